@@ -1,0 +1,254 @@
+/*
+ * lasv_b200.h -- C ABI of the B200-native de Bruijn graph build for laSV.
+ *
+ * One shared library (lasv_b200/liblasv_b200.so) serves MAXK 31/63/95: the
+ * number of 64-bit words per k-mer, N = 2k/64 + 1 (graph_operations.c:620), is
+ * picked at run time from kmer_size where the reference picks it at compile
+ * time (Makefile:8-43).  Plain pointers and sizes only; no torch types.
+ *
+ * Three groups of entry points, each naming the reference interface it stands
+ * in for (paths relative to /root/reference):
+ *
+ *  (A) L-loader drop-ins   : same names and signatures as
+ *        include/dB_graph_operations/file_reader.h:86-118, operating on the
+ *        caller's reference-layout HashTable (include/hash_table/open_hash/
+ *        hash_table.h:40-50).  INTEGRATION.md shows the two-line change that
+ *        makes the reference's own main() (graph_operations.c:746-765) call
+ *        them.
+ *  (B) graph handle        : the hash_table / element / binary_kmer surface
+ *        (hash_table.h:53-86, element.h:89-292) over a device-resident table.
+ *  (C) .ctx wire format    : file_reader.c:2930-2994 (writer), :1652-1715
+ *        (loader), element.c:894-910 (record).
+ *
+ * Error convention: group (A) behaves like the reference -- fatal conditions
+ * print "Error: ..." to stderr and exit(EXIT_FAILURE) (src/basic/global.c:44-63).
+ * Groups (B),(C) return 0 on success or a negative LASV_ERR_* code, with the
+ * message available from lasv_last_error().  There is NO CPU fallback: every
+ * compute entry point fails with LASV_ERR_CUDA if no CUDA device is usable.
+ */
+#ifndef LASV_B200_H_
+#define LASV_B200_H_
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LASV_OK 0
+#define LASV_ERR_ARG (-1)        /* bad argument (k even/out of range, NULL, sizes) */
+#define LASV_ERR_CUDA (-2)       /* CUDA runtime failure, or no device */
+#define LASV_ERR_TABLE_FULL (-3) /* a key met 16 full buckets: hash_table.c:309-317 die() */
+#define LASV_ERR_IO (-4)         /* file could not be opened / parsed */
+#define LASV_ERR_STATE (-5)      /* e.g. inserting into a finalised table */
+#define LASV_ERR_CAPACITY (-6)   /* caller-provided output buffer too small */
+
+typedef struct lasv_graph lasv_graph;
+
+/* Loader bookkeeping, the quantities file_reader.c prints / returns
+ * (file_reader.c:1062-1075) plus the insert counter behind the k-mers/s metric
+ * (= sum of hash_table.c:325 collisions[]). */
+typedef struct {
+  uint64_t n_reads;
+  uint64_t bad_reads;      /* reads with no k consecutive good bases */
+  uint64_t bases_read;     /* all bases seen */
+  uint64_t bases_loaded;   /* sum of contig lengths that entered the graph */
+  uint64_t n_contigs;
+  uint64_t kmers_inserted; /* find_or_insert calls */
+  uint64_t unique_kmers;   /* hash_table_get_unique_kmers */
+} lasv_load_stats;
+
+/* Order-independent digest of the node multiset {(key, coverage, edges)}. */
+typedef struct {
+  uint64_t n_nodes;
+  uint64_t sum_covg;
+  uint64_t sum_edge_bits;
+  uint64_t fingerprint;
+} lasv_table_summary;
+
+/* Reference HashTable layout (hash_table.h:40-50), for the (A) drop-ins. */
+typedef struct {
+  short kmer_size;
+  long long number_buckets;
+  int bucket_size;
+  void *table;             /* Element[number_buckets*bucket_size], element.h:77-82 */
+  short *next_element;
+  long long *collisions;
+  long long unique_kmers;
+  int max_rehash_tries;
+} lasv_ref_hash_table;
+
+const char *lasv_last_error(void);
+int lasv_device_count(void);
+const char *lasv_version(void);
+
+/* ------------------------------------------------------------------ (B) -- */
+/* hash_table_new (hash_table.c:13-53): 2^number_bits buckets x bucket_size
+ * slots of sizeof(Element) = 8N+8 bytes, zeroed, on CUDA device `device`.
+ * Returns NULL on failure (as the reference does on OOM). */
+lasv_graph *lasv_graph_new(int kmer_size, int number_bits, int bucket_size,
+                           int max_rehash_tries, int device);
+/* hash_table_free (hash_table.c:55-62): frees and NULLs the caller's pointer. */
+void lasv_graph_free(lasv_graph **g);
+/* Back to the state right after lasv_graph_new (zero table and counters). */
+int lasv_graph_clear(lasv_graph *g, void *cuda_stream);
+/* hash_table_get_unique_kmers / hash_table_get_capacity (hash_table.c:397-408). */
+long long lasv_graph_unique_kmers(lasv_graph *g);
+long long lasv_graph_capacity(lasv_graph *g);
+int lasv_graph_words_per_kmer(lasv_graph *g);
+size_t lasv_graph_element_bytes(lasv_graph *g);
+/* Device address of the slot array (reference Element layout; pad bytes carry
+ * tags until lasv_graph_finalize). */
+void *lasv_graph_device_table(lasv_graph *g);
+
+/* THE HOT PATH.  One batch of reads as two byte streams (sequence, quality):
+ * reads back to back, every read followed by exactly `1` separator byte '\n'
+ * in BOTH streams; offsets[i] = start of read i, offsets[n_reads] = n_bytes.
+ * Does, for every read: quality/N filter -> k-mers -> canonical key ->
+ * find-or-insert, coverage += 1, edges |= ... (file_reader.c:322-473,589-773).
+ * quality_cutoff is the RAW ASCII cutoff = threshold + offset
+ * (file_reader.c:798,919); qual == NULL means "no quality scores" (FASTA).
+ *
+ * _device: buffers already in HBM, 16-byte aligned, readable up to
+ *   round_up(n_bytes,16); asynchronous on `cuda_stream`; d_offsets may be NULL
+ *   (then the read-level bookkeeping -- bad reads, bases loaded, contig
+ *   histogram -- is skipped; k-mer counters are always kept).
+ * _host:   host buffers (pinned for full speed); copies are chunked and
+ *   overlapped with the kernels; synchronous; returns the batch statistics. */
+int lasv_graph_load_reads_device(lasv_graph *g, const uint8_t *d_seq, const uint8_t *d_qual,
+                                 uint64_t n_bytes, const uint64_t *d_offsets, uint64_t n_reads,
+                                 int quality_cutoff, void *cuda_stream);
+int lasv_graph_load_reads_host(lasv_graph *g, const uint8_t *seq, const uint8_t *qual,
+                               uint64_t n_bytes, const uint64_t *offsets, uint64_t n_reads,
+                               int quality_cutoff, lasv_load_stats *batch_stats);
+/* Cumulative statistics since new/clear (synchronises `cuda_stream`).  Returns
+ * LASV_ERR_TABLE_FULL if any insert overflowed its whole rehash chain.
+ * contig_hist (may be NULL) receives the contig-length histogram,
+ * readlen_count_array of file_reader.c:467-471, hist_size bins. */
+int lasv_graph_stats(lasv_graph *g, lasv_load_stats *out, uint64_t *contig_hist,
+                     uint64_t hist_size, void *cuda_stream);
+/* collisions[r] of hash_table.c:325 (r = 0..15). */
+int lasv_graph_rehash_histogram(lasv_graph *g, long long out16[16]);
+
+/* Hash-sharded build.  A rank's local table has 2^number_bits
+ * buckets; owner(key) = (lookup3(key) >> number_bits) & (n_dest-1).
+ * route: reads -> records binned by owner: d_bins holds n_dest bins of
+ *   bin_capacity records of (2N+1) uint32; d_bin_counts[n_dest] is zeroed by the
+ *   caller and receives the counts (a count above bin_capacity means overflow:
+ *   LASV_ERR_CAPACITY is reported by lasv_graph_stats).
+ * insert_records: the receive side: find-or-insert every record. */
+int lasv_graph_route_reads_device(lasv_graph *g, const uint8_t *d_seq, const uint8_t *d_qual,
+                                  uint64_t n_bytes, int quality_cutoff, int n_dest,
+                                  uint32_t *d_bins, uint64_t bin_capacity,
+                                  unsigned long long *d_bin_counts, void *cuda_stream);
+int lasv_graph_extract_records_device(lasv_graph *g, const uint8_t *d_seq, const uint8_t *d_qual,
+                                      uint64_t n_bytes, int quality_cutoff, uint32_t *d_records,
+                                      uint64_t capacity, unsigned long long *d_count,
+                                      void *cuda_stream);
+int lasv_graph_insert_records_device(lasv_graph *g, const uint32_t *d_records, uint64_t n_records,
+                                     void *cuda_stream);
+int lasv_graph_read_stats_device(lasv_graph *g, const uint8_t *d_seq, const uint8_t *d_qual,
+                                 const uint64_t *d_offsets, uint64_t n_reads, int quality_cutoff,
+                                 void *cuda_stream);
+
+/* hash_table_find (hash_table.c:234-267) for n canonical keys (n x N words,
+ * word 0 most significant).  Host arrays. */
+int lasv_graph_find(lasv_graph *g, const uint64_t *keys, uint64_t n, uint32_t *covg,
+                    uint8_t *edges, uint8_t *found);
+int lasv_graph_summary(lasv_graph *g, lasv_table_summary *out);
+
+/* Squeeze every bucket hole-free and restore pure reference Element bytes: the
+ * device table becomes a valid HashTable->table.  No inserts afterwards. */
+int lasv_graph_finalize(lasv_graph *g);
+/* finalize + copy to host: `elements` receives capacity*element_bytes bytes,
+ * next_element (may be NULL) the per-bucket fill (hash_table.h:46). */
+int lasv_graph_export_table(lasv_graph *g, void *elements, short *next_element);
+/* Merge an existing reference-layout table (e.g. from an earlier CPU load). */
+int lasv_graph_import_table(lasv_graph *g, const void *elements);
+
+/* ------------------------------------------------------------------ (C) -- */
+/* Records in table order, each kmer[N] | uint32 covg | uint8 edges = 8N+5
+ * bytes (element.c:894-910).  Returns the record count, or a negative error. */
+long long lasv_graph_dump_ctx_records(lasv_graph *g, uint8_t *out, uint64_t capacity_records);
+/* db_graph_dump_single_colour_binary_of_colour0 (dB_graph_population.c:3730):
+ * BINVERSION 6 header (file_reader.c:2930-2994) + records. */
+int lasv_graph_write_ctx(lasv_graph *g, const char *path, uint32_t mean_read_len,
+                         uint64_t total_seq);
+int lasv_ctx_header(int kmer_size, uint32_t mean_read_len, uint64_t total_seq, uint8_t *out128);
+/* load_multicolour_binary_from_filename_into_graph (file_reader.c:1652): */
+int lasv_graph_load_ctx_records(lasv_graph *g, const uint8_t *records, uint64_t n_records);
+int lasv_graph_load_ctx_file(lasv_graph *g, const char *path, uint32_t *mean_read_len,
+                             uint64_t *total_seq);
+
+/* Sequence files -> graph.  load_se/pe_seq_data_into_graph_colour
+ * (file_reader.c:475,589): FASTQ / FASTA / plain, optionally gzipped; the
+ * quality cutoff is RAW ASCII here, as in the reference's inner loaders. */
+int lasv_graph_load_se_file(lasv_graph *g, const char *path, int quality_cutoff,
+                            lasv_load_stats *stats);
+int lasv_graph_load_pe_files(lasv_graph *g, const char *path1, const char *path2,
+                             int quality_cutoff, lasv_load_stats *stats);
+/* load_se_filelist / load_pe_filelists (file_reader.c:789,910): qual_thresh +
+ * ascii_fq_offset is the cutoff; paths inside a list are relative to it. */
+int lasv_graph_load_se_filelist(lasv_graph *g, const char *list, int qual_thresh,
+                                int ascii_fq_offset, unsigned int *files_loaded,
+                                lasv_load_stats *stats);
+int lasv_graph_load_pe_filelists(lasv_graph *g, const char *list1, const char *list2,
+                                 int qual_thresh, int ascii_fq_offset, unsigned int *pairs_loaded,
+                                 lasv_load_stats *stats);
+
+/* ------------------------------------------------------------------ (A) -- */
+/* Exact reference signatures (file_reader.h:86-118); `boolean` is signed char
+ * (global.h:37).  They build the graph on the GPU and leave db_graph->table,
+ * next_element, unique_kmers and collisions[] as the reference loader would
+ * (hole-free buckets, reference rehash chain), so every consumer in
+ * src/dB_graph_operations runs unchanged.  Unsupported arguments
+ * (homopol_limit != 0, remove_dups == true, colour lists) die() with a clear
+ * message: laSV never passes them (graph_operations.c:741-765). */
+void load_se_filelist_into_graph_colour(
+    char *se_filelist_path, int qual_thresh, int homopol_limit, signed char remove_dups_se,
+    char ascii_fq_offset, int colour, lasv_ref_hash_table *db_graph, char is_colour_list,
+    unsigned int *total_files_loaded, unsigned long long *total_bad_reads,
+    unsigned long long *total_dup_reads, unsigned long long *total_bases_read,
+    unsigned long long *total_bases_loaded, unsigned long *readlen_count_array,
+    unsigned long readlen_count_array_size);
+void load_pe_filelists_into_graph_colour(
+    char *pe_filelist_path1, char *pe_filelist_path2, int qual_thresh, int homopol_limit,
+    signed char remove_dups_pe, char ascii_fq_offset, int colour, lasv_ref_hash_table *db_graph,
+    char is_colour_lists, unsigned int *total_file_pairs_loaded,
+    unsigned long long *total_bad_reads, unsigned long long *total_dup_reads,
+    unsigned long long *total_bases_read, unsigned long long *total_bases_loaded,
+    unsigned long *readlen_count_array, unsigned long readlen_count_array_size);
+
+/* ------------------------------------------------- bench / test utilities -- */
+typedef struct {
+  uint64_t seed;
+  uint64_t genome_len;
+  uint32_t read_len;
+  uint32_t insert;
+  uint32_t err_q20;      /* probabilities are scaled by 2^20 */
+  uint32_t n_q20;
+  uint32_t lowq_q20;
+  uint32_t err_lowq_pct;
+  uint32_t tail_min;
+  uint32_t tail_max;
+  uint32_t tiling;
+  uint32_t tiling_step;
+} lasv_synth_params;
+/* Deterministic synthetic reads, stride read_len+1 ('\n' after every read).
+ * The host and device versions produce identical bytes. */
+int lasv_synth_reads_device(const lasv_synth_params *p, uint64_t first_read, uint64_t n_reads,
+                            uint8_t *d_seq, uint8_t *d_qual, void *cuda_stream);
+int lasv_synth_reads_host(const lasv_synth_params *p, uint64_t first_read, uint64_t n_reads,
+                          uint8_t *seq, uint8_t *qual);
+/* n_ops uniform random 32-byte read-modify-writes over n_sectors sectors: the
+ * random-access HBM ceiling quoted next to the roofline. */
+int lasv_random_access_probe(void *d_buf, uint64_t n_sectors, uint64_t n_ops, uint64_t seed,
+                             void *cuda_stream);
+/* Number of kernels this library has launched since load (bench gpu_launches). */
+uint64_t lasv_kernel_launches(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LASV_B200_H_ */

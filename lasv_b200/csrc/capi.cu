@@ -1,0 +1,1071 @@
+// capi.cu -- host runtime behind include/lasv_b200.h: graph handle, chunked
+// host->device pipeline, sequence-file loaders, .ctx reader/writer and the
+// reference-named drop-in loaders.  All compute is in graph_kernels.cu; there
+// is no CPU implementation of any of it here.
+#include <cuda_runtime.h>
+#include <errno.h>
+#include <libgen.h>
+#include <limits.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <atomic>
+#include <string>
+#include <vector>
+
+#include "../../include/lasv_b200.h"
+#include "graph_kernels.cuh"
+#include "seq_reader.h"
+
+using namespace lasv;
+
+namespace {
+
+thread_local std::string g_err;
+std::atomic<uint64_t> g_launches{0};
+
+int fail(int code, const char *fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+
+#define CUDA_TRY(expr)                                                                      \
+  do {                                                                                      \
+    cudaError_t e__ = (expr);                                                               \
+    if (e__ != cudaSuccess)                                                                 \
+      return fail(LASV_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__),   \
+                  __FILE__, __LINE__);                                                      \
+  } while (0)
+
+const char *TABLE_FULL_MSG =
+    "Dear user - you have not allocated enough memory to contain your sequence data. Either "
+    "allocate more memory (have you done your calculations right? have you allowed for sequencing "
+    "errors?), or threshold more harshly on quality score, and try again. Aborting mission.";
+
+constexpr uint32_t HIST_BINS = 1u << 16;       // device contig-length histogram (last bin = longer)
+constexpr uint64_t CHUNK_BYTES = 64ull << 20;  // host->device pipeline granularity
+constexpr uint64_t CHUNK_READS = 4ull << 20;
+
+struct Staging {  // one leg of the double-buffered host->device pipeline
+  uint8_t *d_seq = nullptr, *d_qual = nullptr;
+  uint64_t *d_offsets = nullptr;
+  cudaEvent_t copied = nullptr, consumed = nullptr;
+  std::vector<uint64_t> h_offsets;
+};
+
+}  // namespace
+
+struct lasv_graph {
+  int k = 0, N = 0, L = 0, W = 0, max_rehash = 15, device = 0;
+  uint64_t n_buckets = 0, n_slots = 0;
+  size_t slot_bytes = 0;
+  uint8_t *d_slots = nullptr;
+  GraphCounters *d_ctr = nullptr;
+  ReadStats *d_stats = nullptr;
+  unsigned long long *d_hist = nullptr;
+  unsigned long long *d_overflow = nullptr;
+  bool finalized = false;
+  cudaStream_t compute = nullptr, copy = nullptr;
+  Staging stage[2];
+  bool staging_ready = false;
+
+  TableView view() const {
+    TableView t;
+    t.slots = d_slots;
+    t.bucket_mask = (uint32_t)(n_buckets - 1);
+    t.W = (uint32_t)W;
+    t.max_rehash = (uint32_t)max_rehash;
+    return t;
+  }
+};
+
+namespace {
+
+int use(lasv_graph *g) {
+  if (!g) return fail(LASV_ERR_ARG, "NULL graph");
+  CUDA_TRY(cudaSetDevice(g->device));
+  return LASV_OK;
+}
+
+cudaStream_t stream_of(lasv_graph *g, void *s) { return s ? (cudaStream_t)s : g->compute; }
+
+int ensure_staging(lasv_graph *g) {
+  if (g->staging_ready) return LASV_OK;
+  for (auto &s : g->stage) {
+    CUDA_TRY(cudaMalloc(&s.d_seq, CHUNK_BYTES + 256));
+    CUDA_TRY(cudaMalloc(&s.d_qual, CHUNK_BYTES + 256));
+    CUDA_TRY(cudaMalloc(&s.d_offsets, (CHUNK_READS + 1) * sizeof(uint64_t)));
+    CUDA_TRY(cudaEventCreateWithFlags(&s.copied, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&s.consumed, cudaEventDisableTiming));
+  }
+  g->staging_ready = true;
+  return LASV_OK;
+}
+
+void fill_stats(lasv_load_stats *o, const ReadStats &rs, const GraphCounters &c) {
+  o->n_reads = rs.n_reads;
+  o->bad_reads = rs.bad_reads;
+  o->bases_read = rs.bases_read;
+  o->bases_loaded = rs.bases_loaded;
+  o->n_contigs = rs.n_contigs;
+  o->kmers_inserted = c.kmers_inserted;
+  o->unique_kmers = c.unique_kmers;
+}
+
+int fetch_counters(lasv_graph *g, cudaStream_t st, ReadStats *rs, GraphCounters *c,
+                   unsigned long long *overflow) {
+  CUDA_TRY(cudaMemcpyAsync(rs, g->d_stats, sizeof *rs, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(c, g->d_ctr, sizeof *c, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(overflow, g->d_overflow, sizeof *overflow, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  return LASV_OK;
+}
+
+BuildParams build_params(lasv_graph *g, const uint8_t *d_seq, const uint8_t *d_qual,
+                         uint64_t n_bytes, int cutoff) {
+  BuildParams p;
+  memset(&p, 0, sizeof p);
+  p.seq = d_seq;
+  p.qual = d_qual;
+  p.n_bytes = n_bytes;
+  p.k = g->k;
+  p.cutoff = cutoff;
+  p.table = g->view();
+  p.ctr = g->d_ctr;
+  p.rec_overflow = g->d_overflow;
+  p.n_dest = 1;
+  p.owner_shift = g->L;
+  return p;
+}
+
+int check_launch() {
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  CUDA_TRY(cudaGetLastError());
+  return LASV_OK;
+}
+
+int check_aligned(const void *p, const char *what) {
+  if (((uintptr_t)p & 15u) != 0) return fail(LASV_ERR_ARG, "%s must be 16-byte aligned", what);
+  return LASV_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *lasv_last_error(void) { return g_err.c_str(); }
+const char *lasv_version(void) { return "lasv_b200 0.1 (sm_100a)"; }
+uint64_t lasv_kernel_launches(void) { return g_launches.load(); }
+
+int lasv_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+lasv_graph *lasv_graph_new(int kmer_size, int number_bits, int bucket_size, int max_rehash_tries,
+                           int device) {
+  if (kmer_size < 1 || kmer_size > 95 || (kmer_size & 1) == 0) {
+    fail(LASV_ERR_ARG, "kmer_size must be odd and in [1,95] (cmd_line.c:805; MAXK 31/63/95), got %d",
+         kmer_size);
+    return nullptr;
+  }
+  if (number_bits < 1 || number_bits > 31 || bucket_size < 1 || bucket_size > 32767 ||
+      max_rehash_tries < 0 || max_rehash_tries > 15) {
+    fail(LASV_ERR_ARG, "bad table geometry: number_bits=%d bucket_size=%d max_rehash_tries=%d",
+         number_bits, bucket_size, max_rehash_tries);
+    return nullptr;
+  }
+  if (lasv_device_count() <= device || device < 0) {
+    fail(LASV_ERR_CUDA, "no usable CUDA device %d (this library has no CPU fallback)", device);
+    return nullptr;
+  }
+  lasv_graph *g = new lasv_graph();
+  g->k = kmer_size;
+  g->N = (2 * kmer_size) / 64 + 1;  // graph_operations.c:620
+  g->L = number_bits;
+  g->W = bucket_size;
+  g->max_rehash = max_rehash_tries;
+  g->device = device;
+  g->n_buckets = 1ull << number_bits;
+  g->n_slots = g->n_buckets * (uint64_t)bucket_size;
+  g->slot_bytes = 8 * (size_t)g->N + 8;
+  bool ok = cudaSetDevice(device) == cudaSuccess &&
+            cudaMalloc(&g->d_slots, g->n_slots * g->slot_bytes) == cudaSuccess &&
+            cudaMalloc(&g->d_ctr, sizeof(GraphCounters)) == cudaSuccess &&
+            cudaMalloc(&g->d_stats, sizeof(ReadStats)) == cudaSuccess &&
+            cudaMalloc(&g->d_hist, HIST_BINS * sizeof(unsigned long long)) == cudaSuccess &&
+            cudaMalloc(&g->d_overflow, sizeof(unsigned long long)) == cudaSuccess &&
+            cudaStreamCreateWithFlags(&g->compute, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaStreamCreateWithFlags(&g->copy, cudaStreamNonBlocking) == cudaSuccess;
+  if (ok) ok = lasv_graph_clear(g, nullptr) == LASV_OK && cudaStreamSynchronize(g->compute) == cudaSuccess;
+  if (!ok) {
+    if (g_err.empty() || g_err.find("failed") == std::string::npos)
+      fail(LASV_ERR_CUDA, "could not allocate hash table of size %llu: %s",
+           (unsigned long long)g->n_slots, cudaGetErrorString(cudaGetLastError()));
+    lasv_graph_free(&g);
+    return nullptr;
+  }
+  return g;
+}
+
+void lasv_graph_free(lasv_graph **gp) {
+  if (!gp || !*gp) return;
+  lasv_graph *g = *gp;
+  cudaSetDevice(g->device);
+  cudaDeviceSynchronize();
+  cudaFree(g->d_slots);
+  cudaFree(g->d_ctr);
+  cudaFree(g->d_stats);
+  cudaFree(g->d_hist);
+  cudaFree(g->d_overflow);
+  for (auto &s : g->stage) {
+    cudaFree(s.d_seq);
+    cudaFree(s.d_qual);
+    cudaFree(s.d_offsets);
+    if (s.copied) cudaEventDestroy(s.copied);
+    if (s.consumed) cudaEventDestroy(s.consumed);
+  }
+  if (g->compute) cudaStreamDestroy(g->compute);
+  if (g->copy) cudaStreamDestroy(g->copy);
+  delete g;
+  *gp = nullptr;
+}
+
+int lasv_graph_clear(lasv_graph *g, void *cuda_stream) {
+  if (int e = use(g)) return e;
+  cudaStream_t st = stream_of(g, cuda_stream);
+  CUDA_TRY(cudaMemsetAsync(g->d_slots, 0, g->n_slots * g->slot_bytes, st));
+  CUDA_TRY(cudaMemsetAsync(g->d_ctr, 0, sizeof(GraphCounters), st));
+  CUDA_TRY(cudaMemsetAsync(g->d_stats, 0, sizeof(ReadStats), st));
+  CUDA_TRY(cudaMemsetAsync(g->d_hist, 0, HIST_BINS * sizeof(unsigned long long), st));
+  CUDA_TRY(cudaMemsetAsync(g->d_overflow, 0, sizeof(unsigned long long), st));
+  g->finalized = false;
+  return LASV_OK;
+}
+
+long long lasv_graph_unique_kmers(lasv_graph *g) {
+  if (use(g)) return -1;
+  unsigned long long v = 0;
+  if (cudaMemcpy(&v, &g->d_ctr->unique_kmers, sizeof v, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+  return (long long)v;
+}
+
+long long lasv_graph_capacity(lasv_graph *g) { return g ? (long long)g->n_slots : -1; }
+int lasv_graph_words_per_kmer(lasv_graph *g) { return g ? g->N : -1; }
+size_t lasv_graph_element_bytes(lasv_graph *g) { return g ? g->slot_bytes : 0; }
+void *lasv_graph_device_table(lasv_graph *g) { return g ? g->d_slots : nullptr; }
+
+// ------------------------------------------------------------- the hot path
+int lasv_graph_load_reads_device(lasv_graph *g, const uint8_t *d_seq, const uint8_t *d_qual,
+                                 uint64_t n_bytes, const uint64_t *d_offsets, uint64_t n_reads,
+                                 int quality_cutoff, void *cuda_stream) {
+  if (int e = use(g)) return e;
+  if (g->finalized) return fail(LASV_ERR_STATE, "graph is finalised; no further inserts");
+  if (int e = check_aligned(d_seq, "d_seq")) return e;
+  if (d_qual) if (int e = check_aligned(d_qual, "d_qual")) return e;
+  cudaStream_t st = stream_of(g, cuda_stream);
+  if (n_bytes) {
+    launch_build(g->N, MODE_FUSED, build_params(g, d_seq, d_qual, n_bytes, quality_cutoff), st);
+    if (int e = check_launch()) return e;
+  }
+  if (d_offsets && n_reads) {
+    launch_read_stats(d_seq, d_qual, d_offsets, n_reads, 1, g->k, quality_cutoff, g->d_stats,
+                      g->d_hist, HIST_BINS, st);
+    if (int e = check_launch()) return e;
+  }
+  return LASV_OK;
+}
+
+int lasv_graph_read_stats_device(lasv_graph *g, const uint8_t *d_seq, const uint8_t *d_qual,
+                                 const uint64_t *d_offsets, uint64_t n_reads, int quality_cutoff,
+                                 void *cuda_stream) {
+  if (int e = use(g)) return e;
+  if (!n_reads) return LASV_OK;
+  launch_read_stats(d_seq, d_qual, d_offsets, n_reads, 1, g->k, quality_cutoff, g->d_stats,
+                    g->d_hist, HIST_BINS, stream_of(g, cuda_stream));
+  return check_launch();
+}
+
+int lasv_graph_load_reads_host(lasv_graph *g, const uint8_t *seq, const uint8_t *qual,
+                               uint64_t n_bytes, const uint64_t *offsets, uint64_t n_reads,
+                               int quality_cutoff, lasv_load_stats *batch_stats) {
+  if (int e = use(g)) return e;
+  if (g->finalized) return fail(LASV_ERR_STATE, "graph is finalised; no further inserts");
+  if (!seq || !offsets) return fail(LASV_ERR_ARG, "seq and offsets are required");
+  if (offsets[n_reads] != n_bytes) return fail(LASV_ERR_ARG, "offsets[n_reads] != n_bytes");
+  if (int e = ensure_staging(g)) return e;
+
+  ReadStats rs0, rs1;
+  GraphCounters c0, c1;
+  unsigned long long ov = 0;
+  if (batch_stats) if (int e = fetch_counters(g, g->compute, &rs0, &c0, &ov)) return e;
+
+  // chunks are cut at read boundaries, so no k-mer window straddles two chunks
+  uint64_t r0 = 0;
+  int leg = 0;
+  while (r0 < n_reads) {
+    uint64_t r1 = r0;
+    const uint64_t base = offsets[r0];
+    // largest r1 with offsets[r1]-base <= CHUNK_BYTES and r1-r0 <= CHUNK_READS
+    {
+      uint64_t lo = r0 + 1, hi = std::min(n_reads, r0 + CHUNK_READS);
+      if (offsets[lo] - base > CHUNK_BYTES)
+        return fail(LASV_ERR_ARG, "read %llu is longer than the %llu-byte pipeline chunk",
+                    (unsigned long long)r0, (unsigned long long)CHUNK_BYTES);
+      while (lo < hi) {
+        const uint64_t mid = (lo + hi + 1) / 2;
+        if (offsets[mid] - base <= CHUNK_BYTES) lo = mid;
+        else hi = mid - 1;
+      }
+      r1 = lo;
+    }
+    const uint64_t bytes = offsets[r1] - base, nr = r1 - r0;
+    Staging &s = g->stage[leg];
+    CUDA_TRY(cudaEventSynchronize(s.consumed));  // the kernels that read this leg are done
+    s.h_offsets.resize(nr + 1);
+    for (uint64_t i = 0; i <= nr; i++) s.h_offsets[i] = offsets[r0 + i] - base;
+    CUDA_TRY(cudaMemcpyAsync(s.d_seq, seq + base, bytes, cudaMemcpyHostToDevice, g->copy));
+    if (qual) CUDA_TRY(cudaMemcpyAsync(s.d_qual, qual + base, bytes, cudaMemcpyHostToDevice, g->copy));
+    CUDA_TRY(cudaMemcpyAsync(s.d_offsets, s.h_offsets.data(), (nr + 1) * sizeof(uint64_t),
+                             cudaMemcpyHostToDevice, g->copy));
+    CUDA_TRY(cudaEventRecord(s.copied, g->copy));
+    CUDA_TRY(cudaStreamWaitEvent(g->compute, s.copied, 0));
+    if (int e = lasv_graph_load_reads_device(g, s.d_seq, qual ? s.d_qual : nullptr, bytes,
+                                             s.d_offsets, nr, quality_cutoff, g->compute))
+      return e;
+    CUDA_TRY(cudaEventRecord(s.consumed, g->compute));
+    // h_offsets of this leg must stay alive until its copy completed: the next
+    // use of the leg waits on `consumed`, which is ordered after `copied`.
+    leg ^= 1;
+    r0 = r1;
+  }
+  if (int e = fetch_counters(g, g->compute, &rs1, &c1, &ov)) return e;
+  if (c1.table_full) return fail(LASV_ERR_TABLE_FULL, "%s", TABLE_FULL_MSG);
+  if (batch_stats) {
+    ReadStats d;
+    d.n_reads = rs1.n_reads - rs0.n_reads;
+    d.bad_reads = rs1.bad_reads - rs0.bad_reads;
+    d.bases_read = rs1.bases_read - rs0.bases_read;
+    d.bases_loaded = rs1.bases_loaded - rs0.bases_loaded;
+    d.n_contigs = rs1.n_contigs - rs0.n_contigs;
+    GraphCounters dc = c1;
+    dc.kmers_inserted = c1.kmers_inserted - c0.kmers_inserted;
+    fill_stats(batch_stats, d, dc);
+  }
+  return LASV_OK;
+}
+
+int lasv_graph_stats(lasv_graph *g, lasv_load_stats *out, uint64_t *contig_hist, uint64_t hist_size,
+                     void *cuda_stream) {
+  if (int e = use(g)) return e;
+  cudaStream_t st = stream_of(g, cuda_stream);
+  ReadStats rs;
+  GraphCounters c;
+  unsigned long long ov = 0;
+  if (int e = fetch_counters(g, st, &rs, &c, &ov)) return e;
+  if (out) fill_stats(out, rs, c);
+  if (contig_hist && hist_size) {
+    std::vector<unsigned long long> h(HIST_BINS);
+    CUDA_TRY(cudaMemcpy(h.data(), g->d_hist, HIST_BINS * sizeof(unsigned long long),
+                        cudaMemcpyDeviceToHost));
+    for (uint64_t i = 0; i < hist_size; i++) contig_hist[i] = 0;
+    for (uint32_t i = 0; i < HIST_BINS; i++) {
+      if (!h[i]) continue;
+      const uint64_t b = std::min<uint64_t>(i, hist_size - 1);  // file_reader.c:469
+      contig_hist[b] += h[i];
+    }
+  }
+  if (c.table_full) return fail(LASV_ERR_TABLE_FULL, "%s", TABLE_FULL_MSG);
+  if (ov) return fail(LASV_ERR_CAPACITY, "record buffer / exchange bin overflow");
+  return LASV_OK;
+}
+
+int lasv_graph_rehash_histogram(lasv_graph *g, long long out16[16]) {
+  if (int e = use(g)) return e;
+  GraphCounters c;
+  CUDA_TRY(cudaMemcpy(&c, g->d_ctr, sizeof c, cudaMemcpyDeviceToHost));
+  unsigned long long later = 0;
+  for (int r = 1; r < 16; r++) {
+    out16[r] = (long long)c.rehash_hist[r];
+    later += c.rehash_hist[r];
+  }
+  out16[0] = (long long)(c.kmers_inserted - later);
+  return LASV_OK;
+}
+
+// ---------------------------------------------------------- sharded pieces
+int lasv_graph_route_reads_device(lasv_graph *g, const uint8_t *d_seq, const uint8_t *d_qual,
+                                  uint64_t n_bytes, int quality_cutoff, int n_dest, uint32_t *d_bins,
+                                  uint64_t bin_capacity, unsigned long long *d_bin_counts,
+                                  void *cuda_stream) {
+  if (int e = use(g)) return e;
+  if (n_dest < 1 || n_dest > 16 || (n_dest & (n_dest - 1)))
+    return fail(LASV_ERR_ARG, "n_dest must be a power of two <= 16, got %d", n_dest);
+  if (int e = check_aligned(d_seq, "d_seq")) return e;
+  if (!n_bytes) return LASV_OK;
+  BuildParams p = build_params(g, d_seq, d_qual, n_bytes, quality_cutoff);
+  p.rec_out = d_bins;
+  p.rec_count = d_bin_counts;
+  p.rec_capacity = bin_capacity;
+  p.n_dest = n_dest;
+  p.owner_shift = g->L;
+  launch_build(g->N, MODE_ROUTE, p, stream_of(g, cuda_stream));
+  return check_launch();
+}
+
+int lasv_graph_extract_records_device(lasv_graph *g, const uint8_t *d_seq, const uint8_t *d_qual,
+                                      uint64_t n_bytes, int quality_cutoff, uint32_t *d_records,
+                                      uint64_t capacity, unsigned long long *d_count,
+                                      void *cuda_stream) {
+  if (int e = use(g)) return e;
+  if (int e = check_aligned(d_seq, "d_seq")) return e;
+  if (!n_bytes) return LASV_OK;
+  BuildParams p = build_params(g, d_seq, d_qual, n_bytes, quality_cutoff);
+  p.rec_out = d_records;
+  p.rec_count = d_count;
+  p.rec_capacity = capacity;
+  launch_build(g->N, MODE_RECORDS, p, stream_of(g, cuda_stream));
+  return check_launch();
+}
+
+int lasv_graph_insert_records_device(lasv_graph *g, const uint32_t *d_records, uint64_t n_records,
+                                     void *cuda_stream) {
+  if (int e = use(g)) return e;
+  if (g->finalized) return fail(LASV_ERR_STATE, "graph is finalised; no further inserts");
+  if (!n_records) return LASV_OK;
+  launch_insert_records(g->N, d_records, n_records, g->view(), g->d_ctr, stream_of(g, cuda_stream));
+  return check_launch();
+}
+
+// ------------------------------------------------------------------ queries
+int lasv_graph_find(lasv_graph *g, const uint64_t *keys, uint64_t n, uint32_t *covg, uint8_t *edges,
+                    uint8_t *found) {
+  if (int e = use(g)) return e;
+  if (!n) return LASV_OK;
+  uint64_t *d_keys = nullptr;
+  uint32_t *d_covg = nullptr;
+  uint8_t *d_edges = nullptr, *d_found = nullptr;
+  int rc = LASV_OK;
+  auto body = [&]() -> int {
+    CUDA_TRY(cudaMalloc(&d_keys, n * g->N * 8));
+    CUDA_TRY(cudaMalloc(&d_covg, n * 4));
+    CUDA_TRY(cudaMalloc(&d_edges, n));
+    CUDA_TRY(cudaMalloc(&d_found, n));
+    CUDA_TRY(cudaMemcpyAsync(d_keys, keys, n * g->N * 8, cudaMemcpyHostToDevice, g->compute));
+    launch_find(g->N, g->view(), d_keys, n, g->finalized ? 1 : 0, d_covg, d_edges, d_found, g->compute);
+    if (int e = check_launch()) return e;
+    CUDA_TRY(cudaMemcpyAsync(covg, d_covg, n * 4, cudaMemcpyDeviceToHost, g->compute));
+    CUDA_TRY(cudaMemcpyAsync(edges, d_edges, n, cudaMemcpyDeviceToHost, g->compute));
+    CUDA_TRY(cudaMemcpyAsync(found, d_found, n, cudaMemcpyDeviceToHost, g->compute));
+    CUDA_TRY(cudaStreamSynchronize(g->compute));
+    return LASV_OK;
+  };
+  rc = body();
+  cudaFree(d_keys); cudaFree(d_covg); cudaFree(d_edges); cudaFree(d_found);
+  return rc;
+}
+
+int lasv_graph_summary(lasv_graph *g, lasv_table_summary *out) {
+  if (int e = use(g)) return e;
+  TableSummary *d = nullptr;
+  CUDA_TRY(cudaMalloc(&d, sizeof(TableSummary)));
+  int rc = [&]() -> int {
+    CUDA_TRY(cudaMemsetAsync(d, 0, sizeof(TableSummary), g->compute));
+    launch_table_summary(g->N, g->view(), d, g->compute);
+    if (int e = check_launch()) return e;
+    TableSummary h;
+    CUDA_TRY(cudaMemcpyAsync(&h, d, sizeof h, cudaMemcpyDeviceToHost, g->compute));
+    CUDA_TRY(cudaStreamSynchronize(g->compute));
+    out->n_nodes = h.n_nodes;
+    out->sum_covg = h.sum_covg;
+    out->sum_edge_bits = h.sum_edge_bits;
+    out->fingerprint = h.fingerprint;
+    return LASV_OK;
+  }();
+  cudaFree(d);
+  return rc;
+}
+
+static int finalize_impl(lasv_graph *g, int16_t *d_next) {
+  launch_finalize(g->N, g->view(), d_next, g->compute);
+  if (int e = check_launch()) return e;
+  CUDA_TRY(cudaStreamSynchronize(g->compute));
+  g->finalized = true;
+  return LASV_OK;
+}
+
+int lasv_graph_finalize(lasv_graph *g) {
+  if (int e = use(g)) return e;
+  CUDA_TRY(cudaDeviceSynchronize());
+  return finalize_impl(g, nullptr);
+}
+
+int lasv_graph_export_table(lasv_graph *g, void *elements, short *next_element) {
+  if (int e = use(g)) return e;
+  if (!elements) return fail(LASV_ERR_ARG, "elements is NULL");
+  CUDA_TRY(cudaDeviceSynchronize());
+  int16_t *d_next = nullptr;
+  CUDA_TRY(cudaMalloc(&d_next, g->n_buckets * sizeof(int16_t)));
+  int rc = [&]() -> int {
+    if (int e = finalize_impl(g, d_next)) return e;
+    CUDA_TRY(cudaMemcpy(elements, g->d_slots, g->n_slots * g->slot_bytes, cudaMemcpyDeviceToHost));
+    if (next_element)
+      CUDA_TRY(cudaMemcpy(next_element, d_next, g->n_buckets * sizeof(int16_t), cudaMemcpyDeviceToHost));
+    return LASV_OK;
+  }();
+  cudaFree(d_next);
+  return rc;
+}
+
+int lasv_graph_import_table(lasv_graph *g, const void *elements) {
+  if (int e = use(g)) return e;
+  if (g->finalized) return fail(LASV_ERR_STATE, "graph is finalised; no further inserts");
+  // stream the host table through a bounded device buffer, whole slots at a time
+  const uint64_t slots_per_chunk = std::max<uint64_t>(1, (256ull << 20) / g->slot_bytes);
+  uint8_t *d_buf = nullptr;
+  CUDA_TRY(cudaMalloc(&d_buf, slots_per_chunk * g->slot_bytes));
+  int rc = [&]() -> int {
+    for (uint64_t s0 = 0; s0 < g->n_slots; s0 += slots_per_chunk) {
+      const uint64_t ns = std::min(slots_per_chunk, g->n_slots - s0);
+      CUDA_TRY(cudaMemcpyAsync(d_buf, (const uint8_t *)elements + s0 * g->slot_bytes,
+                               ns * g->slot_bytes, cudaMemcpyHostToDevice, g->compute));
+      launch_ingest_elements(g->N, d_buf, ns, g->view(), g->d_ctr, g->compute);
+      if (int e = check_launch()) return e;
+      CUDA_TRY(cudaStreamSynchronize(g->compute));
+    }
+    return LASV_OK;
+  }();
+  cudaFree(d_buf);
+  return rc;
+}
+
+// ------------------------------------------------------------ .ctx records
+static int dump_records_device(lasv_graph *g, uint8_t **d_out, uint64_t *n_out) {
+  uint32_t *d_counts = nullptr;
+  uint64_t *d_offsets = nullptr;
+  void *d_tmp = nullptr;
+  *d_out = nullptr;
+  const size_t tmp_bytes = exclusive_scan_tmp_bytes(g->n_buckets);
+  int rc = [&]() -> int {
+    CUDA_TRY(cudaMalloc(&d_counts, g->n_buckets * 4));
+    CUDA_TRY(cudaMalloc(&d_offsets, g->n_buckets * 8));
+    CUDA_TRY(cudaMalloc(&d_tmp, tmp_bytes));
+    launch_bucket_counts(g->N, g->view(), d_counts, g->compute);
+    if (int e = check_launch()) return e;
+    launch_exclusive_scan_u32_to_u64(d_counts, d_offsets, g->n_buckets, d_tmp, tmp_bytes, g->compute);
+    if (int e = check_launch()) return e;
+    uint64_t last_off = 0;
+    uint32_t last_cnt = 0;
+    CUDA_TRY(cudaMemcpyAsync(&last_off, d_offsets + g->n_buckets - 1, 8, cudaMemcpyDeviceToHost, g->compute));
+    CUDA_TRY(cudaMemcpyAsync(&last_cnt, d_counts + g->n_buckets - 1, 4, cudaMemcpyDeviceToHost, g->compute));
+    CUDA_TRY(cudaStreamSynchronize(g->compute));
+    *n_out = last_off + last_cnt;
+    const size_t rec = 8 * (size_t)g->N + 5;
+    CUDA_TRY(cudaMalloc(d_out, std::max<size_t>(16, *n_out * rec)));
+    launch_dump_ctx(g->N, g->view(), d_offsets, *d_out, g->compute);
+    if (int e = check_launch()) return e;
+    CUDA_TRY(cudaStreamSynchronize(g->compute));
+    return LASV_OK;
+  }();
+  cudaFree(d_counts); cudaFree(d_offsets); cudaFree(d_tmp);
+  if (rc != LASV_OK && *d_out) { cudaFree(*d_out); *d_out = nullptr; }
+  return rc;
+}
+
+long long lasv_graph_dump_ctx_records(lasv_graph *g, uint8_t *out, uint64_t capacity_records) {
+  if (int e = use(g)) return e;
+  CUDA_TRY(cudaDeviceSynchronize());
+  uint8_t *d_out = nullptr;
+  uint64_t n = 0;
+  if (int e = dump_records_device(g, &d_out, &n)) return e;
+  int rc = LASV_OK;
+  if (n > capacity_records) rc = fail(LASV_ERR_CAPACITY, "need room for %llu records, have %llu",
+                                      (unsigned long long)n, (unsigned long long)capacity_records);
+  else if (n && cudaMemcpy(out, d_out, n * (8 * (size_t)g->N + 5), cudaMemcpyDeviceToHost) != cudaSuccess)
+    rc = fail(LASV_ERR_CUDA, "copy of .ctx records to host failed");
+  cudaFree(d_out);
+  return rc == LASV_OK ? (long long)n : rc;
+}
+
+int lasv_ctx_header(int kmer_size, uint32_t mean_read_len, uint64_t total_seq, uint8_t *out) {
+  // print_binary_signature_NEW, file_reader.c:2930-2994, one colour, default
+  // GraphInfo (graph_info.c): sample id "undefined", seq_err 0.01, no cleaning.
+  uint8_t *p = out;
+  auto put = [&](const void *src, size_t n) { memcpy(p, src, n); p += n; };
+  int32_t v;
+  put("CORTEX", 6);
+  v = 6; put(&v, 4);
+  v = kmer_size; put(&v, 4);
+  v = (2 * kmer_size) / 64 + 1; put(&v, 4);
+  v = 1; put(&v, 4);
+  v = (int32_t)mean_read_len; put(&v, 4);
+  long long ts = (long long)total_seq; put(&ts, 8);
+  v = 9; put(&v, 4); put("undefined", 9);
+  uint8_t ld[16];
+  memset(ld, 0, sizeof ld);
+  long double err = 0.01L;
+  memcpy(ld, &err, 10);  // x87 extended: 10 significant bytes of the 16 stored
+  put(ld, 16);
+  uint8_t flags[4] = {0, 0, 0, 0};
+  put(flags, 4);
+  v = -1; put(&v, 4);
+  v = -1; put(&v, 4);
+  v = 9; put(&v, 4); put("undefined", 9);
+  put("CORTEX", 6);
+  return (int)(p - out);
+}
+
+int lasv_graph_write_ctx(lasv_graph *g, const char *path, uint32_t mean_read_len, uint64_t total_seq) {
+  if (int e = use(g)) return e;
+  CUDA_TRY(cudaDeviceSynchronize());
+  uint8_t *d_out = nullptr;
+  uint64_t n = 0;
+  if (int e = dump_records_device(g, &d_out, &n)) return e;
+  FILE *fp = fopen(path, "wb");
+  if (!fp) {
+    cudaFree(d_out);
+    return fail(LASV_ERR_IO, "cannot open %s for writing: %s", path, strerror(errno));
+  }
+  uint8_t hdr[128];
+  const int hl = lasv_ctx_header(g->k, mean_read_len, total_seq, hdr);
+  int rc = LASV_OK;
+  if (fwrite(hdr, 1, (size_t)hl, fp) != (size_t)hl) rc = fail(LASV_ERR_IO, "short write to %s", path);
+  const size_t rec = 8 * (size_t)g->N + 5;
+  const uint64_t per = (64ull << 20) / rec;
+  std::vector<uint8_t> host(per * rec);
+  for (uint64_t i = 0; i < n && rc == LASV_OK; i += per) {
+    const uint64_t m = std::min(per, n - i);
+    if (cudaMemcpy(host.data(), d_out + i * rec, m * rec, cudaMemcpyDeviceToHost) != cudaSuccess)
+      rc = fail(LASV_ERR_CUDA, "copy of .ctx records to host failed");
+    else if (fwrite(host.data(), rec, m, fp) != m) rc = fail(LASV_ERR_IO, "short write to %s", path);
+  }
+  fclose(fp);
+  cudaFree(d_out);
+  return rc;
+}
+
+int lasv_graph_load_ctx_records(lasv_graph *g, const uint8_t *records, uint64_t n_records) {
+  if (int e = use(g)) return e;
+  if (g->finalized) return fail(LASV_ERR_STATE, "graph is finalised; no further inserts");
+  const size_t rec = 8 * (size_t)g->N + 5;
+  const uint64_t per = (256ull << 20) / rec;
+  uint8_t *d_buf = nullptr;
+  CUDA_TRY(cudaMalloc(&d_buf, std::max<uint64_t>(1, std::min(per, n_records)) * rec));
+  int rc = [&]() -> int {
+    for (uint64_t i = 0; i < n_records; i += per) {
+      const uint64_t m = std::min(per, n_records - i);
+      CUDA_TRY(cudaMemcpyAsync(d_buf, records + i * rec, m * rec, cudaMemcpyHostToDevice, g->compute));
+      launch_ingest_ctx(g->N, d_buf, m, g->view(), g->d_ctr, g->compute);
+      if (int e = check_launch()) return e;
+      CUDA_TRY(cudaStreamSynchronize(g->compute));
+    }
+    GraphCounters c;
+    CUDA_TRY(cudaMemcpy(&c, g->d_ctr, sizeof c, cudaMemcpyDeviceToHost));
+    if (c.table_full) return fail(LASV_ERR_TABLE_FULL, "%s", TABLE_FULL_MSG);
+    return LASV_OK;
+  }();
+  cudaFree(d_buf);
+  return rc;
+}
+
+int lasv_graph_load_ctx_file(lasv_graph *g, const char *path, uint32_t *mean_read_len,
+                             uint64_t *total_seq) {
+  if (int e = use(g)) return e;
+  FILE *fp = fopen(path, "rb");
+  if (!fp) return fail(LASV_ERR_IO, "cannot open %s: %s", path, strerror(errno));
+  // query_binary_NEW, file_reader.c:3023-3232 (single colour)
+  auto bad = [&](const char *why) {
+    fclose(fp);
+    return fail(LASV_ERR_IO, "%s is not a loadable .ctx: %s", path, why);
+  };
+  char magic[6];
+  int32_t version, k, nbf, ncols;
+  if (fread(magic, 1, 6, fp) != 6 || memcmp(magic, "CORTEX", 6)) return bad("missing magic number");
+  if (fread(&version, 4, 1, fp) != 1 || version < 4 || version > 6) return bad("version not in [4,6]");
+  if (fread(&k, 4, 1, fp) != 1 || k != g->k) return bad("kmer size differs from the graph's");
+  if (fread(&nbf, 4, 1, fp) != 1 || nbf != g->N) return bad("number of bitfields differs");
+  if (fread(&ncols, 4, 1, fp) != 1 || ncols != 1) return bad("only single-colour binaries are supported");
+  int32_t mrl;
+  long long ts;
+  if (fread(&mrl, 4, 1, fp) != 1 || fread(&ts, 8, 1, fp) != 1) return bad("truncated header");
+  if (version > 5) {
+    int32_t idlen;
+    if (fread(&idlen, 4, 1, fp) != 1 || idlen < 0 || idlen > 100000) return bad("bad sample id");
+    if (fseek(fp, idlen + 16 + 4, SEEK_CUR)) return bad("truncated header");
+    int32_t t1, t2, namelen;
+    if (fread(&t1, 4, 1, fp) != 1 || fread(&t2, 4, 1, fp) != 1 || fread(&namelen, 4, 1, fp) != 1 ||
+        namelen < 0 || namelen > 100000 || fseek(fp, namelen, SEEK_CUR))
+      return bad("truncated header");
+  }
+  if (fread(magic, 1, 6, fp) != 6 || memcmp(magic, "CORTEX", 6)) return bad("missing end-of-header magic");
+  if (mean_read_len) *mean_read_len = (uint32_t)mrl;
+  if (total_seq) *total_seq = (uint64_t)ts;
+  const size_t rec = 8 * (size_t)g->N + 5;
+  const uint64_t per = (64ull << 20) / rec;
+  std::vector<uint8_t> buf(per * rec);
+  int rc = LASV_OK;
+  for (;;) {
+    const size_t got = fread(buf.data(), rec, per, fp);
+    if (!got) break;
+    rc = lasv_graph_load_ctx_records(g, buf.data(), got);
+    if (rc != LASV_OK || got < per) break;
+  }
+  fclose(fp);
+  return rc;
+}
+
+// ---------------------------------------------------------- sequence files
+namespace {
+
+struct PinnedBatch : HostBatch {
+  bool ok = false;
+  PinnedBatch(uint64_t bytes, uint64_t reads) {
+    cap_bytes = bytes;
+    cap_reads = reads;
+    ok = cudaMallocHost(&seq, bytes) == cudaSuccess && cudaMallocHost(&qual, bytes) == cudaSuccess &&
+         cudaMallocHost(&offsets, (reads + 1) * sizeof(uint64_t)) == cudaSuccess;
+    if (ok) reset();
+  }
+  ~PinnedBatch() {
+    if (seq) cudaFreeHost(seq);
+    if (qual) cudaFreeHost(qual);
+    if (offsets) cudaFreeHost(offsets);
+  }
+};
+
+constexpr uint64_t LOADER_BATCH_BYTES = 256ull << 20;
+constexpr uint64_t LOADER_BATCH_READS = 4ull << 20;
+
+int flush_batch(lasv_graph *g, HostBatch &b, bool with_qual, int cutoff) {
+  if (!b.n_reads) return LASV_OK;
+  int rc = lasv_graph_load_reads_host(g, b.seq, with_qual ? b.qual : nullptr, b.n_bytes, b.offsets,
+                                      b.n_reads, cutoff, nullptr);
+  b.reset();
+  return rc;
+}
+
+// Common body of the SE and PE loaders: mates are interleaved (mate 1 then
+// mate 2 of each pair, file_reader.c:636-765) -- the order is irrelevant to the
+// graph but the lock-step read is what detects files of unequal length.
+int load_files(lasv_graph *g, const char *path1, const char *path2, int cutoff,
+               lasv_load_stats *stats) {
+  if (int e = use(g)) return e;
+  std::string err;
+  SeqReader r1, r2;
+  if (!r1.open(path1, err)) return fail(LASV_ERR_IO, "%s", err.c_str());
+  if (path2 && !r2.open(path2, err)) return fail(LASV_ERR_IO, "%s", err.c_str());
+  const bool with_qual = r1.has_quality() || (path2 && r2.has_quality());
+  PinnedBatch batch(LOADER_BATCH_BYTES, LOADER_BATCH_READS);
+  if (!batch.ok) return fail(LASV_ERR_CUDA, "cannot allocate pinned batch buffers");
+  lasv_load_stats before;
+  if (int e = lasv_graph_stats(g, &before, nullptr, 0, nullptr)) return e;
+  for (;;) {
+    const bool got1 = r1.next(err);
+    if (!err.empty()) return fail(LASV_ERR_IO, "%s", err.c_str());
+    bool got2 = false;
+    if (path2) {
+      got2 = r2.next(err);
+      if (!err.empty()) return fail(LASV_ERR_IO, "%s", err.c_str());
+      if (got1 != got2)
+        return fail(LASV_ERR_IO,
+                    "Paired-end files don't have the same number of reads\nfile1: %s\nfile2: %s",
+                    path1, path2);
+    }
+    if (!got1) break;
+    for (int m = 0; m < (path2 ? 2 : 1); m++) {
+      SeqReader &r = m ? r2 : r1;
+      if (!r.append_to(batch, with_qual)) {
+        if (int e = flush_batch(g, batch, with_qual, cutoff)) return e;
+        if (!r.append_to(batch, with_qual))
+          return fail(LASV_ERR_ARG, "read of %zu bases exceeds the loader batch", r.seq().size());
+      }
+    }
+  }
+  if (int e = flush_batch(g, batch, with_qual, cutoff)) return e;
+  lasv_load_stats after;
+  if (int e = lasv_graph_stats(g, &after, nullptr, 0, nullptr)) return e;
+  if (stats) {
+    stats->n_reads = after.n_reads - before.n_reads;
+    stats->bad_reads = after.bad_reads - before.bad_reads;
+    stats->bases_read = after.bases_read - before.bases_read;
+    stats->bases_loaded = after.bases_loaded - before.bases_loaded;
+    stats->n_contigs = after.n_contigs - before.n_contigs;
+    stats->kmers_inserted = after.kmers_inserted - before.kmers_inserted;
+    stats->unique_kmers = after.unique_kmers;
+  }
+  return LASV_OK;
+}
+
+bool read_list_line(FILE *f, std::string &line) {
+  line.clear();
+  int c;
+  bool any = false;
+  while ((c = fgetc(f)) != EOF) {
+    any = true;
+    if (c == '\n') break;
+    line.push_back((char)c);
+  }
+  while (!line.empty() && (line.back() == '\r' || line.back() == '\n')) line.pop_back();
+  return any;
+}
+
+std::string dir_of(const std::string &abs) {
+  std::vector<char> tmp(abs.begin(), abs.end());
+  tmp.push_back('\0');
+  return std::string(dirname(tmp.data())) + "/";
+}
+
+void add_stats(lasv_load_stats *acc, const lasv_load_stats &s) {
+  acc->n_reads += s.n_reads;
+  acc->bad_reads += s.bad_reads;
+  acc->bases_read += s.bases_read;
+  acc->bases_loaded += s.bases_loaded;
+  acc->n_contigs += s.n_contigs;
+  acc->kmers_inserted += s.kmers_inserted;
+  acc->unique_kmers = s.unique_kmers;
+}
+
+}  // namespace
+
+int lasv_graph_load_se_file(lasv_graph *g, const char *path, int quality_cutoff,
+                            lasv_load_stats *stats) {
+  return load_files(g, path, nullptr, quality_cutoff, stats);
+}
+
+int lasv_graph_load_pe_files(lasv_graph *g, const char *path1, const char *path2, int quality_cutoff,
+                             lasv_load_stats *stats) {
+  return load_files(g, path1, path2, quality_cutoff, stats);
+}
+
+int lasv_graph_load_se_filelist(lasv_graph *g, const char *list, int qual_thresh, int ascii_fq_offset,
+                                unsigned int *files_loaded, lasv_load_stats *stats) {
+  // file_reader.c:789-907
+  const int cutoff = (int)(signed char)(qual_thresh + ascii_fq_offset);
+  char abs[PATH_MAX + 1];
+  if (!realpath(list, abs)) return fail(LASV_ERR_IO, "Cannot get absolute path to filelist of SE files: %s", list);
+  FILE *f = fopen(abs, "r");
+  if (!f) return fail(LASV_ERR_IO, "Cannot open filelist of SE files: %s", abs);
+  const std::string dir = dir_of(abs);
+  lasv_load_stats acc;
+  memset(&acc, 0, sizeof acc);
+  std::string line;
+  unsigned int n = 0;
+  int rc = LASV_OK;
+  while (rc == LASV_OK && read_list_line(f, line)) {
+    if (line.empty()) continue;
+    if (line[0] != '/') line = dir + line;
+    char p[PATH_MAX + 1];
+    if (!realpath(line.c_str(), p)) { rc = fail(LASV_ERR_IO, "Cannot find sequence file: %s", line.c_str()); break; }
+    lasv_load_stats s;
+    rc = load_files(g, p, nullptr, cutoff, &s);
+    if (rc == LASV_OK) { add_stats(&acc, s); n++; }
+  }
+  fclose(f);
+  if (rc != LASV_OK) return rc;
+  if (files_loaded) *files_loaded += n;
+  if (stats) *stats = acc;
+  return LASV_OK;
+}
+
+int lasv_graph_load_pe_filelists(lasv_graph *g, const char *list1, const char *list2, int qual_thresh,
+                                 int ascii_fq_offset, unsigned int *pairs_loaded,
+                                 lasv_load_stats *stats) {
+  // file_reader.c:910-1077
+  const int cutoff = (int)(signed char)(qual_thresh + ascii_fq_offset);
+  char abs1[PATH_MAX + 1], abs2[PATH_MAX + 1];
+  if (!realpath(list1, abs1)) return fail(LASV_ERR_IO, "Cannot get absolute path to filelist of PE files: %s", list1);
+  if (!realpath(list2, abs2)) return fail(LASV_ERR_IO, "Cannot get absolute path to filelist of PE files: %s", list2);
+  FILE *f1 = fopen(abs1, "r");
+  if (!f1) return fail(LASV_ERR_IO, "Cannot open filelist of PE files: %s", abs1);
+  FILE *f2 = fopen(abs2, "r");
+  if (!f2) { fclose(f1); return fail(LASV_ERR_IO, "Cannot open filelist of PE files: %s", abs2); }
+  const std::string dir1 = dir_of(abs1), dir2 = dir_of(abs2);
+  lasv_load_stats acc;
+  memset(&acc, 0, sizeof acc);
+  std::string l1, l2;
+  unsigned int n = 0;
+  int rc = LASV_OK;
+  for (;;) {
+    const bool g1 = read_list_line(f1, l1), g2 = read_list_line(f2, l2);
+    if (!g1 && !g2) break;
+    if (l1.empty() != l2.empty()) {
+      rc = fail(LASV_ERR_IO, "Paired-end files don't have the same number of lines:\nFile 1: %s\nFile 2: %s",
+                list1, list2);
+      break;
+    }
+    if (l1.empty()) continue;
+    if (l1[0] != '/') l1 = dir1 + l1;
+    if (l2[0] != '/') l2 = dir2 + l2;
+    char p1[PATH_MAX + 1], p2[PATH_MAX + 1];
+    if (!realpath(l1.c_str(), p1)) { rc = fail(LASV_ERR_IO, "Cannot find sequence file: %s", l1.c_str()); break; }
+    if (!realpath(l2.c_str(), p2)) { rc = fail(LASV_ERR_IO, "Cannot find sequence file: %s", l2.c_str()); break; }
+    lasv_load_stats s;
+    rc = load_files(g, p1, p2, cutoff, &s);
+    if (rc != LASV_OK) break;
+    add_stats(&acc, s);
+    n++;
+  }
+  fclose(f1);
+  fclose(f2);
+  if (rc != LASV_OK) return rc;
+  if (pairs_loaded) *pairs_loaded += n;
+  if (stats) *stats = acc;
+  return LASV_OK;
+}
+
+// ----------------------------------------------- (A) reference-named drop-ins
+namespace {
+
+[[noreturn]] void die_like_reference(const char *msg) {  // src/basic/global.c:44-63
+  fflush(stdout);
+  fprintf(stderr, "Error: %s", msg);
+  const size_t n = strlen(msg);
+  if (!n || msg[n - 1] != '\n') fprintf(stderr, "\n");
+  exit(EXIT_FAILURE);
+}
+
+int log2_exact(long long v) {
+  int l = 0;
+  while ((1ll << l) < v) l++;
+  return ((1ll << l) == v) ? l : -1;
+}
+
+// Build on the GPU into the caller's reference HashTable.
+void dropin_load(lasv_ref_hash_table *t, const char *list1, const char *list2, int qual_thresh,
+                 int homopol_limit, signed char remove_dups, char ascii_fq_offset, char is_colour_list,
+                 unsigned int *files_loaded, unsigned long long *bad_reads,
+                 unsigned long long *dup_reads, unsigned long long *bases_read,
+                 unsigned long long *bases_loaded, unsigned long *hist, unsigned long hist_size) {
+  (void)dup_reads;
+  if (homopol_limit != 0) die_like_reference("lasv_b200: homopolymer cut-off is not supported by the GPU loader");
+  if (remove_dups) die_like_reference("lasv_b200: PCR duplicate removal is not supported by the GPU loader");
+  if (is_colour_list) die_like_reference("lasv_b200: colour lists are not supported by the GPU loader");
+  if (!t || !t->table) die_like_reference("NULL table!");
+  const int L = log2_exact(t->number_buckets);
+  if (L < 0) die_like_reference("lasv_b200: number_buckets is not a power of two");
+  int dev = 0;
+  if (const char *e = getenv("LASV_B200_DEVICE")) dev = atoi(e);
+  lasv_graph *g = lasv_graph_new(t->kmer_size, L, t->bucket_size, t->max_rehash_tries, dev);
+  if (!g) die_like_reference(lasv_last_error());
+  if (t->unique_kmers > 0 && lasv_graph_import_table(g, t->table) != LASV_OK)
+    die_like_reference(lasv_last_error());
+  printf(list2 ? "Load paired-ended files\n" : "Load single-ended files\n");
+  lasv_load_stats s;
+  memset(&s, 0, sizeof s);
+  unsigned int n = 0;
+  const int rc = list2 ? lasv_graph_load_pe_filelists(g, list1, list2, qual_thresh, ascii_fq_offset, &n, &s)
+                       : lasv_graph_load_se_filelist(g, list1, qual_thresh, ascii_fq_offset, &n, &s);
+  if (rc != LASV_OK) die_like_reference(lasv_last_error());
+  if (hist && hist_size) {
+    std::vector<uint64_t> h(hist_size);
+    if (lasv_graph_stats(g, nullptr, h.data(), hist_size, nullptr) != LASV_OK)
+      die_like_reference(lasv_last_error());
+    for (unsigned long i = 0; i < hist_size; i++) hist[i] += (unsigned long)h[i];
+  }
+  long long coll[16];
+  if (lasv_graph_rehash_histogram(g, coll) != LASV_OK) die_like_reference(lasv_last_error());
+  const long long uniq = lasv_graph_unique_kmers(g);
+  if (lasv_graph_export_table(g, t->table, t->next_element) != LASV_OK)
+    die_like_reference(lasv_last_error());
+  t->unique_kmers = uniq;
+  if (t->collisions)
+    for (int r = 0; r < t->max_rehash_tries && r < 16; r++) t->collisions[r] += coll[r];
+  lasv_graph_free(&g);
+  *files_loaded += n;
+  *bad_reads += s.bad_reads;
+  *bases_read += s.bases_read;
+  *bases_loaded += s.bases_loaded;
+  // file_reader.c:898-906 / 1068-1076
+  printf(list2 ? "\nNum PE file pairs loaded:%u\n" : "\nNum SE files loaded:%u\n", n);
+  printf("\tKmers:%lld\n", uniq);
+  printf("\tNumber of bad reads:%llu\n", (unsigned long long)s.bad_reads);
+  printf("\tNumber of dupe reads:%llu\n", 0ull);
+  printf(list2 ? "\tPE sequence parsed:%llu\n" : "\tSE sequence parsed:%llu\n",
+         (unsigned long long)s.bases_read);
+  printf(list2 ? "\tTotal PE sequence that passed filters:%llu\n"
+               : "\tTotal SE sequence that passed filters:%llu\n",
+         (unsigned long long)s.bases_loaded);
+}
+
+}  // namespace
+
+void load_se_filelist_into_graph_colour(
+    char *se_filelist_path, int qual_thresh, int homopol_limit, signed char remove_dups_se,
+    char ascii_fq_offset, int colour, lasv_ref_hash_table *db_graph, char is_colour_list,
+    unsigned int *total_files_loaded, unsigned long long *total_bad_reads,
+    unsigned long long *total_dup_reads, unsigned long long *total_bases_read,
+    unsigned long long *total_bases_loaded, unsigned long *readlen_count_array,
+    unsigned long readlen_count_array_size) {
+  (void)colour;
+  dropin_load(db_graph, se_filelist_path, nullptr, qual_thresh, homopol_limit, remove_dups_se,
+              ascii_fq_offset, is_colour_list, total_files_loaded, total_bad_reads, total_dup_reads,
+              total_bases_read, total_bases_loaded, readlen_count_array, readlen_count_array_size);
+}
+
+void load_pe_filelists_into_graph_colour(
+    char *pe_filelist_path1, char *pe_filelist_path2, int qual_thresh, int homopol_limit,
+    signed char remove_dups_pe, char ascii_fq_offset, int colour, lasv_ref_hash_table *db_graph,
+    char is_colour_lists, unsigned int *total_file_pairs_loaded, unsigned long long *total_bad_reads,
+    unsigned long long *total_dup_reads, unsigned long long *total_bases_read,
+    unsigned long long *total_bases_loaded, unsigned long *readlen_count_array,
+    unsigned long readlen_count_array_size) {
+  (void)colour;
+  dropin_load(db_graph, pe_filelist_path1, pe_filelist_path2, qual_thresh, homopol_limit,
+              remove_dups_pe, ascii_fq_offset, is_colour_lists, total_file_pairs_loaded,
+              total_bad_reads, total_dup_reads, total_bases_read, total_bases_loaded,
+              readlen_count_array, readlen_count_array_size);
+}
+
+// ------------------------------------------------- bench / test utilities
+static SynthParams to_synth(const lasv_synth_params *p) {
+  SynthParams s;
+  s.seed = p->seed; s.genome_len = p->genome_len; s.read_len = p->read_len; s.insert = p->insert;
+  s.err_q20 = p->err_q20; s.n_q20 = p->n_q20; s.lowq_q20 = p->lowq_q20;
+  s.err_lowq_pct = p->err_lowq_pct; s.tail_min = p->tail_min; s.tail_max = p->tail_max;
+  s.tiling = p->tiling; s.tiling_step = p->tiling_step;
+  return s;
+}
+
+static int check_synth(const lasv_synth_params *p) {
+  if (!p || p->read_len < 1 || p->read_len > 1023) return fail(LASV_ERR_ARG, "read_len must be in [1,1023]");
+  if (!p->tiling && (p->insert < p->read_len || p->genome_len < p->insert))
+    return fail(LASV_ERR_ARG, "need read_len <= insert <= genome_len");
+  if (p->tail_max < p->tail_min) return fail(LASV_ERR_ARG, "tail_max < tail_min");
+  if (p->tiling && !p->tiling_step) return fail(LASV_ERR_ARG, "tiling_step must be > 0");
+  return LASV_OK;
+}
+
+int lasv_synth_reads_device(const lasv_synth_params *p, uint64_t first_read, uint64_t n_reads,
+                            uint8_t *d_seq, uint8_t *d_qual, void *cuda_stream) {
+  if (int e = check_synth(p)) return e;
+  launch_synth(to_synth(p), first_read, n_reads, d_seq, d_qual, (cudaStream_t)cuda_stream);
+  return check_launch();
+}
+
+int lasv_synth_reads_host(const lasv_synth_params *p, uint64_t first_read, uint64_t n_reads,
+                          uint8_t *seq, uint8_t *qual) {
+  if (int e = check_synth(p)) return e;
+  synth_host(to_synth(p), first_read, n_reads, seq, qual);
+  return LASV_OK;
+}
+
+int lasv_random_access_probe(void *d_buf, uint64_t n_sectors, uint64_t n_ops, uint64_t seed,
+                             void *cuda_stream) {
+  if (!d_buf || !n_sectors) return fail(LASV_ERR_ARG, "bad buffer");
+  launch_random_rmw((uint64_t *)d_buf, n_sectors, n_ops, seed, (cudaStream_t)cuda_stream);
+  return check_launch();
+}
+
+}  // extern "C"

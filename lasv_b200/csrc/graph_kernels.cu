@@ -1,0 +1,812 @@
+// graph_kernels.cu -- hand-written sm_100a kernels of the de Bruijn graph build.
+//
+//   build_kernel<N,MODE>   K1+K2(+K3): stream tile -> classify/pack (128-bit
+//                          coalesced loads, shared-memory bit strings) -> window
+//                          validity -> O(1) forward / reverse-complement k-mer
+//                          extraction -> canonical key + edge byte -> either
+//                          find-or-insert straight into the table (FUSED), or
+//                          (2N+1)-word records (RECORDS), or records binned by
+//                          owner GPU for the all-to-all (ROUTE).
+//   insert_records_kernel  K3 on records (the receive side of the exchange).
+//   read_stats_kernel      loader bookkeeping: bad reads, bases loaded, contig
+//                          length histogram (file_reader.c:460-470,579).
+//   finalize / dump / ingest / find / summary kernels: K4 and the .ctx wire
+//                          format (element.c:894-910, file_reader.c:1686-1703).
+//
+// Integer hashing only: no tensor cores.  The table traffic is random 32-byte
+// sectors in HBM; everything else is streaming.  Grids are persistent:
+// (#SMs x resident CTAs) CTAs looping over tiles.
+#include <cub/device/device_scan.cuh>
+#include "graph_kernels.cuh"
+#include "synth.cuh"
+
+namespace lasv {
+
+namespace {
+
+constexpr int THREADS = 256;
+constexpr unsigned FULL = 0xFFFFFFFFu;
+
+__device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31u; }
+__device__ __forceinline__ unsigned lanemask_lt() {
+  unsigned m;
+  asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+  return m;
+}
+
+// Warp-level pre-aggregation of identical keys (reads with homopolymer or
+// tandem runs put the same k-mer in neighbouring lanes; 30x coverage makes hot
+// k-mers).  On return `lead` tells whether this lane performs the table update,
+// carrying the group's summed count and OR-ed edges.
+template <int N>
+__device__ __forceinline__ bool warp_aggregate(bool active, const uint64_t (&key)[N],
+                                               uint32_t &edge, uint32_t &count) {
+  uint64_t sig = key[N - 1];
+#pragma unroll
+  for (int i = 0; i < N - 1; i++) sig = sig * 0x9E3779B97F4A7C15ull + key[i];
+  if (!active) sig = ~0ull - lane_id();
+  const unsigned grp = __match_any_sync(FULL, sig);
+  const int leader = __ffs(grp) - 1;
+  bool same = active;
+#pragma unroll
+  for (int i = 0; i < N; i++) same &= (__shfl_sync(FULL, key[i], leader) == key[i]);
+  const unsigned same_mask = __ballot_sync(FULL, same);
+  if (!same) return active;  // signature clash with a different key: go alone
+  const unsigned g = grp & same_mask;  // lanes holding exactly this key (leader included)
+  const uint32_t e = __reduce_or_sync(g, edge);
+  const uint32_t c = __reduce_add_sync(g, count);
+  if ((int)lane_id() != __ffs(g) - 1) return false;
+  edge = e;
+  count = c;
+  return true;
+}
+
+template <int N>
+__device__ __forceinline__ void store_record(uint32_t *dst, const uint64_t (&key)[N], uint32_t edge,
+                                             uint32_t count) {
+#pragma unroll
+  for (int i = 0; i < N; i++) {
+    dst[2 * i] = (uint32_t)key[i];
+    dst[2 * i + 1] = (uint32_t)(key[i] >> 32);
+  }
+  dst[2 * N] = (edge & 0xFFu) | (count << 8);
+}
+
+template <int N>
+__device__ __forceinline__ void load_record(const uint32_t *src, uint64_t (&key)[N], uint32_t &edge,
+                                            uint32_t &count) {
+#pragma unroll
+  for (int i = 0; i < N; i++) key[i] = (uint64_t)src[2 * i] | ((uint64_t)src[2 * i + 1] << 32);
+  const uint32_t m = src[2 * N];
+  edge = m & 0xFFu;
+  count = m >> 8;
+}
+
+// --------------------------------------------------------------------------
+// build_kernel
+// --------------------------------------------------------------------------
+template <int MODE>
+struct TileCfg {
+  static constexpr int T = (MODE == MODE_ROUTE) ? 1024 : 2048;  // window starts per tile
+  static constexpr int R = T + TileGeom::HALO_L + TileGeom::HALO_R;  // region bases (multiple of 64)
+  static constexpr int CHUNKS = R / 16;
+};
+
+template <int N, int MODE>
+__global__ void __launch_bounds__(THREADS) build_kernel(const BuildParams p, const uint64_t n_tiles) {
+  using Cfg = TileCfg<MODE>;
+  constexpr int T = Cfg::T, R = Cfg::R, CHUNKS = Cfg::CHUNKS;
+  static_assert(CHUNKS <= THREADS, "one staging chunk per thread");
+  static_assert(R % 64 == 0, "region must be whole bad-bit words");
+  constexpr int RECW = 2 * N + 1;
+
+  __shared__ uint64_t sP[R / 32 + 2];
+  __shared__ uint64_t sPR[R / 32 + 2];
+  __shared__ uint64_t sBD[R / 64 + 2];
+  __shared__ uint16_t sPos[T];
+  __shared__ uint32_t sCount;
+  __shared__ unsigned long long sTileBase[16];
+  __shared__ uint32_t sBinCount[16];
+  __shared__ uint32_t sBinRank[16];
+  // ROUTE only: records of the tile wait here until the per-destination space is reserved
+  __shared__ uint32_t sStash[(MODE == MODE_ROUTE) ? T * RECW : 1];
+  __shared__ uint8_t sDest[(MODE == MODE_ROUTE) ? T : 1];
+
+  const int tid = threadIdx.x;
+  const bool has_qual = p.qual != nullptr;
+  const int k = p.k;
+
+  if (tid == 0) {
+    sP[0] = 0; sPR[0] = 0;
+    sP[R / 32 + 1] = 0; sPR[R / 32 + 1] = 0;
+    sBD[R / 64] = ~0ull; sBD[R / 64 + 1] = ~0ull;
+  }
+
+  unsigned long long my_new = 0;    // keys this thread created
+  unsigned long long my_kmers = 0;  // thread 0 only: occurrences in this CTA's tiles
+
+  // software pipeline: the staging loads of the next tile are issued before the
+  // heavy phase of the current one
+  uint4 sv = make_uint4(0, 0, 0, 0), qv = make_uint4(0, 0, 0, 0);
+  uint32_t inr = 0;
+  auto issue_stage = [&](uint64_t tile) {
+    inr = 0;
+    if (tid < CHUNKS && tile < n_tiles) {
+      const long long g = (long long)(tile * (uint64_t)T) - TileGeom::HALO_L + 16ll * tid;
+      if (g >= 0 && (uint64_t)g < p.n_bytes) {
+        sv = __ldg(reinterpret_cast<const uint4 *>(p.seq + g));
+        if (has_qual) qv = __ldg(reinterpret_cast<const uint4 *>(p.qual + g));
+        const uint64_t left = p.n_bytes - (uint64_t)g;
+        inr = left >= 16 ? 0xFFFFu : ((1u << left) - 1u);
+      }
+    }
+  };
+
+  uint64_t tile = blockIdx.x;
+  issue_stage(tile);
+
+  for (; tile < n_tiles; tile += gridDim.x) {
+    // ---- stage: classify + pack this thread's 16 bases into the bit strings
+    if (tid < CHUNKS) {
+      uint32_t code32, bad16;
+      classify16(sv, qv, has_qual, p.cutoff, inr, code32, bad16);
+      reinterpret_cast<uint32_t *>(sP)[code_u32_index(tid)] = code32;
+      reinterpret_cast<uint32_t *>(sPR)[code_u32_index(CHUNKS - 1 - tid)] = rc_code32(code32);
+      reinterpret_cast<uint16_t *>(sBD)[bad_u16_index(tid)] = (uint16_t)bad16;
+    }
+    if (tid == 0) sCount = 0;
+    if (MODE == MODE_ROUTE && tid < 16) { sBinCount[tid] = 0; sBinRank[tid] = 0; }
+    __syncthreads();
+
+    issue_stage(tile + gridDim.x);  // next tile's bytes fly during the heavy phase
+
+    // ---- window validity + compaction of the good window starts
+#pragma unroll
+    for (int it = 0; it < T / THREADS; it++) {
+      const int pos = it * THREADS + tid;
+      const bool good = window_good(sBD, TileGeom::HALO_L + pos, k);
+      const unsigned m = __ballot_sync(FULL, good);
+      unsigned base = 0;
+      if (lane_id() == 0 && m) base = atomicAdd(&sCount, (uint32_t)__popc(m));
+      base = __shfl_sync(FULL, base, 0);
+      if (good) sPos[base + __popc(m & lanemask_lt())] = (uint16_t)pos;
+    }
+    __syncthreads();
+    const int M = (int)sCount;
+    if (tid == 0) my_kmers += (unsigned long long)M;
+
+    if (MODE == MODE_RECORDS) {
+      if (tid == 0) sTileBase[0] = M ? atomicAdd(p.rec_count, (unsigned long long)M) : 0ull;
+      __syncthreads();
+    }
+
+    // ---- heavy phase over the dense list of good windows
+    for (int base = 0; base < M; base += THREADS) {
+      const int i = base + tid;
+      const bool active = i < M;
+      uint64_t key[N];
+      uint32_t edge = 0, count = 1;
+      if (active) {
+        const int j = TileGeom::HALO_L + (int)sPos[i];
+        edge = kmer_occurrence<N>(sP, sPR, sBD, R, j, k, key);
+      } else {
+#pragma unroll
+        for (int w = 0; w < N; w++) key[w] = 0;
+      }
+      if (MODE == MODE_FUSED) {
+        const bool lead = warp_aggregate<N>(active, key, edge, count);
+        if (lead) {
+          const int r = table_upsert<N>(p.table, p.ctr, key, edge, count);
+          my_new += (r == 1);
+        }
+      } else if (MODE == MODE_RECORDS) {
+        if (active) {
+          const unsigned long long idx = sTileBase[0] + (unsigned long long)i;
+          if (idx < p.rec_capacity) store_record<N>(p.rec_out + idx * RECW, key, edge, 1u);
+          else atomicExch(p.rec_overflow, 1ull);
+        }
+      } else {  // MODE_ROUTE
+        if (active) {
+          const Hash3 h = lookup3_key<N>(key, 0);
+          const uint32_t d = (h.c >> p.owner_shift) & (uint32_t)(p.n_dest - 1);
+          store_record<N>(sStash + i * RECW, key, edge, 1u);
+          sDest[i] = (uint8_t)d;
+          atomicAdd(&sBinCount[d], 1u);
+        }
+      }
+    }
+
+    if (MODE == MODE_ROUTE) {
+      __syncthreads();
+      if (tid < p.n_dest) {
+        const uint32_t c = sBinCount[tid];
+        sTileBase[tid] = c ? atomicAdd(p.rec_count + tid, (unsigned long long)c) : 0ull;
+      }
+      __syncthreads();
+      for (int i = tid; i < M; i += THREADS) {
+        const uint32_t d = sDest[i];
+        const unsigned long long idx = sTileBase[d] + atomicAdd(&sBinRank[d], 1u);
+        if (idx < p.rec_capacity) {
+          uint32_t *dst = p.rec_out + ((uint64_t)d * p.rec_capacity + idx) * RECW;
+#pragma unroll
+          for (int w = 0; w < RECW; w++) dst[w] = sStash[i * RECW + w];
+        } else {
+          atomicExch(p.rec_overflow, 1ull);
+        }
+      }
+    }
+    __syncthreads();  // smem is re-staged by the next iteration
+  }
+
+  // ---- CTA-level counters
+  if (MODE == MODE_FUSED) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) my_new += __shfl_xor_sync(FULL, my_new, o);
+    if (lane_id() == 0 && my_new) atomicAdd(&p.ctr->unique_kmers, my_new);
+  }
+  if (tid == 0 && my_kmers) atomicAdd(&p.ctr->kmers_inserted, my_kmers);
+}
+
+// --------------------------------------------------------------------------
+// insert_records_kernel: K3 over (2N+1)-word records
+// --------------------------------------------------------------------------
+template <int N>
+__global__ void __launch_bounds__(THREADS) insert_records_kernel(const uint32_t *__restrict__ recs,
+                                                                const uint64_t n_recs,
+                                                                const TableView t,
+                                                                GraphCounters *ctr) {
+  constexpr int RECW = 2 * N + 1;
+  unsigned long long my_new = 0;
+  const uint64_t stride = (uint64_t)gridDim.x * THREADS;
+  const uint64_t n_round = (n_recs + 31) & ~31ull;
+  for (uint64_t i = (uint64_t)blockIdx.x * THREADS + threadIdx.x; i < n_round; i += stride) {
+    const bool active = i < n_recs;
+    uint64_t key[N];
+    uint32_t edge = 0, count = 0;
+    if (active) load_record<N>(recs + i * RECW, key, edge, count);
+    else {
+#pragma unroll
+      for (int w = 0; w < N; w++) key[w] = 0;
+    }
+    const bool lead = warp_aggregate<N>(active, key, edge, count);
+    if (lead) {
+      const int r = table_upsert<N>(t, ctr, key, edge, count);
+      my_new += (r == 1);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) my_new += __shfl_xor_sync(FULL, my_new, o);
+  if (lane_id() == 0 && my_new) atomicAdd(&ctr->unique_kmers, my_new);
+}
+
+// --------------------------------------------------------------------------
+// read_stats_kernel: one warp per read
+// --------------------------------------------------------------------------
+constexpr int HIST_SMEM = 1024;
+
+__global__ void __launch_bounds__(THREADS) read_stats_kernel(
+    const uint8_t *__restrict__ seq, const uint8_t *__restrict__ qual,
+    const uint64_t *__restrict__ offsets, const uint64_t n_reads, const int sep, const int k,
+    const int cutoff, ReadStats *stats, unsigned long long *hist, const uint32_t hist_size) {
+  __shared__ uint32_t sHist[HIST_SMEM];
+  for (int i = threadIdx.x; i < HIST_SMEM; i += THREADS) sHist[i] = 0;
+  __syncthreads();
+  const bool has_qual = qual != nullptr;
+  const unsigned lane = lane_id();
+  const uint64_t warp0 = ((uint64_t)blockIdx.x * THREADS + threadIdx.x) >> 5;
+  const uint64_t nwarps = ((uint64_t)gridDim.x * THREADS) >> 5;
+  unsigned long long bad_reads = 0, bases_read = 0, bases_loaded = 0, contigs = 0;
+
+  auto end_run = [&](uint32_t run, bool &has) {
+    if (run >= (uint32_t)k) {
+      has = true;
+      bases_loaded += run;
+      contigs++;
+      if (lane == 0) {
+        const uint32_t b = run < hist_size - 1 ? run : hist_size - 1;
+        if (b < HIST_SMEM) atomicAdd(&sHist[b], 1u);
+        else atomicAdd(&hist[b], 1ull);
+      }
+    }
+  };
+
+  for (uint64_t r = warp0; r < n_reads; r += nwarps) {
+    const uint64_t beg = offsets[r];
+    const uint64_t len = offsets[r + 1] - beg - (uint64_t)sep;
+    bases_read += len;
+    uint32_t run = 0;
+    bool has = false;
+    for (uint64_t c0 = 0; c0 < len; c0 += 32) {
+      const uint64_t i = c0 + lane;
+      bool good = false;
+      if (i < len) {
+        const uint32_t u = (uint32_t)seq[beg + i] & 0xDFu;
+        good = (u == 0x41u) | (u == 0x43u) | (u == 0x47u) | (u == 0x54u);
+        if (has_qual) good &= ((int)(int8_t)qual[beg + i] > cutoff);
+      }
+      const uint32_t mask = __ballot_sync(FULL, good);
+      const int nbits = (len - c0) < 32 ? (int)(len - c0) : 32;
+      int pos = 0;  // every lane walks the same mask: uniform control flow
+      while (pos < nbits) {
+        const uint32_t rest = mask >> pos;
+        if (rest & 1u) {
+          int ones = __ffs(~rest) - 1;  // trailing ones (32 if rest is all ones)
+          if (ones < 0) ones = 32;
+          if (ones > nbits - pos) ones = nbits - pos;
+          run += ones;
+          pos += ones;
+        } else {
+          end_run(run, has);
+          run = 0;
+          int zeros = rest ? __ffs(rest) - 1 : 32;
+          if (zeros > nbits - pos) zeros = nbits - pos;
+          pos += zeros;
+        }
+      }
+    }
+    end_run(run, has);
+    if (!has) bad_reads++;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < HIST_SMEM; i += THREADS) {
+    const uint32_t v = sHist[i];
+    if (v && (uint32_t)i < hist_size) atomicAdd(&hist[i], (unsigned long long)v);
+  }
+  if (lane == 0) {  // every lane of a warp carries the same totals
+    const unsigned long long nr = (warp0 < n_reads) ? ((n_reads - 1 - warp0) / nwarps + 1) : 0;
+    if (nr) atomicAdd(&stats->n_reads, nr);
+    if (bad_reads) atomicAdd(&stats->bad_reads, bad_reads);
+    if (bases_read) atomicAdd(&stats->bases_read, bases_read);
+    if (bases_loaded) atomicAdd(&stats->bases_loaded, bases_loaded);
+    if (contigs) atomicAdd(&stats->n_contigs, contigs);
+  }
+}
+
+// --------------------------------------------------------------------------
+// table-wide kernels (streaming over slots / buckets)
+// --------------------------------------------------------------------------
+template <int N>
+__global__ void __launch_bounds__(THREADS) table_summary_kernel(const TableView t, TableSummary *out) {
+  constexpr uint32_t STRIDE = 8 * N + 8;
+  const uint64_t n_slots = ((uint64_t)t.bucket_mask + 1) * t.W;
+  unsigned long long n = 0, sc = 0, se = 0, fp = 0;
+  for (uint64_t i = (uint64_t)blockIdx.x * THREADS + threadIdx.x; i < n_slots;
+       i += (uint64_t)gridDim.x * THREADS) {
+    const uint64_t *slot = reinterpret_cast<const uint64_t *>(t.slots + i * STRIDE);
+    const uint64_t m = slot[N];
+    if (meta_status(m) == ST_EMPTY) continue;
+    uint64_t key[N];
+#pragma unroll
+    for (int w = 0; w < N; w++) key[w] = slot[w];
+    n++;
+    sc += meta_covg(m);
+    se += __popc(meta_edges(m));
+    fp += node_fingerprint<N>(key, meta_covg(m), meta_edges(m));
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+    n += __shfl_xor_sync(FULL, n, o);
+    sc += __shfl_xor_sync(FULL, sc, o);
+    se += __shfl_xor_sync(FULL, se, o);
+    fp += __shfl_xor_sync(FULL, fp, o);
+  }
+  if (lane_id() == 0 && n) {
+    atomicAdd(&out->n_nodes, n);
+    atomicAdd(&out->sum_covg, sc);
+    atomicAdd(&out->sum_edge_bits, se);
+    atomicAdd(&out->fingerprint, fp);
+  }
+}
+
+// occupied slots per bucket: one warp per bucket
+template <int N>
+__global__ void __launch_bounds__(THREADS) bucket_counts_kernel(const TableView t, uint32_t *counts) {
+  constexpr uint32_t STRIDE = 8 * N + 8;
+  const uint64_t n_buckets = (uint64_t)t.bucket_mask + 1;
+  const uint64_t warp0 = ((uint64_t)blockIdx.x * THREADS + threadIdx.x) >> 5;
+  const uint64_t nwarps = ((uint64_t)gridDim.x * THREADS) >> 5;
+  for (uint64_t b = warp0; b < n_buckets; b += nwarps) {
+    const uint8_t *bucket = t.slots + b * t.W * STRIDE;
+    uint32_t c = 0;
+    for (uint32_t s = lane_id(); s < t.W; s += 32) {
+      const uint64_t m = reinterpret_cast<const uint64_t *>(bucket + (uint64_t)s * STRIDE)[N];
+      c += (meta_status(m) != ST_EMPTY);
+    }
+    c = __reduce_add_sync(FULL, c);
+    if (lane_id() == 0) counts[b] = c;
+  }
+}
+
+// Squeeze every bucket hole-free, in slot order, and restore the reference
+// Element bytes (status none, pad bytes zero): afterwards the table IS a
+// reference HashTable->table (hash_table.c:69-122 finds every key).  One warp
+// per bucket; chunks of 32 slots are read into registers before any of them is
+// overwritten, and destinations never run ahead of sources.
+template <int N>
+__global__ void __launch_bounds__(THREADS) finalize_kernel(const TableView t, int16_t *next_element) {
+  constexpr uint32_t STRIDE = 8 * N + 8;
+  const uint64_t n_buckets = (uint64_t)t.bucket_mask + 1;
+  const uint64_t warp0 = ((uint64_t)blockIdx.x * THREADS + threadIdx.x) >> 5;
+  const uint64_t nwarps = ((uint64_t)gridDim.x * THREADS) >> 5;
+  const unsigned lane = lane_id();
+  for (uint64_t b = warp0; b < n_buckets; b += nwarps) {
+    uint8_t *bucket = t.slots + b * t.W * STRIDE;
+    uint32_t filled = 0;
+    for (uint32_t s0 = 0; s0 < t.W; s0 += 32) {
+      const uint32_t s = s0 + lane;
+      uint64_t key[N];
+      uint64_t m = 0;
+      if (s < t.W) {
+        const uint64_t *slot = reinterpret_cast<const uint64_t *>(bucket + (uint64_t)s * STRIDE);
+        m = slot[N];
+#pragma unroll
+        for (int w = 0; w < N; w++) key[w] = slot[w];
+      }
+      const bool occ = meta_status(m) != ST_EMPTY;
+      const unsigned om = __ballot_sync(FULL, occ);
+      __syncwarp();
+      if (occ) {
+        const uint32_t d = filled + __popc(om & lanemask_lt());
+        uint64_t *dst = reinterpret_cast<uint64_t *>(bucket + (uint64_t)d * STRIDE);
+#pragma unroll
+        for (int w = 0; w < N; w++) dst[w] = key[w];
+        dst[N] = meta_pack(meta_covg(m), meta_edges(m), ST_NONE, 0);
+      }
+      filled += __popc(om);
+      __syncwarp();
+    }
+    for (uint32_t s = filled + lane; s < t.W; s += 32) {
+      uint64_t *dst = reinterpret_cast<uint64_t *>(bucket + (uint64_t)s * STRIDE);
+#pragma unroll
+      for (int w = 0; w <= N; w++) dst[w] = 0;
+    }
+    if (lane == 0 && next_element) next_element[b] = (int16_t)filled;
+  }
+}
+
+// .ctx records (element.c:894-910) in table order: kmer[N] | uint32 covg | uint8 edges
+template <int N>
+__global__ void __launch_bounds__(THREADS) dump_ctx_kernel(const TableView t,
+                                                          const uint64_t *__restrict__ bucket_offsets,
+                                                          uint8_t *__restrict__ out) {
+  constexpr uint32_t STRIDE = 8 * N + 8;
+  constexpr uint32_t REC = 8 * N + 5;
+  const uint64_t n_buckets = (uint64_t)t.bucket_mask + 1;
+  const uint64_t warp0 = ((uint64_t)blockIdx.x * THREADS + threadIdx.x) >> 5;
+  const uint64_t nwarps = ((uint64_t)gridDim.x * THREADS) >> 5;
+  const unsigned lane = lane_id();
+  for (uint64_t b = warp0; b < n_buckets; b += nwarps) {
+    const uint8_t *bucket = t.slots + b * t.W * STRIDE;
+    uint64_t o = bucket_offsets[b];
+    for (uint32_t s0 = 0; s0 < t.W; s0 += 32) {
+      const uint32_t s = s0 + lane;
+      uint64_t key[N];
+      uint64_t m = 0;
+      if (s < t.W) {
+        const uint64_t *slot = reinterpret_cast<const uint64_t *>(bucket + (uint64_t)s * STRIDE);
+        m = slot[N];
+#pragma unroll
+        for (int w = 0; w < N; w++) key[w] = slot[w];
+      }
+      const bool occ = meta_status(m) != ST_EMPTY;
+      const unsigned om = __ballot_sync(FULL, occ);
+      if (occ) {
+        uint8_t *dst = out + (o + __popc(om & lanemask_lt())) * REC;
+#pragma unroll
+        for (int w = 0; w < N; w++) {
+#pragma unroll
+          for (int by = 0; by < 8; by++) dst[8 * w + by] = (uint8_t)(key[w] >> (8 * by));
+        }
+        const uint32_t c = meta_covg(m);
+        dst[8 * N + 0] = (uint8_t)c;
+        dst[8 * N + 1] = (uint8_t)(c >> 8);
+        dst[8 * N + 2] = (uint8_t)(c >> 16);
+        dst[8 * N + 3] = (uint8_t)(c >> 24);
+        dst[8 * N + 4] = (uint8_t)meta_edges(m);
+      }
+      o += __popc(om);
+    }
+  }
+}
+
+// load packed .ctx records into the table (file_reader.c:1686-1703: insert key,
+// add coverage, OR edges)
+template <int N>
+__global__ void __launch_bounds__(THREADS) ingest_ctx_kernel(const uint8_t *__restrict__ recs,
+                                                            const uint64_t n_recs, const TableView t,
+                                                            GraphCounters *ctr) {
+  constexpr uint32_t REC = 8 * N + 5;
+  unsigned long long my_new = 0;
+  for (uint64_t i = (uint64_t)blockIdx.x * THREADS + threadIdx.x; i < n_recs;
+       i += (uint64_t)gridDim.x * THREADS) {
+    const uint8_t *src = recs + i * REC;
+    uint64_t key[N];
+#pragma unroll
+    for (int w = 0; w < N; w++) {
+      uint64_t v = 0;
+#pragma unroll
+      for (int by = 0; by < 8; by++) v |= (uint64_t)src[8 * w + by] << (8 * by);
+      key[w] = v;
+    }
+    const uint32_t c = (uint32_t)src[8 * N] | ((uint32_t)src[8 * N + 1] << 8) |
+                       ((uint32_t)src[8 * N + 2] << 16) | ((uint32_t)src[8 * N + 3] << 24);
+    const int r = table_upsert<N>(t, ctr, key, src[8 * N + 4], c);
+    my_new += (r == 1);
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) my_new += __shfl_xor_sync(FULL, my_new, o);
+  if (lane_id() == 0 && my_new) atomicAdd(&ctr->unique_kmers, my_new);
+}
+
+// merge an uploaded reference-layout Element[] (any hole pattern) into the table
+template <int N>
+__global__ void __launch_bounds__(THREADS) ingest_elements_kernel(const uint8_t *__restrict__ elems,
+                                                                 const uint64_t n_slots,
+                                                                 const TableView t, GraphCounters *ctr) {
+  constexpr uint32_t STRIDE = 8 * N + 8;
+  unsigned long long my_new = 0;
+  for (uint64_t i = (uint64_t)blockIdx.x * THREADS + threadIdx.x; i < n_slots;
+       i += (uint64_t)gridDim.x * THREADS) {
+    const uint64_t *slot = reinterpret_cast<const uint64_t *>(elems + i * STRIDE);
+    const uint64_t m = slot[N];
+    if (meta_status(m) == ST_EMPTY) continue;
+    uint64_t key[N];
+#pragma unroll
+    for (int w = 0; w < N; w++) key[w] = slot[w];
+    const int r = table_upsert<N>(t, ctr, key, meta_edges(m), meta_covg(m));
+    my_new += (r == 1);
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) my_new += __shfl_xor_sync(FULL, my_new, o);
+  if (lane_id() == 0 && my_new) atomicAdd(&ctr->unique_kmers, my_new);
+}
+
+// hash_table_find for a batch of canonical keys (keys: n x N words).
+// finalized != 0: reference layout (scan each bucket from slot 0 to the first
+// empty slot, hash_table.c:84-111); else the hashed-start device layout.
+template <int N>
+__global__ void __launch_bounds__(THREADS) find_kernel(const TableView t,
+                                                      const uint64_t *__restrict__ keys,
+                                                      const uint64_t n, const int finalized,
+                                                      uint32_t *covg, uint8_t *edges, uint8_t *found) {
+  constexpr uint32_t STRIDE = 8 * N + 8;
+  for (uint64_t i = (uint64_t)blockIdx.x * THREADS + threadIdx.x; i < n;
+       i += (uint64_t)gridDim.x * THREADS) {
+    uint64_t key[N];
+#pragma unroll
+    for (int w = 0; w < N; w++) key[w] = keys[i * N + w];
+    uint64_t m = 0;
+    bool hit = false;
+    if (!finalized) {
+      hit = table_find<N>(t, key, m);
+    } else {
+      for (uint32_t r = 0; r <= t.max_rehash && !hit; ++r) {
+        const Probe pr = probe_of(lookup3_key<N>(key, r), t.bucket_mask, t.W);
+        const uint8_t *bucket = t.slots + (uint64_t)pr.bucket * t.W * STRIDE;
+        uint32_t s = 0;
+        for (; s < t.W; ++s) {
+          const uint64_t *slot = reinterpret_cast<const uint64_t *>(bucket + (uint64_t)s * STRIDE);
+          m = slot[N];
+          if (meta_status(m) == ST_EMPTY) break;
+          bool same = true;
+#pragma unroll
+          for (int w = 0; w < N; w++) same &= (slot[w] == key[w]);
+          if (same) { hit = true; break; }
+        }
+        if (!hit && s < t.W) break;  // met an empty slot: not present
+      }
+    }
+    found[i] = hit ? 1 : 0;
+    covg[i] = hit ? meta_covg(m) : 0;
+    edges[i] = hit ? (uint8_t)meta_edges(m) : 0;
+  }
+}
+
+__global__ void widen_u32_kernel(const uint32_t *in, unsigned long long *out, uint64_t n) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (uint64_t)gridDim.x * blockDim.x)
+    out[i] = in[i];
+}
+
+// --------------------------------------------------------------------------
+// synthetic reads + random-access microbenchmark (bench / test infrastructure)
+// --------------------------------------------------------------------------
+__global__ void __launch_bounds__(THREADS) synth_kernel(const SynthParams p, const uint64_t first_read,
+                                                       const uint64_t n_reads, uint8_t *seq,
+                                                       uint8_t *qual) {
+  const uint64_t stride = (uint64_t)p.read_len + 1;
+  const uint64_t total = n_reads * stride;
+  for (uint64_t t = (uint64_t)blockIdx.x * THREADS + threadIdx.x; t < total;
+       t += (uint64_t)gridDim.x * THREADS) {
+    const uint64_t r = t / stride;
+    const uint32_t i = (uint32_t)(t - r * stride);
+    uint8_t s, q;
+    synth_byte(p, first_read + r, i, s, q);
+    seq[t] = s;
+    qual[t] = q;
+  }
+}
+
+// Uniform random 32-byte read-modify-write over a buffer of n_sectors sectors:
+// the random-access ceiling the insert kernel is compared with.
+__global__ void __launch_bounds__(THREADS) random_rmw_kernel(uint64_t *buf, const uint64_t n_sectors,
+                                                            const uint64_t n_ops, const uint64_t seed) {
+  for (uint64_t i = (uint64_t)blockIdx.x * THREADS + threadIdx.x; i < n_ops;
+       i += (uint64_t)gridDim.x * THREADS) {
+    const uint64_t h = mix64(seed + i);
+    const uint64_t s = (uint64_t)(((unsigned __int128)h * n_sectors) >> 64);
+    uint64_t *p = buf + s * 4;
+    const uint64_t a = ld_strong_u64(p), b = ld_strong_u64(p + 1);
+    if (a + b != 0x123456789ull)  // data-dependent so the loads cannot be dropped
+      atomicAdd(reinterpret_cast<unsigned int *>(p + 2), 1u);
+  }
+}
+
+int g_sm_count = 0;
+
+template <typename F>
+void dispatch_n(int N, F &&f) {
+  if (N == 1) f(std::integral_constant<int, 1>());
+  else if (N == 2) f(std::integral_constant<int, 2>());
+  else f(std::integral_constant<int, 3>());
+}
+
+template <typename K>
+int resident_grid(K kernel, int cap_per_sm = 8) {
+  int per_sm = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, THREADS, 0);
+  if (per_sm < 1) per_sm = 1;
+  if (per_sm > cap_per_sm) per_sm = cap_per_sm;
+  return per_sm * sm_count();
+}
+
+}  // namespace
+
+int sm_count() {
+  if (!g_sm_count) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
+    if (g_sm_count <= 0) g_sm_count = 148;
+  }
+  return g_sm_count;
+}
+
+void launch_build(int N, BuildMode mode, const BuildParams &p, cudaStream_t st) {
+  if (p.n_bytes == 0) return;
+  dispatch_n(N, [&](auto n) {
+    constexpr int NN = decltype(n)::value;
+    auto go = [&](auto kernel, int T) {
+      const uint64_t n_tiles = (p.n_bytes + T - 1) / T;
+      uint64_t grid = (uint64_t)resident_grid(kernel);
+      if (grid > n_tiles) grid = n_tiles;
+      kernel<<<(unsigned)grid, THREADS, 0, st>>>(p, n_tiles);
+    };
+    if (mode == MODE_FUSED) go(build_kernel<NN, MODE_FUSED>, TileCfg<MODE_FUSED>::T);
+    else if (mode == MODE_RECORDS) go(build_kernel<NN, MODE_RECORDS>, TileCfg<MODE_RECORDS>::T);
+    else go(build_kernel<NN, MODE_ROUTE>, TileCfg<MODE_ROUTE>::T);
+  });
+}
+
+void launch_insert_records(int N, const uint32_t *recs, uint64_t n_recs, const TableView &t,
+                           GraphCounters *ctr, cudaStream_t st) {
+  if (!n_recs) return;
+  dispatch_n(N, [&](auto n) {
+    constexpr int NN = decltype(n)::value;
+    uint64_t grid = (uint64_t)resident_grid(insert_records_kernel<NN>);
+    const uint64_t need = (n_recs + THREADS - 1) / THREADS;
+    if (grid > need) grid = need;
+    insert_records_kernel<NN><<<(unsigned)grid, THREADS, 0, st>>>(recs, n_recs, t, ctr);
+  });
+}
+
+void launch_read_stats(const uint8_t *seq, const uint8_t *qual, const uint64_t *offsets,
+                       uint64_t n_reads, int sep, int k, int cutoff, ReadStats *stats,
+                       unsigned long long *hist, uint32_t hist_size, cudaStream_t st) {
+  if (!n_reads) return;
+  uint64_t grid = (uint64_t)resident_grid(read_stats_kernel);
+  const uint64_t need = (n_reads + (THREADS / 32) - 1) / (THREADS / 32);
+  if (grid > need) grid = need;
+  read_stats_kernel<<<(unsigned)grid, THREADS, 0, st>>>(seq, qual, offsets, n_reads, sep, k, cutoff,
+                                                       stats, hist, hist_size);
+}
+
+void launch_table_summary(int N, const TableView &t, TableSummary *out, cudaStream_t st) {
+  dispatch_n(N, [&](auto n) {
+    constexpr int NN = decltype(n)::value;
+    table_summary_kernel<NN><<<resident_grid(table_summary_kernel<NN>), THREADS, 0, st>>>(t, out);
+  });
+}
+
+void launch_bucket_counts(int N, const TableView &t, uint32_t *counts, cudaStream_t st) {
+  dispatch_n(N, [&](auto n) {
+    constexpr int NN = decltype(n)::value;
+    bucket_counts_kernel<NN><<<resident_grid(bucket_counts_kernel<NN>), THREADS, 0, st>>>(t, counts);
+  });
+}
+
+void launch_finalize(int N, const TableView &t, int16_t *next_element, cudaStream_t st) {
+  dispatch_n(N, [&](auto n) {
+    constexpr int NN = decltype(n)::value;
+    finalize_kernel<NN><<<resident_grid(finalize_kernel<NN>), THREADS, 0, st>>>(t, next_element);
+  });
+}
+
+void launch_dump_ctx(int N, const TableView &t, const uint64_t *bucket_offsets, uint8_t *out,
+                     cudaStream_t st) {
+  dispatch_n(N, [&](auto n) {
+    constexpr int NN = decltype(n)::value;
+    dump_ctx_kernel<NN><<<resident_grid(dump_ctx_kernel<NN>), THREADS, 0, st>>>(t, bucket_offsets, out);
+  });
+}
+
+void launch_ingest_ctx(int N, const uint8_t *recs, uint64_t n_recs, const TableView &t,
+                       GraphCounters *ctr, cudaStream_t st) {
+  if (!n_recs) return;
+  dispatch_n(N, [&](auto n) {
+    constexpr int NN = decltype(n)::value;
+    ingest_ctx_kernel<NN><<<resident_grid(ingest_ctx_kernel<NN>), THREADS, 0, st>>>(recs, n_recs, t, ctr);
+  });
+}
+
+void launch_ingest_elements(int N, const uint8_t *elements, uint64_t n_slots, const TableView &t,
+                            GraphCounters *ctr, cudaStream_t st) {
+  if (!n_slots) return;
+  dispatch_n(N, [&](auto n) {
+    constexpr int NN = decltype(n)::value;
+    ingest_elements_kernel<NN><<<resident_grid(ingest_elements_kernel<NN>), THREADS, 0, st>>>(
+        elements, n_slots, t, ctr);
+  });
+}
+
+void launch_find(int N, const TableView &t, const uint64_t *keys, uint64_t n, int finalized,
+                 uint32_t *covg, uint8_t *edges, uint8_t *found, cudaStream_t st) {
+  if (!n) return;
+  dispatch_n(N, [&](auto nn) {
+    constexpr int NN = decltype(nn)::value;
+    uint64_t grid = (n + THREADS - 1) / THREADS;
+    const uint64_t cap = (uint64_t)resident_grid(find_kernel<NN>);
+    if (grid > cap) grid = cap;
+    find_kernel<NN><<<(unsigned)grid, THREADS, 0, st>>>(t, keys, n, finalized, covg, edges, found);
+  });
+}
+
+size_t exclusive_scan_tmp_bytes(uint64_t n) {
+  size_t bytes = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, bytes, (const unsigned long long *)nullptr,
+                                (unsigned long long *)nullptr, (long long)n);
+  return bytes + n * sizeof(unsigned long long);
+}
+
+// out[i] = sum_{j<i} in[j]; tmp must hold exclusive_scan_tmp_bytes(n)
+void launch_exclusive_scan_u32_to_u64(const uint32_t *in, uint64_t *out, uint64_t n, void *tmp,
+                                      size_t tmp_bytes, cudaStream_t st) {
+  if (!n) return;
+  unsigned long long *wide = reinterpret_cast<unsigned long long *>(tmp);
+  widen_u32_kernel<<<sm_count() * 4, 256, 0, st>>>(in, wide, n);
+  void *cub_tmp = reinterpret_cast<uint8_t *>(tmp) + n * sizeof(unsigned long long);
+  size_t cub_bytes = tmp_bytes - n * sizeof(unsigned long long);
+  cub::DeviceScan::ExclusiveSum(cub_tmp, cub_bytes, wide, reinterpret_cast<unsigned long long *>(out),
+                                (long long)n, st);
+}
+
+void launch_synth(const SynthParams &p, uint64_t first_read, uint64_t n_reads, uint8_t *seq,
+                  uint8_t *qual, cudaStream_t st) {
+  if (!n_reads) return;
+  synth_kernel<<<sm_count() * 8, THREADS, 0, st>>>(p, first_read, n_reads, seq, qual);
+}
+
+void synth_host(const SynthParams &p, uint64_t first_read, uint64_t n_reads, uint8_t *seq,
+                uint8_t *qual) {
+  const uint64_t stride = (uint64_t)p.read_len + 1;
+  for (uint64_t r = 0; r < n_reads; r++)
+    for (uint32_t i = 0; i <= p.read_len; i++)
+      synth_byte(p, first_read + r, i, seq[r * stride + i], qual[r * stride + i]);
+}
+
+void launch_random_rmw(uint64_t *buf, uint64_t n_sectors, uint64_t n_ops, uint64_t seed,
+                       cudaStream_t st) {
+  random_rmw_kernel<<<sm_count() * 8, THREADS, 0, st>>>(buf, n_sectors, n_ops, seed);
+}
+
+}  // namespace lasv

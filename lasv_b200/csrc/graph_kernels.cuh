@@ -1,0 +1,93 @@
+// graph_kernels.cuh -- launch interface between the host runtime (capi.cu) and
+// the sm_100a kernels (graph_kernels.cu).  Plain structs, no torch types.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "table.cuh"
+
+namespace lasv {
+
+// Records travelling between the extract kernel, the all-to-all and the insert
+// kernel: (2N+1) uint32 each = key words as (lo,hi) pairs in word order, then
+// one word {edges : 8, count : 24}.
+__host__ __device__ inline int record_u32(int N) { return 2 * N + 1; }
+
+enum BuildMode { MODE_FUSED = 0, MODE_RECORDS = 1, MODE_ROUTE = 2 };
+
+struct BuildParams {
+  const uint8_t *seq;   // sequence stream: reads back to back, each followed by >= 1 separator byte
+  const uint8_t *qual;  // quality stream, byte-aligned with seq; nullptr = no quality filter (FASTA)
+  uint64_t n_bytes;     // stream length; buffers must be readable up to round_up(n_bytes, 16)
+  int k;
+  int cutoff;           // RAW ascii cutoff (threshold + offset), signed-char compare, '<=' is bad
+  TableView table;
+  GraphCounters *ctr;
+  // MODE_RECORDS: one output array; MODE_ROUTE: n_dest bins of bin_capacity records each
+  uint32_t *rec_out;
+  unsigned long long *rec_count;  // [1] (RECORDS) or [n_dest] (ROUTE)
+  uint64_t rec_capacity;          // records (RECORDS) / records per bin (ROUTE)
+  unsigned long long *rec_overflow;
+  int n_dest;       // power of two
+  int owner_shift;  // owner = (hash.c >> owner_shift) & (n_dest-1)
+};
+
+struct ReadStats {  // loader bookkeeping (file_reader.c:460-470,579,584)
+  unsigned long long n_reads;
+  unsigned long long bad_reads;     // reads without k consecutive good bases
+  unsigned long long bases_read;
+  unsigned long long bases_loaded;  // sum of contig lengths
+  unsigned long long n_contigs;
+};
+
+struct TableSummary {  // order-independent digest of the node multiset
+  unsigned long long n_nodes;
+  unsigned long long sum_covg;
+  unsigned long long sum_edge_bits;
+  unsigned long long fingerprint;  // sum over nodes of node_fingerprint() mod 2^64
+};
+
+struct SynthParams {  // synthetic paired-end reads (bench / tests input, not reference behaviour)
+  uint64_t seed;
+  uint64_t genome_len;
+  uint32_t read_len;
+  uint32_t insert;        // outer fragment length
+  uint32_t err_q20;       // P(substitution) * 2^20 per base
+  uint32_t n_q20;         // P(N) * 2^20 per base
+  uint32_t lowq_q20;      // P(isolated low-quality base, Phred 2..5) * 2^20
+  uint32_t err_lowq_pct;  // % of substituted bases that also get a low quality
+  uint32_t tail_min;      // low-quality 3' tail length range (Phred 2); 0,0 = none
+  uint32_t tail_max;
+  uint32_t tiling;        // 1: error-free forward reads tiling the genome with k-1 overlap
+  uint32_t tiling_step;   // read_len - k + 1 in tiling mode
+};
+
+int sm_count();
+
+void launch_build(int N, BuildMode mode, const BuildParams &p, cudaStream_t st);
+void launch_insert_records(int N, const uint32_t *recs, uint64_t n_recs, const TableView &t,
+                           GraphCounters *ctr, cudaStream_t st);
+void launch_read_stats(const uint8_t *seq, const uint8_t *qual, const uint64_t *offsets,
+                       uint64_t n_reads, int sep, int k, int cutoff, ReadStats *stats,
+                       unsigned long long *hist, uint32_t hist_size, cudaStream_t st);
+void launch_table_summary(int N, const TableView &t, TableSummary *out, cudaStream_t st);
+void launch_bucket_counts(int N, const TableView &t, uint32_t *counts, cudaStream_t st);
+void launch_finalize(int N, const TableView &t, int16_t *next_element, cudaStream_t st);
+void launch_dump_ctx(int N, const TableView &t, const uint64_t *bucket_offsets, uint8_t *out,
+                     cudaStream_t st);
+void launch_ingest_ctx(int N, const uint8_t *recs, uint64_t n_recs, const TableView &t,
+                       GraphCounters *ctr, cudaStream_t st);
+void launch_ingest_elements(int N, const uint8_t *elements, uint64_t n_slots, const TableView &t,
+                            GraphCounters *ctr, cudaStream_t st);
+void launch_find(int N, const TableView &t, const uint64_t *keys, uint64_t n, int finalized,
+                 uint32_t *covg, uint8_t *edges, uint8_t *found, cudaStream_t st);
+void launch_exclusive_scan_u32_to_u64(const uint32_t *in, uint64_t *out, uint64_t n, void *tmp,
+                                      size_t tmp_bytes, cudaStream_t st);
+size_t exclusive_scan_tmp_bytes(uint64_t n);
+void launch_synth(const SynthParams &p, uint64_t first_read, uint64_t n_reads, uint8_t *seq,
+                  uint8_t *qual, cudaStream_t st);
+void synth_host(const SynthParams &p, uint64_t first_read, uint64_t n_reads, uint8_t *seq,
+                uint8_t *qual);
+void launch_random_rmw(uint64_t *buf, uint64_t n_sectors, uint64_t n_ops, uint64_t seed,
+                       cudaStream_t st);
+
+}  // namespace lasv

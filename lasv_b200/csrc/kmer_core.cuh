@@ -1,0 +1,324 @@
+// kmer_core.cuh -- host/device arithmetic shared by every kernel of the graph
+// build: base classification + 2-bit packing, window validity, O(1) k-mer /
+// reverse-complement extraction from a packed tile, canonical key, per-occurrence
+// edge byte, and Bob Jenkins lookup3 over 1/2/3-word keys.
+//
+// Everything here is a pure function (no memory side effects beyond its
+// arguments) marked __host__ __device__, so tests/host_emul can run exactly the
+// code the kernels run, on the CPU, against the oracle.
+//
+// Reference semantics restated (file:line under /root/reference):
+//   base codes A0 C1 G2 T3 ............ include/basic/event_encoding/base_encoding/event_encoding.h:37-44
+//   "bad" base (non-ACGT or qual<=cutoff) src/dB_graph_operations/file_reader.c:120-178,389
+//   BinaryKmer word order (word 0 = MSW)  include/basic/binary_kmer.h:41-47, src/basic/binary_kmer.c:115-143
+//   reverse complement .................. src/basic/binary_kmer.c:456-523
+//   canonical key = min(kmer, revcomp) .. src/dB_graph_operations/element.c:308-336, binary_kmer.c:66-97
+//   orientation / edge bits ............. src/dB_graph_operations/element.c:470-560
+//   lookup3 hashlittle(key, 8N, 10) ..... src/hash_table/hash_key/bob_jenkins/hash_value.c:114-158,282-449,767-773
+//   rehash = add r to the last word ..... src/hash_table/open_hash/hash_table.c:73-78
+#pragma once
+#include <stdint.h>
+#include <vector_types.h>
+
+#if defined(__CUDACC__)
+#define LASV_HD __host__ __device__ __forceinline__
+#else
+#define LASV_HD inline
+#endif
+
+namespace lasv {
+
+// ---------------------------------------------------------------- intrinsics
+LASV_HD int clz64(uint64_t x) {
+#if defined(__CUDA_ARCH__)
+  return __clzll((long long)x);
+#else
+  return x ? __builtin_clzll(x) : 64;
+#endif
+}
+LASV_HD uint32_t brev32(uint32_t x) {
+#if defined(__CUDA_ARCH__)
+  return __brev(x);
+#else
+  x = ((x >> 1) & 0x55555555u) | ((x & 0x55555555u) << 1);
+  x = ((x >> 2) & 0x33333333u) | ((x & 0x33333333u) << 2);
+  x = ((x >> 4) & 0x0F0F0F0Fu) | ((x & 0x0F0F0F0Fu) << 4);
+  x = ((x >> 8) & 0x00FF00FFu) | ((x & 0x00FF00FFu) << 8);
+  return (x >> 16) | (x << 16);
+#endif
+}
+LASV_HD uint32_t rot32(uint32_t x, int k) {
+#if defined(__CUDA_ARCH__)
+  return __funnelshift_l(x, x, k);
+#else
+  return (x << k) | (x >> (32 - k));
+#endif
+}
+LASV_HD uint32_t mulhi32(uint32_t a, uint32_t b) {
+#if defined(__CUDA_ARCH__)
+  return __umulhi(a, b);
+#else
+  return (uint32_t)(((uint64_t)a * (uint64_t)b) >> 32);
+#endif
+}
+
+// ------------------------------------------------------------------- lookup3
+struct Hash3 {
+  uint32_t a, b, c;  // c is the reference's hashlittle() value
+};
+
+#define LASV_MIX(a, b, c)                 \
+  {                                       \
+    a -= c; a ^= rot32(c, 4);  c += b;    \
+    b -= a; b ^= rot32(a, 6);  a += c;    \
+    c -= b; c ^= rot32(b, 8);  b += a;    \
+    a -= c; a ^= rot32(c, 16); c += b;    \
+    b -= a; b ^= rot32(a, 19); a += c;    \
+    c -= b; c ^= rot32(b, 4);  b += a;    \
+  }
+#define LASV_FINAL(a, b, c)               \
+  {                                       \
+    c ^= b; c -= rot32(b, 14);            \
+    a ^= c; a -= rot32(c, 11);            \
+    b ^= a; b -= rot32(a, 25);            \
+    c ^= b; c -= rot32(b, 16);            \
+    a ^= c; a -= rot32(c, 4);             \
+    b ^= a; b -= rot32(a, 14);            \
+    c ^= b; c -= rot32(b, 24);            \
+  }
+
+// hashlittle over the 8N key bytes in memory order (word 0 first, each word
+// little-endian), initval 10, with `rehash` added to the last word first.
+// Returns the full final (a,b,c) state: c is what the reference uses for the
+// bucket; a and b are spare, equally mixed bits (used for the in-bucket start
+// slot and the slot tag -- device-layout only, invisible in any output).
+template <int N>
+LASV_HD Hash3 lookup3_key(const uint64_t (&key)[N], uint32_t rehash) {
+  uint32_t w[2 * N];
+#pragma unroll
+  for (int i = 0; i < N; i++) {
+    uint64_t v = key[i] + ((i == N - 1) ? (uint64_t)rehash : 0ull);
+    w[2 * i] = (uint32_t)v;
+    w[2 * i + 1] = (uint32_t)(v >> 32);
+  }
+  uint32_t a, b, c;
+  a = b = c = 0xdeadbeefu + (uint32_t)(8 * N) + 10u;
+  if (N == 1) {
+    a += w[0]; b += w[1];
+  } else if (N == 2) {
+    a += w[0]; b += w[1]; c += w[2];
+    LASV_MIX(a, b, c);
+    a += w[3];
+  } else {
+    a += w[0]; b += w[1]; c += w[2];
+    LASV_MIX(a, b, c);
+    a += w[3]; b += w[4 % (2 * N)]; c += w[5 % (2 * N)];
+  }
+  LASV_FINAL(a, b, c);
+  Hash3 h;
+  h.a = a; h.b = b; h.c = c;
+  return h;
+}
+
+// ------------------------------------------------- base classification (16 B)
+// Classify 16 consecutive bytes of the sequence stream (and the 16 matching
+// quality bytes).  Out:
+//   code32 : 2-bit codes, FIRST base in bits 31:30 ... 16th base in bits 1:0
+//   bad16  : bit 15 = first base ... bit 0 = 16th base; 1 = base breaks k-mers
+// A base is bad iff it is not one of ACGTacgt, or has_qual and the RAW quality
+// byte, compared as signed char, is <= cutoff (file_reader.c:150,389), or its
+// byte lies outside the stream (inrange16 bit clear; bit i <-> byte i).
+// Read separators ('\n') are ordinary non-ACGT bytes, hence bad: no window ever
+// spans two reads.
+LASV_HD void classify16(uint4 sv, uint4 qv, bool has_qual, int cutoff, uint32_t inrange16,
+                        uint32_t &code32, uint32_t &bad16) {
+  const uint32_t sw[4] = {sv.x, sv.y, sv.z, sv.w};
+  const uint32_t qw[4] = {qv.x, qv.y, qv.z, qv.w};
+  uint32_t code = 0, bad = 0;
+#pragma unroll
+  for (int i = 0; i < 16; i++) {
+    uint32_t ch = (sw[i >> 2] >> (8 * (i & 3))) & 0xFFu;
+    uint32_t u = ch & 0xDFu;  // fold lower case onto upper case (clears bit 5 only)
+    bool isb = (u == 0x41u) | (u == 0x43u) | (u == 0x47u) | (u == 0x54u);
+    uint32_t c2 = ((u >> 1) & 3u) ^ ((u >> 2) & 1u);  // A0 C1 G2 T3
+    int q = (int)(int8_t)((qw[i >> 2] >> (8 * (i & 3))) & 0xFFu);
+    bool lowq = has_qual & (q <= cutoff);
+    bool in = (inrange16 >> i) & 1u;
+    bool isbad = (!isb) | lowq | (!in);
+    code |= (isb ? c2 : 0u) << (30 - 2 * i);
+    bad |= (uint32_t)isbad << (15 - i);
+  }
+  code32 = code;
+  bad16 = bad;
+}
+
+// Reverse-complement of a 16-base code word: complement every base (3-c == ~c
+// on two bits) and reverse the base order.
+LASV_HD uint32_t rc_code32(uint32_t code32) {
+  uint32_t y = brev32(~code32);
+  return ((y >> 1) & 0x55555555u) | ((y & 0x55555555u) << 1);
+}
+
+// ------------------------------------------------------------ tile geometry
+// A tile is a window of the byte stream packed into shared memory (or a host
+// array in the emulation).  Region base index j in [0, R): region position 0 is
+// stream position t0 - HALO_L.  All three packed arrays are big-endian bit
+// strings over the region:
+//   P  (uint64)  forward codes, 32 bases per word, ONE pad word in front
+//   PR (uint64)  reverse-complement string (RC position p <-> region R-1-p),
+//                same layout
+//   BD (uint64)  bad bits, 64 bases per word, two all-ones pad words behind
+struct TileGeom {
+  static constexpr int HALO_L = 16;   // bytes before the first window start (need >= 1)
+  static constexpr int HALO_R = 112;  // bytes after the last window start   (need >= k+1, k<=95)
+};
+
+// Index (in uint32 units) inside P/PR for the 16-base chunk c: big-endian
+// halves inside little-endian uint64 words, plus the front pad word.
+LASV_HD int code_u32_index(int chunk) { return (chunk + 2) ^ 1; }
+// Index (in uint16 units) inside BD for chunk c.
+LASV_HD int bad_u16_index(int chunk) { return chunk ^ 3; }
+
+// True iff the k bases starting at region index j are all good.
+// BD must have two pad words of all-ones behind the data (k <= 95).
+LASV_HD bool window_good(const uint64_t *BD, int j, int k) {
+  int w = j >> 6, off = j & 63;
+  uint64_t x = BD[w] << off;
+  if (x) return clz64(x) >= k;
+  int d = 64 - off;
+  if (d >= k) return true;
+  x = BD[w + 1];
+  if (x) return d + clz64(x) >= k;
+  d += 64;
+  if (d >= k) return true;
+  x = BD[w + 2];
+  return d + clz64(x) >= k;
+}
+
+LASV_HD bool base_bad(const uint64_t *BD, int j) { return (BD[j >> 6] >> (63 - (j & 63))) & 1ull; }
+LASV_HD uint32_t base_code(const uint64_t *P, int j) {
+  return (uint32_t)(P[(j >> 5) + 1] >> (62 - 2 * (j & 31))) & 3u;
+}
+
+// Distance from region index j to the next bad base at or after j, scanning at
+// most up to region index `limit` (exclusive).  Returns limit - j if none.
+LASV_HD int next_bad_distance(const uint64_t *BD, int j, int limit) {
+  int p = j;
+  while (p < limit) {
+    int w = p >> 6, off = p & 63;
+    uint64_t x = BD[w] << off;
+    if (x) {
+      int d = p + clz64(x);
+      return (d < limit ? d : limit) - j;
+    }
+    p += 64 - off;
+  }
+  return limit - j;
+}
+
+// The k-mer whose first base is region index j, right-aligned in N words with
+// word 0 most significant (binary_kmer.h:41-47).  P has one pad word in front.
+template <int N>
+LASV_HD void extract_kmer(const uint64_t *P, int j, int k, uint64_t (&out)[N]) {
+#pragma unroll
+  for (int e = 0; e < N; e++) {
+    int b0 = j + k - 32 * e;  // padded base coordinate of the first of 32 bases of word N-1-e
+    int w = b0 >> 5, sh = 2 * (b0 & 31);
+    uint64_t hi = P[w], lo = P[w + 1];
+    out[N - 1 - e] = (hi << sh) | ((lo >> 1) >> (63 - sh));
+  }
+  out[0] &= (~0ull) >> (64 - 2 * (k & 31));
+}
+
+template <int N>
+LASV_HD bool kmer_less(const uint64_t (&a)[N], const uint64_t (&b)[N]) {
+#pragma unroll
+  for (int i = 0; i < N; i++) {
+    if (a[i] != b[i]) return a[i] < b[i];
+  }
+  return false;
+}
+
+template <int N>
+LASV_HD bool kmer_equal(const uint64_t (&a)[N], const uint64_t (&b)[N]) {
+  bool eq = true;
+#pragma unroll
+  for (int i = 0; i < N; i++) eq &= (a[i] == b[i]);
+  return eq;
+}
+
+// One k-mer OCCURRENCE: the canonical key and the 8-bit edge contribution this
+// occurrence makes to its node (element.c:519-560 evaluated on the read alone):
+//   as target of (prev -> this):  bit (3 - f) of the nibble OPPOSITE to this
+//       occurrence's orientation, f = base before the window;
+//   as source of (this -> next):  bit b of the nibble OF this occurrence's
+//       orientation, b = base after the window.
+// Low nibble = forward edges, high nibble = reverse (element.c:501-513).
+// prev/next exist iff the neighbouring window is good, i.e. (given this window
+// is good) iff the base just before / just after it is good.
+template <int N>
+LASV_HD uint32_t kmer_occurrence(const uint64_t *P, const uint64_t *PR, const uint64_t *BD, int R,
+                                 int j, int k, uint64_t (&key)[N]) {
+  uint64_t fw[N], rc[N];
+  extract_kmer<N>(P, j, k, fw);
+  extract_kmer<N>(PR, R - j - k, k, rc);
+  const bool rev = kmer_less<N>(rc, fw);  // k odd => fw != rc
+#pragma unroll
+  for (int i = 0; i < N; i++) key[i] = rev ? rc[i] : fw[i];
+  const uint32_t o = rev ? 1u : 0u;
+  uint32_t edge = 0;
+  if (!base_bad(BD, j - 1)) edge |= (1u << (3u - base_code(P, j - 1))) << (4u * (1u - o));
+  if (!base_bad(BD, j + k)) edge |= (1u << base_code(P, j + k)) << (4u * o);
+  return edge;
+}
+
+// ------------------------------------------------------- device slot layout
+// A slot has the reference Element layout (element.h:77-82): N key words, then
+// one 8-byte word holding {uint32 coverage; int8 edges; int8 status; 2 pad}.
+// While the table lives on the device the two pad bytes carry a 16-bit tag of
+// the key (zeroed again when the table is finalised for the host).
+constexpr uint32_t ST_EMPTY = 0;       // NodeStatus unassigned (element.h:57)
+constexpr uint32_t ST_NONE = 1;        // NodeStatus none
+constexpr uint32_t ST_LOCKED = 0x80;   // device-only: key words not yet published
+
+LASV_HD uint64_t meta_pack(uint32_t covg, uint32_t edges, uint32_t status, uint32_t tag) {
+  return (uint64_t)covg | ((uint64_t)(edges & 0xFFu) << 32) | ((uint64_t)(status & 0xFFu) << 40) |
+         ((uint64_t)(tag & 0xFFFFu) << 48);
+}
+LASV_HD uint32_t meta_covg(uint64_t m) { return (uint32_t)m; }
+LASV_HD uint32_t meta_edges(uint64_t m) { return (uint32_t)(m >> 32) & 0xFFu; }
+LASV_HD uint32_t meta_status(uint64_t m) { return (uint32_t)(m >> 40) & 0xFFu; }
+LASV_HD uint32_t meta_tag(uint64_t m) { return (uint32_t)(m >> 48); }
+
+// Where a key lives: CORTEX bucket from c (hash_value.c:767-773), in-bucket
+// start slot and tag from the spare hash words.
+struct Probe {
+  uint32_t bucket, start, tag;
+};
+LASV_HD Probe probe_of(const Hash3 &h, uint32_t bucket_mask, uint32_t W) {
+  Probe p;
+  p.bucket = h.c & bucket_mask;
+  p.start = mulhi32(h.b, W);
+  p.tag = h.a >> 16;
+  return p;
+}
+
+// 64-bit mixer (splitmix64 finaliser) -- used by the order-independent table
+// checksum and by the synthetic read generator.
+LASV_HD uint64_t mix64(uint64_t x) {
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+
+// Order-independent fingerprint of one node (key words, coverage, edges).
+template <int N>
+LASV_HD uint64_t node_fingerprint(const uint64_t (&key)[N], uint32_t covg, uint32_t edges) {
+  uint64_t h = 0x243F6A8885A308D3ull;
+#pragma unroll
+  for (int i = 0; i < N; i++) h = mix64(h ^ key[i]);
+  return mix64(h ^ ((uint64_t)covg | ((uint64_t)(edges & 0xFFu) << 32)));
+}
+
+}  // namespace lasv

@@ -1,0 +1,200 @@
+// seq_reader.cpp -- see seq_reader.h
+#include "seq_reader.h"
+#include <string.h>
+#include <strings.h>
+
+namespace lasv {
+
+static bool path_has_ext(const std::string &p, const char *ext) {
+  const size_t n = strlen(ext);
+  if (p.size() >= n && strcasecmp(p.c_str() + p.size() - n, ext) == 0) return true;
+  // ".sam.something" style (seq_file.c:126-137 looks for the extension anywhere)
+  std::string lower(p);
+  for (auto &c : lower) c = (char)tolower((unsigned char)c);
+  std::string needle = std::string(ext) + ".";
+  return lower.find(needle) != std::string::npos;
+}
+
+bool SeqReader::open(const std::string &path, std::string &err) {
+  close();
+  path_ = path;
+  if (path_has_ext(path, ".sam") || path_has_ext(path, ".bam")) {
+    err = "SAM/BAM input is not supported by the GPU loader: " + path;
+    return false;
+  }
+  gz_ = gzopen(path.c_str(), "r");
+  if (!gz_) {
+    err = "Couldn't open sequence file '" + path + "'";
+    return false;
+  }
+  gzbuffer(gz_, 1u << 20);
+  buf_.resize(4u << 20);
+  pos_ = end_ = 0;
+  eof_ = false;
+  n_reads_ = 0;
+  // type sniffing on the first byte (seq_file.c:215-259)
+  const int c = getc_();
+  if (c == -1) {
+    type_ = PLAIN;  // empty file: no reads
+  } else if (c == '>') {
+    type_ = FASTA;
+    at_record_start_ = true;
+  } else if (c == '@') {
+    type_ = FASTQ;
+    at_record_start_ = true;
+  } else {
+    type_ = PLAIN;
+    pos_--;  // unget
+  }
+  return true;
+}
+
+void SeqReader::close() {
+  if (gz_) gzclose(gz_);
+  gz_ = nullptr;
+  type_ = UNKNOWN;
+}
+
+bool SeqReader::fill_() {
+  if (eof_) return false;
+  const int n = gzread(gz_, buf_.data(), (unsigned)buf_.size());
+  if (n <= 0) {
+    eof_ = true;
+    pos_ = end_ = 0;
+    return false;
+  }
+  pos_ = 0;
+  end_ = (size_t)n;
+  return true;
+}
+
+int SeqReader::getc_() {
+  if (pos_ == end_ && !fill_()) return -1;
+  return buf_[pos_++];
+}
+
+int SeqReader::peekc_() {
+  if (pos_ == end_ && !fill_()) return -1;
+  return buf_[pos_];
+}
+
+// Consume up to and including the next '\n'; append the line, without its
+// trailing "\r\n", to *dst (strbuf readline + chomp).
+void SeqReader::read_line_(std::string *dst) {
+  for (;;) {
+    if (pos_ == end_ && !fill_()) break;
+    const unsigned char *p = buf_.data() + pos_;
+    const size_t avail = end_ - pos_;
+    const unsigned char *nl = (const unsigned char *)memchr(p, '\n', avail);
+    const size_t take = nl ? (size_t)(nl - p) : avail;
+    if (dst) dst->append((const char *)p, take);
+    pos_ += take;
+    if (nl) {
+      pos_++;
+      break;
+    }
+  }
+  if (dst) {
+    while (!dst->empty() && (dst->back() == '\r' || dst->back() == '\n')) dst->pop_back();
+  }
+}
+
+bool SeqReader::next(std::string &err) {
+  seq_.clear();
+  qual_.clear();
+  if (!gz_) return false;
+  int c;
+  if (type_ == FASTQ) {
+    if (!at_record_start_) {
+      // skip newlines, expect '@' (seq_fastq.c:86-99)
+      while ((c = getc_()) != -1 && (c == '\n' || c == '\r')) {}
+      if (c == -1) return false;
+      if (c != '@') {
+        err = "FASTQ header does not begin with '@' [file: " + path_ + "]";
+        return false;
+      }
+    }
+    at_record_start_ = false;
+    read_line_(nullptr);  // read name
+    // sequence: every line up to one that starts with '+' (seq_fastq.c:24-53)
+    while ((c = getc_()) != -1 && c != '+') {
+      if (c != '\r' && c != '\n') {
+        seq_.push_back((char)c);
+        read_line_(&seq_);
+      }
+    }
+    if (c == -1) {
+      if (seq_.empty()) return false;  // trailing '@name' without a record
+      err = "Missing '+' in FASTQ [file: " + path_ + "]";
+      return false;
+    }
+    read_line_(nullptr);  // rest of the '+' line
+    // qualities: exactly |seq| non-newline bytes, possibly over several lines
+    qual_.reserve(seq_.size());
+    while (qual_.size() < seq_.size()) {
+      c = getc_();
+      if (c == -1) {
+        err = "FASTQ file ended without finishing quality scores [file: " + path_ + "]";
+        return false;
+      }
+      if (c != '\r' && c != '\n') qual_.push_back((char)c);
+    }
+    n_reads_++;
+    return true;
+  }
+  if (type_ == FASTA) {
+    if (!at_record_start_) {
+      // we are positioned just after a '>' or at EOF
+      return false;
+    }
+    at_record_start_ = false;
+    read_line_(nullptr);  // name
+    // bases: everything but newlines up to the next '>' (seq_fasta.c:72-95)
+    for (;;) {
+      if (pos_ == end_ && !fill_()) break;
+      const unsigned char ch = buf_[pos_];
+      if (ch == '>') {
+        pos_++;
+        at_record_start_ = true;
+        break;
+      }
+      if (ch == '\n' || ch == '\r') {
+        pos_++;
+        continue;
+      }
+      // take the run up to the next newline or '>'
+      size_t e = pos_;
+      while (e < end_ && buf_[e] != '\n' && buf_[e] != '\r' && buf_[e] != '>') e++;
+      seq_.append((const char *)buf_.data() + pos_, e - pos_);
+      pos_ = e;
+    }
+    n_reads_++;
+    return true;
+  }
+  if (type_ == PLAIN) {
+    // one read per line terminator (seq_plain.c:24-66): an empty line is an empty read
+    if (peekc_() == -1) return false;
+    while ((c = getc_()) != -1 && c != '\n' && c != '\r') seq_.push_back((char)c);
+    n_reads_++;
+    return true;
+  }
+  return false;
+}
+
+bool SeqReader::append_to(HostBatch &b, bool with_qual) const {
+  const uint64_t need = (uint64_t)seq_.size() + 1;
+  if (b.n_reads >= b.cap_reads || b.n_bytes + need > b.cap_bytes) return false;
+  memcpy(b.seq + b.n_bytes, seq_.data(), seq_.size());
+  b.seq[b.n_bytes + seq_.size()] = '\n';
+  if (with_qual) {
+    if (qual_.size() == seq_.size()) memcpy(b.qual + b.n_bytes, qual_.data(), seq_.size());
+    else memset(b.qual + b.n_bytes, 0x7F, seq_.size());  // reader without qualities in a mixed pair
+    b.qual[b.n_bytes + seq_.size()] = '\n';
+  }
+  b.n_bytes += need;
+  b.n_reads++;
+  b.offsets[b.n_reads] = b.n_bytes;
+  return true;
+}
+
+}  // namespace lasv

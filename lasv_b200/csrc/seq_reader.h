@@ -1,0 +1,66 @@
+// seq_reader.h -- host-side sequence file reader feeding the GPU loader.
+//
+// Re-implements the grammar of the reference's vendored reader for the formats
+// laSV feeds it (libs/seq_file/seq_file.c:191-239 type sniffing on the first
+// byte; seq_fastq.c:24-150; seq_fasta.c:24-100; seq_plain.c), gzip through
+// zlib's gzopen like the reference (seq_file.c:170).  Reads are appended to a
+// batch as two byte streams with a '\n' after each read -- the layout the build
+// kernel consumes -- instead of being handed out base by base.
+#pragma once
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include <zlib.h>
+
+namespace lasv {
+
+// Pinned (or plain) host buffers for one batch of reads.
+struct HostBatch {
+  uint8_t *seq = nullptr;
+  uint8_t *qual = nullptr;
+  uint64_t *offsets = nullptr;  // cap_reads + 1 entries
+  uint64_t cap_bytes = 0, cap_reads = 0;
+  uint64_t n_bytes = 0, n_reads = 0;
+  void reset() { n_bytes = 0; n_reads = 0; if (offsets) offsets[0] = 0; }
+};
+
+class SeqReader {
+ public:
+  enum Type { UNKNOWN, FASTQ, FASTA, PLAIN };
+  SeqReader() {}
+  ~SeqReader() { close(); }
+  // Returns false (and sets err) if the file cannot be opened or is SAM/BAM.
+  bool open(const std::string &path, std::string &err);
+  void close();
+  bool has_quality() const { return type_ == FASTQ; }
+  Type type() const { return type_; }
+  const std::string &path() const { return path_; }
+
+  // Parse the next read into the internal (seq_, qual_) strings.
+  // Returns false at end of file.  err is set on malformed input.
+  bool next(std::string &err);
+  const std::string &seq() const { return seq_; }
+  const std::string &qual() const { return qual_; }
+  uint64_t reads_parsed() const { return n_reads_; }
+
+  // Append the current read to a batch; false if it does not fit.
+  bool append_to(HostBatch &b, bool with_qual) const;
+
+ private:
+  int getc_();
+  int peekc_();
+  bool fill_();
+  void read_line_(std::string *dst);  // rest of the current line, chomped; dst may be null
+
+  gzFile gz_ = nullptr;
+  std::string path_;
+  Type type_ = UNKNOWN;
+  std::vector<unsigned char> buf_;
+  size_t pos_ = 0, end_ = 0;
+  bool eof_ = false;
+  bool at_record_start_ = false;  // header marker already consumed (seq_file.c: read_line_start)
+  std::string seq_, qual_;
+  uint64_t n_reads_ = 0;
+};
+
+}  // namespace lasv

@@ -1,0 +1,176 @@
+// table.cuh -- device side of the CORTEX-style open hash (2^L buckets x W slots):
+// lock-free find-or-insert with coverage / edge accumulation.
+//
+// Replaces, on the device (reference file:line under /root/reference):
+//   hash_table_find_or_insert / find_in_bucket  src/hash_table/open_hash/hash_table.c:69-122,270-327
+//   element_initialise                          src/dB_graph_operations/element.c:339-362
+//   db_node_update_coverage (saturating u32)    src/dB_graph_operations/element.c:395-417
+//   add_edges (OR)                              src/dB_graph_operations/element.c:223-228
+//
+// Same bucket function and rehash chain as the reference (bucket r of a key is
+// lookup3(key + r) & (2^L - 1), r = 0..max_rehash, a key moves to bucket r+1
+// only when bucket r is FULL), so capacity behaviour ("table full" is fatal) and
+// the set of keys a bucket can hold are the reference's.  What differs is only
+// the position INSIDE a bucket: instead of scanning from slot 0 (W/2 slot reads
+// per lookup) a key starts at a hashed slot and probes linearly with wrap-around,
+// so a lookup touches O(1) slots.  lasv_graph_finalize() squeezes every bucket
+// hole-free afterwards, which is exactly the layout hash_table_find expects.
+//
+// Concurrency protocol per slot (meta = the 8-byte word after the key words):
+//   EMPTY  --CAS(meta: 0 -> {covg=c, edges=e, LOCKED, tag})-->  LOCKED
+//   LOCKED --key words stored, __threadfence, meta ^= LOCKED^NONE-->  NONE
+// Readers that find LOCKED with a different tag skip the slot (different key);
+// with the same tag they wait for publication, then compare key words.
+// Updates of a published slot are two independent L2 reductions: 32-bit add on
+// the coverage word, 32-bit OR on the edges word (only when it adds a bit).
+#pragma once
+#include <cuda_runtime.h>
+#include "kmer_core.cuh"
+
+namespace lasv {
+
+struct TableView {
+  uint8_t *slots;        // n_buckets * W slots of (8N+8) bytes
+  uint32_t bucket_mask;  // n_buckets - 1
+  uint32_t W;
+  uint32_t max_rehash;   // 15 in laSV (graph_operations.c:640)
+};
+
+// Per-graph device counters (one cache line each would be nicer; they are only
+// touched once per CTA).
+struct GraphCounters {
+  unsigned long long unique_kmers;     // hash_table.c:305
+  unsigned long long kmers_inserted;   // number of find_or_insert calls
+  unsigned long long table_full;       // != 0: some key found 16 full buckets (reference die()s)
+  unsigned long long rehash_hist[16];  // collisions[r], hash_table.c:325
+  unsigned long long covg_saturated;   // element.c:402-415 warning condition
+};
+
+__device__ __forceinline__ uint64_t ld_strong_u64(const uint64_t *p) {
+  uint64_t v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_strong_u64(uint64_t *p, uint64_t v) {
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ void prefetch_l2(const void *p) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+
+// Saturating coverage add on a published slot (slow path, only near UINT_MAX).
+static __device__ __noinline__ void covg_add_saturating(uint64_t *meta_ptr, uint32_t add,
+                                                 GraphCounters *ctr) {
+  unsigned long long *mp = reinterpret_cast<unsigned long long *>(meta_ptr);
+  unsigned long long old = ld_strong_u64(meta_ptr);
+  for (;;) {
+    uint32_t c = (uint32_t)old;
+    uint32_t nc = (0xFFFFFFFFu - add >= c) ? c + add : 0xFFFFFFFFu;
+    unsigned long long want = (old & 0xFFFFFFFF00000000ull) | nc;
+    unsigned long long got = atomicCAS(mp, old, want);
+    if (got == old) {
+      if (nc == 0xFFFFFFFFu) atomicAdd(&ctr->covg_saturated, 1ull);
+      return;
+    }
+    old = got;
+  }
+}
+
+// find-or-insert `key`, then coverage += covg_add (saturating) and edges |= edge.
+// Returns 1 if the key was new, 0 if it existed, -1 if the table is full.
+template <int N>
+__device__ __forceinline__ int table_upsert(const TableView &t, GraphCounters *ctr,
+                                            const uint64_t (&key)[N], uint32_t edge,
+                                            uint32_t covg_add) {
+  constexpr uint32_t STRIDE = 8 * N + 8;
+  for (uint32_t r = 0; r <= t.max_rehash; ++r) {
+    const Probe pr = probe_of(lookup3_key<N>(key, r), t.bucket_mask, t.W);
+    uint8_t *bucket = t.slots + (uint64_t)pr.bucket * t.W * STRIDE;
+    uint32_t s = pr.start;
+    for (uint32_t i = 0; i < t.W; ++i) {
+      uint64_t *slot = reinterpret_cast<uint64_t *>(bucket + (uint64_t)s * STRIDE);
+      uint64_t *meta_ptr = slot + N;
+      if (N > 1) prefetch_l2(slot);  // key words may sit in the neighbouring sector
+      uint64_t m = ld_strong_u64(meta_ptr);
+      for (;;) {
+        const uint32_t st = meta_status(m);
+        if (st == ST_EMPTY) {
+          const uint64_t want = meta_pack(covg_add, edge, ST_LOCKED, pr.tag);
+          const uint64_t old = atomicCAS(reinterpret_cast<unsigned long long *>(meta_ptr), 0ull,
+                                         (unsigned long long)want);
+          if (old == 0ull) {
+#pragma unroll
+            for (int w = 0; w < N; w++) st_strong_u64(slot + w, key[w]);
+            __threadfence();
+            atomicXor(reinterpret_cast<unsigned long long *>(meta_ptr),
+                      (unsigned long long)(ST_LOCKED ^ ST_NONE) << 40);
+            if (r) atomicAdd(&ctr->rehash_hist[r], 1ull);
+            return 1;
+          }
+          m = old;  // somebody claimed it first: look at what they put there
+          continue;
+        }
+        if (meta_tag(m) != pr.tag) break;  // some other key: next slot
+        if (st == ST_LOCKED) {
+          // same tag, key words not visible yet: wait for the owner to publish
+          do {
+            __nanosleep(40);
+            m = ld_strong_u64(meta_ptr);
+          } while (meta_status(m) == ST_LOCKED);
+          __threadfence();
+        }
+        // published, tag matches: compare the key (loads are issued after the
+        // meta load that saw the slot published, and bypass L1)
+        bool same = true;
+#pragma unroll
+        for (int w = 0; w < N; w++) same &= (ld_strong_u64(slot + w) == key[w]);
+        if (!same) break;
+        // ---- hit: accumulate
+        if (meta_covg(m) < 0xF0000000u && covg_add < 0x01000000u) {
+          atomicAdd(reinterpret_cast<unsigned int *>(meta_ptr), covg_add);
+        } else {
+          covg_add_saturating(meta_ptr, covg_add, ctr);
+        }
+        if ((meta_edges(m) | edge) != meta_edges(m)) {
+          atomicOr(reinterpret_cast<unsigned int *>(meta_ptr) + 1, edge & 0xFFu);
+        }
+        if (r) atomicAdd(&ctr->rehash_hist[r], 1ull);
+        return 0;
+      }
+      if (++s == t.W) s = 0;
+    }
+    // bucket r is full and does not hold the key: follow the rehash chain
+  }
+  atomicExch(&ctr->table_full, 1ull);
+  return -1;
+}
+
+// hash_table_find (hash_table.c:234-267) on the UN-finalised device layout.
+// Returns true and the meta word if present.
+template <int N>
+__device__ __forceinline__ bool table_find(const TableView &t, const uint64_t (&key)[N],
+                                           uint64_t &meta_out) {
+  constexpr uint32_t STRIDE = 8 * N + 8;
+  for (uint32_t r = 0; r <= t.max_rehash; ++r) {
+    const Probe pr = probe_of(lookup3_key<N>(key, r), t.bucket_mask, t.W);
+    const uint8_t *bucket = t.slots + (uint64_t)pr.bucket * t.W * STRIDE;
+    uint32_t s = pr.start;
+    bool saw_empty = false;
+    for (uint32_t i = 0; i < t.W; ++i) {
+      const uint64_t *slot = reinterpret_cast<const uint64_t *>(bucket + (uint64_t)s * STRIDE);
+      uint64_t m = ld_strong_u64(slot + N);
+      if (meta_status(m) == ST_EMPTY) { saw_empty = true; break; }
+      if (meta_tag(m) == pr.tag) {
+        bool same = true;
+#pragma unroll
+        for (int w = 0; w < N; w++) same &= (ld_strong_u64(slot + w) == key[w]);
+        if (same) { meta_out = m; return true; }
+      }
+      if (++s == t.W) s = 0;
+    }
+    if (saw_empty) return false;
+  }
+  return false;
+}
+
+}  // namespace lasv
