@@ -1,0 +1,157 @@
+"""ctypes binding of lasv_b200/liblasv_b200.so (include/lasv_b200.h).
+
+The library is the product; this module only declares its entry points.  It
+fails loudly if the library has not been built -- there is no Python or CPU
+implementation behind any of these calls.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+PKG_DIR = Path(__file__).resolve().parent
+LIB_PATH = PKG_DIR / "liblasv_b200.so"
+
+LASV_OK = 0
+LASV_ERR_ARG = -1
+LASV_ERR_CUDA = -2
+LASV_ERR_TABLE_FULL = -3
+LASV_ERR_IO = -4
+LASV_ERR_STATE = -5
+LASV_ERR_CAPACITY = -6
+
+
+class LoadStats(C.Structure):
+    _fields_ = [("n_reads", C.c_uint64), ("bad_reads", C.c_uint64), ("bases_read", C.c_uint64),
+                ("bases_loaded", C.c_uint64), ("n_contigs", C.c_uint64),
+                ("kmers_inserted", C.c_uint64), ("unique_kmers", C.c_uint64)]
+
+    def as_dict(self):
+        return {f: int(getattr(self, f)) for f, _ in self._fields_}
+
+
+class TableSummary(C.Structure):
+    _fields_ = [("n_nodes", C.c_uint64), ("sum_covg", C.c_uint64), ("sum_edge_bits", C.c_uint64),
+                ("fingerprint", C.c_uint64)]
+
+    def as_dict(self):
+        return {f: int(getattr(self, f)) for f, _ in self._fields_}
+
+
+class SynthParams(C.Structure):
+    _fields_ = [("seed", C.c_uint64), ("genome_len", C.c_uint64), ("read_len", C.c_uint32),
+                ("insert", C.c_uint32), ("err_q20", C.c_uint32), ("n_q20", C.c_uint32),
+                ("lowq_q20", C.c_uint32), ("err_lowq_pct", C.c_uint32), ("tail_min", C.c_uint32),
+                ("tail_max", C.c_uint32), ("tiling", C.c_uint32), ("tiling_step", C.c_uint32)]
+
+
+class RefHashTable(C.Structure):
+    """include/hash_table/open_hash/hash_table.h:40-50"""
+    _fields_ = [("kmer_size", C.c_short), ("number_buckets", C.c_longlong), ("bucket_size", C.c_int),
+                ("table", C.c_void_p), ("next_element", C.c_void_p), ("collisions", C.c_void_p),
+                ("unique_kmers", C.c_longlong), ("max_rehash_tries", C.c_int)]
+
+
+# every symbol include/lasv_b200.h declares (tests check the library exports them all)
+EXPORTS = [
+    "lasv_last_error", "lasv_device_count", "lasv_version", "lasv_graph_new", "lasv_graph_free",
+    "lasv_graph_clear", "lasv_graph_unique_kmers", "lasv_graph_capacity", "lasv_graph_words_per_kmer",
+    "lasv_graph_element_bytes", "lasv_graph_device_table", "lasv_graph_load_reads_device",
+    "lasv_graph_load_reads_host", "lasv_graph_stats", "lasv_graph_rehash_histogram",
+    "lasv_graph_route_reads_device", "lasv_graph_extract_records_device",
+    "lasv_graph_insert_records_device", "lasv_graph_read_stats_device", "lasv_graph_find",
+    "lasv_graph_summary", "lasv_graph_finalize", "lasv_graph_export_table", "lasv_graph_import_table",
+    "lasv_graph_dump_ctx_records", "lasv_graph_write_ctx", "lasv_ctx_header",
+    "lasv_graph_load_ctx_records", "lasv_graph_load_ctx_file", "lasv_graph_load_se_file",
+    "lasv_graph_load_pe_files", "lasv_graph_load_se_filelist", "lasv_graph_load_pe_filelists",
+    "load_se_filelist_into_graph_colour", "load_pe_filelists_into_graph_colour",
+    "lasv_synth_reads_device", "lasv_synth_reads_host", "lasv_random_access_probe",
+    "lasv_kernel_launches",
+]
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "or `make -C lasv_b200/csrc` (there is no fallback implementation)")
+    L = C.CDLL(str(LIB_PATH))
+    vp, u64, i32 = C.c_void_p, C.c_uint64, C.c_int
+    L.lasv_last_error.restype = C.c_char_p
+    L.lasv_version.restype = C.c_char_p
+    L.lasv_device_count.restype = i32
+    L.lasv_kernel_launches.restype = u64
+    L.lasv_graph_new.restype = vp
+    L.lasv_graph_new.argtypes = [i32, i32, i32, i32, i32]
+    L.lasv_graph_free.argtypes = [C.POINTER(vp)]
+    L.lasv_graph_clear.argtypes = [vp, vp]
+    L.lasv_graph_unique_kmers.restype = C.c_longlong
+    L.lasv_graph_unique_kmers.argtypes = [vp]
+    L.lasv_graph_capacity.restype = C.c_longlong
+    L.lasv_graph_capacity.argtypes = [vp]
+    L.lasv_graph_words_per_kmer.argtypes = [vp]
+    L.lasv_graph_element_bytes.restype = C.c_size_t
+    L.lasv_graph_element_bytes.argtypes = [vp]
+    L.lasv_graph_device_table.restype = vp
+    L.lasv_graph_device_table.argtypes = [vp]
+    L.lasv_graph_load_reads_device.argtypes = [vp, vp, vp, u64, vp, u64, i32, vp]
+    L.lasv_graph_load_reads_host.argtypes = [vp, vp, vp, u64, vp, u64, i32, C.POINTER(LoadStats)]
+    L.lasv_graph_stats.argtypes = [vp, C.POINTER(LoadStats), vp, u64, vp]
+    L.lasv_graph_rehash_histogram.argtypes = [vp, vp]
+    L.lasv_graph_route_reads_device.argtypes = [vp, vp, vp, u64, i32, i32, vp, u64, vp, vp]
+    L.lasv_graph_extract_records_device.argtypes = [vp, vp, vp, u64, i32, vp, u64, vp, vp]
+    L.lasv_graph_insert_records_device.argtypes = [vp, vp, u64, vp]
+    L.lasv_graph_read_stats_device.argtypes = [vp, vp, vp, vp, u64, i32, vp]
+    L.lasv_graph_find.argtypes = [vp, vp, u64, vp, vp, vp]
+    L.lasv_graph_summary.argtypes = [vp, C.POINTER(TableSummary)]
+    L.lasv_graph_finalize.argtypes = [vp]
+    L.lasv_graph_export_table.argtypes = [vp, vp, vp]
+    L.lasv_graph_import_table.argtypes = [vp, vp]
+    L.lasv_graph_dump_ctx_records.restype = C.c_longlong
+    L.lasv_graph_dump_ctx_records.argtypes = [vp, vp, u64]
+    L.lasv_graph_write_ctx.argtypes = [vp, C.c_char_p, C.c_uint32, u64]
+    L.lasv_ctx_header.argtypes = [i32, C.c_uint32, u64, vp]
+    L.lasv_graph_load_ctx_records.argtypes = [vp, vp, u64]
+    L.lasv_graph_load_ctx_file.argtypes = [vp, C.c_char_p, C.POINTER(C.c_uint32), C.POINTER(u64)]
+    L.lasv_graph_load_se_file.argtypes = [vp, C.c_char_p, i32, C.POINTER(LoadStats)]
+    L.lasv_graph_load_pe_files.argtypes = [vp, C.c_char_p, C.c_char_p, i32, C.POINTER(LoadStats)]
+    L.lasv_graph_load_se_filelist.argtypes = [vp, C.c_char_p, i32, i32, C.POINTER(C.c_uint),
+                                              C.POINTER(LoadStats)]
+    L.lasv_graph_load_pe_filelists.argtypes = [vp, C.c_char_p, C.c_char_p, i32, i32,
+                                               C.POINTER(C.c_uint), C.POINTER(LoadStats)]
+    ull_p = C.POINTER(C.c_ulonglong)
+    L.load_se_filelist_into_graph_colour.restype = None
+    L.load_se_filelist_into_graph_colour.argtypes = [
+        C.c_char_p, i32, i32, C.c_byte, C.c_char, i32, C.POINTER(RefHashTable), C.c_char,
+        C.POINTER(C.c_uint), ull_p, ull_p, ull_p, ull_p, vp, C.c_ulong]
+    L.load_pe_filelists_into_graph_colour.restype = None
+    L.load_pe_filelists_into_graph_colour.argtypes = [
+        C.c_char_p, C.c_char_p, i32, i32, C.c_byte, C.c_char, i32, C.POINTER(RefHashTable), C.c_char,
+        C.POINTER(C.c_uint), ull_p, ull_p, ull_p, ull_p, vp, C.c_ulong]
+    L.lasv_synth_reads_device.argtypes = [C.POINTER(SynthParams), u64, u64, vp, vp, vp]
+    L.lasv_synth_reads_host.argtypes = [C.POINTER(SynthParams), u64, u64, vp, vp]
+    L.lasv_random_access_probe.argtypes = [vp, u64, u64, u64, vp]
+    _lib = L
+    return L
+
+
+class LasvError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"[{code}] {msg}")
+        self.code = code
+
+
+class TableFullError(LasvError):
+    """hash_table.c:309-317: a key met 16 full buckets (the reference die()s)."""
+
+
+def check(rc: int) -> int:
+    if rc < 0:
+        msg = lib().lasv_last_error().decode(errors="replace")
+        raise (TableFullError if rc == LASV_ERR_TABLE_FULL else LasvError)(rc, msg)
+    return rc

@@ -615,7 +615,7 @@ int lasv_ctx_header(int kmer_size, uint32_t mean_read_len, uint64_t total_seq, u
   v = 9; put(&v, 4); put("undefined", 9);
   uint8_t ld[16];
   memset(ld, 0, sizeof ld);
-  long double err = 0.01L;
+  long double err = (long double)0.01;  // graph_info.c:127 assigns the double literal 0.01
   memcpy(ld, &err, 10);  // x87 extended: 10 significant bytes of the 16 stored
   put(ld, 16);
   uint8_t flags[4] = {0, 0, 0, 0};

@@ -17,6 +17,7 @@
 // sectors in HBM; everything else is streaming.  Grids are persistent:
 // (#SMs x resident CTAs) CTAs looping over tiles.
 #include <cub/device/device_scan.cuh>
+#include <type_traits>
 #include "graph_kernels.cuh"
 #include "synth.cuh"
 
@@ -196,7 +197,7 @@ __global__ void __launch_bounds__(THREADS) build_kernel(const BuildParams p, con
       if (MODE == MODE_FUSED) {
         const bool lead = warp_aggregate<N>(active, key, edge, count);
         if (lead) {
-          const int r = table_upsert<N>(p.table, p.ctr, key, edge, count);
+          const int r = table_upsert<N, DeviceOps>(p.table, p.ctr, key, edge, count);
           my_new += (r == 1);
         }
       } else if (MODE == MODE_RECORDS) {
@@ -270,7 +271,7 @@ __global__ void __launch_bounds__(THREADS) insert_records_kernel(const uint32_t 
     }
     const bool lead = warp_aggregate<N>(active, key, edge, count);
     if (lead) {
-      const int r = table_upsert<N>(t, ctr, key, edge, count);
+      const int r = table_upsert<N, DeviceOps>(t, ctr, key, edge, count);
       my_new += (r == 1);
     }
   }
@@ -530,7 +531,7 @@ __global__ void __launch_bounds__(THREADS) ingest_ctx_kernel(const uint8_t *__re
     }
     const uint32_t c = (uint32_t)src[8 * N] | ((uint32_t)src[8 * N + 1] << 8) |
                        ((uint32_t)src[8 * N + 2] << 16) | ((uint32_t)src[8 * N + 3] << 24);
-    const int r = table_upsert<N>(t, ctr, key, src[8 * N + 4], c);
+    const int r = table_upsert<N, DeviceOps>(t, ctr, key, src[8 * N + 4], c);
     my_new += (r == 1);
   }
 #pragma unroll
@@ -553,7 +554,7 @@ __global__ void __launch_bounds__(THREADS) ingest_elements_kernel(const uint8_t 
     uint64_t key[N];
 #pragma unroll
     for (int w = 0; w < N; w++) key[w] = slot[w];
-    const int r = table_upsert<N>(t, ctr, key, meta_edges(m), meta_covg(m));
+    const int r = table_upsert<N, DeviceOps>(t, ctr, key, meta_edges(m), meta_covg(m));
     my_new += (r == 1);
   }
 #pragma unroll
@@ -578,23 +579,9 @@ __global__ void __launch_bounds__(THREADS) find_kernel(const TableView t,
     uint64_t m = 0;
     bool hit = false;
     if (!finalized) {
-      hit = table_find<N>(t, key, m);
+      hit = table_find<N, DeviceOps>(t, key, m);
     } else {
-      for (uint32_t r = 0; r <= t.max_rehash && !hit; ++r) {
-        const Probe pr = probe_of(lookup3_key<N>(key, r), t.bucket_mask, t.W);
-        const uint8_t *bucket = t.slots + (uint64_t)pr.bucket * t.W * STRIDE;
-        uint32_t s = 0;
-        for (; s < t.W; ++s) {
-          const uint64_t *slot = reinterpret_cast<const uint64_t *>(bucket + (uint64_t)s * STRIDE);
-          m = slot[N];
-          if (meta_status(m) == ST_EMPTY) break;
-          bool same = true;
-#pragma unroll
-          for (int w = 0; w < N; w++) same &= (slot[w] == key[w]);
-          if (same) { hit = true; break; }
-        }
-        if (!hit && s < t.W) break;  // met an empty slot: not present
-      }
+      hit = table_find_finalized<N, DeviceOps>(t, key, m);
     }
     found[i] = hit ? 1 : 0;
     covg[i] = hit ? meta_covg(m) : 0;
@@ -634,7 +621,7 @@ __global__ void __launch_bounds__(THREADS) random_rmw_kernel(uint64_t *buf, cons
   for (uint64_t i = (uint64_t)blockIdx.x * THREADS + threadIdx.x; i < n_ops;
        i += (uint64_t)gridDim.x * THREADS) {
     const uint64_t h = mix64(seed + i);
-    const uint64_t s = (uint64_t)(((unsigned __int128)h * n_sectors) >> 64);
+    const uint64_t s = __umul64hi(h, n_sectors);
     uint64_t *p = buf + s * 4;
     const uint64_t a = ld_strong_u64(p), b = ld_strong_u64(p + 1);
     if (a + b != 0x123456789ull)  // data-dependent so the loads cannot be dropped

@@ -24,7 +24,9 @@
 // Updates of a published slot are two independent L2 reductions: 32-bit add on
 // the coverage word, 32-bit OR on the edges word (only when it adds a bit).
 #pragma once
+#if defined(__CUDACC__)
 #include <cuda_runtime.h>
+#endif
 #include "kmer_core.cuh"
 
 namespace lasv {
@@ -46,6 +48,12 @@ struct GraphCounters {
   unsigned long long covg_saturated;   // element.c:402-415 warning condition
 };
 
+// ---------------------------------------------------------------------------
+// Memory operations of the table protocol.  The kernels use DeviceOps (strong
+// GPU-scope loads/stores that bypass L1, L2 atomics).  tests/host_emul supplies
+// a sequential HostOps with the same interface so the probing / claiming /
+// finalising LOGIC is exercised on the CPU; the product never instantiates it.
+#if defined(__CUDACC__)
 __device__ __forceinline__ uint64_t ld_strong_u64(const uint64_t *p) {
   uint64_t v;
   asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
@@ -54,22 +62,44 @@ __device__ __forceinline__ uint64_t ld_strong_u64(const uint64_t *p) {
 __device__ __forceinline__ void st_strong_u64(uint64_t *p, uint64_t v) {
   asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
-__device__ __forceinline__ void prefetch_l2(const void *p) {
-  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-}
 
-// Saturating coverage add on a published slot (slow path, only near UINT_MAX).
-static __device__ __noinline__ void covg_add_saturating(uint64_t *meta_ptr, uint32_t add,
-                                                 GraphCounters *ctr) {
-  unsigned long long *mp = reinterpret_cast<unsigned long long *>(meta_ptr);
-  unsigned long long old = ld_strong_u64(meta_ptr);
+struct DeviceOps {
+  static __device__ __forceinline__ uint64_t load(const uint64_t *p) { return ld_strong_u64(p); }
+  static __device__ __forceinline__ void store(uint64_t *p, uint64_t v) { st_strong_u64(p, v); }
+  static __device__ __forceinline__ void prefetch(const void *p) {
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+  }
+  static __device__ __forceinline__ uint64_t cas(uint64_t *p, uint64_t expect, uint64_t want) {
+    return atomicCAS(reinterpret_cast<unsigned long long *>(p), (unsigned long long)expect,
+                     (unsigned long long)want);
+  }
+  static __device__ __forceinline__ void xor64(uint64_t *p, uint64_t v) {
+    atomicXor(reinterpret_cast<unsigned long long *>(p), (unsigned long long)v);
+  }
+  static __device__ __forceinline__ void add32(uint32_t *p, uint32_t v) { atomicAdd(p, v); }
+  static __device__ __forceinline__ void or32(uint32_t *p, uint32_t v) { atomicOr(p, v); }
+  static __device__ __forceinline__ void fence() { __threadfence(); }
+  static __device__ __forceinline__ void backoff() { __nanosleep(40); }
+  static __device__ __forceinline__ void count(unsigned long long *p, unsigned long long v) {
+    atomicAdd(p, v);
+  }
+  static __device__ __forceinline__ void flag(unsigned long long *p) { atomicExch(p, 1ull); }
+};
+#endif
+
+// Saturating coverage add on a published slot (slow path, only near UINT_MAX;
+// element.c:395-417).
+#pragma nv_exec_check_disable
+template <class Ops>
+LASV_HD void covg_add_saturating(uint64_t *meta_ptr, uint32_t add, GraphCounters *ctr) {
+  uint64_t old = Ops::load(meta_ptr);
   for (;;) {
-    uint32_t c = (uint32_t)old;
-    uint32_t nc = (0xFFFFFFFFu - add >= c) ? c + add : 0xFFFFFFFFu;
-    unsigned long long want = (old & 0xFFFFFFFF00000000ull) | nc;
-    unsigned long long got = atomicCAS(mp, old, want);
+    const uint32_t c = (uint32_t)old;
+    const uint32_t nc = (0xFFFFFFFFu - add >= c) ? c + add : 0xFFFFFFFFu;
+    const uint64_t want = (old & 0xFFFFFFFF00000000ull) | nc;
+    const uint64_t got = Ops::cas(meta_ptr, old, want);
     if (got == old) {
-      if (nc == 0xFFFFFFFFu) atomicAdd(&ctr->covg_saturated, 1ull);
+      if (nc == 0xFFFFFFFFu) Ops::count(&ctr->covg_saturated, 1ull);
       return;
     }
     old = got;
@@ -78,10 +108,10 @@ static __device__ __noinline__ void covg_add_saturating(uint64_t *meta_ptr, uint
 
 // find-or-insert `key`, then coverage += covg_add (saturating) and edges |= edge.
 // Returns 1 if the key was new, 0 if it existed, -1 if the table is full.
-template <int N>
-__device__ __forceinline__ int table_upsert(const TableView &t, GraphCounters *ctr,
-                                            const uint64_t (&key)[N], uint32_t edge,
-                                            uint32_t covg_add) {
+#pragma nv_exec_check_disable
+template <int N, class Ops>
+LASV_HD int table_upsert(const TableView &t, GraphCounters *ctr, const uint64_t (&key)[N],
+                         uint32_t edge, uint32_t covg_add) {
   constexpr uint32_t STRIDE = 8 * N + 8;
   for (uint32_t r = 0; r <= t.max_rehash; ++r) {
     const Probe pr = probe_of(lookup3_key<N>(key, r), t.bucket_mask, t.W);
@@ -90,21 +120,19 @@ __device__ __forceinline__ int table_upsert(const TableView &t, GraphCounters *c
     for (uint32_t i = 0; i < t.W; ++i) {
       uint64_t *slot = reinterpret_cast<uint64_t *>(bucket + (uint64_t)s * STRIDE);
       uint64_t *meta_ptr = slot + N;
-      if (N > 1) prefetch_l2(slot);  // key words may sit in the neighbouring sector
-      uint64_t m = ld_strong_u64(meta_ptr);
+      if (N > 1) Ops::prefetch(slot);  // key words may sit in the neighbouring sector
+      uint64_t m = Ops::load(meta_ptr);
       for (;;) {
         const uint32_t st = meta_status(m);
         if (st == ST_EMPTY) {
           const uint64_t want = meta_pack(covg_add, edge, ST_LOCKED, pr.tag);
-          const uint64_t old = atomicCAS(reinterpret_cast<unsigned long long *>(meta_ptr), 0ull,
-                                         (unsigned long long)want);
+          const uint64_t old = Ops::cas(meta_ptr, 0ull, want);
           if (old == 0ull) {
 #pragma unroll
-            for (int w = 0; w < N; w++) st_strong_u64(slot + w, key[w]);
-            __threadfence();
-            atomicXor(reinterpret_cast<unsigned long long *>(meta_ptr),
-                      (unsigned long long)(ST_LOCKED ^ ST_NONE) << 40);
-            if (r) atomicAdd(&ctr->rehash_hist[r], 1ull);
+            for (int w = 0; w < N; w++) Ops::store(slot + w, key[w]);
+            Ops::fence();
+            Ops::xor64(meta_ptr, (uint64_t)(ST_LOCKED ^ ST_NONE) << 40);
+            if (r) Ops::count(&ctr->rehash_hist[r], 1ull);
             return 1;
           }
           m = old;  // somebody claimed it first: look at what they put there
@@ -114,61 +142,85 @@ __device__ __forceinline__ int table_upsert(const TableView &t, GraphCounters *c
         if (st == ST_LOCKED) {
           // same tag, key words not visible yet: wait for the owner to publish
           do {
-            __nanosleep(40);
-            m = ld_strong_u64(meta_ptr);
+            Ops::backoff();
+            m = Ops::load(meta_ptr);
           } while (meta_status(m) == ST_LOCKED);
-          __threadfence();
+          Ops::fence();
         }
         // published, tag matches: compare the key (loads are issued after the
         // meta load that saw the slot published, and bypass L1)
         bool same = true;
 #pragma unroll
-        for (int w = 0; w < N; w++) same &= (ld_strong_u64(slot + w) == key[w]);
+        for (int w = 0; w < N; w++) same &= (Ops::load(slot + w) == key[w]);
         if (!same) break;
         // ---- hit: accumulate
         if (meta_covg(m) < 0xF0000000u && covg_add < 0x01000000u) {
-          atomicAdd(reinterpret_cast<unsigned int *>(meta_ptr), covg_add);
+          Ops::add32(reinterpret_cast<uint32_t *>(meta_ptr), covg_add);
         } else {
-          covg_add_saturating(meta_ptr, covg_add, ctr);
+          covg_add_saturating<Ops>(meta_ptr, covg_add, ctr);
         }
         if ((meta_edges(m) | edge) != meta_edges(m)) {
-          atomicOr(reinterpret_cast<unsigned int *>(meta_ptr) + 1, edge & 0xFFu);
+          Ops::or32(reinterpret_cast<uint32_t *>(meta_ptr) + 1, edge & 0xFFu);
         }
-        if (r) atomicAdd(&ctr->rehash_hist[r], 1ull);
+        if (r) Ops::count(&ctr->rehash_hist[r], 1ull);
         return 0;
       }
       if (++s == t.W) s = 0;
     }
     // bucket r is full and does not hold the key: follow the rehash chain
   }
-  atomicExch(&ctr->table_full, 1ull);
+  Ops::flag(&ctr->table_full);
   return -1;
 }
 
 // hash_table_find (hash_table.c:234-267) on the UN-finalised device layout.
 // Returns true and the meta word if present.
-template <int N>
-__device__ __forceinline__ bool table_find(const TableView &t, const uint64_t (&key)[N],
-                                           uint64_t &meta_out) {
+#pragma nv_exec_check_disable
+template <int N, class Ops>
+LASV_HD bool table_find(const TableView &t, const uint64_t (&key)[N], uint64_t &meta_out) {
   constexpr uint32_t STRIDE = 8 * N + 8;
   for (uint32_t r = 0; r <= t.max_rehash; ++r) {
     const Probe pr = probe_of(lookup3_key<N>(key, r), t.bucket_mask, t.W);
-    const uint8_t *bucket = t.slots + (uint64_t)pr.bucket * t.W * STRIDE;
+    uint8_t *bucket = t.slots + (uint64_t)pr.bucket * t.W * STRIDE;
     uint32_t s = pr.start;
     bool saw_empty = false;
     for (uint32_t i = 0; i < t.W; ++i) {
-      const uint64_t *slot = reinterpret_cast<const uint64_t *>(bucket + (uint64_t)s * STRIDE);
-      uint64_t m = ld_strong_u64(slot + N);
+      uint64_t *slot = reinterpret_cast<uint64_t *>(bucket + (uint64_t)s * STRIDE);
+      const uint64_t m = Ops::load(slot + N);
       if (meta_status(m) == ST_EMPTY) { saw_empty = true; break; }
       if (meta_tag(m) == pr.tag) {
         bool same = true;
 #pragma unroll
-        for (int w = 0; w < N; w++) same &= (ld_strong_u64(slot + w) == key[w]);
+        for (int w = 0; w < N; w++) same &= (Ops::load(slot + w) == key[w]);
         if (same) { meta_out = m; return true; }
       }
       if (++s == t.W) s = 0;
     }
     if (saw_empty) return false;
+  }
+  return false;
+}
+
+// hash_table_find on the FINALISED (reference) layout: scan each bucket of the
+// rehash chain from slot 0 to the first empty slot (hash_table.c:84-117,247-264).
+#pragma nv_exec_check_disable
+template <int N, class Ops>
+LASV_HD bool table_find_finalized(const TableView &t, const uint64_t (&key)[N], uint64_t &meta_out) {
+  constexpr uint32_t STRIDE = 8 * N + 8;
+  for (uint32_t r = 0; r <= t.max_rehash; ++r) {
+    const Probe pr = probe_of(lookup3_key<N>(key, r), t.bucket_mask, t.W);
+    uint8_t *bucket = t.slots + (uint64_t)pr.bucket * t.W * STRIDE;
+    uint32_t s = 0;
+    for (; s < t.W; ++s) {
+      uint64_t *slot = reinterpret_cast<uint64_t *>(bucket + (uint64_t)s * STRIDE);
+      const uint64_t m = Ops::load(slot + N);
+      if (meta_status(m) == ST_EMPTY) return false;  // hole-free buckets: not present
+      bool same = true;
+#pragma unroll
+      for (int w = 0; w < N; w++) same &= (Ops::load(slot + w) == key[w]);
+      if (same) { meta_out = m; return true; }
+    }
+    // bucket full and key absent: next bucket of the chain
   }
   return false;
 }

@@ -474,50 +474,68 @@ static int orc_process_read(orc_graph *g, orc_cursor *c, char *kmer_str, char *q
   return 1;
 }
 
-/* file_reader.c:475-587 load_se_seq_data_into_graph_colour, and the per-mate
- * body of load_pe_seq_data_into_graph_colour (:589-773) -- with duplicate
- * removal off (laSV never enables it) the PE loader is the SE loader applied
- * to mate 1 then mate 2 of each pair, so the caller interleaves the mates.
+/* file_reader.c:475-587 load_se_seq_data_into_graph_colour (paired == 0) and
+ * file_reader.c:589-773 load_pe_seq_data_into_graph_colour (paired != 0), with
+ * duplicate removal off (laSV never enables it).  The paired loader looks up the
+ * first k-mer of BOTH mates (:654-694) before it walks mate 1 and then mate 2
+ * (:737-764); that only changes the order in which slots are claimed, never the
+ * node multiset, and is kept so the oracle's table layout equals the reference's.
  *
  * Reads are given in memory: read i occupies seq[offsets[i] .. offsets[i+1]-sep)
  * (and the same span of qual when qual != NULL); `sep` separator bytes follow
- * each read.  `cutoff` is the RAW ASCII cutoff, i.e. threshold + offset
+ * each read; in paired mode reads 2p and 2p+1 are the mates of pair p.
+ * `cutoff` is the RAW ASCII cutoff, i.e. threshold + offset
  * (file_reader.c:798,919), compared as signed char (file_reader.c:150,389).
  * Returns 1, or 0 if the table filled up (the reference would die()).       */
 int orc_load_reads(orc_graph *g, const char *seq, const char *qual,
-                   const uint64_t *offsets, uint64_t n_reads, int sep, int cutoff,
+                   const uint64_t *offsets, uint64_t n_reads, int sep, int cutoff, int paired,
                    orc_stats *st, uint64_t *hist, uint64_t hist_size) {
   int k = g->k, N = g->N, found;
-  char *kmer_str = (char *)malloc((size_t)k + 1), *qual_str = (char *)malloc((size_t)k + 1);
-  uint64_t curr_kmer[ORC_MAXN], key[ORC_MAXN];
+  int group = paired ? 2 : 1, m;
+  char *kmer_str[2], *qual_str[2];
+  uint64_t curr_kmer[2][ORC_MAXN], key[ORC_MAXN];
+  orc_node *node[2];
+  orc_cursor cur[2];
+  int got[2], orient[2];
   uint64_t r;
   int read_qual = qual != NULL, ok = 1;
-  memset(qual_str, 0, (size_t)k + 1);
-  for (r = 0; r < n_reads && ok; r++) {
-    orc_cursor c;
-    c.bases = seq + offsets[r];
-    c.quals = qual ? qual + offsets[r] : NULL;
-    c.len = offsets[r + 1] - offsets[r] - (uint64_t)sep;
-    c.off = 0;
-    c.entry_read = 1;
-    st->n_reads++;
-    st->bases_read += c.len;
-    if (orc_read_first_kmer(&c, kmer_str, qual_str, k, read_qual, (signed char)cutoff)) {
-      orc_seq_to_kmer(kmer_str, k, N, curr_kmer);
-      orc_get_key(curr_kmer, k, N, key);
-      orc_node *node = orc_find_or_insert(g, key, &found);
-      if (!node) { ok = 0; break; }
-      st->kmers_inserted++;
-      int orient = orc_get_orientation(curr_kmer, node, k, N);
-      orc_update_coverage(node, 1);
-      ok = orc_process_read(g, &c, kmer_str, qual_str, read_qual, (signed char)cutoff,
-                            curr_kmer, node, orient, st, hist, hist_size);
-    } else {
-      st->bad_reads++;
+  for (m = 0; m < 2; m++) {
+    kmer_str[m] = (char *)malloc((size_t)k + 1);
+    qual_str[m] = (char *)calloc((size_t)k + 1, 1);
+  }
+  for (r = 0; r + (uint64_t)group <= n_reads && ok; r += (uint64_t)group) {
+    for (m = 0; m < group; m++) {
+      orc_cursor *c = &cur[m];
+      c->bases = seq + offsets[r + m];
+      c->quals = qual ? qual + offsets[r + m] : NULL;
+      c->len = offsets[r + m + 1] - offsets[r + m] - (uint64_t)sep;
+      c->off = 0;
+      c->entry_read = 1;
+      st->n_reads++;
+      st->bases_read += c->len;
+    }
+    for (m = 0; m < group; m++)
+      got[m] = orc_read_first_kmer(&cur[m], kmer_str[m], qual_str[m], k, read_qual, (signed char)cutoff);
+    for (m = 0; m < group && ok; m++) {
+      if (got[m]) {
+        orc_seq_to_kmer(kmer_str[m], k, N, curr_kmer[m]);
+        orc_get_key(curr_kmer[m], k, N, key);
+        node[m] = orc_find_or_insert(g, key, &found);
+        if (!node[m]) { ok = 0; break; }
+        st->kmers_inserted++;
+        orient[m] = orc_get_orientation(curr_kmer[m], node[m], k, N);
+      } else {
+        st->bad_reads++;
+      }
+    }
+    for (m = 0; m < group && ok; m++) {
+      if (!got[m]) continue;
+      orc_update_coverage(node[m], 1);
+      ok = orc_process_read(g, &cur[m], kmer_str[m], qual_str[m], read_qual, (signed char)cutoff,
+                            curr_kmer[m], node[m], orient[m], st, hist, hist_size);
     }
   }
-  free(kmer_str);
-  free(qual_str);
+  for (m = 0; m < 2; m++) { free(kmer_str[m]); free(qual_str[m]); }
   return ok;
 }
 
@@ -588,7 +606,7 @@ int orc_ctx_header(int k, int N, uint32_t mean_read_len, uint64_t total_seq, uin
   v = (int32_t)mean_read_len; memcpy(p, &v, 4); p += 4;
   { long long t = (long long)total_seq; memcpy(p, &t, 8); p += 8; }
   v = 9; memcpy(p, &v, 4); p += 4; memcpy(p, "undefined", 9); p += 9;
-  { long double e = 0.01L; memset(p, 0, 16); memcpy(p, &e, sizeof(long double)); p += 16; }
+  { long double e = (long double)0.01; /* graph_info.c:127 assigns the DOUBLE literal */ memset(p, 0, 16); memcpy(p, &e, sizeof(long double)); p += 16; }
   memset(p, 0, 4); p += 4;                  /* 4 x boolean (1 byte each) cleaning flags */
   v = -1; memcpy(p, &v, 4); p += 4;
   v = -1; memcpy(p, &v, 4); p += 4;

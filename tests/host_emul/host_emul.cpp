@@ -1,0 +1,255 @@
+// tests/host_emul/host_emul.cpp -- TEST HARNESS ONLY.
+//
+// Runs the kernels' own __host__ __device__ arithmetic (lasv_b200/csrc/
+// kmer_core.cuh: classify16, tile bit-string layout, window_good, extract_kmer,
+// kmer_occurrence, lookup3_key; table.cuh: table_upsert / table_find* with a
+// sequential HostOps) on the CPU, tile by tile in the order build_kernel walks
+// them, so that index arithmetic, packing, canonicalisation, edge formula,
+// probing and finalisation are checked against the oracle WITHOUT a GPU.
+// What it cannot check -- atomics under contention, warp intrinsics -- is
+// covered by the -m gpu parity tests.  The product never links this file.
+#include <stdint.h>
+#include <string.h>
+#include <vector>
+
+#include "../../lasv_b200/csrc/kmer_core.cuh"
+#include "../../lasv_b200/csrc/table.cuh"
+
+using namespace lasv;
+
+namespace {
+
+struct HostOps {
+  static uint64_t load(const uint64_t *p) { return *p; }
+  static void store(uint64_t *p, uint64_t v) { *p = v; }
+  static void prefetch(const void *) {}
+  static uint64_t cas(uint64_t *p, uint64_t expect, uint64_t want) {
+    uint64_t old = *p;
+    if (old == expect) *p = want;
+    return old;
+  }
+  static void xor64(uint64_t *p, uint64_t v) { *p ^= v; }
+  static void add32(uint32_t *p, uint32_t v) { *p += v; }
+  static void or32(uint32_t *p, uint32_t v) { *p |= v; }
+  static void fence() {}
+  static void backoff() {}
+  static void count(unsigned long long *p, unsigned long long v) { *p += v; }
+  static void flag(unsigned long long *p) { *p = 1; }
+};
+
+struct Tile {
+  int T, R, CHUNKS;
+  std::vector<uint64_t> P, PR, BD;
+  explicit Tile(int t) : T(t), R(t + TileGeom::HALO_L + TileGeom::HALO_R), CHUNKS(R / 16) {
+    P.assign(R / 32 + 2, 0);
+    PR.assign(R / 32 + 2, 0);
+    BD.assign(R / 64 + 2, 0);
+    BD[R / 64] = ~0ull;
+    BD[R / 64 + 1] = ~0ull;
+  }
+  // mirrors build_kernel's issue_stage + stage phase
+  void stage(const uint8_t *seq, const uint8_t *qual, uint64_t n_bytes, uint64_t tile, int cutoff) {
+    for (int c = 0; c < CHUNKS; c++) {
+      uint4 sv = {0, 0, 0, 0}, qv = {0, 0, 0, 0};
+      uint32_t inr = 0;
+      const long long g = (long long)(tile * (uint64_t)T) - TileGeom::HALO_L + 16ll * c;
+      if (g >= 0 && (uint64_t)g < n_bytes) {
+        const uint64_t left = n_bytes - (uint64_t)g;
+        const size_t take = left >= 16 ? 16 : (size_t)left;
+        uint8_t sb[16], qb[16];
+        memset(sb, 0xAB, 16);  // bytes past the stream are garbage on the device too
+        memset(qb, 0xCD, 16);
+        memcpy(sb, seq + g, take);
+        if (qual) memcpy(qb, qual + g, take);
+        memcpy(&sv, sb, 16);
+        memcpy(&qv, qb, 16);
+        inr = left >= 16 ? 0xFFFFu : ((1u << left) - 1u);
+      }
+      uint32_t code32, bad16;
+      classify16(sv, qv, qual != nullptr, cutoff, inr, code32, bad16);
+      reinterpret_cast<uint32_t *>(P.data())[code_u32_index(c)] = code32;
+      reinterpret_cast<uint32_t *>(PR.data())[code_u32_index(CHUNKS - 1 - c)] = rc_code32(code32);
+      reinterpret_cast<uint16_t *>(BD.data())[bad_u16_index(c)] = (uint16_t)bad16;
+    }
+  }
+};
+
+template <int N, class Sink>
+void walk(const uint8_t *seq, const uint8_t *qual, uint64_t n_bytes, int k, int cutoff, int T,
+          Sink &&sink) {
+  Tile tile(T);
+  const uint64_t n_tiles = (n_bytes + T - 1) / T;
+  for (uint64_t t = 0; t < n_tiles; t++) {
+    tile.stage(seq, qual, n_bytes, t, cutoff);
+    for (int pos = 0; pos < T; pos++) {
+      const int j = TileGeom::HALO_L + pos;
+      if (!window_good(tile.BD.data(), j, k)) continue;
+      uint64_t key[N];
+      const uint32_t edge = kmer_occurrence<N>(tile.P.data(), tile.PR.data(), tile.BD.data(), tile.R, j, k, key);
+      sink(key, edge);
+    }
+  }
+}
+
+TableView view_of(uint8_t *table, int L, int W, int max_rehash) {
+  TableView t;
+  t.slots = table;
+  t.bucket_mask = (uint32_t)((1ull << L) - 1);
+  t.W = (uint32_t)W;
+  t.max_rehash = (uint32_t)max_rehash;
+  return t;
+}
+
+template <int N>
+int build_fused(const uint8_t *seq, const uint8_t *qual, uint64_t n_bytes, int k, int cutoff, int L,
+                int W, int max_rehash, int T, uint8_t *table, GraphCounters *ctr) {
+  const TableView tv = view_of(table, L, W, max_rehash);
+  walk<N>(seq, qual, n_bytes, k, cutoff, T, [&](const uint64_t(&key)[N], uint32_t edge) {
+    ctr->kmers_inserted++;
+    const int r = table_upsert<N, HostOps>(tv, ctr, key, edge, 1u);
+    if (r == 1) ctr->unique_kmers++;
+  });
+  return ctr->table_full ? -3 : 0;
+}
+
+template <int N>
+uint64_t extract(const uint8_t *seq, const uint8_t *qual, uint64_t n_bytes, int k, int cutoff, int T,
+                 uint32_t *out, uint64_t cap) {
+  uint64_t n = 0;
+  walk<N>(seq, qual, n_bytes, k, cutoff, T, [&](const uint64_t(&key)[N], uint32_t edge) {
+    if (n < cap) {
+      uint32_t *dst = out + n * (2 * N + 1);
+      for (int i = 0; i < N; i++) {
+        dst[2 * i] = (uint32_t)key[i];
+        dst[2 * i + 1] = (uint32_t)(key[i] >> 32);
+      }
+      dst[2 * N] = (edge & 0xFFu) | (1u << 8);
+    }
+    n++;
+  });
+  return n;
+}
+
+template <int N>
+int insert_records(const uint32_t *recs, uint64_t n, int L, int W, int max_rehash, uint8_t *table,
+                   GraphCounters *ctr) {
+  const TableView tv = view_of(table, L, W, max_rehash);
+  for (uint64_t i = 0; i < n; i++) {
+    const uint32_t *src = recs + i * (2 * N + 1);
+    uint64_t key[N];
+    for (int w = 0; w < N; w++) key[w] = (uint64_t)src[2 * w] | ((uint64_t)src[2 * w + 1] << 32);
+    const uint32_t m = src[2 * N];
+    const int r = table_upsert<N, HostOps>(tv, ctr, key, m & 0xFFu, m >> 8);
+    if (r == 1) ctr->unique_kmers++;
+  }
+  return ctr->table_full ? -3 : 0;
+}
+
+// finalize_kernel restated with its 32-slot chunking (read a chunk, then write)
+template <int N>
+void finalize(uint8_t *table, int L, int W, int16_t *next) {
+  constexpr uint32_t STRIDE = 8 * N + 8;
+  const uint64_t nb = 1ull << L;
+  for (uint64_t b = 0; b < nb; b++) {
+    uint8_t *bucket = table + b * (uint64_t)W * STRIDE;
+    uint32_t filled = 0;
+    for (uint32_t s0 = 0; s0 < (uint32_t)W; s0 += 32) {
+      uint64_t keys[32][N], metas[32];
+      bool occ[32];
+      for (uint32_t l = 0; l < 32; l++) {
+        const uint32_t s = s0 + l;
+        metas[l] = 0;
+        if (s < (uint32_t)W) {
+          const uint64_t *slot = reinterpret_cast<const uint64_t *>(bucket + (uint64_t)s * STRIDE);
+          metas[l] = slot[N];
+          for (int w = 0; w < N; w++) keys[l][w] = slot[w];
+        }
+        occ[l] = meta_status(metas[l]) != ST_EMPTY;
+      }
+      uint32_t rank = 0;
+      for (uint32_t l = 0; l < 32; l++) {
+        if (!occ[l]) continue;
+        uint64_t *dst = reinterpret_cast<uint64_t *>(bucket + (uint64_t)(filled + rank) * STRIDE);
+        for (int w = 0; w < N; w++) dst[w] = keys[l][w];
+        dst[N] = meta_pack(meta_covg(metas[l]), meta_edges(metas[l]), ST_NONE, 0);
+        rank++;
+      }
+      filled += rank;
+    }
+    for (uint32_t s = filled; s < (uint32_t)W; s++)
+      memset(bucket + (uint64_t)s * STRIDE, 0, STRIDE);
+    if (next) next[b] = (int16_t)filled;
+  }
+}
+
+template <int N>
+void find(uint8_t *table, int L, int W, int max_rehash, int finalized, const uint64_t *keys,
+          uint64_t n, uint32_t *covg, uint8_t *edges, uint8_t *found) {
+  const TableView tv = view_of(table, L, W, max_rehash);
+  for (uint64_t i = 0; i < n; i++) {
+    uint64_t key[N], m = 0;
+    for (int w = 0; w < N; w++) key[w] = keys[i * N + w];
+    const bool hit = finalized ? table_find_finalized<N, HostOps>(tv, key, m)
+                               : table_find<N, HostOps>(tv, key, m);
+    found[i] = hit;
+    covg[i] = hit ? meta_covg(m) : 0;
+    edges[i] = hit ? (uint8_t)meta_edges(m) : 0;
+  }
+}
+
+}  // namespace
+
+#define DISPATCH(N, call) ((N) == 1 ? call<1> : (N) == 2 ? call<2> : call<3>)
+
+extern "C" {
+
+int emul_build_fused(const uint8_t *seq, const uint8_t *qual, uint64_t n_bytes, int k, int cutoff,
+                     int L, int W, int max_rehash, int T, uint8_t *table, uint64_t *counters20) {
+  GraphCounters ctr;
+  memset(&ctr, 0, sizeof ctr);
+  const int N = 2 * k / 64 + 1;
+  const int rc = DISPATCH(N, build_fused)(seq, qual, n_bytes, k, cutoff, L, W, max_rehash, T, table, &ctr);
+  counters20[0] = ctr.unique_kmers;
+  counters20[1] = ctr.kmers_inserted;
+  counters20[2] = ctr.table_full;
+  for (int r = 0; r < 16; r++) counters20[3 + r] = ctr.rehash_hist[r];
+  return rc;
+}
+
+uint64_t emul_extract_records(const uint8_t *seq, const uint8_t *qual, uint64_t n_bytes, int k,
+                              int cutoff, int T, uint32_t *out, uint64_t cap) {
+  const int N = 2 * k / 64 + 1;
+  return DISPATCH(N, extract)(seq, qual, n_bytes, k, cutoff, T, out, cap);
+}
+
+int emul_insert_records(const uint32_t *recs, uint64_t n, int k, int L, int W, int max_rehash,
+                        uint8_t *table, uint64_t *counters20) {
+  GraphCounters ctr;
+  memset(&ctr, 0, sizeof ctr);
+  const int N = 2 * k / 64 + 1;
+  const int rc = DISPATCH(N, insert_records)(recs, n, L, W, max_rehash, table, &ctr);
+  counters20[0] = ctr.unique_kmers;
+  counters20[2] = ctr.table_full;
+  for (int r = 0; r < 16; r++) counters20[3 + r] = ctr.rehash_hist[r];
+  return rc;
+}
+
+void emul_finalize(uint8_t *table, int k, int L, int W, int16_t *next) {
+  const int N = 2 * k / 64 + 1;
+  DISPATCH(N, finalize)(table, L, W, next);
+}
+
+void emul_find(uint8_t *table, int k, int L, int W, int max_rehash, int finalized,
+               const uint64_t *keys, uint64_t n, uint32_t *covg, uint8_t *edges, uint8_t *found) {
+  const int N = 2 * k / 64 + 1;
+  DISPATCH(N, find)(table, L, W, max_rehash, finalized, keys, n, covg, edges, found);
+}
+
+uint32_t emul_hash_c(const uint64_t *key, int N, uint32_t rehash) {
+  if (N == 1) { uint64_t k1[1] = {key[0]}; return lookup3_key<1>(k1, rehash).c; }
+  if (N == 2) { uint64_t k2[2] = {key[0], key[1]}; return lookup3_key<2>(k2, rehash).c; }
+  uint64_t k3[3] = {key[0], key[1], key[2]};
+  return lookup3_key<3>(k3, rehash).c;
+}
+
+}  // extern "C"

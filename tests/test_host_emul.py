@@ -1,0 +1,185 @@
+"""CPU check of the kernels' own arithmetic (tests/host_emul): the __host__
+__device__ functions the CUDA kernels are made of, driven tile by tile on the
+host, against the golden reference outputs and the oracle.  No GPU needed; the
+-m gpu tests repeat the same comparisons through the real kernels."""
+import ctypes as C
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from lasv_b200 import element_dtype, record_dtype, words_per_kmer
+from tests import util
+
+HERE = Path(__file__).resolve().parent / "host_emul"
+
+
+@pytest.fixture(scope="module")
+def emul():
+    so = HERE / "libhost_emul.so"
+    src = HERE / "host_emul.cpp"
+    hdrs = list((HERE.parents[1] / "lasv_b200" / "csrc").glob("*.cuh"))
+    if not so.exists() or so.stat().st_mtime < max(p.stat().st_mtime for p in [src] + hdrs):
+        subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas",
+                        "-I/usr/local/cuda/include", "-o", str(so), str(src)], check=True)
+    L = C.CDLL(str(so))
+    L.emul_build_fused.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64] + [C.c_int] * 6 + [C.c_void_p, C.c_void_p]
+    L.emul_extract_records.restype = C.c_uint64
+    L.emul_extract_records.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_int,
+                                       C.c_void_p, C.c_uint64]
+    L.emul_insert_records.argtypes = [C.c_void_p, C.c_uint64] + [C.c_int] * 4 + [C.c_void_p, C.c_void_p]
+    L.emul_finalize.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    L.emul_find.argtypes = [C.c_void_p] + [C.c_int] * 5 + [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.emul_hash_c.restype = C.c_uint32
+    L.emul_hash_c.argtypes = [C.c_void_p, C.c_int, C.c_uint32]
+    return L
+
+
+def table_records(table):
+    occ = table[table["status"] != 0]
+    out = np.zeros(len(occ), dtype=record_dtype(table["kmer"].shape[1]))
+    out["kmer"], out["covg"], out["edges"] = occ["kmer"], occ["coverage"], occ["edges"]
+    return out
+
+
+def emul_build(emul, meta, seq, qual, T=2048, L=None, W=None):
+    k = meta["k"]
+    L = L or meta["L"]
+    W = W or meta["W"]
+    N = words_per_kmer(k)
+    table = np.zeros((1 << L) * W, dtype=element_dtype(N))
+    ctr = np.zeros(20, dtype=np.uint64)
+    rc = emul.emul_build_fused(seq.ctypes.data, qual.ctypes.data if qual is not None else None, len(seq), k,
+                               util.cutoff_of(meta), L, W, 15, T, table.ctypes.data, ctr.ctypes.data)
+    return rc, table, ctr
+
+
+@pytest.mark.parametrize("name", util.ALL_CASES)
+@pytest.mark.parametrize("T", [2048, 1024])
+def test_emulated_build_matches_reference_golden(emul, name, T):
+    meta = util.case_meta(name)
+    seq, qual, _ = util.case_streams(name)
+    rc, table, ctr = emul_build(emul, meta, seq, qual, T)
+    assert rc == 0
+    util.assert_same_records(table_records(table), util.case_records(name), name)
+    assert int(ctr[1]) == meta["inserts"]
+    assert int(ctr[0]) == meta["n_records"]
+    # pad bytes carry tags until finalisation, status is `none`
+    occ = table[table["status"] != 0]
+    assert (occ["status"] == 1).all()
+
+
+@pytest.mark.parametrize("name", ["synth_cfg0_k53", "synth_cfg1_k31", "synth_cfg2_k95", "synth_full_k53",
+                                  "synth_full_k31", "edge_pe_k33_q5"])
+def test_emulated_finalize_gives_reference_layout(emul, name):
+    """After finalisation every bucket is hole-free and every key is found by the
+    reference's scan-from-slot-0 lookup along the reference's rehash chain."""
+    meta = util.case_meta(name)
+    k, L, W = meta["k"], meta["L"], meta["W"]
+    N = words_per_kmer(k)
+    seq, qual, _ = util.case_streams(name)
+    rc, table, ctr = emul_build(emul, meta, seq, qual)
+    assert rc == 0
+    gold = util.case_records(name)
+    keys = np.ascontiguousarray(gold["kmer"])
+    n = len(keys)
+    covg, edges, found = np.zeros(n, np.uint32), np.zeros(n, np.uint8), np.zeros(n, np.uint8)
+    emul.emul_find(table.ctypes.data, k, L, W, 15, 0, keys.ctypes.data, n, covg.ctypes.data,
+                   edges.ctypes.data, found.ctypes.data)
+    assert found.all() and np.array_equal(covg, gold["covg"]) and np.array_equal(edges, gold["edges"])
+    nxt = np.zeros(1 << L, dtype=np.int16)
+    emul.emul_finalize(table.ctypes.data, k, L, W, nxt.ctypes.data)
+    raw = table.view(np.uint8).reshape(len(table), 8 * N + 8)
+    assert not raw[:, 8 * N + 6:].any()                       # pad bytes zeroed
+    t2 = table.reshape(1 << L, W)
+    occ = t2["status"] != 0
+    assert np.array_equal(occ.sum(axis=1), nxt)
+    assert (occ == (np.arange(W)[None, :] < nxt[:, None])).all()    # hole-free from slot 0
+    assert not raw[~occ.reshape(-1)].any()                    # empty slots are all-zero bytes
+    emul.emul_find(table.ctypes.data, k, L, W, 15, 1, keys.ctypes.data, n, covg.ctypes.data,
+                   edges.ctypes.data, found.ctypes.data)
+    assert found.all() and np.array_equal(covg, gold["covg"]) and np.array_equal(edges, gold["edges"])
+    # independent check with the ORACLE's own find (reference bucket scan + rehash chain):
+    # place the finalised slots into an oracle table slot for slot and look every key up
+    g = O.OracleGraph(k, L, W)
+    for b in range(1 << L):                                   # bucket b holds exactly the keys the
+        for s in range(int(nxt[b])):                          # reference chain would look for there
+            h = [O.hash_value(t2["kmer"][b, s], r, L) for r in range(16)]
+            assert b in h
+            r = h.index(b)
+            assert all(nxt[hb] == W for hb in h[:r])          # earlier buckets of the chain are full
+    g.close()
+    util.assert_same_records(table_records(table), gold, name)
+    absent = keys.copy()
+    absent[:, -1] ^= np.uint64(0x5555)
+    emul.emul_find(table.ctypes.data, k, L, W, 15, 1, absent.ctypes.data, n, covg.ctypes.data,
+                   edges.ctypes.data, found.ctypes.data)
+    present = {tuple(x) for x in keys.tolist()}
+    assert [bool(f) for f in found] == [tuple(x) in present for x in absent.tolist()]
+
+
+@pytest.mark.parametrize("name", ["synth_cfg0_k53", "synth_cfg1_k31", "synth_cfg2_k95", "edge_pe_k65_q5"])
+def test_emulated_records_path(emul, name):
+    """extract -> records -> insert (the split / sharded path) gives the same graph."""
+    meta = util.case_meta(name)
+    k, L, W = meta["k"], meta["L"], meta["W"]
+    N = words_per_kmer(k)
+    seq, qual, _ = util.case_streams(name)
+    cap = meta["inserts"] + 10
+    recs = np.zeros((cap, 2 * N + 1), dtype=np.uint32)
+    n = emul.emul_extract_records(seq.ctypes.data, qual.ctypes.data, len(seq), k, util.cutoff_of(meta), 1024,
+                                  recs.ctypes.data, cap)
+    assert n == meta["inserts"]
+    # shard the records by owner bits exactly as the ROUTE mode does and insert per shard
+    g_bits = 1
+    shards = [np.zeros((1 << (L - g_bits)) * W, dtype=element_dtype(N)) for _ in range(2)]
+    owner = np.zeros(n, dtype=np.int64)
+    for i in range(n):
+        key = np.zeros(N, dtype=np.uint64)
+        for w in range(N):
+            key[w] = np.uint64(recs[i, 2 * w]) | (np.uint64(recs[i, 2 * w + 1]) << np.uint64(32))
+        c = emul.emul_hash_c(key.ctypes.data, N, 0)
+        assert (c & ((1 << L) - 1)) == O.hash_value(key, 0, L)     # lookup3 == reference hash_value
+        owner[i] = (c >> (L - g_bits)) & 1
+    all_recs = []
+    for d in range(2):
+        sub = np.ascontiguousarray(recs[:n][owner == d])
+        ctr = np.zeros(20, dtype=np.uint64)
+        rc = emul.emul_insert_records(sub.ctypes.data, len(sub), k, L - g_bits, W, 15,
+                                      shards[d].ctypes.data, ctr.ctypes.data)
+        assert rc == 0
+        all_recs.append(table_records(shards[d]))
+    util.assert_same_records(np.concatenate(all_recs), util.case_records(name), name)
+
+
+def test_emulated_table_full(emul):
+    meta = util.case_meta("synth_cfg0_k53")
+    seq, qual, _ = util.case_streams("synth_cfg0_k53")
+    rc, table, ctr = emul_build(emul, meta, seq, qual, L=4, W=20)
+    assert rc == -3 and ctr[2] == 1
+
+
+def test_emulated_ragged_and_tiny_inputs(emul):
+    """Empty stream, one short read, reads of every length around k, no trailing
+    newline at a 16-byte boundary: compare with the oracle."""
+    rng = np.random.default_rng(5)
+    for k in (21, 33, 65):
+        reads, quals = [], []
+        for ln in [0, 1, k - 1, k, k + 1, 2 * k, 15, 16, 17, 31, 32, 33, 200, 5000]:
+            reads.append("".join(rng.choice(list("ACGT"), ln)))
+            q = rng.choice([ord("I"), ord("#"), ord("&"), ord("'")], ln, p=[0.9, 0.04, 0.03, 0.03])
+            quals.append(bytes(q.astype(np.uint8)).decode())
+        seq, qual, offs = O.reads_to_streams(reads, quals)
+        meta = {"k": k, "L": 8, "W": 60, "q_thresh": 5}
+        g, ok = util.oracle_build(k, 8, 60, seq, qual, offs, 38)
+        assert ok
+        for T in (1024, 2048):
+            rc, table, ctr = emul_build(emul, meta, seq, qual, T)
+            assert rc == 0
+            util.assert_same_records(table_records(table), g.records(), f"k={k}")
+            assert int(ctr[1]) == g.stats.kmers_inserted
+    rc, table, ctr = emul_build(emul, {"k": 31, "L": 4, "W": 4, "q_thresh": 0}, np.zeros(0, np.uint8),
+                                np.zeros(0, np.uint8))
+    assert rc == 0 and ctr[1] == 0

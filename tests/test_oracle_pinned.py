@@ -1,0 +1,108 @@
+"""Pins the oracle (oracle/dbg_oracle.c) to the reference: SURVEY 8c known-answer
+vectors, golden `.ctx` outputs of the compiled unmodified reference
+(tests/golden, generator make_golden.py) and, where oracle/_ref is present,
+live runs of the reference binary."""
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from tests import util
+
+S = ("ACGTTGCATGCCGATAGGCTAACGTTAGCCATGCATCGGATCGATTACGGCTAGCTAGGATCCGATCGTAGCTAGCTAGGCTAACGATCGA"
+     "TCGGCTAGCTAAGCTT")
+
+# SURVEY.md section 8c, extracted from the compiled reference
+KAT = {
+    31: dict(fw=[0x06f9396329c1bc94], rc=[0x3a706f25cda4e41b], h=[(43, 451), (106539, 62915), (16228395, 10679747)]),
+    53: dict(fw=[0x0000006f9396329c, 0x1bc94e4da363c69c], rc=[0x00000325b0d8d639, 0x3a706f25cda4e41b],
+             h=[(366, 991), (10606, 41951), (16132462, 6071263)]),
+    95: dict(fw=[0x06f9396329c1bc94, 0xe4da363c69c9ca35, 0x8db272729c18d8da],
+             rc=[0x163636f25c9c9c63, 0x68d72725b0d8d639, 0x3a706f25cda4e41b],
+             h=[(787, 538), (127763, 21018), (4846355, 16405018)]),
+}
+
+
+@pytest.mark.parametrize("k", [31, 53, 95])
+def test_known_answers(k):
+    v = KAT[k]
+    fw = O.seq_to_kmer(S[:k], k)
+    assert [int(x) for x in fw] == v["fw"]
+    rc = O.revcomp(fw, k)
+    assert [int(x) for x in rc] == v["rc"]
+    key = O.get_key(fw, k)
+    assert np.array_equal(key, fw)                      # "= fwd" in the table
+    assert np.array_equal(O.get_key(rc, k), fw)         # and from the other strand
+    assert O.kmer_to_seq(fw, k) == S[:k]
+    for L, (h0, h1) in zip((10, 17, 24), v["h"]):
+        assert O.hash_value(key, 0, L) == h0
+        assert O.hash_value(key, 1, L) == h1
+
+
+@pytest.mark.parametrize("name", util.ALL_CASES)
+def test_oracle_matches_reference_golden(name):
+    meta = util.case_meta(name)
+    seq, qual, offs = util.case_streams(name)
+    paired = name.startswith("edge_pe") or name.startswith("synth")
+    g, ok = util.oracle_build(meta["k"], meta["L"], meta["W"], seq, qual, offs, util.cutoff_of(meta),
+                              paired=paired)
+    assert ok
+    util.assert_same_records(g.records(), util.case_records(name), name)
+    assert g.stats.kmers_inserted == meta["inserts"]
+    assert g.stats.bad_reads == meta["bad_reads"]
+    assert g.stats.bases_read == meta["bases_parsed"]
+    assert g.stats.bases_loaded == meta["bases_loaded"]
+    # "tries r: n" (hash_table.c:384-394) -- the oracle keeps the reference's slot layout
+    coll = g.collisions()
+    for r, n in meta["tries"].items():
+        assert int(coll[int(r)]) == n
+    # mean contig length that lands in the .ctx header (graph_operations.c:769-774)
+    tot = int(g.hist.sum())
+    mean = int((g.hist.astype(object) * np.arange(len(g.hist), dtype=object)).sum() // tot) if tot else 0
+    assert mean == meta["ctx_mean_read_len"] == meta["mean_read_len_after_filters"]
+    # header bytes: all but the 6 padding bytes of the x87 long double
+    hdr = bytearray(O.ctx_header(meta["k"], mean, meta["bases_loaded"]))
+    ref = bytearray(bytes.fromhex(meta["ctx_header_hex"]))
+    assert len(hdr) == len(ref) == 94
+    pad = slice(6 + 16 + 12 + 4 + 9 + 10, 6 + 16 + 12 + 4 + 9 + 16)
+    hdr[pad] = ref[pad] = b"\0" * 6
+    assert hdr == ref
+
+
+def test_oracle_table_full_is_reported():
+    meta = util.case_meta("synth_cfg0_k53")
+    seq, qual, offs = util.case_streams("synth_cfg0_k53")
+    g, ok = util.oracle_build(53, 4, 20, seq, qual, offs, util.cutoff_of(meta))   # 320 slots << 7208 keys
+    assert not ok and g.table_full
+
+
+def test_oracle_reload_records_roundtrip():
+    name = "synth_cfg0_k53"
+    recs = util.case_records(name)
+    g = O.OracleGraph(53, 10, 40)
+    assert g.load_records(recs)
+    util.assert_same_records(g.records(), recs)
+    key = recs["kmer"][123]
+    assert g.lookup(key) == (int(recs["covg"][123]), int(recs["edges"][123]))
+
+
+@pytest.mark.skipif(not O.ref_available(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("k,L,W", [(31, 9, 30), (53, 9, 30), (95, 9, 30)])
+def test_oracle_matches_live_reference(tmp_path, k, L, W):
+    from lasv_b200 import synth
+    base = {31: synth.CFG1, 53: synth.CFG0, 95: synth.CFG2}[k]
+    w = synth.scaled(base, 3000, L)
+    w.seed = 7 + k
+    p = w.params()
+    n_pairs = 150
+    seq, qual, offs = synth.reads_host(p, 0, 2 * n_pairs)
+    stride = w.read_len + 1
+    s2, q2 = seq.reshape(-1, stride), qual.reshape(-1, stride)
+    O.write_fastq_fixed(tmp_path / "a.fq", s2[0::2].reshape(-1), q2[0::2].reshape(-1), w.read_len)
+    O.write_fastq_fixed(tmp_path / "b.fq", s2[1::2].reshape(-1), q2[1::2].reshape(-1), w.read_len)
+    ref = O.run_reference(k, L, W, tmp_path / "a.fq", tmp_path / "b.fq", q_thresh=5, workdir=tmp_path)
+    g, ok = util.oracle_build(k, L, W, seq, qual, offs, 38, paired=True)
+    assert ok
+    util.assert_same_records(g.records(), ref["ctx"]["records"])
+    assert g.stats.kmers_inserted == ref["inserts"]
+    # the oracle keeps the reference's slot order too: .ctx record order is identical
+    assert np.array_equal(g.records(), ref["ctx"]["records"])
