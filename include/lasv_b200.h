@@ -245,6 +245,12 @@ int lasv_synth_reads_host(const lasv_synth_params *p, uint64_t first_read, uint6
  * random-access HBM ceiling quoted next to the roofline. */
 int lasv_random_access_probe(void *d_buf, uint64_t n_sectors, uint64_t n_ops, uint64_t seed,
                              void *cuda_stream);
+/* Host-only: parse a whole sequence file with the loader's reader (FASTQ /
+ * FASTA / plain, optionally gzipped; grammar of libs/seq_file) into the stream
+ * layout of lasv_graph_load_reads_host.  Returns the number of reads, or a
+ * negative error; *has_qual tells whether the file carries quality scores. */
+long long lasv_seqfile_to_streams(const char *path, uint8_t *seq, uint8_t *qual, uint64_t cap_bytes,
+                                  uint64_t *offsets, uint64_t cap_reads, int *has_qual);
 /* Number of kernels this library has launched since load (bench gpu_launches). */
 uint64_t lasv_kernel_launches(void);
 

@@ -133,9 +133,12 @@ BuildParams build_params(lasv_graph *g, const uint8_t *d_seq, const uint8_t *d_q
                          uint64_t n_bytes, int cutoff) {
   BuildParams p;
   memset(&p, 0, sizeof p);
-  p.seq = d_seq;
-  p.qual = d_qual;
-  p.n_bytes = n_bytes;
+  // the kernels read 16-byte chunks: align the pointers down, skip the lead bytes
+  const uint32_t lead = (uint32_t)((uintptr_t)d_seq & 15u);
+  p.seq = d_seq - lead;
+  p.qual = d_qual ? d_qual - lead : nullptr;
+  p.lead = lead;
+  p.n_bytes = n_bytes + lead;
   p.k = g->k;
   p.cutoff = cutoff;
   p.table = g->view();
@@ -152,8 +155,10 @@ int check_launch() {
   return LASV_OK;
 }
 
-int check_aligned(const void *p, const char *what) {
-  if (((uintptr_t)p & 15u) != 0) return fail(LASV_ERR_ARG, "%s must be 16-byte aligned", what);
+int check_streams(const void *seq, const void *qual) {
+  if (!seq) return fail(LASV_ERR_ARG, "sequence stream is NULL");
+  if (qual && (((uintptr_t)seq ^ (uintptr_t)qual) & 15u) != 0)
+    return fail(LASV_ERR_ARG, "sequence and quality streams must share their alignment modulo 16");
   return LASV_OK;
 }
 
@@ -273,8 +278,7 @@ int lasv_graph_load_reads_device(lasv_graph *g, const uint8_t *d_seq, const uint
                                  int quality_cutoff, void *cuda_stream) {
   if (int e = use(g)) return e;
   if (g->finalized) return fail(LASV_ERR_STATE, "graph is finalised; no further inserts");
-  if (int e = check_aligned(d_seq, "d_seq")) return e;
-  if (d_qual) if (int e = check_aligned(d_qual, "d_qual")) return e;
+  if (int e = check_streams(d_seq, d_qual)) return e;
   cudaStream_t st = stream_of(g, cuda_stream);
   if (n_bytes) {
     launch_build(g->N, MODE_FUSED, build_params(g, d_seq, d_qual, n_bytes, quality_cutoff), st);
@@ -413,7 +417,7 @@ int lasv_graph_route_reads_device(lasv_graph *g, const uint8_t *d_seq, const uin
   if (int e = use(g)) return e;
   if (n_dest < 1 || n_dest > 16 || (n_dest & (n_dest - 1)))
     return fail(LASV_ERR_ARG, "n_dest must be a power of two <= 16, got %d", n_dest);
-  if (int e = check_aligned(d_seq, "d_seq")) return e;
+  if (int e = check_streams(d_seq, d_qual)) return e;
   if (!n_bytes) return LASV_OK;
   BuildParams p = build_params(g, d_seq, d_qual, n_bytes, quality_cutoff);
   p.rec_out = d_bins;
@@ -430,7 +434,7 @@ int lasv_graph_extract_records_device(lasv_graph *g, const uint8_t *d_seq, const
                                       uint64_t capacity, unsigned long long *d_count,
                                       void *cuda_stream) {
   if (int e = use(g)) return e;
-  if (int e = check_aligned(d_seq, "d_seq")) return e;
+  if (int e = check_streams(d_seq, d_qual)) return e;
   if (!n_bytes) return LASV_OK;
   BuildParams p = build_params(g, d_seq, d_qual, n_bytes, quality_cutoff);
   p.rec_out = d_records;
@@ -1059,6 +1063,24 @@ int lasv_synth_reads_host(const lasv_synth_params *p, uint64_t first_read, uint6
   if (int e = check_synth(p)) return e;
   synth_host(to_synth(p), first_read, n_reads, seq, qual);
   return LASV_OK;
+}
+
+long long lasv_seqfile_to_streams(const char *path, uint8_t *seq, uint8_t *qual, uint64_t cap_bytes,
+                                  uint64_t *offsets, uint64_t cap_reads, int *has_qual) {
+  std::string err;
+  SeqReader r;
+  if (!r.open(path, err)) return fail(LASV_ERR_IO, "%s", err.c_str());
+  HostBatch b;
+  b.seq = seq; b.qual = qual; b.offsets = offsets;
+  b.cap_bytes = cap_bytes; b.cap_reads = cap_reads;
+  b.reset();
+  if (has_qual) *has_qual = r.has_quality() ? 1 : 0;
+  while (r.next(err)) {
+    if (!r.append_to(b, r.has_quality()))
+      return fail(LASV_ERR_CAPACITY, "output buffers too small for %s", path);
+  }
+  if (!err.empty()) return fail(LASV_ERR_IO, "%s", err.c_str());
+  return (long long)b.n_reads;
 }
 
 int lasv_random_access_probe(void *d_buf, uint64_t n_sectors, uint64_t n_ops, uint64_t seed,

@@ -134,11 +134,10 @@ __global__ void __launch_bounds__(THREADS) build_kernel(const BuildParams p, con
     inr = 0;
     if (tid < CHUNKS && tile < n_tiles) {
       const long long g = (long long)(tile * (uint64_t)T) - TileGeom::HALO_L + 16ll * tid;
-      if (g >= 0 && (uint64_t)g < p.n_bytes) {
+      inr = chunk_inrange16(g, p.lead, p.n_bytes);
+      if (inr) {
         sv = __ldg(reinterpret_cast<const uint4 *>(p.seq + g));
         if (has_qual) qv = __ldg(reinterpret_cast<const uint4 *>(p.qual + g));
-        const uint64_t left = p.n_bytes - (uint64_t)g;
-        inr = left >= 16 ? 0xFFFFu : ((1u << left) - 1u);
       }
     }
   };

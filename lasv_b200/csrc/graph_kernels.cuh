@@ -17,7 +17,8 @@ enum BuildMode { MODE_FUSED = 0, MODE_RECORDS = 1, MODE_ROUTE = 2 };
 struct BuildParams {
   const uint8_t *seq;   // sequence stream: reads back to back, each followed by >= 1 separator byte
   const uint8_t *qual;  // quality stream, byte-aligned with seq; nullptr = no quality filter (FASTA)
-  uint64_t n_bytes;     // stream length; buffers must be readable up to round_up(n_bytes, 16)
+  uint64_t n_bytes;     // lead + stream length; buffers must be readable up to round_up(n_bytes, 16)
+  uint32_t lead;        // seq/qual are aligned DOWN to 16 bytes; the stream starts `lead` bytes in
   int k;
   int cutoff;           // RAW ascii cutoff (threshold + offset), signed-char compare, '<=' is bad
   TableView table;

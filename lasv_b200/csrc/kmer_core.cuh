@@ -152,6 +152,17 @@ LASV_HD void classify16(uint4 sv, uint4 qv, bool has_qual, int cutoff, uint32_t 
   bad16 = bad;
 }
 
+// Which of the 16 bytes of the chunk at byte offset g (relative to the 16-byte
+// aligned base of the stream buffer) belong to the stream [lead, n_total):
+// bit i <-> byte g+i.  `lead` (< 16) is the misalignment of the caller's pointer.
+LASV_HD uint32_t chunk_inrange16(long long g, uint32_t lead, uint64_t n_total) {
+  if (g < 0 || (uint64_t)g >= n_total) return 0u;
+  const uint64_t left = n_total - (uint64_t)g;
+  uint32_t m = left >= 16 ? 0xFFFFu : ((1u << left) - 1u);
+  if ((uint64_t)g < lead) m &= ~((1u << (lead - (uint32_t)g)) - 1u);
+  return m;
+}
+
 // Reverse-complement of a 16-base code word: complement every base (3-c == ~c
 // on two bits) and reverse the base order.
 LASV_HD uint32_t rc_code32(uint32_t code32) {

@@ -228,3 +228,16 @@ def mean_contig_length(hist: np.ndarray) -> int:
     if tot == 0:
         return 0
     return int((hist.astype(object) * np.arange(len(hist), dtype=object)).sum() // tot)
+
+
+def seqfile_to_streams(path, cap_bytes: int = 1 << 26, cap_reads: int = 1 << 20):
+    """Parse a sequence file with the loader's own reader (host only).  Returns
+    (seq, qual or None, offsets)."""
+    seq = np.zeros(cap_bytes, dtype=np.uint8)
+    qual = np.zeros(cap_bytes, dtype=np.uint8)
+    offs = np.zeros(cap_reads + 1, dtype=np.uint64)
+    hq = C.c_int(0)
+    n = check(_capi.lib().lasv_seqfile_to_streams(str(path).encode(), seq.ctypes.data, qual.ctypes.data,
+                                                  cap_bytes, offs.ctypes.data, cap_reads, C.byref(hq)))
+    nb = int(offs[n])
+    return seq[:nb], (qual[:nb] if hq.value else None), offs[: n + 1]

@@ -48,12 +48,13 @@ struct Tile {
     BD[R / 64 + 1] = ~0ull;
   }
   // mirrors build_kernel's issue_stage + stage phase
-  void stage(const uint8_t *seq, const uint8_t *qual, uint64_t n_bytes, uint64_t tile, int cutoff) {
+  void stage(const uint8_t *seq, const uint8_t *qual, uint64_t n_bytes, uint32_t lead, uint64_t tile,
+             int cutoff) {
     for (int c = 0; c < CHUNKS; c++) {
       uint4 sv = {0, 0, 0, 0}, qv = {0, 0, 0, 0};
-      uint32_t inr = 0;
       const long long g = (long long)(tile * (uint64_t)T) - TileGeom::HALO_L + 16ll * c;
-      if (g >= 0 && (uint64_t)g < n_bytes) {
+      const uint32_t inr = chunk_inrange16(g, lead, n_bytes);
+      if (inr) {
         const uint64_t left = n_bytes - (uint64_t)g;
         const size_t take = left >= 16 ? 16 : (size_t)left;
         uint8_t sb[16], qb[16];
@@ -63,7 +64,6 @@ struct Tile {
         if (qual) memcpy(qb, qual + g, take);
         memcpy(&sv, sb, 16);
         memcpy(&qv, qb, 16);
-        inr = left >= 16 ? 0xFFFFu : ((1u << left) - 1u);
       }
       uint32_t code32, bad16;
       classify16(sv, qv, qual != nullptr, cutoff, inr, code32, bad16);
@@ -75,12 +75,23 @@ struct Tile {
 };
 
 template <int N, class Sink>
-void walk(const uint8_t *seq, const uint8_t *qual, uint64_t n_bytes, int k, int cutoff, int T,
-          Sink &&sink) {
+void walk(const uint8_t *seq_in, const uint8_t *qual_in, uint64_t n_in, int k, int cutoff, int T,
+          Sink &&sink, uint32_t lead = 0) {
+  // a caller pointer that is `lead` bytes past a 16-byte boundary: the kernels see
+  // the aligned-down buffer, whose first `lead` bytes are foreign (here: valid-looking
+  // bases, so that a wrong in-range mask would show up as extra k-mers)
+  std::vector<uint8_t> sbuf(lead + n_in + 32, (uint8_t)'A'), qbuf(lead + n_in + 32, (uint8_t)'I');
+  if (n_in) {
+    memcpy(sbuf.data() + lead, seq_in, n_in);
+    if (qual_in) memcpy(qbuf.data() + lead, qual_in, n_in);
+  }
+  const uint8_t *seq = sbuf.data();
+  const uint8_t *qual = qual_in ? qbuf.data() : nullptr;
+  const uint64_t n_bytes = n_in + lead;
   Tile tile(T);
   const uint64_t n_tiles = (n_bytes + T - 1) / T;
   for (uint64_t t = 0; t < n_tiles; t++) {
-    tile.stage(seq, qual, n_bytes, t, cutoff);
+    tile.stage(seq, qual, n_bytes, lead, t, cutoff);
     for (int pos = 0; pos < T; pos++) {
       const int j = TileGeom::HALO_L + pos;
       if (!window_good(tile.BD.data(), j, k)) continue;
@@ -104,11 +115,11 @@ template <int N>
 int build_fused(const uint8_t *seq, const uint8_t *qual, uint64_t n_bytes, int k, int cutoff, int L,
                 int W, int max_rehash, int T, uint8_t *table, GraphCounters *ctr) {
   const TableView tv = view_of(table, L, W, max_rehash);
-  walk<N>(seq, qual, n_bytes, k, cutoff, T, [&](const uint64_t(&key)[N], uint32_t edge) {
+  walk<N>(seq, qual, n_bytes, k, cutoff, T & 0xFFFF, [&](const uint64_t(&key)[N], uint32_t edge) {
     ctr->kmers_inserted++;
     const int r = table_upsert<N, HostOps>(tv, ctr, key, edge, 1u);
     if (r == 1) ctr->unique_kmers++;
-  });
+  }, (uint32_t)(T >> 16) & 15u);  // bits 16..19 of T: emulated pointer misalignment
   return ctr->table_full ? -3 : 0;
 }
 

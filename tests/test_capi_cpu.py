@@ -1,0 +1,134 @@
+"""CPU-side checks of the C-ABI library: it loads, exports every symbol
+include/lasv_b200.h declares, refuses to compute without a GPU (no fallback),
+and its host-only pieces (sequence-file reader, synthetic-read generator, .ctx
+header) behave like the reference."""
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import lasv_b200
+from lasv_b200 import _capi, synth
+from lasv_b200.graph import seqfile_to_streams
+from oracle import oracle as O
+from tests import util
+
+ROOT = Path(__file__).resolve().parents[1]
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _capi.lib()
+    hdr = (ROOT / "include" / "lasv_b200.h").read_text()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b((?:lasv|load)_[a-z0-9_]+)\s*\(", hdr))
+    assert declared, "no declarations parsed"
+    assert declared == set(_capi.EXPORTS), declared ^ set(_capi.EXPORTS)
+    for sym in declared:
+        assert hasattr(lib, sym), f"liblasv_b200.so does not export {sym}"
+
+
+def test_no_cpu_fallback_without_gpu():
+    lib = _capi.lib()
+    if lib.lasv_device_count() > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(_capi.LasvError) as e:
+        lasv_b200.DBGraph(31, 10, 20)
+    assert "no usable CUDA device" in str(e.value)
+
+
+def test_argument_validation():
+    lib = _capi.lib()
+    assert not lib.lasv_graph_new(32, 10, 20, 15, 0)          # even k (cmd_line.c:805)
+    assert b"odd" in lib.lasv_last_error()
+    assert not lib.lasv_graph_new(97, 10, 20, 15, 0)          # beyond MAXK=95
+    assert not lib.lasv_graph_new(31, 0, 20, 15, 0)
+
+
+@pytest.mark.parametrize("fname", ["edge_1.fq", "edge_2.fq", "edge_1.fq.gz"])
+def test_fastq_reader_matches_reference_grammar(fname):
+    seq, qual, offs = seqfile_to_streams(util.GOLDEN / fname)
+    reads, quals = O.parse_fastq_python(util.GOLDEN / fname)
+    s2, q2, o2 = O.reads_to_streams(reads, quals)
+    assert np.array_equal(seq, s2) and np.array_equal(qual, q2) and np.array_equal(offs, o2)
+
+
+def test_fasta_and_plain_reader(tmp_path):
+    seq, qual, offs = seqfile_to_streams(util.GOLDEN / "contigs.fa")
+    assert qual is None and len(offs) == 3
+    reads = util._fasta_reads(util.GOLDEN / "contigs.fa")
+    assert seq.tobytes().decode().split("\n")[:-1] == reads
+    p = tmp_path / "plain.txt"
+    p.write_text("ACGT\nGGCC\n\nTT")
+    seq, qual, offs = seqfile_to_streams(p)
+    assert qual is None
+    assert seq.tobytes().decode().split("\n")[:-1] == ["ACGT", "GGCC", "", "TT"]   # seq_plain.c: empty line = empty read
+    q = tmp_path / "x.sam"
+    q.write_text("@HD\n")
+    with pytest.raises(_capi.LasvError):
+        seqfile_to_streams(q)
+    with pytest.raises(_capi.LasvError):
+        seqfile_to_streams(tmp_path / "missing.fq")
+
+
+def test_reader_through_oracle_matches_reference_golden():
+    """The reader's bytes, fed to the oracle, reproduce the reference's output on
+    the file-based golden cases: pins the parser end to end on the CPU."""
+    for name in util.EDGE_PE + util.EDGE_SE:
+        meta = util.case_meta(name)
+        f1, f2 = util.case_files(name)
+        s1, q1, o1 = seqfile_to_streams(f1)
+        if f2 is None:
+            seq, qual, offs, paired = s1, q1, o1, False
+        else:
+            s2, q2, o2 = seqfile_to_streams(f2)
+            r1 = s1.tobytes().decode("latin1").split("\n")[:-1]
+            r2 = s2.tobytes().decode("latin1").split("\n")[:-1]
+            u1 = q1.tobytes().decode("latin1")
+            u2 = q2.tobytes().decode("latin1")
+            qa = [u1[int(o1[i]):int(o1[i + 1]) - 1] for i in range(len(r1))]
+            qb = [u2[int(o2[i]):int(o2[i + 1]) - 1] for i in range(len(r2))]
+            reads, quals = [], []
+            for a, b, c, d in zip(r1, r2, qa, qb):
+                reads += [a, b]
+                quals += [c, d]
+            seq, qual, offs = O.reads_to_streams(reads, quals)
+            paired = True
+        g, ok = util.oracle_build(meta["k"], meta["L"], meta["W"], seq, qual, offs, util.cutoff_of(meta), paired)
+        assert ok
+        util.assert_same_records(g.records(), util.case_records(name), name)
+
+
+def test_synth_generator_is_deterministic_and_sane():
+    w = synth.scaled(synth.CFG2, 5000, 10)
+    p = w.params()
+    a = synth.reads_host(p, 0, 64)
+    b = synth.reads_host(p, 32, 32)
+    stride = w.read_len + 1
+    assert np.array_equal(a[0][32 * stride:], b[0]) and np.array_equal(a[1][32 * stride:], b[1])
+    s = a[0].reshape(64, stride)
+    assert (s[:, -1] == 10).all() and set(np.unique(s[:, :-1])) <= set(b"ACGTN")
+    q = a[1].reshape(64, stride)[:, :-1]
+    assert q.min() >= 33 + 2 and q.max() <= 33 + 40
+    # mates of a pair come from opposite strands of one fragment: with no errors the
+    # reverse complement of mate 2 matches the genome downstream of mate 1
+    w0 = synth.scaled(synth.CFG0, 5000, 10)
+    w0.err = w0.n_rate = w0.lowq = 0.0
+    s0 = synth.reads_host(w0.params(), 0, 2)[0].tobytes().decode().split("\n")
+    tiled = synth.reads_host(w0.params(tiling=True), 0, (5000 // 48) + 2)[0].tobytes().decode().split("\n")
+    genome = tiled[0] + "".join(t[52:] for t in tiled[1:-1])
+    genome = genome.replace("N", "")
+    comp = str.maketrans("ACGT", "TGCA")
+    m1, m2 = s0[0], s0[1]
+    fwd, rev = (m1, m2.translate(comp)[::-1])
+    if fwd not in genome:
+        fwd, rev = (m2, m1.translate(comp)[::-1])
+    i = genome.find(fwd)
+    assert i >= 0 and genome[i + w0.insert - w0.read_len: i + w0.insert] == rev
+
+
+def test_ctx_header_matches_reference_bytes():
+    meta = util.case_meta("synth_cfg0_k53")
+    hdr = lasv_b200.ctx_header(53, meta["ctx_mean_read_len"], meta["ctx_total_seq"])
+    assert hdr.hex() == meta["ctx_header_hex"]
+    assert hdr == O.ctx_header(53, meta["ctx_mean_read_len"], meta["ctx_total_seq"])

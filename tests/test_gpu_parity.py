@@ -1,0 +1,448 @@
+"""GPU parity tests (run with -m gpu on the B200 box): every call goes through
+the C ABI of liblasv_b200.so.  The CUDA graph build is compared bit-exactly
+(sorted multiset of (canonical k-mer, coverage, edges), loader statistics, .ctx
+bytes) with the golden outputs of the compiled reference, with the oracle on
+seeded synthetic reads, and -- at BASELINE.json's full config-0 size -- through
+size-independent properties."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import lasv_b200
+from lasv_b200 import DBGraph, _capi, synth
+from lasv_b200.graph import mean_contig_length
+from oracle import oracle as O
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+
+def _have_gpu():
+    try:
+        return _capi.lib().lasv_device_count() > 0
+    except Exception:
+        return False
+
+
+@pytest.fixture(scope="module", autouse=True)
+def need_gpu():
+    if not _have_gpu():
+        pytest.fail("no CUDA device: the GPU tests need one (the product has no CPU fallback)")
+
+
+def torch_cuda():
+    import torch
+    torch.cuda.set_device(0)
+    return torch
+
+
+# ---------------------------------------------------------------- golden cases
+@pytest.mark.parametrize("name", util.ALL_CASES)
+def test_host_buffer_path_matches_reference_golden(name):
+    meta = util.case_meta(name)
+    seq, qual, offs = util.case_streams(name)
+    with DBGraph(meta["k"], meta["L"], meta["W"]) as g:
+        st = g.load_reads_host(seq, qual, offs, util.cutoff_of(meta))
+        util.assert_same_records(g.records(), util.case_records(name), name)
+        assert st["kmers_inserted"] == meta["inserts"]
+        assert st["unique_kmers"] == meta["n_records"] == g.unique_kmers
+        assert st["bad_reads"] == meta["bad_reads"]
+        assert st["bases_read"] == meta["bases_parsed"]
+        assert st["bases_loaded"] == meta["bases_loaded"]
+        _, hist = g.stats(hist_size=20001)
+        assert mean_contig_length(hist) == meta["ctx_mean_read_len"]
+        assert int(g.rehash_histogram().sum()) == meta["inserts"]
+
+
+@pytest.mark.parametrize("name", util.EDGE_PE + util.EDGE_SE)
+def test_sequence_file_loaders_match_reference_golden(name, tmp_path):
+    meta = util.case_meta(name)
+    f1, f2 = util.case_files(name)
+    with DBGraph(meta["k"], meta["L"], meta["W"]) as g:
+        if f2 is None:
+            lst = tmp_path / "se.list"
+            lst.write_text(f"{f1}\n")
+            st = g.load_se_filelist(lst, meta["q_thresh"], 33)
+        else:
+            (tmp_path / "l").write_text(f"{f1}\n")
+            (tmp_path / "r").write_text(f"{f2}\n")
+            st = g.load_pe_filelists(tmp_path / "l", tmp_path / "r", meta["q_thresh"], 33)
+        assert st["files_loaded"] == 1
+        util.assert_same_records(g.records(), util.case_records(name), name)
+        assert st["kmers_inserted"] == meta["inserts"] and st["bad_reads"] == meta["bad_reads"]
+        assert st["bases_read"] == meta["bases_parsed"] and st["bases_loaded"] == meta["bases_loaded"]
+        # .ctx file: header bytes and record multiset equal the reference's own dump
+        _, hist = g.stats(hist_size=20001)
+        out = tmp_path / "g.ctx"
+        g.dump_binary(out, mean_contig_length(hist), st["bases_loaded"])
+        ctx = O.parse_ctx(out)
+        assert ctx["header"].hex() == meta["ctx_header_hex"]
+        util.assert_same_records(ctx["records"], util.case_records(name), name)
+
+
+def test_paired_files_of_unequal_length_are_an_error(tmp_path):
+    a = tmp_path / "a.fq"
+    a.write_text("@x\nACGT\n+\nIIII\n@y\nACGT\n+\nIIII\n")
+    b = tmp_path / "b.fq"
+    b.write_text("@x\nACGT\n+\nIIII\n")
+    with DBGraph(3, 4, 4) as g:
+        with pytest.raises(_capi.LasvError) as e:
+            g.load_pe_seq_data(a, b, 33)
+        assert "same number of reads" in str(e.value)        # file_reader.c:641-647
+
+
+# ------------------------------------------------------- seeded synthetic reads
+def _synth_oracle(w, n_reads, seed=None):
+    if seed is not None:
+        w.seed = seed
+    p = w.params()
+    seq, qual, offs = synth.reads_host(p, 0, n_reads)
+    og = O.OracleGraph(w.kmer_size, w.number_bits, w.bucket_size)
+    assert og.load_reads(seq, qual, offs, w.cutoff, paired=True)
+    return p, seq, qual, offs, og
+
+
+@pytest.mark.parametrize("base,genome,L,W,n_reads", [
+    (synth.CFG1, 100_000, 13, 60, 30_000),    # k=31, one word
+    (synth.CFG0, 100_000, 13, 60, 30_000),    # k=53, two words
+    (synth.CFG2, 60_000, 12, 60, 20_000),     # k=95, three words, filter-heavy
+    (synth.CFG4, 150_000, 10, 250, 20_000),   # human-scale read model, W=250
+])
+def test_device_resident_path_matches_oracle(base, genome, L, W, n_reads):
+    torch = torch_cuda()
+    w = synth.scaled(base, genome, L)
+    w.bucket_size = W
+    p, seq, qual, offs, og = _synth_oracle(w, n_reads)
+    want = O.sort_records(og.records())
+    n_bytes = len(seq)
+    d_seq = torch.empty(n_bytes + 16, dtype=torch.uint8, device="cuda")
+    d_qual = torch.empty_like(d_seq)
+    st_ = torch.cuda.current_stream().cuda_stream
+    synth.reads_device(p, 0, n_reads, d_seq, d_qual, st_)
+    assert np.array_equal(d_seq[:n_bytes].cpu().numpy(), seq)
+    assert np.array_equal(d_qual[:n_bytes].cpu().numpy(), qual)
+    d_offs = torch.from_numpy(offs.astype(np.int64)).cuda()
+    with DBGraph(w.kmer_size, L, W) as g:
+        # two batches on the caller's stream
+        half = (n_reads // 2) * (w.read_len + 1)
+        g.load_reads_device(d_seq, d_qual, half, d_offs, n_reads // 2, w.cutoff, st_)
+        rest = d_offs[n_reads // 2:] - half
+        g.load_reads_device(d_seq[half:], d_qual[half:], n_bytes - half, rest, n_reads - n_reads // 2,
+                            w.cutoff, st_)
+        torch.cuda.synchronize()
+        st = g.stats(stream=st_)
+        assert np.array_equal(O.sort_records(g.records()), want)
+        assert st["kmers_inserted"] == og.stats.kmers_inserted
+        assert st["unique_kmers"] == og.unique_kmers
+        assert st["bad_reads"] == og.stats.bad_reads and st["bases_loaded"] == og.stats.bases_loaded
+        s = g.summary()
+        assert s["n_nodes"] == len(want) and s["sum_covg"] == og.stats.kmers_inserted
+        # find: present and absent keys
+        keys = want["kmer"][:: max(1, len(want) // 500)]
+        found, covg, edges = g.find(keys)
+        sel = want[:: max(1, len(want) // 500)]
+        assert found.all() and np.array_equal(covg, sel["covg"]) and np.array_equal(edges, sel["edges"])
+        absent = keys.copy()
+        absent[:, -1] ^= np.uint64(0x2AAAA)
+        present = {tuple(x) for x in want["kmer"].tolist()}
+        found, _, _ = g.find(absent)
+        assert found.tolist() == [tuple(x) in present for x in absent.tolist()]
+
+
+@pytest.mark.parametrize("base,world", [(synth.CFG0, 2), (synth.CFG1, 4), (synth.CFG2, 8)])
+def test_route_and_insert_records_match_oracle(base, world):
+    """The sharded path on one GPU: ranks emulated as `world` local graphs; every
+    emulated rank routes its slice of the reads, bins are handed to their owners."""
+    torch = torch_cuda()
+    L, W, n_reads = 13, 40, 24_000
+    w = synth.scaled(base, 80_000, L)
+    w.bucket_size = W
+    p, seq, qual, offs, og = _synth_oracle(w, n_reads, seed=99)
+    want = O.sort_records(og.records())
+    N = lasv_b200.words_per_kmer(w.kmer_size)
+    rw = 2 * N + 1
+    bits = int(np.log2(world))
+    st_ = torch.cuda.current_stream().cuda_stream
+    d_seq = torch.from_numpy(np.concatenate([seq, np.full(16, 10, np.uint8)])).cuda()
+    d_qual = torch.from_numpy(np.concatenate([qual, np.full(16, 10, np.uint8)])).cuda()
+    graphs = [DBGraph(w.kmer_size, L - bits, W) for _ in range(world)]
+    try:
+        cap = int(og.stats.kmers_inserted / world * 1.5) + 4096
+        per = (n_reads // world) * (w.read_len + 1)
+        inbox = [[] for _ in range(world)]
+        total_sent = 0
+        for r in range(world):
+            bins = torch.zeros((world, cap, rw), dtype=torch.int32, device="cuda")
+            counts = torch.zeros(world, dtype=torch.int64, device="cuda")
+            lo, hi = r * per, ((r + 1) * per if r < world - 1 else len(seq))
+            graphs[r].route_reads_device(d_seq[lo:], d_qual[lo:], hi - lo, w.cutoff, world, bins, cap,
+                                         counts, st_)
+            torch.cuda.synchronize()
+            c = counts.cpu().tolist()
+            assert max(c) <= cap
+            total_sent += sum(c)
+            for d in range(world):
+                inbox[d].append(bins[d, : c[d]].clone())
+        assert total_sent == og.stats.kmers_inserted
+        recs = []
+        for d in range(world):
+            mine = torch.cat(inbox[d]).contiguous()
+            graphs[d].insert_records_device(mine, mine.shape[0], st_)
+            torch.cuda.synchronize()
+            graphs[d].stats(stream=st_)
+            recs.append(graphs[d].records())
+        assert np.array_equal(O.sort_records(np.concatenate(recs)), want)
+        # extract-records (single bin) + insert == fused
+        with DBGraph(w.kmer_size, L, W) as g:
+            out = torch.zeros((og.stats.kmers_inserted + 8, rw), dtype=torch.int32, device="cuda")
+            cnt = torch.zeros(1, dtype=torch.int64, device="cuda")
+            g.extract_records_device(d_seq, d_qual, len(seq), w.cutoff, out, out.shape[0], cnt, st_)
+            torch.cuda.synchronize()
+            assert int(cnt.item()) == og.stats.kmers_inserted
+            g.insert_records_device(out, int(cnt.item()), st_)
+            torch.cuda.synchronize()
+            assert np.array_equal(O.sort_records(g.records()), want)
+    finally:
+        for g in graphs:
+            g.free()
+
+
+def test_hot_kmers_and_duplicate_reads_are_counted_exactly():
+    """Thousands of copies of the same reads (and homopolymers): every occurrence is
+    an atomic on the same few slots; warp aggregation and L2 reductions must not
+    lose or double count."""
+    rng = np.random.default_rng(3)
+    base = ["".join(rng.choice(list("ACGT"), 100)) for _ in range(3)] + ["A" * 100, "AC" * 50, "ACG" * 33 + "A"]
+    reads = [base[i % len(base)] for i in range(60_000)]
+    quals = ["I" * 100] * len(reads)
+    seq, qual, offs = O.reads_to_streams(reads, quals)
+    for k in (31, 53, 95):
+        og, ok = util.oracle_build(k, 8, 40, seq, qual, offs, 38)
+        assert ok
+        with DBGraph(k, 8, 40) as g:
+            st = g.load_reads_host(seq, qual, offs, 38)
+            assert st["kmers_inserted"] == og.stats.kmers_inserted
+            util.assert_same_records(g.records(), og.records(), f"k={k}")
+
+
+def test_table_full_is_fatal_not_silent():
+    w = synth.scaled(synth.CFG0, 50_000, 6)
+    w.bucket_size = 20                       # 1280 slots for ~50k distinct k-mers
+    seq, qual, offs = synth.reads_host(w.params(), 0, 4000)
+    with DBGraph(w.kmer_size, 6, 20) as g:
+        with pytest.raises(_capi.TableFullError) as e:
+            g.load_reads_host(seq, qual, offs, w.cutoff)
+        assert "not allocated enough memory" in str(e.value)      # hash_table.c:312-316
+
+
+def test_nearly_full_table_uses_the_rehash_chain():
+    name = "synth_full_k53"
+    meta = util.case_meta(name)
+    seq, qual, offs = util.case_streams(name)
+    with DBGraph(meta["k"], meta["L"], meta["W"]) as g:
+        g.load_reads_host(seq, qual, offs, util.cutoff_of(meta))
+        h = g.rehash_histogram()
+        assert h[1:].sum() > 0 and h.sum() == meta["inserts"]
+        util.assert_same_records(g.records(), util.case_records(name), name)
+        table, nxt = g.export_table()
+        _check_reference_layout(table, nxt, meta["k"], meta["L"], meta["W"])
+
+
+# ---------------------------------------------- reference-layout host HashTable
+def _check_reference_layout(table, nxt, k, L, W):
+    """hole-free buckets; each key sits in a bucket of ITS reference rehash chain
+    with every earlier bucket of the chain full (hash_table.c:69-122,234-267)."""
+    N = lasv_b200.words_per_kmer(k)
+    t2 = table.reshape(1 << L, W)
+    occ = t2["status"] != 0
+    assert np.array_equal(occ.sum(axis=1), nxt)
+    assert (occ == (np.arange(W)[None, :] < nxt[:, None])).all()
+    raw = table.view(np.uint8).reshape(len(table), 8 * N + 8)
+    assert not raw[:, 8 * N + 6:].any() and not raw[~occ.reshape(-1)].any()
+    assert (t2["status"][occ] == 1).all()
+    bs, ss = np.nonzero(occ)
+    step = max(1, len(bs) // 400)
+    for b, s in zip(bs[::step], ss[::step]):
+        chain = [O.hash_value(t2["kmer"][b, s], r, L) for r in range(16)]
+        assert b in chain
+        assert all(nxt[c] == W for c in chain[: chain.index(b)])
+
+
+def _libref(k):
+    so = O.REF_DIR / f"libref_{O.MAXK_OF_N[O.words_per_kmer(k)]}.so"
+    return C.CDLL(str(so)) if so.exists() else None
+
+
+@pytest.mark.parametrize("name", ["synth_cfg1_k31", "synth_cfg0_k53", "synth_cfg2_k95"])
+def test_export_import_and_reference_hash_table_find(name):
+    meta = util.case_meta(name)
+    k, L, W = meta["k"], meta["L"], meta["W"]
+    gold = util.case_records(name)
+    seq, qual, offs = util.case_streams(name)
+    with DBGraph(k, L, W) as g:
+        g.load_reads_host(seq, qual, offs, util.cutoff_of(meta))
+        table, nxt = g.export_table()
+        _check_reference_layout(table, nxt, k, L, W)
+        # finalised tables still answer find() and dump, but refuse inserts
+        found, covg, edges = g.find(gold["kmer"])
+        assert found.all() and np.array_equal(covg, gold["covg"]) and np.array_equal(edges, gold["edges"])
+        util.assert_same_records(g.records(), gold)
+        with pytest.raises(_capi.LasvError):
+            g.load_reads_host(seq, qual, offs, util.cutoff_of(meta))
+    # the REFERENCE's own hash_table_find (compiled from /root/reference) on our table
+    ref = _libref(k)
+    if ref is not None:
+        ht = _capi.RefHashTable(k, 1 << L, W, table.ctypes.data, nxt.ctypes.data, None, len(gold), 15)
+        ref.hash_table_find.restype = C.c_void_p
+        ref.hash_table_find.argtypes = [C.c_void_p, C.POINTER(_capi.RefHashTable)]
+        esz = table.dtype.itemsize
+        for i in range(0, len(gold), 7):
+            key = np.ascontiguousarray(gold["kmer"][i])
+            ptr = ref.hash_table_find(key.ctypes.data, C.byref(ht))
+            assert ptr, "reference hash_table_find misses a key in the exported table"
+            e = table[(ptr - table.ctypes.data) // esz]
+            assert np.array_equal(e["kmer"], key) and e["coverage"] == gold["covg"][i] and e["edges"] == gold["edges"][i]
+        miss = np.ascontiguousarray(gold["kmer"][0] ^ np.uint64(0x15555))
+        if tuple(miss.tolist()) not in {tuple(x) for x in gold["kmer"].tolist()}:
+            assert not ref.hash_table_find(miss.ctypes.data, C.byref(ht))
+    # importing a reference-layout table (an earlier load) and continuing gives the same graph
+    with DBGraph(k, L, W) as g2:
+        g2.import_table(table)
+        util.assert_same_records(g2.records(), gold)
+        g2.load_reads_host(seq, qual, offs, util.cutoff_of(meta))
+        twice = gold.copy()
+        twice["covg"] *= 2
+        util.assert_same_records(g2.records(), twice)
+
+
+def test_dropin_loader_fills_a_reference_hash_table(tmp_path):
+    """(A) of include/lasv_b200.h: the reference-named loader on a calloc'ed
+    reference HashTable, as graph_operations.c:757-765 calls it."""
+    name = "edge_pe_k53_q5"
+    meta = util.case_meta(name)
+    k, L, W = meta["k"], meta["L"], meta["W"]
+    N = lasv_b200.words_per_kmer(k)
+    table = np.zeros((1 << L) * W, dtype=lasv_b200.element_dtype(N))
+    nxt = np.zeros((1 << L) * 2, dtype=np.int16)             # calloc(number_buckets, sizeof(int))
+    coll = np.zeros(15, dtype=np.int64)
+    ht = _capi.RefHashTable(k, 1 << L, W, table.ctypes.data, nxt.ctypes.data, coll.ctypes.data, 0, 15)
+    f1, f2 = util.case_files(name)
+    (tmp_path / "l").write_text(f"{f1}\n")
+    (tmp_path / "r").write_text(f"{f2}\n")
+    files = C.c_uint(0)
+    bad, dup, parsed, loaded = (C.c_ulonglong(0) for _ in range(4))
+    hist = np.zeros(20001, dtype=np.uint64)
+    _capi.lib().load_pe_filelists_into_graph_colour(
+        str(tmp_path / "l").encode(), str(tmp_path / "r").encode(), meta["q_thresh"], 0, 0, bytes([33]), 0,
+        C.byref(ht), b"\0", C.byref(files), C.byref(bad), C.byref(dup), C.byref(parsed), C.byref(loaded),
+        hist.ctypes.data, len(hist))
+    assert files.value == 1 and bad.value == meta["bad_reads"]
+    assert parsed.value == meta["bases_parsed"] and loaded.value == meta["bases_loaded"]
+    assert ht.unique_kmers == meta["n_records"] and coll.sum() == meta["inserts"]
+    assert mean_contig_length(hist) == meta["ctx_mean_read_len"]
+    _check_reference_layout(table, nxt[: 1 << L], k, L, W)
+    occ = table[table["status"] != 0]
+    got = np.zeros(len(occ), dtype=lasv_b200.record_dtype(N))
+    got["kmer"], got["covg"], got["edges"] = occ["kmer"], occ["coverage"], occ["edges"]
+    util.assert_same_records(got, util.case_records(name))
+
+
+# ----------------------------------------------------- .ctx and the consumers
+@pytest.mark.parametrize("name", ["synth_cfg1_k31", "synth_cfg0_k53", "synth_cfg2_k95"])
+def test_ctx_roundtrip_and_reference_consumer(name, tmp_path):
+    """Config 3: the reference's own supernode walk (dB_graph --multicolour_bin ...
+    --output_supernodes) on OUR dumped graph gives the reference's contig set."""
+    meta = util.case_meta(name)
+    k, L, W = meta["k"], meta["L"], meta["W"]
+    gold = util.case_records(name)
+    seq, qual, offs = util.case_streams(name)
+    out = tmp_path / "gpu.ctx"
+    with DBGraph(k, L, W) as g:
+        st = g.load_reads_host(seq, qual, offs, util.cutoff_of(meta))
+        _, hist = g.stats(hist_size=20001)
+        g.dump_binary(out, mean_contig_length(hist), st["bases_loaded"])
+    ctx = O.parse_ctx(out)
+    assert ctx["header"].hex() == meta["ctx_header_hex"]
+    util.assert_same_records(ctx["records"], gold)
+    with DBGraph(k, L, W) as g:                                # load_multicolour_binary_from_filename_into_graph
+        mrl, ts = g.load_binary(out)
+        assert (mrl, ts) == (meta["ctx_mean_read_len"], meta["ctx_total_seq"])
+        util.assert_same_records(g.records(), gold)
+        g.load_records(gold)                                   # merging a second binary adds covg, ORs edges
+        twice = gold.copy()
+        twice["covg"] *= 2
+        util.assert_same_records(g.records(), twice)
+    if O.ref_available(k):
+        res = O.run_reference(k, L, W, None, ctx_in=out, workdir=tmp_path, want_supernodes=True)
+        util.assert_same_records(res["ctx"]["records"], gold)  # reloaded + re-dumped by the reference
+        assert O.canonical_seq_set(res["supernodes"]) == meta["supernodes"]
+
+
+# --------------------------------------------------- BASELINE-size properties
+@pytest.mark.skipif(os.environ.get("LASV_SKIP_FULLSIZE") == "1", reason="LASV_SKIP_FULLSIZE=1")
+def test_config0_full_size_properties():
+    """BASELINE.json config 0 at full size (63 Mbp, 30x, 2x100 bp, k=53, L=22 W=100;
+    ~0.9 G k-mer inserts into a 10 GB table).  Too big for the CPU oracle, so:
+      * sum of coverages == number of inserts, nodes == unique counter;
+      * the order-independent fingerprint is identical when the same reads are
+        loaded in a different batch split and order, and through the
+        records path (extract + insert) instead of the fused kernel;
+      * a 1/256 subsample of the pairs built on the GPU equals the oracle."""
+    torch = torch_cuda()
+    w = synth.CFG0
+    p = w.params()
+    n_pairs = w.n_pairs
+    n_reads = 2 * n_pairs
+    stride = w.read_len + 1
+    st_ = torch.cuda.current_stream().cuda_stream
+    batch = 1 << 21                                            # reads per batch
+    d_seq = torch.empty(batch * stride + 16, dtype=torch.uint8, device="cuda")
+    d_qual = torch.empty_like(d_seq)
+
+    def run(order, records_path=False):
+        with DBGraph(w.kmer_size, w.number_bits, w.bucket_size) as g:
+            N = g.N
+            out = cnt = None
+            if records_path:
+                out = torch.empty((batch * 48 + 8, 2 * N + 1), dtype=torch.int32, device="cuda")
+                cnt = torch.zeros(1, dtype=torch.int64, device="cuda")
+            for b0 in order:
+                nr = min(batch, n_reads - b0)
+                synth.reads_device(p, b0, nr, d_seq, d_qual, st_)
+                if records_path:
+                    cnt.zero_()
+                    g.extract_records_device(d_seq, d_qual, nr * stride, w.cutoff, out, out.shape[0], cnt, st_)
+                    g.insert_records_device(out, int(cnt.item()), st_)
+                else:
+                    g.load_reads_device(d_seq, d_qual, nr * stride, None, 0, w.cutoff, st_)
+            torch.cuda.synchronize()
+            st = g.stats(stream=st_)
+            return st, g.summary()
+
+    starts = list(range(0, n_reads, batch))
+    st1, s1 = run(starts)
+    assert s1["sum_covg"] == st1["kmers_inserted"] > 800_000_000
+    assert s1["n_nodes"] == st1["unique_kmers"]
+    st2, s2 = run(starts[::-1])
+    assert s2 == s1 and st2["kmers_inserted"] == st1["kmers_inserted"]
+    # the records path counts inserts on the extract side only
+    st3, s3 = run(starts[1::2] + starts[0::2], records_path=True)
+    assert s3 == s1
+    # subsample vs oracle: every 256th pair
+    sel = np.arange(0, n_pairs, 256)
+    seqs, quals = [], []
+    for pr in sel:
+        s, q, _ = synth.reads_host(p, 2 * int(pr), 2)
+        seqs.append(s)
+        quals.append(q)
+    seq, qual = np.concatenate(seqs), np.concatenate(quals)
+    offs = synth.offsets_fixed(w.read_len, 2 * len(sel))
+    og = O.OracleGraph(w.kmer_size, 18, 100)
+    assert og.load_reads(seq, qual, offs, w.cutoff, paired=True)
+    with DBGraph(w.kmer_size, 18, 100) as g:
+        st = g.load_reads_host(seq, qual, offs, w.cutoff)
+        assert st["kmers_inserted"] == og.stats.kmers_inserted
+        assert np.array_equal(O.sort_records(g.records()), O.sort_records(og.records()))

@@ -175,7 +175,7 @@ def test_emulated_ragged_and_tiny_inputs(emul):
         meta = {"k": k, "L": 8, "W": 60, "q_thresh": 5}
         g, ok = util.oracle_build(k, 8, 60, seq, qual, offs, 38)
         assert ok
-        for T in (1024, 2048):
+        for T in (1024, 2048, 2048 | (5 << 16), 1024 | (15 << 16)):    # last two: misaligned stream pointer
             rc, table, ctr = emul_build(emul, meta, seq, qual, T)
             assert rc == 0
             util.assert_same_records(table_records(table), g.records(), f"k={k}")
