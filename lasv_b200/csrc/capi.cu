@@ -263,6 +263,7 @@ int lasv_graph_clear(lasv_graph *g, void *cuda_stream) {
 long long lasv_graph_unique_kmers(lasv_graph *g) {
   if (use(g)) return -1;
   unsigned long long v = 0;
+  if (cudaDeviceSynchronize() != cudaSuccess) return -1;  // work may be queued on any stream
   if (cudaMemcpy(&v, &g->d_ctr->unique_kmers, sizeof v, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
   return (long long)v;
 }
@@ -310,6 +311,7 @@ int lasv_graph_load_reads_host(lasv_graph *g, const uint8_t *seq, const uint8_t 
   if (!seq || !offsets) return fail(LASV_ERR_ARG, "seq and offsets are required");
   if (offsets[n_reads] != n_bytes) return fail(LASV_ERR_ARG, "offsets[n_reads] != n_bytes");
   if (int e = ensure_staging(g)) return e;
+  CUDA_TRY(cudaDeviceSynchronize());  // earlier device-API work may sit on a caller's stream
 
   ReadStats rs0, rs1;
   GraphCounters c0, c1;
@@ -399,6 +401,7 @@ int lasv_graph_stats(lasv_graph *g, lasv_load_stats *out, uint64_t *contig_hist,
 int lasv_graph_rehash_histogram(lasv_graph *g, long long out16[16]) {
   if (int e = use(g)) return e;
   GraphCounters c;
+  CUDA_TRY(cudaDeviceSynchronize());
   CUDA_TRY(cudaMemcpy(&c, g->d_ctr, sizeof c, cudaMemcpyDeviceToHost));
   unsigned long long later = 0;
   for (int r = 1; r < 16; r++) {
@@ -458,6 +461,7 @@ int lasv_graph_find(lasv_graph *g, const uint64_t *keys, uint64_t n, uint32_t *c
                     uint8_t *found) {
   if (int e = use(g)) return e;
   if (!n) return LASV_OK;
+  CUDA_TRY(cudaDeviceSynchronize());
   uint64_t *d_keys = nullptr;
   uint32_t *d_covg = nullptr;
   uint8_t *d_edges = nullptr, *d_found = nullptr;
@@ -483,6 +487,7 @@ int lasv_graph_find(lasv_graph *g, const uint64_t *keys, uint64_t n, uint32_t *c
 
 int lasv_graph_summary(lasv_graph *g, lasv_table_summary *out) {
   if (int e = use(g)) return e;
+  CUDA_TRY(cudaDeviceSynchronize());
   TableSummary *d = nullptr;
   CUDA_TRY(cudaMalloc(&d, sizeof(TableSummary)));
   int rc = [&]() -> int {
@@ -536,6 +541,7 @@ int lasv_graph_export_table(lasv_graph *g, void *elements, short *next_element) 
 int lasv_graph_import_table(lasv_graph *g, const void *elements) {
   if (int e = use(g)) return e;
   if (g->finalized) return fail(LASV_ERR_STATE, "graph is finalised; no further inserts");
+  CUDA_TRY(cudaDeviceSynchronize());
   // stream the host table through a bounded device buffer, whole slots at a time
   const uint64_t slots_per_chunk = std::max<uint64_t>(1, (256ull << 20) / g->slot_bytes);
   uint8_t *d_buf = nullptr;
@@ -663,6 +669,7 @@ int lasv_graph_write_ctx(lasv_graph *g, const char *path, uint32_t mean_read_len
 int lasv_graph_load_ctx_records(lasv_graph *g, const uint8_t *records, uint64_t n_records) {
   if (int e = use(g)) return e;
   if (g->finalized) return fail(LASV_ERR_STATE, "graph is finalised; no further inserts");
+  CUDA_TRY(cudaDeviceSynchronize());
   const size_t rec = 8 * (size_t)g->N + 5;
   const uint64_t per = (256ull << 20) / rec;
   uint8_t *d_buf = nullptr;
