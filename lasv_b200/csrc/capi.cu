@@ -95,7 +95,9 @@ int use(lasv_graph *g) {
   return LASV_OK;
 }
 
-cudaStream_t stream_of(lasv_graph *g, void *s) { return s ? (cudaStream_t)s : g->compute; }
+// A NULL stream argument means the CUDA default stream, as everywhere in CUDA (torch's
+// default stream is that stream too, so CUDA events recorded there bracket our launches).
+cudaStream_t stream_of(lasv_graph *, void *s) { return (cudaStream_t)s; }
 
 int ensure_staging(lasv_graph *g) {
   if (g->staging_ready) return LASV_OK;
@@ -214,7 +216,7 @@ lasv_graph *lasv_graph_new(int kmer_size, int number_bits, int bucket_size, int 
             cudaMalloc(&g->d_overflow, sizeof(unsigned long long)) == cudaSuccess &&
             cudaStreamCreateWithFlags(&g->compute, cudaStreamNonBlocking) == cudaSuccess &&
             cudaStreamCreateWithFlags(&g->copy, cudaStreamNonBlocking) == cudaSuccess;
-  if (ok) ok = lasv_graph_clear(g, nullptr) == LASV_OK && cudaStreamSynchronize(g->compute) == cudaSuccess;
+  if (ok) ok = lasv_graph_clear(g, nullptr) == LASV_OK && cudaDeviceSynchronize() == cudaSuccess;
   if (!ok) {
     if (g_err.empty() || g_err.find("failed") == std::string::npos)
       fail(LASV_ERR_CUDA, "could not allocate hash table of size %llu: %s",
@@ -376,11 +378,12 @@ int lasv_graph_load_reads_host(lasv_graph *g, const uint8_t *seq, const uint8_t 
 int lasv_graph_stats(lasv_graph *g, lasv_load_stats *out, uint64_t *contig_hist, uint64_t hist_size,
                      void *cuda_stream) {
   if (int e = use(g)) return e;
-  cudaStream_t st = stream_of(g, cuda_stream);
+  (void)cuda_stream;
   ReadStats rs;
   GraphCounters c;
   unsigned long long ov = 0;
-  if (int e = fetch_counters(g, st, &rs, &c, &ov)) return e;
+  CUDA_TRY(cudaDeviceSynchronize());  // whatever stream the loads were queued on
+  if (int e = fetch_counters(g, g->compute, &rs, &c, &ov)) return e;
   if (out) fill_stats(out, rs, c);
   if (contig_hist && hist_size) {
     std::vector<unsigned long long> h(HIST_BINS);
