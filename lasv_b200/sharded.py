@@ -12,8 +12,9 @@ batch:
 
     reads --route kernel--> per-owner bins --all_to_all--> insert kernel --> shard
 
-The exchange is `torch.distributed.all_to_all` on views of the bins (no packing
-copy); counts travel first in a tiny all_to_all_single.
+The exchange is one grouped send/recv (`torch.distributed.batch_isend_irecv`, a
+single ncclGroup of ncclSend/ncclRecv under NCCL) on views of the bins -- no
+packing copy; counts travel first in a tiny all_to_all_single.
 """
 from __future__ import annotations
 
@@ -51,9 +52,22 @@ def exchange_records(bins: torch.Tensor, send_counts: torch.Tensor, recv_buf: to
         raise OverflowError(f"receive buffer too small: {total} > {recv_buf.shape[0]}")
     starts = torch.zeros(world + 1, dtype=torch.int64)
     starts[1:] = torch.cumsum(rc, 0)
-    ins = [bins[d, : int(sc[d])] for d in range(world)]
-    outs = [recv_buf[int(starts[d]): int(starts[d + 1])] for d in range(world)]
-    dist.all_to_all(outs, ins, group=group)
+    rank = dist.get_rank(group)
+    ops = []
+    for d in range(world):
+        src = bins[d, : int(sc[d])]
+        dst = recv_buf[int(starts[d]): int(starts[d + 1])]
+        if d == rank:
+            dst.copy_(src)                     # own records never leave the GPU
+            continue
+        if src.numel():
+            ops.append(dist.P2POp(dist.isend, src, d if group is None else dist.get_global_rank(group, d), group))
+        if dst.numel():
+            ops.append(dist.P2POp(dist.irecv, dst, d if group is None else dist.get_global_rank(group, d), group))
+    if ops:
+        # one grouped ncclSend/ncclRecv launch under NCCL; plain isend/irecv under gloo
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
     return total, rc
 
 

@@ -381,6 +381,40 @@ def test_ctx_roundtrip_and_reference_consumer(name, tmp_path):
         assert O.canonical_seq_set(res["supernodes"]) == meta["supernodes"]
 
 
+# ------------------------------------ the reference's own main() on the GPU loader
+@pytest.mark.parametrize("name", ["synth_cfg1_k31", "synth_cfg0_k53", "synth_cfg2_k95"])
+def test_reference_cli_with_gpu_loader(name, tmp_path):
+    """integration/_build/dB_graph_gpu_*: reference main(), cmd-line parsing, cleaning,
+    supernode walk and .ctx dump compiled from the reference sources, with ONLY the
+    two loader symbols coming from liblasv_b200.so (INTEGRATION.md level A)."""
+    from pathlib import Path
+    meta = util.case_meta(name)
+    k, L, W = meta["k"], meta["L"], meta["W"]
+    exe = Path(__file__).resolve().parents[1] / "integration" / "_build" / f"dB_graph_gpu_{O.MAXK_OF_N[O.words_per_kmer(k)]}"
+    if not exe.exists():
+        pytest.skip("integration/_build not built (needs /root/reference at build time)")
+    seq, qual, _ = util.case_streams(name)
+    rl = meta["workload"]["read_len"]
+    s2, q2 = seq.reshape(-1, rl + 1), qual.reshape(-1, rl + 1)
+    O.write_fastq_fixed(tmp_path / "a.fq", s2[0::2].reshape(-1), q2[0::2].reshape(-1), rl)
+    O.write_fastq_fixed(tmp_path / "b.fq", s2[1::2].reshape(-1), q2[1::2].reshape(-1), rl)
+    (tmp_path / "l").write_text(f"{tmp_path / 'a.fq'}\n")
+    (tmp_path / "r").write_text(f"{tmp_path / 'b.fq'}\n")
+    cmd = [str(exe), "--kmer_size", str(k), "--mem_height", str(L), "--mem_width", str(W),
+           "--pe_list", f"{tmp_path / 'l'},{tmp_path / 'r'}", "--quality_score_threshold", str(meta["q_thresh"]),
+           "--dump_binary", str(tmp_path / "out.ctx"), "--output_supernodes", str(tmp_path / "sup.fa")]
+    p = subprocess.run(cmd, cwd=tmp_path, capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stderr[-2000:] + p.stdout[-2000:]
+    ctx = O.parse_ctx(tmp_path / "out.ctx")
+    assert ctx["header"].hex() == meta["ctx_header_hex"]                  # incl. mean read length, total seq
+    util.assert_same_records(ctx["records"], util.case_records(name), name)
+    assert O.canonical_seq_set(O.read_fasta_seqs(tmp_path / "sup.fa")) == meta["supernodes"]
+    assert f"Number of bad reads:{meta['bad_reads']}" in p.stdout
+    assert f"Total bases passing filters and loaded into graph:{meta['bases_loaded']}" in p.stdout
+    tries = sum(int(l.split(":")[1]) for l in p.stdout.splitlines() if l.strip().startswith("tries "))
+    assert tries == meta["inserts"]
+
+
 # --------------------------------------------------- BASELINE-size properties
 @pytest.mark.skipif(os.environ.get("LASV_SKIP_FULLSIZE") == "1", reason="LASV_SKIP_FULLSIZE=1")
 def test_config0_full_size_properties():

@@ -1,0 +1,112 @@
+"""world_size-2 gloo test (CPU) of the sharded build's host logic: the
+personalised all-to-all of variable-length record blocks
+(lasv_b200/sharded.py::exchange_records) carrying records produced and consumed
+by the kernels' host emulation (tests/host_emul).  The union of the two shards
+must equal the reference golden graph."""
+import ctypes as C
+import os
+import socket
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, name, outdir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from lasv_b200 import element_dtype, words_per_kmer
+    from lasv_b200.sharded import exchange_records
+    from tests import util
+    emul = C.CDLL(str(ROOT / "tests" / "host_emul" / "libhost_emul.so"))
+    emul.emul_extract_records.restype = C.c_uint64
+    emul.emul_extract_records.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_int,
+                                          C.c_void_p, C.c_uint64]
+    emul.emul_insert_records.argtypes = [C.c_void_p, C.c_uint64] + [C.c_int] * 4 + [C.c_void_p, C.c_void_p]
+    emul.emul_hash_c.restype = C.c_uint32
+    emul.emul_hash_c.argtypes = [C.c_void_p, C.c_int, C.c_uint32]
+    meta = util.case_meta(name)
+    k, L, W = meta["k"], meta["L"], meta["W"]
+    N = words_per_kmer(k)
+    rw = 2 * N + 1
+    seq, qual, offs = util.case_streams(name)
+    # this rank's slice of the reads (cut at a read boundary)
+    n_reads = len(offs) - 1
+    lo, hi = int(offs[n_reads * rank // world]), int(offs[n_reads * (rank + 1) // world])
+    s, q = np.ascontiguousarray(seq[lo:hi]), np.ascontiguousarray(qual[lo:hi])
+    cap = meta["inserts"] + 8
+    recs = np.zeros((cap, rw), dtype=np.uint32)
+    n = emul.emul_extract_records(s.ctypes.data, q.ctypes.data, len(s), k, util.cutoff_of(meta), 1024,
+                                  recs.ctypes.data, cap)
+    recs = recs[:n]
+    bits = int(np.log2(world))
+    owner = np.zeros(n, dtype=np.int64)
+    for i in range(n):
+        key = np.zeros(N, dtype=np.uint64)
+        for w in range(N):
+            key[w] = np.uint64(recs[i, 2 * w]) | (np.uint64(recs[i, 2 * w + 1]) << np.uint64(32))
+        owner[i] = (emul.emul_hash_c(key.ctypes.data, N, 0) >> (L - bits)) & (world - 1)
+    bins = torch.zeros((world, cap, rw), dtype=torch.int32)
+    counts = torch.zeros(world, dtype=torch.int64)
+    for d in range(world):
+        mine = recs[owner == d].view(np.int32)
+        bins[d, : len(mine)] = torch.from_numpy(mine.copy())
+        counts[d] = len(mine)
+    recv = torch.zeros((cap * world, rw), dtype=torch.int32)
+    total, rc = exchange_records(bins, counts, recv)
+    assert total == int(rc.sum())
+    got = np.ascontiguousarray(recv[:total].numpy().view(np.uint32))
+    table = np.zeros((1 << (L - bits)) * W, dtype=element_dtype(N))
+    ctr = np.zeros(20, dtype=np.uint64)
+    assert emul.emul_insert_records(got.ctypes.data, total, k, L - bits, W, 15, table.ctypes.data,
+                                    ctr.ctypes.data) == 0
+    np.save(Path(outdir) / f"shard{rank}.npy", table)
+    # job-wide insert count through a collective, as ShardedDBGraph.stats does
+    t = torch.tensor([n], dtype=torch.int64)
+    dist.all_reduce(t)
+    assert int(t.item()) == meta["inserts"]
+    # an overflowing bin must be reported, not truncated
+    try:
+        exchange_records(bins[:, :1], counts.clamp(min=2), recv)
+        raise AssertionError("overflow not detected")
+    except OverflowError:
+        pass
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("name", ["synth_cfg0_k53", "synth_cfg1_k31"])
+def test_two_rank_exchange_builds_the_reference_graph(name, tmp_path):
+    import subprocess
+    so = ROOT / "tests" / "host_emul" / "libhost_emul.so"
+    if not so.exists():
+        subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas",
+                        "-I/usr/local/cuda/include", "-o", str(so), str(so.with_name("host_emul.cpp"))], check=True)
+    world = 2
+    mp.spawn(_worker, args=(world, _free_port(), name, str(tmp_path)), nprocs=world, join=True)
+    from lasv_b200 import record_dtype
+    from tests import util
+    recs = []
+    for r in range(world):
+        t = np.load(tmp_path / f"shard{r}.npy")
+        occ = t[t["status"] != 0]
+        out = np.zeros(len(occ), dtype=record_dtype(t["kmer"].shape[1]))
+        out["kmer"], out["covg"], out["edges"] = occ["kmer"], occ["coverage"], occ["edges"]
+        recs.append(out)
+    assert all(len(r) > 0 for r in recs)
+    util.assert_same_records(np.concatenate(recs), util.case_records(name), name)
