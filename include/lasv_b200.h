@@ -245,6 +245,12 @@ int lasv_synth_reads_host(const lasv_synth_params *p, uint64_t first_read, uint6
  * random-access HBM ceiling quoted next to the roofline. */
 int lasv_random_access_probe(void *d_buf, uint64_t n_sectors, uint64_t n_ops, uint64_t seed,
                              void *cuda_stream);
+/* mode 0: 16 B read + 32-bit atomic; 1: read only; 2: atomic only; 3: 64 B read + atomic. */
+int lasv_random_access_probe_mode(void *d_buf, uint64_t n_sectors, uint64_t n_ops, uint64_t seed,
+                                  int mode, void *cuda_stream);
+/* First-choice bucket (hash_value.c:767-773, rehash 0) of each record. */
+int lasv_graph_record_buckets_device(lasv_graph *g, const uint32_t *d_records, uint64_t n_records,
+                                     uint32_t *d_buckets, void *cuda_stream);
 /* Host-only: parse a whole sequence file with the loader's reader (FASTQ /
  * FASTA / plain, optionally gzipped; grammar of libs/seq_file) into the stream
  * layout of lasv_graph_load_reads_host.  Returns the number of reads, or a

@@ -66,7 +66,8 @@ EXPORTS = [
     "lasv_graph_load_pe_files", "lasv_graph_load_se_filelist", "lasv_graph_load_pe_filelists",
     "load_se_filelist_into_graph_colour", "load_pe_filelists_into_graph_colour",
     "lasv_synth_reads_device", "lasv_synth_reads_host", "lasv_random_access_probe",
-    "lasv_kernel_launches", "lasv_seqfile_to_streams",
+    "lasv_kernel_launches", "lasv_seqfile_to_streams", "lasv_random_access_probe_mode",
+    "lasv_graph_record_buckets_device",
 ]
 
 _lib = None
@@ -136,6 +137,8 @@ def lib() -> C.CDLL:
     L.lasv_synth_reads_device.argtypes = [C.POINTER(SynthParams), u64, u64, vp, vp, vp]
     L.lasv_synth_reads_host.argtypes = [C.POINTER(SynthParams), u64, u64, vp, vp]
     L.lasv_random_access_probe.argtypes = [vp, u64, u64, u64, vp]
+    L.lasv_random_access_probe_mode.argtypes = [vp, u64, u64, u64, i32, vp]
+    L.lasv_graph_record_buckets_device.argtypes = [vp, vp, u64, vp, vp]
     L.lasv_seqfile_to_streams.restype = C.c_longlong
     L.lasv_seqfile_to_streams.argtypes = [C.c_char_p, vp, vp, u64, vp, u64, C.POINTER(i32)]
     _lib = L

@@ -148,6 +148,9 @@ BuildParams build_params(lasv_graph *g, const uint8_t *d_seq, const uint8_t *d_q
   p.rec_overflow = g->d_overflow;
   p.n_dest = 1;
   p.owner_shift = g->L;
+  p.n_pass = 1;
+  p.pass = 0;
+  p.pass_shift = g->L;
   return p;
 }
 
@@ -284,8 +287,25 @@ int lasv_graph_load_reads_device(lasv_graph *g, const uint8_t *d_seq, const uint
   if (int e = check_streams(d_seq, d_qual)) return e;
   cudaStream_t st = stream_of(g, cuda_stream);
   if (n_bytes) {
-    launch_build(g->N, MODE_FUSED, build_params(g, d_seq, d_qual, n_bytes, quality_cutoff), st);
-    if (int e = check_launch()) return e;
+    // Random access over more than ~64 GB falls off the TLB reach of a B200
+    // (profiles/random_access_sweep_r1.jsonl): walk the batch once per <=50 GB
+    // slice of the table instead.  LASV_B200_PASSES overrides (experiments).
+    BuildParams p = build_params(g, d_seq, d_qual, n_bytes, quality_cutoff);
+    int n_pass = 1;
+    while ((g->n_slots * g->slot_bytes) / (uint64_t)n_pass > (50ull << 30) && (1 << g->L) > 2 * n_pass) n_pass *= 2;
+    if (const char *e = getenv("LASV_B200_PASSES")) {
+      const int v = atoi(e);
+      if (v >= 1 && v <= 64 && (v & (v - 1)) == 0 && v <= (1 << (g->L - 1))) n_pass = v;
+    }
+    int lg = 0;
+    while ((1 << lg) < n_pass) lg++;
+    p.n_pass = n_pass;
+    p.pass_shift = g->L - lg;
+    for (int pass = 0; pass < n_pass; pass++) {
+      p.pass = pass;
+      launch_build(g->N, MODE_FUSED, p, st);
+      if (int e = check_launch()) return e;
+    }
   }
   if (d_offsets && n_reads) {
     launch_read_stats(d_seq, d_qual, d_offsets, n_reads, 1, g->k, quality_cutoff, g->d_stats,
@@ -1095,8 +1115,21 @@ long long lasv_seqfile_to_streams(const char *path, uint8_t *seq, uint8_t *qual,
 
 int lasv_random_access_probe(void *d_buf, uint64_t n_sectors, uint64_t n_ops, uint64_t seed,
                              void *cuda_stream) {
-  if (!d_buf || !n_sectors) return fail(LASV_ERR_ARG, "bad buffer");
-  launch_random_rmw((uint64_t *)d_buf, n_sectors, n_ops, seed, (cudaStream_t)cuda_stream);
+  return lasv_random_access_probe_mode(d_buf, n_sectors, n_ops, seed, 0, cuda_stream);
+}
+
+int lasv_random_access_probe_mode(void *d_buf, uint64_t n_sectors, uint64_t n_ops, uint64_t seed,
+                                  int mode, void *cuda_stream) {
+  if (!d_buf || !n_sectors || mode < 0 || mode > 3) return fail(LASV_ERR_ARG, "bad probe arguments");
+  launch_random_rmw((uint64_t *)d_buf, n_sectors, n_ops, seed, mode, (cudaStream_t)cuda_stream);
+  return check_launch();
+}
+
+int lasv_graph_record_buckets_device(lasv_graph *g, const uint32_t *d_records, uint64_t n_records,
+                                     uint32_t *d_buckets, void *cuda_stream) {
+  if (int e = use(g)) return e;
+  launch_record_buckets(g->N, d_records, n_records, (uint32_t)(g->n_buckets - 1), d_buckets,
+                        (cudaStream_t)cuda_stream);
   return check_launch();
 }
 

@@ -173,7 +173,7 @@ __global__ void __launch_bounds__(THREADS) build_kernel(const BuildParams p, con
     }
     __syncthreads();
     const int M = (int)sCount;
-    if (tid == 0) my_kmers += (unsigned long long)M;
+    if (tid == 0 && (MODE != MODE_FUSED || p.pass == 0)) my_kmers += (unsigned long long)M;
 
     if (MODE == MODE_RECORDS) {
       if (tid == 0) sTileBase[0] = M ? atomicAdd(p.rec_count, (unsigned long long)M) : 0ull;
@@ -194,7 +194,12 @@ __global__ void __launch_bounds__(THREADS) build_kernel(const BuildParams p, con
         for (int w = 0; w < N; w++) key[w] = 0;
       }
       if (MODE == MODE_FUSED) {
-        const bool lead = warp_aggregate<N>(active, key, edge, count);
+        bool mine = active;
+        if (p.n_pass > 1 && active) {
+          const uint32_t b = lookup3_key<N>(key, 0).c & p.table.bucket_mask;
+          mine = (int)(b >> p.pass_shift) == p.pass;
+        }
+        const bool lead = warp_aggregate<N>(mine, key, edge, count);
         if (lead) {
           const int r = table_upsert<N, DeviceOps>(p.table, p.ctr, key, edge, count);
           my_new += (r == 1);
@@ -616,15 +621,42 @@ __global__ void __launch_bounds__(THREADS) synth_kernel(const SynthParams p, con
 // Uniform random 32-byte read-modify-write over a buffer of n_sectors sectors:
 // the random-access ceiling the insert kernel is compared with.
 __global__ void __launch_bounds__(THREADS) random_rmw_kernel(uint64_t *buf, const uint64_t n_sectors,
-                                                            const uint64_t n_ops, const uint64_t seed) {
+                                                            const uint64_t n_ops, const uint64_t seed,
+                                                            const int mode) {
+  // mode 0: 16-byte read + 32-bit atomic (one slot probe + coverage update)
+  // mode 1: read only     mode 2: atomic only     mode 3: 64-byte read (two sectors) + atomic
+  uint64_t acc = 0;
   for (uint64_t i = (uint64_t)blockIdx.x * THREADS + threadIdx.x; i < n_ops;
        i += (uint64_t)gridDim.x * THREADS) {
     const uint64_t h = mix64(seed + i);
     const uint64_t s = __umul64hi(h, n_sectors);
     uint64_t *p = buf + s * 4;
-    const uint64_t a = ld_strong_u64(p), b = ld_strong_u64(p + 1);
+    if (mode == 2) {
+      atomicAdd(reinterpret_cast<unsigned int *>(p + 2), 1u);
+      continue;
+    }
+    uint64_t a = ld_strong_u64(p), b = ld_strong_u64(p + 1);
+    if (mode == 3 && s + 1 < n_sectors) { a ^= ld_strong_u64(p + 4); b ^= ld_strong_u64(p + 5); }
+    if (mode == 1) { acc += a ^ b; continue; }
     if (a + b != 0x123456789ull)  // data-dependent so the loads cannot be dropped
       atomicAdd(reinterpret_cast<unsigned int *>(p + 2), 1u);
+  }
+  if (mode == 1 && acc == 0x123456789ull) buf[0] = acc;
+}
+
+// bucket (rehash 0) of every record: scaffolding for locality experiments
+template <int N>
+__global__ void __launch_bounds__(THREADS) record_buckets_kernel(const uint32_t *__restrict__ recs,
+                                                                const uint64_t n_recs,
+                                                                const uint32_t bucket_mask,
+                                                                uint32_t *__restrict__ buckets) {
+  constexpr int RECW = 2 * N + 1;
+  for (uint64_t i = (uint64_t)blockIdx.x * THREADS + threadIdx.x; i < n_recs;
+       i += (uint64_t)gridDim.x * THREADS) {
+    uint64_t key[N];
+    uint32_t e, c;
+    load_record<N>(recs + i * RECW, key, e, c);
+    buckets[i] = lookup3_key<N>(key, 0).c & bucket_mask;
   }
 }
 
@@ -790,9 +822,18 @@ void synth_host(const SynthParams &p, uint64_t first_read, uint64_t n_reads, uin
       synth_byte(p, first_read + r, i, seq[r * stride + i], qual[r * stride + i]);
 }
 
-void launch_random_rmw(uint64_t *buf, uint64_t n_sectors, uint64_t n_ops, uint64_t seed,
+void launch_random_rmw(uint64_t *buf, uint64_t n_sectors, uint64_t n_ops, uint64_t seed, int mode,
                        cudaStream_t st) {
-  random_rmw_kernel<<<sm_count() * 8, THREADS, 0, st>>>(buf, n_sectors, n_ops, seed);
+  random_rmw_kernel<<<sm_count() * 8, THREADS, 0, st>>>(buf, n_sectors, n_ops, seed, mode);
+}
+
+void launch_record_buckets(int N, const uint32_t *recs, uint64_t n_recs, uint32_t bucket_mask,
+                           uint32_t *buckets, cudaStream_t st) {
+  if (!n_recs) return;
+  dispatch_n(N, [&](auto n) {
+    constexpr int NN = decltype(n)::value;
+    record_buckets_kernel<NN><<<sm_count() * 8, THREADS, 0, st>>>(recs, n_recs, bucket_mask, buckets);
+  });
 }
 
 }  // namespace lasv

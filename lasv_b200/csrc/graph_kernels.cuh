@@ -30,6 +30,10 @@ struct BuildParams {
   unsigned long long *rec_overflow;
   int n_dest;       // power of two
   int owner_shift;  // owner = (hash.c >> owner_shift) & (n_dest-1)
+  // MODE_FUSED over a table larger than the TLB reach: the batch is walked n_pass
+  // times and pass `pass` only inserts the k-mers whose bucket lies in its
+  // 1/n_pass slice of the table (n_pass power of two, pass_shift = L - log2 n_pass)
+  int n_pass, pass, pass_shift;
 };
 
 struct ReadStats {  // loader bookkeeping (file_reader.c:460-470,579,584)
@@ -88,7 +92,9 @@ void launch_synth(const SynthParams &p, uint64_t first_read, uint64_t n_reads, u
                   uint8_t *qual, cudaStream_t st);
 void synth_host(const SynthParams &p, uint64_t first_read, uint64_t n_reads, uint8_t *seq,
                 uint8_t *qual);
-void launch_random_rmw(uint64_t *buf, uint64_t n_sectors, uint64_t n_ops, uint64_t seed,
+void launch_random_rmw(uint64_t *buf, uint64_t n_sectors, uint64_t n_ops, uint64_t seed, int mode,
                        cudaStream_t st);
+void launch_record_buckets(int N, const uint32_t *recs, uint64_t n_recs, uint32_t bucket_mask,
+                           uint32_t *buckets, cudaStream_t st);
 
 }  // namespace lasv
