@@ -204,6 +204,21 @@ __global__ void __launch_bounds__(THREADS) build_kernel(const BuildParams p, con
           const int r = table_upsert<N, DeviceOps>(p.table, p.ctr, key, edge, count);
           my_new += (r == 1);
         }
+      } else if (MODE == MODE_BIN) {
+        const bool lead = warp_aggregate<N>(active, key, edge, count);
+        if (lead) {
+          const uint32_t bin = (lookup3_key<N>(key, 0).c & p.table.bucket_mask) >> p.bins.bin_shift;
+          const uint32_t idx = atomicAdd(&p.bins.count[bin], 1u);
+          if (idx < p.bins.cap) {
+            const uint64_t at = (uint64_t)bin * p.bins.cap + idx;
+            if (N >= 2) p.bins.keyA[at] = make_ulonglong2(key[0], key[1 % N]);
+            if (N & 1) p.bins.keyB[at] = key[N - 1];
+            p.bins.meta[at] = (uint16_t)((edge & 0xFFu) | (count << 8));
+          } else {  // stripe full (skewed batch): this occurrence goes straight to the table
+            const int r = table_upsert<N, DeviceOps>(p.table, p.ctr, key, edge, count);
+            my_new += (r == 1);
+          }
+        }
       } else if (MODE == MODE_RECORDS) {
         if (active) {
           const unsigned long long idx = sTileBase[0] + (unsigned long long)i;
@@ -244,12 +259,105 @@ __global__ void __launch_bounds__(THREADS) build_kernel(const BuildParams p, con
   }
 
   // ---- CTA-level counters
-  if (MODE == MODE_FUSED) {
+  if (MODE == MODE_FUSED || MODE == MODE_BIN) {
 #pragma unroll
     for (int o = 16; o; o >>= 1) my_new += __shfl_xor_sync(FULL, my_new, o);
     if (lane_id() == 0 && my_new) atomicAdd(&p.ctr->unique_kmers, my_new);
   }
   if (tid == 0 && my_kmers) atomicAdd(&p.ctr->kmers_inserted, my_kmers);
+}
+
+// --------------------------------------------------------------------------
+// partitioned insert: prefix over the bins, then K3 region by region
+// --------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) bin_prefix_kernel(const BinView b) {
+  // single CTA: exclusive prefix of min(count, cap) over <= 64 Ki bins
+  __shared__ uint32_t sWarp[32];
+  __shared__ uint32_t sCarry;
+  if (threadIdx.x == 0) sCarry = 0;
+  __syncthreads();
+  for (uint32_t base = 0; base < b.n_bins; base += 1024) {
+    const uint32_t i = base + threadIdx.x;
+    uint32_t v = 0;
+    if (i < b.n_bins) {
+      v = b.count[i];
+      if (v > b.cap) v = b.cap;
+    }
+    uint32_t x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t y = __shfl_up_sync(FULL, x, o);
+      if ((int)lane_id() >= o) x += y;
+    }
+    if (lane_id() == 31) sWarp[threadIdx.x >> 5] = x;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      uint32_t wsum = sWarp[threadIdx.x];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(FULL, wsum, o);
+        if ((int)lane_id() >= o) wsum += y;
+      }
+      sWarp[threadIdx.x] = wsum;
+    }
+    __syncthreads();
+    const uint32_t warp_off = (threadIdx.x >> 5) ? sWarp[(threadIdx.x >> 5) - 1] : 0;
+    const uint32_t carry = sCarry;
+    if (i < b.n_bins) b.prefix[i] = carry + warp_off + x - v;
+    __syncthreads();
+    if (threadIdx.x == 1023) sCarry = carry + warp_off + x;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) b.prefix[b.n_bins] = sCarry;
+}
+
+template <int N>
+__global__ void __launch_bounds__(THREADS) insert_bins_kernel(const BinView b, const TableView t,
+                                                             GraphCounters *ctr) {
+  // Grid-stride over the logical concatenation of the bins: at any moment all
+  // resident CTAs work on neighbouring records, i.e. on a few neighbouring
+  // table regions.
+  const uint32_t total = b.prefix[b.n_bins];
+  unsigned long long my_new = 0;
+  const uint32_t stride = gridDim.x * THREADS;
+  const uint32_t n_round = (total + 31u) & ~31u;
+  for (uint32_t i = blockIdx.x * THREADS + threadIdx.x; i < n_round; i += stride) {
+    // the warp's first index locates the bin by binary search; lanes walk on from there
+    const uint32_t i0 = i & ~31u;
+    uint32_t lo = 0, hi = b.n_bins;  // prefix[lo] <= i0 < prefix[hi]
+    while (hi - lo > 1) {
+      const uint32_t mid = (lo + hi) >> 1;
+      if (__ldg(&b.prefix[mid]) <= i0) lo = mid;
+      else hi = mid;
+    }
+    const bool active = i < total;
+    uint64_t key[N];
+    uint32_t edge = 0, count = 0;
+#pragma unroll
+    for (int w = 0; w < N; w++) key[w] = 0;
+    if (active) {
+      uint32_t bin = lo;
+      while (__ldg(&b.prefix[bin + 1]) <= i) bin++;
+      const uint64_t at = (uint64_t)bin * b.cap + (i - __ldg(&b.prefix[bin]));
+      if (N >= 2) {
+        const ulonglong2 a = b.keyA[at];
+        key[0] = a.x;
+        key[1 % N] = a.y;
+      }
+      if (N & 1) key[N - 1] = b.keyB[at];
+      const uint32_t m = b.meta[at];
+      edge = m & 0xFFu;
+      count = m >> 8;
+    }
+    const bool lead = warp_aggregate<N>(active, key, edge, count);
+    if (lead) {
+      const int r = table_upsert<N, DeviceOps>(t, ctr, key, edge, count);
+      my_new += (r == 1);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) my_new += __shfl_xor_sync(FULL, my_new, o);
+  if (lane_id() == 0 && my_new) atomicAdd(&ctr->unique_kmers, my_new);
 }
 
 // --------------------------------------------------------------------------
@@ -701,6 +809,7 @@ void launch_build(int N, BuildMode mode, const BuildParams &p, cudaStream_t st) 
       kernel<<<(unsigned)grid, THREADS, 0, st>>>(p, n_tiles);
     };
     if (mode == MODE_FUSED) go(build_kernel<NN, MODE_FUSED>, TileCfg<MODE_FUSED>::T);
+    else if (mode == MODE_BIN) go(build_kernel<NN, MODE_BIN>, TileCfg<MODE_BIN>::T);
     else if (mode == MODE_RECORDS) go(build_kernel<NN, MODE_RECORDS>, TileCfg<MODE_RECORDS>::T);
     else go(build_kernel<NN, MODE_ROUTE>, TileCfg<MODE_ROUTE>::T);
   });
@@ -715,6 +824,15 @@ void launch_insert_records(int N, const uint32_t *recs, uint64_t n_recs, const T
     const uint64_t need = (n_recs + THREADS - 1) / THREADS;
     if (grid > need) grid = need;
     insert_records_kernel<NN><<<(unsigned)grid, THREADS, 0, st>>>(recs, n_recs, t, ctr);
+  });
+}
+
+void launch_bin_prefix(const BinView &b, cudaStream_t st) { bin_prefix_kernel<<<1, 1024, 0, st>>>(b); }
+
+void launch_insert_bins(int N, const BinView &b, const TableView &t, GraphCounters *ctr, cudaStream_t st) {
+  dispatch_n(N, [&](auto n) {
+    constexpr int NN = decltype(n)::value;
+    insert_bins_kernel<NN><<<resident_grid(insert_bins_kernel<NN>), THREADS, 0, st>>>(b, t, ctr);
   });
 }
 

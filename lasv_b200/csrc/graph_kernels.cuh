@@ -12,7 +12,22 @@ namespace lasv {
 // one word {edges : 8, count : 24}.
 __host__ __device__ inline int record_u32(int N) { return 2 * N + 1; }
 
-enum BuildMode { MODE_FUSED = 0, MODE_RECORDS = 1, MODE_ROUTE = 2 };
+enum BuildMode { MODE_FUSED = 0, MODE_RECORDS = 1, MODE_ROUTE = 2, MODE_BIN = 3 };
+
+// Region bins of the partitioned insert: k-mer occurrences of a batch grouped by
+// the slice of the table they will touch (bin = bucket >> bin_shift), so that the
+// insert kernel walks the table region by region (L2- and DRAM-row-friendly)
+// instead of at random.  Structure of arrays, one fixed-capacity stripe per bin.
+struct BinView {
+  ulonglong2 *keyA;     // [n_bins*cap] key words 0,1          (N >= 2)
+  uint64_t *keyB;       // [n_bins*cap] last key word          (N odd)
+  uint16_t *meta;       // [n_bins*cap] edges | count << 8
+  unsigned int *count;  // [n_bins]     records wanted per bin (may exceed cap: the excess went straight to the table)
+  uint32_t *prefix;     // [n_bins+1]   exclusive prefix of min(count, cap)
+  uint32_t cap;
+  uint32_t bin_shift;
+  uint32_t n_bins;
+};
 
 struct BuildParams {
   const uint8_t *seq;   // sequence stream: reads back to back, each followed by >= 1 separator byte
@@ -34,6 +49,7 @@ struct BuildParams {
   // times and pass `pass` only inserts the k-mers whose bucket lies in its
   // 1/n_pass slice of the table (n_pass power of two, pass_shift = L - log2 n_pass)
   int n_pass, pass, pass_shift;
+  BinView bins;  // MODE_BIN
 };
 
 struct ReadStats {  // loader bookkeeping (file_reader.c:460-470,579,584)
@@ -71,6 +87,8 @@ int sm_count();
 void launch_build(int N, BuildMode mode, const BuildParams &p, cudaStream_t st);
 void launch_insert_records(int N, const uint32_t *recs, uint64_t n_recs, const TableView &t,
                            GraphCounters *ctr, cudaStream_t st);
+void launch_bin_prefix(const BinView &b, cudaStream_t st);
+void launch_insert_bins(int N, const BinView &b, const TableView &t, GraphCounters *ctr, cudaStream_t st);
 void launch_read_stats(const uint8_t *seq, const uint8_t *qual, const uint64_t *offsets,
                        uint64_t n_reads, int sep, int k, int cutoff, ReadStats *stats,
                        unsigned long long *hist, uint32_t hist_size, cudaStream_t st);
