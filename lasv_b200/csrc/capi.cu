@@ -68,6 +68,7 @@ struct lasv_graph {
   uint64_t n_buckets = 0, n_slots = 0;
   size_t slot_bytes = 0;
   uint8_t *d_slots = nullptr;
+  uint8_t *d_tags = nullptr;  // one tag byte per slot (table.cuh)
   GraphCounters *d_ctr = nullptr;
   ReadStats *d_stats = nullptr;
   unsigned long long *d_hist = nullptr;
@@ -84,6 +85,7 @@ struct lasv_graph {
   TableView view() const {
     TableView t;
     t.slots = d_slots;
+    t.tags = d_tags;
     t.bucket_mask = (uint32_t)(n_buckets - 1);
     t.W = (uint32_t)W;
     t.max_rehash = (uint32_t)max_rehash;
@@ -274,6 +276,7 @@ lasv_graph *lasv_graph_new(int kmer_size, int number_bits, int bucket_size, int 
   g->slot_bytes = 8 * (size_t)g->N + 8;
   bool ok = cudaSetDevice(device) == cudaSuccess &&
             cudaMalloc(&g->d_slots, g->n_slots * g->slot_bytes) == cudaSuccess &&
+            cudaMalloc(&g->d_tags, g->n_slots + 32) == cudaSuccess &&
             cudaMalloc(&g->d_ctr, sizeof(GraphCounters)) == cudaSuccess &&
             cudaMalloc(&g->d_stats, sizeof(ReadStats)) == cudaSuccess &&
             cudaMalloc(&g->d_hist, HIST_BINS * sizeof(unsigned long long)) == cudaSuccess &&
@@ -297,6 +300,7 @@ void lasv_graph_free(lasv_graph **gp) {
   cudaSetDevice(g->device);
   cudaDeviceSynchronize();
   cudaFree(g->d_slots);
+  cudaFree(g->d_tags);
   cudaFree(g->d_ctr);
   cudaFree(g->d_stats);
   cudaFree(g->d_hist);
@@ -319,6 +323,7 @@ int lasv_graph_clear(lasv_graph *g, void *cuda_stream) {
   if (int e = use(g)) return e;
   cudaStream_t st = stream_of(g, cuda_stream);
   CUDA_TRY(cudaMemsetAsync(g->d_slots, 0, g->n_slots * g->slot_bytes, st));
+  CUDA_TRY(cudaMemsetAsync(g->d_tags, 0, g->n_slots + 32, st));
   CUDA_TRY(cudaMemsetAsync(g->d_ctr, 0, sizeof(GraphCounters), st));
   CUDA_TRY(cudaMemsetAsync(g->d_stats, 0, sizeof(ReadStats), st));
   CUDA_TRY(cudaMemsetAsync(g->d_hist, 0, HIST_BINS * sizeof(unsigned long long), st));

@@ -304,14 +304,32 @@ LASV_HD uint32_t meta_tag(uint64_t m) { return (uint32_t)(m >> 48); }
 // Where a key lives: CORTEX bucket from c (hash_value.c:767-773), in-bucket
 // start slot and tag from the spare hash words.
 struct Probe {
-  uint32_t bucket, start, tag;
+  uint32_t bucket, start, tag, tag8;
 };
 LASV_HD Probe probe_of(const Hash3 &h, uint32_t bucket_mask, uint32_t W) {
   Probe p;
   p.bucket = h.c & bucket_mask;
   p.start = mulhi32(h.b, W);
-  p.tag = h.a >> 16;
+  p.tag = h.a >> 16;                       // 16 bits kept in the slot's pad bytes
+  const uint32_t t = h.a & 0xFFu;          // 8 bits kept in the side tag array, never 0
+  p.tag8 = t ? t : 1u;
   return p;
+}
+
+// 16 one-byte tags in a uint4 -> 16-bit mask of the bytes equal to `v`
+// (bit i <-> byte i in memory order).
+LASV_HD uint32_t bytes_equal_mask16(uint4 t, uint32_t v) {
+  const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+  const uint32_t rep = v * 0x01010101u;
+  uint32_t m = 0;
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    uint32_t x = w[i] ^ rep;               // zero byte <=> equal
+    // exact zero-byte detector: high bit of each byte set iff that byte is zero
+    uint32_t z = ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x | 0x7F7F7F7Fu);
+    m |= (((z >> 7) * 0x01020408u) >> 24) << (4 * i);
+  }
+  return m & 0xFFFFu;
 }
 
 // 64-bit mixer (splitmix64 finaliser) -- used by the order-independent table

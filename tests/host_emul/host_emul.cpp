@@ -23,6 +23,12 @@ struct HostOps {
   static uint64_t load(const uint64_t *p) { return *p; }
   static void store(uint64_t *p, uint64_t v) { *p = v; }
   static void prefetch(const void *) {}
+  static uint4 load_tags16(const uint8_t *p) {
+    uint4 v;
+    memcpy(&v, p, 16);
+    return v;
+  }
+  static void store_tag(uint8_t *p, uint32_t v) { *p = (uint8_t)v; }
   static uint64_t cas(uint64_t *p, uint64_t expect, uint64_t want) {
     uint64_t old = *p;
     if (old == expect) *p = want;
@@ -102,9 +108,10 @@ void walk(const uint8_t *seq_in, const uint8_t *qual_in, uint64_t n_in, int k, i
   }
 }
 
-TableView view_of(uint8_t *table, int L, int W, int max_rehash) {
+TableView view_of(uint8_t *table, uint8_t *tags, int L, int W, int max_rehash) {
   TableView t;
   t.slots = table;
+  t.tags = tags;
   t.bucket_mask = (uint32_t)((1ull << L) - 1);
   t.W = (uint32_t)W;
   t.max_rehash = (uint32_t)max_rehash;
@@ -113,8 +120,8 @@ TableView view_of(uint8_t *table, int L, int W, int max_rehash) {
 
 template <int N>
 int build_fused(const uint8_t *seq, const uint8_t *qual, uint64_t n_bytes, int k, int cutoff, int L,
-                int W, int max_rehash, int T, uint8_t *table, GraphCounters *ctr) {
-  const TableView tv = view_of(table, L, W, max_rehash);
+                int W, int max_rehash, int T, uint8_t *table, uint8_t *tags, GraphCounters *ctr) {
+  const TableView tv = view_of(table, tags, L, W, max_rehash);
   walk<N>(seq, qual, n_bytes, k, cutoff, T & 0xFFFF, [&](const uint64_t(&key)[N], uint32_t edge) {
     ctr->kmers_inserted++;
     const int r = table_upsert<N, HostOps>(tv, ctr, key, edge, 1u);
@@ -143,8 +150,8 @@ uint64_t extract(const uint8_t *seq, const uint8_t *qual, uint64_t n_bytes, int 
 
 template <int N>
 int insert_records(const uint32_t *recs, uint64_t n, int L, int W, int max_rehash, uint8_t *table,
-                   GraphCounters *ctr) {
-  const TableView tv = view_of(table, L, W, max_rehash);
+                   uint8_t *tags, GraphCounters *ctr) {
+  const TableView tv = view_of(table, tags, L, W, max_rehash);
   for (uint64_t i = 0; i < n; i++) {
     const uint32_t *src = recs + i * (2 * N + 1);
     uint64_t key[N];
@@ -194,9 +201,9 @@ void finalize(uint8_t *table, int L, int W, int16_t *next) {
 }
 
 template <int N>
-void find(uint8_t *table, int L, int W, int max_rehash, int finalized, const uint64_t *keys,
+void find(uint8_t *table, uint8_t *tags, int L, int W, int max_rehash, int finalized, const uint64_t *keys,
           uint64_t n, uint32_t *covg, uint8_t *edges, uint8_t *found) {
-  const TableView tv = view_of(table, L, W, max_rehash);
+  const TableView tv = view_of(table, tags, L, W, max_rehash);
   for (uint64_t i = 0; i < n; i++) {
     uint64_t key[N], m = 0;
     for (int w = 0; w < N; w++) key[w] = keys[i * N + w];
@@ -215,11 +222,12 @@ void find(uint8_t *table, int L, int W, int max_rehash, int finalized, const uin
 extern "C" {
 
 int emul_build_fused(const uint8_t *seq, const uint8_t *qual, uint64_t n_bytes, int k, int cutoff,
-                     int L, int W, int max_rehash, int T, uint8_t *table, uint64_t *counters20) {
+                     int L, int W, int max_rehash, int T, uint8_t *table, uint8_t *tags,
+                     uint64_t *counters20) {
   GraphCounters ctr;
   memset(&ctr, 0, sizeof ctr);
   const int N = 2 * k / 64 + 1;
-  const int rc = DISPATCH(N, build_fused)(seq, qual, n_bytes, k, cutoff, L, W, max_rehash, T, table, &ctr);
+  const int rc = DISPATCH(N, build_fused)(seq, qual, n_bytes, k, cutoff, L, W, max_rehash, T, table, tags, &ctr);
   counters20[0] = ctr.unique_kmers;
   counters20[1] = ctr.kmers_inserted;
   counters20[2] = ctr.table_full;
@@ -234,11 +242,11 @@ uint64_t emul_extract_records(const uint8_t *seq, const uint8_t *qual, uint64_t 
 }
 
 int emul_insert_records(const uint32_t *recs, uint64_t n, int k, int L, int W, int max_rehash,
-                        uint8_t *table, uint64_t *counters20) {
+                        uint8_t *table, uint8_t *tags, uint64_t *counters20) {
   GraphCounters ctr;
   memset(&ctr, 0, sizeof ctr);
   const int N = 2 * k / 64 + 1;
-  const int rc = DISPATCH(N, insert_records)(recs, n, L, W, max_rehash, table, &ctr);
+  const int rc = DISPATCH(N, insert_records)(recs, n, L, W, max_rehash, table, tags, &ctr);
   counters20[0] = ctr.unique_kmers;
   counters20[2] = ctr.table_full;
   for (int r = 0; r < 16; r++) counters20[3 + r] = ctr.rehash_hist[r];
@@ -250,10 +258,10 @@ void emul_finalize(uint8_t *table, int k, int L, int W, int16_t *next) {
   DISPATCH(N, finalize)(table, L, W, next);
 }
 
-void emul_find(uint8_t *table, int k, int L, int W, int max_rehash, int finalized,
+void emul_find(uint8_t *table, uint8_t *tags, int k, int L, int W, int max_rehash, int finalized,
                const uint64_t *keys, uint64_t n, uint32_t *covg, uint8_t *edges, uint8_t *found) {
   const int N = 2 * k / 64 + 1;
-  DISPATCH(N, find)(table, L, W, max_rehash, finalized, keys, n, covg, edges, found);
+  DISPATCH(N, find)(table, tags, L, W, max_rehash, finalized, keys, n, covg, edges, found);
 }
 
 uint32_t emul_hash_c(const uint64_t *key, int N, uint32_t rehash) {

@@ -25,13 +25,13 @@ def emul():
         subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas",
                         "-I/usr/local/cuda/include", "-o", str(so), str(src)], check=True)
     L = C.CDLL(str(so))
-    L.emul_build_fused.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64] + [C.c_int] * 6 + [C.c_void_p, C.c_void_p]
+    L.emul_build_fused.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64] + [C.c_int] * 6 + [C.c_void_p] * 3
     L.emul_extract_records.restype = C.c_uint64
     L.emul_extract_records.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_int,
                                        C.c_void_p, C.c_uint64]
-    L.emul_insert_records.argtypes = [C.c_void_p, C.c_uint64] + [C.c_int] * 4 + [C.c_void_p, C.c_void_p]
+    L.emul_insert_records.argtypes = [C.c_void_p, C.c_uint64] + [C.c_int] * 4 + [C.c_void_p] * 3
     L.emul_finalize.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
-    L.emul_find.argtypes = [C.c_void_p] + [C.c_int] * 5 + [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.emul_find.argtypes = [C.c_void_p, C.c_void_p] + [C.c_int] * 5 + [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]
     L.emul_hash_c.restype = C.c_uint32
     L.emul_hash_c.argtypes = [C.c_void_p, C.c_int, C.c_uint32]
     return L
@@ -50,9 +50,12 @@ def emul_build(emul, meta, seq, qual, T=2048, L=None, W=None):
     W = W or meta["W"]
     N = words_per_kmer(k)
     table = np.zeros((1 << L) * W, dtype=element_dtype(N))
+    tags = np.zeros((1 << L) * W + 32, dtype=np.uint8)        # one tag byte per slot (+ slack)
     ctr = np.zeros(20, dtype=np.uint64)
     rc = emul.emul_build_fused(seq.ctypes.data, qual.ctypes.data if qual is not None else None, len(seq), k,
-                               util.cutoff_of(meta), L, W, 15, T, table.ctypes.data, ctr.ctypes.data)
+                               util.cutoff_of(meta), L, W, 15, T, table.ctypes.data, tags.ctypes.data,
+                               ctr.ctypes.data)
+    emul_build.tags = tags
     return rc, table, ctr
 
 
@@ -86,9 +89,18 @@ def test_emulated_finalize_gives_reference_layout(emul, name):
     keys = np.ascontiguousarray(gold["kmer"])
     n = len(keys)
     covg, edges, found = np.zeros(n, np.uint32), np.zeros(n, np.uint8), np.zeros(n, np.uint8)
-    emul.emul_find(table.ctypes.data, k, L, W, 15, 0, keys.ctypes.data, n, covg.ctypes.data,
+    tags = emul_build.tags
+    emul.emul_find(table.ctypes.data, tags.ctypes.data, k, L, W, 15, 0, keys.ctypes.data, n, covg.ctypes.data,
                    edges.ctypes.data, found.ctypes.data)
     assert found.all() and np.array_equal(covg, gold["covg"]) and np.array_equal(edges, gold["edges"])
+    # the tag array mirrors the occupancy exactly (0 <=> empty slot)
+    assert np.array_equal(tags[: len(table)] != 0, table["status"] != 0)
+    absent0 = keys.copy()
+    absent0[:, -1] ^= np.uint64(0x5555)
+    emul.emul_find(table.ctypes.data, tags.ctypes.data, k, L, W, 15, 0, absent0.ctypes.data, n, covg.ctypes.data,
+                   edges.ctypes.data, found.ctypes.data)
+    present0 = {tuple(x) for x in keys.tolist()}
+    assert [bool(f) for f in found] == [tuple(x) in present0 for x in absent0.tolist()]
     nxt = np.zeros(1 << L, dtype=np.int16)
     emul.emul_finalize(table.ctypes.data, k, L, W, nxt.ctypes.data)
     raw = table.view(np.uint8).reshape(len(table), 8 * N + 8)
@@ -98,7 +110,7 @@ def test_emulated_finalize_gives_reference_layout(emul, name):
     assert np.array_equal(occ.sum(axis=1), nxt)
     assert (occ == (np.arange(W)[None, :] < nxt[:, None])).all()    # hole-free from slot 0
     assert not raw[~occ.reshape(-1)].any()                    # empty slots are all-zero bytes
-    emul.emul_find(table.ctypes.data, k, L, W, 15, 1, keys.ctypes.data, n, covg.ctypes.data,
+    emul.emul_find(table.ctypes.data, tags.ctypes.data, k, L, W, 15, 1, keys.ctypes.data, n, covg.ctypes.data,
                    edges.ctypes.data, found.ctypes.data)
     assert found.all() and np.array_equal(covg, gold["covg"]) and np.array_equal(edges, gold["edges"])
     # independent check with the ORACLE's own find (reference bucket scan + rehash chain):
@@ -114,7 +126,7 @@ def test_emulated_finalize_gives_reference_layout(emul, name):
     util.assert_same_records(table_records(table), gold, name)
     absent = keys.copy()
     absent[:, -1] ^= np.uint64(0x5555)
-    emul.emul_find(table.ctypes.data, k, L, W, 15, 1, absent.ctypes.data, n, covg.ctypes.data,
+    emul.emul_find(table.ctypes.data, tags.ctypes.data, k, L, W, 15, 1, absent.ctypes.data, n, covg.ctypes.data,
                    edges.ctypes.data, found.ctypes.data)
     present = {tuple(x) for x in keys.tolist()}
     assert [bool(f) for f in found] == [tuple(x) in present for x in absent.tolist()]
@@ -135,6 +147,7 @@ def test_emulated_records_path(emul, name):
     # shard the records by owner bits exactly as the ROUTE mode does and insert per shard
     g_bits = 1
     shards = [np.zeros((1 << (L - g_bits)) * W, dtype=element_dtype(N)) for _ in range(2)]
+    shard_tags = [np.zeros((1 << (L - g_bits)) * W + 32, dtype=np.uint8) for _ in range(2)]
     owner = np.zeros(n, dtype=np.int64)
     for i in range(n):
         key = np.zeros(N, dtype=np.uint64)
@@ -148,7 +161,7 @@ def test_emulated_records_path(emul, name):
         sub = np.ascontiguousarray(recs[:n][owner == d])
         ctr = np.zeros(20, dtype=np.uint64)
         rc = emul.emul_insert_records(sub.ctypes.data, len(sub), k, L - g_bits, W, 15,
-                                      shards[d].ctypes.data, ctr.ctypes.data)
+                                      shards[d].ctypes.data, shard_tags[d].ctypes.data, ctr.ctypes.data)
         assert rc == 0
         all_recs.append(table_records(shards[d]))
     util.assert_same_records(np.concatenate(all_recs), util.case_records(name), name)

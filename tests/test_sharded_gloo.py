@@ -37,7 +37,7 @@ def _worker(rank, world, port, name, outdir):
     emul.emul_extract_records.restype = C.c_uint64
     emul.emul_extract_records.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_int,
                                           C.c_void_p, C.c_uint64]
-    emul.emul_insert_records.argtypes = [C.c_void_p, C.c_uint64] + [C.c_int] * 4 + [C.c_void_p, C.c_void_p]
+    emul.emul_insert_records.argtypes = [C.c_void_p, C.c_uint64] + [C.c_int] * 4 + [C.c_void_p] * 3
     emul.emul_hash_c.restype = C.c_uint32
     emul.emul_hash_c.argtypes = [C.c_void_p, C.c_int, C.c_uint32]
     meta = util.case_meta(name)
@@ -73,8 +73,9 @@ def _worker(rank, world, port, name, outdir):
     got = np.ascontiguousarray(recv[:total].numpy().view(np.uint32))
     table = np.zeros((1 << (L - bits)) * W, dtype=element_dtype(N))
     ctr = np.zeros(20, dtype=np.uint64)
+    tags = np.zeros(len(table) + 32, dtype=np.uint8)
     assert emul.emul_insert_records(got.ctypes.data, total, k, L - bits, W, 15, table.ctypes.data,
-                                    ctr.ctypes.data) == 0
+                                    tags.ctypes.data, ctr.ctypes.data) == 0
     np.save(Path(outdir) / f"shard{rank}.npy", table)
     # job-wide insert count through a collective, as ShardedDBGraph.stats does
     t = torch.tensor([n], dtype=torch.int64)
