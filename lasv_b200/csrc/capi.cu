@@ -264,6 +264,10 @@ lasv_graph *lasv_graph_new(int kmer_size, int number_bits, int bucket_size, int 
     fail(LASV_ERR_CUDA, "no usable CUDA device %d (this library has no CPU fallback)", device);
     return nullptr;
   }
+  if (const char *e = getenv("LASV_B200_L2FETCH")) {  // experiment: L2 fetch granularity (32/64/128)
+    cudaSetDevice(device);
+    cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(e));
+  }
   lasv_graph *g = new lasv_graph();
   g->k = kmer_size;
   g->N = (2 * kmer_size) / 64 + 1;  // graph_operations.c:620

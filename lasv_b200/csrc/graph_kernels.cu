@@ -94,18 +94,20 @@ struct TileCfg {
 };
 
 template <int N, int MODE>
-__global__ void __launch_bounds__(THREADS) build_kernel(const BuildParams p, const uint64_t n_tiles) {
+__global__ void __launch_bounds__(THREADS, 4) build_kernel(const BuildParams p, const uint64_t n_tiles) {
   using Cfg = TileCfg<MODE>;
   constexpr int T = Cfg::T, R = Cfg::R, CHUNKS = Cfg::CHUNKS;
   static_assert(CHUNKS <= THREADS, "one staging chunk per thread");
   static_assert(R % 64 == 0, "region must be whole bad-bit words");
   constexpr int RECW = 2 * N + 1;
 
-  __shared__ uint64_t sP[R / 32 + 2];
-  __shared__ uint64_t sPR[R / 32 + 2];
-  __shared__ uint64_t sBD[R / 64 + 2];
+  constexpr int WORDS = R / 32;  // 32-position words of the bad / valid bit strings
+  static_assert(WORDS <= THREADS, "one validity word per thread");
+  __shared__ uint32_t sP[R / 16 + TileGeom::PADW + 2];
+  __shared__ uint32_t sPR[R / 16 + TileGeom::PADW + 2];
+  __shared__ uint32_t sBD[WORDS + 4];
   __shared__ uint16_t sPos[T];
-  __shared__ uint32_t sCount;
+  __shared__ uint32_t sWarpSum[THREADS / 32];
   __shared__ unsigned long long sTileBase[16];
   __shared__ uint32_t sBinCount[16];
   __shared__ uint32_t sBinRank[16];
@@ -117,10 +119,11 @@ __global__ void __launch_bounds__(THREADS) build_kernel(const BuildParams p, con
   const bool has_qual = p.qual != nullptr;
   const int k = p.k;
 
-  if (tid == 0) {
-    sP[0] = 0; sPR[0] = 0;
-    sP[R / 32 + 1] = 0; sPR[R / 32 + 1] = 0;
-    sBD[R / 64] = ~0ull; sBD[R / 64 + 1] = ~0ull;
+  if (tid < TileGeom::PADW + 2) {  // pad words: zeros around the code strings, all-bad behind BD
+    const int tail = R / 16 + TileGeom::PADW;
+    if (tid < TileGeom::PADW) { sP[tid] = 0; sPR[tid] = 0; }
+    else { sP[tail + tid - TileGeom::PADW] = 0; sPR[tail + tid - TileGeom::PADW] = 0; }
+    sBD[WORDS + tid] = ~0u;
   }
 
   unsigned long long my_new = 0;    // keys this thread created
@@ -150,29 +153,45 @@ __global__ void __launch_bounds__(THREADS) build_kernel(const BuildParams p, con
     if (tid < CHUNKS) {
       uint32_t code32, bad16;
       classify16(sv, qv, has_qual, p.cutoff, inr, code32, bad16);
-      reinterpret_cast<uint32_t *>(sP)[code_u32_index(tid)] = code32;
-      reinterpret_cast<uint32_t *>(sPR)[code_u32_index(CHUNKS - 1 - tid)] = rc_code32(code32);
-      reinterpret_cast<uint16_t *>(sBD)[bad_u16_index(tid)] = (uint16_t)bad16;
+      sP[TileGeom::PADW + tid] = code32;
+      sPR[TileGeom::PADW + (CHUNKS - 1 - tid)] = rc_code32(code32);
+      reinterpret_cast<uint16_t *>(sBD)[tid ^ 1] = (uint16_t)bad16;  // big-endian halves of a 32-bit word
     }
-    if (tid == 0) sCount = 0;
     if (MODE == MODE_ROUTE && tid < 16) { sBinCount[tid] = 0; sBinRank[tid] = 0; }
     __syncthreads();
 
     issue_stage(tile + gridDim.x);  // next tile's bytes fly during the heavy phase
 
-    // ---- window validity + compaction of the good window starts
+    // ---- window validity by word-parallel erosion, then an ordered dense list of
+    //      the good window starts (block scan over one popcount per word)
+    uint32_t vbits = 0;
+    if (tid < WORDS) vbits = valid_window_word(sBD, tid, k) & tile_word_mask(tid, T);
+    const uint32_t vcnt = (uint32_t)__popc(vbits);
+    uint32_t incl = vcnt;
 #pragma unroll
-    for (int it = 0; it < T / THREADS; it++) {
-      const int pos = it * THREADS + tid;
-      const bool good = window_good(sBD, TileGeom::HALO_L + pos, k);
-      const unsigned m = __ballot_sync(FULL, good);
-      unsigned base = 0;
-      if (lane_id() == 0 && m) base = atomicAdd(&sCount, (uint32_t)__popc(m));
-      base = __shfl_sync(FULL, base, 0);
-      if (good) sPos[base + __popc(m & lanemask_lt())] = (uint16_t)pos;
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t y = __shfl_up_sync(FULL, incl, o);
+      if ((int)lane_id() >= o) incl += y;
+    }
+    if (lane_id() == 31) sWarpSum[tid >> 5] = incl;
+    __syncthreads();
+    uint32_t wbase = 0, total = 0;
+#pragma unroll
+    for (int w2 = 0; w2 < THREADS / 32; w2++) {
+      const uint32_t ws = sWarpSum[w2];
+      if (w2 < (tid >> 5)) wbase += ws;
+      total += ws;
+    }
+    {
+      uint32_t idx = wbase + incl - vcnt;
+      while (vbits) {
+        const int b = __clz((int)vbits);
+        sPos[idx++] = (uint16_t)(32 * tid + b - TileGeom::HALO_L);
+        vbits &= ~(0x80000000u >> b);
+      }
     }
     __syncthreads();
-    const int M = (int)sCount;
+    const int M = (int)total;
     if (tid == 0 && (MODE != MODE_FUSED || p.pass == 0)) my_kmers += (unsigned long long)M;
 
     if (MODE == MODE_RECORDS) {
@@ -205,8 +224,7 @@ __global__ void __launch_bounds__(THREADS) build_kernel(const BuildParams p, con
           my_new += (r == 1);
         }
       } else if (MODE == MODE_BIN) {
-        const bool lead = warp_aggregate<N>(active, key, edge, count);
-        if (lead) {
+        if (active) {  // duplicates meet again, side by side, in insert_bins_kernel
           const uint32_t bin = (lookup3_key<N>(key, 0).c & p.table.bucket_mask) >> p.bins.bin_shift;
           const uint32_t idx = atomicAdd(&p.bins.count[bin], 1u);
           if (idx < p.bins.cap) {
@@ -312,7 +330,7 @@ __global__ void __launch_bounds__(1024) bin_prefix_kernel(const BinView b) {
 }
 
 template <int N>
-__global__ void __launch_bounds__(THREADS) insert_bins_kernel(const BinView b, const TableView t,
+__global__ void __launch_bounds__(THREADS, 5) insert_bins_kernel(const BinView b, const TableView t,
                                                              GraphCounters *ctr) {
   // Grid-stride over the logical concatenation of the bins: at any moment all
   // resident CTAs work on neighbouring records, i.e. on a few neighbouring
@@ -364,7 +382,7 @@ __global__ void __launch_bounds__(THREADS) insert_bins_kernel(const BinView b, c
 // insert_records_kernel: K3 over (2N+1)-word records
 // --------------------------------------------------------------------------
 template <int N>
-__global__ void __launch_bounds__(THREADS) insert_records_kernel(const uint32_t *__restrict__ recs,
+__global__ void __launch_bounds__(THREADS, 5) insert_records_kernel(const uint32_t *__restrict__ recs,
                                                                 const uint64_t n_recs,
                                                                 const TableView t,
                                                                 GraphCounters *ctr) {
@@ -625,7 +643,7 @@ __global__ void __launch_bounds__(THREADS) dump_ctx_kernel(const TableView t,
 // load packed .ctx records into the table (file_reader.c:1686-1703: insert key,
 // add coverage, OR edges)
 template <int N>
-__global__ void __launch_bounds__(THREADS) ingest_ctx_kernel(const uint8_t *__restrict__ recs,
+__global__ void __launch_bounds__(THREADS, 5) ingest_ctx_kernel(const uint8_t *__restrict__ recs,
                                                             const uint64_t n_recs, const TableView t,
                                                             GraphCounters *ctr) {
   constexpr uint32_t REC = 8 * N + 5;
@@ -653,7 +671,7 @@ __global__ void __launch_bounds__(THREADS) ingest_ctx_kernel(const uint8_t *__re
 
 // merge an uploaded reference-layout Element[] (any hole pattern) into the table
 template <int N>
-__global__ void __launch_bounds__(THREADS) ingest_elements_kernel(const uint8_t *__restrict__ elems,
+__global__ void __launch_bounds__(THREADS, 5) ingest_elements_kernel(const uint8_t *__restrict__ elems,
                                                                  const uint64_t n_slots,
                                                                  const TableView t, GraphCounters *ctr) {
   constexpr uint32_t STRIDE = 8 * N + 8;

@@ -173,70 +173,112 @@ LASV_HD uint32_t rc_code32(uint32_t code32) {
 // ------------------------------------------------------------ tile geometry
 // A tile is a window of the byte stream packed into shared memory (or a host
 // array in the emulation).  Region base index j in [0, R): region position 0 is
-// stream position t0 - HALO_L.  All three packed arrays are big-endian bit
-// strings over the region:
-//   P  (uint64)  forward codes, 32 bases per word, ONE pad word in front
-//   PR (uint64)  reverse-complement string (RC position p <-> region R-1-p),
-//                same layout
-//   BD (uint64)  bad bits, 64 bases per word, two all-ones pad words behind
+// stream position t0 - HALO_L.  Three big-endian bit strings of 32-bit words:
+//   P  forward 2-bit codes, 16 bases per word (base 16w in bits 31:30), PADW
+//      pad words in front
+//   PR reverse-complement string (RC position p <-> region R-1-p), same layout
+//   BD bad bits, 32 positions per word (position 32w in bit 31)
+// and, derived from BD once per tile,
+//   VD valid-window bits: bit j set <=> the k bases from j on are all good.
+// 32-bit words on purpose: a k-mer word is ONE funnel shift of two neighbouring
+// string words (SHF), where 64-bit variable shifts cost four instructions each.
 struct TileGeom {
   static constexpr int HALO_L = 16;   // bytes before the first window start (need >= 1)
   static constexpr int HALO_R = 112;  // bytes after the last window start   (need >= k+1, k<=95)
+  static constexpr int PADW = 2;      // front pad words of P / PR
 };
 
-// Index (in uint32 units) inside P/PR for the 16-base chunk c: big-endian
-// halves inside little-endian uint64 words, plus the front pad word.
-LASV_HD int code_u32_index(int chunk) { return (chunk + 2) ^ 1; }
-// Index (in uint16 units) inside BD for chunk c.
-LASV_HD int bad_u16_index(int chunk) { return chunk ^ 3; }
-
-// True iff the k bases starting at region index j are all good.
-// BD must have two pad words of all-ones behind the data (k <= 95).
-LASV_HD bool window_good(const uint64_t *BD, int j, int k) {
-  int w = j >> 6, off = j & 63;
-  uint64_t x = BD[w] << off;
-  if (x) return clz64(x) >= k;
-  int d = 64 - off;
-  if (d >= k) return true;
-  x = BD[w + 1];
-  if (x) return d + clz64(x) >= k;
-  d += 64;
-  if (d >= k) return true;
-  x = BD[w + 2];
-  return d + clz64(x) >= k;
+LASV_HD uint32_t funnel_l(uint32_t hi, uint32_t lo, uint32_t sh) {  // upper word of (hi:lo) << sh, 0<=sh<32
+#if defined(__CUDA_ARCH__)
+  return __funnelshift_l(lo, hi, sh);
+#else
+  return sh ? ((hi << sh) | (lo >> (32 - sh))) : hi;
+#endif
+}
+LASV_HD int clz32(uint32_t x) {
+#if defined(__CUDA_ARCH__)
+  return __clz((int)x);
+#else
+  return x ? __builtin_clz(x) : 32;
+#endif
 }
 
-LASV_HD bool base_bad(const uint64_t *BD, int j) { return (BD[j >> 6] >> (63 - (j & 63))) & 1ull; }
-LASV_HD uint32_t base_code(const uint64_t *P, int j) {
-  return (uint32_t)(P[(j >> 5) + 1] >> (62 - 2 * (j & 31))) & 3u;
+LASV_HD bool base_bad(const uint32_t *BD, int j) { return (BD[j >> 5] >> (31 - (j & 31))) & 1u; }
+LASV_HD uint32_t base_code(const uint32_t *P, int j) {
+  return (P[TileGeom::PADW + (j >> 4)] >> (30 - 2 * (j & 15))) & 3u;
 }
 
-// Distance from region index j to the next bad base at or after j, scanning at
-// most up to region index `limit` (exclusive).  Returns limit - j if none.
-LASV_HD int next_bad_distance(const uint64_t *BD, int j, int limit) {
-  int p = j;
-  while (p < limit) {
-    int w = p >> 6, off = p & 63;
-    uint64_t x = BD[w] << off;
-    if (x) {
-      int d = p + clz64(x);
-      return (d < limit ? d : limit) - j;
-    }
-    p += 64 - off;
-  }
-  return limit - j;
+// 128-bit big-endian window (w[0] first) shifted left by s bits (0 <= s < 96),
+// zeros shifted in behind.  No dynamically indexed arrays (they would live in
+// local memory): the word shift is two conditional moves.
+LASV_HD void shl128(const uint32_t (&w)[4], uint32_t s, uint32_t (&out)[4]) {
+  uint32_t x0 = w[0], x1 = w[1], x2 = w[2], x3 = w[3];
+  if (s & 64u) { x0 = x2; x1 = x3; x2 = 0u; x3 = 0u; }
+  if (s & 32u) { x0 = x1; x1 = x2; x2 = x3; x3 = 0u; }
+  const uint32_t bs = s & 31u;
+  out[0] = funnel_l(x0, x1, bs);
+  out[1] = funnel_l(x1, x2, bs);
+  out[2] = funnel_l(x2, x3, bs);
+  out[3] = funnel_l(x3, 0u, bs);
 }
 
-// The k-mer whose first base is region index j, right-aligned in N words with
-// word 0 most significant (binary_kmer.h:41-47).  P has one pad word in front.
-template <int N>
-LASV_HD void extract_kmer(const uint64_t *P, int j, int k, uint64_t (&out)[N]) {
+// Mask of the window-start positions of word `word` that belong to the tile
+// proper, i.e. to region indices [HALO_L, HALO_L + T).
+LASV_HD uint32_t tile_word_mask(int word, int T) {
+  const int lo = TileGeom::HALO_L, hi = TileGeom::HALO_L + T;  // region index range
+  const int b = 32 * word;
+  if (b + 32 <= lo || b >= hi) return 0u;
+  uint32_t m = ~0u;
+  if (b < lo) m &= ~0u >> (lo - b);           // drop the first lo-b positions (top bits)
+  if (b + 32 > hi) m &= ~0u << (b + 32 - hi); // drop the last positions (low bits)
+  return m;
+}
+
+// Valid-window bits of the 32 positions [32*word, 32*word+32): position j is
+// valid iff BD has no bad bit in [j, j+k), 1 <= k <= 95.  Word-parallel erosion:
+// E_2n = E_n & (E_n << n), then E_k assembled from the binary digits of k.
+// BD needs readable words up to index word+3 (pad words must be all-ones).
+LASV_HD uint32_t valid_window_word(const uint32_t *BD, int word, int k) {
+  uint32_t e[4] = {~BD[word], ~BD[word + 1], ~BD[word + 2], ~BD[word + 3]};  // E_1 = good bits
+  uint32_t acc[4] = {~0u, ~0u, ~0u, ~0u};
+  uint32_t off = 0;
+  // digits of k from the lowest: consume E_(2^b) as it is produced
 #pragma unroll
-  for (int e = 0; e < N; e++) {
-    int b0 = j + k - 32 * e;  // padded base coordinate of the first of 32 bases of word N-1-e
-    int w = b0 >> 5, sh = 2 * (b0 & 31);
-    uint64_t hi = P[w], lo = P[w + 1];
-    out[N - 1 - e] = (hi << sh) | ((lo >> 1) >> (63 - sh));
+  for (int b = 0; b < 7; b++) {
+    const uint32_t n = 1u << b;
+    if ((uint32_t)k & n) {
+      uint32_t t[4];
+      shl128(e, off, t);
+#pragma unroll
+      for (int i = 0; i < 4; i++) acc[i] &= t[i];
+      off += n;
+    }
+    if (b < 6) {
+      uint32_t t[4];
+      shl128(e, n, t);
+#pragma unroll
+      for (int i = 0; i < 4; i++) e[i] &= t[i];
+    }
+  }
+  return acc[0];
+}
+
+// The k-mer whose first base is region index j, right-aligned in N 64-bit words
+// with word 0 most significant (binary_kmer.h:41-47).  All 2N 32-bit halves come
+// from 2N+1 consecutive string words through the same funnel shift.
+template <int N>
+LASV_HD void extract_kmer(const uint32_t *P, int j, int k, uint64_t (&out)[N]) {
+  const int b0 = j + k - 32 * N;                 // first base of the top 32-bit half (may be < 0)
+  const int w0 = (b0 >> 4) + TileGeom::PADW;     // arithmetic shift: floor
+  const uint32_t sh = 2u * (uint32_t)(b0 & 15);
+  uint32_t prev = P[w0];
+#pragma unroll
+  for (int t = 0; t < 2 * N; t++) {              // t = 0 is the most significant half
+    const uint32_t next = P[w0 + t + 1];
+    const uint32_t v = funnel_l(prev, next, sh);
+    prev = next;
+    if (t & 1) out[t >> 1] |= (uint64_t)v;
+    else out[t >> 1] = (uint64_t)v << 32;
   }
   out[0] &= (~0ull) >> (64 - 2 * (k & 31));
 }
@@ -268,7 +310,7 @@ LASV_HD bool kmer_equal(const uint64_t (&a)[N], const uint64_t (&b)[N]) {
 // prev/next exist iff the neighbouring window is good, i.e. (given this window
 // is good) iff the base just before / just after it is good.
 template <int N>
-LASV_HD uint32_t kmer_occurrence(const uint64_t *P, const uint64_t *PR, const uint64_t *BD, int R,
+LASV_HD uint32_t kmer_occurrence(const uint32_t *P, const uint32_t *PR, const uint32_t *BD, int R,
                                  int j, int k, uint64_t (&key)[N]) {
   uint64_t fw[N], rc[N];
   extract_kmer<N>(P, j, k, fw);

@@ -44,14 +44,13 @@ struct HostOps {
 };
 
 struct Tile {
-  int T, R, CHUNKS;
-  std::vector<uint64_t> P, PR, BD;
-  explicit Tile(int t) : T(t), R(t + TileGeom::HALO_L + TileGeom::HALO_R), CHUNKS(R / 16) {
-    P.assign(R / 32 + 2, 0);
-    PR.assign(R / 32 + 2, 0);
-    BD.assign(R / 64 + 2, 0);
-    BD[R / 64] = ~0ull;
-    BD[R / 64 + 1] = ~0ull;
+  int T, R, CHUNKS, WORDS;
+  std::vector<uint32_t> P, PR, BD;
+  explicit Tile(int t)
+      : T(t), R(t + TileGeom::HALO_L + TileGeom::HALO_R), CHUNKS(R / 16), WORDS(R / 32) {
+    P.assign(R / 16 + TileGeom::PADW + 2, 0);
+    PR.assign(R / 16 + TileGeom::PADW + 2, 0);
+    BD.assign(WORDS + 4, ~0u);
   }
   // mirrors build_kernel's issue_stage + stage phase
   void stage(const uint8_t *seq, const uint8_t *qual, uint64_t n_bytes, uint32_t lead, uint64_t tile,
@@ -73,9 +72,9 @@ struct Tile {
       }
       uint32_t code32, bad16;
       classify16(sv, qv, qual != nullptr, cutoff, inr, code32, bad16);
-      reinterpret_cast<uint32_t *>(P.data())[code_u32_index(c)] = code32;
-      reinterpret_cast<uint32_t *>(PR.data())[code_u32_index(CHUNKS - 1 - c)] = rc_code32(code32);
-      reinterpret_cast<uint16_t *>(BD.data())[bad_u16_index(c)] = (uint16_t)bad16;
+      P[TileGeom::PADW + c] = code32;
+      PR[TileGeom::PADW + (CHUNKS - 1 - c)] = rc_code32(code32);
+      reinterpret_cast<uint16_t *>(BD.data())[c ^ 1] = (uint16_t)bad16;
     }
   }
 };
@@ -98,12 +97,17 @@ void walk(const uint8_t *seq_in, const uint8_t *qual_in, uint64_t n_in, int k, i
   const uint64_t n_tiles = (n_bytes + T - 1) / T;
   for (uint64_t t = 0; t < n_tiles; t++) {
     tile.stage(seq, qual, n_bytes, lead, t, cutoff);
-    for (int pos = 0; pos < T; pos++) {
-      const int j = TileGeom::HALO_L + pos;
-      if (!window_good(tile.BD.data(), j, k)) continue;
-      uint64_t key[N];
-      const uint32_t edge = kmer_occurrence<N>(tile.P.data(), tile.PR.data(), tile.BD.data(), tile.R, j, k, key);
-      sink(key, edge);
+    // mirrors the validity + ordered compaction phase: one word per "thread"
+    for (int w = 0; w < tile.WORDS; w++) {
+      uint32_t vbits = valid_window_word(tile.BD.data(), w, k) & tile_word_mask(w, T);
+      while (vbits) {
+        const int b = clz32(vbits);
+        vbits &= ~(0x80000000u >> b);
+        const int j = 32 * w + b;  // == HALO_L + pos
+        uint64_t key[N];
+        const uint32_t edge = kmer_occurrence<N>(tile.P.data(), tile.PR.data(), tile.BD.data(), tile.R, j, k, key);
+        sink(key, edge);
+      }
     }
   }
 }
