@@ -86,128 +86,119 @@ __device__ __forceinline__ void load_record(const uint32_t *src, uint64_t (&key)
 // --------------------------------------------------------------------------
 // build_kernel
 // --------------------------------------------------------------------------
+// One WARP owns one tile: it stages, classifies, erodes, compacts and inserts on
+// its own, synchronising with __syncwarp only -- the eight warps of a CTA never
+// wait for each other, so staging in one warp overlaps table probes in another.
 template <int MODE>
 struct TileCfg {
-  static constexpr int T = (MODE == MODE_ROUTE) ? 1024 : 2048;  // window starts per tile
-  static constexpr int R = T + TileGeom::HALO_L + TileGeom::HALO_R;  // region bases (multiple of 64)
-  static constexpr int CHUNKS = R / 16;
+  // window starts per tile; region = T + 128 bases, a whole number of 32-lane rounds
+  static constexpr int T = (MODE == MODE_ROUTE) ? 384 : 896;
+  static constexpr int R = T + TileGeom::HALO_L + TileGeom::HALO_R;
+  static constexpr int CHUNKS = R / 16;  // 16-base chunks: 32 or 64 -> one or two per lane
+  static constexpr int WORDS = R / 32;   // validity words: 16 or 32 -> at most one per lane
 };
 
 template <int N, int MODE>
-__global__ void __launch_bounds__(THREADS, 4) build_kernel(const BuildParams p, const uint64_t n_tiles) {
+struct WarpTile {
   using Cfg = TileCfg<MODE>;
-  constexpr int T = Cfg::T, R = Cfg::R, CHUNKS = Cfg::CHUNKS;
-  static_assert(CHUNKS <= THREADS, "one staging chunk per thread");
-  static_assert(R % 64 == 0, "region must be whole bad-bit words");
+  uint32_t P[Cfg::CHUNKS + TileGeom::PADW + 2];
+  uint32_t PR[Cfg::CHUNKS + TileGeom::PADW + 2];
+  uint32_t BD[Cfg::WORDS + 4];
+  uint16_t pos[Cfg::T];
+  // ROUTE only: the tile's records wait here until per-destination space is reserved
+  uint32_t stash[(MODE == MODE_ROUTE) ? Cfg::T * (2 * N + 1) : 1];
+  uint8_t dest[(MODE == MODE_ROUTE) ? Cfg::T : 4];
+  uint32_t bin_count[16];
+  uint32_t bin_rank[16];
+  unsigned long long tile_base[16];
+};
+
+template <int N, int MODE>
+__global__ void __launch_bounds__(THREADS, (MODE == MODE_ROUTE) ? 3 : 4)
+build_kernel(const BuildParams p, const uint64_t n_tiles) {
+  using Cfg = TileCfg<MODE>;
+  constexpr int T = Cfg::T, R = Cfg::R, CHUNKS = Cfg::CHUNKS, WORDS = Cfg::WORDS;
+  static_assert(CHUNKS % 32 == 0 && WORDS <= 32 && R % 64 == 0, "tile must map onto whole warp rounds");
   constexpr int RECW = 2 * N + 1;
+  constexpr int WARPS = THREADS / 32;
 
-  constexpr int WORDS = R / 32;  // 32-position words of the bad / valid bit strings
-  static_assert(WORDS <= THREADS, "one validity word per thread");
-  __shared__ uint32_t sP[R / 16 + TileGeom::PADW + 2];
-  __shared__ uint32_t sPR[R / 16 + TileGeom::PADW + 2];
-  __shared__ uint32_t sBD[WORDS + 4];
-  __shared__ uint16_t sPos[T];
-  __shared__ uint32_t sWarpSum[THREADS / 32];
-  __shared__ unsigned long long sTileBase[16];
-  __shared__ uint32_t sBinCount[16];
-  __shared__ uint32_t sBinRank[16];
-  // ROUTE only: records of the tile wait here until the per-destination space is reserved
-  __shared__ uint32_t sStash[(MODE == MODE_ROUTE) ? T * RECW : 1];
-  __shared__ uint8_t sDest[(MODE == MODE_ROUTE) ? T : 1];
-
-  const int tid = threadIdx.x;
+  extern __shared__ __align__(16) unsigned char sTilesRaw[];  // WARPS tiles (dynamic: ROUTE exceeds 48 KB)
+  WarpTile<N, MODE> &wt = reinterpret_cast<WarpTile<N, MODE> *>(sTilesRaw)[threadIdx.x >> 5];
+  const unsigned lane = lane_id();
   const bool has_qual = p.qual != nullptr;
   const int k = p.k;
 
-  if (tid < TileGeom::PADW + 2) {  // pad words: zeros around the code strings, all-bad behind BD
-    const int tail = R / 16 + TileGeom::PADW;
-    if (tid < TileGeom::PADW) { sP[tid] = 0; sPR[tid] = 0; }
-    else { sP[tail + tid - TileGeom::PADW] = 0; sPR[tail + tid - TileGeom::PADW] = 0; }
-    sBD[WORDS + tid] = ~0u;
+  if (lane < TileGeom::PADW + 2) {  // pad words: zeros around the code strings, all-bad behind BD
+    if (lane < TileGeom::PADW) { wt.P[lane] = 0; wt.PR[lane] = 0; }
+    else { wt.P[CHUNKS + lane] = 0; wt.PR[CHUNKS + lane] = 0; }
+    wt.BD[WORDS + lane] = ~0u;
   }
 
   unsigned long long my_new = 0;    // keys this thread created
-  unsigned long long my_kmers = 0;  // thread 0 only: occurrences in this CTA's tiles
+  unsigned long long my_kmers = 0;  // lane 0: occurrences in this warp's tiles
 
-  // software pipeline: the staging loads of the next tile are issued before the
-  // heavy phase of the current one
-  uint4 sv = make_uint4(0, 0, 0, 0), qv = make_uint4(0, 0, 0, 0);
-  uint32_t inr = 0;
-  auto issue_stage = [&](uint64_t tile) {
-    inr = 0;
-    if (tid < CHUNKS && tile < n_tiles) {
-      const long long g = (long long)(tile * (uint64_t)T) - TileGeom::HALO_L + 16ll * tid;
-      inr = chunk_inrange16(g, p.lead, p.n_bytes);
+  const uint64_t warp_global = (uint64_t)blockIdx.x * WARPS + (threadIdx.x >> 5);
+  const uint64_t warp_stride = (uint64_t)gridDim.x * WARPS;
+
+  for (uint64_t tile = warp_global; tile < n_tiles; tile += warp_stride) {
+    __syncwarp();  // previous tile fully consumed before its strings are overwritten
+    // ---- stage: 16 bytes of both streams per lane and round, classify, pack
+#pragma unroll
+    for (int c = (int)lane; c < CHUNKS; c += 32) {
+      const long long g = (long long)(tile * (uint64_t)T) - TileGeom::HALO_L + 16ll * c;
+      const uint32_t inr = chunk_inrange16(g, p.lead, p.n_bytes);
+      uint4 sv = make_uint4(0, 0, 0, 0), qv = make_uint4(0, 0, 0, 0);
       if (inr) {
         sv = __ldg(reinterpret_cast<const uint4 *>(p.seq + g));
         if (has_qual) qv = __ldg(reinterpret_cast<const uint4 *>(p.qual + g));
       }
-    }
-  };
-
-  uint64_t tile = blockIdx.x;
-  issue_stage(tile);
-
-  for (; tile < n_tiles; tile += gridDim.x) {
-    // ---- stage: classify + pack this thread's 16 bases into the bit strings
-    if (tid < CHUNKS) {
       uint32_t code32, bad16;
       classify16(sv, qv, has_qual, p.cutoff, inr, code32, bad16);
-      sP[TileGeom::PADW + tid] = code32;
-      sPR[TileGeom::PADW + (CHUNKS - 1 - tid)] = rc_code32(code32);
-      reinterpret_cast<uint16_t *>(sBD)[tid ^ 1] = (uint16_t)bad16;  // big-endian halves of a 32-bit word
+      wt.P[TileGeom::PADW + c] = code32;
+      wt.PR[TileGeom::PADW + (CHUNKS - 1 - c)] = rc_code32(code32);
+      reinterpret_cast<uint16_t *>(wt.BD)[c ^ 1] = (uint16_t)bad16;  // big-endian halves of a 32-bit word
     }
-    if (MODE == MODE_ROUTE && tid < 16) { sBinCount[tid] = 0; sBinRank[tid] = 0; }
-    __syncthreads();
+    if (MODE == MODE_ROUTE && lane < 16) { wt.bin_count[lane] = 0; wt.bin_rank[lane] = 0; }
+    __syncwarp();
 
-    issue_stage(tile + gridDim.x);  // next tile's bytes fly during the heavy phase
-
-    // ---- window validity by word-parallel erosion, then an ordered dense list of
-    //      the good window starts (block scan over one popcount per word)
+    // ---- window validity by word-parallel erosion (one word per lane), then an
+    //      ordered dense list of the good window starts (warp scan of popcounts)
     uint32_t vbits = 0;
-    if (tid < WORDS) vbits = valid_window_word(sBD, tid, k) & tile_word_mask(tid, T);
+    if ((int)lane < WORDS) vbits = valid_window_word(wt.BD, (int)lane, k) & tile_word_mask((int)lane, T);
     const uint32_t vcnt = (uint32_t)__popc(vbits);
     uint32_t incl = vcnt;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       const uint32_t y = __shfl_up_sync(FULL, incl, o);
-      if ((int)lane_id() >= o) incl += y;
+      if ((int)lane >= o) incl += y;
     }
-    if (lane_id() == 31) sWarpSum[tid >> 5] = incl;
-    __syncthreads();
-    uint32_t wbase = 0, total = 0;
-#pragma unroll
-    for (int w2 = 0; w2 < THREADS / 32; w2++) {
-      const uint32_t ws = sWarpSum[w2];
-      if (w2 < (tid >> 5)) wbase += ws;
-      total += ws;
-    }
+    const int M = (int)__shfl_sync(FULL, incl, 31);
     {
-      uint32_t idx = wbase + incl - vcnt;
+      uint32_t idx = incl - vcnt;
       while (vbits) {
         const int b = __clz((int)vbits);
-        sPos[idx++] = (uint16_t)(32 * tid + b - TileGeom::HALO_L);
+        wt.pos[idx++] = (uint16_t)(32 * (int)lane + b - TileGeom::HALO_L);
         vbits &= ~(0x80000000u >> b);
       }
     }
-    __syncthreads();
-    const int M = (int)total;
-    if (tid == 0 && (MODE != MODE_FUSED || p.pass == 0)) my_kmers += (unsigned long long)M;
+    __syncwarp();
+    if (lane == 0 && (MODE != MODE_FUSED || p.pass == 0)) my_kmers += (unsigned long long)M;
 
+    unsigned long long rec_base = 0;
     if (MODE == MODE_RECORDS) {
-      if (tid == 0) sTileBase[0] = M ? atomicAdd(p.rec_count, (unsigned long long)M) : 0ull;
-      __syncthreads();
+      if (lane == 0 && M) rec_base = atomicAdd(p.rec_count, (unsigned long long)M);
+      rec_base = __shfl_sync(FULL, rec_base, 0);
     }
 
     // ---- heavy phase over the dense list of good windows
-    for (int base = 0; base < M; base += THREADS) {
-      const int i = base + tid;
+    for (int base = 0; base < M; base += 32) {
+      const int i = base + (int)lane;
       const bool active = i < M;
       uint64_t key[N];
       uint32_t edge = 0, count = 1;
       if (active) {
-        const int j = TileGeom::HALO_L + (int)sPos[i];
-        edge = kmer_occurrence<N>(sP, sPR, sBD, R, j, k, key);
+        const int j = TileGeom::HALO_L + (int)wt.pos[i];
+        edge = kmer_occurrence<N>(wt.P, wt.PR, wt.BD, R, j, k, key);
       } else {
 #pragma unroll
         for (int w = 0; w < N; w++) key[w] = 0;
@@ -239,7 +230,7 @@ __global__ void __launch_bounds__(THREADS, 4) build_kernel(const BuildParams p, 
         }
       } else if (MODE == MODE_RECORDS) {
         if (active) {
-          const unsigned long long idx = sTileBase[0] + (unsigned long long)i;
+          const unsigned long long idx = rec_base + (unsigned long long)i;
           if (idx < p.rec_capacity) store_record<N>(p.rec_out + idx * RECW, key, edge, 1u);
           else atomicExch(p.rec_overflow, 1ull);
         }
@@ -247,42 +238,41 @@ __global__ void __launch_bounds__(THREADS, 4) build_kernel(const BuildParams p, 
         if (active) {
           const Hash3 h = lookup3_key<N>(key, 0);
           const uint32_t d = (h.c >> p.owner_shift) & (uint32_t)(p.n_dest - 1);
-          store_record<N>(sStash + i * RECW, key, edge, 1u);
-          sDest[i] = (uint8_t)d;
-          atomicAdd(&sBinCount[d], 1u);
+          store_record<N>(wt.stash + i * RECW, key, edge, 1u);
+          wt.dest[i] = (uint8_t)d;
+          atomicAdd(&wt.bin_count[d], 1u);
         }
       }
     }
 
     if (MODE == MODE_ROUTE) {
-      __syncthreads();
-      if (tid < p.n_dest) {
-        const uint32_t c = sBinCount[tid];
-        sTileBase[tid] = c ? atomicAdd(p.rec_count + tid, (unsigned long long)c) : 0ull;
+      __syncwarp();
+      if ((int)lane < p.n_dest) {
+        const uint32_t c = wt.bin_count[lane];
+        wt.tile_base[lane] = c ? atomicAdd(p.rec_count + lane, (unsigned long long)c) : 0ull;
       }
-      __syncthreads();
-      for (int i = tid; i < M; i += THREADS) {
-        const uint32_t d = sDest[i];
-        const unsigned long long idx = sTileBase[d] + atomicAdd(&sBinRank[d], 1u);
+      __syncwarp();
+      for (int i = (int)lane; i < M; i += 32) {
+        const uint32_t d = wt.dest[i];
+        const unsigned long long idx = wt.tile_base[d] + atomicAdd(&wt.bin_rank[d], 1u);
         if (idx < p.rec_capacity) {
           uint32_t *dst = p.rec_out + ((uint64_t)d * p.rec_capacity + idx) * RECW;
 #pragma unroll
-          for (int w = 0; w < RECW; w++) dst[w] = sStash[i * RECW + w];
+          for (int w = 0; w < RECW; w++) dst[w] = wt.stash[i * RECW + w];
         } else {
           atomicExch(p.rec_overflow, 1ull);
         }
       }
     }
-    __syncthreads();  // smem is re-staged by the next iteration
   }
 
-  // ---- CTA-level counters
+  // ---- warp-level counters
   if (MODE == MODE_FUSED || MODE == MODE_BIN) {
 #pragma unroll
     for (int o = 16; o; o >>= 1) my_new += __shfl_xor_sync(FULL, my_new, o);
-    if (lane_id() == 0 && my_new) atomicAdd(&p.ctr->unique_kmers, my_new);
+    if (lane == 0 && my_new) atomicAdd(&p.ctr->unique_kmers, my_new);
   }
-  if (tid == 0 && my_kmers) atomicAdd(&p.ctr->kmers_inserted, my_kmers);
+  if (lane == 0 && my_kmers) atomicAdd(&p.ctr->kmers_inserted, my_kmers);
 }
 
 // --------------------------------------------------------------------------
@@ -700,7 +690,6 @@ __global__ void __launch_bounds__(THREADS) find_kernel(const TableView t,
                                                       const uint64_t *__restrict__ keys,
                                                       const uint64_t n, const int finalized,
                                                       uint32_t *covg, uint8_t *edges, uint8_t *found) {
-  constexpr uint32_t STRIDE = 8 * N + 8;
   for (uint64_t i = (uint64_t)blockIdx.x * THREADS + threadIdx.x; i < n;
        i += (uint64_t)gridDim.x * THREADS) {
     uint64_t key[N];
@@ -796,9 +785,9 @@ void dispatch_n(int N, F &&f) {
 }
 
 template <typename K>
-int resident_grid(K kernel, int cap_per_sm = 8) {
+int resident_grid(K kernel, int cap_per_sm = 8, size_t dyn_smem = 0) {
   int per_sm = 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, THREADS, 0);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, THREADS, dyn_smem);
   if (per_sm < 1) per_sm = 1;
   if (per_sm > cap_per_sm) per_sm = cap_per_sm;
   return per_sm * sm_count();
@@ -820,16 +809,23 @@ void launch_build(int N, BuildMode mode, const BuildParams &p, cudaStream_t st) 
   if (p.n_bytes == 0) return;
   dispatch_n(N, [&](auto n) {
     constexpr int NN = decltype(n)::value;
-    auto go = [&](auto kernel, int T) {
-      const uint64_t n_tiles = (p.n_bytes + T - 1) / T;
-      uint64_t grid = (uint64_t)resident_grid(kernel);
-      if (grid > n_tiles) grid = n_tiles;
-      kernel<<<(unsigned)grid, THREADS, 0, st>>>(p, n_tiles);
+    auto go = [&](auto kernel, int T, size_t smem) {
+      cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      const uint64_t n_tiles = (p.n_bytes + T - 1) / T;  // one tile per warp and round
+      uint64_t grid = (uint64_t)resident_grid(kernel, 8, smem);
+      const uint64_t need = (n_tiles + THREADS / 32 - 1) / (THREADS / 32);
+      if (grid > need) grid = need;
+      kernel<<<(unsigned)grid, THREADS, smem, st>>>(p, n_tiles);
     };
-    if (mode == MODE_FUSED) go(build_kernel<NN, MODE_FUSED>, TileCfg<MODE_FUSED>::T);
-    else if (mode == MODE_BIN) go(build_kernel<NN, MODE_BIN>, TileCfg<MODE_BIN>::T);
-    else if (mode == MODE_RECORDS) go(build_kernel<NN, MODE_RECORDS>, TileCfg<MODE_RECORDS>::T);
-    else go(build_kernel<NN, MODE_ROUTE>, TileCfg<MODE_ROUTE>::T);
+    constexpr int W8 = THREADS / 32;
+    if (mode == MODE_FUSED)
+      go(build_kernel<NN, MODE_FUSED>, TileCfg<MODE_FUSED>::T, W8 * sizeof(WarpTile<NN, MODE_FUSED>));
+    else if (mode == MODE_BIN)
+      go(build_kernel<NN, MODE_BIN>, TileCfg<MODE_BIN>::T, W8 * sizeof(WarpTile<NN, MODE_BIN>));
+    else if (mode == MODE_RECORDS)
+      go(build_kernel<NN, MODE_RECORDS>, TileCfg<MODE_RECORDS>::T, W8 * sizeof(WarpTile<NN, MODE_RECORDS>));
+    else
+      go(build_kernel<NN, MODE_ROUTE>, TileCfg<MODE_ROUTE>::T, W8 * sizeof(WarpTile<NN, MODE_ROUTE>));
   });
 }
 

@@ -44,7 +44,7 @@ def table_records(table):
     return out
 
 
-def emul_build(emul, meta, seq, qual, T=2048, L=None, W=None):
+def emul_build(emul, meta, seq, qual, T=896, L=None, W=None):
     k = meta["k"]
     L = L or meta["L"]
     W = W or meta["W"]
@@ -60,7 +60,7 @@ def emul_build(emul, meta, seq, qual, T=2048, L=None, W=None):
 
 
 @pytest.mark.parametrize("name", util.ALL_CASES)
-@pytest.mark.parametrize("T", [2048, 1024])
+@pytest.mark.parametrize("T", [896, 384, 2048])
 def test_emulated_build_matches_reference_golden(emul, name, T):
     meta = util.case_meta(name)
     seq, qual, _ = util.case_streams(name)
@@ -141,7 +141,7 @@ def test_emulated_records_path(emul, name):
     seq, qual, _ = util.case_streams(name)
     cap = meta["inserts"] + 10
     recs = np.zeros((cap, 2 * N + 1), dtype=np.uint32)
-    n = emul.emul_extract_records(seq.ctypes.data, qual.ctypes.data, len(seq), k, util.cutoff_of(meta), 1024,
+    n = emul.emul_extract_records(seq.ctypes.data, qual.ctypes.data, len(seq), k, util.cutoff_of(meta), 384,
                                   recs.ctypes.data, cap)
     assert n == meta["inserts"]
     # shard the records by owner bits exactly as the ROUTE mode does and insert per shard
@@ -188,7 +188,7 @@ def test_emulated_ragged_and_tiny_inputs(emul):
         meta = {"k": k, "L": 8, "W": 60, "q_thresh": 5}
         g, ok = util.oracle_build(k, 8, 60, seq, qual, offs, 38)
         assert ok
-        for T in (1024, 2048, 2048 | (5 << 16), 1024 | (15 << 16)):    # last two: misaligned stream pointer
+        for T in (384, 896, 896 | (5 << 16), 384 | (15 << 16)):    # last two: misaligned stream pointer
             rc, table, ctr = emul_build(emul, meta, seq, qual, T)
             assert rc == 0
             util.assert_same_records(table_records(table), g.records(), f"k={k}")

@@ -51,7 +51,7 @@ def _worker(rank, world, port, name, outdir):
     s, q = np.ascontiguousarray(seq[lo:hi]), np.ascontiguousarray(qual[lo:hi])
     cap = meta["inserts"] + 8
     recs = np.zeros((cap, rw), dtype=np.uint32)
-    n = emul.emul_extract_records(s.ctypes.data, q.ctypes.data, len(s), k, util.cutoff_of(meta), 1024,
+    n = emul.emul_extract_records(s.ctypes.data, q.ctypes.data, len(s), k, util.cutoff_of(meta), 384,
                                   recs.ctypes.data, cap)
     recs = recs[:n]
     bits = int(np.log2(world))
