@@ -204,7 +204,7 @@ int ensure_bins(lasv_graph *g, uint64_t n_bytes, uint32_t n_bins) {
     if (g->N >= 2) CUDA_TRY(cudaMalloc(&g->bins.keyA, total * sizeof(ulonglong2)));
     if (g->N & 1) CUDA_TRY(cudaMalloc(&g->bins.keyB, total * sizeof(uint64_t)));
     CUDA_TRY(cudaMalloc(&g->bins.meta, total * sizeof(uint16_t)));
-    CUDA_TRY(cudaMalloc(&g->bins.count, n_bins * sizeof(unsigned int)));
+    CUDA_TRY(cudaMalloc(&g->bins.count, (size_t)n_bins * COUNT_STRIDE * sizeof(unsigned int)));
     CUDA_TRY(cudaMalloc(&g->bins.prefix, (n_bins + 1) * sizeof(uint32_t)));
     g->bins.cap = (uint32_t)cap;
     g->bins.n_bins = n_bins;
@@ -366,7 +366,7 @@ int lasv_graph_load_reads_device(lasv_graph *g, const uint8_t *d_seq, const uint
       // the insert rate of uniformly random probes on a 100 GB table).
       if (int e = ensure_bins(g, n_bytes, n_bins)) return e;
       p.bins = g->bins;
-      CUDA_TRY(cudaMemsetAsync(g->bins.count, 0, n_bins * sizeof(unsigned int), st));
+      CUDA_TRY(cudaMemsetAsync(g->bins.count, 0, (size_t)n_bins * COUNT_STRIDE * sizeof(unsigned int), st));
       launch_build(g->N, MODE_BIN, p, st);
       if (int e = check_launch()) return e;
       launch_bin_prefix(g->bins, st);

@@ -217,7 +217,7 @@ build_kernel(const BuildParams p, const uint64_t n_tiles) {
       } else if (MODE == MODE_BIN) {
         if (active) {  // duplicates meet again, side by side, in insert_bins_kernel
           const uint32_t bin = (lookup3_key<N>(key, 0).c & p.table.bucket_mask) >> p.bins.bin_shift;
-          const uint32_t idx = atomicAdd(&p.bins.count[bin], 1u);
+          const uint32_t idx = atomicAdd(&p.bins.count[bin * COUNT_STRIDE], 1u);
           if (idx < p.bins.cap) {
             const uint64_t at = (uint64_t)bin * p.bins.cap + idx;
             if (N >= 2) p.bins.keyA[at] = make_ulonglong2(key[0], key[1 % N]);
@@ -288,7 +288,7 @@ __global__ void __launch_bounds__(1024) bin_prefix_kernel(const BinView b) {
     const uint32_t i = base + threadIdx.x;
     uint32_t v = 0;
     if (i < b.n_bins) {
-      v = b.count[i];
+      v = b.count[i * COUNT_STRIDE];
       if (v > b.cap) v = b.cap;
     }
     uint32_t x = v;

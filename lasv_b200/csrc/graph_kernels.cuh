@@ -18,11 +18,14 @@ enum BuildMode { MODE_FUSED = 0, MODE_RECORDS = 1, MODE_ROUTE = 2, MODE_BIN = 3 
 // the slice of the table they will touch (bin = bucket >> bin_shift), so that the
 // insert kernel walks the table region by region (L2- and DRAM-row-friendly)
 // instead of at random.  Structure of arrays, one fixed-capacity stripe per bin.
+constexpr uint32_t COUNT_STRIDE = 32;  // uint32 units = 128 bytes
 struct BinView {
   ulonglong2 *keyA;     // [n_bins*cap] key words 0,1          (N >= 2)
   uint64_t *keyB;       // [n_bins*cap] last key word          (N odd)
   uint16_t *meta;       // [n_bins*cap] edges | count << 8
-  unsigned int *count;  // [n_bins]     records wanted per bin (may exceed cap: the excess went straight to the table)
+  unsigned int *count;  // [n_bins*COUNT_STRIDE] records wanted per bin, ONE COUNTER PER 128-BYTE LINE: the L2
+                        // atomic unit serialises per line, 8 counters in a line would share one queue
+                        // (a count may exceed cap: the excess went straight to the table)
   uint32_t *prefix;     // [n_bins+1]   exclusive prefix of min(count, cap)
   uint32_t cap;
   uint32_t bin_shift;
