@@ -445,11 +445,13 @@ def main():
     barrier()
     t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     wall0 = time.monotonic()
+    torch.cuda.profiler.start()        # `ncu --profile-from-start off` sees the timed steps only
     t_begin.record()
     for s in range(K):
         step(0 if cfg0 else Wm + s, s)
     t_end.record()
     barrier()
+    torch.cuda.profiler.stop()
     wall1 = time.monotonic()
     launches = lib.lasv_kernel_launches() - l0
     dt = max_over_ranks(t_begin.elapsed_time(t_end) * 1e-3)

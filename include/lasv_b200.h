@@ -98,9 +98,12 @@ long long lasv_graph_unique_kmers(lasv_graph *g);
 long long lasv_graph_capacity(lasv_graph *g);
 int lasv_graph_words_per_kmer(lasv_graph *g);
 size_t lasv_graph_element_bytes(lasv_graph *g);
-/* Device address of the slot array (reference Element layout; pad bytes carry
- * tags until lasv_graph_finalize). */
+/* Device address and size of the table memory.  Until lasv_graph_finalize a
+ * bucket is ceil(W/G) lines of 128 bytes (8 tag bytes + G Elements, G = 7/5/3
+ * for N = 1/2/3); afterwards it is W consecutive reference Elements at the start
+ * of the same bytes.  lasv_graph_export_table packs the buckets for the host. */
 void *lasv_graph_device_table(lasv_graph *g);
+uint64_t lasv_graph_device_table_bytes(lasv_graph *g);
 
 /* THE HOT PATH.  One batch of reads as two byte streams (sequence, quality):
  * reads back to back, every read followed by exactly `1` separator byte '\n'

@@ -56,7 +56,7 @@ class RefHashTable(C.Structure):
 EXPORTS = [
     "lasv_last_error", "lasv_device_count", "lasv_version", "lasv_graph_new", "lasv_graph_free",
     "lasv_graph_clear", "lasv_graph_unique_kmers", "lasv_graph_capacity", "lasv_graph_words_per_kmer",
-    "lasv_graph_element_bytes", "lasv_graph_device_table", "lasv_graph_load_reads_device",
+    "lasv_graph_element_bytes", "lasv_graph_device_table", "lasv_graph_device_table_bytes", "lasv_graph_load_reads_device",
     "lasv_graph_load_reads_host", "lasv_graph_stats", "lasv_graph_rehash_histogram",
     "lasv_graph_route_reads_device", "lasv_graph_extract_records_device",
     "lasv_graph_insert_records_device", "lasv_graph_read_stats_device", "lasv_graph_find",
@@ -100,6 +100,8 @@ def lib() -> C.CDLL:
     L.lasv_graph_element_bytes.argtypes = [vp]
     L.lasv_graph_device_table.restype = vp
     L.lasv_graph_device_table.argtypes = [vp]
+    L.lasv_graph_device_table_bytes.restype = C.c_uint64
+    L.lasv_graph_device_table_bytes.argtypes = [vp]
     L.lasv_graph_load_reads_device.argtypes = [vp, vp, vp, u64, vp, u64, i32, vp]
     L.lasv_graph_load_reads_host.argtypes = [vp, vp, vp, u64, vp, u64, i32, C.POINTER(LoadStats)]
     L.lasv_graph_stats.argtypes = [vp, C.POINTER(LoadStats), vp, u64, vp]

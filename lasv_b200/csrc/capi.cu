@@ -67,8 +67,8 @@ struct lasv_graph {
   int k = 0, N = 0, L = 0, W = 0, max_rehash = 15, device = 0;
   uint64_t n_buckets = 0, n_slots = 0;
   size_t slot_bytes = 0;
-  uint8_t *d_slots = nullptr;
-  uint8_t *d_tags = nullptr;  // one tag byte per slot (table.cuh)
+  uint8_t *d_lines = nullptr;  // 2^L buckets x NL lines of 128 bytes (kmer_core.cuh, "line layout")
+  uint64_t table_bytes = 0;
   GraphCounters *d_ctr = nullptr;
   ReadStats *d_stats = nullptr;
   unsigned long long *d_hist = nullptr;
@@ -83,13 +83,7 @@ struct lasv_graph {
   uint32_t bins_alloc_n = 0;
 
   TableView view() const {
-    TableView t;
-    t.slots = d_slots;
-    t.tags = d_tags;
-    t.bucket_mask = (uint32_t)(n_buckets - 1);
-    t.W = (uint32_t)W;
-    t.max_rehash = (uint32_t)max_rehash;
-    return t;
+    return make_table_view(d_lines, N, L, W, max_rehash, finalized);
   }
 };
 
@@ -161,9 +155,7 @@ BuildParams build_params(lasv_graph *g, const uint8_t *d_seq, const uint8_t *d_q
 }
 
 void free_bins(lasv_graph *g) {
-  cudaFree(g->bins.keyA);
-  cudaFree(g->bins.keyB);
-  cudaFree(g->bins.meta);
+  cudaFree(g->bins.recs);
   cudaFree(g->bins.count);
   cudaFree(g->bins.prefix);
   g->bins = BinView{};
@@ -175,9 +167,12 @@ void free_bins(lasv_graph *g) {
 // puts a useful number of records into every region.  LASV_B200_INSERT=direct|binned
 // overrides the choice (tests, experiments).
 bool want_binned(const lasv_graph *g, uint64_t n_bytes, uint32_t *n_bins_out) {
-  const uint64_t table_bytes = g->n_slots * g->slot_bytes;
+  const uint64_t table_bytes = g->table_bytes;
   uint32_t n_bins = 1;
-  while ((uint64_t)n_bins * (16ull << 20) < table_bytes && n_bins < 65536u && n_bins < g->n_buckets) n_bins <<= 1;
+  // regions of <= 64 MB: the insert rate doubles once the region all SMs work on at a time is
+  // ~100 MB or less and is flat below that (profiles/: bins sweep), while fewer bins keep the
+  // scatter's open write streams few
+  while ((uint64_t)n_bins * (64ull << 20) < table_bytes && n_bins < 65536u && n_bins < g->n_buckets) n_bins <<= 1;
   if (const char *e = getenv("LASV_B200_BINS")) {  // tests: force a bin count on small tables
     const long v = atol(e);
     if (v >= 1 && v <= 65536 && (v & (v - 1)) == 0 && (uint64_t)v <= g->n_buckets) n_bins = (uint32_t)v;
@@ -201,9 +196,7 @@ int ensure_bins(lasv_graph *g, uint64_t n_bytes, uint32_t n_bins) {
     const uint64_t cap = (want + n_bins - 1) / n_bins;
     if (cap > 0xFFFFFFF0ull) return fail(LASV_ERR_ARG, "batch too large for the bin stripes");
     const uint64_t total = cap * n_bins;
-    if (g->N >= 2) CUDA_TRY(cudaMalloc(&g->bins.keyA, total * sizeof(ulonglong2)));
-    if (g->N & 1) CUDA_TRY(cudaMalloc(&g->bins.keyB, total * sizeof(uint64_t)));
-    CUDA_TRY(cudaMalloc(&g->bins.meta, total * sizeof(uint16_t)));
+    CUDA_TRY(cudaMalloc(&g->bins.recs, total * (size_t)bin_record_words(g->N) * sizeof(uint64_t)));
     CUDA_TRY(cudaMalloc(&g->bins.count, (size_t)n_bins * COUNT_STRIDE * sizeof(unsigned int)));
     CUDA_TRY(cudaMalloc(&g->bins.prefix, (n_bins + 1) * sizeof(uint32_t)));
     g->bins.cap = (uint32_t)cap;
@@ -278,9 +271,9 @@ lasv_graph *lasv_graph_new(int kmer_size, int number_bits, int bucket_size, int 
   g->n_buckets = 1ull << number_bits;
   g->n_slots = g->n_buckets * (uint64_t)bucket_size;
   g->slot_bytes = 8 * (size_t)g->N + 8;
+  g->table_bytes = table_bytes(g->view());
   bool ok = cudaSetDevice(device) == cudaSuccess &&
-            cudaMalloc(&g->d_slots, g->n_slots * g->slot_bytes) == cudaSuccess &&
-            cudaMalloc(&g->d_tags, g->n_slots + 32) == cudaSuccess &&
+            cudaMalloc(&g->d_lines, g->table_bytes) == cudaSuccess &&
             cudaMalloc(&g->d_ctr, sizeof(GraphCounters)) == cudaSuccess &&
             cudaMalloc(&g->d_stats, sizeof(ReadStats)) == cudaSuccess &&
             cudaMalloc(&g->d_hist, HIST_BINS * sizeof(unsigned long long)) == cudaSuccess &&
@@ -303,8 +296,7 @@ void lasv_graph_free(lasv_graph **gp) {
   lasv_graph *g = *gp;
   cudaSetDevice(g->device);
   cudaDeviceSynchronize();
-  cudaFree(g->d_slots);
-  cudaFree(g->d_tags);
+  cudaFree(g->d_lines);
   cudaFree(g->d_ctr);
   cudaFree(g->d_stats);
   cudaFree(g->d_hist);
@@ -326,8 +318,7 @@ void lasv_graph_free(lasv_graph **gp) {
 int lasv_graph_clear(lasv_graph *g, void *cuda_stream) {
   if (int e = use(g)) return e;
   cudaStream_t st = stream_of(g, cuda_stream);
-  CUDA_TRY(cudaMemsetAsync(g->d_slots, 0, g->n_slots * g->slot_bytes, st));
-  CUDA_TRY(cudaMemsetAsync(g->d_tags, 0, g->n_slots + 32, st));
+  CUDA_TRY(cudaMemsetAsync(g->d_lines, 0, g->table_bytes, st));
   CUDA_TRY(cudaMemsetAsync(g->d_ctr, 0, sizeof(GraphCounters), st));
   CUDA_TRY(cudaMemsetAsync(g->d_stats, 0, sizeof(ReadStats), st));
   CUDA_TRY(cudaMemsetAsync(g->d_hist, 0, HIST_BINS * sizeof(unsigned long long), st));
@@ -347,7 +338,8 @@ long long lasv_graph_unique_kmers(lasv_graph *g) {
 long long lasv_graph_capacity(lasv_graph *g) { return g ? (long long)g->n_slots : -1; }
 int lasv_graph_words_per_kmer(lasv_graph *g) { return g ? g->N : -1; }
 size_t lasv_graph_element_bytes(lasv_graph *g) { return g ? g->slot_bytes : 0; }
-void *lasv_graph_device_table(lasv_graph *g) { return g ? g->d_slots : nullptr; }
+void *lasv_graph_device_table(lasv_graph *g) { return g ? g->d_lines : nullptr; }
+uint64_t lasv_graph_device_table_bytes(lasv_graph *g) { return g ? g->table_bytes : 0; }
 
 // ------------------------------------------------------------- the hot path
 int lasv_graph_load_reads_device(lasv_graph *g, const uint8_t *d_seq, const uint8_t *d_qual,
@@ -378,7 +370,7 @@ int lasv_graph_load_reads_device(lasv_graph *g, const uint8_t *d_seq, const uint
       // TLB reach of a B200 (profiles/random_access_sweep_r1.jsonl): walk the batch
       // once per <=50 GB slice of the table.  LASV_B200_PASSES overrides.
       int n_pass = 1;
-      while ((g->n_slots * g->slot_bytes) / (uint64_t)n_pass > (50ull << 30) && (1 << g->L) > 2 * n_pass) n_pass *= 2;
+      while (g->table_bytes / (uint64_t)n_pass > (50ull << 30) && (1 << g->L) > 2 * n_pass) n_pass *= 2;
       if (const char *e = getenv("LASV_B200_PASSES")) {
         const int v = atoi(e);
         if (v >= 1 && v <= 64 && (v & (v - 1)) == 0 && v <= (1 << (g->L - 1))) n_pass = v;
@@ -582,7 +574,7 @@ int lasv_graph_find(lasv_graph *g, const uint64_t *keys, uint64_t n, uint32_t *c
     CUDA_TRY(cudaMalloc(&d_edges, n));
     CUDA_TRY(cudaMalloc(&d_found, n));
     CUDA_TRY(cudaMemcpyAsync(d_keys, keys, n * g->N * 8, cudaMemcpyHostToDevice, g->compute));
-    launch_find(g->N, g->view(), d_keys, n, g->finalized ? 1 : 0, d_covg, d_edges, d_found, g->compute);
+    launch_find(g->N, g->view(), d_keys, n, d_covg, d_edges, d_found, g->compute);
     if (int e = check_launch()) return e;
     CUDA_TRY(cudaMemcpyAsync(covg, d_covg, n * 4, cudaMemcpyDeviceToHost, g->compute));
     CUDA_TRY(cudaMemcpyAsync(edges, d_edges, n, cudaMemcpyDeviceToHost, g->compute));
@@ -639,7 +631,15 @@ int lasv_graph_export_table(lasv_graph *g, void *elements, short *next_element) 
   CUDA_TRY(cudaMalloc(&d_next, g->n_buckets * sizeof(int16_t)));
   int rc = [&]() -> int {
     if (int e = finalize_impl(g, d_next)) return e;
-    CUDA_TRY(cudaMemcpy(elements, g->d_slots, g->n_slots * g->slot_bytes, cudaMemcpyDeviceToHost));
+    // bucket b is W consecutive Elements at the start of its NL lines: a pitched copy
+    // (DMA engine) packs the buckets into the reference's contiguous Element[]
+    const size_t row = (size_t)g->W * g->slot_bytes, pitch = (size_t)(g->table_bytes / g->n_buckets);
+    const uint64_t rows_per_copy = 1ull << 20;
+    for (uint64_t b0 = 0; b0 < g->n_buckets; b0 += rows_per_copy) {
+      const uint64_t nb = std::min(rows_per_copy, g->n_buckets - b0);
+      CUDA_TRY(cudaMemcpy2D((uint8_t *)elements + b0 * row, row, g->d_lines + b0 * pitch, pitch, row,
+                            (size_t)nb, cudaMemcpyDeviceToHost));
+    }
     if (next_element)
       CUDA_TRY(cudaMemcpy(next_element, d_next, g->n_buckets * sizeof(int16_t), cudaMemcpyDeviceToHost));
     return LASV_OK;

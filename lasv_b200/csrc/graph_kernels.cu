@@ -47,6 +47,9 @@ __device__ __forceinline__ bool warp_aggregate(bool active, const uint64_t (&key
   for (int i = 0; i < N - 1; i++) sig = sig * 0x9E3779B97F4A7C15ull + key[i];
   if (!active) sig = ~0ull - lane_id();
   const unsigned grp = __match_any_sync(FULL, sig);
+  // Common case: 32 distinct keys.  (The reductions below run once per distinct lane
+  // mask, i.e. 32 times for 32 singleton groups -- never enter them for nothing.)
+  if (!__any_sync(FULL, (grp & (grp - 1u)) != 0u)) return active;
   const int leader = __ffs(grp) - 1;
   bool same = active;
 #pragma unroll
@@ -83,6 +86,99 @@ __device__ __forceinline__ void load_record(const uint32_t *src, uint64_t (&key)
   count = m >> 8;
 }
 
+// Bin records: one vector store / load per record (graph_kernels.cuh, BinView).
+template <int N>
+__device__ __forceinline__ void store_bin_record(uint64_t *dst, const uint64_t (&key)[N], uint64_t aux) {
+  if (N == 1) {
+    asm volatile("st.global.v2.u64 [%0], {%1,%2};" ::"l"(dst), "l"(key[0]), "l"(aux) : "memory");
+  } else {
+    const uint64_t w2 = (N == 2) ? aux : key[2 % N], w3 = (N == 2) ? 0ull : aux;
+    asm volatile("st.global.v4.u64 [%0], {%1,%2,%3,%4};" ::"l"(dst), "l"(key[0]), "l"(key[1 % N]), "l"(w2), "l"(w3)
+                 : "memory");
+  }
+}
+template <int N>
+__device__ __forceinline__ uint64_t load_bin_record(const uint64_t *src, uint64_t (&key)[N]) {
+  uint64_t a, b, c = 0, d = 0;
+  if (N == 1) {
+    asm volatile("ld.global.nc.v2.u64 {%0,%1}, [%2];" : "=l"(a), "=l"(b) : "l"(src));
+    key[0] = a;
+    return b;
+  }
+  asm volatile("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(src));
+  key[0] = a;
+  key[1 % N] = b;
+  if (N == 3) key[2 % N] = c;
+  return (N == 2) ? c : d;
+}
+
+// --------------------------------------------------------------------------
+// upsert_batch: U independent find-or-inserts per lane with the memory accesses
+// of the common case issued together
+// --------------------------------------------------------------------------
+// Steady state of a 30x build: ~99 % of the operations find their key behind a
+// visible tag in the first line probed.  That case is two dependent round trips
+// (header, then meta + key words of the tagged slot) and one reduction; the U
+// items of a lane take it in lock step so that U headers, then U slots, are in
+// flight at once.  Whatever does not finish there (no tag match, tag collision,
+// new key, full line) goes through the complete protocol of table.cuh.
+template <int N, int U>
+__device__ __forceinline__ void upsert_batch(const TableView &t, GraphCounters *ctr,
+                                             const uint64_t (&key)[U][N], const uint32_t (&c)[U],
+                                             const uint32_t (&edge)[U], const uint32_t (&count)[U],
+                                             const bool (&act)[U], unsigned long long &my_new) {
+  constexpr uint32_t SLOT = LineLayout<N>::SLOT, G = LineLayout<N>::G;
+  uint8_t *lp[U];
+  uint64_t hdr[U];
+  uint32_t tag8[U];
+  bool last[U];
+#pragma unroll
+  for (int u = 0; u < U; u++) {
+    const Probe pr = probe_of_key<N>(key[u]);
+    const uint32_t line = mulhi32(pr.h, t.NL);
+    tag8[u] = pr.tag8;
+    last[u] = line == t.NL - 1;
+    lp[u] = bucket_base(t, c[u] & t.bucket_mask) + (uint64_t)line * LINE_BYTES;
+  }
+#pragma unroll
+  for (int u = 0; u < U; u++) hdr[u] = act[u] ? DeviceOps::load(reinterpret_cast<uint64_t *>(lp[u])) : 0ull;
+  uint64_t *slot[U];
+  bool has[U];
+#pragma unroll
+  for (int u = 0; u < U; u++) {
+    const uint64_t valid = header_valid_mask(last[u] ? t.last_slots : G);
+    const uint64_t cand = zero_bytes64(hdr[u] ^ ((uint64_t)tag8[u] * 0x0101010101010101ull)) & valid;
+    has[u] = act[u] && cand != 0ull;
+    const uint32_t i = cand ? first_byte_index(cand) : 0u;
+    slot[u] = reinterpret_cast<uint64_t *>(lp[u] + 8u + i * SLOT);
+  }
+  uint64_t m[U], kw[U][N];
+#pragma unroll
+  for (int u = 0; u < U; u++) {
+    m[u] = 0;
+#pragma unroll
+    for (int w = 0; w < N; w++) kw[u][w] = ~key[u][w];
+    if (has[u]) {
+      m[u] = DeviceOps::load(slot[u] + N);
+#pragma unroll
+      for (int w = 0; w < N; w++) kw[u][w] = DeviceOps::load(slot[u] + w);
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < U; u++) {
+    bool same = has[u];
+#pragma unroll
+    for (int w = 0; w < N; w++) same &= (kw[u][w] == key[u][w]);
+    if (same) {
+      slot_accumulate<DeviceOps>(slot[u] + N, m[u], edge[u], count[u], ctr);
+    } else if (act[u]) {
+      const int r = table_upsert_hashed<N, DeviceOps>(t, ctr, key[u], c[u], edge[u], count[u]);
+      my_new += (r == 1);
+    }
+    __syncwarp();  // lanes that took the long way rejoin here (callers are warp-convergent)
+  }
+}
+
 // --------------------------------------------------------------------------
 // build_kernel
 // --------------------------------------------------------------------------
@@ -96,6 +192,8 @@ struct TileCfg {
   static constexpr int R = T + TileGeom::HALO_L + TileGeom::HALO_R;
   static constexpr int CHUNKS = R / 16;  // 16-base chunks: 32 or 64 -> one or two per lane
   static constexpr int WORDS = R / 32;   // validity words: 16 or 32 -> at most one per lane
+  // k-mers per lane in flight in the heavy phase (independent table probes / bin reservations)
+  static constexpr int U = (MODE == MODE_FUSED || MODE == MODE_BIN) ? 2 : 1;
 };
 
 template <int N, int MODE>
@@ -117,7 +215,7 @@ template <int N, int MODE>
 __global__ void __launch_bounds__(THREADS, (MODE == MODE_ROUTE) ? 3 : 4)
 build_kernel(const BuildParams p, const uint64_t n_tiles) {
   using Cfg = TileCfg<MODE>;
-  constexpr int T = Cfg::T, R = Cfg::R, CHUNKS = Cfg::CHUNKS, WORDS = Cfg::WORDS;
+  constexpr int T = Cfg::T, R = Cfg::R, CHUNKS = Cfg::CHUNKS, WORDS = Cfg::WORDS, U = Cfg::U;
   static_assert(CHUNKS % 32 == 0 && WORDS <= 32 && R % 64 == 0, "tile must map onto whole warp rounds");
   constexpr int RECW = 2 * N + 1;
   constexpr int WARPS = THREADS / 32;
@@ -190,55 +288,70 @@ build_kernel(const BuildParams p, const uint64_t n_tiles) {
       rec_base = __shfl_sync(FULL, rec_base, 0);
     }
 
-    // ---- heavy phase over the dense list of good windows
-    for (int base = 0; base < M; base += 32) {
-      const int i = base + (int)lane;
-      const bool active = i < M;
-      uint64_t key[N];
-      uint32_t edge = 0, count = 1;
-      if (active) {
-        const int j = TileGeom::HALO_L + (int)wt.pos[i];
-        edge = kmer_occurrence<N>(wt.P, wt.PR, wt.BD, R, j, k, key);
-      } else {
+    // ---- heavy phase over the dense list of good windows, U rounds of 32 at a time
+    for (int base = 0; base < M; base += 32 * U) {
+      __syncwarp();
+      uint64_t key[U][N];
+      uint32_t edge[U], count[U], hc[U];
+      bool lead[U];
 #pragma unroll
-        for (int w = 0; w < N; w++) key[w] = 0;
+      for (int u = 0; u < U; u++) {
+        const int i = base + 32 * u + (int)lane;
+        const bool active = i < M;
+        edge[u] = 0;
+        count[u] = 1;
+        hc[u] = 0;
+        if (active) {
+          const int j = TileGeom::HALO_L + (int)wt.pos[i];
+          edge[u] = kmer_occurrence<N>(wt.P, wt.PR, wt.BD, R, j, k, key[u]);
+        } else {
+#pragma unroll
+          for (int w = 0; w < N; w++) key[u][w] = 0;
+        }
+        lead[u] = active;
+        if (MODE != MODE_RECORDS) hc[u] = lookup3_key<N>(key[u], 0).c;
+        if (MODE == MODE_FUSED || MODE == MODE_BIN) {
+          bool mine = active;
+          if (MODE == MODE_FUSED && p.n_pass > 1)
+            mine = active && (int)((hc[u] & p.table.bucket_mask) >> p.pass_shift) == p.pass;
+          // identical keys of a round (homopolymer and tandem runs) become one update
+          lead[u] = warp_aggregate<N>(mine, key[u], edge[u], count[u]);
+        }
       }
       if (MODE == MODE_FUSED) {
-        bool mine = active;
-        if (p.n_pass > 1 && active) {
-          const uint32_t b = lookup3_key<N>(key, 0).c & p.table.bucket_mask;
-          mine = (int)(b >> p.pass_shift) == p.pass;
-        }
-        const bool lead = warp_aggregate<N>(mine, key, edge, count);
-        if (lead) {
-          const int r = table_upsert<N, DeviceOps>(p.table, p.ctr, key, edge, count);
-          my_new += (r == 1);
-        }
+        upsert_batch<N, U>(p.table, p.ctr, key, hc, edge, count, lead, my_new);
       } else if (MODE == MODE_BIN) {
-        if (active) {  // duplicates meet again, side by side, in insert_bins_kernel
-          const uint32_t bin = (lookup3_key<N>(key, 0).c & p.table.bucket_mask) >> p.bins.bin_shift;
-          const uint32_t idx = atomicAdd(&p.bins.count[bin * COUNT_STRIDE], 1u);
-          if (idx < p.bins.cap) {
-            const uint64_t at = (uint64_t)bin * p.bins.cap + idx;
-            if (N >= 2) p.bins.keyA[at] = make_ulonglong2(key[0], key[1 % N]);
-            if (N & 1) p.bins.keyB[at] = key[N - 1];
-            p.bins.meta[at] = (uint16_t)((edge & 0xFFu) | (count << 8));
+        uint32_t idx[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+          const uint32_t bin = (hc[u] & p.table.bucket_mask) >> p.bins.bin_shift;
+          idx[u] = lead[u] ? atomicAdd(&p.bins.count[bin * COUNT_STRIDE], 1u) : 0u;
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+          if (!lead[u]) continue;
+          const uint32_t bin = (hc[u] & p.table.bucket_mask) >> p.bins.bin_shift;
+          if (idx[u] < p.bins.cap) {
+            store_bin_record<N>(p.bins.recs + ((uint64_t)bin * p.bins.cap + idx[u]) * bin_record_words(N), key[u],
+                                bin_aux(hc[u], edge[u], count[u]));
           } else {  // stripe full (skewed batch): this occurrence goes straight to the table
-            const int r = table_upsert<N, DeviceOps>(p.table, p.ctr, key, edge, count);
+            const int r = table_upsert_hashed<N, DeviceOps>(p.table, p.ctr, key[u], hc[u], edge[u], count[u]);
             my_new += (r == 1);
           }
         }
+        __syncwarp();
       } else if (MODE == MODE_RECORDS) {
-        if (active) {
+        const int i = base + (int)lane;
+        if (lead[0]) {
           const unsigned long long idx = rec_base + (unsigned long long)i;
-          if (idx < p.rec_capacity) store_record<N>(p.rec_out + idx * RECW, key, edge, 1u);
+          if (idx < p.rec_capacity) store_record<N>(p.rec_out + idx * RECW, key[0], edge[0], 1u);
           else atomicExch(p.rec_overflow, 1ull);
         }
       } else {  // MODE_ROUTE
-        if (active) {
-          const Hash3 h = lookup3_key<N>(key, 0);
-          const uint32_t d = (h.c >> p.owner_shift) & (uint32_t)(p.n_dest - 1);
-          store_record<N>(wt.stash + i * RECW, key, edge, 1u);
+        const int i = base + (int)lane;
+        if (lead[0]) {
+          const uint32_t d = (hc[0] >> p.owner_shift) & (uint32_t)(p.n_dest - 1);
+          store_record<N>(wt.stash + i * RECW, key[0], edge[0], 1u);
           wt.dest[i] = (uint8_t)d;
           atomicAdd(&wt.bin_count[d], 1u);
         }
@@ -319,81 +432,91 @@ __global__ void __launch_bounds__(1024) bin_prefix_kernel(const BinView b) {
   if (threadIdx.x == 0) b.prefix[b.n_bins] = sCarry;
 }
 
-template <int N>
-__global__ void __launch_bounds__(THREADS, 5) insert_bins_kernel(const BinView b, const TableView t,
+// Walks the logical concatenation of the bins: a warp takes 32*U consecutive
+// records per round and the rounds of all resident warps are neighbours, so at
+// any moment the whole GPU works on a few adjacent table regions.  One binary
+// search per warp round locates the bin; lanes walk on from there.
+template <int N, int U>
+__global__ void __launch_bounds__(THREADS, 4) insert_bins_kernel(const BinView b, const TableView t,
                                                              GraphCounters *ctr) {
-  // Grid-stride over the logical concatenation of the bins: at any moment all
-  // resident CTAs work on neighbouring records, i.e. on a few neighbouring
-  // table regions.
   const uint32_t total = b.prefix[b.n_bins];
   unsigned long long my_new = 0;
-  const uint32_t stride = gridDim.x * THREADS;
-  const uint32_t n_round = (total + 31u) & ~31u;
-  for (uint32_t i = blockIdx.x * THREADS + threadIdx.x; i < n_round; i += stride) {
-    // the warp's first index locates the bin by binary search; lanes walk on from there
-    const uint32_t i0 = i & ~31u;
-    uint32_t lo = 0, hi = b.n_bins;  // prefix[lo] <= i0 < prefix[hi]
+  const unsigned lane = lane_id();
+  constexpr uint32_t CHUNK = 32u * U;
+  const uint32_t warp_global = (blockIdx.x * THREADS + threadIdx.x) >> 5;
+  const uint32_t n_warps = (gridDim.x * THREADS) >> 5;
+  for (uint64_t base64 = (uint64_t)warp_global * CHUNK; base64 < total; base64 += (uint64_t)n_warps * CHUNK) {
+    __syncwarp();
+    const uint32_t base = (uint32_t)base64;
+    // bin of `base`: 32-ary search, every lane tests one pivot (prefix is non-decreasing)
+    uint32_t lo = 0, hi = b.n_bins;  // prefix[lo] <= base < prefix[hi]
     while (hi - lo > 1) {
-      const uint32_t mid = (lo + hi) >> 1;
-      if (__ldg(&b.prefix[mid]) <= i0) lo = mid;
-      else hi = mid;
+      const uint32_t step = (hi - lo + 31u) >> 5;
+      const uint32_t piv = lo + (lane + 1u) * step;
+      const bool le = piv < hi && __ldg(&b.prefix[piv]) <= base;
+      const uint32_t n_le = (uint32_t)__popc(__ballot_sync(FULL, le));
+      const uint32_t nlo = lo + n_le * step;
+      hi = min(hi, nlo + step);
+      lo = nlo;
     }
-    const bool active = i < total;
-    uint64_t key[N];
-    uint32_t edge = 0, count = 0;
+    uint64_t key[U][N];
+    uint32_t c[U], edge[U], count[U];
+    bool act[U];
+    uint32_t bin = lo;
 #pragma unroll
-    for (int w = 0; w < N; w++) key[w] = 0;
-    if (active) {
-      uint32_t bin = lo;
-      while (__ldg(&b.prefix[bin + 1]) <= i) bin++;
-      const uint64_t at = (uint64_t)bin * b.cap + (i - __ldg(&b.prefix[bin]));
-      if (N >= 2) {
-        const ulonglong2 a = b.keyA[at];
-        key[0] = a.x;
-        key[1 % N] = a.y;
+    for (int u = 0; u < U; u++) {
+      const uint32_t i = base + 32u * u + lane;
+      act[u] = i < total;
+      c[u] = 0; edge[u] = 0; count[u] = 0;
+#pragma unroll
+      for (int w = 0; w < N; w++) key[u][w] = 0;
+      if (act[u]) {
+        while (__ldg(&b.prefix[bin + 1]) <= i) bin++;
+        const uint64_t aux = load_bin_record<N>(
+            b.recs + ((uint64_t)bin * b.cap + (i - __ldg(&b.prefix[bin]))) * bin_record_words(N), key[u]);
+        c[u] = (uint32_t)aux;
+        edge[u] = (uint32_t)(aux >> 32) & 0xFFu;
+        count[u] = (uint32_t)(aux >> 40);
       }
-      if (N & 1) key[N - 1] = b.keyB[at];
-      const uint32_t m = b.meta[at];
-      edge = m & 0xFFu;
-      count = m >> 8;
     }
-    const bool lead = warp_aggregate<N>(active, key, edge, count);
-    if (lead) {
-      const int r = table_upsert<N, DeviceOps>(t, ctr, key, edge, count);
-      my_new += (r == 1);
-    }
+    upsert_batch<N, U>(t, ctr, key, c, edge, count, act, my_new);
   }
 #pragma unroll
   for (int o = 16; o; o >>= 1) my_new += __shfl_xor_sync(FULL, my_new, o);
-  if (lane_id() == 0 && my_new) atomicAdd(&ctr->unique_kmers, my_new);
+  if (lane == 0 && my_new) atomicAdd(&ctr->unique_kmers, my_new);
 }
 
 // --------------------------------------------------------------------------
 // insert_records_kernel: K3 over (2N+1)-word records
 // --------------------------------------------------------------------------
 template <int N>
-__global__ void __launch_bounds__(THREADS, 5) insert_records_kernel(const uint32_t *__restrict__ recs,
+__global__ void __launch_bounds__(THREADS, 4) insert_records_kernel(const uint32_t *__restrict__ recs,
                                                                 const uint64_t n_recs,
                                                                 const TableView t,
                                                                 GraphCounters *ctr) {
   constexpr int RECW = 2 * N + 1;
+  constexpr int U = 2;
   unsigned long long my_new = 0;
-  const uint64_t stride = (uint64_t)gridDim.x * THREADS;
-  const uint64_t n_round = (n_recs + 31) & ~31ull;
-  for (uint64_t i = (uint64_t)blockIdx.x * THREADS + threadIdx.x; i < n_round; i += stride) {
-    const bool active = i < n_recs;
-    uint64_t key[N];
-    uint32_t edge = 0, count = 0;
-    if (active) load_record<N>(recs + i * RECW, key, edge, count);
-    else {
+  const uint64_t warp_global = ((uint64_t)blockIdx.x * THREADS + threadIdx.x) >> 5;
+  const uint64_t n_warps = ((uint64_t)gridDim.x * THREADS) >> 5;
+  for (uint64_t base = warp_global * 32 * U; base < n_recs; base += n_warps * 32 * U) {
+    __syncwarp();
+    const uint64_t i0 = base + lane_id();
+    uint64_t key[U][N];
+    uint32_t c[U], edge[U], count[U];
+    bool act[U];
 #pragma unroll
-      for (int w = 0; w < N; w++) key[w] = 0;
+    for (int u = 0; u < U; u++) {
+      const uint64_t i = i0 + 32ull * u;
+      act[u] = i < n_recs;
+      edge[u] = 0; count[u] = 0;
+#pragma unroll
+      for (int w = 0; w < N; w++) key[u][w] = 0;
+      if (act[u]) load_record<N>(recs + i * RECW, key[u], edge[u], count[u]);
+      c[u] = lookup3_key<N>(key[u], 0).c;
+      act[u] = warp_aggregate<N>(act[u], key[u], edge[u], count[u]);
     }
-    const bool lead = warp_aggregate<N>(active, key, edge, count);
-    if (lead) {
-      const int r = table_upsert<N, DeviceOps>(t, ctr, key, edge, count);
-      my_new += (r == 1);
-    }
+    upsert_batch<N, U>(t, ctr, key, c, edge, count, act, my_new);
   }
 #pragma unroll
   for (int o = 16; o; o >>= 1) my_new += __shfl_xor_sync(FULL, my_new, o);
@@ -488,12 +611,12 @@ __global__ void __launch_bounds__(THREADS) read_stats_kernel(
 // --------------------------------------------------------------------------
 template <int N>
 __global__ void __launch_bounds__(THREADS) table_summary_kernel(const TableView t, TableSummary *out) {
-  constexpr uint32_t STRIDE = 8 * N + 8;
   const uint64_t n_slots = ((uint64_t)t.bucket_mask + 1) * t.W;
   unsigned long long n = 0, sc = 0, se = 0, fp = 0;
   for (uint64_t i = (uint64_t)blockIdx.x * THREADS + threadIdx.x; i < n_slots;
        i += (uint64_t)gridDim.x * THREADS) {
-    const uint64_t *slot = reinterpret_cast<const uint64_t *>(t.slots + i * STRIDE);
+    const uint32_t bucket = (uint32_t)(i / t.W);
+    const uint64_t *slot = slot_ptr<N>(t, bucket, (uint32_t)(i - (uint64_t)bucket * t.W));
     const uint64_t m = slot[N];
     if (meta_status(m) == ST_EMPTY) continue;
     uint64_t key[N];
@@ -522,15 +645,13 @@ __global__ void __launch_bounds__(THREADS) table_summary_kernel(const TableView 
 // occupied slots per bucket: one warp per bucket
 template <int N>
 __global__ void __launch_bounds__(THREADS) bucket_counts_kernel(const TableView t, uint32_t *counts) {
-  constexpr uint32_t STRIDE = 8 * N + 8;
   const uint64_t n_buckets = (uint64_t)t.bucket_mask + 1;
   const uint64_t warp0 = ((uint64_t)blockIdx.x * THREADS + threadIdx.x) >> 5;
   const uint64_t nwarps = ((uint64_t)gridDim.x * THREADS) >> 5;
   for (uint64_t b = warp0; b < n_buckets; b += nwarps) {
-    const uint8_t *bucket = t.slots + b * t.W * STRIDE;
     uint32_t c = 0;
     for (uint32_t s = lane_id(); s < t.W; s += 32) {
-      const uint64_t m = reinterpret_cast<const uint64_t *>(bucket + (uint64_t)s * STRIDE)[N];
+      const uint64_t m = slot_ptr<N>(t, (uint32_t)b, s)[N];
       c += (meta_status(m) != ST_EMPTY);
     }
     c = __reduce_add_sync(FULL, c);
@@ -538,27 +659,29 @@ __global__ void __launch_bounds__(THREADS) bucket_counts_kernel(const TableView 
   }
 }
 
-// Squeeze every bucket hole-free, in slot order, and restore the reference
-// Element bytes (status none, pad bytes zero): afterwards the table IS a
-// reference HashTable->table (hash_table.c:69-122 finds every key).  One warp
-// per bucket; chunks of 32 slots are read into registers before any of them is
-// overwritten, and destinations never run ahead of sources.
+// Rewrite every bucket, in place, from lines of tagged slots to W hole-free
+// consecutive Elements in slot order (status none, pad bytes zero) at the start of
+// its NL*128 bytes: afterwards a bucket IS a reference bucket (hash_table.c:69-122
+// finds every key) and the table is copied out bucket by bucket.  One warp per
+// bucket; 32 slots are read into registers before any of them is overwritten, and
+// a destination never runs ahead of a source: slot s of the line layout starts at
+// byte 128*(s/G) + 8 + SLOT*(s%G) >= SLOT*s + 8, its destination at SLOT*d, d <= s.
 template <int N>
 __global__ void __launch_bounds__(THREADS) finalize_kernel(const TableView t, int16_t *next_element) {
-  constexpr uint32_t STRIDE = 8 * N + 8;
+  constexpr uint32_t SLOT = LineLayout<N>::SLOT;
   const uint64_t n_buckets = (uint64_t)t.bucket_mask + 1;
   const uint64_t warp0 = ((uint64_t)blockIdx.x * THREADS + threadIdx.x) >> 5;
   const uint64_t nwarps = ((uint64_t)gridDim.x * THREADS) >> 5;
   const unsigned lane = lane_id();
   for (uint64_t b = warp0; b < n_buckets; b += nwarps) {
-    uint8_t *bucket = t.slots + b * t.W * STRIDE;
+    uint8_t *bucket = bucket_base(t, (uint32_t)b);
     uint32_t filled = 0;
     for (uint32_t s0 = 0; s0 < t.W; s0 += 32) {
       const uint32_t s = s0 + lane;
       uint64_t key[N];
       uint64_t m = 0;
       if (s < t.W) {
-        const uint64_t *slot = reinterpret_cast<const uint64_t *>(bucket + (uint64_t)s * STRIDE);
+        const uint64_t *slot = slot_ptr<N>(t, (uint32_t)b, s);
         m = slot[N];
 #pragma unroll
         for (int w = 0; w < N; w++) key[w] = slot[w];
@@ -568,7 +691,7 @@ __global__ void __launch_bounds__(THREADS) finalize_kernel(const TableView t, in
       __syncwarp();
       if (occ) {
         const uint32_t d = filled + __popc(om & lanemask_lt());
-        uint64_t *dst = reinterpret_cast<uint64_t *>(bucket + (uint64_t)d * STRIDE);
+        uint64_t *dst = reinterpret_cast<uint64_t *>(bucket + (uint64_t)d * SLOT);
 #pragma unroll
         for (int w = 0; w < N; w++) dst[w] = key[w];
         dst[N] = meta_pack(meta_covg(m), meta_edges(m), ST_NONE, 0);
@@ -576,11 +699,10 @@ __global__ void __launch_bounds__(THREADS) finalize_kernel(const TableView t, in
       filled += __popc(om);
       __syncwarp();
     }
-    for (uint32_t s = filled + lane; s < t.W; s += 32) {
-      uint64_t *dst = reinterpret_cast<uint64_t *>(bucket + (uint64_t)s * STRIDE);
-#pragma unroll
-      for (int w = 0; w <= N; w++) dst[w] = 0;
-    }
+    // everything behind the last Element, line slack included, becomes zero
+    uint64_t *words = reinterpret_cast<uint64_t *>(bucket);
+    const uint32_t w_end = t.NL * (LINE_BYTES / 8);
+    for (uint32_t w = filled * (SLOT / 8) + lane; w < w_end; w += 32) words[w] = 0;
     if (lane == 0 && next_element) next_element[b] = (int16_t)filled;
   }
 }
@@ -590,21 +712,19 @@ template <int N>
 __global__ void __launch_bounds__(THREADS) dump_ctx_kernel(const TableView t,
                                                           const uint64_t *__restrict__ bucket_offsets,
                                                           uint8_t *__restrict__ out) {
-  constexpr uint32_t STRIDE = 8 * N + 8;
   constexpr uint32_t REC = 8 * N + 5;
   const uint64_t n_buckets = (uint64_t)t.bucket_mask + 1;
   const uint64_t warp0 = ((uint64_t)blockIdx.x * THREADS + threadIdx.x) >> 5;
   const uint64_t nwarps = ((uint64_t)gridDim.x * THREADS) >> 5;
   const unsigned lane = lane_id();
   for (uint64_t b = warp0; b < n_buckets; b += nwarps) {
-    const uint8_t *bucket = t.slots + b * t.W * STRIDE;
     uint64_t o = bucket_offsets[b];
     for (uint32_t s0 = 0; s0 < t.W; s0 += 32) {
       const uint32_t s = s0 + lane;
       uint64_t key[N];
       uint64_t m = 0;
       if (s < t.W) {
-        const uint64_t *slot = reinterpret_cast<const uint64_t *>(bucket + (uint64_t)s * STRIDE);
+        const uint64_t *slot = slot_ptr<N>(t, (uint32_t)b, s);
         m = slot[N];
 #pragma unroll
         for (int w = 0; w < N; w++) key[w] = slot[w];
@@ -688,7 +808,7 @@ __global__ void __launch_bounds__(THREADS, 5) ingest_elements_kernel(const uint8
 template <int N>
 __global__ void __launch_bounds__(THREADS) find_kernel(const TableView t,
                                                       const uint64_t *__restrict__ keys,
-                                                      const uint64_t n, const int finalized,
+                                                      const uint64_t n,
                                                       uint32_t *covg, uint8_t *edges, uint8_t *found) {
   for (uint64_t i = (uint64_t)blockIdx.x * THREADS + threadIdx.x; i < n;
        i += (uint64_t)gridDim.x * THREADS) {
@@ -697,7 +817,7 @@ __global__ void __launch_bounds__(THREADS) find_kernel(const TableView t,
     for (int w = 0; w < N; w++) key[w] = keys[i * N + w];
     uint64_t m = 0;
     bool hit = false;
-    if (!finalized) {
+    if (!t.finalized) {
       hit = table_find<N, DeviceOps>(t, key, m);
     } else {
       hit = table_find_finalized<N, DeviceOps>(t, key, m);
@@ -846,7 +966,7 @@ void launch_bin_prefix(const BinView &b, cudaStream_t st) { bin_prefix_kernel<<<
 void launch_insert_bins(int N, const BinView &b, const TableView &t, GraphCounters *ctr, cudaStream_t st) {
   dispatch_n(N, [&](auto n) {
     constexpr int NN = decltype(n)::value;
-    insert_bins_kernel<NN><<<resident_grid(insert_bins_kernel<NN>), THREADS, 0, st>>>(b, t, ctr);
+    insert_bins_kernel<NN, 2><<<resident_grid(insert_bins_kernel<NN, 2>), THREADS, 0, st>>>(b, t, ctr);
   });
 }
 
@@ -909,15 +1029,15 @@ void launch_ingest_elements(int N, const uint8_t *elements, uint64_t n_slots, co
   });
 }
 
-void launch_find(int N, const TableView &t, const uint64_t *keys, uint64_t n, int finalized,
-                 uint32_t *covg, uint8_t *edges, uint8_t *found, cudaStream_t st) {
+void launch_find(int N, const TableView &t, const uint64_t *keys, uint64_t n, uint32_t *covg,
+                 uint8_t *edges, uint8_t *found, cudaStream_t st) {
   if (!n) return;
   dispatch_n(N, [&](auto nn) {
     constexpr int NN = decltype(nn)::value;
     uint64_t grid = (n + THREADS - 1) / THREADS;
     const uint64_t cap = (uint64_t)resident_grid(find_kernel<NN>);
     if (grid > cap) grid = cap;
-    find_kernel<NN><<<(unsigned)grid, THREADS, 0, st>>>(t, keys, n, finalized, covg, edges, found);
+    find_kernel<NN><<<(unsigned)grid, THREADS, 0, st>>>(t, keys, n, covg, edges, found);
   });
 }
 

@@ -16,13 +16,16 @@ enum BuildMode { MODE_FUSED = 0, MODE_RECORDS = 1, MODE_ROUTE = 2, MODE_BIN = 3 
 
 // Region bins of the partitioned insert: k-mer occurrences of a batch grouped by
 // the slice of the table they will touch (bin = bucket >> bin_shift), so that the
-// insert kernel walks the table region by region (L2- and DRAM-row-friendly)
-// instead of at random.  Structure of arrays, one fixed-capacity stripe per bin.
+// insert kernel walks the table region by region (TLB-, L2- and DRAM-row-friendly)
+// instead of at random.  One fixed-capacity stripe of records per bin.  A record is
+// the key words, then {lookup3 c : 32, edges : 8, count : 24} (the insert side does
+// not hash again), padded to 16 bytes (N = 1) or 32 bytes (N = 2, 3) and written
+// with ONE vector store: scattered stores cost per request, not per byte
+// (tools/ubench: 3 x 8 B = 15 ms, 1 x 32 B = 5 ms per 180 M records).
+__host__ __device__ inline uint32_t bin_record_words(int N) { return N == 1 ? 2u : 4u; }
 constexpr uint32_t COUNT_STRIDE = 32;  // uint32 units = 128 bytes
 struct BinView {
-  ulonglong2 *keyA;     // [n_bins*cap] key words 0,1          (N >= 2)
-  uint64_t *keyB;       // [n_bins*cap] last key word          (N odd)
-  uint16_t *meta;       // [n_bins*cap] edges | count << 8
+  uint64_t *recs;       // [n_bins*cap*bin_record_words(N)]
   unsigned int *count;  // [n_bins*COUNT_STRIDE] records wanted per bin, ONE COUNTER PER 128-BYTE LINE: the L2
                         // atomic unit serialises per line, 8 counters in a line would share one queue
                         // (a count may exceed cap: the excess went straight to the table)
@@ -31,6 +34,9 @@ struct BinView {
   uint32_t bin_shift;
   uint32_t n_bins;
 };
+__host__ __device__ inline uint64_t bin_aux(uint32_t c, uint32_t edge, uint32_t count) {
+  return (uint64_t)c | ((uint64_t)(edge & 0xFFu) << 32) | ((uint64_t)count << 40);
+}
 
 struct BuildParams {
   const uint8_t *seq;   // sequence stream: reads back to back, each followed by >= 1 separator byte
@@ -104,8 +110,8 @@ void launch_ingest_ctx(int N, const uint8_t *recs, uint64_t n_recs, const TableV
                        GraphCounters *ctr, cudaStream_t st);
 void launch_ingest_elements(int N, const uint8_t *elements, uint64_t n_slots, const TableView &t,
                             GraphCounters *ctr, cudaStream_t st);
-void launch_find(int N, const TableView &t, const uint64_t *keys, uint64_t n, int finalized,
-                 uint32_t *covg, uint8_t *edges, uint8_t *found, cudaStream_t st);
+void launch_find(int N, const TableView &t, const uint64_t *keys, uint64_t n, uint32_t *covg,
+                 uint8_t *edges, uint8_t *found, cudaStream_t st);
 void launch_exclusive_scan_u32_to_u64(const uint32_t *in, uint64_t *out, uint64_t n, void *tmp,
                                       size_t tmp_bytes, cudaStream_t st);
 size_t exclusive_scan_tmp_bytes(uint64_t n);

@@ -343,35 +343,80 @@ LASV_HD uint32_t meta_edges(uint64_t m) { return (uint32_t)(m >> 32) & 0xFFu; }
 LASV_HD uint32_t meta_status(uint64_t m) { return (uint32_t)(m >> 40) & 0xFFu; }
 LASV_HD uint32_t meta_tag(uint64_t m) { return (uint32_t)(m >> 48); }
 
-// Where a key lives: CORTEX bucket from c (hash_value.c:767-773), in-bucket
-// start slot and tag from the spare hash words.
-struct Probe {
-  uint32_t bucket, start, tag, tag8;
+// ------------------------------------------------------------ line layout
+// On the device a bucket is not W consecutive Elements but NL = ceil(W / G)
+// LINES of 128 bytes (one L2 line, two 64-byte DRAM atoms):
+//   bytes 0..7    header: one tag byte per slot of the line (0 = never claimed,
+//                 else 8 hash bits of the key, 1..255); bytes >= G stay 0
+//   bytes 8..     G slots of 8N+8 bytes in the reference Element layout
+// so the tag probe and the slot it leads to share a line (mostly a 64-byte
+// atom): one random DRAM location per lookup instead of two.  G = 7 / 5 / 3 for
+// 1 / 2 / 3-word k-mers.  lasv_graph_finalize() rewrites every bucket, in place,
+// as W hole-free consecutive Elements at the start of its NL*128 bytes.
+constexpr uint32_t LINE_BYTES = 128;
+template <int N>
+struct LineLayout {
+  static constexpr uint32_t SLOT = 8 * N + 8;
+  static constexpr uint32_t G = (LINE_BYTES - 8) / SLOT;
 };
-LASV_HD Probe probe_of(const Hash3 &h, uint32_t bucket_mask, uint32_t W) {
+LASV_HD uint32_t slots_per_line(int N) { return (LINE_BYTES - 8) / (8u * (uint32_t)N + 8u); }
+LASV_HD uint32_t lines_per_bucket(int N, uint32_t W) {
+  const uint32_t g = slots_per_line(N);
+  return (W + g - 1) / g;
+}
+// header mask with 0x80 in the byte of every usable slot 0..n-1
+LASV_HD uint64_t header_valid_mask(uint32_t n) {
+  return n == 0 ? 0ull : 0x8080808080808080ull >> (8u * (8u - (n > 8u ? 8u : n)));
+}
+
+// Where a key probes inside its bucket: start line and tags.  Device layout only
+// (invisible in any output), so a cheap multiplicative mix of the key words is
+// enough; the bucket itself is the reference's lookup3 value (hash_value.c:767).
+struct Probe {
+  uint32_t h;      // 32 mixed bits: start line = mulhi(h, NL)
+  uint32_t tag8;   // header tag, 1..255
+  uint32_t tag16;  // kept in the slot's pad bytes while on the device
+};
+LASV_HD uint32_t fmix32(uint32_t x) {
+  x ^= x >> 16; x *= 0x85EBCA6Bu;
+  x ^= x >> 13; x *= 0xC2B2AE35u;
+  x ^= x >> 16;
+  return x;
+}
+template <int N>
+LASV_HD Probe probe_of_key(const uint64_t (&key)[N]) {
+  constexpr uint32_t MA[6] = {0x9E3779B1u, 0x85EBCA77u, 0xC2B2AE3Du, 0x27D4EB2Fu, 0x165667B1u, 0xD3A2646Du};
+  constexpr uint32_t MB[6] = {0xCC9E2D51u, 0x1B873593u, 0xE6546B64u, 0x38B34AE5u, 0xA1E38B93u, 0x7FEB352Du};
+  uint32_t xa = 0x2545F491u, xb = 0x9E3779B9u;
+#pragma unroll
+  for (int i = 0; i < N; i++) {
+    const uint32_t lo = (uint32_t)key[i], hi = (uint32_t)(key[i] >> 32);
+    xa += lo * MA[2 * i] + hi * MA[2 * i + 1];
+    xb += lo * MB[2 * i] + hi * MB[2 * i + 1];
+  }
+  const uint32_t ya = fmix32(xa ^ rot32(xb, 15));
+  const uint32_t yb = fmix32(xb + ya);
   Probe p;
-  p.bucket = h.c & bucket_mask;
-  p.start = mulhi32(h.b, W);
-  p.tag = h.a >> 16;                       // 16 bits kept in the slot's pad bytes
-  const uint32_t t = h.a & 0xFFu;          // 8 bits kept in the side tag array, never 0
-  p.tag8 = t ? t : 1u;
+  p.h = ya;
+  const uint32_t t = yb & 0xFFu;
+  p.tag8 = t ? t : 0x55u;
+  p.tag16 = yb >> 16;
   return p;
 }
 
-// 16 one-byte tags in a uint4 -> 16-bit mask of the bytes equal to `v`
-// (bit i <-> byte i in memory order).
-LASV_HD uint32_t bytes_equal_mask16(uint4 t, uint32_t v) {
-  const uint32_t w[4] = {t.x, t.y, t.z, t.w};
-  const uint32_t rep = v * 0x01010101u;
-  uint32_t m = 0;
-#pragma unroll
-  for (int i = 0; i < 4; i++) {
-    uint32_t x = w[i] ^ rep;               // zero byte <=> equal
-    // exact zero-byte detector: high bit of each byte set iff that byte is zero
-    uint32_t z = ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x | 0x7F7F7F7Fu);
-    m |= (((z >> 7) * 0x01020408u) >> 24) << (4 * i);
-  }
-  return m & 0xFFFFu;
+// bit 8i+7 of the result is set iff byte i of x is zero (exact, no carries across bytes)
+LASV_HD uint64_t zero_bytes64(uint64_t x) {
+  const uint32_t lo = (uint32_t)x, hi = (uint32_t)(x >> 32);
+  const uint32_t zl = ~(((lo & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | lo | 0x7F7F7F7Fu);
+  const uint32_t zh = ~(((hi & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | hi | 0x7F7F7F7Fu);
+  return (uint64_t)zl | ((uint64_t)zh << 32);
+}
+LASV_HD uint32_t first_byte_index(uint64_t m) {  // m != 0, bits only at 8i+7
+#if defined(__CUDA_ARCH__)
+  return (uint32_t)(__ffsll((long long)m) - 1) >> 3;
+#else
+  return (uint32_t)__builtin_ctzll(m) >> 3;
+#endif
 }
 
 // 64-bit mixer (splitmix64 finaliser) -- used by the order-independent table

@@ -9,30 +9,31 @@
 //
 // Same bucket function and rehash chain as the reference (bucket r of a key is
 // lookup3(key + r) & (2^L - 1), r = 0..max_rehash, a key moves to bucket r+1
-// only when bucket r is FULL), so capacity behaviour ("table full" is fatal) and
-// the set of keys a bucket can hold are the reference's.  What differs is only
-// the position INSIDE a bucket: instead of scanning from slot 0 (W/2 slot reads
-// per lookup) a key starts at a hashed slot and probes linearly with wrap-around.
-// lasv_graph_finalize() squeezes every bucket hole-free afterwards, which is
-// exactly the layout hash_table_find expects.
-//
-// Probing does not read slots: a side array holds ONE TAG BYTE PER SLOT (0 =
-// never claimed, else 8 hash bits of the key).  A lookup loads 16 tags with one
-// 16-byte access (a 74 %-full bucket needs 2.4 probes on average, 16 tags cover
-// the tail), compares them in-register, and touches only slots whose tag matches
-// -- one or two 32-byte sectors per k-mer instead of the whole probe run, and no
-// per-lane probe loop for the warp to diverge on.  The tag array is a HINT: the
-// slot's meta word stays authoritative.
+// only when bucket r holds W keys), so capacity behaviour ("table full" is
+// fatal) and the set of keys a bucket can hold are the reference's.  What
+// differs is only the arrangement INSIDE a bucket while it lives on the device
+// (kmer_core.cuh, "line layout"): a bucket is NL lines of 128 bytes, each an
+// 8-byte header of tag bytes followed by G reference-layout slots.  A key starts
+// at a hashed line and walks the lines of its bucket with wrap-around; inside a
+// line the header tells which slots can hold it.  A steady-state lookup is one
+// header read plus one slot read in the SAME line (the reference scans from
+// slot 0: ~W*fill/2 slot reads).  lasv_graph_finalize() rewrites every bucket
+// as W hole-free consecutive Elements, which is what hash_table_find expects.
 //
 // Concurrency protocol per slot (meta = the 8-byte word after the key words):
-//   EMPTY  --CAS(meta: 0 -> {covg=c, edges=e, LOCKED, tag16})-->  LOCKED
-//   LOCKED --key words and tag byte stored, __threadfence, meta ^= LOCKED^NONE-->  NONE
-// A reader that sees tag byte 0 claims the slot by CAS; if the CAS fails somebody
-// else got there first (tag byte not visible yet) and the slot is examined like a
-// tag match: 16-bit meta tag differs -> other key; LOCKED -> wait for publication;
-// then compare key words.  A non-zero tag byte never changes (no deletions).
-// Updates of a published slot are two independent L2 reductions: 32-bit add on
-// the coverage word, 32-bit OR on the edges word (only when it adds a bit).
+//   EMPTY  --CAS(meta: 0 -> {covg, edges, LOCKED, tag16})-->  LOCKED
+//   LOCKED --key words stored, __threadfence, tag byte stored, status ^= LOCKED^NONE-->  NONE
+// The tag byte is written AFTER the key words are visible: whoever reaches a
+// slot through a non-zero tag byte may read its key words at once, without
+// looking at the status.  A slot reached through a zero tag byte is claimed by
+// CAS; a failed CAS means somebody else got there first (tag byte not visible
+// yet) and the slot is examined through its meta word: 16-bit tag differs ->
+// other key; LOCKED -> wait for publication; then compare the key words.
+// Slots are claimed in header order and never released, hence the invariant:
+// a key sits behind claimed slots only, and every prober meets it before it
+// meets a claimable slot.
+// Updates of a slot are independent 32-bit L2 reductions: add on the coverage
+// word, OR on the edges word (only when it adds a bit).
 #pragma once
 #if defined(__CUDACC__)
 #include <cuda_runtime.h>
@@ -42,15 +43,43 @@
 namespace lasv {
 
 struct TableView {
-  uint8_t *slots;        // n_buckets * W slots of (8N+8) bytes
-  uint8_t *tags;         // n_buckets * W tag bytes (+16 readable bytes of slack), 16-byte aligned
+  uint8_t *lines;        // n_buckets * NL lines of 128 bytes (16-byte aligned at least)
   uint32_t bucket_mask;  // n_buckets - 1
-  uint32_t W;
+  uint32_t W;            // slots per bucket (the reference's bucket_size)
+  uint32_t NL;           // lines per bucket = ceil(W / G)
+  uint32_t last_slots;   // usable slots of a bucket's last line = W - (NL-1)*G
   uint32_t max_rehash;   // 15 in laSV (graph_operations.c:640)
+  uint32_t finalized;    // != 0: every bucket is W consecutive Elements at the start of its NL lines
 };
 
-// Per-graph device counters (one cache line each would be nicer; they are only
-// touched once per CTA).
+LASV_HD TableView make_table_view(uint8_t *lines, int N, int L, int W, int max_rehash, bool finalized) {
+  TableView t;
+  t.lines = lines;
+  t.bucket_mask = (uint32_t)((1ull << L) - 1);
+  t.W = (uint32_t)W;
+  t.NL = lines_per_bucket(N, (uint32_t)W);
+  t.last_slots = (uint32_t)W - (t.NL - 1) * slots_per_line(N);
+  t.max_rehash = (uint32_t)max_rehash;
+  t.finalized = finalized ? 1u : 0u;
+  return t;
+}
+LASV_HD uint64_t table_bytes(const TableView &t) {
+  return ((uint64_t)t.bucket_mask + 1) * t.NL * LINE_BYTES;
+}
+LASV_HD uint8_t *bucket_base(const TableView &t, uint32_t bucket) {
+  return t.lines + (uint64_t)bucket * t.NL * LINE_BYTES;
+}
+// slot s (0 <= s < W) of a bucket, in whichever arrangement the table is in
+template <int N>
+LASV_HD uint64_t *slot_ptr(const TableView &t, uint32_t bucket, uint32_t s) {
+  constexpr uint32_t SLOT = LineLayout<N>::SLOT, G = LineLayout<N>::G;
+  uint8_t *b = bucket_base(t, bucket);
+  if (t.finalized) return reinterpret_cast<uint64_t *>(b + (uint64_t)s * SLOT);
+  const uint32_t line = s / G, i = s - line * G;
+  return reinterpret_cast<uint64_t *>(b + (uint64_t)line * LINE_BYTES + 8u + i * SLOT);
+}
+
+// Per-graph device counters (touched once per warp).
 struct GraphCounters {
   unsigned long long unique_kmers;     // hash_table.c:305
   unsigned long long kmers_inserted;   // number of find_or_insert calls
@@ -77,15 +106,6 @@ __device__ __forceinline__ void st_strong_u64(uint64_t *p, uint64_t v) {
 struct DeviceOps {
   static __device__ __forceinline__ uint64_t load(const uint64_t *p) { return ld_strong_u64(p); }
   static __device__ __forceinline__ void store(uint64_t *p, uint64_t v) { st_strong_u64(p, v); }
-  static __device__ __forceinline__ void prefetch(const void *p) {
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-  }
-  static __device__ __forceinline__ uint4 load_tags16(const uint8_t *p) {  // p 16-byte aligned
-    uint4 v;
-    asm volatile("ld.relaxed.gpu.global.v4.u32 {%0,%1,%2,%3}, [%4];"
-                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
-    return v;
-  }
   static __device__ __forceinline__ void store_tag(uint8_t *p, uint32_t v) {
     asm volatile("st.relaxed.gpu.global.u8 [%0], %1;" ::"l"(p), "r"(v) : "memory");
   }
@@ -93,9 +113,7 @@ struct DeviceOps {
     return atomicCAS(reinterpret_cast<unsigned long long *>(p), (unsigned long long)expect,
                      (unsigned long long)want);
   }
-  static __device__ __forceinline__ void xor64(uint64_t *p, uint64_t v) {
-    atomicXor(reinterpret_cast<unsigned long long *>(p), (unsigned long long)v);
-  }
+  static __device__ __forceinline__ void xor32(uint32_t *p, uint32_t v) { atomicXor(p, v); }
   static __device__ __forceinline__ void add32(uint32_t *p, uint32_t v) { atomicAdd(p, v); }
   static __device__ __forceinline__ void or32(uint32_t *p, uint32_t v) { atomicOr(p, v); }
   static __device__ __forceinline__ void fence() { __threadfence(); }
@@ -107,8 +125,7 @@ struct DeviceOps {
 };
 #endif
 
-// Saturating coverage add on a published slot (slow path, only near UINT_MAX;
-// element.c:395-417).
+// Saturating coverage add (slow path, only near UINT_MAX; element.c:395-417).
 #pragma nv_exec_check_disable
 template <class Ops>
 LASV_HD void covg_add_saturating(uint64_t *meta_ptr, uint32_t add, GraphCounters *ctr) {
@@ -126,28 +143,12 @@ LASV_HD void covg_add_saturating(uint64_t *meta_ptr, uint32_t add, GraphCounters
   }
 }
 
-// A slot whose meta word `m` is known to be non-EMPTY: is it `key`?  If so
-// accumulate.  Returns 0 (hit, updated) or 2 (some other key).
+// coverage += covg_add (saturating), edges |= edge, on a slot known to hold the
+// key; m is a recent copy of its meta word.
 #pragma nv_exec_check_disable
-template <int N, class Ops>
-LASV_HD int slot_examine(uint64_t *slot, uint64_t m, const Probe &pr, GraphCounters *ctr,
-                         const uint64_t (&key)[N], uint32_t edge, uint32_t covg_add) {
-  uint64_t *meta_ptr = slot + N;
-  if (meta_tag(m) != pr.tag) return 2;
-  if (meta_status(m) == ST_LOCKED) {
-    // same tag, key words not visible yet: wait for the owner to publish
-    do {
-      Ops::backoff();
-      m = Ops::load(meta_ptr);
-    } while (meta_status(m) == ST_LOCKED);
-    Ops::fence();
-  }
-  // published: compare the key (loads issued after the meta load that saw the
-  // slot published, and bypassing L1)
-  bool same = true;
-#pragma unroll
-  for (int w = 0; w < N; w++) same &= (Ops::load(slot + w) == key[w]);
-  if (!same) return 2;
+template <class Ops>
+LASV_HD void slot_accumulate(uint64_t *meta_ptr, uint64_t m, uint32_t edge, uint32_t covg_add,
+                             GraphCounters *ctr) {
   if (meta_covg(m) < 0xF0000000u && covg_add < 0x01000000u) {
     Ops::add32(reinterpret_cast<uint32_t *>(meta_ptr), covg_add);
   } else {
@@ -156,110 +157,145 @@ LASV_HD int slot_examine(uint64_t *slot, uint64_t m, const Probe &pr, GraphCount
   if ((meta_edges(m) | edge) != meta_edges(m)) {
     Ops::or32(reinterpret_cast<uint32_t *>(meta_ptr) + 1, edge & 0xFFu);
   }
-  return 0;
+}
+
+// A slot reached through a visible tag byte: its key words are readable.
+#pragma nv_exec_check_disable
+template <int N, class Ops>
+LASV_HD bool slot_hit_tagged(uint64_t *slot, GraphCounters *ctr, const uint64_t (&key)[N],
+                             uint32_t edge, uint32_t covg_add) {
+  const uint64_t m = Ops::load(slot + N);
+  bool same = true;
+#pragma unroll
+  for (int w = 0; w < N; w++) same &= (Ops::load(slot + w) == key[w]);
+  if (!same) return false;
+  slot_accumulate<Ops>(slot + N, m, edge, covg_add, ctr);
+  return true;
+}
+
+// A slot somebody else claimed before our CAS (m = its meta word, non-zero).
+#pragma nv_exec_check_disable
+template <int N, class Ops>
+LASV_HD bool slot_hit_claimed(uint64_t *slot, uint64_t m, const Probe &pr, GraphCounters *ctr,
+                              const uint64_t (&key)[N], uint32_t edge, uint32_t covg_add) {
+  uint64_t *meta_ptr = slot + N;
+  if (meta_tag(m) != pr.tag16) return false;
+  while (meta_status(m) == ST_LOCKED) {  // same tag, key words not published yet
+    Ops::backoff();
+    m = Ops::load(meta_ptr);
+  }
+  Ops::fence();
+  bool same = true;
+#pragma unroll
+  for (int w = 0; w < N; w++) same &= (Ops::load(slot + w) == key[w]);
+  if (!same) return false;
+  slot_accumulate<Ops>(meta_ptr, m, edge, covg_add, ctr);
+  return true;
+}
+
+// find-or-insert `key` in bucket `bucket` only (one step of the rehash chain).
+// Returns 1 if the key was new, 0 if it existed, -1 if the bucket holds W other keys.
+#pragma nv_exec_check_disable
+template <int N, class Ops>
+LASV_HD int bucket_upsert(const TableView &t, GraphCounters *ctr, uint32_t bucket, const Probe &pr,
+                          const uint64_t (&key)[N], uint32_t edge, uint32_t covg_add) {
+  constexpr uint32_t SLOT = LineLayout<N>::SLOT, G = LineLayout<N>::G;
+  const uint64_t full_valid = header_valid_mask(G);
+  const uint64_t last_valid = header_valid_mask(t.last_slots);
+  const uint64_t rep = (uint64_t)pr.tag8 * 0x0101010101010101ull;
+  uint8_t *base = bucket_base(t, bucket);
+  uint32_t line = mulhi32(pr.h, t.NL);
+#pragma unroll 1
+  for (uint32_t step = 0; step < t.NL; ++step) {
+    uint8_t *lp = base + (uint64_t)line * LINE_BYTES;
+    const uint64_t hdr = Ops::load(reinterpret_cast<uint64_t *>(lp));
+    const uint64_t valid = (line == t.NL - 1) ? last_valid : full_valid;
+    uint64_t cand = zero_bytes64(hdr ^ rep) & valid;
+    uint64_t empt = zero_bytes64(hdr) & valid;
+    while (cand) {  // visible tags equal to ours, in slot order
+      const uint32_t i = first_byte_index(cand);
+      cand &= cand - 1;
+      uint64_t *slot = reinterpret_cast<uint64_t *>(lp + 8u + i * SLOT);
+      if (slot_hit_tagged<N, Ops>(slot, ctr, key, edge, covg_add)) return 0;
+    }
+    while (empt) {  // never-claimed slots (as far as the header told), in slot order
+      const uint32_t i = first_byte_index(empt);
+      empt &= empt - 1;
+      uint64_t *slot = reinterpret_cast<uint64_t *>(lp + 8u + i * SLOT);
+      const uint64_t want = meta_pack(covg_add, edge, ST_LOCKED, pr.tag16);
+      const uint64_t m = Ops::cas(slot + N, 0ull, want);
+      if (m == 0ull) {
+#pragma unroll
+        for (int w = 0; w < N; w++) Ops::store(slot + w, key[w]);
+        Ops::fence();
+        Ops::store_tag(lp + i, pr.tag8);
+        Ops::xor32(reinterpret_cast<uint32_t *>(slot + N) + 1, (ST_LOCKED ^ ST_NONE) << 8);
+        return 1;
+      }
+      if (slot_hit_claimed<N, Ops>(slot, m, pr, ctr, key, edge, covg_add)) return 0;
+    }
+    line = (line + 1 == t.NL) ? 0u : line + 1;  // line full without the key
+  }
+  return -1;
 }
 
 // find-or-insert `key`, then coverage += covg_add (saturating) and edges |= edge.
-// Returns 1 if the key was new, 0 if it existed, -1 if the table is full.
+// c0 = lookup3(key, 0).c when the caller has it already (have_c0), so that the
+// records path hashes once.  Returns 1 if the key was new, 0 if it existed, -1
+// if the table is full.
 #pragma nv_exec_check_disable
 template <int N, class Ops>
-LASV_HD int table_upsert(const TableView &t, GraphCounters *ctr, const uint64_t (&key)[N],
-                         uint32_t edge, uint32_t covg_add) {
-  constexpr uint32_t STRIDE = 8 * N + 8;
-  for (uint32_t r = 0; r <= t.max_rehash; ++r) {
-    const Probe pr = probe_of(lookup3_key<N>(key, r), t.bucket_mask, t.W);
-    const uint64_t b0 = (uint64_t)pr.bucket * t.W;  // global index of the bucket's slot 0
-    // the bucket is walked as two runs: [start, W) then [0, start)
-#pragma unroll 1
-    for (int seg = 0; seg < 2; ++seg) {
-      const uint64_t lo = seg ? b0 : b0 + pr.start;
-      const uint64_t hi = seg ? b0 + pr.start : b0 + t.W;
-#pragma unroll 1
-      for (uint64_t gb = lo & ~15ull; gb < hi; gb += 16) {
-        const uint4 tg = Ops::load_tags16(t.tags + gb);
-        // bytes of this group that belong to [lo, hi)
-        uint32_t valid = 0xFFFFu;
-        if (gb < lo) valid &= 0xFFFFu << (uint32_t)(lo - gb);
-        if (gb + 16 > hi) valid &= 0xFFFFu >> (uint32_t)(gb + 16 - hi);
-        const uint32_t empty = bytes_equal_mask16(tg, 0u) & valid;
-        uint32_t ev = (bytes_equal_mask16(tg, pr.tag8) & valid) | empty;
-        while (ev) {
-          const uint32_t pbit = ev & (0u - ev);
-          ev ^= pbit;
-          uint32_t p = 0;
-#if defined(__CUDA_ARCH__)
-          p = (uint32_t)__ffs((int)pbit) - 1u;
-#else
-          p = (uint32_t)__builtin_ctz(pbit);
-#endif
-          const uint64_t sidx = gb + p;
-          uint64_t *slot = reinterpret_cast<uint64_t *>(t.slots + sidx * STRIDE);
-          uint64_t *meta_ptr = slot + N;
-          uint64_t m;
-          if (empty & pbit) {
-            // first never-claimed slot of the probe order: the key is absent (unless a
-            // concurrent claim is in flight, which the CAS detects)
-            const uint64_t want = meta_pack(covg_add, edge, ST_LOCKED, pr.tag);
-            m = Ops::cas(meta_ptr, 0ull, want);
-            if (m == 0ull) {
-#pragma unroll
-              for (int w = 0; w < N; w++) Ops::store(slot + w, key[w]);
-              Ops::store_tag(t.tags + sidx, pr.tag8);
-              Ops::fence();
-              Ops::xor64(meta_ptr, (uint64_t)(ST_LOCKED ^ ST_NONE) << 40);
-              if (r) Ops::count(&ctr->rehash_hist[r], 1ull);
-              return 1;
-            }
-          } else {
-            m = Ops::load(meta_ptr);
-          }
-          if (slot_examine<N, Ops>(slot, m, pr, ctr, key, edge, covg_add) == 0) {
-            if (r) Ops::count(&ctr->rehash_hist[r], 1ull);
-            return 0;
-          }
-        }
-      }
+LASV_HD int table_upsert_hashed(const TableView &t, GraphCounters *ctr, const uint64_t (&key)[N],
+                                uint32_t c0, uint32_t edge, uint32_t covg_add) {
+  const Probe pr = probe_of_key<N>(key);
+  uint32_t c = c0;
+  for (uint32_t r = 0;;) {
+    const int res = bucket_upsert<N, Ops>(t, ctr, c & t.bucket_mask, pr, key, edge, covg_add);
+    if (res >= 0) {
+      if (r) Ops::count(&ctr->rehash_hist[r], 1ull);
+      return res;
     }
-    // bucket r is full and does not hold the key: follow the rehash chain
+    if (++r > t.max_rehash) break;
+    c = lookup3_key<N>(key, r).c;  // bucket r-1 is full and does not hold the key
   }
   Ops::flag(&ctr->table_full);
   return -1;
 }
 
-// hash_table_find (hash_table.c:234-267) on the UN-finalised device layout, with
+#pragma nv_exec_check_disable
+template <int N, class Ops>
+LASV_HD int table_upsert(const TableView &t, GraphCounters *ctr, const uint64_t (&key)[N],
+                         uint32_t edge, uint32_t covg_add) {
+  return table_upsert_hashed<N, Ops>(t, ctr, key, lookup3_key<N>(key, 0).c, edge, covg_add);
+}
+
+// hash_table_find (hash_table.c:234-267) on the un-finalised device layout, with
 // no insert in flight.  Returns true and the meta word if present.
 #pragma nv_exec_check_disable
 template <int N, class Ops>
 LASV_HD bool table_find(const TableView &t, const uint64_t (&key)[N], uint64_t &meta_out) {
-  constexpr uint32_t STRIDE = 8 * N + 8;
+  constexpr uint32_t SLOT = LineLayout<N>::SLOT, G = LineLayout<N>::G;
+  const Probe pr = probe_of_key<N>(key);
+  const uint64_t rep = (uint64_t)pr.tag8 * 0x0101010101010101ull;
   for (uint32_t r = 0; r <= t.max_rehash; ++r) {
-    const Probe pr = probe_of(lookup3_key<N>(key, r), t.bucket_mask, t.W);
-    const uint64_t b0 = (uint64_t)pr.bucket * t.W;
-    for (int seg = 0; seg < 2; ++seg) {
-      const uint64_t lo = seg ? b0 : b0 + pr.start;
-      const uint64_t hi = seg ? b0 + pr.start : b0 + t.W;
-      for (uint64_t gb = lo & ~15ull; gb < hi; gb += 16) {
-        const uint4 tg = Ops::load_tags16(t.tags + gb);
-        uint32_t valid = 0xFFFFu;
-        if (gb < lo) valid &= 0xFFFFu << (uint32_t)(lo - gb);
-        if (gb + 16 > hi) valid &= 0xFFFFu >> (uint32_t)(gb + 16 - hi);
-        const uint32_t empty = bytes_equal_mask16(tg, 0u) & valid;
-        uint32_t ev = (bytes_equal_mask16(tg, pr.tag8) & valid) | empty;
-        while (ev) {
-          const uint32_t pbit = ev & (0u - ev);
-          ev ^= pbit;
-          if (empty & pbit) return false;  // an empty slot ends the probe run
-          uint32_t p = 0;
-          while (!((pbit >> p) & 1u)) p++;
-          uint64_t *slot = reinterpret_cast<uint64_t *>(t.slots + (gb + p) * STRIDE);
-          const uint64_t m = Ops::load(slot + N);
-          if (meta_tag(m) != pr.tag) continue;
-          bool same = true;
+    uint8_t *base = bucket_base(t, lookup3_key<N>(key, r).c & t.bucket_mask);
+    uint32_t line = mulhi32(pr.h, t.NL);
+    for (uint32_t step = 0; step < t.NL; ++step) {
+      uint8_t *lp = base + (uint64_t)line * LINE_BYTES;
+      const uint64_t hdr = Ops::load(reinterpret_cast<uint64_t *>(lp));
+      const uint64_t valid = header_valid_mask((line == t.NL - 1) ? t.last_slots : G);
+      uint64_t cand = zero_bytes64(hdr ^ rep) & valid;
+      while (cand) {
+        const uint32_t i = first_byte_index(cand);
+        cand &= cand - 1;
+        uint64_t *slot = reinterpret_cast<uint64_t *>(lp + 8u + i * SLOT);
+        bool same = true;
 #pragma unroll
-          for (int w = 0; w < N; w++) same &= (Ops::load(slot + w) == key[w]);
-          if (same) { meta_out = m; return true; }
-        }
+        for (int w = 0; w < N; w++) same &= (Ops::load(slot + w) == key[w]);
+        if (same) { meta_out = Ops::load(slot + N); return true; }
       }
+      if (zero_bytes64(hdr) & valid) return false;  // a claimable slot ends the probe
+      line = (line + 1 == t.NL) ? 0u : line + 1;
     }
     // bucket full without the key: next bucket of the chain
   }
@@ -271,13 +307,11 @@ LASV_HD bool table_find(const TableView &t, const uint64_t (&key)[N], uint64_t &
 #pragma nv_exec_check_disable
 template <int N, class Ops>
 LASV_HD bool table_find_finalized(const TableView &t, const uint64_t (&key)[N], uint64_t &meta_out) {
-  constexpr uint32_t STRIDE = 8 * N + 8;
+  constexpr uint32_t SLOT = LineLayout<N>::SLOT;
   for (uint32_t r = 0; r <= t.max_rehash; ++r) {
-    const Probe pr = probe_of(lookup3_key<N>(key, r), t.bucket_mask, t.W);
-    uint8_t *bucket = t.slots + (uint64_t)pr.bucket * t.W * STRIDE;
-    uint32_t s = 0;
-    for (; s < t.W; ++s) {
-      uint64_t *slot = reinterpret_cast<uint64_t *>(bucket + (uint64_t)s * STRIDE);
+    uint8_t *bucket = bucket_base(t, lookup3_key<N>(key, r).c & t.bucket_mask);
+    for (uint32_t s = 0; s < t.W; ++s) {
+      uint64_t *slot = reinterpret_cast<uint64_t *>(bucket + (uint64_t)s * SLOT);
       const uint64_t m = Ops::load(slot + N);
       if (meta_status(m) == ST_EMPTY) return false;  // hole-free buckets: not present
       bool same = true;

@@ -22,19 +22,13 @@ namespace {
 struct HostOps {
   static uint64_t load(const uint64_t *p) { return *p; }
   static void store(uint64_t *p, uint64_t v) { *p = v; }
-  static void prefetch(const void *) {}
-  static uint4 load_tags16(const uint8_t *p) {
-    uint4 v;
-    memcpy(&v, p, 16);
-    return v;
-  }
   static void store_tag(uint8_t *p, uint32_t v) { *p = (uint8_t)v; }
   static uint64_t cas(uint64_t *p, uint64_t expect, uint64_t want) {
     uint64_t old = *p;
     if (old == expect) *p = want;
     return old;
   }
-  static void xor64(uint64_t *p, uint64_t v) { *p ^= v; }
+  static void xor32(uint32_t *p, uint32_t v) { *p ^= v; }
   static void add32(uint32_t *p, uint32_t v) { *p += v; }
   static void or32(uint32_t *p, uint32_t v) { *p |= v; }
   static void fence() {}
@@ -112,20 +106,10 @@ void walk(const uint8_t *seq_in, const uint8_t *qual_in, uint64_t n_in, int k, i
   }
 }
 
-TableView view_of(uint8_t *table, uint8_t *tags, int L, int W, int max_rehash) {
-  TableView t;
-  t.slots = table;
-  t.tags = tags;
-  t.bucket_mask = (uint32_t)((1ull << L) - 1);
-  t.W = (uint32_t)W;
-  t.max_rehash = (uint32_t)max_rehash;
-  return t;
-}
-
 template <int N>
 int build_fused(const uint8_t *seq, const uint8_t *qual, uint64_t n_bytes, int k, int cutoff, int L,
-                int W, int max_rehash, int T, uint8_t *table, uint8_t *tags, GraphCounters *ctr) {
-  const TableView tv = view_of(table, tags, L, W, max_rehash);
+                int W, int max_rehash, int T, uint8_t *table, GraphCounters *ctr) {
+  const TableView tv = make_table_view(table, N, L, W, max_rehash, false);
   walk<N>(seq, qual, n_bytes, k, cutoff, T & 0xFFFF, [&](const uint64_t(&key)[N], uint32_t edge) {
     ctr->kmers_inserted++;
     const int r = table_upsert<N, HostOps>(tv, ctr, key, edge, 1u);
@@ -154,14 +138,15 @@ uint64_t extract(const uint8_t *seq, const uint8_t *qual, uint64_t n_bytes, int 
 
 template <int N>
 int insert_records(const uint32_t *recs, uint64_t n, int L, int W, int max_rehash, uint8_t *table,
-                   uint8_t *tags, GraphCounters *ctr) {
-  const TableView tv = view_of(table, tags, L, W, max_rehash);
+                   GraphCounters *ctr) {
+  const TableView tv = make_table_view(table, N, L, W, max_rehash, false);
   for (uint64_t i = 0; i < n; i++) {
     const uint32_t *src = recs + i * (2 * N + 1);
     uint64_t key[N];
     for (int w = 0; w < N; w++) key[w] = (uint64_t)src[2 * w] | ((uint64_t)src[2 * w + 1] << 32);
     const uint32_t m = src[2 * N];
-    const int r = table_upsert<N, HostOps>(tv, ctr, key, m & 0xFFu, m >> 8);
+    // the records path hands the first-bucket hash over instead of hashing twice
+    const int r = table_upsert_hashed<N, HostOps>(tv, ctr, key, lookup3_key<N>(key, 0).c, m & 0xFFu, m >> 8);
     if (r == 1) ctr->unique_kmers++;
   }
   return ctr->table_full ? -3 : 0;
@@ -170,10 +155,11 @@ int insert_records(const uint32_t *recs, uint64_t n, int L, int W, int max_rehas
 // finalize_kernel restated with its 32-slot chunking (read a chunk, then write)
 template <int N>
 void finalize(uint8_t *table, int L, int W, int16_t *next) {
-  constexpr uint32_t STRIDE = 8 * N + 8;
+  constexpr uint32_t SLOT = LineLayout<N>::SLOT;
+  const TableView tv = make_table_view(table, N, L, W, 15, false);
   const uint64_t nb = 1ull << L;
   for (uint64_t b = 0; b < nb; b++) {
-    uint8_t *bucket = table + b * (uint64_t)W * STRIDE;
+    uint8_t *bucket = bucket_base(tv, (uint32_t)b);
     uint32_t filled = 0;
     for (uint32_t s0 = 0; s0 < (uint32_t)W; s0 += 32) {
       uint64_t keys[32][N], metas[32];
@@ -182,7 +168,7 @@ void finalize(uint8_t *table, int L, int W, int16_t *next) {
         const uint32_t s = s0 + l;
         metas[l] = 0;
         if (s < (uint32_t)W) {
-          const uint64_t *slot = reinterpret_cast<const uint64_t *>(bucket + (uint64_t)s * STRIDE);
+          const uint64_t *slot = slot_ptr<N>(tv, (uint32_t)b, s);
           metas[l] = slot[N];
           for (int w = 0; w < N; w++) keys[l][w] = slot[w];
         }
@@ -191,23 +177,32 @@ void finalize(uint8_t *table, int L, int W, int16_t *next) {
       uint32_t rank = 0;
       for (uint32_t l = 0; l < 32; l++) {
         if (!occ[l]) continue;
-        uint64_t *dst = reinterpret_cast<uint64_t *>(bucket + (uint64_t)(filled + rank) * STRIDE);
+        uint64_t *dst = reinterpret_cast<uint64_t *>(bucket + (uint64_t)(filled + rank) * SLOT);
         for (int w = 0; w < N; w++) dst[w] = keys[l][w];
         dst[N] = meta_pack(meta_covg(metas[l]), meta_edges(metas[l]), ST_NONE, 0);
         rank++;
       }
       filled += rank;
     }
-    for (uint32_t s = filled; s < (uint32_t)W; s++)
-      memset(bucket + (uint64_t)s * STRIDE, 0, STRIDE);
+    memset(bucket + (uint64_t)filled * SLOT, 0, (size_t)tv.NL * LINE_BYTES - (size_t)filled * SLOT);
     if (next) next[b] = (int16_t)filled;
   }
 }
 
+// slot s of bucket b -> out[b*W + s] (reference Element bytes), either arrangement
 template <int N>
-void find(uint8_t *table, uint8_t *tags, int L, int W, int max_rehash, int finalized, const uint64_t *keys,
+void gather(uint8_t *table, int L, int W, int finalized, uint8_t *out) {
+  constexpr uint32_t SLOT = LineLayout<N>::SLOT;
+  const TableView tv = make_table_view(table, N, L, W, 15, finalized != 0);
+  for (uint64_t b = 0; b < (1ull << L); b++)
+    for (uint32_t s = 0; s < (uint32_t)W; s++)
+      memcpy(out + (b * (uint64_t)W + s) * SLOT, slot_ptr<N>(tv, (uint32_t)b, s), SLOT);
+}
+
+template <int N>
+void find(uint8_t *table, int L, int W, int max_rehash, int finalized, const uint64_t *keys,
           uint64_t n, uint32_t *covg, uint8_t *edges, uint8_t *found) {
-  const TableView tv = view_of(table, tags, L, W, max_rehash);
+  const TableView tv = make_table_view(table, N, L, W, max_rehash, finalized != 0);
   for (uint64_t i = 0; i < n; i++) {
     uint64_t key[N], m = 0;
     for (int w = 0; w < N; w++) key[w] = keys[i * N + w];
@@ -225,13 +220,18 @@ void find(uint8_t *table, uint8_t *tags, int L, int W, int max_rehash, int final
 
 extern "C" {
 
+// bytes of the device table for (k, L, W): 2^L buckets x ceil(W/G) lines x 128
+uint64_t emul_table_bytes(int k, int L, int W) {
+  const int N = 2 * k / 64 + 1;
+  return table_bytes(make_table_view(nullptr, N, L, W, 15, false));
+}
+
 int emul_build_fused(const uint8_t *seq, const uint8_t *qual, uint64_t n_bytes, int k, int cutoff,
-                     int L, int W, int max_rehash, int T, uint8_t *table, uint8_t *tags,
-                     uint64_t *counters20) {
+                     int L, int W, int max_rehash, int T, uint8_t *table, uint64_t *counters20) {
   GraphCounters ctr;
   memset(&ctr, 0, sizeof ctr);
   const int N = 2 * k / 64 + 1;
-  const int rc = DISPATCH(N, build_fused)(seq, qual, n_bytes, k, cutoff, L, W, max_rehash, T, table, tags, &ctr);
+  const int rc = DISPATCH(N, build_fused)(seq, qual, n_bytes, k, cutoff, L, W, max_rehash, T, table, &ctr);
   counters20[0] = ctr.unique_kmers;
   counters20[1] = ctr.kmers_inserted;
   counters20[2] = ctr.table_full;
@@ -246,11 +246,11 @@ uint64_t emul_extract_records(const uint8_t *seq, const uint8_t *qual, uint64_t 
 }
 
 int emul_insert_records(const uint32_t *recs, uint64_t n, int k, int L, int W, int max_rehash,
-                        uint8_t *table, uint8_t *tags, uint64_t *counters20) {
+                        uint8_t *table, uint64_t *counters20) {
   GraphCounters ctr;
   memset(&ctr, 0, sizeof ctr);
   const int N = 2 * k / 64 + 1;
-  const int rc = DISPATCH(N, insert_records)(recs, n, L, W, max_rehash, table, tags, &ctr);
+  const int rc = DISPATCH(N, insert_records)(recs, n, L, W, max_rehash, table, &ctr);
   counters20[0] = ctr.unique_kmers;
   counters20[2] = ctr.table_full;
   for (int r = 0; r < 16; r++) counters20[3 + r] = ctr.rehash_hist[r];
@@ -262,10 +262,15 @@ void emul_finalize(uint8_t *table, int k, int L, int W, int16_t *next) {
   DISPATCH(N, finalize)(table, L, W, next);
 }
 
-void emul_find(uint8_t *table, uint8_t *tags, int k, int L, int W, int max_rehash, int finalized,
+void emul_gather(uint8_t *table, int k, int L, int W, int finalized, uint8_t *out) {
+  const int N = 2 * k / 64 + 1;
+  DISPATCH(N, gather)(table, L, W, finalized, out);
+}
+
+void emul_find(uint8_t *table, int k, int L, int W, int max_rehash, int finalized,
                const uint64_t *keys, uint64_t n, uint32_t *covg, uint8_t *edges, uint8_t *found) {
   const int N = 2 * k / 64 + 1;
-  DISPATCH(N, find)(table, tags, L, W, max_rehash, finalized, keys, n, covg, edges, found);
+  DISPATCH(N, find)(table, L, W, max_rehash, finalized, keys, n, covg, edges, found);
 }
 
 uint32_t emul_hash_c(const uint64_t *key, int N, uint32_t rehash) {

@@ -25,16 +25,55 @@ def emul():
         subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas",
                         "-I/usr/local/cuda/include", "-o", str(so), str(src)], check=True)
     L = C.CDLL(str(so))
-    L.emul_build_fused.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64] + [C.c_int] * 6 + [C.c_void_p] * 3
+    L.emul_table_bytes.restype = C.c_uint64
+    L.emul_table_bytes.argtypes = [C.c_int] * 3
+    L.emul_build_fused.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64] + [C.c_int] * 6 + [C.c_void_p] * 2
     L.emul_extract_records.restype = C.c_uint64
     L.emul_extract_records.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_int,
                                        C.c_void_p, C.c_uint64]
-    L.emul_insert_records.argtypes = [C.c_void_p, C.c_uint64] + [C.c_int] * 4 + [C.c_void_p] * 3
+    L.emul_insert_records.argtypes = [C.c_void_p, C.c_uint64] + [C.c_int] * 4 + [C.c_void_p] * 2
     L.emul_finalize.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
-    L.emul_find.argtypes = [C.c_void_p, C.c_void_p] + [C.c_int] * 5 + [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.emul_gather.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    L.emul_find.argtypes = [C.c_void_p] + [C.c_int] * 5 + [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]
     L.emul_hash_c.restype = C.c_uint32
     L.emul_hash_c.argtypes = [C.c_void_p, C.c_int, C.c_uint32]
     return L
+
+
+class EmulTable:
+    """The device table as the kernels see it: 2^L buckets x ceil(W/G) lines of 128
+    bytes (kmer_core.cuh "line layout"), in host memory."""
+
+    def __init__(self, emul, k, L, W):
+        self.emul, self.k, self.L, self.W, self.N = emul, k, L, W, words_per_kmer(k)
+        self.raw = np.zeros(int(emul.emul_table_bytes(k, L, W)), dtype=np.uint8)
+        self.finalized = False
+
+    @property
+    def ptr(self):
+        return self.raw.ctypes.data
+
+    def elements(self):
+        """Slot s of bucket b -> out[b*W+s], as reference Elements (holes included)."""
+        out = np.zeros((1 << self.L) * self.W, dtype=element_dtype(self.N))
+        self.emul.emul_gather(self.ptr, self.k, self.L, self.W, int(self.finalized), out.ctypes.data)
+        return out
+
+    def finalize(self):
+        nxt = np.zeros(1 << self.L, dtype=np.int16)
+        self.emul.emul_finalize(self.ptr, self.k, self.L, self.W, nxt.ctypes.data)
+        self.finalized = True
+        return nxt
+
+    def find(self, keys):
+        n = len(keys)
+        covg, edges, found = np.zeros(n, np.uint32), np.zeros(n, np.uint8), np.zeros(n, np.uint8)
+        self.emul.emul_find(self.ptr, self.k, self.L, self.W, 15, int(self.finalized), keys.ctypes.data, n,
+                            covg.ctypes.data, edges.ctypes.data, found.ctypes.data)
+        return found.astype(bool), covg, edges
+
+    def records(self):
+        return table_records(self.elements())
 
 
 def table_records(table):
@@ -48,15 +87,11 @@ def emul_build(emul, meta, seq, qual, T=896, L=None, W=None):
     k = meta["k"]
     L = L or meta["L"]
     W = W or meta["W"]
-    N = words_per_kmer(k)
-    table = np.zeros((1 << L) * W, dtype=element_dtype(N))
-    tags = np.zeros((1 << L) * W + 32, dtype=np.uint8)        # one tag byte per slot (+ slack)
+    tab = EmulTable(emul, k, L, W)
     ctr = np.zeros(20, dtype=np.uint64)
     rc = emul.emul_build_fused(seq.ctypes.data, qual.ctypes.data if qual is not None else None, len(seq), k,
-                               util.cutoff_of(meta), L, W, 15, T, table.ctypes.data, tags.ctypes.data,
-                               ctr.ctypes.data)
-    emul_build.tags = tags
-    return rc, table, ctr
+                               util.cutoff_of(meta), L, W, 15, T, tab.ptr, ctr.ctypes.data)
+    return rc, tab, ctr
 
 
 @pytest.mark.parametrize("name", util.ALL_CASES)
@@ -64,8 +99,9 @@ def emul_build(emul, meta, seq, qual, T=896, L=None, W=None):
 def test_emulated_build_matches_reference_golden(emul, name, T):
     meta = util.case_meta(name)
     seq, qual, _ = util.case_streams(name)
-    rc, table, ctr = emul_build(emul, meta, seq, qual, T)
+    rc, tab, ctr = emul_build(emul, meta, seq, qual, T)
     assert rc == 0
+    table = tab.elements()
     util.assert_same_records(table_records(table), util.case_records(name), name)
     assert int(ctr[1]) == meta["inserts"]
     assert int(ctr[0]) == meta["n_records"]
@@ -83,26 +119,34 @@ def test_emulated_finalize_gives_reference_layout(emul, name):
     k, L, W = meta["k"], meta["L"], meta["W"]
     N = words_per_kmer(k)
     seq, qual, _ = util.case_streams(name)
-    rc, table, ctr = emul_build(emul, meta, seq, qual)
+    rc, tab, ctr = emul_build(emul, meta, seq, qual)
     assert rc == 0
     gold = util.case_records(name)
     keys = np.ascontiguousarray(gold["kmer"])
     n = len(keys)
-    covg, edges, found = np.zeros(n, np.uint32), np.zeros(n, np.uint8), np.zeros(n, np.uint8)
-    tags = emul_build.tags
-    emul.emul_find(table.ctypes.data, tags.ctypes.data, k, L, W, 15, 0, keys.ctypes.data, n, covg.ctypes.data,
-                   edges.ctypes.data, found.ctypes.data)
+    found, covg, edges = tab.find(keys)
     assert found.all() and np.array_equal(covg, gold["covg"]) and np.array_equal(edges, gold["edges"])
-    # the tag array mirrors the occupancy exactly (0 <=> empty slot)
-    assert np.array_equal(tags[: len(table)] != 0, table["status"] != 0)
+    # the header tag bytes mirror the occupancy exactly (0 <=> empty slot), slots fill each
+    # line in order, and bytes past the line's slots stay zero
+    G = (128 - 8) // (8 * N + 8)
+    NL = -(-W // G)
+    lines = tab.raw.reshape(1 << L, NL, 128)
+    hdr = lines[:, :, :8]
+    assert not hdr[:, :, G:].any()
+    occ_dev = (tab.elements()["status"] != 0).reshape(1 << L, W)
+    tag_occ = (hdr[:, :, :G] != 0).reshape(1 << L, NL * G)
+    assert np.array_equal(tag_occ[:, :W], occ_dev) and not tag_occ[:, W:].any()
     absent0 = keys.copy()
     absent0[:, -1] ^= np.uint64(0x5555)
-    emul.emul_find(table.ctypes.data, tags.ctypes.data, k, L, W, 15, 0, absent0.ctypes.data, n, covg.ctypes.data,
-                   edges.ctypes.data, found.ctypes.data)
+    found, _, _ = tab.find(absent0)
     present0 = {tuple(x) for x in keys.tolist()}
     assert [bool(f) for f in found] == [tuple(x) in present0 for x in absent0.tolist()]
-    nxt = np.zeros(1 << L, dtype=np.int16)
-    emul.emul_finalize(table.ctypes.data, k, L, W, nxt.ctypes.data)
+    nxt = tab.finalize()
+    table = tab.elements()
+    # every bucket: W consecutive Elements at the start of its lines, zero slack behind
+    pitched = tab.raw.reshape(1 << L, NL * 128)
+    assert np.array_equal(pitched[:, : W * (8 * N + 8)].reshape(-1), table.view(np.uint8).reshape(-1))
+    assert not pitched[:, W * (8 * N + 8):].any()
     raw = table.view(np.uint8).reshape(len(table), 8 * N + 8)
     assert not raw[:, 8 * N + 6:].any()                       # pad bytes zeroed
     t2 = table.reshape(1 << L, W)
@@ -110,24 +154,19 @@ def test_emulated_finalize_gives_reference_layout(emul, name):
     assert np.array_equal(occ.sum(axis=1), nxt)
     assert (occ == (np.arange(W)[None, :] < nxt[:, None])).all()    # hole-free from slot 0
     assert not raw[~occ.reshape(-1)].any()                    # empty slots are all-zero bytes
-    emul.emul_find(table.ctypes.data, tags.ctypes.data, k, L, W, 15, 1, keys.ctypes.data, n, covg.ctypes.data,
-                   edges.ctypes.data, found.ctypes.data)
+    found, covg, edges = tab.find(keys)
     assert found.all() and np.array_equal(covg, gold["covg"]) and np.array_equal(edges, gold["edges"])
-    # independent check with the ORACLE's own find (reference bucket scan + rehash chain):
-    # place the finalised slots into an oracle table slot for slot and look every key up
-    g = O.OracleGraph(k, L, W)
+    # independent check against the reference's placement rule (bucket scan + rehash chain)
     for b in range(1 << L):                                   # bucket b holds exactly the keys the
         for s in range(int(nxt[b])):                          # reference chain would look for there
             h = [O.hash_value(t2["kmer"][b, s], r, L) for r in range(16)]
             assert b in h
             r = h.index(b)
             assert all(nxt[hb] == W for hb in h[:r])          # earlier buckets of the chain are full
-    g.close()
     util.assert_same_records(table_records(table), gold, name)
     absent = keys.copy()
     absent[:, -1] ^= np.uint64(0x5555)
-    emul.emul_find(table.ctypes.data, tags.ctypes.data, k, L, W, 15, 1, absent.ctypes.data, n, covg.ctypes.data,
-                   edges.ctypes.data, found.ctypes.data)
+    found, _, _ = tab.find(absent)
     present = {tuple(x) for x in keys.tolist()}
     assert [bool(f) for f in found] == [tuple(x) in present for x in absent.tolist()]
 
@@ -146,8 +185,7 @@ def test_emulated_records_path(emul, name):
     assert n == meta["inserts"]
     # shard the records by owner bits exactly as the ROUTE mode does and insert per shard
     g_bits = 1
-    shards = [np.zeros((1 << (L - g_bits)) * W, dtype=element_dtype(N)) for _ in range(2)]
-    shard_tags = [np.zeros((1 << (L - g_bits)) * W + 32, dtype=np.uint8) for _ in range(2)]
+    shards = [EmulTable(emul, k, L - g_bits, W) for _ in range(2)]
     owner = np.zeros(n, dtype=np.int64)
     for i in range(n):
         key = np.zeros(N, dtype=np.uint64)
@@ -161,9 +199,9 @@ def test_emulated_records_path(emul, name):
         sub = np.ascontiguousarray(recs[:n][owner == d])
         ctr = np.zeros(20, dtype=np.uint64)
         rc = emul.emul_insert_records(sub.ctypes.data, len(sub), k, L - g_bits, W, 15,
-                                      shards[d].ctypes.data, shard_tags[d].ctypes.data, ctr.ctypes.data)
+                                      shards[d].ptr, ctr.ctypes.data)
         assert rc == 0
-        all_recs.append(table_records(shards[d]))
+        all_recs.append(shards[d].records())
     util.assert_same_records(np.concatenate(all_recs), util.case_records(name), name)
 
 
@@ -191,7 +229,7 @@ def test_emulated_ragged_and_tiny_inputs(emul):
         for T in (384, 896, 896 | (5 << 16), 384 | (15 << 16)):    # last two: misaligned stream pointer
             rc, table, ctr = emul_build(emul, meta, seq, qual, T)
             assert rc == 0
-            util.assert_same_records(table_records(table), g.records(), f"k={k}")
+            util.assert_same_records(table.records(), g.records(), f"k={k}")
             assert int(ctr[1]) == g.stats.kmers_inserted
     rc, table, ctr = emul_build(emul, {"k": 31, "L": 4, "W": 4, "q_thresh": 0}, np.zeros(0, np.uint8),
                                 np.zeros(0, np.uint8))

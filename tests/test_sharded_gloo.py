@@ -37,7 +37,10 @@ def _worker(rank, world, port, name, outdir):
     emul.emul_extract_records.restype = C.c_uint64
     emul.emul_extract_records.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_int,
                                           C.c_void_p, C.c_uint64]
-    emul.emul_insert_records.argtypes = [C.c_void_p, C.c_uint64] + [C.c_int] * 4 + [C.c_void_p] * 3
+    emul.emul_insert_records.argtypes = [C.c_void_p, C.c_uint64] + [C.c_int] * 4 + [C.c_void_p] * 2
+    emul.emul_table_bytes.restype = C.c_uint64
+    emul.emul_table_bytes.argtypes = [C.c_int] * 3
+    emul.emul_gather.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
     emul.emul_hash_c.restype = C.c_uint32
     emul.emul_hash_c.argtypes = [C.c_void_p, C.c_int, C.c_uint32]
     meta = util.case_meta(name)
@@ -71,11 +74,12 @@ def _worker(rank, world, port, name, outdir):
     total, rc = exchange_records(bins, counts, recv)
     assert total == int(rc.sum())
     got = np.ascontiguousarray(recv[:total].numpy().view(np.uint32))
-    table = np.zeros((1 << (L - bits)) * W, dtype=element_dtype(N))
+    raw = np.zeros(int(emul.emul_table_bytes(k, L - bits, W)), dtype=np.uint8)   # device line layout
     ctr = np.zeros(20, dtype=np.uint64)
-    tags = np.zeros(len(table) + 32, dtype=np.uint8)
-    assert emul.emul_insert_records(got.ctypes.data, total, k, L - bits, W, 15, table.ctypes.data,
-                                    tags.ctypes.data, ctr.ctypes.data) == 0
+    assert emul.emul_insert_records(got.ctypes.data, total, k, L - bits, W, 15, raw.ctypes.data,
+                                    ctr.ctypes.data) == 0
+    table = np.zeros((1 << (L - bits)) * W, dtype=element_dtype(N))
+    emul.emul_gather(raw.ctypes.data, k, L - bits, W, 0, table.ctypes.data)
     np.save(Path(outdir) / f"shard{rank}.npy", table)
     # job-wide insert count through a collective, as ShardedDBGraph.stats does
     t = torch.tensor([n], dtype=torch.int64)

@@ -1,0 +1,18 @@
+# usage: bash tools/run_gpu.sh <tag> [steps...]   (runs on the GPU box via gpurun)
+tag=$1; shift
+out=gpurun_out/$tag; mkdir -p $out
+MET=gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,smsp__inst_executed.sum,smsp__thread_inst_executed_per_inst_executed.ratio,sm__inst_executed.avg.per_cycle_elapsed
+for step in "$@"; do
+case $step in
+  pytest) timeout 900 python -m pytest tests -m gpu -x -q > $out/pytest.log 2>&1; echo "pytest rc=$?" >> $out/pytest.log;;
+  bench) timeout 600 python bench.py --steps 5 --warmup 3 > $out/bench_default.log 2> $out/bench_default.err;;
+  direct) LASV_B200_INSERT=direct timeout 600 python bench.py --steps 5 --warmup 3 --no-e2e --no-cpu-baseline > $out/bench_direct.log 2>&1;;
+  binned) LASV_B200_INSERT=binned timeout 600 python bench.py --steps 5 --warmup 3 --no-e2e --no-cpu-baseline > $out/bench_binned.log 2>&1;;
+  cfg0) timeout 600 python bench.py --workload cfg0 --steps 3 --warmup 3 --no-cpu-baseline > $out/bench_cfg0.log 2>&1;;
+  launches) timeout 900 ncu --metrics $MET --clock-control none --profile-from-start off --csv --log-file $out/launches.csv python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline > $out/ncu_launches.log 2>&1;;
+  launches_direct) LASV_B200_INSERT=direct timeout 900 ncu --metrics $MET --clock-control none --profile-from-start off --csv --log-file $out/launches_direct.csv python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline > $out/ncu_launches_direct.log 2>&1;;
+  full) timeout 900 ncu --set full --import-source on --clock-control none --profile-from-start off -k regex:"build_kernel|insert_" -c 2 -o $out/prof python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu-baseline > $out/ncu_full.log 2>&1;;
+  *) echo "unknown step $step";;
+esac
+done
+ls -la $out
