@@ -361,8 +361,6 @@ int lasv_graph_load_reads_device(lasv_graph *g, const uint8_t *d_seq, const uint
       CUDA_TRY(cudaMemsetAsync(g->bins.count, 0, (size_t)n_bins * COUNT_STRIDE * sizeof(unsigned int), st));
       launch_build(g->N, MODE_BIN, p, st);
       if (int e = check_launch()) return e;
-      launch_bin_prefix(g->bins, st);
-      if (int e = check_launch()) return e;
       launch_insert_bins(g->N, g->bins, g->view(), g->d_ctr, st);
       if (int e = check_launch()) return e;
     } else {

@@ -17,6 +17,7 @@
 // sectors in HBM; everything else is streaming.  Grids are persistent:
 // (#SMs x resident CTAs) CTAs looping over tiles.
 #include <cub/device/device_scan.cuh>
+#include <stdlib.h>
 #include <type_traits>
 #include "graph_kernels.cuh"
 #include "synth.cuh"
@@ -114,16 +115,70 @@ __device__ __forceinline__ uint64_t load_bin_record(const uint64_t *src, uint64_
 
 // --------------------------------------------------------------------------
 // upsert_batch: U independent find-or-inserts per lane with the memory accesses
-// of the common case issued together
+// of the common case issued together; the uncommon cases are set aside and run
+// 32 at a time
 // --------------------------------------------------------------------------
-// Steady state of a 30x build: ~99 % of the operations find their key behind a
-// visible tag in the first line probed.  That case is two dependent round trips
-// (header, then meta + key words of the tagged slot) and one reduction; the U
-// items of a lane take it in lock step so that U headers, then U slots, are in
-// flight at once.  Whatever does not finish there (no tag match, tag collision,
-// new key, full line) goes through the complete protocol of table.cuh.
+// Steady state of a 30x build: ~99 % of the operations find their key, ~90 % of
+// them behind a visible tag in the first line probed.  That case is two dependent
+// round trips (header, then meta + key words of the tagged slot) and one
+// reduction; the U items of a lane take it in lock step so that U headers, then U
+// slots, are in flight at once.  Whatever does not finish there (no tag match in
+// the first line, tag collision, new key) needs the complete protocol of
+// table.cuh, whose loops would run with two or three lanes of the warp alive if
+// entered on the spot.  Those items are pushed to a per-warp queue in shared
+// memory instead and drained 32 at a time (operations on the table commute, so
+// the order does not matter).
+template <int N>
+struct DeferItem {
+  uint64_t key[N];
+  uint32_t c;
+  uint32_t em;  // edges | count << 8
+};
+constexpr int DEFER_CAP = 64;  // < 32 queued between calls, + at most 32 per push
+
+template <int N>
+struct DeferQueue {
+  DeferItem<N> *q;  // DEFER_CAP items of this warp, shared memory
+  uint32_t n;       // warp-uniform
+
+  __device__ __forceinline__ void drain32(const TableView &t, GraphCounters *ctr, unsigned long long &my_new,
+                                          uint32_t take) {
+    // `take` <= 32 items off the top; lanes >= take idle
+    const unsigned lane = lane_id();
+    n -= take;
+    __syncwarp();
+    if (lane < take) {
+      const DeferItem<N> it = q[n + lane];
+      uint64_t key[N];
+#pragma unroll
+      for (int w = 0; w < N; w++) key[w] = it.key[w];
+      const int r = table_upsert_hashed<N, DeviceOps>(t, ctr, key, it.c, it.em & 0xFFu, it.em >> 8);
+      my_new += (r == 1);
+    }
+    __syncwarp();
+  }
+  __device__ __forceinline__ void push(const TableView &t, GraphCounters *ctr, unsigned long long &my_new,
+                                       bool want, const uint64_t (&key)[N], uint32_t c, uint32_t edge,
+                                       uint32_t count) {
+    const unsigned m = __ballot_sync(FULL, want);
+    if (m == 0u) return;
+    if (want) {
+      DeferItem<N> &d = q[n + __popc(m & lanemask_lt())];
+#pragma unroll
+      for (int w = 0; w < N; w++) d.key[w] = key[w];
+      d.c = c;
+      d.em = (edge & 0xFFu) | (count << 8);
+    }
+    n += __popc(m);
+    if (n >= 32u) drain32(t, ctr, my_new, 32u);
+  }
+  __device__ __forceinline__ void flush(const TableView &t, GraphCounters *ctr, unsigned long long &my_new) {
+    while (n) drain32(t, ctr, my_new, n < 32u ? n : 32u);
+  }
+};
+
 template <int N, int U>
-__device__ __forceinline__ void upsert_batch(const TableView &t, GraphCounters *ctr,
+__device__ __forceinline__ void upsert_batch(const TableView &t, GraphCounters *ctr, DeferQueue<N> &dq,
                                              const uint64_t (&key)[U][N], const uint32_t (&c)[U],
                                              const uint32_t (&edge)[U], const uint32_t (&count)[U],
                                              const bool (&act)[U], unsigned long long &my_new) {
@@ -152,30 +207,21 @@ __device__ __forceinline__ void upsert_batch(const TableView &t, GraphCounters *
     const uint32_t i = cand ? first_byte_index(cand) : 0u;
     slot[u] = reinterpret_cast<uint64_t *>(lp[u] + 8u + i * SLOT);
   }
-  uint64_t m[U], kw[U][N];
+  uint64_t sw[U][N + 1];
 #pragma unroll
   for (int u = 0; u < U; u++) {
-    m[u] = 0;
 #pragma unroll
-    for (int w = 0; w < N; w++) kw[u][w] = ~key[u][w];
-    if (has[u]) {
-      m[u] = DeviceOps::load(slot[u] + N);
-#pragma unroll
-      for (int w = 0; w < N; w++) kw[u][w] = DeviceOps::load(slot[u] + w);
-    }
+    for (int w = 0; w < N; w++) sw[u][w] = ~key[u][w];
+    sw[u][N] = 0;
+    if (has[u]) slot_load_words<N, DeviceOps>(slot[u], sw[u]);
   }
 #pragma unroll
   for (int u = 0; u < U; u++) {
     bool same = has[u];
 #pragma unroll
-    for (int w = 0; w < N; w++) same &= (kw[u][w] == key[u][w]);
-    if (same) {
-      slot_accumulate<DeviceOps>(slot[u] + N, m[u], edge[u], count[u], ctr);
-    } else if (act[u]) {
-      const int r = table_upsert_hashed<N, DeviceOps>(t, ctr, key[u], c[u], edge[u], count[u]);
-      my_new += (r == 1);
-    }
-    __syncwarp();  // lanes that took the long way rejoin here (callers are warp-convergent)
+    for (int w = 0; w < N; w++) same &= (sw[u][w] == key[u][w]);
+    if (same) slot_accumulate<DeviceOps>(slot[u] + N, sw[u][N], edge[u], count[u], ctr);
+    dq.push(t, ctr, my_new, act[u] && !same, key[u], c[u], edge[u], count[u]);
   }
 }
 
@@ -209,6 +255,7 @@ struct WarpTile {
   uint32_t bin_count[16];
   uint32_t bin_rank[16];
   unsigned long long tile_base[16];
+  DeferItem<N> defer[(MODE == MODE_FUSED) ? DEFER_CAP : 1];
 };
 
 template <int N, int MODE>
@@ -234,6 +281,7 @@ build_kernel(const BuildParams p, const uint64_t n_tiles) {
 
   unsigned long long my_new = 0;    // keys this thread created
   unsigned long long my_kmers = 0;  // lane 0: occurrences in this warp's tiles
+  DeferQueue<N> dq{wt.defer, 0u};
 
   const uint64_t warp_global = (uint64_t)blockIdx.x * WARPS + (threadIdx.x >> 5);
   const uint64_t warp_stride = (uint64_t)gridDim.x * WARPS;
@@ -319,7 +367,7 @@ build_kernel(const BuildParams p, const uint64_t n_tiles) {
         }
       }
       if (MODE == MODE_FUSED) {
-        upsert_batch<N, U>(p.table, p.ctr, key, hc, edge, count, lead, my_new);
+        upsert_batch<N, U>(p.table, p.ctr, dq, key, hc, edge, count, lead, my_new);
       } else if (MODE == MODE_BIN) {
         uint32_t idx[U];
 #pragma unroll
@@ -379,6 +427,8 @@ build_kernel(const BuildParams p, const uint64_t n_tiles) {
     }
   }
 
+  if (MODE == MODE_FUSED) dq.flush(p.table, p.ctr, my_new);
+
   // ---- warp-level counters
   if (MODE == MODE_FUSED || MODE == MODE_BIN) {
 #pragma unroll
@@ -432,55 +482,93 @@ __global__ void __launch_bounds__(1024) bin_prefix_kernel(const BinView b) {
   if (threadIdx.x == 0) b.prefix[b.n_bins] = sCarry;
 }
 
-// Walks the logical concatenation of the bins: a warp takes 32*U consecutive
-// records per round and the rounds of all resident warps are neighbours, so at
-// any moment the whole GPU works on a few adjacent table regions.  One binary
-// search per warp round locates the bin; lanes walk on from there.
+// All warps of the grid sweep the bins in the same order, bin by bin, so that at
+// any moment the whole GPU works inside one or two table regions (<= 64 MB each:
+// TLB-, L2- and DRAM-row-friendly).  A bin is cut into chunks of 32 records and
+// chunk j of bin b belongs to warp (j + first_b) mod n_warps, first_b = number of
+// chunks of all earlier bins: a round robin over the concatenation of the bins
+// that every warp derives by itself from the bin counters -- no prefix pass, no
+// search.  A warp collects U of its chunks into a batch, loads the records together
+// and runs them through upsert_batch.  (A three-stage software pipeline with L2
+// prefetches of records and table lines was tried and was slower: the kernel is
+// bound by scattered DRAM write-backs -- tools/ubench "sweep": ~21 G dirty
+// sectors/s whatever the instruction that dirties them -- not by load latency,
+// and FEWER resident warps do better, hence the small grid.)
+template <int U>
+struct BinBatch {
+  uint64_t at[U];  // record index of this lane in each chunk
+  bool live[U];
+};
+
 template <int N, int U>
 __global__ void __launch_bounds__(THREADS, 4) insert_bins_kernel(const BinView b, const TableView t,
                                                              GraphCounters *ctr) {
-  const uint32_t total = b.prefix[b.n_bins];
+  __shared__ DeferItem<N> sDefer[THREADS / 32][DEFER_CAP];
+  DeferQueue<N> dq{sDefer[threadIdx.x >> 5], 0u};
   unsigned long long my_new = 0;
   const unsigned lane = lane_id();
-  constexpr uint32_t CHUNK = 32u * U;
-  const uint32_t warp_global = (blockIdx.x * THREADS + threadIdx.x) >> 5;
   const uint32_t n_warps = (gridDim.x * THREADS) >> 5;
-  for (uint64_t base64 = (uint64_t)warp_global * CHUNK; base64 < total; base64 += (uint64_t)n_warps * CHUNK) {
-    __syncwarp();
-    const uint32_t base = (uint32_t)base64;
-    // bin of `base`: 32-ary search, every lane tests one pivot (prefix is non-decreasing)
-    uint32_t lo = 0, hi = b.n_bins;  // prefix[lo] <= base < prefix[hi]
-    while (hi - lo > 1) {
-      const uint32_t step = (hi - lo + 31u) >> 5;
-      const uint32_t piv = lo + (lane + 1u) * step;
-      const bool le = piv < hi && __ldg(&b.prefix[piv]) <= base;
-      const uint32_t n_le = (uint32_t)__popc(__ballot_sync(FULL, le));
-      const uint32_t nlo = lo + n_le * step;
-      hi = min(hi, nlo + step);
-      lo = nlo;
-    }
+  const uint32_t warp = (blockIdx.x * THREADS + threadIdx.x) >> 5;
+  constexpr uint32_t RW = (N == 1) ? 2u : 4u;
+
+  BinBatch<U> s0;  // being collected
+  int n_have = 0;  // chunks in s0, warp-uniform
+#pragma unroll
+  for (int u = 0; u < U; u++) { s0.at[u] = 0; s0.live[u] = false; }
+
+  auto advance = [&]() {
     uint64_t key[U][N];
     uint32_t c[U], edge[U], count[U];
-    bool act[U];
-    uint32_t bin = lo;
 #pragma unroll
     for (int u = 0; u < U; u++) {
-      const uint32_t i = base + 32u * u + lane;
-      act[u] = i < total;
       c[u] = 0; edge[u] = 0; count[u] = 0;
 #pragma unroll
       for (int w = 0; w < N; w++) key[u][w] = 0;
-      if (act[u]) {
-        while (__ldg(&b.prefix[bin + 1]) <= i) bin++;
-        const uint64_t aux = load_bin_record<N>(
-            b.recs + ((uint64_t)bin * b.cap + (i - __ldg(&b.prefix[bin]))) * bin_record_words(N), key[u]);
+      if (s0.live[u]) {
+        const uint64_t aux = load_bin_record<N>(b.recs + s0.at[u] * RW, key[u]);
         c[u] = (uint32_t)aux;
         edge[u] = (uint32_t)(aux >> 32) & 0xFFu;
         count[u] = (uint32_t)(aux >> 40);
       }
     }
-    upsert_batch<N, U>(t, ctr, key, c, edge, count, act, my_new);
+    upsert_batch<N, U>(t, ctr, dq, key, c, edge, count, s0.live, my_new);
+#pragma unroll
+    for (int u = 0; u < U; u++) s0.live[u] = false;
+    n_have = 0;
+  };
+
+  uint32_t first = 0;  // (chunks of all earlier bins) mod n_warps, warp-uniform
+  for (uint32_t b0 = 0; b0 < b.n_bins; b0 += 32) {
+    __syncwarp();
+    uint32_t cnt_l = 0;
+    if (b0 + lane < b.n_bins) {
+      cnt_l = __ldg(&b.count[(b0 + lane) * COUNT_STRIDE]);
+      if (cnt_l > b.cap) cnt_l = b.cap;
+    }
+    const uint32_t n_here = min(32u, b.n_bins - b0);
+    for (uint32_t tb = 0; tb < n_here; tb++) {
+      const uint32_t cnt = __shfl_sync(FULL, cnt_l, (int)tb);
+      const uint32_t n_chunks = (cnt + 31u) >> 5;
+      uint32_t j = warp >= first ? warp - first : warp + n_warps - first;  // first chunk of this bin that is ours
+      for (; j < n_chunks; j += n_warps) {
+        const uint32_t i = j * 32u + lane;
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+          if (u == n_have) {
+            s0.live[u] = i < cnt;
+            s0.at[u] = (uint64_t)(b0 + tb) * b.cap + i;
+          }
+        }
+        if (++n_have == U) advance();
+      }
+      uint32_t adv = n_chunks;
+      while (adv >= n_warps) adv -= n_warps;
+      first += adv;
+      if (first >= n_warps) first -= n_warps;
+    }
   }
+  if (n_have) advance();
+  dq.flush(t, ctr, my_new);
 #pragma unroll
   for (int o = 16; o; o >>= 1) my_new += __shfl_xor_sync(FULL, my_new, o);
   if (lane == 0 && my_new) atomicAdd(&ctr->unique_kmers, my_new);
@@ -496,6 +584,8 @@ __global__ void __launch_bounds__(THREADS, 4) insert_records_kernel(const uint32
                                                                 GraphCounters *ctr) {
   constexpr int RECW = 2 * N + 1;
   constexpr int U = 2;
+  __shared__ DeferItem<N> sDefer[THREADS / 32][DEFER_CAP];
+  DeferQueue<N> dq{sDefer[threadIdx.x >> 5], 0u};
   unsigned long long my_new = 0;
   const uint64_t warp_global = ((uint64_t)blockIdx.x * THREADS + threadIdx.x) >> 5;
   const uint64_t n_warps = ((uint64_t)gridDim.x * THREADS) >> 5;
@@ -516,8 +606,9 @@ __global__ void __launch_bounds__(THREADS, 4) insert_records_kernel(const uint32
       c[u] = lookup3_key<N>(key[u], 0).c;
       act[u] = warp_aggregate<N>(act[u], key[u], edge[u], count[u]);
     }
-    upsert_batch<N, U>(t, ctr, key, c, edge, count, act, my_new);
+    upsert_batch<N, U>(t, ctr, dq, key, c, edge, count, act, my_new);
   }
+  dq.flush(t, ctr, my_new);
 #pragma unroll
   for (int o = 16; o; o >>= 1) my_new += __shfl_xor_sync(FULL, my_new, o);
   if (lane_id() == 0 && my_new) atomicAdd(&ctr->unique_kmers, my_new);
@@ -966,7 +1057,10 @@ void launch_bin_prefix(const BinView &b, cudaStream_t st) { bin_prefix_kernel<<<
 void launch_insert_bins(int N, const BinView &b, const TableView &t, GraphCounters *ctr, cudaStream_t st) {
   dispatch_n(N, [&](auto n) {
     constexpr int NN = decltype(n)::value;
-    insert_bins_kernel<NN, 2><<<resident_grid(insert_bins_kernel<NN, 2>), THREADS, 0, st>>>(b, t, ctr);
+    // few resident warps on purpose (see the kernel's comment); LASV_B200_INSERT_CTAS overrides
+    int per_sm = 3;
+    if (const char *e = getenv("LASV_B200_INSERT_CTAS")) per_sm = atoi(e) > 0 ? atoi(e) : per_sm;
+    insert_bins_kernel<NN, 2><<<resident_grid(insert_bins_kernel<NN, 2>, per_sm), THREADS, 0, st>>>(b, t, ctr);
   });
 }
 

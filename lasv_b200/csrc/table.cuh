@@ -94,10 +94,16 @@ struct GraphCounters {
 // a sequential HostOps with the same interface so the probing / claiming /
 // finalising LOGIC is exercised on the CPU; the product never instantiates it.
 #if defined(__CUDACC__)
+// L2::64B: a miss fetches one 64-byte DRAM atom instead of the default whole 128-byte
+// line (tools/ubench "gran": 64 vs 128 bytes of DRAM read per random 8-byte load) --
+// the table is touched one slot at a time, the other half of the line would be waste.
 __device__ __forceinline__ uint64_t ld_strong_u64(const uint64_t *p) {
   uint64_t v;
-  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  asm volatile("ld.relaxed.gpu.global.L2::64B.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
+}
+__device__ __forceinline__ void ld_strong_v2u64(const uint64_t *p, uint64_t &a, uint64_t &b) {
+  asm volatile("ld.relaxed.gpu.global.L2::64B.v2.u64 {%0,%1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
 }
 __device__ __forceinline__ void st_strong_u64(uint64_t *p, uint64_t v) {
   asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
@@ -105,6 +111,9 @@ __device__ __forceinline__ void st_strong_u64(uint64_t *p, uint64_t v) {
 
 struct DeviceOps {
   static __device__ __forceinline__ uint64_t load(const uint64_t *p) { return ld_strong_u64(p); }
+  static __device__ __forceinline__ void load16(const uint64_t *p, uint64_t &a, uint64_t &b) {  // p 16-byte aligned
+    ld_strong_v2u64(p, a, b);
+  }
   static __device__ __forceinline__ void store(uint64_t *p, uint64_t v) { st_strong_u64(p, v); }
   static __device__ __forceinline__ void store_tag(uint8_t *p, uint32_t v) {
     asm volatile("st.relaxed.gpu.global.u8 [%0], %1;" ::"l"(p), "r"(v) : "memory");
@@ -159,17 +168,40 @@ LASV_HD void slot_accumulate(uint64_t *meta_ptr, uint64_t m, uint32_t edge, uint
   }
 }
 
+// The N+1 words of a slot (key words, then meta) with as few memory requests as
+// possible: 16-byte pieces from the enclosing 16-byte boundary on (scattered
+// requests cost per request -- address translation -- not per byte).  Slots start
+// 8 bytes past a 16-byte boundary or on one.  The pieces are independent loads:
+// only for slots whose key words are known to be visible.
+#pragma nv_exec_check_disable
+template <int N, class Ops>
+LASV_HD void slot_load_words(const uint64_t *slot, uint64_t (&w)[N + 1]) {
+  constexpr int PIECES = (8 * N + 8 + 8 + 15) / 16;  // window of SLOT + 8 bytes
+  const bool odd = (reinterpret_cast<uintptr_t>(slot) & 8u) != 0;
+  const uint64_t *p16 = reinterpret_cast<const uint64_t *>(reinterpret_cast<uintptr_t>(slot) & ~(uintptr_t)15);
+  uint64_t x[2 * PIECES];
+#pragma unroll
+  for (int i = 0; i < PIECES; i++) {
+    // a slot on a 16-byte boundary does not reach into the last piece of the window
+    if (i < PIECES - 1 || odd || (8 * N + 8) > 16 * (PIECES - 1)) Ops::load16(p16 + 2 * i, x[2 * i], x[2 * i + 1]);
+    else { x[2 * i] = 0; x[2 * i + 1] = 0; }
+  }
+#pragma unroll
+  for (int i = 0; i <= N; i++) w[i] = odd ? x[i + 1] : x[i];
+}
+
 // A slot reached through a visible tag byte: its key words are readable.
 #pragma nv_exec_check_disable
 template <int N, class Ops>
 LASV_HD bool slot_hit_tagged(uint64_t *slot, GraphCounters *ctr, const uint64_t (&key)[N],
                              uint32_t edge, uint32_t covg_add) {
-  const uint64_t m = Ops::load(slot + N);
+  uint64_t sw[N + 1];
+  slot_load_words<N, Ops>(slot, sw);
   bool same = true;
 #pragma unroll
-  for (int w = 0; w < N; w++) same &= (Ops::load(slot + w) == key[w]);
+  for (int w = 0; w < N; w++) same &= (sw[w] == key[w]);
   if (!same) return false;
-  slot_accumulate<Ops>(slot + N, m, edge, covg_add, ctr);
+  slot_accumulate<Ops>(slot + N, sw[N], edge, covg_add, ctr);
   return true;
 }
 

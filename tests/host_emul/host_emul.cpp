@@ -21,6 +21,7 @@ namespace {
 
 struct HostOps {
   static uint64_t load(const uint64_t *p) { return *p; }
+  static void load16(const uint64_t *p, uint64_t &a, uint64_t &b) { a = p[0]; b = p[1]; }
   static void store(uint64_t *p, uint64_t v) { *p = v; }
   static void store_tag(uint8_t *p, uint32_t v) { *p = (uint8_t)v; }
   static uint64_t cas(uint64_t *p, uint64_t expect, uint64_t want) {

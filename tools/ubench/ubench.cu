@@ -75,6 +75,107 @@ __global__ void __launch_bounds__(256) scatter_kernel(uint64_t *recs, unsigned *
   }
 }
 
+// DRAM fetch granularity: random lines of a big buffer, a few accesses per line (run under ncu)
+// pat 0: ld s0 | 1: ld s0,s1 | 2: ld s0,s2 | 3: ld s0,s3 | 4: ld s0 + red s1 | 5: ld s0 + red s0 | 6: ld s1,s2 (straddle atoms)
+// 7: ld s0 (L1-cached plain ld) | 8: red s0 only | 9: ld s0, then dependent ld s3
+__global__ void __launch_bounds__(256) gran_kernel(uint64_t *buf, uint64_t n_lines, uint64_t n_ops, int pat, uint64_t seed) {
+  uint64_t acc = 0;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_ops; i += (uint64_t)gridDim.x * blockDim.x) {
+    uint64_t *line = buf + (mix64(seed + i) % n_lines) * 16;
+    auto ld = [&](int sector) { uint64_t v; asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(line + 4 * sector) : "memory"); return v; };
+    if (pat == 0) acc += ld(0);
+    else if (pat == 1) acc += ld(0) + ld(1);
+    else if (pat == 2) acc += ld(0) + ld(2);
+    else if (pat == 3) acc += ld(0) + ld(3);
+    else if (pat == 4) { uint64_t v = ld(0); if (v != 0x1234567ull) atomicAdd(reinterpret_cast<unsigned *>(line + 4), 1u); }
+    else if (pat == 5) { uint64_t v = ld(0); if (v != 0x1234567ull) atomicAdd(reinterpret_cast<unsigned *>(line + 1), 1u); }
+    else if (pat == 6) acc += ld(1) + ld(2);
+    else if (pat == 7) acc += line[0];
+    else if (pat == 8) atomicAdd(reinterpret_cast<unsigned *>(line + 1), 1u);
+    else if (pat == 9) { uint64_t v = ld(0); acc += line[12 + (v & 1)]; }
+    else if (pat == 10) { uint64_t a, b; asm volatile("ld.relaxed.gpu.global.v2.u64 {%0,%1}, [%2];" : "=l"(a), "=l"(b) : "l"(line) : "memory"); acc += a + b; }
+    else if (pat == 11) { uint64_t a, b, c, d; asm volatile("ld.global.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(line) : "memory"); acc += a + b + c + d; }
+    else if (pat == 12) { acc += line[0] + line[4]; }
+    else if (pat == 13) { uint64_t v = ld(0); uint64_t *s = line + 4 + (v & 1); uint64_t a = ld(1), b, c;
+      asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(b) : "l"(s + 1) : "memory");
+      asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(c) : "l"(s + 2) : "memory");
+      if (a + b + c != 0x1234567ull) atomicAdd(reinterpret_cast<unsigned *>(s), 1u); }
+    else if (pat == 14) { uint64_t v = ld(0); uint64_t *s = line + 4 + 4 * (v & 1); uint64_t a, b, c, d;
+      asm volatile("ld.relaxed.gpu.global.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(s) : "memory");
+      if (a + b + c + d != 0x1234567ull) atomicAdd(reinterpret_cast<unsigned *>(s), 1u); }
+    else if (pat == 15) { uint64_t a, b, c, d; asm volatile("ld.relaxed.gpu.global.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(line) : "memory");
+      if (a + b + c + d != 0x1234567ull) atomicAdd(reinterpret_cast<unsigned *>(line + 1), 1u); }
+    else if (pat == 16) { // two independent ops per iteration (MLP 2): ld s0 each, then red each
+      uint64_t *l2 = buf + (mix64(seed + i + 0x5555555ull) % n_lines) * 16;
+      uint64_t v = ld(0), w; asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(w) : "l"(l2) : "memory");
+      if (v != 0x1234567ull) atomicAdd(reinterpret_cast<unsigned *>(line + 1), 1u);
+      if (w != 0x1234567ull) atomicAdd(reinterpret_cast<unsigned *>(l2 + 1), 1u); }
+    else if (pat == 18) { uint64_t v; asm volatile("ld.global.L2::64B.u64 %0, [%1];" : "=l"(v) : "l"(line) : "memory"); acc += v; }
+    else if (pat == 19) { uint64_t v; asm volatile("ld.global.L1::no_allocate.L2::64B.u64 %0, [%1];" : "=l"(v) : "l"(line) : "memory"); acc += v; }
+    else if (pat == 20) { uint64_t v; asm volatile("ld.global.cv.u64 %0, [%1];" : "=l"(v) : "l"(line) : "memory"); acc += v; }
+    else if (pat == 21) { uint64_t v; asm volatile("ld.global.cs.u64 %0, [%1];" : "=l"(v) : "l"(line) : "memory"); acc += v; }
+    else if (pat == 22) { uint64_t v; asm volatile("ld.global.lu.u64 %0, [%1];" : "=l"(v) : "l"(line) : "memory"); acc += v; }
+    else if (pat == 23) { uint64_t v; asm volatile("ld.global.nc.L2::64B.u64 %0, [%1];" : "=l"(v) : "l"(line) : "memory"); acc += v; }
+    else if (pat == 24) { unsigned r = atomicAdd(reinterpret_cast<unsigned *>(line + 1), 0u); acc += r; }
+    else { // 17: whole line as 4 x v4 loads issued together
+      uint64_t t = 0;
+      for (int q = 0; q < 4; q++) { uint64_t a, b, c, d; asm volatile("ld.global.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(line + 4 * q)); t += a + b + c + d; }
+      acc += t; }
+  }
+  if (acc == 0x9999) buf[0] = acc;
+}
+
+// "sorted insert" access: ops sweep the table region by region (all CTAs inside the same region at a time),
+// inside a region each op goes to a random 128-byte line, ~one op per 5 lines.
+template <int PAT, bool L64>
+__device__ __forceinline__ uint64_t sweep_op(uint64_t *line) {
+  auto ld8 = [&](uint64_t *p) { uint64_t v; if (L64) asm volatile("ld.relaxed.gpu.global.L2::64B.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory"); else asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory"); return v; };
+  auto ld16 = [&](uint64_t *p) { uint64_t a, b; if (L64) asm volatile("ld.relaxed.gpu.global.L2::64B.v2.u64 {%0,%1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory"); else asm volatile("ld.relaxed.gpu.global.v2.u64 {%0,%1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory"); return a + b; };
+  auto ld32 = [&](uint64_t *p) { uint64_t a, b, c, d; if (L64) asm volatile("ld.relaxed.gpu.global.L2::64B.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p) : "memory"); else asm volatile("ld.relaxed.gpu.global.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p) : "memory"); return a + b + c + d; };
+  if (PAT == 0) return ld8(line);
+  if (PAT == 1) { uint64_t v = ld8(line); return v + ld16(line + 2 + 2 * (v & 1)); }
+  if (PAT == 2) { uint64_t v = ld8(line); uint64_t *s = line + 2 + 2 * (v & 1); uint64_t x = ld16(s) + ld16(s + 2); if (x != 0x1234567ull) atomicAdd(reinterpret_cast<unsigned *>(s + 2), 1u); return x; }
+  if (PAT == 3) { uint64_t v = ld8(line); uint64_t *s = line + 4 + 4 * (v & 1); uint64_t x = ld32(s); if (x != 0x1234567ull) atomicAdd(reinterpret_cast<unsigned *>(s + 2), 1u); return x; }
+  if (PAT == 4) { uint64_t x = ld32(line); if (x != 0x1234567ull) atomicAdd(reinterpret_cast<unsigned *>(line + 2), 1u); return x; }
+  if (PAT == 5) { atomicAdd(reinterpret_cast<unsigned *>(line + 2), 1u); return 0; }
+  if (PAT == 6) { uint64_t v = ld8(line); uint64_t *s = line + 2 + 2 * (v & 1); uint64_t x = ld16(s) + ld16(s + 2); return x; }
+  if (PAT == 7) { uint64_t v = ld8(line); uint64_t *s = line + 2 + 2 * (v & 1); uint64_t x = ld16(s) + ld16(s + 2); if (x != 0x1234567ull) asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(s + 2), "l"(x + 1) : "memory"); return x; }
+  if (PAT == 8) { uint64_t v = ld8(line); uint64_t *s = line + 4 + 4 * (v & 1); uint64_t x = ld32(s); if (x != 0x1234567ull) asm volatile("st.global.v4.u64 [%0], {%1,%2,%3,%4};" ::"l"(s), "l"(x), "l"(x + 1), "l"(x + 2), "l"(x + 3) : "memory"); return x; }
+  if (PAT == 9) { uint64_t v = ld8(line); uint64_t *s = line + 2 + 2 * (v & 1); uint64_t x = ld16(s) + ld16(s + 2); if (x != 0x1234567ull) atomicAdd(reinterpret_cast<unsigned long long *>(s + 2), 1ull); return x; }
+  if (PAT == 10) { uint64_t v = ld8(line); uint64_t *s = line + 2 + 2 * (v & 1); uint64_t x = ld16(s) + ld16(s + 2); if (x != 0x1234567ull) x += atomicAdd(reinterpret_cast<unsigned *>(s + 2), 1u); return x; }
+  if (PAT == 11) { uint64_t v = ld8(line); uint64_t *s = line + 2 + 2 * (v & 1); uint64_t x = ld16(s) + ld16(s + 2); if (x != 0x1234567ull) asm volatile("st.global.u64 [%0], %1;" ::"l"(s + 2), "l"(x + 1) : "memory"); return x; }
+  return 0;
+}
+template <int PAT, bool L64, int U>
+__global__ void __launch_bounds__(256) sweep_kernel(uint64_t *buf, uint64_t region_lines, uint64_t ops_per_region, uint64_t n_ops, uint64_t seed) {
+  uint64_t acc = 0;
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t g0 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g0 < n_ops; g0 += stride * U) {
+    uint64_t *line[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const uint64_t g = (g0 + u * stride) % n_ops;
+      const uint64_t region = g / ops_per_region;
+      line[u] = buf + (region * region_lines + mix64(seed + g) % region_lines) * 16;
+    }
+    if (U == 1) acc += sweep_op<PAT, L64>(line[0]);
+    else {
+      // U independent ops with their stages interleaved by hand for PAT 2 (hdr, slot pieces, red)
+      uint64_t v[U], x[U]; uint64_t *s[U];
+#pragma unroll
+      for (int u = 0; u < U; u++) { if (L64) asm volatile("ld.relaxed.gpu.global.L2::64B.u64 %0, [%1];" : "=l"(v[u]) : "l"(line[u]) : "memory"); else asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v[u]) : "l"(line[u]) : "memory"); }
+#pragma unroll
+      for (int u = 0; u < U; u++) { s[u] = line[u] + 2 + 2 * (v[u] & 1); uint64_t a, b, c, d;
+        if (L64) { asm volatile("ld.relaxed.gpu.global.L2::64B.v2.u64 {%0,%1}, [%2];" : "=l"(a), "=l"(b) : "l"(s[u]) : "memory"); asm volatile("ld.relaxed.gpu.global.L2::64B.v2.u64 {%0,%1}, [%2];" : "=l"(c), "=l"(d) : "l"(s[u] + 2) : "memory"); }
+        else { asm volatile("ld.relaxed.gpu.global.v2.u64 {%0,%1}, [%2];" : "=l"(a), "=l"(b) : "l"(s[u]) : "memory"); asm volatile("ld.relaxed.gpu.global.v2.u64 {%0,%1}, [%2];" : "=l"(c), "=l"(d) : "l"(s[u] + 2) : "memory"); }
+        x[u] = a + b + c + d; }
+#pragma unroll
+      for (int u = 0; u < U; u++) { if (x[u] != 0x1234567ull) atomicAdd(reinterpret_cast<unsigned *>(s[u] + 2), 1u); acc += x[u]; }
+    }
+  }
+  if (acc == 0x9999) buf[0] = acc;
+}
+
 static float time_ms(cudaEvent_t a, cudaEvent_t b) { float ms; cudaEventElapsedTime(&ms, a, b); return ms; }
 
 int main(int argc, char **argv) {
@@ -103,6 +204,57 @@ int main(int argc, char **argv) {
                  (double)w / (1 << 20), opw, ops / best / 1e6);
           fflush(stdout);
         }
+    CK(cudaFree(buf));
+  }
+  if (argc > 2) { size_t g = (size_t)atoi(argv[2]); cudaError_t e = cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, g); size_t got = 0; cudaDeviceGetLimit(&got, cudaLimitMaxL2FetchGranularity); printf("{\"l2fetch_req\":%zu,\"rc\":%d,\"got\":%zu}\n", g, (int)e, got); }
+  if (!strcmp(what, "sweep")) {
+    const uint64_t total = 100ull << 30;
+    uint64_t *buf; CK(cudaMalloc(&buf, total)); CK(cudaMemset(buf, 0, total));
+    const uint64_t n_ops = 180000000ull;
+    for (uint64_t region_mb : {64ull}) {
+      const uint64_t region_lines = (region_mb << 20) / 128;
+      const uint64_t n_regions = total / (region_mb << 20);
+      const uint64_t opr = n_ops / n_regions;
+      auto run = [&](const char *name, auto kern, int ctas_per_sm) {
+        float best = 1e30f;
+        for (int rep = 0; rep < 2; rep++) {
+          CK(cudaEventRecord(e0));
+          kern<<<sms * ctas_per_sm, 256>>>(buf, region_lines, opr, opr * n_regions, 777 + rep);
+          CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
+          best = fminf(best, time_ms(e0, e1));
+        }
+        printf("{\"bench\":\"sweep\",\"region_MB\":%llu,\"kernel\":\"%s\",\"ctas_per_sm\":%d,\"ms\":%.3f,\"Gops\":%.2f}\n",
+               (unsigned long long)region_mb, name, ctas_per_sm, best, n_ops / best / 1e6);
+        fflush(stdout);
+      };
+      run("hdr", sweep_kernel<0, false, 1>, 8);
+      run("hdr+2v2 (no red)", sweep_kernel<6, false, 1>, 8);
+      for (int c : {2, 3, 4, 6, 8}) run("hdr+2v2+red", sweep_kernel<2, false, 1>, c);
+      for (int c : {2, 4, 8}) run("hdr+2v2+red_64B", sweep_kernel<2, true, 1>, c);
+      for (int c : {2, 4}) run("hdr+2v2+red U2", sweep_kernel<2, false, 2>, c);
+      for (int c : {1, 2}) run("hdr+2v2+red U4", sweep_kernel<2, false, 4>, c);
+      for (int c : {4, 8}) run("hdr+2v2+st8 strong", sweep_kernel<7, false, 1>, c);
+      for (int c : {4, 8}) run("hdr+2v2+st8 weak", sweep_kernel<11, false, 1>, c);
+      for (int c : {4, 8}) run("hdr+v4+st32", sweep_kernel<8, false, 1>, c);
+      for (int c : {4, 8}) run("hdr+2v2+red64", sweep_kernel<9, false, 1>, c);
+      for (int c : {4, 8}) run("hdr+2v2+atom32", sweep_kernel<10, false, 1>, c);
+      for (int c : {4, 8}) run("hdr+v4+red", sweep_kernel<3, false, 1>, c);
+      for (int c : {4, 8}) run("v4+red", sweep_kernel<4, false, 1>, c);
+      for (int c : {4, 8}) run("red only", sweep_kernel<5, false, 1>, c);
+    }
+    CK(cudaFree(buf));
+  }
+  if (!strcmp(what, "gran")) {
+    const uint64_t total = 32ull << 30;
+    uint64_t *buf; CK(cudaMalloc(&buf, total)); CK(cudaMemset(buf, 0, total));
+    const uint64_t n_ops = 64ull << 20;
+    for (int pat = 0; pat < 25; pat++) {
+      if (argc > 3 && pat != 0 && pat < 17) continue;
+      CK(cudaEventRecord(e0));
+      gran_kernel<<<sms * 8, 256>>>(buf, total / 128, n_ops, pat, 4242 + pat);
+      CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
+      printf("{\"bench\":\"gran\",\"pat\":%d,\"ms\":%.3f,\"Gops\":%.2f}\n", pat, time_ms(e0, e1), n_ops / time_ms(e0, e1) / 1e6);
+    }
     CK(cudaFree(buf));
   }
   if (!strcmp(what, "all") || !strcmp(what, "scatter")) {
