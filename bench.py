@@ -362,7 +362,8 @@ def main():
     stream = torch.cuda.current_stream().cuda_stream
 
     graph = ShardedDBGraph(w.kmer_size, w.number_bits, w.bucket_size, rank, world, local_rank,
-                           max_kmers_per_batch=reads_per_step * kpr)
+                           max_kmers_per_batch=reads_per_step * kpr, max_bytes_per_batch=n_bytes,
+                           max_reads_per_batch=reads_per_step)
     g = graph.graph
     table_bytes = g.capacity * g.element_bytes
 
@@ -449,6 +450,7 @@ def main():
     t_begin.record()
     for s in range(K):
         step(0 if cfg0 else Wm + s, s)
+    graph.flush()                      # side-stream inserts of the last batches join the timed stream
     t_end.record()
     barrier()
     torch.cuda.profiler.stop()
@@ -470,8 +472,8 @@ def main():
         kname = "build_kernel<2,FUSED>"
     else:
         kt = dt / K                                          # step time bounds every kernel in it
-        alg_bytes = kmers_per_launch * (2 * slot + 4 * graph.rec_words) + 2 * n_bytes
-        kname = "route+exchange+insert step"
+        alg_bytes = kmers_per_launch * (2 * slot + 2 * graph.rec_bytes) + 2 * n_bytes
+        kname = "bin+exchange+insert step"
     achieved = alg_bytes / kt / 1e9
     roofline = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "peak_source": peak_src,
@@ -524,7 +526,7 @@ def main():
                "h2d_bytes_per_step": int(2 * n_bytes + 8 * (reads_per_step + 1)),
                "d2h_bytes_per_step": 7 * 8 + 20 * 8 + 8, "ms_per_step": 1e3 * dte / K,
                "api": "lasv_graph_load_reads_host (C ABI, pinned host buffers)" if world == 1 else
-                      "pinned host -> device copy + sharded route/all_to_all/insert + counter read-back"}
+                      "pinned host -> device copy + sharded bin/all_to_all/insert + counter read-back"}
 
     sampler.stop()
 

@@ -151,6 +151,29 @@ int lasv_graph_extract_records_device(lasv_graph *g, const uint8_t *d_seq, const
                                       void *cuda_stream);
 int lasv_graph_insert_records_device(lasv_graph *g, const uint32_t *d_records, uint64_t n_records,
                                      void *cuda_stream);
+
+/* The same exchange for large tables, region by region (the production path of a
+ * hash-sharded build).  bin_reads: K1+K2 over this rank's reads, each k-mer
+ * occurrence written as one fixed-size record (key words, lookup3 value, edges,
+ * count) into the stripe of the 64 MB TABLE REGION it will touch on its owner:
+ * stripe index = owner * bins_per_owner + region, `stripe_capacity_records` records
+ * each, counters one per 128-byte line.  The stripes of one owner are one contiguous
+ * block, so the all-to-all moves fixed-size blocks (no host round trip for sizes).
+ * insert_bins: the receive side: sweeps the stripes of all senders region by region
+ * (stripe index = sender * bins_per_src + region) and find-or-inserts every record.
+ * bin_geometry sizes the buffers for a batch (reads known: k-mers <= n_bytes -
+ * n_reads*k).  An overfull stripe sets the overflow flag reported by lasv_graph_stats
+ * (single owner: the excess goes straight into the table instead). */
+int lasv_graph_bin_geometry(lasv_graph *g, int n_owners, uint64_t n_bytes, uint64_t n_reads,
+                            uint32_t *bins_per_owner, uint32_t *stripe_capacity_records,
+                            uint32_t *record_bytes, uint32_t *count_stride_bytes);
+int lasv_graph_bin_reads_device(lasv_graph *g, const uint8_t *d_seq, const uint8_t *d_qual,
+                                uint64_t n_bytes, int quality_cutoff, int n_owners,
+                                uint32_t bins_per_owner, uint32_t stripe_capacity_records,
+                                void *d_records, void *d_counts, void *cuda_stream);
+int lasv_graph_insert_bins_device(lasv_graph *g, const void *d_records, const void *d_counts, int n_src,
+                                  uint32_t bins_per_src, uint32_t stripe_capacity_records,
+                                  void *cuda_stream);
 int lasv_graph_read_stats_device(lasv_graph *g, const uint8_t *d_seq, const uint8_t *d_qual,
                                  const uint64_t *d_offsets, uint64_t n_reads, int quality_cutoff,
                                  void *cuda_stream);

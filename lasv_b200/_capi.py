@@ -67,7 +67,8 @@ EXPORTS = [
     "load_se_filelist_into_graph_colour", "load_pe_filelists_into_graph_colour",
     "lasv_synth_reads_device", "lasv_synth_reads_host", "lasv_random_access_probe",
     "lasv_kernel_launches", "lasv_seqfile_to_streams", "lasv_random_access_probe_mode",
-    "lasv_graph_record_buckets_device",
+    "lasv_graph_record_buckets_device", "lasv_graph_bin_geometry", "lasv_graph_bin_reads_device",
+    "lasv_graph_insert_bins_device",
 ]
 
 _lib = None
@@ -110,6 +111,10 @@ def lib() -> C.CDLL:
     L.lasv_graph_extract_records_device.argtypes = [vp, vp, vp, u64, i32, vp, u64, vp, vp]
     L.lasv_graph_insert_records_device.argtypes = [vp, vp, u64, vp]
     L.lasv_graph_read_stats_device.argtypes = [vp, vp, vp, vp, u64, i32, vp]
+    u32p = C.POINTER(C.c_uint32)
+    L.lasv_graph_bin_geometry.argtypes = [vp, i32, u64, u64, u32p, u32p, u32p, u32p]
+    L.lasv_graph_bin_reads_device.argtypes = [vp, vp, vp, u64, i32, i32, C.c_uint32, C.c_uint32, vp, vp, vp]
+    L.lasv_graph_insert_bins_device.argtypes = [vp, vp, vp, i32, C.c_uint32, C.c_uint32, vp]
     L.lasv_graph_find.argtypes = [vp, vp, u64, vp, vp, vp]
     L.lasv_graph_summary.argtypes = [vp, C.POINTER(TableSummary)]
     L.lasv_graph_finalize.argtypes = [vp]

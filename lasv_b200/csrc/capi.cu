@@ -6,6 +6,7 @@
 #include <errno.h>
 #include <libgen.h>
 #include <limits.h>
+#include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -157,7 +158,6 @@ BuildParams build_params(lasv_graph *g, const uint8_t *d_seq, const uint8_t *d_q
 void free_bins(lasv_graph *g) {
   cudaFree(g->bins.recs);
   cudaFree(g->bins.count);
-  cudaFree(g->bins.prefix);
   g->bins = BinView{};
   g->bins_alloc_records = 0;
   g->bins_alloc_n = 0;
@@ -186,27 +186,44 @@ bool want_binned(const lasv_graph *g, uint64_t n_bytes, uint32_t *n_bins_out) {
   return binned;
 }
 
-int ensure_bins(lasv_graph *g, uint64_t n_bytes, uint32_t n_bins) {
-  // expected k-mers of a batch are <= ~0.8 per stream byte; a fuller stripe spills
-  // its excess straight into the table, so this is a sizing choice, not a limit
-  const uint64_t want = (uint64_t)((double)n_bytes * 0.85) + (uint64_t)n_bins * 1024u;
+int log2_u32(uint32_t v) {
+  int lg = 0;
+  while ((1u << lg) < v) lg++;
+  return lg;
+}
+
+// Records per stripe for a batch of n_bytes stream bytes in n_reads reads spread over n_bins stripes.
+// A read of length l yields at most l-k+1 k-mers and occupies l+1 stream bytes, so a batch yields at
+// most n_bytes - n_reads*k; without the read count, at most n_bytes.  Stripes fill like balls into
+// bins by a well-mixed hash: mean + 8 sigma (+ a little) is never reached in practice.
+uint64_t stripe_capacity(const lasv_graph *g, uint64_t n_bytes, uint64_t n_reads, uint32_t n_bins) {
+  uint64_t bound = n_bytes;
+  if (n_reads && n_reads * (uint64_t)g->k < n_bytes) bound = n_bytes - n_reads * (uint64_t)g->k;
+  else if (!n_reads) bound = (uint64_t)((double)n_bytes * 0.85);  // k >= ~21 on reads of <= ~150 bases
+  const double mean = (double)bound / n_bins;
+  return (uint64_t)(mean * 1.01 + 8.0 * sqrt(mean) + 64.0);
+}
+
+int ensure_bins(lasv_graph *g, uint64_t n_bytes, uint64_t n_reads, uint32_t n_bins) {
+  // a fuller stripe spills its excess straight into the table, so this is a sizing choice, not a limit
+  const uint64_t cap = stripe_capacity(g, n_bytes, n_reads, n_bins);
+  if (cap > 0xFFFFFFF0ull) return fail(LASV_ERR_ARG, "batch too large for the bin stripes");
+  const uint64_t want = cap * n_bins;
   if (g->bins_alloc_records < want || g->bins_alloc_n != n_bins) {
     CUDA_TRY(cudaDeviceSynchronize());
     free_bins(g);
-    const uint64_t cap = (want + n_bins - 1) / n_bins;
-    if (cap > 0xFFFFFFF0ull) return fail(LASV_ERR_ARG, "batch too large for the bin stripes");
-    const uint64_t total = cap * n_bins;
-    CUDA_TRY(cudaMalloc(&g->bins.recs, total * (size_t)bin_record_words(g->N) * sizeof(uint64_t)));
+    CUDA_TRY(cudaMalloc(&g->bins.recs, want * (size_t)bin_record_words(g->N) * sizeof(uint64_t)));
     CUDA_TRY(cudaMalloc(&g->bins.count, (size_t)n_bins * COUNT_STRIDE * sizeof(unsigned int)));
-    CUDA_TRY(cudaMalloc(&g->bins.prefix, (n_bins + 1) * sizeof(uint32_t)));
-    g->bins.cap = (uint32_t)cap;
-    g->bins.n_bins = n_bins;
-    int lg = 0;
-    while ((1u << lg) < n_bins) lg++;
-    g->bins.bin_shift = (uint32_t)(g->L - lg);
-    g->bins_alloc_records = total;
+    g->bins_alloc_records = want;
     g->bins_alloc_n = n_bins;
   }
+  g->bins.cap = (uint32_t)(g->bins_alloc_records / n_bins);
+  g->bins.n_bins = n_bins;
+  g->bins.bin_mask = (uint32_t)(g->n_buckets - 1);
+  g->bins.bin_shift = (uint32_t)(g->L - log2_u32(n_bins));
+  g->bins.spill_ok = 1;
+  g->bins.src_shift = 0;
+  g->bins.bins_per_src = n_bins;
   return LASV_OK;
 }
 
@@ -356,7 +373,7 @@ int lasv_graph_load_reads_device(lasv_graph *g, const uint8_t *d_seq, const uint
       // Partitioned insert: group the batch's k-mers by 16 MB table region, then
       // insert region by region (profiles/exp_sorted_insert_r1_cfg4.jsonl: 3.3x
       // the insert rate of uniformly random probes on a 100 GB table).
-      if (int e = ensure_bins(g, n_bytes, n_bins)) return e;
+      if (int e = ensure_bins(g, n_bytes, d_offsets ? n_reads : 0, n_bins)) return e;
       p.bins = g->bins;
       CUDA_TRY(cudaMemsetAsync(g->bins.count, 0, (size_t)n_bins * COUNT_STRIDE * sizeof(unsigned int), st));
       launch_build(g->N, MODE_BIN, p, st);
@@ -553,6 +570,77 @@ int lasv_graph_insert_records_device(lasv_graph *g, const uint32_t *d_records, u
   if (g->finalized) return fail(LASV_ERR_STATE, "graph is finalised; no further inserts");
   if (!n_records) return LASV_OK;
   launch_insert_records(g->N, d_records, n_records, g->view(), g->d_ctr, stream_of(g, cuda_stream));
+  return check_launch();
+}
+
+int lasv_graph_bin_geometry(lasv_graph *g, int n_owners, uint64_t n_bytes, uint64_t n_reads,
+                            uint32_t *bins_per_owner, uint32_t *stripe_capacity_out,
+                            uint32_t *record_bytes, uint32_t *count_stride_bytes) {
+  if (!g) return fail(LASV_ERR_ARG, "NULL graph");
+  if (n_owners < 1 || n_owners > 16 || (n_owners & (n_owners - 1)))
+    return fail(LASV_ERR_ARG, "n_owners must be a power of two <= 16, got %d", n_owners);
+  uint32_t per = 1;
+  while ((uint64_t)per * (64ull << 20) < g->table_bytes && per < 65536u && per < g->n_buckets) per <<= 1;
+  if (const char *e = getenv("LASV_B200_BINS")) {
+    const long v = atol(e);
+    if (v >= 1 && v <= 65536 && (v & (v - 1)) == 0 && (uint64_t)v <= g->n_buckets) per = (uint32_t)v;
+  }
+  const uint64_t cap = stripe_capacity(g, n_bytes, n_reads, per * (uint32_t)n_owners);
+  if (cap > 0xFFFFFFF0ull) return fail(LASV_ERR_ARG, "batch too large for the bin stripes");
+  if (bins_per_owner) *bins_per_owner = per;
+  if (stripe_capacity_out) *stripe_capacity_out = (uint32_t)cap;
+  if (record_bytes) *record_bytes = 8u * bin_record_words(g->N);
+  if (count_stride_bytes) *count_stride_bytes = COUNT_STRIDE * (uint32_t)sizeof(unsigned int);
+  return LASV_OK;
+}
+
+int lasv_graph_bin_reads_device(lasv_graph *g, const uint8_t *d_seq, const uint8_t *d_qual,
+                                uint64_t n_bytes, int quality_cutoff, int n_owners,
+                                uint32_t bins_per_owner, uint32_t stripe_capacity_records,
+                                void *d_records, void *d_counts, void *cuda_stream) {
+  if (int e = use(g)) return e;
+  if (n_owners < 1 || n_owners > 16 || (n_owners & (n_owners - 1)) || !bins_per_owner ||
+      (bins_per_owner & (bins_per_owner - 1)) || bins_per_owner > g->n_buckets || !stripe_capacity_records)
+    return fail(LASV_ERR_ARG, "bad bin geometry: %d owners x %u bins x %u records", n_owners, bins_per_owner,
+                stripe_capacity_records);
+  if (!d_records || !d_counts) return fail(LASV_ERR_ARG, "NULL bin buffers");
+  if (int e = check_streams(d_seq, d_qual)) return e;
+  cudaStream_t st = stream_of(g, cuda_stream);
+  const uint32_t n_bins = bins_per_owner * (uint32_t)n_owners;
+  CUDA_TRY(cudaMemsetAsync(d_counts, 0, (size_t)n_bins * COUNT_STRIDE * sizeof(unsigned int), st));
+  if (!n_bytes) return LASV_OK;
+  BuildParams p = build_params(g, d_seq, d_qual, n_bytes, quality_cutoff);
+  p.bins.recs = (uint64_t *)d_records;
+  p.bins.count = (unsigned int *)d_counts;
+  p.bins.cap = stripe_capacity_records;
+  p.bins.n_bins = n_bins;
+  // this graph is one of n_owners shards: the global bucket index has log2(n_owners) more bits
+  const int Lg = g->L + log2_u32((uint32_t)n_owners);
+  p.bins.bin_mask = Lg >= 32 ? 0xFFFFFFFFu : ((1u << Lg) - 1u);
+  p.bins.bin_shift = (uint32_t)(Lg - log2_u32(n_bins));
+  p.bins.spill_ok = n_owners == 1 ? 1u : 0u;
+  p.bins.src_shift = 0;
+  p.bins.bins_per_src = n_bins;
+  launch_build(g->N, MODE_BIN, p, st);
+  return check_launch();
+}
+
+int lasv_graph_insert_bins_device(lasv_graph *g, const void *d_records, const void *d_counts, int n_src,
+                                  uint32_t bins_per_src, uint32_t stripe_capacity_records,
+                                  void *cuda_stream) {
+  if (int e = use(g)) return e;
+  if (g->finalized) return fail(LASV_ERR_STATE, "graph is finalised; no further inserts");
+  if (n_src < 1 || n_src > 16 || (n_src & (n_src - 1)) || !bins_per_src || (bins_per_src & (bins_per_src - 1)))
+    return fail(LASV_ERR_ARG, "bad bin geometry: %d senders x %u bins", n_src, bins_per_src);
+  if (!d_records || !d_counts) return fail(LASV_ERR_ARG, "NULL bin buffers");
+  BinView b{};
+  b.recs = (uint64_t *)d_records;
+  b.count = (unsigned int *)d_counts;
+  b.cap = stripe_capacity_records;
+  b.n_bins = bins_per_src * (uint32_t)n_src;
+  b.src_shift = (uint32_t)log2_u32((uint32_t)n_src);
+  b.bins_per_src = bins_per_src;
+  launch_insert_bins(g->N, b, g->view(), g->d_ctr, stream_of(g, cuda_stream));
   return check_launch();
 }
 

@@ -372,19 +372,21 @@ build_kernel(const BuildParams p, const uint64_t n_tiles) {
         uint32_t idx[U];
 #pragma unroll
         for (int u = 0; u < U; u++) {
-          const uint32_t bin = (hc[u] & p.table.bucket_mask) >> p.bins.bin_shift;
+          const uint32_t bin = (hc[u] & p.bins.bin_mask) >> p.bins.bin_shift;
           idx[u] = lead[u] ? atomicAdd(&p.bins.count[bin * COUNT_STRIDE], 1u) : 0u;
         }
 #pragma unroll
         for (int u = 0; u < U; u++) {
           if (!lead[u]) continue;
-          const uint32_t bin = (hc[u] & p.table.bucket_mask) >> p.bins.bin_shift;
+          const uint32_t bin = (hc[u] & p.bins.bin_mask) >> p.bins.bin_shift;
           if (idx[u] < p.bins.cap) {
             store_bin_record<N>(p.bins.recs + ((uint64_t)bin * p.bins.cap + idx[u]) * bin_record_words(N), key[u],
                                 bin_aux(hc[u], edge[u], count[u]));
-          } else {  // stripe full (skewed batch): this occurrence goes straight to the table
+          } else if (p.bins.spill_ok) {  // stripe full (skewed batch): straight into the table
             const int r = table_upsert_hashed<N, DeviceOps>(p.table, p.ctr, key[u], hc[u], edge[u], count[u]);
             my_new += (r == 1);
+          } else {
+            atomicExch(p.rec_overflow, 1ull);
           }
         }
         __syncwarp();
@@ -441,52 +443,11 @@ build_kernel(const BuildParams p, const uint64_t n_tiles) {
 // --------------------------------------------------------------------------
 // partitioned insert: prefix over the bins, then K3 region by region
 // --------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) bin_prefix_kernel(const BinView b) {
-  // single CTA: exclusive prefix of min(count, cap) over <= 64 Ki bins
-  __shared__ uint32_t sWarp[32];
-  __shared__ uint32_t sCarry;
-  if (threadIdx.x == 0) sCarry = 0;
-  __syncthreads();
-  for (uint32_t base = 0; base < b.n_bins; base += 1024) {
-    const uint32_t i = base + threadIdx.x;
-    uint32_t v = 0;
-    if (i < b.n_bins) {
-      v = b.count[i * COUNT_STRIDE];
-      if (v > b.cap) v = b.cap;
-    }
-    uint32_t x = v;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const uint32_t y = __shfl_up_sync(FULL, x, o);
-      if ((int)lane_id() >= o) x += y;
-    }
-    if (lane_id() == 31) sWarp[threadIdx.x >> 5] = x;
-    __syncthreads();
-    if (threadIdx.x < 32) {
-      uint32_t wsum = sWarp[threadIdx.x];
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t y = __shfl_up_sync(FULL, wsum, o);
-        if ((int)lane_id() >= o) wsum += y;
-      }
-      sWarp[threadIdx.x] = wsum;
-    }
-    __syncthreads();
-    const uint32_t warp_off = (threadIdx.x >> 5) ? sWarp[(threadIdx.x >> 5) - 1] : 0;
-    const uint32_t carry = sCarry;
-    if (i < b.n_bins) b.prefix[i] = carry + warp_off + x - v;
-    __syncthreads();
-    if (threadIdx.x == 1023) sCarry = carry + warp_off + x;
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) b.prefix[b.n_bins] = sCarry;
-}
-
 // All warps of the grid sweep the bins in the same order, bin by bin, so that at
 // any moment the whole GPU works inside one or two table regions (<= 64 MB each:
 // TLB-, L2- and DRAM-row-friendly).  A bin is cut into chunks of 32 records and
 // chunk j of bin b belongs to warp (j + first_b) mod n_warps, first_b = number of
-// chunks of all earlier bins: a round robin over the concatenation of the bins
+// chunks of all earlier bins (a bin = the stripes of all senders for one region): a round robin over the concatenation of the bins
 // that every warp derives by itself from the bin counters -- no prefix pass, no
 // search.  A warp collects U of its chunks into a batch, loads the records together
 // and runs them through upsert_batch.  (A three-stage software pipeline with L2
@@ -537,12 +498,15 @@ __global__ void __launch_bounds__(THREADS, 4) insert_bins_kernel(const BinView b
     n_have = 0;
   };
 
-  uint32_t first = 0;  // (chunks of all earlier bins) mod n_warps, warp-uniform
+  // sweep position g = region * n_src + sender  ->  stripe index sender * bins_per_src + region
+  const uint32_t src_mask = (1u << b.src_shift) - 1u;
+  auto stripe_of = [&](uint32_t g) { return (g & src_mask) * b.bins_per_src + (g >> b.src_shift); };
+  uint32_t first = 0;  // (chunks of all earlier stripes) mod n_warps, warp-uniform
   for (uint32_t b0 = 0; b0 < b.n_bins; b0 += 32) {
     __syncwarp();
     uint32_t cnt_l = 0;
     if (b0 + lane < b.n_bins) {
-      cnt_l = __ldg(&b.count[(b0 + lane) * COUNT_STRIDE]);
+      cnt_l = __ldg(&b.count[stripe_of(b0 + lane) * COUNT_STRIDE]);
       if (cnt_l > b.cap) cnt_l = b.cap;
     }
     const uint32_t n_here = min(32u, b.n_bins - b0);
@@ -556,7 +520,7 @@ __global__ void __launch_bounds__(THREADS, 4) insert_bins_kernel(const BinView b
         for (int u = 0; u < U; u++) {
           if (u == n_have) {
             s0.live[u] = i < cnt;
-            s0.at[u] = (uint64_t)(b0 + tb) * b.cap + i;
+            s0.at[u] = (uint64_t)stripe_of(b0 + tb) * b.cap + i;
           }
         }
         if (++n_have == U) advance();
@@ -1051,8 +1015,6 @@ void launch_insert_records(int N, const uint32_t *recs, uint64_t n_recs, const T
     insert_records_kernel<NN><<<(unsigned)grid, THREADS, 0, st>>>(recs, n_recs, t, ctr);
   });
 }
-
-void launch_bin_prefix(const BinView &b, cudaStream_t st) { bin_prefix_kernel<<<1, 1024, 0, st>>>(b); }
 
 void launch_insert_bins(int N, const BinView &b, const TableView &t, GraphCounters *ctr, cudaStream_t st) {
   dispatch_n(N, [&](auto n) {

@@ -25,14 +25,24 @@ enum BuildMode { MODE_FUSED = 0, MODE_RECORDS = 1, MODE_ROUTE = 2, MODE_BIN = 3 
 __host__ __device__ inline uint32_t bin_record_words(int N) { return N == 1 ? 2u : 4u; }
 constexpr uint32_t COUNT_STRIDE = 32;  // uint32 units = 128 bytes
 struct BinView {
-  uint64_t *recs;       // [n_bins*cap*bin_record_words(N)]
+  uint64_t *recs;       // [n_bins*cap*bin_record_words(N)], stripe of bin i at i*cap
   unsigned int *count;  // [n_bins*COUNT_STRIDE] records wanted per bin, ONE COUNTER PER 128-BYTE LINE: the L2
                         // atomic unit serialises per line, 8 counters in a line would share one queue
-                        // (a count may exceed cap: the excess went straight to the table)
-  uint32_t *prefix;     // [n_bins+1]   exclusive prefix of min(count, cap)
+                        // (a count may exceed cap: see spill_ok)
   uint32_t cap;
-  uint32_t bin_shift;
   uint32_t n_bins;
+  // producer side (build_kernel<MODE_BIN>): bin = (lookup3 c & bin_mask) >> bin_shift.  In a hash-sharded
+  // job bin_mask covers the GLOBAL bucket index, so the owner GPU is the top bits of the bin and the
+  // stripes of one owner are contiguous (they travel as one block of the all-to-all).
+  uint32_t bin_mask;
+  uint32_t bin_shift;
+  uint32_t spill_ok;    // 1: a record that finds its stripe full goes straight into the (local) table;
+                        // 0: it raises the overflow flag (its owner may be another GPU)
+  // consumer side (insert_bins_kernel): the stripes are swept region by region; with n_src senders the
+  // stripe of (sender s, local region r) is at index s*bins_per_src + r and the sweep takes all senders
+  // of a region before the next region (n_src = 1 << src_shift, n_bins = n_src*bins_per_src)
+  uint32_t src_shift;
+  uint32_t bins_per_src;
 };
 __host__ __device__ inline uint64_t bin_aux(uint32_t c, uint32_t edge, uint32_t count) {
   return (uint64_t)c | ((uint64_t)(edge & 0xFFu) << 32) | ((uint64_t)count << 40);
@@ -96,7 +106,6 @@ int sm_count();
 void launch_build(int N, BuildMode mode, const BuildParams &p, cudaStream_t st);
 void launch_insert_records(int N, const uint32_t *recs, uint64_t n_recs, const TableView &t,
                            GraphCounters *ctr, cudaStream_t st);
-void launch_bin_prefix(const BinView &b, cudaStream_t st);
 void launch_insert_bins(int N, const BinView &b, const TableView &t, GraphCounters *ctr, cudaStream_t st);
 void launch_read_stats(const uint8_t *seq, const uint8_t *qual, const uint64_t *offsets,
                        uint64_t n_reads, int sep, int k, int cutoff, ReadStats *stats,

@@ -7,14 +7,21 @@ i.e. by the HIGH bits of its reference bucket index (hash_value.c:767-773), and
 is inserted there with the LOW bits as the local bucket -- so the shards laid
 end to end in rank order are the reference's table for every key that sits in
 its first-choice bucket.  Node updates commute (coverage +, edges |), so the
-only communication is one personalised all-to-all of (2N+1)-word records per
-batch:
+only communication is one personalised all-to-all of k-mer records per batch:
 
-    reads --route kernel--> per-owner bins --all_to_all--> insert kernel --> shard
+    reads --bin kernel--> stripes[owner][region] --all_to_all--> insert kernel --> shard
 
-The exchange is one grouped send/recv (`torch.distributed.batch_isend_irecv`, a
-single ncclGroup of ncclSend/ncclRecv under NCCL) on views of the bins -- no
-packing copy; counts travel first in a tiny all_to_all_single.
+The bin kernel writes every k-mer occurrence into the stripe of the 64 MB table
+region it will touch ON ITS OWNER; the stripes of one owner are one contiguous,
+fixed-size block, so the exchange is a plain `all_to_all_single` with equal
+splits (NCCL over NVLink) -- no packing copy and no host round trip for sizes;
+the per-stripe counters travel the same way.  The insert kernel then sweeps the
+received stripes region by region, all senders of a region together.  With
+`pipeline=True` batch i+1 is binned and exchanged while batch i is inserted
+(two sets of buffers, side streams).
+
+`exchange_records` / route / insert_records is the older variable-length path
+(kept: small tables, the world_size-2 gloo test).
 """
 from __future__ import annotations
 
@@ -71,11 +78,46 @@ def exchange_records(bins: torch.Tensor, send_counts: torch.Tensor, recv_buf: to
     return total, rc
 
 
+def exchange_stripes(send: torch.Tensor, recv: torch.Tensor, group=None):
+    """Equal-split personalised all-to-all of the stripe blocks: block d of `send`
+    goes to rank d, block s of `recv` comes from rank s.  NCCL: all_to_all_single;
+    gloo (CPU tests): list all_to_all, or send/recv pairs if that is missing."""
+    world = send.shape[0]
+    if send.is_cuda:
+        dist.all_to_all_single(recv.view(world, -1), send.view(world, -1), group=group)
+        return
+    try:
+        dist.all_to_all(list(recv.view(world, -1).unbind(0)), list(send.view(world, -1).unbind(0)), group=group)
+    except (RuntimeError, NotImplementedError):
+        rank = dist.get_rank(group)
+        ops = []
+        for d in range(world):
+            if d == rank:
+                recv[d].copy_(send[d])
+            else:
+                ops.append(dist.P2POp(dist.isend, send[d].contiguous(), d, group))
+                ops.append(dist.P2POp(dist.irecv, recv[d], d, group))
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+
+
+class _StripeBuffers:
+    def __init__(self, world, bins_per_owner, cap, rec_bytes, count_stride_bytes, device):
+        self.send = torch.empty((world, bins_per_owner, cap, rec_bytes // 8), dtype=torch.int64, device=device)
+        self.recv = torch.empty_like(self.send)
+        self.send_counts = torch.zeros((world, bins_per_owner, count_stride_bytes // 4), dtype=torch.int32,
+                                       device=device)
+        self.recv_counts = torch.zeros_like(self.send_counts)
+        self.inserted = None     # event: the insert kernel that read `recv` is done
+        self.exchanged = None    # event: `send` may be overwritten, `recv` is complete
+
+
 class ShardedDBGraph:
     """The rank-local part of a graph sharded over `world` GPUs."""
 
     def __init__(self, kmer_size: int, number_bits: int, bucket_size: int, rank: int, world: int,
-                 device: int, max_kmers_per_batch: int, group=None, slack: float = 1.08):
+                 device: int, max_kmers_per_batch: int, group=None, slack: float = 1.08,
+                 max_bytes_per_batch: int = 0, max_reads_per_batch: int = 0, pipeline: bool = True):
         if not is_pow2(world) or world > 16:
             raise ValueError("world size must be a power of two <= 16")
         self.rank, self.world, self.group = rank, world, group
@@ -86,27 +128,88 @@ class ShardedDBGraph:
             raise ValueError("too few buckets for this many ranks")
         self.graph = DBGraph(kmer_size, self.local_bits, bucket_size, device=device)
         self.device = torch.device("cuda", device)
+        self.pipeline = pipeline and world > 1
+        self.buffers = []
+        self.turn = 0
         if world > 1:
-            # a rank sends ~1/world of its k-mers to each owner and receives about as many as it sent
-            self.bin_capacity = int(max_kmers_per_batch / world * slack) + 4096
-            self.bins = torch.empty((world, self.bin_capacity, self.rec_words), dtype=torch.int32,
-                                    device=self.device)
-            self.recv = torch.empty((int(max_kmers_per_batch * slack) + 4096 * world, self.rec_words),
-                                    dtype=torch.int32, device=self.device)
-            self.counts = torch.zeros(world, dtype=torch.int64, device=self.device)
+            if not max_bytes_per_batch:       # k-mers <= bytes: a safe stand-in for callers that only know k-mers
+                max_bytes_per_batch = int(max_kmers_per_batch * 1.7)
+            geo = self.graph.bin_geometry(world, max_bytes_per_batch, max_reads_per_batch)
+            self.bins_per_owner, self.cap = geo["bins_per_owner"], geo["stripe_capacity"]
+            self.rec_bytes = geo["record_bytes"]
+            for _ in range(2 if self.pipeline else 1):
+                self.buffers.append(_StripeBuffers(world, self.bins_per_owner, self.cap, self.rec_bytes,
+                                                   geo["count_stride_bytes"], self.device))
+            self.comm_stream = torch.cuda.Stream(device=self.device)
+            self.insert_stream = torch.cuda.Stream(device=self.device)
 
     def free(self):
         self.graph.free()
 
     def load_reads_device(self, d_seq, d_qual, n_bytes: int, quality_cutoff: int, d_offsets=None,
                           n_reads: int = 0):
-        """One batch: every rank passes ITS reads; returns after the local inserts
-        are queued on the current stream."""
-        stream = torch.cuda.current_stream().cuda_stream
+        """One batch: every rank passes ITS reads.  Returns once the batch's work is
+        queued; with the pipeline on, the inserts of this batch may still be running
+        on a side stream when the caller's stream is done -- `flush()` joins them
+        (stats/summary/free do it themselves)."""
+        cur = torch.cuda.current_stream()
+        stream = cur.cuda_stream
         g = self.graph
         if self.world == 1:
             g.load_reads_device(d_seq, d_qual, n_bytes, d_offsets, n_reads, quality_cutoff, stream)
             return
+        buf = self.buffers[self.turn % len(self.buffers)]
+        self.turn += 1
+        # the previous user of this buffer set must be done with it
+        if buf.exchanged is not None:
+            cur.wait_event(buf.exchanged)       # its send block is free again
+        g.bin_reads_device(d_seq, d_qual, n_bytes, quality_cutoff, self.world, self.bins_per_owner, self.cap,
+                           buf.send, buf.send_counts, stream)
+        if d_offsets is not None and n_reads:
+            g.read_stats_device(d_seq, d_qual, d_offsets, n_reads, quality_cutoff, stream)
+        if not self.pipeline:
+            exchange_stripes(buf.send, buf.recv, self.group)
+            exchange_stripes(buf.send_counts, buf.recv_counts, self.group)
+            g.insert_bins_device(buf.recv, buf.recv_counts, self.world, self.bins_per_owner, self.cap, stream)
+            return
+        binned = torch.cuda.Event()
+        binned.record(cur)
+        with torch.cuda.stream(self.comm_stream):
+            self.comm_stream.wait_event(binned)
+            if buf.inserted is not None:
+                self.comm_stream.wait_event(buf.inserted)   # recv block free again
+            exchange_stripes(buf.send, buf.recv, self.group)
+            exchange_stripes(buf.send_counts, buf.recv_counts, self.group)
+            buf.exchanged = torch.cuda.Event()
+            buf.exchanged.record(self.comm_stream)
+        with torch.cuda.stream(self.insert_stream):
+            self.insert_stream.wait_event(buf.exchanged)
+            g.insert_bins_device(buf.recv, buf.recv_counts, self.world, self.bins_per_owner, self.cap,
+                                 self.insert_stream.cuda_stream)
+            buf.inserted = torch.cuda.Event()
+            buf.inserted.record(self.insert_stream)
+
+    def flush(self):
+        """Make the caller's current stream wait for everything queued on the side streams."""
+        if self.world > 1 and self.pipeline:
+            cur = torch.cuda.current_stream()
+            for buf in self.buffers:
+                if buf.inserted is not None:
+                    cur.wait_event(buf.inserted)
+
+    def load_reads_device_routed(self, d_seq, d_qual, n_bytes: int, quality_cutoff: int, d_offsets=None,
+                                 n_reads: int = 0):
+        """The older path: per-owner record bins of variable length, sizes via the host."""
+        stream = torch.cuda.current_stream().cuda_stream
+        g = self.graph
+        if not hasattr(self, "bins"):
+            kmers = int(n_bytes)
+            self.bin_capacity = int(kmers / self.world * 1.08) + 4096
+            self.bins = torch.empty((self.world, self.bin_capacity, self.rec_words), dtype=torch.int32,
+                                    device=self.device)
+            self.recv = torch.empty((int(kmers * 1.08) + 4096 * self.world, self.rec_words),
+                                    dtype=torch.int32, device=self.device)
+            self.counts = torch.zeros(self.world, dtype=torch.int64, device=self.device)
         self.counts.zero_()
         g.route_reads_device(d_seq, d_qual, n_bytes, quality_cutoff, self.world, self.bins,
                              self.bin_capacity, self.counts, stream)
@@ -117,6 +220,7 @@ class ShardedDBGraph:
 
     def stats(self) -> dict:
         """Job-wide statistics (sum over ranks)."""
+        self.flush()
         st = self.graph.stats(stream=torch.cuda.current_stream().cuda_stream)
         keys = sorted(st)
         t = torch.tensor([st[k] for k in keys], dtype=torch.int64, device=self.device)
@@ -125,6 +229,7 @@ class ShardedDBGraph:
         return dict(zip(keys, (int(x) for x in t.cpu())))
 
     def summary(self) -> dict:
+        self.flush()
         s = self.graph.summary()
         keys = sorted(s)
         # fingerprints add modulo 2^64: reduce as two 32-bit halves to stay inside int64

@@ -210,6 +210,80 @@ def test_route_and_insert_records_match_oracle(base, world):
             g.free()
 
 
+@pytest.mark.parametrize("base,world,bins", [(synth.CFG0, 2, 4), (synth.CFG1, 4, 1), (synth.CFG2, 8, 8),
+                                              (synth.CFG0, 1, 16)])
+def test_binned_exchange_matches_oracle(base, world, bins, monkeypatch):
+    """The production sharded path on one GPU: ranks emulated as `world` local graphs.
+    Every emulated rank bins its slice of the reads by (owner, table region); the
+    all-to-all is emulated by handing block d of every sender to graph d; the owners
+    sweep the received stripes region by region."""
+    torch = torch_cuda()
+    monkeypatch.setenv("LASV_B200_BINS", str(bins))
+    L, W, n_reads = 13, 40, 24_000
+    w = synth.scaled(base, 80_000, L)
+    w.bucket_size = W
+    p, seq, qual, offs, og = _synth_oracle(w, n_reads, seed=77)
+    want = O.sort_records(og.records())
+    bits = int(np.log2(world))
+    st_ = torch.cuda.current_stream().cuda_stream
+    d_seq = torch.from_numpy(np.concatenate([seq, np.full(16, 10, np.uint8)])).cuda()
+    d_qual = torch.from_numpy(np.concatenate([qual, np.full(16, 10, np.uint8)])).cuda()
+    graphs = [DBGraph(w.kmer_size, L - bits, W) for _ in range(world)]
+    try:
+        per_reads = n_reads // world
+        per = per_reads * (w.read_len + 1)
+        geo = graphs[0].bin_geometry(world, len(seq) - (world - 1) * per, n_reads - (world - 1) * per_reads)
+        assert geo["bins_per_owner"] == bins
+        B, cap, rw, cw = geo["bins_per_owner"], geo["stripe_capacity"], geo["record_bytes"] // 8, geo["count_stride_bytes"] // 4
+        send = torch.zeros((world, world, B, cap, rw), dtype=torch.int64, device="cuda")       # [sender][owner]...
+        send_counts = torch.zeros((world, world, B, cw), dtype=torch.int32, device="cuda")
+        for r in range(world):
+            lo, hi = r * per, ((r + 1) * per if r < world - 1 else len(seq))
+            graphs[r].bin_reads_device(d_seq[lo:], d_qual[lo:], hi - lo, w.cutoff, world, B, cap, send[r],
+                                       send_counts[r], st_)
+        torch.cuda.synchronize()
+        cnt = send_counts[..., 0].cpu().numpy()
+        # (a record may stand for several occurrences: identical keys of a warp round are merged)
+        assert cnt.max() <= cap and 0 < int(cnt.sum()) <= og.stats.kmers_inserted
+        assert sum(g.stats(stream=st_)["kmers_inserted"] for g in graphs) == og.stats.kmers_inserted
+        for g in graphs:
+            g.stats(stream=st_)                                   # raises if a stripe overflowed
+        recs = []
+        for d in range(world):
+            recv = send[:, d].contiguous()                        # what all_to_all_single delivers to rank d
+            recv_counts = send_counts[:, d].contiguous()
+            graphs[d].insert_bins_device(recv, recv_counts, world, B, cap, st_)
+            torch.cuda.synchronize()
+            st = graphs[d].stats(stream=st_)
+            recs.append(graphs[d].records())
+            assert st["unique_kmers"] == len(recs[-1])
+        assert np.array_equal(O.sort_records(np.concatenate(recs)), want)
+    finally:
+        for g in graphs:
+            g.free()
+
+
+def test_binned_exchange_overflow_is_reported(monkeypatch):
+    """A stripe that is too small must raise, never drop records silently."""
+    torch = torch_cuda()
+    monkeypatch.setenv("LASV_B200_BINS", "2")
+    w = synth.scaled(synth.CFG0, 50_000, 10)
+    seq, qual, offs = synth.reads_host(w.params(), 0, 4000)
+    st_ = torch.cuda.current_stream().cuda_stream
+    d_seq = torch.from_numpy(np.concatenate([seq, np.full(16, 10, np.uint8)])).cuda()
+    d_qual = torch.from_numpy(np.concatenate([qual, np.full(16, 10, np.uint8)])).cuda()
+    with DBGraph(w.kmer_size, 9, w.bucket_size) as g:
+        geo = g.bin_geometry(2, len(seq), len(offs) - 1)
+        B, rw, cw = geo["bins_per_owner"], geo["record_bytes"] // 8, geo["count_stride_bytes"] // 4
+        cap = 100
+        send = torch.zeros((2, B, cap, rw), dtype=torch.int64, device="cuda")
+        counts = torch.zeros((2, B, cw), dtype=torch.int32, device="cuda")
+        g.bin_reads_device(d_seq, d_qual, len(seq), w.cutoff, 2, B, cap, send, counts, st_)
+        torch.cuda.synchronize()
+        with pytest.raises(_capi.LasvError):
+            g.stats(stream=st_)
+
+
 def test_hot_kmers_and_duplicate_reads_are_counted_exactly():
     """Thousands of copies of the same reads (and homopolymers): every occurrence is
     an atomic on the same few slots; warp aggregation and L2 reductions must not
