@@ -57,6 +57,8 @@ def parse_args():
     ap.add_argument("--workload", default="cfg4", choices=["cfg4", "cfg0"])
     ap.add_argument("--pairs-per-step", type=int, default=1 << 20)
     ap.add_argument("--no-prefill", action="store_true")
+    ap.add_argument("--no-pipeline", action="store_true",
+                    help="insert each batch before the next one is partitioned (one stream)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-pairs", type=int, default=100_000)
@@ -363,7 +365,7 @@ def main():
 
     graph = ShardedDBGraph(w.kmer_size, w.number_bits, w.bucket_size, rank, world, local_rank,
                            max_kmers_per_batch=reads_per_step * kpr, max_bytes_per_batch=n_bytes,
-                           max_reads_per_batch=reads_per_step)
+                           max_reads_per_batch=reads_per_step, pipeline=not args.no_pipeline)
     g = graph.graph
     table_bytes = g.capacity * g.element_bytes
 
@@ -466,10 +468,14 @@ def main():
     peak, peak_src = measured_peaks()
     slot = g.element_bytes
     kmers_per_launch = kmers / (K * world)
-    if world == 1:
+    if world == 1 and args.no_pipeline:
         kt = statistics.mean(e[0].elapsed_time(e[1]) for e in ev) * 1e-3
         alg_bytes = kmers_per_launch * 2 * slot + 2 * n_bytes
-        kname = "build_kernel<2,FUSED>"
+        kname = "build_kernel<MODE_BIN> + insert_bins_kernel (one batch, back to back)"
+    elif world == 1:
+        kt = dt / K                                          # the two kernels of consecutive batches overlap:
+        alg_bytes = kmers_per_launch * 2 * slot + 2 * n_bytes   # the step time is the per-batch kernel time
+        kname = "build_kernel<MODE_BIN> || insert_bins_kernel (pipelined, per batch)"
     else:
         kt = dt / K                                          # step time bounds every kernel in it
         alg_bytes = kmers_per_launch * (2 * slot + 2 * graph.rec_bytes) + 2 * n_bytes
@@ -478,7 +484,7 @@ def main():
     roofline = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "peak_source": peak_src,
                 "algorithmic_bytes_per_kmer": alg_bytes / kmers_per_launch,
-                "kernel_ms": kt * 1e3, "traffic": ncu_traffic(kname)}
+                "kernel_ms": kt * 1e3, "traffic": ncu_traffic("step")}
     if ra:
         ra["kernel_kmers_per_s"] = kmers_per_launch / kt
         ra["frac_of_random_access_ceiling"] = (kmers_per_launch / kt) / ra["ops_per_s"]

@@ -93,6 +93,14 @@ lasv_graph *lasv_graph_new(int kmer_size, int number_bits, int bucket_size,
 void lasv_graph_free(lasv_graph **g);
 /* Back to the state right after lasv_graph_new (zero table and counters). */
 int lasv_graph_clear(lasv_graph *g, void *cuda_stream);
+/* Pipelined inserts (large tables): with `on`, batch i is inserted on an internal
+ * stream while the caller's stream already partitions batch i+1.  Library calls that
+ * read the table join the internal stream themselves; a caller that reads the table
+ * with its own kernels, or times with events on its stream, calls lasv_graph_flush
+ * (the stream then waits for all queued inserts).  Default off; the environment
+ * variable LASV_B200_PIPELINE=1 turns it on at lasv_graph_new. */
+int lasv_graph_set_pipeline(lasv_graph *g, int on);
+int lasv_graph_flush(lasv_graph *g, void *cuda_stream);
 /* hash_table_get_unique_kmers / hash_table_get_capacity (hash_table.c:397-408). */
 long long lasv_graph_unique_kmers(lasv_graph *g);
 long long lasv_graph_capacity(lasv_graph *g);

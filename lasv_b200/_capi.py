@@ -68,7 +68,7 @@ EXPORTS = [
     "lasv_synth_reads_device", "lasv_synth_reads_host", "lasv_random_access_probe",
     "lasv_kernel_launches", "lasv_seqfile_to_streams", "lasv_random_access_probe_mode",
     "lasv_graph_record_buckets_device", "lasv_graph_bin_geometry", "lasv_graph_bin_reads_device",
-    "lasv_graph_insert_bins_device",
+    "lasv_graph_insert_bins_device", "lasv_graph_set_pipeline", "lasv_graph_flush",
 ]
 
 _lib = None
@@ -92,6 +92,8 @@ def lib() -> C.CDLL:
     L.lasv_graph_new.argtypes = [i32, i32, i32, i32, i32]
     L.lasv_graph_free.argtypes = [C.POINTER(vp)]
     L.lasv_graph_clear.argtypes = [vp, vp]
+    L.lasv_graph_set_pipeline.argtypes = [vp, i32]
+    L.lasv_graph_flush.argtypes = [vp, vp]
     L.lasv_graph_unique_kmers.restype = C.c_longlong
     L.lasv_graph_unique_kmers.argtypes = [vp]
     L.lasv_graph_capacity.restype = C.c_longlong

@@ -78,10 +78,18 @@ struct lasv_graph {
   cudaStream_t compute = nullptr, copy = nullptr;
   Staging stage[2];
   bool staging_ready = false;
-  // scratch of the partitioned insert (region bins), grown on demand
-  BinView bins{};
-  uint64_t bins_alloc_records = 0;
-  uint32_t bins_alloc_n = 0;
+  // scratch of the partitioned insert (region bins), grown on demand.  Pipelined mode uses both legs:
+  // batch i+1 is binned on the caller's stream while batch i is inserted on `ins`.
+  struct BinLeg {
+    BinView v{};
+    uint64_t alloc_records = 0;
+    uint32_t alloc_n = 0;
+    cudaEvent_t binned = nullptr, inserted = nullptr;
+    bool in_flight = false;
+  } leg[2];
+  int turn = 0;
+  bool pipeline = false;
+  cudaStream_t ins = nullptr;
 
   TableView view() const {
     return make_table_view(d_lines, N, L, W, max_rehash, finalized);
@@ -156,11 +164,20 @@ BuildParams build_params(lasv_graph *g, const uint8_t *d_seq, const uint8_t *d_q
 }
 
 void free_bins(lasv_graph *g) {
-  cudaFree(g->bins.recs);
-  cudaFree(g->bins.count);
-  g->bins = BinView{};
-  g->bins_alloc_records = 0;
-  g->bins_alloc_n = 0;
+  for (auto &l : g->leg) {
+    cudaFree(l.v.recs);
+    cudaFree(l.v.count);
+    l.v = BinView{};
+    l.alloc_records = 0;
+    l.alloc_n = 0;
+  }
+}
+
+// The caller's stream waits for every insert queued on the internal stream.
+int join_inserts(lasv_graph *g, cudaStream_t st) {
+  for (auto &l : g->leg)
+    if (l.in_flight) CUDA_TRY(cudaStreamWaitEvent(st, l.inserted, 0));
+  return LASV_OK;
 }
 
 // Partitioned insert applies when the table is much larger than L2 and the batch
@@ -204,26 +221,28 @@ uint64_t stripe_capacity(const lasv_graph *g, uint64_t n_bytes, uint64_t n_reads
   return (uint64_t)(mean * 1.01 + 8.0 * sqrt(mean) + 64.0);
 }
 
-int ensure_bins(lasv_graph *g, uint64_t n_bytes, uint64_t n_reads, uint32_t n_bins) {
+int ensure_bins(lasv_graph *g, lasv_graph::BinLeg &l, uint64_t n_bytes, uint64_t n_reads, uint32_t n_bins) {
   // a fuller stripe spills its excess straight into the table, so this is a sizing choice, not a limit
   const uint64_t cap = stripe_capacity(g, n_bytes, n_reads, n_bins);
   if (cap > 0xFFFFFFF0ull) return fail(LASV_ERR_ARG, "batch too large for the bin stripes");
   const uint64_t want = cap * n_bins;
-  if (g->bins_alloc_records < want || g->bins_alloc_n != n_bins) {
+  if (l.alloc_records < want || l.alloc_n != n_bins) {
     CUDA_TRY(cudaDeviceSynchronize());
-    free_bins(g);
-    CUDA_TRY(cudaMalloc(&g->bins.recs, want * (size_t)bin_record_words(g->N) * sizeof(uint64_t)));
-    CUDA_TRY(cudaMalloc(&g->bins.count, (size_t)n_bins * COUNT_STRIDE * sizeof(unsigned int)));
-    g->bins_alloc_records = want;
-    g->bins_alloc_n = n_bins;
+    cudaFree(l.v.recs);
+    cudaFree(l.v.count);
+    l.v = BinView{};
+    CUDA_TRY(cudaMalloc(&l.v.recs, want * (size_t)bin_record_words(g->N) * sizeof(uint64_t)));
+    CUDA_TRY(cudaMalloc(&l.v.count, (size_t)n_bins * COUNT_STRIDE * sizeof(unsigned int)));
+    l.alloc_records = want;
+    l.alloc_n = n_bins;
   }
-  g->bins.cap = (uint32_t)(g->bins_alloc_records / n_bins);
-  g->bins.n_bins = n_bins;
-  g->bins.bin_mask = (uint32_t)(g->n_buckets - 1);
-  g->bins.bin_shift = (uint32_t)(g->L - log2_u32(n_bins));
-  g->bins.spill_ok = 1;
-  g->bins.src_shift = 0;
-  g->bins.bins_per_src = n_bins;
+  l.v.cap = (uint32_t)(l.alloc_records / n_bins);
+  l.v.n_bins = n_bins;
+  l.v.bin_mask = (uint32_t)(g->n_buckets - 1);
+  l.v.bin_shift = (uint32_t)(g->L - log2_u32(n_bins));
+  l.v.spill_ok = 1;
+  l.v.src_shift = 0;
+  l.v.bins_per_src = n_bins;
   return LASV_OK;
 }
 
@@ -296,7 +315,12 @@ lasv_graph *lasv_graph_new(int kmer_size, int number_bits, int bucket_size, int 
             cudaMalloc(&g->d_hist, HIST_BINS * sizeof(unsigned long long)) == cudaSuccess &&
             cudaMalloc(&g->d_overflow, sizeof(unsigned long long)) == cudaSuccess &&
             cudaStreamCreateWithFlags(&g->compute, cudaStreamNonBlocking) == cudaSuccess &&
-            cudaStreamCreateWithFlags(&g->copy, cudaStreamNonBlocking) == cudaSuccess;
+            cudaStreamCreateWithFlags(&g->copy, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaStreamCreateWithFlags(&g->ins, cudaStreamNonBlocking) == cudaSuccess;
+  for (auto &l : g->leg)
+    ok = ok && cudaEventCreateWithFlags(&l.binned, cudaEventDisableTiming) == cudaSuccess &&
+         cudaEventCreateWithFlags(&l.inserted, cudaEventDisableTiming) == cudaSuccess;
+  if (const char *e = getenv("LASV_B200_PIPELINE")) g->pipeline = atoi(e) != 0;
   if (ok) ok = lasv_graph_clear(g, nullptr) == LASV_OK && cudaDeviceSynchronize() == cudaSuccess;
   if (!ok) {
     if (g_err.empty() || g_err.find("failed") == std::string::npos)
@@ -326,6 +350,11 @@ void lasv_graph_free(lasv_graph **gp) {
     if (s.copied) cudaEventDestroy(s.copied);
     if (s.consumed) cudaEventDestroy(s.consumed);
   }
+  for (auto &l : g->leg) {
+    if (l.binned) cudaEventDestroy(l.binned);
+    if (l.inserted) cudaEventDestroy(l.inserted);
+  }
+  if (g->ins) cudaStreamDestroy(g->ins);
   if (g->compute) cudaStreamDestroy(g->compute);
   if (g->copy) cudaStreamDestroy(g->copy);
   delete g;
@@ -335,6 +364,7 @@ void lasv_graph_free(lasv_graph **gp) {
 int lasv_graph_clear(lasv_graph *g, void *cuda_stream) {
   if (int e = use(g)) return e;
   cudaStream_t st = stream_of(g, cuda_stream);
+  if (int e = join_inserts(g, st)) return e;
   CUDA_TRY(cudaMemsetAsync(g->d_lines, 0, g->table_bytes, st));
   CUDA_TRY(cudaMemsetAsync(g->d_ctr, 0, sizeof(GraphCounters), st));
   CUDA_TRY(cudaMemsetAsync(g->d_stats, 0, sizeof(ReadStats), st));
@@ -350,6 +380,23 @@ long long lasv_graph_unique_kmers(lasv_graph *g) {
   if (cudaDeviceSynchronize() != cudaSuccess) return -1;  // work may be queued on any stream
   if (cudaMemcpy(&v, &g->d_ctr->unique_kmers, sizeof v, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
   return (long long)v;
+}
+
+/* Pipelined inserts: with `on`, the partitioned path inserts batch i on an internal stream while
+ * the caller's stream already bins batch i+1 (both kernels are then sized to share the SMs).  Every
+ * entry point of this library that reads the table joins the internal stream itself; a caller that
+ * reads the table with its OWN kernels, or times with events on its stream, calls lasv_graph_flush. */
+int lasv_graph_set_pipeline(lasv_graph *g, int on) {
+  if (int e = use(g)) return e;
+  CUDA_TRY(cudaDeviceSynchronize());
+  for (auto &l : g->leg) l.in_flight = false;
+  g->pipeline = on != 0;
+  return LASV_OK;
+}
+
+int lasv_graph_flush(lasv_graph *g, void *cuda_stream) {
+  if (int e = use(g)) return e;
+  return join_inserts(g, stream_of(g, cuda_stream));
 }
 
 long long lasv_graph_capacity(lasv_graph *g) { return g ? (long long)g->n_slots : -1; }
@@ -373,13 +420,25 @@ int lasv_graph_load_reads_device(lasv_graph *g, const uint8_t *d_seq, const uint
       // Partitioned insert: group the batch's k-mers by 16 MB table region, then
       // insert region by region (profiles/exp_sorted_insert_r1_cfg4.jsonl: 3.3x
       // the insert rate of uniformly random probes on a 100 GB table).
-      if (int e = ensure_bins(g, n_bytes, d_offsets ? n_reads : 0, n_bins)) return e;
-      p.bins = g->bins;
-      CUDA_TRY(cudaMemsetAsync(g->bins.count, 0, (size_t)n_bins * COUNT_STRIDE * sizeof(unsigned int), st));
+      lasv_graph::BinLeg &l = g->leg[g->pipeline ? (g->turn++ & 1) : 0];
+      if (l.in_flight) CUDA_TRY(cudaStreamWaitEvent(st, l.inserted, 0));  // the insert that read this leg
+      if (int e = ensure_bins(g, l, n_bytes, d_offsets ? n_reads : 0, n_bins)) return e;
+      p.bins = l.v;
+      p.ctas_per_sm = g->pipeline ? 2 : 0;  // pipelined: this kernel shares the SMs with the previous batch's insert
+      CUDA_TRY(cudaMemsetAsync(l.v.count, 0, (size_t)n_bins * COUNT_STRIDE * sizeof(unsigned int), st));
       launch_build(g->N, MODE_BIN, p, st);
       if (int e = check_launch()) return e;
-      launch_insert_bins(g->N, g->bins, g->view(), g->d_ctr, st);
-      if (int e = check_launch()) return e;
+      if (!g->pipeline) {
+        launch_insert_bins(g->N, l.v, g->view(), g->d_ctr, 0, st);
+        if (int e = check_launch()) return e;
+      } else {
+        CUDA_TRY(cudaEventRecord(l.binned, st));
+        CUDA_TRY(cudaStreamWaitEvent(g->ins, l.binned, 0));
+        launch_insert_bins(g->N, l.v, g->view(), g->d_ctr, 2, g->ins);
+        if (int e = check_launch()) return e;
+        CUDA_TRY(cudaEventRecord(l.inserted, g->ins));
+        l.in_flight = true;
+      }
     } else {
       // Direct fused insert.  Random access over more than ~64 GB falls off the
       // TLB reach of a B200 (profiles/random_access_sweep_r1.jsonl): walk the batch
@@ -473,6 +532,7 @@ int lasv_graph_load_reads_host(lasv_graph *g, const uint8_t *seq, const uint8_t 
     leg ^= 1;
     r0 = r1;
   }
+  if (int e = join_inserts(g, g->compute)) return e;  // pipelined inserts of the last chunks
   if (int e = fetch_counters(g, g->compute, &rs1, &c1, &ov)) return e;
   if (c1.table_full) return fail(LASV_ERR_TABLE_FULL, "%s", TABLE_FULL_MSG);
   if (batch_stats) {
@@ -621,6 +681,7 @@ int lasv_graph_bin_reads_device(lasv_graph *g, const uint8_t *d_seq, const uint8
   p.bins.spill_ok = n_owners == 1 ? 1u : 0u;
   p.bins.src_shift = 0;
   p.bins.bins_per_src = n_bins;
+  p.ctas_per_sm = g->pipeline ? 2 : 0;
   launch_build(g->N, MODE_BIN, p, st);
   return check_launch();
 }
@@ -640,7 +701,7 @@ int lasv_graph_insert_bins_device(lasv_graph *g, const void *d_records, const vo
   b.n_bins = bins_per_src * (uint32_t)n_src;
   b.src_shift = (uint32_t)log2_u32((uint32_t)n_src);
   b.bins_per_src = bins_per_src;
-  launch_insert_bins(g->N, b, g->view(), g->d_ctr, stream_of(g, cuda_stream));
+  launch_insert_bins(g->N, b, g->view(), g->d_ctr, g->pipeline ? 2 : 0, stream_of(g, cuda_stream));
   return check_launch();
 }
 

@@ -987,7 +987,7 @@ void launch_build(int N, BuildMode mode, const BuildParams &p, cudaStream_t st) 
     auto go = [&](auto kernel, int T, size_t smem) {
       cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       const uint64_t n_tiles = (p.n_bytes + T - 1) / T;  // one tile per warp and round
-      uint64_t grid = (uint64_t)resident_grid(kernel, 8, smem);
+      uint64_t grid = (uint64_t)resident_grid(kernel, p.ctas_per_sm > 0 ? p.ctas_per_sm : 8, smem);
       const uint64_t need = (n_tiles + THREADS / 32 - 1) / (THREADS / 32);
       if (grid > need) grid = need;
       kernel<<<(unsigned)grid, THREADS, smem, st>>>(p, n_tiles);
@@ -1016,11 +1016,12 @@ void launch_insert_records(int N, const uint32_t *recs, uint64_t n_recs, const T
   });
 }
 
-void launch_insert_bins(int N, const BinView &b, const TableView &t, GraphCounters *ctr, cudaStream_t st) {
+void launch_insert_bins(int N, const BinView &b, const TableView &t, GraphCounters *ctr, int ctas_per_sm,
+                        cudaStream_t st) {
   dispatch_n(N, [&](auto n) {
     constexpr int NN = decltype(n)::value;
     // few resident warps on purpose (see the kernel's comment); LASV_B200_INSERT_CTAS overrides
-    int per_sm = 3;
+    int per_sm = ctas_per_sm > 0 ? ctas_per_sm : 3;
     if (const char *e = getenv("LASV_B200_INSERT_CTAS")) per_sm = atoi(e) > 0 ? atoi(e) : per_sm;
     insert_bins_kernel<NN, 2><<<resident_grid(insert_bins_kernel<NN, 2>, per_sm), THREADS, 0, st>>>(b, t, ctr);
   });

@@ -69,6 +69,7 @@ struct BuildParams {
   // 1/n_pass slice of the table (n_pass power of two, pass_shift = L - log2 n_pass)
   int n_pass, pass, pass_shift;
   BinView bins;  // MODE_BIN
+  int ctas_per_sm;  // > 0: cap on resident CTAs per SM (kernels that share the GPU with another kernel)
 };
 
 struct ReadStats {  // loader bookkeeping (file_reader.c:460-470,579,584)
@@ -106,7 +107,8 @@ int sm_count();
 void launch_build(int N, BuildMode mode, const BuildParams &p, cudaStream_t st);
 void launch_insert_records(int N, const uint32_t *recs, uint64_t n_recs, const TableView &t,
                            GraphCounters *ctr, cudaStream_t st);
-void launch_insert_bins(int N, const BinView &b, const TableView &t, GraphCounters *ctr, cudaStream_t st);
+void launch_insert_bins(int N, const BinView &b, const TableView &t, GraphCounters *ctr, int ctas_per_sm,
+                        cudaStream_t st);
 void launch_read_stats(const uint8_t *seq, const uint8_t *qual, const uint64_t *offsets,
                        uint64_t n_reads, int sep, int k, int cutoff, ReadStats *stats,
                        unsigned long long *hist, uint32_t hist_size, cudaStream_t st);

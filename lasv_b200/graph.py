@@ -81,6 +81,14 @@ class DBGraph:
     def clear(self, stream=None):
         check(self._lib.lasv_graph_clear(self._h, stream))
 
+    def set_pipeline(self, on: bool = True):
+        """Insert batch i on an internal stream while batch i+1 is partitioned (large tables)."""
+        check(self._lib.lasv_graph_set_pipeline(self._h, int(on)))
+
+    def flush(self, stream=None):
+        """`stream` waits for every insert queued on the internal stream."""
+        check(self._lib.lasv_graph_flush(self._h, stream))
+
     # -- properties
     @property
     def unique_kmers(self) -> int:

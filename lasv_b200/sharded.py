@@ -128,7 +128,9 @@ class ShardedDBGraph:
             raise ValueError("too few buckets for this many ranks")
         self.graph = DBGraph(kmer_size, self.local_bits, bucket_size, device=device)
         self.device = torch.device("cuda", device)
-        self.pipeline = pipeline and world > 1
+        self.pipeline = pipeline
+        if pipeline:
+            self.graph.set_pipeline(True)     # kernels sized to share the SMs with the neighbouring stage
         self.buffers = []
         self.turn = 0
         if world > 1:
@@ -191,8 +193,10 @@ class ShardedDBGraph:
 
     def flush(self):
         """Make the caller's current stream wait for everything queued on the side streams."""
-        if self.world > 1 and self.pipeline:
-            cur = torch.cuda.current_stream()
+        cur = torch.cuda.current_stream()
+        if self.world == 1:
+            self.graph.flush(cur.cuda_stream)
+        elif self.pipeline:
             for buf in self.buffers:
                 if buf.inserted is not None:
                     cur.wait_event(buf.inserted)
