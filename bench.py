@@ -365,7 +365,7 @@ def main():
 
     graph = ShardedDBGraph(w.kmer_size, w.number_bits, w.bucket_size, rank, world, local_rank,
                            max_kmers_per_batch=reads_per_step * kpr, max_bytes_per_batch=n_bytes,
-                           max_reads_per_batch=reads_per_step, pipeline=not args.no_pipeline)
+                           max_reads_per_batch=reads_per_step, pipeline=(world > 1 and not args.no_pipeline))
     g = graph.graph
     table_bytes = g.capacity * g.element_bytes
 
@@ -445,6 +445,8 @@ def main():
     barrier()
     st0 = graph.stats()
     l0 = lib.lasv_kernel_launches()
+    if world == 1:
+        g.enable_kernel_timing(True)   # CUDA events around every launch of the two kernels, on their stream
     barrier()
     t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     wall0 = time.monotonic()
@@ -458,6 +460,9 @@ def main():
     torch.cuda.profiler.stop()
     wall1 = time.monotonic()
     launches = lib.lasv_kernel_launches() - l0
+    ktimes = g.kernel_times() if world == 1 else None
+    if world == 1:
+        g.enable_kernel_timing(False)
     dt = max_over_ranks(t_begin.elapsed_time(t_end) * 1e-3)
     st1 = graph.stats()
     kmers = st1["kmers_inserted"] - st0["kmers_inserted"] if not cfg0 else st1["kmers_inserted"] * K
@@ -468,14 +473,22 @@ def main():
     peak, peak_src = measured_peaks()
     slot = g.element_bytes
     kmers_per_launch = kmers / (K * world)
-    if world == 1 and args.no_pipeline:
-        kt = statistics.mean(e[0].elapsed_time(e[1]) for e in ev) * 1e-3
-        alg_bytes = kmers_per_launch * 2 * slot + 2 * n_bytes
-        kname = "build_kernel<MODE_BIN> + insert_bins_kernel (one batch, back to back)"
+    step_alg_bytes = kmers_per_launch * 2 * slot + 2 * n_bytes       # 2*sizeof(Element) + 2 B/base
+    extra = {}
+    if world == 1 and ktimes and ktimes["batches"]:
+        # dominant kernel: insert_bins_kernel (the find-or-insert); its algorithmic bytes are the
+        # slot read + write-back, the 2 B/base of input belong to the partition kernel
+        kt = ktimes["insert_ms"] / ktimes["batches"] * 1e-3
+        alg_bytes = kmers_per_launch * 2 * slot
+        kname = "insert_bins_kernel"
+        extra = {"partition_kernel": "build_kernel<MODE_BIN>",
+                 "partition_kernel_ms": ktimes["partition_ms"] / ktimes["batches"],
+                 "launches_timed": ktimes["batches"],
+                 "step_achieved": step_alg_bytes / (dt / K) / 1e9, "step_frac": step_alg_bytes / (dt / K) / 1e9 / peak}
     elif world == 1:
-        kt = dt / K                                          # the two kernels of consecutive batches overlap:
-        alg_bytes = kmers_per_launch * 2 * slot + 2 * n_bytes   # the step time is the per-batch kernel time
-        kname = "build_kernel<MODE_BIN> || insert_bins_kernel (pipelined, per batch)"
+        kt = statistics.mean(e[0].elapsed_time(e[1]) for e in ev) * 1e-3
+        alg_bytes = step_alg_bytes
+        kname = "build_kernel<FUSED>"
     else:
         kt = dt / K                                          # step time bounds every kernel in it
         alg_bytes = kmers_per_launch * (2 * slot + 2 * graph.rec_bytes) + 2 * n_bytes
@@ -484,7 +497,8 @@ def main():
     roofline = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "peak_source": peak_src,
                 "algorithmic_bytes_per_kmer": alg_bytes / kmers_per_launch,
-                "kernel_ms": kt * 1e3, "traffic": ncu_traffic("step")}
+                "kernel_ms": kt * 1e3, "traffic": ncu_traffic(kname)}
+    roofline.update(extra)
     if ra:
         ra["kernel_kmers_per_s"] = kmers_per_launch / kt
         ra["frac_of_random_access_ceiling"] = (kmers_per_launch / kt) / ra["ops_per_s"]
@@ -505,15 +519,35 @@ def main():
         offs_host = (np.arange(reads_per_step + 1, dtype=np.uint64) * np.uint64(stride))
         barrier()
 
+        copy_stream = torch.cuda.Stream(device=dev)
+        copied = [torch.cuda.Event(), torch.cuda.Event()]
+        consumed = [None, None]
+        results = torch.zeros((K + Wm + 1, 9), dtype=torch.int64).pin_memory()    # one statistics row per step
+        step_no = [0]
+
         def e2e_step(b):
             if cfg0:
                 g.clear(None)
             if world == 1:
                 return g.load_reads_host(host_seq[b], host_qual[b], offs_host, w.cutoff)   # C-ABI, host buffers
-            seqs[0].copy_(host_seq[b], non_blocking=True)
-            quals[0].copy_(host_qual[b], non_blocking=True)
-            graph.load_reads_device(seqs[0], quals[0], n_bytes, w.cutoff, offs_dev, reads_per_step)
-            return g.stats(stream=stream)                                                # D2H of the counters
+            # sharded: pinned host -> device on a copy stream (two device buffers), binned exchange and
+            # inserts behind it, the step's statistics copied back behind the inserts -- nothing blocks the host
+            i = step_no[0]
+            step_no[0] += 1
+            k2 = i % min(2, len(seqs))
+            cur = torch.cuda.current_stream()
+            with torch.cuda.stream(copy_stream):
+                if consumed[k2] is not None:
+                    copy_stream.wait_event(consumed[k2])
+                seqs[k2].copy_(host_seq[b], non_blocking=True)
+                quals[k2].copy_(host_qual[b], non_blocking=True)
+                copied[k2].record(copy_stream)
+            cur.wait_event(copied[k2])
+            graph.load_reads_device(seqs[k2], quals[k2], n_bytes, w.cutoff, offs_dev, reads_per_step)
+            consumed[k2] = torch.cuda.Event()
+            consumed[k2].record(cur)
+            graph.stats_async(results[i])                                                  # D2H of the counters
+            return None
 
         for s in range(Wm):
             e2e_step(0 if cfg0 else s)
@@ -524,15 +558,17 @@ def main():
             e2e_step(0 if cfg0 else Wm + s)
         torch.cuda.synchronize()
         t1 = time.perf_counter()
+        if world > 1 and int(results[step_no[0] - 1, 6]) <= int(results[Wm - 1, 6]):
+            raise RuntimeError("e2e: the per-step statistics did not advance")
         dte = max_over_ranks(t1 - t0)
         barrier()
         sb = graph.stats()
         ke = sb["kmers_inserted"] - sa["kmers_inserted"] if not cfg0 else sb["kmers_inserted"] * K
         e2e = {"value": ke / dte, "unit": UNIT,
                "h2d_bytes_per_step": int(2 * n_bytes + 8 * (reads_per_step + 1)),
-               "d2h_bytes_per_step": 7 * 8 + 20 * 8 + 8, "ms_per_step": 1e3 * dte / K,
+               "d2h_bytes_per_step": (7 * 8 + 20 * 8 + 8) if world == 1 else 9 * 8, "ms_per_step": 1e3 * dte / K,
                "api": "lasv_graph_load_reads_host (C ABI, pinned host buffers)" if world == 1 else
-                      "pinned host -> device copy + sharded bin/all_to_all/insert + counter read-back"}
+                      "pinned host -> device copies on a copy stream + sharded bin/all_to_all/insert + per-step statistics read-back (async)"}
 
     sampler.stop()
 

@@ -101,6 +101,12 @@ int lasv_graph_clear(lasv_graph *g, void *cuda_stream);
  * variable LASV_B200_PIPELINE=1 turns it on at lasv_graph_new. */
 int lasv_graph_set_pipeline(lasv_graph *g, int on);
 int lasv_graph_flush(lasv_graph *g, void *cuda_stream);
+/* Measurement aid: CUDA events around every launch of the partitioned path's two
+ * kernels (partition = build_kernel<MODE_BIN>, insert = insert_bins_kernel), each on
+ * the stream the kernel is launched on.  enable(1) starts and resets the collection;
+ * kernel_times synchronises the device and sums the durations collected so far. */
+int lasv_graph_enable_kernel_timing(lasv_graph *g, int on);
+int lasv_graph_kernel_times(lasv_graph *g, double *partition_ms, double *insert_ms, uint64_t *n_batches);
 /* hash_table_get_unique_kmers / hash_table_get_capacity (hash_table.c:397-408). */
 long long lasv_graph_unique_kmers(lasv_graph *g);
 long long lasv_graph_capacity(lasv_graph *g);
@@ -139,6 +145,11 @@ int lasv_graph_load_reads_host(lasv_graph *g, const uint8_t *seq, const uint8_t 
  * readlen_count_array of file_reader.c:467-471, hist_size bins. */
 int lasv_graph_stats(lasv_graph *g, lasv_load_stats *out, uint64_t *contig_hist,
                      uint64_t hist_size, void *cuda_stream);
+/* Non-blocking variant for pipelined callers: the statistics as they stand when
+ * `cuda_stream` reaches this point, copied to PINNED host memory: n_reads, bad_reads,
+ * bases_read, bases_loaded, n_contigs, unique_kmers, kmers_inserted, table_full,
+ * exchange_overflow (9 x uint64).  Valid once the stream has passed the copy. */
+int lasv_graph_stats_async(lasv_graph *g, uint64_t *pinned_out9, void *cuda_stream);
 /* collisions[r] of hash_table.c:325 (r = 0..15). */
 int lasv_graph_rehash_histogram(lasv_graph *g, long long out16[16]);
 

@@ -69,6 +69,7 @@ EXPORTS = [
     "lasv_kernel_launches", "lasv_seqfile_to_streams", "lasv_random_access_probe_mode",
     "lasv_graph_record_buckets_device", "lasv_graph_bin_geometry", "lasv_graph_bin_reads_device",
     "lasv_graph_insert_bins_device", "lasv_graph_set_pipeline", "lasv_graph_flush",
+    "lasv_graph_enable_kernel_timing", "lasv_graph_kernel_times", "lasv_graph_stats_async",
 ]
 
 _lib = None
@@ -94,6 +95,8 @@ def lib() -> C.CDLL:
     L.lasv_graph_clear.argtypes = [vp, vp]
     L.lasv_graph_set_pipeline.argtypes = [vp, i32]
     L.lasv_graph_flush.argtypes = [vp, vp]
+    L.lasv_graph_enable_kernel_timing.argtypes = [vp, i32]
+    L.lasv_graph_kernel_times.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(u64)]
     L.lasv_graph_unique_kmers.restype = C.c_longlong
     L.lasv_graph_unique_kmers.argtypes = [vp]
     L.lasv_graph_capacity.restype = C.c_longlong
@@ -109,6 +112,7 @@ def lib() -> C.CDLL:
     L.lasv_graph_load_reads_host.argtypes = [vp, vp, vp, u64, vp, u64, i32, C.POINTER(LoadStats)]
     L.lasv_graph_stats.argtypes = [vp, C.POINTER(LoadStats), vp, u64, vp]
     L.lasv_graph_rehash_histogram.argtypes = [vp, vp]
+    L.lasv_graph_stats_async.argtypes = [vp, vp, vp]
     L.lasv_graph_route_reads_device.argtypes = [vp, vp, vp, u64, i32, i32, vp, u64, vp, vp]
     L.lasv_graph_extract_records_device.argtypes = [vp, vp, vp, u64, i32, vp, u64, vp, vp]
     L.lasv_graph_insert_records_device.argtypes = [vp, vp, u64, vp]

@@ -90,6 +90,11 @@ struct lasv_graph {
   int turn = 0;
   bool pipeline = false;
   cudaStream_t ins = nullptr;
+  // optional per-launch timing of the two kernels of the partitioned path (bench: roofline of the
+  // dominant kernel from CUDA events on the stream the kernel is launched on)
+  bool timing = false;
+  std::vector<cudaEvent_t> t_events;  // 4 per batch: bin begin/end, insert begin/end
+  size_t t_used = 0;
 
   TableView view() const {
     return make_table_view(d_lines, N, L, W, max_rehash, finalized);
@@ -171,6 +176,20 @@ void free_bins(lasv_graph *g) {
     l.alloc_records = 0;
     l.alloc_n = 0;
   }
+}
+
+// next timing event (created on demand, reused after a reset); nullptr when timing is off
+cudaEvent_t timing_event(lasv_graph *g) {
+  if (!g->timing) return nullptr;
+  if (g->t_used == g->t_events.size()) {
+    cudaEvent_t e = nullptr;
+    if (cudaEventCreate(&e) != cudaSuccess) return nullptr;
+    g->t_events.push_back(e);
+  }
+  return g->t_events[g->t_used++];
+}
+void mark(cudaEvent_t e, cudaStream_t st) {
+  if (e) cudaEventRecord(e, st);
 }
 
 // The caller's stream waits for every insert queued on the internal stream.
@@ -354,6 +373,7 @@ void lasv_graph_free(lasv_graph **gp) {
     if (l.binned) cudaEventDestroy(l.binned);
     if (l.inserted) cudaEventDestroy(l.inserted);
   }
+  for (cudaEvent_t e : g->t_events) cudaEventDestroy(e);
   if (g->ins) cudaStreamDestroy(g->ins);
   if (g->compute) cudaStreamDestroy(g->compute);
   if (g->copy) cudaStreamDestroy(g->copy);
@@ -394,6 +414,35 @@ int lasv_graph_set_pipeline(lasv_graph *g, int on) {
   return LASV_OK;
 }
 
+/* Per-launch CUDA-event timing of the partitioned path's two kernels.  enable: start (and reset) or
+ * stop collecting; kernel_times: device-synchronises, then sums the durations collected so far. */
+int lasv_graph_enable_kernel_timing(lasv_graph *g, int on) {
+  if (int e = use(g)) return e;
+  CUDA_TRY(cudaDeviceSynchronize());
+  g->timing = on != 0;
+  g->t_used = 0;
+  return LASV_OK;
+}
+
+int lasv_graph_kernel_times(lasv_graph *g, double *partition_ms, double *insert_ms, uint64_t *n_batches) {
+  if (int e = use(g)) return e;
+  CUDA_TRY(cudaDeviceSynchronize());
+  double a = 0, b = 0;
+  uint64_t n = 0;
+  for (size_t i = 0; i + 3 < g->t_used; i += 4) {
+    float x = 0, y = 0;
+    CUDA_TRY(cudaEventElapsedTime(&x, g->t_events[i], g->t_events[i + 1]));
+    CUDA_TRY(cudaEventElapsedTime(&y, g->t_events[i + 2], g->t_events[i + 3]));
+    a += x;
+    b += y;
+    n++;
+  }
+  if (partition_ms) *partition_ms = a;
+  if (insert_ms) *insert_ms = b;
+  if (n_batches) *n_batches = n;
+  return LASV_OK;
+}
+
 int lasv_graph_flush(lasv_graph *g, void *cuda_stream) {
   if (int e = use(g)) return e;
   return join_inserts(g, stream_of(g, cuda_stream));
@@ -426,16 +475,23 @@ int lasv_graph_load_reads_device(lasv_graph *g, const uint8_t *d_seq, const uint
       p.bins = l.v;
       p.ctas_per_sm = g->pipeline ? 2 : 0;  // pipelined: this kernel shares the SMs with the previous batch's insert
       CUDA_TRY(cudaMemsetAsync(l.v.count, 0, (size_t)n_bins * COUNT_STRIDE * sizeof(unsigned int), st));
+      cudaEvent_t tb0 = timing_event(g), tb1 = timing_event(g), ti0 = timing_event(g), ti1 = timing_event(g);
+      mark(tb0, st);
       launch_build(g->N, MODE_BIN, p, st);
       if (int e = check_launch()) return e;
+      mark(tb1, st);
       if (!g->pipeline) {
+        mark(ti0, st);
         launch_insert_bins(g->N, l.v, g->view(), g->d_ctr, 0, st);
         if (int e = check_launch()) return e;
+        mark(ti1, st);
       } else {
         CUDA_TRY(cudaEventRecord(l.binned, st));
         CUDA_TRY(cudaStreamWaitEvent(g->ins, l.binned, 0));
+        mark(ti0, g->ins);
         launch_insert_bins(g->N, l.v, g->view(), g->d_ctr, 2, g->ins);
         if (int e = check_launch()) return e;
+        mark(ti1, g->ins);
         CUDA_TRY(cudaEventRecord(l.inserted, g->ins));
         l.in_flight = true;
       }
@@ -572,6 +628,20 @@ int lasv_graph_stats(lasv_graph *g, lasv_load_stats *out, uint64_t *contig_hist,
   }
   if (c.table_full) return fail(LASV_ERR_TABLE_FULL, "%s", TABLE_FULL_MSG);
   if (ov) return fail(LASV_ERR_CAPACITY, "record buffer / exchange bin overflow");
+  return LASV_OK;
+}
+
+/* Asynchronous read-back of the load statistics as they stand when `cuda_stream` reaches this
+ * point: 7 uint64 (lasv_load_stats order) + table_full + overflow into pinned host memory. */
+int lasv_graph_stats_async(lasv_graph *g, uint64_t *pinned_out9, void *cuda_stream) {
+  if (int e = use(g)) return e;
+  if (!pinned_out9) return fail(LASV_ERR_ARG, "NULL output");
+  cudaStream_t st = stream_of(g, cuda_stream);
+  // ReadStats = {n_reads, bad_reads, bases_read, bases_loaded, n_contigs}; GraphCounters starts with
+  // {unique_kmers, kmers_inserted, table_full}
+  CUDA_TRY(cudaMemcpyAsync(pinned_out9, g->d_stats, 5 * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(pinned_out9 + 5, g->d_ctr, 3 * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(pinned_out9 + 8, g->d_overflow, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
   return LASV_OK;
 }
 

@@ -85,6 +85,15 @@ class DBGraph:
         """Insert batch i on an internal stream while batch i+1 is partitioned (large tables)."""
         check(self._lib.lasv_graph_set_pipeline(self._h, int(on)))
 
+    def enable_kernel_timing(self, on: bool = True):
+        check(self._lib.lasv_graph_enable_kernel_timing(self._h, int(on)))
+
+    def kernel_times(self) -> dict:
+        """Summed CUDA-event durations of the partition / insert kernels since enable_kernel_timing."""
+        a, b, n = C.c_double(0), C.c_double(0), C.c_uint64(0)
+        check(self._lib.lasv_graph_kernel_times(self._h, C.byref(a), C.byref(b), C.byref(n)))
+        return {"partition_ms": a.value, "insert_ms": b.value, "batches": int(n.value)}
+
     def flush(self, stream=None):
         """`stream` waits for every insert queued on the internal stream."""
         check(self._lib.lasv_graph_flush(self._h, stream))
@@ -121,6 +130,13 @@ class DBGraph:
         hist = np.zeros(hist_size, dtype=np.uint64) if hist_size else None
         check(self._lib.lasv_graph_stats(self._h, C.byref(st), _ptr(hist), hist_size, stream))
         return (st.as_dict(), hist) if hist_size else st.as_dict()
+
+    STATS_ASYNC_FIELDS = ("n_reads", "bad_reads", "bases_read", "bases_loaded", "n_contigs", "unique_kmers",
+                          "kmers_inserted", "table_full", "exchange_overflow")
+
+    def stats_async(self, pinned_out, stream=None):
+        """Queue a copy of the statistics (9 x uint64, STATS_ASYNC_FIELDS) into pinned host memory."""
+        check(self._lib.lasv_graph_stats_async(self._h, _ptr(pinned_out), stream))
 
     def rehash_histogram(self) -> np.ndarray:
         out = np.zeros(16, dtype=np.int64)

@@ -191,6 +191,15 @@ class ShardedDBGraph:
             buf.inserted = torch.cuda.Event()
             buf.inserted.record(self.insert_stream)
 
+    def stats_async(self, pinned_out):
+        """Queue a device->host copy of this rank's statistics behind the inserts of the batches
+        loaded so far (no host synchronisation); see DBGraph.stats_async for the layout."""
+        if self.world > 1 and self.pipeline:
+            with torch.cuda.stream(self.insert_stream):
+                self.graph.stats_async(pinned_out, self.insert_stream.cuda_stream)
+        else:
+            self.graph.stats_async(pinned_out, torch.cuda.current_stream().cuda_stream)
+
     def flush(self):
         """Make the caller's current stream wait for everything queued on the side streams."""
         cur = torch.cuda.current_stream()
