@@ -529,6 +529,7 @@ int lasv_graph_read_stats_device(lasv_graph *g, const uint8_t *d_seq, const uint
                                  void *cuda_stream) {
   if (int e = use(g)) return e;
   if (!n_reads) return LASV_OK;
+  if (int e = check_streams(d_seq, d_qual)) return e;
   launch_read_stats(d_seq, d_qual, d_offsets, n_reads, 1, g->k, quality_cutoff, g->d_stats,
                     g->d_hist, HIST_BINS, stream_of(g, cuda_stream));
   return check_launch();

@@ -579,8 +579,13 @@ __global__ void __launch_bounds__(THREADS, 4) insert_records_kernel(const uint32
 }
 
 // --------------------------------------------------------------------------
-// read_stats_kernel: one warp per read
+// read_stats_kernel: one LANE per read
 // --------------------------------------------------------------------------
+// Loader bookkeeping (file_reader.c:460-470,579): reads without a run of k good
+// bases, bases in such runs, number of runs, run-length histogram.  A lane walks
+// its read in aligned 8-byte words of both streams; per base: class lookup in a
+// 32-bit constant, signed quality compare, run counter.  (One warp per read with
+// ballots over 32 bases cost 49 thread instructions per base, this costs ~12.)
 constexpr int HIST_SMEM = 1024;
 
 __global__ void __launch_bounds__(THREADS) read_stats_kernel(
@@ -591,55 +596,45 @@ __global__ void __launch_bounds__(THREADS) read_stats_kernel(
   for (int i = threadIdx.x; i < HIST_SMEM; i += THREADS) sHist[i] = 0;
   __syncthreads();
   const bool has_qual = qual != nullptr;
-  const unsigned lane = lane_id();
-  const uint64_t warp0 = ((uint64_t)blockIdx.x * THREADS + threadIdx.x) >> 5;
-  const uint64_t nwarps = ((uint64_t)gridDim.x * THREADS) >> 5;
-  unsigned long long bad_reads = 0, bases_read = 0, bases_loaded = 0, contigs = 0;
+  // A=0x41 C=0x43 G=0x47 T=0x54 after folding case: bits 1, 3, 7, 20 of the 0x40..0x5F block
+  constexpr uint32_t ACGT = (1u << 1) | (1u << 3) | (1u << 7) | (1u << 20);
+  unsigned long long bad_reads = 0, bases_read = 0, bases_loaded = 0, contigs = 0, reads = 0;
 
   auto end_run = [&](uint32_t run, bool &has) {
     if (run >= (uint32_t)k) {
       has = true;
       bases_loaded += run;
       contigs++;
-      if (lane == 0) {
-        const uint32_t b = run < hist_size - 1 ? run : hist_size - 1;
-        if (b < HIST_SMEM) atomicAdd(&sHist[b], 1u);
-        else atomicAdd(&hist[b], 1ull);
-      }
+      const uint32_t b = run < hist_size - 1 ? run : hist_size - 1;
+      if (b < HIST_SMEM) atomicAdd(&sHist[b], 1u);
+      else atomicAdd(&hist[b], 1ull);
     }
   };
 
-  for (uint64_t r = warp0; r < n_reads; r += nwarps) {
+  for (uint64_t r = (uint64_t)blockIdx.x * THREADS + threadIdx.x; r < n_reads; r += (uint64_t)gridDim.x * THREADS) {
     const uint64_t beg = offsets[r];
     const uint64_t len = offsets[r + 1] - beg - (uint64_t)sep;
+    reads++;
     bases_read += len;
     uint32_t run = 0;
     bool has = false;
-    for (uint64_t c0 = 0; c0 < len; c0 += 32) {
-      const uint64_t i = c0 + lane;
-      bool good = false;
-      if (i < len) {
-        const uint32_t u = (uint32_t)seq[beg + i] & 0xDFu;
-        good = (u == 0x41u) | (u == 0x43u) | (u == 0x47u) | (u == 0x54u);
-        if (has_qual) good &= ((int)(int8_t)qual[beg + i] > cutoff);
-      }
-      const uint32_t mask = __ballot_sync(FULL, good);
-      const int nbits = (len - c0) < 32 ? (int)(len - c0) : 32;
-      int pos = 0;  // every lane walks the same mask: uniform control flow
-      while (pos < nbits) {
-        const uint32_t rest = mask >> pos;
-        if (rest & 1u) {
-          int ones = __ffs(~rest) - 1;  // trailing ones (32 if rest is all ones)
-          if (ones < 0) ones = 32;
-          if (ones > nbits - pos) ones = nbits - pos;
-          run += ones;
-          pos += ones;
+    const uintptr_t s0 = reinterpret_cast<uintptr_t>(seq) + beg, s1 = s0 + len;
+    const uintptr_t q0 = reinterpret_cast<uintptr_t>(qual) + beg;
+    // seq and qual share their alignment modulo 16 (checked by the host), so one word walk serves both
+    for (uintptr_t wa = s0 & ~(uintptr_t)7; wa < s1; wa += 8) {
+      const uint64_t sw = __ldg(reinterpret_cast<const uint64_t *>(wa));
+      const uint64_t qw = has_qual ? __ldg(reinterpret_cast<const uint64_t *>(wa - s0 + q0)) : 0ull;
+      const int lo = wa < s0 ? (int)(s0 - wa) : 0;
+      const int hi = (s1 - wa) < 8 ? (int)(s1 - wa) : 8;
+      for (int i = lo; i < hi; i++) {
+        const uint32_t u = (uint32_t)(sw >> (8 * i)) & 0xDFu;
+        bool good = ((u & 0xE0u) == 0x40u) && ((ACGT >> (u & 31u)) & 1u);
+        if (has_qual) good = good && ((int)(int8_t)(qw >> (8 * i)) > cutoff);
+        if (good) {
+          run++;
         } else {
           end_run(run, has);
           run = 0;
-          int zeros = rest ? __ffs(rest) - 1 : 32;
-          if (zeros > nbits - pos) zeros = nbits - pos;
-          pos += zeros;
         }
       }
     }
@@ -651,9 +646,16 @@ __global__ void __launch_bounds__(THREADS) read_stats_kernel(
     const uint32_t v = sHist[i];
     if (v && (uint32_t)i < hist_size) atomicAdd(&hist[i], (unsigned long long)v);
   }
-  if (lane == 0) {  // every lane of a warp carries the same totals
-    const unsigned long long nr = (warp0 < n_reads) ? ((n_reads - 1 - warp0) / nwarps + 1) : 0;
-    if (nr) atomicAdd(&stats->n_reads, nr);
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+    reads += __shfl_xor_sync(FULL, reads, o);
+    bad_reads += __shfl_xor_sync(FULL, bad_reads, o);
+    bases_read += __shfl_xor_sync(FULL, bases_read, o);
+    bases_loaded += __shfl_xor_sync(FULL, bases_loaded, o);
+    contigs += __shfl_xor_sync(FULL, contigs, o);
+  }
+  if (lane_id() == 0) {
+    if (reads) atomicAdd(&stats->n_reads, reads);
     if (bad_reads) atomicAdd(&stats->bad_reads, bad_reads);
     if (bases_read) atomicAdd(&stats->bases_read, bases_read);
     if (bases_loaded) atomicAdd(&stats->bases_loaded, bases_loaded);
@@ -1032,7 +1034,7 @@ void launch_read_stats(const uint8_t *seq, const uint8_t *qual, const uint64_t *
                        unsigned long long *hist, uint32_t hist_size, cudaStream_t st) {
   if (!n_reads) return;
   uint64_t grid = (uint64_t)resident_grid(read_stats_kernel);
-  const uint64_t need = (n_reads + (THREADS / 32) - 1) / (THREADS / 32);
+  const uint64_t need = (n_reads + THREADS - 1) / THREADS;  // one lane per read
   if (grid > need) grid = need;
   read_stats_kernel<<<(unsigned)grid, THREADS, 0, st>>>(seq, qual, offsets, n_reads, sep, k, cutoff,
                                                        stats, hist, hist_size);

@@ -12,6 +12,10 @@ case $step in
   launches) timeout 900 ncu --metrics $MET --clock-control none --profile-from-start off --csv --log-file $out/launches.csv python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline > $out/ncu_launches.log 2>&1;;
   launches_direct) LASV_B200_INSERT=direct timeout 900 ncu --metrics $MET --clock-control none --profile-from-start off --csv --log-file $out/launches_direct.csv python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline > $out/ncu_launches_direct.log 2>&1;;
   full) timeout 900 ncu --set full --import-source on --clock-control none --profile-from-start off -k regex:"build_kernel|insert_" -c 2 -o $out/prof python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu-baseline > $out/ncu_full.log 2>&1;;
+  cfg1) timeout 600 python bench.py --workload cfg1 --steps 3 --warmup 3 --no-cpu-baseline > $out/bench_cfg1.log 2>&1;;
+  cfg2) timeout 600 python bench.py --workload cfg2 --steps 3 --warmup 3 --no-cpu-baseline > $out/bench_cfg2.log 2>&1;;
+  big2) timeout 600 python bench.py --steps 4 --warmup 3 --no-cpu-baseline --no-e2e --pairs-per-step 2097152 > $out/bench_big2.log 2>&1;;
+  big4) timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e --pairs-per-step 4194304 > $out/bench_big4.log 2>&1;;
   n2) timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 5 --warmup 3 --no-cpu-baseline > $out/bench_n2.log 2> $out/bench_n2.err;;
   n4) timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 4 --steps 5 --warmup 3 --no-cpu-baseline > $out/bench_n4.log 2> $out/bench_n4.err;;
   n8) timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus 8 --steps 5 --warmup 3 --no-cpu-baseline > $out/bench_n8.log 2> $out/bench_n8.err;;
