@@ -237,7 +237,8 @@ uint64_t stripe_capacity(const lasv_graph *g, uint64_t n_bytes, uint64_t n_reads
   if (n_reads && n_reads * (uint64_t)g->k < n_bytes) bound = n_bytes - n_reads * (uint64_t)g->k;
   else if (!n_reads) bound = (uint64_t)((double)n_bytes * 0.85);  // k >= ~21 on reads of <= ~150 bases
   const double mean = (double)bound / n_bins;
-  return (uint64_t)(mean * 1.01 + 8.0 * sqrt(mean) + 64.0);
+  const uint64_t cap = (uint64_t)(mean * 1.01 + 8.0 * sqrt(mean) + 64.0);
+  return (cap + STRIPE_RUN - 1) / STRIPE_RUN * STRIPE_RUN;  // whole runs (stripe_record_at)
 }
 
 int ensure_bins(lasv_graph *g, lasv_graph::BinLeg &l, uint64_t n_bytes, uint64_t n_reads, uint32_t n_bins) {
@@ -255,7 +256,8 @@ int ensure_bins(lasv_graph *g, lasv_graph::BinLeg &l, uint64_t n_bytes, uint64_t
     l.alloc_records = want;
     l.alloc_n = n_bins;
   }
-  l.v.cap = (uint32_t)(l.alloc_records / n_bins);
+  l.v.cap = (uint32_t)(l.alloc_records / n_bins / STRIPE_RUN * STRIPE_RUN);
+  l.v.block_shift = (uint32_t)log2_u32(n_bins);
   l.v.n_bins = n_bins;
   l.v.bin_mask = (uint32_t)(g->n_buckets - 1);
   l.v.bin_shift = (uint32_t)(g->L - log2_u32(n_bins));
@@ -735,6 +737,8 @@ int lasv_graph_bin_reads_device(lasv_graph *g, const uint8_t *d_seq, const uint8
     return fail(LASV_ERR_ARG, "bad bin geometry: %d owners x %u bins x %u records", n_owners, bins_per_owner,
                 stripe_capacity_records);
   if (!d_records || !d_counts) return fail(LASV_ERR_ARG, "NULL bin buffers");
+  if (stripe_capacity_records % STRIPE_RUN)
+    return fail(LASV_ERR_ARG, "stripe capacity must be a multiple of %u records", STRIPE_RUN);
   if (int e = check_streams(d_seq, d_qual)) return e;
   cudaStream_t st = stream_of(g, cuda_stream);
   const uint32_t n_bins = bins_per_owner * (uint32_t)n_owners;
@@ -752,6 +756,7 @@ int lasv_graph_bin_reads_device(lasv_graph *g, const uint8_t *d_seq, const uint8
   p.bins.spill_ok = n_owners == 1 ? 1u : 0u;
   p.bins.src_shift = 0;
   p.bins.bins_per_src = n_bins;
+  p.bins.block_shift = (uint32_t)log2_u32(bins_per_owner);
   p.ctas_per_sm = g->pipeline ? 2 : 0;
   launch_build(g->N, MODE_BIN, p, st);
   return check_launch();
@@ -765,6 +770,8 @@ int lasv_graph_insert_bins_device(lasv_graph *g, const void *d_records, const vo
   if (n_src < 1 || n_src > 16 || (n_src & (n_src - 1)) || !bins_per_src || (bins_per_src & (bins_per_src - 1)))
     return fail(LASV_ERR_ARG, "bad bin geometry: %d senders x %u bins", n_src, bins_per_src);
   if (!d_records || !d_counts) return fail(LASV_ERR_ARG, "NULL bin buffers");
+  if (stripe_capacity_records % STRIPE_RUN)
+    return fail(LASV_ERR_ARG, "stripe capacity must be a multiple of %u records", STRIPE_RUN);
   BinView b{};
   b.recs = (uint64_t *)d_records;
   b.count = (unsigned int *)d_counts;
@@ -772,6 +779,7 @@ int lasv_graph_insert_bins_device(lasv_graph *g, const void *d_records, const vo
   b.n_bins = bins_per_src * (uint32_t)n_src;
   b.src_shift = (uint32_t)log2_u32((uint32_t)n_src);
   b.bins_per_src = bins_per_src;
+  b.block_shift = (uint32_t)log2_u32(bins_per_src);
   launch_insert_bins(g->N, b, g->view(), g->d_ctr, g->pipeline ? 2 : 0, stream_of(g, cuda_stream));
   return check_launch();
 }

@@ -380,7 +380,7 @@ build_kernel(const BuildParams p, const uint64_t n_tiles) {
           if (!lead[u]) continue;
           const uint32_t bin = (hc[u] & p.bins.bin_mask) >> p.bins.bin_shift;
           if (idx[u] < p.bins.cap) {
-            store_bin_record<N>(p.bins.recs + ((uint64_t)bin * p.bins.cap + idx[u]) * bin_record_words(N), key[u],
+            store_bin_record<N>(p.bins.recs + stripe_record_at(p.bins, bin, idx[u]) * bin_record_words(N), key[u],
                                 bin_aux(hc[u], edge[u], count[u]));
           } else if (p.bins.spill_ok) {  // stripe full (skewed batch): straight into the table
             const int r = table_upsert_hashed<N, DeviceOps>(p.table, p.ctr, key[u], hc[u], edge[u], count[u]);
@@ -520,7 +520,7 @@ __global__ void __launch_bounds__(THREADS, 4) insert_bins_kernel(const BinView b
         for (int u = 0; u < U; u++) {
           if (u == n_have) {
             s0.live[u] = i < cnt;
-            s0.at[u] = (uint64_t)stripe_of(b0 + tb) * b.cap + i;
+            s0.at[u] = stripe_record_at(b, stripe_of(b0 + tb), i);
           }
         }
         if (++n_have == U) advance();

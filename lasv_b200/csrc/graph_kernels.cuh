@@ -25,7 +25,7 @@ enum BuildMode { MODE_FUSED = 0, MODE_RECORDS = 1, MODE_ROUTE = 2, MODE_BIN = 3 
 __host__ __device__ inline uint32_t bin_record_words(int N) { return N == 1 ? 2u : 4u; }
 constexpr uint32_t COUNT_STRIDE = 32;  // uint32 units = 128 bytes
 struct BinView {
-  uint64_t *recs;       // [n_bins*cap*bin_record_words(N)], stripe of bin i at i*cap
+  uint64_t *recs;       // [n_bins*cap*bin_record_words(N)], see stripe_record_at
   unsigned int *count;  // [n_bins*COUNT_STRIDE] records wanted per bin, ONE COUNTER PER 128-BYTE LINE: the L2
                         // atomic unit serialises per line, 8 counters in a line would share one queue
                         // (a count may exceed cap: see spill_ok)
@@ -43,7 +43,20 @@ struct BinView {
   // of a region before the next region (n_src = 1 << src_shift, n_bins = n_src*bins_per_src)
   uint32_t src_shift;
   uint32_t bins_per_src;
+  // Record placement, both sides.  The stripes of one owner (producer) / one sender (consumer) form a
+  // BLOCK of `1 << block_shift` stripes that is stored interleaved in runs of STRIPE_RUN records:
+  //   record idx of stripe (o, r)  ->  o*block*cap + ((idx / RUN)*block + r)*RUN + idx % RUN
+  // Bins fill at the same pace, so at any moment the write frontiers of ALL stripes of a block lie in
+  // the same few pages (block * RUN * 32 B = 1-8 MB) instead of one page per stripe: the scatter of the
+  // partition kernel stops missing the TLB on every store.  The consumer reads a stripe in 4 KB runs.
+  uint32_t block_shift;
 };
+constexpr uint32_t STRIPE_RUN = 128;  // records; cap is a multiple of it
+__host__ __device__ inline uint64_t stripe_record_at(const BinView &b, uint32_t stripe, uint32_t idx) {
+  const uint32_t o = stripe >> b.block_shift, r = stripe & ((1u << b.block_shift) - 1u);
+  return (((uint64_t)o * b.cap + (uint64_t)(idx / STRIPE_RUN) * STRIPE_RUN) << b.block_shift) +
+         (uint64_t)r * STRIPE_RUN + (idx % STRIPE_RUN);
+}
 __host__ __device__ inline uint64_t bin_aux(uint32_t c, uint32_t edge, uint32_t count) {
   return (uint64_t)c | ((uint64_t)(edge & 0xFFu) << 32) | ((uint64_t)count << 40);
 }

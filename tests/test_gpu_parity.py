@@ -275,13 +275,58 @@ def test_binned_exchange_overflow_is_reported(monkeypatch):
     with DBGraph(w.kmer_size, 9, w.bucket_size) as g:
         geo = g.bin_geometry(2, len(seq), len(offs) - 1)
         B, rw, cw = geo["bins_per_owner"], geo["record_bytes"] // 8, geo["count_stride_bytes"] // 4
-        cap = 100
+        cap = 128                                                # far too small (one run of records)
         send = torch.zeros((2, B, cap, rw), dtype=torch.int64, device="cuda")
         counts = torch.zeros((2, B, cw), dtype=torch.int32, device="cuda")
         g.bin_reads_device(d_seq, d_qual, len(seq), w.cutoff, 2, B, cap, send, counts, st_)
         torch.cuda.synchronize()
         with pytest.raises(_capi.LasvError):
             g.stats(stream=st_)
+
+
+def test_pipelined_inserts_and_async_statistics(monkeypatch):
+    """lasv_graph_set_pipeline: batch i is inserted on the library's own stream while
+    batch i+1 is partitioned on the caller's; the result, the asynchronous statistics
+    read-back and the per-kernel timing events must match the one-stream build."""
+    torch = torch_cuda()
+    monkeypatch.setenv("LASV_B200_BINS", "8")
+    monkeypatch.setenv("LASV_B200_INSERT", "binned")
+    L, W, n_reads = 13, 40, 24_000
+    w = synth.scaled(synth.CFG0, 80_000, L)
+    w.bucket_size = W
+    p, seq, qual, offs, og = _synth_oracle(w, n_reads, seed=5)
+    want = O.sort_records(og.records())
+    st_ = torch.cuda.current_stream().cuda_stream
+    d_seq = torch.from_numpy(np.concatenate([seq, np.full(16, 10, np.uint8)])).cuda()
+    d_qual = torch.from_numpy(np.concatenate([qual, np.full(16, 10, np.uint8)])).cuda()
+    d_offs = torch.from_numpy(offs.astype(np.int64)).cuda()
+    n_batches = 6
+    per_reads = n_reads // n_batches
+    per = per_reads * (w.read_len + 1)
+    with DBGraph(w.kmer_size, L, W) as g:
+        g.set_pipeline(True)
+        g.enable_kernel_timing(True)
+        rows = torch.zeros((n_batches, 9), dtype=torch.int64).pin_memory()
+        for b in range(n_batches):
+            lo = b * per
+            nr = per_reads if b < n_batches - 1 else n_reads - b * per_reads
+            nb = nr * (w.read_len + 1)
+            d_off_b = (d_offs[b * per_reads: b * per_reads + nr + 1] - lo).contiguous()
+            g.load_reads_device(d_seq[lo:], d_qual[lo:], nb, d_off_b, nr, w.cutoff, st_)
+            g.flush(st_)                                       # the statistics row of THIS batch
+            g.stats_async(rows[b], st_)
+        torch.cuda.synchronize()
+        kt = g.kernel_times()
+        assert kt["batches"] == n_batches and kt["partition_ms"] > 0 and kt["insert_ms"] > 0
+        names = DBGraph.STATS_ASYNC_FIELDS
+        last = dict(zip(names, rows[-1].tolist()))
+        assert last["kmers_inserted"] == og.stats.kmers_inserted and last["n_reads"] == n_reads
+        assert last["bad_reads"] == og.stats.bad_reads and last["table_full"] == 0
+        ins = rows[:, names.index("kmers_inserted")].tolist()
+        assert all(a < b for a, b in zip(ins, ins[1:]))        # every batch's row advanced
+        st = g.stats(stream=st_)
+        assert st["unique_kmers"] == len(want) == last["unique_kmers"]
+        assert np.array_equal(O.sort_records(g.records()), want)
 
 
 def test_hot_kmers_and_duplicate_reads_are_counted_exactly():
