@@ -1025,7 +1025,10 @@ void launch_insert_bins(int N, const BinView &b, const TableView &t, GraphCounte
     // few resident warps on purpose (see the kernel's comment); LASV_B200_INSERT_CTAS overrides
     int per_sm = ctas_per_sm > 0 ? ctas_per_sm : 3;
     if (const char *e = getenv("LASV_B200_INSERT_CTAS")) per_sm = atoi(e) > 0 ? atoi(e) : per_sm;
-    insert_bins_kernel<NN, 2><<<resident_grid(insert_bins_kernel<NN, 2>, per_sm), THREADS, 0, st>>>(b, t, ctr);
+    int u = 2;
+    if (const char *e = getenv("LASV_B200_INSERT_U")) u = atoi(e);
+    if (u == 1) insert_bins_kernel<NN, 1><<<resident_grid(insert_bins_kernel<NN, 1>, per_sm), THREADS, 0, st>>>(b, t, ctr);
+    else insert_bins_kernel<NN, 2><<<resident_grid(insert_bins_kernel<NN, 2>, per_sm), THREADS, 0, st>>>(b, t, ctr);
   });
 }
 

@@ -143,6 +143,9 @@ __device__ __forceinline__ uint64_t sweep_op(uint64_t *line) {
   if (PAT == 8) { uint64_t v = ld8(line); uint64_t *s = line + 4 + 4 * (v & 1); uint64_t x = ld32(s); if (x != 0x1234567ull) asm volatile("st.global.v4.u64 [%0], {%1,%2,%3,%4};" ::"l"(s), "l"(x), "l"(x + 1), "l"(x + 2), "l"(x + 3) : "memory"); return x; }
   if (PAT == 9) { uint64_t v = ld8(line); uint64_t *s = line + 2 + 2 * (v & 1); uint64_t x = ld16(s) + ld16(s + 2); if (x != 0x1234567ull) atomicAdd(reinterpret_cast<unsigned long long *>(s + 2), 1ull); return x; }
   if (PAT == 10) { uint64_t v = ld8(line); uint64_t *s = line + 2 + 2 * (v & 1); uint64_t x = ld16(s) + ld16(s + 2); if (x != 0x1234567ull) x += atomicAdd(reinterpret_cast<unsigned *>(s + 2), 1u); return x; }
+  if (PAT == 12) { uint64_t v = ld8(line); uint64_t *s = line + 2 + 2 * (v & 1); uint64_t x = ld16(s) + ld16(s + 2); if (x != 0x1234567ull) { atomicAdd(reinterpret_cast<unsigned *>(s + 2), 1u); atomicAdd(reinterpret_cast<unsigned *>(reinterpret_cast<uintptr_t>(s + 2) ^ 32), 0u); } return x; }
+  if (PAT == 13) { uint64_t v = ld8(line); uint64_t *s = line + 2 + 2 * (v & 1); uint64_t x = ld16(s) + ld16(s + 2); if (x != 0x1234567ull) { unsigned *q = reinterpret_cast<unsigned *>(reinterpret_cast<uintptr_t>(s + 2) & ~(uintptr_t)127); atomicAdd(q + 1, 1u); atomicAdd(q + 9, 0u); atomicAdd(q + 17, 0u); atomicAdd(q + 25, 0u); } return x; }
+  if (PAT == 14) { uint64_t v = ld8(line); uint64_t *s = line + 2 + 2 * (v & 1); uint64_t x = ld16(s) + ld16(s + 2); if (x != 0x1234567ull) asm volatile("red.global.add.L2::cache_hint.u32 [%0], %1, %2;" ::"l"(s + 2), "r"(1u), "l"(0x12F0000000000000ull) : "memory"); return x; }
   if (PAT == 11) { uint64_t v = ld8(line); uint64_t *s = line + 2 + 2 * (v & 1); uint64_t x = ld16(s) + ld16(s + 2); if (x != 0x1234567ull) asm volatile("st.global.u64 [%0], %1;" ::"l"(s + 2), "l"(x + 1) : "memory"); return x; }
   return 0;
 }
@@ -233,6 +236,8 @@ int main(int argc, char **argv) {
       for (int c : {2, 4, 8}) run("hdr+2v2+red_64B", sweep_kernel<2, true, 1>, c);
       for (int c : {2, 4}) run("hdr+2v2+red U2", sweep_kernel<2, false, 2>, c);
       for (int c : {1, 2}) run("hdr+2v2+red U4", sweep_kernel<2, false, 4>, c);
+      for (int c : {2, 4}) run("hdr+2v2+red+red0(other sector of atom)", sweep_kernel<12, false, 1>, c);
+      for (int c : {2, 4}) run("hdr+2v2+red all 4 sectors", sweep_kernel<13, false, 1>, c);
       for (int c : {4, 8}) run("hdr+2v2+st8 strong", sweep_kernel<7, false, 1>, c);
       for (int c : {4, 8}) run("hdr+2v2+st8 weak", sweep_kernel<11, false, 1>, c);
       for (int c : {4, 8}) run("hdr+v4+st32", sweep_kernel<8, false, 1>, c);
