@@ -453,6 +453,8 @@ def main():
     wall0 = time.monotonic()
     torch.cuda.profiler.start()        # `ncu --profile-from-start off` sees the timed steps only
     t_begin.record()
+    if os.environ.get("LASV_BENCH_TRACE") and world > 1 and graph.pipeline:
+        graph.trace = []
     for s in range(K):
         step(0 if cfg0 else Wm + s, s)
     graph.flush()                      # side-stream inserts of the last batches join the timed stream
@@ -590,6 +592,12 @@ def main():
         except Exception as ex:  # the baseline is reported, never required
             cpu = {"value": None, "unit": UNIT, "cores": 1, "kind": "unavailable", "sample": repr(ex)[:200]}
 
+    if getattr(graph, "trace", None):
+        tl = graph.timeline()
+        print(f"[rank {rank}] stage timeline (ms): partition, exchange, insert", file=sys.stderr)
+        for row in tl:
+            print(f"[rank {rank}]   " + "  ".join(f"{a:7.2f}-{b:7.2f}" for a, b in zip(row[0::2], row[1::2])), file=sys.stderr)
+        graph.trace = None
     summary = graph.summary()
     final = graph.stats()
     if rank == 0:

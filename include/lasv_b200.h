@@ -181,18 +181,27 @@ int lasv_graph_insert_records_device(lasv_graph *g, const uint32_t *d_records, u
  * insert_bins: the receive side: sweeps the stripes of all senders region by region
  * (stripe index = sender * bins_per_src + region) and find-or-inserts every record.
  * bin_geometry sizes the buffers for a batch (reads known: k-mers <= n_bytes -
- * n_reads*k).  An overfull stripe sets the overflow flag reported by lasv_graph_stats
- * (single owner: the excess goes straight into the table instead). */
+ * n_reads*k).  Buffer layout, per owner / sender, contiguous:
+ *   records: bins_per_owner * stripe_capacity records (the stripes, interleaved in
+ *            runs of 128 records) followed by spill_capacity records
+ *   counts : bins_per_owner + 1 counters, count_stride_bytes apart (the last one
+ *            counts the spill area)
+ * A record that finds its stripe full (a k-mer occurring very often in one batch)
+ * goes to its owner's spill area, which the owner inserts after its regions; only if
+ * that is full too is the overflow flag raised (reported by lasv_graph_stats).  With a
+ * single owner and spill_capacity 0 the excess goes straight into the table. */
 int lasv_graph_bin_geometry(lasv_graph *g, int n_owners, uint64_t n_bytes, uint64_t n_reads,
                             uint32_t *bins_per_owner, uint32_t *stripe_capacity_records,
-                            uint32_t *record_bytes, uint32_t *count_stride_bytes);
+                            uint32_t *spill_capacity_records, uint32_t *record_bytes,
+                            uint32_t *count_stride_bytes);
 int lasv_graph_bin_reads_device(lasv_graph *g, const uint8_t *d_seq, const uint8_t *d_qual,
                                 uint64_t n_bytes, int quality_cutoff, int n_owners,
                                 uint32_t bins_per_owner, uint32_t stripe_capacity_records,
-                                void *d_records, void *d_counts, void *cuda_stream);
+                                uint32_t spill_capacity_records, void *d_records, void *d_counts,
+                                void *cuda_stream);
 int lasv_graph_insert_bins_device(lasv_graph *g, const void *d_records, const void *d_counts, int n_src,
                                   uint32_t bins_per_src, uint32_t stripe_capacity_records,
-                                  void *cuda_stream);
+                                  uint32_t spill_capacity_records, void *cuda_stream);
 int lasv_graph_read_stats_device(lasv_graph *g, const uint8_t *d_seq, const uint8_t *d_qual,
                                  const uint64_t *d_offsets, uint64_t n_reads, int quality_cutoff,
                                  void *cuda_stream);

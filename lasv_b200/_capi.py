@@ -118,9 +118,9 @@ def lib() -> C.CDLL:
     L.lasv_graph_insert_records_device.argtypes = [vp, vp, u64, vp]
     L.lasv_graph_read_stats_device.argtypes = [vp, vp, vp, vp, u64, i32, vp]
     u32p = C.POINTER(C.c_uint32)
-    L.lasv_graph_bin_geometry.argtypes = [vp, i32, u64, u64, u32p, u32p, u32p, u32p]
-    L.lasv_graph_bin_reads_device.argtypes = [vp, vp, vp, u64, i32, i32, C.c_uint32, C.c_uint32, vp, vp, vp]
-    L.lasv_graph_insert_bins_device.argtypes = [vp, vp, vp, i32, C.c_uint32, C.c_uint32, vp]
+    L.lasv_graph_bin_geometry.argtypes = [vp, i32, u64, u64, u32p, u32p, u32p, u32p, u32p]
+    L.lasv_graph_bin_reads_device.argtypes = [vp, vp, vp, u64, i32, i32, C.c_uint32, C.c_uint32, C.c_uint32, vp, vp, vp]
+    L.lasv_graph_insert_bins_device.argtypes = [vp, vp, vp, i32, C.c_uint32, C.c_uint32, C.c_uint32, vp]
     L.lasv_graph_find.argtypes = [vp, vp, u64, vp, vp, vp]
     L.lasv_graph_summary.argtypes = [vp, C.POINTER(TableSummary)]
     L.lasv_graph_finalize.argtypes = [vp]

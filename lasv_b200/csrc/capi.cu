@@ -252,12 +252,13 @@ int ensure_bins(lasv_graph *g, lasv_graph::BinLeg &l, uint64_t n_bytes, uint64_t
     cudaFree(l.v.count);
     l.v = BinView{};
     CUDA_TRY(cudaMalloc(&l.v.recs, want * (size_t)bin_record_words(g->N) * sizeof(uint64_t)));
-    CUDA_TRY(cudaMalloc(&l.v.count, (size_t)n_bins * COUNT_STRIDE * sizeof(unsigned int)));
+    CUDA_TRY(cudaMalloc(&l.v.count, (size_t)(n_bins + 1) * COUNT_STRIDE * sizeof(unsigned int)));
     l.alloc_records = want;
     l.alloc_n = n_bins;
   }
   l.v.cap = (uint32_t)(l.alloc_records / n_bins / STRIPE_RUN * STRIPE_RUN);
   l.v.block_shift = (uint32_t)log2_u32(n_bins);
+  l.v.spill_cap = 0;  // one owner: an overfull stripe spills straight into the table
   l.v.n_bins = n_bins;
   l.v.bin_mask = (uint32_t)(g->n_buckets - 1);
   l.v.bin_shift = (uint32_t)(g->L - log2_u32(n_bins));
@@ -476,7 +477,7 @@ int lasv_graph_load_reads_device(lasv_graph *g, const uint8_t *d_seq, const uint
       if (int e = ensure_bins(g, l, n_bytes, d_offsets ? n_reads : 0, n_bins)) return e;
       p.bins = l.v;
       p.ctas_per_sm = g->pipeline ? 2 : 0;  // pipelined: this kernel shares the SMs with the previous batch's insert
-      CUDA_TRY(cudaMemsetAsync(l.v.count, 0, (size_t)n_bins * COUNT_STRIDE * sizeof(unsigned int), st));
+      CUDA_TRY(cudaMemsetAsync(l.v.count, 0, (size_t)(n_bins + 1) * COUNT_STRIDE * sizeof(unsigned int), st));
       cudaEvent_t tb0 = timing_event(g), tb1 = timing_event(g), ti0 = timing_event(g), ti1 = timing_event(g);
       mark(tb0, st);
       launch_build(g->N, MODE_BIN, p, st);
@@ -708,7 +709,8 @@ int lasv_graph_insert_records_device(lasv_graph *g, const uint32_t *d_records, u
 
 int lasv_graph_bin_geometry(lasv_graph *g, int n_owners, uint64_t n_bytes, uint64_t n_reads,
                             uint32_t *bins_per_owner, uint32_t *stripe_capacity_out,
-                            uint32_t *record_bytes, uint32_t *count_stride_bytes) {
+                            uint32_t *spill_capacity_out, uint32_t *record_bytes,
+                            uint32_t *count_stride_bytes) {
   if (!g) return fail(LASV_ERR_ARG, "NULL graph");
   if (n_owners < 1 || n_owners > 16 || (n_owners & (n_owners - 1)))
     return fail(LASV_ERR_ARG, "n_owners must be a power of two <= 16, got %d", n_owners);
@@ -722,6 +724,11 @@ int lasv_graph_bin_geometry(lasv_graph *g, int n_owners, uint64_t n_bytes, uint6
   if (cap > 0xFFFFFFF0ull) return fail(LASV_ERR_ARG, "batch too large for the bin stripes");
   if (bins_per_owner) *bins_per_owner = per;
   if (stripe_capacity_out) *stripe_capacity_out = (uint32_t)cap;
+  // spill area per owner: 1/16 of its stripes (a single k-mer may be that share of a batch), >= 4096 records
+  if (spill_capacity_out) {
+    const uint64_t sp = std::max<uint64_t>(4096, cap * per / 16);
+    *spill_capacity_out = n_owners == 1 ? 0u : (uint32_t)std::min<uint64_t>(0xFFFFFF80ull, (sp + STRIPE_RUN - 1) / STRIPE_RUN * STRIPE_RUN);
+  }
   if (record_bytes) *record_bytes = 8u * bin_record_words(g->N);
   if (count_stride_bytes) *count_stride_bytes = COUNT_STRIDE * (uint32_t)sizeof(unsigned int);
   return LASV_OK;
@@ -730,19 +737,20 @@ int lasv_graph_bin_geometry(lasv_graph *g, int n_owners, uint64_t n_bytes, uint6
 int lasv_graph_bin_reads_device(lasv_graph *g, const uint8_t *d_seq, const uint8_t *d_qual,
                                 uint64_t n_bytes, int quality_cutoff, int n_owners,
                                 uint32_t bins_per_owner, uint32_t stripe_capacity_records,
-                                void *d_records, void *d_counts, void *cuda_stream) {
+                                uint32_t spill_capacity_records, void *d_records, void *d_counts,
+                                void *cuda_stream) {
   if (int e = use(g)) return e;
   if (n_owners < 1 || n_owners > 16 || (n_owners & (n_owners - 1)) || !bins_per_owner ||
       (bins_per_owner & (bins_per_owner - 1)) || bins_per_owner > g->n_buckets || !stripe_capacity_records)
     return fail(LASV_ERR_ARG, "bad bin geometry: %d owners x %u bins x %u records", n_owners, bins_per_owner,
                 stripe_capacity_records);
   if (!d_records || !d_counts) return fail(LASV_ERR_ARG, "NULL bin buffers");
-  if (stripe_capacity_records % STRIPE_RUN)
-    return fail(LASV_ERR_ARG, "stripe capacity must be a multiple of %u records", STRIPE_RUN);
+  if (stripe_capacity_records % STRIPE_RUN || spill_capacity_records % STRIPE_RUN)
+    return fail(LASV_ERR_ARG, "stripe and spill capacities must be multiples of %u records", STRIPE_RUN);
   if (int e = check_streams(d_seq, d_qual)) return e;
   cudaStream_t st = stream_of(g, cuda_stream);
   const uint32_t n_bins = bins_per_owner * (uint32_t)n_owners;
-  CUDA_TRY(cudaMemsetAsync(d_counts, 0, (size_t)n_bins * COUNT_STRIDE * sizeof(unsigned int), st));
+  CUDA_TRY(cudaMemsetAsync(d_counts, 0, (size_t)(n_bins + n_owners) * COUNT_STRIDE * sizeof(unsigned int), st));
   if (!n_bytes) return LASV_OK;
   BuildParams p = build_params(g, d_seq, d_qual, n_bytes, quality_cutoff);
   p.bins.recs = (uint64_t *)d_records;
@@ -753,7 +761,8 @@ int lasv_graph_bin_reads_device(lasv_graph *g, const uint8_t *d_seq, const uint8
   const int Lg = g->L + log2_u32((uint32_t)n_owners);
   p.bins.bin_mask = Lg >= 32 ? 0xFFFFFFFFu : ((1u << Lg) - 1u);
   p.bins.bin_shift = (uint32_t)(Lg - log2_u32(n_bins));
-  p.bins.spill_ok = n_owners == 1 ? 1u : 0u;
+  p.bins.spill_ok = (n_owners == 1 && !spill_capacity_records) ? 1u : 0u;
+  p.bins.spill_cap = spill_capacity_records;
   p.bins.src_shift = 0;
   p.bins.bins_per_src = n_bins;
   p.bins.block_shift = (uint32_t)log2_u32(bins_per_owner);
@@ -764,15 +773,16 @@ int lasv_graph_bin_reads_device(lasv_graph *g, const uint8_t *d_seq, const uint8
 
 int lasv_graph_insert_bins_device(lasv_graph *g, const void *d_records, const void *d_counts, int n_src,
                                   uint32_t bins_per_src, uint32_t stripe_capacity_records,
-                                  void *cuda_stream) {
+                                  uint32_t spill_capacity_records, void *cuda_stream) {
   if (int e = use(g)) return e;
   if (g->finalized) return fail(LASV_ERR_STATE, "graph is finalised; no further inserts");
   if (n_src < 1 || n_src > 16 || (n_src & (n_src - 1)) || !bins_per_src || (bins_per_src & (bins_per_src - 1)))
     return fail(LASV_ERR_ARG, "bad bin geometry: %d senders x %u bins", n_src, bins_per_src);
   if (!d_records || !d_counts) return fail(LASV_ERR_ARG, "NULL bin buffers");
-  if (stripe_capacity_records % STRIPE_RUN)
-    return fail(LASV_ERR_ARG, "stripe capacity must be a multiple of %u records", STRIPE_RUN);
+  if (stripe_capacity_records % STRIPE_RUN || spill_capacity_records % STRIPE_RUN)
+    return fail(LASV_ERR_ARG, "stripe and spill capacities must be multiples of %u records", STRIPE_RUN);
   BinView b{};
+  b.spill_cap = spill_capacity_records;
   b.recs = (uint64_t *)d_records;
   b.count = (unsigned int *)d_counts;
   b.cap = stripe_capacity_records;

@@ -373,7 +373,8 @@ build_kernel(const BuildParams p, const uint64_t n_tiles) {
 #pragma unroll
         for (int u = 0; u < U; u++) {
           const uint32_t bin = (hc[u] & p.bins.bin_mask) >> p.bins.bin_shift;
-          idx[u] = lead[u] ? atomicAdd(&p.bins.count[bin * COUNT_STRIDE], 1u) : 0u;
+          const uint32_t ci = stripe_counter_at(p.bins, bin >> p.bins.block_shift, bin & ((1u << p.bins.block_shift) - 1u));
+          idx[u] = lead[u] ? atomicAdd(&p.bins.count[ci], 1u) : 0u;
         }
 #pragma unroll
         for (int u = 0; u < U; u++) {
@@ -385,8 +386,14 @@ build_kernel(const BuildParams p, const uint64_t n_tiles) {
           } else if (p.bins.spill_ok) {  // stripe full (skewed batch): straight into the table
             const int r = table_upsert_hashed<N, DeviceOps>(p.table, p.ctr, key[u], hc[u], edge[u], count[u]);
             my_new += (r == 1);
-          } else {
-            atomicExch(p.rec_overflow, 1ull);
+          } else {  // the owner's spill area
+            const uint32_t owner = bin >> p.bins.block_shift;
+            const uint32_t si = atomicAdd(&p.bins.count[stripe_counter_at(p.bins, owner, 1u << p.bins.block_shift)], 1u);
+            if (si < p.bins.spill_cap)
+              store_bin_record<N>(p.bins.recs + spill_record_at(p.bins, owner, si) * bin_record_words(N), key[u],
+                                  bin_aux(hc[u], edge[u], count[u]));
+            else
+              atomicExch(p.rec_overflow, 1ull);
           }
         }
         __syncwarp();
@@ -498,18 +505,26 @@ __global__ void __launch_bounds__(THREADS, 4) insert_bins_kernel(const BinView b
     n_have = 0;
   };
 
-  // sweep position g = region * n_src + sender  ->  stripe index sender * bins_per_src + region
+  // sweep position g < n_bins: region g / n_src of sender g % n_src; then one spill stripe per sender
   const uint32_t src_mask = (1u << b.src_shift) - 1u;
-  auto stripe_of = [&](uint32_t g) { return (g & src_mask) * b.bins_per_src + (g >> b.src_shift); };
-  uint32_t first = 0;  // (chunks of all earlier stripes) mod n_warps, warp-uniform
-  for (uint32_t b0 = 0; b0 < b.n_bins; b0 += 32) {
-    __syncwarp();
-    uint32_t cnt_l = 0;
-    if (b0 + lane < b.n_bins) {
-      cnt_l = __ldg(&b.count[stripe_of(b0 + lane) * COUNT_STRIDE]);
-      if (cnt_l > b.cap) cnt_l = b.cap;
+  const uint32_t n_sweep = b.n_bins + (b.spill_cap ? (1u << b.src_shift) : 0u);
+  auto count_of = [&](uint32_t g) -> uint32_t {
+    if (g < b.n_bins) {
+      const uint32_t c = __ldg(&b.count[stripe_counter_at(b, g & src_mask, g >> b.src_shift)]);
+      return c > b.cap ? b.cap : c;
     }
-    const uint32_t n_here = min(32u, b.n_bins - b0);
+    const uint32_t c = __ldg(&b.count[stripe_counter_at(b, g - b.n_bins, b.bins_per_src)]);
+    return c > b.spill_cap ? b.spill_cap : c;
+  };
+  auto record_of = [&](uint32_t g, uint32_t i) -> uint64_t {
+    if (g < b.n_bins) return stripe_record_at(b, (g & src_mask) * b.bins_per_src + (g >> b.src_shift), i);
+    return spill_record_at(b, g - b.n_bins, i);
+  };
+  uint32_t first = 0;  // (chunks of all earlier stripes) mod n_warps, warp-uniform
+  for (uint32_t b0 = 0; b0 < n_sweep; b0 += 32) {
+    __syncwarp();
+    const uint32_t cnt_l = b0 + lane < n_sweep ? count_of(b0 + lane) : 0u;
+    const uint32_t n_here = min(32u, n_sweep - b0);
     for (uint32_t tb = 0; tb < n_here; tb++) {
       const uint32_t cnt = __shfl_sync(FULL, cnt_l, (int)tb);
       const uint32_t n_chunks = (cnt + 31u) >> 5;
@@ -520,7 +535,7 @@ __global__ void __launch_bounds__(THREADS, 4) insert_bins_kernel(const BinView b
         for (int u = 0; u < U; u++) {
           if (u == n_have) {
             s0.live[u] = i < cnt;
-            s0.at[u] = stripe_record_at(b, stripe_of(b0 + tb), i);
+            s0.at[u] = record_of(b0 + tb, i);
           }
         }
         if (++n_have == U) advance();

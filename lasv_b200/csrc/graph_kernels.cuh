@@ -26,7 +26,7 @@ __host__ __device__ inline uint32_t bin_record_words(int N) { return N == 1 ? 2u
 constexpr uint32_t COUNT_STRIDE = 32;  // uint32 units = 128 bytes
 struct BinView {
   uint64_t *recs;       // [n_bins*cap*bin_record_words(N)], see stripe_record_at
-  unsigned int *count;  // [n_bins*COUNT_STRIDE] records wanted per bin, ONE COUNTER PER 128-BYTE LINE: the L2
+  unsigned int *count;  // [(block+1)*n_owners*COUNT_STRIDE] records wanted per stripe (stripe_counter_at), ONE COUNTER PER 128-BYTE LINE: the L2
                         // atomic unit serialises per line, 8 counters in a line would share one queue
                         // (a count may exceed cap: see spill_ok)
   uint32_t cap;
@@ -37,7 +37,7 @@ struct BinView {
   uint32_t bin_mask;
   uint32_t bin_shift;
   uint32_t spill_ok;    // 1: a record that finds its stripe full goes straight into the (local) table;
-                        // 0: it raises the overflow flag (its owner may be another GPU)
+                        // 0: it goes to its owner's spill area (overflow flag if that is full too)
   // consumer side (insert_bins_kernel): the stripes are swept region by region; with n_src senders the
   // stripe of (sender s, local region r) is at index s*bins_per_src + r and the sweep takes all senders
   // of a region before the next region (n_src = 1 << src_shift, n_bins = n_src*bins_per_src)
@@ -45,18 +45,33 @@ struct BinView {
   uint32_t bins_per_src;
   // Record placement, both sides.  The stripes of one owner (producer) / one sender (consumer) form a
   // BLOCK of `1 << block_shift` stripes that is stored interleaved in runs of STRIPE_RUN records:
-  //   record idx of stripe (o, r)  ->  o*block*cap + ((idx / RUN)*block + r)*RUN + idx % RUN
+  //   record idx of stripe (o, r)  ->  o*owner_stride + ((idx / RUN)*block + r)*RUN + idx % RUN
   // Bins fill at the same pace, so at any moment the write frontiers of ALL stripes of a block lie in
   // the same few pages (block * RUN * 32 B = 1-8 MB) instead of one page per stripe: the scatter of the
   // partition kernel stops missing the TLB on every store.  The consumer reads a stripe in 4 KB runs.
+  // Behind the block of every owner sit `spill_cap` records for whatever found its stripe full (a k-mer
+  // that occurs a million times in one batch lands in ONE stripe): the owner inserts them after its
+  // regions.  owner_stride = (cap << block_shift) + spill_cap records; every owner has block+1 counters.
   uint32_t block_shift;
+  uint32_t spill_cap;
 };
-constexpr uint32_t STRIPE_RUN = 128;  // records; cap is a multiple of it
+constexpr uint32_t STRIPE_RUN = 128;  // records; cap and spill_cap are multiples of it
+__host__ __device__ inline uint64_t owner_stride_records(const BinView &b) {
+  return ((uint64_t)b.cap << b.block_shift) + b.spill_cap;
+}
 __host__ __device__ inline uint64_t stripe_record_at(const BinView &b, uint32_t stripe, uint32_t idx) {
   const uint32_t o = stripe >> b.block_shift, r = stripe & ((1u << b.block_shift) - 1u);
-  return (((uint64_t)o * b.cap + (uint64_t)(idx / STRIPE_RUN) * STRIPE_RUN) << b.block_shift) +
+  return (uint64_t)o * owner_stride_records(b) + (((uint64_t)(idx / STRIPE_RUN) * STRIPE_RUN) << b.block_shift) +
          (uint64_t)r * STRIPE_RUN + (idx % STRIPE_RUN);
 }
+__host__ __device__ inline uint64_t spill_record_at(const BinView &b, uint32_t owner, uint32_t idx) {
+  return (uint64_t)owner * owner_stride_records(b) + ((uint64_t)b.cap << b.block_shift) + idx;
+}
+// counter of stripe (o, r), r == block: the owner's spill area
+__host__ __device__ inline uint32_t stripe_counter_at(const BinView &b, uint32_t owner, uint32_t r) {
+  return (owner * ((1u << b.block_shift) + 1u) + r) * COUNT_STRIDE;
+}
+
 __host__ __device__ inline uint64_t bin_aux(uint32_t c, uint32_t edge, uint32_t count) {
   return (uint64_t)c | ((uint64_t)(edge & 0xFFu) << 32) | ((uint64_t)count << 40);
 }

@@ -160,22 +160,26 @@ class DBGraph:
         check(self._lib.lasv_graph_insert_records_device(self._h, _ptr(d_records), n_records, stream))
 
     def bin_geometry(self, n_owners: int, n_bytes: int, n_reads: int = 0) -> dict:
-        """Buffer sizes of the region-binned exchange for one batch."""
-        a, b, c, d = (C.c_uint32(0) for _ in range(4))
+        """Buffer sizes of the region-binned exchange for one batch (include/lasv_b200.h)."""
+        a, b, sp, c, d = (C.c_uint32(0) for _ in range(5))
         check(self._lib.lasv_graph_bin_geometry(self._h, n_owners, n_bytes, n_reads, C.byref(a), C.byref(b),
-                                                C.byref(c), C.byref(d)))
-        return {"bins_per_owner": int(a.value), "stripe_capacity": int(b.value), "record_bytes": int(c.value),
-                "count_stride_bytes": int(d.value)}
+                                                C.byref(sp), C.byref(c), C.byref(d)))
+        geo = {"bins_per_owner": int(a.value), "stripe_capacity": int(b.value), "spill_capacity": int(sp.value),
+               "record_bytes": int(c.value), "count_stride_bytes": int(d.value)}
+        geo["records_per_owner"] = geo["bins_per_owner"] * geo["stripe_capacity"] + geo["spill_capacity"]
+        geo["counters_per_owner"] = geo["bins_per_owner"] + 1
+        return geo
 
     def bin_reads_device(self, d_seq, d_qual, n_bytes, quality_cutoff, n_owners, bins_per_owner,
-                         stripe_capacity, d_records, d_counts, stream=None):
+                         stripe_capacity, spill_capacity, d_records, d_counts, stream=None):
         check(self._lib.lasv_graph_bin_reads_device(self._h, _ptr(d_seq), _ptr(d_qual), n_bytes, quality_cutoff,
-                                                    n_owners, bins_per_owner, stripe_capacity, _ptr(d_records),
-                                                    _ptr(d_counts), stream))
+                                                    n_owners, bins_per_owner, stripe_capacity, spill_capacity,
+                                                    _ptr(d_records), _ptr(d_counts), stream))
 
-    def insert_bins_device(self, d_records, d_counts, n_src, bins_per_src, stripe_capacity, stream=None):
+    def insert_bins_device(self, d_records, d_counts, n_src, bins_per_src, stripe_capacity, spill_capacity,
+                           stream=None):
         check(self._lib.lasv_graph_insert_bins_device(self._h, _ptr(d_records), _ptr(d_counts), n_src,
-                                                      bins_per_src, stripe_capacity, stream))
+                                                      bins_per_src, stripe_capacity, spill_capacity, stream))
 
     def read_stats_device(self, d_seq, d_qual, d_offsets, n_reads, quality_cutoff, stream=None):
         check(self._lib.lasv_graph_read_stats_device(self._h, _ptr(d_seq), _ptr(d_qual), _ptr(d_offsets),

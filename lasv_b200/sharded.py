@@ -15,7 +15,13 @@ The bin kernel writes every k-mer occurrence into the stripe of the 64 MB table
 region it will touch ON ITS OWNER; the stripes of one owner are one contiguous,
 fixed-size block, so the exchange is a plain `all_to_all_single` with equal
 splits (NCCL over NVLink) -- no packing copy and no host round trip for sizes;
-the per-stripe counters travel the same way.  The insert kernel then sweeps the
+the per-stripe counters travel the same way.  By default the blocks do not even go
+through NCCL: the receive buffers live in symmetric memory (every rank maps every
+rank's allocation, torch.distributed._symmetric_memory) and each rank PUSHES its
+blocks into its peers' buffers with peer-to-peer DMA copies -- copy engines over
+NVLink, no SM of either side involved -- bracketed by two stream-ordered barriers
+(`LASV_B200_EXCHANGE=nccl` selects the all_to_all_single path; it is also the
+fallback when peer access is unavailable).  The insert kernel then sweeps the
 received stripes region by region, all senders of a region together.  With
 `pipeline=True` batch i+1 is binned and exchanged while batch i is inserted
 (two sets of buffers, side streams).
@@ -26,6 +32,8 @@ received stripes region by region, all senders of a region together.  With
 from __future__ import annotations
 
 import math
+import os
+import sys
 
 import torch
 import torch.distributed as dist
@@ -102,11 +110,12 @@ def exchange_stripes(send: torch.Tensor, recv: torch.Tensor, group=None):
 
 
 class _StripeBuffers:
-    def __init__(self, world, bins_per_owner, cap, rec_bytes, count_stride_bytes, device):
-        self.send = torch.empty((world, bins_per_owner, cap, rec_bytes // 8), dtype=torch.int64, device=device)
+    def __init__(self, world, geo, device):
+        self.send = torch.empty((world, geo["records_per_owner"], geo["record_bytes"] // 8), dtype=torch.int64,
+                                device=device)
         self.recv = torch.empty_like(self.send)
-        self.send_counts = torch.zeros((world, bins_per_owner, count_stride_bytes // 4), dtype=torch.int32,
-                                       device=device)
+        self.send_counts = torch.zeros((world, geo["counters_per_owner"], geo["count_stride_bytes"] // 4),
+                                       dtype=torch.int32, device=device)
         self.recv_counts = torch.zeros_like(self.send_counts)
         self.inserted = None     # event: the insert kernel that read `recv` is done
         self.exchanged = None    # event: `send` may be overwritten, `recv` is complete
@@ -133,17 +142,66 @@ class ShardedDBGraph:
             self.graph.set_pipeline(True)     # kernels sized to share the SMs with the neighbouring stage
         self.buffers = []
         self.turn = 0
+        self.trace = None                     # set to [] to collect per-stage CUDA events (timeline())
         if world > 1:
             if not max_bytes_per_batch:       # k-mers <= bytes: a safe stand-in for callers that only know k-mers
                 max_bytes_per_batch = int(max_kmers_per_batch * 1.7)
             geo = self.graph.bin_geometry(world, max_bytes_per_batch, max_reads_per_batch)
-            self.bins_per_owner, self.cap = geo["bins_per_owner"], geo["stripe_capacity"]
+            self.bins_per_owner, self.cap, self.spill = geo["bins_per_owner"], geo["stripe_capacity"], geo["spill_capacity"]
             self.rec_bytes = geo["record_bytes"]
             for _ in range(2 if self.pipeline else 1):
-                self.buffers.append(_StripeBuffers(world, self.bins_per_owner, self.cap, self.rec_bytes,
-                                                   geo["count_stride_bytes"], self.device))
+                self.buffers.append(_StripeBuffers(world, geo, self.device))
             self.comm_stream = torch.cuda.Stream(device=self.device)
             self.insert_stream = torch.cuda.Stream(device=self.device)
+            self.exchange = "nccl"
+            want = os.environ.get("LASV_B200_EXCHANGE", "p2p")
+            if want == "p2p":
+                try:
+                    self._setup_p2p(geo)
+                    self.exchange = "p2p"
+                except Exception as ex:           # no peer access / no symmetric memory: NCCL does the job
+                    print(f"[lasv_b200] peer-memory exchange unavailable ({type(ex).__name__}: {ex}); using NCCL",
+                          file=sys.stderr)
+
+    def _setup_p2p(self, geo):
+        """Receive buffers in symmetric memory (every rank maps every rank's allocation): the exchange
+        becomes `world` peer-to-peer DMA copies per batch -- copy engines over NVLink, no SM of the
+        sender or the receiver involved -- bracketed by two stream-ordered barriers."""
+        import torch.distributed._symmetric_memory as symm_mem
+        group = self.group if self.group is not None else dist.group.WORLD
+        world, rw, cw = self.world, geo["record_bytes"] // 8, geo["count_stride_bytes"] // 4
+        rec_words = geo["records_per_owner"] * rw                       # int64 words per owner block
+        cnt_words = geo["counters_per_owner"] * cw // 2                 # int32 counters viewed as int64 words
+        set_words = world * (rec_words + cnt_words)
+        self.symm = symm_mem.empty(len(self.buffers) * set_words, dtype=torch.int64, device=self.device)
+        self.symm_hdl = symm_mem.rendezvous(self.symm, group)
+        for k, buf in enumerate(self.buffers):
+            base = k * set_words
+            buf.recv = self.symm[base: base + world * rec_words].view(world, geo["records_per_owner"], rw)
+            cbase = base + world * rec_words
+            buf.recv_counts = self.symm[cbase: cbase + world * cnt_words].view(torch.int32).view(
+                world, geo["counters_per_owner"], cw)
+            # where MY block lands on every peer: slot `rank` of the peer's receive buffer
+            buf.peer_recv = [self.symm_hdl.get_buffer(d, (geo["records_per_owner"], rw), torch.int64,
+                                                      base + self.rank * rec_words) for d in range(world)]
+            buf.peer_counts = [self.symm_hdl.get_buffer(d, (cnt_words,), torch.int64,
+                                                        cbase + self.rank * cnt_words) for d in range(world)]
+            buf.send_counts64 = buf.send_counts.view(torch.int64).view(world, cnt_words)
+        self.symm_hdl.barrier(0)
+        torch.cuda.synchronize()
+
+    def _exchange(self, buf, k):
+        """On the current (communication) stream: blocks and counters of `buf.send*` to their owners."""
+        if self.exchange == "p2p":
+            self.symm_hdl.barrier(k)                 # every rank's receive buffer of this set is free
+            for i in range(self.world):
+                d = (self.rank + i) % self.world     # start with the local block, spread the peers
+                buf.peer_recv[d].copy_(buf.send[d], non_blocking=True)
+                buf.peer_counts[d].copy_(buf.send_counts64[d], non_blocking=True)
+            self.symm_hdl.barrier(k)                 # every block addressed to this rank has landed
+        else:
+            exchange_stripes(buf.send, buf.recv, self.group)
+            exchange_stripes(buf.send_counts, buf.recv_counts, self.group)
 
     def free(self):
         self.graph.free()
@@ -165,14 +223,21 @@ class ShardedDBGraph:
         # the previous user of this buffer set must be done with it
         if buf.exchanged is not None:
             cur.wait_event(buf.exchanged)       # its send block is free again
+        ev = None
+        if self.trace is not None:
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
+            self.trace.append(ev)
+            ev[0].record(cur)
         g.bin_reads_device(d_seq, d_qual, n_bytes, quality_cutoff, self.world, self.bins_per_owner, self.cap,
-                           buf.send, buf.send_counts, stream)
+                           self.spill, buf.send, buf.send_counts, stream)
+        if ev:
+            ev[1].record(cur)
         if d_offsets is not None and n_reads:
             g.read_stats_device(d_seq, d_qual, d_offsets, n_reads, quality_cutoff, stream)
         if not self.pipeline:
-            exchange_stripes(buf.send, buf.recv, self.group)
-            exchange_stripes(buf.send_counts, buf.recv_counts, self.group)
-            g.insert_bins_device(buf.recv, buf.recv_counts, self.world, self.bins_per_owner, self.cap, stream)
+            self._exchange(buf, 0)
+            g.insert_bins_device(buf.recv, buf.recv_counts, self.world, self.bins_per_owner, self.cap, self.spill,
+                                 stream)
             return
         binned = torch.cuda.Event()
         binned.record(cur)
@@ -180,14 +245,21 @@ class ShardedDBGraph:
             self.comm_stream.wait_event(binned)
             if buf.inserted is not None:
                 self.comm_stream.wait_event(buf.inserted)   # recv block free again
-            exchange_stripes(buf.send, buf.recv, self.group)
-            exchange_stripes(buf.send_counts, buf.recv_counts, self.group)
+            if ev:
+                ev[2].record(self.comm_stream)
+            self._exchange(buf, (self.turn - 1) % len(self.buffers))
+            if ev:
+                ev[3].record(self.comm_stream)
             buf.exchanged = torch.cuda.Event()
             buf.exchanged.record(self.comm_stream)
         with torch.cuda.stream(self.insert_stream):
             self.insert_stream.wait_event(buf.exchanged)
-            g.insert_bins_device(buf.recv, buf.recv_counts, self.world, self.bins_per_owner, self.cap,
+            if ev:
+                ev[4].record(self.insert_stream)
+            g.insert_bins_device(buf.recv, buf.recv_counts, self.world, self.bins_per_owner, self.cap, self.spill,
                                  self.insert_stream.cuda_stream)
+            if ev:
+                ev[5].record(self.insert_stream)
             buf.inserted = torch.cuda.Event()
             buf.inserted.record(self.insert_stream)
 
@@ -199,6 +271,15 @@ class ShardedDBGraph:
                 self.graph.stats_async(pinned_out, self.insert_stream.cuda_stream)
         else:
             self.graph.stats_async(pinned_out, torch.cuda.current_stream().cuda_stream)
+
+    def timeline(self):
+        """[(partition start, end, exchange start, end, insert start, end)] in ms relative to the first
+        traced batch (after a device synchronisation)."""
+        torch.cuda.synchronize()
+        if not self.trace:
+            return []
+        t0 = self.trace[0][0]
+        return [[t0.elapsed_time(e) for e in ev] for ev in self.trace]
 
     def flush(self):
         """Make the caller's current stream wait for everything queued on the side streams."""

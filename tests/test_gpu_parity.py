@@ -210,9 +210,10 @@ def test_route_and_insert_records_match_oracle(base, world):
             g.free()
 
 
-@pytest.mark.parametrize("base,world,bins", [(synth.CFG0, 2, 4), (synth.CFG1, 4, 1), (synth.CFG2, 8, 8),
-                                              (synth.CFG0, 1, 16)])
-def test_binned_exchange_matches_oracle(base, world, bins, monkeypatch):
+@pytest.mark.parametrize("base,world,bins,tiny_stripes", [(synth.CFG0, 2, 4, False), (synth.CFG1, 4, 1, False),
+                                                           (synth.CFG2, 8, 8, False), (synth.CFG0, 1, 16, False),
+                                                           (synth.CFG0, 2, 4, True), (synth.CFG2, 4, 2, True)])
+def test_binned_exchange_matches_oracle(base, world, bins, tiny_stripes, monkeypatch):
     """The production sharded path on one GPU: ranks emulated as `world` local graphs.
     Every emulated rank bins its slice of the reads by (owner, table region); the
     all-to-all is emulated by handing block d of every sender to graph d; the owners
@@ -234,25 +235,31 @@ def test_binned_exchange_matches_oracle(base, world, bins, monkeypatch):
         per = per_reads * (w.read_len + 1)
         geo = graphs[0].bin_geometry(world, len(seq) - (world - 1) * per, n_reads - (world - 1) * per_reads)
         assert geo["bins_per_owner"] == bins
-        B, cap, rw, cw = geo["bins_per_owner"], geo["stripe_capacity"], geo["record_bytes"] // 8, geo["count_stride_bytes"] // 4
-        send = torch.zeros((world, world, B, cap, rw), dtype=torch.int64, device="cuda")       # [sender][owner]...
-        send_counts = torch.zeros((world, world, B, cw), dtype=torch.int32, device="cuda")
+        B, cap, spill = geo["bins_per_owner"], geo["stripe_capacity"], geo["spill_capacity"]
+        if tiny_stripes:                      # most records overflow their stripe and take the spill path
+            cap, spill = 128, (int(og.stats.kmers_inserted / world / world * 1.3) + 127) // 128 * 128
+        rw, cw = geo["record_bytes"] // 8, geo["count_stride_bytes"] // 4
+        send = torch.zeros((world, world, B * cap + spill, rw), dtype=torch.int64, device="cuda")  # [sender][owner]
+        send_counts = torch.zeros((world, world, B + 1, cw), dtype=torch.int32, device="cuda")
         for r in range(world):
             lo, hi = r * per, ((r + 1) * per if r < world - 1 else len(seq))
-            graphs[r].bin_reads_device(d_seq[lo:], d_qual[lo:], hi - lo, w.cutoff, world, B, cap, send[r],
+            graphs[r].bin_reads_device(d_seq[lo:], d_qual[lo:], hi - lo, w.cutoff, world, B, cap, spill, send[r],
                                        send_counts[r], st_)
         torch.cuda.synchronize()
-        cnt = send_counts[..., 0].cpu().numpy()
+        cnt = send_counts[..., 0].cpu().numpy().astype(np.int64)
+        stored = np.minimum(cnt[..., :B], cap).sum() + np.minimum(cnt[..., B], spill).sum()
         # (a record may stand for several occurrences: identical keys of a warp round are merged)
-        assert cnt.max() <= cap and 0 < int(cnt.sum()) <= og.stats.kmers_inserted
+        assert 0 < int(stored) <= og.stats.kmers_inserted
+        if world > 1 or tiny_stripes:
+            assert (cnt[..., B] <= spill).all()
+        if tiny_stripes:
+            assert cnt[..., B].sum() > 0.5 * stored
         assert sum(g.stats(stream=st_)["kmers_inserted"] for g in graphs) == og.stats.kmers_inserted
-        for g in graphs:
-            g.stats(stream=st_)                                   # raises if a stripe overflowed
         recs = []
         for d in range(world):
             recv = send[:, d].contiguous()                        # what all_to_all_single delivers to rank d
             recv_counts = send_counts[:, d].contiguous()
-            graphs[d].insert_bins_device(recv, recv_counts, world, B, cap, st_)
+            graphs[d].insert_bins_device(recv, recv_counts, world, B, cap, spill, st_)
             torch.cuda.synchronize()
             st = graphs[d].stats(stream=st_)
             recs.append(graphs[d].records())
@@ -275,10 +282,10 @@ def test_binned_exchange_overflow_is_reported(monkeypatch):
     with DBGraph(w.kmer_size, 9, w.bucket_size) as g:
         geo = g.bin_geometry(2, len(seq), len(offs) - 1)
         B, rw, cw = geo["bins_per_owner"], geo["record_bytes"] // 8, geo["count_stride_bytes"] // 4
-        cap = 128                                                # far too small (one run of records)
-        send = torch.zeros((2, B, cap, rw), dtype=torch.int64, device="cuda")
-        counts = torch.zeros((2, B, cw), dtype=torch.int32, device="cuda")
-        g.bin_reads_device(d_seq, d_qual, len(seq), w.cutoff, 2, B, cap, send, counts, st_)
+        cap, spill = 128, 128                                    # far too small, spill area included
+        send = torch.zeros((2, B * cap + spill, rw), dtype=torch.int64, device="cuda")
+        counts = torch.zeros((2, B + 1, cw), dtype=torch.int32, device="cuda")
+        g.bin_reads_device(d_seq, d_qual, len(seq), w.cutoff, 2, B, cap, spill, send, counts, st_)
         torch.cuda.synchronize()
         with pytest.raises(_capi.LasvError):
             g.stats(stream=st_)

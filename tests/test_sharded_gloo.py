@@ -115,3 +115,102 @@ def test_two_rank_exchange_builds_the_reference_graph(name, tmp_path):
         recs.append(out)
     assert all(len(r) > 0 for r in recs)
     util.assert_same_records(np.concatenate(recs), util.case_records(name), name)
+
+
+def _stripe_worker(rank, world, port, name, outdir):
+    """The production exchange on the CPU: every rank bins its records by (owner, region) into the
+    fixed-size per-owner blocks the partition kernel writes (stripe counters one per 128-byte line, a
+    spill area behind every block), `exchange_stripes` moves the blocks, and the owner inserts what it
+    received sender by sender -- through the kernels' host emulation."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from lasv_b200 import element_dtype, words_per_kmer
+    from lasv_b200.sharded import exchange_stripes
+    from tests import util
+    emul = C.CDLL(str(ROOT / "tests" / "host_emul" / "libhost_emul.so"))
+    emul.emul_extract_records.restype = C.c_uint64
+    emul.emul_extract_records.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_int,
+                                          C.c_void_p, C.c_uint64]
+    emul.emul_insert_records.argtypes = [C.c_void_p, C.c_uint64] + [C.c_int] * 4 + [C.c_void_p] * 2
+    emul.emul_table_bytes.restype = C.c_uint64
+    emul.emul_table_bytes.argtypes = [C.c_int] * 3
+    emul.emul_gather.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    emul.emul_hash_c.restype = C.c_uint32
+    emul.emul_hash_c.argtypes = [C.c_void_p, C.c_int, C.c_uint32]
+    meta = util.case_meta(name)
+    k, L, W = meta["k"], meta["L"], meta["W"]
+    N = words_per_kmer(k)
+    rw = 2 * N + 1
+    seq, qual, offs = util.case_streams(name)
+    n_reads = len(offs) - 1
+    lo, hi = int(offs[n_reads * rank // world]), int(offs[n_reads * (rank + 1) // world])
+    s, q = np.ascontiguousarray(seq[lo:hi]), np.ascontiguousarray(qual[lo:hi])
+    cap_all = meta["inserts"] + 8
+    recs = np.zeros((cap_all, rw), dtype=np.uint32)
+    n = emul.emul_extract_records(s.ctypes.data, q.ctypes.data, len(s), k, util.cutoff_of(meta), 384,
+                                  recs.ctypes.data, cap_all)
+    recs = recs[:n]
+    bits = int(np.log2(world))
+    B, cap, spill, cstride = 4, 64, cap_all, 32        # tiny stripes: the spill areas carry real traffic
+    per_owner = B * cap + spill
+    send = torch.zeros((world, per_owner, rw), dtype=torch.int32)
+    send_counts = torch.zeros((world, B + 1, cstride), dtype=torch.int32)
+    region_shift = L - bits - 2                        # B = 4 regions per owner
+    for i in range(n):
+        key = np.zeros(N, dtype=np.uint64)
+        for w in range(N):
+            key[w] = np.uint64(recs[i, 2 * w]) | (np.uint64(recs[i, 2 * w + 1]) << np.uint64(32))
+        c = emul.emul_hash_c(key.ctypes.data, N, 0) & ((1 << L) - 1)
+        owner, region = c >> (L - bits), (c >> region_shift) & (B - 1)
+        idx = int(send_counts[owner, region, 0])
+        send_counts[owner, region, 0] += 1
+        if idx < cap:
+            send[owner, region * cap + idx] = torch.from_numpy(recs[i].view(np.int32).copy())
+        else:
+            si = int(send_counts[owner, B, 0])
+            send_counts[owner, B, 0] += 1
+            assert si < spill
+            send[owner, B * cap + si] = torch.from_numpy(recs[i].view(np.int32).copy())
+    recv, recv_counts = torch.zeros_like(send), torch.zeros_like(send_counts)
+    exchange_stripes(send, recv, None)
+    exchange_stripes(send_counts, recv_counts, None)
+    raw = np.zeros(int(emul.emul_table_bytes(k, L - bits, W)), dtype=np.uint8)
+    ctr = np.zeros(20, dtype=np.uint64)
+    total = 0
+    for region in list(range(B)) + [B]:               # regions in order, every sender; then the spill areas
+        for src in range(world):
+            cnt = int(recv_counts[src, region, 0])
+            if region < B:
+                cnt = min(cnt, cap)
+                blk = recv[src, region * cap: region * cap + cnt]
+            else:
+                blk = recv[src, B * cap: B * cap + cnt]
+            got = np.ascontiguousarray(blk.numpy().view(np.uint32))
+            assert emul.emul_insert_records(got.ctypes.data, cnt, k, L - bits, W, 15, raw.ctypes.data,
+                                            ctr.ctypes.data) == 0
+            total += cnt
+    t = torch.tensor([total, n], dtype=torch.int64)
+    dist.all_reduce(t)
+    assert int(t[0]) == int(t[1]) == meta["inserts"]
+    assert int(recv_counts[:, B, 0].sum()) > 0
+    table = np.zeros((1 << (L - bits)) * W, dtype=element_dtype(N))
+    emul.emul_gather(raw.ctypes.data, k, L - bits, W, 0, table.ctypes.data)
+    np.save(Path(outdir) / f"shard{rank}.npy", table)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_stripe_exchange_builds_the_reference_graph(tmp_path):
+    name = "synth_cfg0_k53"
+    world = 2
+    mp.spawn(_stripe_worker, args=(world, _free_port(), name, str(tmp_path)), nprocs=world, join=True)
+    from lasv_b200 import record_dtype
+    from tests import util
+    recs = []
+    for r in range(world):
+        t = np.load(tmp_path / f"shard{r}.npy")
+        occ = t[t["status"] != 0]
+        out = np.zeros(len(occ), dtype=record_dtype(t["kmer"].shape[1]))
+        out["kmer"], out["covg"], out["edges"] = occ["kmer"], occ["coverage"], occ["edges"]
+        recs.append(out)
+    util.assert_same_records(np.concatenate(recs), util.case_records(name), name)
