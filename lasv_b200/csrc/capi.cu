@@ -555,21 +555,24 @@ int lasv_graph_load_reads_host(lasv_graph *g, const uint8_t *seq, const uint8_t 
 
   // chunks are cut at read boundaries, so no k-mer window straddles two chunks
   uint64_t r0 = 0;
-  int leg = 0;
+  int leg = 0, n_chunk = 0;
   while (r0 < n_reads) {
     uint64_t r1 = r0;
     const uint64_t base = offsets[r0];
-    // largest r1 with offsets[r1]-base <= CHUNK_BYTES and r1-r0 <= CHUNK_READS
+    // largest r1 with offsets[r1]-base <= limit and r1-r0 <= CHUNK_READS.  The first chunks are short so
+    // that the kernels start early (nothing overlaps the first copy): 1/8, 1/4, 1/2, then whole chunks.
     {
+      const uint64_t limit = n_chunk < 3 ? (CHUNK_BYTES >> (3 - n_chunk)) : CHUNK_BYTES;
       uint64_t lo = r0 + 1, hi = std::min(n_reads, r0 + CHUNK_READS);
       if (offsets[lo] - base > CHUNK_BYTES)
         return fail(LASV_ERR_ARG, "read %llu is longer than the %llu-byte pipeline chunk",
                     (unsigned long long)r0, (unsigned long long)CHUNK_BYTES);
       while (lo < hi) {
         const uint64_t mid = (lo + hi + 1) / 2;
-        if (offsets[mid] - base <= CHUNK_BYTES) lo = mid;
+        if (offsets[mid] - base <= limit) lo = mid;
         else hi = mid - 1;
       }
+      n_chunk++;
       r1 = lo;
     }
     const uint64_t bytes = offsets[r1] - base, nr = r1 - r0;
