@@ -67,15 +67,33 @@ def parse_args():
 
 # ----------------------------------------------------------------------- clocks
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+    """SM clock and throttle reasons DURING the timed region: NVML polled every few ms from a thread
+    (nvidia-smi -lms as the fallback when the NVML binding is missing)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NVML_REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown",
+                    0x4: "sw_power_cap"}
 
     def __init__(self, device_index: int):
-        self.idx, self.proc, self.lines = device_index, None, []
+        self.idx, self.proc, self.lines, self.samples = device_index, None, [], []
+        self.stop_flag = threading.Event()
+        self.nvml = None
 
     def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[self.idx]) if vis and vis.split(",")[self.idx].isdigit() else self.idx
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
@@ -85,14 +103,31 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        n = self.nvml
+        while not self.stop_flag.is_set():
+            try:
+                mhz = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+                try:
+                    mask = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+                except Exception:
+                    mask = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+                self.samples.append((time.monotonic(), mhz, mask))
+            except Exception:
+                pass
+            time.sleep(0.004)
+
     def _pump(self):
         for line in self.proc.stdout:
             self.lines.append((time.monotonic(), line.strip()))
 
     def window(self, t0, t1):
+        if self.nvml:
+            return [x for x in self.samples if t0 <= x[0] <= t1] or self.samples[-3:]
         return [l for t, l in self.lines if t0 <= t <= t1] or [l for _, l in self.lines[-3:]]
 
     def stop(self):
+        self.stop_flag.set()
         if self.proc:
             self.proc.terminate()
             try:
@@ -100,8 +135,17 @@ class ClockSampler:
             except Exception:
                 self.proc.kill()
 
-    @staticmethod
-    def summarise(lines):
+    def summarise(self, lines):
+        if self.nvml:
+            if not lines:
+                return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+            reasons = set()
+            for _, _, mask in lines:
+                for bit, name in self.NVML_REASONS.items():
+                    if mask & bit:
+                        reasons.add(name)
+            return {"sm_mhz": statistics.median(x[1] for x in lines), "sm_max_mhz": self.max_mhz,
+                    "reasons": sorted(reasons), "samples": len(lines), "source": "nvml"}
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for l in lines:
@@ -119,7 +163,7 @@ class ClockSampler:
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "source": "nvidia-smi"}
 
 
 def measured_peaks():
@@ -470,7 +514,7 @@ def main():
     st1 = graph.stats()
     kmers = st1["kmers_inserted"] - st0["kmers_inserted"] if not cfg0 else st1["kmers_inserted"] * K
     value = kmers / dt
-    clocks = ClockSampler.summarise(sampler.window(wall0, wall1)) if rank == 0 else None
+    clocks = sampler.summarise(sampler.window(wall0, wall1)) if rank == 0 else None
 
     # ---- roofline of the dominant kernel (N=1: the fused build kernel)
     peak, peak_src = measured_peaks()
