@@ -252,6 +252,17 @@ int lasv_graph_load_pe_filelists(lasv_graph *g, const char *list1, const char *l
                                  lasv_load_stats *stats);
 
 /* ------------------------------------------------------------------ (A) -- */
+/* The record loop of load_multicolour_binary_from_filename_into_graph
+ * (file_reader.c:1652-1710: hash_table_insert + add_edges + db_node_update_coverage
+ * per record, single-threaded -- SURVEY 8f rank 1) on the GPU.  The caller parses the
+ * header with the reference's own check_binary_signature_NEW (which also updates its
+ * GraphInfo) and passes the file offset of the first record; the caller's
+ * reference-layout table is merged in first if it already holds k-mers and is then
+ * replaced by the result (hole-free buckets, next_element[], unique_kmers,
+ * collisions[]).  Returns the number of records read or a negative LASV_ERR_*.
+ * integration/ctx_loader_shim.c is the reference-side binding. */
+long long lasv_ref_hash_table_load_ctx_records(lasv_ref_hash_table *t, const char *path, long record_offset);
+
 /* Exact reference signatures (file_reader.h:86-118); `boolean` is signed char
  * (global.h:37).  They build the graph on the GPU and leave db_graph->table,
  * next_element, unique_kmers and collisions[] as the reference loader would

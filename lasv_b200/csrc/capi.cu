@@ -1040,6 +1040,24 @@ int lasv_graph_load_ctx_records(lasv_graph *g, const uint8_t *records, uint64_t 
   return rc;
 }
 
+// packed .ctx records from the current position of `fp` to its end, into the device table
+static int stream_ctx_records(lasv_graph *g, FILE *fp, unsigned long long *n_records) {
+  const size_t rec = 8 * (size_t)g->N + 5;
+  const uint64_t per = (64ull << 20) / rec;
+  std::vector<uint8_t> buf(per * rec);
+  unsigned long long n = 0;
+  int rc = LASV_OK;
+  for (;;) {
+    const size_t got = fread(buf.data(), rec, per, fp);
+    if (!got) break;
+    rc = lasv_graph_load_ctx_records(g, buf.data(), got);
+    n += got;
+    if (rc != LASV_OK || got < per) break;
+  }
+  if (n_records) *n_records = n;
+  return rc;
+}
+
 int lasv_graph_load_ctx_file(lasv_graph *g, const char *path, uint32_t *mean_read_len,
                              uint64_t *total_seq) {
   if (int e = use(g)) return e;
@@ -1072,16 +1090,7 @@ int lasv_graph_load_ctx_file(lasv_graph *g, const char *path, uint32_t *mean_rea
   if (fread(magic, 1, 6, fp) != 6 || memcmp(magic, "CORTEX", 6)) return bad("missing end-of-header magic");
   if (mean_read_len) *mean_read_len = (uint32_t)mrl;
   if (total_seq) *total_seq = (uint64_t)ts;
-  const size_t rec = 8 * (size_t)g->N + 5;
-  const uint64_t per = (64ull << 20) / rec;
-  std::vector<uint8_t> buf(per * rec);
-  int rc = LASV_OK;
-  for (;;) {
-    const size_t got = fread(buf.data(), rec, per, fp);
-    if (!got) break;
-    rc = lasv_graph_load_ctx_records(g, buf.data(), got);
-    if (rc != LASV_OK || got < per) break;
-  }
+  const int rc = stream_ctx_records(g, fp, nullptr);
   fclose(fp);
   return rc;
 }
@@ -1360,6 +1369,54 @@ void dropin_load(lasv_ref_hash_table *t, const char *list1, const char *list2, i
 }
 
 }  // namespace
+
+/* The record loop of load_multicolour_binary_from_filename_into_graph (file_reader.c:1686-1703:
+ * hash_table_insert + add_edges + db_node_update_coverage per record, single-threaded) on the GPU,
+ * for a caller that has parsed the header with the reference's own check_binary_signature_NEW and
+ * hands over the file offset of the first record.  The caller's reference-layout table is merged in
+ * first if it already holds k-mers, then replaced by the result.  Returns the number of records read,
+ * or a negative error code. */
+long long lasv_ref_hash_table_load_ctx_records(lasv_ref_hash_table *t, const char *path, long record_offset) {
+  if (!t || !t->table) return fail(LASV_ERR_ARG, "NULL table!");
+  const int L = log2_exact(t->number_buckets);
+  if (L < 0) return fail(LASV_ERR_ARG, "number_buckets is not a power of two");
+  FILE *fp = fopen(path, "rb");
+  if (!fp) return fail(LASV_ERR_IO, "load_multicolour_binary_from_filename_into_graph cannot open file:%s", path);
+  if (fseek(fp, record_offset, SEEK_SET)) {
+    fclose(fp);
+    return fail(LASV_ERR_IO, "cannot seek to the records of %s", path);
+  }
+  int dev = 0;
+  if (const char *e = getenv("LASV_B200_DEVICE")) dev = atoi(e);
+  lasv_graph *g = lasv_graph_new(t->kmer_size, L, t->bucket_size, t->max_rehash_tries, dev);
+  if (!g) {
+    fclose(fp);
+    return LASV_ERR_CUDA;
+  }
+  unsigned long long n = 0;
+  int rc = LASV_OK;
+  if (t->unique_kmers > 0) rc = lasv_graph_import_table(g, t->table);
+  if (rc == LASV_OK) rc = stream_ctx_records(g, fp, &n);
+  fclose(fp);
+  long long coll[16];
+  if (rc == LASV_OK) rc = lasv_graph_rehash_histogram(g, coll);
+  const long long uniq = rc == LASV_OK ? lasv_graph_unique_kmers(g) : -1;
+  if (rc == LASV_OK) rc = lasv_graph_export_table(g, t->table, t->next_element);
+  if (rc == LASV_OK) {
+    t->unique_kmers = uniq;
+    // one hash_table_insert per record (hash_table.c:333-382 counts collisions[] like find_or_insert)
+    if (t->collisions) {
+      long long later = 0;
+      for (int r = 1; r < t->max_rehash_tries && r < 16; r++) {
+        t->collisions[r] += coll[r];
+        later += coll[r];
+      }
+      t->collisions[0] += (long long)n - later;
+    }
+  }
+  lasv_graph_free(&g);
+  return rc == LASV_OK ? (long long)n : rc;
+}
 
 void load_se_filelist_into_graph_colour(
     char *se_filelist_path, int qual_thresh, int homopol_limit, signed char remove_dups_se,

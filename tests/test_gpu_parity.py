@@ -541,6 +541,41 @@ def test_reference_cli_with_gpu_loader(name, tmp_path):
     assert tries == meta["inserts"]
 
 
+@pytest.mark.parametrize("name", ["synth_cfg1_k31", "synth_cfg0_k53", "synth_cfg2_k95", "synth_full_k53"])
+def test_reference_cli_reloads_ctx_through_the_gpu(name, tmp_path):
+    """`dB_graph --multicolour_bin x.ctx` with the record loop of
+    load_multicolour_binary_from_filename_into_graph replaced by the GPU loader
+    (integration/ctx_loader_shim.c + lasv_ref_hash_table_load_ctx_records): the
+    reference's own consumers (supernode walk, binary dump) must see exactly the graph
+    the reference's single-threaded hash_table_insert loop would have built."""
+    from pathlib import Path
+    meta = util.case_meta(name)
+    k, L, W = meta["k"], meta["L"], meta["W"]
+    exe = Path(__file__).resolve().parents[1] / "integration" / "_build" / f"dB_graph_gpu_{O.MAXK_OF_N[O.words_per_kmer(k)]}"
+    if not exe.exists():
+        pytest.skip("integration/_build not built (needs /root/reference at build time)")
+    gold = util.case_records(name)
+    src = tmp_path / "in.ctx"
+    src.write_bytes(bytes.fromhex(meta["ctx_header_hex"]) + gold.tobytes())      # a reference-format binary of the golden graph
+    cmd = [str(exe), "--kmer_size", str(k), "--mem_height", str(L), "--mem_width", str(W),
+           "--multicolour_bin", str(src), "--dump_binary", str(tmp_path / "out.ctx"),
+           "--output_supernodes", str(tmp_path / "sup.fa")]
+    p = subprocess.run(cmd, cwd=tmp_path, capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stderr[-2000:] + p.stdout[-2000:]
+    assert f"got {len(gold)} kmers" in p.stdout                                   # graph_operations.c:834
+    ctx = O.parse_ctx(tmp_path / "out.ctx")
+    assert ctx["header"].hex() == meta["ctx_header_hex"]                          # GraphInfo carried over by the reference's parser
+    util.assert_same_records(ctx["records"], gold, name)
+    if "supernodes" in meta:                                  # (the 90 %-full rehash-chain cases carry none)
+        assert O.canonical_seq_set(O.read_fasta_seqs(tmp_path / "sup.fa")) == meta["supernodes"]
+    # a file that is not a binary dies like the reference does
+    bad = tmp_path / "bad.ctx"
+    bad.write_bytes(b"NOTCORTEX" + bytes(100))
+    p = subprocess.run(cmd[:7] + ["--multicolour_bin", str(bad), "--dump_binary", str(tmp_path / "out2.ctx")],
+                       cwd=tmp_path, capture_output=True, text=True, timeout=600)
+    assert p.returncode != 0 and "not compatible" in (p.stderr + p.stdout)       # cmd_line.c checks the header first
+
+
 # --------------------------------------------------- BASELINE-size properties
 @pytest.mark.skipif(os.environ.get("LASV_SKIP_FULLSIZE") == "1", reason="LASV_SKIP_FULLSIZE=1")
 def test_config0_full_size_properties():
