@@ -14,6 +14,11 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
+#include <condition_variable>
+#include <memory>
+#include <mutex>
+#include <thread>
 #include <string>
 #include <vector>
 
@@ -1114,7 +1119,7 @@ struct PinnedBatch : HostBatch {
   }
 };
 
-constexpr uint64_t LOADER_BATCH_BYTES = 256ull << 20;
+constexpr uint64_t LOADER_BATCH_BYTES = 128ull << 20;  // x 2 slots x (1 or 2 files), pinned
 constexpr uint64_t LOADER_BATCH_READS = 4ull << 20;
 
 int flush_batch(lasv_graph *g, HostBatch &b, bool with_qual, int cutoff) {
@@ -1125,44 +1130,117 @@ int flush_batch(lasv_graph *g, HostBatch &b, bool with_qual, int cutoff) {
   return rc;
 }
 
-// Common body of the SE and PE loaders: mates are interleaved (mate 1 then
-// mate 2 of each pair, file_reader.c:636-765) -- the order is irrelevant to the
-// graph but the lock-step read is what detects files of unequal length.
+// One parser thread per file: it fills two pinned batches in turn while the caller's thread hands the
+// full ones to the GPU.  (The text parse is the slow end of the file loaders by two orders of magnitude;
+// the two mates of a pair need not be interleaved -- the order of reads is irrelevant to the graph,
+// SURVEY 8a-B -- so each file streams on its own and only the read counts are compared.)
+struct FileProducer {
+  SeqReader reader;
+  std::string err;
+  bool with_qual = false;
+  PinnedBatch *slot[2] = {nullptr, nullptr};
+  int full[2] = {0, 0};  // guarded by m
+  bool done = false;     // guarded by m: no further batches will be produced
+  bool too_long = false;
+  uint64_t reads = 0;
+  std::mutex m;
+  std::condition_variable cv;
+  std::thread th;
+
+  void run() {
+    int k = 0;
+    bool have = false;  // a parsed read waits for room
+    for (;;) {
+      {
+        std::unique_lock<std::mutex> lk(m);
+        cv.wait(lk, [&] { return !full[k]; });
+      }
+      HostBatch &b = *slot[k];
+      b.reset();
+      bool eof = false;
+      for (;;) {
+        if (!have) {
+          if (!reader.next(err)) { eof = true; break; }
+          have = true;
+        }
+        if (!reader.append_to(b, with_qual)) {
+          if (b.n_reads == 0) { too_long = true; eof = true; }
+          break;  // batch full: the read stays pending
+        }
+        have = false;
+        reads++;
+      }
+      {
+        std::lock_guard<std::mutex> lk(m);
+        if (b.n_reads) full[k] = 1;
+        if (eof) done = true;
+      }
+      cv.notify_all();
+      if (eof) return;
+      k ^= 1;
+    }
+  }
+};
+
+// Common body of the SE and PE loaders (file_reader.c:475-773).
 int load_files(lasv_graph *g, const char *path1, const char *path2, int cutoff,
                lasv_load_stats *stats) {
   if (int e = use(g)) return e;
   std::string err;
-  SeqReader r1, r2;
-  if (!r1.open(path1, err)) return fail(LASV_ERR_IO, "%s", err.c_str());
-  if (path2 && !r2.open(path2, err)) return fail(LASV_ERR_IO, "%s", err.c_str());
-  const bool with_qual = r1.has_quality() || (path2 && r2.has_quality());
-  PinnedBatch batch(LOADER_BATCH_BYTES, LOADER_BATCH_READS);
-  if (!batch.ok) return fail(LASV_ERR_CUDA, "cannot allocate pinned batch buffers");
-  lasv_load_stats before;
-  if (int e = lasv_graph_stats(g, &before, nullptr, 0, nullptr)) return e;
-  for (;;) {
-    const bool got1 = r1.next(err);
-    if (!err.empty()) return fail(LASV_ERR_IO, "%s", err.c_str());
-    bool got2 = false;
-    if (path2) {
-      got2 = r2.next(err);
-      if (!err.empty()) return fail(LASV_ERR_IO, "%s", err.c_str());
-      if (got1 != got2)
-        return fail(LASV_ERR_IO,
-                    "Paired-end files don't have the same number of reads\nfile1: %s\nfile2: %s",
-                    path1, path2);
-    }
-    if (!got1) break;
-    for (int m = 0; m < (path2 ? 2 : 1); m++) {
-      SeqReader &r = m ? r2 : r1;
-      if (!r.append_to(batch, with_qual)) {
-        if (int e = flush_batch(g, batch, with_qual, cutoff)) return e;
-        if (!r.append_to(batch, with_qual))
-          return fail(LASV_ERR_ARG, "read of %zu bases exceeds the loader batch", r.seq().size());
-      }
+  const int n_files = path2 ? 2 : 1;
+  FileProducer prod[2];
+  if (!prod[0].reader.open(path1, err)) return fail(LASV_ERR_IO, "%s", err.c_str());
+  if (path2 && !prod[1].reader.open(path2, err)) return fail(LASV_ERR_IO, "%s", err.c_str());
+  const bool with_qual = prod[0].reader.has_quality() || (path2 && prod[1].reader.has_quality());
+  std::vector<std::unique_ptr<PinnedBatch>> batches;
+  for (int f = 0; f < n_files; f++) {
+    prod[f].with_qual = with_qual;
+    for (int k = 0; k < 2; k++) {
+      batches.emplace_back(new PinnedBatch(LOADER_BATCH_BYTES, LOADER_BATCH_READS));
+      if (!batches.back()->ok) return fail(LASV_ERR_CUDA, "cannot allocate pinned batch buffers");
+      prod[f].slot[k] = batches.back().get();
     }
   }
-  if (int e = flush_batch(g, batch, with_qual, cutoff)) return e;
+  lasv_load_stats before;
+  if (int e = lasv_graph_stats(g, &before, nullptr, 0, nullptr)) return e;
+  for (int f = 0; f < n_files; f++) prod[f].th = std::thread([&prod, f] { prod[f].run(); });
+
+  int rc = LASV_OK;
+  int next_slot[2] = {0, 0};
+  bool finished[2] = {false, n_files < 2};
+  while (!(finished[0] && finished[1])) {
+    for (int f = 0; f < n_files; f++) {
+      if (finished[f]) continue;
+      FileProducer &p = prod[f];
+      const int k = next_slot[f];
+      bool ready = false;
+      {
+        std::unique_lock<std::mutex> lk(p.m);
+        // with two files, do not sleep on one while the other may have a batch ready
+        if (n_files == 1 || finished[f ^ 1]) p.cv.wait(lk, [&] { return p.full[k] || p.done; });
+        else p.cv.wait_for(lk, std::chrono::milliseconds(1), [&] { return p.full[k] || p.done; });
+        ready = p.full[k] != 0;
+        if (!ready && p.done) finished[f] = true;
+      }
+      if (!ready) continue;
+      if (rc == LASV_OK) rc = flush_batch(g, *p.slot[k], with_qual, cutoff);  // after an error: just drain
+      {
+        std::lock_guard<std::mutex> lk(p.m);
+        p.full[k] = 0;
+      }
+      p.cv.notify_all();
+      next_slot[f] ^= 1;
+    }
+  }
+  for (int f = 0; f < n_files; f++) prod[f].th.join();
+  if (rc != LASV_OK) return rc;
+  for (int f = 0; f < n_files; f++) {
+    if (!prod[f].err.empty()) return fail(LASV_ERR_IO, "%s", prod[f].err.c_str());
+    if (prod[f].too_long) return fail(LASV_ERR_ARG, "a read of %s exceeds the loader batch", f ? path2 : path1);
+  }
+  if (path2 && prod[0].reads != prod[1].reads)
+    return fail(LASV_ERR_IO, "Paired-end files don't have the same number of reads\nfile1: %s\nfile2: %s",
+                path1, path2);
   lasv_load_stats after;
   if (int e = lasv_graph_stats(g, &after, nullptr, 0, nullptr)) return e;
   if (stats) {

@@ -132,12 +132,21 @@ bool SeqReader::next(std::string &err) {
     // qualities: exactly |seq| non-newline bytes, possibly over several lines
     qual_.reserve(seq_.size());
     while (qual_.size() < seq_.size()) {
-      c = getc_();
-      if (c == -1) {
+      if (pos_ == end_ && !fill_()) {
         err = "FASTQ file ended without finishing quality scores [file: " + path_ + "]";
         return false;
       }
-      if (c != '\r' && c != '\n') qual_.push_back((char)c);
+      // bulk: the run of quality bytes up to the next line terminator (or as many as are still wanted)
+      const unsigned char *p = buf_.data() + pos_;
+      size_t want = seq_.size() - qual_.size();
+      if (want > end_ - pos_) want = end_ - pos_;
+      const unsigned char *nl = (const unsigned char *)memchr(p, '\n', want);
+      size_t take = nl ? (size_t)(nl - p) : want;
+      const unsigned char *cr = take ? (const unsigned char *)memchr(p, '\r', take) : nullptr;
+      if (cr) take = (size_t)(cr - p);
+      qual_.append((const char *)p, take);
+      pos_ += take;
+      if (nl || cr) pos_++;  // the terminator itself is not a quality byte
     }
     n_reads_++;
     return true;
