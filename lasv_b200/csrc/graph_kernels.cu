@@ -43,13 +43,29 @@ __device__ __forceinline__ unsigned lanemask_lt() {
 template <int N>
 __device__ __forceinline__ bool warp_aggregate(bool active, const uint64_t (&key)[N],
                                                uint32_t &edge, uint32_t &count) {
+  // Common case: no two NEIGHBOURING lanes hold the same key (consecutive windows of a read are
+  // neighbours; a homopolymer or tandem run is what this function is for) -- one shuffle per key
+  // word and a vote.  Only then the general grouping below (match.any costs ~20 % of the
+  // partition kernel if run every round; a repeated key in non-neighbouring lanes just stays
+  // two updates).
+  {
+    bool same_prev = active && lane_id() > 0;
+#pragma unroll
+    for (int i = 0; i < N; i++) same_prev &= (__shfl_up_sync(FULL, key[i], 1) == key[i]);
+    same_prev &= (__shfl_up_sync(FULL, active ? 1 : 0, 1) != 0);
+    bool same_prev2 = active && lane_id() > 1;   // period-2 repeats: (AC)n alternates two keys
+#pragma unroll
+    for (int i = 0; i < N; i++) same_prev2 &= (__shfl_up_sync(FULL, key[i], 2) == key[i]);
+    same_prev2 &= (__shfl_up_sync(FULL, active ? 1 : 0, 2) != 0);
+    if (!__any_sync(FULL, same_prev | same_prev2)) return active;
+  }
   uint64_t sig = key[N - 1];
 #pragma unroll
   for (int i = 0; i < N - 1; i++) sig = sig * 0x9E3779B97F4A7C15ull + key[i];
   if (!active) sig = ~0ull - lane_id();
   const unsigned grp = __match_any_sync(FULL, sig);
-  // Common case: 32 distinct keys.  (The reductions below run once per distinct lane
-  // mask, i.e. 32 times for 32 singleton groups -- never enter them for nothing.)
+  // (The reductions below run once per distinct lane mask, i.e. 32 times for 32 singleton
+  // groups -- never enter them for nothing.)
   if (!__any_sync(FULL, (grp & (grp - 1u)) != 0u)) return active;
   const int leader = __ffs(grp) - 1;
   bool same = active;
