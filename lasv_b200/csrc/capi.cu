@@ -256,13 +256,14 @@ int ensure_bins(lasv_graph *g, lasv_graph::BinLeg &l, uint64_t n_bytes, uint64_t
     cudaFree(l.v.recs);
     cudaFree(l.v.count);
     l.v = BinView{};
-    CUDA_TRY(cudaMalloc(&l.v.recs, want * (size_t)bin_record_words(g->N) * sizeof(uint64_t)));
+    CUDA_TRY(cudaMalloc(&l.v.recs, want * (size_t)bin_record_words(g->N, g->k) * sizeof(uint64_t)));
     CUDA_TRY(cudaMalloc(&l.v.count, (size_t)(n_bins + 1) * COUNT_STRIDE * sizeof(unsigned int)));
     l.alloc_records = want;
     l.alloc_n = n_bins;
   }
   l.v.cap = (uint32_t)(l.alloc_records / n_bins / STRIPE_RUN * STRIPE_RUN);
   l.v.block_shift = (uint32_t)log2_u32(n_bins);
+  l.v.rec_words = bin_record_words(g->N, g->k);
   l.v.spill_cap = 0;  // one owner: an overfull stripe spills straight into the table
   l.v.n_bins = n_bins;
   l.v.bin_mask = (uint32_t)(g->n_buckets - 1);
@@ -737,7 +738,7 @@ int lasv_graph_bin_geometry(lasv_graph *g, int n_owners, uint64_t n_bytes, uint6
     const uint64_t sp = std::max<uint64_t>(4096, cap * per / 16);
     *spill_capacity_out = n_owners == 1 ? 0u : (uint32_t)std::min<uint64_t>(0xFFFFFF80ull, (sp + STRIPE_RUN - 1) / STRIPE_RUN * STRIPE_RUN);
   }
-  if (record_bytes) *record_bytes = 8u * bin_record_words(g->N);
+  if (record_bytes) *record_bytes = 8u * bin_record_words(g->N, g->k);
   if (count_stride_bytes) *count_stride_bytes = COUNT_STRIDE * (uint32_t)sizeof(unsigned int);
   return LASV_OK;
 }
@@ -774,6 +775,7 @@ int lasv_graph_bin_reads_device(lasv_graph *g, const uint8_t *d_seq, const uint8
   p.bins.src_shift = 0;
   p.bins.bins_per_src = n_bins;
   p.bins.block_shift = (uint32_t)log2_u32(bins_per_owner);
+  p.bins.rec_words = bin_record_words(g->N, g->k);
   p.ctas_per_sm = g->pipeline ? 2 : 0;
   launch_build(g->N, MODE_BIN, p, st);
   return check_launch();
@@ -798,6 +800,7 @@ int lasv_graph_insert_bins_device(lasv_graph *g, const void *d_records, const vo
   b.src_shift = (uint32_t)log2_u32((uint32_t)n_src);
   b.bins_per_src = bins_per_src;
   b.block_shift = (uint32_t)log2_u32(bins_per_src);
+  b.rec_words = bin_record_words(g->N, g->k);
   launch_insert_bins(g->N, b, g->view(), g->d_ctr, g->pipeline ? 2 : 0, stream_of(g, cuda_stream));
   return check_launch();
 }

@@ -105,28 +105,48 @@ __device__ __forceinline__ void load_record(const uint32_t *src, uint64_t (&key)
 
 // Bin records: one vector store / load per record (graph_kernels.cuh, BinView).
 template <int N>
-__device__ __forceinline__ void store_bin_record(uint64_t *dst, const uint64_t (&key)[N], uint64_t aux) {
+__device__ __forceinline__ void store_bin_record(uint64_t *dst, uint32_t rec_words, const uint64_t (&key)[N],
+                                                 uint32_t c, uint32_t edge, uint32_t count) {
   if (N == 1) {
-    asm volatile("st.global.v2.u64 [%0], {%1,%2};" ::"l"(dst), "l"(key[0]), "l"(aux) : "memory");
+    asm volatile("st.global.v2.u64 [%0], {%1,%2};" ::"l"(dst), "l"(key[0]), "l"(bin_aux(c, edge, count)) : "memory");
+  } else if (N == 2 && rec_words == 2) {  // k <= 56: edges and count ride in the top key word (count <= 32 per round)
+    const uint64_t w0 = key[0] | ((uint64_t)(edge & 0xFFu) << 48) | ((uint64_t)(count & 0xFFu) << 56);
+    asm volatile("st.global.v2.u64 [%0], {%1,%2};" ::"l"(dst), "l"(w0), "l"(key[1 % N]) : "memory");
   } else {
+    const uint64_t aux = bin_aux(c, edge, count);
     const uint64_t w2 = (N == 2) ? aux : key[2 % N], w3 = (N == 2) ? 0ull : aux;
     asm volatile("st.global.v4.u64 [%0], {%1,%2,%3,%4};" ::"l"(dst), "l"(key[0]), "l"(key[1 % N]), "l"(w2), "l"(w3)
                  : "memory");
   }
 }
 template <int N>
-__device__ __forceinline__ uint64_t load_bin_record(const uint64_t *src, uint64_t (&key)[N]) {
-  uint64_t a, b, c = 0, d = 0;
-  if (N == 1) {
+__device__ __forceinline__ void load_bin_record(const uint64_t *src, uint32_t rec_words, uint64_t (&key)[N],
+                                                uint32_t &c, uint32_t &edge, uint32_t &count) {
+  uint64_t a, b, x = 0, y = 0;
+  if (N == 1 || rec_words == 2) {
     asm volatile("ld.global.nc.v2.u64 {%0,%1}, [%2];" : "=l"(a), "=l"(b) : "l"(src));
-    key[0] = a;
-    return b;
+    if (N == 1) {
+      key[0] = a;
+      c = (uint32_t)b;
+      edge = (uint32_t)(b >> 32) & 0xFFu;
+      count = (uint32_t)(b >> 40);
+    } else {
+      key[0] = a & 0x0000FFFFFFFFFFFFull;
+      key[1 % N] = b;
+      edge = (uint32_t)(a >> 48) & 0xFFu;
+      count = (uint32_t)(a >> 56);
+      c = lookup3_key<N>(key, 0).c;
+    }
+    return;
   }
-  asm volatile("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(src));
+  asm volatile("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(x), "=l"(y) : "l"(src));
   key[0] = a;
   key[1 % N] = b;
-  if (N == 3) key[2 % N] = c;
-  return (N == 2) ? c : d;
+  if (N == 3) key[2 % N] = x;
+  const uint64_t aux = (N == 2) ? x : y;
+  c = (uint32_t)aux;
+  edge = (uint32_t)(aux >> 32) & 0xFFu;
+  count = (uint32_t)(aux >> 40);
 }
 
 // --------------------------------------------------------------------------
@@ -397,8 +417,8 @@ build_kernel(const BuildParams p, const uint64_t n_tiles) {
           if (!lead[u]) continue;
           const uint32_t bin = (hc[u] & p.bins.bin_mask) >> p.bins.bin_shift;
           if (idx[u] < p.bins.cap) {
-            store_bin_record<N>(p.bins.recs + stripe_record_at(p.bins, bin, idx[u]) * bin_record_words(N), key[u],
-                                bin_aux(hc[u], edge[u], count[u]));
+            store_bin_record<N>(p.bins.recs + stripe_record_at(p.bins, bin, idx[u]) * p.bins.rec_words,
+                                p.bins.rec_words, key[u], hc[u], edge[u], count[u]);
           } else if (p.bins.spill_ok) {  // stripe full (skewed batch): straight into the table
             const int r = table_upsert_hashed<N, DeviceOps>(p.table, p.ctr, key[u], hc[u], edge[u], count[u]);
             my_new += (r == 1);
@@ -406,8 +426,8 @@ build_kernel(const BuildParams p, const uint64_t n_tiles) {
             const uint32_t owner = bin >> p.bins.block_shift;
             const uint32_t si = atomicAdd(&p.bins.count[stripe_counter_at(p.bins, owner, 1u << p.bins.block_shift)], 1u);
             if (si < p.bins.spill_cap)
-              store_bin_record<N>(p.bins.recs + spill_record_at(p.bins, owner, si) * bin_record_words(N), key[u],
-                                  bin_aux(hc[u], edge[u], count[u]));
+              store_bin_record<N>(p.bins.recs + spill_record_at(p.bins, owner, si) * p.bins.rec_words,
+                                  p.bins.rec_words, key[u], hc[u], edge[u], count[u]);
             else
               atomicExch(p.rec_overflow, 1ull);
           }
@@ -493,7 +513,6 @@ __global__ void __launch_bounds__(THREADS, 4) insert_bins_kernel(const BinView b
   const unsigned lane = lane_id();
   const uint32_t n_warps = (gridDim.x * THREADS) >> 5;
   const uint32_t warp = (blockIdx.x * THREADS + threadIdx.x) >> 5;
-  constexpr uint32_t RW = (N == 1) ? 2u : 4u;
 
   BinBatch<U> s0;  // being collected
   int n_have = 0;  // chunks in s0, warp-uniform
@@ -508,12 +527,7 @@ __global__ void __launch_bounds__(THREADS, 4) insert_bins_kernel(const BinView b
       c[u] = 0; edge[u] = 0; count[u] = 0;
 #pragma unroll
       for (int w = 0; w < N; w++) key[u][w] = 0;
-      if (s0.live[u]) {
-        const uint64_t aux = load_bin_record<N>(b.recs + s0.at[u] * RW, key[u]);
-        c[u] = (uint32_t)aux;
-        edge[u] = (uint32_t)(aux >> 32) & 0xFFu;
-        count[u] = (uint32_t)(aux >> 40);
-      }
+      if (s0.live[u]) load_bin_record<N>(b.recs + s0.at[u] * b.rec_words, b.rec_words, key[u], c[u], edge[u], count[u]);
     }
     upsert_batch<N, U>(t, ctr, dq, key, c, edge, count, s0.live, my_new);
 #pragma unroll

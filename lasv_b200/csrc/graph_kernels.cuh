@@ -18,14 +18,20 @@ enum BuildMode { MODE_FUSED = 0, MODE_RECORDS = 1, MODE_ROUTE = 2, MODE_BIN = 3 
 // the slice of the table they will touch (bin = bucket >> bin_shift), so that the
 // insert kernel walks the table region by region (TLB-, L2- and DRAM-row-friendly)
 // instead of at random.  One fixed-capacity stripe of records per bin.  A record is
-// the key words, then {lookup3 c : 32, edges : 8, count : 24} (the insert side does
-// not hash again), padded to 16 bytes (N = 1) or 32 bytes (N = 2, 3) and written
-// with ONE vector store: scattered stores cost per request, not per byte
-// (tools/ubench: 3 x 8 B = 15 ms, 1 x 32 B = 5 ms per 180 M records).
-__host__ __device__ inline uint32_t bin_record_words(int N) { return N == 1 ? 2u : 4u; }
+// written with ONE vector store: scattered stores cost per request, not per byte
+// (tools/ubench: 3 x 8 B = 15 ms, 1 x 32 B = 5 ms per 180 M records) -- but every
+// record byte is DRAM traffic three times over (partition write, exchange copy,
+// insert read) in kernels that are bound by exactly that, so records are as small as
+// the key allows:
+//   16 bytes  N = 1: {key, aux};  N = 2 and k <= 56: {key0 | edges << 48 | count << 56, key1}
+//             (the top key word has 16 spare bits; the insert side hashes again)
+//   32 bytes  N = 2 and k > 56: {key0, key1, aux, 0};  N = 3: {key0, key1, key2, aux}
+// aux = {lookup3 c : 32, edges : 8, count : 24}.
+__host__ __device__ inline uint32_t bin_record_words(int N, int k) { return (N == 1 || (N == 2 && k <= 56)) ? 2u : 4u; }
 constexpr uint32_t COUNT_STRIDE = 32;  // uint32 units = 128 bytes
 struct BinView {
-  uint64_t *recs;       // [n_bins*cap*bin_record_words(N)], see stripe_record_at
+  uint64_t *recs;       // [n_bins*cap*rec_words], see stripe_record_at
+  uint32_t rec_words;   // 2 or 4 64-bit words per record (bin_record_words)
   unsigned int *count;  // [(block+1)*n_owners*COUNT_STRIDE] records wanted per stripe (stripe_counter_at), ONE COUNTER PER 128-BYTE LINE: the L2
                         // atomic unit serialises per line, 8 counters in a line would share one queue
                         // (a count may exceed cap: see spill_ok)

@@ -5,6 +5,7 @@ bytes) with the golden outputs of the compiled reference, with the oracle on
 seeded synthetic reads, and -- at BASELINE.json's full config-0 size -- through
 size-independent properties."""
 import ctypes as C
+import dataclasses
 import os
 import subprocess
 
@@ -212,7 +213,10 @@ def test_route_and_insert_records_match_oracle(base, world):
 
 @pytest.mark.parametrize("base,world,bins,tiny_stripes", [(synth.CFG0, 2, 4, False), (synth.CFG1, 4, 1, False),
                                                            (synth.CFG2, 8, 8, False), (synth.CFG0, 1, 16, False),
-                                                           (synth.CFG0, 2, 4, True), (synth.CFG2, 4, 2, True)])
+                                                           (synth.CFG0, 2, 4, True), (synth.CFG2, 4, 2, True),
+                                                           # two-word k-mers too long for the 16-byte record
+                                                           (dataclasses.replace(synth.CFG0, kmer_size=63), 2, 2, False),
+                                                           (dataclasses.replace(synth.CFG0, kmer_size=57), 1, 4, False)])
 def test_binned_exchange_matches_oracle(base, world, bins, tiny_stripes, monkeypatch):
     """The production sharded path on one GPU: ranks emulated as `world` local graphs.
     Every emulated rank bins its slice of the reads by (owner, table region); the
