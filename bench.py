@@ -166,6 +166,32 @@ class ClockSampler:
                 "samples": len(sm), "source": "nvidia-smi"}
 
 
+def bind_to_gpu_numa_node(device_index: int):
+    """Run this process on the CPUs of the NUMA node the GPU hangs off, BEFORE any pinned host memory is
+    allocated (first touch puts the pages on that node): at 8 ranks the host->device copies otherwise all
+    read one socket's memory.  Returns the node, or None if the topology cannot be read."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(device_index)).busId
+        bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()
+        dom, b, rest = bus.split(":")
+        node = int(Path(f"/sys/bus/pci/devices/{dom[-4:]}:{b}:{rest}/numa_node").read_text())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in Path(f"/sys/devices/system/node/node{node}/cpulist").read_text().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:
+        return None
+
+
 def measured_peaks():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -371,6 +397,7 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if world != args.gpus and world > 1:
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    numa_node = bind_to_gpu_numa_node(local_rank)
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -652,7 +679,7 @@ def main():
             "config": workload_config(args, w, world),
             "kmers_per_step": kmers // K, "gpu_launches": int(launches),
             "roofline": roofline, "random_access": ra, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
-            "prefill": prefill,
+            "prefill": prefill, "host": {"numa_node_of_rank0": numa_node, "cpus_of_rank0": len(os.sched_getaffinity(0))},
             "graph": {"unique_kmers": final["unique_kmers"], "fill": final["unique_kmers"] / (g.capacity * world),
                       "sum_covg": summary["sum_covg"], "kmers_inserted_total": final["kmers_inserted"],
                       "bad_reads": final["bad_reads"], "fingerprint": f"{summary['fingerprint']:016x}"},
