@@ -1196,10 +1196,15 @@ int load_files(lasv_graph *g, const char *path1, const char *path2, int cutoff,
   if (path2 && !prod[1].reader.open(path2, err)) return fail(LASV_ERR_IO, "%s", err.c_str());
   const bool with_qual = prod[0].reader.has_quality() || (path2 && prod[1].reader.has_quality());
   std::vector<std::unique_ptr<PinnedBatch>> batches;
+  uint64_t batch_bytes = LOADER_BATCH_BYTES;
+  if (const char *e = getenv("LASV_B200_LOADER_BATCH_BYTES")) {  // tests: many small batches per file
+    const long long v = atoll(e);
+    if (v >= 1024 && (uint64_t)v <= LOADER_BATCH_BYTES) batch_bytes = (uint64_t)v;
+  }
   for (int f = 0; f < n_files; f++) {
     prod[f].with_qual = with_qual;
     for (int k = 0; k < 2; k++) {
-      batches.emplace_back(new PinnedBatch(LOADER_BATCH_BYTES, LOADER_BATCH_READS));
+      batches.emplace_back(new PinnedBatch(batch_bytes, LOADER_BATCH_READS));
       if (!batches.back()->ok) return fail(LASV_ERR_CUDA, "cannot allocate pinned batch buffers");
       prod[f].slot[k] = batches.back().get();
     }

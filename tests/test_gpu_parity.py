@@ -84,6 +84,28 @@ def test_sequence_file_loaders_match_reference_golden(name, tmp_path):
         util.assert_same_records(ctx["records"], util.case_records(name), name)
 
 
+@pytest.mark.parametrize("name", ["synth_cfg0_k53", "synth_cfg2_k95"])
+@pytest.mark.parametrize("batch_bytes", [4096, 50_000])
+def test_file_loaders_with_many_small_batches(name, batch_bytes, tmp_path, monkeypatch):
+    """The parser threads hand their pinned batches to the GPU in turn: with batches of a few KB every
+    file spans hundreds of them (slot hand-off, the read that did not fit, the last partial batch)."""
+    monkeypatch.setenv("LASV_B200_LOADER_BATCH_BYTES", str(batch_bytes))
+    meta = util.case_meta(name)
+    seq, qual, _ = util.case_streams(name)
+    rl = meta["workload"]["read_len"]
+    s2, q2 = seq.reshape(-1, rl + 1), qual.reshape(-1, rl + 1)
+    O.write_fastq_fixed(tmp_path / "a.fq", s2[0::2].reshape(-1), q2[0::2].reshape(-1), rl)
+    O.write_fastq_fixed(tmp_path / "b.fq", s2[1::2].reshape(-1), q2[1::2].reshape(-1), rl)
+    with DBGraph(meta["k"], meta["L"], meta["W"]) as g:
+        st = g.load_pe_seq_data(tmp_path / "a.fq", tmp_path / "b.fq", util.cutoff_of(meta))
+        assert st["n_reads"] == len(s2) and st["kmers_inserted"] == meta["inserts"]
+        assert st["bad_reads"] == meta["bad_reads"] and st["bases_loaded"] == meta["bases_loaded"]
+        util.assert_same_records(g.records(), util.case_records(name), name)
+    with DBGraph(meta["k"], meta["L"], meta["W"]) as g:      # single-ended: one parser thread
+        st = g.load_se_seq_data(tmp_path / "a.fq", util.cutoff_of(meta))
+        assert st["n_reads"] == len(s2) // 2
+
+
 def test_paired_files_of_unequal_length_are_an_error(tmp_path):
     a = tmp_path / "a.fq"
     a.write_text("@x\nACGT\n+\nIIII\n@y\nACGT\n+\nIIII\n")
