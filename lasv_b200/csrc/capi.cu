@@ -476,7 +476,7 @@ int lasv_graph_load_reads_device(lasv_graph *g, const uint8_t *d_seq, const uint
     uint32_t n_bins = 1;
     if (want_binned(g, n_bytes, &n_bins)) {
       // Partitioned insert: group the batch's k-mers by 16 MB table region, then
-      // insert region by region (profiles/exp_sorted_insert_r1_cfg4.jsonl: 3.3x
+      // insert region by region (profiles/bins_sweep_r1.txt: 2x
       // the insert rate of uniformly random probes on a 100 GB table).
       lasv_graph::BinLeg &l = g->leg[g->pipeline ? (g->turn++ & 1) : 0];
       if (l.in_flight) CUDA_TRY(cudaStreamWaitEvent(st, l.inserted, 0));  // the insert that read this leg

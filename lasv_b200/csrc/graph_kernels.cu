@@ -1,21 +1,29 @@
 // graph_kernels.cu -- hand-written sm_100a kernels of the de Bruijn graph build.
 //
-//   build_kernel<N,MODE>   K1+K2(+K3): stream tile -> classify/pack (128-bit
-//                          coalesced loads, shared-memory bit strings) -> window
-//                          validity -> O(1) forward / reverse-complement k-mer
-//                          extraction -> canonical key + edge byte -> either
-//                          find-or-insert straight into the table (FUSED), or
-//                          (2N+1)-word records (RECORDS), or records binned by
-//                          owner GPU for the all-to-all (ROUTE).
-//   insert_records_kernel  K3 on records (the receive side of the exchange).
+//   build_kernel<N,MODE>   K1+K2: stream tile -> classify/pack (128-bit coalesced
+//                          loads, shared-memory bit strings) -> window validity ->
+//                          O(1) forward / reverse-complement k-mer extraction ->
+//                          canonical key + edge byte -> then, by MODE:
+//                            BIN     one record per k-mer into the stripe of the
+//                                    (owner GPU, 64 MB table region) it will touch
+//                                    -- the production path (partition kernel)
+//                            FUSED   find-or-insert straight into the table (K3
+//                                    in the same pass; small tables)
+//                            RECORDS / ROUTE  (2N+1)-word records, flat or per
+//                                    owner (older variable-length exchange)
+//   insert_bins_kernel     K3: sweeps the stripes region by region with the whole
+//                          grid, find-or-insert + coverage / edge accumulation
+//                          (upsert_batch: lock-step fast path, deferred 32-wide
+//                          slow path).
+//   insert_records_kernel  K3 on (2N+1)-word records.
 //   read_stats_kernel      loader bookkeeping: bad reads, bases loaded, contig
 //                          length histogram (file_reader.c:460-470,579).
 //   finalize / dump / ingest / find / summary kernels: K4 and the .ctx wire
 //                          format (element.c:894-910, file_reader.c:1686-1703).
 //
-// Integer hashing only: no tensor cores.  The table traffic is random 32-byte
-// sectors in HBM; everything else is streaming.  Grids are persistent:
-// (#SMs x resident CTAs) CTAs looping over tiles.
+// Integer hashing only: no tensor cores.  What bounds the kernels, and why they
+// look the way they do, is measured in tools/ubench.  Grids
+// are persistent: (#SMs x resident CTAs) CTAs looping over tiles / chunks.
 #include <cub/device/device_scan.cuh>
 #include <stdlib.h>
 #include <type_traits>
