@@ -475,9 +475,9 @@ int lasv_graph_load_reads_device(lasv_graph *g, const uint8_t *d_seq, const uint
     BuildParams p = build_params(g, d_seq, d_qual, n_bytes, quality_cutoff);
     uint32_t n_bins = 1;
     if (want_binned(g, n_bytes, &n_bins)) {
-      // Partitioned insert: group the batch's k-mers by 16 MB table region, then
-      // insert region by region (profiles/bins_sweep_r1.txt: 2x
-      // the insert rate of uniformly random probes on a 100 GB table).
+      // Partitioned insert: group the batch's k-mers by 64 MB table region, then insert region by
+      // region with the whole grid (profiles/bins_sweep_r1.txt: twice the insert rate of probes spread
+      // over the whole 100 GB table, on top of the 2x lost to the TLB beyond 64 GB).
       lasv_graph::BinLeg &l = g->leg[g->pipeline ? (g->turn++ & 1) : 0];
       if (l.in_flight) CUDA_TRY(cudaStreamWaitEvent(st, l.inserted, 0));  // the insert that read this leg
       if (int e = ensure_bins(g, l, n_bytes, d_offsets ? n_reads : 0, n_bins)) return e;
