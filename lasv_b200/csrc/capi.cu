@@ -15,6 +15,7 @@
 #include <algorithm>
 #include <atomic>
 #include <chrono>
+#include <functional>
 #include <condition_variable>
 #include <memory>
 #include <mutex>
@@ -919,50 +920,74 @@ int lasv_graph_import_table(lasv_graph *g, const void *elements) {
 }
 
 // ------------------------------------------------------------ .ctx records
-static int dump_records_device(lasv_graph *g, uint8_t **d_out, uint64_t *n_out) {
+// .ctx records in table order, streamed through a bounded device buffer: the table is walked in ranges
+// of buckets whose records fit DUMP_CHUNK_BYTES even if every slot is occupied (a 100 GB table holds
+// ~65 GB of records -- they cannot be materialised next to it); each range is counted, scanned, packed
+// by dump_ctx_kernel and handed to `sink` in host memory.
+constexpr uint64_t DUMP_CHUNK_BYTES = 256ull << 20;
+
+using CtxSink = std::function<int(const uint8_t *records, uint64_t n, uint64_t n_before)>;
+static int stream_ctx_records_out(lasv_graph *g, uint64_t *n_out, const CtxSink &sink) {
+  const size_t rec = 8 * (size_t)g->N + 5;
+  uint64_t chunk_bytes = DUMP_CHUNK_BYTES;
+  if (const char *e = getenv("LASV_B200_DUMP_CHUNK_BYTES")) {  // tests: many ranges on small tables
+    const long long v = atoll(e);
+    if (v >= 64 && (uint64_t)v <= DUMP_CHUNK_BYTES) chunk_bytes = (uint64_t)v;
+  }
+  const uint64_t per_range = std::max<uint64_t>(1, chunk_bytes / ((uint64_t)g->W * rec));
+  const uint64_t range = std::min<uint64_t>(g->n_buckets, per_range);
   uint32_t *d_counts = nullptr;
   uint64_t *d_offsets = nullptr;
   void *d_tmp = nullptr;
-  *d_out = nullptr;
-  const size_t tmp_bytes = exclusive_scan_tmp_bytes(g->n_buckets);
+  uint8_t *d_out = nullptr, *h_out = nullptr;
+  const size_t tmp_bytes = exclusive_scan_tmp_bytes(range);
+  const size_t out_bytes = std::max<size_t>(16, range * (size_t)g->W * rec);
+  uint64_t total = 0;
   int rc = [&]() -> int {
-    CUDA_TRY(cudaMalloc(&d_counts, g->n_buckets * 4));
-    CUDA_TRY(cudaMalloc(&d_offsets, g->n_buckets * 8));
+    CUDA_TRY(cudaMalloc(&d_counts, range * 4));
+    CUDA_TRY(cudaMalloc(&d_offsets, range * 8));
     CUDA_TRY(cudaMalloc(&d_tmp, tmp_bytes));
-    launch_bucket_counts(g->N, g->view(), d_counts, g->compute);
-    if (int e = check_launch()) return e;
-    launch_exclusive_scan_u32_to_u64(d_counts, d_offsets, g->n_buckets, d_tmp, tmp_bytes, g->compute);
-    if (int e = check_launch()) return e;
-    uint64_t last_off = 0;
-    uint32_t last_cnt = 0;
-    CUDA_TRY(cudaMemcpyAsync(&last_off, d_offsets + g->n_buckets - 1, 8, cudaMemcpyDeviceToHost, g->compute));
-    CUDA_TRY(cudaMemcpyAsync(&last_cnt, d_counts + g->n_buckets - 1, 4, cudaMemcpyDeviceToHost, g->compute));
-    CUDA_TRY(cudaStreamSynchronize(g->compute));
-    *n_out = last_off + last_cnt;
-    const size_t rec = 8 * (size_t)g->N + 5;
-    CUDA_TRY(cudaMalloc(d_out, std::max<size_t>(16, *n_out * rec)));
-    launch_dump_ctx(g->N, g->view(), d_offsets, *d_out, g->compute);
-    if (int e = check_launch()) return e;
-    CUDA_TRY(cudaStreamSynchronize(g->compute));
+    CUDA_TRY(cudaMalloc(&d_out, out_bytes));
+    CUDA_TRY(cudaMallocHost(&h_out, out_bytes));
+    for (uint64_t b0 = 0; b0 < g->n_buckets; b0 += range) {
+      const uint64_t nb = std::min(range, g->n_buckets - b0);
+      launch_bucket_counts(g->N, g->view(), b0, nb, d_counts, g->compute);
+      if (int e = check_launch()) return e;
+      launch_exclusive_scan_u32_to_u64(d_counts, d_offsets, nb, d_tmp, tmp_bytes, g->compute);
+      if (int e = check_launch()) return e;
+      uint64_t last_off = 0;
+      uint32_t last_cnt = 0;
+      CUDA_TRY(cudaMemcpyAsync(&last_off, d_offsets + nb - 1, 8, cudaMemcpyDeviceToHost, g->compute));
+      CUDA_TRY(cudaMemcpyAsync(&last_cnt, d_counts + nb - 1, 4, cudaMemcpyDeviceToHost, g->compute));
+      CUDA_TRY(cudaStreamSynchronize(g->compute));
+      const uint64_t n = last_off + last_cnt;
+      if (!n) continue;
+      launch_dump_ctx(g->N, g->view(), b0, nb, d_offsets, d_out, g->compute);
+      if (int e = check_launch()) return e;
+      CUDA_TRY(cudaMemcpyAsync(h_out, d_out, n * rec, cudaMemcpyDeviceToHost, g->compute));
+      CUDA_TRY(cudaStreamSynchronize(g->compute));
+      if (int e = sink(h_out, n, total)) return e;
+      total += n;
+    }
     return LASV_OK;
   }();
-  cudaFree(d_counts); cudaFree(d_offsets); cudaFree(d_tmp);
-  if (rc != LASV_OK && *d_out) { cudaFree(*d_out); *d_out = nullptr; }
+  cudaFree(d_counts); cudaFree(d_offsets); cudaFree(d_tmp); cudaFree(d_out);
+  if (h_out) cudaFreeHost(h_out);
+  if (n_out) *n_out = total;
   return rc;
 }
 
 long long lasv_graph_dump_ctx_records(lasv_graph *g, uint8_t *out, uint64_t capacity_records) {
   if (int e = use(g)) return e;
   CUDA_TRY(cudaDeviceSynchronize());
-  uint8_t *d_out = nullptr;
+  const size_t rec = 8 * (size_t)g->N + 5;
   uint64_t n = 0;
-  if (int e = dump_records_device(g, &d_out, &n)) return e;
-  int rc = LASV_OK;
-  if (n > capacity_records) rc = fail(LASV_ERR_CAPACITY, "need room for %llu records, have %llu",
-                                      (unsigned long long)n, (unsigned long long)capacity_records);
-  else if (n && cudaMemcpy(out, d_out, n * (8 * (size_t)g->N + 5), cudaMemcpyDeviceToHost) != cudaSuccess)
-    rc = fail(LASV_ERR_CUDA, "copy of .ctx records to host failed");
-  cudaFree(d_out);
+  const int rc = stream_ctx_records_out(g, &n, [&](const uint8_t *h, uint64_t m, uint64_t done) -> int {
+    if (done + m > capacity_records)
+      return fail(LASV_ERR_CAPACITY, "need room for more than %llu records", (unsigned long long)capacity_records);
+    memcpy(out + done * rec, h, m * rec);
+    return LASV_OK;
+  });
   return rc == LASV_OK ? (long long)n : rc;
 }
 
@@ -997,29 +1022,19 @@ int lasv_ctx_header(int kmer_size, uint32_t mean_read_len, uint64_t total_seq, u
 int lasv_graph_write_ctx(lasv_graph *g, const char *path, uint32_t mean_read_len, uint64_t total_seq) {
   if (int e = use(g)) return e;
   CUDA_TRY(cudaDeviceSynchronize());
-  uint8_t *d_out = nullptr;
-  uint64_t n = 0;
-  if (int e = dump_records_device(g, &d_out, &n)) return e;
   FILE *fp = fopen(path, "wb");
-  if (!fp) {
-    cudaFree(d_out);
-    return fail(LASV_ERR_IO, "cannot open %s for writing: %s", path, strerror(errno));
-  }
+  if (!fp) return fail(LASV_ERR_IO, "cannot open %s for writing: %s", path, strerror(errno));
   uint8_t hdr[128];
   const int hl = lasv_ctx_header(g->k, mean_read_len, total_seq, hdr);
   int rc = LASV_OK;
   if (fwrite(hdr, 1, (size_t)hl, fp) != (size_t)hl) rc = fail(LASV_ERR_IO, "short write to %s", path);
   const size_t rec = 8 * (size_t)g->N + 5;
-  const uint64_t per = (64ull << 20) / rec;
-  std::vector<uint8_t> host(per * rec);
-  for (uint64_t i = 0; i < n && rc == LASV_OK; i += per) {
-    const uint64_t m = std::min(per, n - i);
-    if (cudaMemcpy(host.data(), d_out + i * rec, m * rec, cudaMemcpyDeviceToHost) != cudaSuccess)
-      rc = fail(LASV_ERR_CUDA, "copy of .ctx records to host failed");
-    else if (fwrite(host.data(), rec, m, fp) != m) rc = fail(LASV_ERR_IO, "short write to %s", path);
-  }
-  fclose(fp);
-  cudaFree(d_out);
+  if (rc == LASV_OK)
+    rc = stream_ctx_records_out(g, nullptr, [&](const uint8_t *h, uint64_t m, uint64_t) -> int {
+      if (fwrite(h, rec, m, fp) != m) return fail(LASV_ERR_IO, "short write to %s", path);
+      return LASV_OK;
+    });
+  if (fclose(fp) != 0 && rc == LASV_OK) rc = fail(LASV_ERR_IO, "cannot close %s: %s", path, strerror(errno));
   return rc;
 }
 

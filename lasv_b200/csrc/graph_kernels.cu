@@ -754,14 +754,15 @@ __global__ void __launch_bounds__(THREADS) table_summary_kernel(const TableView 
 
 // occupied slots per bucket: one warp per bucket
 template <int N>
-__global__ void __launch_bounds__(THREADS) bucket_counts_kernel(const TableView t, uint32_t *counts) {
-  const uint64_t n_buckets = (uint64_t)t.bucket_mask + 1;
+__global__ void __launch_bounds__(THREADS) bucket_counts_kernel(const TableView t, const uint64_t first,
+                                                               const uint64_t n_buckets, uint32_t *counts) {
+  // buckets [first, first + n_buckets); counts[] is relative to `first`
   const uint64_t warp0 = ((uint64_t)blockIdx.x * THREADS + threadIdx.x) >> 5;
   const uint64_t nwarps = ((uint64_t)gridDim.x * THREADS) >> 5;
   for (uint64_t b = warp0; b < n_buckets; b += nwarps) {
     uint32_t c = 0;
     for (uint32_t s = lane_id(); s < t.W; s += 32) {
-      const uint64_t m = slot_ptr<N>(t, (uint32_t)b, s)[N];
+      const uint64_t m = slot_ptr<N>(t, (uint32_t)(first + b), s)[N];
       c += (meta_status(m) != ST_EMPTY);
     }
     c = __reduce_add_sync(FULL, c);
@@ -819,16 +820,18 @@ __global__ void __launch_bounds__(THREADS) finalize_kernel(const TableView t, in
 
 // .ctx records (element.c:894-910) in table order: kmer[N] | uint32 covg | uint8 edges
 template <int N>
-__global__ void __launch_bounds__(THREADS) dump_ctx_kernel(const TableView t,
+__global__ void __launch_bounds__(THREADS) dump_ctx_kernel(const TableView t, const uint64_t first,
+                                                          const uint64_t n_buckets,
                                                           const uint64_t *__restrict__ bucket_offsets,
                                                           uint8_t *__restrict__ out) {
+  // buckets [first, first + n_buckets); bucket_offsets[] and out are relative to `first`
   constexpr uint32_t REC = 8 * N + 5;
-  const uint64_t n_buckets = (uint64_t)t.bucket_mask + 1;
   const uint64_t warp0 = ((uint64_t)blockIdx.x * THREADS + threadIdx.x) >> 5;
   const uint64_t nwarps = ((uint64_t)gridDim.x * THREADS) >> 5;
   const unsigned lane = lane_id();
-  for (uint64_t b = warp0; b < n_buckets; b += nwarps) {
-    uint64_t o = bucket_offsets[b];
+  for (uint64_t bb = warp0; bb < n_buckets; bb += nwarps) {
+    const uint64_t b = first + bb;
+    uint64_t o = bucket_offsets[bb];
     for (uint32_t s0 = 0; s0 < t.W; s0 += 32) {
       const uint32_t s = s0 + lane;
       uint64_t key[N];
@@ -1103,10 +1106,11 @@ void launch_table_summary(int N, const TableView &t, TableSummary *out, cudaStre
   });
 }
 
-void launch_bucket_counts(int N, const TableView &t, uint32_t *counts, cudaStream_t st) {
+void launch_bucket_counts(int N, const TableView &t, uint64_t first, uint64_t n_buckets, uint32_t *counts,
+                          cudaStream_t st) {
   dispatch_n(N, [&](auto n) {
     constexpr int NN = decltype(n)::value;
-    bucket_counts_kernel<NN><<<resident_grid(bucket_counts_kernel<NN>), THREADS, 0, st>>>(t, counts);
+    bucket_counts_kernel<NN><<<resident_grid(bucket_counts_kernel<NN>), THREADS, 0, st>>>(t, first, n_buckets, counts);
   });
 }
 
@@ -1117,11 +1121,11 @@ void launch_finalize(int N, const TableView &t, int16_t *next_element, cudaStrea
   });
 }
 
-void launch_dump_ctx(int N, const TableView &t, const uint64_t *bucket_offsets, uint8_t *out,
-                     cudaStream_t st) {
+void launch_dump_ctx(int N, const TableView &t, uint64_t first, uint64_t n_buckets, const uint64_t *bucket_offsets,
+                     uint8_t *out, cudaStream_t st) {
   dispatch_n(N, [&](auto n) {
     constexpr int NN = decltype(n)::value;
-    dump_ctx_kernel<NN><<<resident_grid(dump_ctx_kernel<NN>), THREADS, 0, st>>>(t, bucket_offsets, out);
+    dump_ctx_kernel<NN><<<resident_grid(dump_ctx_kernel<NN>), THREADS, 0, st>>>(t, first, n_buckets, bucket_offsets, out);
   });
 }
 

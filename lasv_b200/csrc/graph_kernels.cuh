@@ -147,10 +147,11 @@ void launch_read_stats(const uint8_t *seq, const uint8_t *qual, const uint64_t *
                        uint64_t n_reads, int sep, int k, int cutoff, ReadStats *stats,
                        unsigned long long *hist, uint32_t hist_size, cudaStream_t st);
 void launch_table_summary(int N, const TableView &t, TableSummary *out, cudaStream_t st);
-void launch_bucket_counts(int N, const TableView &t, uint32_t *counts, cudaStream_t st);
+void launch_bucket_counts(int N, const TableView &t, uint64_t first, uint64_t n_buckets, uint32_t *counts,
+                          cudaStream_t st);
 void launch_finalize(int N, const TableView &t, int16_t *next_element, cudaStream_t st);
-void launch_dump_ctx(int N, const TableView &t, const uint64_t *bucket_offsets, uint8_t *out,
-                     cudaStream_t st);
+void launch_dump_ctx(int N, const TableView &t, uint64_t first, uint64_t n_buckets, const uint64_t *bucket_offsets,
+                     uint8_t *out, cudaStream_t st);
 void launch_ingest_ctx(int N, const uint8_t *recs, uint64_t n_recs, const TableView &t,
                        GraphCounters *ctr, cudaStream_t st);
 void launch_ingest_elements(int N, const uint8_t *elements, uint64_t n_slots, const TableView &t,

@@ -533,6 +533,25 @@ def test_ctx_roundtrip_and_reference_consumer(name, tmp_path):
         assert O.canonical_seq_set(res["supernodes"]) == meta["supernodes"]
 
 
+def test_ctx_dump_streams_through_a_bounded_buffer(tmp_path, monkeypatch):
+    """A table larger than the spare device memory is dumped range of buckets by range of buckets
+    (a 100 GB table holds ~65 GB of records): force hundreds of ranges on a small table."""
+    name = "synth_cfg0_k53"
+    meta = util.case_meta(name)
+    seq, qual, offs = util.case_streams(name)
+    gold = util.case_records(name)
+    with DBGraph(meta["k"], meta["L"], meta["W"]) as g:
+        g.load_reads_host(seq, qual, offs, util.cutoff_of(meta))
+        whole = g.records()
+        monkeypatch.setenv("LASV_B200_DUMP_CHUNK_BYTES", str(meta["W"] * 21 * 3))     # three buckets per range
+        parts = g.records()
+        assert np.array_equal(parts, whole)                      # same records, same (table) order
+        util.assert_same_records(parts, gold, name)
+        g.dump_binary(tmp_path / "x.ctx", 7, 11)
+        ctx = O.parse_ctx(tmp_path / "x.ctx")
+        assert np.array_equal(ctx["records"], whole)
+
+
 # ------------------------------------ the reference's own main() on the GPU loader
 @pytest.mark.parametrize("name", ["synth_cfg1_k31", "synth_cfg0_k53", "synth_cfg2_k95"])
 def test_reference_cli_with_gpu_loader(name, tmp_path):
