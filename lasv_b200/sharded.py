@@ -113,10 +113,10 @@ class _StripeBuffers:
     def __init__(self, world, geo, device):
         self.send = torch.empty((world, geo["records_per_owner"], geo["record_bytes"] // 8), dtype=torch.int64,
                                 device=device)
-        self.recv = torch.empty_like(self.send)
+        self.recv = None                     # allocated by the exchange set-up: symmetric memory or plain
         self.send_counts = torch.zeros((world, geo["counters_per_owner"], geo["count_stride_bytes"] // 4),
                                        dtype=torch.int32, device=device)
-        self.recv_counts = torch.zeros_like(self.send_counts)
+        self.recv_counts = None
         self.inserted = None     # event: the insert kernel that read `recv` is done
         self.exchanged = None    # event: `send` may be overwritten, `recv` is complete
 
@@ -162,6 +162,10 @@ class ShardedDBGraph:
                 except Exception as ex:           # no peer access / no symmetric memory: NCCL does the job
                     print(f"[lasv_b200] peer-memory exchange unavailable ({type(ex).__name__}: {ex}); using NCCL",
                           file=sys.stderr)
+            if self.exchange == "nccl":
+                for buf in self.buffers:
+                    buf.recv = torch.empty_like(buf.send)
+                    buf.recv_counts = torch.zeros_like(buf.send_counts)
 
     def _setup_p2p(self, geo):
         """Receive buffers in symmetric memory (every rank maps every rank's allocation): the exchange
