@@ -25,7 +25,14 @@
 //   LOCKED --key words stored, __threadfence, tag byte stored, status ^= LOCKED^NONE-->  NONE
 // The tag byte is written AFTER the key words are visible: whoever reaches a
 // slot through a non-zero tag byte may read its key words at once, without
-// looking at the status.  A slot reached through a zero tag byte is claimed by
+// looking at the status.  (Why that holds: header and slot loads are strong GPU-scope
+// loads served by L2, the point of coherence; the writer's fence makes the key stores
+// reach L2 before the tag store; the reader cannot ISSUE the slot load before the
+// header load has returned -- the slot address is computed from the header -- so the
+// slot load reaches L2 after the tag, hence after the key words.  An acquire load on
+// the header would say the same in memory-model terms but compiles to CCTL.IVALL,
+// which throws away the L1 lines the record loads live in.)
+// A slot reached through a zero tag byte is claimed by
 // CAS; a failed CAS means somebody else got there first (tag byte not visible
 // yet) and the slot is examined through its meta word: 16-bit tag differs ->
 // other key; LOCKED -> wait for publication; then compare the key words.
