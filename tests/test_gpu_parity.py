@@ -362,6 +362,50 @@ def test_pipelined_inserts_and_async_statistics(monkeypatch):
         assert np.array_equal(O.sort_records(g.records()), want)
 
 
+@pytest.mark.parametrize("mode", ["direct", "binned"])
+def test_random_inputs_match_oracle(mode, monkeypatch):
+    """Seeded random reads (bad characters, low qualities, low-complexity, empty and short reads) and
+    random table geometries -- bucket sizes that are not a multiple of the slots per line, tables that
+    overflow -- through the real kernels, fused and partitioned, against the oracle."""
+    monkeypatch.setenv("LASV_B200_INSERT", mode)
+    rng = np.random.default_rng(20261019)
+    alphabet = np.array(list("ACGT" * 12 + "acgt" * 2 + "NnX-"))
+    quals = np.array([chr(q) for q in (73, 73, 73, 73, 73, 60, 40, 39, 38, 37, 35, 34, 33)])
+    for case in range(24):
+        k = int(rng.choice([3, 5, 21, 31, 33, 53, 63, 65, 95]))
+        L, W = int(rng.integers(2, 8)), int(rng.choice([1, 2, 3, 5, 7, 8, 13, 40, 100]))
+        q_thresh = int(rng.choice([0, 5, 20]))
+        monkeypatch.setenv("LASV_B200_BINS", str(1 << int(rng.integers(0, L + 1))))
+        reads, qs = [], []
+        for _ in range(int(rng.integers(0, 400))):
+            n = int(rng.integers(0, 300))
+            if rng.integers(0, 10) == 0:
+                unit = str(rng.choice(["A", "AC", "ACG", "T", "GC"]))
+                reads.append((unit * (n // len(unit) + 1))[:n])
+            else:
+                reads.append("".join(rng.choice(alphabet, n)))
+            qs.append("".join(rng.choice(quals, n)))
+        seq, qual, offs = O.reads_to_streams(reads, qs)
+        og, ok = util.oracle_build(k, L + 6, W, seq, qual, offs, q_thresh + 33)       # roomy: the true node set
+        assert ok
+        distinct, capacity = og.unique_kmers, (1 << L) * W
+        if 0.6 * capacity < distinct <= capacity:
+            continue          # whether a 16-bucket rehash chain fills up first depends on the insertion order
+        with DBGraph(k, L, W) as g:
+            if distinct > capacity:
+                with pytest.raises(_capi.TableFullError):
+                    g.load_reads_host(seq, qual, offs, q_thresh + 33)
+                continue
+            st = g.load_reads_host(seq, qual, offs, q_thresh + 33)
+            tag = f"case {case}: k={k} L={L} W={W} mode={mode}"
+            assert st["kmers_inserted"] == og.stats.kmers_inserted and st["bad_reads"] == og.stats.bad_reads, tag
+            assert st["bases_loaded"] == og.stats.bases_loaded, tag
+            util.assert_same_records(g.records(), og.records(), tag)
+            table, nxt = g.export_table()
+            occ = (table["status"] != 0).reshape(1 << L, W)
+            assert (occ == (np.arange(W)[None, :] < nxt[:, None])).all(), tag
+
+
 def test_hot_kmers_and_duplicate_reads_are_counted_exactly():
     """Thousands of copies of the same reads (and homopolymers): every occurrence is
     an atomic on the same few slots; warp aggregation and L2 reductions must not

@@ -234,3 +234,52 @@ def test_emulated_ragged_and_tiny_inputs(emul):
     rc, table, ctr = emul_build(emul, {"k": 31, "L": 4, "W": 4, "q_thresh": 0}, np.zeros(0, np.uint8),
                                 np.zeros(0, np.uint8))
     assert rc == 0 and ctr[1] == 0
+
+
+# --------------------------------------------------------------- property test
+from hypothesis import given, settings, strategies as st, HealthCheck  # noqa: E402
+
+_BASES = st.sampled_from(list("ACGT") * 12 + list("acgt") * 2 + ["N", "n", "X", "-"])
+_QUALS = st.sampled_from([chr(q) for q in (73, 73, 73, 73, 73, 60, 40, 39, 38, 37, 35, 34, 33)])
+
+
+@st.composite
+def _read(draw):
+    n = draw(st.integers(min_value=0, max_value=260))
+    if draw(st.integers(0, 9)) == 0:                       # a low-complexity read now and then
+        unit = draw(st.sampled_from(["A", "AC", "ACG", "T", "GC"]))
+        seq = (unit * (n // len(unit) + 1))[:n]
+    else:
+        seq = "".join(draw(st.lists(_BASES, min_size=n, max_size=n)))
+    qual = "".join(draw(st.lists(_QUALS, min_size=n, max_size=n)))
+    return seq, qual
+
+
+@settings(max_examples=int(__import__("os").environ.get("LASV_FUZZ_EXAMPLES", "40")), deadline=None, suppress_health_check=[HealthCheck.too_slow, HealthCheck.function_scoped_fixture])
+@given(reads=st.lists(_read(), min_size=0, max_size=40),
+       k=st.sampled_from([3, 5, 21, 31, 33, 53, 63, 65, 95]),
+       L=st.integers(min_value=2, max_value=6),
+       W=st.sampled_from([1, 2, 3, 5, 7, 8, 13, 40, 100]),
+       q_thresh=st.sampled_from([0, 5, 20]),
+       T=st.sampled_from([384, 896, 896 | (7 << 16)]))
+def test_emulated_build_equals_oracle_on_random_inputs(emul, reads, k, L, W, q_thresh, T):
+    """Random reads (bad characters, low qualities, homopolymers, empty and short reads), random table
+    geometry incl. bucket sizes that are not a multiple of the slots per line and tables that overflow:
+    the kernels' arithmetic + the line-layout table == the oracle, or both report a full table."""
+    seq, qual, offs = O.reads_to_streams([r[0] for r in reads], [r[1] for r in reads])
+    g, ok = util.oracle_build(k, L, W, seq, qual, offs, q_thresh + 33)
+    meta = {"k": k, "L": L, "W": W, "q_thresh": q_thresh}
+    rc, table, ctr = emul_build(emul, meta, seq, qual, T)
+    if not ok:
+        assert rc == -3                                       # hash table full: fatal on both sides
+        return
+    assert rc == 0
+    util.assert_same_records(table.records(), g.records(), f"k={k} L={L} W={W}")
+    assert int(ctr[1]) == g.stats.kmers_inserted and int(ctr[0]) == g.unique_kmers
+    nxt = table.finalize()
+    fin = table.elements().reshape(1 << L, W)
+    occ = fin["status"] != 0
+    assert (occ == (np.arange(W)[None, :] < nxt[:, None])).all()
+    if len(g.records()):
+        found, covg, edges = table.find(np.ascontiguousarray(g.records()["kmer"]))
+        assert found.all() and np.array_equal(covg, g.records()["covg"]) and np.array_equal(edges, g.records()["edges"])
