@@ -58,14 +58,14 @@ const char *TABLE_FULL_MSG =
     "errors?), or threshold more harshly on quality score, and try again. Aborting mission.";
 
 constexpr uint32_t HIST_BINS = 1u << 16;       // device contig-length histogram (last bin = longer)
-constexpr uint64_t CHUNK_BYTES = 64ull << 20;  // host->device pipeline granularity
+constexpr uint64_t CHUNK_BYTES = 64ull << 20;  // host->device pipeline granularity (staging buffers are this big)
 constexpr uint64_t CHUNK_READS = 4ull << 20;
 
 struct Staging {  // one leg of the double-buffered host->device pipeline
   uint8_t *d_seq = nullptr, *d_qual = nullptr;
   uint64_t *d_offsets = nullptr;
   cudaEvent_t copied = nullptr, consumed = nullptr;
-  std::vector<uint64_t> h_offsets;
+  uint64_t *h_offsets = nullptr;  // pinned: a pageable source would make the "async" copy block the host
 };
 
 }  // namespace
@@ -82,7 +82,7 @@ struct lasv_graph {
   unsigned long long *d_overflow = nullptr;
   bool finalized = false;
   cudaStream_t compute = nullptr, copy = nullptr;
-  Staging stage[2];
+  Staging stage[3];  // three legs: the copy of chunk i+1 may start while chunk i-1 is still being consumed
   bool staging_ready = false;
   // scratch of the partitioned insert (region bins), grown on demand.  Pipelined mode uses both legs:
   // batch i+1 is binned on the caller's stream while batch i is inserted on `ins`.
@@ -125,6 +125,7 @@ int ensure_staging(lasv_graph *g) {
     CUDA_TRY(cudaMalloc(&s.d_seq, CHUNK_BYTES + 256));
     CUDA_TRY(cudaMalloc(&s.d_qual, CHUNK_BYTES + 256));
     CUDA_TRY(cudaMalloc(&s.d_offsets, (CHUNK_READS + 1) * sizeof(uint64_t)));
+    CUDA_TRY(cudaMallocHost(&s.h_offsets, (CHUNK_READS + 1) * sizeof(uint64_t)));
     CUDA_TRY(cudaEventCreateWithFlags(&s.copied, cudaEventDisableTiming));
     CUDA_TRY(cudaEventCreateWithFlags(&s.consumed, cudaEventDisableTiming));
   }
@@ -376,6 +377,7 @@ void lasv_graph_free(lasv_graph **gp) {
     cudaFree(s.d_seq);
     cudaFree(s.d_qual);
     cudaFree(s.d_offsets);
+    if (s.h_offsets) cudaFreeHost(s.h_offsets);
     if (s.copied) cudaEventDestroy(s.copied);
     if (s.consumed) cudaEventDestroy(s.consumed);
   }
@@ -569,7 +571,12 @@ int lasv_graph_load_reads_host(lasv_graph *g, const uint8_t *seq, const uint8_t 
     // largest r1 with offsets[r1]-base <= limit and r1-r0 <= CHUNK_READS.  The first chunks are short so
     // that the kernels start early (nothing overlaps the first copy): 1/8, 1/4, 1/2, then whole chunks.
     {
-      const uint64_t limit = n_chunk < 3 ? (CHUNK_BYTES >> (3 - n_chunk)) : CHUNK_BYTES;
+      uint64_t chunk = CHUNK_BYTES;
+      if (const char *e = getenv("LASV_B200_CHUNK_MB")) {  // experiments: 1..64
+        const long v = atol(e);
+        if (v >= 1 && (uint64_t)v <= (CHUNK_BYTES >> 20)) chunk = (uint64_t)v << 20;
+      }
+      const uint64_t limit = n_chunk < 3 ? (chunk >> (3 - n_chunk)) : chunk;
       uint64_t lo = r0 + 1, hi = std::min(n_reads, r0 + CHUNK_READS);
       if (offsets[lo] - base > CHUNK_BYTES)
         return fail(LASV_ERR_ARG, "read %llu is longer than the %llu-byte pipeline chunk",
@@ -585,11 +592,10 @@ int lasv_graph_load_reads_host(lasv_graph *g, const uint8_t *seq, const uint8_t 
     const uint64_t bytes = offsets[r1] - base, nr = r1 - r0;
     Staging &s = g->stage[leg];
     CUDA_TRY(cudaEventSynchronize(s.consumed));  // the kernels that read this leg are done
-    s.h_offsets.resize(nr + 1);
     for (uint64_t i = 0; i <= nr; i++) s.h_offsets[i] = offsets[r0 + i] - base;
     CUDA_TRY(cudaMemcpyAsync(s.d_seq, seq + base, bytes, cudaMemcpyHostToDevice, g->copy));
     if (qual) CUDA_TRY(cudaMemcpyAsync(s.d_qual, qual + base, bytes, cudaMemcpyHostToDevice, g->copy));
-    CUDA_TRY(cudaMemcpyAsync(s.d_offsets, s.h_offsets.data(), (nr + 1) * sizeof(uint64_t),
+    CUDA_TRY(cudaMemcpyAsync(s.d_offsets, s.h_offsets, (nr + 1) * sizeof(uint64_t),
                              cudaMemcpyHostToDevice, g->copy));
     CUDA_TRY(cudaEventRecord(s.copied, g->copy));
     CUDA_TRY(cudaStreamWaitEvent(g->compute, s.copied, 0));
@@ -599,7 +605,7 @@ int lasv_graph_load_reads_host(lasv_graph *g, const uint8_t *seq, const uint8_t 
     CUDA_TRY(cudaEventRecord(s.consumed, g->compute));
     // h_offsets of this leg must stay alive until its copy completed: the next
     // use of the leg waits on `consumed`, which is ordered after `copied`.
-    leg ^= 1;
+    leg = (leg + 1) % 3;
     r0 = r1;
   }
   if (int e = join_inserts(g, g->compute)) return e;  // pipelined inserts of the last chunks

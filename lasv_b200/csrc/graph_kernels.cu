@@ -561,28 +561,38 @@ __global__ void __launch_bounds__(THREADS, 4) insert_bins_kernel(const BinView b
   uint32_t first = 0;  // (chunks of all earlier stripes) mod n_warps, warp-uniform
   for (uint32_t b0 = 0; b0 < n_sweep; b0 += 32) {
     __syncwarp();
+    // 32 stripes at a time, one per lane: chunk counts, their running sum, and whether THIS warp owns a
+    // chunk of the lane's stripe -- the warp then visits only the stripes where it has work (a sweep
+    // that looks at every stripe costs 0.2 ms per launch, which small batches cannot amortise)
     const uint32_t cnt_l = b0 + lane < n_sweep ? count_of(b0 + lane) : 0u;
-    const uint32_t n_here = min(32u, n_sweep - b0);
-    for (uint32_t tb = 0; tb < n_here; tb++) {
-      const uint32_t cnt = __shfl_sync(FULL, cnt_l, (int)tb);
+    const uint32_t chunks_l = (cnt_l + 31u) >> 5;
+    uint32_t incl = chunks_l;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t y = __shfl_up_sync(FULL, incl, o);
+      if ((int)lane >= o) incl += y;
+    }
+    const uint32_t first_l = (first + (incl - chunks_l)) % n_warps;         // first chunk index base of my stripe
+    const uint32_t j0_l = warp >= first_l ? warp - first_l : warp + n_warps - first_l;
+    unsigned todo = __ballot_sync(FULL, j0_l < chunks_l);
+    while (todo) {
+      const int tb = __ffs(todo) - 1;
+      todo &= todo - 1;
+      const uint32_t cnt = __shfl_sync(FULL, cnt_l, tb);
       const uint32_t n_chunks = (cnt + 31u) >> 5;
-      uint32_t j = warp >= first ? warp - first : warp + n_warps - first;  // first chunk of this bin that is ours
-      for (; j < n_chunks; j += n_warps) {
+      for (uint32_t j = __shfl_sync(FULL, j0_l, tb); j < n_chunks; j += n_warps) {
         const uint32_t i = j * 32u + lane;
 #pragma unroll
         for (int u = 0; u < U; u++) {
           if (u == n_have) {
             s0.live[u] = i < cnt;
-            s0.at[u] = record_of(b0 + tb, i);
+            s0.at[u] = record_of(b0 + (uint32_t)tb, i);
           }
         }
         if (++n_have == U) advance();
       }
-      uint32_t adv = n_chunks;
-      while (adv >= n_warps) adv -= n_warps;
-      first += adv;
-      if (first >= n_warps) first -= n_warps;
     }
+    first = (first + __shfl_sync(FULL, incl, 31)) % n_warps;
   }
   if (n_have) advance();
   dq.flush(t, ctr, my_new);
