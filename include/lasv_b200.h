@@ -316,6 +316,15 @@ int lasv_random_access_probe_mode(void *d_buf, uint64_t n_sectors, uint64_t n_op
 /* First-choice bucket (hash_value.c:767-773, rehash 0) of each record. */
 int lasv_graph_record_buckets_device(lasv_graph *g, const uint32_t *d_records, uint64_t n_records,
                                      uint32_t *d_buckets, void *cuda_stream);
+/* The file loaders' parser on its own (host only, no GPU): reads per file, bases and
+ * an order-independent checksum of every (sequence, quality) pair, parsed with
+ * `threads` parser threads per file exactly as the loaders do (large uncompressed
+ * FASTQ files are cut at record boundaries and parsed slice by slice; anything else
+ * gets one sequential parser).  out4 = {reads of file 1, reads of file 2, bases,
+ * checksum}.  Used by the tests to check the parallel parse against the sequential. */
+int lasv_seqfile_parse_check(const char *path1, const char *path2, int threads, uint64_t batch_bytes,
+                             uint64_t *out4, int *producers_used);
+
 /* Host-only: parse a whole sequence file with the loader's reader (FASTQ /
  * FASTA / plain, optionally gzipped; grammar of libs/seq_file) into the stream
  * layout of lasv_graph_load_reads_host.  Returns the number of reads, or a

@@ -70,7 +70,7 @@ EXPORTS = [
     "lasv_graph_record_buckets_device", "lasv_graph_bin_geometry", "lasv_graph_bin_reads_device",
     "lasv_graph_insert_bins_device", "lasv_graph_set_pipeline", "lasv_graph_flush",
     "lasv_graph_enable_kernel_timing", "lasv_graph_kernel_times", "lasv_graph_stats_async",
-    "lasv_ref_hash_table_load_ctx_records",
+    "lasv_ref_hash_table_load_ctx_records", "lasv_seqfile_parse_check",
 ]
 
 _lib = None
@@ -155,6 +155,7 @@ def lib() -> C.CDLL:
     L.lasv_graph_record_buckets_device.argtypes = [vp, vp, u64, vp, vp]
     L.lasv_seqfile_to_streams.restype = C.c_longlong
     L.lasv_seqfile_to_streams.argtypes = [C.c_char_p, vp, vp, u64, vp, u64, C.POINTER(i32)]
+    L.lasv_seqfile_parse_check.argtypes = [C.c_char_p, C.c_char_p, i32, u64, vp, C.POINTER(i32)]
     L.lasv_ref_hash_table_load_ctx_records.restype = C.c_longlong
     L.lasv_ref_hash_table_load_ctx_records.argtypes = [C.POINTER(RefHashTable), C.c_char_p, C.c_long]
     _lib = L

@@ -4,6 +4,10 @@
 // is no CPU implementation of any of it here.
 #include <cuda_runtime.h>
 #include <errno.h>
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 #include <libgen.h>
 #include <limits.h>
 #include <math.h>
@@ -70,7 +74,26 @@ struct Staging {  // one leg of the double-buffered host->device pipeline
 
 }  // namespace
 
+// Pinned host buffers for one batch of parsed reads (file loaders).  Kept by the graph between loader
+// calls: pinning memory costs more than parsing a few hundred MB of FASTQ.
+struct PinnedBatch : lasv::HostBatch {
+  bool ok = false;
+  PinnedBatch(uint64_t bytes, uint64_t reads) {
+    cap_bytes = bytes;
+    cap_reads = reads;
+    ok = cudaMallocHost(&seq, bytes) == cudaSuccess && cudaMallocHost(&qual, bytes) == cudaSuccess &&
+         cudaMallocHost(&offsets, (reads + 1) * sizeof(uint64_t)) == cudaSuccess;
+    if (ok) reset();
+  }
+  ~PinnedBatch() {
+    if (seq) cudaFreeHost(seq);
+    if (qual) cudaFreeHost(qual);
+    if (offsets) cudaFreeHost(offsets);
+  }
+};
+
 struct lasv_graph {
+  std::vector<std::unique_ptr<PinnedBatch>> host_pool;  // loader batches, all of one size
   int k = 0, N = 0, L = 0, W = 0, max_rehash = 15, device = 0;
   uint64_t n_buckets = 0, n_slots = 0;
   size_t slot_bytes = 0;
@@ -1127,23 +1150,7 @@ int lasv_graph_load_ctx_file(lasv_graph *g, const char *path, uint32_t *mean_rea
 // ---------------------------------------------------------- sequence files
 namespace {
 
-struct PinnedBatch : HostBatch {
-  bool ok = false;
-  PinnedBatch(uint64_t bytes, uint64_t reads) {
-    cap_bytes = bytes;
-    cap_reads = reads;
-    ok = cudaMallocHost(&seq, bytes) == cudaSuccess && cudaMallocHost(&qual, bytes) == cudaSuccess &&
-         cudaMallocHost(&offsets, (reads + 1) * sizeof(uint64_t)) == cudaSuccess;
-    if (ok) reset();
-  }
-  ~PinnedBatch() {
-    if (seq) cudaFreeHost(seq);
-    if (qual) cudaFreeHost(qual);
-    if (offsets) cudaFreeHost(offsets);
-  }
-};
-
-constexpr uint64_t LOADER_BATCH_BYTES = 128ull << 20;  // x 2 slots x (1 or 2 files), pinned
+constexpr uint64_t LOADER_BATCH_BYTES = 32ull << 20;  // x 2 slots x parser threads, pinned, kept by the graph
 constexpr uint64_t LOADER_BATCH_READS = 4ull << 20;
 
 int flush_batch(lasv_graph *g, HostBatch &b, bool with_qual, int cutoff) {
@@ -1162,7 +1169,7 @@ struct FileProducer {
   SeqReader reader;
   std::string err;
   bool with_qual = false;
-  PinnedBatch *slot[2] = {nullptr, nullptr};
+  HostBatch *slot[2] = {nullptr, nullptr};
   int full[2] = {0, 0};  // guarded by m
   bool done = false;     // guarded by m: no further batches will be produced
   bool too_long = false;
@@ -1206,68 +1213,232 @@ struct FileProducer {
   }
 };
 
+// An uncompressed FASTQ file mapped read-only, for the parser threads that share it.
+struct MappedFile {
+  int fd = -1;
+  const unsigned char *data = nullptr;
+  size_t size = 0;
+  bool map(const char *path) {
+    fd = ::open(path, O_RDONLY);
+    if (fd < 0) return false;
+    struct stat st;
+    if (fstat(fd, &st) != 0 || st.st_size <= 0) return false;
+    void *p = mmap(nullptr, (size_t)st.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+    if (p == MAP_FAILED) return false;
+    data = (const unsigned char *)p;
+    size = (size_t)st.st_size;
+    madvise(p, size, MADV_SEQUENTIAL);
+    return true;
+  }
+  ~MappedFile() {
+    if (data) munmap((void *)data, size);
+    if (fd >= 0) ::close(fd);
+  }
+};
+
+// Start of the first FASTQ record at or after the line that follows position `from` (from == 0: the file
+// start), recognised by the shape of the record that begins there: '@' line, sequence line, '+' line,
+// quality line of the sequence's length, and then end of data or another '@'.  A quality line may start
+// with '@' too, but then the line after the next one is a sequence, not a '+' line.  Multi-line records
+// never match: the caller falls back to one sequential parser.  SIZE_MAX if nothing matches nearby.
+size_t find_fastq_record(const unsigned char *d, size_t n, size_t from) {
+  auto line_end = [&](size_t p) -> size_t {  // index of the '\n' ending the line at p, or n
+    const void *nl = p < n ? memchr(d + p, '\n', n - p) : nullptr;
+    return nl ? (size_t)((const unsigned char *)nl - d) : n;
+  };
+  auto content = [&](size_t b, size_t e) -> size_t {  // line length without a trailing '\r'
+    return (e > b && d[e - 1] == '\r') ? e - b - 1 : e - b;
+  };
+  size_t p = from;
+  if (p != 0) {
+    p = line_end(p);
+    if (p >= n) return SIZE_MAX;
+    p++;
+  }
+  for (int tries = 0; tries < 64 && p < n; tries++) {
+    const size_t e1 = line_end(p);
+    if (d[p] == '@' && e1 < n) {
+      const size_t e2 = line_end(e1 + 1);
+      if (e2 < n && e2 + 1 < n && d[e2 + 1] == '+') {
+        const size_t e3 = line_end(e2 + 1);
+        if (e3 < n) {
+          const size_t e4 = line_end(e3 + 1);
+          if (content(e3 + 1, e4) == content(e1 + 1, e2) && content(e1 + 1, e2) > 0 &&
+              (e4 + 1 >= n || d[e4 + 1] == '@'))
+            return p;
+        }
+      }
+    }
+    if (e1 >= n) return SIZE_MAX;
+    p = e1 + 1;
+  }
+  return SIZE_MAX;
+}
+
+// Parser threads of one or two sequence files: one per file, or -- for a large uncompressed FASTQ file --
+// several, each on its own slice of the mapped file (the text parse is the slow end).
+struct ParseJob {
+  std::vector<std::unique_ptr<FileProducer>> prod;
+  std::vector<int> file_of;  // producer -> file index
+  MappedFile maps[2];
+  bool with_qual = false;
+  std::string err;
+
+  // `threads` per file (>= 1); `alloc` hands out the two batches of every producer
+  bool open(const char *path1, const char *path2, int threads, size_t min_slice_bytes,
+            const std::function<HostBatch *()> &alloc) {
+    const char *paths[2] = {path1, path2};
+    const int n_files = path2 ? 2 : 1;
+    std::vector<std::unique_ptr<FileProducer>> heads;
+    for (int f = 0; f < n_files; f++) {
+      heads.emplace_back(new FileProducer());
+      if (!heads.back()->reader.open(paths[f], err)) return false;
+    }
+    with_qual = heads[0]->reader.has_quality() || (path2 && heads[1]->reader.has_quality());
+    for (int f = 0; f < n_files; f++) {
+      std::vector<size_t> cuts;
+      SeqReader &r = heads[f]->reader;
+      if (threads > 1 && r.type() == SeqReader::FASTQ && r.is_plain_file() && maps[f].map(paths[f]) &&
+          maps[f].size >= (size_t)threads * min_slice_bytes) {
+        const MappedFile &m = maps[f];
+        cuts.push_back(find_fastq_record(m.data, m.size, 0));
+        for (int w = 1; w < threads && cuts.back() != SIZE_MAX; w++) {
+          const size_t c = find_fastq_record(m.data, m.size, m.size / (size_t)threads * (size_t)w);
+          if (c == SIZE_MAX || c <= cuts.back()) { cuts.assign(1, SIZE_MAX); break; }
+          cuts.push_back(c);
+        }
+        if (cuts.back() == SIZE_MAX || cuts[0] != 0) cuts.clear();  // not the 4-line shape: sequential
+      }
+      if (cuts.size() > 1) {
+        cuts.push_back(maps[f].size);
+        for (size_t w = 0; w + 1 < cuts.size(); w++) {
+          prod.emplace_back(new FileProducer());
+          prod.back()->reader.open_memory(maps[f].data + cuts[w], cuts[w + 1] - cuts[w], paths[f]);
+          file_of.push_back(f);
+        }
+      } else {
+        prod.emplace_back(std::move(heads[f]));
+        file_of.push_back(f);
+      }
+    }
+    for (auto &p : prod) {
+      p->with_qual = with_qual;
+      for (int k = 0; k < 2; k++) {
+        p->slot[k] = alloc();
+        if (!p->slot[k]) { err = "cannot allocate batch buffers"; return false; }
+      }
+    }
+    return true;
+  }
+
+  // runs the producers; `consume(batch)` is called from this thread for every full batch
+  void run(const std::function<void(HostBatch &)> &consume) {
+    for (auto &p : prod) {
+      FileProducer *fp = p.get();
+      fp->th = std::thread([fp] { fp->run(); });
+    }
+    const size_t n = prod.size();
+    std::vector<int> next_slot(n, 0);
+    std::vector<char> finished(n, 0);
+    size_t n_finished = 0;
+    while (n_finished < n) {
+      bool progressed = false;
+      for (size_t i = 0; i < n; i++) {
+        if (finished[i]) continue;
+        FileProducer &p = *prod[i];
+        const int k = next_slot[i];
+        bool ready = false;
+        {
+          std::unique_lock<std::mutex> lk(p.m);
+          // never sleep long on one producer while another may have a batch ready
+          if (n - n_finished == 1) p.cv.wait(lk, [&] { return p.full[k] || p.done; });
+          else p.cv.wait_for(lk, std::chrono::microseconds(200), [&] { return p.full[k] || p.done; });
+          ready = p.full[k] != 0;
+          if (!ready && p.done) {
+            finished[i] = 1;
+            n_finished++;
+          }
+        }
+        if (!ready) continue;
+        consume(*p.slot[k]);
+        {
+          std::lock_guard<std::mutex> lk(p.m);
+          p.full[k] = 0;
+        }
+        p.cv.notify_all();
+        next_slot[i] ^= 1;
+        progressed = true;
+      }
+      (void)progressed;
+    }
+    for (auto &p : prod) p->th.join();
+  }
+
+  uint64_t reads_of_file(int f) const {
+    uint64_t n = 0;
+    for (size_t i = 0; i < prod.size(); i++)
+      if (file_of[i] == f) n += prod[i]->reads;
+    return n;
+  }
+};
+
+// Parser threads per file and the smallest slice worth a thread of its own (every thread brings two pinned
+// batches whose allocation costs more than parsing a small file).  LASV_B200_PARSE_THREADS overrides both.
+int parse_threads_per_file(int n_files, size_t *min_slice_bytes) {
+  *min_slice_bytes = 32u << 20;
+  if (const char *e = getenv("LASV_B200_PARSE_THREADS")) {
+    const int v = atoi(e);
+    if (v >= 1 && v <= 64) {
+      *min_slice_bytes = 1u << 20;
+      return v;
+    }
+  }
+  const unsigned hw = std::thread::hardware_concurrency();
+  const int per = hw ? (int)hw / (2 * n_files) : 1;  // leave half of the cores to the rest of the process
+  return std::max(1, std::min(4, per));
+}
+
 // Common body of the SE and PE loaders (file_reader.c:475-773).
 int load_files(lasv_graph *g, const char *path1, const char *path2, int cutoff,
                lasv_load_stats *stats) {
   if (int e = use(g)) return e;
-  std::string err;
   const int n_files = path2 ? 2 : 1;
-  FileProducer prod[2];
-  if (!prod[0].reader.open(path1, err)) return fail(LASV_ERR_IO, "%s", err.c_str());
-  if (path2 && !prod[1].reader.open(path2, err)) return fail(LASV_ERR_IO, "%s", err.c_str());
-  const bool with_qual = prod[0].reader.has_quality() || (path2 && prod[1].reader.has_quality());
-  std::vector<std::unique_ptr<PinnedBatch>> batches;
+  size_t min_slice = 0;
+  const int threads = parse_threads_per_file(n_files, &min_slice);
   uint64_t batch_bytes = LOADER_BATCH_BYTES;
   if (const char *e = getenv("LASV_B200_LOADER_BATCH_BYTES")) {  // tests: many small batches per file
     const long long v = atoll(e);
     if (v >= 1024 && (uint64_t)v <= LOADER_BATCH_BYTES) batch_bytes = (uint64_t)v;
   }
-  for (int f = 0; f < n_files; f++) {
-    prod[f].with_qual = with_qual;
-    for (int k = 0; k < 2; k++) {
-      batches.emplace_back(new PinnedBatch(batch_bytes, LOADER_BATCH_READS));
-      if (!batches.back()->ok) return fail(LASV_ERR_CUDA, "cannot allocate pinned batch buffers");
-      prod[f].slot[k] = batches.back().get();
-    }
-  }
+  if (!g->host_pool.empty() && g->host_pool[0]->cap_bytes != batch_bytes) g->host_pool.clear();
+  size_t pool_next = 0;
+  ParseJob job;
+  if (!job.open(path1, path2, threads, min_slice, [&]() -> HostBatch * {
+        if (pool_next == g->host_pool.size()) {
+          // reads of >= 15 bases fill the bytes first; shorter ones fill the read slots first -- either way a batch
+          g->host_pool.emplace_back(new PinnedBatch(batch_bytes, std::min<uint64_t>(LOADER_BATCH_READS, batch_bytes / 16 + 16)));
+          if (!g->host_pool.back()->ok) {
+            g->host_pool.pop_back();
+            return nullptr;
+          }
+        }
+        return g->host_pool[pool_next++].get();
+      }))
+    return fail(job.err.find("batch buffers") != std::string::npos ? LASV_ERR_CUDA : LASV_ERR_IO, "%s",
+                job.err.c_str());
   lasv_load_stats before;
   if (int e = lasv_graph_stats(g, &before, nullptr, 0, nullptr)) return e;
-  for (int f = 0; f < n_files; f++) prod[f].th = std::thread([&prod, f] { prod[f].run(); });
-
   int rc = LASV_OK;
-  int next_slot[2] = {0, 0};
-  bool finished[2] = {false, n_files < 2};
-  while (!(finished[0] && finished[1])) {
-    for (int f = 0; f < n_files; f++) {
-      if (finished[f]) continue;
-      FileProducer &p = prod[f];
-      const int k = next_slot[f];
-      bool ready = false;
-      {
-        std::unique_lock<std::mutex> lk(p.m);
-        // with two files, do not sleep on one while the other may have a batch ready
-        if (n_files == 1 || finished[f ^ 1]) p.cv.wait(lk, [&] { return p.full[k] || p.done; });
-        else p.cv.wait_for(lk, std::chrono::milliseconds(1), [&] { return p.full[k] || p.done; });
-        ready = p.full[k] != 0;
-        if (!ready && p.done) finished[f] = true;
-      }
-      if (!ready) continue;
-      if (rc == LASV_OK) rc = flush_batch(g, *p.slot[k], with_qual, cutoff);  // after an error: just drain
-      {
-        std::lock_guard<std::mutex> lk(p.m);
-        p.full[k] = 0;
-      }
-      p.cv.notify_all();
-      next_slot[f] ^= 1;
-    }
-  }
-  for (int f = 0; f < n_files; f++) prod[f].th.join();
+  job.run([&](HostBatch &b) {
+    if (rc == LASV_OK) rc = flush_batch(g, b, job.with_qual, cutoff);  // after an error: just drain
+  });
   if (rc != LASV_OK) return rc;
-  for (int f = 0; f < n_files; f++) {
-    if (!prod[f].err.empty()) return fail(LASV_ERR_IO, "%s", prod[f].err.c_str());
-    if (prod[f].too_long) return fail(LASV_ERR_ARG, "a read of %s exceeds the loader batch", f ? path2 : path1);
+  for (size_t i = 0; i < job.prod.size(); i++) {
+    if (!job.prod[i]->err.empty()) return fail(LASV_ERR_IO, "%s", job.prod[i]->err.c_str());
+    if (job.prod[i]->too_long)
+      return fail(LASV_ERR_ARG, "a read of %s exceeds the loader batch", job.file_of[i] ? path2 : path1);
   }
-  if (path2 && prod[0].reads != prod[1].reads)
+  if (path2 && job.reads_of_file(0) != job.reads_of_file(1))
     return fail(LASV_ERR_IO, "Paired-end files don't have the same number of reads\nfile1: %s\nfile2: %s",
                 path1, path2);
   lasv_load_stats after;
@@ -1582,6 +1753,52 @@ int lasv_synth_reads_host(const lasv_synth_params *p, uint64_t first_read, uint6
                           uint8_t *seq, uint8_t *qual) {
   if (int e = check_synth(p)) return e;
   synth_host(to_synth(p), first_read, n_reads, seq, qual);
+  return LASV_OK;
+}
+
+/* The file loaders' parser on its own (no GPU): reads, bases and an order-independent checksum of all
+ * (sequence, quality) pairs of one or two files, parsed with `threads` parser threads per file exactly as
+ * the loaders do (threads <= 1: one sequential parser per file).  out4 = {reads of file 1, reads of file
+ * 2, bases, checksum}; producers_used reports how many parser threads ran. */
+int lasv_seqfile_parse_check(const char *path1, const char *path2, int threads, uint64_t batch_bytes,
+                             uint64_t *out4, int *producers_used) {
+  if (!path1 || !out4) return fail(LASV_ERR_ARG, "NULL argument");
+  if (batch_bytes < 1024) batch_bytes = 1024;
+  struct PlainBatch : HostBatch {
+    std::vector<uint8_t> s, q;
+    std::vector<uint64_t> o;
+    PlainBatch(uint64_t bytes, uint64_t reads) : s(bytes), q(bytes), o(reads + 1) {
+      seq = s.data(); qual = q.data(); offsets = o.data();
+      cap_bytes = bytes; cap_reads = reads;
+      reset();
+    }
+  };
+  std::vector<std::unique_ptr<PlainBatch>> batches;
+  ParseJob job;
+  if (!job.open(path1, path2, threads < 1 ? 1 : threads, 1u << 20, [&]() -> HostBatch * {
+        batches.emplace_back(new PlainBatch(batch_bytes, batch_bytes / 16 + 16));
+        return batches.back().get();
+      }))
+    return fail(LASV_ERR_IO, "%s", job.err.c_str());
+  uint64_t bases = 0, sum = 0;
+  const bool wq = job.with_qual;
+  job.run([&](HostBatch &b) {
+    for (uint64_t r = 0; r < b.n_reads; r++) {
+      const uint64_t lo = b.offsets[r], hi = b.offsets[r + 1] - 1;  // without the separator
+      uint64_t h = 0xCBF29CE484222325ull;
+      for (uint64_t i = lo; i < hi; i++) h = (h ^ b.seq[i]) * 0x100000001B3ull;
+      if (wq) for (uint64_t i = lo; i < hi; i++) h = (h ^ b.qual[i]) * 0x100000001B3ull;
+      sum += mix64(h ^ (hi - lo));
+      bases += hi - lo;
+    }
+  });
+  for (auto &p : job.prod)
+    if (!p->err.empty()) return fail(LASV_ERR_IO, "%s", p->err.c_str());
+  out4[0] = job.reads_of_file(0);
+  out4[1] = path2 ? job.reads_of_file(1) : 0;
+  out4[2] = bases;
+  out4[3] = sum;
+  if (producers_used) *producers_used = (int)job.prod.size();
   return LASV_OK;
 }
 

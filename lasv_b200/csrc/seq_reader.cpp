@@ -28,7 +28,9 @@ bool SeqReader::open(const std::string &path, std::string &err) {
     return false;
   }
   gzbuffer(gz_, 1u << 20);
-  buf_.resize(4u << 20);
+  own_.resize(4u << 20);
+  buf_ = own_.data();
+  memory_ = false;
   pos_ = end_ = 0;
   eof_ = false;
   n_reads_ = 0;
@@ -49,15 +51,34 @@ bool SeqReader::open(const std::string &path, std::string &err) {
   return true;
 }
 
+void SeqReader::open_memory(const unsigned char *data, size_t n, const std::string &path) {
+  close();
+  path_ = path;
+  buf_ = data;
+  memory_ = true;
+  pos_ = 0;
+  end_ = n;
+  eof_ = false;
+  n_reads_ = 0;
+  type_ = FASTQ;
+  at_record_start_ = false;  // the slice begins AT the '@' of a record header
+}
+
 void SeqReader::close() {
   if (gz_) gzclose(gz_);
   gz_ = nullptr;
   type_ = UNKNOWN;
+  memory_ = false;
 }
 
 bool SeqReader::fill_() {
   if (eof_) return false;
-  const int n = gzread(gz_, buf_.data(), (unsigned)buf_.size());
+  if (memory_) {  // the whole slice was the window
+    eof_ = true;
+    pos_ = end_ = 0;
+    return false;
+  }
+  const int n = gzread(gz_, own_.data(), (unsigned)own_.size());
   if (n <= 0) {
     eof_ = true;
     pos_ = end_ = 0;
@@ -83,7 +104,7 @@ int SeqReader::peekc_() {
 void SeqReader::read_line_(std::string *dst) {
   for (;;) {
     if (pos_ == end_ && !fill_()) break;
-    const unsigned char *p = buf_.data() + pos_;
+    const unsigned char *p = buf_ + pos_;
     const size_t avail = end_ - pos_;
     const unsigned char *nl = (const unsigned char *)memchr(p, '\n', avail);
     const size_t take = nl ? (size_t)(nl - p) : avail;
@@ -102,7 +123,7 @@ void SeqReader::read_line_(std::string *dst) {
 bool SeqReader::next(std::string &err) {
   seq_.clear();
   qual_.clear();
-  if (!gz_) return false;
+  if (!gz_ && !memory_) return false;
   int c;
   if (type_ == FASTQ) {
     if (!at_record_start_) {
@@ -137,7 +158,7 @@ bool SeqReader::next(std::string &err) {
         return false;
       }
       // bulk: the run of quality bytes up to the next line terminator (or as many as are still wanted)
-      const unsigned char *p = buf_.data() + pos_;
+      const unsigned char *p = buf_ + pos_;
       size_t want = seq_.size() - qual_.size();
       if (want > end_ - pos_) want = end_ - pos_;
       const unsigned char *nl = (const unsigned char *)memchr(p, '\n', want);
@@ -174,7 +195,7 @@ bool SeqReader::next(std::string &err) {
       // take the run up to the next newline or '>'
       size_t e = pos_;
       while (e < end_ && buf_[e] != '\n' && buf_[e] != '\r' && buf_[e] != '>') e++;
-      seq_.append((const char *)buf_.data() + pos_, e - pos_);
+      seq_.append((const char *)buf_ + pos_, e - pos_);
       pos_ = e;
     }
     n_reads_++;

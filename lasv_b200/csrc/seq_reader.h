@@ -31,6 +31,11 @@ class SeqReader {
   ~SeqReader() { close(); }
   // Returns false (and sets err) if the file cannot be opened or is SAM/BAM.
   bool open(const std::string &path, std::string &err);
+  // Parse records from a byte range already in memory (a slice of an mmap'ed, uncompressed FASTQ file that
+  // starts at a record header): the parallel loader gives every parser thread its own slice.
+  void open_memory(const unsigned char *data, size_t n, const std::string &path);
+  // True if the file is stored uncompressed (gzopen reads it transparently either way).
+  bool is_plain_file() const { return gz_ && gzdirect(gz_) == 1; }
   void close();
   bool has_quality() const { return type_ == FASTQ; }
   Type type() const { return type_; }
@@ -55,7 +60,9 @@ class SeqReader {
   gzFile gz_ = nullptr;
   std::string path_;
   Type type_ = UNKNOWN;
-  std::vector<unsigned char> buf_;
+  std::vector<unsigned char> own_;      // gz mode: the refill buffer
+  const unsigned char *buf_ = nullptr;  // current window (own_.data() or the caller's memory)
+  bool memory_ = false;
   size_t pos_ = 0, end_ = 0;
   bool eof_ = false;
   bool at_record_start_ = false;  // header marker already consumed (seq_file.c: read_line_start)

@@ -132,3 +132,58 @@ def test_ctx_header_matches_reference_bytes():
     hdr = lasv_b200.ctx_header(53, meta["ctx_mean_read_len"], meta["ctx_total_seq"])
     assert hdr.hex() == meta["ctx_header_hex"]
     assert hdr == O.ctx_header(53, meta["ctx_mean_read_len"], meta["ctx_total_seq"])
+
+
+# ------------------------------------------------ parallel parse of large FASTQ files
+def _parse_check(path1, path2, threads, batch_bytes=1 << 16):
+    import ctypes as C
+    out = (C.c_uint64 * 4)()
+    used = C.c_int(0)
+    rc = _capi.lib().lasv_seqfile_parse_check(str(path1).encode(), str(path2).encode() if path2 else None, threads,
+                                              batch_bytes, out, C.byref(used))
+    assert rc == 0, _capi.lib().lasv_last_error()
+    return tuple(int(x) for x in out), used.value
+
+
+def test_parallel_fastq_parse_equals_sequential(tmp_path):
+    """Large uncompressed FASTQ files are cut at record boundaries and parsed slice by slice by several
+    threads; everything else (gzip, multi-line records, FASTA, small files) gets one sequential parser.
+    Either way: same reads, same bases, same checksum of all (sequence, quality) pairs."""
+    rng = np.random.default_rng(11)
+    n = 30_000
+    lens = rng.integers(1, 220, n)
+    with open(tmp_path / "a.fq", "w") as fa, open(tmp_path / "crlf.fq", "w", newline="") as fc, \
+            open(tmp_path / "wrapped.fq", "w") as fw:
+        for i, ln in enumerate(lens):
+            s = "".join(rng.choice(list("ACGTNacgt"), ln))
+            # quality lines that start with '@' or '+' are the classic trap for boundary detection
+            q = "".join(rng.choice(list("@+IIIIIIFF#5&'"), ln))
+            fa.write(f"@r{i} x\n{s}\n+\n{q}\n")
+            fc.write(f"@r{i}\r\n{s}\r\n+r{i}\r\n{q}\r\n")
+            h = ln // 2
+            fw.write(f"@r{i}\n{s[:h]}\n{s[h:]}\n+\n{q[:h]}\n{q[h:]}\n")        # multi-line record
+    import gzip, shutil
+    with open(tmp_path / "a.fq", "rb") as src, gzip.open(tmp_path / "a.fq.gz", "wb", compresslevel=1) as dst:
+        shutil.copyfileobj(src, dst)
+    ref, used = _parse_check(tmp_path / "a.fq", None, 1)
+    assert used == 1 and ref[0] == n and ref[2] == int(lens.sum())
+    size = (tmp_path / "a.fq").stat().st_size
+    for threads in (2, 3, 4, 6, 64):
+        got, used = _parse_check(tmp_path / "a.fq", None, threads)
+        assert used == (threads if size >= threads << 20 else 1) and got == ref, (threads, got, ref)
+    got, used = _parse_check(tmp_path / "crlf.fq", None, 4)
+    assert used == 4 and got == ref                                   # '\r' is not part of a read
+    got, used = _parse_check(tmp_path / "wrapped.fq", None, 4)
+    assert used == 1 and got == ref                                   # multi-line: sequential fallback
+    got, used = _parse_check(tmp_path / "a.fq.gz", None, 4)
+    assert used == 1 and got == ref                                   # compressed: sequential
+    got, used = _parse_check(tmp_path / "a.fq", tmp_path / "crlf.fq", 3)
+    assert used == 6 and got == (n, n, 2 * ref[2], (2 * ref[3]) % (1 << 64))
+    # tiny batches: many hand-offs per slice
+    got, used = _parse_check(tmp_path / "a.fq", None, 4, batch_bytes=2048)
+    assert got == ref
+    # the golden edge-case files (too small to be cut): unchanged
+    for f in ("edge_1.fq", "edge_2.fq", "edge_1.fq.gz", "contigs.fa"):
+        one, u1 = _parse_check(util.GOLDEN / f, None, 1)
+        four, u4 = _parse_check(util.GOLDEN / f, None, 4)
+        assert one == four and u1 == u4 == 1
