@@ -108,6 +108,10 @@ acgttgcatgccgataggctaacgttagccatgcatcggatcgattacggctagctagg
 """
 
 
+REF_FIXTURES = ["multiline.fastq", "ncbi.fastq", "reads.fq", "small.fq", "reads.fa", "small.fa", "reads.txt",
+                "small.txt", "single.txt"]
+
+
 def ref_case(name, k, L, W, q, fq1, fq2=None, supernodes=False, extra=None):
     wd = Path(tempfile.mkdtemp(prefix="lasv_golden_"))
     try:
@@ -188,6 +192,16 @@ def main():
     ref_case("edge_se_gz_k31_q5", 31, 10, 20, 5, HERE / "edge_1.fq.gz")
     ref_case("fasta_se_k31", 31, 10, 20, 5, HERE / "contigs.fa")
     ref_case("fasta_se_k53", 53, 10, 20, 0, HERE / "contigs.fa")
+
+    # the fixtures of the reference's own (assert-free) reader smoke test, libs/seq_file/test/: multi-line
+    # records, quality lines starting with '@', '+name' separator lines, lower case, FASTA, plain text
+    # with empty lines.  The inputs are copied as test data; the expected output is the reference's.
+    ref_fix = Path(O.REFERENCE_ROOT) / "libs" / "seq_file" / "test" if hasattr(O, "REFERENCE_ROOT") else \
+        Path("/root/reference/libs/seq_file/test")
+    (HERE / "reffix").mkdir(exist_ok=True)
+    for fname in REF_FIXTURES:
+        shutil.copyfile(ref_fix / fname, HERE / "reffix" / fname)
+        ref_case("reffix_" + fname.replace(".", "_") + "_k15", 15, 8, 20, 5, HERE / "reffix" / fname)
 
     # synthetic PE reads (regenerated bit-exactly from the stored synth parameters)
     synth_case("synth_cfg0_k53", synth.CFG0, 4000, 10, 40, 400, supernodes=True)

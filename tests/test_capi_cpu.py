@@ -74,7 +74,7 @@ def test_fasta_and_plain_reader(tmp_path):
 def test_reader_through_oracle_matches_reference_golden():
     """The reader's bytes, fed to the oracle, reproduce the reference's output on
     the file-based golden cases: pins the parser end to end on the CPU."""
-    for name in util.EDGE_PE + util.EDGE_SE:
+    for name in util.EDGE_PE + util.EDGE_SE + util.REFFIX:      # REFFIX: the reference's own reader fixtures
         meta = util.case_meta(name)
         f1, f2 = util.case_files(name)
         s1, q1, o1 = seqfile_to_streams(f1)
@@ -97,6 +97,8 @@ def test_reader_through_oracle_matches_reference_golden():
         g, ok = util.oracle_build(meta["k"], meta["L"], meta["W"], seq, qual, offs, util.cutoff_of(meta), paired)
         assert ok
         util.assert_same_records(g.records(), util.case_records(name), name)
+        assert g.stats.kmers_inserted == meta["inserts"] and g.stats.bad_reads == meta["bad_reads"], name
+        assert g.stats.bases_loaded == meta["bases_loaded"], name
 
 
 def test_synth_generator_is_deterministic_and_sane():

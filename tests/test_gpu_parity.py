@@ -58,7 +58,7 @@ def test_host_buffer_path_matches_reference_golden(name):
         assert int(g.rehash_histogram().sum()) == meta["inserts"]
 
 
-@pytest.mark.parametrize("name", util.EDGE_PE + util.EDGE_SE)
+@pytest.mark.parametrize("name", util.EDGE_PE + util.EDGE_SE + util.REFFIX)
 def test_sequence_file_loaders_match_reference_golden(name, tmp_path):
     meta = util.case_meta(name)
     f1, f2 = util.case_files(name)

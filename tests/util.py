@@ -16,6 +16,10 @@ GOLDEN = Path(__file__).resolve().parent / "golden"
 EDGE_PE = [f"edge_pe_k{k}_q5" for k in (21, 31, 33, 53, 63, 65, 95)] + ["edge_pe_k31_q0"]
 EDGE_SE = ["edge_se_k53_q20", "edge_se_gz_k31_q5", "fasta_se_k31", "fasta_se_k53"]
 SYNTH = ["synth_cfg0_k53", "synth_cfg1_k31", "synth_cfg2_k95", "synth_full_k53", "synth_full_k31"]
+# the reference's own reader fixtures (libs/seq_file/test), expected output from the compiled reference
+REFFIX_FILES = ["multiline.fastq", "ncbi.fastq", "reads.fq", "small.fq", "reads.fa", "small.fa", "reads.txt",
+                "small.txt", "single.txt"]
+REFFIX = ["reffix_" + f.replace(".", "_") + "_k15" for f in REFFIX_FILES]
 ALL_CASES = EDGE_PE + EDGE_SE + SYNTH
 
 
@@ -37,6 +41,8 @@ def case_files(name: str):
         return GOLDEN / "edge_1.fq", None
     if name.startswith("fasta"):
         return GOLDEN / "contigs.fa", None
+    if name.startswith("reffix_"):
+        return GOLDEN / "reffix" / REFFIX_FILES[REFFIX.index(name)], None
     raise KeyError(name)
 
 
