@@ -83,7 +83,11 @@ class ClockSampler:
     def start(self):
         try:
             import pynvml
-            pynvml.nvmlInit()
+            try:
+                pynvml.nvmlInit()
+            except Exception:
+                time.sleep(0.2)
+                pynvml.nvmlInit()
             vis = os.environ.get("CUDA_VISIBLE_DEVICES")
             phys = int(vis.split(",")[self.idx]) if vis and vis.split(",")[self.idx].isdigit() else self.idx
             self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
@@ -96,7 +100,7 @@ class ClockSampler:
             self.nvml = None
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                  "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
@@ -124,7 +128,15 @@ class ClockSampler:
     def window(self, t0, t1):
         if self.nvml:
             return [x for x in self.samples if t0 <= x[0] <= t1] or self.samples[-3:]
-        return [l for t, l in self.lines if t0 <= t <= t1] or [l for _, l in self.lines[-3:]]
+        got = [l for t, l in self.lines if t0 <= t <= t1] or [l for _, l in self.lines[-3:]]
+        if not got:   # the sampler never produced a line (slow start): one synchronous reading instead
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
+                                      str(self.idx)], capture_output=True, text=True, timeout=10).stdout
+                got = [l.strip() for l in out.splitlines() if l.strip()]
+            except Exception:
+                got = []
+        return got
 
     def stop(self):
         self.stop_flag.set()
