@@ -1,7 +1,6 @@
 """Shared helpers for the tests: golden cases, inputs, comparisons."""
 from __future__ import annotations
 
-import ctypes as C
 import json
 from pathlib import Path
 

@@ -3,7 +3,6 @@
 import os, sys, time, json
 from pathlib import Path
 sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
-import numpy as np
 from lasv_b200 import DBGraph, synth
 from oracle import oracle as O   # FASTQ writer only (test infrastructure)
 
