@@ -146,6 +146,7 @@ class ShardedDBGraph:
         if world > 1:
             if not max_bytes_per_batch:       # k-mers <= bytes: a safe stand-in for callers that only know k-mers
                 max_bytes_per_batch = int(max_kmers_per_batch * 1.7)
+            self.max_bytes_per_batch = max_bytes_per_batch
             geo = self.graph.bin_geometry(world, max_bytes_per_batch, max_reads_per_batch)
             self.bins_per_owner, self.cap, self.spill = geo["bins_per_owner"], geo["stripe_capacity"], geo["spill_capacity"]
             self.rec_bytes = geo["record_bytes"]
@@ -222,6 +223,9 @@ class ShardedDBGraph:
         if self.world == 1:
             g.load_reads_device(d_seq, d_qual, n_bytes, d_offsets, n_reads, quality_cutoff, stream)
             return
+        if n_bytes > self.max_bytes_per_batch:
+            raise ValueError(f"batch of {n_bytes} stream bytes exceeds the {self.max_bytes_per_batch} the exchange "
+                             "buffers were sized for (max_bytes_per_batch)")
         buf = self.buffers[self.turn % len(self.buffers)]
         self.turn += 1
         # the previous user of this buffer set must be done with it
