@@ -28,6 +28,18 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, sym), f"liblasv_b200.so does not export {sym}"
 
 
+def test_header_is_plain_c(tmp_path):
+    """The boundary is a C ABI: include/lasv_b200.h must compile as C99 (no C++, no torch types)."""
+    import shutil
+    import subprocess
+    if not shutil.which("gcc"):
+        pytest.skip("no gcc")
+    src = tmp_path / "hdr.c"
+    src.write_text('#include "include/lasv_b200.h"\nint main(void) { return 0; }\n')
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-I", str(ROOT),
+                    str(src)], check=True)
+
+
 def test_no_cpu_fallback_without_gpu():
     lib = _capi.lib()
     if lib.lasv_device_count() > 0:
