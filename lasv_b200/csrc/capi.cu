@@ -1279,50 +1279,56 @@ size_t find_fastq_record(const unsigned char *d, size_t n, size_t from) {
 // several, each on its own slice of the mapped file (the text parse is the slow end).
 struct ParseJob {
   std::vector<std::unique_ptr<FileProducer>> prod;
-  std::vector<int> file_of;  // producer -> file index
-  MappedFile maps[2];
-  bool with_qual = false;
+  std::vector<int> file_of;  // producer -> file index (entry e: files 2e and 2e+1)
+  std::vector<std::unique_ptr<MappedFile>> maps;
   std::string err;
 
-  // `threads` per file (>= 1); `alloc` hands out the two batches of every producer
-  bool open(const char *path1, const char *path2, int threads, size_t min_slice_bytes,
+  // entries: (file 1, file 2 or "") -- every file of every entry is parsed concurrently; `threads` parser
+  // threads per large uncompressed FASTQ file (>= 1); `alloc` hands out the two batches of every producer
+  bool open(const std::vector<std::pair<std::string, std::string>> &entries, int threads, size_t min_slice_bytes,
             const std::function<HostBatch *()> &alloc) {
-    const char *paths[2] = {path1, path2};
-    const int n_files = path2 ? 2 : 1;
-    std::vector<std::unique_ptr<FileProducer>> heads;
-    for (int f = 0; f < n_files; f++) {
-      heads.emplace_back(new FileProducer());
-      if (!heads.back()->reader.open(paths[f], err)) return false;
-    }
-    with_qual = heads[0]->reader.has_quality() || (path2 && heads[1]->reader.has_quality());
-    for (int f = 0; f < n_files; f++) {
-      std::vector<size_t> cuts;
-      SeqReader &r = heads[f]->reader;
-      if (threads > 1 && r.type() == SeqReader::FASTQ && r.is_plain_file() && maps[f].map(paths[f]) &&
-          maps[f].size >= (size_t)threads * min_slice_bytes) {
-        const MappedFile &m = maps[f];
-        cuts.push_back(find_fastq_record(m.data, m.size, 0));
-        for (int w = 1; w < threads && cuts.back() != SIZE_MAX; w++) {
-          const size_t c = find_fastq_record(m.data, m.size, m.size / (size_t)threads * (size_t)w);
-          if (c == SIZE_MAX || c <= cuts.back()) { cuts.assign(1, SIZE_MAX); break; }
-          cuts.push_back(c);
-        }
-        if (cuts.back() == SIZE_MAX || cuts[0] != 0) cuts.clear();  // not the 4-line shape: sequential
+    for (size_t e = 0; e < entries.size(); e++) {
+      const std::string paths[2] = {entries[e].first, entries[e].second};
+      const int n_files = paths[1].empty() ? 1 : 2;
+      std::vector<std::unique_ptr<FileProducer>> heads;
+      for (int f = 0; f < n_files; f++) {
+        heads.emplace_back(new FileProducer());
+        if (!heads.back()->reader.open(paths[f], err)) return false;
       }
-      if (cuts.size() > 1) {
-        cuts.push_back(maps[f].size);
-        for (size_t w = 0; w + 1 < cuts.size(); w++) {
-          prod.emplace_back(new FileProducer());
-          prod.back()->reader.open_memory(maps[f].data + cuts[w], cuts[w + 1] - cuts[w], paths[f]);
-          file_of.push_back(f);
+      // quality filtering applies to an entry if either of its files carries qualities (file_reader.c:389)
+      const bool with_qual = heads[0]->reader.has_quality() || (n_files == 2 && heads[1]->reader.has_quality());
+      for (int f = 0; f < n_files; f++) {
+        std::vector<size_t> cuts;
+        SeqReader &r = heads[f]->reader;
+        maps.emplace_back(new MappedFile());
+        MappedFile &m = *maps.back();
+        if (threads > 1 && r.type() == SeqReader::FASTQ && r.is_plain_file() && m.map(paths[f].c_str()) &&
+            m.size >= (size_t)threads * min_slice_bytes) {
+          cuts.push_back(find_fastq_record(m.data, m.size, 0));
+          for (int w = 1; w < threads && cuts.back() != SIZE_MAX; w++) {
+            const size_t c = find_fastq_record(m.data, m.size, m.size / (size_t)threads * (size_t)w);
+            if (c == SIZE_MAX || c <= cuts.back()) { cuts.assign(1, SIZE_MAX); break; }
+            cuts.push_back(c);
+          }
+          if (cuts.back() == SIZE_MAX || cuts[0] != 0) cuts.clear();  // not the 4-line shape: sequential
         }
-      } else {
-        prod.emplace_back(std::move(heads[f]));
-        file_of.push_back(f);
+        const size_t first = prod.size();
+        if (cuts.size() > 1) {
+          cuts.push_back(m.size);
+          for (size_t w = 0; w + 1 < cuts.size(); w++) {
+            prod.emplace_back(new FileProducer());
+            prod.back()->reader.open_memory(m.data + cuts[w], cuts[w + 1] - cuts[w], paths[f]);
+          }
+        } else {
+          prod.emplace_back(std::move(heads[f]));
+        }
+        for (size_t i = first; i < prod.size(); i++) {
+          file_of.push_back((int)(2 * e) + f);
+          prod[i]->with_qual = with_qual;
+        }
       }
     }
     for (auto &p : prod) {
-      p->with_qual = with_qual;
       for (int k = 0; k < 2; k++) {
         p->slot[k] = alloc();
         if (!p->slot[k]) { err = "cannot allocate batch buffers"; return false; }
@@ -1332,7 +1338,7 @@ struct ParseJob {
   }
 
   // runs the producers; `consume(batch)` is called from this thread for every full batch
-  void run(const std::function<void(HostBatch &)> &consume) {
+  void run(const std::function<void(HostBatch &, const FileProducer &)> &consume) {
     for (auto &p : prod) {
       FileProducer *fp = p.get();
       fp->th = std::thread([fp] { fp->run(); });
@@ -1360,7 +1366,7 @@ struct ParseJob {
           }
         }
         if (!ready) continue;
-        consume(*p.slot[k]);
+        consume(*p.slot[k], p);
         {
           std::lock_guard<std::mutex> lk(p.m);
           p.full[k] = 0;
@@ -1398,13 +1404,24 @@ int parse_threads_per_file(int n_files, size_t *min_slice_bytes) {
   return std::max(1, std::min(4, per));
 }
 
-// Common body of the SE and PE loaders (file_reader.c:475-773).
-int load_files(lasv_graph *g, const char *path1, const char *path2, int cutoff,
-               lasv_load_stats *stats) {
+void add_stats(lasv_load_stats *acc, const lasv_load_stats &s);
+
+constexpr size_t LOADER_GROUP = 4;  // entries (files or file pairs) of a filelist parsed at the same time
+
+// Common body of the SE and PE loaders (file_reader.c:475-773) for a group of files / file pairs that
+// are parsed concurrently (gzip input is bound by inflate: one file, one thread -- but a filelist usually
+// names several files).
+int load_file_group(lasv_graph *g, const std::vector<std::pair<std::string, std::string>> &entries, int cutoff,
+                    lasv_load_stats *stats) {
   if (int e = use(g)) return e;
-  const int n_files = path2 ? 2 : 1;
+  if (entries.empty()) {
+    if (stats) memset(stats, 0, sizeof *stats);
+    return LASV_OK;
+  }
+  size_t n_files = 0;
+  for (auto &e : entries) n_files += e.second.empty() ? 1 : 2;
   size_t min_slice = 0;
-  const int threads = parse_threads_per_file(n_files, &min_slice);
+  const int threads = parse_threads_per_file((int)n_files, &min_slice);
   uint64_t batch_bytes = LOADER_BATCH_BYTES;
   if (const char *e = getenv("LASV_B200_LOADER_BATCH_BYTES")) {  // tests: many small batches per file
     const long long v = atoll(e);
@@ -1413,7 +1430,7 @@ int load_files(lasv_graph *g, const char *path1, const char *path2, int cutoff,
   if (!g->host_pool.empty() && g->host_pool[0]->cap_bytes != batch_bytes) g->host_pool.clear();
   size_t pool_next = 0;
   ParseJob job;
-  if (!job.open(path1, path2, threads, min_slice, [&]() -> HostBatch * {
+  if (!job.open(entries, threads, min_slice, [&]() -> HostBatch * {
         if (pool_next == g->host_pool.size()) {
           // reads of >= 15 bases fill the bytes first; shorter ones fill the read slots first -- either way a batch
           g->host_pool.emplace_back(new PinnedBatch(batch_bytes, std::min<uint64_t>(LOADER_BATCH_READS, batch_bytes / 16 + 16)));
@@ -1429,18 +1446,20 @@ int load_files(lasv_graph *g, const char *path1, const char *path2, int cutoff,
   lasv_load_stats before;
   if (int e = lasv_graph_stats(g, &before, nullptr, 0, nullptr)) return e;
   int rc = LASV_OK;
-  job.run([&](HostBatch &b) {
-    if (rc == LASV_OK) rc = flush_batch(g, b, job.with_qual, cutoff);  // after an error: just drain
+  job.run([&](HostBatch &b, const FileProducer &p) {
+    if (rc == LASV_OK) rc = flush_batch(g, b, p.with_qual, cutoff);  // after an error: just drain
   });
   if (rc != LASV_OK) return rc;
   for (size_t i = 0; i < job.prod.size(); i++) {
+    const auto &e = entries[(size_t)job.file_of[i] / 2];
+    const std::string &path = (job.file_of[i] & 1) ? e.second : e.first;
     if (!job.prod[i]->err.empty()) return fail(LASV_ERR_IO, "%s", job.prod[i]->err.c_str());
-    if (job.prod[i]->too_long)
-      return fail(LASV_ERR_ARG, "a read of %s exceeds the loader batch", job.file_of[i] ? path2 : path1);
+    if (job.prod[i]->too_long) return fail(LASV_ERR_ARG, "a read of %s exceeds the loader batch", path.c_str());
   }
-  if (path2 && job.reads_of_file(0) != job.reads_of_file(1))
-    return fail(LASV_ERR_IO, "Paired-end files don't have the same number of reads\nfile1: %s\nfile2: %s",
-                path1, path2);
+  for (size_t e = 0; e < entries.size(); e++)
+    if (!entries[e].second.empty() && job.reads_of_file((int)(2 * e)) != job.reads_of_file((int)(2 * e + 1)))
+      return fail(LASV_ERR_IO, "Paired-end files don't have the same number of reads\nfile1: %s\nfile2: %s",
+                  entries[e].first.c_str(), entries[e].second.c_str());
   lasv_load_stats after;
   if (int e = lasv_graph_stats(g, &after, nullptr, 0, nullptr)) return e;
   if (stats) {
@@ -1451,6 +1470,23 @@ int load_files(lasv_graph *g, const char *path1, const char *path2, int cutoff,
     stats->n_contigs = after.n_contigs - before.n_contigs;
     stats->kmers_inserted = after.kmers_inserted - before.kmers_inserted;
     stats->unique_kmers = after.unique_kmers;
+  }
+  return LASV_OK;
+}
+
+int load_files(lasv_graph *g, const char *path1, const char *path2, int cutoff, lasv_load_stats *stats) {
+  return load_file_group(g, {{std::string(path1), std::string(path2 ? path2 : "")}}, cutoff, stats);
+}
+
+// the entries of a filelist, LOADER_GROUP at a time
+int load_entries(lasv_graph *g, const std::vector<std::pair<std::string, std::string>> &entries, int cutoff,
+                 lasv_load_stats *acc) {
+  for (size_t i = 0; i < entries.size(); i += LOADER_GROUP) {
+    const std::vector<std::pair<std::string, std::string>> group(
+        entries.begin() + (long)i, entries.begin() + (long)std::min(entries.size(), i + LOADER_GROUP));
+    lasv_load_stats s;
+    if (int e = load_file_group(g, group, cutoff, &s)) return e;
+    add_stats(acc, s);
   }
   return LASV_OK;
 }
@@ -1508,19 +1544,19 @@ int lasv_graph_load_se_filelist(lasv_graph *g, const char *list, int qual_thresh
   lasv_load_stats acc;
   memset(&acc, 0, sizeof acc);
   std::string line;
-  unsigned int n = 0;
+  std::vector<std::pair<std::string, std::string>> entries;
   int rc = LASV_OK;
   while (rc == LASV_OK && read_list_line(f, line)) {
     if (line.empty()) continue;
     if (line[0] != '/') line = dir + line;
     char p[PATH_MAX + 1];
     if (!realpath(line.c_str(), p)) { rc = fail(LASV_ERR_IO, "Cannot find sequence file: %s", line.c_str()); break; }
-    lasv_load_stats s;
-    rc = load_files(g, p, nullptr, cutoff, &s);
-    if (rc == LASV_OK) { add_stats(&acc, s); n++; }
+    entries.emplace_back(std::string(p), std::string());
   }
   fclose(f);
+  if (rc == LASV_OK) rc = load_entries(g, entries, cutoff, &acc);
   if (rc != LASV_OK) return rc;
+  const unsigned int n = (unsigned int)entries.size();
   if (files_loaded) *files_loaded += n;
   if (stats) *stats = acc;
   return LASV_OK;
@@ -1542,7 +1578,7 @@ int lasv_graph_load_pe_filelists(lasv_graph *g, const char *list1, const char *l
   lasv_load_stats acc;
   memset(&acc, 0, sizeof acc);
   std::string l1, l2;
-  unsigned int n = 0;
+  std::vector<std::pair<std::string, std::string>> entries;
   int rc = LASV_OK;
   for (;;) {
     const bool g1 = read_list_line(f1, l1), g2 = read_list_line(f2, l2);
@@ -1558,15 +1594,13 @@ int lasv_graph_load_pe_filelists(lasv_graph *g, const char *list1, const char *l
     char p1[PATH_MAX + 1], p2[PATH_MAX + 1];
     if (!realpath(l1.c_str(), p1)) { rc = fail(LASV_ERR_IO, "Cannot find sequence file: %s", l1.c_str()); break; }
     if (!realpath(l2.c_str(), p2)) { rc = fail(LASV_ERR_IO, "Cannot find sequence file: %s", l2.c_str()); break; }
-    lasv_load_stats s;
-    rc = load_files(g, p1, p2, cutoff, &s);
-    if (rc != LASV_OK) break;
-    add_stats(&acc, s);
-    n++;
+    entries.emplace_back(std::string(p1), std::string(p2));
   }
   fclose(f1);
   fclose(f2);
+  if (rc == LASV_OK) rc = load_entries(g, entries, cutoff, &acc);
   if (rc != LASV_OK) return rc;
+  const unsigned int n = (unsigned int)entries.size();
   if (pairs_loaded) *pairs_loaded += n;
   if (stats) *stats = acc;
   return LASV_OK;
@@ -1775,14 +1809,15 @@ int lasv_seqfile_parse_check(const char *path1, const char *path2, int threads, 
   };
   std::vector<std::unique_ptr<PlainBatch>> batches;
   ParseJob job;
-  if (!job.open(path1, path2, threads < 1 ? 1 : threads, 1u << 20, [&]() -> HostBatch * {
-        batches.emplace_back(new PlainBatch(batch_bytes, batch_bytes / 16 + 16));
-        return batches.back().get();
-      }))
+  if (!job.open({{std::string(path1), std::string(path2 ? path2 : "")}}, threads < 1 ? 1 : threads, 1u << 20,
+                [&]() -> HostBatch * {
+                  batches.emplace_back(new PlainBatch(batch_bytes, batch_bytes / 16 + 16));
+                  return batches.back().get();
+                }))
     return fail(LASV_ERR_IO, "%s", job.err.c_str());
   uint64_t bases = 0, sum = 0;
-  const bool wq = job.with_qual;
-  job.run([&](HostBatch &b) {
+  job.run([&](HostBatch &b, const FileProducer &fp) {
+    const bool wq = fp.with_qual;
     for (uint64_t r = 0; r < b.n_reads; r++) {
       const uint64_t lo = b.offsets[r], hi = b.offsets[r + 1] - 1;  // without the separator
       uint64_t h = 0xCBF29CE484222325ull;

@@ -106,6 +106,51 @@ def test_file_loaders_with_many_small_batches(name, batch_bytes, tmp_path, monke
         assert st["n_reads"] == len(s2) // 2
 
 
+def _merge_records(*arrays):
+    acc = {}
+    for a in arrays:
+        for r in a:
+            key = tuple(int(x) for x in r["kmer"])
+            c, e = acc.get(key, (0, 0))
+            acc[key] = (c + int(r["covg"]), e | int(r["edges"]))
+    out = np.zeros(len(acc), dtype=arrays[0].dtype)
+    for i, (key, (c, e)) in enumerate(acc.items()):
+        out[i]["kmer"], out[i]["covg"], out[i]["edges"] = key, c, e
+    return out
+
+
+def test_filelists_with_several_files_are_parsed_concurrently(tmp_path):
+    """A filelist names several files: they are parsed at the same time, four entries per group.  Five
+    copies of a pair (two groups) give five times the coverage; a list that mixes FASTQ and FASTA applies
+    the quality filter only where there are qualities."""
+    name = "synth_cfg0_k53"
+    meta = util.case_meta(name)
+    seq, qual, _ = util.case_streams(name)
+    rl = meta["workload"]["read_len"]
+    s2, q2 = seq.reshape(-1, rl + 1), qual.reshape(-1, rl + 1)
+    O.write_fastq_fixed(tmp_path / "a.fq", s2[0::2].reshape(-1), q2[0::2].reshape(-1), rl)
+    O.write_fastq_fixed(tmp_path / "b.fq", s2[1::2].reshape(-1), q2[1::2].reshape(-1), rl)
+    (tmp_path / "l").write_text("a.fq\n" * 5)                   # relative to the list's directory
+    (tmp_path / "r").write_text("b.fq\n" * 5)
+    gold = util.case_records(name)
+    with DBGraph(meta["k"], meta["L"], meta["W"]) as g:
+        st = g.load_pe_filelists(tmp_path / "l", tmp_path / "r", meta["q_thresh"], 33)
+        assert st["files_loaded"] == 5 and st["kmers_inserted"] == 5 * meta["inserts"]
+        assert st["bad_reads"] == 5 * meta["bad_reads"] and st["n_reads"] == 5 * len(s2)
+        five = gold.copy()
+        five["covg"] *= 5
+        util.assert_same_records(g.records(), five, name)
+    # SE list: FASTQ (quality threshold 20 applies) + FASTA (no qualities) at k=53
+    mq, mf = util.case_meta("edge_se_k53_q20"), util.case_meta("fasta_se_k53")
+    assert (mq["k"], mq["L"], mq["W"]) == (mf["k"], mf["L"], mf["W"])
+    (tmp_path / "se").write_text(f"{util.GOLDEN / 'edge_1.fq'}\n{util.GOLDEN / 'contigs.fa'}\n")
+    with DBGraph(mq["k"], mq["L"], mq["W"]) as g:
+        st = g.load_se_filelist(tmp_path / "se", mq["q_thresh"], 33)
+        assert st["files_loaded"] == 2 and st["kmers_inserted"] == mq["inserts"] + mf["inserts"]
+        want = _merge_records(util.case_records("edge_se_k53_q20"), util.case_records("fasta_se_k53"))
+        util.assert_same_records(g.records(), want, "fastq+fasta list")
+
+
 def test_paired_files_of_unequal_length_are_an_error(tmp_path):
     a = tmp_path / "a.fq"
     a.write_text("@x\nACGT\n+\nIIII\n@y\nACGT\n+\nIIII\n")
