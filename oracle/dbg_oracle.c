@@ -614,3 +614,168 @@ int orc_ctx_header(int k, int N, uint32_t mean_read_len, uint64_t total_seq, uin
   memcpy(p, "CORTEX", 6); p += 6;
   return (int)(p - out);
 }
+
+/* ------------------------------------------------------------------------ */
+/* Supernode (maximal unambiguous contig) printing, restated step by step from
+ * the reference: the sequential table traversal with `visited` marks, the
+ * reverse walk to the end of the supernode, the forward walk that prints it.
+ * The product (lasv_b200/csrc/supernodes.cuh) derives the same output from a
+ * parallel path decomposition plus an event replay; this is its checker. */
+
+/* element.c:653-679  db_node_has_precisely_one_edge_in_subgraph_...; *nuc is
+ * left at the LAST edge seen, as in the reference */
+static int orc_has_precisely_one_edge(const orc_node *e, int orient, int *nuc) {
+  unsigned edges = e->edges;
+  int n, count = 0;
+  if (orient == 1) edges >>= 4;
+  for (n = 0; n < 4; n++) {
+    if (edges & 1u) { *nuc = n; count++; }
+    edges >>= 1;
+  }
+  return count == 1;
+}
+
+/* dB_graph_population.c:156-206  db_graph_get_next_node_in_subgraph_...
+ * (status pruned never occurs here; a node without edges is "not in the
+ * subgraph", element.c:850-868) */
+static orc_node *orc_get_next_node(orc_graph *g, const orc_node *cur, int cur_o, int *next_o,
+                                   int edge, int *reverse_edge) {
+  uint64_t local[ORC_MAXN], rev[ORC_MAXN], key[ORC_MAXN];
+  int i;
+  orc_node *next;
+  for (i = 0; i < g->N; i++) local[i] = cur->kmer[i];
+  orc_revcomp(local, g->k, g->N, rev);
+  if (cur_o == 1) {
+    *reverse_edge = (int)(local[g->N - 1] & 3);
+    for (i = 0; i < g->N; i++) local[i] = rev[i];
+  } else {
+    *reverse_edge = (int)(rev[g->N - 1] & 3);
+  }
+  orc_shift_insert(local, edge, g->k, g->N);
+  orc_get_key(local, g->k, g->N, key);
+  next = orc_find(g, key);
+  if (next) *next_o = orc_get_orientation(local, next, g->k, g->N);
+  if (!next || next->edges == 0) return NULL;
+  return next;
+}
+
+typedef struct {
+  orc_node **nodes;
+  int *orients;
+  int *labels;
+  char *seq;
+} orc_path;
+
+/* dB_graph_population.c:783-896  ..._get_perfect_path_with_first_edge_...;
+ * mark != 0: node_action = set status visited (2) on interior nodes.
+ * Returns -1 where the reference die()s (edge to a node that is not there). */
+static int orc_perfect_path_with_first_edge(orc_graph *g, orc_node *node, int orient, int limit,
+                                            int fst_nuc, int mark, orc_path *p, int *is_cycle) {
+  static const char nuc_char[4] = {'A', 'C', 'G', 'T'};
+  orc_node *cur = node, *next = NULL;
+  int cur_o = orient, next_o = 0, nuc = fst_nuc, rev_nuc, nuc2, length = 0;
+  if (node->edges == 0) return 0; /* "This node is not in the graph of this person" */
+  *is_cycle = 0;
+  p->nodes[0] = node;
+  p->orients[0] = orient;
+  do {
+    if (length > 0 && mark) cur->status = 2;
+    next = orc_get_next_node(g, cur, cur_o, &next_o, nuc, &rev_nuc);
+    if (!next) return -1;
+    p->labels[length] = nuc;
+    p->seq[length] = nuc_char[nuc];
+    length++;
+    p->nodes[length] = next;
+    p->orients[length] = next_o;
+    cur = next;
+    cur_o = next_o;
+  } while (length < limit && !(next == node && next_o == orient) &&
+           orc_has_precisely_one_edge(next, next_o ^ 1, &nuc2) &&
+           orc_has_precisely_one_edge(cur, cur_o, &nuc));
+  if (next == node && next_o == orient) *is_cycle = 1;
+  p->seq[length] = '\0';
+  return length;
+}
+
+/* dB_graph_population.c:900-940  ..._get_perfect_path_... */
+static int orc_perfect_path(orc_graph *g, orc_node *node, int orient, int limit, int mark,
+                            orc_path *p, int *is_cycle) {
+  int nuc;
+  p->nodes[0] = node;
+  p->orients[0] = orient;
+  if (orc_has_precisely_one_edge(node, orient, &nuc))
+    return orc_perfect_path_with_first_edge(g, node, orient, limit, nuc, mark, p, is_cycle);
+  p->seq[0] = '\0';
+  return 0;
+}
+
+/* dB_graph_population.c:1454-1527  db_graph_supernode_in_subgraph_... */
+static int orc_supernode(orc_graph *g, orc_node *node, int limit, orc_path *p, int *is_cycle) {
+  int is_cycler, length, length_reverse;
+  length_reverse = orc_perfect_path(g, node, 1, limit, 0, p, &is_cycler);
+  if (length_reverse < 0) return -1;
+  if (length_reverse > 0) {
+    int label, next_o;
+    orc_node *lst = orc_get_next_node(g, p->nodes[length_reverse - 1], p->orients[length_reverse - 1],
+                                      &next_o, p->labels[length_reverse - 1], &label);
+    if (lst != p->nodes[length_reverse]) return -1; /* "db_graph_supernode broken!" */
+    length = orc_perfect_path_with_first_edge(g, p->nodes[length_reverse],
+                                              p->orients[length_reverse] ^ 1, limit, label, 1, p,
+                                              is_cycle);
+  } else {
+    length = orc_perfect_path(g, node, 0, limit, 1, p, is_cycle);
+  }
+  if (length < 0) return -1;
+  p->nodes[0]->status = 2;
+  p->nodes[length]->status = 2;
+  return length;
+}
+
+/* dB_graph_population.c:2696-2803  db_graph_print_supernodes_... with
+ * filename_sings == "" (graph_operations.c:1281-1287), record format of
+ * print_ultra_minimal_fasta_from_path (:6125-6178), then the status reset of
+ * graph_operations.c:1290.  counts[0] = supernodes printed, [1] = singletons,
+ * [2] = nodes visited, [3] = supernodes of exactly max_length edges.
+ * Returns 0, or -1 on I/O error / inconsistent graph. */
+int orc_print_supernodes(orc_graph *g, const char *path, int max_length, uint64_t *counts) {
+  uint64_t i, cap = g->n_buckets * (uint64_t)g->W;
+  orc_path p;
+  int rc = 0;
+  FILE *f = fopen(path, "w");
+  if (!f) return -1;
+  p.nodes = (orc_node **)calloc((size_t)max_length + 1, sizeof(orc_node *));
+  p.orients = (int *)calloc((size_t)max_length + 1, sizeof(int));
+  p.labels = (int *)calloc((size_t)max_length + 1, sizeof(int));
+  p.seq = (char *)calloc((size_t)max_length + 1 + (size_t)g->k, 1);
+  counts[0] = counts[1] = counts[2] = counts[3] = 0;
+  for (i = 0; i < cap && rc == 0; i++) {
+    orc_node *e = &g->table[i];
+    int is_cycle = 0, length;
+    if (e->status == 0) continue; /* hash_table_traverse skips unassigned slots */
+    counts[2]++;
+    if (e->status != 1) continue;
+    length = orc_supernode(g, e, max_length, &p, &is_cycle);
+    if (length < 0) { rc = -1; break; }
+    if (length > 0) {
+      uint64_t fst[ORC_MAXN];
+      char *fst_seq = (char *)malloc((size_t)g->k + 1);
+      int w;
+      if (p.orients[0] == 1) orc_revcomp(p.nodes[0]->kmer, g->k, g->N, fst);
+      else for (w = 0; w < g->N; w++) fst[w] = p.nodes[0]->kmer[w];
+      orc_kmer_to_seq(fst, g->k, g->N, fst_seq);
+      fst_seq[g->k] = '\0';
+      fprintf(f, ">node_%llu length:%i INFO:KMER=%d\n%s%s\n", (unsigned long long)counts[0],
+              length + g->k, g->k, fst_seq, p.seq);
+      free(fst_seq);
+      if (length == max_length) counts[3]++;
+      counts[0]++;
+    } else {
+      counts[1]++;
+    }
+  }
+  for (i = 0; i < cap; i++)
+    if (g->table[i].status == 2) g->table[i].status = 1;
+  free(p.nodes); free(p.orients); free(p.labels); free(p.seq);
+  if (fclose(f) != 0) rc = -1;
+  return rc;
+}

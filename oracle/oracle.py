@@ -67,6 +67,8 @@ def lib() -> C.CDLL:
         L.orc_kmer_to_seq.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_char_p]
         L.orc_revcomp.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         L.orc_get_key.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        L.orc_print_supernodes.restype = C.c_int
+        L.orc_print_supernodes.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_void_p]
         L.orc_ctx_header.restype = C.c_int
         L.orc_ctx_header.argtypes = [C.c_int, C.c_int, C.c_uint32, C.c_uint64, C.c_void_p]
         _lib = L
@@ -144,6 +146,15 @@ class OracleGraph:
     def load_records(self, recs: np.ndarray) -> bool:
         recs = np.ascontiguousarray(recs)
         return bool(lib().orc_load_records(self._g, recs.ctypes.data, len(recs)))
+
+    def print_supernodes(self, path, max_length: int = 10000) -> dict:
+        """`--output_supernodes` (dB_graph_population.c:2696-2803) on this table, in table order."""
+        counts = np.zeros(4, dtype=np.uint64)
+        rc = lib().orc_print_supernodes(self._g, str(path).encode(), max_length, counts.ctypes.data)
+        if rc != 0:
+            raise RuntimeError("oracle supernode walk failed (I/O error or an edge to a missing node)")
+        return {"supernodes": int(counts[0]), "singletons": int(counts[1]), "nodes": int(counts[2]),
+                "at_max_length": int(counts[3])}
 
     def lookup(self, key_words):
         key = np.asarray(key_words, dtype=np.uint64)

@@ -106,3 +106,50 @@ def test_oracle_matches_live_reference(tmp_path, k, L, W):
     assert g.stats.kmers_inserted == ref["inserts"]
     # the oracle keeps the reference's slot order too: .ctx record order is identical
     assert np.array_equal(g.records(), ref["ctx"]["records"])
+
+
+# ---- supernodes (config 3): the oracle's restatement of the reference's sequential walk ----
+SUPERNODE_CASES = [n for n in util.ALL_CASES if "supernodes" in util.case_meta(n)]
+
+
+@pytest.mark.parametrize("name", SUPERNODE_CASES)
+def test_oracle_supernodes_match_reference_golden(name, tmp_path):
+    meta = util.case_meta(name)
+    seq, qual, offs = util.case_streams(name)
+    g, ok = util.oracle_build(meta["k"], meta["L"], meta["W"], seq, qual, offs, util.cutoff_of(meta), paired=True)
+    assert ok
+    st = g.print_supernodes(tmp_path / "sup.fa")
+    seqs = O.read_fasta_seqs(tmp_path / "sup.fa")
+    assert st["supernodes"] == len(seqs)
+    assert O.canonical_seq_set(seqs) == meta["supernodes"]
+    # the walk leaves the graph as it found it (graph_operations.c:1290)
+    st2 = g.print_supernodes(tmp_path / "sup2.fa")
+    assert st2 == st and (tmp_path / "sup2.fa").read_bytes() == (tmp_path / "sup.fa").read_bytes()
+
+
+@pytest.mark.skipif(not O.ref_available(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("k,L,W,err", [(31, 9, 30, None), (53, 9, 30, None), (95, 9, 30, None), (21, 10, 30, 30000)])
+def test_oracle_supernodes_match_live_reference_bytes(tmp_path, k, L, W, err):
+    """Same table order (the oracle keeps the reference's slot layout), so the FASTA the
+    reference prints -- names, order, strand -- must come out byte for byte; the k=21 case
+    has 3 % errors: junction next to junction, where what gets printed depends on the order."""
+    from lasv_b200 import synth
+    base = {21: synth.CFG1, 31: synth.CFG1, 53: synth.CFG0, 95: synth.CFG2}[k]
+    w = synth.scaled(base, 3000, L)
+    w.seed = 11 + k
+    w.kmer_size = k
+    p = w.params()
+    if err is not None:
+        p.err_q20 = err
+    n_pairs = 150
+    seq, qual, offs = synth.reads_host(p, 0, 2 * n_pairs)
+    stride = w.read_len + 1
+    s2, q2 = seq.reshape(-1, stride), qual.reshape(-1, stride)
+    O.write_fastq_fixed(tmp_path / "a.fq", s2[0::2].reshape(-1), q2[0::2].reshape(-1), w.read_len)
+    O.write_fastq_fixed(tmp_path / "b.fq", s2[1::2].reshape(-1), q2[1::2].reshape(-1), w.read_len)
+    O.run_reference(k, L, W, tmp_path / "a.fq", tmp_path / "b.fq", q_thresh=5, workdir=tmp_path,
+                    want_supernodes=True)
+    g, ok = util.oracle_build(k, L, W, seq, qual, offs, 38, paired=True)
+    assert ok
+    g.print_supernodes(tmp_path / "ours.fa")
+    assert (tmp_path / "ours.fa").read_bytes() == (tmp_path / "sup.fa").read_bytes()
