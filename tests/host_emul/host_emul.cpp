@@ -14,6 +14,8 @@
 
 #include "../../lasv_b200/csrc/kmer_core.cuh"
 #include "../../lasv_b200/csrc/table.cuh"
+#include "../../lasv_b200/csrc/supernodes.cuh"
+#include "../../lasv_b200/csrc/supernodes_host.h"
 
 using namespace lasv;
 
@@ -215,6 +217,60 @@ void find(uint8_t *table, int L, int W, int max_rehash, int finalized, const uin
   }
 }
 
+// the supernode kernels of supernode_kernels.cu, slot by slot / start by start, + the replay
+template <int N>
+int supernodes(uint8_t *table, int k, int L, int W, int finalized, const char *path, uint64_t *counts8) {
+  const TableView tv = make_table_view(table, N, L, W, 15, finalized != 0);
+  const uint64_t n_slots = (1ull << L) * (uint64_t)W;
+  const uint64_t max_steps = 2 * n_slots + 2;
+  std::vector<uint8_t> covered(n_slots, 0);
+  std::vector<SnPath> recs;
+  uint64_t nodes = 0, interior = 0, starts = 0, dangling = 0;
+  for (uint64_t q = 0; q < n_slots; q++) {  // sn_count_kernel + sn_starts_kernel + sn_paths_kernel
+    const uint32_t v = sn_classify<N, HostOps>(tv, q);
+    nodes += v & 1u;
+    interior += (v >> 1) & 1u;
+    starts += v >> 2;
+    if (!(v & 1u) || (v & 2u)) continue;
+    uint64_t key[N];
+    const uint64_t m = sn_load_node<N, HostOps>(tv, q, key);
+    const uint32_t e = meta_edges(m);
+    for (uint32_t bit = 0; bit < 8; bit++) {
+      if (!((e >> bit) & 1u)) continue;
+      SnPath rec;
+      bool d = false;
+      if (sn_walk_path<N, HostOps>(tv, k, q, key, e, bit >> 2, bit & 3u, max_steps, covered.data(), rec, d))
+        recs.push_back(rec);
+      dangling += d;
+    }
+  }
+  const uint64_t n_paths = recs.size();
+  uint64_t uncovered = 0;
+  for (uint64_t q = 0; q < n_slots; q++) {  // sn_uncovered_kernel + sn_cycles_kernel
+    if (covered[q] || (sn_classify<N, HostOps>(tv, q) & 3u) != 3u) continue;
+    uncovered++;
+    uint64_t key[N];
+    const uint64_t m = sn_load_node<N, HostOps>(tv, q, key);
+    SnPath rec;
+    bool d = false;
+    if (sn_walk_cycle<N, HostOps>(tv, k, q, key, meta_edges(m), max_steps, rec, d)) recs.push_back(rec);
+    dangling += d;
+  }
+  std::vector<SnPrint> prints;
+  const SnReplayStats st = sn_replay(recs, k, prints);
+  std::vector<char> seqs(sn_assign_offsets(prints, k) + 1);
+  for (const SnPrint &p : prints)  // sn_write_kernel
+    if (!sn_write_sequence<N, HostOps>(tv, k, p, seqs.data())) dangling++;
+  FILE *fp = fopen(path, "w");
+  if (!fp) return -1;
+  const bool ok = sn_write_fasta(fp, prints, seqs.data(), k);
+  if (fclose(fp) != 0 || !ok) return -1;
+  counts8[0] = st.printed; counts8[1] = nodes; counts8[2] = interior; counts8[3] = starts;
+  counts8[4] = n_paths; counts8[5] = recs.size() - n_paths; counts8[6] = st.never_printed; counts8[7] = dangling;
+  (void)uncovered;
+  return dangling ? -2 : 0;
+}
+
 }  // namespace
 
 #define DISPATCH(N, call) ((N) == 1 ? call<1> : (N) == 2 ? call<2> : call<3>)
@@ -272,6 +328,19 @@ void emul_find(uint8_t *table, int k, int L, int W, int max_rehash, int finalize
                const uint64_t *keys, uint64_t n, uint32_t *covg, uint8_t *edges, uint8_t *found) {
   const int N = 2 * k / 64 + 1;
   DISPATCH(N, find)(table, L, W, max_rehash, finalized, keys, n, covg, edges, found);
+}
+
+int emul_supernodes(uint8_t *table, int k, int L, int W, int finalized, const char *path, uint64_t *counts8) {
+  const int N = 2 * k / 64 + 1;
+  return DISPATCH(N, supernodes)(table, k, L, W, finalized, path, counts8);
+}
+
+// kmer_revcomp of supernodes.cuh, for known-answer checks
+void emul_revcomp(const uint64_t *in, int k, uint64_t *out) {
+  const int N = 2 * k / 64 + 1;
+  if (N == 1) { uint64_t a[1] = {in[0]}, b[1]; kmer_revcomp<1>(a, k, b); out[0] = b[0]; }
+  else if (N == 2) { uint64_t a[2] = {in[0], in[1]}, b[2]; kmer_revcomp<2>(a, k, b); out[0] = b[0]; out[1] = b[1]; }
+  else { uint64_t a[3] = {in[0], in[1], in[2]}, b[3]; kmer_revcomp<3>(a, k, b); out[0] = b[0]; out[1] = b[1]; out[2] = b[2]; }
 }
 
 uint32_t emul_hash_c(const uint64_t *key, int N, uint32_t rehash) {

@@ -35,6 +35,8 @@ def emul():
     L.emul_finalize.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
     L.emul_gather.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
     L.emul_find.argtypes = [C.c_void_p] + [C.c_int] * 5 + [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.emul_supernodes.argtypes = [C.c_void_p] + [C.c_int] * 4 + [C.c_char_p, C.c_void_p]
+    L.emul_revcomp.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
     L.emul_hash_c.restype = C.c_uint32
     L.emul_hash_c.argtypes = [C.c_void_p, C.c_int, C.c_uint32]
     return L
@@ -283,3 +285,86 @@ def test_emulated_build_equals_oracle_on_random_inputs(emul, reads, k, L, W, q_t
     if len(g.records()):
         found, covg, edges = table.find(np.ascontiguousarray(g.records()["kmer"]))
         assert found.all() and np.array_equal(covg, g.records()["covg"]) and np.array_equal(edges, g.records()["edges"])
+
+
+# ---- supernodes: supernodes.cuh (walks) + supernodes_host.h (replay) on the CPU ----
+SN_COUNTS = ["printed", "nodes", "interior", "starts", "paths", "cycles", "never_printed", "dangling"]
+
+
+def emul_supernodes(emul, tab, path):
+    counts = np.zeros(8, dtype=np.uint64)
+    rc = emul.emul_supernodes(tab.ptr, tab.k, tab.L, tab.W, int(tab.finalized), str(path).encode(), counts.ctypes.data)
+    assert rc == 0, f"emulated supernode extraction failed ({rc}): {dict(zip(SN_COUNTS, counts.tolist()))}"
+    return dict(zip(SN_COUNTS, (int(c) for c in counts)))
+
+
+def oracle_supernodes_in_order(tab, path):
+    """The oracle's restatement of the reference's sequential walk over OUR slot order."""
+    g = O.OracleGraph(tab.k, tab.L, tab.W)
+    assert g.load_records(tab.records())
+    return g.print_supernodes(path, max_length=1 << 20)
+
+
+@pytest.mark.parametrize("k", [21, 31, 33, 53, 63, 65, 95])
+def test_closed_form_revcomp_matches_oracle(emul, k):
+    rng = np.random.default_rng(k)
+    N = words_per_kmer(k)
+    for _ in range(200):
+        s = "".join(rng.choice(list("ACGT"), size=k))
+        km = O.seq_to_kmer(s, k)
+        out = np.zeros(N, dtype=np.uint64)
+        emul.emul_revcomp(km.ctypes.data, k, out.ctypes.data)
+        assert np.array_equal(out, O.revcomp(km, k)), s
+
+
+@pytest.mark.parametrize("name", [n for n in util.ALL_CASES if "supernodes" in util.case_meta(n)])
+@pytest.mark.parametrize("finalized", [False, True])
+def test_emulated_supernodes_match_reference_golden(emul, name, finalized, tmp_path):
+    meta = util.case_meta(name)
+    seq, qual, _ = util.case_streams(name)
+    rc, tab, _ = emul_build(emul, meta, seq, qual)
+    assert rc == 0
+    if finalized:
+        tab.finalize()
+    st = emul_supernodes(emul, tab, tmp_path / "ours.fa")
+    seqs = O.read_fasta_seqs(tmp_path / "ours.fa")
+    assert st["printed"] == len(seqs) and st["nodes"] == meta["n_records"]
+    # the contig set the compiled reference printed for its own build of the same reads
+    assert O.canonical_seq_set(seqs) == meta["supernodes"]
+    # and, for OUR slot order, the reference's sequential walk (oracle) prints the same bytes
+    ost = oracle_supernodes_in_order(tab, tmp_path / "oracle.fa")
+    assert (tmp_path / "ours.fa").read_bytes() == (tmp_path / "oracle.fa").read_bytes()
+    assert ost["supernodes"] == st["printed"] and ost["nodes"] == st["nodes"]
+
+
+@pytest.mark.parametrize("k,err_q20,seed", [(21, 30000, 3), (21, 60000, 4), (31, 40000, 5), (53, 30000, 6),
+                                             (95, 20000, 7), (15, 80000, 8)])
+def test_emulated_supernodes_order_dependent_cases(emul, k, err_q20, seed, tmp_path):
+    """Dense errors: junctions next to junctions, where whether a one-edge supernode is printed
+    depends on which of its end nodes the traversal visited first.  Ours must equal the
+    reference's sequential walk over the same slot order, byte for byte -- the oracle's
+    restatement always, the compiled reference (reloading our .ctx) where it is available."""
+    from lasv_b200 import synth
+    base = synth.CFG1 if k <= 31 else synth.CFG0 if k <= 63 else synth.CFG2
+    w = synth.scaled(base, 3000, 10)
+    w.seed = seed
+    w.kmer_size = k
+    p = w.params()
+    p.err_q20 = err_q20
+    seq, qual, _ = synth.reads_host(p, 0, 400)
+    meta = {"k": k, "L": 10, "W": 40, "q_thresh": 5}
+    rc, tab, _ = emul_build(emul, meta, seq, qual)
+    assert rc == 0
+    st = emul_supernodes(emul, tab, tmp_path / "ours.fa")
+    oracle_supernodes_in_order(tab, tmp_path / "oracle.fa")
+    ours = (tmp_path / "ours.fa").read_bytes()
+    assert ours == (tmp_path / "oracle.fa").read_bytes()
+    assert st["never_printed"] > 0 or k == 95, "case does not exercise the order dependence"
+    if O.ref_available(k):
+        recs = tab.records()
+        with open(tmp_path / "ours.ctx", "wb") as f:
+            f.write(O.ctx_header(k, 100, 1000))
+            f.write(recs.tobytes())
+        O.run_reference(k, 10, 40, None, ctx_in=tmp_path / "ours.ctx", workdir=tmp_path, want_supernodes=True,
+                        extra_args=["--max_var_len", str(1 << 20)])
+        assert ours == (tmp_path / "sup.fa").read_bytes()
