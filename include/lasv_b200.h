@@ -221,6 +221,32 @@ int lasv_graph_export_table(lasv_graph *g, void *elements, short *next_element);
 /* Merge an existing reference-layout table (e.g. from an earlier CPU load). */
 int lasv_graph_import_table(lasv_graph *g, const void *elements);
 
+/* Supernodes = maximal unambiguous contigs of the graph on the device
+ * (`--output_supernodes FILE`, graph_operations.c:1276-1293 ->
+ * db_graph_print_supernodes_defined_by_func_of_colours, dB_graph_population.c:
+ * 2696-2803, with db_graph_supernode_... :1454-1527 and ..._get_perfect_path_
+ * with_first_edge_... :783-896).  Writes the reference's FASTA (">node_<i>
+ * length:<bases> INFO:KMER=<k>", print_ultra_minimal_fasta_from_path :6125-6178)
+ * for a traversal in table order -- the order of the .ctx records this library
+ * dumps -- byte for byte what the reference prints after reloading that .ctx;
+ * singletons are not printed (filename_sings == "").  The reference's walk limit
+ * (--max_var_len, default 10000 edges, after which it prints overlapping pieces)
+ * is not applied: a supernode is always whole, `over_max_length` counts those
+ * longer than `max_length`.  The graph is left unchanged. */
+typedef struct {
+  uint64_t n_supernodes;     /* records written */
+  uint64_t n_nodes;          /* nodes in the graph */
+  uint64_t n_interior;       /* nodes with exactly one edge on each side */
+  uint64_t n_paths;          /* distinct paths between non-interior nodes */
+  uint64_t n_cycles;         /* cycles of interior nodes */
+  uint64_t n_not_printed;    /* one-edge paths whose end nodes were both visited first (the reference skips them) */
+  uint64_t longest_edges;    /* edges of the longest supernode */
+  uint64_t total_bases;      /* sum of sequence lengths */
+  uint64_t over_max_length;  /* supernodes with more than max_length edges */
+} lasv_supernode_stats;
+int lasv_graph_write_supernodes(lasv_graph *g, const char *fasta_path, int max_length,
+                                lasv_supernode_stats *stats /* may be NULL */);
+
 /* ------------------------------------------------------------------ (C) -- */
 /* Records in table order, each kmer[N] | uint32 covg | uint8 edges = 8N+5
  * bytes (element.c:894-910).  Returns the record count, or a negative error. */

@@ -38,6 +38,15 @@ class TableSummary(C.Structure):
         return {f: int(getattr(self, f)) for f, _ in self._fields_}
 
 
+class SupernodeStats(C.Structure):
+    _fields_ = [("n_supernodes", C.c_uint64), ("n_nodes", C.c_uint64), ("n_interior", C.c_uint64),
+                ("n_paths", C.c_uint64), ("n_cycles", C.c_uint64), ("n_not_printed", C.c_uint64),
+                ("longest_edges", C.c_uint64), ("total_bases", C.c_uint64), ("over_max_length", C.c_uint64)]
+
+    def as_dict(self):
+        return {f: int(getattr(self, f)) for f, _ in self._fields_}
+
+
 class SynthParams(C.Structure):
     _fields_ = [("seed", C.c_uint64), ("genome_len", C.c_uint64), ("read_len", C.c_uint32),
                 ("insert", C.c_uint32), ("err_q20", C.c_uint32), ("n_q20", C.c_uint32),
@@ -61,7 +70,7 @@ EXPORTS = [
     "lasv_graph_route_reads_device", "lasv_graph_extract_records_device",
     "lasv_graph_insert_records_device", "lasv_graph_read_stats_device", "lasv_graph_find",
     "lasv_graph_summary", "lasv_graph_finalize", "lasv_graph_export_table", "lasv_graph_import_table",
-    "lasv_graph_dump_ctx_records", "lasv_graph_write_ctx", "lasv_ctx_header",
+    "lasv_graph_dump_ctx_records", "lasv_graph_write_ctx", "lasv_ctx_header", "lasv_graph_write_supernodes",
     "lasv_graph_load_ctx_records", "lasv_graph_load_ctx_file", "lasv_graph_load_se_file",
     "lasv_graph_load_pe_files", "lasv_graph_load_se_filelist", "lasv_graph_load_pe_filelists",
     "load_se_filelist_into_graph_colour", "load_pe_filelists_into_graph_colour",
@@ -131,6 +140,7 @@ def lib() -> C.CDLL:
     L.lasv_graph_dump_ctx_records.argtypes = [vp, vp, u64]
     L.lasv_graph_write_ctx.argtypes = [vp, C.c_char_p, C.c_uint32, u64]
     L.lasv_ctx_header.argtypes = [i32, C.c_uint32, u64, vp]
+    L.lasv_graph_write_supernodes.argtypes = [vp, C.c_char_p, i32, C.POINTER(SupernodeStats)]
     L.lasv_graph_load_ctx_records.argtypes = [vp, vp, u64]
     L.lasv_graph_load_ctx_file.argtypes = [vp, C.c_char_p, C.POINTER(C.c_uint32), C.POINTER(u64)]
     L.lasv_graph_load_se_file.argtypes = [vp, C.c_char_p, i32, C.POINTER(LoadStats)]

@@ -29,6 +29,7 @@
 
 #include "../../include/lasv_b200.h"
 #include "graph_kernels.cuh"
+#include "supernodes_host.h"
 #include "seq_reader.h"
 
 using namespace lasv;
@@ -946,6 +947,138 @@ int lasv_graph_import_table(lasv_graph *g, const void *elements) {
   }();
   cudaFree(d_buf);
   return rc;
+}
+
+// ------------------------------------------------------------- supernodes
+// `--output_supernodes`: enumerate all paths on the device, replay the reference's
+// sequential traversal over the path records on the host, write the sequences on
+// the device (supernodes.cuh has the argument and the reference lines).
+int lasv_graph_write_supernodes(lasv_graph *g, const char *fasta_path, int max_length,
+                                lasv_supernode_stats *stats) {
+  if (int e = use(g)) return e;
+  if (!fasta_path) return fail(LASV_ERR_ARG, "fasta_path is NULL");
+  CUDA_TRY(cudaDeviceSynchronize());
+  const TableView tv = g->view();
+  SnCounters *d_c = nullptr, h_c;
+  uint64_t *d_starts = nullptr, *d_list = nullptr;
+  unsigned long long *d_n = nullptr;
+  uint8_t *d_covered = nullptr;
+  SnPath *d_recs = nullptr, *d_cyc = nullptr;
+  SnPrint *d_prints = nullptr;
+  char *d_seqs = nullptr;
+  std::vector<SnPath> recs;
+  std::vector<SnPrint> prints;
+  std::vector<char> seqs;
+  SnReplayStats rs;
+  uint64_t over = 0;
+  // LASV_B200_SN_TRACE=1: stage times on stderr (tools/supernodes_speed.py)
+  const bool trace = getenv("LASV_B200_SN_TRACE") != nullptr;
+  auto t_last = std::chrono::steady_clock::now();
+  auto stage = [&](const char *what) {
+    if (!trace) return;
+    cudaStreamSynchronize(g->compute);
+    const auto now = std::chrono::steady_clock::now();
+    fprintf(stderr, "[supernodes] %-28s %9.3f ms\n", what, std::chrono::duration<double, std::milli>(now - t_last).count());
+    t_last = now;
+  };
+  auto counters = [&]() -> int {
+    CUDA_TRY(cudaMemcpyAsync(&h_c, d_c, sizeof h_c, cudaMemcpyDeviceToHost, g->compute));
+    CUDA_TRY(cudaStreamSynchronize(g->compute));
+    return LASV_OK;
+  };
+  int rc = [&]() -> int {
+    CUDA_TRY(cudaMalloc(&d_c, sizeof(SnCounters)));
+    CUDA_TRY(cudaMalloc(&d_n, sizeof(unsigned long long)));
+    CUDA_TRY(cudaMemsetAsync(d_c, 0, sizeof(SnCounters), g->compute));
+    CUDA_TRY(cudaMemsetAsync(d_n, 0, sizeof(unsigned long long), g->compute));
+    launch_sn_count(g->N, tv, d_c, g->compute);
+    if (int e = check_launch()) return e;
+    if (int e = counters()) return e;
+    stage("count nodes and starts");
+    const uint64_t n_starts = h_c.n_starts;
+    // every path has two starts (twins) and keeps one record; self-twins keep theirs
+    CUDA_TRY(cudaMalloc(&d_starts, std::max<uint64_t>(1, n_starts) * sizeof(uint64_t)));
+    CUDA_TRY(cudaMalloc(&d_recs, std::max<uint64_t>(1, n_starts) * sizeof(SnPath)));
+    CUDA_TRY(cudaMalloc(&d_covered, g->n_slots));
+    CUDA_TRY(cudaMemsetAsync(d_covered, 0, g->n_slots, g->compute));
+    launch_sn_starts(g->N, tv, d_starts, n_starts, d_n, d_c, g->compute);
+    if (int e = check_launch()) return e;
+    stage("list starts");
+    launch_sn_paths(g->N, tv, g->k, d_starts, n_starts, d_covered, d_recs, n_starts, d_c, g->compute);
+    if (n_starts)
+      if (int e = check_launch()) return e;
+    stage("walk paths");
+    // interior nodes no path crossed lie on cycles: count, list, walk
+    launch_sn_uncovered(g->N, tv, d_covered, nullptr, 0, d_c, g->compute);
+    if (int e = check_launch()) return e;
+    if (int e = counters()) return e;
+    const uint64_t n_unc = h_c.n_uncovered;
+    stage("find uncovered interior nodes");
+    if (n_unc) {
+      CUDA_TRY(cudaMalloc(&d_list, n_unc * sizeof(uint64_t)));
+      CUDA_TRY(cudaMalloc(&d_cyc, n_unc * sizeof(SnPath)));
+      CUDA_TRY(cudaMemsetAsync(&d_c->n_uncovered, 0, sizeof(unsigned long long), g->compute));
+      launch_sn_uncovered(g->N, tv, d_covered, d_list, n_unc, d_c, g->compute);
+      if (int e = check_launch()) return e;
+      launch_sn_cycles(g->N, tv, g->k, d_list, n_unc, d_cyc, n_unc, d_c, g->compute);
+      if (int e = check_launch()) return e;
+      if (int e = counters()) return e;
+      stage("walk cycles");
+    }
+    if (h_c.n_overflow) return fail(LASV_ERR_STATE, "supernode record buffers overflowed (internal sizing error)");
+    if (h_c.n_dangling)
+      return fail(LASV_ERR_STATE, "%llu walks met an edge to a node that is not in the graph (the reference "
+                  "die()s: dB_graph_population.c:842-850)", (unsigned long long)h_c.n_dangling);
+    recs.resize(h_c.n_paths + h_c.n_cycles);
+    if (h_c.n_paths)
+      CUDA_TRY(cudaMemcpy(recs.data(), d_recs, h_c.n_paths * sizeof(SnPath), cudaMemcpyDeviceToHost));
+    if (h_c.n_cycles)
+      CUDA_TRY(cudaMemcpy(recs.data() + h_c.n_paths, d_cyc, h_c.n_cycles * sizeof(SnPath), cudaMemcpyDeviceToHost));
+    cudaFree(d_starts); d_starts = nullptr;
+    cudaFree(d_recs); d_recs = nullptr;
+    cudaFree(d_covered); d_covered = nullptr;
+    // the records arrive in atomic-append order; the replay sorts its events by slot, so the
+    // output does not depend on it
+    stage("copy path records to the host");
+    rs = sn_replay(recs, g->k, prints);
+    stage("replay the traversal (host)");
+    for (const SnPrint &p : prints) over += max_length > 0 && p.len > (uint32_t)max_length;
+    const uint64_t seq_bytes = sn_assign_offsets(prints, g->k);
+    if (!prints.empty()) {
+      CUDA_TRY(cudaMalloc(&d_prints, prints.size() * sizeof(SnPrint)));
+      CUDA_TRY(cudaMalloc(&d_seqs, seq_bytes));
+      CUDA_TRY(cudaMemcpyAsync(d_prints, prints.data(), prints.size() * sizeof(SnPrint), cudaMemcpyHostToDevice,
+                               g->compute));
+      launch_sn_write(g->N, tv, g->k, d_prints, prints.size(), d_seqs, d_c, g->compute);
+      if (int e = check_launch()) return e;
+      seqs.resize(seq_bytes);
+      CUDA_TRY(cudaMemcpyAsync(seqs.data(), d_seqs, seq_bytes, cudaMemcpyDeviceToHost, g->compute));
+      if (int e = counters()) return e;
+      if (h_c.n_dangling) return fail(LASV_ERR_STATE, "supernode sequence walk left the graph");
+      stage("write sequences + copy back");
+    }
+    return LASV_OK;
+  }();
+  cudaFree(d_c); cudaFree(d_n); cudaFree(d_starts); cudaFree(d_list); cudaFree(d_covered);
+  cudaFree(d_recs); cudaFree(d_cyc); cudaFree(d_prints); cudaFree(d_seqs);
+  if (rc != LASV_OK) return rc;
+  FILE *fp = fopen(fasta_path, "w");
+  if (!fp) return fail(LASV_ERR_IO, "cannot open %s for writing: %s", fasta_path, strerror(errno));
+  const bool ok = sn_write_fasta(fp, prints, seqs.data(), g->k);
+  if (fclose(fp) != 0 || !ok) return fail(LASV_ERR_IO, "short write to %s", fasta_path);
+  stage("write the FASTA file");
+  if (stats) {
+    stats->n_supernodes = rs.printed;
+    stats->n_nodes = h_c.n_nodes;
+    stats->n_interior = h_c.n_interior;
+    stats->n_paths = h_c.n_paths;
+    stats->n_cycles = h_c.n_cycles;
+    stats->n_not_printed = rs.never_printed;
+    stats->longest_edges = rs.longest;
+    stats->total_bases = rs.total_bases;
+    stats->over_max_length = over;
+  }
+  return LASV_OK;
 }
 
 // ------------------------------------------------------------ .ctx records

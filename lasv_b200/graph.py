@@ -227,6 +227,13 @@ class DBGraph:
     def dump_binary(self, path, mean_read_len: int = 0, total_seq: int = 0):
         check(self._lib.lasv_graph_write_ctx(self._h, str(path).encode(), mean_read_len, total_seq))
 
+    def output_supernodes(self, path, max_length: int = 10000) -> dict:
+        """`--output_supernodes path` (graph_operations.c:1276-1293): the reference's FASTA of
+        maximal unambiguous contigs for a traversal in table (= dumped .ctx) order."""
+        st = _capi.SupernodeStats()
+        check(self._lib.lasv_graph_write_supernodes(self._h, str(path).encode(), max_length, C.byref(st)))
+        return st.as_dict()
+
     def load_binary(self, path):
         mrl, ts = C.c_uint32(), C.c_uint64()
         check(self._lib.lasv_graph_load_ctx_file(self._h, str(path).encode(), C.byref(mrl), C.byref(ts)))

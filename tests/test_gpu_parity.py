@@ -622,6 +622,93 @@ def test_ctx_roundtrip_and_reference_consumer(name, tmp_path):
         assert O.canonical_seq_set(res["supernodes"]) == meta["supernodes"]
 
 
+def _oracle_supernodes_in_table_order(k, L, W, recs, path):
+    """The reference's sequential supernode walk (oracle restatement) over the given record order."""
+    og = O.OracleGraph(k, L, W)
+    assert og.load_records(recs)
+    return og.print_supernodes(path, max_length=1 << 20)
+
+
+@pytest.mark.parametrize("name", [n for n in util.ALL_CASES if "supernodes" in util.case_meta(n)])
+def test_gpu_supernodes_match_reference(name, tmp_path):
+    """SURVEY 8f rank 2, `--output_supernodes` on the device graph: the reference's contig set
+    (golden), and byte for byte the FASTA the reference's traversal prints for OUR slot order --
+    before and after finalisation, against the oracle's restatement and the compiled reference."""
+    meta = util.case_meta(name)
+    k, L, W = meta["k"], meta["L"], meta["W"]
+    seq, qual, offs = util.case_streams(name)
+    with DBGraph(k, L, W) as g:
+        g.load_reads_host(seq, qual, offs, util.cutoff_of(meta))
+        st = g.output_supernodes(tmp_path / "gpu.fa")
+        recs = g.records()
+        g.dump_binary(tmp_path / "gpu.ctx", 100, 1000)
+        seqs = O.read_fasta_seqs(tmp_path / "gpu.fa")
+        assert st["n_supernodes"] == len(seqs) and st["n_nodes"] == meta["n_records"]
+        assert O.canonical_seq_set(seqs) == meta["supernodes"]
+        ost = _oracle_supernodes_in_table_order(k, L, W, recs, tmp_path / "oracle.fa")
+        gpu = (tmp_path / "gpu.fa").read_bytes()
+        assert gpu == (tmp_path / "oracle.fa").read_bytes()
+        assert ost["supernodes"] == st["n_supernodes"]
+        g.finalize()                                            # reference layout: same order, same output
+        st2 = g.output_supernodes(tmp_path / "gpu_final.fa")
+        assert (tmp_path / "gpu_final.fa").read_bytes() == gpu and st2 == st
+    if O.ref_available(k):
+        O.run_reference(k, L, W, None, ctx_in=tmp_path / "gpu.ctx", workdir=tmp_path, want_supernodes=True,
+                        extra_args=["--max_var_len", str(1 << 20)])
+        assert (tmp_path / "sup.fa").read_bytes() == gpu
+
+
+@pytest.mark.parametrize("k,err_q20,n_reads,genome,L", [(21, 30000, 400, 3000, 10), (15, 80000, 400, 3000, 10),
+                                                        (53, 30000, 400, 3000, 10), (95, 20000, 400, 3000, 10),
+                                                        (31, 20000, 40000, 200000, 14)])
+def test_gpu_supernodes_order_dependent_cases(k, err_q20, n_reads, genome, L, tmp_path):
+    """Dense errors put junction next to junction: whether a one-edge supernode is printed depends on
+    which end node the traversal visited first.  The device enumeration + replay must print exactly
+    what the reference's sequential walk prints over the same slot order."""
+    base = synth.CFG1 if k <= 31 else synth.CFG0 if k <= 63 else synth.CFG2
+    w = synth.scaled(base, genome, L)
+    w.seed = 100 + k
+    w.kmer_size = k
+    p = w.params()
+    p.err_q20 = err_q20
+    seq, qual, offs = synth.reads_host(p, 0, n_reads)
+    with DBGraph(k, L, 40) as g:
+        g.load_reads_host(seq, qual, offs, 38)
+        st = g.output_supernodes(tmp_path / "gpu.fa")
+        recs = g.records()
+        g.dump_binary(tmp_path / "gpu.ctx", 100, 1000)
+    gpu = (tmp_path / "gpu.fa").read_bytes()
+    _oracle_supernodes_in_table_order(k, L, 40, recs, tmp_path / "oracle.fa")
+    assert gpu == (tmp_path / "oracle.fa").read_bytes()
+    assert st["n_not_printed"] > 0 or k == 95
+    assert st["n_nodes"] == len(recs) and st["total_bases"] == sum(len(s) for s in O.read_fasta_seqs(tmp_path / "gpu.fa"))
+    if O.ref_available(k) and n_reads <= 1000:
+        O.run_reference(k, L, 40, None, ctx_in=tmp_path / "gpu.ctx", workdir=tmp_path, want_supernodes=True,
+                        extra_args=["--max_var_len", str(1 << 20)])
+        assert (tmp_path / "sup.fa").read_bytes() == gpu
+
+
+def test_gpu_supernodes_cycles_and_long_paths(tmp_path):
+    """A circular genome read without errors is one cycle of interior nodes (no node ends a path);
+    an error-free linear genome is one long path (thousands of edges walked by one thread)."""
+    rng = np.random.default_rng(5)
+    k = 31
+    circ = "".join(rng.choice(list("ACGT"), size=500))
+    lin = "".join(rng.choice(list("ACGT"), size=6000))
+    reads = [(circ + circ)[i:i + 100] for i in range(0, 500, 7)] + [lin[i:i + 150] for i in range(0, 5851, 50)]
+    seq, _, offs = O.reads_to_streams(reads)
+    with DBGraph(k, 10, 40) as g:
+        g.load_reads_host(seq, None, offs, 0)
+        st = g.output_supernodes(tmp_path / "gpu.fa", max_length=1000)
+        recs = g.records()
+    _oracle_supernodes_in_table_order(k, 10, 40, recs, tmp_path / "oracle.fa")
+    assert (tmp_path / "gpu.fa").read_bytes() == (tmp_path / "oracle.fa").read_bytes()
+    assert st["n_cycles"] == 1 and st["n_supernodes"] == 2
+    assert st["longest_edges"] == 6000 - k and st["over_max_length"] == 1
+    seqs = sorted(O.read_fasta_seqs(tmp_path / "gpu.fa"), key=len)
+    assert len(seqs[0]) == 500 + k and len(seqs[1]) == 6000
+
+
 def test_ctx_dump_streams_through_a_bounded_buffer(tmp_path, monkeypatch):
     """A table larger than the spare device memory is dumped range of buckets by range of buckets
     (a 100 GB table holds ~65 GB of records): force hundreds of ranges on a small table."""

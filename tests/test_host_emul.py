@@ -368,3 +368,22 @@ def test_emulated_supernodes_order_dependent_cases(emul, k, err_q20, seed, tmp_p
         O.run_reference(k, 10, 40, None, ctx_in=tmp_path / "ours.ctx", workdir=tmp_path, want_supernodes=True,
                         extra_args=["--max_var_len", str(1 << 20)])
         assert ours == (tmp_path / "sup.fa").read_bytes()
+
+
+def test_emulated_supernodes_cycles_and_long_paths(emul, tmp_path):
+    """A circular genome read without errors is one cycle of interior nodes; an error-free
+    linear genome is one long path."""
+    rng = np.random.default_rng(5)
+    k = 31
+    circ = "".join(rng.choice(list("ACGT"), size=500))
+    lin = "".join(rng.choice(list("ACGT"), size=6000))
+    reads = [(circ + circ)[i:i + 100] for i in range(0, 500, 7)] + [lin[i:i + 150] for i in range(0, 5851, 50)]
+    seq, _, _ = O.reads_to_streams(reads)
+    rc, tab, _ = emul_build(emul, {"k": k, "L": 10, "W": 40, "q_thresh": 0}, seq, None)
+    assert rc == 0
+    st = emul_supernodes(emul, tab, tmp_path / "ours.fa")
+    oracle_supernodes_in_order(tab, tmp_path / "oracle.fa")
+    assert (tmp_path / "ours.fa").read_bytes() == (tmp_path / "oracle.fa").read_bytes()
+    assert st["cycles"] == 1 and st["printed"] == 2 and st["paths"] == 1
+    seqs = sorted(O.read_fasta_seqs(tmp_path / "ours.fa"), key=len)
+    assert len(seqs[0]) == 500 + k and len(seqs[1]) == 6000
