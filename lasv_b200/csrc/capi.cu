@@ -968,7 +968,9 @@ int lasv_graph_write_supernodes(lasv_graph *g, const char *fasta_path, int max_l
   char *d_seqs = nullptr;
   std::vector<SnPath> recs;
   std::vector<SnPrint> prints;
-  std::vector<char> seqs;
+  std::vector<uint64_t> hdr_at;
+  std::vector<char> image;  // the whole FASTA file
+  uint64_t image_bytes = 0;
   SnReplayStats rs;
   uint64_t over = 0;
   // LASV_B200_SN_TRACE=1: stage times on stderr (tools/supernodes_speed.py)
@@ -1034,28 +1036,31 @@ int lasv_graph_write_supernodes(lasv_graph *g, const char *fasta_path, int max_l
       CUDA_TRY(cudaMemcpy(recs.data(), d_recs, h_c.n_paths * sizeof(SnPath), cudaMemcpyDeviceToHost));
     if (h_c.n_cycles)
       CUDA_TRY(cudaMemcpy(recs.data() + h_c.n_paths, d_cyc, h_c.n_cycles * sizeof(SnPath), cudaMemcpyDeviceToHost));
+    stage("copy path records to the host");
     cudaFree(d_starts); d_starts = nullptr;
     cudaFree(d_recs); d_recs = nullptr;
     cudaFree(d_covered); d_covered = nullptr;
+    stage("free the scan buffers");
     // the records arrive in atomic-append order; the replay sorts its events by slot, so the
     // output does not depend on it
-    stage("copy path records to the host");
-    rs = sn_replay(recs, g->k, prints);
-    stage("replay the traversal (host)");
+    rs = sn_replay(recs, g->k, g->n_slots, prints);
     for (const SnPrint &p : prints) over += max_length > 0 && p.len > (uint32_t)max_length;
-    const uint64_t seq_bytes = sn_assign_offsets(prints, g->k);
+    image_bytes = sn_layout_fasta(prints, g->k, hdr_at);
+    stage("replay the traversal (host)");
     if (!prints.empty()) {
       CUDA_TRY(cudaMalloc(&d_prints, prints.size() * sizeof(SnPrint)));
-      CUDA_TRY(cudaMalloc(&d_seqs, seq_bytes));
+      CUDA_TRY(cudaMalloc(&d_seqs, image_bytes));
+      image.resize(image_bytes);
       CUDA_TRY(cudaMemcpyAsync(d_prints, prints.data(), prints.size() * sizeof(SnPrint), cudaMemcpyHostToDevice,
                                g->compute));
       launch_sn_write(g->N, tv, g->k, d_prints, prints.size(), d_seqs, d_c, g->compute);
       if (int e = check_launch()) return e;
-      seqs.resize(seq_bytes);
-      CUDA_TRY(cudaMemcpyAsync(seqs.data(), d_seqs, seq_bytes, cudaMemcpyDeviceToHost, g->compute));
+      // the device wrote the sequence lines into the image; the header lines are filled in here
+      CUDA_TRY(cudaMemcpyAsync(image.data(), d_seqs, image_bytes, cudaMemcpyDeviceToHost, g->compute));
       if (int e = counters()) return e;
       if (h_c.n_dangling) return fail(LASV_ERR_STATE, "supernode sequence walk left the graph");
-      stage("write sequences + copy back");
+      sn_fill_headers(image.data(), prints, g->k, hdr_at);
+      stage("write sequences, copy back, headers");
     }
     return LASV_OK;
   }();
@@ -1064,7 +1069,7 @@ int lasv_graph_write_supernodes(lasv_graph *g, const char *fasta_path, int max_l
   if (rc != LASV_OK) return rc;
   FILE *fp = fopen(fasta_path, "w");
   if (!fp) return fail(LASV_ERR_IO, "cannot open %s for writing: %s", fasta_path, strerror(errno));
-  const bool ok = sn_write_fasta(fp, prints, seqs.data(), g->k);
+  const bool ok = image_bytes == 0 || fwrite(image.data(), 1, image_bytes, fp) == image_bytes;
   if (fclose(fp) != 0 || !ok) return fail(LASV_ERR_IO, "short write to %s", fasta_path);
   stage("write the FASTA file");
   if (stats) {

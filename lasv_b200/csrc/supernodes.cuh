@@ -312,13 +312,14 @@ LASV_HD bool sn_walk_cycle(const TableView &t, int k, uint64_t q, const uint64_t
 // What the replay hands back for every printed supernode: where to start reading.
 struct SnPrint {
   uint64_t q;       // first node
-  uint64_t offset;  // byte offset of the sequence in the output buffer
+  uint64_t offset;  // byte offset of the sequence line in the FASTA image
   uint32_t len;     // edges; the sequence has k + len bases
   uint32_t on;      // orientation | first nucleotide << 1
 };
 
-// Sequence of one printed supernode: the first k-mer as read in the start
-// orientation, then one base per edge (print_ultra_minimal_fasta_from_path).
+// Sequence line of one printed supernode: the first k-mer as read in the start
+// orientation, then one base per edge, then the newline
+// (print_ultra_minimal_fasta_from_path).
 #pragma nv_exec_check_disable
 template <int N, class Ops>
 LASV_HD bool sn_write_sequence(const TableView &t, int k, const SnPrint &p, char *out) {
@@ -334,6 +335,7 @@ LASV_HD bool sn_write_sequence(const TableView &t, int k, const SnPrint &p, char
   char *dst = out + p.offset;
   for (int i = 0; i < k; i++) dst[i] = base_char(kmer_base_at<N>(km, k, i));
   dst += k;
+  dst[p.len] = '\n';
   for (uint32_t i = 0; i < p.len; i++) {
     uint64_t m2 = 0;
     dst[i] = base_char(cn);

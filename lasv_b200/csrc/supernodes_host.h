@@ -6,6 +6,7 @@
 #pragma once
 #include <stdint.h>
 #include <stdio.h>
+#include <string.h>
 
 #include <algorithm>
 #include <vector>
@@ -24,9 +25,10 @@ struct SnReplayStats {
   uint64_t total_bases = 0;    // sum of k + len over the printed supernodes
 };
 
-// paths: records of the path scan followed by the cycle records.  out: the printed
-// supernodes in the reference's print order (offsets not filled in).
-inline SnReplayStats sn_replay(const std::vector<SnPath> &paths, int k, std::vector<SnPrint> &out) {
+// paths: records of the path scan followed by the cycle records; n_slots: size of the
+// table (slot numbers are < n_slots).  out: the printed supernodes in the reference's
+// print order (offsets not filled in).
+inline SnReplayStats sn_replay(const std::vector<SnPath> &paths, int k, uint64_t n_slots, std::vector<SnPrint> &out) {
   struct Event {
     uint64_t pos;   // slot at which the traversal fires it
     uint32_t path;  // index into paths
@@ -34,8 +36,6 @@ inline SnReplayStats sn_replay(const std::vector<SnPath> &paths, int k, std::vec
   };
   std::vector<Event> ev;
   ev.reserve(paths.size() * 2);
-  std::vector<uint64_t> ends;  // the non-interior nodes that end some path: their `visited` marks matter
-  ends.reserve(paths.size() * 2);
   for (size_t i = 0; i < paths.size(); i++) {
     const SnPath &p = paths[i];
     if (p.bits & SNB_CYCLE) {
@@ -47,16 +47,15 @@ inline SnReplayStats sn_replay(const std::vector<SnPath> &paths, int k, std::vec
     // a path that is its own twin carries both flags for the same (node, side): one event
     const bool self_twin = p.s_q == p.t_q && ((p.bits & SNB_S_O) != 0) == ((p.bits & SNB_T_O) != 0);
     if ((p.bits & SNB_TRIG_T) && !self_twin) ev.push_back({p.t_q, (uint32_t)i, 2u});
-    ends.push_back(p.s_q);
-    ends.push_back(p.t_q);
   }
-  std::sort(ends.begin(), ends.end());
-  ends.erase(std::unique(ends.begin(), ends.end()), ends.end());
   std::sort(ev.begin(), ev.end(), [](const Event &a, const Event &b) {
     return a.pos != b.pos ? a.pos < b.pos : a.role < b.role;
   });
-  std::vector<uint8_t> visited(ends.size(), 0), printed(paths.size(), 0);
-  auto end_index = [&](uint64_t q) { return (size_t)(std::lower_bound(ends.begin(), ends.end(), q) - ends.begin()); };
+  // `visited` marks of the nodes that end paths (interior nodes are never asked): one bit per slot
+  std::vector<uint64_t> visited((n_slots + 63) / 64, 0);
+  std::vector<uint8_t> printed(paths.size(), 0);
+  auto is_visited = [&](uint64_t q) { return (visited[q >> 6] >> (q & 63)) & 1ull; };
+  auto visit = [&](uint64_t q) { visited[q >> 6] |= 1ull << (q & 63); };
 
   SnReplayStats st;
   out.clear();
@@ -73,7 +72,7 @@ inline SnReplayStats sn_replay(const std::vector<SnPath> &paths, int k, std::vec
       st.by_interior++;
     } else {
       const uint64_t x = e.role == 1 ? p.s_q : p.t_q;
-      if (visited[end_index(x)]) continue;  // an earlier supernode ended here: status != none
+      if (is_visited(x)) continue;  // an earlier supernode ended here: status != none
       const uint32_t side = (p.bits >> (e.role == 1 ? SNB_S_SIDE : SNB_T_SIDE)) & 3u;
       // reverse-side trigger: walk to the far end, print from there; forward-side: print from x
       from_t = (e.role == 1) == (side == 1u);
@@ -81,8 +80,8 @@ inline SnReplayStats sn_replay(const std::vector<SnPath> &paths, int k, std::vec
     }
     printed[e.path] = 1;
     if (!(p.bits & SNB_CYCLE)) {
-      visited[end_index(p.s_q)] = 1;
-      visited[end_index(p.t_q)] = 1;
+      visit(p.s_q);
+      visit(p.t_q);
     }
     SnPrint pr;
     pr.offset = 0;
@@ -103,27 +102,30 @@ inline SnReplayStats sn_replay(const std::vector<SnPath> &paths, int k, std::vec
   return st;
 }
 
-// Byte offsets of the sequences in one packed buffer; returns its size.
-inline uint64_t sn_assign_offsets(std::vector<SnPrint> &prints, int k) {
+// Layout of the reference's FASTA as one file image: per supernode a header line
+// ">node_<i> length:<bases> INFO:KMER=<k>" (print_ultra_minimal_fasta_from_path with the
+// first k-mer, dB_graph_population.c:6167-6169; names in print order, :2761) followed by
+// the sequence line.  Sets every SnPrint::offset to where its sequence starts (the device
+// writes sequence + newline there), returns the image size; hdr_at[i] = where header i starts.
+inline uint64_t sn_layout_fasta(std::vector<SnPrint> &prints, int k, std::vector<uint64_t> &hdr_at) {
+  hdr_at.resize(prints.size());
   uint64_t off = 0;
-  for (SnPrint &p : prints) {
-    p.offset = off;
-    off += (uint64_t)k + p.len;
+  char tmp[96];
+  for (size_t i = 0; i < prints.size(); i++) {
+    hdr_at[i] = off;
+    off += (uint64_t)snprintf(tmp, sizeof tmp, ">node_%zu length:%zu INFO:KMER=%d\n", i, (size_t)k + prints[i].len, k);
+    prints[i].offset = off;
+    off += (uint64_t)k + prints[i].len + 1;
   }
   return off;
 }
 
-// The reference's FASTA (print_ultra_minimal_fasta_from_path with the first k-mer,
-// dB_graph_population.c:6167-6169; names node_0, node_1, ... in print order, :2761).
-inline bool sn_write_fasta(FILE *fp, const std::vector<SnPrint> &prints, const char *seqs, int k) {
+inline void sn_fill_headers(char *image, const std::vector<SnPrint> &prints, int k, const std::vector<uint64_t> &hdr_at) {
+  char tmp[96];
   for (size_t i = 0; i < prints.size(); i++) {
-    const SnPrint &p = prints[i];
-    const size_t n = (size_t)k + p.len;
-    if (fprintf(fp, ">node_%zu length:%zu INFO:KMER=%d\n", i, n, k) < 0) return false;
-    if (fwrite(seqs + p.offset, 1, n, fp) != n) return false;
-    if (fputc('\n', fp) == EOF) return false;
+    const int n = snprintf(tmp, sizeof tmp, ">node_%zu length:%zu INFO:KMER=%d\n", i, (size_t)k + prints[i].len, k);
+    memcpy(image + hdr_at[i], tmp, (size_t)n);
   }
-  return true;
 }
 
 }  // namespace lasv

@@ -257,13 +257,15 @@ int supernodes(uint8_t *table, int k, int L, int W, int finalized, const char *p
     dangling += d;
   }
   std::vector<SnPrint> prints;
-  const SnReplayStats st = sn_replay(recs, k, prints);
-  std::vector<char> seqs(sn_assign_offsets(prints, k) + 1);
+  const SnReplayStats st = sn_replay(recs, k, n_slots, prints);
+  std::vector<uint64_t> hdr_at;
+  std::vector<char> image(sn_layout_fasta(prints, k, hdr_at) + 1);
   for (const SnPrint &p : prints)  // sn_write_kernel
-    if (!sn_write_sequence<N, HostOps>(tv, k, p, seqs.data())) dangling++;
+    if (!sn_write_sequence<N, HostOps>(tv, k, p, image.data())) dangling++;
+  sn_fill_headers(image.data(), prints, k, hdr_at);
   FILE *fp = fopen(path, "w");
   if (!fp) return -1;
-  const bool ok = sn_write_fasta(fp, prints, seqs.data(), k);
+  const bool ok = fwrite(image.data(), 1, image.size() - 1, fp) == image.size() - 1;
   if (fclose(fp) != 0 || !ok) return -1;
   counts8[0] = st.printed; counts8[1] = nodes; counts8[2] = interior; counts8[3] = starts;
   counts8[4] = n_paths; counts8[5] = recs.size() - n_paths; counts8[6] = st.never_printed; counts8[7] = dangling;

@@ -660,7 +660,7 @@ def test_gpu_supernodes_match_reference(name, tmp_path):
 
 @pytest.mark.parametrize("k,err_q20,n_reads,genome,L", [(21, 30000, 400, 3000, 10), (15, 80000, 400, 3000, 10),
                                                         (53, 30000, 400, 3000, 10), (95, 20000, 400, 3000, 10),
-                                                        (31, 20000, 40000, 200000, 14)])
+                                                        (31, 20000, 40000, 200000, 17)])
 def test_gpu_supernodes_order_dependent_cases(k, err_q20, n_reads, genome, L, tmp_path):
     """Dense errors put junction next to junction: whether a one-edge supernode is printed depends on
     which end node the traversal visited first.  The device enumeration + replay must print exactly
