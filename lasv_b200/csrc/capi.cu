@@ -960,17 +960,19 @@ int lasv_graph_write_supernodes(lasv_graph *g, const char *fasta_path, int max_l
   CUDA_TRY(cudaDeviceSynchronize());
   const TableView tv = g->view();
   SnCounters *d_c = nullptr, h_c;
-  uint64_t *d_starts = nullptr, *d_list = nullptr;
+  uint64_t *d_starts = nullptr, *d_list = nullptr, *d_keys = nullptr, *d_keys_alt = nullptr;
+  uint32_t *d_vals = nullptr, *d_vals_alt = nullptr;
   unsigned long long *d_n = nullptr;
   uint8_t *d_covered = nullptr;
   SnPath *d_recs = nullptr, *d_cyc = nullptr;
+  SnEvent *d_events = nullptr;
   SnPrint *d_prints = nullptr;
-  char *d_seqs = nullptr;
-  std::vector<SnPath> recs;
+  char *d_image = nullptr, *h_stage[2] = {nullptr, nullptr};
+  void *d_tmp = nullptr;
+  cudaEvent_t copied[2] = {nullptr, nullptr};
+  FILE *fp = nullptr;
+  std::unique_ptr<SnEvent[]> events;
   std::vector<SnPrint> prints;
-  std::vector<uint64_t> hdr_at;
-  std::vector<char> image;  // the whole FASTA file
-  uint64_t image_bytes = 0;
   SnReplayStats rs;
   uint64_t over = 0;
   // LASV_B200_SN_TRACE=1: stage times on stderr (tools/supernodes_speed.py)
@@ -980,7 +982,7 @@ int lasv_graph_write_supernodes(lasv_graph *g, const char *fasta_path, int max_l
     if (!trace) return;
     cudaStreamSynchronize(g->compute);
     const auto now = std::chrono::steady_clock::now();
-    fprintf(stderr, "[supernodes] %-28s %9.3f ms\n", what, std::chrono::duration<double, std::milli>(now - t_last).count());
+    fprintf(stderr, "[supernodes] %-36s %9.3f ms\n", what, std::chrono::duration<double, std::milli>(now - t_last).count());
     t_last = now;
   };
   auto counters = [&]() -> int {
@@ -1031,47 +1033,108 @@ int lasv_graph_write_supernodes(lasv_graph *g, const char *fasta_path, int max_l
     if (h_c.n_dangling)
       return fail(LASV_ERR_STATE, "%llu walks met an edge to a node that is not in the graph (the reference "
                   "die()s: dB_graph_population.c:842-850)", (unsigned long long)h_c.n_dangling);
-    recs.resize(h_c.n_paths + h_c.n_cycles);
-    if (h_c.n_paths)
-      CUDA_TRY(cudaMemcpy(recs.data(), d_recs, h_c.n_paths * sizeof(SnPath), cudaMemcpyDeviceToHost));
-    if (h_c.n_cycles)
-      CUDA_TRY(cudaMemcpy(recs.data() + h_c.n_paths, d_cyc, h_c.n_cycles * sizeof(SnPath), cudaMemcpyDeviceToHost));
-    stage("copy path records to the host");
     cudaFree(d_starts); d_starts = nullptr;
-    cudaFree(d_recs); d_recs = nullptr;
     cudaFree(d_covered); d_covered = nullptr;
-    stage("free the scan buffers");
-    // the records arrive in atomic-append order; the replay sorts its events by slot, so the
-    // output does not depend on it
-    rs = sn_replay(recs, g->k, g->n_slots, prints);
+    cudaFree(d_list); d_list = nullptr;
+
+    // replay events: (slot, path << 2 | role) pairs, sorted by slot on the device, expanded to
+    // SnEvent records in that order (the path records arrive in atomic-append order; sorting the
+    // events by slot makes the output independent of it)
+    const uint64_t n_rec = h_c.n_paths + h_c.n_cycles;
+    if (n_rec >= (1ull << 30)) return fail(LASV_ERR_CAPACITY, "more than 2^30 paths");
+    uint64_t n_ev = 0;
+    if (n_rec) {
+      CUDA_TRY(cudaMalloc(&d_keys, 3 * n_rec * sizeof(uint64_t)));
+      CUDA_TRY(cudaMalloc(&d_keys_alt, 3 * n_rec * sizeof(uint64_t)));
+      CUDA_TRY(cudaMalloc(&d_vals, 3 * n_rec * sizeof(uint32_t)));
+      CUDA_TRY(cudaMalloc(&d_vals_alt, 3 * n_rec * sizeof(uint32_t)));
+      CUDA_TRY(cudaMemsetAsync(d_n, 0, sizeof(unsigned long long), g->compute));
+      launch_sn_events(d_recs, h_c.n_paths, 0u, d_keys, d_vals, d_n, g->compute);
+      if (h_c.n_paths)
+        if (int e = check_launch()) return e;
+      launch_sn_events(d_cyc, h_c.n_cycles, (uint32_t)h_c.n_paths, d_keys, d_vals, d_n, g->compute);
+      if (h_c.n_cycles)
+        if (int e = check_launch()) return e;
+      unsigned long long nev = 0;
+      CUDA_TRY(cudaMemcpyAsync(&nev, d_n, sizeof nev, cudaMemcpyDeviceToHost, g->compute));
+      CUDA_TRY(cudaStreamSynchronize(g->compute));
+      n_ev = nev;
+    }
+    if (n_ev) {
+      int key_bits = 1;
+      while (key_bits < 64 && (g->n_slots >> key_bits)) key_bits++;
+      const size_t tmp_bytes = sn_sort_tmp_bytes(n_ev);
+      CUDA_TRY(cudaMalloc(&d_tmp, std::max<size_t>(tmp_bytes, 16)));
+      CUDA_TRY(cudaMalloc(&d_events, n_ev * sizeof(SnEvent)));
+      launch_sn_sort_events(d_keys, d_keys_alt, d_vals, d_vals_alt, n_ev, key_bits, d_tmp, tmp_bytes, d_recs,
+                            h_c.n_paths, d_cyc, d_events, g->compute);
+      if (int e = check_launch()) return e;
+      stage("events: build, sort, expand");
+      events.reset(new SnEvent[n_ev]);
+      CUDA_TRY(cudaMemcpyAsync(events.get(), d_events, n_ev * sizeof(SnEvent), cudaMemcpyDeviceToHost, g->compute));
+      CUDA_TRY(cudaStreamSynchronize(g->compute));
+      stage("copy events to the host");
+    }
+    cudaFree(d_recs); d_recs = nullptr;
+    cudaFree(d_cyc); d_cyc = nullptr;
+    cudaFree(d_keys); d_keys = nullptr;
+    cudaFree(d_keys_alt); d_keys_alt = nullptr;
+    cudaFree(d_vals); d_vals = nullptr;
+    cudaFree(d_vals_alt); d_vals_alt = nullptr;
+    cudaFree(d_tmp); d_tmp = nullptr;
+    cudaFree(d_events); d_events = nullptr;
+
+    rs = sn_replay_events(events.get(), n_ev, n_rec, g->n_slots, g->k, prints);
+    events.reset();
     for (const SnPrint &p : prints) over += max_length > 0 && p.len > (uint32_t)max_length;
-    image_bytes = sn_layout_fasta(prints, g->k, hdr_at);
+    const uint64_t image_bytes = sn_layout_fasta(prints, g->k);
     stage("replay the traversal (host)");
+
+    fp = fopen(fasta_path, "w");
+    if (!fp) return fail(LASV_ERR_IO, "cannot open %s for writing: %s", fasta_path, strerror(errno));
     if (!prints.empty()) {
       CUDA_TRY(cudaMalloc(&d_prints, prints.size() * sizeof(SnPrint)));
-      CUDA_TRY(cudaMalloc(&d_seqs, image_bytes));
-      image.resize(image_bytes);
+      CUDA_TRY(cudaMalloc(&d_image, image_bytes));
       CUDA_TRY(cudaMemcpyAsync(d_prints, prints.data(), prints.size() * sizeof(SnPrint), cudaMemcpyHostToDevice,
                                g->compute));
-      launch_sn_write(g->N, tv, g->k, d_prints, prints.size(), d_seqs, d_c, g->compute);
+      // the device writes the whole file image: header lines and sequence lines
+      launch_sn_write(g->N, tv, g->k, d_prints, prints.size(), d_image, d_c, g->compute);
       if (int e = check_launch()) return e;
-      // the device wrote the sequence lines into the image; the header lines are filled in here
-      CUDA_TRY(cudaMemcpyAsync(image.data(), d_seqs, image_bytes, cudaMemcpyDeviceToHost, g->compute));
       if (int e = counters()) return e;
       if (h_c.n_dangling) return fail(LASV_ERR_STATE, "supernode sequence walk left the graph");
-      sn_fill_headers(image.data(), prints, g->k, hdr_at);
-      stage("write sequences, copy back, headers");
+      stage("write the FASTA image (device)");
+      // image -> file through two pinned staging buffers: the copy of chunk i+1 runs under the fwrite of chunk i
+      const uint64_t chunk = 16ull << 20;
+      for (int b = 0; b < 2; b++) {
+        CUDA_TRY(cudaMallocHost(&h_stage[b], chunk));
+        CUDA_TRY(cudaEventCreateWithFlags(&copied[b], cudaEventDisableTiming));
+      }
+      const uint64_t n_chunks = (image_bytes + chunk - 1) / chunk;
+      auto bytes_of = [&](uint64_t c) { return std::min(chunk, image_bytes - c * chunk); };
+      for (uint64_t c = 0; c <= n_chunks; c++) {
+        if (c < n_chunks) {
+          CUDA_TRY(cudaMemcpyAsync(h_stage[c & 1], d_image + c * chunk, bytes_of(c), cudaMemcpyDeviceToHost, g->compute));
+          CUDA_TRY(cudaEventRecord(copied[c & 1], g->compute));
+        }
+        if (c > 0) {
+          CUDA_TRY(cudaEventSynchronize(copied[(c - 1) & 1]));
+          if (fwrite(h_stage[(c - 1) & 1], 1, bytes_of(c - 1), fp) != bytes_of(c - 1))
+            return fail(LASV_ERR_IO, "short write to %s", fasta_path);
+        }
+      }
+      stage("copy back + write the file");
     }
     return LASV_OK;
   }();
   cudaFree(d_c); cudaFree(d_n); cudaFree(d_starts); cudaFree(d_list); cudaFree(d_covered);
-  cudaFree(d_recs); cudaFree(d_cyc); cudaFree(d_prints); cudaFree(d_seqs);
+  cudaFree(d_recs); cudaFree(d_cyc); cudaFree(d_keys); cudaFree(d_keys_alt); cudaFree(d_vals); cudaFree(d_vals_alt);
+  cudaFree(d_tmp); cudaFree(d_events); cudaFree(d_prints); cudaFree(d_image);
+  for (int b = 0; b < 2; b++) {
+    if (h_stage[b]) cudaFreeHost(h_stage[b]);
+    if (copied[b]) cudaEventDestroy(copied[b]);
+  }
+  if (fp && fclose(fp) != 0 && rc == LASV_OK) rc = fail(LASV_ERR_IO, "cannot close %s: %s", fasta_path, strerror(errno));
   if (rc != LASV_OK) return rc;
-  FILE *fp = fopen(fasta_path, "w");
-  if (!fp) return fail(LASV_ERR_IO, "cannot open %s for writing: %s", fasta_path, strerror(errno));
-  const bool ok = image_bytes == 0 || fwrite(image.data(), 1, image_bytes, fp) == image_bytes;
-  if (fclose(fp) != 0 || !ok) return fail(LASV_ERR_IO, "short write to %s", fasta_path);
-  stage("write the FASTA file");
   if (stats) {
     stats->n_supernodes = rs.printed;
     stats->n_nodes = h_c.n_nodes;

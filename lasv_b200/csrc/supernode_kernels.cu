@@ -11,12 +11,15 @@
 //                        if this start is the smaller twin
 //   sn_uncovered_kernel  per slot: interior nodes no walk crossed (cycles) -> list
 //   sn_cycles_kernel     one thread per such node: walk the cycle, lowest slot keeps it
-//   sn_write_kernel      one thread per printed supernode: first k-mer + one base per edge
+//   sn_events_kernel     per path record: its replay events as (slot, path << 2 | role) pairs
+//   cub radix sort       the events by slot; sn_expand_events_kernel: SnEvent records in that order
+//   sn_write_kernel      one thread per printed supernode: header line, first k-mer, one base per edge
 //
 // All of them are latency-bound pointer chases except the per-slot sweeps, which
 // stream the table once; grids are sized to the resident-CTA limit of the device.
 #include <stdint.h>
 
+#include <cub/device/device_radix_sort.cuh>
 #include <type_traits>
 
 #include "graph_kernels.cuh"
@@ -140,11 +143,49 @@ __global__ void __launch_bounds__(SN_THREADS) sn_cycles_kernel(const TableView t
 template <int N>
 __global__ void __launch_bounds__(SN_THREADS) sn_write_kernel(const TableView t, const int k,
                                                              const SnPrint *__restrict__ prints, const uint64_t n,
-                                                             char *out, SnCounters *c) {
+                                                             char *image, SnCounters *c) {
   for (uint64_t i = (uint64_t)blockIdx.x * SN_THREADS + threadIdx.x; i < n;
        i += (uint64_t)gridDim.x * SN_THREADS) {
     const SnPrint p = prints[i];
-    if (!sn_write_sequence<N, DeviceOps>(t, k, p, out)) atomicAdd(&c->n_dangling, 1ull);
+    if (!sn_write_record<N, DeviceOps>(t, k, p, i, image)) atomicAdd(&c->n_dangling, 1ull);
+  }
+}
+
+__global__ void __launch_bounds__(SN_THREADS) sn_events_kernel(const SnPath *__restrict__ recs, const uint64_t n,
+                                                              const uint32_t index_base, uint64_t *keys,
+                                                              uint32_t *vals, unsigned long long *n_events) {
+  for (uint64_t i = (uint64_t)blockIdx.x * SN_THREADS + threadIdx.x; i < n;
+       i += (uint64_t)gridDim.x * SN_THREADS) {
+    uint64_t pos[3];
+    uint32_t role[3];
+    const int m = sn_path_events(recs[i], pos, role);
+    if (!m) continue;
+    const uint64_t at = atomicAdd(n_events, (unsigned long long)m);
+    for (int j = 0; j < m; j++) {
+      keys[at + j] = pos[j];
+      vals[at + j] = ((index_base + (uint32_t)i) << 2) | role[j];
+    }
+  }
+}
+
+__global__ void __launch_bounds__(SN_THREADS) sn_expand_events_kernel(const uint32_t *__restrict__ vals,
+                                                                     const uint64_t n_events,
+                                                                     const SnPath *__restrict__ paths,
+                                                                     const uint64_t n_paths,
+                                                                     const SnPath *__restrict__ cycles,
+                                                                     SnEvent *events) {
+  for (uint64_t i = (uint64_t)blockIdx.x * SN_THREADS + threadIdx.x; i < n_events;
+       i += (uint64_t)gridDim.x * SN_THREADS) {
+    const uint32_t v = vals[i], idx = v >> 2;
+    const SnPath p = idx < n_paths ? paths[idx] : cycles[idx - n_paths];
+    SnEvent e;
+    e.s_q = p.s_q;
+    e.t_q = p.t_q;
+    e.len = p.len;
+    e.bits = p.bits;
+    e.path = idx;
+    e.role = v & 3u;
+    events[i] = e;
   }
 }
 
@@ -215,13 +256,37 @@ void launch_sn_cycles(int N, const TableView &t, int k, const uint64_t *list, ui
   });
 }
 
-void launch_sn_write(int N, const TableView &t, int k, const SnPrint *prints, uint64_t n, char *out,
+void launch_sn_write(int N, const TableView &t, int k, const SnPrint *prints, uint64_t n, char *image,
                      SnCounters *c, cudaStream_t st) {
   if (!n) return;
   sn_dispatch(N, [&](auto nn) {
     constexpr int NN = decltype(nn)::value;
-    sn_write_kernel<NN><<<sn_grid(sn_write_kernel<NN>, n), SN_THREADS, 0, st>>>(t, k, prints, n, out, c);
+    sn_write_kernel<NN><<<sn_grid(sn_write_kernel<NN>, n), SN_THREADS, 0, st>>>(t, k, prints, n, image, c);
   });
+}
+
+void launch_sn_events(const SnPath *recs, uint64_t n, uint32_t index_base, uint64_t *keys, uint32_t *vals,
+                      unsigned long long *n_events, cudaStream_t st) {
+  if (!n) return;
+  sn_events_kernel<<<sn_grid(sn_events_kernel, n), SN_THREADS, 0, st>>>(recs, n, index_base, keys, vals, n_events);
+}
+
+size_t sn_sort_tmp_bytes(uint64_t n_events) {
+  size_t bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const uint64_t *)nullptr, (uint64_t *)nullptr,
+                                  (const uint32_t *)nullptr, (uint32_t *)nullptr, (long long)n_events, 0, 64);
+  return bytes;
+}
+
+void launch_sn_sort_events(uint64_t *keys, uint64_t *keys_alt, uint32_t *vals, uint32_t *vals_alt, uint64_t n_events,
+                           int key_bits, void *tmp, size_t tmp_bytes, const SnPath *paths, uint64_t n_paths,
+                           const SnPath *cycles, SnEvent *events, cudaStream_t st) {
+  if (!n_events) return;
+  // slots are distinct per event, so any order of equal keys would do; the sort is stable anyway
+  cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, (const uint64_t *)keys, keys_alt, (const uint32_t *)vals, vals_alt,
+                                  (long long)n_events, 0, key_bits, st);
+  sn_expand_events_kernel<<<sn_grid(sn_expand_events_kernel, n_events), SN_THREADS, 0, st>>>(vals_alt, n_events, paths,
+                                                                                           n_paths, cycles, events);
 }
 
 }  // namespace lasv

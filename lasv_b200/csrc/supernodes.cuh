@@ -309,20 +309,74 @@ LASV_HD bool sn_walk_cycle(const TableView &t, int k, uint64_t q, const uint64_t
   return true;
 }
 
-// What the replay hands back for every printed supernode: where to start reading.
+// One trigger of the replay: at slot `pos` the traversal reaches a node that would
+// print path `path` (role 0: its lowest interior node, or a cycle; 1: its start node;
+// 2: its end node -- the node must still be unvisited for roles 1 and 2).  Events are
+// processed in slot order; they carry what the replay needs of the path record.
+struct SnEvent {
+  uint64_t s_q, t_q;
+  uint32_t len, bits;
+  uint32_t path;
+  uint32_t role;
+};
+
+LASV_HD int sn_path_events(const SnPath &p, uint64_t (&pos)[3], uint32_t (&role)[3]) {
+  if (p.bits & SNB_CYCLE) {
+    pos[0] = p.min_q;
+    role[0] = 0u;
+    return 1;
+  }
+  int n = 0;
+  if (p.min_q != SN_NONE) { pos[n] = p.min_q; role[n++] = 0u; }
+  if (p.bits & SNB_TRIG_S) { pos[n] = p.s_q; role[n++] = 1u; }
+  // a path that is its own twin carries both flags for the same (node, side): one event
+  const bool self_twin = p.s_q == p.t_q && ((p.bits & SNB_S_O) != 0) == ((p.bits & SNB_T_O) != 0);
+  if ((p.bits & SNB_TRIG_T) && !self_twin) { pos[n] = p.t_q; role[n++] = 2u; }
+  return n;
+}
+
+// What the replay hands back for every printed supernode: where to start reading,
+// and where its record starts in the FASTA image.
 struct SnPrint {
   uint64_t q;       // first node
-  uint64_t offset;  // byte offset of the sequence line in the FASTA image
+  uint64_t offset;  // byte offset of the record (header line) in the FASTA image
   uint32_t len;     // edges; the sequence has k + len bases
   uint32_t on;      // orientation | first nucleotide << 1
 };
 
-// Sequence line of one printed supernode: the first k-mer as read in the start
-// orientation, then one base per edge, then the newline
+// ">node_<i> length:<bases> INFO:KMER=<k>\n" (dB_graph_population.c:2761, :6167)
+LASV_HD uint32_t dec_digits(uint64_t v) {
+  uint32_t d = 1;
+  while (v >= 10) { v /= 10; d++; }
+  return d;
+}
+LASV_HD uint32_t put_dec(char *dst, uint64_t v) {
+  const uint32_t d = dec_digits(v);
+  for (uint32_t i = d; i-- > 0;) { dst[i] = (char)('0' + (int)(v % 10)); v /= 10; }
+  return d;
+}
+LASV_HD uint32_t sn_header_bytes(uint64_t i, uint64_t bases, int k) {
+  return 6u + dec_digits(i) + 8u + dec_digits(bases) + 11u + dec_digits((uint64_t)k) + 1u;
+}
+LASV_HD uint32_t sn_write_header(char *dst, uint64_t i, uint64_t bases, int k) {
+  const char a[] = ">node_", b[] = " length:", c[] = " INFO:KMER=";
+  uint32_t n = 0;
+  for (int j = 0; j < 6; j++) dst[n++] = a[j];
+  n += put_dec(dst + n, i);
+  for (int j = 0; j < 8; j++) dst[n++] = b[j];
+  n += put_dec(dst + n, bases);
+  for (int j = 0; j < 11; j++) dst[n++] = c[j];
+  n += put_dec(dst + n, (uint64_t)k);
+  dst[n++] = '\n';
+  return n;
+}
+
+// Record i of the FASTA: header line, then the first k-mer as read in the start
+// orientation and one base per edge, then the newline
 // (print_ultra_minimal_fasta_from_path).
 #pragma nv_exec_check_disable
 template <int N, class Ops>
-LASV_HD bool sn_write_sequence(const TableView &t, int k, const SnPrint &p, char *out) {
+LASV_HD bool sn_write_record(const TableView &t, int k, const SnPrint &p, uint64_t i, char *image) {
   uint64_t key[N], key2[N], km[N];
   const uint64_t m = sn_load_node<N, Ops>(t, p.q, key);
   if (!m) return false;
@@ -332,14 +386,15 @@ LASV_HD bool sn_write_sequence(const TableView &t, int k, const SnPrint &p, char
 #pragma unroll
     for (int w = 0; w < N; w++) km[w] = key[w];
   }
-  char *dst = out + p.offset;
-  for (int i = 0; i < k; i++) dst[i] = base_char(kmer_base_at<N>(km, k, i));
+  char *dst = image + p.offset;
+  dst += sn_write_header(dst, i, (uint64_t)k + p.len, k);
+  for (int b = 0; b < k; b++) dst[b] = base_char(kmer_base_at<N>(km, k, b));
   dst += k;
   dst[p.len] = '\n';
-  for (uint32_t i = 0; i < p.len; i++) {
+  for (uint32_t e = 0; e < p.len; e++) {
     uint64_t m2 = 0;
-    dst[i] = base_char(cn);
-    if (i + 1 == p.len) break;
+    dst[e] = base_char(cn);
+    if (e + 1 == p.len) break;
     if (sn_step<N, Ops>(t, k, key, co, cn, key2, m2, o2, back) == SN_NONE) return false;
 #pragma unroll
     for (int w = 0; w < N; w++) key[w] = key2[w];
@@ -360,8 +415,16 @@ void launch_sn_uncovered(int N, const TableView &t, const uint8_t *covered, uint
                          SnCounters *c, cudaStream_t st);
 void launch_sn_cycles(int N, const TableView &t, int k, const uint64_t *list, uint64_t n, SnPath *recs,
                       uint64_t cap, SnCounters *c, cudaStream_t st);
-void launch_sn_write(int N, const TableView &t, int k, const SnPrint *prints, uint64_t n, char *out,
+void launch_sn_write(int N, const TableView &t, int k, const SnPrint *prints, uint64_t n, char *image,
                      SnCounters *c, cudaStream_t st);
+// events of recs[0..n) appended to (keys, vals) at *n_events; val = (index_base + i) << 2 | role
+void launch_sn_events(const SnPath *recs, uint64_t n, uint32_t index_base, uint64_t *keys, uint32_t *vals,
+                      unsigned long long *n_events, cudaStream_t st);
+// sort the events by slot (keys_alt / vals_alt / tmp: scratch), then expand them to SnEvent in that order
+size_t sn_sort_tmp_bytes(uint64_t n_events);
+void launch_sn_sort_events(uint64_t *keys, uint64_t *keys_alt, uint32_t *vals, uint32_t *vals_alt, uint64_t n_events,
+                           int key_bits, void *tmp, size_t tmp_bytes, const SnPath *paths, uint64_t n_paths,
+                           const SnPath *cycles, SnEvent *events, cudaStream_t st);
 #endif
 
 }  // namespace lasv

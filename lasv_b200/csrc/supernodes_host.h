@@ -25,107 +25,92 @@ struct SnReplayStats {
   uint64_t total_bases = 0;    // sum of k + len over the printed supernodes
 };
 
-// paths: records of the path scan followed by the cycle records; n_slots: size of the
-// table (slot numbers are < n_slots).  out: the printed supernodes in the reference's
-// print order (offsets not filled in).
-inline SnReplayStats sn_replay(const std::vector<SnPath> &paths, int k, uint64_t n_slots, std::vector<SnPrint> &out) {
-  struct Event {
-    uint64_t pos;   // slot at which the traversal fires it
-    uint32_t path;  // index into paths
-    uint32_t role;  // 0 interior node / cycle, 1 start node, 2 end node
-  };
-  std::vector<Event> ev;
-  ev.reserve(paths.size() * 2);
-  for (size_t i = 0; i < paths.size(); i++) {
-    const SnPath &p = paths[i];
-    if (p.bits & SNB_CYCLE) {
-      ev.push_back({p.min_q, (uint32_t)i, 0u});
-      continue;
-    }
-    if (p.min_q != SN_NONE) ev.push_back({p.min_q, (uint32_t)i, 0u});
-    if (p.bits & SNB_TRIG_S) ev.push_back({p.s_q, (uint32_t)i, 1u});
-    // a path that is its own twin carries both flags for the same (node, side): one event
-    const bool self_twin = p.s_q == p.t_q && ((p.bits & SNB_S_O) != 0) == ((p.bits & SNB_T_O) != 0);
-    if ((p.bits & SNB_TRIG_T) && !self_twin) ev.push_back({p.t_q, (uint32_t)i, 2u});
-  }
-  std::sort(ev.begin(), ev.end(), [](const Event &a, const Event &b) {
-    return a.pos != b.pos ? a.pos < b.pos : a.role < b.role;
-  });
+// events: the triggers of all paths in slot order.  out: the printed supernodes in the
+// reference's print order (offsets not filled in).
+inline SnReplayStats sn_replay_events(const SnEvent *ev, size_t n_events, size_t n_paths, uint64_t n_slots, int k,
+                                      std::vector<SnPrint> &out) {
   // `visited` marks of the nodes that end paths (interior nodes are never asked): one bit per slot
   std::vector<uint64_t> visited((n_slots + 63) / 64, 0);
-  std::vector<uint8_t> printed(paths.size(), 0);
+  std::vector<uint8_t> printed(n_paths, 0);
   auto is_visited = [&](uint64_t q) { return (visited[q >> 6] >> (q & 63)) & 1ull; };
   auto visit = [&](uint64_t q) { visited[q >> 6] |= 1ull << (q & 63); };
-
   SnReplayStats st;
   out.clear();
-  for (const Event &e : ev) {
-    const SnPath &p = paths[e.path];
+  out.reserve(n_paths);
+  for (size_t i = 0; i < n_events; i++) {
+    const SnEvent &e = ev[i];
     if (printed[e.path]) continue;
     bool from_t = false;  // print the twin (start at the t end)
-    if (p.bits & SNB_CYCLE) {
+    if (e.bits & SNB_CYCLE) {
       st.cycles++;
     } else if (e.role == 0) {
       // the interior node min_q walks against its own reverse orientation to the end of the
       // supernode and the print starts there: crossed in reverse by the s->t walk => that end is t
-      from_t = (p.bits & SNB_MIN_O) != 0;
+      from_t = (e.bits & SNB_MIN_O) != 0;
       st.by_interior++;
     } else {
-      const uint64_t x = e.role == 1 ? p.s_q : p.t_q;
-      if (is_visited(x)) continue;  // an earlier supernode ended here: status != none
-      const uint32_t side = (p.bits >> (e.role == 1 ? SNB_S_SIDE : SNB_T_SIDE)) & 3u;
+      if (is_visited(e.role == 1 ? e.s_q : e.t_q)) continue;  // an earlier supernode ended here: status != none
+      const uint32_t side = (e.bits >> (e.role == 1 ? SNB_S_SIDE : SNB_T_SIDE)) & 3u;
       // reverse-side trigger: walk to the far end, print from there; forward-side: print from x
       from_t = (e.role == 1) == (side == 1u);
       st.by_end_node++;
     }
     printed[e.path] = 1;
-    if (!(p.bits & SNB_CYCLE)) {
-      visit(p.s_q);
-      visit(p.t_q);
+    if (!(e.bits & SNB_CYCLE)) {
+      visit(e.s_q);
+      visit(e.t_q);
     }
     SnPrint pr;
     pr.offset = 0;
-    pr.len = p.len;
+    pr.len = e.len;
     if (from_t) {
-      pr.q = p.t_q;
-      pr.on = ((p.bits & SNB_T_O) ? 1u : 0u) | (((p.bits >> SNB_T_N) & 3u) << 1);
+      pr.q = e.t_q;
+      pr.on = ((e.bits & SNB_T_O) ? 1u : 0u) | (((e.bits >> SNB_T_N) & 3u) << 1);
     } else {
-      pr.q = p.s_q;
-      pr.on = ((p.bits & SNB_S_O) ? 1u : 0u) | (((p.bits >> SNB_S_N) & 3u) << 1);
+      pr.q = e.s_q;
+      pr.on = ((e.bits & SNB_S_O) ? 1u : 0u) | (((e.bits >> SNB_S_N) & 3u) << 1);
     }
     out.push_back(pr);
     st.printed++;
-    st.longest = std::max<uint64_t>(st.longest, p.len);
-    st.total_bases += (uint64_t)k + p.len;
+    st.longest = std::max<uint64_t>(st.longest, e.len);
+    st.total_bases += (uint64_t)k + e.len;
   }
-  for (size_t i = 0; i < paths.size(); i++) st.never_printed += !printed[i];
+  st.never_printed = n_paths - st.printed;
   return st;
 }
 
-// Layout of the reference's FASTA as one file image: per supernode a header line
-// ">node_<i> length:<bases> INFO:KMER=<k>" (print_ultra_minimal_fasta_from_path with the
-// first k-mer, dB_graph_population.c:6167-6169; names in print order, :2761) followed by
-// the sequence line.  Sets every SnPrint::offset to where its sequence starts (the device
-// writes sequence + newline there), returns the image size; hdr_at[i] = where header i starts.
-inline uint64_t sn_layout_fasta(std::vector<SnPrint> &prints, int k, std::vector<uint64_t> &hdr_at) {
-  hdr_at.resize(prints.size());
-  uint64_t off = 0;
-  char tmp[96];
-  for (size_t i = 0; i < prints.size(); i++) {
-    hdr_at[i] = off;
-    off += (uint64_t)snprintf(tmp, sizeof tmp, ">node_%zu length:%zu INFO:KMER=%d\n", i, (size_t)k + prints[i].len, k);
-    prints[i].offset = off;
-    off += (uint64_t)k + prints[i].len + 1;
+// The same from the path records (path scan, then cycles): builds and sorts the events on
+// the host.  tests/host_emul uses this; the library sorts on the device (supernode_kernels.cu).
+inline SnReplayStats sn_replay(const std::vector<SnPath> &paths, int k, uint64_t n_slots, std::vector<SnPrint> &out) {
+  struct Keyed {
+    uint64_t pos;
+    SnEvent e;
+  };
+  std::vector<Keyed> ev;
+  ev.reserve(paths.size() * 2);
+  for (size_t i = 0; i < paths.size(); i++) {
+    const SnPath &p = paths[i];
+    uint64_t pos[3];
+    uint32_t role[3];
+    const int n = sn_path_events(p, pos, role);
+    for (int j = 0; j < n; j++) ev.push_back({pos[j], {p.s_q, p.t_q, p.len, p.bits, (uint32_t)i, role[j]}});
   }
-  return off;
+  std::sort(ev.begin(), ev.end(), [](const Keyed &a, const Keyed &b) { return a.pos < b.pos; });
+  std::vector<SnEvent> sorted(ev.size());
+  for (size_t i = 0; i < ev.size(); i++) sorted[i] = ev[i].e;
+  return sn_replay_events(sorted.data(), sorted.size(), paths.size(), n_slots, k, out);
 }
 
-inline void sn_fill_headers(char *image, const std::vector<SnPrint> &prints, int k, const std::vector<uint64_t> &hdr_at) {
-  char tmp[96];
+// Layout of the reference's FASTA as one file image: record i = header line + sequence
+// line.  Sets every SnPrint::offset to where its record starts, returns the image size.
+inline uint64_t sn_layout_fasta(std::vector<SnPrint> &prints, int k) {
+  uint64_t off = 0;
   for (size_t i = 0; i < prints.size(); i++) {
-    const int n = snprintf(tmp, sizeof tmp, ">node_%zu length:%zu INFO:KMER=%d\n", i, (size_t)k + prints[i].len, k);
-    memcpy(image + hdr_at[i], tmp, (size_t)n);
+    prints[i].offset = off;
+    const uint64_t bases = (uint64_t)k + prints[i].len;
+    off += sn_header_bytes(i, bases, k) + bases + 1;
   }
+  return off;
 }
 
 }  // namespace lasv

@@ -258,11 +258,9 @@ int supernodes(uint8_t *table, int k, int L, int W, int finalized, const char *p
   }
   std::vector<SnPrint> prints;
   const SnReplayStats st = sn_replay(recs, k, n_slots, prints);
-  std::vector<uint64_t> hdr_at;
-  std::vector<char> image(sn_layout_fasta(prints, k, hdr_at) + 1);
-  for (const SnPrint &p : prints)  // sn_write_kernel
-    if (!sn_write_sequence<N, HostOps>(tv, k, p, image.data())) dangling++;
-  sn_fill_headers(image.data(), prints, k, hdr_at);
+  std::vector<char> image(sn_layout_fasta(prints, k) + 1);
+  for (size_t i = 0; i < prints.size(); i++)  // sn_write_kernel
+    if (!sn_write_record<N, HostOps>(tv, k, prints[i], i, image.data())) dangling++;
   FILE *fp = fopen(path, "w");
   if (!fp) return -1;
   const bool ok = fwrite(image.data(), 1, image.size() - 1, fp) == image.size() - 1;
