@@ -971,7 +971,7 @@ int lasv_graph_write_supernodes(lasv_graph *g, const char *fasta_path, int max_l
   void *d_tmp = nullptr;
   cudaEvent_t copied[2] = {nullptr, nullptr};
   FILE *fp = nullptr;
-  std::unique_ptr<SnEvent[]> events;
+  constexpr uint64_t STAGE_BYTES = 16ull << 20;
   std::vector<SnPrint> prints;
   SnReplayStats rs;
   uint64_t over = 0;
@@ -1070,10 +1070,6 @@ int lasv_graph_write_supernodes(lasv_graph *g, const char *fasta_path, int max_l
                             h_c.n_paths, d_cyc, d_events, g->compute);
       if (int e = check_launch()) return e;
       stage("events: build, sort, expand");
-      events.reset(new SnEvent[n_ev]);
-      CUDA_TRY(cudaMemcpyAsync(events.get(), d_events, n_ev * sizeof(SnEvent), cudaMemcpyDeviceToHost, g->compute));
-      CUDA_TRY(cudaStreamSynchronize(g->compute));
-      stage("copy events to the host");
     }
     cudaFree(d_recs); d_recs = nullptr;
     cudaFree(d_cyc); d_cyc = nullptr;
@@ -1082,10 +1078,33 @@ int lasv_graph_write_supernodes(lasv_graph *g, const char *fasta_path, int max_l
     cudaFree(d_vals); d_vals = nullptr;
     cudaFree(d_vals_alt); d_vals_alt = nullptr;
     cudaFree(d_tmp); d_tmp = nullptr;
-    cudaFree(d_events); d_events = nullptr;
 
-    rs = sn_replay_events(events.get(), n_ev, n_rec, g->n_slots, g->k, prints);
-    events.reset();
+    // the replay consumes the events in order, so they stream through the two pinned staging
+    // buffers: the copy of piece i+1 runs under the replay of piece i
+    for (int b = 0; b < 2; b++) {
+      CUDA_TRY(cudaMallocHost(&h_stage[b], STAGE_BYTES));
+      CUDA_TRY(cudaEventCreateWithFlags(&copied[b], cudaEventDisableTiming));
+    }
+    SnReplayer replayer(n_rec, g->n_slots, g->k);
+    {
+      const uint64_t per = STAGE_BYTES / sizeof(SnEvent);
+      const uint64_t n_pieces = (n_ev + per - 1) / per;
+      auto count_of = [&](uint64_t c) { return std::min(per, n_ev - c * per); };
+      for (uint64_t c = 0; c <= n_pieces; c++) {
+        if (c < n_pieces) {
+          CUDA_TRY(cudaMemcpyAsync(h_stage[c & 1], d_events + c * per, count_of(c) * sizeof(SnEvent),
+                                   cudaMemcpyDeviceToHost, g->compute));
+          CUDA_TRY(cudaEventRecord(copied[c & 1], g->compute));
+        }
+        if (c > 0) {
+          CUDA_TRY(cudaEventSynchronize(copied[(c - 1) & 1]));
+          replayer.feed(reinterpret_cast<const SnEvent *>(h_stage[(c - 1) & 1]), count_of(c - 1));
+        }
+      }
+    }
+    cudaFree(d_events); d_events = nullptr;
+    rs = replayer.finish();
+    prints.swap(replayer.prints);
     for (const SnPrint &p : prints) over += max_length > 0 && p.len > (uint32_t)max_length;
     const uint64_t image_bytes = sn_layout_fasta(prints, g->k);
     stage("replay the traversal (host)");
@@ -1104,11 +1123,7 @@ int lasv_graph_write_supernodes(lasv_graph *g, const char *fasta_path, int max_l
       if (h_c.n_dangling) return fail(LASV_ERR_STATE, "supernode sequence walk left the graph");
       stage("write the FASTA image (device)");
       // image -> file through two pinned staging buffers: the copy of chunk i+1 runs under the fwrite of chunk i
-      const uint64_t chunk = 16ull << 20;
-      for (int b = 0; b < 2; b++) {
-        CUDA_TRY(cudaMallocHost(&h_stage[b], chunk));
-        CUDA_TRY(cudaEventCreateWithFlags(&copied[b], cudaEventDisableTiming));
-      }
+      const uint64_t chunk = STAGE_BYTES;
       const uint64_t n_chunks = (image_bytes + chunk - 1) / chunk;
       auto bytes_of = [&](uint64_t c) { return std::min(chunk, image_bytes - c * chunk); };
       for (uint64_t c = 0; c <= n_chunks; c++) {

@@ -371,6 +371,34 @@ LASV_HD uint32_t sn_write_header(char *dst, uint64_t i, uint64_t bases, int k) {
   return n;
 }
 
+// Sequential byte output with 8-byte stores: single bytes up to the first 8-byte boundary,
+// then whole words (one thread writes one record; byte stores were 85 % of sn_write_kernel).
+struct ByteWriter {
+  char *p;       // next byte to be stored
+  uint64_t acc;  // bytes collected for the word at p (p is 8-byte aligned whenever n > 0)
+  uint32_t n;
+  LASV_HD explicit ByteWriter(char *dst) : p(dst), acc(0), n(0) {}
+  LASV_HD void put(char c) {
+    if (n == 0 && (reinterpret_cast<uintptr_t>(p) & 7u) != 0) {
+      *p++ = c;
+      return;
+    }
+    acc |= (uint64_t)(uint8_t)c << (8u * n);
+    if (++n == 8u) {
+      *reinterpret_cast<uint64_t *>(p) = acc;  // little-endian: byte j of the word is p[j]
+      p += 8;
+      acc = 0;
+      n = 0;
+    }
+  }
+  LASV_HD void flush() {
+    for (uint32_t j = 0; j < n; j++) p[j] = (char)(acc >> (8u * j));
+    p += n;
+    acc = 0;
+    n = 0;
+  }
+};
+
 // Record i of the FASTA: header line, then the first k-mer as read in the start
 // orientation and one base per edge, then the newline
 // (print_ultra_minimal_fasta_from_path).
@@ -386,22 +414,25 @@ LASV_HD bool sn_write_record(const TableView &t, int k, const SnPrint &p, uint64
 #pragma unroll
     for (int w = 0; w < N; w++) km[w] = key[w];
   }
-  char *dst = image + p.offset;
-  dst += sn_write_header(dst, i, (uint64_t)k + p.len, k);
-  for (int b = 0; b < k; b++) dst[b] = base_char(kmer_base_at<N>(km, k, b));
-  dst += k;
-  dst[p.len] = '\n';
+  char hdr[72];
+  const uint32_t hn = sn_write_header(hdr, i, (uint64_t)k + p.len, k);
+  ByteWriter out(image + p.offset);
+  for (uint32_t b = 0; b < hn; b++) out.put(hdr[b]);
+  for (int b = 0; b < k; b++) out.put(base_char(kmer_base_at<N>(km, k, b)));
+  bool ok = true;
   for (uint32_t e = 0; e < p.len; e++) {
     uint64_t m2 = 0;
-    dst[e] = base_char(cn);
+    out.put(base_char(cn));
     if (e + 1 == p.len) break;
-    if (sn_step<N, Ops>(t, k, key, co, cn, key2, m2, o2, back) == SN_NONE) return false;
+    if (sn_step<N, Ops>(t, k, key, co, cn, key2, m2, o2, back) == SN_NONE) { ok = false; break; }
 #pragma unroll
     for (int w = 0; w < N; w++) key[w] = key2[w];
     co = o2;
     cn = low_bit4(sn_side(meta_edges(m2), o2));
   }
-  return true;
+  out.put('\n');
+  out.flush();
+  return ok;
 }
 
 #if defined(__CUDACC__)

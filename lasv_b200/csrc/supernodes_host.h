@@ -25,59 +25,78 @@ struct SnReplayStats {
   uint64_t total_bases = 0;    // sum of k + len over the printed supernodes
 };
 
-// events: the triggers of all paths in slot order.  out: the printed supernodes in the
-// reference's print order (offsets not filled in).
-inline SnReplayStats sn_replay_events(const SnEvent *ev, size_t n_events, size_t n_paths, uint64_t n_slots, int k,
-                                      std::vector<SnPrint> &out) {
-  // `visited` marks of the nodes that end paths (interior nodes are never asked): one bit per slot
-  std::vector<uint64_t> visited((n_slots + 63) / 64, 0);
-  std::vector<uint8_t> printed(n_paths, 0);
-  auto is_visited = [&](uint64_t q) { return (visited[q >> 6] >> (q & 63)) & 1ull; };
-  auto visit = [&](uint64_t q) { visited[q >> 6] |= 1ull << (q & 63); };
-  SnReplayStats st;
-  out.clear();
-  out.reserve(n_paths);
-  for (size_t i = 0; i < n_events; i++) {
-    const SnEvent &e = ev[i];
-    if (printed[e.path]) continue;
-    bool from_t = false;  // print the twin (start at the t end)
-    if (e.bits & SNB_CYCLE) {
-      st.cycles++;
-    } else if (e.role == 0) {
-      // the interior node min_q walks against its own reverse orientation to the end of the
-      // supernode and the print starts there: crossed in reverse by the s->t walk => that end is t
-      from_t = (e.bits & SNB_MIN_O) != 0;
-      st.by_interior++;
-    } else {
-      if (is_visited(e.role == 1 ? e.s_q : e.t_q)) continue;  // an earlier supernode ended here: status != none
-      const uint32_t side = (e.bits >> (e.role == 1 ? SNB_S_SIDE : SNB_T_SIDE)) & 3u;
-      // reverse-side trigger: walk to the far end, print from there; forward-side: print from x
-      from_t = (e.role == 1) == (side == 1u);
-      st.by_end_node++;
-    }
-    printed[e.path] = 1;
-    if (!(e.bits & SNB_CYCLE)) {
-      visit(e.s_q);
-      visit(e.t_q);
-    }
-    SnPrint pr;
-    pr.offset = 0;
-    pr.len = e.len;
-    if (from_t) {
-      pr.q = e.t_q;
-      pr.on = ((e.bits & SNB_T_O) ? 1u : 0u) | (((e.bits >> SNB_T_N) & 3u) << 1);
-    } else {
-      pr.q = e.s_q;
-      pr.on = ((e.bits & SNB_S_O) ? 1u : 0u) | (((e.bits >> SNB_S_N) & 3u) << 1);
-    }
-    out.push_back(pr);
-    st.printed++;
-    st.longest = std::max<uint64_t>(st.longest, e.len);
-    st.total_bases += (uint64_t)k + e.len;
+// The replay proper: feed it the triggers of all paths in slot order (in as many pieces
+// as convenient -- the library streams them from the device); `prints` collects the
+// printed supernodes in the reference's print order (offsets not filled in).
+class SnReplayer {
+ public:
+  SnReplayer(size_t n_paths, uint64_t n_slots, int k)
+      : visited_((n_slots + 63) / 64, 0), printed_(n_paths, 0), n_paths_(n_paths), k_(k) {
+    prints.reserve(n_paths);
   }
-  st.never_printed = n_paths - st.printed;
-  return st;
-}
+  void feed(const SnEvent *ev, size_t n) {
+    constexpr size_t AHEAD = 16;  // the marks are random accesses into tens of MB: fetch them early
+    for (size_t i = 0; i < n; i++) {
+      if (i + AHEAD < n) {
+        const SnEvent &f = ev[i + AHEAD];
+        __builtin_prefetch(&printed_[f.path]);
+        __builtin_prefetch(&visited_[f.s_q >> 6]);
+        __builtin_prefetch(&visited_[f.t_q >> 6]);
+      }
+      const SnEvent &e = ev[i];
+      if (printed_[e.path]) continue;
+      bool from_t = false;  // print the twin (start at the t end)
+      if (e.bits & SNB_CYCLE) {
+        stats_.cycles++;
+      } else if (e.role == 0) {
+        // the interior node min_q walks against its own reverse orientation to the end of the
+        // supernode and the print starts there: crossed in reverse by the s->t walk => that end is t
+        from_t = (e.bits & SNB_MIN_O) != 0;
+        stats_.by_interior++;
+      } else {
+        if (is_visited(e.role == 1 ? e.s_q : e.t_q)) continue;  // an earlier supernode ended here: status != none
+        const uint32_t side = (e.bits >> (e.role == 1 ? SNB_S_SIDE : SNB_T_SIDE)) & 3u;
+        // reverse-side trigger: walk to the far end, print from there; forward-side: print from x
+        from_t = (e.role == 1) == (side == 1u);
+        stats_.by_end_node++;
+      }
+      printed_[e.path] = 1;
+      if (!(e.bits & SNB_CYCLE)) {
+        visit(e.s_q);
+        visit(e.t_q);
+      }
+      SnPrint pr;
+      pr.offset = 0;
+      pr.len = e.len;
+      if (from_t) {
+        pr.q = e.t_q;
+        pr.on = ((e.bits & SNB_T_O) ? 1u : 0u) | (((e.bits >> SNB_T_N) & 3u) << 1);
+      } else {
+        pr.q = e.s_q;
+        pr.on = ((e.bits & SNB_S_O) ? 1u : 0u) | (((e.bits >> SNB_S_N) & 3u) << 1);
+      }
+      prints.push_back(pr);
+      stats_.printed++;
+      stats_.longest = std::max<uint64_t>(stats_.longest, e.len);
+      stats_.total_bases += (uint64_t)k_ + e.len;
+    }
+  }
+  SnReplayStats finish() {
+    stats_.never_printed = n_paths_ - stats_.printed;
+    return stats_;
+  }
+  std::vector<SnPrint> prints;
+
+ private:
+  bool is_visited(uint64_t q) const { return (visited_[q >> 6] >> (q & 63)) & 1ull; }
+  void visit(uint64_t q) { visited_[q >> 6] |= 1ull << (q & 63); }
+  // `visited` marks of the nodes that end paths (interior nodes are never asked): one bit per slot
+  std::vector<uint64_t> visited_;
+  std::vector<uint8_t> printed_;
+  size_t n_paths_;
+  int k_;
+  SnReplayStats stats_;
+};
 
 // The same from the path records (path scan, then cycles): builds and sorts the events on
 // the host.  tests/host_emul uses this; the library sorts on the device (supernode_kernels.cu).
@@ -98,7 +117,12 @@ inline SnReplayStats sn_replay(const std::vector<SnPath> &paths, int k, uint64_t
   std::sort(ev.begin(), ev.end(), [](const Keyed &a, const Keyed &b) { return a.pos < b.pos; });
   std::vector<SnEvent> sorted(ev.size());
   for (size_t i = 0; i < ev.size(); i++) sorted[i] = ev[i].e;
-  return sn_replay_events(sorted.data(), sorted.size(), paths.size(), n_slots, k, out);
+  SnReplayer rp(paths.size(), n_slots, k);
+  // in uneven pieces, as the library feeds it
+  for (size_t at = 0, step = 1; at < sorted.size(); at += step, step = step * 3 + 1)
+    rp.feed(sorted.data() + at, std::min(step, sorted.size() - at));
+  out.swap(rp.prints);
+  return rp.finish();
 }
 
 // Layout of the reference's FASTA as one file image: record i = header line + sequence
