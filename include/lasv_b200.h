@@ -289,6 +289,16 @@ int lasv_graph_load_pe_filelists(lasv_graph *g, const char *list1, const char *l
  * integration/ctx_loader_shim.c is the reference-side binding. */
 long long lasv_ref_hash_table_load_ctx_records(lasv_ref_hash_table *t, const char *path, long record_offset);
 
+/* db_graph_print_supernodes_defined_by_func_of_colours (dB_graph_population.c:2696-2803)
+ * on the caller's reference-layout table: the table is copied to the device as it is
+ * (same slot order, so the traversal order is the caller's), the supernodes are
+ * enumerated there (lasv_graph_write_supernodes above) and the reference's FASTA is
+ * written to fasta_path.  Nodes whose edges were reset by the reference's cleaning
+ * (pruned) are isolated and print nothing, as in the reference.  The table is not
+ * modified.  integration/supernode_shim.c is the reference-side binding. */
+int lasv_ref_hash_table_write_supernodes(lasv_ref_hash_table *t, const char *fasta_path, int max_length,
+                                         lasv_supernode_stats *stats /* may be NULL */);
+
 /* Exact reference signatures (file_reader.h:86-118); `boolean` is signed char
  * (global.h:37).  They build the graph on the GPU and leave db_graph->table,
  * next_element, unique_kmers and collisions[] as the reference loader would

@@ -70,7 +70,7 @@ EXPORTS = [
     "lasv_graph_route_reads_device", "lasv_graph_extract_records_device",
     "lasv_graph_insert_records_device", "lasv_graph_read_stats_device", "lasv_graph_find",
     "lasv_graph_summary", "lasv_graph_finalize", "lasv_graph_export_table", "lasv_graph_import_table",
-    "lasv_graph_dump_ctx_records", "lasv_graph_write_ctx", "lasv_ctx_header", "lasv_graph_write_supernodes",
+    "lasv_graph_dump_ctx_records", "lasv_graph_write_ctx", "lasv_ctx_header", "lasv_graph_write_supernodes", "lasv_ref_hash_table_write_supernodes",
     "lasv_graph_load_ctx_records", "lasv_graph_load_ctx_file", "lasv_graph_load_se_file",
     "lasv_graph_load_pe_files", "lasv_graph_load_se_filelist", "lasv_graph_load_pe_filelists",
     "load_se_filelist_into_graph_colour", "load_pe_filelists_into_graph_colour",

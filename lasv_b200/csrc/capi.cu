@@ -1904,6 +1904,32 @@ void dropin_load(lasv_ref_hash_table *t, const char *list1, const char *list2, i
  * hands over the file offset of the first record.  The caller's reference-layout table is merged in
  * first if it already holds k-mers, then replaced by the result.  Returns the number of records read,
  * or a negative error code. */
+int lasv_ref_hash_table_write_supernodes(lasv_ref_hash_table *t, const char *fasta_path, int max_length,
+                                         lasv_supernode_stats *stats) {
+  if (!t || !t->table) return fail(LASV_ERR_ARG, "NULL table!");
+  const int L = log2_exact(t->number_buckets);
+  if (L < 0) return fail(LASV_ERR_ARG, "number_buckets is not a power of two");
+  int dev = 0;
+  if (const char *e = getenv("LASV_B200_DEVICE")) dev = atoi(e);
+  lasv_graph *g = lasv_graph_new(t->kmer_size, L, t->bucket_size, t->max_rehash_tries, dev);
+  if (!g) return LASV_ERR_CUDA;
+  int rc = [&]() -> int {
+    // the inverse of lasv_graph_export_table: bucket b = W consecutive Elements at the start of its
+    // NL lines (the finalised arrangement), slack bytes stay zero
+    const size_t row = (size_t)g->W * g->slot_bytes, pitch = (size_t)(g->table_bytes / g->n_buckets);
+    const uint64_t rows_per_copy = 1ull << 20;
+    for (uint64_t b0 = 0; b0 < g->n_buckets; b0 += rows_per_copy) {
+      const uint64_t nb = std::min(rows_per_copy, g->n_buckets - b0);
+      CUDA_TRY(cudaMemcpy2D(g->d_lines + b0 * pitch, pitch, (const uint8_t *)t->table + b0 * row, row, row,
+                            (size_t)nb, cudaMemcpyHostToDevice));
+    }
+    g->finalized = true;
+    return lasv_graph_write_supernodes(g, fasta_path, max_length, stats);
+  }();
+  lasv_graph_free(&g);
+  return rc;
+}
+
 long long lasv_ref_hash_table_load_ctx_records(lasv_ref_hash_table *t, const char *path, long record_offset) {
   if (!t || !t->table) return fail(LASV_ERR_ARG, "NULL table!");
   const int L = log2_exact(t->number_buckets);

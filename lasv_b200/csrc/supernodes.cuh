@@ -372,7 +372,7 @@ LASV_HD uint32_t sn_write_header(char *dst, uint64_t i, uint64_t bases, int k) {
 }
 
 // Sequential byte output with 8-byte stores: single bytes up to the first 8-byte boundary,
-// then whole words (one thread writes one record; byte stores were 85 % of sn_write_kernel).
+// then whole words (one thread writes one record; neighbouring records never share a word store).
 struct ByteWriter {
   char *p;       // next byte to be stored
   uint64_t acc;  // bytes collected for the word at p (p is 8-byte aligned whenever n > 0)

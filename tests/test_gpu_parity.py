@@ -762,6 +762,47 @@ def test_reference_cli_with_gpu_loader(name, tmp_path):
     assert tries == meta["inserts"]
 
 
+@pytest.mark.parametrize("name", ["synth_cfg1_k31", "synth_cfg0_k53", "synth_cfg2_k95"])
+@pytest.mark.parametrize("clean", [False, True])
+def test_reference_cli_prints_supernodes_through_the_gpu(name, clean, tmp_path):
+    """the reference's main() with `--output_supernodes` bound to the GPU
+    (integration/supernode_shim.c + lasv_ref_hash_table_write_supernodes), on the table the GPU
+    loader left in host memory -- raw, and after the reference's own tip clipping and
+    low-coverage supernode removal (pruned nodes stay in the table, isolated).  The FASTA must be
+    what the reference's sequential walk prints for that table: the oracle's restatement walks the
+    `.ctx` the same run dumped (same slot order) and must produce the same bytes."""
+    from pathlib import Path
+    meta = util.case_meta(name)
+    k, L, W = meta["k"], meta["L"], meta["W"]
+    exe = Path(__file__).resolve().parents[1] / "integration" / "_build" / f"dB_graph_gpusn_{O.MAXK_OF_N[O.words_per_kmer(k)]}"
+    if not exe.exists():
+        pytest.skip("integration/_build not built (needs /root/reference at build time)")
+    seq, qual, _ = util.case_streams(name)
+    rl = meta["workload"]["read_len"]
+    s2, q2 = seq.reshape(-1, rl + 1), qual.reshape(-1, rl + 1)
+    O.write_fastq_fixed(tmp_path / "a.fq", s2[0::2].reshape(-1), q2[0::2].reshape(-1), rl)
+    O.write_fastq_fixed(tmp_path / "b.fq", s2[1::2].reshape(-1), q2[1::2].reshape(-1), rl)
+    (tmp_path / "l").write_text(f"{tmp_path / 'a.fq'}\n")
+    (tmp_path / "r").write_text(f"{tmp_path / 'b.fq'}\n")
+    cmd = [str(exe), "--kmer_size", str(k), "--mem_height", str(L), "--mem_width", str(W),
+           "--pe_list", f"{tmp_path / 'l'},{tmp_path / 'r'}", "--quality_score_threshold", str(meta["q_thresh"]),
+           "--dump_binary", str(tmp_path / "out.ctx"), "--output_supernodes", str(tmp_path / "sup.fa")]
+    if clean:
+        cmd += ["--remove_low_coverage_supernodes", "2"]
+    p = subprocess.run(cmd, cwd=tmp_path, capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stderr[-2000:] + p.stdout[-2000:]
+    assert "nodes visted" in p.stdout
+    ctx = O.parse_ctx(tmp_path / "out.ctx")
+    seqs = O.read_fasta_seqs(tmp_path / "sup.fa")
+    if not clean:
+        util.assert_same_records(ctx["records"], util.case_records(name), name)
+        assert O.canonical_seq_set(seqs) == meta["supernodes"]
+    else:
+        assert 0 < len(ctx["records"]) < meta["n_records"]
+    _oracle_supernodes_in_table_order(k, L, W, ctx["records"], tmp_path / "oracle.fa")
+    assert (tmp_path / "sup.fa").read_bytes() == (tmp_path / "oracle.fa").read_bytes()
+
+
 @pytest.mark.parametrize("name", ["synth_cfg1_k31", "synth_cfg0_k53", "synth_cfg2_k95", "synth_full_k53"])
 def test_reference_cli_reloads_ctx_through_the_gpu(name, tmp_path):
     """`dB_graph --multicolour_bin x.ctx` with the record loop of
