@@ -555,7 +555,7 @@ uint64_t orc_dump_records(const orc_graph *g, uint8_t *out) {
   size_t rec = 8 * (size_t)g->N + 5;
   for (i = 0; i < cap; i++) {
     const orc_node *e = &g->table[i];
-    if (e->status == 0) continue; /* db_node_check_for_flag_ALL_OFF */
+    if (e->status != 1 && e->status != 2) continue; /* db_node_check_status_not_pruned, element.c:795-802 */
     memcpy(out + n * rec, e->kmer, 8 * (size_t)g->N);
     memcpy(out + n * rec + 8 * (size_t)g->N, &e->covg, 4);
     out[n * rec + 8 * (size_t)g->N + 4] = e->edges;
@@ -655,7 +655,7 @@ static orc_node *orc_get_next_node(orc_graph *g, const orc_node *cur, int cur_o,
   orc_get_key(local, g->k, g->N, key);
   next = orc_find(g, key);
   if (next) *next_o = orc_get_orientation(local, next, g->k, g->N);
-  if (!next || next->edges == 0) return NULL;
+  if (!next || next->status == 3 || next->edges == 0) return NULL; /* element.c:850-868 */
   return next;
 }
 
@@ -778,4 +778,144 @@ int orc_print_supernodes(orc_graph *g, const char *path, int max_length, uint64_
   free(p.nodes); free(p.orients); free(p.labels); free(p.seq);
   if (fclose(f) != 0) rc = -1;
   return rc;
+}
+
+/* ------------------------------------------------------------------------ */
+/* Cleaning, as `--remove_low_coverage_supernodes T` runs it (graph_operations.c:
+ * 1069-1090): clip tips, then prune low-coverage supernodes.  Both mutate the
+ * graph while they traverse it, so what they leave depends on the slot order. */
+
+/* element.c:249-267  reset_one_edge */
+static void orc_reset_one_edge(orc_node *e, int orient, int nuc) {
+  e->edges &= (uint8_t)~(1u << (nuc + 4 * orient));
+}
+
+/* dB_graph_population.c:365-441  ..._clip_tip_with_orientation_...; node_action =
+ * db_node_action_set_status_pruned, edges of the tip reset, back edge of the
+ * junction reset.  Returns the tip length, 0 if nothing was clipped, -1 where the
+ * reference die()s. */
+static int orc_clip_tip_with_orientation(orc_graph *g, orc_node *node, int orientation, int limit,
+                                         orc_node **nodes) {
+  int nuc = 0, rev_nuc = 0, next_o = 0, length = 0, i;
+  orc_node *next = NULL;
+  unsigned other = node->edges;
+  if ((orientation ^ 1) == 1) other >>= 4;
+  if ((other & 15u) != 0) return 0; /* not a blunt end against the walk (element.c:761-774) */
+  {
+    int join_main_trunk = 0;
+    while (orc_has_precisely_one_edge(node, orientation, &nuc)) {
+      nodes[length] = node;
+      next = orc_get_next_node(g, node, orientation, &next_o, nuc, &rev_nuc);
+      if (!next) return -1;
+      length++;
+      if (length > limit) break;
+      if (!orc_has_precisely_one_edge(next, next_o ^ 1, &nuc)) { join_main_trunk = 1; break; }
+      node = next;
+      orientation = next_o;
+    }
+    if (!join_main_trunk) {
+      length = 0;
+    } else {
+      for (i = 0; i < length; i++) { nodes[i]->status = 3; nodes[i]->edges = 0; }
+      orc_reset_one_edge(next, next_o ^ 1, rev_nuc);
+    }
+  }
+  return length;
+}
+
+/* dB_graph_population.c:485-530  db_graph_db_node_prune_low_coverage (the raw
+ * db_graph_get_next_node of dB_graph.c:22-62: no subgraph check) */
+static int orc_prune_low_coverage(orc_graph *g, orc_node *node, uint32_t coverage) {
+  int nuc, orient;
+  if (node->covg > coverage) return 0;
+  for (nuc = 0; nuc < 4; nuc++) {
+    for (orient = 0; orient < 2; orient++) {
+      if ((node->edges >> (nuc + 4 * orient)) & 1u) {
+        uint64_t local[ORC_MAXN], rev[ORC_MAXN], key[ORC_MAXN];
+        int i, next_o, rev_nuc;
+        orc_node *next;
+        for (i = 0; i < g->N; i++) local[i] = node->kmer[i];
+        orc_revcomp(local, g->k, g->N, rev);
+        if (orient == 1) {
+          rev_nuc = (int)(local[g->N - 1] & 3);
+          for (i = 0; i < g->N; i++) local[i] = rev[i];
+        } else {
+          rev_nuc = (int)(rev[g->N - 1] & 3);
+        }
+        orc_shift_insert(local, nuc, g->k, g->N);
+        orc_get_key(local, g->k, g->N, key);
+        next = orc_find(g, key);
+        if (!next) return -1; /* the reference dereferences NULL here */
+        next_o = orc_get_orientation(local, next, g->k, g->N);
+        orc_reset_one_edge(next, next_o ^ 1, rev_nuc);
+      }
+    }
+  }
+  node->status = 3;
+  node->edges = 0;
+  return 1;
+}
+
+/* graph_operations.c:1069-1090: db_graph_clip_tips_in_union_of_all_colours
+ * (dB_graph_population.c:2563-2608, limit k+1) then
+ * db_graph_remove_errors_considering_covg_and_topology (:3595-3649 with
+ * :3371-3462), then visited -> none (:3640).  counts[0] = tips clipped,
+ * [1] = nodes pruned as tips, [2] = supernodes pruned, [3] = nodes left.
+ * Returns 0, or -1 where the reference would die. */
+int orc_clean(orc_graph *g, int threshold, int max_var_len, uint64_t *counts) {
+  uint64_t i, cap = g->n_buckets * (uint64_t)g->W;
+  int limit = 1 + g->k, rc = 0;
+  orc_node **nodes = (orc_node **)calloc((size_t)limit + 2, sizeof(orc_node *));
+  orc_path p;
+  counts[0] = counts[1] = counts[2] = counts[3] = 0;
+  for (i = 0; i < cap && rc == 0; i++) {
+    orc_node *e = &g->table[i];
+    int len;
+    if (e->status != 1) continue;
+    len = orc_clip_tip_with_orientation(g, e, 0, limit, nodes);
+    if (len == 0) len = orc_clip_tip_with_orientation(g, e, 1, limit, nodes);
+    if (len < 0) rc = -1;
+    else if (len > 0) { counts[0]++; counts[1] += (uint64_t)len; }
+  }
+  free(nodes);
+  p.nodes = (orc_node **)calloc((size_t)max_var_len + 2, sizeof(orc_node *));
+  p.orients = (int *)calloc((size_t)max_var_len + 2, sizeof(int));
+  p.labels = (int *)calloc((size_t)max_var_len + 2, sizeof(int));
+  p.seq = (char *)calloc((size_t)max_var_len + 2 + (size_t)g->k, 1);
+  for (i = 0; i < cap && rc == 0; i++) {
+    orc_node *e = &g->table[i];
+    int is_cycle = 0, length_sup, j, all_low = 1;
+    if (e->status != 1) continue;
+    if (!(e->covg > 0 && e->covg <= (uint32_t)threshold)) continue;
+    length_sup = orc_supernode(g, e, max_var_len, &p, &is_cycle);
+    if (length_sup < 0) { rc = -1; break; }
+    if (length_sup <= 1 || length_sup > 2 * g->k + 2) continue;
+    for (j = 1; j <= length_sup - 1 && all_low; j++)
+      if (p.nodes[j]->covg > (uint32_t)threshold) all_low = 0;
+    if (!all_low) continue;
+    for (j = 1; j <= length_sup - 1; j++)
+      if (orc_prune_low_coverage(g, p.nodes[j], (uint32_t)threshold) < 0) rc = -1;
+    counts[2]++;
+  }
+  free(p.nodes); free(p.orients); free(p.labels); free(p.seq);
+  for (i = 0; i < cap; i++) {
+    if (g->table[i].status == 2) g->table[i].status = 1;
+    if (g->table[i].status == 1) counts[3]++;
+  }
+  return rc;
+}
+
+/* print_binary_signature_NEW (file_reader.c:2930-2994) after cleaning: the
+ * error-cleaning object carries tip_clipping, remv_low_cov_sups and its threshold
+ * (graph_info.c:147-173, graph_operations.c:1084-1088). */
+int orc_ctx_header_cleaned(int k, int N, uint32_t mean_read_len, uint64_t total_seq, int threshold,
+                           uint8_t *out) {
+  int n = orc_ctx_header(k, N, mean_read_len, total_seq, out);
+  /* flags sit behind magic(6) ints(16) mean(4) total(8) idlen(4) id(9) seq_err(16) */
+  uint8_t *flags = out + 6 + 16 + 4 + 8 + 4 + 9 + 16;
+  int32_t v = threshold;
+  flags[0] = 1; /* tip_clipping */
+  flags[1] = 1; /* remv_low_cov_sups */
+  memcpy(flags + 4, &v, 4);
+  return n;
 }

@@ -69,6 +69,10 @@ def lib() -> C.CDLL:
         L.orc_get_key.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         L.orc_print_supernodes.restype = C.c_int
         L.orc_print_supernodes.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_void_p]
+        L.orc_clean.restype = C.c_int
+        L.orc_clean.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        L.orc_ctx_header_cleaned.restype = C.c_int
+        L.orc_ctx_header_cleaned.argtypes = [C.c_int, C.c_int, C.c_uint32, C.c_uint64, C.c_int, C.c_void_p]
         L.orc_ctx_header.restype = C.c_int
         L.orc_ctx_header.argtypes = [C.c_int, C.c_int, C.c_uint32, C.c_uint64, C.c_void_p]
         _lib = L
@@ -139,9 +143,18 @@ class OracleGraph:
 
     def records(self) -> np.ndarray:
         out = np.zeros(self.unique_kmers, dtype=record_dtype(self.N))
-        n = lib().orc_dump_records(self._g, out.ctypes.data)
-        assert n == len(out)
-        return out
+        n = lib().orc_dump_records(self._g, out.ctypes.data)   # pruned nodes are not dumped
+        assert n <= len(out)
+        return out[:n]
+
+    def clean(self, threshold: int, max_var_len: int = 10000) -> dict:
+        """`--remove_low_coverage_supernodes threshold` (graph_operations.c:1069-1090): clip tips, then
+        prune low-coverage supernodes, in table order."""
+        counts = np.zeros(4, dtype=np.uint64)
+        if lib().orc_clean(self._g, threshold, max_var_len, counts.ctypes.data) != 0:
+            raise RuntimeError("oracle cleaning met an edge to a missing node (the reference dies there)")
+        return {"tips": int(counts[0]), "tip_nodes": int(counts[1]), "supernodes_pruned": int(counts[2]),
+                "nodes_left": int(counts[3])}
 
     def load_records(self, recs: np.ndarray) -> bool:
         recs = np.ascontiguousarray(recs)
@@ -197,9 +210,13 @@ def get_key(words, k: int) -> np.ndarray:
     return out
 
 
-def ctx_header(k: int, mean_read_len: int, total_seq: int) -> bytes:
+def ctx_header(k: int, mean_read_len: int, total_seq: int, cleaned_threshold=None) -> bytes:
     buf = np.zeros(128, dtype=np.uint8)
-    n = lib().orc_ctx_header(k, words_per_kmer(k), mean_read_len, total_seq, buf.ctypes.data)
+    if cleaned_threshold is None:
+        n = lib().orc_ctx_header(k, words_per_kmer(k), mean_read_len, total_seq, buf.ctypes.data)
+    else:
+        n = lib().orc_ctx_header_cleaned(k, words_per_kmer(k), mean_read_len, total_seq, cleaned_threshold,
+                                         buf.ctypes.data)
     return buf[:n].tobytes()
 
 

@@ -153,3 +153,41 @@ def test_oracle_supernodes_match_live_reference_bytes(tmp_path, k, L, W, err):
     assert ok
     g.print_supernodes(tmp_path / "ours.fa")
     assert (tmp_path / "ours.fa").read_bytes() == (tmp_path / "sup.fa").read_bytes()
+
+
+# ---- cleaning (`--remove_low_coverage_supernodes T`, always on in laSV: run_laSV.sh) ----
+@pytest.mark.skipif(not O.ref_available(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("name,thresh", [("synth_cfg1_k31", 2), ("synth_cfg0_k53", 2), ("synth_cfg2_k95", 2),
+                                         ("synth_cfg0_k53", 1), ("synth_cfg1_k31", 5), ("edge_pe_k21_q5", 1)])
+def test_oracle_cleaning_matches_live_reference(name, thresh, tmp_path):
+    """Tip clipping + low-coverage supernode removal restated from the reference (they mutate the
+    graph as they traverse it): same slot order in, same `.ctx` out -- records in the same order,
+    header with the cleaning flags -- and the same supernodes printed afterwards, byte for byte."""
+    meta = util.case_meta(name)
+    k, L, W = meta["k"], meta["L"], meta["W"]
+    f1, f2 = (tmp_path / "a.fq", tmp_path / "b.fq")
+    seq, qual, offs = util.case_streams(name)
+    if "synth" in meta:
+        rl = meta["workload"]["read_len"]
+        s2, q2 = seq.reshape(-1, rl + 1), qual.reshape(-1, rl + 1)
+        O.write_fastq_fixed(f1, s2[0::2].reshape(-1), q2[0::2].reshape(-1), rl)
+        O.write_fastq_fixed(f2, s2[1::2].reshape(-1), q2[1::2].reshape(-1), rl)
+    else:
+        f1, f2 = util.case_files(name)
+    ref = O.run_reference(k, L, W, f1, f2, q_thresh=meta["q_thresh"], workdir=tmp_path, want_supernodes=True,
+                          extra_args=["--remove_low_coverage_supernodes", str(thresh)])
+    g, ok = util.oracle_build(k, L, W, seq, qual, offs, util.cutoff_of(meta), paired=True)
+    assert ok
+    st = g.clean(thresh)
+    recs = g.records()
+    assert st["nodes_left"] == len(recs) == len(ref["ctx"]["records"])
+    assert np.array_equal(recs, ref["ctx"]["records"])          # same nodes, coverage, edges, in the same order
+    if name.startswith("synth"):
+        assert st["tips"] > 0 and st["supernodes_pruned"] > 0 and len(recs) < meta["n_records"]
+    hdr = bytearray(O.ctx_header(k, meta["ctx_mean_read_len"], meta["ctx_total_seq"], cleaned_threshold=thresh))
+    got = bytearray(ref["ctx"]["header"])
+    pad = slice(6 + 16 + 12 + 4 + 9 + 10, 6 + 16 + 12 + 4 + 9 + 16)
+    hdr[pad] = got[pad] = b"\0" * 6
+    assert hdr == got
+    g.print_supernodes(tmp_path / "oracle.fa")
+    assert (tmp_path / "oracle.fa").read_bytes() == (tmp_path / "sup.fa").read_bytes()
