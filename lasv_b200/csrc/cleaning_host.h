@@ -1,0 +1,307 @@
+// cleaning_host.h -- the sequential decisions of the reference's graph cleaning
+// (`--remove_low_coverage_supernodes T`: tip clipping, then low-coverage supernode
+// removal; graph_operations.c:1069-1090), taken on the PATH RECORDS the supernode
+// kernels enumerate instead of on the table.
+//
+// Both passes of the reference walk the table slot by slot and mutate the graph as
+// they go, so their result depends on the slot order.  But every walk they make runs
+// along whole paths between non-interior nodes, and every mutation either removes
+// whole paths or clears one edge bit of a non-interior node.  The graph they see is
+// therefore the COMPRESSED graph -- one vertex per non-interior node, one edge per
+// path record (length, coverage summary) -- a few per cent of the table, and replaying
+// the reference's traversal on it, in slot order, is cheap and exact:
+//
+//   clip tips      a node with no edges on one side walks out of its other side while
+//                  every node has one way on; it is a tip iff within k+1 edges it meets a
+//                  node with another way in (dB_graph_population.c:365-441).  Clipping
+//                  clears that node's edge bit -- which may let a LATER walk run on
+//                  through it.
+//   low coverage   a node with 0 < coverage <= T and status none gets its supernode
+//                  computed and marked visited; if it has 2..2k+2 edges and no interior
+//                  node above T, its interior is pruned and its two end nodes lose the
+//                  edge into it -- which may merge the supernodes around them
+//                  (:3371-3462).  A path's interior nodes share their fate, so one event
+//                  per path (its lowest low-coverage interior slot) and one per
+//                  low-coverage non-interior node are all the triggers there are.
+//
+// The result is a list of actions (prune the interior of a path, prune a node, clear
+// edge bits of a node) that the device applies.  Not reproduced: the reference's walk
+// limit inside the supernode computation (--max_var_len, 10 000 edges).
+//
+// STATUS: host-emulated only (tests/host_emul); see cleaning.cuh.
+#pragma once
+#include <stdint.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "supernodes.cuh"
+
+namespace lasv {
+
+struct ClNode {  // a non-interior node
+  uint64_t q;
+  uint32_t covg;
+  uint8_t edges;
+  uint8_t status;  // 1 none, 2 visited, 3 pruned
+  int32_t adj[8];  // path leaving through edge bit (side * 4 + nucleotide), -1 if none
+};
+
+struct ClPath {
+  int32_t a, b;           // end nodes (indices into nodes)
+  uint8_t a_bit, b_bit;   // the edge bit of each end node that leads into the path
+  uint8_t alive, visited;
+  uint32_t len;           // edges
+  uint32_t max_covg;      // over the interior nodes
+  uint64_t min_low_q;     // lowest interior slot with 0 < coverage <= T, SN_NONE if none
+  uint64_t s_q;           // how to walk it: start node, orientation | nucleotide << 1
+  uint32_t s_on;
+};
+
+struct ClCycle {  // a cycle of interior nodes (record walked forward from its lowest slot s_q)
+  uint64_t s_q;
+  uint32_t s_on, len;
+  uint32_t s_covg, max_covg;  // of the start node / of all the others
+  uint64_t min_low_q;         // lowest slot of the whole cycle with 0 < coverage <= T
+};
+
+struct ClActions {
+  struct PathPrune {
+    uint64_t q;       // walk from this node ...
+    uint32_t on;      // ... in this orientation | nucleotide << 1 ...
+    uint32_t len;     // ... over len edges, pruning the len - 1 nodes in between,
+    uint64_t keep_q;  // except this one, which only loses its edges (SN_NONE: none)
+  };
+  struct EdgeReset {
+    uint64_t q;
+    uint32_t mask;
+  };
+  std::vector<PathPrune> paths;
+  std::vector<uint64_t> nodes;
+  std::vector<EdgeReset> resets;
+  uint64_t tips = 0, tip_edges = 0, supernodes_pruned = 0;
+};
+
+class ClGraph {
+ public:
+  std::vector<ClNode> nodes;  // sorted by slot
+  std::vector<ClPath> paths;
+  std::vector<ClCycle> cycles;
+
+  // node list: every occupied, un-pruned, non-interior node with at least one edge, in any order
+  void add_node(uint64_t q, uint32_t covg, uint32_t edges) {
+    ClNode n;
+    n.q = q;
+    n.covg = covg;
+    n.edges = (uint8_t)edges;
+    n.status = 1;
+    for (int i = 0; i < 8; i++) n.adj[i] = -1;
+    nodes.push_back(n);
+  }
+  void seal_nodes() {
+    std::sort(nodes.begin(), nodes.end(), [](const ClNode &x, const ClNode &y) { return x.q < y.q; });
+  }
+  int32_t index_of(uint64_t q) const {
+    auto it = std::lower_bound(nodes.begin(), nodes.end(), q, [](const ClNode &x, uint64_t v) { return x.q < v; });
+    return (it != nodes.end() && it->q == q) ? (int32_t)(it - nodes.begin()) : -1;
+  }
+  // path record (not a cycle) with its coverage summary; false if an end node is unknown
+  bool add_path(const SnPath &p, uint32_t max_covg, uint64_t min_low_q) {
+    ClPath c;
+    c.a = index_of(p.s_q);
+    c.b = index_of(p.t_q);
+    if (c.a < 0 || c.b < 0) return false;
+    c.a_bit = (uint8_t)(((p.bits & SNB_S_O) ? 4u : 0u) | ((p.bits >> SNB_S_N) & 3u));
+    c.b_bit = (uint8_t)(((p.bits & SNB_T_O) ? 4u : 0u) | ((p.bits >> SNB_T_N) & 3u));
+    c.alive = 1;
+    c.visited = 0;
+    c.len = p.len;
+    c.max_covg = max_covg;
+    c.min_low_q = min_low_q;
+    c.s_q = p.s_q;
+    c.s_on = ((p.bits & SNB_S_O) ? 1u : 0u) | (((p.bits >> SNB_S_N) & 3u) << 1);
+    const int32_t id = (int32_t)paths.size();
+    nodes[c.a].adj[c.a_bit] = id;
+    nodes[c.b].adj[c.b_bit] = id;
+    paths.push_back(c);
+    return true;
+  }
+
+  // ------------------------------------------------------------------ helpers
+  static uint32_t side_bits(const ClNode &n, uint32_t side) { return (n.edges >> (4u * side)) & 15u; }
+  static bool interior_now(const ClNode &n) { return popc4(side_bits(n, 0)) == 1u && popc4(side_bits(n, 1)) == 1u; }
+  void other_end(int32_t pid, int32_t node, uint32_t bit, int32_t &node2, uint32_t &bit2) const {
+    const ClPath &p = paths[pid];
+    if (p.a == node && p.a_bit == bit) { node2 = p.b; bit2 = p.b_bit; }
+    else { node2 = p.a; bit2 = p.a_bit; }
+  }
+  void drop_edge(int32_t node, uint32_t bit, ClActions &act) {
+    nodes[node].edges &= (uint8_t)~(1u << bit);
+    nodes[node].adj[bit] = -1;
+    act.resets.push_back({nodes[node].q, 1u << bit});
+  }
+  void prune_node(int32_t node, ClActions &act) {
+    nodes[node].status = 3;
+    nodes[node].edges = 0;
+    act.nodes.push_back(nodes[node].q);
+  }
+  void prune_path(int32_t pid, uint64_t keep_q, ClActions &act) {
+    paths[pid].alive = 0;
+    if (paths[pid].len > 1) act.paths.push_back({paths[pid].s_q, paths[pid].s_on, paths[pid].len, keep_q});
+  }
+
+  // ------------------------------------------------------------------ pass 1
+  // db_graph_clip_tips_in_union_of_all_colours (dB_graph_population.c:2563-2608, 445-470, 365-441)
+  void clip_tips(int k, ClActions &act) {
+    const uint64_t limit = 1 + (uint64_t)k;
+    std::vector<int32_t> wn, wp;
+    for (int32_t i = 0; i < (int32_t)nodes.size(); i++) {
+      if (nodes[i].status != 1) continue;
+      for (uint32_t o = 0; o < 2; o++) {  // forward first, reverse only if nothing was clipped
+        if (side_bits(nodes[i], o ^ 1u) != 0) continue;  // not a blunt end against the walk
+        wn.clear();
+        wp.clear();
+        int32_t cur = i, y = -1;
+        uint32_t side = o, ybit = 0;
+        uint64_t length = 0;
+        bool join = false;
+        for (;;) {
+          const uint32_t e = side_bits(nodes[cur], side);
+          if (popc4(e) != 1u) break;
+          const uint32_t bit = side * 4u + low_bit4(e);
+          const int32_t pid = nodes[cur].adj[bit];
+          if (pid < 0) break;  // inconsistent input
+          other_end(pid, cur, bit, y, ybit);
+          wn.push_back(cur);
+          wp.push_back(pid);
+          length += paths[pid].len;
+          if (length > limit) break;
+          if (popc4(side_bits(nodes[y], ybit >> 2)) != 1u) { join = true; break; }
+          cur = y;
+          side = (ybit >> 2) ^ 1u;
+        }
+        if (!join) continue;
+        for (int32_t n : wn) prune_node(n, act);
+        for (int32_t p : wp) prune_path(p, SN_NONE, act);
+        drop_edge(y, ybit, act);
+        act.tips++;
+        act.tip_edges += length;
+        break;
+      }
+    }
+  }
+
+  // ------------------------------------------------------------------ pass 2
+  // db_graph_remove_errors_considering_covg_and_topology (dB_graph_population.c:3595-3649, 3371-3462)
+  void remove_low_coverage_supernodes(int k, uint32_t T, ClActions &act) {
+    struct Event {
+      uint64_t q;
+      uint32_t kind;  // 0 path (its lowest low-coverage interior node), 1 node, 2 cycle
+      int32_t id;
+    };
+    std::vector<Event> ev;
+    for (int32_t i = 0; i < (int32_t)paths.size(); i++)
+      if (paths[i].min_low_q != SN_NONE) ev.push_back({paths[i].min_low_q, 0u, i});
+    for (int32_t i = 0; i < (int32_t)nodes.size(); i++)
+      if (nodes[i].covg > 0 && nodes[i].covg <= T) ev.push_back({nodes[i].q, 1u, i});
+    for (int32_t i = 0; i < (int32_t)cycles.size(); i++)
+      if (cycles[i].min_low_q != SN_NONE) ev.push_back({cycles[i].min_low_q, 2u, i});
+    std::sort(ev.begin(), ev.end(), [](const Event &x, const Event &y) { return x.q < y.q; });
+
+    std::vector<int32_t> cp, cn;  // paths and interior-now nodes of the supernode at hand
+    for (const Event &e : ev) {
+      if (e.kind == 2) {  // a cycle of interior nodes: printed from its first low node, which stays
+        const ClCycle &c = cycles[e.id];
+        if (c.len <= 1 || c.len > 2u * (uint32_t)k + 2u) continue;
+        if (c.max_covg > T || c.s_covg > T) continue;
+        act.paths.push_back({c.s_q, c.s_on, c.len, e.q});
+        if (c.s_q == e.q) act.resets.push_back({c.s_q, 0xFFu});
+        else act.nodes.push_back(c.s_q);
+        act.supernodes_pruned++;
+        continue;
+      }
+      cp.clear();
+      cn.clear();
+      int32_t term[2] = {-1, -1};  // end nodes of the supernode and their edge bits into it
+      uint32_t term_bit[2] = {0, 0};
+      bool cycle = false;
+      int32_t cycle_start_node = -1;  // a cycle printed from a (now interior) node: that node stays
+      // grow from (node, bit): take the path behind that edge, go on through interior nodes
+      auto grow = [&](int32_t node, uint32_t bit, int which, int32_t stop_path, int32_t stop_node) {
+        for (;;) {
+          const int32_t pid = nodes[node].adj[bit];
+          if (pid < 0) { term[which] = node; term_bit[which] = bit; return; }  // inconsistent input
+          if (pid == stop_path) { cycle = true; return; }
+          cp.push_back(pid);
+          int32_t y;
+          uint32_t ybit;
+          other_end(pid, node, bit, y, ybit);
+          if (y == stop_node) { cycle = true; return; }
+          if (!interior_now(nodes[y])) { term[which] = y; term_bit[which] = ybit; return; }
+          cn.push_back(y);
+          const uint32_t side = (ybit >> 2) ^ 1u;
+          node = y;
+          bit = side * 4u + low_bit4(side_bits(nodes[y], side));
+        }
+      };
+      // beyond end node `node` of the trigger path (its bit `bit` leads INTO that path)
+      auto beyond = [&](int32_t node, uint32_t bit, int which, int32_t stop_path) {
+        if (!interior_now(nodes[node])) { term[which] = node; term_bit[which] = bit; return; }
+        cn.push_back(node);
+        const uint32_t side = (bit >> 2) ^ 1u;
+        grow(node, side * 4u + low_bit4(side_bits(nodes[node], side)), which, stop_path, -1);
+      };
+      uint64_t keep_q = SN_NONE;
+      if (e.kind == 0) {
+        const ClPath &p = paths[e.id];
+        if (!p.alive || p.visited) continue;
+        cp.push_back(e.id);
+        beyond(p.a, p.a_bit, 0, e.id);
+        if (!cycle) beyond(p.b, p.b_bit, 1, e.id);
+        if (cycle) keep_q = e.q;  // printed from this interior node: everything else is "interior"
+      } else {
+        ClNode &j = nodes[e.id];
+        if (j.status != 1) continue;
+        if (interior_now(j)) {
+          cycle_start_node = e.id;
+          grow(e.id, 0u * 4u + low_bit4(side_bits(j, 0)), 0, -1, e.id);
+          if (!cycle) grow(e.id, 1u * 4u + low_bit4(side_bits(j, 1)), 1, -1, e.id);
+          if (!cycle) cn.push_back(e.id);
+        } else {
+          // the reference walks against the node's reverse side first (dB_graph_population.c:1481-1512)
+          const uint32_t side = popc4(side_bits(j, 1)) == 1u ? 1u : popc4(side_bits(j, 0)) == 1u ? 0u : 2u;
+          if (side == 2u) { j.status = 2; continue; }
+          term[0] = e.id;
+          term_bit[0] = side * 4u + low_bit4(side_bits(j, side));
+          grow(e.id, term_bit[0], 1, -1, -1);
+        }
+      }
+      // db_node_action_set_status_visited on every node of the supernode
+      for (int32_t p : cp) paths[p].visited = 1;
+      for (int32_t n : cn) nodes[n].status = 2;
+      if (cycle && cycle_start_node >= 0) nodes[cycle_start_node].status = 2;
+      for (int w = 0; w < 2; w++)
+        if (term[w] >= 0) nodes[term[w]].status = 2;
+      uint64_t length = 0;
+      bool all_low = true;
+      for (int32_t p : cp) {
+        length += paths[p].len;
+        all_low = all_low && paths[p].max_covg <= T;
+      }
+      for (int32_t n : cn) all_low = all_low && nodes[n].covg <= T;
+      if (length <= 1 || length > 2ull * (uint64_t)k + 2ull || !all_low) continue;
+      for (int32_t n : cn) prune_node(n, act);
+      for (int32_t p : cp) prune_path(p, keep_q, act);
+      if (cycle && cycle_start_node >= 0) {  // the start node stays, without edges
+        nodes[cycle_start_node].edges = 0;
+        for (int b = 0; b < 8; b++) nodes[cycle_start_node].adj[b] = -1;
+        act.resets.push_back({nodes[cycle_start_node].q, 0xFFu});
+      }
+      for (int w = 0; w < 2; w++)
+        if (term[w] >= 0) drop_edge(term[w], term_bit[w], act);
+      act.supernodes_pruned++;
+    }
+  }
+};
+
+}  // namespace lasv

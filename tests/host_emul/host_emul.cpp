@@ -16,6 +16,8 @@
 #include "../../lasv_b200/csrc/table.cuh"
 #include "../../lasv_b200/csrc/supernodes.cuh"
 #include "../../lasv_b200/csrc/supernodes_host.h"
+#include "../../lasv_b200/csrc/cleaning.cuh"
+#include "../../lasv_b200/csrc/cleaning_host.h"
 
 using namespace lasv;
 
@@ -271,6 +273,97 @@ int supernodes(uint8_t *table, int k, int L, int W, int finalized, const char *p
   return dangling ? -2 : 0;
 }
 
+// The cleaning as the library will run it: enumerate the paths (the supernode kernels' walks),
+// take the reference's sequential decisions on the compressed graph (cleaning_host.h), apply the
+// actions to the table (cleaning.cuh); once for the tips, once more for the low-coverage supernodes.
+template <int N>
+bool build_cl_graph(const TableView &tv, int k, uint32_t T, ClGraph &g) {
+  const uint64_t n_slots = ((uint64_t)tv.bucket_mask + 1) * tv.W;
+  const uint64_t max_steps = 2 * n_slots + 2;
+  std::vector<uint8_t> covered(n_slots, 0);
+  for (uint64_t q = 0; q < n_slots; q++) {
+    uint64_t key[N];
+    const uint64_t m = sn_load_node<N, HostOps>(tv, q, key);
+    if (!m || meta_status(m) == ST_PRUNED) continue;
+    const uint32_t e = meta_edges(m);
+    if (e != 0 && !sn_interior(e)) g.add_node(q, meta_covg(m), e);
+  }
+  g.seal_nodes();
+  bool ok = true;
+  const size_t n_nodes = g.nodes.size();
+  for (size_t i = 0; i < n_nodes; i++) {
+    const uint64_t q = g.nodes[i].q;
+    uint64_t key[N];
+    const uint64_t m = sn_load_node<N, HostOps>(tv, q, key);
+    const uint32_t e = meta_edges(m);
+    for (uint32_t bit = 0; bit < 8; bit++) {
+      if (!((e >> bit) & 1u)) continue;
+      SnPath rec;
+      bool d = false;
+      if (sn_walk_path<N, HostOps>(tv, k, q, key, e, bit >> 2, bit & 3u, max_steps, covered.data(), rec, d)) {
+        uint32_t mx = 0;
+        uint64_t lo = SN_NONE;
+        ok = ok && cl_path_coverage<N, HostOps>(tv, k, rec, T, mx, lo) && g.add_path(rec, mx, lo);
+      }
+      ok = ok && !d;
+    }
+  }
+  for (uint64_t q = 0; q < n_slots; q++) {
+    if (covered[q] || (sn_classify<N, HostOps>(tv, q) & 3u) != 3u) continue;
+    uint64_t key[N];
+    const uint64_t m = sn_load_node<N, HostOps>(tv, q, key);
+    if (meta_status(m) == ST_PRUNED) continue;
+    SnPath rec;
+    bool d = false;
+    if (sn_walk_cycle<N, HostOps>(tv, k, q, key, meta_edges(m), max_steps, rec, d)) {
+      ClCycle c;
+      c.s_q = q;
+      c.s_on = ((rec.bits >> SNB_S_N) & 3u) << 1;
+      c.len = rec.len;
+      c.s_covg = meta_covg(m);
+      uint64_t lo = SN_NONE;
+      ok = ok && cl_path_coverage<N, HostOps>(tv, k, rec, T, c.max_covg, lo);
+      if (c.s_covg > 0 && c.s_covg <= T && q < lo) lo = q;
+      c.min_low_q = lo;
+      g.cycles.push_back(c);
+    }
+    ok = ok && !d;
+  }
+  return ok;
+}
+
+template <int N>
+bool apply_cl_actions(const TableView &tv, int k, const ClActions &act) {
+  bool ok = true;
+  for (const auto &p : act.paths) ok = cl_prune_path<N, HostOps>(tv, k, p.q, p.on & 1u, p.on >> 1, p.len, p.keep_q) && ok;
+  for (uint64_t q : act.nodes) cl_prune_node<N, HostOps>(tv, q);
+  for (const auto &r : act.resets) cl_reset_edges<N, HostOps>(tv, r.q, r.mask);
+  return ok;
+}
+
+template <int N>
+int clean(uint8_t *table, int k, int L, int W, int finalized, int threshold, uint64_t *counts4) {
+  const TableView tv = make_table_view(table, N, L, W, 15, finalized != 0);
+  ClActions tips, sups;
+  {
+    ClGraph g;
+    if (!build_cl_graph<N>(tv, k, (uint32_t)threshold, g)) return -2;
+    g.clip_tips(k, tips);
+    if (!apply_cl_actions<N>(tv, k, tips)) return -3;
+  }
+  {
+    ClGraph g;  // the paths of the clipped graph
+    if (!build_cl_graph<N>(tv, k, (uint32_t)threshold, g)) return -4;
+    g.remove_low_coverage_supernodes(k, (uint32_t)threshold, sups);
+    if (!apply_cl_actions<N>(tv, k, sups)) return -5;
+  }
+  counts4[0] = tips.tips;
+  counts4[1] = tips.tip_edges;
+  counts4[2] = sups.supernodes_pruned;
+  counts4[3] = tips.paths.size() + sups.paths.size();
+  return 0;
+}
+
 }  // namespace
 
 #define DISPATCH(N, call) ((N) == 1 ? call<1> : (N) == 2 ? call<2> : call<3>)
@@ -333,6 +426,11 @@ void emul_find(uint8_t *table, int k, int L, int W, int max_rehash, int finalize
 int emul_supernodes(uint8_t *table, int k, int L, int W, int finalized, const char *path, uint64_t *counts8) {
   const int N = 2 * k / 64 + 1;
   return DISPATCH(N, supernodes)(table, k, L, W, finalized, path, counts8);
+}
+
+int emul_clean(uint8_t *table, int k, int L, int W, int finalized, int threshold, uint64_t *counts4) {
+  const int N = 2 * k / 64 + 1;
+  return DISPATCH(N, clean)(table, k, L, W, finalized, threshold, counts4);
 }
 
 // kmer_revcomp of supernodes.cuh, for known-answer checks

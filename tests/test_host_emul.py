@@ -37,6 +37,7 @@ def emul():
     L.emul_find.argtypes = [C.c_void_p] + [C.c_int] * 5 + [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]
     L.emul_supernodes.argtypes = [C.c_void_p] + [C.c_int] * 4 + [C.c_char_p, C.c_void_p]
     L.emul_revcomp.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    L.emul_clean.argtypes = [C.c_void_p] + [C.c_int] * 5 + [C.c_void_p]
     L.emul_hash_c.restype = C.c_uint32
     L.emul_hash_c.argtypes = [C.c_void_p, C.c_int, C.c_uint32]
     return L
@@ -79,7 +80,7 @@ class EmulTable:
 
 
 def table_records(table):
-    occ = table[table["status"] != 0]
+    occ = table[(table["status"] == 1) | (table["status"] == 2)]       # pruned nodes are not part of the graph
     out = np.zeros(len(occ), dtype=record_dtype(table["kmer"].shape[1]))
     out["kmer"], out["covg"], out["edges"] = occ["kmer"], occ["coverage"], occ["edges"]
     return out
@@ -387,3 +388,45 @@ def test_emulated_supernodes_cycles_and_long_paths(emul, tmp_path):
     assert st["cycles"] == 1 and st["printed"] == 2 and st["paths"] == 1
     seqs = sorted(O.read_fasta_seqs(tmp_path / "ours.fa"), key=len)
     assert len(seqs[0]) == 500 + k and len(seqs[1]) == 6000
+
+
+# ---- cleaning: cleaning.cuh (per-path work) + cleaning_host.h (the reference's decisions on the compressed graph) ----
+def emul_clean(emul, tab, threshold):
+    counts = np.zeros(4, dtype=np.uint64)
+    rc = emul.emul_clean(tab.ptr, tab.k, tab.L, tab.W, int(tab.finalized), threshold, counts.ctypes.data)
+    assert rc == 0, f"emulated cleaning failed ({rc})"
+    return dict(zip(["tips", "tip_edges", "supernodes_pruned", "paths_pruned"], (int(c) for c in counts)))
+
+
+def oracle_clean_in_order(tab, threshold):
+    g = O.OracleGraph(tab.k, tab.L, tab.W)
+    assert g.load_records(tab.records())
+    st = g.clean(threshold)
+    return g, st
+
+
+@pytest.mark.parametrize("name,thresh", [("synth_cfg1_k31", 2), ("synth_cfg0_k53", 2), ("synth_cfg2_k95", 2),
+                                         ("synth_cfg0_k53", 1), ("synth_cfg1_k31", 5), ("edge_pe_k21_q5", 1),
+                                         ("edge_pe_k31_q5", 3)])
+@pytest.mark.parametrize("finalized", [False, True])
+def test_emulated_cleaning_matches_reference_walk(emul, name, thresh, finalized, tmp_path):
+    """`--remove_low_coverage_supernodes T` decided on the path records: the table it leaves must hold
+    exactly the nodes, coverages and edges the reference's sequential cleaning (oracle restatement,
+    pinned on the compiled reference) leaves for the same slot order."""
+    meta = util.case_meta(name)
+    seq, qual, _ = util.case_streams(name)
+    rc, tab, _ = emul_build(emul, meta, seq, qual)
+    assert rc == 0
+    if finalized:
+        tab.finalize()
+    og, ost = oracle_clean_in_order(tab, thresh)          # before the emulation mutates the table
+    st = emul_clean(emul, tab, thresh)
+    assert np.array_equal(tab.records(), og.records())
+    assert st["tips"] == ost["tips"] and st["tip_edges"] == ost["tip_nodes"]
+    assert st["supernodes_pruned"] == ost["supernodes_pruned"]
+    if name.startswith("synth"):
+        assert st["tips"] > 0 and st["supernodes_pruned"] > 0
+    # and the supernodes of the cleaned graph
+    emul_supernodes(emul, tab, tmp_path / "ours.fa")
+    og.print_supernodes(tmp_path / "oracle.fa", max_length=1 << 20)
+    assert (tmp_path / "ours.fa").read_bytes() == (tmp_path / "oracle.fa").read_bytes()
