@@ -299,6 +299,29 @@ long long lasv_ref_hash_table_load_ctx_records(lasv_ref_hash_table *t, const cha
 int lasv_ref_hash_table_write_supernodes(lasv_ref_hash_table *t, const char *fasta_path, int max_length,
                                          lasv_supernode_stats *stats /* may be NULL */);
 
+/* The cleaning laSV always runs, `--remove_low_coverage_supernodes T` (graph_operations.c:
+ * 1069-1090), on the caller's reference-layout table:
+ *   LASV_CLEAN_TIPS        db_graph_clip_tips_in_union_of_all_colours (dB_graph_population.c:
+ *                          2563-2608 with :365-470; tips of up to kmer_size + 1 edges)
+ *   LASV_CLEAN_SUPERNODES  db_graph_remove_errors_considering_covg_and_topology (:3595-3649
+ *                          with :3371-3462 and :485-530), coverage threshold `threshold`
+ * Both passes of the reference mutate the graph while they traverse it; the result here is the
+ * reference's for the caller's slot order: the table is copied to the device as it is, the paths
+ * between non-interior nodes are enumerated there, the reference's traversal is replayed on those
+ * path records (cleaning_host.h) and the decisions are applied on the device; the table comes
+ * back with pruned nodes marked `pruned` (status 3) and their edges reset, everything else
+ * `none`, as the reference leaves it.  Not reproduced: the --max_var_len walk limit inside the
+ * supernode computation.  integration/clean_shim.c is the reference-side binding. */
+#define LASV_CLEAN_TIPS 1
+#define LASV_CLEAN_SUPERNODES 2
+typedef struct {
+  uint64_t tips_clipped;
+  uint64_t tip_nodes_pruned;
+  uint64_t supernodes_pruned;
+  uint64_t nodes_pruned;     /* all nodes that went from none to pruned */
+} lasv_clean_stats;
+int lasv_ref_hash_table_clean(lasv_ref_hash_table *t, int what, int threshold, lasv_clean_stats *stats /* may be NULL */);
+
 /* Exact reference signatures (file_reader.h:86-118); `boolean` is signed char
  * (global.h:37).  They build the graph on the GPU and leave db_graph->table,
  * next_element, unique_kmers and collisions[] as the reference loader would

@@ -47,6 +47,17 @@ class SupernodeStats(C.Structure):
         return {f: int(getattr(self, f)) for f, _ in self._fields_}
 
 
+class CleanStats(C.Structure):
+    _fields_ = [("tips_clipped", C.c_uint64), ("tip_nodes_pruned", C.c_uint64), ("supernodes_pruned", C.c_uint64),
+                ("nodes_pruned", C.c_uint64)]
+
+    def as_dict(self):
+        return {f: int(getattr(self, f)) for f, _ in self._fields_}
+
+
+CLEAN_TIPS, CLEAN_SUPERNODES = 1, 2
+
+
 class SynthParams(C.Structure):
     _fields_ = [("seed", C.c_uint64), ("genome_len", C.c_uint64), ("read_len", C.c_uint32),
                 ("insert", C.c_uint32), ("err_q20", C.c_uint32), ("n_q20", C.c_uint32),
@@ -70,7 +81,7 @@ EXPORTS = [
     "lasv_graph_route_reads_device", "lasv_graph_extract_records_device",
     "lasv_graph_insert_records_device", "lasv_graph_read_stats_device", "lasv_graph_find",
     "lasv_graph_summary", "lasv_graph_finalize", "lasv_graph_export_table", "lasv_graph_import_table",
-    "lasv_graph_dump_ctx_records", "lasv_graph_write_ctx", "lasv_ctx_header", "lasv_graph_write_supernodes", "lasv_ref_hash_table_write_supernodes",
+    "lasv_graph_dump_ctx_records", "lasv_graph_write_ctx", "lasv_ctx_header", "lasv_graph_write_supernodes", "lasv_ref_hash_table_write_supernodes", "lasv_ref_hash_table_clean",
     "lasv_graph_load_ctx_records", "lasv_graph_load_ctx_file", "lasv_graph_load_se_file",
     "lasv_graph_load_pe_files", "lasv_graph_load_se_filelist", "lasv_graph_load_pe_filelists",
     "load_se_filelist_into_graph_colour", "load_pe_filelists_into_graph_colour",
@@ -166,6 +177,8 @@ def lib() -> C.CDLL:
     L.lasv_seqfile_to_streams.restype = C.c_longlong
     L.lasv_seqfile_to_streams.argtypes = [C.c_char_p, vp, vp, u64, vp, u64, C.POINTER(i32)]
     L.lasv_seqfile_parse_check.argtypes = [C.c_char_p, C.c_char_p, i32, u64, vp, C.POINTER(i32)]
+    L.lasv_ref_hash_table_write_supernodes.argtypes = [C.POINTER(RefHashTable), C.c_char_p, i32, C.POINTER(SupernodeStats)]
+    L.lasv_ref_hash_table_clean.argtypes = [C.POINTER(RefHashTable), i32, i32, C.POINTER(CleanStats)]
     L.lasv_ref_hash_table_load_ctx_records.restype = C.c_longlong
     L.lasv_ref_hash_table_load_ctx_records.argtypes = [C.POINTER(RefHashTable), C.c_char_p, C.c_long]
     _lib = L

@@ -30,6 +30,7 @@
 #include "../../include/lasv_b200.h"
 #include "graph_kernels.cuh"
 #include "supernodes_host.h"
+#include "cleaning_host.h"
 #include "seq_reader.h"
 
 using namespace lasv;
@@ -1904,6 +1905,201 @@ void dropin_load(lasv_ref_hash_table *t, const char *list1, const char *list2, i
  * hands over the file offset of the first record.  The caller's reference-layout table is merged in
  * first if it already holds k-mers, then replaced by the result.  Returns the number of records read,
  * or a negative error code. */
+// ---------------------------------------------------------------- cleaning
+// One pass of the cleaning on the device table: enumerate the paths (the supernode kernels),
+// summarise their coverage, copy the compressed graph to the host, let cleaning_host.h take the
+// reference's decisions in slot order, apply them on the device.
+static int clean_pass(lasv_graph *g, int what, uint32_t threshold, lasv_clean_stats *st) {
+  const TableView tv = g->view();
+  SnCounters *d_c = nullptr, h_c;
+  ClCounters *d_cc = nullptr, h_cc;
+  uint64_t *d_starts = nullptr, *d_list = nullptr, *d_low = nullptr, *d_anodes = nullptr;
+  unsigned long long *d_n = nullptr;
+  uint8_t *d_covered = nullptr;
+  SnPath *d_recs = nullptr, *d_cyc = nullptr;
+  ClNodeRec *d_nodes = nullptr;
+  uint32_t *d_max = nullptr, *d_scov = nullptr;
+  ClPathPrune *d_apaths = nullptr;
+  ClEdgeReset *d_aresets = nullptr;
+  auto sync_counters = [&]() -> int {
+    CUDA_TRY(cudaMemcpyAsync(&h_c, d_c, sizeof h_c, cudaMemcpyDeviceToHost, g->compute));
+    CUDA_TRY(cudaMemcpyAsync(&h_cc, d_cc, sizeof h_cc, cudaMemcpyDeviceToHost, g->compute));
+    CUDA_TRY(cudaStreamSynchronize(g->compute));
+    return LASV_OK;
+  };
+  int rc = [&]() -> int {
+    CUDA_TRY(cudaMalloc(&d_c, sizeof(SnCounters)));
+    CUDA_TRY(cudaMalloc(&d_cc, sizeof(ClCounters)));
+    CUDA_TRY(cudaMalloc(&d_n, sizeof(unsigned long long)));
+    CUDA_TRY(cudaMemsetAsync(d_c, 0, sizeof(SnCounters), g->compute));
+    CUDA_TRY(cudaMemsetAsync(d_cc, 0, sizeof(ClCounters), g->compute));
+    CUDA_TRY(cudaMemsetAsync(d_n, 0, sizeof(unsigned long long), g->compute));
+    // vertices of the compressed graph: count, then list
+    launch_sn_count(g->N, tv, d_c, g->compute);
+    if (int e = check_launch()) return e;
+    launch_cl_nodes(g->N, tv, nullptr, 0, d_cc, g->compute);
+    if (int e = check_launch()) return e;
+    if (int e = sync_counters()) return e;
+    const uint64_t n_starts = h_c.n_starts, n_nodes = h_cc.n_nodes;
+    CUDA_TRY(cudaMalloc(&d_nodes, std::max<uint64_t>(1, n_nodes) * sizeof(ClNodeRec)));
+    CUDA_TRY(cudaMemsetAsync(&d_cc->n_nodes, 0, sizeof(unsigned long long), g->compute));
+    launch_cl_nodes(g->N, tv, d_nodes, n_nodes, d_cc, g->compute);
+    if (int e = check_launch()) return e;
+    // its edges: the paths between them, and the cycles of interior nodes
+    CUDA_TRY(cudaMalloc(&d_starts, std::max<uint64_t>(1, n_starts) * sizeof(uint64_t)));
+    CUDA_TRY(cudaMalloc(&d_recs, std::max<uint64_t>(1, n_starts) * sizeof(SnPath)));
+    CUDA_TRY(cudaMalloc(&d_covered, g->n_slots));
+    CUDA_TRY(cudaMemsetAsync(d_covered, 0, g->n_slots, g->compute));
+    launch_sn_starts(g->N, tv, d_starts, n_starts, d_n, d_c, g->compute);
+    if (int e = check_launch()) return e;
+    launch_sn_paths(g->N, tv, g->k, d_starts, n_starts, d_covered, d_recs, n_starts, d_c, g->compute);
+    if (n_starts)
+      if (int e = check_launch()) return e;
+    launch_sn_uncovered(g->N, tv, d_covered, nullptr, 0, d_c, g->compute);
+    if (int e = check_launch()) return e;
+    if (int e = sync_counters()) return e;
+    const uint64_t n_unc = h_c.n_uncovered;
+    if (n_unc) {
+      CUDA_TRY(cudaMalloc(&d_list, n_unc * sizeof(uint64_t)));
+      CUDA_TRY(cudaMalloc(&d_cyc, n_unc * sizeof(SnPath)));
+      CUDA_TRY(cudaMemsetAsync(&d_c->n_uncovered, 0, sizeof(unsigned long long), g->compute));
+      launch_sn_uncovered(g->N, tv, d_covered, d_list, n_unc, d_c, g->compute);
+      if (int e = check_launch()) return e;
+      launch_sn_cycles(g->N, tv, g->k, d_list, n_unc, d_cyc, n_unc, d_c, g->compute);
+      if (int e = check_launch()) return e;
+      if (int e = sync_counters()) return e;
+    }
+    if (h_c.n_overflow) return fail(LASV_ERR_STATE, "path record buffers overflowed (internal sizing error)");
+    if (h_c.n_dangling)
+      return fail(LASV_ERR_STATE, "%llu walks met an edge to a node that is not in the graph (the reference die()s)",
+                  (unsigned long long)h_c.n_dangling);
+    const uint64_t n_paths = h_c.n_paths, n_cycles = h_c.n_cycles, n_rec = n_paths + n_cycles;
+    if (n_rec >= (1ull << 31) || n_nodes >= (1ull << 31)) return fail(LASV_ERR_CAPACITY, "more than 2^31 paths");
+    // coverage summaries (the path records first, the cycle records behind them)
+    CUDA_TRY(cudaMalloc(&d_max, std::max<uint64_t>(1, n_rec) * sizeof(uint32_t)));
+    CUDA_TRY(cudaMalloc(&d_scov, std::max<uint64_t>(1, n_rec) * sizeof(uint32_t)));
+    CUDA_TRY(cudaMalloc(&d_low, std::max<uint64_t>(1, n_rec) * sizeof(uint64_t)));
+    launch_cl_coverage(g->N, tv, g->k, d_recs, n_paths, threshold, d_max, d_low, d_scov, d_cc, g->compute);
+    if (n_paths)
+      if (int e = check_launch()) return e;
+    launch_cl_coverage(g->N, tv, g->k, d_cyc, n_cycles, threshold, d_max + n_paths, d_low + n_paths, d_scov + n_paths,
+                       d_cc, g->compute);
+    if (n_cycles)
+      if (int e = check_launch()) return e;
+    std::vector<ClNodeRec> nodes(n_nodes);
+    std::vector<SnPath> recs(n_rec);
+    std::vector<uint32_t> mx(n_rec), scov(n_rec);
+    std::vector<uint64_t> low(n_rec);
+    if (n_nodes) CUDA_TRY(cudaMemcpyAsync(nodes.data(), d_nodes, n_nodes * sizeof(ClNodeRec), cudaMemcpyDeviceToHost, g->compute));
+    if (n_paths) CUDA_TRY(cudaMemcpyAsync(recs.data(), d_recs, n_paths * sizeof(SnPath), cudaMemcpyDeviceToHost, g->compute));
+    if (n_cycles)
+      CUDA_TRY(cudaMemcpyAsync(recs.data() + n_paths, d_cyc, n_cycles * sizeof(SnPath), cudaMemcpyDeviceToHost, g->compute));
+    if (n_rec) {
+      CUDA_TRY(cudaMemcpyAsync(mx.data(), d_max, n_rec * sizeof(uint32_t), cudaMemcpyDeviceToHost, g->compute));
+      CUDA_TRY(cudaMemcpyAsync(scov.data(), d_scov, n_rec * sizeof(uint32_t), cudaMemcpyDeviceToHost, g->compute));
+      CUDA_TRY(cudaMemcpyAsync(low.data(), d_low, n_rec * sizeof(uint64_t), cudaMemcpyDeviceToHost, g->compute));
+    }
+    if (int e = sync_counters()) return e;
+    if (h_cc.n_failed) return fail(LASV_ERR_STATE, "coverage walks left the graph");
+    cudaFree(d_starts); d_starts = nullptr;
+    cudaFree(d_recs); d_recs = nullptr;
+    cudaFree(d_cyc); d_cyc = nullptr;
+    cudaFree(d_covered); d_covered = nullptr;
+
+    // the reference's decisions, in slot order, on the compressed graph
+    ClGraph cg;
+    cg.nodes.reserve(n_nodes);
+    for (const ClNodeRec &r : nodes) cg.add_node(r.q, r.covg, r.edges);
+    cg.seal_nodes();
+    cg.paths.reserve(n_paths);
+    for (uint64_t i = 0; i < n_paths; i++)
+      if (!cg.add_path(recs[i], mx[i], low[i])) return fail(LASV_ERR_STATE, "a path ends in a node that is not in the node list");
+    for (uint64_t i = n_paths; i < n_rec; i++) {
+      ClCycle c;
+      c.s_q = recs[i].s_q;
+      c.s_on = ((recs[i].bits >> SNB_S_N) & 3u) << 1;
+      c.len = recs[i].len;
+      c.s_covg = scov[i];
+      c.max_covg = mx[i];
+      c.min_low_q = low[i];
+      if (c.s_covg > 0 && c.s_covg <= threshold && c.s_q < c.min_low_q) c.min_low_q = c.s_q;
+      c.both_ways = (recs[i].bits & SNB_BOTH_WAYS) ? 1u : 0u;
+      cg.cycles.push_back(c);
+    }
+    ClActions act;
+    if (what == LASV_CLEAN_TIPS) cg.clip_tips(g->k, act);
+    else cg.remove_low_coverage_supernodes(g->k, threshold, act);
+
+    // apply
+    const uint64_t np = act.paths.size(), nn = act.nodes.size(), nr = act.resets.size();
+    if (np) {
+      CUDA_TRY(cudaMalloc(&d_apaths, np * sizeof(ClPathPrune)));
+      CUDA_TRY(cudaMemcpyAsync(d_apaths, act.paths.data(), np * sizeof(ClPathPrune), cudaMemcpyHostToDevice, g->compute));
+    }
+    if (nn) {
+      CUDA_TRY(cudaMalloc(&d_anodes, nn * sizeof(uint64_t)));
+      CUDA_TRY(cudaMemcpyAsync(d_anodes, act.nodes.data(), nn * sizeof(uint64_t), cudaMemcpyHostToDevice, g->compute));
+    }
+    if (nr) {
+      CUDA_TRY(cudaMalloc(&d_aresets, nr * sizeof(ClEdgeReset)));
+      CUDA_TRY(cudaMemcpyAsync(d_aresets, act.resets.data(), nr * sizeof(ClEdgeReset), cudaMemcpyHostToDevice, g->compute));
+    }
+    launch_cl_apply(g->N, tv, g->k, d_apaths, np, d_anodes, nn, d_aresets, nr, d_cc, g->compute);
+    if (np + nn + nr)
+      if (int e = check_launch()) return e;
+    if (int e = sync_counters()) return e;
+    if (h_cc.n_failed) return fail(LASV_ERR_STATE, "pruning walks left the graph");
+    if (st) {
+      st->tips_clipped += act.tips;
+      st->tip_nodes_pruned += act.tip_edges;
+      st->supernodes_pruned += act.supernodes_pruned;
+      st->nodes_pruned += act.nodes_pruned();
+    }
+    return LASV_OK;
+  }();
+  cudaFree(d_c); cudaFree(d_cc); cudaFree(d_n); cudaFree(d_starts); cudaFree(d_list); cudaFree(d_low); cudaFree(d_anodes);
+  cudaFree(d_covered); cudaFree(d_recs); cudaFree(d_cyc); cudaFree(d_nodes); cudaFree(d_max); cudaFree(d_scov);
+  cudaFree(d_apaths); cudaFree(d_aresets);
+  return rc;
+}
+
+int lasv_ref_hash_table_clean(lasv_ref_hash_table *t, int what, int threshold, lasv_clean_stats *stats) {
+  if (!t || !t->table) return fail(LASV_ERR_ARG, "NULL table!");
+  if (!(what & (LASV_CLEAN_TIPS | LASV_CLEAN_SUPERNODES)) || (what & ~(LASV_CLEAN_TIPS | LASV_CLEAN_SUPERNODES)))
+    return fail(LASV_ERR_ARG, "what must be LASV_CLEAN_TIPS, LASV_CLEAN_SUPERNODES or both");
+  if ((what & LASV_CLEAN_SUPERNODES) && threshold < 0) return fail(LASV_ERR_ARG, "negative coverage threshold");
+  const int L = log2_exact(t->number_buckets);
+  if (L < 0) return fail(LASV_ERR_ARG, "number_buckets is not a power of two");
+  int dev = 0;
+  if (const char *e = getenv("LASV_B200_DEVICE")) dev = atoi(e);
+  lasv_graph *g = lasv_graph_new(t->kmer_size, L, t->bucket_size, t->max_rehash_tries, dev);
+  if (!g) return LASV_ERR_CUDA;
+  if (stats) memset(stats, 0, sizeof *stats);
+  int rc = [&]() -> int {
+    // the table as it is (the finalised arrangement: bucket b = W consecutive Elements at the start of its lines)
+    const size_t row = (size_t)g->W * g->slot_bytes, pitch = (size_t)(g->table_bytes / g->n_buckets);
+    const uint64_t rows_per_copy = 1ull << 20;
+    for (uint64_t b0 = 0; b0 < g->n_buckets; b0 += rows_per_copy) {
+      const uint64_t nb = std::min(rows_per_copy, g->n_buckets - b0);
+      CUDA_TRY(cudaMemcpy2D(g->d_lines + b0 * pitch, pitch, (const uint8_t *)t->table + b0 * row, row, row,
+                            (size_t)nb, cudaMemcpyHostToDevice));
+    }
+    g->finalized = true;
+    if (what & LASV_CLEAN_TIPS)
+      if (int e = clean_pass(g, LASV_CLEAN_TIPS, (uint32_t)std::max(threshold, 0), stats)) return e;
+    if (what & LASV_CLEAN_SUPERNODES)
+      if (int e = clean_pass(g, LASV_CLEAN_SUPERNODES, (uint32_t)threshold, stats)) return e;
+    for (uint64_t b0 = 0; b0 < g->n_buckets; b0 += rows_per_copy) {
+      const uint64_t nb = std::min(rows_per_copy, g->n_buckets - b0);
+      CUDA_TRY(cudaMemcpy2D((uint8_t *)t->table + b0 * row, row, g->d_lines + b0 * pitch, pitch, row, (size_t)nb,
+                            cudaMemcpyDeviceToHost));
+    }
+    return LASV_OK;
+  }();
+  lasv_graph_free(&g);
+  return rc;
+}
+
 int lasv_ref_hash_table_write_supernodes(lasv_ref_hash_table *t, const char *fasta_path, int max_length,
                                          lasv_supernode_stats *stats) {
   if (!t || !t->table) return fail(LASV_ERR_ARG, "NULL table!");

@@ -5,14 +5,36 @@
 // (future) kernels and tests/host_emul; the sequential decisions are taken on the
 // path records by cleaning_host.h.
 //
-// STATUS: host-emulated only (tests/test_host_emul.py against the oracle's
-// restatement of the reference); not yet part of the C ABI -- see DESIGN 6d.
+// The kernels are in cleaning_kernels.cu; the entry point is
+// lasv_ref_hash_table_clean (capi.cu), on the caller's reference-layout table.
 #pragma once
 #include "supernodes.cuh"
 
 namespace lasv {
 
 constexpr uint32_t ST_PRUNED = 3;  // NodeStatus pruned (element.h:57-75)
+
+// What the sequential decisions (cleaning_host.h) ask the device to do.
+struct ClPathPrune {
+  uint64_t q;       // walk from this node ...
+  uint32_t on;      // ... in this orientation | nucleotide << 1 ...
+  uint32_t len;     // ... over len edges, pruning the len - 1 nodes in between,
+  uint64_t keep_q;  // except this one, which only loses its edges (SN_NONE: none)
+};
+struct ClEdgeReset {
+  uint64_t q;
+  uint32_t mask;
+  uint32_t pad;
+};
+struct ClNodeRec {  // a non-interior node as the decisions see it
+  uint64_t q;
+  uint32_t covg;
+  uint32_t edges;
+};
+struct ClCounters {
+  unsigned long long n_nodes;
+  unsigned long long n_failed;  // walks that left the graph
+};
 
 LASV_HD uint64_t meta_with(uint64_t m, uint32_t edges, uint32_t status) {
   return (m & 0xFFFF0000FFFFFFFFull) | ((uint64_t)(edges & 0xFFu) << 32) | ((uint64_t)(status & 0xFFu) << 40);
@@ -39,8 +61,8 @@ LASV_HD void cl_prune_node(const TableView &t, uint64_t q) {
 template <int N, class Ops>
 LASV_HD void cl_reset_edges(const TableView &t, uint64_t q, uint32_t mask) {
   uint64_t *mp = cl_meta_ptr<N, Ops>(t, q);
-  const uint64_t m = Ops::load(mp);
-  Ops::store(mp, meta_with(m, meta_edges(m) & ~mask, meta_status(m)));
+  // the edges byte is the low byte of the meta word's upper half (kmer_core.cuh, meta_pack)
+  Ops::and32(reinterpret_cast<uint32_t *>(mp) + 1, ~(mask & 0xFFu));
 }
 
 // Coverage summary of the interior nodes of a path record (walked from its s end):
@@ -71,10 +93,14 @@ LASV_HD bool cl_path_coverage(const TableView &t, int k, const SnPath &p, uint32
   return true;
 }
 
-// Prune the interior nodes of a path, walked from (q, orientation, nucleotide) over
-// len edges; the node `keep_q` (SN_NONE: none) is spared -- the start node of a
-// cycle the reference printed from one of its own interior nodes -- and only loses
-// its edges.  The next node is located BEFORE the current one loses its edges.
+// Mark the interior nodes of a path as pruned, walked from (q, orientation, nucleotide) over
+// len edges; the node `keep_q` (SN_NONE: none) is spared -- the start node of a cycle the
+// reference printed from one of its own interior nodes -- and only loses its edges.  Only the
+// STATUS changes here: a path that is its own reverse complement turns round in the middle and
+// runs back over its own nodes, so the edges must stay readable until every walk is done;
+// cl_settle_node clears them afterwards, in one sweep over the table.
+constexpr uint32_t ST_CLEARED = 0x7E;  // transient, device only: keeps status none, loses its edges
+
 #pragma nv_exec_check_disable
 template <int N, class Ops>
 LASV_HD bool cl_prune_path(const TableView &t, int k, uint64_t q, uint32_t o, uint32_t n, uint32_t len,
@@ -82,26 +108,38 @@ LASV_HD bool cl_prune_path(const TableView &t, int k, uint64_t q, uint32_t o, ui
   uint64_t key[N], key2[N];
   if (!sn_load_node<N, Ops>(t, q, key)) return false;
   uint32_t co = o, cn = n, o2 = 0, back = 0;
-  uint64_t prev_q = SN_NONE;  // interior node whose successor is known by now
   for (uint32_t e = 0; e + 1 < len; e++) {
     uint64_t m2 = 0;
     const uint64_t q2 = sn_step<N, Ops>(t, k, key, co, cn, key2, m2, o2, back);
     if (q2 == SN_NONE) return false;
-    if (prev_q != SN_NONE) {
-      if (prev_q == keep_q) cl_reset_edges<N, Ops>(t, prev_q, 0xFFu);
-      else cl_prune_node<N, Ops>(t, prev_q);
-    }
-    prev_q = q2;
+    const uint32_t want = q2 == keep_q ? ST_CLEARED : ST_PRUNED;
+    if (meta_status(m2) != want) Ops::store(cl_meta_ptr<N, Ops>(t, q2), meta_with(m2, meta_edges(m2), want));
 #pragma unroll
     for (int w = 0; w < N; w++) key[w] = key2[w];
     co = o2;
     cn = low_bit4(sn_side(meta_edges(m2), o2));
   }
-  if (prev_q != SN_NONE) {
-    if (prev_q == keep_q) cl_reset_edges<N, Ops>(t, prev_q, 0xFFu);
-    else cl_prune_node<N, Ops>(t, prev_q);
-  }
   return true;
 }
+
+// After all walks: pruned nodes lose their edges (db_node_reset_edges), spared ones too but stay `none`.
+#pragma nv_exec_check_disable
+template <int N, class Ops>
+LASV_HD void cl_settle_node(const TableView &t, uint64_t q) {
+  uint64_t *mp = cl_meta_ptr<N, Ops>(t, q);
+  const uint64_t m = Ops::load(mp);
+  const uint32_t st = meta_status(m);
+  if (st == ST_CLEARED) Ops::store(mp, meta_with(m, 0u, ST_NONE));
+  else if (st == ST_PRUNED && meta_edges(m) != 0) Ops::store(mp, meta_with(m, 0u, ST_PRUNED));
+}
+
+#if defined(__CUDACC__)
+// launch interface (cleaning_kernels.cu)
+void launch_cl_nodes(int N, const TableView &t, ClNodeRec *out, uint64_t cap, ClCounters *c, cudaStream_t st);
+void launch_cl_coverage(int N, const TableView &t, int k, const SnPath *recs, uint64_t n, uint32_t threshold,
+                        uint32_t *max_covg, uint64_t *min_low_q, uint32_t *s_covg, ClCounters *c, cudaStream_t st);
+void launch_cl_apply(int N, const TableView &t, int k, const ClPathPrune *paths, uint64_t n_paths, const uint64_t *nodes,
+                     uint64_t n_nodes, const ClEdgeReset *resets, uint64_t n_resets, ClCounters *c, cudaStream_t st);
+#endif
 
 }  // namespace lasv

@@ -28,14 +28,13 @@
 // edge bits of a node) that the device applies.  Not reproduced: the reference's walk
 // limit inside the supernode computation (--max_var_len, 10 000 edges).
 //
-// STATUS: host-emulated only (tests/host_emul); see cleaning.cuh.
 #pragma once
 #include <stdint.h>
 
 #include <algorithm>
 #include <vector>
 
-#include "supernodes.cuh"
+#include "cleaning.cuh"
 
 namespace lasv {
 
@@ -63,23 +62,21 @@ struct ClCycle {  // a cycle of interior nodes (record walked forward from its l
   uint32_t s_on, len;
   uint32_t s_covg, max_covg;  // of the start node / of all the others
   uint64_t min_low_q;         // lowest slot of the whole cycle with 0 < coverage <= T
+  uint32_t both_ways;         // crosses every node in both orientations: the node it is printed from is interior too
 };
 
 struct ClActions {
-  struct PathPrune {
-    uint64_t q;       // walk from this node ...
-    uint32_t on;      // ... in this orientation | nucleotide << 1 ...
-    uint32_t len;     // ... over len edges, pruning the len - 1 nodes in between,
-    uint64_t keep_q;  // except this one, which only loses its edges (SN_NONE: none)
-  };
-  struct EdgeReset {
-    uint64_t q;
-    uint32_t mask;
-  };
-  std::vector<PathPrune> paths;
+  std::vector<ClPathPrune> paths;
   std::vector<uint64_t> nodes;
-  std::vector<EdgeReset> resets;
+  std::vector<ClEdgeReset> resets;
   uint64_t tips = 0, tip_edges = 0, supernodes_pruned = 0;
+  uint64_t twice = 0;  // interior nodes that a pruning walk meets a second time (paths that turn round)
+  // nodes that go from none to pruned when the actions are applied
+  uint64_t nodes_pruned() const {
+    uint64_t n = nodes.size();
+    for (const ClPathPrune &p : paths) n += p.len - 1 - (p.keep_q != SN_NONE ? 1u : 0u);
+    return n - twice;
+  }
 };
 
 class ClGraph {
@@ -138,7 +135,7 @@ class ClGraph {
   void drop_edge(int32_t node, uint32_t bit, ClActions &act) {
     nodes[node].edges &= (uint8_t)~(1u << bit);
     nodes[node].adj[bit] = -1;
-    act.resets.push_back({nodes[node].q, 1u << bit});
+    act.resets.push_back({nodes[node].q, 1u << bit, 0u});
   }
   void prune_node(int32_t node, ClActions &act) {
     nodes[node].status = 3;
@@ -146,8 +143,12 @@ class ClGraph {
     act.nodes.push_back(nodes[node].q);
   }
   void prune_path(int32_t pid, uint64_t keep_q, ClActions &act) {
-    paths[pid].alive = 0;
-    if (paths[pid].len > 1) act.paths.push_back({paths[pid].s_q, paths[pid].s_on, paths[pid].len, keep_q});
+    ClPath &p = paths[pid];
+    if (!p.alive) return;
+    p.alive = 0;
+    if (p.len <= 1) return;
+    act.paths.push_back({p.s_q, p.s_on, p.len, keep_q});
+    if (p.a == p.b && p.a_bit == p.b_bit) act.twice += (p.len - 1) / 2;  // its own reverse complement: out and back
   }
 
   // ------------------------------------------------------------------ pass 1
@@ -214,9 +215,14 @@ class ClGraph {
         const ClCycle &c = cycles[e.id];
         if (c.len <= 1 || c.len > 2u * (uint32_t)k + 2u) continue;
         if (c.max_covg > T || c.s_covg > T) continue;
-        act.paths.push_back({c.s_q, c.s_on, c.len, e.q});
-        if (c.s_q == e.q) act.resets.push_back({c.s_q, 0xFFu});
-        else act.nodes.push_back(c.s_q);
+        if (c.both_ways) {  // no node is spared; the walk from s meets every other node twice and s once more
+          act.paths.push_back({c.s_q, c.s_on, c.len, SN_NONE});
+          act.twice += (c.len - 1) - c.len / 2;
+        } else {
+          act.paths.push_back({c.s_q, c.s_on, c.len, c.s_q == e.q ? SN_NONE : e.q});
+          if (c.s_q == e.q) act.resets.push_back({c.s_q, 0xFFu, 0u});
+          else act.nodes.push_back(c.s_q);
+        }
         act.supernodes_pruned++;
         continue;
       }
@@ -226,6 +232,12 @@ class ClGraph {
       uint32_t term_bit[2] = {0, 0};
       bool cycle = false;
       int32_t cycle_start_node = -1;  // a cycle printed from a (now interior) node: that node stays
+      // A path that is its own reverse complement leaves and re-enters its node through the same
+      // edge: the reference's walk turns round there and runs back over the chain it came along
+      // (every node once more, in the other orientation) to whatever ends the supernode on the
+      // OTHER side.  Such a side has no end node of its own; its paths count twice in the length.
+      bool reflect[2] = {false, false};
+      uint64_t hairpin_len = 0;
       // grow from (node, bit): take the path behind that edge, go on through interior nodes
       auto grow = [&](int32_t node, uint32_t bit, int which, int32_t stop_path, int32_t stop_node) {
         for (;;) {
@@ -236,6 +248,7 @@ class ClGraph {
           int32_t y;
           uint32_t ybit;
           other_end(pid, node, bit, y, ybit);
+          if (y == node && ybit == bit) { reflect[which] = true; hairpin_len += paths[pid].len; return; }
           if (y == stop_node) { cycle = true; return; }
           if (!interior_now(nodes[y])) { term[which] = y; term_bit[which] = ybit; return; }
           cn.push_back(y);
@@ -257,7 +270,12 @@ class ClGraph {
         if (!p.alive || p.visited) continue;
         cp.push_back(e.id);
         beyond(p.a, p.a_bit, 0, e.id);
-        if (!cycle) beyond(p.b, p.b_bit, 1, e.id);
+        if (p.a == p.b && p.a_bit == p.b_bit) {  // the path itself turns round: it has one end only
+          reflect[1] = true;
+          hairpin_len += p.len;
+        } else if (!cycle) {
+          beyond(p.b, p.b_bit, 1, e.id);
+        }
         if (cycle) keep_q = e.q;  // printed from this interior node: everything else is "interior"
       } else {
         ClNode &j = nodes[e.id];
@@ -276,6 +294,8 @@ class ClGraph {
           grow(e.id, term_bit[0], 1, -1, -1);
         }
       }
+      std::sort(cn.begin(), cn.end());
+      cn.erase(std::unique(cn.begin(), cn.end()), cn.end());
       // db_node_action_set_status_visited on every node of the supernode
       for (int32_t p : cp) paths[p].visited = 1;
       for (int32_t n : cn) nodes[n].status = 2;
@@ -288,14 +308,23 @@ class ClGraph {
         length += paths[p].len;
         all_low = all_low && paths[p].max_covg <= T;
       }
+      if (reflect[0] || reflect[1]) {
+        length = 2 * (length - hairpin_len) + hairpin_len;
+        if (reflect[0] && reflect[1]) {
+          // turned round at both ends: a cycle through both orientations of every node, the one it
+          // is printed from included -- nothing is spared and there are no end nodes
+          cycle = true;
+          cycle_start_node = -1;
+        }
+      }
       for (int32_t n : cn) all_low = all_low && nodes[n].covg <= T;
       if (length <= 1 || length > 2ull * (uint64_t)k + 2ull || !all_low) continue;
       for (int32_t n : cn) prune_node(n, act);
-      for (int32_t p : cp) prune_path(p, keep_q, act);
+      for (int32_t p : cp) prune_path(p, (e.kind == 0 && p == e.id) ? keep_q : SN_NONE, act);
       if (cycle && cycle_start_node >= 0) {  // the start node stays, without edges
         nodes[cycle_start_node].edges = 0;
         for (int b = 0; b < 8; b++) nodes[cycle_start_node].adj[b] = -1;
-        act.resets.push_back({nodes[cycle_start_node].q, 0xFFu});
+        act.resets.push_back({nodes[cycle_start_node].q, 0xFFu, 0u});
       }
       for (int w = 0; w < 2; w++)
         if (term[w] >= 0) drop_edge(term[w], term_bit[w], act);

@@ -204,7 +204,8 @@ struct SnPath {
 // node min_q, trigger flags (s / t is a node that prints this path when the
 // traversal reaches it unvisited), trigger sides of s and t, cycle flag
 constexpr uint32_t SNB_S_O = 1u << 0, SNB_T_O = 1u << 3, SNB_MIN_O = 1u << 6, SNB_TRIG_S = 1u << 7,
-                   SNB_TRIG_T = 1u << 8, SNB_CYCLE = 1u << 13;
+                   SNB_TRIG_T = 1u << 8, SNB_CYCLE = 1u << 13,
+                   SNB_BOTH_WAYS = 1u << 14;  // a cycle that crosses every node in both orientations
 constexpr int SNB_S_N = 1, SNB_T_N = 4, SNB_S_SIDE = 9, SNB_T_SIDE = 11;
 
 struct SnCounters {
@@ -287,6 +288,7 @@ LASV_HD bool sn_walk_cycle(const TableView &t, int k, uint64_t q, const uint64_t
   const uint32_t n0 = low_bit4(sn_side(q_edges, 0u));
   uint32_t co = 0, cn = n0, o2 = 0, back = 0;
   uint64_t q2 = SN_NONE, m2 = 0, len = 0;
+  bool both_ways = false;
   dangling = false;
   for (;;) {
     q2 = sn_step<N, Ops>(t, k, key, co, cn, key2, m2, o2, back);
@@ -294,6 +296,7 @@ LASV_HD bool sn_walk_cycle(const TableView &t, int k, uint64_t q, const uint64_t
     len++;
     if (q2 < q) return false;                 // a lower slot of the same cycle keeps the record
     if ((q2 == q && o2 == 0u) || len >= max_steps) break;
+    if (q2 == q) both_ways = true;            // back at q in the other orientation: half way round
     const uint32_t e2 = meta_edges(m2);
     if (!sn_interior(e2)) { dangling = true; return false; }  // cannot happen in a consistent graph
 #pragma unroll
@@ -305,7 +308,7 @@ LASV_HD bool sn_walk_cycle(const TableView &t, int k, uint64_t q, const uint64_t
   rec.t_q = q;
   rec.min_q = q;
   rec.len = (uint32_t)len;
-  rec.bits = SNB_CYCLE | (n0 << SNB_S_N);
+  rec.bits = SNB_CYCLE | (n0 << SNB_S_N) | (both_ways ? SNB_BOTH_WAYS : 0u);
   return true;
 }
 

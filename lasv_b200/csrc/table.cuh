@@ -132,6 +132,7 @@ struct DeviceOps {
   static __device__ __forceinline__ void xor32(uint32_t *p, uint32_t v) { atomicXor(p, v); }
   static __device__ __forceinline__ void add32(uint32_t *p, uint32_t v) { atomicAdd(p, v); }
   static __device__ __forceinline__ void or32(uint32_t *p, uint32_t v) { atomicOr(p, v); }
+  static __device__ __forceinline__ void and32(uint32_t *p, uint32_t v) { atomicAnd(p, v); }
   static __device__ __forceinline__ void fence() { __threadfence(); }
   static __device__ __forceinline__ void backoff() { __nanosleep(40); }
   static __device__ __forceinline__ void count(unsigned long long *p, unsigned long long v) {

@@ -36,6 +36,7 @@ struct HostOps {
   static void xor32(uint32_t *p, uint32_t v) { *p ^= v; }
   static void add32(uint32_t *p, uint32_t v) { *p += v; }
   static void or32(uint32_t *p, uint32_t v) { *p |= v; }
+  static void and32(uint32_t *p, uint32_t v) { *p &= v; }
   static void fence() {}
   static void backoff() {}
   static void count(unsigned long long *p, unsigned long long v) { *p += v; }
@@ -325,6 +326,7 @@ bool build_cl_graph(const TableView &tv, int k, uint32_t T, ClGraph &g) {
       ok = ok && cl_path_coverage<N, HostOps>(tv, k, rec, T, c.max_covg, lo);
       if (c.s_covg > 0 && c.s_covg <= T && q < lo) lo = q;
       c.min_low_q = lo;
+      c.both_ways = (rec.bits & SNB_BOTH_WAYS) ? 1u : 0u;
       g.cycles.push_back(c);
     }
     ok = ok && !d;
@@ -336,6 +338,10 @@ template <int N>
 bool apply_cl_actions(const TableView &tv, int k, const ClActions &act) {
   bool ok = true;
   for (const auto &p : act.paths) ok = cl_prune_path<N, HostOps>(tv, k, p.q, p.on & 1u, p.on >> 1, p.len, p.keep_q) && ok;
+  if (!act.paths.empty()) {  // cl_settle_kernel
+    const uint64_t n_slots = ((uint64_t)tv.bucket_mask + 1) * tv.W;
+    for (uint64_t q = 0; q < n_slots; q++) cl_settle_node<N, HostOps>(tv, q);
+  }
   for (uint64_t q : act.nodes) cl_prune_node<N, HostOps>(tv, q);
   for (const auto &r : act.resets) cl_reset_edges<N, HostOps>(tv, r.q, r.mask);
   return ok;
@@ -360,7 +366,7 @@ int clean(uint8_t *table, int k, int L, int W, int finalized, int threshold, uin
   counts4[0] = tips.tips;
   counts4[1] = tips.tip_edges;
   counts4[2] = sups.supernodes_pruned;
-  counts4[3] = tips.paths.size() + sups.paths.size();
+  counts4[3] = tips.nodes_pruned() + sups.nodes_pruned();
   return 0;
 }
 

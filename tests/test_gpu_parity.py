@@ -803,6 +803,116 @@ def test_reference_cli_prints_supernodes_through_the_gpu(name, clean, tmp_path):
     assert (tmp_path / "sup.fa").read_bytes() == (tmp_path / "oracle.fa").read_bytes()
 
 
+def _table_records(table):
+    occ = table[table["status"] == 1]
+    out = np.zeros(len(occ), dtype=lasv_b200.record_dtype(table["kmer"].shape[1]))
+    out["kmer"], out["covg"], out["edges"] = occ["kmer"], occ["coverage"], occ["edges"]
+    return out
+
+
+def _clean_case(name, thresh, tmp_path, dense=None):
+    """Build on the GPU, export the reference-layout table, clean it through
+    lasv_ref_hash_table_clean and compare with the reference's sequential cleaning (oracle
+    restatement, pinned on the compiled reference) of the same slot order."""
+    if dense is None:
+        meta = util.case_meta(name)
+        k, L, W = meta["k"], meta["L"], meta["W"]
+        seq, qual, offs = util.case_streams(name)
+        cutoff = util.cutoff_of(meta)
+    else:
+        k, err_q20, n_reads, genome, L = dense
+        W, cutoff = 40, 38
+        base = synth.CFG1 if k <= 31 else synth.CFG0 if k <= 63 else synth.CFG2
+        w = synth.scaled(base, genome, L)
+        w.seed, w.kmer_size = 300 + k, k
+        p = w.params()
+        p.err_q20 = err_q20
+        seq, qual, offs = synth.reads_host(p, 0, n_reads)
+    with DBGraph(k, L, W) as g:
+        g.load_reads_host(seq, qual, offs, cutoff)
+        table, nxt = g.export_table()
+    raw = _table_records(table)
+    og = O.OracleGraph(k, L, W)
+    assert og.load_records(raw)
+    ost = og.clean(thresh)
+    ht = _capi.RefHashTable(k, 1 << L, W, table.ctypes.data, nxt.ctypes.data, None, len(raw), 15)
+    st = _capi.CleanStats()
+    _capi.check(_capi.lib().lasv_ref_hash_table_clean(C.byref(ht), _capi.CLEAN_TIPS | _capi.CLEAN_SUPERNODES, thresh,
+                                                    C.byref(st)))
+    st = st.as_dict()
+    assert np.array_equal(_table_records(table), og.records())          # same nodes, coverage, edges, same order
+    assert int((table["status"] == 3).sum()) == st["nodes_pruned"] == len(raw) - ost["nodes_left"]
+    assert not table["edges"][table["status"] == 3].any()
+    assert st["tips_clipped"] == ost["tips"] and st["tip_nodes_pruned"] == ost["tip_nodes"]
+    assert st["supernodes_pruned"] == ost["supernodes_pruned"]
+    # the supernodes of the cleaned table, through the reference-table entry point as well
+    sst = _capi.SupernodeStats()
+    _capi.check(_capi.lib().lasv_ref_hash_table_write_supernodes(C.byref(ht), str(tmp_path / "gpu.fa").encode(), 10000,
+                                                               C.byref(sst)))
+    og.print_supernodes(tmp_path / "oracle.fa", max_length=1 << 20)
+    assert (tmp_path / "gpu.fa").read_bytes() == (tmp_path / "oracle.fa").read_bytes()
+    return st
+
+
+@pytest.mark.parametrize("name,thresh", [("synth_cfg1_k31", 2), ("synth_cfg0_k53", 2), ("synth_cfg2_k95", 2),
+                                         ("synth_cfg0_k53", 1), ("edge_pe_k21_q5", 1)])
+def test_ref_table_clean_matches_reference_walk(name, thresh, tmp_path):
+    """`--remove_low_coverage_supernodes T` (tip clipping + low-coverage supernode
+    removal, both order-dependent) on the device, exact for the caller's slot order."""
+    st = _clean_case(name, thresh, tmp_path)
+    if name.startswith("synth"):
+        assert st["tips_clipped"] > 0 and st["supernodes_pruned"] > 0
+
+
+@pytest.mark.parametrize("dense", [(21, 40000, 600, 3000, 11), (53, 20000, 600, 3000, 11), (95, 20000, 600, 3000, 11),
+                                   (31, 20000, 40000, 200000, 17)])
+def test_ref_table_clean_dense_errors(dense, tmp_path):
+    """Junction next to junction, several tips on one node, supernodes that merge once a
+    neighbour is pruned: where the order of the traversal decides."""
+    st = _clean_case(None, 2, tmp_path, dense=dense)
+    assert st["tips_clipped"] > 0 and st["supernodes_pruned"] > 0
+
+
+@pytest.mark.parametrize("name", ["synth_cfg1_k31", "synth_cfg0_k53", "synth_cfg2_k95"])
+def test_reference_cli_cleans_through_the_gpu(name, tmp_path):
+    """The reference's main() with loaders, cleaning and supernode printing all bound to the GPU
+    (integration/_build/dB_graph_gpuall_*): `--remove_low_coverage_supernodes 2` leaves a `.ctx`
+    whose header carries the cleaning flags and whose records the oracle's supernode walk turns
+    into the FASTA the same run printed."""
+    from pathlib import Path
+    meta = util.case_meta(name)
+    k, L, W = meta["k"], meta["L"], meta["W"]
+    exe = Path(__file__).resolve().parents[1] / "integration" / "_build" / f"dB_graph_gpuall_{O.MAXK_OF_N[O.words_per_kmer(k)]}"
+    if not exe.exists():
+        pytest.skip("integration/_build not built (needs /root/reference at build time)")
+    seq, qual, _ = util.case_streams(name)
+    rl = meta["workload"]["read_len"]
+    s2, q2 = seq.reshape(-1, rl + 1), qual.reshape(-1, rl + 1)
+    O.write_fastq_fixed(tmp_path / "a.fq", s2[0::2].reshape(-1), q2[0::2].reshape(-1), rl)
+    O.write_fastq_fixed(tmp_path / "b.fq", s2[1::2].reshape(-1), q2[1::2].reshape(-1), rl)
+    (tmp_path / "l").write_text(f"{tmp_path / 'a.fq'}\n")
+    (tmp_path / "r").write_text(f"{tmp_path / 'b.fq'}\n")
+    cmd = [str(exe), "--kmer_size", str(k), "--mem_height", str(L), "--mem_width", str(W),
+           "--pe_list", f"{tmp_path / 'l'},{tmp_path / 'r'}", "--quality_score_threshold", str(meta["q_thresh"]),
+           "--remove_low_coverage_supernodes", "2", "--dump_binary", str(tmp_path / "out.ctx"),
+           "--output_supernodes", str(tmp_path / "sup.fa")]
+    p = subprocess.run(cmd, cwd=tmp_path, capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stderr[-2000:] + p.stdout[-2000:]
+    assert "tips clipped" in p.stdout
+    ctx = O.parse_ctx(tmp_path / "out.ctx")
+    want = bytearray(O.ctx_header(k, meta["ctx_mean_read_len"], meta["ctx_total_seq"], cleaned_threshold=2))
+    got = bytearray(ctx["header"])
+    pad = slice(6 + 16 + 12 + 4 + 9 + 10, 6 + 16 + 12 + 4 + 9 + 16)
+    want[pad] = got[pad] = b"\0" * 6
+    assert want == got
+    assert 0 < len(ctx["records"]) < meta["n_records"]
+    gold = util.case_records(name)                       # cleaning removes nodes and edges, never adds any
+    keys = {tuple(r) for r in gold["kmer"].tolist()}
+    assert all(tuple(r) in keys for r in ctx["records"]["kmer"].tolist())
+    _oracle_supernodes_in_table_order(k, L, W, ctx["records"], tmp_path / "oracle.fa")
+    assert (tmp_path / "sup.fa").read_bytes() == (tmp_path / "oracle.fa").read_bytes()
+
+
 @pytest.mark.parametrize("name", ["synth_cfg1_k31", "synth_cfg0_k53", "synth_cfg2_k95", "synth_full_k53"])
 def test_reference_cli_reloads_ctx_through_the_gpu(name, tmp_path):
     """`dB_graph --multicolour_bin x.ctx` with the record loop of

@@ -395,7 +395,7 @@ def emul_clean(emul, tab, threshold):
     counts = np.zeros(4, dtype=np.uint64)
     rc = emul.emul_clean(tab.ptr, tab.k, tab.L, tab.W, int(tab.finalized), threshold, counts.ctypes.data)
     assert rc == 0, f"emulated cleaning failed ({rc})"
-    return dict(zip(["tips", "tip_edges", "supernodes_pruned", "paths_pruned"], (int(c) for c in counts)))
+    return dict(zip(["tips", "tip_edges", "supernodes_pruned", "nodes_pruned"], (int(c) for c in counts)))
 
 
 def oracle_clean_in_order(tab, threshold):
@@ -424,9 +424,54 @@ def test_emulated_cleaning_matches_reference_walk(emul, name, thresh, finalized,
     assert np.array_equal(tab.records(), og.records())
     assert st["tips"] == ost["tips"] and st["tip_edges"] == ost["tip_nodes"]
     assert st["supernodes_pruned"] == ost["supernodes_pruned"]
+    elems = tab.elements()
+    assert int((elems["status"] == 3).sum()) == st["nodes_pruned"] and not elems["edges"][elems["status"] == 3].any()
     if name.startswith("synth"):
         assert st["tips"] > 0 and st["supernodes_pruned"] > 0
     # and the supernodes of the cleaned graph
     emul_supernodes(emul, tab, tmp_path / "ours.fa")
     og.print_supernodes(tmp_path / "oracle.fa", max_length=1 << 20)
     assert (tmp_path / "ours.fa").read_bytes() == (tmp_path / "oracle.fa").read_bytes()
+
+
+@pytest.mark.parametrize("alphabet,seed", [("AC", 1), ("CG", 2), ("ACG", 3), ("ACGT", 4)])
+def test_emulated_cleaning_and_supernodes_on_repetitive_graphs(emul, alphabet, seed, tmp_path):
+    """Small random graphs over reduced alphabets: short cycles, tips on tips, and -- with C and G --
+    paths that are their own reverse complement (the reference's walk turns round in them and runs
+    back over its own nodes).  Cleaning and the supernodes printed afterwards must equal the
+    reference's sequential result (oracle restatement) for the same slot order."""
+    rng = np.random.default_rng(seed)
+    comp = str.maketrans("ACGT", "TGCA")
+    checked = cycles = 0
+    for _ in range(120):
+        k = int(rng.choice([9, 11, 15, 21]))
+        glen = int(rng.integers(30, 400))
+        genome = "".join(rng.choice(list(alphabet), size=glen))
+        src = genome * 3 if rng.random() < 0.5 else genome
+        reads = []
+        for _ in range(int(rng.integers(1, 40))):
+            s, rl = int(rng.integers(0, glen)), int(rng.integers(k, k + 60))
+            r = src[s:s + rl]
+            if len(r) < k:
+                continue
+            if rng.random() < 0.3:
+                r = list(r)
+                r[int(rng.integers(0, len(r)))] = str(rng.choice(list("ACGT")))
+                r = "".join(r)
+            reads.append(r.translate(comp)[::-1] if rng.random() < 0.5 else r)
+        if not reads:
+            continue
+        seq, _, _ = O.reads_to_streams(reads)
+        thresh = int(rng.integers(1, 4))
+        rc, tab, _ = emul_build(emul, {"k": k, "L": 6, "W": 40, "q_thresh": 0}, seq, None)
+        if rc != 0:
+            continue
+        og, _ = oracle_clean_in_order(tab, thresh)
+        emul_clean(emul, tab, thresh)
+        assert np.array_equal(tab.records(), og.records()), (alphabet, k, thresh, reads)
+        st = emul_supernodes(emul, tab, tmp_path / "ours.fa")
+        og.print_supernodes(tmp_path / "oracle.fa", max_length=1 << 20)
+        assert (tmp_path / "ours.fa").read_bytes() == (tmp_path / "oracle.fa").read_bytes(), (alphabet, k, thresh, reads)
+        checked += 1
+        cycles += st["cycles"]
+    assert checked > 100 and cycles > 0
