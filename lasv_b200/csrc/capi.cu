@@ -2085,6 +2085,9 @@ int lasv_ref_hash_table_clean(lasv_ref_hash_table *t, int what, int threshold, l
                             (size_t)nb, cudaMemcpyHostToDevice));
     }
     g->finalized = true;
+    // a copy from pageable host memory may return before its last DMA has landed, and the kernels run
+    // on a non-blocking stream that does not wait for the legacy stream the copy was issued on
+    CUDA_TRY(cudaDeviceSynchronize());
     if (what & LASV_CLEAN_TIPS)
       if (int e = clean_pass(g, LASV_CLEAN_TIPS, (uint32_t)std::max(threshold, 0), stats)) return e;
     if (what & LASV_CLEAN_SUPERNODES)
@@ -2120,7 +2123,7 @@ int lasv_ref_hash_table_write_supernodes(lasv_ref_hash_table *t, const char *fas
                             (size_t)nb, cudaMemcpyHostToDevice));
     }
     g->finalized = true;
-    return lasv_graph_write_supernodes(g, fasta_path, max_length, stats);
+    return lasv_graph_write_supernodes(g, fasta_path, max_length, stats);  // starts with a device synchronisation
   }();
   lasv_graph_free(&g);
   return rc;
