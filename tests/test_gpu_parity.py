@@ -864,15 +864,11 @@ def test_ref_table_clean_matches_reference_walk(name, thresh, tmp_path):
         assert st["tips_clipped"] > 0 and st["supernodes_pruned"] > 0
 
 
-# The last GPU session of round 1 ran the five cases above and dense0 (green) and dense1, which hit a race between
-# the pageable upload and the first kernel (fixed since: device synchronisation after the upload); the budget
-# ended before the fix, the remaining dense cases and the CLI binding could be run on a device.  They are exact
-# on the CPU emulation (tests/test_host_emul.py); LASV_B200_UNVERIFIED=1 runs them on the GPU.
-_unverified = pytest.mark.skipif(os.environ.get("LASV_B200_UNVERIFIED") != "1",
-                                 reason="cleaning: dense and CLI cases not yet run on a device (set LASV_B200_UNVERIFIED=1)")
+# dense1 once failed on the device with "path record buffers overflowed": a race between the pageable table upload
+# and the first kernel on the non-blocking stream (the count pass saw fewer nodes than the list pass).  Fixed by a
+# device synchronisation after the upload; all cases below green on a B200 since (profiles/r1/cleaning_gpu_pytest_*.log).
 
 
-@_unverified
 @pytest.mark.parametrize("dense", [(21, 40000, 600, 3000, 11), (53, 20000, 600, 3000, 11), (95, 20000, 600, 3000, 11),
                                    (31, 20000, 40000, 200000, 17)])
 def test_ref_table_clean_dense_errors(dense, tmp_path):
@@ -882,7 +878,6 @@ def test_ref_table_clean_dense_errors(dense, tmp_path):
     assert st["tips_clipped"] > 0 and st["supernodes_pruned"] > 0
 
 
-@_unverified
 @pytest.mark.parametrize("name", ["synth_cfg1_k31", "synth_cfg0_k53", "synth_cfg2_k95"])
 def test_reference_cli_cleans_through_the_gpu(name, tmp_path):
     """The reference's main() with loaders, cleaning and supernode printing all bound to the GPU
