@@ -919,3 +919,137 @@ int orc_ctx_header_cleaned(int k, int N, uint32_t mean_read_len, uint64_t total_
   memcpy(flags + 4, &v, 4);
   return n;
 }
+
+/* ------------------------------------------------------------------------ */
+/* Branch printing, as `--mode build` runs it after the cleaning
+ * (graph_operations.c:1145-1152): for every node with more than one edge on a
+ * side, every neighbour on that side starts a "branch" -- the neighbour's
+ * k-mer, then on through nodes with one edge each way, at most 300 of them --
+ * unless an earlier branch has marked that neighbour `visited`.  Sequential,
+ * order-dependent through the marks; the marks are left in the table.  The
+ * product (lasv_b200/csrc/branches.cuh, branches_host.h) replays it on the
+ * compressed graph; this is its checker. */
+
+static int orc_degree(const orc_node *e, int orient) { /* element.c:1429-1447 db_node_get_degree */
+  unsigned edges = e->edges;
+  int j, d = 0;
+  if (orient == 1) edges >>= 4;
+  for (j = 0; j < 4; j++) { d += (int)(edges & 1u); edges >>= 1; }
+  return d;
+}
+
+static int orc_edge_exists(const orc_node *e, int nuc, int orient) { /* element.c db_node_edge_exist */
+  return (e->edges >> (nuc + 4 * orient)) & 1u;
+}
+
+/* print_branches.c:16-127  db_graph_get_sequence_for_a_single_branch_for_specific_person_or_pop
+ * (seq has room for k + 400 characters; the reference's buffer is char[500]).
+ * Returns the length in nodes, or -1 where the reference would die / dereference NULL. */
+static int orc_single_branch(orc_graph *g, orc_node *node, int orientation, char *seq) {
+  uint64_t km[ORC_MAXN];
+  int length = 1, i, w, n;
+  int reverse_edge = 0, next_o = 0, curr_o = 0, degree1, degree2;
+  orc_node *node_ptr = NULL, *next_node = NULL;
+  if (orientation == 0) for (w = 0; w < g->N; w++) km[w] = node->kmer[w];
+  else orc_revcomp(node->kmer, g->k, g->N, km);
+  orc_kmer_to_seq(km, g->k, g->N, seq);
+  seq[g->k] = '\0';
+  n = g->k;
+  node->status = 2; /* visited */
+  if (orc_degree(node, orientation) > 1) return length; /* :50-54 */
+  if (orc_degree(node, orientation) == 0) return length; /* :56-59 */
+  for (i = 0; i < 4; i++) { /* :61-73 */
+    if (orc_edge_exists(node, i, orientation)) {
+      next_o = 0;
+      reverse_edge = 0;
+      node_ptr = orc_get_next_node(g, node, orientation, &next_o, i, &reverse_edge);
+      seq[n++] = "ACGT"[i];
+      seq[n] = '\0';
+    }
+  }
+  if (!node_ptr) return -1;
+  curr_o = next_o;
+  degree1 = orc_degree(node_ptr, 0);
+  degree2 = orc_degree(node_ptr, 1);
+  while (degree1 == 1 && degree2 == 1 && length <= 300) { /* :82-110 */
+    int j;
+    if (node_ptr->status == 2) break; /* "if in a circle" */
+    length++;
+    node_ptr->status = 2;
+    next_node = NULL;
+    for (j = 0; j < 4; j++) {
+      if (orc_edge_exists(node_ptr, j, curr_o)) {
+        next_o = 0;
+        reverse_edge = 0;
+        next_node = orc_get_next_node(g, node_ptr, curr_o, &next_o, j, &reverse_edge);
+        seq[n++] = "ACGT"[j];
+        seq[n] = '\0';
+      }
+    }
+    if (!next_node) return -1; /* "Unexpected disruption ..." */
+    node_ptr = next_node;
+    curr_o = next_o;
+    degree1 = orc_degree(node_ptr, 0);
+    degree2 = orc_degree(node_ptr, 1);
+  }
+  if (curr_o == 0 && degree1 != 1 && degree2 == 1) { /* :112-123 */
+    node_ptr->status = 2;
+    length++;
+  } else if (curr_o == 1 && degree2 != 1 && degree1 == 1) {
+    node_ptr->status = 2;
+    length++;
+  } else {
+    seq[--n] = '\0';
+  }
+  return length;
+}
+
+/* print_branches.c:131-199  db_graph_print_all_branches_for_specific_person_or_pop.
+ * counts[0] = branches printed, [1] = branching nodes, [2] = nodes left `visited`.
+ * keep_marks = 0 additionally resets the marks afterwards (a convenience the reference
+ * does not have: there the marks stay, graph_operations.c:1145-1152).
+ * Returns 0, or -1 on I/O error / inconsistent graph. */
+int orc_print_branches(orc_graph *g, const char *path, int keep_marks, uint64_t *counts) {
+  uint64_t i, cap = g->n_buckets * (uint64_t)g->W;
+  char *seq = (char *)malloc((size_t)g->k + 512);
+  int rc = 0;
+  FILE *f = fopen(path, "w");
+  if (!f || !seq) { free(seq); if (f) fclose(f); return -1; }
+  counts[0] = counts[1] = counts[2] = 0;
+  for (i = 0; i < cap; i++) /* :133 visited -> none */
+    if (g->table[i].status == 2) g->table[i].status = 1;
+  for (i = 0; i < cap && rc == 0; i++) {
+    orc_node *cur = &g->table[i];
+    int k;
+    if (cur->status == 0) continue; /* an empty slot has coverage 0 */
+    if (!(cur->covg > 0 && cur->status != 3 && (orc_degree(cur, 0) > 1 || orc_degree(cur, 1) > 1))) continue;
+    counts[1]++;
+    for (k = 0; k < 2 && rc == 0; k++) {
+      int j;
+      if (orc_degree(cur, k) <= 1) continue;
+      for (j = 0; j < 4; j++) {
+        int next_o = 0, reverse_edge = 0, length;
+        orc_node *next;
+        if (!orc_edge_exists(cur, j, k)) continue;
+        next = orc_get_next_node(g, cur, k, &next_o, j, &reverse_edge);
+        if (!next) { rc = -1; break; } /* the reference reads next_node->status of NULL */
+        if (next->status == 2) continue;
+        length = orc_single_branch(g, next, next_o, seq);
+        if (length < 0) { rc = -1; break; }
+        if (length > 0) {
+          fprintf(f, ">b_%.*s\n%s\n", g->k, seq, seq);
+          counts[0]++;
+        }
+      }
+    }
+  }
+  for (i = 0; i < cap; i++) {
+    if (g->table[i].status == 2) {
+      counts[2]++;
+      if (!keep_marks) g->table[i].status = 1;
+    }
+  }
+  free(seq);
+  if (fclose(f) != 0) rc = -1;
+  return rc;
+}

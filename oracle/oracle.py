@@ -69,6 +69,8 @@ def lib() -> C.CDLL:
         L.orc_get_key.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         L.orc_print_supernodes.restype = C.c_int
         L.orc_print_supernodes.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_void_p]
+        L.orc_print_branches.restype = C.c_int
+        L.orc_print_branches.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_void_p]
         L.orc_clean.restype = C.c_int
         L.orc_clean.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         L.orc_ctx_header_cleaned.restype = C.c_int
@@ -168,6 +170,15 @@ class OracleGraph:
             raise RuntimeError("oracle supernode walk failed (I/O error or an edge to a missing node)")
         return {"supernodes": int(counts[0]), "singletons": int(counts[1]), "nodes": int(counts[2]),
                 "at_max_length": int(counts[3])}
+
+    def print_branches(self, path, keep_marks: bool = False) -> dict:
+        """`--mode build`'s branches.fa (print_branches.c:131-199) on this table, in table order.
+        keep_marks=True leaves the `visited` marks in the table, as the reference does."""
+        counts = np.zeros(3, dtype=np.uint64)
+        rc = lib().orc_print_branches(self._g, str(path).encode(), 1 if keep_marks else 0, counts.ctypes.data)
+        if rc != 0:
+            raise RuntimeError("oracle branch walk failed (I/O error or an edge to a missing node)")
+        return {"branches": int(counts[0]), "branching_nodes": int(counts[1]), "visited": int(counts[2])}
 
     def lookup(self, key_words):
         key = np.asarray(key_words, dtype=np.uint64)

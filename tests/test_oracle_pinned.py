@@ -191,3 +191,67 @@ def test_oracle_cleaning_matches_live_reference(name, thresh, tmp_path):
     assert hdr == got
     g.print_supernodes(tmp_path / "oracle.fa")
     assert (tmp_path / "oracle.fa").read_bytes() == (tmp_path / "sup.fa").read_bytes()
+
+
+# ---- branch printing (`--mode build` writes ./branches.fa after the cleaning: graph_operations.c:1145-1152) ----
+@pytest.mark.skipif(not O.ref_available(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("name,thresh", [("synth_cfg1_k31", None), ("synth_cfg0_k53", None), ("synth_cfg2_k95", None),
+                                         ("synth_cfg1_k31", 2), ("synth_cfg0_k53", 2), ("synth_cfg2_k95", 2),
+                                         ("edge_pe_k21_q5", None), ("edge_pe_k21_q5", 1)])
+def test_oracle_branches_match_live_reference(name, thresh, tmp_path):
+    """print_branches.c restated: same slot order in, the same branches.fa out byte for byte, raw and
+    after the cleaning; the `visited` marks it leaves behind are pinned through the supernodes the same
+    run prints afterwards (the printer skips marked nodes)."""
+    meta = util.case_meta(name)
+    k, L, W = meta["k"], meta["L"], meta["W"]
+    f1, f2 = (tmp_path / "a.fq", tmp_path / "b.fq")
+    seq, qual, offs = util.case_streams(name)
+    if "synth" in meta:
+        rl = meta["workload"]["read_len"]
+        s2, q2 = seq.reshape(-1, rl + 1), qual.reshape(-1, rl + 1)
+        O.write_fastq_fixed(f1, s2[0::2].reshape(-1), q2[0::2].reshape(-1), rl)
+        O.write_fastq_fixed(f2, s2[1::2].reshape(-1), q2[1::2].reshape(-1), rl)
+    else:
+        f1, f2 = util.case_files(name)
+    extra = ["--mode", "build"] + (["--remove_low_coverage_supernodes", str(thresh)] if thresh is not None else [])
+    ref = O.run_reference(k, L, W, f1, f2, q_thresh=meta["q_thresh"], workdir=tmp_path, want_supernodes=True,
+                          extra_args=extra)
+    g, ok = util.oracle_build(k, L, W, seq, qual, offs, util.cutoff_of(meta), paired=True)
+    assert ok
+    if thresh is not None:
+        g.clean(thresh)
+    st = g.print_branches(tmp_path / "oracle_branches.fa", keep_marks=True)
+    want = (tmp_path / "branches.fa").read_bytes()
+    assert (tmp_path / "oracle_branches.fa").read_bytes() == want
+    assert st["branches"] == want.count(b">b_")
+    if name.startswith("synth") and thresh is None:     # the cleaning may leave no junction at all
+        assert st["branches"] > 0 and st["visited"] >= st["branches"]
+    assert np.array_equal(g.records(), ref["ctx"]["records"])     # marks do not change what is dumped
+    g.print_supernodes(tmp_path / "oracle.fa")
+    assert (tmp_path / "oracle.fa").read_bytes() == (tmp_path / "sup.fa").read_bytes()
+
+
+@pytest.mark.skipif(not O.ref_available(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("k,L,W,err,genome,pairs", [(21, 10, 30, 30000, 3000, 150), (31, 12, 40, 20000, 20000, 1500),
+                                                    (53, 11, 40, 600, 1500, 400), (95, 11, 40, 20000, 3000, 300)])
+def test_oracle_branches_dense_errors_live_reference(tmp_path, k, L, W, err, genome, pairs):
+    """Junction next to junction and long error-free stretches (walks cut at 300 nodes, walks that
+    run into marks left from the other end)."""
+    from lasv_b200 import synth
+    base = {21: synth.CFG1, 31: synth.CFG1, 53: synth.CFG0, 95: synth.CFG2}[k]
+    w = synth.scaled(base, genome, L)
+    w.seed, w.kmer_size = 500 + k, k
+    p = w.params()
+    p.err_q20 = err
+    seq, qual, offs = synth.reads_host(p, 0, 2 * pairs)
+    stride = w.read_len + 1
+    s2, q2 = seq.reshape(-1, stride), qual.reshape(-1, stride)
+    O.write_fastq_fixed(tmp_path / "a.fq", s2[0::2].reshape(-1), q2[0::2].reshape(-1), w.read_len)
+    O.write_fastq_fixed(tmp_path / "b.fq", s2[1::2].reshape(-1), q2[1::2].reshape(-1), w.read_len)
+    O.run_reference(k, L, W, tmp_path / "a.fq", tmp_path / "b.fq", q_thresh=5, workdir=tmp_path,
+                    extra_args=["--mode", "build"])
+    g, ok = util.oracle_build(k, L, W, seq, qual, offs, 38, paired=True)
+    assert ok
+    st = g.print_branches(tmp_path / "ours.fa")
+    assert st["branches"] > 0
+    assert (tmp_path / "ours.fa").read_bytes() == (tmp_path / "branches.fa").read_bytes()
