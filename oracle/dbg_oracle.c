@@ -564,6 +564,17 @@ uint64_t orc_dump_records(const orc_graph *g, uint8_t *out) {
   return n;
 }
 
+/* test helper: status byte of every dumped record, in the order of orc_dump_records */
+uint64_t orc_dump_status(const orc_graph *g, uint8_t *out) {
+  uint64_t i, n = 0, cap = g->n_buckets * (uint64_t)g->W;
+  for (i = 0; i < cap; i++) {
+    const orc_node *e = &g->table[i];
+    if (e->status != 1 && e->status != 2) continue;
+    out[n++] = e->status;
+  }
+  return n;
+}
+
 /* file_reader.c:1686-1703 + hash_table.c:333-382: reload records through
  * find_or_insert semantics (keys are unique in a .ctx), adding covg/edges. */
 int orc_load_records(orc_graph *g, const uint8_t *recs, uint64_t n) {

@@ -56,6 +56,8 @@ def lib() -> C.CDLL:
         L.orc_collisions.argtypes = [C.c_void_p, C.c_void_p]
         L.orc_dump_records.restype = C.c_uint64
         L.orc_dump_records.argtypes = [C.c_void_p, C.c_void_p]
+        L.orc_dump_status.restype = C.c_uint64
+        L.orc_dump_status.argtypes = [C.c_void_p, C.c_void_p]
         L.orc_load_records.restype = C.c_int
         L.orc_load_records.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
         L.orc_lookup.restype = C.c_int
@@ -147,6 +149,12 @@ class OracleGraph:
         out = np.zeros(self.unique_kmers, dtype=record_dtype(self.N))
         n = lib().orc_dump_records(self._g, out.ctypes.data)   # pruned nodes are not dumped
         assert n <= len(out)
+        return out[:n]
+
+    def status(self) -> np.ndarray:
+        """Status byte (1 none, 2 visited) of every record of records(), in that order."""
+        out = np.zeros(self.unique_kmers, dtype=np.uint8)
+        n = lib().orc_dump_status(self._g, out.ctypes.data)
         return out[:n]
 
     def clean(self, threshold: int, max_var_len: int = 10000) -> dict:

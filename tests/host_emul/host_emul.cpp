@@ -18,6 +18,8 @@
 #include "../../lasv_b200/csrc/supernodes_host.h"
 #include "../../lasv_b200/csrc/cleaning.cuh"
 #include "../../lasv_b200/csrc/cleaning_host.h"
+#include "../../lasv_b200/csrc/branches.cuh"
+#include "../../lasv_b200/csrc/branches_host.h"
 
 using namespace lasv;
 
@@ -370,6 +372,29 @@ int clean(uint8_t *table, int k, int L, int W, int finalized, int threshold, uin
   return 0;
 }
 
+// Branch printing as the library runs it: the paths (supernode kernels' walks) -> compressed
+// graph -> replay of the reference's traversal (branches_host.h) -> one record writer per branch
+// (branches.cuh), optionally leaving the reference's `visited` marks in the table.
+template <int N>
+int branches(uint8_t *table, int k, int L, int W, int finalized, const char *path, int mark, uint64_t *counts6) {
+  const TableView tv = make_table_view(table, N, L, W, 15, finalized != 0);
+  ClGraph g;
+  if (!build_cl_graph<N>(tv, k, 0u, g)) return -2;
+  std::vector<BrPrint> prints;
+  BrReplay replay(g, k);
+  const BrStats st = replay.run(prints);
+  std::vector<char> image(st.image_bytes + 8);
+  bool ok = true;
+  for (const BrPrint &p : prints) ok = br_write_record<N, HostOps>(tv, k, p, image.data(), mark) && ok;  // br_write_kernel
+  FILE *fp = fopen(path, "w");
+  if (!fp) return -1;
+  const bool wrote = fwrite(image.data(), 1, st.image_bytes, fp) == st.image_bytes;
+  if (fclose(fp) != 0 || !wrote) return -1;
+  counts6[0] = st.branches; counts6[1] = st.branching_nodes; counts6[2] = st.nodes; counts6[3] = st.refused;
+  counts6[4] = st.cut; counts6[5] = st.inconsistent;
+  return (ok && !st.inconsistent) ? 0 : -3;
+}
+
 }  // namespace
 
 #define DISPATCH(N, call) ((N) == 1 ? call<1> : (N) == 2 ? call<2> : call<3>)
@@ -437,6 +462,11 @@ int emul_supernodes(uint8_t *table, int k, int L, int W, int finalized, const ch
 int emul_clean(uint8_t *table, int k, int L, int W, int finalized, int threshold, uint64_t *counts4) {
   const int N = 2 * k / 64 + 1;
   return DISPATCH(N, clean)(table, k, L, W, finalized, threshold, counts4);
+}
+
+int emul_branches(uint8_t *table, int k, int L, int W, int finalized, const char *path, int mark, uint64_t *counts6) {
+  const int N = 2 * k / 64 + 1;
+  return DISPATCH(N, branches)(table, k, L, W, finalized, path, mark, counts6);
 }
 
 // kmer_revcomp of supernodes.cuh, for known-answer checks

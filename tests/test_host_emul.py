@@ -20,7 +20,7 @@ HERE = Path(__file__).resolve().parent / "host_emul"
 def emul():
     so = HERE / "libhost_emul.so"
     src = HERE / "host_emul.cpp"
-    hdrs = list((HERE.parents[1] / "lasv_b200" / "csrc").glob("*.cuh"))
+    hdrs = list((HERE.parents[1] / "lasv_b200" / "csrc").glob("*.cuh")) + list((HERE.parents[1] / "lasv_b200" / "csrc").glob("*_host.h"))
     if not so.exists() or so.stat().st_mtime < max(p.stat().st_mtime for p in [src] + hdrs):
         subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas",
                         "-I/usr/local/cuda/include", "-o", str(so), str(src)], check=True)
@@ -38,6 +38,7 @@ def emul():
     L.emul_supernodes.argtypes = [C.c_void_p] + [C.c_int] * 4 + [C.c_char_p, C.c_void_p]
     L.emul_revcomp.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
     L.emul_clean.argtypes = [C.c_void_p] + [C.c_int] * 5 + [C.c_void_p]
+    L.emul_branches.argtypes = [C.c_void_p] + [C.c_int] * 4 + [C.c_char_p, C.c_int, C.c_void_p]
     L.emul_hash_c.restype = C.c_uint32
     L.emul_hash_c.argtypes = [C.c_void_p, C.c_int, C.c_uint32]
     return L
@@ -475,3 +476,109 @@ def test_emulated_cleaning_and_supernodes_on_repetitive_graphs(emul, alphabet, s
         checked += 1
         cycles += st["cycles"]
     assert checked > 100 and cycles > 0
+
+
+# ---- branch printing: branches.cuh (record writer) + branches_host.h (the reference's traversal on the compressed graph) ----
+def emul_branches(emul, tab, path, mark=False):
+    counts = np.zeros(6, dtype=np.uint64)
+    rc = emul.emul_branches(tab.ptr, tab.k, tab.L, tab.W, int(tab.finalized), str(path).encode(), int(mark),
+                            counts.ctypes.data)
+    assert rc == 0, f"emulated branch printing failed ({rc})"
+    return dict(zip(["branches", "branching_nodes", "nodes", "refused", "cut", "inconsistent"], (int(c) for c in counts)))
+
+
+def check_branches(emul, tab, tmp_path, what=""):
+    """branches.fa of the emulated pipeline == the reference's sequential walk (oracle restatement,
+    pinned on the compiled reference) over the same slot order, and the same `visited` marks left."""
+    og = O.OracleGraph(tab.k, tab.L, tab.W)
+    recs = tab.records()
+    assert og.load_records(recs)
+    ost = og.print_branches(tmp_path / "oracle_br.fa", keep_marks=True)
+    st = emul_branches(emul, tab, tmp_path / "ours_br.fa", mark=True)
+    assert (tmp_path / "ours_br.fa").read_bytes() == (tmp_path / "oracle_br.fa").read_bytes(), what
+    assert st["branches"] == ost["branches"] and st["branching_nodes"] == ost["branching_nodes"], what
+    elems = tab.elements()
+    occ = elems[(elems["status"] == 1) | (elems["status"] == 2)]
+    ours = {tuple(r) for r in occ["kmer"][occ["status"] == 2].tolist()}             # the marks, node for node
+    orecs = og.records()
+    assert ours == {tuple(r) for r in orecs["kmer"][og.status() == 2].tolist()}, what
+    assert np.array_equal(tab.records(), recs), what                                # nothing else changed
+    return st
+
+
+@pytest.mark.parametrize("name,thresh", [("synth_cfg1_k31", None), ("synth_cfg0_k53", None), ("synth_cfg2_k95", None),
+                                         ("synth_cfg0_k53", 2), ("synth_cfg2_k95", 1), ("edge_pe_k21_q5", None),
+                                         ("edge_pe_k31_q5", None), ("synth_full_k53", None)])
+@pytest.mark.parametrize("finalized", [False, True])
+def test_emulated_branches_match_reference_walk(emul, name, thresh, finalized, tmp_path):
+    meta = util.case_meta(name)
+    seq, qual, _ = util.case_streams(name)
+    rc, tab, _ = emul_build(emul, meta, seq, qual)
+    assert rc == 0
+    if finalized:
+        tab.finalize()
+    if thresh is not None:
+        emul_clean(emul, tab, thresh)
+    st = check_branches(emul, tab, tmp_path, name)
+    if name.startswith("synth") and thresh is None:
+        assert st["branches"] > 0
+
+
+@pytest.mark.parametrize("k,err_q20,n_reads,genome,L", [(21, 40000, 600, 3000, 11), (53, 20000, 600, 3000, 11),
+                                                        (95, 20000, 600, 3000, 11), (31, 3000, 3000, 60000, 14),
+                                                        (31, 20000, 40000, 200000, 17)])
+def test_emulated_branches_dense_errors_and_long_runs(emul, k, err_q20, n_reads, genome, L, tmp_path):
+    """Junction next to junction (neighbours refused because an earlier branch marked them) and long
+    error-free stretches (walks cut at 300 nodes, walks that meet marks left from the other end)."""
+    from lasv_b200 import synth
+    base = synth.CFG1 if k <= 31 else synth.CFG0 if k <= 63 else synth.CFG2
+    w = synth.scaled(base, genome, L)
+    w.seed, w.kmer_size = 700 + k, k
+    p = w.params()
+    p.err_q20 = err_q20
+    seq, qual, _ = synth.reads_host(p, 0, n_reads)
+    rc, tab, _ = emul_build(emul, {"k": k, "L": L, "W": 40, "q_thresh": 5}, seq, qual)
+    assert rc == 0
+    st = check_branches(emul, tab, tmp_path)
+    assert st["branches"] > 0
+    if k <= 53:
+        assert st["refused"] > 0
+    if err_q20 <= 3000:
+        assert st["cut"] > 0
+
+
+@pytest.mark.parametrize("alphabet,seed", [("AC", 11), ("CG", 12), ("ACG", 13), ("ACGT", 14)])
+def test_emulated_branches_on_repetitive_graphs(emul, alphabet, seed, tmp_path):
+    """Small random graphs over reduced alphabets: loops through a branching node, paths that are
+    their own reverse complement, branching nodes that are each other's neighbours; raw and cleaned."""
+    rng = np.random.default_rng(seed)
+    comp = str.maketrans("ACGT", "TGCA")
+    checked = printed = 0
+    for _ in range(150):
+        k = int(rng.choice([9, 11, 15, 21]))
+        glen = int(rng.integers(30, 400))
+        genome = "".join(rng.choice(list(alphabet), size=glen))
+        src = genome * 3 if rng.random() < 0.5 else genome
+        reads = []
+        for _ in range(int(rng.integers(1, 40))):
+            s, rl = int(rng.integers(0, glen)), int(rng.integers(k, k + 60))
+            r = src[s:s + rl]
+            if len(r) < k:
+                continue
+            if rng.random() < 0.3:
+                r = list(r)
+                r[int(rng.integers(0, len(r)))] = str(rng.choice(list("ACGT")))
+                r = "".join(r)
+            reads.append(r.translate(comp)[::-1] if rng.random() < 0.5 else r)
+        if not reads:
+            continue
+        seq, _, _ = O.reads_to_streams(reads)
+        rc, tab, _ = emul_build(emul, {"k": k, "L": 6, "W": 40, "q_thresh": 0}, seq, None)
+        if rc != 0:
+            continue
+        if rng.random() < 0.4:
+            emul_clean(emul, tab, int(rng.integers(1, 3)))
+        st = check_branches(emul, tab, tmp_path, (alphabet, k, reads))
+        checked += 1
+        printed += st["branches"]
+    assert checked > 120 and printed > 0
