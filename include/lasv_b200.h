@@ -247,6 +247,25 @@ typedef struct {
 int lasv_graph_write_supernodes(lasv_graph *g, const char *fasta_path, int max_length,
                                 lasv_supernode_stats *stats /* may be NULL */);
 
+/* Branch sequences of the device graph: what `--mode build` writes to ./branches.fa after
+ * the cleaning (graph_operations.c:1145-1152 -> db_graph_print_all_branches_for_specific_
+ * person_or_pop, print_branches.c:131-199, with db_graph_get_sequence_for_a_single_branch_...
+ * :16-127): every neighbour X of a node with more than one edge on a side starts a record
+ * ">b_<k-mer of X>\n<X and the nodes with one edge each way that follow, at most 300>\n",
+ * unless an earlier record left X `visited`.  Byte for byte the reference's file for a
+ * traversal in table order.  mark_visited != 0 also leaves the reference's `visited` marks
+ * (status 2) on the nodes of the printed branches; pruned nodes are skipped either way. */
+typedef struct {
+  uint64_t n_branches;         /* records written */
+  uint64_t n_branching_nodes;  /* nodes with more than one edge on a side */
+  uint64_t n_nodes;            /* sum of the record lengths in nodes */
+  uint64_t n_refused;          /* neighbours an earlier branch had marked */
+  uint64_t n_cut;              /* walks stopped by the 300-node limit */
+  uint64_t bytes;              /* size of the file */
+} lasv_branch_stats;
+int lasv_graph_write_branches(lasv_graph *g, const char *fasta_path, int mark_visited,
+                              lasv_branch_stats *stats /* may be NULL */);
+
 /* ------------------------------------------------------------------ (C) -- */
 /* Records in table order, each kmer[N] | uint32 covg | uint8 edges = 8N+5
  * bytes (element.c:894-910).  Returns the record count, or a negative error. */
@@ -321,6 +340,14 @@ typedef struct {
   uint64_t nodes_pruned;     /* all nodes that went from none to pruned */
 } lasv_clean_stats;
 int lasv_ref_hash_table_clean(lasv_ref_hash_table *t, int what, int threshold, lasv_clean_stats *stats /* may be NULL */);
+
+/* db_graph_print_all_branches_for_specific_person_or_pop (print_branches.c:131-199) on the
+ * caller's reference-layout table (lasv_graph_write_branches above, in the caller's slot
+ * order).  As in the reference, `visited` marks are cleared first (:133) and the nodes of the
+ * printed branches come back `visited`; nothing else changes.  integration/branch_shim.c is
+ * the reference-side binding. */
+int lasv_ref_hash_table_write_branches(lasv_ref_hash_table *t, const char *fasta_path,
+                                       lasv_branch_stats *stats /* may be NULL */);
 
 /* Exact reference signatures (file_reader.h:86-118); `boolean` is signed char
  * (global.h:37).  They build the graph on the GPU and leave db_graph->table,

@@ -79,10 +79,20 @@ LASV_HD bool br_write_record(const TableView &t, int k, const BrPrint &p, char *
   return ok;
 }
 
+// print_branches.c:133 (db_node_action_unset_status_visited_...): visited -> none
+#pragma nv_exec_check_disable
+template <int N, class Ops>
+LASV_HD void br_reset_mark(const TableView &t, uint64_t q) {
+  uint64_t *mp = cl_meta_ptr<N, Ops>(t, q);
+  const uint64_t m = Ops::load(mp);
+  if (meta_status(m) == ST_VISITED) Ops::store(mp, meta_with(m, meta_edges(m), ST_NONE));
+}
+
 #if defined(__CUDACC__)
 // launch interface (cleaning_kernels.cu); failures are counted in c->n_failed
 void launch_br_write(int N, const TableView &t, int k, const BrPrint *prints, uint64_t n, char *image, int mark,
                      ClCounters *c, cudaStream_t st);
+void launch_br_reset_marks(int N, const TableView &t, cudaStream_t st);
 #endif
 
 }  // namespace lasv

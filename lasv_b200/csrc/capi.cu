@@ -31,6 +31,7 @@
 #include "graph_kernels.cuh"
 #include "supernodes_host.h"
 #include "cleaning_host.h"
+#include "branches_host.h"
 #include "seq_reader.h"
 
 using namespace lasv;
@@ -2093,6 +2094,174 @@ int lasv_ref_hash_table_clean(lasv_ref_hash_table *t, int what, int threshold, l
     if (what & LASV_CLEAN_SUPERNODES)
       if (int e = clean_pass(g, LASV_CLEAN_SUPERNODES, (uint32_t)threshold, stats)) return e;
     for (uint64_t b0 = 0; b0 < g->n_buckets; b0 += rows_per_copy) {
+      const uint64_t nb = std::min(rows_per_copy, g->n_buckets - b0);
+      CUDA_TRY(cudaMemcpy2D((uint8_t *)t->table + b0 * row, row, g->d_lines + b0 * pitch, pitch, row, (size_t)nb,
+                            cudaMemcpyDeviceToHost));
+    }
+    return LASV_OK;
+  }();
+  lasv_graph_free(&g);
+  return rc;
+}
+
+// ------------------------------------------------------------- branches
+// `--mode build`'s ./branches.fa (print_branches.c:131-199): enumerate the paths between
+// non-interior nodes on the device (the supernode kernels), replay the reference's traversal with
+// its `visited` marks on those records on the host (branches_host.h, O(1) per branch), write the
+// records on the device (br_write_kernel), stream the image to the file.
+int lasv_graph_write_branches(lasv_graph *g, const char *fasta_path, int mark_visited, lasv_branch_stats *stats) {
+  if (int e = use(g)) return e;
+  if (!fasta_path) return fail(LASV_ERR_ARG, "fasta_path is NULL");
+  CUDA_TRY(cudaDeviceSynchronize());
+  const TableView tv = g->view();
+  SnCounters *d_c = nullptr, h_c;
+  ClCounters *d_cc = nullptr, h_cc;
+  uint64_t *d_starts = nullptr;
+  unsigned long long *d_n = nullptr;
+  SnPath *d_recs = nullptr;
+  ClNodeRec *d_nodes = nullptr;
+  BrPrint *d_prints = nullptr;
+  char *d_image = nullptr, *h_stage[2] = {nullptr, nullptr};
+  cudaEvent_t copied[2] = {nullptr, nullptr};
+  FILE *fp = nullptr;
+  constexpr uint64_t STAGE_BYTES = 16ull << 20;
+  BrStats bs;
+  auto sync_counters = [&]() -> int {
+    CUDA_TRY(cudaMemcpyAsync(&h_c, d_c, sizeof h_c, cudaMemcpyDeviceToHost, g->compute));
+    CUDA_TRY(cudaMemcpyAsync(&h_cc, d_cc, sizeof h_cc, cudaMemcpyDeviceToHost, g->compute));
+    CUDA_TRY(cudaStreamSynchronize(g->compute));
+    return LASV_OK;
+  };
+  int rc = [&]() -> int {
+    CUDA_TRY(cudaMalloc(&d_c, sizeof(SnCounters)));
+    CUDA_TRY(cudaMalloc(&d_cc, sizeof(ClCounters)));
+    CUDA_TRY(cudaMalloc(&d_n, sizeof(unsigned long long)));
+    CUDA_TRY(cudaMemsetAsync(d_c, 0, sizeof(SnCounters), g->compute));
+    CUDA_TRY(cudaMemsetAsync(d_cc, 0, sizeof(ClCounters), g->compute));
+    CUDA_TRY(cudaMemsetAsync(d_n, 0, sizeof(unsigned long long), g->compute));
+    if (mark_visited) {  // print_branches.c:133
+      launch_br_reset_marks(g->N, tv, g->compute);
+      if (int e = check_launch()) return e;
+    }
+    // the compressed graph: non-interior nodes, and the paths between them (cycles of interior
+    // nodes are out of reach of any branching node and are not enumerated)
+    launch_sn_count(g->N, tv, d_c, g->compute);
+    if (int e = check_launch()) return e;
+    launch_cl_nodes(g->N, tv, nullptr, 0, d_cc, g->compute);
+    if (int e = check_launch()) return e;
+    if (int e = sync_counters()) return e;
+    const uint64_t n_starts = h_c.n_starts, n_nodes = h_cc.n_nodes;
+    CUDA_TRY(cudaMalloc(&d_nodes, std::max<uint64_t>(1, n_nodes) * sizeof(ClNodeRec)));
+    CUDA_TRY(cudaMemsetAsync(&d_cc->n_nodes, 0, sizeof(unsigned long long), g->compute));
+    launch_cl_nodes(g->N, tv, d_nodes, n_nodes, d_cc, g->compute);
+    if (int e = check_launch()) return e;
+    CUDA_TRY(cudaMalloc(&d_starts, std::max<uint64_t>(1, n_starts) * sizeof(uint64_t)));
+    CUDA_TRY(cudaMalloc(&d_recs, std::max<uint64_t>(1, n_starts) * sizeof(SnPath)));
+    launch_sn_starts(g->N, tv, d_starts, n_starts, d_n, d_c, g->compute);
+    if (int e = check_launch()) return e;
+    launch_sn_paths(g->N, tv, g->k, d_starts, n_starts, nullptr, d_recs, n_starts, d_c, g->compute);
+    if (n_starts)
+      if (int e = check_launch()) return e;
+    if (int e = sync_counters()) return e;
+    if (h_c.n_overflow) return fail(LASV_ERR_STATE, "path record buffers overflowed (internal sizing error)");
+    if (h_c.n_dangling)
+      return fail(LASV_ERR_STATE, "%llu walks met an edge to a node that is not in the graph (the reference die()s)",
+                  (unsigned long long)h_c.n_dangling);
+    const uint64_t n_paths = h_c.n_paths;
+    if (n_paths >= (1ull << 31) || n_nodes >= (1ull << 31)) return fail(LASV_ERR_CAPACITY, "more than 2^31 paths");
+    std::vector<ClNodeRec> nodes(n_nodes);
+    std::vector<SnPath> recs(n_paths);
+    if (n_nodes) CUDA_TRY(cudaMemcpyAsync(nodes.data(), d_nodes, n_nodes * sizeof(ClNodeRec), cudaMemcpyDeviceToHost, g->compute));
+    if (n_paths) CUDA_TRY(cudaMemcpyAsync(recs.data(), d_recs, n_paths * sizeof(SnPath), cudaMemcpyDeviceToHost, g->compute));
+    CUDA_TRY(cudaStreamSynchronize(g->compute));
+    cudaFree(d_starts); d_starts = nullptr;
+    cudaFree(d_recs); d_recs = nullptr;
+    cudaFree(d_nodes); d_nodes = nullptr;
+
+    // the reference's traversal, in slot order, on the compressed graph
+    ClGraph cg;
+    cg.nodes.reserve(n_nodes);
+    for (const ClNodeRec &r : nodes) cg.add_node(r.q, r.covg, r.edges);
+    cg.seal_nodes();
+    cg.paths.reserve(n_paths);
+    for (uint64_t i = 0; i < n_paths; i++)
+      if (!cg.add_path(recs[i], 0u, SN_NONE)) return fail(LASV_ERR_STATE, "a path ends in a node that is not in the node list");
+    std::vector<BrPrint> prints;
+    BrReplay replay(cg, g->k);
+    bs = replay.run(prints);
+    if (bs.inconsistent) return fail(LASV_ERR_STATE, "%llu edges of branching nodes have no path record", (unsigned long long)bs.inconsistent);
+
+    fp = fopen(fasta_path, "w");
+    if (!fp) return fail(LASV_ERR_IO, "cannot open %s for writing: %s", fasta_path, strerror(errno));
+    if (!prints.empty()) {
+      const uint64_t image_bytes = bs.image_bytes;
+      CUDA_TRY(cudaMalloc(&d_prints, prints.size() * sizeof(BrPrint)));
+      CUDA_TRY(cudaMalloc(&d_image, image_bytes + 8));
+      CUDA_TRY(cudaMemcpyAsync(d_prints, prints.data(), prints.size() * sizeof(BrPrint), cudaMemcpyHostToDevice, g->compute));
+      launch_br_write(g->N, tv, g->k, d_prints, prints.size(), d_image, mark_visited ? 1 : 0, d_cc, g->compute);
+      if (int e = check_launch()) return e;
+      if (int e = sync_counters()) return e;
+      if (h_cc.n_failed) return fail(LASV_ERR_STATE, "branch sequence walk left the graph");
+      for (int b = 0; b < 2; b++) {
+        CUDA_TRY(cudaMallocHost(&h_stage[b], STAGE_BYTES));
+        CUDA_TRY(cudaEventCreateWithFlags(&copied[b], cudaEventDisableTiming));
+      }
+      // image -> file through two pinned staging buffers: the copy of chunk i+1 runs under the fwrite of chunk i
+      const uint64_t n_chunks = (image_bytes + STAGE_BYTES - 1) / STAGE_BYTES;
+      auto bytes_of = [&](uint64_t c) { return std::min(STAGE_BYTES, image_bytes - c * STAGE_BYTES); };
+      for (uint64_t c = 0; c <= n_chunks; c++) {
+        if (c < n_chunks) {
+          CUDA_TRY(cudaMemcpyAsync(h_stage[c & 1], d_image + c * STAGE_BYTES, bytes_of(c), cudaMemcpyDeviceToHost, g->compute));
+          CUDA_TRY(cudaEventRecord(copied[c & 1], g->compute));
+        }
+        if (c > 0) {
+          CUDA_TRY(cudaEventSynchronize(copied[(c - 1) & 1]));
+          if (fwrite(h_stage[(c - 1) & 1], 1, bytes_of(c - 1), fp) != bytes_of(c - 1))
+            return fail(LASV_ERR_IO, "short write to %s", fasta_path);
+        }
+      }
+    }
+    return LASV_OK;
+  }();
+  cudaFree(d_c); cudaFree(d_cc); cudaFree(d_n); cudaFree(d_starts); cudaFree(d_recs); cudaFree(d_nodes);
+  cudaFree(d_prints); cudaFree(d_image);
+  for (int b = 0; b < 2; b++) {
+    if (h_stage[b]) cudaFreeHost(h_stage[b]);
+    if (copied[b]) cudaEventDestroy(copied[b]);
+  }
+  if (fp && fclose(fp) != 0 && rc == LASV_OK) rc = fail(LASV_ERR_IO, "cannot close %s: %s", fasta_path, strerror(errno));
+  if (rc != LASV_OK) return rc;
+  if (stats) {
+    stats->n_branches = bs.branches;
+    stats->n_branching_nodes = bs.branching_nodes;
+    stats->n_nodes = bs.nodes;
+    stats->n_refused = bs.refused;
+    stats->n_cut = bs.cut;
+    stats->bytes = bs.image_bytes;
+  }
+  return LASV_OK;
+}
+
+int lasv_ref_hash_table_write_branches(lasv_ref_hash_table *t, const char *fasta_path, lasv_branch_stats *stats) {
+  if (!t || !t->table) return fail(LASV_ERR_ARG, "NULL table!");
+  const int L = log2_exact(t->number_buckets);
+  if (L < 0) return fail(LASV_ERR_ARG, "number_buckets is not a power of two");
+  int dev = 0;
+  if (const char *e = getenv("LASV_B200_DEVICE")) dev = atoi(e);
+  lasv_graph *g = lasv_graph_new(t->kmer_size, L, t->bucket_size, t->max_rehash_tries, dev);
+  if (!g) return LASV_ERR_CUDA;
+  int rc = [&]() -> int {
+    // the table as it is (the finalised arrangement), as in lasv_ref_hash_table_clean
+    const size_t row = (size_t)g->W * g->slot_bytes, pitch = (size_t)(g->table_bytes / g->n_buckets);
+    const uint64_t rows_per_copy = 1ull << 20;
+    for (uint64_t b0 = 0; b0 < g->n_buckets; b0 += rows_per_copy) {
+      const uint64_t nb = std::min(rows_per_copy, g->n_buckets - b0);
+      CUDA_TRY(cudaMemcpy2D(g->d_lines + b0 * pitch, pitch, (const uint8_t *)t->table + b0 * row, row, row,
+                            (size_t)nb, cudaMemcpyHostToDevice));
+    }
+    g->finalized = true;
+    if (int e = lasv_graph_write_branches(g, fasta_path, 1, stats)) return e;  // starts with a device synchronisation
+    for (uint64_t b0 = 0; b0 < g->n_buckets; b0 += rows_per_copy) {            // the marks
       const uint64_t nb = std::min(rows_per_copy, g->n_buckets - b0);
       CUDA_TRY(cudaMemcpy2D((uint8_t *)t->table + b0 * row, row, g->d_lines + b0 * pitch, pitch, row, (size_t)nb,
                             cudaMemcpyDeviceToHost));

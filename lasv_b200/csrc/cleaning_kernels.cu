@@ -11,10 +11,13 @@
 //                        prune a node, clear edge bits of a node (atomic AND: several
 //                        paths may end in one node)
 //   cl_settle_kernel     per slot: nodes marked by the walks lose their edges
+//   br_write_kernel      branch printing (branches.cuh): one thread per printed branch writes its
+//                        FASTA record into the file image and, if asked, leaves the `visited` marks
 #include <stdint.h>
 
 #include <type_traits>
 
+#include "branches.cuh"
 #include "cleaning.cuh"
 #include "graph_kernels.cuh"
 
@@ -97,6 +100,23 @@ __global__ void __launch_bounds__(CL_THREADS) cl_settle_kernel(const TableView t
     cl_settle_node<N, DeviceOps>(t, q);
 }
 
+template <int N>
+__global__ void __launch_bounds__(CL_THREADS) br_write_kernel(const TableView t, const int k,
+                                                             const BrPrint *__restrict__ prints, const uint64_t n,
+                                                             char *image, const int mark, ClCounters *c) {
+  for (uint64_t i = (uint64_t)blockIdx.x * CL_THREADS + threadIdx.x; i < n;
+       i += (uint64_t)gridDim.x * CL_THREADS)
+    if (!br_write_record<N, DeviceOps>(t, k, prints[i], image, mark)) atomicAdd(&c->n_failed, 1ull);
+}
+
+template <int N>
+__global__ void __launch_bounds__(CL_THREADS) br_reset_marks_kernel(const TableView t) {
+  const uint64_t n_slots = ((uint64_t)t.bucket_mask + 1) * t.W;
+  for (uint64_t q = (uint64_t)blockIdx.x * CL_THREADS + threadIdx.x; q < n_slots;
+       q += (uint64_t)gridDim.x * CL_THREADS)
+    br_reset_mark<N, DeviceOps>(t, q);
+}
+
 template <typename F>
 void cl_dispatch(int N, F &&f) {
   if (N == 1) f(std::integral_constant<int, 1>());
@@ -150,6 +170,23 @@ void launch_cl_apply(int N, const TableView &t, int k, const ClPathPrune *paths,
       cl_apply_nodes_kernel<NN><<<cl_grid(cl_apply_nodes_kernel<NN>, n_nodes), CL_THREADS, 0, st>>>(t, nodes, n_nodes);
     if (n_resets)
       cl_apply_resets_kernel<NN><<<cl_grid(cl_apply_resets_kernel<NN>, n_resets), CL_THREADS, 0, st>>>(t, resets, n_resets);
+  });
+}
+
+void launch_br_write(int N, const TableView &t, int k, const BrPrint *prints, uint64_t n, char *image, int mark,
+                     ClCounters *c, cudaStream_t st) {
+  if (!n) return;
+  cl_dispatch(N, [&](auto nn) {
+    constexpr int NN = decltype(nn)::value;
+    br_write_kernel<NN><<<cl_grid(br_write_kernel<NN>, n), CL_THREADS, 0, st>>>(t, k, prints, n, image, mark, c);
+  });
+}
+
+void launch_br_reset_marks(int N, const TableView &t, cudaStream_t st) {
+  const uint64_t n_slots = ((uint64_t)t.bucket_mask + 1) * t.W;
+  cl_dispatch(N, [&](auto nn) {
+    constexpr int NN = decltype(nn)::value;
+    br_reset_marks_kernel<NN><<<cl_grid(br_reset_marks_kernel<NN>, n_slots), CL_THREADS, 0, st>>>(t);
   });
 }
 

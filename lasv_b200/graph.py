@@ -234,6 +234,13 @@ class DBGraph:
         check(self._lib.lasv_graph_write_supernodes(self._h, str(path).encode(), max_length, C.byref(st)))
         return st.as_dict()
 
+    def output_branches(self, path, mark_visited: bool = False) -> dict:
+        """`--mode build`'s ./branches.fa (graph_operations.c:1145-1152, print_branches.c:131-199) for a
+        traversal in table order; mark_visited leaves the reference's `visited` marks on the device table."""
+        st = _capi.BranchStats()
+        check(self._lib.lasv_graph_write_branches(self._h, str(path).encode(), 1 if mark_visited else 0, C.byref(st)))
+        return st.as_dict()
+
     def load_binary(self, path):
         mrl, ts = C.c_uint32(), C.c_uint64()
         check(self._lib.lasv_graph_load_ctx_file(self._h, str(path).encode(), C.byref(mrl), C.byref(ts)))

@@ -378,6 +378,10 @@ int clean(uint8_t *table, int k, int L, int W, int finalized, int threshold, uin
 template <int N>
 int branches(uint8_t *table, int k, int L, int W, int finalized, const char *path, int mark, uint64_t *counts6) {
   const TableView tv = make_table_view(table, N, L, W, 15, finalized != 0);
+  if (mark) {  // br_reset_marks_kernel
+    const uint64_t n_slots = ((uint64_t)tv.bucket_mask + 1) * tv.W;
+    for (uint64_t q = 0; q < n_slots; q++) br_reset_mark<N, HostOps>(tv, q);
+  }
   ClGraph g;
   if (!build_cl_graph<N>(tv, k, 0u, g)) return -2;
   std::vector<BrPrint> prints;

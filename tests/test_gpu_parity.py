@@ -1018,3 +1018,117 @@ def test_config0_full_size_properties():
         st = g.load_reads_host(seq, qual, offs, w.cutoff)
         assert st["kmers_inserted"] == og.stats.kmers_inserted
         assert np.array_equal(O.sort_records(g.records()), O.sort_records(og.records()))
+
+
+# ---- branch printing: `--mode build`'s ./branches.fa on the device ------------------------------
+# Written after the round's GPU minutes were spent: exact against the oracle on the CPU emulation
+# (tests/test_host_emul.py, same record writer and replay), NOT YET RUN ON A DEVICE.  The cases sit at the very end
+# of the GPU suite and are non-strict xfail until they have: an XPASS in the log is their first green run on a
+# B200, a failure cannot hide or cut short any verified test above.  Remove the marker once seen green.
+_first_device_run = pytest.mark.xfail(strict=False, reason="branch printing: first run on a device (see comment)")
+
+
+def _oracle_branches_in_table_order(k, L, W, recs, path):
+    og = O.OracleGraph(k, L, W)
+    assert og.load_records(recs)
+    st = og.print_branches(path, keep_marks=True)
+    return og, st
+
+
+@_first_device_run
+@pytest.mark.parametrize("name", ["synth_cfg1_k31", "synth_cfg0_k53", "synth_cfg2_k95", "edge_pe_k21_q5"])
+def test_gpu_branches_match_reference_walk(name, tmp_path):
+    """The reference's branches.fa for OUR slot order, byte for byte, in both arrangements of the table."""
+    meta = util.case_meta(name)
+    k, L, W = meta["k"], meta["L"], meta["W"]
+    seq, qual, offs = util.case_streams(name)
+    with DBGraph(k, L, W) as g:
+        g.load_reads_host(seq, qual, offs, util.cutoff_of(meta))
+        recs = g.records()
+        st = g.output_branches(tmp_path / "gpu.fa")
+        _, ost = _oracle_branches_in_table_order(k, L, W, recs, tmp_path / "oracle.fa")
+        gpu = (tmp_path / "gpu.fa").read_bytes()
+        assert gpu == (tmp_path / "oracle.fa").read_bytes()
+        assert st["n_branches"] == ost["branches"] and st["n_branching_nodes"] == ost["branching_nodes"]
+        assert st["bytes"] == len(gpu)
+        if name.startswith("synth"):
+            assert st["n_branches"] > 0
+        assert np.array_equal(g.records(), recs)                # the graph is left as it was
+        g.finalize()
+        st2 = g.output_branches(tmp_path / "gpu_final.fa")
+        assert (tmp_path / "gpu_final.fa").read_bytes() == gpu and st2 == st
+
+
+@_first_device_run
+@pytest.mark.parametrize("dense", [(21, 40000, 600, 3000, 11, None), (53, 20000, 600, 3000, 11, 2),
+                                   (31, 3000, 3000, 60000, 14, None), (31, 20000, 40000, 200000, 17, 2)])
+def test_ref_table_branches_and_marks(dense, tmp_path):
+    """lasv_ref_hash_table_write_branches on the caller's reference-layout table, raw or after the GPU cleaning:
+    the file, and the `visited` marks it leaves in the table, against the reference's sequential walk."""
+    k, err_q20, n_reads, genome, L, thresh = dense
+    W, cutoff = 40, 38
+    base = synth.CFG1 if k <= 31 else synth.CFG0 if k <= 63 else synth.CFG2
+    w = synth.scaled(base, genome, L)
+    w.seed, w.kmer_size = 700 + k, k
+    p = w.params()
+    p.err_q20 = err_q20
+    seq, qual, offs = synth.reads_host(p, 0, n_reads)
+    with DBGraph(k, L, W) as g:
+        g.load_reads_host(seq, qual, offs, cutoff)
+        table, nxt = g.export_table()
+    n_raw = int((table["status"] == 1).sum())
+    ht = _capi.RefHashTable(k, 1 << L, W, table.ctypes.data, nxt.ctypes.data, None, n_raw, 15)
+    if thresh is not None:
+        _capi.check(_capi.lib().lasv_ref_hash_table_clean(C.byref(ht), _capi.CLEAN_TIPS | _capi.CLEAN_SUPERNODES, thresh,
+                                                        None))
+    before = table.copy()
+    og, ost = _oracle_branches_in_table_order(k, L, W, _table_records(table), tmp_path / "oracle.fa")
+    st = _capi.BranchStats()
+    _capi.check(_capi.lib().lasv_ref_hash_table_write_branches(C.byref(ht), str(tmp_path / "gpu.fa").encode(), C.byref(st)))
+    st = st.as_dict()
+    assert (tmp_path / "gpu.fa").read_bytes() == (tmp_path / "oracle.fa").read_bytes()
+    assert st["n_branches"] == ost["branches"] > 0
+    if err_q20 <= 3000:
+        assert st["n_cut"] > 0
+    # marks: exactly the reference's; nothing else in the table changed
+    marked = {tuple(r) for r in table["kmer"][table["status"] == 2].tolist()}
+    orecs = og.records()
+    assert marked == {tuple(r) for r in orecs["kmer"][og.status() == 2].tolist()}
+    after = table.copy()
+    after["status"][after["status"] == 2] = 1
+    assert np.array_equal(after, before)
+
+
+@_first_device_run
+@pytest.mark.parametrize("name,clean", [("synth_cfg1_k31", False), ("synth_cfg0_k53", False), ("synth_cfg0_k53", True),
+                                        ("synth_cfg2_k95", True)])
+def test_reference_cli_build_mode_through_the_gpu(name, clean, tmp_path):
+    """run_laSV.sh:178 -- `dB_graph --mode build ... --dump_binary x.ctx` -- with loaders, cleaning and branch
+    printing all bound to the GPU (integration/_build/dB_graph_gpubuild_*): ./branches.fa is what the reference's
+    walk prints for the table the same run dumped."""
+    from pathlib import Path
+    meta = util.case_meta(name)
+    k, L, W = meta["k"], meta["L"], meta["W"]
+    exe = Path(__file__).resolve().parents[1] / "integration" / "_build" / f"dB_graph_gpubuild_{O.MAXK_OF_N[O.words_per_kmer(k)]}"
+    if not exe.exists():
+        pytest.skip("integration/_build not built (needs /root/reference at build time)")
+    seq, qual, _ = util.case_streams(name)
+    rl = meta["workload"]["read_len"]
+    s2, q2 = seq.reshape(-1, rl + 1), qual.reshape(-1, rl + 1)
+    O.write_fastq_fixed(tmp_path / "a.fq", s2[0::2].reshape(-1), q2[0::2].reshape(-1), rl)
+    O.write_fastq_fixed(tmp_path / "b.fq", s2[1::2].reshape(-1), q2[1::2].reshape(-1), rl)
+    (tmp_path / "l").write_text(f"{tmp_path / 'a.fq'}\n")
+    (tmp_path / "r").write_text(f"{tmp_path / 'b.fq'}\n")
+    cmd = [str(exe), "--kmer_size", str(k), "--mode", "build", "--mem_height", str(L), "--mem_width", str(W),
+           "--pe_list", f"{tmp_path / 'l'},{tmp_path / 'r'}", "--quality_score_threshold", str(meta["q_thresh"]),
+           "--dump_binary", str(tmp_path / "out.ctx")]
+    if clean:
+        cmd += ["--remove_low_coverage_supernodes", "2"]
+    p = subprocess.run(cmd, cwd=tmp_path, capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stderr[-2000:] + p.stdout[-2000:]
+    assert "branches printed from" in p.stdout and "Branches printed" in p.stdout
+    ctx = O.parse_ctx(tmp_path / "out.ctx")
+    if not clean:
+        util.assert_same_records(ctx["records"], util.case_records(name), name)
+    _oracle_branches_in_table_order(k, L, W, ctx["records"], tmp_path / "oracle.fa")
+    assert (tmp_path / "branches.fa").read_bytes() == (tmp_path / "oracle.fa").read_bytes()
