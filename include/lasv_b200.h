@@ -340,6 +340,16 @@ typedef struct {
   uint64_t nodes_pruned;     /* all nodes that went from none to pruned */
 } lasv_clean_stats;
 int lasv_ref_hash_table_clean(lasv_ref_hash_table *t, int what, int threshold, lasv_clean_stats *stats /* may be NULL */);
+/* The same on a graph handle, in either arrangement of the device table -- no host copy of the table.
+ * Pruned nodes stay in the table with status `pruned` and no edges, as in the reference: they are
+ * skipped by lasv_graph_dump_ctx_records / lasv_graph_write_ctx (db_node_check_status_not_pruned,
+ * element.c:795-802), lasv_graph_summary, the supernode and branch printers, and exported as `pruned`
+ * by lasv_graph_export_table; lasv_graph_unique_kmers keeps counting them (hash_table->unique_kmers
+ * does too).  lasv_graph_write_ctx afterwards writes the cleaning flags and the threshold into the
+ * header as the reference's --dump_binary does after --remove_low_coverage_supernodes
+ * (file_reader.c:2930-2994, graph_operations.c:1084-1088).  With lasv_graph_write_branches this is the
+ * whole of `--mode build` after the load (run_laSV.sh:178) on the device. */
+int lasv_graph_clean(lasv_graph *g, int what, int threshold, lasv_clean_stats *stats /* may be NULL */);
 
 /* db_graph_print_all_branches_for_specific_person_or_pop (print_branches.c:131-199) on the
  * caller's reference-layout table (lasv_graph_write_branches above, in the caller's slot

@@ -107,6 +107,9 @@ struct lasv_graph {
   unsigned long long *d_hist = nullptr;
   unsigned long long *d_overflow = nullptr;
   bool finalized = false;
+  // set by lasv_graph_clean, written into the .ctx header (graph_info.c:147-173, graph_operations.c:1084-1088)
+  bool cleaned_tips = false, cleaned_sups = false;
+  int clean_threshold = -1;
   cudaStream_t compute = nullptr, copy = nullptr;
   Staging stage[3];  // three legs: the copy of chunk i+1 may start while chunk i-1 is still being consumed
   bool staging_ready = false;
@@ -1273,6 +1276,15 @@ int lasv_graph_write_ctx(lasv_graph *g, const char *path, uint32_t mean_read_len
   if (!fp) return fail(LASV_ERR_IO, "cannot open %s for writing: %s", path, strerror(errno));
   uint8_t hdr[128];
   const int hl = lasv_ctx_header(g->k, mean_read_len, total_seq, hdr);
+  {  // the error-cleaning object of print_binary_signature_NEW: 4 flags, then the supernode threshold
+    uint8_t *flags = hdr + 6 + 16 + 4 + 8 + 4 + 9 + 16;
+    flags[0] = g->cleaned_tips ? 1 : 0;
+    flags[1] = g->cleaned_sups ? 1 : 0;
+    if (g->cleaned_sups) {
+      const int32_t v = g->clean_threshold;
+      memcpy(flags + 4, &v, 4);
+    }
+  }
   int rc = LASV_OK;
   if (fwrite(hdr, 1, (size_t)hl, fp) != (size_t)hl) rc = fail(LASV_ERR_IO, "short write to %s", path);
   const size_t rec = 8 * (size_t)g->N + 5;
@@ -2062,6 +2074,25 @@ static int clean_pass(lasv_graph *g, int what, uint32_t threshold, lasv_clean_st
   cudaFree(d_covered); cudaFree(d_recs); cudaFree(d_cyc); cudaFree(d_nodes); cudaFree(d_max); cudaFree(d_scov);
   cudaFree(d_apaths); cudaFree(d_aresets);
   return rc;
+}
+
+int lasv_graph_clean(lasv_graph *g, int what, int threshold, lasv_clean_stats *stats) {
+  if (int e = use(g)) return e;
+  if (!(what & (LASV_CLEAN_TIPS | LASV_CLEAN_SUPERNODES)) || (what & ~(LASV_CLEAN_TIPS | LASV_CLEAN_SUPERNODES)))
+    return fail(LASV_ERR_ARG, "what must be LASV_CLEAN_TIPS, LASV_CLEAN_SUPERNODES or both");
+  if ((what & LASV_CLEAN_SUPERNODES) && threshold < 0) return fail(LASV_ERR_ARG, "negative coverage threshold");
+  CUDA_TRY(cudaDeviceSynchronize());
+  if (stats) memset(stats, 0, sizeof *stats);
+  if (what & LASV_CLEAN_TIPS) {
+    if (int e = clean_pass(g, LASV_CLEAN_TIPS, (uint32_t)std::max(threshold, 0), stats)) return e;
+    g->cleaned_tips = true;
+  }
+  if (what & LASV_CLEAN_SUPERNODES) {
+    if (int e = clean_pass(g, LASV_CLEAN_SUPERNODES, (uint32_t)threshold, stats)) return e;
+    g->cleaned_sups = true;
+    g->clean_threshold = threshold;
+  }
+  return LASV_OK;
 }
 
 int lasv_ref_hash_table_clean(lasv_ref_hash_table *t, int what, int threshold, lasv_clean_stats *stats) {

@@ -12,7 +12,7 @@
 
 namespace lasv {
 
-constexpr uint32_t ST_PRUNED = 3;  // NodeStatus pruned (element.h:57-75)
+// ST_PRUNED (NodeStatus pruned) lives in kmer_core.cuh: the dump and summary kernels skip such nodes too
 
 // What the sequential decisions (cleaning_host.h) ask the device to do.
 struct ClPathPrune {

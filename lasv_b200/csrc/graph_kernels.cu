@@ -738,7 +738,7 @@ __global__ void __launch_bounds__(THREADS) table_summary_kernel(const TableView 
     const uint32_t bucket = (uint32_t)(i / t.W);
     const uint64_t *slot = slot_ptr<N>(t, bucket, (uint32_t)(i - (uint64_t)bucket * t.W));
     const uint64_t m = slot[N];
-    if (meta_status(m) == ST_EMPTY) continue;
+    if (meta_status(m) == ST_EMPTY || meta_status(m) == ST_PRUNED) continue;  // db_node_check_status_not_pruned
     uint64_t key[N];
 #pragma unroll
     for (int w = 0; w < N; w++) key[w] = slot[w];
@@ -762,7 +762,7 @@ __global__ void __launch_bounds__(THREADS) table_summary_kernel(const TableView 
   }
 }
 
-// occupied slots per bucket: one warp per bucket
+// slots per bucket that hold a node of the graph (occupied and not pruned): one warp per bucket
 template <int N>
 __global__ void __launch_bounds__(THREADS) bucket_counts_kernel(const TableView t, const uint64_t first,
                                                                const uint64_t n_buckets, uint32_t *counts) {
@@ -773,7 +773,7 @@ __global__ void __launch_bounds__(THREADS) bucket_counts_kernel(const TableView 
     uint32_t c = 0;
     for (uint32_t s = lane_id(); s < t.W; s += 32) {
       const uint64_t m = slot_ptr<N>(t, (uint32_t)(first + b), s)[N];
-      c += (meta_status(m) != ST_EMPTY);
+      c += (meta_status(m) != ST_EMPTY && meta_status(m) != ST_PRUNED);  // what dump_ctx_kernel writes
     }
     c = __reduce_add_sync(FULL, c);
     if (lane_id() == 0) counts[b] = c;
@@ -781,7 +781,7 @@ __global__ void __launch_bounds__(THREADS) bucket_counts_kernel(const TableView 
 }
 
 // Rewrite every bucket, in place, from lines of tagged slots to W hole-free
-// consecutive Elements in slot order (status none, pad bytes zero) at the start of
+// consecutive Elements in slot order (status none -- pruned stays pruned --, pad bytes zero) at the start of
 // its NL*128 bytes: afterwards a bucket IS a reference bucket (hash_table.c:69-122
 // finds every key) and the table is copied out bucket by bucket.  One warp per
 // bucket; 32 slots are read into registers before any of them is overwritten, and
@@ -815,7 +815,7 @@ __global__ void __launch_bounds__(THREADS) finalize_kernel(const TableView t, in
         uint64_t *dst = reinterpret_cast<uint64_t *>(bucket + (uint64_t)d * SLOT);
 #pragma unroll
         for (int w = 0; w < N; w++) dst[w] = key[w];
-        dst[N] = meta_pack(meta_covg(m), meta_edges(m), ST_NONE, 0);
+        dst[N] = meta_pack(meta_covg(m), meta_edges(m), meta_status(m) == ST_PRUNED ? ST_PRUNED : ST_NONE, 0);
       }
       filled += __popc(om);
       __syncwarp();
@@ -852,7 +852,7 @@ __global__ void __launch_bounds__(THREADS) dump_ctx_kernel(const TableView t, co
 #pragma unroll
         for (int w = 0; w < N; w++) key[w] = slot[w];
       }
-      const bool occ = meta_status(m) != ST_EMPTY;
+      const bool occ = meta_status(m) != ST_EMPTY && meta_status(m) != ST_PRUNED;  // db_node_check_status_not_pruned (element.c:795-802)
       const unsigned om = __ballot_sync(FULL, occ);
       if (occ) {
         uint8_t *dst = out + (o + __popc(om & lanemask_lt())) * REC;

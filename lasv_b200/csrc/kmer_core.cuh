@@ -332,6 +332,7 @@ LASV_HD uint32_t kmer_occurrence(const uint32_t *P, const uint32_t *PR, const ui
 // the key (zeroed again when the table is finalised for the host).
 constexpr uint32_t ST_EMPTY = 0;       // NodeStatus unassigned (element.h:57)
 constexpr uint32_t ST_NONE = 1;        // NodeStatus none
+constexpr uint32_t ST_PRUNED = 3;      // NodeStatus pruned (element.h:57-75): left by the cleaning, not part of the graph
 constexpr uint32_t ST_LOCKED = 0x80;   // device-only: key words not yet published
 
 LASV_HD uint64_t meta_pack(uint32_t covg, uint32_t edges, uint32_t status, uint32_t tag) {

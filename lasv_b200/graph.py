@@ -234,6 +234,13 @@ class DBGraph:
         check(self._lib.lasv_graph_write_supernodes(self._h, str(path).encode(), max_length, C.byref(st)))
         return st.as_dict()
 
+    def clean(self, threshold: int, what: int = _capi.CLEAN_TIPS | _capi.CLEAN_SUPERNODES) -> dict:
+        """`--remove_low_coverage_supernodes threshold` (graph_operations.c:1069-1090) on the device table: tip
+        clipping, then low-coverage supernode removal, exact for the table's slot order."""
+        st = _capi.CleanStats()
+        check(self._lib.lasv_graph_clean(self._h, what, threshold, C.byref(st)))
+        return st.as_dict()
+
     def output_branches(self, path, mark_visited: bool = False) -> dict:
         """`--mode build`'s ./branches.fa (graph_operations.c:1145-1152, print_branches.c:131-199) for a
         traversal in table order; mark_visited leaves the reference's `visited` marks on the device table."""

@@ -187,7 +187,8 @@ void finalize(uint8_t *table, int L, int W, int16_t *next) {
         if (!occ[l]) continue;
         uint64_t *dst = reinterpret_cast<uint64_t *>(bucket + (uint64_t)(filled + rank) * SLOT);
         for (int w = 0; w < N; w++) dst[w] = keys[l][w];
-        dst[N] = meta_pack(meta_covg(metas[l]), meta_edges(metas[l]), ST_NONE, 0);
+        dst[N] = meta_pack(meta_covg(metas[l]), meta_edges(metas[l]),
+                           meta_status(metas[l]) == ST_PRUNED ? ST_PRUNED : ST_NONE, 0);
         rank++;
       }
       filled += rank;

@@ -1132,3 +1132,44 @@ def test_reference_cli_build_mode_through_the_gpu(name, clean, tmp_path):
         util.assert_same_records(ctx["records"], util.case_records(name), name)
     _oracle_branches_in_table_order(k, L, W, ctx["records"], tmp_path / "oracle.fa")
     assert (tmp_path / "branches.fa").read_bytes() == (tmp_path / "oracle.fa").read_bytes()
+
+
+@_first_device_run
+@pytest.mark.parametrize("name,thresh,finalized", [("synth_cfg1_k31", 2, False), ("synth_cfg0_k53", 2, False),
+                                                   ("synth_cfg2_k95", 2, True), ("synth_cfg0_k53", 1, True)])
+def test_gpu_build_mode_stays_on_the_device(name, thresh, finalized, tmp_path):
+    """`--mode build --remove_low_coverage_supernodes T --dump_binary` (run_laSV.sh:178) on a graph handle, nothing
+    but files leaving the device: lasv_graph_clean -> lasv_graph_write_branches -> lasv_graph_write_ctx (pruned
+    nodes skipped, cleaning flags in the header) -> supernodes; all against the reference's sequential passes
+    (oracle restatement) over the same slot order."""
+    meta = util.case_meta(name)
+    k, L, W = meta["k"], meta["L"], meta["W"]
+    seq, qual, offs = util.case_streams(name)
+    with DBGraph(k, L, W) as g:
+        g.load_reads_host(seq, qual, offs, util.cutoff_of(meta))
+        raw = g.records()
+        if finalized:
+            g.finalize()
+        og = O.OracleGraph(k, L, W)
+        assert og.load_records(raw)
+        ost = og.clean(thresh)
+        st = g.clean(thresh)
+        assert st["tips_clipped"] == ost["tips"] and st["supernodes_pruned"] == ost["supernodes_pruned"]
+        assert st["nodes_pruned"] == len(raw) - ost["nodes_left"] > 0
+        recs = g.records()
+        assert np.array_equal(recs, og.records())              # same nodes, coverage, edges, same order
+        assert g.summary()["n_nodes"] == len(recs)
+        g.dump_binary(tmp_path / "gpu.ctx", 100, 1000)
+        ctx = O.parse_ctx(tmp_path / "gpu.ctx")
+        assert np.array_equal(ctx["records"], recs)
+        assert bytes(ctx["header"]) == O.ctx_header(k, 100, 1000, cleaned_threshold=thresh)
+        g.output_branches(tmp_path / "gpu_br.fa")
+        og.print_branches(tmp_path / "oracle_br.fa")
+        assert (tmp_path / "gpu_br.fa").read_bytes() == (tmp_path / "oracle_br.fa").read_bytes()
+        g.output_supernodes(tmp_path / "gpu.fa")
+        og.print_supernodes(tmp_path / "oracle.fa", max_length=1 << 20)
+        assert (tmp_path / "gpu.fa").read_bytes() == (tmp_path / "oracle.fa").read_bytes()
+        table, _ = g.export_table()                              # pruned nodes keep their place and status
+        assert int((table["status"] == 3).sum()) == st["nodes_pruned"]
+        assert not table["edges"][table["status"] == 3].any()
+        assert np.array_equal(_table_records(table), recs)

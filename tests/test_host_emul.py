@@ -582,3 +582,26 @@ def test_emulated_branches_on_repetitive_graphs(emul, alphabet, seed, tmp_path):
         checked += 1
         printed += st["branches"]
     assert checked > 120 and printed > 0
+
+
+def test_emulated_clean_then_finalize_keeps_pruned_nodes_pruned(emul, tmp_path):
+    """lasv_graph_clean on the line layout, then finalisation (export): pruned nodes keep their place and their
+    status, as in the reference's table; the records of the graph (pruned skipped) and everything printed
+    from it are the same before and after."""
+    name, thresh = "synth_cfg0_k53", 2
+    meta = util.case_meta(name)
+    seq, qual, _ = util.case_streams(name)
+    rc, tab, _ = emul_build(emul, meta, seq, qual)
+    assert rc == 0
+    og, _ = oracle_clean_in_order(tab, thresh)
+    st = emul_clean(emul, tab, thresh)
+    recs = tab.records()
+    assert np.array_equal(recs, og.records())
+    emul_supernodes(emul, tab, tmp_path / "a.fa")
+    tab.finalize()
+    elems = tab.elements()
+    assert int((elems["status"] == 3).sum()) == st["nodes_pruned"] > 0
+    assert np.array_equal(tab.records(), recs)
+    emul_supernodes(emul, tab, tmp_path / "b.fa")
+    assert (tmp_path / "a.fa").read_bytes() == (tmp_path / "b.fa").read_bytes()
+    check_branches(emul, tab, tmp_path)
