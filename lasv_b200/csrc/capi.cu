@@ -2023,7 +2023,7 @@ static int clean_pass(lasv_graph *g, int what, uint32_t threshold, lasv_clean_st
     ClGraph cg;
     cg.nodes.reserve(n_nodes);
     for (const ClNodeRec &r : nodes) cg.add_node(r.q, r.covg, r.edges);
-    cg.seal_nodes();
+    cg.seal_nodes(g->n_slots);
     cg.paths.reserve(n_paths);
     for (uint64_t i = 0; i < n_paths; i++)
       if (!cg.add_path(recs[i], mx[i], low[i])) return fail(LASV_ERR_STATE, "a path ends in a node that is not in the node list");
@@ -2213,7 +2213,7 @@ int lasv_graph_write_branches(lasv_graph *g, const char *fasta_path, int mark_vi
     ClGraph cg;
     cg.nodes.reserve(n_nodes);
     for (const ClNodeRec &r : nodes) cg.add_node(r.q, r.covg, r.edges);
-    cg.seal_nodes();
+    cg.seal_nodes(g->n_slots);
     cg.paths.reserve(n_paths);
     for (uint64_t i = 0; i < n_paths; i++)
       if (!cg.add_path(recs[i], 0u, SN_NONE)) return fail(LASV_ERR_STATE, "a path ends in a node that is not in the node list");

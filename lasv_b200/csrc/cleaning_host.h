@@ -85,6 +85,11 @@ class ClGraph {
   std::vector<ClPath> paths;
   std::vector<ClCycle> cycles;
 
+ private:
+  std::vector<uint64_t> bits_;   // one bit per slot: a node of the list sits there
+  std::vector<uint32_t> rank_;   // nodes in the slots before each 64-slot word
+
+ public:
   // node list: every occupied, un-pruned, non-interior node with at least one edge, in any order
   void add_node(uint64_t q, uint32_t covg, uint32_t edges) {
     ClNode n;
@@ -95,12 +100,29 @@ class ClGraph {
     for (int i = 0; i < 8; i++) n.adj[i] = -1;
     nodes.push_back(n);
   }
-  void seal_nodes() {
-    std::sort(nodes.begin(), nodes.end(), [](const ClNode &x, const ClNode &y) { return x.q < y.q; });
+  // Put the nodes in slot order and build the slot -> index map: one bit per slot plus a running count
+  // per 64 slots, so placing a node and finding the end node of a path are O(1) (the node list arrives
+  // in atomic-append order; sorting millions of records and a binary search per path end dominated
+  // the host side of a pass otherwise).
+  void seal_nodes(uint64_t n_slots) {
+    bits_.assign((size_t)((n_slots + 63) / 64), 0ull);
+    for (const ClNode &n : nodes)
+      if (n.q < n_slots) bits_[(size_t)(n.q >> 6)] |= 1ull << (n.q & 63);
+    rank_.assign(bits_.size() + 1, 0u);
+    for (size_t w = 0; w < bits_.size(); w++) rank_[w + 1] = rank_[w] + (uint32_t)__builtin_popcountll(bits_[w]);
+    std::vector<ClNode> placed(rank_.back());
+    for (const ClNode &n : nodes) {
+      const int32_t i = index_of(n.q);
+      if (i >= 0) placed[(size_t)i] = n;
+    }
+    nodes.swap(placed);
   }
   int32_t index_of(uint64_t q) const {
-    auto it = std::lower_bound(nodes.begin(), nodes.end(), q, [](const ClNode &x, uint64_t v) { return x.q < v; });
-    return (it != nodes.end() && it->q == q) ? (int32_t)(it - nodes.begin()) : -1;
+    const size_t w = (size_t)(q >> 6);
+    if (w >= bits_.size()) return -1;
+    const uint64_t bit = 1ull << (q & 63);
+    if (!(bits_[w] & bit)) return -1;
+    return (int32_t)(rank_[w] + (uint32_t)__builtin_popcountll(bits_[w] & (bit - 1)));
   }
   // path record (not a cycle) with its coverage summary; false if an end node is unknown
   bool add_path(const SnPath &p, uint32_t max_covg, uint64_t min_low_q) {

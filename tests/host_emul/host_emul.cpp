@@ -292,7 +292,7 @@ bool build_cl_graph(const TableView &tv, int k, uint32_t T, ClGraph &g) {
     const uint32_t e = meta_edges(m);
     if (e != 0 && !sn_interior(e)) g.add_node(q, meta_covg(m), e);
   }
-  g.seal_nodes();
+  g.seal_nodes(n_slots);
   bool ok = true;
   const size_t n_nodes = g.nodes.size();
   for (size_t i = 0; i < n_nodes; i++) {
