@@ -57,6 +57,30 @@ def test_argument_validation():
     assert not lib.lasv_graph_new(31, 0, 20, 15, 0)
 
 
+def test_reference_table_entry_points_fail_loudly():
+    """The entries a reference-side shim binds (cleaning, supernodes, branches, .ctx reload) never fall back to
+    the CPU: bad arguments are refused with a message, and without a GPU they report the missing device."""
+    import ctypes as C
+    lib = _capi.lib()
+    for call in (lambda: lib.lasv_ref_hash_table_clean(None, _capi.CLEAN_TIPS, 0, None),
+                 lambda: lib.lasv_ref_hash_table_write_supernodes(None, b"/dev/null", 10000, None),
+                 lambda: lib.lasv_ref_hash_table_write_branches(None, b"/dev/null", None),
+                 lambda: lib.lasv_graph_write_branches(None, b"/dev/null", 0, None),
+                 lambda: lib.lasv_graph_clean(None, _capi.CLEAN_TIPS, 0, None)):
+        assert call() < 0 and lib.lasv_last_error()
+    table = np.zeros(4 * 8, dtype=lasv_b200.element_dtype(1))
+    ht = _capi.RefHashTable(31, 3, 8, table.ctypes.data, None, None, 0, 15)    # 3 buckets: not a power of two
+    assert lib.lasv_ref_hash_table_write_branches(C.byref(ht), b"/dev/null", None) < 0
+    assert b"power of two" in lib.lasv_last_error()
+    ht = _capi.RefHashTable(31, 4, 8, table.ctypes.data, None, None, 0, 15)
+    assert lib.lasv_ref_hash_table_clean(C.byref(ht), 8, 0, None) < 0          # unknown pass
+    if lib.lasv_device_count() == 0:
+        for call in (lambda: lib.lasv_ref_hash_table_write_branches(C.byref(ht), b"/dev/null", None),
+                     lambda: lib.lasv_ref_hash_table_clean(C.byref(ht), _capi.CLEAN_TIPS, 0, None)):
+            assert call() < 0
+            assert b"CUDA" in lib.lasv_last_error()
+
+
 @pytest.mark.parametrize("fname", ["edge_1.fq", "edge_2.fq", "edge_1.fq.gz"])
 def test_fastq_reader_matches_reference_grammar(fname):
     seq, qual, offs = seqfile_to_streams(util.GOLDEN / fname)
