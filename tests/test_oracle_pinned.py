@@ -255,3 +255,31 @@ def test_oracle_branches_dense_errors_live_reference(tmp_path, k, L, W, err, gen
     st = g.print_branches(tmp_path / "ours.fa")
     assert st["branches"] > 0
     assert (tmp_path / "ours.fa").read_bytes() == (tmp_path / "branches.fa").read_bytes()
+
+
+def _golden_branches():
+    import json
+    return json.loads((util.GOLDEN / "branches.json").read_text())
+
+
+@pytest.mark.parametrize("key", sorted(_golden_branches()))
+def test_oracle_cleaning_and_branches_match_committed_reference_digests(key, tmp_path):
+    """The same pinning without oracle/_ref: tests/golden/branches.json holds, from the compiled reference
+    (generator: tests/golden/make_golden_branches.py), the SHA-256 of ./branches.fa and of the `.ctx` records a
+    `--mode build [--remove_low_coverage_supernodes T]` run leaves for every golden case."""
+    import hashlib
+    gold = _golden_branches()[key]
+    name, what = key.split(":")
+    meta = util.case_meta(name)
+    seq, qual, offs = util.case_streams(name)
+    g, ok = util.oracle_build(meta["k"], meta["L"], meta["W"], seq, qual, offs, util.cutoff_of(meta), paired=True)
+    assert ok
+    if what != "raw":
+        g.clean(int(what))
+    st = g.print_branches(tmp_path / "br.fa")
+    fa = (tmp_path / "br.fa").read_bytes()
+    assert (len(fa), st["branches"]) == (gold["branches_bytes"], gold["branches"])
+    assert hashlib.sha256(fa).hexdigest() == gold["branches_sha256"]
+    recs = g.records()
+    assert len(recs) == gold["ctx_records"]
+    assert hashlib.sha256(recs.tobytes()).hexdigest() == gold["ctx_records_sha256"]
