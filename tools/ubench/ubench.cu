@@ -2,6 +2,7 @@
 // (tools only; not part of the product library).
 //   A. locality: random 8-byte read + 32-bit reduction inside a WINDOW of the table;
 //      the window is global (all CTAs share it and it slides), per SM, or per CTA.
+//   C. groups: stream groups of lines through shared memory, update them there (the planned insert).
 //   B. scatter: N records appended to n_bins stripes, one global atomic each, for
 //      several record sizes / store shapes; atomics alone; stores alone.
 #include <cuda_runtime.h>
@@ -179,6 +180,81 @@ __global__ void __launch_bounds__(256) sweep_kernel(uint64_t *buf, uint64_t regi
   if (acc == 0x9999) buf[0] = acc;
 }
 
+// C. groups: the access pattern of the planned streamed insert: the table is cut into GROUPS of
+//    lines (a few buckets, tens of KB); a CTA brings one group into shared memory, applies `ops` random
+//    header-read + slot-read + shared-memory atomic updates there, and streams the group back.
+//    V = 0: LDG.128 -> STS, LDS -> STG.128 through registers.  V = 1: cp.async.bulk (TMA 1-D copies) both ways,
+//    double buffered: group i+1 is loaded and group i-1 written back while group i is updated.
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void group_ops(uint64_t *lines, uint32_t n_lines, uint32_t ops, uint64_t seed) {
+  uint64_t acc = 0;
+  for (uint32_t i = threadIdx.x; i < ops; i += blockDim.x) {
+    uint64_t *line = lines + (uint64_t)(mix64(seed + i) % n_lines) * 16;
+    const uint64_t hdr = line[0];
+    uint64_t *slot = line + 1 + 3 * (hdr & 3);  // a 24-byte slot behind the 8-byte header
+    acc += slot[0] + slot[1];
+    atomicAdd(reinterpret_cast<unsigned *>(slot + 2), 1u);
+  }
+  if (acc == 0x1234567ull) lines[0] = acc;
+}
+template <int V>
+__global__ void __launch_bounds__(256) groups_kernel(uint64_t *buf, uint64_t n_groups, uint32_t group_bytes, uint32_t ops,
+                                                    uint64_t seed) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const uint32_t n_lines = group_bytes / 128, n_vec = group_bytes / 16;
+  if (V == 0) {
+    uint4 *sm = reinterpret_cast<uint4 *>(smem_raw);
+    for (uint64_t g = blockIdx.x; g < n_groups; g += gridDim.x) {
+      uint4 *src = reinterpret_cast<uint4 *>(reinterpret_cast<unsigned char *>(buf) + g * group_bytes);
+      for (uint32_t i = threadIdx.x; i < n_vec; i += blockDim.x) sm[i] = src[i];
+      __syncthreads();
+      group_ops(reinterpret_cast<uint64_t *>(sm), n_lines, ops, seed + g * 7919);
+      __syncthreads();
+      for (uint32_t i = threadIdx.x; i < n_vec; i += blockDim.x) src[i] = sm[i];
+      __syncthreads();
+    }
+  } else {
+    __shared__ __align__(8) uint64_t mbar[2];
+    unsigned char *bufs[2] = {smem_raw, smem_raw + group_bytes};
+    if (threadIdx.x == 0) {
+      for (int b = 0; b < 2; b++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar[b])));
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    auto load = [&](uint64_t g, int b) {  // one thread
+      const unsigned char *src = reinterpret_cast<unsigned char *>(buf) + g * group_bytes;
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&mbar[b])), "r"(group_bytes) : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(bufs[b])),
+                   "l"(src), "r"(group_bytes), "r"(smem_u32(&mbar[b]))
+                   : "memory");
+    };
+    if (threadIdx.x == 0 && blockIdx.x < n_groups) load(blockIdx.x, 0);
+    uint32_t it = 0;
+    for (uint64_t g = blockIdx.x; g < n_groups; g += gridDim.x, it++) {
+      const int b = it & 1;
+      if (threadIdx.x == 0) {
+        // the write-back of the group that used the other buffer must have read it before it is refilled
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        if (g + gridDim.x < n_groups) load(g + gridDim.x, b ^ 1);
+      }
+      const uint32_t parity = (it >> 1) & 1u;
+      uint32_t done = 0;
+      while (!done)
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(done) : "r"(smem_u32(&mbar[b])), "r"(parity) : "memory");
+      group_ops(reinterpret_cast<uint64_t *>(bufs[b]), n_lines, ops, seed + g * 7919);
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        unsigned char *dst = reinterpret_cast<unsigned char *>(buf) + g * group_bytes;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the bulk copy
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(bufs[b])), "r"(group_bytes) : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+    }
+    if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
+}
+
 static float time_ms(cudaEvent_t a, cudaEvent_t b) { float ms; cudaEventElapsedTime(&ms, a, b); return ms; }
 
 int main(int argc, char **argv) {
@@ -246,6 +322,34 @@ int main(int argc, char **argv) {
       for (int c : {4, 8}) run("hdr+v4+red", sweep_kernel<3, false, 1>, c);
       for (int c : {4, 8}) run("v4+red", sweep_kernel<4, false, 1>, c);
       for (int c : {4, 8}) run("red only", sweep_kernel<5, false, 1>, c);
+    }
+    CK(cudaFree(buf));
+  }
+  if (!strcmp(what, "groups")) {
+    // ./ubench groups [table_GB] : default 12.5 GB (one GPU's share of the human-scale table at 8 GPUs)
+    const uint64_t total = (uint64_t)((argc > 2 ? atof(argv[2]) : 12.5) * (1ull << 30));
+    uint64_t *buf; CK(cudaMalloc(&buf, total)); CK(cudaMemset(buf, 0, total));
+    const uint64_t n_ops = 180000000ull;
+    for (uint32_t group_bytes : {6400u, 12800u, 25600u, 51200u}) {  // 1, 2, 4, 8 buckets of 50 lines
+      const uint64_t n_groups = total / group_bytes;
+      const uint32_t ops = (uint32_t)(n_ops / n_groups) + 1;
+      auto run = [&](const char *name, auto kern, int ctas_per_sm, uint32_t smem) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); return; }
+        float best = 1e30f;
+        for (int rep = 0; rep < 3; rep++) {
+          CK(cudaEventRecord(e0));
+          kern<<<sms * ctas_per_sm, 256, smem>>>(buf, n_groups, group_bytes, ops, 4242 + rep);
+          CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
+          if (cudaGetLastError() != cudaSuccess) return;
+          best = fminf(best, time_ms(e0, e1));
+        }
+        printf("{\"bench\":\"groups\",\"table_GB\":%.1f,\"group_bytes\":%u,\"ops_per_group\":%u,\"kernel\":\"%s\",\"ctas_per_sm\":%d,"
+               "\"ms\":%.3f,\"GBps_in_plus_out\":%.0f,\"Gops\":%.2f}\n", (double)total / (1ull << 30), group_bytes, ops, name,
+               ctas_per_sm, best, 2.0 * (double)n_groups * group_bytes / best / 1e6, (double)n_groups * ops / best / 1e6);
+        fflush(stdout);
+      };
+      for (int c : {2, 4, 8}) if ((uint64_t)c * group_bytes <= 200u * 1024u) run("ldg/stg", groups_kernel<0>, c, group_bytes);
+      for (int c : {1, 2, 4}) if ((uint64_t)c * 2 * group_bytes <= 200u * 1024u) run("bulk copy, double buffered", groups_kernel<1>, c, 2 * group_bytes);
     }
     CK(cudaFree(buf));
   }
