@@ -39,6 +39,7 @@ using namespace lasv;
 namespace {
 
 thread_local std::string g_err;
+thread_local int g_err_code = 0;  // of the last fail(), for callers that got a NULL handle back
 std::atomic<uint64_t> g_launches{0};
 
 int fail(int code, const char *fmt, ...) {
@@ -48,8 +49,11 @@ int fail(int code, const char *fmt, ...) {
   vsnprintf(buf, sizeof buf, fmt, ap);
   va_end(ap);
   g_err = buf;
+  g_err_code = code;
   return code;
 }
+
+int last_error_code() { return g_err_code < 0 ? g_err_code : LASV_ERR_CUDA; }
 
 #define CUDA_TRY(expr)                                                                      \
   do {                                                                                      \
@@ -2095,41 +2099,59 @@ int lasv_graph_clean(lasv_graph *g, int what, int threshold, lasv_clean_stats *s
   return LASV_OK;
 }
 
+// The caller's reference-layout table <-> a device table of the same geometry in the finalised arrangement
+// (bucket b = W consecutive Elements at the start of its NL lines, slack bytes zero): the inverse of
+// lasv_graph_export_table, slot order preserved, so a traversal in table order is the caller's.
+static lasv_graph *graph_for_reference_table(const lasv_ref_hash_table *t) {
+  if (!t || !t->table) { fail(LASV_ERR_ARG, "NULL table!"); return nullptr; }
+  const int L = log2_exact(t->number_buckets);
+  if (L < 0) { fail(LASV_ERR_ARG, "number_buckets is not a power of two"); return nullptr; }
+  int dev = 0;
+  if (const char *e = getenv("LASV_B200_DEVICE")) dev = atoi(e);
+  return lasv_graph_new(t->kmer_size, L, t->bucket_size, t->max_rehash_tries, dev);
+}
+
+static int upload_reference_table(lasv_graph *g, const lasv_ref_hash_table *t) {
+  const size_t row = (size_t)g->W * g->slot_bytes, pitch = (size_t)(g->table_bytes / g->n_buckets);
+  const uint64_t rows_per_copy = 1ull << 20;
+  for (uint64_t b0 = 0; b0 < g->n_buckets; b0 += rows_per_copy) {
+    const uint64_t nb = std::min(rows_per_copy, g->n_buckets - b0);
+    CUDA_TRY(cudaMemcpy2D(g->d_lines + b0 * pitch, pitch, (const uint8_t *)t->table + b0 * row, row, row, (size_t)nb,
+                          cudaMemcpyHostToDevice));
+  }
+  g->finalized = true;
+  // a copy from pageable host memory may return before its last DMA has landed, and the kernels run
+  // on a non-blocking stream that does not wait for the legacy stream the copy was issued on
+  CUDA_TRY(cudaDeviceSynchronize());
+  return LASV_OK;
+}
+
+static int download_reference_table(lasv_graph *g, lasv_ref_hash_table *t) {
+  CUDA_TRY(cudaDeviceSynchronize());
+  const size_t row = (size_t)g->W * g->slot_bytes, pitch = (size_t)(g->table_bytes / g->n_buckets);
+  const uint64_t rows_per_copy = 1ull << 20;
+  for (uint64_t b0 = 0; b0 < g->n_buckets; b0 += rows_per_copy) {
+    const uint64_t nb = std::min(rows_per_copy, g->n_buckets - b0);
+    CUDA_TRY(cudaMemcpy2D((uint8_t *)t->table + b0 * row, row, g->d_lines + b0 * pitch, pitch, row, (size_t)nb,
+                          cudaMemcpyDeviceToHost));
+  }
+  return LASV_OK;
+}
+
 int lasv_ref_hash_table_clean(lasv_ref_hash_table *t, int what, int threshold, lasv_clean_stats *stats) {
-  if (!t || !t->table) return fail(LASV_ERR_ARG, "NULL table!");
   if (!(what & (LASV_CLEAN_TIPS | LASV_CLEAN_SUPERNODES)) || (what & ~(LASV_CLEAN_TIPS | LASV_CLEAN_SUPERNODES)))
     return fail(LASV_ERR_ARG, "what must be LASV_CLEAN_TIPS, LASV_CLEAN_SUPERNODES or both");
   if ((what & LASV_CLEAN_SUPERNODES) && threshold < 0) return fail(LASV_ERR_ARG, "negative coverage threshold");
-  const int L = log2_exact(t->number_buckets);
-  if (L < 0) return fail(LASV_ERR_ARG, "number_buckets is not a power of two");
-  int dev = 0;
-  if (const char *e = getenv("LASV_B200_DEVICE")) dev = atoi(e);
-  lasv_graph *g = lasv_graph_new(t->kmer_size, L, t->bucket_size, t->max_rehash_tries, dev);
-  if (!g) return LASV_ERR_CUDA;
+  lasv_graph *g = graph_for_reference_table(t);
+  if (!g) return last_error_code();
   if (stats) memset(stats, 0, sizeof *stats);
   int rc = [&]() -> int {
-    // the table as it is (the finalised arrangement: bucket b = W consecutive Elements at the start of its lines)
-    const size_t row = (size_t)g->W * g->slot_bytes, pitch = (size_t)(g->table_bytes / g->n_buckets);
-    const uint64_t rows_per_copy = 1ull << 20;
-    for (uint64_t b0 = 0; b0 < g->n_buckets; b0 += rows_per_copy) {
-      const uint64_t nb = std::min(rows_per_copy, g->n_buckets - b0);
-      CUDA_TRY(cudaMemcpy2D(g->d_lines + b0 * pitch, pitch, (const uint8_t *)t->table + b0 * row, row, row,
-                            (size_t)nb, cudaMemcpyHostToDevice));
-    }
-    g->finalized = true;
-    // a copy from pageable host memory may return before its last DMA has landed, and the kernels run
-    // on a non-blocking stream that does not wait for the legacy stream the copy was issued on
-    CUDA_TRY(cudaDeviceSynchronize());
+    if (int e = upload_reference_table(g, t)) return e;
     if (what & LASV_CLEAN_TIPS)
       if (int e = clean_pass(g, LASV_CLEAN_TIPS, (uint32_t)std::max(threshold, 0), stats)) return e;
     if (what & LASV_CLEAN_SUPERNODES)
       if (int e = clean_pass(g, LASV_CLEAN_SUPERNODES, (uint32_t)threshold, stats)) return e;
-    for (uint64_t b0 = 0; b0 < g->n_buckets; b0 += rows_per_copy) {
-      const uint64_t nb = std::min(rows_per_copy, g->n_buckets - b0);
-      CUDA_TRY(cudaMemcpy2D((uint8_t *)t->table + b0 * row, row, g->d_lines + b0 * pitch, pitch, row, (size_t)nb,
-                            cudaMemcpyDeviceToHost));
-    }
-    return LASV_OK;
+    return download_reference_table(g, t);  // pruned nodes marked `pruned`, their edges reset
   }();
   lasv_graph_free(&g);
   return rc;
@@ -2274,30 +2296,12 @@ int lasv_graph_write_branches(lasv_graph *g, const char *fasta_path, int mark_vi
 }
 
 int lasv_ref_hash_table_write_branches(lasv_ref_hash_table *t, const char *fasta_path, lasv_branch_stats *stats) {
-  if (!t || !t->table) return fail(LASV_ERR_ARG, "NULL table!");
-  const int L = log2_exact(t->number_buckets);
-  if (L < 0) return fail(LASV_ERR_ARG, "number_buckets is not a power of two");
-  int dev = 0;
-  if (const char *e = getenv("LASV_B200_DEVICE")) dev = atoi(e);
-  lasv_graph *g = lasv_graph_new(t->kmer_size, L, t->bucket_size, t->max_rehash_tries, dev);
-  if (!g) return LASV_ERR_CUDA;
+  lasv_graph *g = graph_for_reference_table(t);
+  if (!g) return last_error_code();
   int rc = [&]() -> int {
-    // the table as it is (the finalised arrangement), as in lasv_ref_hash_table_clean
-    const size_t row = (size_t)g->W * g->slot_bytes, pitch = (size_t)(g->table_bytes / g->n_buckets);
-    const uint64_t rows_per_copy = 1ull << 20;
-    for (uint64_t b0 = 0; b0 < g->n_buckets; b0 += rows_per_copy) {
-      const uint64_t nb = std::min(rows_per_copy, g->n_buckets - b0);
-      CUDA_TRY(cudaMemcpy2D(g->d_lines + b0 * pitch, pitch, (const uint8_t *)t->table + b0 * row, row, row,
-                            (size_t)nb, cudaMemcpyHostToDevice));
-    }
-    g->finalized = true;
-    if (int e = lasv_graph_write_branches(g, fasta_path, 1, stats)) return e;  // starts with a device synchronisation
-    for (uint64_t b0 = 0; b0 < g->n_buckets; b0 += rows_per_copy) {            // the marks
-      const uint64_t nb = std::min(rows_per_copy, g->n_buckets - b0);
-      CUDA_TRY(cudaMemcpy2D((uint8_t *)t->table + b0 * row, row, g->d_lines + b0 * pitch, pitch, row, (size_t)nb,
-                            cudaMemcpyDeviceToHost));
-    }
-    return LASV_OK;
+    if (int e = upload_reference_table(g, t)) return e;
+    if (int e = lasv_graph_write_branches(g, fasta_path, 1, stats)) return e;
+    return download_reference_table(g, t);  // the marks
   }();
   lasv_graph_free(&g);
   return rc;
@@ -2305,26 +2309,10 @@ int lasv_ref_hash_table_write_branches(lasv_ref_hash_table *t, const char *fasta
 
 int lasv_ref_hash_table_write_supernodes(lasv_ref_hash_table *t, const char *fasta_path, int max_length,
                                          lasv_supernode_stats *stats) {
-  if (!t || !t->table) return fail(LASV_ERR_ARG, "NULL table!");
-  const int L = log2_exact(t->number_buckets);
-  if (L < 0) return fail(LASV_ERR_ARG, "number_buckets is not a power of two");
-  int dev = 0;
-  if (const char *e = getenv("LASV_B200_DEVICE")) dev = atoi(e);
-  lasv_graph *g = lasv_graph_new(t->kmer_size, L, t->bucket_size, t->max_rehash_tries, dev);
-  if (!g) return LASV_ERR_CUDA;
-  int rc = [&]() -> int {
-    // the inverse of lasv_graph_export_table: bucket b = W consecutive Elements at the start of its
-    // NL lines (the finalised arrangement), slack bytes stay zero
-    const size_t row = (size_t)g->W * g->slot_bytes, pitch = (size_t)(g->table_bytes / g->n_buckets);
-    const uint64_t rows_per_copy = 1ull << 20;
-    for (uint64_t b0 = 0; b0 < g->n_buckets; b0 += rows_per_copy) {
-      const uint64_t nb = std::min(rows_per_copy, g->n_buckets - b0);
-      CUDA_TRY(cudaMemcpy2D(g->d_lines + b0 * pitch, pitch, (const uint8_t *)t->table + b0 * row, row, row,
-                            (size_t)nb, cudaMemcpyHostToDevice));
-    }
-    g->finalized = true;
-    return lasv_graph_write_supernodes(g, fasta_path, max_length, stats);  // starts with a device synchronisation
-  }();
+  lasv_graph *g = graph_for_reference_table(t);
+  if (!g) return last_error_code();
+  int rc = upload_reference_table(g, t);
+  if (rc == LASV_OK) rc = lasv_graph_write_supernodes(g, fasta_path, max_length, stats);
   lasv_graph_free(&g);
   return rc;
 }
