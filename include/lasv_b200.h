@@ -247,6 +247,21 @@ typedef struct {
 int lasv_graph_write_supernodes(lasv_graph *g, const char *fasta_path, int max_length,
                                 lasv_supernode_stats *stats /* may be NULL */);
 
+/* `--health_check` (db_graph_health_check, dB_graph_population.c:6274-6350) on the device graph, in
+ * either arrangement: every edge of every node (pruned ones have none) must lead to a node that is in
+ * the graph -- present, not pruned, with at least one edge (db_graph_get_next_node_for_specific_person_
+ * or_pop, :100-152) -- and that node must hold the return arrow.  Problems are counted (the reference
+ * prints one line each); nothing is fixed.  A graph built by the loaders, and one left by the cleaning,
+ * has none: a size-independent invariant for graphs too large to compare record by record. */
+typedef struct {
+  uint64_t nodes_checked;         /* the reference's return value */
+  uint64_t edges_checked;
+  uint64_t missing_target;        /* "didnt find node in hash table" */
+  uint64_t missing_return_arrow;  /* "inconsitency return arrow missing" */
+  uint64_t zero_kmers;            /* nodes whose k-mer is all A (more than one is an error in the reference) */
+} lasv_health_stats;
+int lasv_graph_health_check(lasv_graph *g, lasv_health_stats *out);
+
 /* Branch sequences of the device graph: what `--mode build` writes to ./branches.fa after
  * the cleaning (graph_operations.c:1145-1152 -> db_graph_print_all_branches_for_specific_
  * person_or_pop, print_branches.c:131-199, with db_graph_get_sequence_for_a_single_branch_...

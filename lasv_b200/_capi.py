@@ -55,6 +55,14 @@ class CleanStats(C.Structure):
         return {f: int(getattr(self, f)) for f, _ in self._fields_}
 
 
+class HealthStats(C.Structure):
+    _fields_ = [("nodes_checked", C.c_uint64), ("edges_checked", C.c_uint64), ("missing_target", C.c_uint64),
+                ("missing_return_arrow", C.c_uint64), ("zero_kmers", C.c_uint64)]
+
+    def as_dict(self):
+        return {f: int(getattr(self, f)) for f, _ in self._fields_}
+
+
 class BranchStats(C.Structure):
     _fields_ = [("n_branches", C.c_uint64), ("n_branching_nodes", C.c_uint64), ("n_nodes", C.c_uint64),
                 ("n_refused", C.c_uint64), ("n_cut", C.c_uint64), ("bytes", C.c_uint64)]
@@ -89,7 +97,7 @@ EXPORTS = [
     "lasv_graph_route_reads_device", "lasv_graph_extract_records_device",
     "lasv_graph_insert_records_device", "lasv_graph_read_stats_device", "lasv_graph_find",
     "lasv_graph_summary", "lasv_graph_finalize", "lasv_graph_export_table", "lasv_graph_import_table",
-    "lasv_graph_dump_ctx_records", "lasv_graph_write_ctx", "lasv_ctx_header", "lasv_graph_write_supernodes", "lasv_ref_hash_table_write_supernodes", "lasv_ref_hash_table_clean", "lasv_graph_write_branches", "lasv_graph_clean", "lasv_ref_hash_table_write_branches",
+    "lasv_graph_dump_ctx_records", "lasv_graph_write_ctx", "lasv_ctx_header", "lasv_graph_write_supernodes", "lasv_ref_hash_table_write_supernodes", "lasv_ref_hash_table_clean", "lasv_graph_write_branches", "lasv_graph_clean", "lasv_graph_health_check", "lasv_ref_hash_table_write_branches",
     "lasv_graph_load_ctx_records", "lasv_graph_load_ctx_file", "lasv_graph_load_se_file",
     "lasv_graph_load_pe_files", "lasv_graph_load_se_filelist", "lasv_graph_load_pe_filelists",
     "load_se_filelist_into_graph_colour", "load_pe_filelists_into_graph_colour",
@@ -187,6 +195,7 @@ def lib() -> C.CDLL:
     L.lasv_seqfile_parse_check.argtypes = [C.c_char_p, C.c_char_p, i32, u64, vp, C.POINTER(i32)]
     L.lasv_ref_hash_table_write_supernodes.argtypes = [C.POINTER(RefHashTable), C.c_char_p, i32, C.POINTER(SupernodeStats)]
     L.lasv_ref_hash_table_clean.argtypes = [C.POINTER(RefHashTable), i32, i32, C.POINTER(CleanStats)]
+    L.lasv_graph_health_check.argtypes = [vp, C.POINTER(HealthStats)]
     L.lasv_graph_clean.argtypes = [vp, i32, i32, C.POINTER(CleanStats)]
     L.lasv_graph_write_branches.argtypes = [vp, C.c_char_p, i32, C.POINTER(BranchStats)]
     L.lasv_ref_hash_table_write_branches.argtypes = [C.POINTER(RefHashTable), C.c_char_p, C.POINTER(BranchStats)]

@@ -2080,6 +2080,31 @@ static int clean_pass(lasv_graph *g, int what, uint32_t threshold, lasv_clean_st
   return rc;
 }
 
+// `--health_check` (db_graph_health_check, dB_graph_population.c:6274-6350): every edge leads to a node of
+// the graph that holds the return arrow.  Problems are counted, not fixed or printed.
+int lasv_graph_health_check(lasv_graph *g, lasv_health_stats *out) {
+  if (int e = use(g)) return e;
+  if (!out) return fail(LASV_ERR_ARG, "out is NULL");
+  CUDA_TRY(cudaDeviceSynchronize());
+  HcCounters *d = nullptr, h;
+  CUDA_TRY(cudaMalloc(&d, sizeof(HcCounters)));
+  int rc = [&]() -> int {
+    CUDA_TRY(cudaMemsetAsync(d, 0, sizeof(HcCounters), g->compute));
+    launch_hc_check(g->N, g->view(), g->k, d, g->compute);
+    if (int e = check_launch()) return e;
+    CUDA_TRY(cudaMemcpyAsync(&h, d, sizeof h, cudaMemcpyDeviceToHost, g->compute));
+    CUDA_TRY(cudaStreamSynchronize(g->compute));
+    out->nodes_checked = h.nodes;
+    out->edges_checked = h.edges;
+    out->missing_target = h.missing_target;
+    out->missing_return_arrow = h.missing_return;
+    out->zero_kmers = h.zero_kmers;
+    return LASV_OK;
+  }();
+  cudaFree(d);
+  return rc;
+}
+
 int lasv_graph_clean(lasv_graph *g, int what, int threshold, lasv_clean_stats *stats) {
   if (int e = use(g)) return e;
   if (!(what & (LASV_CLEAN_TIPS | LASV_CLEAN_SUPERNODES)) || (what & ~(LASV_CLEAN_TIPS | LASV_CLEAN_SUPERNODES)))

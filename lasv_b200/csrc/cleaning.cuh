@@ -133,7 +133,40 @@ LASV_HD void cl_settle_node(const TableView &t, uint64_t q) {
   else if (st == ST_PRUNED && meta_edges(m) != 0) Ops::store(mp, meta_with(m, 0u, ST_PRUNED));
 }
 
+// db_graph_health_check (dB_graph_population.c:6274-6350; `--health_check`) for one node: every edge
+// must lead to a node that is in the graph (present, not pruned, with at least one edge:
+// db_graph_get_next_node_for_specific_person_or_pop, :100-152) and that node must hold the return
+// arrow.  Returns the number of edges checked; adds to the two problem counts.
+#pragma nv_exec_check_disable
+template <int N, class Ops>
+LASV_HD uint32_t hc_check_node(const TableView &t, int k, uint64_t q, uint32_t &missing_target, uint32_t &missing_return,
+                               bool &zero_kmer) {
+  uint64_t key[N], key2[N];
+  const uint64_t m = sn_load_node<N, Ops>(t, q, key);
+  if (!m) return 0u;
+  zero_kmer = true;
+#pragma unroll
+  for (int w = 0; w < N; w++) zero_kmer = zero_kmer && key[w] == 0ull;
+  const uint32_t e = meta_edges(m);
+  uint32_t n = 0;
+  for (uint32_t bit = 0; bit < 8; bit++) {
+    if (!((e >> bit) & 1u)) continue;
+    n++;
+    uint32_t o2 = 0, back = 0;
+    uint64_t m2 = 0;
+    const uint64_t q2 = sn_step<N, Ops>(t, k, key, bit >> 2, bit & 3u, key2, m2, o2, back);
+    if (q2 == SN_NONE || meta_status(m2) == ST_PRUNED || meta_edges(m2) == 0u) { missing_target++; continue; }
+    if (!((meta_edges(m2) >> (4u * (o2 ^ 1u) + back)) & 1u)) missing_return++;
+  }
+  return n;
+}
+
+struct HcCounters {
+  unsigned long long nodes, edges, missing_target, missing_return, zero_kmers;
+};
+
 #if defined(__CUDACC__)
+void launch_hc_check(int N, const TableView &t, int k, HcCounters *c, cudaStream_t st);
 // launch interface (cleaning_kernels.cu)
 void launch_cl_nodes(int N, const TableView &t, ClNodeRec *out, uint64_t cap, ClCounters *c, cudaStream_t st);
 void launch_cl_coverage(int N, const TableView &t, int k, const SnPath *recs, uint64_t n, uint32_t threshold,

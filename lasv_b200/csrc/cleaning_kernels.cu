@@ -117,6 +117,39 @@ __global__ void __launch_bounds__(CL_THREADS) br_reset_marks_kernel(const TableV
     br_reset_mark<N, DeviceOps>(t, q);
 }
 
+// `--health_check`: one thread per slot, every edge followed once (a random table read per edge)
+template <int N>
+__global__ void __launch_bounds__(CL_THREADS) hc_check_kernel(const TableView t, const int k, HcCounters *c) {
+  const uint64_t n_slots = ((uint64_t)t.bucket_mask + 1) * t.W;
+  unsigned long long nodes = 0, edges = 0, mt = 0, mr = 0, zk = 0;
+  for (uint64_t q = (uint64_t)blockIdx.x * CL_THREADS + threadIdx.x; q < n_slots;
+       q += (uint64_t)gridDim.x * CL_THREADS) {
+    if (meta_status(DeviceOps::load(cl_meta_ptr<N, DeviceOps>(t, q))) == ST_EMPTY) continue;
+    uint32_t a = 0, b = 0;
+    bool z = false;
+    edges += hc_check_node<N, DeviceOps>(t, k, q, a, b, z);
+    nodes++;
+    mt += a;
+    mr += b;
+    zk += z;
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+    nodes += __shfl_xor_sync(0xFFFFFFFFu, nodes, o);
+    edges += __shfl_xor_sync(0xFFFFFFFFu, edges, o);
+    mt += __shfl_xor_sync(0xFFFFFFFFu, mt, o);
+    mr += __shfl_xor_sync(0xFFFFFFFFu, mr, o);
+    zk += __shfl_xor_sync(0xFFFFFFFFu, zk, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (nodes) atomicAdd(&c->nodes, nodes);
+    if (edges) atomicAdd(&c->edges, edges);
+    if (mt) atomicAdd(&c->missing_target, mt);
+    if (mr) atomicAdd(&c->missing_return, mr);
+    if (zk) atomicAdd(&c->zero_kmers, zk);
+  }
+}
+
 template <typename F>
 void cl_dispatch(int N, F &&f) {
   if (N == 1) f(std::integral_constant<int, 1>());
@@ -179,6 +212,14 @@ void launch_br_write(int N, const TableView &t, int k, const BrPrint *prints, ui
   cl_dispatch(N, [&](auto nn) {
     constexpr int NN = decltype(nn)::value;
     br_write_kernel<NN><<<cl_grid(br_write_kernel<NN>, n), CL_THREADS, 0, st>>>(t, k, prints, n, image, mark, c);
+  });
+}
+
+void launch_hc_check(int N, const TableView &t, int k, HcCounters *c, cudaStream_t st) {
+  const uint64_t n_slots = ((uint64_t)t.bucket_mask + 1) * t.W;
+  cl_dispatch(N, [&](auto nn) {
+    constexpr int NN = decltype(nn)::value;
+    hc_check_kernel<NN><<<cl_grid(hc_check_kernel<NN>, n_slots), CL_THREADS, 0, st>>>(t, k, c);
   });
 }
 

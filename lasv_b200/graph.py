@@ -234,6 +234,13 @@ class DBGraph:
         check(self._lib.lasv_graph_write_supernodes(self._h, str(path).encode(), max_length, C.byref(st)))
         return st.as_dict()
 
+    def health_check(self) -> dict:
+        """`--health_check` (dB_graph_population.c:6274-6350): every edge leads to a node of the graph
+        that holds the return arrow; problems are counted."""
+        st = _capi.HealthStats()
+        check(self._lib.lasv_graph_health_check(self._h, C.byref(st)))
+        return st.as_dict()
+
     def clean(self, threshold: int, what: int = _capi.CLEAN_TIPS | _capi.CLEAN_SUPERNODES) -> dict:
         """`--remove_low_coverage_supernodes threshold` (graph_operations.c:1069-1090) on the device table: tip
         clipping, then low-coverage supernode removal, exact for the table's slot order."""

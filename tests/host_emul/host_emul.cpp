@@ -400,6 +400,24 @@ int branches(uint8_t *table, int k, int L, int W, int finalized, const char *pat
   return (ok && !st.inconsistent) ? 0 : -3;
 }
 
+// hc_check_kernel: `--health_check`
+template <int N>
+void health(uint8_t *table, int k, int L, int W, int finalized, uint64_t *counts5) {
+  const TableView tv = make_table_view(table, N, L, W, 15, finalized != 0);
+  const uint64_t n_slots = (1ull << L) * (uint64_t)W;
+  for (int i = 0; i < 5; i++) counts5[i] = 0;
+  for (uint64_t q = 0; q < n_slots; q++) {
+    if (meta_status(HostOps::load(cl_meta_ptr<N, HostOps>(tv, q))) == ST_EMPTY) continue;
+    uint32_t a = 0, b = 0;
+    bool z = false;
+    counts5[1] += hc_check_node<N, HostOps>(tv, k, q, a, b, z);
+    counts5[0]++;
+    counts5[2] += a;
+    counts5[3] += b;
+    counts5[4] += z;
+  }
+}
+
 }  // namespace
 
 #define DISPATCH(N, call) ((N) == 1 ? call<1> : (N) == 2 ? call<2> : call<3>)
@@ -472,6 +490,11 @@ int emul_clean(uint8_t *table, int k, int L, int W, int finalized, int threshold
 int emul_branches(uint8_t *table, int k, int L, int W, int finalized, const char *path, int mark, uint64_t *counts6) {
   const int N = 2 * k / 64 + 1;
   return DISPATCH(N, branches)(table, k, L, W, finalized, path, mark, counts6);
+}
+
+void emul_health(uint8_t *table, int k, int L, int W, int finalized, uint64_t *counts5) {
+  const int N = 2 * k / 64 + 1;
+  DISPATCH(N, health)(table, k, L, W, finalized, counts5);
 }
 
 // kmer_revcomp of supernodes.cuh, for known-answer checks

@@ -1173,3 +1173,50 @@ def test_gpu_build_mode_stays_on_the_device(name, thresh, finalized, tmp_path):
         assert int((table["status"] == 3).sum()) == st["nodes_pruned"]
         assert not table["edges"][table["status"] == 3].any()
         assert np.array_equal(_table_records(table), recs)
+
+
+@_first_device_run
+@pytest.mark.parametrize("name", ["synth_cfg1_k31", "synth_cfg0_k53", "synth_cfg2_k95", "synth_full_k53"])
+def test_gpu_health_check(name):
+    """`--health_check` on the device graph: every edge has its return arrow, raw, finalised and cleaned."""
+    meta = util.case_meta(name)
+    k, L, W = meta["k"], meta["L"], meta["W"]
+    seq, qual, offs = util.case_streams(name)
+    with DBGraph(k, L, W) as g:
+        g.load_reads_host(seq, qual, offs, util.cutoff_of(meta))
+        recs = g.records()
+        want = {"nodes_checked": len(recs), "edges_checked": int(np.unpackbits(recs["edges"]).sum()),
+                "missing_target": 0, "missing_return_arrow": 0, "zero_kmers": 0}
+        assert g.health_check() == want
+        if name != "synth_full_k53":
+            g.clean(2)
+            h = g.health_check()
+            assert h["missing_target"] == h["missing_return_arrow"] == 0 and h["nodes_checked"] == len(recs)
+            assert h["edges_checked"] == int(np.unpackbits(g.records()["edges"]).sum()) < want["edges_checked"]
+        g.finalize()
+        h = g.health_check()
+        assert h["missing_target"] == h["missing_return_arrow"] == 0
+
+
+@_first_device_run
+def test_gpu_health_check_at_full_config0_size():
+    """Size-independent invariant at BASELINE configs[0] scale (63 Mbp, 30x, k=53, L=22 W=100): the graph of the
+    full build has a return arrow for every edge, and edges_checked equals the summary's edge-bit count."""
+    import torch
+    w = synth.WORKLOADS["cfg0"]
+    p = w.params()
+    n_reads, batch, stride = 2 * w.n_pairs, 1 << 20, w.read_len + 1
+    d_seq = torch.empty(batch * stride + 16, dtype=torch.uint8, device="cuda")
+    d_qual = torch.empty_like(d_seq)
+    st_ = torch.cuda.current_stream().cuda_stream
+    with DBGraph(w.kmer_size, w.number_bits, w.bucket_size) as g:
+        for b0 in range(0, n_reads, batch):
+            nr = min(batch, n_reads - b0)
+            synth.reads_device(p, b0, nr, d_seq, d_qual, st_)
+            g.load_reads_device(d_seq, d_qual, nr * stride, None, 0, w.cutoff, st_)
+        torch.cuda.synchronize()
+        s = g.summary()
+        h = g.health_check()
+        assert h["nodes_checked"] == s["n_nodes"] > 100_000_000
+        assert h["edges_checked"] == s["sum_edge_bits"]
+        assert h["missing_target"] == h["missing_return_arrow"] == 0

@@ -38,6 +38,7 @@ def emul():
     L.emul_supernodes.argtypes = [C.c_void_p] + [C.c_int] * 4 + [C.c_char_p, C.c_void_p]
     L.emul_revcomp.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
     L.emul_clean.argtypes = [C.c_void_p] + [C.c_int] * 5 + [C.c_void_p]
+    L.emul_health.argtypes = [C.c_void_p] + [C.c_int] * 4 + [C.c_void_p]
     L.emul_branches.argtypes = [C.c_void_p] + [C.c_int] * 4 + [C.c_char_p, C.c_int, C.c_void_p]
     L.emul_hash_c.restype = C.c_uint32
     L.emul_hash_c.argtypes = [C.c_void_p, C.c_int, C.c_uint32]
@@ -605,3 +606,51 @@ def test_emulated_clean_then_finalize_keeps_pruned_nodes_pruned(emul, tmp_path):
     emul_supernodes(emul, tab, tmp_path / "b.fa")
     assert (tmp_path / "a.fa").read_bytes() == (tmp_path / "b.fa").read_bytes()
     check_branches(emul, tab, tmp_path)
+
+
+# ---- `--health_check` (dB_graph_population.c:6274-6350): hc_check_node of cleaning.cuh ----
+def emul_health(emul, tab):
+    counts = np.zeros(5, dtype=np.uint64)
+    emul.emul_health(tab.ptr, tab.k, tab.L, tab.W, int(tab.finalized), counts.ctypes.data)
+    return dict(zip(["nodes_checked", "edges_checked", "missing_target", "missing_return_arrow", "zero_kmers"],
+                    (int(c) for c in counts)))
+
+
+@pytest.mark.parametrize("name", ["synth_cfg1_k31", "synth_cfg0_k53", "synth_cfg2_k95", "edge_pe_k21_q5", "synth_full_k53"])
+def test_emulated_health_check(emul, name):
+    """A graph built from reads has a return arrow for every edge, before and after the cleaning, in both table
+    arrangements; a flipped edge bit is found."""
+    meta = util.case_meta(name)
+    seq, qual, _ = util.case_streams(name)
+    rc, tab, _ = emul_build(emul, meta, seq, qual)
+    assert rc == 0
+    recs = tab.records()
+    n_edges = int(np.unpackbits(recs["edges"]).sum())
+    zero = int((recs["kmer"] == 0).all(axis=1).sum())          # the poly-A k-mer of the homopolymer reads, if any
+    want = {"nodes_checked": len(recs), "edges_checked": n_edges, "missing_target": 0, "missing_return_arrow": 0,
+            "zero_kmers": zero}
+    assert zero <= 1 and emul_health(emul, tab) == want
+    tab.finalize()
+    assert emul_health(emul, tab) == want
+    if name.startswith("synth") and name != "synth_full_k53":
+        st = emul_clean(emul, tab, 2)
+        h = emul_health(emul, tab)
+        assert h["missing_target"] == h["missing_return_arrow"] == 0
+        assert h["nodes_checked"] == len(recs) and st["nodes_pruned"] > 0        # pruned nodes are visited, they have no edges
+        assert h["edges_checked"] == int(np.unpackbits(tab.records()["edges"]).sum()) < n_edges
+    # corrupt the finalised table: drop one arrow (its twin loses the return arrow), add one that leads nowhere
+    N, slot = tab.N, 8 * tab.N + 8
+    bucket_bytes = len(tab.raw) >> tab.L
+    elems = tab.elements()
+    victim = int(np.flatnonzero((elems["status"] == 1) & (elems["edges"] != 0) & (elems["edges"] != 0xFF))[0])
+    at = (victim // tab.W) * bucket_bytes + (victim % tab.W) * slot + 8 * N + 4
+    before = emul_health(emul, tab)
+    old = int(tab.raw[at])
+    low = old & -old
+    tab.raw[at] = old & ~low
+    h = emul_health(emul, tab)
+    assert h["missing_return_arrow"] == 1 and h["edges_checked"] == before["edges_checked"] - 1
+    free = next(b for b in range(8) if not (old >> b) & 1)
+    tab.raw[at] = old | (1 << free)
+    h = emul_health(emul, tab)
+    assert h["missing_target"] + h["missing_return_arrow"] == 1 and h["edges_checked"] == before["edges_checked"] + 1
