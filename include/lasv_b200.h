@@ -290,6 +290,10 @@ long long lasv_graph_dump_ctx_records(lasv_graph *g, uint8_t *out, uint64_t capa
 int lasv_graph_write_ctx(lasv_graph *g, const char *path, uint32_t mean_read_len,
                          uint64_t total_seq);
 int lasv_ctx_header(int kmer_size, uint32_t mean_read_len, uint64_t total_seq, uint8_t *out128);
+/* The records alone, appended to an existing file: the ranks of a hash-sharded build write one `.ctx` by
+ * appending their shards in rank order behind rank 0's header (the shards hold disjoint key sets and, laid end to
+ * end, are the reference's table order -- SURVEY 8e).  Returns the number of records written or a negative error. */
+long long lasv_graph_append_ctx_records(lasv_graph *g, const char *path);
 /* load_multicolour_binary_from_filename_into_graph (file_reader.c:1652): */
 int lasv_graph_load_ctx_records(lasv_graph *g, const uint8_t *records, uint64_t n_records);
 int lasv_graph_load_ctx_file(lasv_graph *g, const char *path, uint32_t *mean_read_len,

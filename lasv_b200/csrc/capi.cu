@@ -1301,6 +1301,22 @@ int lasv_graph_write_ctx(lasv_graph *g, const char *path, uint32_t mean_read_len
   return rc;
 }
 
+long long lasv_graph_append_ctx_records(lasv_graph *g, const char *path) {
+  if (int e = use(g)) return e;
+  if (!path) return fail(LASV_ERR_ARG, "path is NULL");
+  CUDA_TRY(cudaDeviceSynchronize());
+  FILE *fp = fopen(path, "ab");
+  if (!fp) return fail(LASV_ERR_IO, "cannot open %s for appending: %s", path, strerror(errno));
+  const size_t rec = 8 * (size_t)g->N + 5;
+  uint64_t n = 0;
+  int rc = stream_ctx_records_out(g, &n, [&](const uint8_t *h, uint64_t m, uint64_t) -> int {
+    if (fwrite(h, rec, m, fp) != m) return fail(LASV_ERR_IO, "short write to %s", path);
+    return LASV_OK;
+  });
+  if (fclose(fp) != 0 && rc == LASV_OK) rc = fail(LASV_ERR_IO, "cannot close %s: %s", path, strerror(errno));
+  return rc == LASV_OK ? (long long)n : rc;
+}
+
 int lasv_graph_load_ctx_records(lasv_graph *g, const uint8_t *records, uint64_t n_records) {
   if (int e = use(g)) return e;
   if (g->finalized) return fail(LASV_ERR_STATE, "graph is finalised; no further inserts");

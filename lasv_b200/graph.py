@@ -227,6 +227,10 @@ class DBGraph:
     def dump_binary(self, path, mean_read_len: int = 0, total_seq: int = 0):
         check(self._lib.lasv_graph_write_ctx(self._h, str(path).encode(), mean_read_len, total_seq))
 
+    def append_binary_records(self, path) -> int:
+        """The `.ctx` records of this table, appended to `path` (one shard of a sharded dump)."""
+        return check(self._lib.lasv_graph_append_ctx_records(self._h, str(path).encode()))
+
     def output_supernodes(self, path, max_length: int = 10000) -> dict:
         """`--output_supernodes path` (graph_operations.c:1276-1293): the reference's FASTA of
         maximal unambiguous contigs for a traversal in table (= dumped .ctx) order."""

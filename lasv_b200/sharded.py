@@ -109,6 +109,27 @@ def exchange_stripes(send: torch.Tensor, recv: torch.Tensor, group=None):
             w.wait()
 
 
+def write_sharded_ctx(path, header: bytes, append_records, group=None) -> int:
+    """One `.ctx` from a hash-sharded graph: rank 0 writes the header, then every rank in turn
+    appends its shard's records with `append_records(path) -> count` (the ranks share the file system of
+    the node).  Owner = high bits of the reference bucket index, so the shards laid end to end are in the
+    reference's table order.  Returns the job-wide record count on every rank."""
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    mine = 0
+    for r in range(world):
+        if r == rank:
+            if rank == 0:
+                with open(path, "wb") as f:
+                    f.write(header)
+            mine = int(append_records(path))
+        dist.barrier(group=group)        # rank r's bytes are in the file before rank r+1 opens it
+    total = torch.tensor([mine], dtype=torch.int64)
+    if dist.get_backend(group) == "nccl":
+        total = total.cuda()
+    dist.all_reduce(total, group=group)
+    return int(total.item())
+
+
 class _StripeBuffers:
     def __init__(self, world, geo, device):
         self.send = torch.empty((world, geo["records_per_owner"], geo["record_bytes"] // 8), dtype=torch.int64,
@@ -319,6 +340,17 @@ class ShardedDBGraph:
             g.read_stats_device(d_seq, d_qual, d_offsets, n_reads, quality_cutoff, stream)
         total, _ = exchange_records(self.bins, self.counts, self.recv, self.group)
         g.insert_records_device(self.recv, total, stream)
+
+    def dump_binary(self, path, mean_read_len: int = 0, total_seq: int = 0) -> int:
+        """`--dump_binary path` of the whole sharded graph: BINVERSION 6 header + the records of all shards in
+        rank order (db_graph_dump_single_colour_binary_of_colour0, dB_graph_population.c:3730).  Collective."""
+        from .graph import ctx_header
+        self.flush()
+        if self.world == 1:
+            self.graph.dump_binary(path, mean_read_len, total_seq)
+            return self.graph.summary()["n_nodes"]
+        return write_sharded_ctx(path, ctx_header(self.graph.kmer_size, mean_read_len, total_seq),
+                                 self.graph.append_binary_records, self.group)
 
     def stats(self) -> dict:
         """Job-wide statistics (sum over ranks)."""

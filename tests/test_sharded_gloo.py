@@ -81,6 +81,21 @@ def _worker(rank, world, port, name, outdir):
     table = np.zeros((1 << (L - bits)) * W, dtype=element_dtype(N))
     emul.emul_gather(raw.ctypes.data, k, L - bits, W, 0, table.ctypes.data)
     np.save(Path(outdir) / f"shard{rank}.npy", table)
+    # one `.ctx` from all shards, as ShardedDBGraph.dump_binary writes it: rank 0's header, then every rank's
+    # records in rank order
+    from lasv_b200 import ctx_header, record_dtype
+    from lasv_b200.sharded import write_sharded_ctx
+
+    def append_records(path):
+        occ = table[table["status"] != 0]
+        out = np.zeros(len(occ), dtype=record_dtype(N))
+        out["kmer"], out["covg"], out["edges"] = occ["kmer"], occ["coverage"], occ["edges"]
+        with open(path, "ab") as f:
+            f.write(out.tobytes())
+        return len(out)
+
+    n_all = write_sharded_ctx(Path(outdir) / "all.ctx", ctx_header(k, 100, 1000), append_records)
+    assert n_all == meta["n_records"]
     # job-wide insert count through a collective, as ShardedDBGraph.stats does
     t = torch.tensor([n], dtype=torch.int64)
     dist.all_reduce(t)
@@ -115,6 +130,12 @@ def test_two_rank_exchange_builds_the_reference_graph(name, tmp_path):
         recs.append(out)
     assert all(len(r) > 0 for r in recs)
     util.assert_same_records(np.concatenate(recs), util.case_records(name), name)
+    # the sharded dump: a valid BINVERSION 6 file, shard 0's records first, then shard 1's
+    from oracle import oracle as O
+    ctx = O.parse_ctx(tmp_path / "all.ctx")
+    meta = util.case_meta(name)
+    assert bytes(ctx["header"]) == O.ctx_header(meta["k"], 100, 1000)
+    assert np.array_equal(ctx["records"], np.concatenate(recs))
 
 
 def _stripe_worker(rank, world, port, name, outdir):
