@@ -1441,6 +1441,7 @@ struct FileProducer {
       bool eof = false;
       for (;;) {
         if (!have) {
+          reads += reader.fill_batch_fast(b, with_qual);  // plain four-line records of a mapped slice
           if (!reader.next(err)) { eof = true; break; }
           have = true;
         }
@@ -2466,7 +2467,8 @@ int lasv_synth_reads_host(const lasv_synth_params *p, uint64_t first_read, uint6
  * 2, bases, checksum}; producers_used reports how many parser threads ran. */
 int lasv_seqfile_parse_check(const char *path1, const char *path2, int threads, uint64_t batch_bytes,
                              uint64_t *out4, int *producers_used) {
-  if (!path1 || !out4) return fail(LASV_ERR_ARG, "NULL argument");
+  if (!path1) return fail(LASV_ERR_ARG, "NULL argument");
+  const bool checksum = out4 != nullptr;  // out4 == NULL: parse only (parser timing)
   if (batch_bytes < 1024) batch_bytes = 1024;
   struct PlainBatch : HostBatch {
     std::vector<uint8_t> s, q;
@@ -2488,6 +2490,7 @@ int lasv_seqfile_parse_check(const char *path1, const char *path2, int threads, 
   uint64_t bases = 0, sum = 0;
   job.run([&](HostBatch &b, const FileProducer &fp) {
     const bool wq = fp.with_qual;
+    if (!checksum) { bases += b.n_bytes - b.n_reads; return; }
     for (uint64_t r = 0; r < b.n_reads; r++) {
       const uint64_t lo = b.offsets[r], hi = b.offsets[r + 1] - 1;  // without the separator
       uint64_t h = 0xCBF29CE484222325ull;
@@ -2499,10 +2502,12 @@ int lasv_seqfile_parse_check(const char *path1, const char *path2, int threads, 
   });
   for (auto &p : job.prod)
     if (!p->err.empty()) return fail(LASV_ERR_IO, "%s", p->err.c_str());
-  out4[0] = job.reads_of_file(0);
-  out4[1] = path2 ? job.reads_of_file(1) : 0;
-  out4[2] = bases;
-  out4[3] = sum;
+  if (out4) {
+    out4[0] = job.reads_of_file(0);
+    out4[1] = path2 ? job.reads_of_file(1) : 0;
+    out4[2] = bases;
+    out4[3] = sum;
+  }
   if (producers_used) *producers_used = (int)job.prod.size();
   return LASV_OK;
 }

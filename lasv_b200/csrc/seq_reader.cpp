@@ -211,6 +211,42 @@ bool SeqReader::next(std::string &err) {
   return false;
 }
 
+uint64_t SeqReader::fill_batch_fast(HostBatch &b, bool with_qual) {
+  if (!memory_ || type_ != FASTQ || at_record_start_) return 0;
+  uint64_t added = 0;
+  const unsigned char *const base = buf_, *const end = buf_ + end_;
+  while (pos_ < end_) {
+    const unsigned char *p = base + pos_;
+    if (*p != '@') break;  // blank lines before a header, or garbage: the slow path decides
+    const unsigned char *h = (const unsigned char *)memchr(p, '\n', (size_t)(end - p));
+    if (!h) break;
+    const unsigned char *sq = h + 1;
+    const unsigned char *se = sq < end ? (const unsigned char *)memchr(sq, '\n', (size_t)(end - sq)) : nullptr;
+    if (!se || se == sq || se[-1] == '\r' || se + 1 >= end || se[1] != '+') break;  // empty / CRLF / multi-line sequence
+    const unsigned char *pl = (const unsigned char *)memchr(se + 1, '\n', (size_t)(end - (se + 1)));
+    if (!pl) break;
+    const size_t len = (size_t)(se - sq);
+    const unsigned char *q = pl + 1;
+    if ((size_t)(end - q) < len) break;                                  // truncated quality line
+    if (q + len < end && q[len] != '\n') break;                          // quality line longer / CRLF / wrapped
+    if (memchr(q, '\n', len) || memchr(q, '\r', len)) break;             // wrapped quality line
+    if (b.n_reads >= b.cap_reads || b.n_bytes + len + 1 > b.cap_bytes) break;  // batch full
+    memcpy(b.seq + b.n_bytes, sq, len);
+    b.seq[b.n_bytes + len] = '\n';
+    if (with_qual) {
+      memcpy(b.qual + b.n_bytes, q, len);
+      b.qual[b.n_bytes + len] = '\n';
+    }
+    b.n_bytes += len + 1;
+    b.n_reads++;
+    b.offsets[b.n_reads] = b.n_bytes;
+    pos_ = (size_t)(q - base) + len + (q + len < end ? 1 : 0);
+    n_reads_++;
+    added++;
+  }
+  return added;
+}
+
 bool SeqReader::append_to(HostBatch &b, bool with_qual) const {
   const uint64_t need = (uint64_t)seq_.size() + 1;
   if (b.n_reads >= b.cap_reads || b.n_bytes + need > b.cap_bytes) return false;

@@ -48,6 +48,12 @@ class SeqReader {
   const std::string &qual() const { return qual_; }
   uint64_t reads_parsed() const { return n_reads_; }
 
+  // Fast path of the parallel loader: as many plain four-line FASTQ records ('@name', one sequence line, '+...',
+  // one quality line of the same length, LF line ends) as fit, straight from an in-memory slice into the batch
+  // -- one copy, no intermediate strings.  Stops in front of the first record that does not have that shape
+  // (next() handles it, with the reference's full grammar) or does not fit.  Returns the number of reads added.
+  uint64_t fill_batch_fast(HostBatch &b, bool with_qual);
+
   // Append the current read to a batch; false if it does not fit.
   bool append_to(HostBatch &b, bool with_qual) const;
 

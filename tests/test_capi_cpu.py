@@ -217,6 +217,25 @@ def test_parallel_fastq_parse_equals_sequential(tmp_path):
     assert used == 1 and got == ref                                   # compressed: sequential
     got, used = _parse_check(tmp_path / "a.fq", tmp_path / "crlf.fq", 3)
     assert used == 6 and got == (n, n, 2 * ref[2], (2 * ref[3]) % (1 << 64))
+    # mostly plain four-line records (taken by the slice parsers' fast path) with odd ones in between: wrapped,
+    # CRLF, an empty read, blank lines between records -- the full grammar takes over for those and hands back
+    with open(tmp_path / "mixed.fq", "w", newline="") as fm:
+        for i, ln in enumerate(lens):
+            s_ = "".join(rng.choice(list("ACGTN"), ln))
+            q_ = "".join(rng.choice(list("@+IIIIFF#5"), ln))
+            if i > 2000 and i % 1000 == 0 and ln > 3:
+                fm.write(f"@m{i}\n{s_[:2]}\n{s_[2:]}\n+\n{q_[:1]}\n{q_[1:]}\n")
+            elif i > 2000 and i % 777 == 0:
+                fm.write(f"@m{i}\r\n{s_}\r\n+\r\n{q_}\r\n")
+            elif i > 2000 and i % 1501 == 0:
+                fm.write(f"\n\n@m{i}\n{s_}\n+m{i}\n{q_}\n")
+            else:
+                fm.write(f"@m{i}\n{s_}\n+\n{q_}\n")
+    one, u1 = _parse_check(tmp_path / "mixed.fq", None, 1)
+    assert u1 == 1 and one[0] == n and one[2] == int(lens.sum())
+    for threads in (2, 4):
+        got, used = _parse_check(tmp_path / "mixed.fq", None, threads)
+        assert got == one, (threads, used, got, one)
     # tiny batches: many hand-offs per slice
     got, used = _parse_check(tmp_path / "a.fq", None, 4, batch_bytes=2048)
     assert got == ref
