@@ -2,11 +2,11 @@
 // (`--remove_low_coverage_supernodes T`, graph_operations.c:1069-1090): tip
 // clipping (dB_graph_population.c:365-470, 2563-2608) and removal of low-coverage
 // supernodes (:3371-3462, 3595-3649, node pruning :485-530).  Shared by the
-// (future) kernels and tests/host_emul; the sequential decisions are taken on the
+// kernels (cleaning_kernels.cu) and tests/host_emul; the sequential decisions are taken on the
 // path records by cleaning_host.h.
 //
-// The kernels are in cleaning_kernels.cu; the entry point is
-// lasv_ref_hash_table_clean (capi.cu), on the caller's reference-layout table.
+// Entry points (capi.cu): lasv_ref_hash_table_clean on the caller's reference-layout table,
+// lasv_graph_clean on a graph handle, lasv_graph_health_check (`--health_check`, below).
 #pragma once
 #include "supernodes.cuh"
 
