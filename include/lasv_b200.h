@@ -431,6 +431,16 @@ int lasv_random_access_probe_mode(void *d_buf, uint64_t n_sectors, uint64_t n_op
 /* First-choice bucket (hash_value.c:767-773, rehash 0) of each record. */
 int lasv_graph_record_buckets_device(lasv_graph *g, const uint32_t *d_records, uint64_t n_records,
                                      uint32_t *d_buckets, void *cuda_stream);
+/* PROTOTYPE, not used by the loaders: the streamed insert planned for the next round.  The
+ * records of lasv_graph_extract_records_device, SORTED by group = first-choice bucket / buckets_per_group
+ * (buckets from lasv_graph_record_buckets_device), with d_group_offsets[g] .. [g+1] delimiting the records of
+ * group g (n_buckets / buckets_per_group + 1 entries): one CTA per group brings the group's lines into shared
+ * memory, applies its records there (same find-or-insert protocol, shared-memory atomics) and streams the lines
+ * back; a record whose bucket holds W other keys leaves the group and is inserted through the ordinary path
+ * afterwards (*n_spilled counts them).  Same graph as lasv_graph_insert_records_device. */
+int lasv_graph_insert_grouped_records_device(lasv_graph *g, const uint32_t *d_records, uint64_t n_records,
+                                             const uint64_t *d_group_offsets, uint32_t buckets_per_group,
+                                             uint64_t *n_spilled /* may be NULL */, void *cuda_stream);
 /* The file loaders' parser on its own (host only, no GPU): reads per file, bases and
  * an order-independent checksum of every (sequence, quality) pair, parsed with
  * `threads` parser threads per file exactly as the loaders do (large uncompressed

@@ -32,6 +32,7 @@
 #include "supernodes_host.h"
 #include "cleaning_host.h"
 #include "branches_host.h"
+#include "groups.cuh"
 #include "seq_reader.h"
 
 using namespace lasv;
@@ -754,6 +755,47 @@ int lasv_graph_insert_records_device(lasv_graph *g, const uint32_t *d_records, u
   if (!n_records) return LASV_OK;
   launch_insert_records(g->N, d_records, n_records, g->view(), g->d_ctr, stream_of(g, cuda_stream));
   return check_launch();
+}
+
+// PROTOTYPE of the streamed insert (groups.cuh): records sorted by group, one CTA per group
+// updates the group's lines in shared memory; records whose bucket is full follow through the ordinary path.
+int lasv_graph_insert_grouped_records_device(lasv_graph *g, const uint32_t *d_records, uint64_t n_records,
+                                             const uint64_t *d_group_offsets, uint32_t buckets_per_group,
+                                             uint64_t *n_spilled, void *cuda_stream) {
+  if (int e = use(g)) return e;
+  if (g->finalized) return fail(LASV_ERR_STATE, "graph is finalised; no further inserts");
+  if (!buckets_per_group || (buckets_per_group & (buckets_per_group - 1)) || buckets_per_group > g->n_buckets)
+    return fail(LASV_ERR_ARG, "buckets_per_group must be a power of two <= the number of buckets");
+  const TableView tv = g->view();
+  if (group_bytes(tv, buckets_per_group) > insert_groups_smem_limit())
+    return fail(LASV_ERR_ARG, "a group of %u buckets (%llu bytes) does not fit in shared memory", buckets_per_group,
+                (unsigned long long)group_bytes(tv, buckets_per_group));
+  if (n_records >= (1ull << 32)) return fail(LASV_ERR_ARG, "at most 2^32 - 1 records per call");
+  if (n_spilled) *n_spilled = 0;
+  if (!n_records) return LASV_OK;
+  if (!d_records || !d_group_offsets) return fail(LASV_ERR_ARG, "NULL argument");
+  cudaStream_t st = stream_of(g, cuda_stream);
+  uint32_t *d_spill = nullptr;
+  unsigned long long *d_n = nullptr, h_n = 0;
+  int rc = [&]() -> int {
+    CUDA_TRY(cudaMalloc(&d_spill, n_records * sizeof(uint32_t)));
+    CUDA_TRY(cudaMalloc(&d_n, sizeof(unsigned long long)));
+    CUDA_TRY(cudaMemsetAsync(d_n, 0, sizeof(unsigned long long), st));
+    launch_insert_groups(g->N, d_records, d_group_offsets, g->n_buckets / buckets_per_group, buckets_per_group, tv, g->d_ctr,
+                         d_spill, d_n, n_records, st);
+    if (int e = check_launch()) return e;
+    CUDA_TRY(cudaMemcpyAsync(&h_n, d_n, sizeof h_n, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    launch_insert_spilled(g->N, d_records, d_spill, h_n, tv, g->d_ctr, st);  // after ALL groups are back in the table
+    if (h_n)
+      if (int e = check_launch()) return e;
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return LASV_OK;
+  }();
+  cudaFree(d_spill);
+  cudaFree(d_n);
+  if (n_spilled) *n_spilled = h_n;
+  return rc;
 }
 
 int lasv_graph_bin_geometry(lasv_graph *g, int n_owners, uint64_t n_bytes, uint64_t n_reads,

@@ -1,0 +1,136 @@
+// group_kernels.cu -- sm_100a kernels of the streamed-insert PROTOTYPE (groups.cuh has the scheme and
+// its status: not on the default path).
+//
+//   insert_groups_kernel   persistent CTAs; per group: lines global -> shared (128-bit loads, whole lines,
+//                          coalesced), records applied in shared memory, lines shared -> global
+//   insert_spilled_kernel  the records whose bucket was full, through the ordinary table_upsert
+#include <stdint.h>
+
+#include <type_traits>
+
+#include "graph_kernels.cuh"
+#include "groups.cuh"
+
+namespace lasv {
+
+namespace {
+
+constexpr int GR_THREADS = 256;
+
+// The table protocol on shared memory: same loads / CAS / reductions as DeviceOps, CTA scope.
+struct SmemOps {
+  static __device__ __forceinline__ uint64_t load(const uint64_t *p) { return *reinterpret_cast<const volatile uint64_t *>(p); }
+  static __device__ __forceinline__ void load16(const uint64_t *p, uint64_t &a, uint64_t &b) {
+    a = *reinterpret_cast<const volatile uint64_t *>(p);
+    b = *reinterpret_cast<const volatile uint64_t *>(p + 1);
+  }
+  static __device__ __forceinline__ void store(uint64_t *p, uint64_t v) { *reinterpret_cast<volatile uint64_t *>(p) = v; }
+  static __device__ __forceinline__ void store_tag(uint8_t *p, uint32_t v) { *reinterpret_cast<volatile uint8_t *>(p) = (uint8_t)v; }
+  static __device__ __forceinline__ uint64_t cas(uint64_t *p, uint64_t expect, uint64_t want) {
+    return atomicCAS(reinterpret_cast<unsigned long long *>(p), (unsigned long long)expect, (unsigned long long)want);
+  }
+  static __device__ __forceinline__ void xor32(uint32_t *p, uint32_t v) { atomicXor(p, v); }
+  static __device__ __forceinline__ void add32(uint32_t *p, uint32_t v) { atomicAdd(p, v); }
+  static __device__ __forceinline__ void or32(uint32_t *p, uint32_t v) { atomicOr(p, v); }
+  static __device__ __forceinline__ void and32(uint32_t *p, uint32_t v) { atomicAnd(p, v); }
+  static __device__ __forceinline__ void fence() { __threadfence_block(); }
+  static __device__ __forceinline__ void backoff() { __nanosleep(20); }
+  static __device__ __forceinline__ void count(unsigned long long *p, unsigned long long v) { atomicAdd(p, v); }  // global counters
+  static __device__ __forceinline__ void flag(unsigned long long *p) { atomicExch(p, 1ull); }
+};
+
+template <int N>
+__global__ void __launch_bounds__(GR_THREADS) insert_groups_kernel(const uint32_t *__restrict__ recs,
+                                                                  const uint64_t *__restrict__ group_offsets,
+                                                                  const uint64_t n_groups, const uint32_t buckets_per_group,
+                                                                  const TableView t, GraphCounters *ctr, uint32_t *spill,
+                                                                  unsigned long long *n_spill, const uint64_t spill_cap) {
+  constexpr int RECW = 2 * N + 1;
+  extern __shared__ __align__(128) unsigned char staged[];
+  const uint64_t gbytes = group_bytes(t, buckets_per_group);
+  const uint32_t n_vec = (uint32_t)(gbytes / 16);
+  uint4 *sm = reinterpret_cast<uint4 *>(staged);
+  unsigned long long my_new = 0;
+  for (uint64_t g = blockIdx.x; g < n_groups; g += gridDim.x) {
+    const uint64_t lo = group_offsets[g], hi = group_offsets[g + 1];
+    if (lo == hi) continue;  // the same for every thread of the CTA: no line of this group is touched
+    uint4 *lines = reinterpret_cast<uint4 *>(t.lines + g * gbytes);
+    for (uint32_t i = threadIdx.x; i < n_vec; i += GR_THREADS) sm[i] = lines[i];
+    __syncthreads();
+    const TableView local = group_local_view(t, staged, g, buckets_per_group);
+    for (uint64_t i = lo + threadIdx.x; i < hi; i += GR_THREADS) {
+      const int r = group_upsert<N, SmemOps>(local, ctr, recs + i * RECW);
+      my_new += (r == 1);
+      if (r < 0) {
+        const unsigned long long at = atomicAdd(n_spill, 1ull);
+        if (at < spill_cap) spill[at] = (uint32_t)i;
+      }
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < n_vec; i += GR_THREADS) lines[i] = sm[i];
+    __syncthreads();  // the staging buffer is free for the next group
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) my_new += __shfl_xor_sync(0xFFFFFFFFu, my_new, o);
+  if ((threadIdx.x & 31) == 0 && my_new) atomicAdd(&ctr->unique_kmers, my_new);
+}
+
+template <int N>
+__global__ void __launch_bounds__(GR_THREADS) insert_spilled_kernel(const uint32_t *__restrict__ recs,
+                                                                   const uint32_t *__restrict__ spill, const uint64_t n,
+                                                                   const TableView t, GraphCounters *ctr) {
+  constexpr int RECW = 2 * N + 1;
+  unsigned long long my_new = 0;
+  for (uint64_t j = (uint64_t)blockIdx.x * GR_THREADS + threadIdx.x; j < n; j += (uint64_t)gridDim.x * GR_THREADS) {
+    uint64_t key[N];
+    uint32_t edge, count;
+    group_load_record<N>(recs + (uint64_t)spill[j] * RECW, key, edge, count);
+    my_new += (table_upsert<N, DeviceOps>(t, ctr, key, edge, count) == 1);
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) my_new += __shfl_xor_sync(0xFFFFFFFFu, my_new, o);
+  if ((threadIdx.x & 31) == 0 && my_new) atomicAdd(&ctr->unique_kmers, my_new);
+}
+
+template <typename F>
+void gr_dispatch(int N, F &&f) {
+  if (N == 1) f(std::integral_constant<int, 1>());
+  else if (N == 2) f(std::integral_constant<int, 2>());
+  else f(std::integral_constant<int, 3>());
+}
+
+}  // namespace
+
+size_t insert_groups_smem_limit() { return 200u * 1024u; }  // of the 227 KB a CTA may have on sm_100a
+
+void launch_insert_groups(int N, const uint32_t *recs, const uint64_t *group_offsets, uint64_t n_groups,
+                          uint32_t buckets_per_group, const TableView &t, GraphCounters *ctr, uint32_t *spill,
+                          unsigned long long *n_spill, uint64_t spill_cap, cudaStream_t st) {
+  if (!n_groups) return;
+  const size_t smem = (size_t)group_bytes(t, buckets_per_group);
+  gr_dispatch(N, [&](auto nn) {
+    constexpr int NN = decltype(nn)::value;
+    cudaFuncSetAttribute(insert_groups_kernel<NN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    int per_sm = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, insert_groups_kernel<NN>, GR_THREADS, smem);
+    if (per_sm < 1) per_sm = 1;
+    uint64_t grid = (uint64_t)per_sm * (uint64_t)sm_count();  // persistent: resident CTAs x SMs
+    if (grid > n_groups) grid = n_groups;
+    insert_groups_kernel<NN><<<(unsigned)grid, GR_THREADS, smem, st>>>(recs, group_offsets, n_groups, buckets_per_group, t,
+                                                                        ctr, spill, n_spill, spill_cap);
+  });
+}
+
+void launch_insert_spilled(int N, const uint32_t *recs, const uint32_t *spill, uint64_t n_spill, const TableView &t,
+                           GraphCounters *ctr, cudaStream_t st) {
+  if (!n_spill) return;
+  gr_dispatch(N, [&](auto nn) {
+    constexpr int NN = decltype(nn)::value;
+    uint64_t grid = (n_spill + GR_THREADS - 1) / GR_THREADS;
+    const uint64_t cap = (uint64_t)sm_count() * 8;
+    if (grid > cap) grid = cap;
+    insert_spilled_kernel<NN><<<(unsigned)grid, GR_THREADS, 0, st>>>(recs, spill, n_spill, t, ctr);
+  });
+}
+
+}  // namespace lasv

@@ -159,6 +159,16 @@ class DBGraph:
     def insert_records_device(self, d_records, n_records, stream=None):
         check(self._lib.lasv_graph_insert_records_device(self._h, _ptr(d_records), n_records, stream))
 
+    def insert_grouped_records_device(self, d_sorted_records, n_records, d_group_offsets, buckets_per_group: int,
+                                      stream=None) -> int:
+        """PROTOTYPE of the streamed insert: records sorted by group, offsets per group; returns
+        the number of records whose bucket was full (they went through the ordinary path)."""
+        spilled = C.c_uint64(0)
+        check(self._lib.lasv_graph_insert_grouped_records_device(self._h, _ptr(d_sorted_records), n_records,
+                                                                  _ptr(d_group_offsets), buckets_per_group,
+                                                                  C.byref(spilled), stream))
+        return int(spilled.value)
+
     def bin_geometry(self, n_owners: int, n_bytes: int, n_reads: int = 0) -> dict:
         """Buffer sizes of the region-binned exchange for one batch (include/lasv_b200.h)."""
         a, b, sp, c, d = (C.c_uint32(0) for _ in range(5))

@@ -20,6 +20,7 @@
 #include "../../lasv_b200/csrc/cleaning_host.h"
 #include "../../lasv_b200/csrc/branches.cuh"
 #include "../../lasv_b200/csrc/branches_host.h"
+#include "../../lasv_b200/csrc/groups.cuh"
 
 using namespace lasv;
 
@@ -418,6 +419,40 @@ void health(uint8_t *table, int k, int L, int W, int finalized, uint64_t *counts
   }
 }
 
+// insert_groups_kernel + insert_spilled_kernel (groups.cuh): records grouped by their first-choice bucket,
+// every group updated in a STAGED COPY of its lines (the kernel's shared memory), copied back, and the
+// records that found their bucket full inserted through the ordinary path afterwards.
+template <int N>
+int insert_grouped(const uint32_t *recs, uint64_t n, int L, int W, int max_rehash, uint32_t bpg, uint8_t *table,
+                   GraphCounters *ctr, uint64_t *n_spilled) {
+  constexpr int RECW = 2 * N + 1;
+  const TableView tv = make_table_view(table, N, L, W, max_rehash, false);
+  const uint64_t n_groups = ((uint64_t)tv.bucket_mask + 1) / bpg, gbytes = group_bytes(tv, bpg);
+  std::vector<std::vector<uint64_t>> by_group(n_groups);  // the caller's sort by group
+  for (uint64_t i = 0; i < n; i++) by_group[group_of_record<N>(tv, recs + i * RECW, bpg)].push_back(i);
+  std::vector<uint8_t> staged(gbytes);
+  std::vector<uint64_t> spill;
+  for (uint64_t g = 0; g < n_groups; g++) {
+    if (by_group[g].empty()) continue;
+    memcpy(staged.data(), tv.lines + g * gbytes, gbytes);
+    const TableView local = group_local_view(tv, staged.data(), g, bpg);
+    for (uint64_t i : by_group[g]) {
+      const int r = group_upsert<N, HostOps>(local, ctr, recs + i * RECW);
+      if (r == 1) ctr->unique_kmers++;
+      if (r < 0) spill.push_back(i);
+    }
+    memcpy(tv.lines + g * gbytes, staged.data(), gbytes);
+  }
+  for (uint64_t i : spill) {
+    uint64_t key[N];
+    uint32_t edge, count;
+    group_load_record<N>(recs + i * RECW, key, edge, count);
+    if (table_upsert<N, HostOps>(tv, ctr, key, edge, count) == 1) ctr->unique_kmers++;
+  }
+  *n_spilled = spill.size();
+  return ctr->table_full ? -3 : 0;
+}
+
 }  // namespace
 
 #define DISPATCH(N, call) ((N) == 1 ? call<1> : (N) == 2 ? call<2> : call<3>)
@@ -495,6 +530,18 @@ int emul_branches(uint8_t *table, int k, int L, int W, int finalized, const char
 void emul_health(uint8_t *table, int k, int L, int W, int finalized, uint64_t *counts5) {
   const int N = 2 * k / 64 + 1;
   DISPATCH(N, health)(table, k, L, W, finalized, counts5);
+}
+
+int emul_insert_grouped(const uint32_t *recs, uint64_t n, int k, int L, int W, int max_rehash, uint32_t buckets_per_group,
+                        uint8_t *table, uint64_t *counters20, uint64_t *n_spilled) {
+  GraphCounters ctr;
+  memset(&ctr, 0, sizeof ctr);
+  const int N = 2 * k / 64 + 1;
+  const int rc = DISPATCH(N, insert_grouped)(recs, n, L, W, max_rehash, buckets_per_group, table, &ctr, n_spilled);
+  counters20[0] = ctr.unique_kmers;
+  counters20[2] = ctr.table_full;
+  for (int r = 0; r < 16; r++) counters20[3 + r] = ctr.rehash_hist[r];
+  return rc;
 }
 
 // kmer_revcomp of supernodes.cuh, for known-answer checks

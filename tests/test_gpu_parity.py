@@ -1220,3 +1220,47 @@ def test_gpu_health_check_at_full_config0_size():
         assert h["nodes_checked"] == s["n_nodes"] > 100_000_000
         assert h["edges_checked"] == s["sum_edge_bits"]
         assert h["missing_target"] == h["missing_return_arrow"] == 0
+
+
+@_first_device_run
+@pytest.mark.parametrize("name,bpg", [("synth_cfg0_k53", 4), ("synth_cfg1_k31", 2), ("synth_cfg2_k95", 4),
+                                      ("synth_full_k53", 4), ("synth_full_k53", 1)])
+def test_gpu_grouped_insert_prototype(name, bpg):
+    """The streamed-insert prototype (groups.cuh): records sorted by group, every group updated in
+    shared memory and written back, full buckets spill to the ordinary path -- same graph as the reference, in one
+    batch and in two (the second meets the keys of the first)."""
+    import torch
+    meta = util.case_meta(name)
+    k, L, W = meta["k"], meta["L"], meta["W"]
+    N = lasv_b200.words_per_kmer(k)
+    seq, qual, _ = util.case_streams(name)
+    d_seq, d_qual = torch.from_numpy(seq).cuda(), torch.from_numpy(qual).cuda()
+    st_ = torch.cuda.current_stream().cuda_stream
+    n_groups = (1 << L) // bpg
+
+    def grouped(g, recs):
+        n = recs.shape[0]
+        buckets = torch.empty(n, dtype=torch.int32, device="cuda")
+        _capi.check(_capi.lib().lasv_graph_record_buckets_device(g._h, recs.data_ptr(), n, buckets.data_ptr(), st_))
+        groups = (buckets.to(torch.int64) & 0xFFFFFFFF) // bpg
+        order = torch.argsort(groups, stable=True)
+        offsets = torch.searchsorted(groups[order].contiguous(),
+                                     torch.arange(n_groups + 1, device="cuda", dtype=torch.int64)).to(torch.int64)
+        torch.cuda.synchronize()
+        return g.insert_grouped_records_device(recs[order].contiguous(), n, offsets.contiguous(), bpg, st_)
+
+    for pieces in (1, 2):
+        with DBGraph(k, L, W) as g:
+            out = torch.zeros((meta["inserts"] + 8, 2 * N + 1), dtype=torch.int32, device="cuda")
+            cnt = torch.zeros(1, dtype=torch.int64, device="cuda")
+            g.extract_records_device(d_seq, d_qual, len(seq), util.cutoff_of(meta), out, out.shape[0], cnt, st_)
+            torch.cuda.synchronize()
+            n = int(cnt.item())
+            assert n == meta["inserts"]
+            spilled = 0
+            for part in torch.chunk(out[:n], pieces):
+                spilled += grouped(g, part.contiguous())
+            torch.cuda.synchronize()
+            util.assert_same_records(g.records(), util.case_records(name), name)
+            assert g.unique_kmers == meta["n_records"]
+            assert (spilled > 0) == (name == "synth_full_k53")

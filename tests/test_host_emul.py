@@ -38,6 +38,7 @@ def emul():
     L.emul_supernodes.argtypes = [C.c_void_p] + [C.c_int] * 4 + [C.c_char_p, C.c_void_p]
     L.emul_revcomp.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
     L.emul_clean.argtypes = [C.c_void_p] + [C.c_int] * 5 + [C.c_void_p]
+    L.emul_insert_grouped.argtypes = [C.c_void_p, C.c_uint64] + [C.c_int] * 4 + [C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
     L.emul_health.argtypes = [C.c_void_p] + [C.c_int] * 4 + [C.c_void_p]
     L.emul_branches.argtypes = [C.c_void_p] + [C.c_int] * 4 + [C.c_char_p, C.c_int, C.c_void_p]
     L.emul_hash_c.restype = C.c_uint32
@@ -654,3 +655,42 @@ def test_emulated_health_check(emul, name):
     tab.raw[at] = old | (1 << free)
     h = emul_health(emul, tab)
     assert h["missing_target"] + h["missing_return_arrow"] == 1 and h["edges_checked"] == before["edges_checked"] + 1
+
+
+# ---- streamed-insert prototype (groups.cuh): records grouped by first-choice bucket, groups updated in a staged copy ----
+@pytest.mark.parametrize("name,bpg", [("synth_cfg0_k53", 4), ("synth_cfg1_k31", 1), ("synth_cfg2_k95", 8),
+                                      ("edge_pe_k65_q5", 2), ("synth_full_k53", 4), ("synth_full_k53", 1)])
+def test_emulated_grouped_insert(emul, name, bpg):
+    """Same graph as the random-access insert -- also when buckets fill up and keys leave their group through
+    the rehash chain (synth_full_k53: 90 % full table) -- and the same rehash histogram."""
+    meta = util.case_meta(name)
+    k, L, W = meta["k"], meta["L"], meta["W"]
+    N = words_per_kmer(k)
+    seq, qual, _ = util.case_streams(name)
+    cap = meta["inserts"] + 10
+    recs = np.zeros((cap, 2 * N + 1), dtype=np.uint32)
+    n = emul.emul_extract_records(seq.ctypes.data, qual.ctypes.data, len(seq), k, util.cutoff_of(meta), 384,
+                                  recs.ctypes.data, cap)
+    assert n == meta["inserts"]
+    tab = EmulTable(emul, k, L, W)
+    ctr, spilled = np.zeros(20, dtype=np.uint64), C.c_uint64(0)
+    rc = emul.emul_insert_grouped(recs.ctypes.data, n, k, L, W, 15, bpg, tab.ptr, ctr.ctypes.data, C.byref(spilled))
+    assert rc == 0
+    util.assert_same_records(tab.records(), util.case_records(name), name)
+    assert int(ctr[0]) == meta["n_records"]
+    if name == "synth_full_k53":
+        assert spilled.value > 0                                   # keys that left their group
+        # every key sits on its reference rehash chain: the reference's find locates all of them after finalisation
+        tab.finalize()
+        keys = np.ascontiguousarray(util.case_records(name)["kmer"])
+        found, _, _ = tab.find(keys)
+        assert found.all()
+    else:
+        assert spilled.value == 0
+    # in two halves (a second batch meets the keys of the first)
+    tab2 = EmulTable(emul, k, L, W)
+    for part in (recs[: n // 2], recs[n // 2: n]):
+        part = np.ascontiguousarray(part)
+        assert emul.emul_insert_grouped(part.ctypes.data, len(part), k, L, W, 15, bpg, tab2.ptr, ctr.ctypes.data,
+                                        C.byref(spilled)) == 0
+    util.assert_same_records(tab2.records(), util.case_records(name), name)
