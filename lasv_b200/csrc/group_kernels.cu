@@ -3,8 +3,10 @@
 //
 //   insert_groups_kernel   persistent CTAs; per group: lines global -> shared (128-bit loads, whole lines,
 //                          coalesced), records applied in shared memory, lines shared -> global
+//   insert_groups_bulk_kernel  the same with cp.async.bulk staging, double buffered (LASV_B200_GROUPS_BULK=1)
 //   insert_spilled_kernel  the records whose bucket was full, through the ordinary table_upsert
 #include <stdint.h>
+#include <stdlib.h>
 
 #include <type_traits>
 
@@ -75,6 +77,79 @@ __global__ void __launch_bounds__(GR_THREADS) insert_groups_kernel(const uint32_
   if ((threadIdx.x & 31) == 0 && my_new) atomicAdd(&ctr->unique_kmers, my_new);
 }
 
+// The same with the copy engines of the SM doing the staging (cp.async.bulk, 1-D TMA copies), double buffered:
+// while the records of group i are applied in one buffer, group i+1 (the CTA's next group that has records)
+// arrives in the other and group i-1 is on its way back.  One thread issues the copies; an mbarrier per buffer
+// counts the arriving bytes; the write-back of a buffer must have READ it before the buffer is refilled
+// (wait_group.read), and the updates made through the generic proxy are fenced before the async proxy reads them.
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+template <int N>
+__global__ void __launch_bounds__(GR_THREADS) insert_groups_bulk_kernel(const uint32_t *__restrict__ recs,
+                                                                       const uint64_t *__restrict__ group_offsets,
+                                                                       const uint64_t n_groups, const uint32_t buckets_per_group,
+                                                                       const TableView t, GraphCounters *ctr, uint32_t *spill,
+                                                                       unsigned long long *n_spill, const uint64_t spill_cap) {
+  constexpr int RECW = 2 * N + 1;
+  extern __shared__ __align__(128) unsigned char staged[];
+  __shared__ __align__(8) uint64_t mbar[2];
+  const uint32_t gbytes = (uint32_t)group_bytes(t, buckets_per_group);
+  unsigned char *bufs[2] = {staged, staged + gbytes};
+  if (threadIdx.x == 0) {
+    for (int b = 0; b < 2; b++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(&mbar[b])));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  auto next_with_records = [&](uint64_t g) {  // the same value in every thread
+    for (; g < n_groups; g += gridDim.x)
+      if (group_offsets[g] != group_offsets[g + 1]) return g;
+    return n_groups;
+  };
+  auto load = [&](uint64_t g, int b) {  // one thread
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(&mbar[b])), "r"(gbytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(bufs[b])),
+                 "l"(t.lines + g * (uint64_t)gbytes), "r"(gbytes), "r"(smem_addr(&mbar[b]))
+                 : "memory");
+  };
+  unsigned long long my_new = 0;
+  uint64_t g = next_with_records(blockIdx.x);
+  if (threadIdx.x == 0 && g < n_groups) load(g, 0);
+  for (uint32_t it = 0; g < n_groups; it++) {
+    const int b = it & 1;
+    const uint64_t gn = next_with_records(g + gridDim.x);
+    if (threadIdx.x == 0) {
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the other buffer's write-back has read it
+      if (gn < n_groups) load(gn, b ^ 1);
+    }
+    const uint32_t parity = (it >> 1) & 1u;
+    uint32_t done = 0;
+    while (!done)
+      asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                   : "=r"(done) : "r"(smem_addr(&mbar[b])), "r"(parity) : "memory");
+    const TableView local = group_local_view(t, bufs[b], g, buckets_per_group);
+    for (uint64_t i = group_offsets[g] + threadIdx.x, hi = group_offsets[g + 1]; i < hi; i += GR_THREADS) {
+      const int r = group_upsert<N, SmemOps>(local, ctr, recs + i * RECW);
+      my_new += (r == 1);
+      if (r < 0) {
+        const unsigned long long at = atomicAdd(n_spill, 1ull);
+        if (at < spill_cap) spill[at] = (uint32_t)i;
+      }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // my updates -> visible to the bulk copy
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(t.lines + g * (uint64_t)gbytes),
+                   "r"(smem_addr(bufs[b])), "r"(gbytes) : "memory");
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+    g = gn;
+  }
+  if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+#pragma unroll
+  for (int o = 16; o; o >>= 1) my_new += __shfl_xor_sync(0xFFFFFFFFu, my_new, o);
+  if ((threadIdx.x & 31) == 0 && my_new) atomicAdd(&ctr->unique_kmers, my_new);
+}
+
 template <int N>
 __global__ void __launch_bounds__(GR_THREADS) insert_spilled_kernel(const uint32_t *__restrict__ recs,
                                                                    const uint32_t *__restrict__ spill, const uint64_t n,
@@ -107,17 +182,21 @@ void launch_insert_groups(int N, const uint32_t *recs, const uint64_t *group_off
                           uint32_t buckets_per_group, const TableView &t, GraphCounters *ctr, uint32_t *spill,
                           unsigned long long *n_spill, uint64_t spill_cap, cudaStream_t st) {
   if (!n_groups) return;
-  const size_t smem = (size_t)group_bytes(t, buckets_per_group);
+  // LASV_B200_GROUPS_BULK=1: staging by cp.async.bulk, double buffered (two buffers per CTA)
+  const char *e = getenv("LASV_B200_GROUPS_BULK");
+  const bool bulk = e && atoi(e) != 0 && 2 * group_bytes(t, buckets_per_group) <= insert_groups_smem_limit();
+  const size_t smem = (size_t)group_bytes(t, buckets_per_group) * (bulk ? 2 : 1);
   gr_dispatch(N, [&](auto nn) {
     constexpr int NN = decltype(nn)::value;
-    cudaFuncSetAttribute(insert_groups_kernel<NN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    auto kernel = bulk ? insert_groups_bulk_kernel<NN> : insert_groups_kernel<NN>;
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     int per_sm = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, insert_groups_kernel<NN>, GR_THREADS, smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, GR_THREADS, smem);
     if (per_sm < 1) per_sm = 1;
     uint64_t grid = (uint64_t)per_sm * (uint64_t)sm_count();  // persistent: resident CTAs x SMs
     if (grid > n_groups) grid = n_groups;
-    insert_groups_kernel<NN><<<(unsigned)grid, GR_THREADS, smem, st>>>(recs, group_offsets, n_groups, buckets_per_group, t,
-                                                                        ctr, spill, n_spill, spill_cap);
+    kernel<<<(unsigned)grid, GR_THREADS, smem, st>>>(recs, group_offsets, n_groups, buckets_per_group, t, ctr, spill, n_spill,
+                                                    spill_cap);
   });
 }
 

@@ -1223,13 +1223,15 @@ def test_gpu_health_check_at_full_config0_size():
 
 
 @_first_device_run
+@pytest.mark.parametrize("bulk", [0, 1])
 @pytest.mark.parametrize("name,bpg", [("synth_cfg0_k53", 4), ("synth_cfg1_k31", 2), ("synth_cfg2_k95", 4),
                                       ("synth_full_k53", 4), ("synth_full_k53", 1)])
-def test_gpu_grouped_insert_prototype(name, bpg):
+def test_gpu_grouped_insert_prototype(name, bpg, bulk, monkeypatch):
     """The streamed-insert prototype (groups.cuh): records sorted by group, every group updated in
     shared memory and written back, full buckets spill to the ordinary path -- same graph as the reference, in one
     batch and in two (the second meets the keys of the first)."""
     import torch
+    monkeypatch.setenv("LASV_B200_GROUPS_BULK", str(bulk))      # 1: cp.async.bulk staging, double buffered
     meta = util.case_meta(name)
     k, L, W = meta["k"], meta["L"], meta["W"]
     N = lasv_b200.words_per_kmer(k)

@@ -9,6 +9,7 @@ the bins instead).  Both graphs must have the same fingerprint.
     python tools/grouped_insert_speed.py [pairs_per_batch] [buckets_per_group] [L]
 """
 import json
+import os
 import sys
 from pathlib import Path
 
@@ -29,7 +30,8 @@ batch = 1 << 20
 d_seq = torch.empty(2 * max(pairs, batch) * stride + 16, dtype=torch.uint8, device="cuda")
 d_qual = torch.empty_like(d_seq)
 out = {"what": "insert_groups_kernel (prototype) vs insert_records_kernel", "k": w.kmer_size, "L": L, "W": w.bucket_size,
-       "pairs_per_batch": pairs, "buckets_per_group": bpg}
+       "pairs_per_batch": pairs, "buckets_per_group": bpg,
+       "staging": "cp.async.bulk, double buffered" if os.environ.get("LASV_B200_GROUPS_BULK", "0") != "0" else "ldg/stg"}
 
 
 def event_ms(fn):
