@@ -1020,12 +1020,13 @@ def test_config0_full_size_properties():
         assert np.array_equal(O.sort_records(g.records()), O.sort_records(og.records()))
 
 
-# ---- branch printing: `--mode build`'s ./branches.fa on the device ------------------------------
-# Written after the round's GPU minutes were spent: exact against the oracle on the CPU emulation
-# (tests/test_host_emul.py, same record writer and replay), NOT YET RUN ON A DEVICE.  The cases sit at the very end
-# of the GPU suite and are non-strict xfail until they have: an XPASS in the log is their first green run on a
+# ---- written after the round's GPU minutes were spent: NOT YET RUN ON A DEVICE -------------------------------------
+# Branch printing (`--mode build`'s ./branches.fa), the cleaning on a graph handle with the pruned-aware
+# `.ctx` dump, `--health_check`, and the streamed-insert prototype.  All are exact against the oracle on the CPU emulation
+# (tests/test_host_emul.py: same record writers, same replay, same table protocol).  The cases sit at the very end of the
+# GPU suite and are non-strict xfail until they have run: an XPASS in the log (`-rxX`) is their first green run on a
 # B200, a failure cannot hide or cut short any verified test above.  Remove the marker once seen green.
-_first_device_run = pytest.mark.xfail(strict=False, reason="branch printing: first run on a device (see comment)")
+_first_device_run = pytest.mark.xfail(strict=False, reason="first run on a device pending (see the comment above the marker)")
 
 
 def _oracle_branches_in_table_order(k, L, W, recs, path):
