@@ -472,6 +472,8 @@ def test_emulated_cleaning_and_supernodes_on_repetitive_graphs(emul, alphabet, s
         og, _ = oracle_clean_in_order(tab, thresh)
         emul_clean(emul, tab, thresh)
         assert np.array_equal(tab.records(), og.records()), (alphabet, k, thresh, reads)
+        h = emul_health(emul, tab)                        # the cleaning keeps every remaining arrow paired
+        assert h["missing_target"] == h["missing_return_arrow"] == 0, (alphabet, k, thresh, reads)
         st = emul_supernodes(emul, tab, tmp_path / "ours.fa")
         og.print_supernodes(tmp_path / "oracle.fa", max_length=1 << 20)
         assert (tmp_path / "ours.fa").read_bytes() == (tmp_path / "oracle.fa").read_bytes(), (alphabet, k, thresh, reads)
