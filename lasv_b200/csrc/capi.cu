@@ -1026,7 +1026,7 @@ int lasv_graph_write_supernodes(lasv_graph *g, const char *fasta_path, int max_l
   std::vector<SnPrint> prints;
   SnReplayStats rs;
   uint64_t over = 0;
-  // LASV_B200_SN_TRACE=1: stage times on stderr (tools/supernodes_speed.py)
+  // LASV_B200_SN_TRACE=1: stage times on stderr (tests/perf/supernodes_speed.py)
   const bool trace = getenv("LASV_B200_SN_TRACE") != nullptr;
   auto t_last = std::chrono::steady_clock::now();
   auto stage = [&](const char *what) {

@@ -10,7 +10,7 @@ exports the reference table, times the three calls, then lets the reference relo
 `.ctx` (same slot order) and run the same steps, and compares branches.fa and the cleaned
 `.ctx` byte for byte / record for record.
 
-    python tools/build_mode_speed.py [genome_len] [L] [threshold] [--no-ref]
+    python tests/perf/build_mode_speed.py [genome_len] [L] [threshold] [--no-ref]
 """
 import ctypes as C
 import json
@@ -22,7 +22,7 @@ from pathlib import Path
 
 import numpy as np
 
-sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
+sys.path.insert(0, str(Path(__file__).resolve().parents[2]))
 import torch  # noqa: E402
 from lasv_b200 import DBGraph, _capi, synth  # noqa: E402
 from oracle import oracle as O  # noqa: E402  (reference runner only: test infrastructure)

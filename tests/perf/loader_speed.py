@@ -2,7 +2,7 @@
 """End-to-end speed of the file loaders (FASTQ text -> graph): the parse is the slow end."""
 import os, sys, time, json
 from pathlib import Path
-sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
+sys.path.insert(0, str(Path(__file__).resolve().parents[2]))
 from lasv_b200 import DBGraph, synth
 from oracle import oracle as O   # FASTQ writer only (test infrastructure)
 

@@ -4,7 +4,7 @@
 device-generated reads, times DBGraph.output_supernodes, then lets the reference reload the
 dumped `.ctx` and print its supernodes, and compares the two FASTA files byte for byte.
 
-    python tools/supernodes_speed.py [genome_len] [L] [--no-ref]
+    python tests/perf/supernodes_speed.py [genome_len] [L] [--no-ref]
 """
 import json
 import os
@@ -13,7 +13,7 @@ import sys
 import time
 from pathlib import Path
 
-sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
+sys.path.insert(0, str(Path(__file__).resolve().parents[2]))
 import torch  # noqa: E402
 from lasv_b200 import DBGraph, synth  # noqa: E402
 from oracle import oracle as O  # noqa: E402  (reference runner only: test infrastructure)
