@@ -2087,9 +2087,8 @@ static int clean_pass(lasv_graph *g, int what, uint32_t threshold, lasv_clean_st
     cg.nodes.reserve(n_nodes);
     for (const ClNodeRec &r : nodes) cg.add_node(r.q, r.covg, r.edges);
     cg.seal_nodes(g->n_slots);
-    cg.paths.reserve(n_paths);
-    for (uint64_t i = 0; i < n_paths; i++)
-      if (!cg.add_path(recs[i], mx[i], low[i])) return fail(LASV_ERR_STATE, "a path ends in a node that is not in the node list");
+    if (!cg.add_paths(recs.data(), mx.data(), low.data(), n_paths))
+      return fail(LASV_ERR_STATE, "a path ends in a node that is not in the node list");
     for (uint64_t i = n_paths; i < n_rec; i++) {
       ClCycle c;
       c.s_q = recs[i].s_q;
@@ -2320,9 +2319,8 @@ int lasv_graph_write_branches(lasv_graph *g, const char *fasta_path, int mark_vi
     cg.nodes.reserve(n_nodes);
     for (const ClNodeRec &r : nodes) cg.add_node(r.q, r.covg, r.edges);
     cg.seal_nodes(g->n_slots);
-    cg.paths.reserve(n_paths);
-    for (uint64_t i = 0; i < n_paths; i++)
-      if (!cg.add_path(recs[i], 0u, SN_NONE)) return fail(LASV_ERR_STATE, "a path ends in a node that is not in the node list");
+    if (!cg.add_paths(recs.data(), nullptr, nullptr, n_paths))
+      return fail(LASV_ERR_STATE, "a path ends in a node that is not in the node list");
     std::vector<BrPrint> prints;
     BrReplay replay(cg, g->k);
     bs = replay.run(prints);

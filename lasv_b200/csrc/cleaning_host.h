@@ -32,6 +32,8 @@
 #include <stdint.h>
 
 #include <algorithm>
+#include <atomic>
+#include <thread>
 #include <vector>
 
 #include "cleaning.cuh"
@@ -144,6 +146,53 @@ class ClGraph {
     nodes[c.b].adj[c.b_bit] = id;
     paths.push_back(c);
     return true;
+  }
+
+  // All path records at once (cycles excluded): the ends of a path are looked up in the slot map and its id
+  // is written into two adjacency entries that no other path writes (an edge bit of a node leads into exactly
+  // one path), so ranges of records go to threads without any locking.  max_covg / min_low_q may be NULL
+  // (branch printing needs neither).  False if an end node is unknown.
+  static uint64_t &parallel_min() {  // fewer records than this are not worth threads (tests lower it)
+    static uint64_t v = 1u << 18;
+    return v;
+  }
+  bool add_paths(const SnPath *recs, const uint32_t *max_covg, const uint64_t *min_low_q, uint64_t n) {
+    const size_t base = paths.size();
+    paths.resize(base + (size_t)n);
+    std::atomic<bool> ok(true);
+    auto work = [&](uint64_t lo, uint64_t hi) {
+      for (uint64_t i = lo; i < hi; i++) {
+        const SnPath &p = recs[i];
+        ClPath c;
+        c.a = index_of(p.s_q);
+        c.b = index_of(p.t_q);
+        if (c.a < 0 || c.b < 0) { ok = false; c.a = c.b = 0; }
+        c.a_bit = (uint8_t)(((p.bits & SNB_S_O) ? 4u : 0u) | ((p.bits >> SNB_S_N) & 3u));
+        c.b_bit = (uint8_t)(((p.bits & SNB_T_O) ? 4u : 0u) | ((p.bits >> SNB_T_N) & 3u));
+        c.alive = 1;
+        c.visited = 0;
+        c.len = p.len;
+        c.max_covg = max_covg ? max_covg[i] : 0u;
+        c.min_low_q = min_low_q ? min_low_q[i] : SN_NONE;
+        c.s_q = p.s_q;
+        c.s_on = ((p.bits & SNB_S_O) ? 1u : 0u) | (((p.bits >> SNB_S_N) & 3u) << 1);
+        const int32_t id = (int32_t)(base + i);
+        if (ok) {
+          nodes[(size_t)c.a].adj[c.a_bit] = id;
+          nodes[(size_t)c.b].adj[c.b_bit] = id;
+        }
+        paths[(size_t)id] = c;
+      }
+    };
+    unsigned threads = n >= parallel_min() ? std::min(8u, std::max(2u, std::thread::hardware_concurrency() / 2)) : 1u;
+    if (threads <= 1) {
+      work(0, n);
+    } else {
+      std::vector<std::thread> pool;
+      for (unsigned t = 0; t < threads; t++) pool.emplace_back(work, n * t / threads, n * (t + 1) / threads);
+      for (auto &th : pool) th.join();
+    }
+    return ok;
   }
 
   // ------------------------------------------------------------------ helpers

@@ -295,6 +295,9 @@ bool build_cl_graph(const TableView &tv, int k, uint32_t T, ClGraph &g) {
   }
   g.seal_nodes(n_slots);
   bool ok = true;
+  std::vector<SnPath> p_recs;
+  std::vector<uint32_t> p_max;
+  std::vector<uint64_t> p_low;
   const size_t n_nodes = g.nodes.size();
   for (size_t i = 0; i < n_nodes; i++) {
     const uint64_t q = g.nodes[i].q;
@@ -308,11 +311,15 @@ bool build_cl_graph(const TableView &tv, int k, uint32_t T, ClGraph &g) {
       if (sn_walk_path<N, HostOps>(tv, k, q, key, e, bit >> 2, bit & 3u, max_steps, covered.data(), rec, d)) {
         uint32_t mx = 0;
         uint64_t lo = SN_NONE;
-        ok = ok && cl_path_coverage<N, HostOps>(tv, k, rec, T, mx, lo) && g.add_path(rec, mx, lo);
+        ok = ok && cl_path_coverage<N, HostOps>(tv, k, rec, T, mx, lo);
+        p_recs.push_back(rec);
+        p_max.push_back(mx);
+        p_low.push_back(lo);
       }
       ok = ok && !d;
     }
   }
+  ok = g.add_paths(p_recs.data(), p_max.data(), p_low.data(), p_recs.size()) && ok;  // as the library does
   for (uint64_t q = 0; q < n_slots; q++) {
     if (covered[q] || (sn_classify<N, HostOps>(tv, q) & 3u) != 3u) continue;
     uint64_t key[N];
@@ -543,6 +550,9 @@ int emul_insert_grouped(const uint32_t *recs, uint64_t n, int k, int L, int W, i
   for (int r = 0; r < 16; r++) counters20[3 + r] = ctr.rehash_hist[r];
   return rc;
 }
+
+// threads for ClGraph::add_paths from this many path records on (tests force the threaded branch)
+void emul_set_parallel_min(uint64_t n) { ClGraph::parallel_min() = n; }
 
 // kmer_revcomp of supernodes.cuh, for known-answer checks
 void emul_revcomp(const uint64_t *in, int k, uint64_t *out) {

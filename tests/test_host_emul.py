@@ -39,6 +39,7 @@ def emul():
     L.emul_revcomp.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
     L.emul_clean.argtypes = [C.c_void_p] + [C.c_int] * 5 + [C.c_void_p]
     L.emul_insert_grouped.argtypes = [C.c_void_p, C.c_uint64] + [C.c_int] * 4 + [C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.emul_set_parallel_min.argtypes = [C.c_uint64]
     L.emul_health.argtypes = [C.c_void_p] + [C.c_int] * 4 + [C.c_void_p]
     L.emul_branches.argtypes = [C.c_void_p] + [C.c_int] * 4 + [C.c_char_p, C.c_int, C.c_void_p]
     L.emul_hash_c.restype = C.c_uint32
@@ -696,3 +697,21 @@ def test_emulated_grouped_insert(emul, name, bpg):
         assert emul.emul_insert_grouped(part.ctypes.data, len(part), k, L, W, 15, bpg, tab2.ptr, ctr.ctypes.data,
                                         C.byref(spilled)) == 0
     util.assert_same_records(tab2.records(), util.case_records(name), name)
+
+
+def test_emulated_compressed_graph_built_by_threads(emul, tmp_path):
+    """ClGraph::add_paths hands ranges of path records to threads (no two paths write the same adjacency entry):
+    forced on for a small graph, cleaning and branch printing must not change."""
+    name, thresh = "synth_cfg0_k53", 2
+    meta = util.case_meta(name)
+    seq, qual, _ = util.case_streams(name)
+    emul.emul_set_parallel_min(1)
+    try:
+        rc, tab, _ = emul_build(emul, meta, seq, qual)
+        assert rc == 0
+        check_branches(emul, tab, tmp_path)
+        og, ost = oracle_clean_in_order(tab, thresh)
+        st = emul_clean(emul, tab, thresh)
+        assert np.array_equal(tab.records(), og.records()) and st["supernodes_pruned"] == ost["supernodes_pruned"] > 0
+    finally:
+        emul.emul_set_parallel_min(1 << 18)
