@@ -33,6 +33,7 @@
 #include "cleaning_host.h"
 #include "branches_host.h"
 #include "groups.cuh"
+#include "ranking.cuh"
 #include "seq_reader.h"
 
 using namespace lasv;
@@ -1000,6 +1001,21 @@ int lasv_graph_import_table(lasv_graph *g, const void *elements) {
   return rc;
 }
 
+// Path records of all starts: one walk per start (launch_sn_paths), or -- LASV_B200_SN_RANKING=1, for graphs with long
+// paths; opt-in until it has run on a device -- by list ranking (ranking.cuh).  Same records either way.
+static int enumerate_paths(lasv_graph *g, const TableView &tv, const uint64_t *d_starts, uint64_t n_starts,
+                           uint64_t n_interior, uint8_t *d_covered, SnPath *d_recs, SnCounters *d_c) {
+  const char *e = getenv("LASV_B200_SN_RANKING");
+  if (e && atoi(e) != 0) {
+    const cudaError_t err = sn_paths_ranked(g->N, tv, g->k, d_starts, n_starts, n_interior, d_covered, d_recs, n_starts,
+                                            d_c, g->compute);
+    if (err != cudaSuccess) return fail(LASV_ERR_CUDA, "path enumeration by list ranking failed: %s", cudaGetErrorString(err));
+    return LASV_OK;
+  }
+  launch_sn_paths(g->N, tv, g->k, d_starts, n_starts, d_covered, d_recs, n_starts, d_c, g->compute);
+  return n_starts ? check_launch() : LASV_OK;
+}
+
 // ------------------------------------------------------------- supernodes
 // `--output_supernodes`: enumerate all paths on the device, replay the reference's
 // sequential traversal over the path records on the host, write the sequences on
@@ -1059,9 +1075,7 @@ int lasv_graph_write_supernodes(lasv_graph *g, const char *fasta_path, int max_l
     launch_sn_starts(g->N, tv, d_starts, n_starts, d_n, d_c, g->compute);
     if (int e = check_launch()) return e;
     stage("list starts");
-    launch_sn_paths(g->N, tv, g->k, d_starts, n_starts, d_covered, d_recs, n_starts, d_c, g->compute);
-    if (n_starts)
-      if (int e = check_launch()) return e;
+    if (int e = enumerate_paths(g, tv, d_starts, n_starts, h_c.n_interior, d_covered, d_recs, d_c)) return e;
     stage("walk paths");
     // interior nodes no path crossed lie on cycles: count, list, walk
     launch_sn_uncovered(g->N, tv, d_covered, nullptr, 0, d_c, g->compute);
@@ -2028,9 +2042,7 @@ static int clean_pass(lasv_graph *g, int what, uint32_t threshold, lasv_clean_st
     CUDA_TRY(cudaMemsetAsync(d_covered, 0, g->n_slots, g->compute));
     launch_sn_starts(g->N, tv, d_starts, n_starts, d_n, d_c, g->compute);
     if (int e = check_launch()) return e;
-    launch_sn_paths(g->N, tv, g->k, d_starts, n_starts, d_covered, d_recs, n_starts, d_c, g->compute);
-    if (n_starts)
-      if (int e = check_launch()) return e;
+    if (int e = enumerate_paths(g, tv, d_starts, n_starts, h_c.n_interior, d_covered, d_recs, d_c)) return e;
     launch_sn_uncovered(g->N, tv, d_covered, nullptr, 0, d_c, g->compute);
     if (int e = check_launch()) return e;
     if (int e = sync_counters()) return e;
@@ -2295,9 +2307,7 @@ int lasv_graph_write_branches(lasv_graph *g, const char *fasta_path, int mark_vi
     CUDA_TRY(cudaMalloc(&d_recs, std::max<uint64_t>(1, n_starts) * sizeof(SnPath)));
     launch_sn_starts(g->N, tv, d_starts, n_starts, d_n, d_c, g->compute);
     if (int e = check_launch()) return e;
-    launch_sn_paths(g->N, tv, g->k, d_starts, n_starts, nullptr, d_recs, n_starts, d_c, g->compute);
-    if (n_starts)
-      if (int e = check_launch()) return e;
+    if (int e = enumerate_paths(g, tv, d_starts, n_starts, h_c.n_interior, nullptr, d_recs, d_c)) return e;
     if (int e = sync_counters()) return e;
     if (h_c.n_overflow) return fail(LASV_ERR_STATE, "path record buffers overflowed (internal sizing error)");
     if (h_c.n_dangling)

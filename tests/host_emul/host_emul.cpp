@@ -21,6 +21,7 @@
 #include "../../lasv_b200/csrc/branches.cuh"
 #include "../../lasv_b200/csrc/branches_host.h"
 #include "../../lasv_b200/csrc/groups.cuh"
+#include "../../lasv_b200/csrc/ranking.cuh"
 
 using namespace lasv;
 
@@ -225,6 +226,48 @@ void find(uint8_t *table, int L, int W, int max_rehash, int finalized, const uin
 }
 
 // the supernode kernels of supernode_kernels.cu, slot by slot / start by start, + the replay
+// sn_paths_ranked (ranking_kernels.cu): the path records by list ranking instead of one walk per start
+bool g_ranked = false;
+template <int N>
+void ranked_enumerate(const TableView &tv, int k, const std::vector<uint64_t> &starts, std::vector<SnPath> &recs,
+                      std::vector<uint8_t> &covered, uint64_t &dangling) {
+  const uint64_t n_slots = ((uint64_t)tv.bucket_mask + 1) * tv.W, n_words = (n_slots + 63) / 64;
+  std::vector<uint64_t> bits(n_words, 0), rank(n_words, 0);
+  for (uint64_t q = 0; q < n_slots; q++)  // rk_flags_kernel
+    if ((sn_classify<N, HostOps>(tv, q) & 3u) == 3u) bits[q >> 6] |= 1ull << (q & 63);
+  uint64_t n_int = 0;
+  for (uint64_t w = 0; w < n_words; w++) { rank[w] = n_int; n_int += rk_popc64(bits[w]); }  // rk_popc_kernel + scan
+  const RkMap map{bits.data(), rank.data()};
+  std::vector<RkElem> el[2] = {std::vector<RkElem>(2 * n_int + 1), std::vector<RkElem>(2 * n_int + 1)};
+  for (uint64_t q = 0; q < n_slots; q++) {  // rk_init_kernel
+    if (!((bits[q >> 6] >> (q & 63)) & 1ull)) continue;
+    for (uint32_t o = 0; o < 2; o++)
+      if (!rk_init<N, HostOps>(tv, k, map, q, o, el[0][2u * rk_cid(map, q) + o])) dangling++;
+  }
+  int cur = 0;
+  uint64_t prev = ~0ull;
+  for (int round = 0; round < 64 && n_int; round++) {  // rk_jump_kernel
+    uint64_t active = 0;
+    for (uint64_t i = 0; i < 2 * n_int; i++) active += rk_jump(el[cur].data(), (uint32_t)i, el[cur ^ 1][i]);
+    cur ^= 1;
+    if (active == 0 || active == prev) break;
+    prev = active;
+  }
+  for (uint64_t s : starts) {  // rk_paths_kernel
+    const uint64_t q = s >> 3;
+    uint64_t key[N];
+    const uint64_t m = sn_load_node<N, HostOps>(tv, q, key);
+    SnPath rec;
+    bool d = false, u = false;
+    if (rk_path_of_start<N, HostOps>(tv, k, map, el[cur].data(), q, key, meta_edges(m), (uint32_t)(s >> 2) & 1u,
+                                     (uint32_t)s & 3u, rec, d, u))
+      recs.push_back(rec);
+    dangling += d || u;
+  }
+  for (uint64_t q = 0; q < n_slots; q++)  // rk_covered_kernel
+    if ((bits[q >> 6] >> (q & 63)) & 1ull) covered[q] = el[cur][2u * rk_cid(map, q)].succ == RK_DONE ? 1 : 0;
+}
+
 template <int N>
 int supernodes(uint8_t *table, int k, int L, int W, int finalized, const char *path, uint64_t *counts8) {
   const TableView tv = make_table_view(table, N, L, W, 15, finalized != 0);
@@ -233,6 +276,7 @@ int supernodes(uint8_t *table, int k, int L, int W, int finalized, const char *p
   std::vector<uint8_t> covered(n_slots, 0);
   std::vector<SnPath> recs;
   uint64_t nodes = 0, interior = 0, starts = 0, dangling = 0;
+  std::vector<uint64_t> rk_starts;
   for (uint64_t q = 0; q < n_slots; q++) {  // sn_count_kernel + sn_starts_kernel + sn_paths_kernel
     const uint32_t v = sn_classify<N, HostOps>(tv, q);
     nodes += v & 1u;
@@ -244,6 +288,7 @@ int supernodes(uint8_t *table, int k, int L, int W, int finalized, const char *p
     const uint32_t e = meta_edges(m);
     for (uint32_t bit = 0; bit < 8; bit++) {
       if (!((e >> bit) & 1u)) continue;
+      if (g_ranked) { rk_starts.push_back((q << 3) | bit); continue; }
       SnPath rec;
       bool d = false;
       if (sn_walk_path<N, HostOps>(tv, k, q, key, e, bit >> 2, bit & 3u, max_steps, covered.data(), rec, d))
@@ -251,6 +296,7 @@ int supernodes(uint8_t *table, int k, int L, int W, int finalized, const char *p
       dangling += d;
     }
   }
+  if (g_ranked) ranked_enumerate<N>(tv, k, rk_starts, recs, covered, dangling);
   const uint64_t n_paths = recs.size();
   uint64_t uncovered = 0;
   for (uint64_t q = 0; q < n_slots; q++) {  // sn_uncovered_kernel + sn_cycles_kernel
@@ -295,6 +341,7 @@ bool build_cl_graph(const TableView &tv, int k, uint32_t T, ClGraph &g) {
   }
   g.seal_nodes(n_slots);
   bool ok = true;
+  std::vector<uint64_t> rk_starts;
   std::vector<SnPath> p_recs;
   std::vector<uint32_t> p_max;
   std::vector<uint64_t> p_low;
@@ -306,6 +353,7 @@ bool build_cl_graph(const TableView &tv, int k, uint32_t T, ClGraph &g) {
     const uint32_t e = meta_edges(m);
     for (uint32_t bit = 0; bit < 8; bit++) {
       if (!((e >> bit) & 1u)) continue;
+      if (g_ranked) { rk_starts.push_back((q << 3) | bit); continue; }
       SnPath rec;
       bool d = false;
       if (sn_walk_path<N, HostOps>(tv, k, q, key, e, bit >> 2, bit & 3u, max_steps, covered.data(), rec, d)) {
@@ -317,6 +365,18 @@ bool build_cl_graph(const TableView &tv, int k, uint32_t T, ClGraph &g) {
         p_low.push_back(lo);
       }
       ok = ok && !d;
+    }
+  }
+  if (g_ranked) {
+    uint64_t dangling = 0;
+    ranked_enumerate<N>(tv, k, rk_starts, p_recs, covered, dangling);
+    ok = ok && !dangling;
+    for (const SnPath &rec : p_recs) {
+      uint32_t mx = 0;
+      uint64_t lo = SN_NONE;
+      ok = ok && cl_path_coverage<N, HostOps>(tv, k, rec, T, mx, lo);
+      p_max.push_back(mx);
+      p_low.push_back(lo);
     }
   }
   ok = g.add_paths(p_recs.data(), p_max.data(), p_low.data(), p_recs.size()) && ok;  // as the library does
@@ -550,6 +610,9 @@ int emul_insert_grouped(const uint32_t *recs, uint64_t n, int k, int L, int W, i
   for (int r = 0; r < 16; r++) counters20[3 + r] = ctr.rehash_hist[r];
   return rc;
 }
+
+// path enumeration by list ranking (ranking.cuh) instead of one walk per start, for everything that follows
+void emul_set_ranking(int on) { g_ranked = on != 0; }
 
 // threads for ClGraph::add_paths from this many path records on (tests force the threaded branch)
 void emul_set_parallel_min(uint64_t n) { ClGraph::parallel_min() = n; }

@@ -1267,3 +1267,25 @@ def test_gpu_grouped_insert_prototype(name, bpg, bulk, monkeypatch):
             util.assert_same_records(g.records(), util.case_records(name), name)
             assert g.unique_kmers == meta["n_records"]
             assert (spilled > 0) == (name == "synth_full_k53")
+
+
+@_first_device_run
+@pytest.mark.parametrize("name", ["synth_cfg1_k31", "synth_cfg0_k53", "synth_cfg2_k95", "edge_pe_k21_q5"])
+def test_gpu_ranked_path_enumeration(name, tmp_path, monkeypatch):
+    """LASV_B200_SN_RANKING=1: the path records come from list ranking (ranking.cuh) instead of one walk per start;
+    supernodes, cleaning and branches built on them must be what the verified walks give."""
+    monkeypatch.setenv("LASV_B200_SN_RANKING", "1")
+    test_gpu_supernodes_match_reference(name, tmp_path)
+    if name.startswith("synth"):
+        (tmp_path / "c").mkdir()
+        test_ref_table_clean_matches_reference_walk(name, 2, tmp_path / "c")
+        (tmp_path / "b").mkdir()
+        test_gpu_branches_match_reference_walk(name, tmp_path / "b")
+
+
+@_first_device_run
+def test_gpu_ranked_cycles_long_paths_and_dense_errors(tmp_path, monkeypatch):
+    monkeypatch.setenv("LASV_B200_SN_RANKING", "1")
+    test_gpu_supernodes_cycles_and_long_paths(tmp_path)
+    (tmp_path / "d").mkdir()
+    test_ref_table_clean_dense_errors((31, 20000, 40000, 200000, 17), tmp_path / "d")

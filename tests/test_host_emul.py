@@ -40,6 +40,7 @@ def emul():
     L.emul_clean.argtypes = [C.c_void_p] + [C.c_int] * 5 + [C.c_void_p]
     L.emul_insert_grouped.argtypes = [C.c_void_p, C.c_uint64] + [C.c_int] * 4 + [C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
     L.emul_set_parallel_min.argtypes = [C.c_uint64]
+    L.emul_set_ranking.argtypes = [C.c_int]
     L.emul_health.argtypes = [C.c_void_p] + [C.c_int] * 4 + [C.c_void_p]
     L.emul_branches.argtypes = [C.c_void_p] + [C.c_int] * 4 + [C.c_char_p, C.c_int, C.c_void_p]
     L.emul_hash_c.restype = C.c_uint32
@@ -715,3 +716,42 @@ def test_emulated_compressed_graph_built_by_threads(emul, tmp_path):
         assert np.array_equal(tab.records(), og.records()) and st["supernodes_pruned"] == ost["supernodes_pruned"] > 0
     finally:
         emul.emul_set_parallel_min(1 << 18)
+
+
+# ---- path enumeration by list ranking (ranking.cuh) instead of one walk per path start ----
+@pytest.fixture
+def ranked(emul):
+    emul.emul_set_ranking(1)
+    yield emul
+    emul.emul_set_ranking(0)
+
+
+@pytest.mark.parametrize("name", ["synth_cfg1_k31", "synth_cfg0_k53", "synth_cfg2_k95", "edge_pe_k21_q5"])
+@pytest.mark.parametrize("finalized", [False, True])
+def test_ranked_supernodes_match_reference_golden(ranked, name, finalized, tmp_path):
+    test_emulated_supernodes_match_reference_golden(ranked, name, finalized, tmp_path)
+
+
+@pytest.mark.parametrize("k,err_q20,seed", [(21, 30000, 3), (31, 40000, 5), (53, 30000, 6)])
+def test_ranked_supernodes_order_dependent_cases(ranked, k, err_q20, seed, tmp_path):
+    test_emulated_supernodes_order_dependent_cases(ranked, k, err_q20, seed, tmp_path)
+
+
+def test_ranked_supernodes_cycles_and_long_paths(ranked, tmp_path):
+    """A pure cycle (elements that never finish) and a 5 969-edge path (13 rounds instead of 5 969 steps)."""
+    test_emulated_supernodes_cycles_and_long_paths(ranked, tmp_path)
+
+
+@pytest.mark.parametrize("name,thresh", [("synth_cfg1_k31", 2), ("synth_cfg0_k53", 2), ("synth_cfg2_k95", 2),
+                                         ("edge_pe_k31_q5", 3)])
+def test_ranked_cleaning_and_branches(ranked, name, thresh, tmp_path):
+    test_emulated_cleaning_matches_reference_walk(ranked, name, thresh, False, tmp_path)
+    test_emulated_branches_match_reference_walk(ranked, name, None, True, tmp_path)
+
+
+@pytest.mark.parametrize("alphabet,seed", [("CG", 22), ("ACG", 23), ("AT", 24)])
+def test_ranked_on_repetitive_graphs(ranked, alphabet, seed, tmp_path):
+    """Short cycles, palindromic paths (a node crossed in both orientations: the earlier crossing decides) and loops
+    through a junction: cleaning, supernodes and branches from ranked records equal the reference's."""
+    test_emulated_cleaning_and_supernodes_on_repetitive_graphs(ranked, alphabet, seed, tmp_path)
+    test_emulated_branches_on_repetitive_graphs(ranked, alphabet, seed, tmp_path)
