@@ -40,6 +40,23 @@ def test_header_is_plain_c(tmp_path):
                     str(src)], check=True)
 
 
+def test_product_and_tools_never_touch_the_oracle():
+    """oracle/ is test infrastructure: nothing under lasv_b200/, include/, integration/*.c or tools/ imports, links,
+    loads or executes it (bench.py and __graft_entry__.smoke() use it as the checker / CPU baseline only)."""
+    import subprocess
+    pat = re.compile(r"^\s*(from|import)\s+oracle\b|liboracle|oracle/_ref|dbg_oracle|oracle\.py", re.M)
+    offenders = []
+    for sub, globs in (("lasv_b200", ("*.py", "csrc/*.cu", "csrc/*.cuh", "csrc/*.h", "csrc/*.cpp", "csrc/Makefile")),
+                       ("include", ("*.h",)), ("integration", ("*.c",)), ("tools", ("*.py", "*.sh", "ubench/*.cu"))):
+        for g in globs:
+            for f in (ROOT / sub).glob(g):
+                if pat.search(f.read_text(errors="replace")):
+                    offenders.append(str(f.relative_to(ROOT)))
+    assert not offenders, offenders
+    out = subprocess.run(["ldd", str(ROOT / "lasv_b200" / "liblasv_b200.so")], capture_output=True, text=True).stdout
+    assert "oracle" not in out
+
+
 def test_no_cpu_fallback_without_gpu():
     lib = _capi.lib()
     if lib.lasv_device_count() > 0:
