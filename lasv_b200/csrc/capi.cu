@@ -1003,12 +1003,17 @@ int lasv_graph_import_table(lasv_graph *g, const void *elements) {
 
 // Path records of all starts: one walk per start (launch_sn_paths), or -- LASV_B200_SN_RANKING=1, for graphs with long
 // paths; opt-in until it has run on a device -- by list ranking (ranking.cuh).  Same records either way.
-static int enumerate_paths(lasv_graph *g, const TableView &tv, const uint64_t *d_starts, uint64_t n_starts,
-                           uint64_t n_interior, uint8_t *d_covered, SnPath *d_recs, SnCounters *d_c) {
+static bool ranking_wanted() {
   const char *e = getenv("LASV_B200_SN_RANKING");
-  if (e && atoi(e) != 0) {
+  return e && atoi(e) != 0;
+}
+
+static int enumerate_paths(lasv_graph *g, const TableView &tv, const uint64_t *d_starts, uint64_t n_starts,
+                           uint64_t n_interior, uint8_t *d_covered, SnPath *d_recs, SnCounters *d_c,
+                           RkState *keep = nullptr) {
+  if (ranking_wanted()) {
     const cudaError_t err = sn_paths_ranked(g->N, tv, g->k, d_starts, n_starts, n_interior, d_covered, d_recs, n_starts,
-                                            d_c, g->compute);
+                                            d_c, g->compute, keep);
     if (err != cudaSuccess) return fail(LASV_ERR_CUDA, "path enumeration by list ranking failed: %s", cudaGetErrorString(err));
     return LASV_OK;
   }
@@ -1040,6 +1045,10 @@ int lasv_graph_write_supernodes(lasv_graph *g, const char *fasta_path, int max_l
   FILE *fp = nullptr;
   constexpr uint64_t STAGE_BYTES = 16ull << 20;
   std::vector<SnPrint> prints;
+  std::vector<uint64_t> end_keys;
+  RkState ranked;  // LASV_B200_SN_RANKING=1: the ranked elements, kept for the per-node writer
+  RkPrintKey *d_print_keys = nullptr;
+  uint64_t *d_end_keys = nullptr;
   SnReplayStats rs;
   uint64_t over = 0;
   // LASV_B200_SN_TRACE=1: stage times on stderr (tests/perf/supernodes_speed.py)
@@ -1075,7 +1084,7 @@ int lasv_graph_write_supernodes(lasv_graph *g, const char *fasta_path, int max_l
     launch_sn_starts(g->N, tv, d_starts, n_starts, d_n, d_c, g->compute);
     if (int e = check_launch()) return e;
     stage("list starts");
-    if (int e = enumerate_paths(g, tv, d_starts, n_starts, h_c.n_interior, d_covered, d_recs, d_c)) return e;
+    if (int e = enumerate_paths(g, tv, d_starts, n_starts, h_c.n_interior, d_covered, d_recs, d_c, &ranked)) return e;
     stage("walk paths");
     // interior nodes no path crossed lie on cycles: count, list, walk
     launch_sn_uncovered(g->N, tv, d_covered, nullptr, 0, d_c, g->compute);
@@ -1151,6 +1160,7 @@ int lasv_graph_write_supernodes(lasv_graph *g, const char *fasta_path, int max_l
       CUDA_TRY(cudaEventCreateWithFlags(&copied[b], cudaEventDisableTiming));
     }
     SnReplayer replayer(n_rec, g->n_slots, g->k);
+    replayer.want_end_keys = ranked.el != nullptr;
     {
       const uint64_t per = STAGE_BYTES / sizeof(SnEvent);
       const uint64_t n_pieces = (n_ev + per - 1) / per;
@@ -1170,6 +1180,7 @@ int lasv_graph_write_supernodes(lasv_graph *g, const char *fasta_path, int max_l
     cudaFree(d_events); d_events = nullptr;
     rs = replayer.finish();
     prints.swap(replayer.prints);
+    end_keys.swap(replayer.end_keys);
     for (const SnPrint &p : prints) over += max_length > 0 && p.len > (uint32_t)max_length;
     const uint64_t image_bytes = sn_layout_fasta(prints, g->k);
     stage("replay the traversal (host)");
@@ -1182,7 +1193,23 @@ int lasv_graph_write_supernodes(lasv_graph *g, const char *fasta_path, int max_l
       CUDA_TRY(cudaMemcpyAsync(d_prints, prints.data(), prints.size() * sizeof(SnPrint), cudaMemcpyHostToDevice,
                                g->compute));
       // the device writes the whole file image: header lines and sequence lines
-      launch_sn_write(g->N, tv, g->k, d_prints, prints.size(), d_image, d_c, g->compute);
+      if (ranked.el) {  // one thread per record frame and one per interior node instead of one walk per record
+        std::vector<RkPrintKey> keys;
+        keys.reserve(prints.size());
+        for (size_t i = 0; i < prints.size(); i++)
+          if (end_keys[i] != SN_NONE) keys.push_back({end_keys[i], (uint64_t)i});
+        std::sort(keys.begin(), keys.end(), [](const RkPrintKey &a, const RkPrintKey &b) { return a.key < b.key; });
+        CUDA_TRY(cudaMalloc(&d_print_keys, std::max<size_t>(1, keys.size()) * sizeof(RkPrintKey)));
+        CUDA_TRY(cudaMalloc(&d_end_keys, prints.size() * sizeof(uint64_t)));
+        CUDA_TRY(cudaMemcpyAsync(d_print_keys, keys.data(), keys.size() * sizeof(RkPrintKey), cudaMemcpyHostToDevice, g->compute));
+        CUDA_TRY(cudaMemcpyAsync(d_end_keys, end_keys.data(), prints.size() * sizeof(uint64_t), cudaMemcpyHostToDevice,
+                                 g->compute));
+        rk_write_supernodes(g->N, tv, g->k, ranked, d_print_keys, keys.size(), d_prints, d_end_keys, prints.size(), d_image, d_c,
+                            g->compute);
+        CUDA_TRY(cudaStreamSynchronize(g->compute));  // keys / end_keys go out of scope
+      } else {
+        launch_sn_write(g->N, tv, g->k, d_prints, prints.size(), d_image, d_c, g->compute);
+      }
       if (int e = check_launch()) return e;
       if (int e = counters()) return e;
       if (h_c.n_dangling) return fail(LASV_ERR_STATE, "supernode sequence walk left the graph");
@@ -1208,7 +1235,8 @@ int lasv_graph_write_supernodes(lasv_graph *g, const char *fasta_path, int max_l
   }();
   cudaFree(d_c); cudaFree(d_n); cudaFree(d_starts); cudaFree(d_list); cudaFree(d_covered);
   cudaFree(d_recs); cudaFree(d_cyc); cudaFree(d_keys); cudaFree(d_keys_alt); cudaFree(d_vals); cudaFree(d_vals_alt);
-  cudaFree(d_tmp); cudaFree(d_events); cudaFree(d_prints); cudaFree(d_image);
+  cudaFree(d_tmp); cudaFree(d_events); cudaFree(d_prints); cudaFree(d_image); cudaFree(d_print_keys); cudaFree(d_end_keys);
+  rk_release(ranked);
   for (int b = 0; b < 2; b++) {
     if (h_stage[b]) cudaFreeHost(h_stage[b]);
     if (copied[b]) cudaEventDestroy(copied[b]);

@@ -118,13 +118,100 @@ LASV_HD bool rk_path_of_start(const TableView &t, int k, const RkMap &map, const
   return true;
 }
 
+// ------------------------------------------------------------------ writing long supernodes, one thread per NODE
+// A supernode is one path; printed from one of its ends it is a walk that ends in a known state: the node at the
+// other end, the orientation it is reached in, the nucleotide that leads back (SN_NONE for cycles, which keep the
+// per-record writer).  Every ranked element (q, o) that walks in that direction carries exactly this state in
+// `term` and its distance to it in `len`, so it can place the base node q contributes -- the last base of its
+// k-mer read in orientation o -- without anyone walking the path: sequence index k - 1 + (edges - len).
+struct RkPrintKey {
+  uint64_t key;    // end state of a printed supernode
+  uint64_t print;  // its index in the print list
+};
+LASV_HD uint64_t rk_end_key(uint64_t end_q, uint32_t arrival_o, uint32_t back) {
+  return (end_q << 3) | ((uint64_t)(arrival_o & 1u) << 2) | (back & 3u);
+}
+LASV_HD bool rk_find_print(const RkPrintKey *keys, uint64_t n, uint64_t key, uint64_t &print) {
+  uint64_t lo = 0, hi = n;
+  while (lo < hi) {
+    const uint64_t mid = (lo + hi) >> 1;
+    if (keys[mid].key < key) lo = mid + 1;
+    else hi = mid;
+  }
+  if (lo < n && keys[lo].key == key) { print = keys[lo].print; return true; }
+  return false;
+}
+template <int N>
+LASV_HD uint32_t rk_last_base(const uint64_t (&key)[N], int k, uint32_t o) {  // last base of the k-mer read in orientation o
+  return o ? 3u - kmer_first_base<N>(key, k) : (uint32_t)(key[N - 1] & 3u);
+}
+
+// the bases interior node q contributes (it may be crossed in both orientations by a path that turns round)
+#pragma nv_exec_check_disable
+template <int N, class Ops>
+LASV_HD void rk_write_node(const TableView &t, int k, const RkMap &map, const RkElem *el, const RkPrintKey *keys,
+                           uint64_t n_keys, const SnPrint *prints, uint64_t q, char *image) {
+  uint64_t key[N];
+  if (!sn_load_node<N, Ops>(t, q, key)) return;
+  const uint32_t cid = rk_cid(map, q);
+  for (uint32_t o = 0; o < 2; o++) {
+    const RkElem e = el[2u * cid + o];
+    uint64_t i = 0;
+    if (e.succ != RK_DONE || !rk_find_print(keys, n_keys, e.term, i)) continue;
+    const SnPrint p = prints[i];
+    if (e.len > p.len) continue;  // cannot happen: the element lies on that path
+    const uint64_t bases = (uint64_t)k + p.len;
+    image[p.offset + sn_header_bytes(i, bases, k) + (uint64_t)(k - 1) + (p.len - e.len)] = base_char(rk_last_base<N>(key, k, o));
+  }
+}
+
+// everything else of record i: header line, first k-mer, the base of the end node, newline; a cycle (end_key SN_NONE)
+// is written whole by the per-record walker
+#pragma nv_exec_check_disable
+template <int N, class Ops>
+LASV_HD bool rk_write_frame(const TableView &t, int k, const SnPrint &p, uint64_t end_key, uint64_t i, char *image) {
+  if (end_key == SN_NONE) return sn_write_record<N, Ops>(t, k, p, i, image);
+  uint64_t key[N], km[N];
+  if (!sn_load_node<N, Ops>(t, p.q, key)) return false;
+  if (p.on & 1u) kmer_revcomp<N>(key, k, km);
+  else {
+#pragma unroll
+    for (int w = 0; w < N; w++) km[w] = key[w];
+  }
+  char hdr[72];
+  const uint64_t bases = (uint64_t)k + p.len;
+  const uint32_t hn = sn_write_header(hdr, i, bases, k);
+  char *out = image + p.offset;
+  for (uint32_t b = 0; b < hn; b++) out[b] = hdr[b];
+  for (int b = 0; b < k; b++) out[hn + b] = base_char(kmer_base_at<N>(km, k, b));
+  uint64_t ekey[N];
+  if (!sn_load_node<N, Ops>(t, end_key >> 3, ekey)) return false;
+  out[hn + bases - 1] = base_char(rk_last_base<N>(ekey, k, (uint32_t)(end_key >> 2) & 1u));
+  out[hn + bases] = '\n';
+  return true;
+}
+
 #if defined(__CUDACC__)
+// What the ranking leaves on the device for the per-node writer (rk_release frees it).
+struct RkState {
+  unsigned long long *bits = nullptr;
+  uint64_t *rank = nullptr;
+  RkElem *el = nullptr;
+};
+void rk_release(RkState &s);
 // Drop-in for launch_sn_paths (same arguments plus the number of interior nodes from sn_count): allocates its
-// working arrays (48 bytes per element while it runs), fills recs / covered / the counters in c.  Returns
-// cudaSuccess or the error of a failed allocation / launch.
+// working arrays (48 bytes per element while it runs), fills recs / covered / the counters in c; with `keep` the
+// ranked elements stay on the device for rk_write_supernodes.  Returns cudaSuccess or the error of a failed
+// allocation / launch.
 cudaError_t sn_paths_ranked(int N, const TableView &t, int k, const uint64_t *starts, uint64_t n_starts,
                             uint64_t n_interior, uint8_t *covered, SnPath *recs, uint64_t cap, SnCounters *c,
-                            cudaStream_t st);
+                            cudaStream_t st, RkState *keep = nullptr);
+// The FASTA image of the printed supernodes without anyone walking a path: one thread per record writes its frame
+// (cycles: the whole record), one thread per interior node its base(s).  keys: the end states of the non-cycle
+// prints, sorted; end_keys[i]: the end state of print i (SN_NONE: cycle).  Failures are counted in c->n_dangling.
+void rk_write_supernodes(int N, const TableView &t, int k, const RkState &s, const RkPrintKey *keys, uint64_t n_keys,
+                         const SnPrint *prints, const uint64_t *end_keys, uint64_t n_prints, char *image, SnCounters *c,
+                         cudaStream_t st);
 #endif
 
 }  // namespace lasv

@@ -90,6 +90,25 @@ __global__ void __launch_bounds__(RK_THREADS) rk_covered_kernel(const RkMap map,
     if ((map.bits[q >> 6] >> (q & 63)) & 1ull) covered[q] = el[2u * rk_cid(map, q)].succ == RK_DONE ? 1 : 0;
 }
 
+template <int N>
+__global__ void __launch_bounds__(RK_THREADS) rk_write_frames_kernel(const TableView t, const int k,
+                                                                    const SnPrint *__restrict__ prints,
+                                                                    const uint64_t *__restrict__ end_keys, const uint64_t n,
+                                                                    char *image, SnCounters *c) {
+  for (uint64_t i = (uint64_t)blockIdx.x * RK_THREADS + threadIdx.x; i < n; i += (uint64_t)gridDim.x * RK_THREADS)
+    if (!rk_write_frame<N, DeviceOps>(t, k, prints[i], end_keys[i], i, image)) atomicAdd(&c->n_dangling, 1ull);
+}
+
+template <int N>
+__global__ void __launch_bounds__(RK_THREADS) rk_write_nodes_kernel(const TableView t, const int k, const RkMap map,
+                                                                   const RkElem *__restrict__ el,
+                                                                   const RkPrintKey *__restrict__ keys, const uint64_t n_keys,
+                                                                   const SnPrint *__restrict__ prints, char *image) {
+  const uint64_t n_slots = ((uint64_t)t.bucket_mask + 1) * t.W;
+  for (uint64_t q = (uint64_t)blockIdx.x * RK_THREADS + threadIdx.x; q < n_slots; q += (uint64_t)gridDim.x * RK_THREADS)
+    if ((map.bits[q >> 6] >> (q & 63)) & 1ull) rk_write_node<N, DeviceOps>(t, k, map, el, keys, n_keys, prints, q, image);
+}
+
 template <typename F>
 void rk_dispatch(int N, F &&f) {
   if (N == 1) f(std::integral_constant<int, 1>());
@@ -114,7 +133,7 @@ unsigned rk_grid(uint64_t items) {
 
 cudaError_t sn_paths_ranked(int N, const TableView &t, int k, const uint64_t *starts, uint64_t n_starts,
                             uint64_t n_interior, uint8_t *covered, SnPath *recs, uint64_t cap, SnCounters *c,
-                            cudaStream_t st) {
+                            cudaStream_t st, RkState *keep) {
   const uint64_t n_slots = ((uint64_t)t.bucket_mask + 1) * t.W, n_words = (n_slots + 63) / 64;
   const uint64_t n_el = 2 * n_interior;
   if (n_el >= RK_DONE) return cudaErrorInvalidValue;  // element indices are 32-bit
@@ -168,9 +187,39 @@ cudaError_t sn_paths_ranked(int N, const TableView &t, int k, const uint64_t *st
   RK_TRY(cudaGetLastError());
   RK_TRY(cudaStreamSynchronize(st));
 done:
+  if (keep && err == cudaSuccess) {  // the final elements and the interior-node map stay for the per-node writer
+    keep->bits = d_bits;
+    keep->rank = d_rank;
+    keep->el = d_el[cur];
+    d_bits = nullptr;
+    d_rank = nullptr;
+    d_el[cur] = nullptr;
+  }
   cudaFree(d_bits); cudaFree(d_rank); cudaFree(d_counts); cudaFree(d_tmp); cudaFree(d_active);
   cudaFree(d_el[0]); cudaFree(d_el[1]);
   return err;
+}
+
+void rk_release(RkState &s) {
+  cudaFree(s.bits);
+  cudaFree(s.rank);
+  cudaFree(s.el);
+  s = RkState();
+}
+
+void rk_write_supernodes(int N, const TableView &t, int k, const RkState &s, const RkPrintKey *keys, uint64_t n_keys,
+                         const SnPrint *prints, const uint64_t *end_keys, uint64_t n_prints, char *image, SnCounters *c,
+                         cudaStream_t st) {
+  if (!n_prints) return;
+  const uint64_t n_slots = ((uint64_t)t.bucket_mask + 1) * t.W;
+  RkMap map;
+  map.bits = reinterpret_cast<const uint64_t *>(s.bits);
+  map.rank = s.rank;
+  rk_dispatch(N, [&](auto nn) {
+    constexpr int NN = decltype(nn)::value;
+    rk_write_frames_kernel<NN><<<rk_grid(n_prints), RK_THREADS, 0, st>>>(t, k, prints, end_keys, n_prints, image, c);
+    if (n_keys) rk_write_nodes_kernel<NN><<<rk_grid(n_slots), RK_THREADS, 0, st>>>(t, k, map, s.el, keys, n_keys, prints, image);
+  });
 }
 
 }  // namespace lasv

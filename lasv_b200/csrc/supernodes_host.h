@@ -76,6 +76,18 @@ class SnReplayer {
         pr.on = ((e.bits & SNB_S_O) ? 1u : 0u) | (((e.bits >> SNB_S_N) & 3u) << 1);
       }
       prints.push_back(pr);
+      if (want_end_keys) {
+        // where the printed walk ends: node, orientation it is reached in (the opposite of the twin start there),
+        // nucleotide that leads back -- what the per-node writer of ranking.cuh looks its elements up by
+        uint64_t key = SN_NONE;
+        if (!(e.bits & SNB_CYCLE)) {
+          const uint64_t end_q = from_t ? e.s_q : e.t_q;
+          const uint32_t twin_o = from_t ? ((e.bits & SNB_S_O) ? 1u : 0u) : ((e.bits & SNB_T_O) ? 1u : 0u);
+          const uint32_t back = (e.bits >> (from_t ? SNB_S_N : SNB_T_N)) & 3u;
+          key = (end_q << 3) | ((uint64_t)(twin_o ^ 1u) << 2) | back;
+        }
+        end_keys.push_back(key);
+      }
       stats_.printed++;
       stats_.longest = std::max<uint64_t>(stats_.longest, e.len);
       stats_.total_bases += (uint64_t)k_ + e.len;
@@ -86,6 +98,8 @@ class SnReplayer {
     return stats_;
   }
   std::vector<SnPrint> prints;
+  bool want_end_keys = false;      // set before feeding: also collect end_keys[i] for prints[i]
+  std::vector<uint64_t> end_keys;
 
  private:
   bool is_visited(uint64_t q) const { return (visited_[q >> 6] >> (q & 63)) & 1ull; }
@@ -100,7 +114,8 @@ class SnReplayer {
 
 // The same from the path records (path scan, then cycles): builds and sorts the events on
 // the host.  tests/host_emul uses this; the library sorts on the device (supernode_kernels.cu).
-inline SnReplayStats sn_replay(const std::vector<SnPath> &paths, int k, uint64_t n_slots, std::vector<SnPrint> &out) {
+inline SnReplayStats sn_replay(const std::vector<SnPath> &paths, int k, uint64_t n_slots, std::vector<SnPrint> &out,
+                               std::vector<uint64_t> *end_keys = nullptr) {
   struct Keyed {
     uint64_t pos;
     SnEvent e;
@@ -118,10 +133,12 @@ inline SnReplayStats sn_replay(const std::vector<SnPath> &paths, int k, uint64_t
   std::vector<SnEvent> sorted(ev.size());
   for (size_t i = 0; i < ev.size(); i++) sorted[i] = ev[i].e;
   SnReplayer rp(paths.size(), n_slots, k);
+  rp.want_end_keys = end_keys != nullptr;
   // in uneven pieces, as the library feeds it
   for (size_t at = 0, step = 1; at < sorted.size(); at += step, step = step * 3 + 1)
     rp.feed(sorted.data() + at, std::min(step, sorted.size() - at));
   out.swap(rp.prints);
+  if (end_keys) end_keys->swap(rp.end_keys);
   return rp.finish();
 }
 

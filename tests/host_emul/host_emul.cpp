@@ -228,9 +228,13 @@ void find(uint8_t *table, int L, int W, int max_rehash, int finalized, const uin
 // the supernode kernels of supernode_kernels.cu, slot by slot / start by start, + the replay
 // sn_paths_ranked (ranking_kernels.cu): the path records by list ranking instead of one walk per start
 bool g_ranked = false;
+struct RankedState {  // what sn_paths_ranked leaves on the device for the per-node writer
+  std::vector<uint64_t> bits, rank;
+  std::vector<RkElem> el;
+};
 template <int N>
 void ranked_enumerate(const TableView &tv, int k, const std::vector<uint64_t> &starts, std::vector<SnPath> &recs,
-                      std::vector<uint8_t> &covered, uint64_t &dangling) {
+                      std::vector<uint8_t> &covered, uint64_t &dangling, RankedState *keep = nullptr) {
   const uint64_t n_slots = ((uint64_t)tv.bucket_mask + 1) * tv.W, n_words = (n_slots + 63) / 64;
   std::vector<uint64_t> bits(n_words, 0), rank(n_words, 0);
   for (uint64_t q = 0; q < n_slots; q++)  // rk_flags_kernel
@@ -266,6 +270,11 @@ void ranked_enumerate(const TableView &tv, int k, const std::vector<uint64_t> &s
   }
   for (uint64_t q = 0; q < n_slots; q++)  // rk_covered_kernel
     if ((bits[q >> 6] >> (q & 63)) & 1ull) covered[q] = el[cur][2u * rk_cid(map, q)].succ == RK_DONE ? 1 : 0;
+  if (keep) {
+    keep->el.swap(el[cur]);
+    keep->bits.swap(bits);
+    keep->rank.swap(rank);
+  }
 }
 
 template <int N>
@@ -296,7 +305,8 @@ int supernodes(uint8_t *table, int k, int L, int W, int finalized, const char *p
       dangling += d;
     }
   }
-  if (g_ranked) ranked_enumerate<N>(tv, k, rk_starts, recs, covered, dangling);
+  RankedState ranked;
+  if (g_ranked) ranked_enumerate<N>(tv, k, rk_starts, recs, covered, dangling, &ranked);
   const uint64_t n_paths = recs.size();
   uint64_t uncovered = 0;
   for (uint64_t q = 0; q < n_slots; q++) {  // sn_uncovered_kernel + sn_cycles_kernel
@@ -310,10 +320,24 @@ int supernodes(uint8_t *table, int k, int L, int W, int finalized, const char *p
     dangling += d;
   }
   std::vector<SnPrint> prints;
-  const SnReplayStats st = sn_replay(recs, k, n_slots, prints);
+  std::vector<uint64_t> end_keys;
+  const SnReplayStats st = sn_replay(recs, k, n_slots, prints, g_ranked ? &end_keys : nullptr);
   std::vector<char> image(sn_layout_fasta(prints, k) + 1);
-  for (size_t i = 0; i < prints.size(); i++)  // sn_write_kernel
-    if (!sn_write_record<N, HostOps>(tv, k, prints[i], i, image.data())) dangling++;
+  if (g_ranked) {  // rk_write_frames_kernel + rk_write_nodes_kernel: one thread per record frame, one per interior node
+    std::vector<RkPrintKey> keys;
+    for (size_t i = 0; i < prints.size(); i++)
+      if (end_keys[i] != SN_NONE) keys.push_back({end_keys[i], (uint64_t)i});
+    std::sort(keys.begin(), keys.end(), [](const RkPrintKey &a, const RkPrintKey &b) { return a.key < b.key; });
+    const RkMap map{ranked.bits.data(), ranked.rank.data()};
+    for (size_t i = 0; i < prints.size(); i++)
+      if (!rk_write_frame<N, HostOps>(tv, k, prints[i], end_keys[i], i, image.data())) dangling++;
+    for (uint64_t q = 0; q < n_slots; q++)
+      if ((ranked.bits[q >> 6] >> (q & 63)) & 1ull)
+        rk_write_node<N, HostOps>(tv, k, map, ranked.el.data(), keys.data(), keys.size(), prints.data(), q, image.data());
+  } else {
+    for (size_t i = 0; i < prints.size(); i++)  // sn_write_kernel
+      if (!sn_write_record<N, HostOps>(tv, k, prints[i], i, image.data())) dangling++;
+  }
   FILE *fp = fopen(path, "w");
   if (!fp) return -1;
   const bool ok = fwrite(image.data(), 1, image.size() - 1, fp) == image.size() - 1;
