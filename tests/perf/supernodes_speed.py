@@ -4,7 +4,7 @@
 device-generated reads, times DBGraph.output_supernodes, then lets the reference reload the
 dumped `.ctx` and print its supernodes, and compares the two FASTA files byte for byte.
 
-    python tests/perf/supernodes_speed.py [genome_len] [L] [--no-ref]
+    python tests/perf/supernodes_speed.py [genome_len] [L] [--no-ref] [--clean T]
 """
 import json
 import os
@@ -18,10 +18,17 @@ import torch  # noqa: E402
 from lasv_b200 import DBGraph, synth  # noqa: E402
 from oracle import oracle as O  # noqa: E402  (reference runner only: test infrastructure)
 
-args = [a for a in sys.argv[1:] if not a.startswith("--")]
+_argv = list(sys.argv[1:])
+if "--clean" in _argv:
+    del _argv[_argv.index("--clean") + 1]
+args = [a for a in _argv if not a.startswith("--")]
 genome_len = int(args[0]) if len(args) > 0 else 2_000_000
 L = int(args[1]) if len(args) > 1 else 18
 with_ref = "--no-ref" not in sys.argv
+# --clean T: run the cleaning (tip clipping + low-coverage supernodes, threshold T) on the device first -- a cleaned
+# graph is a few very long paths, the case for LASV_B200_SN_RANKING=1 (list ranking + one writer thread per node)
+clean_T = int(sys.argv[sys.argv.index("--clean") + 1]) if "--clean" in sys.argv else None
+
 w = synth.scaled(synth.CFG0, genome_len, L)
 tmp = Path(os.environ.get("TMPDIR", "/tmp")) / "sn_speed"
 tmp.mkdir(parents=True, exist_ok=True)
@@ -44,7 +51,13 @@ with DBGraph(w.kmer_size, L, w.bucket_size) as g:
         done += nr
     torch.cuda.synchronize()
     out["unique_kmers"] = g.unique_kmers
+    out["ranking"] = os.environ.get("LASV_B200_SN_RANKING", "0")
+    if clean_T is not None:
+        t = time.perf_counter()
+        out["clean"] = g.clean(clean_T)
+        out["clean_seconds"] = time.perf_counter() - t
     os.environ["LASV_B200_SN_TRACE"] = "1"
+
     for rep in range(2):
         t = time.perf_counter()
         stats = g.output_supernodes(tmp / "gpu.fa", max_length=10000)

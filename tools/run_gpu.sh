@@ -22,6 +22,7 @@ case $step in
   first_run) timeout 900 python -m pytest tests -m gpu -q -rxX -k "branches or build_mode or health_check or grouped_insert or ranked" > $out/pytest_first_run.log 2>&1; echo "rc=$?" >> $out/pytest_first_run.log;;
   groups) (cd tools/ubench && ./ubench groups 12.5 && ./ubench groups 100) > $out/ubench_groups.txt 2>&1;;
   grouped) for bulk in 0 1; do for b in 1 2 4 8; do LASV_B200_GROUPS_BULK=$bulk timeout 600 python tools/grouped_insert_speed.py 1048576 $b 21; done; done > $out/grouped_insert_speed.jsonl 2> $out/grouped_insert_speed.err;;
+  ranked_speed) for r in 0 1; do LASV_B200_SN_RANKING=$r timeout 900 python tests/perf/supernodes_speed.py 2000000 18 --clean 2; LASV_B200_SN_RANKING=$r timeout 900 python tests/perf/supernodes_speed.py 2000000 18 --no-ref; done > $out/ranked_speed.jsonl 2> $out/ranked_speed.err;;
   build_mode_2M) timeout 900 python tests/perf/build_mode_speed.py 2000000 18 2 > $out/build_mode_2Mbp.json 2> $out/build_mode_2Mbp.err;;
   build_mode_16M) timeout 1800 python tests/perf/build_mode_speed.py 16000000 21 2 > $out/build_mode_16Mbp.json 2> $out/build_mode_16Mbp.err;;
   build_mode_cfg0) timeout 1800 python tests/perf/build_mode_speed.py 63025520 22 2 --no-ref > $out/build_mode_cfg0.json 2> $out/build_mode_cfg0.err;;
