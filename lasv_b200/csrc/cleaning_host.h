@@ -108,16 +108,33 @@ class ClGraph {
   // the host side of a pass otherwise).
   void seal_nodes(uint64_t n_slots) {
     bits_.assign((size_t)((n_slots + 63) / 64), 0ull);
-    for (const ClNode &n : nodes)
-      if (n.q < n_slots) bits_[(size_t)(n.q >> 6)] |= 1ull << (n.q & 63);
+    const std::vector<ClNode> &in = nodes;
+    parallel_for(in.size(), [&](uint64_t lo, uint64_t hi) {
+      for (uint64_t i = lo; i < hi; i++)
+        if (in[i].q < n_slots) __atomic_fetch_or(&bits_[(size_t)(in[i].q >> 6)], 1ull << (in[i].q & 63), __ATOMIC_RELAXED);
+    });
     rank_.assign(bits_.size() + 1, 0u);
     for (size_t w = 0; w < bits_.size(); w++) rank_[w + 1] = rank_[w] + (uint32_t)__builtin_popcountll(bits_[w]);
     std::vector<ClNode> placed(rank_.back());
-    for (const ClNode &n : nodes) {
-      const int32_t i = index_of(n.q);
-      if (i >= 0) placed[(size_t)i] = n;
-    }
+    parallel_for(in.size(), [&](uint64_t lo, uint64_t hi) {  // every node has a place of its own
+      for (uint64_t i = lo; i < hi; i++) {
+        const int32_t at = index_of(in[i].q);
+        if (at >= 0) placed[(size_t)at] = in[i];
+      }
+    });
     nodes.swap(placed);
+  }
+  // ranges of [0, n) on up to 8 host threads (one below parallel_min() items)
+  template <class F>
+  static void parallel_for(uint64_t n, F &&work) {
+    const unsigned threads = n >= parallel_min() ? std::min(8u, std::max(2u, std::thread::hardware_concurrency() / 2)) : 1u;
+    if (threads <= 1) {
+      work(0, n);
+      return;
+    }
+    std::vector<std::thread> pool;
+    for (unsigned t = 0; t < threads; t++) pool.emplace_back([&work, n, t, threads] { work(n * t / threads, n * (t + 1) / threads); });
+    for (auto &th : pool) th.join();
   }
   int32_t index_of(uint64_t q) const {
     const size_t w = (size_t)(q >> 6);
@@ -184,14 +201,7 @@ class ClGraph {
         paths[(size_t)id] = c;
       }
     };
-    unsigned threads = n >= parallel_min() ? std::min(8u, std::max(2u, std::thread::hardware_concurrency() / 2)) : 1u;
-    if (threads <= 1) {
-      work(0, n);
-    } else {
-      std::vector<std::thread> pool;
-      for (unsigned t = 0; t < threads; t++) pool.emplace_back(work, n * t / threads, n * (t + 1) / threads);
-      for (auto &th : pool) th.join();
-    }
+    parallel_for(n, work);
     return ok;
   }
 
