@@ -123,9 +123,11 @@ __global__ void __launch_bounds__(GR_THREADS) insert_groups_bulk_kernel(const ui
     }
     const uint32_t parity = (it >> 1) & 1u;
     uint32_t done = 0;
-    while (!done)
+    for (uint32_t tries = 0; !done; tries++) {
       asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
                    : "=r"(done) : "r"(smem_addr(&mbar[b])), "r"(parity) : "memory");
+      if (tries > (1u << 24)) __trap();  // a copy that never lands must end the kernel with an error, not hang the GPU
+    }
     const TableView local = group_local_view(t, bufs[b], g, buckets_per_group);
     for (uint64_t i = group_offsets[g] + threadIdx.x, hi = group_offsets[g + 1]; i < hi; i += GR_THREADS) {
       const int r = group_upsert<N, SmemOps>(local, ctr, recs + i * RECW);

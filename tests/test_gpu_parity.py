@@ -1224,7 +1224,9 @@ def test_gpu_health_check_at_full_config0_size():
 
 
 @_first_device_run
-@pytest.mark.parametrize("bulk", [0, 1])
+@pytest.mark.parametrize("bulk", [0, pytest.param(1, marks=pytest.mark.skipif(
+    os.environ.get("LASV_B200_TEST_BULK") != "1",
+    reason="cp.async.bulk staging waits on an mbarrier: first run by hand under `timeout` (LASV_B200_TEST_BULK=1)"))])
 @pytest.mark.parametrize("name,bpg", [("synth_cfg0_k53", 4), ("synth_cfg1_k31", 2), ("synth_cfg2_k95", 4),
                                       ("synth_full_k53", 4), ("synth_full_k53", 1)])
 def test_gpu_grouped_insert_prototype(name, bpg, bulk, monkeypatch):

@@ -19,7 +19,7 @@ case $step in
   n2) timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 5 --warmup 3 --no-cpu-baseline > $out/bench_n2.log 2> $out/bench_n2.err;;
   n4) timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 4 --steps 5 --warmup 3 --no-cpu-baseline > $out/bench_n4.log 2> $out/bench_n4.err;;
   n8) timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus 8 --steps 5 --warmup 3 --no-cpu-baseline > $out/bench_n8.log 2> $out/bench_n8.err;;
-  first_run) timeout 900 python -m pytest tests -m gpu -q -rxX -k "branches or build_mode or health_check or grouped_insert or ranked" > $out/pytest_first_run.log 2>&1; echo "rc=$?" >> $out/pytest_first_run.log;;
+  first_run) LASV_B200_TEST_BULK=1 timeout 900 python -m pytest tests -m gpu -q -rxX -k "branches or build_mode or health_check or grouped_insert or ranked" > $out/pytest_first_run.log 2>&1; echo "rc=$?" >> $out/pytest_first_run.log;;
   groups) (cd tools/ubench && ./ubench groups 12.5 && ./ubench groups 100) > $out/ubench_groups.txt 2>&1;;
   grouped) for bulk in 0 1; do for b in 1 2 4 8; do LASV_B200_GROUPS_BULK=$bulk timeout 600 python tools/grouped_insert_speed.py 1048576 $b 21; done; done > $out/grouped_insert_speed.jsonl 2> $out/grouped_insert_speed.err;;
   ranked_speed) for r in 0 1; do LASV_B200_SN_RANKING=$r timeout 900 python tests/perf/supernodes_speed.py 2000000 18 --clean 2; LASV_B200_SN_RANKING=$r timeout 900 python tests/perf/supernodes_speed.py 2000000 18 --no-ref; done > $out/ranked_speed.jsonl 2> $out/ranked_speed.err;;

@@ -239,9 +239,11 @@ __global__ void __launch_bounds__(256) groups_kernel(uint64_t *buf, uint64_t n_g
       }
       const uint32_t parity = (it >> 1) & 1u;
       uint32_t done = 0;
-      while (!done)
+      for (uint32_t tries = 0; !done; tries++) {
         asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
                      : "=r"(done) : "r"(smem_u32(&mbar[b])), "r"(parity) : "memory");
+        if (tries > (1u << 24)) __trap();  // never hang the GPU box
+      }
       group_ops(reinterpret_cast<uint64_t *>(bufs[b]), n_lines, ops, seed + g * 7919);
       __syncthreads();
       if (threadIdx.x == 0) {
