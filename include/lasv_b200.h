@@ -441,6 +441,11 @@ int lasv_graph_record_buckets_device(lasv_graph *g, const uint32_t *d_records, u
 int lasv_graph_insert_grouped_records_device(lasv_graph *g, const uint32_t *d_records, uint64_t n_records,
                                              const uint64_t *d_group_offsets, uint32_t buckets_per_group,
                                              uint64_t *n_spilled /* may be NULL */, void *cuda_stream);
+/* The sort it needs, in the library (counting sort by group: histogram, scan, scatter): d_sorted gets the n_records
+ * records grouped, d_group_offsets the n_buckets / buckets_per_group + 1 group boundaries. */
+int lasv_graph_group_records_device(lasv_graph *g, const uint32_t *d_records, uint64_t n_records,
+                                    uint32_t buckets_per_group, uint32_t *d_sorted, uint64_t *d_group_offsets,
+                                    void *cuda_stream);
 /* The file loaders' parser on its own (host only, no GPU): reads per file, bases and
  * an order-independent checksum of every (sequence, quality) pair, parsed with
  * `threads` parser threads per file exactly as the loaders do (large uncompressed

@@ -97,7 +97,7 @@ EXPORTS = [
     "lasv_graph_route_reads_device", "lasv_graph_extract_records_device",
     "lasv_graph_insert_records_device", "lasv_graph_read_stats_device", "lasv_graph_find",
     "lasv_graph_summary", "lasv_graph_finalize", "lasv_graph_export_table", "lasv_graph_import_table",
-    "lasv_graph_dump_ctx_records", "lasv_graph_write_ctx", "lasv_ctx_header", "lasv_graph_write_supernodes", "lasv_ref_hash_table_write_supernodes", "lasv_ref_hash_table_clean", "lasv_graph_insert_grouped_records_device", "lasv_graph_write_branches", "lasv_graph_append_ctx_records", "lasv_graph_clean", "lasv_graph_health_check", "lasv_ref_hash_table_write_branches",
+    "lasv_graph_dump_ctx_records", "lasv_graph_write_ctx", "lasv_ctx_header", "lasv_graph_write_supernodes", "lasv_ref_hash_table_write_supernodes", "lasv_ref_hash_table_clean", "lasv_graph_insert_grouped_records_device", "lasv_graph_group_records_device", "lasv_graph_write_branches", "lasv_graph_append_ctx_records", "lasv_graph_clean", "lasv_graph_health_check", "lasv_ref_hash_table_write_branches",
     "lasv_graph_load_ctx_records", "lasv_graph_load_ctx_file", "lasv_graph_load_se_file",
     "lasv_graph_load_pe_files", "lasv_graph_load_se_filelist", "lasv_graph_load_pe_filelists",
     "load_se_filelist_into_graph_colour", "load_pe_filelists_into_graph_colour",
@@ -198,6 +198,7 @@ def lib() -> C.CDLL:
     L.lasv_ref_hash_table_write_supernodes.argtypes = [C.POINTER(RefHashTable), C.c_char_p, i32, C.POINTER(SupernodeStats)]
     L.lasv_ref_hash_table_clean.argtypes = [C.POINTER(RefHashTable), i32, i32, C.POINTER(CleanStats)]
     L.lasv_graph_health_check.argtypes = [vp, C.POINTER(HealthStats)]
+    L.lasv_graph_group_records_device.argtypes = [vp, vp, u64, C.c_uint32, vp, vp, vp]
     L.lasv_graph_insert_grouped_records_device.argtypes = [vp, vp, u64, vp, C.c_uint32, C.POINTER(C.c_uint64), vp]
     L.lasv_graph_clean.argtypes = [vp, i32, i32, C.POINTER(CleanStats)]
     L.lasv_graph_write_branches.argtypes = [vp, C.c_char_p, i32, C.POINTER(BranchStats)]

@@ -799,6 +799,32 @@ int lasv_graph_insert_grouped_records_device(lasv_graph *g, const uint32_t *d_re
   return rc;
 }
 
+// The grouping the prototype needs, in the library: counting sort of the records by group.
+int lasv_graph_group_records_device(lasv_graph *g, const uint32_t *d_records, uint64_t n_records, uint32_t buckets_per_group,
+                                    uint32_t *d_sorted, uint64_t *d_group_offsets, void *cuda_stream) {
+  if (int e = use(g)) return e;
+  if (!buckets_per_group || (buckets_per_group & (buckets_per_group - 1)) || buckets_per_group > g->n_buckets)
+    return fail(LASV_ERR_ARG, "buckets_per_group must be a power of two <= the number of buckets");
+  if (!d_group_offsets || (n_records && (!d_records || !d_sorted))) return fail(LASV_ERR_ARG, "NULL argument");
+  cudaStream_t st = stream_of(g, cuda_stream);
+  const uint64_t n_groups = g->n_buckets / buckets_per_group;
+  uint32_t *d_counts = nullptr;
+  void *d_tmp = nullptr;
+  const size_t tmp_bytes = exclusive_scan_tmp_bytes(n_groups);
+  int rc = [&]() -> int {
+    CUDA_TRY(cudaMalloc(&d_counts, n_groups * sizeof(uint32_t)));
+    CUDA_TRY(cudaMalloc(&d_tmp, std::max<size_t>(tmp_bytes, 16)));
+    launch_group_records(g->N, d_records, n_records, buckets_per_group, g->view(), d_counts, d_group_offsets, d_tmp, tmp_bytes,
+                         d_sorted, st);
+    if (int e = check_launch()) return e;
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return LASV_OK;
+  }();
+  cudaFree(d_counts);
+  cudaFree(d_tmp);
+  return rc;
+}
+
 int lasv_graph_bin_geometry(lasv_graph *g, int n_owners, uint64_t n_bytes, uint64_t n_reads,
                             uint32_t *bins_per_owner, uint32_t *stripe_capacity_out,
                             uint32_t *spill_capacity_out, uint32_t *record_bytes,

@@ -169,6 +169,33 @@ __global__ void __launch_bounds__(GR_THREADS) insert_spilled_kernel(const uint32
   if ((threadIdx.x & 31) == 0 && my_new) atomicAdd(&ctr->unique_kmers, my_new);
 }
 
+// counting sort of the records by group: histogram ...
+template <int N>
+__global__ void __launch_bounds__(GR_THREADS) group_count_kernel(const uint32_t *__restrict__ recs, const uint64_t n,
+                                                                const uint32_t buckets_per_group, const TableView t,
+                                                                uint32_t *counts) {
+  constexpr int RECW = 2 * N + 1;
+  for (uint64_t i = (uint64_t)blockIdx.x * GR_THREADS + threadIdx.x; i < n; i += (uint64_t)gridDim.x * GR_THREADS)
+    atomicAdd(&counts[group_of_record<N>(t, recs + i * RECW, buckets_per_group)], 1u);
+}
+
+// ... and scatter (the order inside a group is whatever the atomics make it: the graph does not depend on it)
+template <int N>
+__global__ void __launch_bounds__(GR_THREADS) group_scatter_kernel(const uint32_t *__restrict__ recs, const uint64_t n,
+                                                                  const uint32_t buckets_per_group, const TableView t,
+                                                                  const uint64_t *__restrict__ offsets, uint32_t *cursor,
+                                                                  uint32_t *sorted) {
+  constexpr int RECW = 2 * N + 1;
+  for (uint64_t i = (uint64_t)blockIdx.x * GR_THREADS + threadIdx.x; i < n; i += (uint64_t)gridDim.x * GR_THREADS) {
+    const uint64_t g = group_of_record<N>(t, recs + i * RECW, buckets_per_group);
+    const uint64_t at = offsets[g] + atomicAdd(&cursor[g], 1u);
+#pragma unroll
+    for (int w = 0; w < RECW; w++) sorted[at * RECW + w] = recs[i * RECW + w];
+  }
+}
+
+__global__ void group_set_last_offset_kernel(uint64_t *offsets, uint64_t n_groups, uint64_t n) { offsets[n_groups] = n; }
+
 template <typename F>
 void gr_dispatch(int N, F &&f) {
   if (N == 1) f(std::integral_constant<int, 1>());
@@ -199,6 +226,28 @@ void launch_insert_groups(int N, const uint32_t *recs, const uint64_t *group_off
     if (grid > n_groups) grid = n_groups;
     kernel<<<(unsigned)grid, GR_THREADS, smem, st>>>(recs, group_offsets, n_groups, buckets_per_group, t, ctr, spill, n_spill,
                                                     spill_cap);
+  });
+}
+
+void launch_group_records(int N, const uint32_t *recs, uint64_t n, uint32_t buckets_per_group, const TableView &t,
+                          uint32_t *counts, uint64_t *offsets, void *scan_tmp, size_t scan_tmp_bytes, uint32_t *sorted,
+                          cudaStream_t st) {
+  const uint64_t n_groups = ((uint64_t)t.bucket_mask + 1) / buckets_per_group;
+  uint64_t grid = (n + GR_THREADS - 1) / GR_THREADS;
+  const uint64_t cap = (uint64_t)sm_count() * 8;
+  if (grid > cap) grid = cap;
+  if (grid < 1) grid = 1;
+  cudaMemsetAsync(counts, 0, n_groups * sizeof(uint32_t), st);
+  gr_dispatch(N, [&](auto nn) {
+    constexpr int NN = decltype(nn)::value;
+    if (n) group_count_kernel<NN><<<(unsigned)grid, GR_THREADS, 0, st>>>(recs, n, buckets_per_group, t, counts);
+  });
+  launch_exclusive_scan_u32_to_u64(counts, offsets, n_groups, scan_tmp, scan_tmp_bytes, st);
+  group_set_last_offset_kernel<<<1, 1, 0, st>>>(offsets, n_groups, n);
+  cudaMemsetAsync(counts, 0, n_groups * sizeof(uint32_t), st);  // now the per-group cursors
+  gr_dispatch(N, [&](auto nn) {
+    constexpr int NN = decltype(nn)::value;
+    if (n) group_scatter_kernel<NN><<<(unsigned)grid, GR_THREADS, 0, st>>>(recs, n, buckets_per_group, t, offsets, counts, sorted);
   });
 }
 

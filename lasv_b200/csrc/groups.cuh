@@ -71,6 +71,11 @@ void launch_insert_groups(int N, const uint32_t *recs, const uint64_t *group_off
 void launch_insert_spilled(int N, const uint32_t *recs, const uint32_t *spill, uint64_t n_spill, const TableView &t,
                            GraphCounters *ctr, cudaStream_t st);
 size_t insert_groups_smem_limit();
+// The caller's sort, in the library: a counting sort of the records by group (histogram, exclusive scan, scatter).
+// counts: n_groups uint32 of scratch; offsets: n_groups + 1 entries out; sorted: room for n records out.
+void launch_group_records(int N, const uint32_t *recs, uint64_t n, uint32_t buckets_per_group, const TableView &t,
+                          uint32_t *counts, uint64_t *offsets, void *scan_tmp, size_t scan_tmp_bytes, uint32_t *sorted,
+                          cudaStream_t st);
 #endif
 
 }  // namespace lasv

@@ -159,6 +159,11 @@ class DBGraph:
     def insert_records_device(self, d_records, n_records, stream=None):
         check(self._lib.lasv_graph_insert_records_device(self._h, _ptr(d_records), n_records, stream))
 
+    def group_records_device(self, d_records, n_records, buckets_per_group: int, d_sorted, d_group_offsets, stream=None):
+        """Counting sort of records by group (first-choice bucket // buckets_per_group) for insert_grouped_records_device."""
+        check(self._lib.lasv_graph_group_records_device(self._h, _ptr(d_records), n_records, buckets_per_group,
+                                                        _ptr(d_sorted), _ptr(d_group_offsets), stream))
+
     def insert_grouped_records_device(self, d_sorted_records, n_records, d_group_offsets, buckets_per_group: int,
                                       stream=None) -> int:
         """PROTOTYPE of the streamed insert: records sorted by group, offsets per group; returns

@@ -1245,6 +1245,14 @@ def test_gpu_grouped_insert_prototype(name, bpg, bulk, monkeypatch):
 
     def grouped(g, recs):
         n = recs.shape[0]
+        if bpg == 4:                                # the library's own counting sort by group
+            srt = torch.empty_like(recs)
+            offsets = torch.empty(n_groups + 1, dtype=torch.int64, device="cuda")
+            g.group_records_device(recs, n, bpg, srt, offsets, st_)
+            torch.cuda.synchronize()
+            assert int(offsets[0].item()) == 0 and int(offsets[-1].item()) == n
+            assert bool((offsets[1:] >= offsets[:-1]).all())
+            return g.insert_grouped_records_device(srt, n, offsets, bpg, st_)
         buckets = torch.empty(n, dtype=torch.int32, device="cuda")
         _capi.check(_capi.lib().lasv_graph_record_buckets_device(g._h, recs.data_ptr(), n, buckets.data_ptr(), st_))
         groups = (buckets.to(torch.int64) & 0xFFFFFFFF) // bpg

@@ -81,6 +81,13 @@ for mode in ("records", "grouped"):
             offs = torch.searchsorted(groups[order].contiguous(),
                                       torch.arange((1 << L) // bpg + 1, device="cuda", dtype=torch.int64))
             return recs[:n][order].contiguous(), offs.contiguous()
+        def sort_in_library():
+            srt = torch.empty((n, 2 * N + 1), dtype=torch.int32, device="cuda")
+            offs_ = torch.empty((1 << L) // bpg + 1, dtype=torch.int64, device="cuda")
+            g.group_records_device(recs, n, bpg, srt, offs_, st)
+            return srt, offs_
+        ms_lib, _ = event_ms(sort_in_library)
+        out["group_records_ms_library"] = ms_lib
         ms_sort, (srecs, offs) = event_ms(sort_by_group)
         ms, spilled = event_ms(lambda: g.insert_grouped_records_device(srecs, n, offs, bpg, st))
         out["sort_by_group_ms_torch"] = ms_sort
