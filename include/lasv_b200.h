@@ -107,6 +107,42 @@ int lasv_graph_flush(lasv_graph *g, void *cuda_stream);
  * kernel_times synchronises the device and sums the durations collected so far. */
 int lasv_graph_enable_kernel_timing(lasv_graph *g, int on);
 int lasv_graph_kernel_times(lasv_graph *g, double *partition_ms, double *insert_ms, uint64_t *n_batches);
+/* The same collection broken down by kind of launch: total milliseconds and number of timed spans per kind.
+ * LASV_T_INSERT spans a whole insert (random-access kernel, or every launch of a streamed insert); the
+ * streamed insert's parts are timed inside it: LASV_T_SORT (count + scan + scatter of a slab's records by
+ * group), LASV_T_STREAM (sg_insert_kernel: group lines through shared memory) and LASV_T_DRAIN (records that
+ * left their group + the senders' spill stripes). */
+#define LASV_T_PARTITION 0
+#define LASV_T_INSERT 1
+#define LASV_T_SORT 2
+#define LASV_T_STREAM 3
+#define LASV_T_DRAIN 4
+#define LASV_T_KINDS 5
+int lasv_graph_kernel_times_by_kind(lasv_graph *g, double ms[LASV_T_KINDS], uint64_t n[LASV_T_KINDS]);
+/* Which insert follows the partition kernel on large tables (hash_table_find_or_insert,
+ * hash_table.c:270-327, either way -- same buckets, same rehash chain, same multiset):
+ *   LASV_INSERT_RANDOM    one random table access per record, region by region (insert_bins_kernel)
+ *   LASV_INSERT_STREAMED  the table streamed through shared memory group by group, the records of a group
+ *                         applied there (streamed_insert.cuh): two sequential passes over the table's lines
+ *                         per insert, whatever the number of records
+ *   LASV_INSERT_AUTO      streamed once the records to insert number `min_records_per_line` (default 0.75;
+ *                         <= 0 keeps the current value) per 128-byte table line, random access below that
+ * Default AUTO; LASV_B200_INSERT=random|streamed at lasv_graph_new overrides. */
+#define LASV_INSERT_AUTO 0
+#define LASV_INSERT_RANDOM 1
+#define LASV_INSERT_STREAMED 2
+int lasv_graph_set_insert_mode(lasv_graph *g, int mode, double min_records_per_line);
+/* Inserts issued so far, by kind. */
+int lasv_graph_insert_counts(lasv_graph *g, uint64_t *n_streamed, uint64_t *n_random);
+/* Accumulation: with max_stream_bytes != 0, lasv_graph_load_reads_device only PARTITIONS each batch into the
+ * graph's region stripes; the stripes are inserted once they hold batches of max_stream_bytes stream bytes
+ * in total (clamped to what the free device memory can hold; UINT64_MAX = as much as fits), on
+ * lasv_graph_flush, and by every library call that reads the table or its counters (stats, find, dumps,
+ * finalize, ...; NOT by lasv_graph_stats_async, whose k-mer counters then lag behind the reads).  The cost of
+ * an insert per record falls with the number of records per table line, so few large inserts beat many small
+ * ones.  Returns the clamped limit through *granted (may be NULL).  0 switches accumulation off (after a
+ * flush).  The host-buffer and file loaders accumulate the chunks of ONE call by themselves. */
+int lasv_graph_set_accumulation(lasv_graph *g, uint64_t max_stream_bytes, uint64_t *granted);
 /* hash_table_get_unique_kmers / hash_table_get_capacity (hash_table.c:397-408). */
 long long lasv_graph_unique_kmers(lasv_graph *g);
 long long lasv_graph_capacity(lasv_graph *g);

@@ -107,7 +107,12 @@ EXPORTS = [
     "lasv_graph_insert_bins_device", "lasv_graph_set_pipeline", "lasv_graph_flush",
     "lasv_graph_enable_kernel_timing", "lasv_graph_kernel_times", "lasv_graph_stats_async",
     "lasv_ref_hash_table_load_ctx_records", "lasv_seqfile_parse_check",
+    "lasv_graph_kernel_times_by_kind", "lasv_graph_set_insert_mode", "lasv_graph_insert_counts",
+    "lasv_graph_set_accumulation",
 ]
+
+INSERT_AUTO, INSERT_RANDOM, INSERT_STREAMED = 0, 1, 2
+T_KINDS = ("partition", "insert", "sort", "stream", "drain")  # LASV_T_* of include/lasv_b200.h
 
 _lib = None
 
@@ -134,6 +139,10 @@ def lib() -> C.CDLL:
     L.lasv_graph_flush.argtypes = [vp, vp]
     L.lasv_graph_enable_kernel_timing.argtypes = [vp, i32]
     L.lasv_graph_kernel_times.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(u64)]
+    L.lasv_graph_kernel_times_by_kind.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(u64)]
+    L.lasv_graph_set_insert_mode.argtypes = [vp, i32, C.c_double]
+    L.lasv_graph_insert_counts.argtypes = [vp, C.POINTER(u64), C.POINTER(u64)]
+    L.lasv_graph_set_accumulation.argtypes = [vp, u64, C.POINTER(u64)]
     L.lasv_graph_unique_kmers.restype = C.c_longlong
     L.lasv_graph_unique_kmers.argtypes = [vp]
     L.lasv_graph_capacity.restype = C.c_longlong

@@ -33,6 +33,7 @@
 #include "cleaning_host.h"
 #include "branches_host.h"
 #include "groups.cuh"
+#include "streamed_insert.cuh"
 #include "ranking.cuh"
 #include "seq_reader.h"
 
@@ -74,6 +75,19 @@ constexpr uint32_t HIST_BINS = 1u << 16;       // device contig-length histogram
 constexpr uint64_t CHUNK_BYTES = 64ull << 20;  // host->device pipeline granularity (staging buffers are this big)
 constexpr uint64_t CHUNK_READS = 4ull << 20;
 
+// Environment knobs of the insert path, read ONCE per graph (lasv_graph_new), never on a hot entry point.
+//   LASV_B200_INSERT = direct | binned | random | streamed   (tests, experiments)
+//       direct    fused find-or-insert from the partition kernel's tiles, no partition
+//       binned    force the partition even on small tables; the insert kind is chosen as usual
+//       random    partition + random-access insert (insert_bins_kernel), never streamed
+//       streamed  partition + streamed insert (streamed_insert.cuh), whatever the batch size
+//   LASV_B200_BINS = regions to partition into (power of two), LASV_B200_PASSES, LASV_B200_CHUNK_MB
+struct Knobs {
+  int insert = 0;  // 0 none, 1 direct, 2 binned
+  long bins = 0;
+  int passes = 0;
+  long chunk_mb = 0;
+};
 struct Staging {  // one leg of the double-buffered host->device pipeline
   uint8_t *d_seq = nullptr, *d_qual = nullptr;
   uint64_t *d_offsets = nullptr;
@@ -131,10 +145,27 @@ struct lasv_graph {
   int turn = 0;
   bool pipeline = false;
   cudaStream_t ins = nullptr;
+  // which insert follows the partition kernel (read once from LASV_B200_INSERT at creation; lasv_graph_set_insert_mode):
+  // AUTO = streamed (streamed_insert.cuh) when the batch puts ~a record on every table line, else random access
+  int insert_mode = LASV_INSERT_AUTO;
+  double streamed_min_per_line = 0.75;  // records (stripe capacity) per 128-byte table line from which streaming pays
+  StreamedScratch ss;
+  // stripes that accumulate several partition launches before ONE insert (host-buffer and file loaders): stream bytes
+  // binned into leg 0 since its last insert, and the batch size its stripes are sized for (0 = not accumulating)
+  // acc_limit: stream bytes the caller (lasv_graph_set_accumulation: acc_user) or a loader call wants per insert;
+  // acc_cap_records: records the stripes were sized for; acc_records: sum of the k-mer bounds of the batches binned
+  // since the last insert (an insert is due before a batch whose bound does not fit any more); acc_stream: the stream
+  // those partition launches were queued on (the insert follows on it)
+  uint64_t acc_bytes = 0, acc_limit = 0, acc_cap_records = 0, acc_records = 0;
+  bool acc_user = false, acc_stream_used = false;
+  cudaStream_t acc_stream = nullptr;
+  uint64_t n_streamed = 0, n_random = 0;  // inserts by kind (lasv_graph_insert_counts)
+  Knobs knobs;
   // optional per-launch timing of the two kernels of the partitioned path (bench: roofline of the
   // dominant kernel from CUDA events on the stream the kernel is launched on)
   bool timing = false;
-  std::vector<cudaEvent_t> t_events;  // 4 per batch: bin begin/end, insert begin/end
+  std::vector<cudaEvent_t> t_events;  // pairs (begin, end), kind of pair i in t_kind[i] (LASV_T_*)
+  std::vector<int> t_kind;
   size_t t_used = 0;
 
   TableView view() const {
@@ -144,9 +175,22 @@ struct lasv_graph {
 
 namespace {
 
-int use(lasv_graph *g) {
+// Entry points of the load path itself: no side effects beyond selecting the device.
+int use_hot(lasv_graph *g) {
   if (!g) return fail(LASV_ERR_ARG, "NULL graph");
   CUDA_TRY(cudaSetDevice(g->device));
+  return LASV_OK;
+}
+int flush_accumulated(lasv_graph *g, cudaStream_t st);
+// Every other entry point: records that were partitioned but not inserted yet (lasv_graph_set_accumulation) go into
+// the table first, so that whatever reads the table or its counters sees every read loaded so far.
+int use(lasv_graph *g) {
+  if (int e = use_hot(g)) return e;
+  if (g->acc_records) {
+    cudaStream_t st = g->acc_stream;
+    if (int e = flush_accumulated(g, st)) return e;
+    CUDA_TRY(cudaStreamSynchronize(st));
+  }
   return LASV_OK;
 }
 
@@ -210,7 +254,20 @@ BuildParams build_params(lasv_graph *g, const uint8_t *d_seq, const uint8_t *d_q
   return p;
 }
 
+void free_streamed(lasv_graph *g) {
+  StreamedScratch &s = g->ss;
+  cudaFree(s.counts);
+  cudaFree(s.offsets);
+  cudaFree(s.cursor);
+  cudaFree(s.scan_tmp);
+  cudaFree(s.sorted);
+  cudaFree(s.spill);
+  cudaFree(s.n_spill);
+  s = StreamedScratch{};
+}
+
 void free_bins(lasv_graph *g) {
+  free_streamed(g);
   for (auto &l : g->leg) {
     cudaFree(l.v.recs);
     cudaFree(l.v.count);
@@ -222,7 +279,6 @@ void free_bins(lasv_graph *g) {
 
 // next timing event (created on demand, reused after a reset); nullptr when timing is off
 cudaEvent_t timing_event(lasv_graph *g) {
-  if (!g->timing) return nullptr;
   if (g->t_used == g->t_events.size()) {
     cudaEvent_t e = nullptr;
     if (cudaEventCreate(&e) != cudaSuccess) return nullptr;
@@ -230,9 +286,24 @@ cudaEvent_t timing_event(lasv_graph *g) {
   }
   return g->t_events[g->t_used++];
 }
-void mark(cudaEvent_t e, cudaStream_t st) {
-  if (e) cudaEventRecord(e, st);
-}
+// A timed span of kind `kind` on stream st: records its begin event on construction, its end event on end().
+struct Span {
+  cudaEvent_t e1 = nullptr;
+  cudaStream_t st;
+  Span(lasv_graph *g, int kind, cudaStream_t st_) : st(st_) {
+    if (!g->timing) return;
+    cudaEvent_t e0 = timing_event(g);
+    e1 = timing_event(g);
+    if (!e0 || !e1) { e1 = nullptr; return; }
+    g->t_kind.resize(g->t_used / 2);
+    g->t_kind[g->t_used / 2 - 1] = kind;
+    cudaEventRecord(e0, st);
+  }
+  void end() {
+    if (e1) cudaEventRecord(e1, st);
+    e1 = nullptr;
+  }
+};
 
 // The caller's stream waits for every insert queued on the internal stream.
 int join_inserts(lasv_graph *g, cudaStream_t st) {
@@ -241,26 +312,44 @@ int join_inserts(lasv_graph *g, cudaStream_t st) {
   return LASV_OK;
 }
 
-// Partitioned insert applies when the table is much larger than L2 and the batch
-// puts a useful number of records into every region.  LASV_B200_INSERT=direct|binned
-// overrides the choice (tests, experiments).
-bool want_binned(const lasv_graph *g, uint64_t n_bytes, uint32_t *n_bins_out) {
-  const uint64_t table_bytes = g->table_bytes;
-  uint32_t n_bins = 1;
-  // regions of <= 64 MB: the insert rate doubles once the region all SMs work on at a time is
-  // ~100 MB or less and is flat below that (profiles/: bins sweep), while fewer bins keep the
-  // scatter's open write streams few
-  while ((uint64_t)n_bins * (64ull << 20) < table_bytes && n_bins < 65536u && n_bins < g->n_buckets) n_bins <<= 1;
-  if (const char *e = getenv("LASV_B200_BINS")) {  // tests: force a bin count on small tables
-    const long v = atol(e);
-    if (v >= 1 && v <= 65536 && (v & (v - 1)) == 0 && (uint64_t)v <= g->n_buckets) n_bins = (uint32_t)v;
-  }
-  *n_bins_out = n_bins;
-  bool binned = table_bytes >= (256ull << 20) && n_bytes >= (uint64_t)n_bins * 256u;
+Knobs read_knobs(int *insert_mode) {
+  Knobs k;
   if (const char *e = getenv("LASV_B200_INSERT")) {
-    if (!strcmp(e, "direct")) binned = false;
-    else if (!strcmp(e, "binned")) binned = n_bins > 1 || g->n_buckets > 1;
+    if (!strcmp(e, "direct")) k.insert = 1;
+    else if (!strcmp(e, "binned")) k.insert = 2;
+    else if (!strcmp(e, "random")) { k.insert = 2; *insert_mode = LASV_INSERT_RANDOM; }
+    else if (!strcmp(e, "streamed")) { k.insert = 2; *insert_mode = LASV_INSERT_STREAMED; }
   }
+  if (const char *e = getenv("LASV_B200_BINS")) k.bins = atol(e);
+  if (const char *e = getenv("LASV_B200_PASSES")) k.passes = atoi(e);
+  if (const char *e = getenv("LASV_B200_CHUNK_MB")) k.chunk_mb = atol(e);
+  return k;
+}
+
+uint32_t region_count(const lasv_graph *g) {
+  uint32_t n_bins = 1;
+  // regions of <= 64 MB: the random-access insert doubles its rate once the region all SMs work on at a time is
+  // ~100 MB or less and is flat below that (profiles/: bins sweep), while fewer bins keep the scatter's open
+  // write streams few
+  while ((uint64_t)n_bins * (64ull << 20) < g->table_bytes && n_bins < 65536u && n_bins < g->n_buckets) n_bins <<= 1;
+  // ... and of <= 256 buckets on large tables: the sorting passes of the streamed insert rank a chunk of one
+  // region's records by bucket in shared memory, and their output runs are chunk / buckets-per-region records long
+  // (the partition kernel costs the same from 2 K to 16 K stripes, +11 % at 64 K: profiles/r2)
+  if (g->table_bytes >= (256ull << 20))
+    while ((uint64_t)n_bins * 256u < g->n_buckets && n_bins < 65536u) n_bins <<= 1;
+  const long v = g->knobs.bins;  // tests: force a bin count on small tables
+  if (v >= 1 && v <= 65536 && (v & (v - 1)) == 0 && (uint64_t)v <= g->n_buckets) n_bins = (uint32_t)v;
+  return n_bins;
+}
+
+// Partitioned insert applies when the table is much larger than L2 and the batch
+// puts a useful number of records into every region.
+bool want_binned(const lasv_graph *g, uint64_t n_bytes, uint32_t *n_bins_out) {
+  const uint32_t n_bins = region_count(g);
+  *n_bins_out = n_bins;
+  bool binned = g->table_bytes >= (256ull << 20) && n_bytes >= (uint64_t)n_bins * 256u;
+  if (g->knobs.insert == 1) binned = false;
+  else if (g->knobs.insert == 2) binned = n_bins > 1 || g->n_buckets > 1;
   return binned;
 }
 
@@ -270,22 +359,25 @@ int log2_u32(uint32_t v) {
   return lg;
 }
 
-// Records per stripe for a batch of n_bytes stream bytes in n_reads reads spread over n_bins stripes.
-// A read of length l yields at most l-k+1 k-mers and occupies l+1 stream bytes, so a batch yields at
-// most n_bytes - n_reads*k; without the read count, at most n_bytes.  Stripes fill like balls into
-// bins by a well-mixed hash: mean + 8 sigma (+ a little) is never reached in practice.
-uint64_t stripe_capacity(const lasv_graph *g, uint64_t n_bytes, uint64_t n_reads, uint32_t n_bins) {
-  uint64_t bound = n_bytes;
-  if (n_reads && n_reads * (uint64_t)g->k < n_bytes) bound = n_bytes - n_reads * (uint64_t)g->k;
-  else if (!n_reads) bound = (uint64_t)((double)n_bytes * 0.85);  // k >= ~21 on reads of <= ~150 bases
+// Upper bound on the k-mers of a batch of n_bytes stream bytes in n_reads reads: a read of length l yields at
+// most l-k+1 k-mers and occupies l+1 stream bytes; without the read count, n_bytes itself (ANY batch of that
+// many bytes: few long reads, FASTA contigs, small k).
+uint64_t kmer_bound(const lasv_graph *g, uint64_t n_bytes, uint64_t n_reads) {
+  if (n_reads && n_reads * (uint64_t)g->k < n_bytes) return n_bytes - n_reads * (uint64_t)g->k;
+  return n_bytes;
+}
+
+// Records per stripe for `bound` records spread over n_bins stripes.  Stripes fill like balls into bins by a
+// well-mixed hash: mean + 8 sigma (+ a little) is never reached in practice.
+uint64_t stripe_capacity(uint64_t bound, uint32_t n_bins) {
   const double mean = (double)bound / n_bins;
   const uint64_t cap = (uint64_t)(mean * 1.01 + 8.0 * sqrt(mean) + 64.0);
   return (cap + STRIPE_RUN - 1) / STRIPE_RUN * STRIPE_RUN;  // whole runs (stripe_record_at)
 }
 
-int ensure_bins(lasv_graph *g, lasv_graph::BinLeg &l, uint64_t n_bytes, uint64_t n_reads, uint32_t n_bins) {
+int ensure_bins(lasv_graph *g, lasv_graph::BinLeg &l, uint64_t bound, uint32_t n_bins) {
   // a fuller stripe spills its excess straight into the table, so this is a sizing choice, not a limit
-  const uint64_t cap = stripe_capacity(g, n_bytes, n_reads, n_bins);
+  const uint64_t cap = stripe_capacity(bound, n_bins);
   if (cap > 0xFFFFFFF0ull) return fail(LASV_ERR_ARG, "batch too large for the bin stripes");
   const uint64_t want = cap * n_bins;
   if (l.alloc_records < want || l.alloc_n != n_bins) {
@@ -293,8 +385,10 @@ int ensure_bins(lasv_graph *g, lasv_graph::BinLeg &l, uint64_t n_bytes, uint64_t
     cudaFree(l.v.recs);
     cudaFree(l.v.count);
     l.v = BinView{};
+    l.alloc_records = 0;
     CUDA_TRY(cudaMalloc(&l.v.recs, want * (size_t)bin_record_words(g->N, g->k) * sizeof(uint64_t)));
     CUDA_TRY(cudaMalloc(&l.v.count, (size_t)(n_bins + 1) * COUNT_STRIDE * sizeof(unsigned int)));
+    CUDA_TRY(cudaMemset(l.v.count, 0, (size_t)(n_bins + 1) * COUNT_STRIDE * sizeof(unsigned int)));
     l.alloc_records = want;
     l.alloc_n = n_bins;
   }
@@ -308,6 +402,36 @@ int ensure_bins(lasv_graph *g, lasv_graph::BinLeg &l, uint64_t n_bytes, uint64_t
   l.v.spill_ok = 1;
   l.v.src_shift = 0;
   l.v.bins_per_src = n_bins;
+  return LASV_OK;
+}
+
+// Streamed or random-access insert for these stripes?  Streaming costs two passes over the table's lines
+// whatever the batch; it pays from about 0.75 records per line on.
+bool want_streamed(const lasv_graph *g, const BinView &v, uint64_t n_records, StreamedGeom *geom) {
+  if (g->insert_mode == LASV_INSERT_RANDOM) return false;
+  if (!streamed_geometry(g->view(), v, geom)) return false;
+  if (g->insert_mode == LASV_INSERT_STREAMED) return true;
+  const double lines = (double)g->table_bytes / LINE_BYTES;
+  return (double)n_records >= g->streamed_min_per_line * lines;
+}
+
+int ensure_streamed(lasv_graph *g, const StreamedGeom &geom, uint32_t rec_words) {
+  StreamedScratch &s = g->ss;
+  const uint32_t buckets = geom.buckets_per_slab;
+  if (s.alloc_records >= geom.slab_cap && s.alloc_buckets >= buckets && s.n_spill) return LASV_OK;
+  CUDA_TRY(cudaDeviceSynchronize());
+  free_streamed(g);
+  const uint64_t recs = std::max<uint64_t>(geom.slab_cap, 1);
+  CUDA_TRY(cudaMalloc(&s.counts, ((size_t)buckets + 1) * sizeof(uint32_t)));
+  CUDA_TRY(cudaMalloc(&s.offsets, ((size_t)buckets + 1) * sizeof(uint32_t)));
+  CUDA_TRY(cudaMalloc(&s.cursor, (size_t)buckets * sizeof(uint32_t)));
+  s.scan_tmp_bytes = std::max<size_t>(streamed_scan_tmp_bytes(buckets + 1), 16);
+  CUDA_TRY(cudaMalloc(&s.scan_tmp, s.scan_tmp_bytes));
+  CUDA_TRY(cudaMalloc(&s.sorted, recs * rec_words * sizeof(uint64_t)));
+  CUDA_TRY(cudaMalloc(&s.spill, recs * sizeof(uint32_t)));
+  CUDA_TRY(cudaMalloc(&s.n_spill, sizeof(unsigned long long)));
+  s.alloc_records = recs;
+  s.alloc_buckets = buckets;
   return LASV_OK;
 }
 
@@ -386,6 +510,7 @@ lasv_graph *lasv_graph_new(int kmer_size, int number_bits, int bucket_size, int 
     ok = ok && cudaEventCreateWithFlags(&l.binned, cudaEventDisableTiming) == cudaSuccess &&
          cudaEventCreateWithFlags(&l.inserted, cudaEventDisableTiming) == cudaSuccess;
   if (const char *e = getenv("LASV_B200_PIPELINE")) g->pipeline = atoi(e) != 0;
+  g->knobs = read_knobs(&g->insert_mode);
   if (ok) ok = lasv_graph_clear(g, nullptr) == LASV_OK && cudaDeviceSynchronize() == cudaSuccess;
   if (!ok) {
     if (g_err.empty() || g_err.find("failed") == std::string::npos)
@@ -429,7 +554,7 @@ void lasv_graph_free(lasv_graph **gp) {
 }
 
 int lasv_graph_clear(lasv_graph *g, void *cuda_stream) {
-  if (int e = use(g)) return e;
+  if (int e = use_hot(g)) return e;
   cudaStream_t st = stream_of(g, cuda_stream);
   if (int e = join_inserts(g, st)) return e;
   CUDA_TRY(cudaMemsetAsync(g->d_lines, 0, g->table_bytes, st));
@@ -437,6 +562,12 @@ int lasv_graph_clear(lasv_graph *g, void *cuda_stream) {
   CUDA_TRY(cudaMemsetAsync(g->d_stats, 0, sizeof(ReadStats), st));
   CUDA_TRY(cudaMemsetAsync(g->d_hist, 0, HIST_BINS * sizeof(unsigned long long), st));
   CUDA_TRY(cudaMemsetAsync(g->d_overflow, 0, sizeof(unsigned long long), st));
+  if (g->acc_records) {  // records binned but not yet inserted belong to the graph that is being cleared
+    CUDA_TRY(cudaStreamSynchronize(g->acc_stream));
+    CUDA_TRY(cudaMemsetAsync(g->leg[0].v.count, 0, (size_t)(g->leg[0].v.n_bins + 1) * COUNT_STRIDE * sizeof(unsigned int), st));
+    g->acc_records = 0;
+    g->acc_bytes = 0;
+  }
   g->finalized = false;
   return LASV_OK;
 }
@@ -468,31 +599,63 @@ int lasv_graph_enable_kernel_timing(lasv_graph *g, int on) {
   CUDA_TRY(cudaDeviceSynchronize());
   g->timing = on != 0;
   g->t_used = 0;
+  g->t_kind.clear();
+  return LASV_OK;
+}
+
+int lasv_graph_kernel_times_by_kind(lasv_graph *g, double ms[LASV_T_KINDS], uint64_t n[LASV_T_KINDS]) {
+  if (int e = use(g)) return e;
+  CUDA_TRY(cudaDeviceSynchronize());
+  for (int k = 0; k < LASV_T_KINDS; k++) { ms[k] = 0; n[k] = 0; }
+  for (size_t i = 0; 2 * i + 1 < g->t_used && i < g->t_kind.size(); i++) {
+    float x = 0;
+    CUDA_TRY(cudaEventElapsedTime(&x, g->t_events[2 * i], g->t_events[2 * i + 1]));
+    const int k = g->t_kind[i];
+    if (k < 0 || k >= LASV_T_KINDS) continue;
+    ms[k] += x;
+    n[k]++;
+  }
   return LASV_OK;
 }
 
 int lasv_graph_kernel_times(lasv_graph *g, double *partition_ms, double *insert_ms, uint64_t *n_batches) {
+  double ms[LASV_T_KINDS];
+  uint64_t n[LASV_T_KINDS];
+  if (int e = lasv_graph_kernel_times_by_kind(g, ms, n)) return e;
+  if (partition_ms) *partition_ms = ms[LASV_T_PARTITION];
+  if (insert_ms) *insert_ms = ms[LASV_T_INSERT];
+  if (n_batches) *n_batches = n[LASV_T_INSERT];
+  return LASV_OK;
+}
+
+int lasv_graph_set_insert_mode(lasv_graph *g, int mode, double min_records_per_line) {
   if (int e = use(g)) return e;
-  CUDA_TRY(cudaDeviceSynchronize());
-  double a = 0, b = 0;
-  uint64_t n = 0;
-  for (size_t i = 0; i + 3 < g->t_used; i += 4) {
-    float x = 0, y = 0;
-    CUDA_TRY(cudaEventElapsedTime(&x, g->t_events[i], g->t_events[i + 1]));
-    CUDA_TRY(cudaEventElapsedTime(&y, g->t_events[i + 2], g->t_events[i + 3]));
-    a += x;
-    b += y;
-    n++;
-  }
-  if (partition_ms) *partition_ms = a;
-  if (insert_ms) *insert_ms = b;
-  if (n_batches) *n_batches = n;
+  if (mode != LASV_INSERT_AUTO && mode != LASV_INSERT_RANDOM && mode != LASV_INSERT_STREAMED)
+    return fail(LASV_ERR_ARG, "insert mode must be LASV_INSERT_AUTO, _RANDOM or _STREAMED");
+  g->insert_mode = mode;
+  if (min_records_per_line > 0) g->streamed_min_per_line = min_records_per_line;
+  return LASV_OK;
+}
+
+int lasv_graph_insert_counts(lasv_graph *g, uint64_t *n_streamed, uint64_t *n_random) {
+  if (!g) return fail(LASV_ERR_ARG, "NULL graph");
+  if (n_streamed) *n_streamed = g->n_streamed;
+  if (n_random) *n_random = g->n_random;
   return LASV_OK;
 }
 
 int lasv_graph_flush(lasv_graph *g, void *cuda_stream) {
-  if (int e = use(g)) return e;
-  return join_inserts(g, stream_of(g, cuda_stream));
+  if (int e = use_hot(g)) return e;
+  cudaStream_t st = stream_of(g, cuda_stream);
+  if (g->acc_records) {  // accumulated stripes: the insert is queued on the stream of their partition launches
+    cudaStream_t as = g->acc_stream;
+    if (int e = flush_accumulated(g, as)) return e;
+    if (as != st) {
+      CUDA_TRY(cudaEventRecord(g->leg[0].inserted, as));
+      CUDA_TRY(cudaStreamWaitEvent(st, g->leg[0].inserted, 0));
+    }
+  }
+  return join_inserts(g, st);
 }
 
 long long lasv_graph_capacity(lasv_graph *g) { return g ? (long long)g->n_slots : -1; }
@@ -502,43 +665,145 @@ void *lasv_graph_device_table(lasv_graph *g) { return g ? g->d_lines : nullptr; 
 uint64_t lasv_graph_device_table_bytes(lasv_graph *g) { return g ? g->table_bytes : 0; }
 
 // ------------------------------------------------------------- the hot path
+namespace {
+
+// K3 for everything the stripes `v` hold (about n_records of them), queued on st: the streamed insert when the
+// batch is dense enough on the table's lines, else the random-access insert.  own_counters: the stripes are the
+// graph's (counters zeroed afterwards, ready for the next partition launch).
+int insert_stripes(lasv_graph *g, const BinView &v, uint64_t n_records, int ctas_per_sm, bool allow_streamed,
+                   bool own_counters, cudaStream_t st) {
+  StreamedGeom geom;
+  Span total(g, LASV_T_INSERT, st);
+  if (allow_streamed && want_streamed(g, v, n_records, &geom)) {
+    if (int e = ensure_streamed(g, geom, v.rec_words)) return e;
+    std::function<void(int, int)> span;
+    std::vector<Span> open;
+    if (g->timing)
+      span = [&](int kind, int begin) {
+        if (begin) open.emplace_back(g, kind, st);
+        else { open.back().end(); open.pop_back(); }
+      };
+    uint64_t launches = 0;
+    if (launch_streamed_insert(g->N, v, g->view(), g->d_ctr, g->d_overflow, geom, g->ss, st, &launches, span))
+      return fail(LASV_ERR_CUDA, "streamed insert: kernel attributes: %s", cudaGetErrorString(cudaGetLastError()));
+    g_launches.fetch_add(launches, std::memory_order_relaxed);
+    CUDA_TRY(cudaGetLastError());
+    g->n_streamed++;
+  } else {
+    launch_insert_bins(g->N, v, g->view(), g->d_ctr, ctas_per_sm, st);
+    if (int e = check_launch()) return e;
+    g->n_random++;
+  }
+  total.end();
+  if (own_counters)
+    CUDA_TRY(cudaMemsetAsync(v.count, 0, (size_t)(v.n_bins + 1) * COUNT_STRIDE * sizeof(unsigned int), st));
+  return LASV_OK;
+}
+
+// Records of bin records + streamed-insert scratch that fit in the free device memory, at most `want`.
+uint64_t accumulation_records(lasv_graph *g, uint64_t want) {
+  size_t free_b = 0, total_b = 0;
+  if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) return 0;
+  const uint64_t rec_bytes = 8ull * bin_record_words(g->N, g->k);
+  // what the graph holds already for this purpose is reallocated, so it counts as free
+  const uint64_t have = g->leg[0].alloc_records * rec_bytes + g->ss.alloc_records * (rec_bytes + 4);
+  const uint64_t reserve = 3ull << 30;  // staging legs, statistics, the caller's next buffers
+  if (free_b + have <= reserve) return 0;
+  const double budget = (double)(free_b + have - reserve);
+  // stripes (1.03: mean + 8 sigma + whole runs) and one slab (<= 1/8 of them) of sorted records + spill indices
+  const double per_record = 1.03 * ((double)rec_bytes + ((double)rec_bytes + 4.0) / 8.0);
+  const uint64_t fit = (uint64_t)(budget / per_record);
+  return std::min(want, fit);
+}
+
+}  // namespace
+
+extern "C++" {
+namespace {
+// Insert what leg 0 has accumulated since its last insert.
+int flush_accumulated(lasv_graph *g, cudaStream_t st) {
+  if (!g->acc_records) return LASV_OK;
+  const uint64_t n = g->acc_records;
+  g->acc_records = 0;
+  g->acc_bytes = 0;
+  return insert_stripes(g, g->leg[0].v, n, 0, true, true, st);
+}
+}  // namespace
+}
+
+int lasv_graph_set_accumulation(lasv_graph *g, uint64_t max_stream_bytes, uint64_t *granted) {
+  if (int e = use(g)) return e;  // inserts what the previous setting left in the stripes
+  g->acc_limit = max_stream_bytes;
+  g->acc_user = max_stream_bytes != 0;
+  g->acc_cap_records = 0;  // sized by the first batch
+  if (granted) {
+    // a stream byte yields at most one k-mer
+    const uint64_t fit = accumulation_records(g, max_stream_bytes);
+    *granted = std::min(max_stream_bytes, fit);
+  }
+  return LASV_OK;
+}
+
 int lasv_graph_load_reads_device(lasv_graph *g, const uint8_t *d_seq, const uint8_t *d_qual,
                                  uint64_t n_bytes, const uint64_t *d_offsets, uint64_t n_reads,
                                  int quality_cutoff, void *cuda_stream) {
-  if (int e = use(g)) return e;
+  if (int e = use_hot(g)) return e;
   if (g->finalized) return fail(LASV_ERR_STATE, "graph is finalised; no further inserts");
   if (int e = check_streams(d_seq, d_qual)) return e;
   cudaStream_t st = stream_of(g, cuda_stream);
   if (n_bytes) {
     BuildParams p = build_params(g, d_seq, d_qual, n_bytes, quality_cutoff);
     uint32_t n_bins = 1;
-    if (want_binned(g, n_bytes, &n_bins)) {
+    const bool accumulate = g->acc_limit != 0 && !g->pipeline;
+    if (want_binned(g, accumulate ? std::max(g->acc_limit, n_bytes) : n_bytes, &n_bins)) {
       // Partitioned insert: group the batch's k-mers by 64 MB table region, then insert region by
-      // region with the whole grid (profiles/bins_sweep_r1.txt: twice the insert rate of probes spread
-      // over the whole 100 GB table, on top of the 2x lost to the TLB beyond 64 GB).
-      lasv_graph::BinLeg &l = g->leg[g->pipeline ? (g->turn++ & 1) : 0];
+      // region: streamed through shared memory when the batch is dense on the table's lines
+      // (streamed_insert.cuh), at random inside one region at a time otherwise.
+      lasv_graph::BinLeg &l = g->leg[(g->pipeline && !accumulate) ? (g->turn++ & 1) : 0];
       if (l.in_flight) CUDA_TRY(cudaStreamWaitEvent(st, l.inserted, 0));  // the insert that read this leg
-      if (int e = ensure_bins(g, l, n_bytes, d_offsets ? n_reads : 0, n_bins)) return e;
+      const uint64_t bound = kmer_bound(g, n_bytes, d_offsets ? n_reads : 0);
+      if (accumulate) {
+        // several partition launches fill the same stripes; ONE insert when the next batch might not fit
+        if (g->acc_records && (g->acc_stream != st || g->acc_records + bound > g->acc_cap_records))
+          if (int e = flush_accumulated(g, g->acc_stream)) return e;
+        if (!g->acc_records) {
+          if (g->acc_stream != st && g->acc_stream_used) {  // the insert just queued there reads the stripes
+            CUDA_TRY(cudaEventRecord(l.inserted, g->acc_stream));
+            CUDA_TRY(cudaStreamWaitEvent(st, l.inserted, 0));
+          }
+          if (!g->acc_cap_records || bound > g->acc_cap_records) {
+            // as many records as `acc_limit` stream bytes of batches like this one hold, if they fit in memory
+            const double ratio = (double)bound / (double)n_bytes;
+            const double want_d = (double)std::max(g->acc_limit, n_bytes) * ratio;
+            const uint64_t want = want_d >= 1.8e19 ? ~0ull : (uint64_t)want_d + 1;
+            g->acc_cap_records = std::max(bound, accumulation_records(g, want));
+          }
+          if (int e = ensure_bins(g, l, g->acc_cap_records, n_bins)) return e;
+        }
+        g->acc_stream = st;
+        g->acc_stream_used = true;
+      } else {
+        if (int e = ensure_bins(g, l, bound, n_bins)) return e;
+      }
       p.bins = l.v;
       p.ctas_per_sm = g->pipeline ? 2 : 0;  // pipelined: this kernel shares the SMs with the previous batch's insert
-      CUDA_TRY(cudaMemsetAsync(l.v.count, 0, (size_t)(n_bins + 1) * COUNT_STRIDE * sizeof(unsigned int), st));
-      cudaEvent_t tb0 = timing_event(g), tb1 = timing_event(g), ti0 = timing_event(g), ti1 = timing_event(g);
-      mark(tb0, st);
-      launch_build(g->N, MODE_BIN, p, st);
-      if (int e = check_launch()) return e;
-      mark(tb1, st);
-      if (!g->pipeline) {
-        mark(ti0, st);
-        launch_insert_bins(g->N, l.v, g->view(), g->d_ctr, 0, st);
+      {
+        Span sp(g, LASV_T_PARTITION, st);
+        launch_build(g->N, MODE_BIN, p, st);
         if (int e = check_launch()) return e;
-        mark(ti1, st);
+        sp.end();
+      }
+      if (accumulate) {
+        g->acc_bytes += n_bytes;
+        g->acc_records += bound;
+      } else if (!g->pipeline) {
+        if (int e = insert_stripes(g, l.v, bound, 0, true, true, st)) return e;
       } else {
+        // (random access only: the next batch's partition kernel may spill straight into the table while
+        // this insert runs, which the streamed insert's staged copies would overwrite)
         CUDA_TRY(cudaEventRecord(l.binned, st));
         CUDA_TRY(cudaStreamWaitEvent(g->ins, l.binned, 0));
-        mark(ti0, g->ins);
-        launch_insert_bins(g->N, l.v, g->view(), g->d_ctr, 2, g->ins);
-        if (int e = check_launch()) return e;
-        mark(ti1, g->ins);
+        if (int e = insert_stripes(g, l.v, bound, 2, false, true, g->ins)) return e;
         CUDA_TRY(cudaEventRecord(l.inserted, g->ins));
         l.in_flight = true;
       }
@@ -546,10 +811,12 @@ int lasv_graph_load_reads_device(lasv_graph *g, const uint8_t *d_seq, const uint
       // Direct fused insert.  Random access over more than ~64 GB falls off the
       // TLB reach of a B200 (profiles/random_access_sweep_r1.jsonl): walk the batch
       // once per <=50 GB slice of the table.  LASV_B200_PASSES overrides.
+      if (g->acc_records)  // (a batch too small to partition arrives while larger ones wait in the stripes)
+        if (int e = flush_accumulated(g, g->acc_stream)) return e;
       int n_pass = 1;
       while (g->table_bytes / (uint64_t)n_pass > (50ull << 30) && (1 << g->L) > 2 * n_pass) n_pass *= 2;
-      if (const char *e = getenv("LASV_B200_PASSES")) {
-        const int v = atoi(e);
+      {
+        const int v = g->knobs.passes;
         if (v >= 1 && v <= 64 && (v & (v - 1)) == 0 && v <= (1 << (g->L - 1))) n_pass = v;
       }
       int lg = 0;
@@ -574,7 +841,7 @@ int lasv_graph_load_reads_device(lasv_graph *g, const uint8_t *d_seq, const uint
 int lasv_graph_read_stats_device(lasv_graph *g, const uint8_t *d_seq, const uint8_t *d_qual,
                                  const uint64_t *d_offsets, uint64_t n_reads, int quality_cutoff,
                                  void *cuda_stream) {
-  if (int e = use(g)) return e;
+  if (int e = use_hot(g)) return e;
   if (!n_reads) return LASV_OK;
   if (int e = check_streams(d_seq, d_qual)) return e;
   launch_read_stats(d_seq, d_qual, d_offsets, n_reads, 1, g->k, quality_cutoff, g->d_stats,
@@ -585,7 +852,7 @@ int lasv_graph_read_stats_device(lasv_graph *g, const uint8_t *d_seq, const uint
 int lasv_graph_load_reads_host(lasv_graph *g, const uint8_t *seq, const uint8_t *qual,
                                uint64_t n_bytes, const uint64_t *offsets, uint64_t n_reads,
                                int quality_cutoff, lasv_load_stats *batch_stats) {
-  if (int e = use(g)) return e;
+  if (int e = use_hot(g)) return e;
   if (g->finalized) return fail(LASV_ERR_STATE, "graph is finalised; no further inserts");
   if (!seq || !offsets) return fail(LASV_ERR_ARG, "seq and offsets are required");
   if (offsets[n_reads] != n_bytes) return fail(LASV_ERR_ARG, "offsets[n_reads] != n_bytes");
@@ -597,6 +864,35 @@ int lasv_graph_load_reads_host(lasv_graph *g, const uint8_t *seq, const uint8_t 
   unsigned long long ov = 0;
   if (batch_stats) if (int e = fetch_counters(g, g->compute, &rs0, &c0, &ov)) return e;
 
+  // The chunks of this call are partitioned one by one (each as soon as its copy has landed) into the SAME
+  // stripes, which are inserted once they hold as much as the device memory allows, and at the end of the call:
+  // the insert's cost per record falls with the number of records per table line (streamed_insert.cuh).
+  // With lasv_graph_set_accumulation in force the chunks join the caller's accumulation instead (and stay there).
+  struct Accumulate {
+    lasv_graph *g;
+    bool mine;
+    Accumulate(lasv_graph *g_, uint64_t limit) : g(g_), mine(g_->acc_limit == 0 && limit != 0) {
+      if (mine) {
+        g->acc_limit = limit;
+        g->acc_cap_records = 0;
+      }
+    }
+    ~Accumulate() {
+      if (!mine) return;
+      if (g->acc_records) {  // error exit: drop what was binned but not inserted
+        cudaStreamSynchronize(g->compute);
+        cudaMemset(g->leg[0].v.count, 0, (size_t)(g->leg[0].v.n_bins + 1) * COUNT_STRIDE * sizeof(unsigned int));
+        g->acc_records = 0;
+        g->acc_bytes = 0;
+      }
+      g->acc_limit = 0;
+      g->acc_cap_records = 0;
+    }
+  };
+  uint32_t n_bins_call = 1;
+  const bool binned_call = !g->pipeline && want_binned(g, n_bytes, &n_bins_call);
+  Accumulate acc(g, binned_call ? n_bytes : 0);
+
   // chunks are cut at read boundaries, so no k-mer window straddles two chunks
   uint64_t r0 = 0;
   int leg = 0, n_chunk = 0;
@@ -607,10 +903,8 @@ int lasv_graph_load_reads_host(lasv_graph *g, const uint8_t *seq, const uint8_t 
     // that the kernels start early (nothing overlaps the first copy): 1/8, 1/4, 1/2, then whole chunks.
     {
       uint64_t chunk = CHUNK_BYTES;
-      if (const char *e = getenv("LASV_B200_CHUNK_MB")) {  // experiments: 1..64
-        const long v = atol(e);
-        if (v >= 1 && (uint64_t)v <= (CHUNK_BYTES >> 20)) chunk = (uint64_t)v << 20;
-      }
+      if (g->knobs.chunk_mb >= 1 && (uint64_t)g->knobs.chunk_mb <= (CHUNK_BYTES >> 20))  // experiments: 1..64
+        chunk = (uint64_t)g->knobs.chunk_mb << 20;
       const uint64_t limit = n_chunk < 3 ? (chunk >> (3 - n_chunk)) : chunk;
       uint64_t lo = r0 + 1, hi = std::min(n_reads, r0 + CHUNK_READS);
       if (offsets[lo] - base > CHUNK_BYTES)
@@ -643,6 +937,8 @@ int lasv_graph_load_reads_host(lasv_graph *g, const uint8_t *seq, const uint8_t 
     leg = (leg + 1) % 3;
     r0 = r1;
   }
+  if (acc.mine)
+    if (int e = flush_accumulated(g, g->compute)) return e;
   if (int e = join_inserts(g, g->compute)) return e;  // pipelined inserts of the last chunks
   if (int e = fetch_counters(g, g->compute, &rs1, &c1, &ov)) return e;
   if (c1.table_full) return fail(LASV_ERR_TABLE_FULL, "%s", TABLE_FULL_MSG);
@@ -689,7 +985,7 @@ int lasv_graph_stats(lasv_graph *g, lasv_load_stats *out, uint64_t *contig_hist,
 /* Asynchronous read-back of the load statistics as they stand when `cuda_stream` reaches this
  * point: 7 uint64 (lasv_load_stats order) + table_full + overflow into pinned host memory. */
 int lasv_graph_stats_async(lasv_graph *g, uint64_t *pinned_out9, void *cuda_stream) {
-  if (int e = use(g)) return e;
+  if (int e = use_hot(g)) return e;
   if (!pinned_out9) return fail(LASV_ERR_ARG, "NULL output");
   cudaStream_t st = stream_of(g, cuda_stream);
   // ReadStats = {n_reads, bad_reads, bases_read, bases_loaded, n_contigs}; GraphCounters starts with
@@ -832,13 +1128,8 @@ int lasv_graph_bin_geometry(lasv_graph *g, int n_owners, uint64_t n_bytes, uint6
   if (!g) return fail(LASV_ERR_ARG, "NULL graph");
   if (n_owners < 1 || n_owners > 16 || (n_owners & (n_owners - 1)))
     return fail(LASV_ERR_ARG, "n_owners must be a power of two <= 16, got %d", n_owners);
-  uint32_t per = 1;
-  while ((uint64_t)per * (64ull << 20) < g->table_bytes && per < 65536u && per < g->n_buckets) per <<= 1;
-  if (const char *e = getenv("LASV_B200_BINS")) {
-    const long v = atol(e);
-    if (v >= 1 && v <= 65536 && (v & (v - 1)) == 0 && (uint64_t)v <= g->n_buckets) per = (uint32_t)v;
-  }
-  const uint64_t cap = stripe_capacity(g, n_bytes, n_reads, per * (uint32_t)n_owners);
+  const uint32_t per = region_count(g);
+  const uint64_t cap = stripe_capacity(kmer_bound(g, n_bytes, n_reads), per * (uint32_t)n_owners);
   if (cap > 0xFFFFFFF0ull) return fail(LASV_ERR_ARG, "batch too large for the bin stripes");
   if (bins_per_owner) *bins_per_owner = per;
   if (stripe_capacity_out) *stripe_capacity_out = (uint32_t)cap;
@@ -910,8 +1201,12 @@ int lasv_graph_insert_bins_device(lasv_graph *g, const void *d_records, const vo
   b.bins_per_src = bins_per_src;
   b.block_shift = (uint32_t)log2_u32(bins_per_src);
   b.rec_words = bin_record_words(g->N, g->k);
-  launch_insert_bins(g->N, b, g->view(), g->d_ctr, g->pipeline ? 2 : 0, stream_of(g, cuda_stream));
-  return check_launch();
+  // (the stripes hold about their capacity less the 8-sigma margin; the counts themselves are on the device)
+  const uint64_t about = (uint64_t)((double)b.n_bins * (double)b.cap / 1.03);
+  // Streamed only when no partition kernel of this graph can write into the table meanwhile: with several
+  // owners an overfull stripe spills into the spill area, never into the table.
+  const bool may_stream = !g->pipeline || n_src > 1 || spill_capacity_records != 0;
+  return insert_stripes(g, b, about, g->pipeline ? 2 : 0, may_stream, false, stream_of(g, cuda_stream));
 }
 
 // ------------------------------------------------------------------ queries

@@ -94,8 +94,31 @@ class DBGraph:
         check(self._lib.lasv_graph_kernel_times(self._h, C.byref(a), C.byref(b), C.byref(n)))
         return {"partition_ms": a.value, "insert_ms": b.value, "batches": int(n.value)}
 
+    def kernel_times_by_kind(self) -> dict:
+        """{kind: (ms, spans)} for partition / insert / sort / stream / drain (LASV_T_*)."""
+        ms = (C.c_double * len(_capi.T_KINDS))()
+        n = (C.c_uint64 * len(_capi.T_KINDS))()
+        check(self._lib.lasv_graph_kernel_times_by_kind(self._h, ms, n))
+        return {k: (ms[i], int(n[i])) for i, k in enumerate(_capi.T_KINDS)}
+
+    def set_insert_mode(self, mode: int, min_records_per_line: float = 0.0):
+        """_capi.INSERT_AUTO / INSERT_RANDOM / INSERT_STREAMED (streamed_insert.cuh)."""
+        check(self._lib.lasv_graph_set_insert_mode(self._h, int(mode), float(min_records_per_line)))
+
+    def insert_counts(self) -> dict:
+        a, b = C.c_uint64(0), C.c_uint64(0)
+        check(self._lib.lasv_graph_insert_counts(self._h, C.byref(a), C.byref(b)))
+        return {"streamed": int(a.value), "random": int(b.value)}
+
+    def set_accumulation(self, max_stream_bytes: int) -> int:
+        """load_reads_device only partitions; one insert per `max_stream_bytes` of batches (or flush()).
+        Returns the limit granted (free device memory may hold less)."""
+        got = C.c_uint64(0)
+        check(self._lib.lasv_graph_set_accumulation(self._h, int(max_stream_bytes), C.byref(got)))
+        return int(got.value)
+
     def flush(self, stream=None):
-        """`stream` waits for every insert queued on the internal stream."""
+        """`stream` waits for every insert queued so far (accumulated stripes are inserted first)."""
         check(self._lib.lasv_graph_flush(self._h, stream))
 
     # -- properties

@@ -284,13 +284,16 @@ def test_route_and_insert_records_match_oracle(base, world):
                                                            # two-word k-mers too long for the 16-byte record
                                                            (dataclasses.replace(synth.CFG0, kmer_size=63), 2, 2, False),
                                                            (dataclasses.replace(synth.CFG0, kmer_size=57), 1, 4, False)])
-def test_binned_exchange_matches_oracle(base, world, bins, tiny_stripes, monkeypatch):
+@pytest.mark.parametrize("insert", ["random", "streamed"])
+def test_binned_exchange_matches_oracle(base, world, bins, tiny_stripes, insert, monkeypatch):
     """The production sharded path on one GPU: ranks emulated as `world` local graphs.
     Every emulated rank bins its slice of the reads by (owner, table region); the
     all-to-all is emulated by handing block d of every sender to graph d; the owners
-    sweep the received stripes region by region."""
+    sweep the received stripes region by region (random access) or stream their table
+    through shared memory (streamed_insert.cuh), senders' spill areas included."""
     torch = torch_cuda()
     monkeypatch.setenv("LASV_B200_BINS", str(bins))
+    monkeypatch.setenv("LASV_B200_INSERT", insert)
     L, W, n_reads = 13, 40, 24_000
     w = synth.scaled(base, 80_000, L)
     w.bucket_size = W
@@ -335,6 +338,7 @@ def test_binned_exchange_matches_oracle(base, world, bins, tiny_stripes, monkeyp
             st = graphs[d].stats(stream=st_)
             recs.append(graphs[d].records())
             assert st["unique_kmers"] == len(recs[-1])
+            assert graphs[d].insert_counts()[insert] == 1
         assert np.array_equal(O.sort_records(np.concatenate(recs)), want)
     finally:
         for g in graphs:
@@ -407,7 +411,64 @@ def test_pipelined_inserts_and_async_statistics(monkeypatch):
         assert np.array_equal(O.sort_records(g.records()), want)
 
 
-@pytest.mark.parametrize("mode", ["direct", "binned"])
+@pytest.mark.parametrize("base,L,W,bins,n_batches", [(synth.CFG0, 13, 40, 4, 5), (synth.CFG1, 12, 100, 1, 3),
+                                                     (synth.CFG2, 13, 40, 16, 4), (synth.CFG0, 10, 250, 2, 1),
+                                                     (dataclasses.replace(synth.CFG0, kmer_size=63), 13, 33, 8, 2)])
+def test_streamed_insert_with_accumulation_matches_oracle(base, L, W, bins, n_batches):
+    """lasv_graph_set_accumulation + the streamed insert (streamed_insert.cuh): load_reads_device only partitions,
+    the stripes are inserted by flush / by the first call that reads the table, through sort-by-group, shared-memory
+    upserts behind cp.async.bulk copies, and the drain of full buckets.  Same multiset as the oracle, and the same
+    as the random-access insert."""
+    torch = torch_cuda()
+    n_reads = 24_000
+    w = synth.scaled(base, 80_000, L)
+    w.bucket_size = W
+    p, seq, qual, offs, og = _synth_oracle(w, n_reads, seed=91)
+    want = O.sort_records(og.records())
+    st_ = torch.cuda.current_stream().cuda_stream
+    d_seq = torch.from_numpy(np.concatenate([seq, np.full(16, 10, np.uint8)])).cuda()
+    d_qual = torch.from_numpy(np.concatenate([qual, np.full(16, 10, np.uint8)])).cuda()
+    d_offs = torch.from_numpy(offs.astype(np.int64)).cuda()
+    per_reads = n_reads // n_batches
+    per = per_reads * (w.read_len + 1)
+    os.environ["LASV_B200_BINS"] = str(bins)
+    os.environ["LASV_B200_INSERT"] = "binned"
+    try:
+        with DBGraph(w.kmer_size, L, W) as g:
+            g.set_insert_mode(_capi.INSERT_STREAMED)
+            g.enable_kernel_timing(True)
+            # room for two batches and a bit: the third one forces an insert by itself
+            granted = g.set_accumulation(int(2.5 * per))
+            assert granted == int(2.5 * per)
+            for b in range(n_batches):
+                lo = b * per
+                nr = per_reads if b < n_batches - 1 else n_reads - b * per_reads
+                d_off_b = (d_offs[b * per_reads: b * per_reads + nr + 1] - lo).contiguous()
+                g.load_reads_device(d_seq[lo:], d_qual[lo:], nr * (w.read_len + 1), d_off_b, nr, w.cutoff, st_)
+            before = g.insert_counts()
+            assert before["random"] == 0 and before["streamed"] == (n_batches - 1) // 2
+            st = g.stats(stream=st_)                   # reads the counters: inserts what is still in the stripes
+            assert g.insert_counts()["streamed"] == before["streamed"] + 1
+            assert st["kmers_inserted"] == og.stats.kmers_inserted and st["unique_kmers"] == len(want)
+            assert st["bad_reads"] == og.stats.bad_reads
+            assert np.array_equal(O.sort_records(g.records()), want)
+            kt = g.kernel_times_by_kind()
+            assert kt["partition"][1] == n_batches and kt["insert"][1] == before["streamed"] + 1
+            assert kt["sort"][0] > 0 and kt["stream"][0] > 0 and kt["stream"][1] == kt["sort"][1] >= kt["insert"][1]
+            # a second load after the flush, accumulation off again: one insert per batch
+            g.set_accumulation(0)
+            g.set_insert_mode(_capi.INSERT_RANDOM)
+            g.load_reads_device(d_seq, d_qual, len(seq), d_offs, n_reads, w.cutoff, st_)
+            recs = O.sort_records(g.records())
+            assert g.insert_counts()["random"] == 1
+            assert np.array_equal(recs["kmer"], want["kmer"]) and np.array_equal(recs["edges"], want["edges"])
+            assert np.array_equal(recs["covg"].astype(np.int64), 2 * want["covg"].astype(np.int64))
+    finally:
+        os.environ.pop("LASV_B200_BINS", None)
+        os.environ.pop("LASV_B200_INSERT", None)
+
+
+@pytest.mark.parametrize("mode", ["direct", "binned", "random", "streamed"])
 def test_random_inputs_match_oracle(mode, monkeypatch):
     """Seeded random reads (bad characters, low qualities, low-complexity, empty and short reads) and
     random table geometries -- bucket sizes that are not a multiple of the slots per line, tables that
@@ -451,10 +512,15 @@ def test_random_inputs_match_oracle(mode, monkeypatch):
             assert (occ == (np.arange(W)[None, :] < nxt[:, None])).all(), tag
 
 
-def test_hot_kmers_and_duplicate_reads_are_counted_exactly():
+@pytest.mark.parametrize("mode", [None, "streamed"])
+def test_hot_kmers_and_duplicate_reads_are_counted_exactly(mode, monkeypatch):
     """Thousands of copies of the same reads (and homopolymers): every occurrence is
-    an atomic on the same few slots; warp aggregation and L2 reductions must not
-    lose or double count."""
+    an atomic on the same few slots; warp aggregation and L2 reductions (shared-memory
+    atomics in the streamed insert, where all copies of a key meet in ONE group) must
+    not lose or double count."""
+    if mode:
+        monkeypatch.setenv("LASV_B200_INSERT", mode)
+        monkeypatch.setenv("LASV_B200_BINS", "4")
     rng = np.random.default_rng(3)
     base = ["".join(rng.choice(list("ACGT"), 100)) for _ in range(3)] + ["A" * 100, "AC" * 50, "ACG" * 33 + "A"]
     reads = [base[i % len(base)] for i in range(60_000)]
@@ -1020,13 +1086,8 @@ def test_config0_full_size_properties():
         assert np.array_equal(O.sort_records(g.records()), O.sort_records(og.records()))
 
 
-# ---- written after the round's GPU minutes were spent: NOT YET RUN ON A DEVICE -------------------------------------
-# Branch printing (`--mode build`'s ./branches.fa), the cleaning on a graph handle with the pruned-aware
-# `.ctx` dump, `--health_check`, and the streamed-insert prototype.  All are exact against the oracle on the CPU emulation
-# (tests/test_host_emul.py: same record writers, same replay, same table protocol).  The cases sit at the very end of the
-# GPU suite and are non-strict xfail until they have run: an XPASS in the log (`-rxX`) is their first green run on a
-# B200, a failure cannot hide or cut short any verified test above.  Remove the marker once seen green.
-_first_device_run = pytest.mark.xfail(strict=False, reason="first run on a device pending (see the comment above the marker)")
+# ---- branch printing, cleaning on a graph handle, --health_check, list ranking, grouped insert -----------------------
+# (first green device run: round 1's round-end suite; plain tests since round 2)
 
 
 def _oracle_branches_in_table_order(k, L, W, recs, path):
@@ -1036,7 +1097,6 @@ def _oracle_branches_in_table_order(k, L, W, recs, path):
     return og, st
 
 
-@_first_device_run
 @pytest.mark.parametrize("name", ["synth_cfg1_k31", "synth_cfg0_k53", "synth_cfg2_k95", "edge_pe_k21_q5"])
 def test_gpu_branches_match_reference_walk(name, tmp_path):
     """The reference's branches.fa for OUR slot order, byte for byte, in both arrangements of the table."""
@@ -1060,8 +1120,8 @@ def test_gpu_branches_match_reference_walk(name, tmp_path):
         assert (tmp_path / "gpu_final.fa").read_bytes() == gpu and st2 == st
 
 
-@_first_device_run
-@pytest.mark.parametrize("dense", [(21, 40000, 600, 3000, 11, None), (53, 20000, 600, 3000, 11, 2),
+@pytest.mark.parametrize("dense", [(21, 40000, 600, 3000, 11, None), (53, 20000, 600, 3000, 11, 1),
+                                   (53, 20000, 600, 3000, 11, 2),
                                    (31, 3000, 3000, 60000, 14, None), (31, 20000, 40000, 200000, 17, 2)])
 def test_ref_table_branches_and_marks(dense, tmp_path):
     """lasv_ref_hash_table_write_branches on the caller's reference-layout table, raw or after the GPU cleaning:
@@ -1088,7 +1148,10 @@ def test_ref_table_branches_and_marks(dense, tmp_path):
     _capi.check(_capi.lib().lasv_ref_hash_table_write_branches(C.byref(ht), str(tmp_path / "gpu.fa").encode(), C.byref(st)))
     st = st.as_dict()
     assert (tmp_path / "gpu.fa").read_bytes() == (tmp_path / "oracle.fa").read_bytes()
-    assert st["n_branches"] == ost["branches"] > 0
+    assert st["n_branches"] == ost["branches"]
+    # (53, ..., T=2): the cleaning leaves a graph without a single branching node -- the reference prints an empty
+    # file (the compiled reference agrees: tests/golden/branches.json holds such cases); everywhere else there are branches
+    assert (st["n_branches"] > 0) == (dense != (53, 20000, 600, 3000, 11, 2))
     if err_q20 <= 3000:
         assert st["n_cut"] > 0
     # marks: exactly the reference's; nothing else in the table changed
@@ -1100,7 +1163,6 @@ def test_ref_table_branches_and_marks(dense, tmp_path):
     assert np.array_equal(after, before)
 
 
-@_first_device_run
 @pytest.mark.parametrize("name,clean", [("synth_cfg1_k31", False), ("synth_cfg0_k53", False), ("synth_cfg0_k53", True),
                                         ("synth_cfg2_k95", True)])
 def test_reference_cli_build_mode_through_the_gpu(name, clean, tmp_path):
@@ -1135,7 +1197,6 @@ def test_reference_cli_build_mode_through_the_gpu(name, clean, tmp_path):
     assert (tmp_path / "branches.fa").read_bytes() == (tmp_path / "oracle.fa").read_bytes()
 
 
-@_first_device_run
 @pytest.mark.parametrize("name,thresh,finalized", [("synth_cfg1_k31", 2, False), ("synth_cfg0_k53", 2, False),
                                                    ("synth_cfg2_k95", 2, True), ("synth_cfg0_k53", 1, True)])
 def test_gpu_build_mode_stays_on_the_device(name, thresh, finalized, tmp_path):
@@ -1176,7 +1237,6 @@ def test_gpu_build_mode_stays_on_the_device(name, thresh, finalized, tmp_path):
         assert np.array_equal(_table_records(table), recs)
 
 
-@_first_device_run
 @pytest.mark.parametrize("name", ["synth_cfg1_k31", "synth_cfg0_k53", "synth_cfg2_k95", "synth_full_k53"])
 def test_gpu_health_check(name):
     """`--health_check` on the device graph: every edge has its return arrow, raw, finalised and cleaned."""
@@ -1199,7 +1259,6 @@ def test_gpu_health_check(name):
         assert h["missing_target"] == h["missing_return_arrow"] == 0
 
 
-@_first_device_run
 def test_gpu_health_check_at_full_config0_size():
     """Size-independent invariant at BASELINE configs[0] scale (63 Mbp, 30x, k=53, L=22 W=100): the graph of the
     full build has a return arrow for every edge, and edges_checked equals the summary's edge-bit count."""
@@ -1223,10 +1282,7 @@ def test_gpu_health_check_at_full_config0_size():
         assert h["missing_target"] == h["missing_return_arrow"] == 0
 
 
-@_first_device_run
-@pytest.mark.parametrize("bulk", [0, pytest.param(1, marks=pytest.mark.skipif(
-    os.environ.get("LASV_B200_TEST_BULK") != "1",
-    reason="cp.async.bulk staging waits on an mbarrier: first run by hand under `timeout` (LASV_B200_TEST_BULK=1)"))])
+@pytest.mark.parametrize("bulk", [0, 1])
 @pytest.mark.parametrize("name,bpg", [("synth_cfg0_k53", 4), ("synth_cfg1_k31", 2), ("synth_cfg2_k95", 4),
                                       ("synth_full_k53", 4), ("synth_full_k53", 1)])
 def test_gpu_grouped_insert_prototype(name, bpg, bulk, monkeypatch):
@@ -1279,7 +1335,6 @@ def test_gpu_grouped_insert_prototype(name, bpg, bulk, monkeypatch):
             assert (spilled > 0) == (name == "synth_full_k53")
 
 
-@_first_device_run
 @pytest.mark.parametrize("name", ["synth_cfg1_k31", "synth_cfg0_k53", "synth_cfg2_k95", "edge_pe_k21_q5"])
 def test_gpu_ranked_path_enumeration(name, tmp_path, monkeypatch):
     """LASV_B200_SN_RANKING=1: the path records come from list ranking (ranking.cuh) instead of one walk per start;
@@ -1293,7 +1348,6 @@ def test_gpu_ranked_path_enumeration(name, tmp_path, monkeypatch):
         test_gpu_branches_match_reference_walk(name, tmp_path / "b")
 
 
-@_first_device_run
 def test_gpu_ranked_cycles_long_paths_and_dense_errors(tmp_path, monkeypatch):
     monkeypatch.setenv("LASV_B200_SN_RANKING", "1")
     test_gpu_supernodes_cycles_and_long_paths(tmp_path)
