@@ -1,28 +1,29 @@
 #!/usr/bin/env python
 """bench.py -- k-mers/s inserted into the de Bruijn graph (k=53) on N B200s.
 
-Workload (default `cfg4`, BASELINE.json configs[4]): human-scale table geometry
-(k=53, L=24, W=250 -> 4.19 G slots x 24 B = 100.7 GB, hash-sharded over the N
-GPUs), 2x150 bp paired-end reads drawn by a counter-based generator from a
-synthetic 3.1 Gbp genome.  Before the timed region the table is PRE-FILLED,
-untimed, with every genomic k-mer once (error-free reads tiling the genome), so
-that the timed steps run in the steady state of a 30x build: ~99 % of the
-operations update an existing node and the rest insert novel error k-mers into a
-~75 % full table.  One step = one batch of `--pairs-per-step` read pairs PER
-GPU (weak scaling) through the whole hot path: quality/N filter -> 2-bit k-mers
--> canonical key + edge byte -> (N>1: route + all-to-all) -> find-or-insert.
+Workload (default `cfg4`, BASELINE.json configs[4]): THE WHOLE JOB -- the complete 30x build of the human-scale
+graph from an EMPTY table (k=53, L=24, W=250 -> 4.19 G slots x 24 B = 100.7 GB, hash-sharded over the N GPUs;
+310 M pairs of 2x150 bp reads drawn by a counter-based generator from a synthetic 3.1 Gbp genome; 53 G k-mer
+insertions).  The job is cut into K equal steps (`--steps`); the reads of a step are generated on the device and
+are resident in HBM before the step's timed region starts; a step partitions its batches (2^20 read pairs each)
+into the graph's region stripes and ends with the insert of what the stripes hold (N=1: streamed insert over
+the accumulated stripes, lasv_graph_set_accumulation; N>1: bin / exchange / insert per batch).  The W warm-up
+steps run the first step's reads into the table, which is then cleared (untimed).  The same read set is used for
+every N (strong scaling), so the graph's order-independent fingerprint must be equal at N = 1, 2, 4, 8.
 
-  value : k-mers/s with the batch already resident in HBM (CUDA-event timed)
-  e2e   : the same through the C-ABI host-buffer call (pinned host memory ->
-          device copies and the statistics read-back inside the timed region)
-  roofline    : dominant kernel, algorithmic bytes / CUDA-event kernel time over
-                the measured HBM copy bandwidth (MEASURED_PEAKS.json)
-  cpu_baseline: the compiled reference (oracle/_ref/libref_63.so) timed on one
-                host core on a bounded sample of the same reads (N=1 only)
+  value : k-mers/s of the whole job, reads already resident in HBM (CUDA events around every step, max over ranks)
+  steady_state : the same after the job, on the finished table (99 % of the operations update an existing node)
+  e2e   : k-mers/s through the C-ABI host-buffer call (pinned host memory -> device copies and the statistics
+          read-back inside the timed region), on the finished table
+  roofline    : dominant kernel of the job, algorithmic bytes / CUDA-event kernel time over the measured HBM
+                copy bandwidth (MEASURED_PEAKS.json); the other kernels' shares next to it
+  parity      : a fixed small read set through the same (sharded) path into a second small graph, its sorted
+                records compared on rank 0 with the compiled reference's own table (oracle/_ref)
+  cpu_baseline: the compiled reference (oracle/_ref/libref_63.so) timed on one host core on a bounded sample
+                of the same reads (N=1 only)
 
 `--impl reference` times the reference's own single-threaded CPU loader instead.
-`--workload cfg0` runs BASELINE.json configs[0] (63 Mbp, 2x100 bp, L=22 W=100)
-as one complete graph build per step.
+`--workload cfg0|cfg1|cfg2` runs the small configs as one complete graph build per step.
 """
 from __future__ import annotations
 
@@ -51,11 +52,21 @@ UNIT = "k-mers/s"
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg4", choices=["cfg4", "cfg0", "cfg1", "cfg2"])
-    ap.add_argument("--pairs-per-step", type=int, default=1 << 20)
+    ap.add_argument("--pairs-per-step", type=int, default=1 << 20,
+                    help="cfg0/1/2 only; cfg4 cuts the whole job into --steps steps")
+    ap.add_argument("--pairs-per-batch", type=int, default=1 << 20, help="cfg4: read pairs per partition launch")
+    ap.add_argument("--fraction", type=float, default=1.0, help="cfg4: part of the 30x read set to load (experiments)")
+    ap.add_argument("--accumulate-gb", type=float, default=-1.0,
+                    help="cfg4, N=1: read stream per insert in GB (-1: all that fits next to the table, 0: one insert per batch)")
+    ap.add_argument("--insert", choices=["auto", "random", "streamed"], default="auto")
+    ap.add_argument("--steady-steps", type=int, default=3)
+    ap.add_argument("--e2e-pairs", type=int, default=4 << 20, help="cfg4: read pairs per host-buffer call of the e2e leg")
+    ap.add_argument("--parity-pairs", type=int, default=20_000)
+    ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--no-prefill", action="store_true")
     ap.add_argument("--no-pipeline", action="store_true",
                     help="insert each batch before the next one is partitioned (one stream)")
@@ -373,15 +384,28 @@ def run_reference_arm(args, w):
     print(json.dumps(line), flush=True)
 
 
+def job_geometry(args, w, world):
+    """cfg4: the whole read set cut into K steps of whole batches; every rank takes part in every batch round."""
+    ppb = args.pairs_per_batch
+    total_pairs = int(w.n_pairs * args.fraction)
+    n_batches = (total_pairs + ppb - 1) // ppb
+    per_step = (n_batches + args.steps - 1) // args.steps           # global batches per step
+    per_step = (per_step + world - 1) // world * world
+    return {"pairs_per_batch": ppb, "batches_per_step": per_step, "batches": per_step * args.steps,
+            "pairs": per_step * args.steps * ppb}
+
+
 def workload_config(args, w, n_gpus):
     if args.workload == "cfg4":
-        return {"workload": "cfg4 human-scale steady state: synthetic 3.1 Gbp genome, 2x150 bp PE, k=53 "
-                            "(MAXK=63), -s 5, table L=24 W=250 (100.7 GB) hash-sharded over the GPUs, "
-                            "pre-filled with the genome's k-mers, then batches of random reads",
+        geo = job_geometry(args, w, n_gpus)
+        return {"workload": "cfg4 human-scale, the whole job: synthetic 3.1 Gbp genome, 30x of 2x150 bp PE reads, k=53 "
+                            "(MAXK=63), -s 5, table L=24 W=250 (100.7 GB) hash-sharded over the GPUs, built from an "
+                            "empty table in `steps` equal steps",
                 "kmer_size": w.kmer_size, "mem_height": w.number_bits, "mem_width": w.bucket_size,
-                "read_pairs_per_gpu_per_step": args.pairs_per_step, "read_len": w.read_len,
-                "prefill": not args.no_prefill, "sharding": f"hash x{n_gpus}",
-                "l2_policy": "inputs (0.6 GB/step) and table (>=12.6 GB/GPU) exceed the 126 MB L2"}
+                "read_pairs_total": geo["pairs"], "read_pairs_per_step": geo["batches_per_step"] * geo["pairs_per_batch"],
+                "read_pairs_per_batch": geo["pairs_per_batch"], "read_len": w.read_len, "fraction_of_30x": args.fraction,
+                "sharding": f"hash x{n_gpus}",
+                "l2_policy": "inputs (>= 0.6 GB per batch), stripes (GBs) and table (>= 13 GB/GPU) exceed the 126 MB L2"}
     return {"workload": f"{w.name}: synthetic {w.genome_len / 1e6:.0f} Mbp genome, 2x{w.read_len} bp PE at {w.coverage:.0f}x, "
                         f"k={w.kmer_size} (MAXK={32 * ((2 * w.kmer_size) // 64 + 1) - 1}), -s {w.q_thresh}, L={w.number_bits} "
                         f"W={w.bucket_size}; one complete graph build (table zeroing included) per step",
@@ -397,7 +421,405 @@ def main():
     w = synth.WORKLOADS[args.workload]
     if args.impl == "reference":
         run_reference_arm(args, w)
-        return
+    elif args.workload == "cfg4":
+        main_job(args, w)
+    else:
+        main_small(args, w)
+
+
+def reference_records(ref, N):
+    """Sorted-able records (kmer, covg, edges) of whatever a ReferenceLoader has built: the reference's own
+    HashTable memory (element.h:77-82) when the compiled reference runs, else the oracle port's dump."""
+    from lasv_b200.graph import element_dtype, record_dtype
+    if ref.kind != "reference":
+        return ref.graph.records()
+    n_slots = int(ref.view.number_buckets) * int(ref.view.bucket_size)
+    ed = element_dtype(N)
+    raw = (C.c_ubyte * (n_slots * ed.itemsize)).from_address(ref.view.table)
+    table = np.frombuffer(raw, dtype=ed)
+    live = table[table["status"] != 0]
+    out = np.zeros(len(live), dtype=record_dtype(N))
+    out["kmer"], out["covg"], out["edges"] = live["kmer"], live["coverage"], live["edges"]
+    return out
+
+
+def parity_leg(args, w, rank, world, local_rank, dev):
+    """A fixed small read set through the same path as the job (partition -> [exchange] -> streamed insert) into a
+    second, small graph; its records, gathered on rank 0, against the compiled reference's table for the same
+    reads.  Collective."""
+    import torch
+    import torch.distributed as dist
+    from lasv_b200 import synth
+    from lasv_b200.sharded import ShardedDBGraph
+    from oracle import oracle as O
+    pairs = args.parity_pairs
+    n_reads = 2 * pairs
+    L = max(sample_table_bits(w, pairs, 1), 9 + int(np.log2(world)))
+    stride = w.read_len + 1
+    seq, qual, _ = synth.reads_host(w.params(), 0, n_reads)
+    per = (n_reads // world) // 2 * 2
+    lo_r, hi_r = rank * per, (n_reads if rank == world - 1 else (rank + 1) * per)
+    nb = (hi_r - lo_r) * stride
+    saved = {k: os.environ.get(k) for k in ("LASV_B200_INSERT", "LASV_B200_BINS")}
+    os.environ["LASV_B200_INSERT"] = "streamed"        # the job's insert kind, on a table too small to choose it itself
+    os.environ["LASV_B200_BINS"] = str(max(1, (1 << L) // world // 256))
+    try:
+        small = ShardedDBGraph(w.kmer_size, L, w.bucket_size, rank, world, local_rank,
+                               max_kmers_per_batch=(n_reads - (world - 1) * per) * stride,
+                               max_bytes_per_batch=(n_reads - (world - 1) * per) * stride,
+                               max_reads_per_batch=n_reads - (world - 1) * per, pipeline=False)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+    pad = np.full(16, 10, np.uint8)
+    d_seq = torch.from_numpy(np.concatenate([seq[lo_r * stride: hi_r * stride], pad])).to(dev)
+    d_qual = torch.from_numpy(np.concatenate([qual[lo_r * stride: hi_r * stride], pad])).to(dev)
+    d_offs = torch.arange(hi_r - lo_r + 1, dtype=torch.int64, device=dev) * stride
+    small.load_reads_device(d_seq, d_qual, nb, w.cutoff, d_offs, hi_r - lo_r)
+    small.flush()
+    torch.cuda.synchronize()
+    st = small.stats()
+    counts = small.graph.insert_counts()
+    mine = small.graph.records()
+    raw = torch.from_numpy(mine.view(np.uint8).reshape(-1).copy()).to(dev)
+    if world > 1:
+        sizes = torch.zeros(world, dtype=torch.int64, device=dev)
+        sizes[rank] = raw.numel()
+        dist.all_reduce(sizes)
+        cap = int(sizes.max().item())
+        padded = torch.zeros(cap, dtype=torch.uint8, device=dev)
+        padded[: raw.numel()] = raw
+        parts = [torch.empty(cap, dtype=torch.uint8, device=dev) for _ in range(world)]
+        dist.all_gather(parts, padded)
+        blobs = [parts[r][: int(sizes[r].item())].cpu().numpy() for r in range(world)] if rank == 0 else []
+    else:
+        blobs = [raw.cpu().numpy()]
+    small.free()
+    if rank != 0:
+        return None
+    ours = np.concatenate([b.view(mine.dtype) for b in blobs]) if blobs else mine
+    t0 = time.perf_counter()
+    ref = ReferenceLoader(w.kmer_size, L, w.bucket_size)
+    n_ref, _ = ref.load(seq, qual, w.read_len, w.q_thresh)
+    theirs = reference_records(ref, small.N)
+    kind = ref.kind
+    ref.close()
+    same = len(ours) == len(theirs) and np.array_equal(O.sort_records(ours), O.sort_records(theirs))
+    out = {"status": "ok" if same and st["kmers_inserted"] == n_ref else "FAILED",
+           "against": "compiled reference (oracle/_ref), its own HashTable" if kind == "reference" else "oracle port",
+           "read_pairs": pairs, "table": f"2^{L}x{w.bucket_size} over {world} GPU(s)", "nodes": int(len(ours)),
+           "nodes_reference": int(len(theirs)), "kmers_inserted": int(st["kmers_inserted"]), "kmers_reference": int(n_ref),
+           "inserts_by_kind_rank0": counts, "reference_seconds": time.perf_counter() - t0}
+    return out
+
+
+def main_job(args, w):
+    """cfg4: the whole job in K steps (see the module docstring)."""
+    import torch
+    import torch.distributed as dist
+    from lasv_b200 import _capi, synth
+    from lasv_b200.sharded import ShardedDBGraph
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    numa_node = bind_to_gpu_numa_node(local_rank)
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _capi.lib()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(xs):
+        t = torch.tensor(list(xs), dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [float(x) for x in t.cpu()]
+
+    K, Wm = args.steps, args.warmup
+    geo = job_geometry(args, w, world)
+    stride = w.read_len + 1
+    reads_per_batch = 2 * geo["pairs_per_batch"]
+    n_bytes = reads_per_batch * stride
+    local_per_step = geo["batches_per_step"] // world
+    stream = torch.cuda.current_stream().cuda_stream
+    p = w.params()
+
+    graph = ShardedDBGraph(w.kmer_size, w.number_bits, w.bucket_size, rank, world, local_rank,
+                           max_kmers_per_batch=reads_per_batch * (w.read_len - w.kmer_size + 1),
+                           max_bytes_per_batch=n_bytes, max_reads_per_batch=reads_per_batch,
+                           pipeline=(world > 1 and not args.no_pipeline))
+    g = graph.graph
+    slot = g.element_bytes
+    g.set_insert_mode({"auto": _capi.INSERT_AUTO, "random": _capi.INSERT_RANDOM, "streamed": _capi.INSERT_STREAMED}[args.insert])
+
+    # the reads of one step, resident in HBM before the step is timed (if they fit next to the table: else two
+    # buffers and the generator runs inside the timed region)
+    free_b, _ = torch.cuda.mem_get_info()
+    resident = local_per_step * 2 * (n_bytes + 16) <= max(0, free_b - (36 << 30))
+    n_pool = local_per_step if resident else 2
+    pool = [(torch.empty(n_bytes + 16, dtype=torch.uint8, device=dev), torch.empty(n_bytes + 16, dtype=torch.uint8, device=dev))
+            for _ in range(n_pool)]
+    offs_dev = torch.arange(reads_per_batch + 1, dtype=torch.int64, device=dev) * stride
+    granted = 0
+    if world == 1 and args.accumulate_gb:
+        granted = g.set_accumulation((1 << 64) - 1 if args.accumulate_gb < 0 else int(args.accumulate_gb * 1e9))
+
+    def first_read(step, i):           # global batch (step, local i of this rank) -> its first read
+        return ((step * geo["batches_per_step"]) + i * world + rank) * reads_per_batch
+
+    def run_step(step, e0=None, e1=None):
+        """One step: its batches through the hot path, then the insert of what the stripes hold."""
+        if resident:
+            for i in range(local_per_step):
+                synth.reads_device(p, first_read(step, i), reads_per_batch, pool[i][0], pool[i][1], stream)
+            barrier()
+        l0 = lib.lasv_kernel_launches()
+        if e0 is not None:
+            e0.record()
+        for i in range(local_per_step):
+            sq = pool[i % n_pool]
+            if not resident:
+                synth.reads_device(p, first_read(step, i), reads_per_batch, sq[0], sq[1], stream)
+            graph.load_reads_device(sq[0], sq[1], n_bytes, w.cutoff, offs_dev, reads_per_batch)
+        graph.flush()                  # N=1: the accumulated stripes are inserted; N>1: side-stream inserts join
+        if e1 is not None:
+            e1.record()
+        return lib.lasv_kernel_launches() - l0
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+
+    # ---------------------------------------------------------------- warm-up, then an empty table again
+    for _ in range(Wm):
+        run_step(0)
+    barrier()
+    graph.stats()                      # (raises if anything overflowed)
+    g.clear(stream)
+    barrier()
+
+    # ---------------------------------------------------------------- the job
+    if world == 1:
+        g.enable_kernel_timing(True)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    launches = 0
+    wall0 = time.monotonic()
+    torch.cuda.profiler.start()        # `ncu --profile-from-start off` sees the timed steps only
+    for s_ in range(K):
+        launches += run_step(s_, *ev[s_])
+    barrier()
+    torch.cuda.profiler.stop()
+    wall1 = time.monotonic()
+    step_ms = max_over_ranks(e0.elapsed_time(e1) for e0, e1 in ev)
+    dt = sum(step_ms) * 1e-3
+    kinds = g.kernel_times_by_kind() if world == 1 else None
+    if world == 1:
+        g.enable_kernel_timing(False)
+    st_job = graph.stats()
+    summary = graph.summary()
+    kmers = st_job["kmers_inserted"]
+    value = kmers / dt
+    clocks = sampler.summarise(sampler.window(wall0, wall1)) if rank == 0 else None
+    inserts_by_kind = g.insert_counts()
+
+    # ---------------------------------------------------------------- steady state on the finished table
+    steady = None
+    if args.steady_steps > 0:
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steady_steps)]
+        for s_ in range(args.steady_steps):
+            run_step(K + s_, *evs[s_])
+        barrier()
+        sms = max_over_ranks(e0.elapsed_time(e1) for e0, e1 in evs)
+        st2 = graph.stats()
+        steady = {"value": (st2["kmers_inserted"] - kmers) / (sum(sms) * 1e-3), "unit": UNIT, "steps": args.steady_steps,
+                  "ms_per_step": sum(sms) / len(sms), "novel_kmers": st2["unique_kmers"] - st_job["unique_kmers"],
+                  "what": "further steps of fresh reads on the finished table (80 % full)"}
+
+    # ---------------------------------------------------------------- roofline
+    peak, peak_src = measured_peaks()
+    bases = geo["pairs"] * 2 * w.read_len
+    step_alg_bytes = kmers * 2 * slot + 2 * bases * stride / w.read_len      # SURVEY 8d: 2*sizeof(Element) + 2 B/base
+    rec_bytes = 16
+    if world == 1 and kinds:
+        alg = {"partition": 2 * bases * stride / w.read_len + kmers * rec_bytes,   # reads in, one record out
+               "sort": kmers * rec_bytes * 3,                                      # records: two reads, one write
+               "stream": kmers * 2 * slot,                                         # find-or-insert: slot in, slot out
+               "insert": kmers * 2 * slot}
+        names = {"partition": "build_kernel<MODE_BIN>", "sort": "sg_sort_kernel", "stream": "sg_insert_kernel",
+                 "insert": "insert_bins_kernel"}
+        cands = ["partition", "sort", "stream"] if kinds["stream"][1] else ["partition", "insert"]
+        dom = max(cands, key=lambda k_: kinds[k_][0])
+        if dom == "partition" and kinds["stream"][1]:
+            dom = "stream"             # the find-or-insert is the kernel the roofline is asked of; the shares are below
+        ms_tot, n_l = kinds[dom]
+        achieved = alg[dom] / (ms_tot * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "kernel": names[dom], "achieved": achieved, "peak": peak, "unit": "GB/s",
+                    "frac": achieved / peak, "peak_source": peak_src,
+                    "algorithmic_bytes_per_kmer": alg[dom] / kmers, "kernel_ms": ms_tot / max(n_l, 1), "launches_timed": n_l,
+                    "kmers_per_launch": kmers / max(n_l, 1), "traffic": ncu_traffic(names[dom]),
+                    "kernels": {k_: {"ms_total": kinds[k_][0], "launches": kinds[k_][1], "share_of_job": kinds[k_][0] * 1e-3 / dt,
+                                     "algorithmic_GBps": (alg[k_] / (kinds[k_][0] * 1e-3) / 1e9) if k_ in alg and kinds[k_][0] else None}
+                                for k_ in kinds},
+                    "step_achieved": step_alg_bytes / dt / 1e9, "step_frac": step_alg_bytes / dt / 1e9 / peak}
+    else:
+        alg_bytes = kmers * (2 * slot + 2 * getattr(graph, "rec_bytes", rec_bytes)) + 2 * bases * stride / w.read_len
+        achieved = alg_bytes / world / dt / 1e9
+        roofline = {"bound": "hbm", "kernel": "bin+exchange+insert step (per GPU)", "achieved": achieved, "peak": peak,
+                    "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
+                    "algorithmic_bytes_per_kmer": alg_bytes / kmers, "kernel_ms": 1e3 * dt / K, "traffic": None}
+
+    # ---------------------------------------------------------------- e2e: host buffers through the public call
+    e2e = None
+    if not args.no_e2e:
+        if world == 1:
+            ep = max(geo["pairs_per_batch"], args.e2e_pairs // geo["pairs_per_batch"] * geo["pairs_per_batch"])
+            sub = ep // geo["pairs_per_batch"]
+            nb_e = sub * n_bytes
+            host = []
+            for b_ in range(2):
+                hs, hq = torch.empty(nb_e + 16, dtype=torch.uint8).pin_memory(), torch.empty(nb_e + 16, dtype=torch.uint8).pin_memory()
+                for i in range(sub):
+                    synth.reads_device(p, ((K + args.steady_steps + 1) * geo["batches_per_step"] + b_ * sub + i) * reads_per_batch,
+                                       reads_per_batch, pool[0][0], pool[0][1], stream)
+                    torch.cuda.synchronize()
+                    hs[i * n_bytes: (i + 1) * n_bytes].copy_(pool[0][0][:n_bytes])
+                    hq[i * n_bytes: (i + 1) * n_bytes].copy_(pool[0][1][:n_bytes])
+                host.append((hs, hq))
+            offs_host = np.arange(sub * reads_per_batch + 1, dtype=np.uint64) * np.uint64(stride)
+            g.set_accumulation(0)      # the host-buffer call accumulates the chunks of ONE call by itself
+            for s_ in range(Wm):
+                g.load_reads_host(host[s_ % 2][0][:nb_e], host[s_ % 2][1][:nb_e], offs_host, w.cutoff)
+            torch.cuda.synchronize()
+            ke = 0
+            t0 = time.perf_counter()
+            for s_ in range(K):
+                ke += g.load_reads_host(host[s_ % 2][0][:nb_e], host[s_ % 2][1][:nb_e], offs_host, w.cutoff)["kmers_inserted"]
+            torch.cuda.synchronize()
+            dte = time.perf_counter() - t0
+            e2e = {"value": ke / dte, "unit": UNIT, "h2d_bytes_per_step": int(2 * nb_e + 8 * (sub * reads_per_batch + 1)),
+                   "d2h_bytes_per_step": 2 * (5 * 8 + 20 * 8 + 8), "ms_per_step": 1e3 * dte / K, "read_pairs_per_step": ep,
+                   "steps": K, "table": "the finished graph (steady state)",
+                   "api": "lasv_graph_load_reads_host (C ABI, pinned host buffers; one call per step)"}
+        else:
+            host_seq = [torch.empty(n_bytes + 16, dtype=torch.uint8).pin_memory() for _ in range(2)]
+            host_qual = [torch.empty(n_bytes + 16, dtype=torch.uint8).pin_memory() for _ in range(2)]
+            for b_ in range(2):
+                synth.reads_device(p, (((K + args.steady_steps + 1) * geo["batches_per_step"]) + b_ * world + rank) * reads_per_batch,
+                                   reads_per_batch, pool[0][0], pool[0][1], stream)
+                torch.cuda.synchronize()
+                host_seq[b_].copy_(pool[0][0])
+                host_qual[b_].copy_(pool[0][1])
+            barrier()
+            copy_stream = torch.cuda.Stream(device=dev)
+            copied = [torch.cuda.Event(), torch.cuda.Event()]
+            consumed = [None, None]
+            results = torch.zeros((K + Wm + 1, 9), dtype=torch.int64).pin_memory()    # one statistics row per step
+            step_no = [0]
+
+            def e2e_step(b_):
+                # pinned host -> device on a copy stream (two device buffers), binned exchange and inserts behind
+                # it, the step's statistics copied back behind the inserts -- nothing blocks the host
+                i = step_no[0]
+                step_no[0] += 1
+                k2 = i % 2
+                cur = torch.cuda.current_stream()
+                with torch.cuda.stream(copy_stream):
+                    if consumed[k2] is not None:
+                        copy_stream.wait_event(consumed[k2])
+                    pool[k2][0].copy_(host_seq[b_], non_blocking=True)
+                    pool[k2][1].copy_(host_qual[b_], non_blocking=True)
+                    copied[k2].record(copy_stream)
+                cur.wait_event(copied[k2])
+                graph.load_reads_device(pool[k2][0], pool[k2][1], n_bytes, w.cutoff, offs_dev, reads_per_batch)
+                consumed[k2] = torch.cuda.Event()
+                consumed[k2].record(cur)
+                graph.stats_async(results[i])
+
+            for s_ in range(Wm):
+                e2e_step(s_ % 2)
+            barrier()
+            sa = graph.stats()
+            t0 = time.perf_counter()
+            for s_ in range(K):
+                e2e_step(s_ % 2)
+            torch.cuda.synchronize()
+            dte = max_over_ranks([time.perf_counter() - t0])[0]
+            barrier()
+            sb = graph.stats()
+            e2e = {"value": (sb["kmers_inserted"] - sa["kmers_inserted"]) / dte, "unit": UNIT,
+                   "h2d_bytes_per_step": int(2 * n_bytes), "d2h_bytes_per_step": 9 * 8, "ms_per_step": 1e3 * dte / K,
+                   "read_pairs_per_step": geo["pairs_per_batch"] * world, "steps": K, "table": "the finished graph (steady state)",
+                   "api": "pinned host -> device copies on a copy stream + sharded bin/exchange/insert + per-step statistics read-back (async)"}
+    sampler.stop()
+    final = graph.stats()
+    capacity = g.capacity * world
+    graph.free()
+    del pool
+    torch.cuda.empty_cache()
+
+    # ---------------------------------------------------------------- parity leg, CPU baseline
+    parity = None
+    if not args.no_parity:
+        try:
+            parity = parity_leg(args, w, rank, world, local_rank, dev)
+        except Exception as ex:          # reported as a failure, never silently dropped
+            parity = {"status": "FAILED", "error": repr(ex)[:300]}
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            sp = args.cpu_sample_pairs
+            L = sample_table_bits(w, sp, 1)
+            ref = ReferenceLoader(w.kmer_size, L, w.bucket_size)
+            seq, qual, _ = synth.reads_host(p, 0, 2 * sp)
+            n, secs = ref.load(seq, qual, w.read_len, w.q_thresh)
+            ref.close()
+            cpu = {"value": n / secs, "unit": UNIT, "cores": 1, "kind": ref.kind,
+                   "sample": f"first {sp} read pairs of the same synthetic reads ({n} k-mers, {secs:.1f} s) into a "
+                             f"2^{L}x{w.bucket_size} reference table; the reference loader is single-threaded; "
+                             f"host {host_cpu_name()}, {os.cpu_count()} logical cores present"}
+        except Exception as ex:  # the baseline is reported, never required
+            cpu = {"value": None, "unit": UNIT, "cores": 1, "kind": "unavailable", "sample": repr(ex)[:200]}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
+            "ms_per_step": 1e3 * dt / K, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "config": workload_config(args, w, world),
+            "job": {"seconds": dt, "kmers_inserted": kmers, "read_pairs": geo["pairs"], "unique_kmers": st_job["unique_kmers"],
+                    "fill": st_job["unique_kmers"] / capacity, "sum_covg": summary["sum_covg"],
+                    "covg_equals_inserts": summary["sum_covg"] == kmers, "bad_reads": st_job["bad_reads"],
+                    "fingerprint": f"{summary['fingerprint']:016x}", "inputs_resident_before_each_step": bool(resident),
+                    "accumulate_stream_bytes_granted": granted, "inserts_by_kind": inserts_by_kind,
+                    "wall_seconds_incl_read_generation": wall1 - wall0, "step_ms": step_ms},
+            "fingerprint": f"{summary['fingerprint']:016x}",
+            "parity": parity["status"] if parity else None, "parity_detail": parity,
+            "kmers_per_step": kmers // K, "gpu_launches": int(launches),
+            "roofline": roofline, "steady_state": steady, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
+            "host": {"numa_node_of_rank0": numa_node, "cpus_of_rank0": len(os.sched_getaffinity(0))},
+            "graph": {"unique_kmers": final["unique_kmers"], "kmers_inserted_total": final["kmers_inserted"],
+                      "fill": final["unique_kmers"] / capacity},
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main_small(args, w):
+    """cfg0 / cfg1 / cfg2: one complete graph build (table zeroing included) per step."""
+    from lasv_b200 import synth
 
     import torch
     import torch.distributed as dist

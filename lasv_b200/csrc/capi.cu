@@ -1754,14 +1754,24 @@ static int stream_ctx_records(lasv_graph *g, FILE *fp, unsigned long long *n_rec
   std::vector<uint8_t> buf(per * rec);
   unsigned long long n = 0;
   int rc = LASV_OK;
+  // read in BYTES: a trailing partial record (truncated file) must be an error, not a silently shorter graph
+  size_t carry = 0;
   for (;;) {
-    const size_t got = fread(buf.data(), rec, per, fp);
-    if (!got) break;
-    rc = lasv_graph_load_ctx_records(g, buf.data(), got);
-    n += got;
-    if (rc != LASV_OK || got < per) break;
+    const size_t got = fread(buf.data() + carry, 1, buf.size() - carry, fp);
+    const size_t have = carry + got, whole = have / rec;
+    if (whole) {
+      rc = lasv_graph_load_ctx_records(g, buf.data(), whole);
+      n += whole;
+      if (rc != LASV_OK) break;
+    }
+    carry = have - whole * rec;
+    if (carry) memmove(buf.data(), buf.data() + whole * rec, carry);
+    if (got == 0 || feof(fp) || ferror(fp)) break;
   }
   if (n_records) *n_records = n;
+  if (rc == LASV_OK && ferror(fp)) rc = fail(LASV_ERR_IO, "read error in the .ctx records: %s", strerror(errno));
+  if (rc == LASV_OK && carry)
+    rc = fail(LASV_ERR_IO, "truncated .ctx: %zu trailing bytes are not a whole %zu-byte record (after %llu records)", carry, rec, n);
   return rc;
 }
 

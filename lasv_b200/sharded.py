@@ -38,6 +38,7 @@ import sys
 import torch
 import torch.distributed as dist
 
+from . import _capi
 from .graph import DBGraph, words_per_kmer
 
 
@@ -168,6 +169,9 @@ class ShardedDBGraph:
             if not max_bytes_per_batch:       # k-mers <= bytes: a safe stand-in for callers that only know k-mers
                 max_bytes_per_batch = int(max_kmers_per_batch * 1.7)
             self.max_bytes_per_batch = max_bytes_per_batch
+            kk = kmer_size
+            self.kmer_bound = (max_bytes_per_batch - max_reads_per_batch * kk
+                               if max_reads_per_batch and max_reads_per_batch * kk < max_bytes_per_batch else max_bytes_per_batch)
             geo = self.graph.bin_geometry(world, max_bytes_per_batch, max_reads_per_batch)
             self.bins_per_owner, self.cap, self.spill = geo["bins_per_owner"], geo["stripe_capacity"], geo["spill_capacity"]
             self.rec_bytes = geo["record_bytes"]
@@ -247,6 +251,13 @@ class ShardedDBGraph:
         if n_bytes > self.max_bytes_per_batch:
             raise ValueError(f"batch of {n_bytes} stream bytes exceeds the {self.max_bytes_per_batch} the exchange "
                              "buffers were sized for (max_bytes_per_batch)")
+        # the stripes hold what a batch of max_bytes in max_reads reads can yield (k-mers <= bytes - reads * k);
+        # a batch of fewer, longer reads yields more per byte and must not be dropped on the floor
+        k = self.graph.kmer_size
+        bound = n_bytes - n_reads * k if (d_offsets is not None and n_reads and n_reads * k < n_bytes) else n_bytes
+        if bound > self.kmer_bound:
+            raise ValueError(f"batch may hold {bound} k-mers, the exchange stripes were sized for {self.kmer_bound} "
+                             "(max_bytes_per_batch / max_reads_per_batch: pass fewer bytes or state fewer reads)")
         buf = self.buffers[self.turn % len(self.buffers)]
         self.turn += 1
         # the previous user of this buffer set must be done with it
@@ -352,10 +363,28 @@ class ShardedDBGraph:
         return write_sharded_ctx(path, ctx_header(self.graph.kmer_size, mean_read_len, total_seq),
                                  self.graph.append_binary_records, self.group)
 
+    def _local(self, call):
+        """A rank-local library call that may raise (table full, stripe overflow, ...): the error is agreed on by
+        all ranks BEFORE anybody raises, so that no rank is left alone in the collective that follows."""
+        err = None
+        try:
+            out = call()
+        except _capi.LasvError as ex:
+            err, out = ex, None
+        if self.world > 1:
+            flag = torch.tensor([0 if err is None else 1], dtype=torch.int64, device=self.device)
+            dist.all_reduce(flag, group=self.group)
+            if int(flag.item()) and err is None:
+                raise _capi.LasvError(_capi.LASV_ERR_STATE, f"{int(flag.item())} other rank(s) of the sharded graph failed "
+                                                              "(table full or exchange stripe overflow there)")
+        if err is not None:
+            raise err
+        return out
+
     def stats(self) -> dict:
         """Job-wide statistics (sum over ranks)."""
         self.flush()
-        st = self.graph.stats(stream=torch.cuda.current_stream().cuda_stream)
+        st = self._local(lambda: self.graph.stats(stream=torch.cuda.current_stream().cuda_stream))
         keys = sorted(st)
         t = torch.tensor([st[k] for k in keys], dtype=torch.int64, device=self.device)
         if self.world > 1:
@@ -364,7 +393,7 @@ class ShardedDBGraph:
 
     def summary(self) -> dict:
         self.flush()
-        s = self.graph.summary()
+        s = self._local(self.graph.summary)
         keys = sorted(s)
         # fingerprints add modulo 2^64: reduce as two 32-bit halves to stay inside int64
         lo = torch.tensor([s[k] & 0xFFFFFFFF for k in keys], dtype=torch.int64, device=self.device)

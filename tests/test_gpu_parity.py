@@ -686,6 +686,12 @@ def test_ctx_roundtrip_and_reference_consumer(name, tmp_path):
         res = O.run_reference(k, L, W, None, ctx_in=out, workdir=tmp_path, want_supernodes=True)
         util.assert_same_records(res["ctx"]["records"], gold)  # reloaded + re-dumped by the reference
         assert O.canonical_seq_set(res["supernodes"]) == meta["supernodes"]
+    # a truncated file is an error, not a silently smaller graph
+    cut = tmp_path / "cut.ctx"
+    cut.write_bytes(out.read_bytes()[:-3])
+    with DBGraph(k, L, W) as g:
+        with pytest.raises(_capi.LasvError, match="truncated"):
+            g.load_binary(cut)
 
 
 def _oracle_supernodes_in_table_order(k, L, W, recs, path):
