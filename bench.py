@@ -65,6 +65,8 @@ def parse_args():
     ap.add_argument("--insert", choices=["auto", "random", "streamed"], default="auto")
     ap.add_argument("--steady-steps", type=int, default=3)
     ap.add_argument("--e2e-pairs", type=int, default=4 << 20, help="cfg4: read pairs per host-buffer call of the e2e leg")
+    ap.add_argument("--e2e-steps", type=int, default=0, help="cfg4, N=1: host-buffer calls of the e2e leg (0: --steps)")
+    ap.add_argument("--e2e-staging-gb", type=float, default=6.0, help="cfg4, N=1: device staging ring of the host-buffer calls")
     ap.add_argument("--parity-pairs", type=int, default=20_000)
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--no-prefill", action="store_true")
@@ -698,20 +700,42 @@ def main_job(args, w):
                     hq[i * n_bytes: (i + 1) * n_bytes].copy_(pool[0][1][:n_bytes])
                 host.append((hs, hq))
             offs_host = np.arange(sub * reads_per_batch + 1, dtype=np.uint64) * np.uint64(stride)
-            g.set_accumulation(0)      # the host-buffer call accumulates the chunks of ONE call by itself
-            for s_ in range(Wm):
-                g.load_reads_host(host[s_ % 2][0][:nb_e], host[s_ % 2][1][:nb_e], offs_host, w.cutoff)
+            # Asynchronous host-buffer calls: a call returns when its copies have left the pinned buffers; the copies
+            # run ahead of the kernels through a staging ring in HBM, the chunks join the graph's accumulation and
+            # the stripes are inserted whenever they are full -- so the host->device traffic of the next calls
+            # overlaps the insert.  Every call queues a device->host copy of the statistics behind its kernels.
+            # The timed region ends with the flush of what the stripes still hold and a device synchronisation.
+            g.set_accumulation(0)
+            del pool[1:]
+            torch.cuda.empty_cache()
+            ring = g.set_staging(int(args.e2e_staging_gb * (1 << 30)))
+            granted_e = g.set_accumulation((1 << 64) - 1)
+            Ke = args.e2e_steps or K
+            rows = torch.zeros((Ke + Wm, 9), dtype=torch.int64).pin_memory()
             torch.cuda.synchronize()
-            ke = 0
+            for s_ in range(Wm):
+                g.load_reads_host_async(host[s_ % 2][0][:nb_e], host[s_ % 2][1][:nb_e], offs_host, w.cutoff, rows[s_])
+            g.flush(stream)
+            torch.cuda.synchronize()
+            sa = g.stats()
             t0 = time.perf_counter()
-            for s_ in range(K):
-                ke += g.load_reads_host(host[s_ % 2][0][:nb_e], host[s_ % 2][1][:nb_e], offs_host, w.cutoff)["kmers_inserted"]
+            for s_ in range(Ke):
+                g.load_reads_host_async(host[s_ % 2][0][:nb_e], host[s_ % 2][1][:nb_e], offs_host, w.cutoff, rows[Wm + s_])
+            g.flush(stream)
             torch.cuda.synchronize()
             dte = time.perf_counter() - t0
+            sb = g.stats()
+            ke = sb["kmers_inserted"] - sa["kmers_inserted"]
+            reads_seen = int(rows[Wm + Ke - 1][0]) - int(rows[Wm - 1][0]) if Wm else int(rows[Ke - 1][0])
+            if reads_seen != Ke * sub * reads_per_batch or ke <= 0:
+                raise RuntimeError(f"e2e: the per-call statistics did not advance as expected ({reads_seen} reads, {ke} k-mers)")
             e2e = {"value": ke / dte, "unit": UNIT, "h2d_bytes_per_step": int(2 * nb_e + 8 * (sub * reads_per_batch + 1)),
-                   "d2h_bytes_per_step": 2 * (5 * 8 + 20 * 8 + 8), "ms_per_step": 1e3 * dte / K, "read_pairs_per_step": ep,
-                   "steps": K, "table": "the finished graph (steady state)",
-                   "api": "lasv_graph_load_reads_host (C ABI, pinned host buffers; one call per step)"}
+                   "d2h_bytes_per_step": 9 * 8, "ms_per_step": 1e3 * dte / Ke, "read_pairs_per_step": ep,
+                   "steps": Ke, "table": "the finished graph (steady state)",
+                   "staging_ring_bytes": ring, "accumulate_stream_bytes_granted": granted_e,
+                   "inserts_by_kind_total": g.insert_counts(),
+                   "api": "lasv_graph_load_reads_host_async (C ABI, pinned host buffers, one call per step, statistics "
+                          "copied back per call) + lasv_graph_flush and a device synchronisation before the clock stops"}
         else:
             host_seq = [torch.empty(n_bytes + 16, dtype=torch.uint8).pin_memory() for _ in range(2)]
             host_qual = [torch.empty(n_bytes + 16, dtype=torch.uint8).pin_memory() for _ in range(2)]

@@ -175,6 +175,27 @@ int lasv_graph_load_reads_device(lasv_graph *g, const uint8_t *d_seq, const uint
 int lasv_graph_load_reads_host(lasv_graph *g, const uint8_t *seq, const uint8_t *qual,
                                uint64_t n_bytes, const uint64_t *offsets, uint64_t n_reads,
                                int quality_cutoff, lasv_load_stats *batch_stats);
+/* Asynchronous host-buffer call: the same chunked copies and partition launches, but nothing waits for a
+ * kernel.  It returns once the last copy has LEFT the caller's buffers (they may be reused at once); the
+ * kernels of the call -- and, with lasv_graph_set_accumulation in force, the insert of stripes that filled
+ * up -- are still queued or running.  The copies run ahead of the kernels through the staging ring
+ * (lasv_graph_set_staging), so that the next call's host->device traffic overlaps this call's insert.
+ * pinned_stats9 (may be NULL): PINNED host memory that receives the statistics as they stand behind this
+ * call's kernels (layout of lasv_graph_stats_async; valid after lasv_graph_flush + a stream synchronisation,
+ * or any synchronous statistics call).  Table-full and overflow conditions are reported by the next
+ * synchronous call (lasv_graph_stats, lasv_graph_load_reads_host, ...).  Earlier work queued on the caller's
+ * own streams (lasv_graph_clear, device-buffer loads) must be complete before the first asynchronous call.
+ * Replaces the reference's one-read-at-a-time loop of load_se/pe_seq_data_into_graph_colour
+ * (file_reader.c:475-773) for callers that parse ahead of the graph. */
+int lasv_graph_load_reads_host_async(lasv_graph *g, const uint8_t *seq, const uint8_t *qual,
+                                     uint64_t n_bytes, const uint64_t *offsets, uint64_t n_reads,
+                                     int quality_cutoff, uint64_t *pinned_stats9);
+/* Size of the device staging ring of the host-buffer calls in bytes (legs of 2 x 64 MB; at least three legs,
+ * at most 256, never more than half of the free device memory).  Three legs (the default) overlap a copy with
+ * the partition kernel of the previous chunk; a ring of a few GB lets lasv_graph_load_reads_host_async keep
+ * copying while an insert of accumulated stripes (~0.1 s on a human-scale table) occupies the GPU.  Call it
+ * BEFORE lasv_graph_set_accumulation (which sizes the stripes from the memory that is left). */
+int lasv_graph_set_staging(lasv_graph *g, uint64_t bytes, uint64_t *granted);
 /* Cumulative statistics since new/clear (synchronises `cuda_stream`).  Returns
  * LASV_ERR_TABLE_FULL if any insert overflowed its whole rehash chain.
  * contig_hist (may be NULL) receives the contig-length histogram,

@@ -108,7 +108,7 @@ EXPORTS = [
     "lasv_graph_enable_kernel_timing", "lasv_graph_kernel_times", "lasv_graph_stats_async",
     "lasv_ref_hash_table_load_ctx_records", "lasv_seqfile_parse_check",
     "lasv_graph_kernel_times_by_kind", "lasv_graph_set_insert_mode", "lasv_graph_insert_counts",
-    "lasv_graph_set_accumulation",
+    "lasv_graph_set_accumulation", "lasv_graph_load_reads_host_async", "lasv_graph_set_staging",
 ]
 
 INSERT_AUTO, INSERT_RANDOM, INSERT_STREAMED = 0, 1, 2
@@ -156,6 +156,8 @@ def lib() -> C.CDLL:
     L.lasv_graph_device_table_bytes.argtypes = [vp]
     L.lasv_graph_load_reads_device.argtypes = [vp, vp, vp, u64, vp, u64, i32, vp]
     L.lasv_graph_load_reads_host.argtypes = [vp, vp, vp, u64, vp, u64, i32, C.POINTER(LoadStats)]
+    L.lasv_graph_load_reads_host_async.argtypes = [vp, vp, vp, u64, vp, u64, i32, vp]
+    L.lasv_graph_set_staging.argtypes = [vp, u64, C.POINTER(u64)]
     L.lasv_graph_stats.argtypes = [vp, C.POINTER(LoadStats), vp, u64, vp]
     L.lasv_graph_rehash_histogram.argtypes = [vp, vp]
     L.lasv_graph_stats_async.argtypes = [vp, vp, vp]

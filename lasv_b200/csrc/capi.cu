@@ -81,12 +81,13 @@ constexpr uint64_t CHUNK_READS = 4ull << 20;
 //       binned    force the partition even on small tables; the insert kind is chosen as usual
 //       random    partition + random-access insert (insert_bins_kernel), never streamed
 //       streamed  partition + streamed insert (streamed_insert.cuh), whatever the batch size
-//   LASV_B200_BINS = regions to partition into (power of two), LASV_B200_PASSES, LASV_B200_CHUNK_MB
+//   LASV_B200_BINS = regions to partition into (power of two), LASV_B200_PASSES, LASV_B200_CHUNK_MB / _KB
 struct Knobs {
   int insert = 0;  // 0 none, 1 direct, 2 binned
   long bins = 0;
   int passes = 0;
   long chunk_mb = 0;
+  long chunk_kb = 0;  // tests: chunks of a few KB make a small input wrap the staging ring many times
 };
 struct Staging {  // one leg of the double-buffered host->device pipeline
   uint8_t *d_seq = nullptr, *d_qual = nullptr;
@@ -131,8 +132,13 @@ struct lasv_graph {
   bool cleaned_tips = false, cleaned_sups = false;
   int clean_threshold = -1;
   cudaStream_t compute = nullptr, copy = nullptr;
-  Staging stage[3];  // three legs: the copy of chunk i+1 may start while chunk i-1 is still being consumed
+  // >= 3 legs: the copy of chunk i+1 may start while chunk i-1 is still being consumed.  More legs (a ring,
+  // lasv_graph_set_staging) let the copies of the asynchronous host call run ahead of the kernels for as long as an
+  // insert of the accumulated stripes keeps the compute stream busy.
+  std::vector<Staging> stage = std::vector<Staging>(3);
+  uint64_t stage_reads = CHUNK_READS;  // reads a leg's offset arrays hold
   bool staging_ready = false;
+  int stage_turn = 0;  // the leg the next chunk goes to (the ring carries over from call to call)
   // scratch of the partitioned insert (region bins), grown on demand.  Pipelined mode uses both legs:
   // batch i+1 is binned on the caller's stream while batch i is inserted on `ins`.
   struct BinLeg {
@@ -198,13 +204,26 @@ int use(lasv_graph *g) {
 // default stream is that stream too, so CUDA events recorded there bracket our launches).
 cudaStream_t stream_of(lasv_graph *, void *s) { return (cudaStream_t)s; }
 
+void free_staging(lasv_graph *g) {
+  for (auto &s : g->stage) {
+    cudaFree(s.d_seq);
+    cudaFree(s.d_qual);
+    cudaFree(s.d_offsets);
+    if (s.h_offsets) cudaFreeHost(s.h_offsets);
+    if (s.copied) cudaEventDestroy(s.copied);
+    if (s.consumed) cudaEventDestroy(s.consumed);
+    s = Staging{};
+  }
+  g->staging_ready = false;
+}
+
 int ensure_staging(lasv_graph *g) {
   if (g->staging_ready) return LASV_OK;
   for (auto &s : g->stage) {
     CUDA_TRY(cudaMalloc(&s.d_seq, CHUNK_BYTES + 256));
     CUDA_TRY(cudaMalloc(&s.d_qual, CHUNK_BYTES + 256));
-    CUDA_TRY(cudaMalloc(&s.d_offsets, (CHUNK_READS + 1) * sizeof(uint64_t)));
-    CUDA_TRY(cudaMallocHost(&s.h_offsets, (CHUNK_READS + 1) * sizeof(uint64_t)));
+    CUDA_TRY(cudaMalloc(&s.d_offsets, (g->stage_reads + 1) * sizeof(uint64_t)));
+    CUDA_TRY(cudaMallocHost(&s.h_offsets, (g->stage_reads + 1) * sizeof(uint64_t)));
     CUDA_TRY(cudaEventCreateWithFlags(&s.copied, cudaEventDisableTiming));
     CUDA_TRY(cudaEventCreateWithFlags(&s.consumed, cudaEventDisableTiming));
   }
@@ -323,6 +342,7 @@ Knobs read_knobs(int *insert_mode) {
   if (const char *e = getenv("LASV_B200_BINS")) k.bins = atol(e);
   if (const char *e = getenv("LASV_B200_PASSES")) k.passes = atoi(e);
   if (const char *e = getenv("LASV_B200_CHUNK_MB")) k.chunk_mb = atol(e);
+  if (const char *e = getenv("LASV_B200_CHUNK_KB")) k.chunk_kb = atol(e);
   return k;
 }
 
@@ -533,14 +553,7 @@ void lasv_graph_free(lasv_graph **gp) {
   cudaFree(g->d_hist);
   cudaFree(g->d_overflow);
   free_bins(g);
-  for (auto &s : g->stage) {
-    cudaFree(s.d_seq);
-    cudaFree(s.d_qual);
-    cudaFree(s.d_offsets);
-    if (s.h_offsets) cudaFreeHost(s.h_offsets);
-    if (s.copied) cudaEventDestroy(s.copied);
-    if (s.consumed) cudaEventDestroy(s.consumed);
-  }
+  free_staging(g);
   for (auto &l : g->leg) {
     if (l.binned) cudaEventDestroy(l.binned);
     if (l.inserted) cudaEventDestroy(l.inserted);
@@ -849,15 +862,42 @@ int lasv_graph_read_stats_device(lasv_graph *g, const uint8_t *d_seq, const uint
   return check_launch();
 }
 
-int lasv_graph_load_reads_host(lasv_graph *g, const uint8_t *seq, const uint8_t *qual,
-                               uint64_t n_bytes, const uint64_t *offsets, uint64_t n_reads,
-                               int quality_cutoff, lasv_load_stats *batch_stats) {
+int lasv_graph_set_staging(lasv_graph *g, uint64_t bytes, uint64_t *granted) {
+  if (int e = use_hot(g)) return e;
+  CUDA_TRY(cudaDeviceSynchronize());
+  const uint64_t leg_bytes = 2 * CHUNK_BYTES;
+  size_t legs = (size_t)std::min<uint64_t>(256, std::max<uint64_t>(3, bytes / leg_bytes));
+  // never more than half of what is free (the ring must not starve the stripes of the insert path)
+  size_t free_b = 0, total_b = 0;
+  if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
+    const uint64_t have = g->staging_ready ? g->stage.size() * leg_bytes : 0;
+    legs = (size_t)std::min<uint64_t>(legs, std::max<uint64_t>(3, (free_b + have) / 2 / leg_bytes));
+  }
+  if (legs != g->stage.size() || !g->staging_ready) {
+    free_staging(g);
+    g->stage.assign(legs, Staging{});
+    // a ring's legs hold the offsets of 2^20 reads each (64 MB of reads of >= 63 bytes); three legs keep the 2^22
+    g->stage_reads = legs > 3 ? (1ull << 20) : CHUNK_READS;
+    if (int e = ensure_staging(g)) return e;
+  }
+  if (granted) *granted = (uint64_t)legs * leg_bytes;
+  return LASV_OK;
+}
+
+extern "C++" {
+namespace {
+// Both host-buffer calls.  async: nothing here waits for a kernel -- the call returns once its last copy has left
+// the host buffers (copy stream drained); statistics, if wanted, are copied to pinned memory behind the kernels.
+int load_reads_host_impl(lasv_graph *g, const uint8_t *seq, const uint8_t *qual,
+                         uint64_t n_bytes, const uint64_t *offsets, uint64_t n_reads,
+                         int quality_cutoff, lasv_load_stats *batch_stats, bool async, uint64_t *pinned_stats9) {
   if (int e = use_hot(g)) return e;
   if (g->finalized) return fail(LASV_ERR_STATE, "graph is finalised; no further inserts");
   if (!seq || !offsets) return fail(LASV_ERR_ARG, "seq and offsets are required");
   if (offsets[n_reads] != n_bytes) return fail(LASV_ERR_ARG, "offsets[n_reads] != n_bytes");
+  if (async && g->pipeline) return fail(LASV_ERR_STATE, "the asynchronous host call does not combine with lasv_graph_set_pipeline");
   if (int e = ensure_staging(g)) return e;
-  CUDA_TRY(cudaDeviceSynchronize());  // earlier device-API work may sit on a caller's stream
+  if (!async) CUDA_TRY(cudaDeviceSynchronize());  // earlier device-API work may sit on a caller's stream
 
   ReadStats rs0, rs1;
   GraphCounters c0, c1;
@@ -895,7 +935,7 @@ int lasv_graph_load_reads_host(lasv_graph *g, const uint8_t *seq, const uint8_t 
 
   // chunks are cut at read boundaries, so no k-mer window straddles two chunks
   uint64_t r0 = 0;
-  int leg = 0, n_chunk = 0;
+  int leg = g->stage_turn % (int)g->stage.size(), n_chunk = async ? 3 : 0;
   while (r0 < n_reads) {
     uint64_t r1 = r0;
     const uint64_t base = offsets[r0];
@@ -905,8 +945,10 @@ int lasv_graph_load_reads_host(lasv_graph *g, const uint8_t *seq, const uint8_t 
       uint64_t chunk = CHUNK_BYTES;
       if (g->knobs.chunk_mb >= 1 && (uint64_t)g->knobs.chunk_mb <= (CHUNK_BYTES >> 20))  // experiments: 1..64
         chunk = (uint64_t)g->knobs.chunk_mb << 20;
+      if (g->knobs.chunk_kb >= 1 && (uint64_t)g->knobs.chunk_kb <= (CHUNK_BYTES >> 10))
+        chunk = (uint64_t)g->knobs.chunk_kb << 10;
       const uint64_t limit = n_chunk < 3 ? (chunk >> (3 - n_chunk)) : chunk;
-      uint64_t lo = r0 + 1, hi = std::min(n_reads, r0 + CHUNK_READS);
+      uint64_t lo = r0 + 1, hi = std::min(n_reads, r0 + g->stage_reads);
       if (offsets[lo] - base > CHUNK_BYTES)
         return fail(LASV_ERR_ARG, "read %llu is longer than the %llu-byte pipeline chunk",
                     (unsigned long long)r0, (unsigned long long)CHUNK_BYTES);
@@ -934,11 +976,18 @@ int lasv_graph_load_reads_host(lasv_graph *g, const uint8_t *seq, const uint8_t 
     CUDA_TRY(cudaEventRecord(s.consumed, g->compute));
     // h_offsets of this leg must stay alive until its copy completed: the next
     // use of the leg waits on `consumed`, which is ordered after `copied`.
-    leg = (leg + 1) % 3;
+    g->stage_turn = (leg + 1) % (int)g->stage.size();
+    leg = g->stage_turn;
     r0 = r1;
   }
   if (acc.mine)
     if (int e = flush_accumulated(g, g->compute)) return e;
+  if (async) {
+    if (pinned_stats9)
+      if (int e = lasv_graph_stats_async(g, pinned_stats9, g->compute)) return e;
+    CUDA_TRY(cudaStreamSynchronize(g->copy));  // the caller may reuse its buffers
+    return LASV_OK;
+  }
   if (int e = join_inserts(g, g->compute)) return e;  // pipelined inserts of the last chunks
   if (int e = fetch_counters(g, g->compute, &rs1, &c1, &ov)) return e;
   if (c1.table_full) return fail(LASV_ERR_TABLE_FULL, "%s", TABLE_FULL_MSG);
@@ -954,6 +1003,20 @@ int lasv_graph_load_reads_host(lasv_graph *g, const uint8_t *seq, const uint8_t 
     fill_stats(batch_stats, d, dc);
   }
   return LASV_OK;
+}
+}  // namespace
+}
+
+int lasv_graph_load_reads_host(lasv_graph *g, const uint8_t *seq, const uint8_t *qual,
+                               uint64_t n_bytes, const uint64_t *offsets, uint64_t n_reads,
+                               int quality_cutoff, lasv_load_stats *batch_stats) {
+  return load_reads_host_impl(g, seq, qual, n_bytes, offsets, n_reads, quality_cutoff, batch_stats, false, nullptr);
+}
+
+int lasv_graph_load_reads_host_async(lasv_graph *g, const uint8_t *seq, const uint8_t *qual,
+                                     uint64_t n_bytes, const uint64_t *offsets, uint64_t n_reads,
+                                     int quality_cutoff, uint64_t *pinned_stats9) {
+  return load_reads_host_impl(g, seq, qual, n_bytes, offsets, n_reads, quality_cutoff, nullptr, true, pinned_stats9);
 }
 
 int lasv_graph_stats(lasv_graph *g, lasv_load_stats *out, uint64_t *contig_hist, uint64_t hist_size,

@@ -148,6 +148,20 @@ class DBGraph:
                                                    _ptr(offsets), n_reads, quality_cutoff, C.byref(st)))
         return st.as_dict()
 
+    def load_reads_host_async(self, seq, qual, offsets, quality_cutoff: int = QUALITY_OFFSET_DEFAULT, pinned_stats=None):
+        """Returns once the copies have left `seq` / `qual`; kernels (and inserts of full stripes) still run.
+        `pinned_stats`: pinned uint64[9] that receives the statistics behind this call's kernels."""
+        n_reads = len(offsets) - 1
+        n_bytes = int(offsets[n_reads])
+        check(self._lib.lasv_graph_load_reads_host_async(self._h, _ptr(seq), _ptr(qual), n_bytes, _ptr(offsets),
+                                                         n_reads, quality_cutoff, _ptr(pinned_stats)))
+
+    def set_staging(self, n_bytes: int) -> int:
+        """Device staging ring of the host-buffer calls (before set_accumulation).  Returns the bytes granted."""
+        got = C.c_uint64(0)
+        check(self._lib.lasv_graph_set_staging(self._h, int(n_bytes), C.byref(got)))
+        return int(got.value)
+
     def stats(self, hist_size: int = 0, stream=None):
         st = LoadStats()
         hist = np.zeros(hist_size, dtype=np.uint64) if hist_size else None

@@ -468,6 +468,53 @@ def test_streamed_insert_with_accumulation_matches_oracle(base, L, W, bins, n_ba
         os.environ.pop("LASV_B200_INSERT", None)
 
 
+
+@pytest.mark.parametrize("accumulate", [0, 2.5])
+def test_asynchronous_host_calls_through_the_staging_ring(accumulate, monkeypatch):
+    """lasv_graph_load_reads_host_async + lasv_graph_set_staging: the calls return when their copies have left the
+    host buffers, the chunks wrap a five-leg ring many times (64 KB chunks), full stripes are inserted while later
+    copies are already on their way, the per-call statistics arrive in pinned memory.  Same graph as the oracle."""
+    torch = torch_cuda()
+    monkeypatch.setenv("LASV_B200_BINS", "4")
+    monkeypatch.setenv("LASV_B200_INSERT", "binned")
+    monkeypatch.setenv("LASV_B200_CHUNK_KB", "64")
+    L, W, n_reads, n_calls = 13, 40, 24_000, 4
+    w = synth.scaled(synth.CFG0, 80_000, L)
+    w.bucket_size = W
+    p, seq, qual, offs, og = _synth_oracle(w, n_reads, seed=17)
+    want = O.sort_records(og.records())
+    per_reads = n_reads // n_calls
+    per = per_reads * (w.read_len + 1)
+    h_seq = torch.from_numpy(seq.copy()).pin_memory()
+    h_qual = torch.from_numpy(qual.copy()).pin_memory()
+    rows = torch.zeros((n_calls, 9), dtype=torch.int64).pin_memory()
+    with DBGraph(w.kmer_size, L, W) as g:
+        assert g.set_staging(5 * (128 << 20)) == 5 * (128 << 20)
+        g.set_insert_mode(_capi.INSERT_STREAMED)
+        if accumulate:
+            g.set_accumulation(int(accumulate * per))
+        torch.cuda.synchronize()
+        for c in range(n_calls):
+            lo = c * per
+            o = (offs[c * per_reads: (c + 1) * per_reads + 1] - np.uint64(lo)).astype(np.uint64)
+            g.load_reads_host_async(h_seq[lo: lo + per], h_qual[lo: lo + per], o, w.cutoff, rows[c])
+            if c == 1:      # the buffers of a finished call may be overwritten at once
+                h_seq[:per].fill_(ord("N"))
+        st = g.stats()      # synchronous: inserts what the stripes still hold
+        names = DBGraph.STATS_ASYNC_FIELDS
+        reads = rows[:, names.index("n_reads")].tolist()
+        assert reads == [per_reads * (c + 1) for c in range(n_calls)]
+        assert st["kmers_inserted"] == og.stats.kmers_inserted and st["unique_kmers"] == len(want)
+        assert st["bad_reads"] == og.stats.bad_reads and st["bases_loaded"] == og.stats.bases_loaded
+        assert np.array_equal(O.sort_records(g.records()), want)
+        n_ins = g.insert_counts()
+        assert n_ins["random"] == 0 and n_ins["streamed"] == (n_calls if not accumulate else 2)
+        # and the synchronous call still works on the same ring
+        h_seq[:per].copy_(torch.from_numpy(seq[:per].copy()))
+        o = offs[: per_reads + 1].astype(np.uint64)
+        st2 = g.load_reads_host(h_seq[:per], h_qual[:per], o, w.cutoff)
+        assert st2["n_reads"] == per_reads and st2["kmers_inserted"] > 0
+
 @pytest.mark.parametrize("mode", ["direct", "binned", "random", "streamed"])
 def test_random_inputs_match_oracle(mode, monkeypatch):
     """Seeded random reads (bad characters, low qualities, low-complexity, empty and short reads) and
