@@ -62,6 +62,8 @@ def parse_args():
     ap.add_argument("--fraction", type=float, default=1.0, help="cfg4: part of the 30x read set to load (experiments)")
     ap.add_argument("--accumulate-gb", type=float, default=-1.0,
                     help="cfg4, N=1: read stream per insert in GB (-1: all that fits next to the table, 0: one insert per batch)")
+    ap.add_argument("--accumulate-batches", type=int, default=0,
+                    help="cfg4, N>1: batches a rank bins before one exchange + insert (0: from the free memory)")
     ap.add_argument("--insert", choices=["auto", "random", "streamed"], default="auto")
     ap.add_argument("--steady-steps", type=int, default=3)
     ap.add_argument("--e2e-pairs", type=int, default=4 << 20, help="cfg4: read pairs per host-buffer call of the e2e leg")
@@ -391,10 +393,19 @@ def job_geometry(args, w, world):
     ppb = args.pairs_per_batch
     total_pairs = int(w.n_pairs * args.fraction)
     n_batches = (total_pairs + ppb - 1) // ppb
-    per_step = (n_batches + args.steps - 1) // args.steps           # global batches per step
-    per_step = (per_step + world - 1) // world * world
-    return {"pairs_per_batch": ppb, "batches_per_step": per_step, "batches": per_step * args.steps,
-            "pairs": per_step * args.steps * ppb}
+    # the same read set at N = 1, 2, 4, 8: whole batches, a multiple of 8 of them (of the world size beyond 8)
+    mult = 8 if 8 % world == 0 else world
+    n_batches = (n_batches + mult - 1) // mult * mult
+    per_rank = n_batches // world
+    K = args.steps
+    # batches of rank r in step s: per_rank / K, the first per_rank % K steps one more
+    counts = [per_rank // K + (1 if s_ < per_rank % K else 0) for s_ in range(K)]
+    prefix = [0]
+    for c in counts:
+        prefix.append(prefix[-1] + c)
+    return {"pairs_per_batch": ppb, "batches": n_batches, "pairs": n_batches * ppb, "per_rank": per_rank,
+            "step_counts": counts, "step_prefix": prefix, "max_per_step": max(counts) if counts else 0,
+            "batches_per_step": max(counts) * world if counts else 0}
 
 
 def workload_config(args, w, n_gpus):
@@ -404,7 +415,7 @@ def workload_config(args, w, n_gpus):
                             "(MAXK=63), -s 5, table L=24 W=250 (100.7 GB) hash-sharded over the GPUs, built from an "
                             "empty table in `steps` equal steps",
                 "kmer_size": w.kmer_size, "mem_height": w.number_bits, "mem_width": w.bucket_size,
-                "read_pairs_total": geo["pairs"], "read_pairs_per_step": geo["batches_per_step"] * geo["pairs_per_batch"],
+                "read_pairs_total": geo["pairs"], "read_pairs_per_step": geo["pairs"] / max(args.steps, 1),
                 "read_pairs_per_batch": geo["pairs_per_batch"], "read_len": w.read_len, "fraction_of_30x": args.fraction,
                 "sharding": f"hash x{n_gpus}",
                 "l2_policy": "inputs (>= 0.6 GB per batch), stripes (GBs) and table (>= 13 GB/GPU) exceed the 126 MB L2"}
@@ -466,10 +477,15 @@ def parity_leg(args, w, rank, world, local_rank, dev):
     os.environ["LASV_B200_INSERT"] = "streamed"        # the job's insert kind, on a table too small to choose it itself
     os.environ["LASV_B200_BINS"] = str(max(1, (1 << L) // world // 256))
     try:
+        # three batches per rank, two of them accumulated per exchange / insert, pipelined like the job
+        n_mine = hi_r - lo_r
+        chunk = ((n_mine + 2) // 3 + 1) // 2 * 2
         small = ShardedDBGraph(w.kmer_size, L, w.bucket_size, rank, world, local_rank,
-                               max_kmers_per_batch=(n_reads - (world - 1) * per) * stride,
-                               max_bytes_per_batch=(n_reads - (world - 1) * per) * stride,
-                               max_reads_per_batch=n_reads - (world - 1) * per, pipeline=False)
+                               max_kmers_per_batch=chunk * stride, max_bytes_per_batch=chunk * stride,
+                               max_reads_per_batch=chunk, pipeline=(world > 1 and not args.no_pipeline),
+                               accumulate_batches=2)
+        if world == 1:
+            small.graph.set_accumulation(2 * chunk * stride)
     finally:
         for k, v in saved.items():
             if v is None:
@@ -479,8 +495,10 @@ def parity_leg(args, w, rank, world, local_rank, dev):
     pad = np.full(16, 10, np.uint8)
     d_seq = torch.from_numpy(np.concatenate([seq[lo_r * stride: hi_r * stride], pad])).to(dev)
     d_qual = torch.from_numpy(np.concatenate([qual[lo_r * stride: hi_r * stride], pad])).to(dev)
-    d_offs = torch.arange(hi_r - lo_r + 1, dtype=torch.int64, device=dev) * stride
-    small.load_reads_device(d_seq, d_qual, nb, w.cutoff, d_offs, hi_r - lo_r)
+    d_offs = torch.arange(chunk + 1, dtype=torch.int64, device=dev) * stride
+    for c0 in range(0, n_mine, chunk):
+        nr = min(chunk, n_mine - c0)
+        small.load_reads_device(d_seq[c0 * stride:], d_qual[c0 * stride:], nr * stride, w.cutoff, d_offs[: nr + 1], nr)
     small.flush()
     torch.cuda.synchronize()
     st = small.stats()
@@ -554,23 +572,48 @@ def main_job(args, w):
     stride = w.read_len + 1
     reads_per_batch = 2 * geo["pairs_per_batch"]
     n_bytes = reads_per_batch * stride
-    local_per_step = geo["batches_per_step"] // world
+    local_per_step = geo["max_per_step"]
     stream = torch.cuda.current_stream().cuda_stream
     p = w.params()
+    batch_dev_bytes = 2 * (n_bytes + 16)
 
+    # The reads of R consecutive steps (a "window") are generated on the device and are resident in HBM before the
+    # window's timed region starts.  N = 1: R = 1 -- everything runs on one stream, so the generator of the next
+    # step simply queues behind this step's kernels and no flush is needed between steps.  N > 1: the exchange and
+    # the inserts run on side streams, so a timed region must end with everything joined; R is as many steps as
+    # fit in a fifth of the memory next to the shard (N >= 4: the whole job), and the steps inside a window follow
+    # each other without a flush.
+    free0, _ = torch.cuda.mem_get_info()
+    shard_bytes = (1 << w.number_bits) // world * ((w.bucket_size + 4) // 5) * 128
+    if world == 1:
+        R = 1
+        resident = local_per_step * batch_dev_bytes <= max(0, free0 - shard_bytes - (36 << 30))
+    else:
+        budget = min(48 << 30, (free0 - shard_bytes) // 5)
+        R = int(max(1, min(K, budget // max(1, local_per_step * batch_dev_bytes))))
+        resident = True
+    windows = [(s0, min(K, s0 + R)) for s0 in range(0, K, R)]
+    n_pool = R * local_per_step if resident else 2
+
+    # N > 1: a rank bins A batches into the same stripes before ONE exchange and ONE insert on the owners (two buffer
+    # sets: the next A batches are binned while the previous ones travel and are inserted).  A from the memory next
+    # to the shard and the resident reads (4 x 3 GB of stripes per batch: send + receive, two sets, + the insert's
+    # scratch), at least ~6 rounds per job.
+    acc_batches = 1
+    if world > 1 and args.accumulate_gb:
+        per_batch = 4 * 1.04 * 16 * reads_per_batch * (w.read_len - w.kmer_size + 1) * 1.13
+        room = free0 - shard_bytes - n_pool * batch_dev_bytes - (16 << 30)
+        acc_batches = int(max(1, min(room / per_batch, (geo["per_rank"] + 5) // 6, 16)))
+        if args.accumulate_batches > 0:
+            acc_batches = args.accumulate_batches
     graph = ShardedDBGraph(w.kmer_size, w.number_bits, w.bucket_size, rank, world, local_rank,
                            max_kmers_per_batch=reads_per_batch * (w.read_len - w.kmer_size + 1),
                            max_bytes_per_batch=n_bytes, max_reads_per_batch=reads_per_batch,
-                           pipeline=(world > 1 and not args.no_pipeline))
+                           pipeline=(world > 1 and not args.no_pipeline), accumulate_batches=acc_batches)
     g = graph.graph
     slot = g.element_bytes
     g.set_insert_mode({"auto": _capi.INSERT_AUTO, "random": _capi.INSERT_RANDOM, "streamed": _capi.INSERT_STREAMED}[args.insert])
 
-    # the reads of one step, resident in HBM before the step is timed (if they fit next to the table: else two
-    # buffers and the generator runs inside the timed region)
-    free_b, _ = torch.cuda.mem_get_info()
-    resident = local_per_step * 2 * (n_bytes + 16) <= max(0, free_b - (36 << 30))
-    n_pool = local_per_step if resident else 2
     pool = [(torch.empty(n_bytes + 16, dtype=torch.uint8, device=dev), torch.empty(n_bytes + 16, dtype=torch.uint8, device=dev))
             for _ in range(n_pool)]
     offs_dev = torch.arange(reads_per_batch + 1, dtype=torch.int64, device=dev) * stride
@@ -578,24 +621,37 @@ def main_job(args, w):
     if world == 1 and args.accumulate_gb:
         granted = g.set_accumulation((1 << 64) - 1 if args.accumulate_gb < 0 else int(args.accumulate_gb * 1e9))
 
-    def first_read(step, i):           # global batch (step, local i of this rank) -> its first read
-        return ((step * geo["batches_per_step"]) + i * world + rank) * reads_per_batch
+    def step_count(step):              # batches of this rank in a step (steps past the job: the largest step)
+        return geo["step_counts"][step] if step < K else local_per_step
 
-    def run_step(step, e0=None, e1=None):
-        """One step: its batches through the hot path, then the insert of what the stripes hold."""
+    def first_read(step, i):           # (step, local batch i of this rank) -> first read of that batch
+        if step < K:
+            mine = geo["step_prefix"][step] + i
+        else:
+            mine = geo["per_rank"] + (step - K) * local_per_step + i
+        return (mine * world + rank) * reads_per_batch
+
+    def run_window(s0, s1, e0=None, e1=None, flush=True):
+        """Steps s0 .. s1-1: their batches through the hot path.  The stripes are inserted whenever they are full
+        (N=1: lasv_graph_set_accumulation; N>1: every `acc_batches` batches); at the end of the window everything
+        queued on side streams is joined (N>1: what the stripes still hold is exchanged and inserted first), and
+        with `flush` (the end of the job) the same happens at N=1."""
+        todo = [(s_, i) for s_ in range(s0, s1) for i in range(step_count(s_))]
         if resident:
-            for i in range(local_per_step):
-                synth.reads_device(p, first_read(step, i), reads_per_batch, pool[i][0], pool[i][1], stream)
-            barrier()
+            for slot_, (s_, i) in enumerate(todo):
+                synth.reads_device(p, first_read(s_, i), reads_per_batch, pool[slot_][0], pool[slot_][1], stream)
+            if world > 1:
+                barrier()              # (N=1: same stream as the kernels, nothing to wait for)
         l0 = lib.lasv_kernel_launches()
         if e0 is not None:
             e0.record()
-        for i in range(local_per_step):
-            sq = pool[i % n_pool]
+        for slot_, (s_, i) in enumerate(todo):
+            sq = pool[slot_ % n_pool]
             if not resident:
-                synth.reads_device(p, first_read(step, i), reads_per_batch, sq[0], sq[1], stream)
+                synth.reads_device(p, first_read(s_, i), reads_per_batch, sq[0], sq[1], stream)
             graph.load_reads_device(sq[0], sq[1], n_bytes, w.cutoff, offs_dev, reads_per_batch)
-        graph.flush()                  # N=1: the accumulated stripes are inserted; N>1: side-stream inserts join
+        if flush or world > 1:
+            graph.flush()
         if e1 is not None:
             e1.record()
         return lib.lasv_kernel_launches() - l0
@@ -606,7 +662,7 @@ def main_job(args, w):
 
     # ---------------------------------------------------------------- warm-up, then an empty table again
     for _ in range(Wm):
-        run_step(0)
+        run_window(0, 1)
     barrier()
     graph.stats()                      # (raises if anything overflowed)
     g.clear(stream)
@@ -615,12 +671,14 @@ def main_job(args, w):
     # ---------------------------------------------------------------- the job
     if world == 1:
         g.enable_kernel_timing(True)
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in windows]
     launches = 0
+    barrier()
     wall0 = time.monotonic()
     torch.cuda.profiler.start()        # `ncu --profile-from-start off` sees the timed steps only
-    for s_ in range(K):
-        launches += run_step(s_, *ev[s_])
+    # K steps in windows of R; the job ends with the insert of what the stripes still hold
+    for wi, (s0, s1) in enumerate(windows):
+        launches += run_window(s0, s1, *ev[wi], flush=(s1 == K))
     barrier()
     torch.cuda.profiler.stop()
     wall1 = time.monotonic()
@@ -639,14 +697,15 @@ def main_job(args, w):
     # ---------------------------------------------------------------- steady state on the finished table
     steady = None
     if args.steady_steps > 0:
-        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steady_steps)]
-        for s_ in range(args.steady_steps):
-            run_step(K + s_, *evs[s_])
+        sw = [(s0, min(args.steady_steps, s0 + R)) for s0 in range(0, args.steady_steps, R)]
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in sw]
+        for wi, (s0, s1) in enumerate(sw):
+            run_window(K + s0, K + s1, *evs[wi], flush=(s1 == args.steady_steps))
         barrier()
         sms = max_over_ranks(e0.elapsed_time(e1) for e0, e1 in evs)
         st2 = graph.stats()
         steady = {"value": (st2["kmers_inserted"] - kmers) / (sum(sms) * 1e-3), "unit": UNIT, "steps": args.steady_steps,
-                  "ms_per_step": sum(sms) / len(sms), "novel_kmers": st2["unique_kmers"] - st_job["unique_kmers"],
+                  "ms_per_step": sum(sms) / args.steady_steps, "novel_kmers": st2["unique_kmers"] - st_job["unique_kmers"],
                   "what": "further steps of fresh reads on the finished table (80 % full)"}
 
     # ---------------------------------------------------------------- roofline
@@ -693,7 +752,7 @@ def main_job(args, w):
             for b_ in range(2):
                 hs, hq = torch.empty(nb_e + 16, dtype=torch.uint8).pin_memory(), torch.empty(nb_e + 16, dtype=torch.uint8).pin_memory()
                 for i in range(sub):
-                    synth.reads_device(p, ((K + args.steady_steps + 1) * geo["batches_per_step"] + b_ * sub + i) * reads_per_batch,
+                    synth.reads_device(p, (geo["batches"] + (args.steady_steps + 1) * geo["batches_per_step"] + b_ * sub + i) * reads_per_batch,
                                        reads_per_batch, pool[0][0], pool[0][1], stream)
                     torch.cuda.synchronize()
                     hs[i * n_bytes: (i + 1) * n_bytes].copy_(pool[0][0][:n_bytes])
@@ -740,7 +799,7 @@ def main_job(args, w):
             host_seq = [torch.empty(n_bytes + 16, dtype=torch.uint8).pin_memory() for _ in range(2)]
             host_qual = [torch.empty(n_bytes + 16, dtype=torch.uint8).pin_memory() for _ in range(2)]
             for b_ in range(2):
-                synth.reads_device(p, (((K + args.steady_steps + 1) * geo["batches_per_step"]) + b_ * world + rank) * reads_per_batch,
+                synth.reads_device(p, (geo["batches"] + (args.steady_steps + 1) * geo["batches_per_step"] + b_ * world + rank) * reads_per_batch,
                                    reads_per_batch, pool[0][0], pool[0][1], stream)
                 torch.cuda.synchronize()
                 host_seq[b_].copy_(pool[0][0])
@@ -778,6 +837,7 @@ def main_job(args, w):
             t0 = time.perf_counter()
             for s_ in range(K):
                 e2e_step(s_ % 2)
+            graph.flush()              # what the stripes still hold is exchanged and inserted inside the timed region
             torch.cuda.synchronize()
             dte = max_over_ranks([time.perf_counter() - t0])[0]
             barrier()
@@ -827,7 +887,8 @@ def main_job(args, w):
                     "covg_equals_inserts": summary["sum_covg"] == kmers, "bad_reads": st_job["bad_reads"],
                     "fingerprint": f"{summary['fingerprint']:016x}", "inputs_resident_before_each_step": bool(resident),
                     "accumulate_stream_bytes_granted": granted, "inserts_by_kind": inserts_by_kind,
-                    "wall_seconds_incl_read_generation": wall1 - wall0, "step_ms": step_ms},
+                    "wall_seconds_incl_read_generation": wall1 - wall0, "window_ms": step_ms, "steps_per_window": R,
+                    "batches_accumulated_per_exchange": acc_batches if world > 1 else None},
             "fingerprint": f"{summary['fingerprint']:016x}",
             "parity": parity["status"] if parity else None, "parity_detail": parity,
             "kmers_per_step": kmers // K, "gpu_launches": int(launches),

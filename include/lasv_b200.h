@@ -256,6 +256,15 @@ int lasv_graph_bin_reads_device(lasv_graph *g, const uint8_t *d_seq, const uint8
                                 uint32_t bins_per_owner, uint32_t stripe_capacity_records,
                                 uint32_t spill_capacity_records, void *d_records, void *d_counts,
                                 void *cuda_stream);
+/* The same, APPENDING to stripes that already hold earlier batches (the counters are not reset): a rank of a
+ * hash-sharded build accumulates several batches in stripes sized for all of them (lasv_graph_bin_geometry
+ * with the summed bytes and reads), exchanges them once and the owners insert them once -- the insert's
+ * cost per record falls with the records per table line (see lasv_graph_set_accumulation). */
+int lasv_graph_bin_reads_append_device(lasv_graph *g, const uint8_t *d_seq, const uint8_t *d_qual,
+                                       uint64_t n_bytes, int quality_cutoff, int n_owners,
+                                       uint32_t bins_per_owner, uint32_t stripe_capacity_records,
+                                       uint32_t spill_capacity_records, void *d_records, void *d_counts,
+                                       void *cuda_stream);
 int lasv_graph_insert_bins_device(lasv_graph *g, const void *d_records, const void *d_counts, int n_src,
                                   uint32_t bins_per_src, uint32_t stripe_capacity_records,
                                   uint32_t spill_capacity_records, void *cuda_stream);

@@ -109,6 +109,7 @@ EXPORTS = [
     "lasv_ref_hash_table_load_ctx_records", "lasv_seqfile_parse_check",
     "lasv_graph_kernel_times_by_kind", "lasv_graph_set_insert_mode", "lasv_graph_insert_counts",
     "lasv_graph_set_accumulation", "lasv_graph_load_reads_host_async", "lasv_graph_set_staging",
+    "lasv_graph_bin_reads_append_device",
 ]
 
 INSERT_AUTO, INSERT_RANDOM, INSERT_STREAMED = 0, 1, 2
@@ -168,6 +169,7 @@ def lib() -> C.CDLL:
     u32p = C.POINTER(C.c_uint32)
     L.lasv_graph_bin_geometry.argtypes = [vp, i32, u64, u64, u32p, u32p, u32p, u32p, u32p]
     L.lasv_graph_bin_reads_device.argtypes = [vp, vp, vp, u64, i32, i32, C.c_uint32, C.c_uint32, C.c_uint32, vp, vp, vp]
+    L.lasv_graph_bin_reads_append_device.argtypes = L.lasv_graph_bin_reads_device.argtypes
     L.lasv_graph_insert_bins_device.argtypes = [vp, vp, vp, i32, C.c_uint32, C.c_uint32, C.c_uint32, vp]
     L.lasv_graph_find.argtypes = [vp, vp, u64, vp, vp, vp]
     L.lasv_graph_summary.argtypes = [vp, C.POINTER(TableSummary)]

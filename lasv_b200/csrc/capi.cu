@@ -1206,11 +1206,13 @@ int lasv_graph_bin_geometry(lasv_graph *g, int n_owners, uint64_t n_bytes, uint6
   return LASV_OK;
 }
 
-int lasv_graph_bin_reads_device(lasv_graph *g, const uint8_t *d_seq, const uint8_t *d_qual,
-                                uint64_t n_bytes, int quality_cutoff, int n_owners,
-                                uint32_t bins_per_owner, uint32_t stripe_capacity_records,
-                                uint32_t spill_capacity_records, void *d_records, void *d_counts,
-                                void *cuda_stream) {
+extern "C++" {
+namespace {
+int bin_reads_impl(lasv_graph *g, const uint8_t *d_seq, const uint8_t *d_qual,
+                   uint64_t n_bytes, int quality_cutoff, int n_owners,
+                   uint32_t bins_per_owner, uint32_t stripe_capacity_records,
+                   uint32_t spill_capacity_records, void *d_records, void *d_counts,
+                   void *cuda_stream, bool append) {
   if (int e = use(g)) return e;
   if (n_owners < 1 || n_owners > 16 || (n_owners & (n_owners - 1)) || !bins_per_owner ||
       (bins_per_owner & (bins_per_owner - 1)) || bins_per_owner > g->n_buckets || !stripe_capacity_records)
@@ -1222,7 +1224,8 @@ int lasv_graph_bin_reads_device(lasv_graph *g, const uint8_t *d_seq, const uint8
   if (int e = check_streams(d_seq, d_qual)) return e;
   cudaStream_t st = stream_of(g, cuda_stream);
   const uint32_t n_bins = bins_per_owner * (uint32_t)n_owners;
-  CUDA_TRY(cudaMemsetAsync(d_counts, 0, (size_t)(n_bins + n_owners) * COUNT_STRIDE * sizeof(unsigned int), st));
+  if (!append)
+    CUDA_TRY(cudaMemsetAsync(d_counts, 0, (size_t)(n_bins + n_owners) * COUNT_STRIDE * sizeof(unsigned int), st));
   if (!n_bytes) return LASV_OK;
   BuildParams p = build_params(g, d_seq, d_qual, n_bytes, quality_cutoff);
   p.bins.recs = (uint64_t *)d_records;
@@ -1240,8 +1243,31 @@ int lasv_graph_bin_reads_device(lasv_graph *g, const uint8_t *d_seq, const uint8
   p.bins.block_shift = (uint32_t)log2_u32(bins_per_owner);
   p.bins.rec_words = bin_record_words(g->N, g->k);
   p.ctas_per_sm = g->pipeline ? 2 : 0;
+  Span sp(g, LASV_T_PARTITION, st);
   launch_build(g->N, MODE_BIN, p, st);
-  return check_launch();
+  if (int e = check_launch()) return e;
+  sp.end();
+  return LASV_OK;
+}
+}  // namespace
+}
+
+int lasv_graph_bin_reads_device(lasv_graph *g, const uint8_t *d_seq, const uint8_t *d_qual,
+                                uint64_t n_bytes, int quality_cutoff, int n_owners,
+                                uint32_t bins_per_owner, uint32_t stripe_capacity_records,
+                                uint32_t spill_capacity_records, void *d_records, void *d_counts,
+                                void *cuda_stream) {
+  return bin_reads_impl(g, d_seq, d_qual, n_bytes, quality_cutoff, n_owners, bins_per_owner, stripe_capacity_records,
+                        spill_capacity_records, d_records, d_counts, cuda_stream, false);
+}
+
+int lasv_graph_bin_reads_append_device(lasv_graph *g, const uint8_t *d_seq, const uint8_t *d_qual,
+                                       uint64_t n_bytes, int quality_cutoff, int n_owners,
+                                       uint32_t bins_per_owner, uint32_t stripe_capacity_records,
+                                       uint32_t spill_capacity_records, void *d_records, void *d_counts,
+                                       void *cuda_stream) {
+  return bin_reads_impl(g, d_seq, d_qual, n_bytes, quality_cutoff, n_owners, bins_per_owner, stripe_capacity_records,
+                        spill_capacity_records, d_records, d_counts, cuda_stream, true);
 }
 
 int lasv_graph_insert_bins_device(lasv_graph *g, const void *d_records, const void *d_counts, int n_src,

@@ -223,10 +223,11 @@ class DBGraph:
         return geo
 
     def bin_reads_device(self, d_seq, d_qual, n_bytes, quality_cutoff, n_owners, bins_per_owner,
-                         stripe_capacity, spill_capacity, d_records, d_counts, stream=None):
-        check(self._lib.lasv_graph_bin_reads_device(self._h, _ptr(d_seq), _ptr(d_qual), n_bytes, quality_cutoff,
-                                                    n_owners, bins_per_owner, stripe_capacity, spill_capacity,
-                                                    _ptr(d_records), _ptr(d_counts), stream))
+                         stripe_capacity, spill_capacity, d_records, d_counts, stream=None, append=False):
+        """append: the stripes keep what earlier batches put there (lasv_graph_bin_reads_append_device)."""
+        fn = self._lib.lasv_graph_bin_reads_append_device if append else self._lib.lasv_graph_bin_reads_device
+        check(fn(self._h, _ptr(d_seq), _ptr(d_qual), n_bytes, quality_cutoff,
+                 n_owners, bins_per_owner, stripe_capacity, spill_capacity, _ptr(d_records), _ptr(d_counts), stream))
 
     def insert_bins_device(self, d_records, d_counts, n_src, bins_per_src, stripe_capacity, spill_capacity,
                            stream=None):

@@ -148,7 +148,8 @@ class ShardedDBGraph:
 
     def __init__(self, kmer_size: int, number_bits: int, bucket_size: int, rank: int, world: int,
                  device: int, max_kmers_per_batch: int, group=None, slack: float = 1.08,
-                 max_bytes_per_batch: int = 0, max_reads_per_batch: int = 0, pipeline: bool = True):
+                 max_bytes_per_batch: int = 0, max_reads_per_batch: int = 0, pipeline: bool = True,
+                 accumulate_batches: int = 1):
         if not is_pow2(world) or world > 16:
             raise ValueError("world size must be a power of two <= 16")
         self.rank, self.world, self.group = rank, world, group
@@ -164,6 +165,11 @@ class ShardedDBGraph:
             self.graph.set_pipeline(True)     # kernels sized to share the SMs with the neighbouring stage
         self.buffers = []
         self.turn = 0
+        # accumulate_batches = A: a rank bins A batches into the SAME stripes (sized for all of them) before the
+        # exchange, and the owners insert A batches' records at once -- the streamed insert's cost per record falls
+        # with the records per table line (streamed_insert.cuh), and the exchange moves few large blocks
+        self.accumulate = max(1, int(accumulate_batches))
+        self.pending = 0                      # batches binned into the current buffer set since its last exchange
         self.trace = None                     # set to [] to collect per-stage CUDA events (timeline())
         if world > 1:
             if not max_bytes_per_batch:       # k-mers <= bytes: a safe stand-in for callers that only know k-mers
@@ -172,7 +178,8 @@ class ShardedDBGraph:
             kk = kmer_size
             self.kmer_bound = (max_bytes_per_batch - max_reads_per_batch * kk
                                if max_reads_per_batch and max_reads_per_batch * kk < max_bytes_per_batch else max_bytes_per_batch)
-            geo = self.graph.bin_geometry(world, max_bytes_per_batch, max_reads_per_batch)
+            geo = self.graph.bin_geometry(world, self.accumulate * max_bytes_per_batch,
+                                          self.accumulate * max_reads_per_batch)
             self.bins_per_owner, self.cap, self.spill = geo["bins_per_owner"], geo["stripe_capacity"], geo["spill_capacity"]
             self.rec_bytes = geo["record_bytes"]
             for _ in range(2 if self.pipeline else 1):
@@ -259,21 +266,37 @@ class ShardedDBGraph:
             raise ValueError(f"batch may hold {bound} k-mers, the exchange stripes were sized for {self.kmer_bound} "
                              "(max_bytes_per_batch / max_reads_per_batch: pass fewer bytes or state fewer reads)")
         buf = self.buffers[self.turn % len(self.buffers)]
-        self.turn += 1
+        first = self.pending == 0
         # the previous user of this buffer set must be done with it
-        if buf.exchanged is not None:
+        if first and buf.exchanged is not None:
             cur.wait_event(buf.exchanged)       # its send block is free again
         ev = None
-        if self.trace is not None:
+        if self.trace is not None and first:
             ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
             self.trace.append(ev)
             ev[0].record(cur)
         g.bin_reads_device(d_seq, d_qual, n_bytes, quality_cutoff, self.world, self.bins_per_owner, self.cap,
-                           self.spill, buf.send, buf.send_counts, stream)
-        if ev:
-            ev[1].record(cur)
+                           self.spill, buf.send, buf.send_counts, stream, append=not first)
         if d_offsets is not None and n_reads:
             g.read_stats_device(d_seq, d_qual, d_offsets, n_reads, quality_cutoff, stream)
+        self.pending += 1
+        if self.pending >= self.accumulate:
+            self._ship()
+
+    def _ship(self):
+        """Exchange what the current buffer set has accumulated and insert it on its owners."""
+        if not self.pending:
+            return
+        cur = torch.cuda.current_stream()
+        stream = cur.cuda_stream
+        g = self.graph
+        k = self.turn % len(self.buffers)
+        buf = self.buffers[k]
+        self.turn += 1
+        self.pending = 0
+        ev = self.trace[-1] if self.trace else None
+        if ev:
+            ev[1].record(cur)
         if not self.pipeline:
             self._exchange(buf, 0)
             g.insert_bins_device(buf.recv, buf.recv_counts, self.world, self.bins_per_owner, self.cap, self.spill,
@@ -287,7 +310,7 @@ class ShardedDBGraph:
                 self.comm_stream.wait_event(buf.inserted)   # recv block free again
             if ev:
                 ev[2].record(self.comm_stream)
-            self._exchange(buf, (self.turn - 1) % len(self.buffers))
+            self._exchange(buf, k)
             if ev:
                 ev[3].record(self.comm_stream)
             buf.exchanged = torch.cuda.Event()
@@ -326,7 +349,9 @@ class ShardedDBGraph:
         cur = torch.cuda.current_stream()
         if self.world == 1:
             self.graph.flush(cur.cuda_stream)
-        elif self.pipeline:
+            return
+        self._ship()                     # (collective: every rank has binned the same number of batches)
+        if self.pipeline:
             for buf in self.buffers:
                 if buf.inserted is not None:
                     cur.wait_event(buf.inserted)

@@ -317,8 +317,12 @@ def test_binned_exchange_matches_oracle(base, world, bins, tiny_stripes, insert,
         send_counts = torch.zeros((world, world, B + 1, cw), dtype=torch.int32, device="cuda")
         for r in range(world):
             lo, hi = r * per, ((r + 1) * per if r < world - 1 else len(seq))
-            graphs[r].bin_reads_device(d_seq[lo:], d_qual[lo:], hi - lo, w.cutoff, world, B, cap, spill, send[r],
+            # in two batches: the second one is APPENDED to the stripes of the first (accumulation before the exchange)
+            mid = lo + (per_reads // 2) * (w.read_len + 1)
+            graphs[r].bin_reads_device(d_seq[lo:], d_qual[lo:], mid - lo, w.cutoff, world, B, cap, spill, send[r],
                                        send_counts[r], st_)
+            graphs[r].bin_reads_device(d_seq[mid:], d_qual[mid:], hi - mid, w.cutoff, world, B, cap, spill, send[r],
+                                       send_counts[r], st_, append=True)
         torch.cuda.synchronize()
         cnt = send_counts[..., 0].cpu().numpy().astype(np.int64)
         stored = np.minimum(cnt[..., :B], cap).sum() + np.minimum(cnt[..., B], spill).sum()
