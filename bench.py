@@ -581,7 +581,7 @@ def main_job(args, w):
     # window's timed region starts.  N = 1: R = 1 -- everything runs on one stream, so the generator of the next
     # step simply queues behind this step's kernels and no flush is needed between steps.  N > 1: the exchange and
     # the inserts run on side streams, so a timed region must end with everything joined; R is as many steps as
-    # fit in a fifth of the memory next to the shard (N >= 4: the whole job), and the steps inside a window follow
+    # fit in an eighth of the memory next to the shard (N >= 4: the whole job), and the steps inside a window follow
     # each other without a flush.
     free0, _ = torch.cuda.mem_get_info()
     shard_bytes = (1 << w.number_bits) // world * ((w.bucket_size + 4) // 5) * 128
@@ -589,7 +589,7 @@ def main_job(args, w):
         R = 1
         resident = local_per_step * batch_dev_bytes <= max(0, free0 - shard_bytes - (36 << 30))
     else:
-        budget = min(48 << 30, (free0 - shard_bytes) // 5)
+        budget = min(48 << 30, (free0 - shard_bytes) // 8)
         R = int(max(1, min(K, budget // max(1, local_per_step * batch_dev_bytes))))
         resident = True
     windows = [(s0, min(K, s0 + R)) for s0 in range(0, K, R)]

@@ -38,7 +38,11 @@ constexpr int SO_THREADS = 512;        // fused sorting kernel
 constexpr uint32_t SO_MAXB = 4096;     // buckets per region the fused sorting kernel handles
 constexpr uint32_t SO_SMEM = 100u << 10;  // its shared memory (two CTAs per SM)
 constexpr int SO_U = 4;                // record loads in flight per thread
-constexpr int SI_WARPS = 4;            // warps per CTA of the insert kernel
+constexpr int SI_UNITS = 4;            // units a CTA of the insert kernel works on at a time
+constexpr int SI_TEAM = 2;             // warps that share one unit (occupancy: the staging buffers bound the units per
+                                       // SM at 16, and 16 warps leave every scheduler with 4 -- too few to cover the
+                                       // shared-memory and record-load latencies of the state machine)
+constexpr int SI_WARPS = SI_UNITS * SI_TEAM;  // warps per CTA of the insert kernel
 constexpr uint32_t SI_MAX_UNIT = 8;    // buckets per unit at most
 constexpr uint32_t SG_CHUNK = 4096;    // records per work item of the direct sorting passes
 constexpr int SG_U = 4;                // records in flight per thread in the direct sorting passes
@@ -403,18 +407,20 @@ template <int N>
 __global__ void __launch_bounds__(SI_WARPS * 32) sg_insert_kernel(const InsertJob j, const TableView t, GraphCounters *ctr) {
   constexpr uint32_t SLOT = LineLayout<N>::SLOT, G = LineLayout<N>::G;
   extern __shared__ __align__(128) unsigned char staged[];
-  __shared__ __align__(8) uint64_t mbar_all[SI_WARPS][2];
+  __shared__ __align__(8) uint64_t mbar_all[SI_UNITS][2];
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t team = warp / SI_TEAM, member = warp % SI_TEAM;  // the warps of a team share one unit; member 0 leads
+  const bool leader = member == 0 && lane == 0;                   // issues the team's copies
   const uint32_t ubytes = j.unit_bytes, upu = 1u << j.unit_shift, bucket_bytes = t.NL * LINE_BYTES;
-  unsigned char *bufs[2] = {staged + (size_t)(2 * warp) * ubytes, staged + (size_t)(2 * warp + 1) * ubytes};
-  uint64_t *mbar = mbar_all[warp];
-  if (lane == 0) {
+  unsigned char *bufs[2] = {staged + (size_t)(2 * team) * ubytes, staged + (size_t)(2 * team + 1) * ubytes};
+  uint64_t *mbar = mbar_all[team];
+  if (leader) {
     for (int b = 0; b < 2; b++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(&mbar[b])));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  __syncwarp();
+  __syncthreads();
   const uint64_t full_valid = header_valid_mask(G), last_valid = header_valid_mask(t.last_slots);
-  const uint32_t n_warps = gridDim.x * SI_WARPS, gw = blockIdx.x * SI_WARPS + warp;
+  const uint32_t n_warps = gridDim.x * SI_UNITS, gw = blockIdx.x * SI_UNITS + team;  // (teams, in fact)
   auto next_with_records = [&](uint32_t u) {  // the same value in every lane
     for (; u < j.n_units; u += n_warps)
       if (__ldg(&j.offsets[u << j.unit_shift]) != __ldg(&j.offsets[(u + 1) << j.unit_shift])) return u;
@@ -429,17 +435,17 @@ __global__ void __launch_bounds__(SI_WARPS * 32) sg_insert_kernel(const InsertJo
   };
   unsigned long long my_new = 0;
   uint32_t u = next_with_records(gw);
-  if (lane == 0 && u < j.n_units) load(u, 0);
+  if (leader && u < j.n_units) load(u, 0);
   for (uint32_t it = 0; u < j.n_units; it++) {
     const int b = it & 1;
     const uint32_t un = next_with_records(u + n_warps);
-    if (lane == 0) {
+    if (leader) {
       asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the other buffer's write-back has read it
       if (un < j.n_units) load(un, b ^ 1);
     }
     const uint32_t lo = __ldg(&j.offsets[u << j.unit_shift]), hi = __ldg(&j.offsets[(u + 1) << j.unit_shift]);
     // this lane's first record is on its way while the lines arrive
-    uint32_t i = lo + lane;
+    uint32_t i = lo + member * 32u + lane;  // the team's lanes take the unit's records in turn
     bool have = i < hi;
     uint64_t w[4] = {0, 0, 0, 0};
     if (have) load_record_words(j.sorted + (uint64_t)i * j.rec_words, j.rec_words, w);
@@ -477,7 +483,7 @@ __global__ void __launch_bounds__(SI_WARPS * 32) sg_insert_kernel(const InsertJo
         steps = 0;
         rejected = 0;
         busy = true;
-        i += 32;
+        i += 32u * SI_TEAM;
         have = i < hi;
         if (have) load_record_words(j.sorted + (uint64_t)i * j.rec_words, j.rec_words, w);  // travels while this one is applied
       }
@@ -530,8 +536,8 @@ __global__ void __launch_bounds__(SI_WARPS * 32) sg_insert_kernel(const InsertJo
       }
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // my updates -> visible to the bulk copy
-    __syncwarp();
-    if (lane == 0) {
+    asm volatile("bar.sync %0, %1;" ::"r"(1u + team), "r"(32u * SI_TEAM) : "memory");  // the whole team is done with the unit
+    if (leader) {
       uint8_t *dst = t.lines + (uint64_t)(j.unit0 + u) * ubytes;
       asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_addr(bufs[b])), "r"(ubytes)
                    : "memory");
@@ -539,7 +545,7 @@ __global__ void __launch_bounds__(SI_WARPS * 32) sg_insert_kernel(const InsertJo
     }
     u = un;
   }
-  if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  if (leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 #pragma unroll
   for (int o = 16; o; o >>= 1) my_new += __shfl_xor_sync(0xFFFFFFFFu, my_new, o);
   if (lane == 0 && my_new) atomicAdd(&ctr->unique_kmers, my_new);
@@ -582,7 +588,7 @@ bool streamed_geometry(const TableView &t, const BinView &b, StreamedGeom *out) 
   const uint64_t bucket_bytes = (uint64_t)t.NL * LINE_BYTES;
   const uint64_t n_buckets = (uint64_t)t.bucket_mask + 1;
   // two staging buffers for each of the four warps of a CTA must fit in shared memory
-  if (2ull * SI_WARPS * bucket_bytes > 200u * 1024u) return false;
+  if (2ull * SI_UNITS * bucket_bytes > 200u * 1024u) return false;
   if (!b.bins_per_src || n_buckets % b.bins_per_src) return false;
   const uint64_t buckets_per_region = n_buckets / b.bins_per_src;
   // units of <= 6.5 KB (one bucket if a bucket is larger): 16 warps with two buffers each share the 227 KB of an SM
@@ -628,7 +634,7 @@ int launch_streamed_insert(int N, const BinView &b, const TableView &t, GraphCou
   };
   sg_dispatch(N, [&](auto nn) {
     constexpr int NN = decltype(nn)::value;
-    const size_t smem = 2 * (size_t)SI_WARPS * geom.unit_bytes;
+    const size_t smem = 2 * (size_t)SI_UNITS * geom.unit_bytes;
     static int per_sm_cached[4] = {0, 0, 0, 0};
     static size_t smem_cached[4] = {0, 0, 0, 0};
     static int sort_per_sm[4] = {0, 0, 0, 0};
@@ -665,7 +671,8 @@ int launch_streamed_insert(int N, const BinView &b, const TableView &t, GraphCou
       mark(LASV_T_SORT, 1);
       if (geom.fused) {
         sg_region_base_kernel<<<1, 1024, 0, st>>>(j, s.counts, s.offsets);
-        const uint32_t grid = std::min<uint32_t>(j.n_regions, (uint32_t)(sm_count() * sort_per_sm[NN]));
+        static const int sort_ctas = [] { const char *e = getenv("LASV_B200_SORT_CTAS"); return e ? atoi(e) : 0; }();  // experiments
+        const uint32_t grid = std::min<uint32_t>(j.n_regions, sort_ctas > 0 ? (uint32_t)sort_ctas : (uint32_t)(sm_count() * sort_per_sm[NN]));
         sg_sort_kernel<NN><<<grid, SO_THREADS, SO_SMEM, st>>>(j, s.counts, s.offsets, s.sorted, overflow);
         if (launches) *launches += 2;
       } else {
@@ -692,7 +699,7 @@ int launch_streamed_insert(int N, const BinView &b, const TableView &t, GraphCou
       ij.spill = s.spill;
       ij.n_spill = s.n_spill;
       uint32_t igrid = (uint32_t)per_sm_cached[NN] * (uint32_t)sm_count();  // persistent: resident CTAs x SMs
-      igrid = std::min<uint32_t>(igrid, (units_per_slab + SI_WARPS - 1) / SI_WARPS);
+      igrid = std::min<uint32_t>(igrid, (units_per_slab + SI_UNITS - 1) / SI_UNITS);
       mark(LASV_T_STREAM, 1);
       sg_insert_kernel<NN><<<igrid, SI_WARPS * 32, smem, st>>>(ij, t, ctr);
       mark(LASV_T_STREAM, 0);

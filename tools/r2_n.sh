@@ -6,5 +6,5 @@ python - <<PY
 import json
 d=json.loads(open('$out/bench_n${n}.json').read().strip().splitlines()[-1])
 print('N', d['n_gpus'], 'value', d['value']/1e9, 'job s', d['job']['seconds'], 'fp', d['fingerprint'], 'parity', d['parity'], 'steady', d['steady_state'] and d['steady_state']['value']/1e9)
-print('e2e', d['e2e'] and d['e2e']['value']/1e9, d['job']['inserts_by_kind'], d['job']['step_ms'])
+print('e2e', d['e2e'] and d['e2e']['value']/1e9, d['job']['inserts_by_kind'], d['job']['window_ms'], d['job']['steps_per_window'], d['job']['batches_accumulated_per_exchange'])
 PY
