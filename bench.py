@@ -456,6 +456,79 @@ def reference_records(ref, N):
     return out
 
 
+PARITY_EVERY = 64     # BASELINE.md section 3 / SURVEY 8d: a deterministic every-64th-pair subsample goes through the reference
+
+
+def parity_reads(w, pairs):
+    """Pairs 0, 64, 128, ... of the job's read set (host arrays in loader order: mate 1, mate 2)."""
+    from lasv_b200 import synth
+    p = w.params()
+    seqs, quals = [], []
+    for i in range(pairs):
+        sq, ql, _ = synth.reads_host(p, 2 * PARITY_EVERY * i, 2)
+        seqs.append(sq)
+        quals.append(ql)
+    return np.concatenate(seqs), np.concatenate(quals)
+
+
+_REF_CACHE = {}
+
+
+def reference_graph_of(w, seq, qual, L, N):
+    """(records of the compiled reference's own table for these reads, k-mers it inserted, kind, seconds)."""
+    key = (L, len(seq))
+    if key not in _REF_CACHE:
+        t0 = time.perf_counter()
+        ref = ReferenceLoader(w.kmer_size, L, w.bucket_size)
+        n_ref, _ = ref.load(seq, qual, w.read_len, w.q_thresh)
+        theirs = reference_records(ref, N)
+        kind = ref.kind
+        ref.close()
+        _REF_CACHE[key] = (theirs, n_ref, kind, time.perf_counter() - t0)
+    return _REF_CACHE[key]
+
+
+def full_geometry_leg(args, w, g, dev):
+    """N = 1: the same subsample through the job's own path into THE JOB'S OWN TABLE (2^24 x 250, 107 GB of lines:
+    64-bit line offsets, 50 lines per bucket), cleared first; every node read back and compared with the compiled
+    reference's table for the same reads (file_reader.c:910-1077 -> hash_table.c:270-327)."""
+    import torch
+    from lasv_b200 import _capi
+    from oracle import oracle as O
+    pairs = args.parity_pairs
+    seq, qual = parity_reads(w, pairs)
+    stride = w.read_len + 1
+    n_reads = 2 * pairs
+    stream = torch.cuda.current_stream().cuda_stream
+    g.set_accumulation(0)
+    g.clear(stream)
+    torch.cuda.synchronize()
+    g.set_insert_mode(_capi.INSERT_STREAMED)       # the job's insert kind (a batch this small would choose random access)
+    chunk = ((n_reads + 2) // 3 + 1) // 2 * 2
+    g.set_accumulation(2 * chunk * stride)
+    pad = np.full(16, 10, np.uint8)
+    d_seq = torch.from_numpy(np.concatenate([seq, pad])).to(dev)
+    d_qual = torch.from_numpy(np.concatenate([qual, pad])).to(dev)
+    d_offs = torch.arange(chunk + 1, dtype=torch.int64, device=dev) * stride
+    for c0 in range(0, n_reads, chunk):
+        nr = min(chunk, n_reads - c0)
+        g.load_reads_device(d_seq[c0 * stride:], d_qual[c0 * stride:], nr * stride, d_offs[: nr + 1], nr, w.cutoff, stream)
+    g.flush(stream)
+    torch.cuda.synchronize()
+    st = g.stats()
+    counts = g.insert_counts()
+    ours = g.records()
+    L = max(sample_table_bits(w, pairs, 1), 9)
+    theirs, n_ref, kind, secs = reference_graph_of(w, seq, qual, L, g.N)
+    same = len(ours) == len(theirs) and np.array_equal(O.sort_records(ours), O.sort_records(theirs))
+    return {"status": "ok" if same and st["kmers_inserted"] == n_ref else "FAILED",
+            "against": "compiled reference (oracle/_ref), its own HashTable" if kind == "reference" else "oracle port",
+            "table": f"the job's own 2^{w.number_bits}x{w.bucket_size} table ({g.table_bytes / 1e9:.1f} GB of lines), cleared",
+            "reads": f"every {PARITY_EVERY}th pair of the job's read set, {pairs} pairs",
+            "nodes": int(len(ours)), "nodes_reference": int(len(theirs)), "kmers_inserted": int(st["kmers_inserted"]),
+            "kmers_reference": int(n_ref), "inserts_by_kind_total": counts}
+
+
 def parity_leg(args, w, rank, world, local_rank, dev):
     """A fixed small read set through the same path as the job (partition -> [exchange] -> streamed insert) into a
     second, small graph; its records, gathered on rank 0, against the compiled reference's table for the same
@@ -469,7 +542,7 @@ def parity_leg(args, w, rank, world, local_rank, dev):
     n_reads = 2 * pairs
     L = max(sample_table_bits(w, pairs, 1), 9 + int(np.log2(world)))
     stride = w.read_len + 1
-    seq, qual, _ = synth.reads_host(w.params(), 0, n_reads)
+    seq, qual = parity_reads(w, pairs)
     per = (n_reads // world) // 2 * 2
     lo_r, hi_r = rank * per, (n_reads if rank == world - 1 else (rank + 1) * per)
     nb = (hi_r - lo_r) * stride
@@ -521,18 +594,14 @@ def parity_leg(args, w, rank, world, local_rank, dev):
     if rank != 0:
         return None
     ours = np.concatenate([b.view(mine.dtype) for b in blobs]) if blobs else mine
-    t0 = time.perf_counter()
-    ref = ReferenceLoader(w.kmer_size, L, w.bucket_size)
-    n_ref, _ = ref.load(seq, qual, w.read_len, w.q_thresh)
-    theirs = reference_records(ref, small.N)
-    kind = ref.kind
-    ref.close()
+    theirs, n_ref, kind, ref_secs = reference_graph_of(w, seq, qual, L, small.N)
     same = len(ours) == len(theirs) and np.array_equal(O.sort_records(ours), O.sort_records(theirs))
     out = {"status": "ok" if same and st["kmers_inserted"] == n_ref else "FAILED",
            "against": "compiled reference (oracle/_ref), its own HashTable" if kind == "reference" else "oracle port",
-           "read_pairs": pairs, "table": f"2^{L}x{w.bucket_size} over {world} GPU(s)", "nodes": int(len(ours)),
+           "read_pairs": pairs, "reads": f"every {PARITY_EVERY}th pair of the job's read set",
+           "table": f"2^{L}x{w.bucket_size} over {world} GPU(s)", "nodes": int(len(ours)),
            "nodes_reference": int(len(theirs)), "kmers_inserted": int(st["kmers_inserted"]), "kmers_reference": int(n_ref),
-           "inserts_by_kind_rank0": counts, "reference_seconds": time.perf_counter() - t0}
+           "inserts_by_kind_rank0": counts, "reference_seconds": ref_secs}
     return out
 
 
@@ -849,6 +918,12 @@ def main_job(args, w):
     sampler.stop()
     final = graph.stats()
     capacity = g.capacity * world
+    parity_full = None
+    if world == 1 and not args.no_parity:
+        try:
+            parity_full = full_geometry_leg(args, w, g, dev)
+        except Exception as ex:          # reported as a failure, never silently dropped
+            parity_full = {"status": "FAILED", "error": repr(ex)[:300]}
     graph.free()
     del pool
     torch.cuda.empty_cache()
@@ -890,7 +965,9 @@ def main_job(args, w):
                     "wall_seconds_incl_read_generation": wall1 - wall0, "window_ms": step_ms, "steps_per_window": R,
                     "batches_accumulated_per_exchange": acc_batches if world > 1 else None},
             "fingerprint": f"{summary['fingerprint']:016x}",
-            "parity": parity["status"] if parity else None, "parity_detail": parity,
+            "parity": (("ok" if all(x["status"] == "ok" for x in (parity, parity_full) if x) else "FAILED")
+                       if (parity or parity_full) else None),
+            "parity_detail": parity, "parity_full_geometry": parity_full,
             "kmers_per_step": kmers // K, "gpu_launches": int(launches),
             "roofline": roofline, "steady_state": steady, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
             "host": {"numa_node_of_rank0": numa_node, "cpus_of_rank0": len(os.sched_getaffinity(0))},

@@ -7,10 +7,13 @@ implementation behind any of these calls.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 
 PKG_DIR = Path(__file__).resolve().parent
 LIB_PATH = PKG_DIR / "liblasv_b200.so"
+if os.environ.get("LASV_B200_LIBRARY"):   # experiments: a variant build of the same library (tools/variants.sh)
+    LIB_PATH = Path(os.environ["LASV_B200_LIBRARY"]).resolve()
 
 LASV_OK = 0
 LASV_ERR_ARG = -1

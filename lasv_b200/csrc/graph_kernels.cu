@@ -230,6 +230,12 @@ __device__ __forceinline__ void upsert_batch(const TableView &t, GraphCounters *
 // One WARP owns one tile: it stages, classifies, erodes, compacts and inserts on
 // its own, synchronising with __syncwarp only -- the eight warps of a CTA never
 // wait for each other, so staging in one warp overlaps table probes in another.
+#ifndef LASV_BIN_U
+#define LASV_BIN_U 2     // rounds of 32 k-mers in flight per warp in the partition kernel
+#endif
+#ifndef LASV_BIN_CTAS
+#define LASV_BIN_CTAS 4  // resident CTAs per SM the partition kernel is compiled for
+#endif
 template <int MODE>
 struct TileCfg {
   // window starts per tile; region = T + 128 bases, a whole number of 32-lane rounds
@@ -238,7 +244,8 @@ struct TileCfg {
   static constexpr int CHUNKS = R / 16;  // 16-base chunks: 32 or 64 -> one or two per lane
   static constexpr int WORDS = R / 32;   // validity words: 16 or 32 -> at most one per lane
   // k-mers per lane in flight in the heavy phase (independent table probes / bin reservations)
-  static constexpr int U = (MODE == MODE_FUSED || MODE == MODE_BIN) ? 2 : 1;
+  static constexpr int U = (MODE == MODE_BIN) ? LASV_BIN_U : (MODE == MODE_FUSED) ? 2 : 1;
+  static constexpr int MIN_CTAS = (MODE == MODE_ROUTE) ? 3 : (MODE == MODE_BIN) ? LASV_BIN_CTAS : 4;
 };
 
 template <int N, int MODE>
@@ -258,7 +265,7 @@ struct WarpTile {
 };
 
 template <int N, int MODE>
-__global__ void __launch_bounds__(THREADS, (MODE == MODE_ROUTE) ? 3 : 4)
+__global__ void __launch_bounds__(THREADS, TileCfg<MODE>::MIN_CTAS)
 build_kernel(const BuildParams p, const uint64_t n_tiles) {
   using Cfg = TileCfg<MODE>;
   constexpr int T = Cfg::T, R = Cfg::R, CHUNKS = Cfg::CHUNKS, WORDS = Cfg::WORDS, U = Cfg::U;

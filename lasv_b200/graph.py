@@ -131,6 +131,11 @@ class DBGraph:
         return int(self._lib.lasv_graph_capacity(self._h))
 
     @property
+    def table_bytes(self) -> int:
+        """Bytes of the device table (lines of 128 bytes until finalize)."""
+        return int(self._lib.lasv_graph_device_table_bytes(self._h))
+
+    @property
     def element_bytes(self) -> int:
         return int(self._lib.lasv_graph_element_bytes(self._h))
 

@@ -519,6 +519,56 @@ def test_asynchronous_host_calls_through_the_staging_ring(accumulate, monkeypatc
         st2 = g.load_reads_host(h_seq[:per], h_qual[:per], o, w.cutoff)
         assert st2["n_reads"] == per_reads and st2["kmers_inserted"] > 0
 
+
+def test_human_scale_table_geometry_matches_oracle():
+    """BASELINE.json configs[4] at its REAL geometry: k=53, 2^24 buckets x 250 slots = 107 GB of 128-byte lines
+    (64-bit line offsets, 50 lines per bucket, 65 536 regions).  A deterministic subsample of the config's read set
+    (every 64th pair) goes through the streamed insert with accumulation and through the random-access insert into
+    that table; every node is read back and compared with the oracle's graph of the same reads (the multiset does
+    not depend on the table geometry as long as no bucket chain overflows)."""
+    torch = torch_cuda()
+    free_b, _ = torch.cuda.mem_get_info()
+    w = synth.CFG4
+    if free_b < (112 << 30):
+        pytest.skip("the human-scale table needs 107 GB of device memory")
+    pairs, every = 8_000, 64
+    p = w.params()
+    parts = [synth.reads_host(p, 2 * every * i, 2) for i in range(pairs)]
+    seq = np.concatenate([a for a, _, _ in parts])
+    qual = np.concatenate([b for _, b, _ in parts])
+    n_reads, stride = 2 * pairs, w.read_len + 1
+    offs = (np.arange(n_reads + 1, dtype=np.uint64) * np.uint64(stride))
+    og = O.OracleGraph(w.kmer_size, 14, w.bucket_size)
+    assert og.load_reads(seq, qual, offs, w.cutoff, paired=True)
+    want = O.sort_records(og.records())
+    st_ = torch.cuda.current_stream().cuda_stream
+    pad = np.full(16, 10, np.uint8)
+    d_seq = torch.from_numpy(np.concatenate([seq, pad])).cuda()
+    d_qual = torch.from_numpy(np.concatenate([qual, pad])).cuda()
+    chunk = ((n_reads + 2) // 3 + 1) // 2 * 2
+    d_offs = torch.arange(chunk + 1, dtype=torch.int64, device="cuda") * stride
+    with DBGraph(w.kmer_size, w.number_bits, w.bucket_size) as g:
+        assert g.table_bytes == (1 << 24) * 50 * 128
+        for mode, kind in ((_capi.INSERT_STREAMED, "streamed"), (_capi.INSERT_RANDOM, "random")):
+            g.set_accumulation(0)
+            g.clear(st_)
+            torch.cuda.synchronize()
+            before = g.insert_counts()
+            g.set_insert_mode(mode)
+            g.set_accumulation(2 * chunk * stride)      # two of the three batches per insert
+            for c0 in range(0, n_reads, chunk):
+                nr = min(chunk, n_reads - c0)
+                g.load_reads_device(d_seq[c0 * stride:], d_qual[c0 * stride:], nr * stride, d_offs[: nr + 1], nr,
+                                    w.cutoff, st_)
+            st = g.stats(stream=st_)
+            after = g.insert_counts()
+            assert after[kind] - before[kind] == 2, (kind, before, after)
+            assert st["kmers_inserted"] == og.stats.kmers_inserted and st["unique_kmers"] == len(want)
+            assert st["bad_reads"] == og.stats.bad_reads
+            assert np.array_equal(O.sort_records(g.records()), want), kind
+            s = g.summary()
+            assert s["sum_covg"] == og.stats.kmers_inserted and s["n_nodes"] == len(want)
+
 @pytest.mark.parametrize("mode", ["direct", "binned", "random", "streamed"])
 def test_random_inputs_match_oracle(mode, monkeypatch):
     """Seeded random reads (bad characters, low qualities, low-complexity, empty and short reads) and
