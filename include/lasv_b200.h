@@ -126,7 +126,10 @@ int lasv_graph_kernel_times_by_kind(lasv_graph *g, double ms[LASV_T_KINDS], uint
  *                         applied there (streamed_insert.cuh): two sequential passes over the table's lines
  *                         per insert, whatever the number of records
  *   LASV_INSERT_AUTO      streamed once the records to insert number `min_records_per_line` (default 0.75;
- *                         <= 0 keeps the current value) per 128-byte table line, random access below that
+ *                         <= 0 keeps the current value) per 128-byte table line, random access below that;
+ *                         batches too small to partition (< 256 bytes per region) or tables below 256 MB
+ *                         take the fused find-or-insert without a partition
+ * RANDOM and STREAMED, asked for by name, partition every batch whatever its size.
  * Default AUTO; LASV_B200_INSERT=random|streamed at lasv_graph_new overrides. */
 #define LASV_INSERT_AUTO 0
 #define LASV_INSERT_RANDOM 1

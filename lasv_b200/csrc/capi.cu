@@ -369,7 +369,8 @@ bool want_binned(const lasv_graph *g, uint64_t n_bytes, uint32_t *n_bins_out) {
   *n_bins_out = n_bins;
   bool binned = g->table_bytes >= (256ull << 20) && n_bytes >= (uint64_t)n_bins * 256u;
   if (g->knobs.insert == 1) binned = false;
-  else if (g->knobs.insert == 2) binned = n_bins > 1 || g->n_buckets > 1;
+  // an insert kind asked for by name (LASV_B200_INSERT, lasv_graph_set_insert_mode) implies the partition
+  else if (g->knobs.insert == 2 || g->insert_mode != LASV_INSERT_AUTO) binned = n_bins > 1 || g->n_buckets > 1;
   return binned;
 }
 
