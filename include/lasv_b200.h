@@ -447,8 +447,49 @@ int lasv_graph_clean(lasv_graph *g, int what, int threshold, lasv_clean_stats *s
 int lasv_ref_hash_table_write_branches(lasv_ref_hash_table *t, const char *fasta_path,
                                        lasv_branch_stats *stats /* may be NULL */);
 
+/* ------------------------------------------- one process, several GPUs -- */
+/* The hash-sharded build of SURVEY 8e for callers that are ONE process and one thread, like the reference's
+ * main() (graph_operations.c:746-765): a graph of 2^number_bits buckets x bucket_size slots split over
+ * n_devices GPUs (a power of two <= 16; the same device may be named more than once), shard o = the buckets
+ * whose index has high bits o, on devices[o].  Host batches go to the devices in turn: copy + partition kernel
+ * there (records by owner and table region into that device's send stripes), one exchange of fixed-size blocks
+ * per `round_bytes` of reads and device (cudaMemcpyPeerAsync: copy engines over NVLink between peers), one insert
+ * per exchange on every owner (streamed when dense).  round_bytes = 0: 2 GB, less if memory is short.
+ * Replaces hash_table_find_or_insert's single table (hash_table.c:270-327) by n of them with the same
+ * bucket-of-key rule; the result is handed back as ONE reference-layout table by
+ * lasv_multi_graph_export_table (keys that left their first-choice bucket are re-inserted along the
+ * reference's own rehash chain over all 2^number_bits buckets).  Everything is synchronous for the caller
+ * except the queued GPU work; statistics / export / flush wait for it. */
+typedef struct lasv_multi_graph lasv_multi_graph;
+lasv_multi_graph *lasv_multi_graph_new(int kmer_size, int number_bits, int bucket_size, int max_rehash_tries,
+                                       const int *devices, int n_devices, uint64_t round_bytes);
+void lasv_multi_graph_free(lasv_multi_graph **m);
+int lasv_multi_graph_n_shards(lasv_multi_graph *m);
+/* One batch in the layout of lasv_graph_load_reads_host (pinned buffers for full speed); the buffers may be
+ * reused when the call returns. */
+int lasv_multi_graph_load_reads_host(lasv_multi_graph *m, const uint8_t *seq, const uint8_t *qual,
+                                     uint64_t n_bytes, const uint64_t *offsets, uint64_t n_reads,
+                                     int quality_cutoff);
+/* load_se_filelist_into_graph_colour / load_pe_filelists_into_graph_colour (file_reader.c:789,910) over all shards. */
+int lasv_multi_graph_load_se_filelist(lasv_multi_graph *m, const char *list, int qual_thresh, int ascii_fq_offset,
+                                      unsigned int *files_loaded, lasv_load_stats *stats);
+int lasv_multi_graph_load_pe_filelists(lasv_multi_graph *m, const char *list1, const char *list2, int qual_thresh,
+                                       int ascii_fq_offset, unsigned int *pairs_loaded, lasv_load_stats *stats);
+/* Exchange and insert what the send stripes still hold; wait for all devices. */
+int lasv_multi_graph_flush(lasv_multi_graph *m);
+/* Sums over the shards (lasv_graph_stats, lasv_graph_rehash_histogram, lasv_graph_summary). */
+int lasv_multi_graph_stats(lasv_multi_graph *m, lasv_load_stats *out, uint64_t *contig_hist, uint64_t hist_size);
+int lasv_multi_graph_rehash_histogram(lasv_multi_graph *m, long long out16[16]);
+int lasv_multi_graph_summary(lasv_multi_graph *m, lasv_table_summary *out);
+/* The whole graph as one reference-layout HashTable: `elements` receives 2^number_bits * bucket_size Elements,
+ * next_element (may be NULL) the fill of every bucket, *unique_kmers (may be NULL) the node count.  The shards
+ * are finalised: no inserts afterwards. */
+int lasv_multi_graph_export_table(lasv_multi_graph *m, void *elements, short *next_element, long long *unique_kmers);
+
 /* Exact reference signatures (file_reader.h:86-118); `boolean` is signed char
- * (global.h:37).  They build the graph on the GPU and leave db_graph->table,
+ * (global.h:37).  With LASV_B200_DEVICES=0,1,... (or "all") in the environment and an empty table they
+ * build on several GPUs (lasv_multi_graph above), else on LASV_B200_DEVICE (default 0).
+ * They build the graph on the GPU and leave db_graph->table,
  * next_element, unique_kmers and collisions[] as the reference loader would
  * (hole-free buckets, reference rehash chain), so every consumer in
  * src/dB_graph_operations runs unchanged.  Unsupported arguments

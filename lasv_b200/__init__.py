@@ -8,6 +8,7 @@ implementation.
 from ._capi import LasvError, TableFullError, lib  # noqa: F401
 from .graph import DBGraph, ctx_header, element_dtype, mean_contig_length, record_dtype, words_per_kmer  # noqa: F401
 from . import synth  # noqa: F401
+from .multi import MultiDBGraph  # noqa: F401
 
 __all__ = ["DBGraph", "LasvError", "TableFullError", "ctx_header", "element_dtype", "record_dtype",
            "words_per_kmer", "mean_contig_length", "synth", "lib"]

@@ -113,6 +113,10 @@ EXPORTS = [
     "lasv_graph_kernel_times_by_kind", "lasv_graph_set_insert_mode", "lasv_graph_insert_counts",
     "lasv_graph_set_accumulation", "lasv_graph_load_reads_host_async", "lasv_graph_set_staging",
     "lasv_graph_bin_reads_append_device",
+    "lasv_multi_graph_new", "lasv_multi_graph_free", "lasv_multi_graph_n_shards", "lasv_multi_graph_load_reads_host",
+    "lasv_multi_graph_load_se_filelist", "lasv_multi_graph_load_pe_filelists", "lasv_multi_graph_flush",
+    "lasv_multi_graph_stats", "lasv_multi_graph_rehash_histogram", "lasv_multi_graph_summary",
+    "lasv_multi_graph_export_table",
 ]
 
 INSERT_AUTO, INSERT_RANDOM, INSERT_STREAMED = 0, 1, 2
@@ -173,6 +177,19 @@ def lib() -> C.CDLL:
     L.lasv_graph_bin_geometry.argtypes = [vp, i32, u64, u64, u32p, u32p, u32p, u32p, u32p]
     L.lasv_graph_bin_reads_device.argtypes = [vp, vp, vp, u64, i32, i32, C.c_uint32, C.c_uint32, C.c_uint32, vp, vp, vp]
     L.lasv_graph_bin_reads_append_device.argtypes = L.lasv_graph_bin_reads_device.argtypes
+    L.lasv_multi_graph_new.restype = vp
+    L.lasv_multi_graph_new.argtypes = [i32, i32, i32, i32, C.POINTER(i32), i32, u64]
+    L.lasv_multi_graph_free.argtypes = [C.POINTER(vp)]
+    L.lasv_multi_graph_free.restype = None
+    L.lasv_multi_graph_n_shards.argtypes = [vp]
+    L.lasv_multi_graph_load_reads_host.argtypes = [vp, vp, vp, u64, vp, u64, i32]
+    L.lasv_multi_graph_load_se_filelist.argtypes = [vp, C.c_char_p, i32, i32, C.POINTER(C.c_uint), C.POINTER(LoadStats)]
+    L.lasv_multi_graph_load_pe_filelists.argtypes = [vp, C.c_char_p, C.c_char_p, i32, i32, C.POINTER(C.c_uint), C.POINTER(LoadStats)]
+    L.lasv_multi_graph_flush.argtypes = [vp]
+    L.lasv_multi_graph_stats.argtypes = [vp, C.POINTER(LoadStats), vp, u64]
+    L.lasv_multi_graph_rehash_histogram.argtypes = [vp, vp]
+    L.lasv_multi_graph_summary.argtypes = [vp, vp]
+    L.lasv_multi_graph_export_table.argtypes = [vp, vp, vp, C.POINTER(C.c_longlong)]
     L.lasv_graph_insert_bins_device.argtypes = [vp, vp, vp, i32, C.c_uint32, C.c_uint32, C.c_uint32, vp]
     L.lasv_graph_find.argtypes = [vp, vp, u64, vp, vp, vp]
     L.lasv_graph_summary.argtypes = [vp, C.POINTER(TableSummary)]

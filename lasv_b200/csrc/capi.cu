@@ -166,6 +166,16 @@ struct lasv_graph {
   bool acc_user = false, acc_stream_used = false;
   cudaStream_t acc_stream = nullptr;
   uint64_t n_streamed = 0, n_random = 0;  // inserts by kind (lasv_graph_insert_counts)
+  // One shard of a lasv_multi_graph: the chunks of the host-buffer calls are binned by (owner, region) into the
+  // multi graph's send stripes of this device instead of this graph's own stripes
+  struct ShardSink {
+    int n_owners = 0;
+    uint32_t bins_per_owner = 0, cap = 0, spill = 0;
+    void *records = nullptr, *counts = nullptr;
+    bool fresh = true;          // the next launch resets the counters (first batch after an exchange)
+    uint64_t bound = 0;         // k-mer bounds of the batches binned since the last exchange
+  } *sink = nullptr;
+  struct lasv_multi_graph *multi = nullptr;  // set on shard 0 while a file loader drives the multi graph through it
   Knobs knobs;
   // optional per-launch timing of the two kernels of the partitioned path (bench: roofline of the
   // dominant kernel from CUDA events on the stream the kernel is launched on)
@@ -188,6 +198,9 @@ int use_hot(lasv_graph *g) {
   return LASV_OK;
 }
 int flush_accumulated(lasv_graph *g, cudaStream_t st);
+int bin_reads_impl(lasv_graph *g, const uint8_t *d_seq, const uint8_t *d_qual, uint64_t n_bytes, int quality_cutoff,
+                   int n_owners, uint32_t bins_per_owner, uint32_t stripe_capacity_records,
+                   uint32_t spill_capacity_records, void *d_records, void *d_counts, void *cuda_stream, bool append);
 // Every other entry point: records that were partitioned but not inserted yet (lasv_graph_set_accumulation) go into
 // the table first, so that whatever reads the table or its counters sees every read loaded so far.
 int use(lasv_graph *g) {
@@ -931,7 +944,7 @@ int load_reads_host_impl(lasv_graph *g, const uint8_t *seq, const uint8_t *qual,
     }
   };
   uint32_t n_bins_call = 1;
-  const bool binned_call = !g->pipeline && want_binned(g, n_bytes, &n_bins_call);
+  const bool binned_call = !g->sink && !g->pipeline && want_binned(g, n_bytes, &n_bins_call);
   Accumulate acc(g, binned_call ? n_bytes : 0);
 
   // chunks are cut at read boundaries, so no k-mer window straddles two chunks
@@ -971,9 +984,20 @@ int load_reads_host_impl(lasv_graph *g, const uint8_t *seq, const uint8_t *qual,
                              cudaMemcpyHostToDevice, g->copy));
     CUDA_TRY(cudaEventRecord(s.copied, g->copy));
     CUDA_TRY(cudaStreamWaitEvent(g->compute, s.copied, 0));
-    if (int e = lasv_graph_load_reads_device(g, s.d_seq, qual ? s.d_qual : nullptr, bytes,
-                                             s.d_offsets, nr, quality_cutoff, g->compute))
+    if (g->sink) {
+      lasv_graph::ShardSink &k = *g->sink;
+      if (int e = bin_reads_impl(g, s.d_seq, qual ? s.d_qual : nullptr, bytes, quality_cutoff, k.n_owners, k.bins_per_owner,
+                                 k.cap, k.spill, k.records, k.counts, g->compute, !k.fresh))
+        return e;
+      k.fresh = false;
+      k.bound += kmer_bound(g, bytes, nr);
+      launch_read_stats(s.d_seq, qual ? s.d_qual : nullptr, s.d_offsets, nr, 1, g->k, quality_cutoff, g->d_stats, g->d_hist,
+                        HIST_BINS, g->compute);
+      if (int e = check_launch()) return e;
+    } else if (int e = lasv_graph_load_reads_device(g, s.d_seq, qual ? s.d_qual : nullptr, bytes,
+                                                    s.d_offsets, nr, quality_cutoff, g->compute)) {
       return e;
+    }
     CUDA_TRY(cudaEventRecord(s.consumed, g->compute));
     // h_offsets of this leg must stay alive until its copy completed: the next
     // use of the leg waits on `consumed`, which is ordered after `copied`.
@@ -1364,14 +1388,43 @@ int lasv_graph_finalize(lasv_graph *g) {
   return finalize_impl(g, nullptr);
 }
 
-int lasv_graph_export_table(lasv_graph *g, void *elements, short *next_element) {
+extern "C++" {
+namespace {
+// finalize + copy to the host.  `moved` (shards of a multi-GPU graph): the Elements that do not sit in their
+// first-choice bucket are taken out first and returned there instead (extract_misplaced_kernel).
+int export_table_impl(lasv_graph *g, void *elements, short *next_element, std::vector<uint8_t> *moved) {
   if (int e = use(g)) return e;
   if (!elements) return fail(LASV_ERR_ARG, "elements is NULL");
   CUDA_TRY(cudaDeviceSynchronize());
   int16_t *d_next = nullptr;
+  uint8_t *d_moved = nullptr;
+  unsigned long long *d_n_moved = nullptr;
   CUDA_TRY(cudaMalloc(&d_next, g->n_buckets * sizeof(int16_t)));
   int rc = [&]() -> int {
     if (int e = finalize_impl(g, d_next)) return e;
+    if (moved) {
+      // room for 1/64 of the slots (a W=250 bucket of an 80 %-full table overflows about once in 10^4), less if the
+      // device is short of memory; more than that is an error, reported below
+      uint64_t cap = std::max<uint64_t>(4096, g->n_slots / 64);
+      size_t free_b = 0, total_b = 0;
+      CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+      cap = std::max<uint64_t>(1, std::min<uint64_t>(cap, (uint64_t)(free_b / 2) / g->slot_bytes));
+      CUDA_TRY(cudaMalloc(&d_n_moved, sizeof(unsigned long long)));
+      CUDA_TRY(cudaMalloc(&d_moved, cap * g->slot_bytes));
+      CUDA_TRY(cudaMemsetAsync(d_n_moved, 0, sizeof(unsigned long long), g->compute));
+      launch_extract_misplaced(g->N, g->view(), d_next, d_moved, d_n_moved, cap, g->compute);
+      if (int e = check_launch()) return e;
+      unsigned long long n_moved = 0;
+      CUDA_TRY(cudaMemcpyAsync(&n_moved, d_n_moved, sizeof n_moved, cudaMemcpyDeviceToHost, g->compute));
+      CUDA_TRY(cudaStreamSynchronize(g->compute));
+      if (n_moved > cap)
+        return fail(LASV_ERR_CAPACITY, "%llu keys of a shard sit outside their first-choice bucket, more than the %llu the "
+                    "export can move (the table is too full to be sharded)", n_moved, (unsigned long long)cap);
+      const size_t old = moved->size();
+      moved->resize(old + (size_t)n_moved * g->slot_bytes);
+      if (n_moved)
+        CUDA_TRY(cudaMemcpy(moved->data() + old, d_moved, (size_t)n_moved * g->slot_bytes, cudaMemcpyDeviceToHost));
+    }
     // bucket b is W consecutive Elements at the start of its NL lines: a pitched copy
     // (DMA engine) packs the buckets into the reference's contiguous Element[]
     const size_t row = (size_t)g->W * g->slot_bytes, pitch = (size_t)(g->table_bytes / g->n_buckets);
@@ -1386,7 +1439,15 @@ int lasv_graph_export_table(lasv_graph *g, void *elements, short *next_element) 
     return LASV_OK;
   }();
   cudaFree(d_next);
+  cudaFree(d_moved);
+  cudaFree(d_n_moved);
   return rc;
+}
+}  // namespace
+}
+
+int lasv_graph_export_table(lasv_graph *g, void *elements, short *next_element) {
+  return export_table_impl(g, elements, next_element, nullptr);
 }
 
 int lasv_graph_import_table(lasv_graph *g, const void *elements) {
@@ -1902,6 +1963,350 @@ int lasv_graph_load_ctx_file(lasv_graph *g, const char *path, uint32_t *mean_rea
   return rc;
 }
 
+
+// ------------------------------------------------------------ one process, several GPUs
+// lasv_multi_graph: the hash-sharded build of SURVEY 8e driven by ONE host thread, for callers that are one process
+// (the reference's main(): graph_operations.c:746-765 calls the loader once and expects its HashTable filled).
+// Shard o of n (a power of two) lives on devices[o] and owns the buckets whose index has high bits o
+// (lasv_b200/sharded.py is the same scheme with one process per GPU).  Host batches go to the shards in turn:
+//   copy + bin kernel on the batch's device (records by (owner, region) into that device's SEND stripes, appended
+//   until the stripes hold `round_bytes` of reads)
+//   exchange: block (sender d -> owner o) by cudaMemcpyPeerAsync into slot d of o's RECEIVE stripes -- copy engines
+//   over NVLink when the devices are peers
+//   insert: every owner inserts the received stripes of all senders (streamed when dense, lasv_graph_insert_bins_device)
+struct lasv_multi_graph {
+  int n = 0, k = 0, L = 0, W = 0, max_rehash = 15;
+  std::vector<int> devices;
+  std::vector<lasv_graph *> shard;
+  struct Dev {
+    void *send = nullptr, *send_counts = nullptr, *recv = nullptr, *recv_counts = nullptr;
+    cudaStream_t comm = nullptr;
+    cudaEvent_t binned = nullptr, sent = nullptr, received = nullptr, inserted = nullptr;
+    lasv_graph::ShardSink sink;
+  };
+  std::vector<Dev> dev;
+  uint32_t bins_per_owner = 0, cap = 0, spill = 0, rec_bytes = 0, count_stride = 0;
+  uint64_t records_per_owner = 0, counters_per_owner = 0, round_bound = 0;
+  int turn = 0;
+  bool any_binned = false;
+};
+
+extern "C++" {
+namespace {
+void multi_release(lasv_multi_graph *m) {
+  for (int d = 0; d < (int)m->dev.size(); d++) {
+    cudaSetDevice(m->devices[d]);
+    cudaDeviceSynchronize();
+    auto &x = m->dev[d];
+    cudaFree(x.send); cudaFree(x.send_counts); cudaFree(x.recv); cudaFree(x.recv_counts);
+    if (x.comm) cudaStreamDestroy(x.comm);
+    for (cudaEvent_t e : {x.binned, x.sent, x.received, x.inserted}) if (e) cudaEventDestroy(e);
+  }
+  for (auto &g : m->shard) if (g) { g->sink = nullptr; g->multi = nullptr; lasv_graph_free(&g); }
+  delete m;
+}
+
+// Exchange what the send stripes hold and insert it on the owners.  Everything is queued; nothing waits.
+int multi_ship(lasv_multi_graph *m) {
+  if (!m->any_binned) return LASV_OK;
+  const int n = m->n;
+  const size_t block_bytes = (size_t)m->records_per_owner * m->rec_bytes;
+  const size_t count_bytes = (size_t)m->counters_per_owner * m->count_stride;
+  for (int d = 0; d < n; d++) {
+    CUDA_TRY(cudaSetDevice(m->devices[d]));
+    CUDA_TRY(cudaEventRecord(m->dev[d].binned, m->shard[d]->compute));
+  }
+  for (int d = 0; d < n; d++) {  // sender d pushes its n blocks
+    auto &x = m->dev[d];
+    CUDA_TRY(cudaSetDevice(m->devices[d]));
+    CUDA_TRY(cudaStreamWaitEvent(x.comm, x.binned, 0));
+    for (int i = 0; i < n; i++) {
+      const int o = (d + i) % n;  // start with the local block, spread the peers
+      CUDA_TRY(cudaStreamWaitEvent(x.comm, m->dev[o].inserted, 0));  // o's receive stripes are free again
+      if (x.sink.fresh) {  // this device binned nothing in this round: its counters on the owners must say so
+        CUDA_TRY(cudaMemsetAsync((uint8_t *)m->dev[o].recv_counts + (size_t)d * count_bytes, 0, count_bytes, x.comm));
+        continue;
+      }
+      CUDA_TRY(cudaMemcpyPeerAsync((uint8_t *)m->dev[o].recv + (size_t)d * block_bytes, m->devices[o],
+                                   (uint8_t *)x.send + (size_t)o * block_bytes, m->devices[d], block_bytes, x.comm));
+      CUDA_TRY(cudaMemcpyPeerAsync((uint8_t *)m->dev[o].recv_counts + (size_t)d * count_bytes, m->devices[o],
+                                   (uint8_t *)x.send_counts + (size_t)o * count_bytes, m->devices[d], count_bytes, x.comm));
+    }
+    CUDA_TRY(cudaEventRecord(x.sent, x.comm));
+    CUDA_TRY(cudaStreamWaitEvent(m->shard[d]->compute, x.sent, 0));  // the send stripes may be refilled after this
+    x.sink.fresh = true;
+    x.sink.bound = 0;
+  }
+  for (int o = 0; o < n; o++) {  // owner o inserts the blocks of all senders
+    CUDA_TRY(cudaSetDevice(m->devices[o]));
+    lasv_graph *g = m->shard[o];
+    for (int d = 0; d < n; d++) CUDA_TRY(cudaStreamWaitEvent(g->compute, m->dev[d].sent, 0));
+    g->sink = nullptr;  // (an ordinary entry point of the shard)
+    const int rc = lasv_graph_insert_bins_device(g, m->dev[o].recv, m->dev[o].recv_counts, n, m->bins_per_owner, m->cap,
+                                                 m->spill, g->compute);
+    g->sink = &m->dev[o].sink;
+    if (rc) return rc;
+    CUDA_TRY(cudaEventRecord(m->dev[o].inserted, g->compute));
+  }
+  m->any_binned = false;
+  return LASV_OK;
+}
+
+int multi_load_host(lasv_multi_graph *m, const uint8_t *seq, const uint8_t *qual, uint64_t n_bytes,
+                    const uint64_t *offsets, uint64_t n_reads, int cutoff) {
+  if (!n_reads) return LASV_OK;
+  const int d = m->turn;
+  lasv_graph *g = m->shard[d];
+  const uint64_t bound = kmer_bound(g, n_bytes, n_reads);
+  if (bound > m->round_bound) return fail(LASV_ERR_ARG, "a host batch of %llu bytes exceeds the exchange stripes of the multi-GPU graph",
+                                          (unsigned long long)n_bytes);
+  if (m->dev[d].sink.bound + bound > m->round_bound)
+    if (int e = multi_ship(m)) return e;
+  m->turn = (d + 1) % m->n;
+  m->any_binned = true;
+  return load_reads_host_impl(g, seq, qual, n_bytes, offsets, n_reads, cutoff, nullptr, true, nullptr);
+}
+
+int multi_sync(lasv_multi_graph *m) {
+  if (int e = multi_ship(m)) return e;
+  for (int d = 0; d < m->n; d++) {
+    CUDA_TRY(cudaSetDevice(m->devices[d]));
+    CUDA_TRY(cudaDeviceSynchronize());
+  }
+  return LASV_OK;
+}
+
+int multi_stats(lasv_multi_graph *m, lasv_load_stats *out, uint64_t *hist, uint64_t hist_size) {
+  if (int e = multi_sync(m)) return e;
+  lasv_load_stats acc;
+  memset(&acc, 0, sizeof acc);
+  std::vector<uint64_t> h(hist_size);
+  if (hist) for (uint64_t i = 0; i < hist_size; i++) hist[i] = 0;
+  for (int d = 0; d < m->n; d++) {
+    lasv_load_stats s;
+    lasv_graph *g = m->shard[d];
+    g->sink = nullptr;
+    const int rc = lasv_graph_stats(g, &s, hist ? h.data() : nullptr, hist ? hist_size : 0, nullptr);
+    g->sink = &m->dev[d].sink;
+    if (rc) return rc;
+    acc.n_reads += s.n_reads;
+    acc.bad_reads += s.bad_reads;
+    acc.bases_read += s.bases_read;
+    acc.bases_loaded += s.bases_loaded;
+    acc.n_contigs += s.n_contigs;
+    acc.kmers_inserted += s.kmers_inserted;
+    acc.unique_kmers += s.unique_kmers;
+    if (hist) for (uint64_t i = 0; i < hist_size; i++) hist[i] += h[i];
+  }
+  if (out) *out = acc;
+  return LASV_OK;
+}
+}  // namespace
+}
+
+lasv_multi_graph *lasv_multi_graph_new(int kmer_size, int number_bits, int bucket_size, int max_rehash_tries,
+                                       const int *devices, int n_devices, uint64_t round_bytes) {
+  if (!devices || n_devices < 1 || n_devices > 16 || (n_devices & (n_devices - 1))) {
+    fail(LASV_ERR_ARG, "the number of devices must be a power of two <= 16, got %d", n_devices);
+    return nullptr;
+  }
+  const int bits = log2_u32((uint32_t)n_devices);
+  if (number_bits - bits < 1) {
+    fail(LASV_ERR_ARG, "too few buckets for %d shards", n_devices);
+    return nullptr;
+  }
+  lasv_multi_graph *m = new lasv_multi_graph();
+  m->n = n_devices;
+  m->k = kmer_size;
+  m->L = number_bits;
+  m->W = bucket_size;
+  m->max_rehash = max_rehash_tries;
+  m->devices.assign(devices, devices + n_devices);
+  m->shard.assign((size_t)n_devices, nullptr);
+  m->dev.resize((size_t)n_devices);
+  auto bail = [&](const char *what) -> lasv_multi_graph * {
+    if (what) fail(LASV_ERR_CUDA, "multi-GPU graph: %s: %s", what, cudaGetErrorString(cudaGetLastError()));
+    multi_release(m);
+    return nullptr;
+  };
+  for (int d = 0; d < n_devices; d++) {
+    m->shard[d] = lasv_graph_new(kmer_size, number_bits - bits, bucket_size, max_rehash_tries, devices[d]);
+    if (!m->shard[d]) return bail(nullptr);
+  }
+  for (int d = 0; d < n_devices; d++) {  // peers where the hardware allows it (else the copies are staged by the driver)
+    cudaSetDevice(devices[d]);
+    for (int o = 0; o < n_devices; o++) {
+      if (devices[o] == devices[d]) continue;
+      int can = 0;
+      if (cudaDeviceCanAccessPeer(&can, devices[d], devices[o]) == cudaSuccess && can) cudaDeviceEnablePeerAccess(devices[o], 0);
+      cudaGetLastError();  // "already enabled" is fine
+    }
+  }
+  // exchange stripes for `round_bytes` of reads per device and round: at most a quarter of what is free next to the
+  // smallest shard (send + receive), 2 GB of reads by default
+  uint64_t want = round_bytes ? round_bytes : (2ull << 30);
+  {
+    size_t min_free = ~(size_t)0;
+    for (int d = 0; d < n_devices; d++) {
+      size_t f = 0, t = 0;
+      cudaSetDevice(devices[d]);
+      if (cudaMemGetInfo(&f, &t) != cudaSuccess) return bail("cudaMemGetInfo");
+      int sharing = 0;  // shards on the same device (tests) share its memory
+      for (int o = 0; o < n_devices; o++) sharing += devices[o] == devices[d];
+      min_free = std::min(min_free, f / (size_t)sharing);
+    }
+    const uint64_t per_byte = 2ull * 17ull;  // send + receive, <= 1 record of 16 (32: below) bytes per stream byte + slack
+    const uint64_t rec = 8ull * bin_record_words(m->shard[0]->N, kmer_size);
+    const uint64_t fit = (uint64_t)(min_free / 4) / (per_byte * rec / 16);
+    want = std::max<uint64_t>(std::min(want, fit), 1ull << 20);
+  }
+  uint32_t rb = 0, cs = 0;
+  if (lasv_graph_bin_geometry(m->shard[0], n_devices, want, 0, &m->bins_per_owner, &m->cap, &m->spill, &rb, &cs) != LASV_OK)
+    return bail(nullptr);
+  m->rec_bytes = rb;
+  m->count_stride = cs;
+  m->records_per_owner = (uint64_t)m->bins_per_owner * m->cap + m->spill;
+  m->counters_per_owner = (uint64_t)m->bins_per_owner + 1;
+  m->round_bound = want;  // (no read count assumed: a stream byte yields at most one k-mer)
+  const size_t block = (size_t)m->records_per_owner * rb * (size_t)n_devices;
+  const size_t cblock = (size_t)m->counters_per_owner * cs * (size_t)n_devices;
+  for (int d = 0; d < n_devices; d++) {
+    auto &x = m->dev[d];
+    cudaSetDevice(devices[d]);
+    if (cudaMalloc(&x.send, block) != cudaSuccess || cudaMalloc(&x.recv, block) != cudaSuccess ||
+        cudaMalloc(&x.send_counts, cblock) != cudaSuccess || cudaMalloc(&x.recv_counts, cblock) != cudaSuccess ||
+        cudaMemset(x.send_counts, 0, cblock) != cudaSuccess || cudaMemset(x.recv_counts, 0, cblock) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&x.comm, cudaStreamNonBlocking) != cudaSuccess)
+      return bail("exchange stripes");
+    for (cudaEvent_t *e : {&x.binned, &x.sent, &x.received, &x.inserted})
+      if (cudaEventCreateWithFlags(e, cudaEventDisableTiming) != cudaSuccess) return bail("events");
+    x.sink.n_owners = n_devices;
+    x.sink.bins_per_owner = m->bins_per_owner;
+    x.sink.cap = m->cap;
+    x.sink.spill = m->spill;
+    x.sink.records = x.send;
+    x.sink.counts = x.send_counts;
+    m->shard[d]->sink = &x.sink;
+  }
+  return m;
+}
+
+void lasv_multi_graph_free(lasv_multi_graph **mp) {
+  if (!mp || !*mp) return;
+  multi_release(*mp);
+  *mp = nullptr;
+}
+
+int lasv_multi_graph_n_shards(lasv_multi_graph *m) { return m ? m->n : -1; }
+
+int lasv_multi_graph_load_reads_host(lasv_multi_graph *m, const uint8_t *seq, const uint8_t *qual, uint64_t n_bytes,
+                                     const uint64_t *offsets, uint64_t n_reads, int quality_cutoff) {
+  if (!m) return fail(LASV_ERR_ARG, "NULL multi graph");
+  return multi_load_host(m, seq, qual, n_bytes, offsets, n_reads, quality_cutoff);
+}
+
+int lasv_multi_graph_flush(lasv_multi_graph *m) {
+  if (!m) return fail(LASV_ERR_ARG, "NULL multi graph");
+  return multi_sync(m);
+}
+
+int lasv_multi_graph_stats(lasv_multi_graph *m, lasv_load_stats *out, uint64_t *contig_hist, uint64_t hist_size) {
+  if (!m) return fail(LASV_ERR_ARG, "NULL multi graph");
+  return multi_stats(m, out, contig_hist, hist_size);
+}
+
+int lasv_multi_graph_rehash_histogram(lasv_multi_graph *m, long long out16[16]) {
+  if (!m) return fail(LASV_ERR_ARG, "NULL multi graph");
+  if (int e = multi_sync(m)) return e;
+  for (int r = 0; r < 16; r++) out16[r] = 0;
+  for (int d = 0; d < m->n; d++) {
+    long long h[16];
+    lasv_graph *g = m->shard[d];
+    g->sink = nullptr;
+    const int rc = lasv_graph_rehash_histogram(g, h);
+    g->sink = &m->dev[d].sink;
+    if (rc) return rc;
+    for (int r = 0; r < 16; r++) out16[r] += h[r];
+  }
+  return LASV_OK;
+}
+
+int lasv_multi_graph_summary(lasv_multi_graph *m, lasv_table_summary *out) {
+  if (!m || !out) return fail(LASV_ERR_ARG, "NULL argument");
+  if (int e = multi_sync(m)) return e;
+  memset(out, 0, sizeof *out);
+  for (int d = 0; d < m->n; d++) {
+    lasv_table_summary s;
+    lasv_graph *g = m->shard[d];
+    g->sink = nullptr;
+    const int rc = lasv_graph_summary(g, &s);
+    g->sink = &m->dev[d].sink;
+    if (rc) return rc;
+    out->n_nodes += s.n_nodes;
+    out->sum_covg += s.sum_covg;
+    out->sum_edge_bits += s.sum_edge_bits;
+    out->fingerprint += s.fingerprint;
+  }
+  return LASV_OK;
+}
+
+// The whole sharded graph as ONE reference-layout HashTable (hash_table.h:40-50).  Owner = high bits of the bucket
+// index, so the exported shards laid end to end are the reference's table for every key that sits in its first-choice
+// bucket.  A key that left its first-choice bucket (full) was rehashed INSIDE its shard; the reference's chain
+// (hash_table.c:69-122,270-327: bucket(key, r) over ALL 2^L buckets) leads elsewhere, so those keys are taken out
+// of the exported shards and inserted again by the reference's own rule on the merged table -- bucket r+1 only if
+// bucket r holds W keys.  (At the fill the reference recommends, < 80 %, a W=250 bucket overflows about once in 10^4.)
+int lasv_multi_graph_export_table(lasv_multi_graph *m, void *elements, short *next_element, long long *unique_kmers) {
+  if (!m || !elements) return fail(LASV_ERR_ARG, "NULL argument");
+  if (int e = multi_sync(m)) return e;
+  lasv_graph *g0 = m->shard[0];
+  const size_t slot = g0->slot_bytes;
+  const uint64_t shard_buckets = g0->n_buckets, shard_slots = g0->n_slots, n_buckets = shard_buckets * (uint64_t)m->n;
+  std::vector<short> next_local;
+  short *next = next_element;
+  if (!next) {
+    next_local.resize(n_buckets);
+    next = next_local.data();
+  }
+  long long uniq = 0;
+  std::vector<uint8_t> moved;  // Elements outside their first-choice bucket, back to back
+  for (int d = 0; d < m->n; d++) {
+    lasv_graph *g = m->shard[d];
+    g->sink = nullptr;
+    uniq += lasv_graph_unique_kmers(g);
+    const int rc = export_table_impl(g, (uint8_t *)elements + (size_t)d * shard_slots * slot, next + (size_t)d * shard_buckets,
+                                     m->n > 1 ? &moved : nullptr);
+    g->sink = &m->dev[d].sink;
+    if (rc) return rc;
+  }
+  if (unique_kmers) *unique_kmers = uniq;
+  if (m->n == 1) return LASV_OK;
+  // back in by the reference's rule: bucket(key, r) over all 2^L buckets, r+1 only if bucket r holds W keys
+  const int N = g0->N;
+  const uint32_t mask = (uint32_t)(n_buckets - 1), W = (uint32_t)m->W;
+  auto bucket_of = [&](const uint64_t *key, uint32_t r) -> uint32_t {
+    if (N == 1) { uint64_t k1[1] = {key[0]}; return lookup3_key<1>(k1, r).c & mask; }
+    if (N == 2) { uint64_t k2[2] = {key[0], key[1]}; return lookup3_key<2>(k2, r).c & mask; }
+    uint64_t k3[3] = {key[0], key[1], key[2]};
+    return lookup3_key<3>(k3, r).c & mask;
+  };
+  uint8_t *tab = (uint8_t *)elements;
+  for (size_t i = 0; i < moved.size(); i += slot) {
+    const uint64_t *key = reinterpret_cast<const uint64_t *>(&moved[i]);
+    bool placed = false;
+    for (int r = 0; r <= m->max_rehash && !placed; r++) {
+      const uint32_t b = bucket_of(key, (uint32_t)r);
+      if ((uint32_t)next[b] < W) {
+        memcpy(tab + ((uint64_t)b * W + (uint32_t)next[b]) * slot, &moved[i], slot);
+        next[b]++;
+        placed = true;
+      }
+    }
+    if (!placed) return fail(LASV_ERR_TABLE_FULL, "%s", TABLE_FULL_MSG);
+  }
+  return LASV_OK;
+}
+
 // ---------------------------------------------------------- sequence files
 namespace {
 
@@ -1910,10 +2315,18 @@ constexpr uint64_t LOADER_BATCH_READS = 4ull << 20;
 
 int flush_batch(lasv_graph *g, HostBatch &b, bool with_qual, int cutoff) {
   if (!b.n_reads) return LASV_OK;
-  int rc = lasv_graph_load_reads_host(g, b.seq, with_qual ? b.qual : nullptr, b.n_bytes, b.offsets,
-                                      b.n_reads, cutoff, nullptr);
+  int rc;
+  if (g->multi)  // shard 0 of a multi-GPU graph stands in for the whole graph: the batch goes to the next device in turn
+    rc = multi_load_host(g->multi, b.seq, with_qual ? b.qual : nullptr, b.n_bytes, b.offsets, b.n_reads, cutoff);
+  else
+    rc = lasv_graph_load_reads_host(g, b.seq, with_qual ? b.qual : nullptr, b.n_bytes, b.offsets, b.n_reads, cutoff, nullptr);
   b.reset();
   return rc;
+}
+// the loaders' statistics: of the graph, or of the multi-GPU graph it stands in for
+int loader_stats(lasv_graph *g, lasv_load_stats *s) {
+  if (g->multi) return multi_stats(g->multi, s, nullptr, 0);
+  return lasv_graph_stats(g, s, nullptr, 0, nullptr);
 }
 
 // One parser thread per file: it fills two pinned batches in turn while the caller's thread hands the
@@ -2200,7 +2613,7 @@ int load_file_group(lasv_graph *g, const std::vector<std::pair<std::string, std:
     return fail(job.err.find("batch buffers") != std::string::npos ? LASV_ERR_CUDA : LASV_ERR_IO, "%s",
                 job.err.c_str());
   lasv_load_stats before;
-  if (int e = lasv_graph_stats(g, &before, nullptr, 0, nullptr)) return e;
+  if (int e = loader_stats(g, &before)) return e;
   int rc = LASV_OK;
   job.run([&](HostBatch &b, const FileProducer &p) {
     if (rc == LASV_OK) rc = flush_batch(g, b, p.with_qual, cutoff);  // after an error: just drain
@@ -2217,7 +2630,7 @@ int load_file_group(lasv_graph *g, const std::vector<std::pair<std::string, std:
       return fail(LASV_ERR_IO, "Paired-end files don't have the same number of reads\nfile1: %s\nfile2: %s",
                   entries[e].first.c_str(), entries[e].second.c_str());
   lasv_load_stats after;
-  if (int e = lasv_graph_stats(g, &after, nullptr, 0, nullptr)) return e;
+  if (int e = loader_stats(g, &after)) return e;
   if (stats) {
     stats->n_reads = after.n_reads - before.n_reads;
     stats->bad_reads = after.bad_reads - before.bad_reads;
@@ -2362,6 +2775,26 @@ int lasv_graph_load_pe_filelists(lasv_graph *g, const char *list1, const char *l
   return LASV_OK;
 }
 
+int lasv_multi_graph_load_se_filelist(lasv_multi_graph *m, const char *list, int qual_thresh, int ascii_fq_offset,
+                                      unsigned int *files_loaded, lasv_load_stats *stats) {
+  if (!m) return fail(LASV_ERR_ARG, "NULL multi graph");
+  lasv_graph *g = m->shard[0];
+  g->multi = m;
+  const int rc = lasv_graph_load_se_filelist(g, list, qual_thresh, ascii_fq_offset, files_loaded, stats);
+  g->multi = nullptr;
+  return rc;
+}
+
+int lasv_multi_graph_load_pe_filelists(lasv_multi_graph *m, const char *list1, const char *list2, int qual_thresh,
+                                       int ascii_fq_offset, unsigned int *pairs_loaded, lasv_load_stats *stats) {
+  if (!m) return fail(LASV_ERR_ARG, "NULL multi graph");
+  lasv_graph *g = m->shard[0];
+  g->multi = m;
+  const int rc = lasv_graph_load_pe_filelists(g, list1, list2, qual_thresh, ascii_fq_offset, pairs_loaded, stats);
+  g->multi = nullptr;
+  return rc;
+}
+
 // ----------------------------------------------- (A) reference-named drop-ins
 namespace {
 
@@ -2394,32 +2827,64 @@ void dropin_load(lasv_ref_hash_table *t, const char *list1, const char *list2, i
   if (L < 0) die_like_reference("lasv_b200: number_buckets is not a power of two");
   int dev = 0;
   if (const char *e = getenv("LASV_B200_DEVICE")) dev = atoi(e);
-  lasv_graph *g = lasv_graph_new(t->kmer_size, L, t->bucket_size, t->max_rehash_tries, dev);
-  if (!g) die_like_reference(lasv_last_error());
-  if (t->unique_kmers > 0 && lasv_graph_import_table(g, t->table) != LASV_OK)
-    die_like_reference(lasv_last_error());
-  printf(list2 ? "Load paired-ended files\n" : "Load single-ended files\n");
+  // LASV_B200_DEVICES=0,1,2,3 (or "all"): the table is hash-sharded over these GPUs (lasv_multi_graph) -- a power of
+  // two of them; the caller's table must be empty (loading on top of an existing graph stays on one device)
+  std::vector<int> devs;
+  if (const char *e = getenv("LASV_B200_DEVICES")) {
+    if (!strcmp(e, "all")) {
+      for (int i = 0, n_dev = lasv_device_count(); i < n_dev; i++) devs.push_back(i);
+      while (devs.size() & (devs.size() - 1)) devs.pop_back();
+    } else {
+      for (const char *q = e; *q;) {
+        devs.push_back(atoi(q));
+        while (*q && *q != ',') q++;
+        if (*q == ',') q++;
+      }
+    }
+  }
   lasv_load_stats s;
   memset(&s, 0, sizeof s);
   unsigned int n = 0;
-  const int rc = list2 ? lasv_graph_load_pe_filelists(g, list1, list2, qual_thresh, ascii_fq_offset, &n, &s)
-                       : lasv_graph_load_se_filelist(g, list1, qual_thresh, ascii_fq_offset, &n, &s);
-  if (rc != LASV_OK) die_like_reference(lasv_last_error());
-  if (hist && hist_size) {
-    std::vector<uint64_t> h(hist_size);
-    if (lasv_graph_stats(g, nullptr, h.data(), hist_size, nullptr) != LASV_OK)
-      die_like_reference(lasv_last_error());
-    for (unsigned long i = 0; i < hist_size; i++) hist[i] += (unsigned long)h[i];
-  }
   long long coll[16];
-  if (lasv_graph_rehash_histogram(g, coll) != LASV_OK) die_like_reference(lasv_last_error());
-  const long long uniq = lasv_graph_unique_kmers(g);
-  if (lasv_graph_export_table(g, t->table, t->next_element) != LASV_OK)
-    die_like_reference(lasv_last_error());
+  long long uniq = 0;
+  printf(list2 ? "Load paired-ended files\n" : "Load single-ended files\n");
+  if (devs.size() > 1 && t->unique_kmers == 0) {
+    lasv_multi_graph *m = lasv_multi_graph_new(t->kmer_size, L, t->bucket_size, t->max_rehash_tries, devs.data(), (int)devs.size(), 0);
+    if (!m) die_like_reference(lasv_last_error());
+    const int rc = list2 ? lasv_multi_graph_load_pe_filelists(m, list1, list2, qual_thresh, ascii_fq_offset, &n, &s)
+                         : lasv_multi_graph_load_se_filelist(m, list1, qual_thresh, ascii_fq_offset, &n, &s);
+    if (rc != LASV_OK) die_like_reference(lasv_last_error());
+    if (hist && hist_size) {
+      std::vector<uint64_t> h(hist_size);
+      if (lasv_multi_graph_stats(m, nullptr, h.data(), hist_size) != LASV_OK) die_like_reference(lasv_last_error());
+      for (unsigned long i = 0; i < hist_size; i++) hist[i] += (unsigned long)h[i];
+    }
+    if (lasv_multi_graph_rehash_histogram(m, coll) != LASV_OK) die_like_reference(lasv_last_error());
+    if (lasv_multi_graph_export_table(m, t->table, t->next_element, &uniq) != LASV_OK) die_like_reference(lasv_last_error());
+    lasv_multi_graph_free(&m);
+  } else {
+    lasv_graph *g = lasv_graph_new(t->kmer_size, L, t->bucket_size, t->max_rehash_tries, devs.size() == 1 ? devs[0] : dev);
+    if (!g) die_like_reference(lasv_last_error());
+    if (t->unique_kmers > 0 && lasv_graph_import_table(g, t->table) != LASV_OK)
+      die_like_reference(lasv_last_error());
+    const int rc = list2 ? lasv_graph_load_pe_filelists(g, list1, list2, qual_thresh, ascii_fq_offset, &n, &s)
+                         : lasv_graph_load_se_filelist(g, list1, qual_thresh, ascii_fq_offset, &n, &s);
+    if (rc != LASV_OK) die_like_reference(lasv_last_error());
+    if (hist && hist_size) {
+      std::vector<uint64_t> h(hist_size);
+      if (lasv_graph_stats(g, nullptr, h.data(), hist_size, nullptr) != LASV_OK)
+        die_like_reference(lasv_last_error());
+      for (unsigned long i = 0; i < hist_size; i++) hist[i] += (unsigned long)h[i];
+    }
+    if (lasv_graph_rehash_histogram(g, coll) != LASV_OK) die_like_reference(lasv_last_error());
+    uniq = lasv_graph_unique_kmers(g);
+    if (lasv_graph_export_table(g, t->table, t->next_element) != LASV_OK)
+      die_like_reference(lasv_last_error());
+    lasv_graph_free(&g);
+  }
   t->unique_kmers = uniq;
   if (t->collisions)
     for (int r = 0; r < t->max_rehash_tries && r < 16; r++) t->collisions[r] += coll[r];
-  lasv_graph_free(&g);
   *files_loaded += n;
   *bad_reads += s.bad_reads;
   *bases_read += s.bases_read;

@@ -790,6 +790,67 @@ __global__ void __launch_bounds__(THREADS) finalize_kernel(const TableView t, in
   }
 }
 
+// A shard of a hash-sharded graph after finalize_kernel: keys that do not sit in their first-choice bucket were
+// rehashed inside the shard; their place in the merged reference table is elsewhere (capi.cu:
+// lasv_multi_graph_export_table).  One warp per bucket: such Elements are copied to `out` (whole Elements, in no
+// particular order), the others are squeezed together, next_element is corrected.
+template <int N>
+__global__ void __launch_bounds__(THREADS) extract_misplaced_kernel(const TableView t, int16_t *next_element, uint8_t *out,
+                                                                   unsigned long long *n_out, const uint64_t cap) {
+  constexpr uint32_t SLOT = LineLayout<N>::SLOT;
+  const uint64_t n_buckets = (uint64_t)t.bucket_mask + 1;
+  const uint64_t warp0 = ((uint64_t)blockIdx.x * THREADS + threadIdx.x) >> 5;
+  const uint64_t nwarps = ((uint64_t)gridDim.x * THREADS) >> 5;
+  const unsigned lane = lane_id();
+  for (uint64_t b = warp0; b < n_buckets; b += nwarps) {
+    uint8_t *bucket = bucket_base(t, (uint32_t)b);
+    const uint32_t filled = (uint32_t)next_element[b];
+    uint32_t kept = 0;
+    for (uint32_t s0 = 0; s0 < filled; s0 += 32) {
+      const uint32_t s = s0 + lane;
+      uint64_t key[N];
+      uint64_t m = 0;
+      bool have = s < filled;
+      if (have) {
+        const uint64_t *slot = reinterpret_cast<const uint64_t *>(bucket + (uint64_t)s * SLOT);
+        m = slot[N];
+#pragma unroll
+        for (int w = 0; w < N; w++) key[w] = slot[w];
+      } else {
+#pragma unroll
+        for (int w = 0; w < N; w++) key[w] = 0;
+      }
+      const bool home = have && (lookup3_key<N>(key, 0).c & t.bucket_mask) == (uint32_t)b;
+      const unsigned km = __ballot_sync(FULL, home), mm = __ballot_sync(FULL, have && !home);
+      unsigned long long at = 0;
+      if (lane == 0 && mm) at = atomicAdd(n_out, (unsigned long long)__popc(mm));
+      at = __shfl_sync(FULL, at, 0);
+      __syncwarp();
+      if (home) {
+        uint64_t *dst = reinterpret_cast<uint64_t *>(bucket + (uint64_t)(kept + __popc(km & lanemask_lt())) * SLOT);
+#pragma unroll
+        for (int w = 0; w < N; w++) dst[w] = key[w];
+        dst[N] = m;
+      } else if (have) {
+        const unsigned long long i = at + __popc(mm & lanemask_lt());
+        if (i < cap) {
+          uint64_t *dst = reinterpret_cast<uint64_t *>(out + i * SLOT);
+#pragma unroll
+          for (int w = 0; w < N; w++) dst[w] = key[w];
+          dst[N] = m;
+        }
+      }
+      kept += __popc(km);
+      __syncwarp();
+    }
+    if (kept != filled) {
+      uint64_t *words = reinterpret_cast<uint64_t *>(bucket);
+      for (uint32_t w = kept * (SLOT / 8) + lane; w < filled * (SLOT / 8); w += 32) words[w] = 0;
+      if (lane == 0) next_element[b] = (int16_t)kept;
+    }
+  }
+}
+
 // .ctx records (element.c:894-910) in table order: kmer[N] | uint32 covg | uint8 edges
 template <int N>
 __global__ void __launch_bounds__(THREADS) dump_ctx_kernel(const TableView t, const uint64_t first,
@@ -1090,6 +1151,14 @@ void launch_finalize(int N, const TableView &t, int16_t *next_element, cudaStrea
   dispatch_n(N, [&](auto n) {
     constexpr int NN = decltype(n)::value;
     finalize_kernel<NN><<<resident_grid(finalize_kernel<NN>), THREADS, 0, st>>>(t, next_element);
+  });
+}
+
+void launch_extract_misplaced(int N, const TableView &t, int16_t *next_element, uint8_t *out, unsigned long long *n_out,
+                              uint64_t cap, cudaStream_t st) {
+  dispatch_n(N, [&](auto n) {
+    constexpr int NN = decltype(n)::value;
+    extract_misplaced_kernel<NN><<<resident_grid(extract_misplaced_kernel<NN>), THREADS, 0, st>>>(t, next_element, out, n_out, cap);
   });
 }
 

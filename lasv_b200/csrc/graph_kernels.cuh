@@ -150,6 +150,8 @@ void launch_table_summary(int N, const TableView &t, TableSummary *out, cudaStre
 void launch_bucket_counts(int N, const TableView &t, uint64_t first, uint64_t n_buckets, uint32_t *counts,
                           cudaStream_t st);
 void launch_finalize(int N, const TableView &t, int16_t *next_element, cudaStream_t st);
+void launch_extract_misplaced(int N, const TableView &t, int16_t *next_element, uint8_t *out, unsigned long long *n_out,
+                              uint64_t cap, cudaStream_t st);
 void launch_dump_ctx(int N, const TableView &t, uint64_t first, uint64_t n_buckets, const uint64_t *bucket_offsets,
                      uint8_t *out, cudaStream_t st);
 void launch_ingest_ctx(int N, const uint8_t *recs, uint64_t n_recs, const TableView &t,

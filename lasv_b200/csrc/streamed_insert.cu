@@ -635,10 +635,19 @@ int launch_streamed_insert(int N, const BinView &b, const TableView &t, GraphCou
   sg_dispatch(N, [&](auto nn) {
     constexpr int NN = decltype(nn)::value;
     const size_t smem = 2 * (size_t)SI_UNITS * geom.unit_bytes;
-    static int per_sm_cached[4] = {0, 0, 0, 0};
-    static size_t smem_cached[4] = {0, 0, 0, 0};
-    static int sort_per_sm[4] = {0, 0, 0, 0};
-    if (smem_cached[NN] != smem) {  // once per geometry, not per launch
+    // kernel attributes belong to a device: cached per (device, N), set once per geometry, not per launch
+    constexpr int MAX_DEV = 64;
+    static int per_sm_all[MAX_DEV][4] = {};
+    static size_t smem_all[MAX_DEV][4] = {};
+    static int sort_all[MAX_DEV][4] = {};
+    int dev_id = 0;
+    if (cudaGetDevice(&dev_id) != cudaSuccess || dev_id < 0 || dev_id >= MAX_DEV) {
+      rc = -1;
+      return;
+    }
+    int *per_sm_cached = per_sm_all[dev_id], *sort_per_sm = sort_all[dev_id];
+    size_t *smem_cached = smem_all[dev_id];
+    if (smem_cached[NN] != smem) {
       int per_sm = 0;
       if (cudaFuncSetAttribute(sg_insert_kernel<NN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
           cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sg_insert_kernel<NN>, SI_WARPS * 32, smem) != cudaSuccess) {

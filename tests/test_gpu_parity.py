@@ -726,9 +726,72 @@ def test_export_import_and_reference_hash_table_find(name):
         util.assert_same_records(g2.records(), twice)
 
 
-def test_dropin_loader_fills_a_reference_hash_table(tmp_path):
+def _reference_finds_every_key(table, nxt, gold, k, L, W):
+    ref = _libref(k)
+    if ref is None:
+        return
+    ht = _capi.RefHashTable(k, 1 << L, W, table.ctypes.data, nxt.ctypes.data, None, len(gold), 15)
+    ref.hash_table_find.restype = C.c_void_p
+    ref.hash_table_find.argtypes = [C.c_void_p, C.POINTER(_capi.RefHashTable)]
+    esz = table.dtype.itemsize
+    for i in range(0, len(gold), 5):
+        key = np.ascontiguousarray(gold["kmer"][i])
+        ptr = ref.hash_table_find(key.ctypes.data, C.byref(ht))
+        assert ptr, "reference hash_table_find misses a key in the merged table"
+        e = table[(ptr - table.ctypes.data) // esz]
+        assert np.array_equal(e["kmer"], key) and e["coverage"] == gold["covg"][i] and e["edges"] == gold["edges"][i]
+
+
+@pytest.mark.parametrize("name,shards", [("synth_full_k53", 2), ("synth_full_k53", 4), ("synth_full_k31", 2),
+                                         ("synth_cfg2_k95", 4), ("synth_cfg0_k53", 8)])
+def test_multi_gpu_graph_in_one_process(name, shards, monkeypatch):
+    """lasv_multi_graph: the hash-sharded build driven by one host thread (the drop-in loaders with
+    LASV_B200_DEVICES).  With one GPU all shards live on device 0 -- same code, the peer copies become local ones.
+    The 90 %-full cases fill buckets, so keys are rehashed INSIDE their shard; the export must put them back on
+    the reference's own chain over all buckets: hole-free buckets, every key behind full buckets only, and the
+    compiled reference's hash_table_find finds every key with its coverage and edges."""
+    monkeypatch.setenv("LASV_B200_BINS", "2")
+    monkeypatch.setenv("LASV_B200_CHUNK_KB", "256")
+    meta = util.case_meta(name)
+    k, L, W = meta["k"], meta["L"], meta["W"]
+    gold = util.case_records(name)
+    seq, qual, offs = util.case_streams(name)
+    n_dev = _capi.lib().lasv_device_count()
+    devices = [i % n_dev for i in range(shards)]
+    n_reads = len(offs) - 1
+    import torch
+    h_seq, h_qual = torch.from_numpy(seq.copy()).pin_memory(), torch.from_numpy(qual.copy()).pin_memory()
+    with lasv_b200.MultiDBGraph(k, L, W, devices, round_bytes=len(seq) // 3) as mg:
+        assert mg.n_shards == shards
+        pieces = 7
+        for c in range(pieces):
+            r0, r1 = n_reads * c // pieces, n_reads * (c + 1) // pieces
+            lo, hi = int(offs[r0]), int(offs[r1])
+            mg.load_reads_host(h_seq[lo:hi], h_qual[lo:hi], (offs[r0: r1 + 1] - offs[r0]).astype(np.uint64),
+                               util.cutoff_of(meta))
+        st = mg.stats()
+        assert st["kmers_inserted"] == meta["inserts"] and st["unique_kmers"] == len(gold)
+        assert st["bad_reads"] == meta["bad_reads"] and st["bases_loaded"] == meta["bases_loaded"]
+        assert int(mg.rehash_histogram().sum()) == meta["inserts"]
+        s = mg.summary()
+        assert s["n_nodes"] == len(gold) and s["sum_covg"] == meta["inserts"]
+        table, nxt, uniq = mg.export_table()
+    assert uniq == len(gold)
+    _check_reference_layout(table, nxt, k, L, W)
+    occ = table["status"] != 0
+    got = np.zeros(int(occ.sum()), dtype=gold.dtype)
+    got["kmer"], got["covg"], got["edges"] = table["kmer"][occ], table["coverage"][occ], table["edges"][occ]
+    util.assert_same_records(got, gold, name)
+    _reference_finds_every_key(table, nxt, gold, k, L, W)
+
+
+@pytest.mark.parametrize("devices", [None, "0,0", "all"])
+def test_dropin_loader_fills_a_reference_hash_table(devices, tmp_path, monkeypatch):
     """(A) of include/lasv_b200.h: the reference-named loader on a calloc'ed
-    reference HashTable, as graph_operations.c:757-765 calls it."""
+    reference HashTable, as graph_operations.c:757-765 calls it -- on one GPU, and hash-sharded over several
+    (LASV_B200_DEVICES: two shards on device 0, or every GPU of the box)."""
+    if devices:
+        monkeypatch.setenv("LASV_B200_DEVICES", devices)
     name = "edge_pe_k53_q5"
     meta = util.case_meta(name)
     k, L, W = meta["k"], meta["L"], meta["W"]
@@ -902,12 +965,16 @@ def test_ctx_dump_streams_through_a_bounded_buffer(tmp_path, monkeypatch):
 
 
 # ------------------------------------ the reference's own main() on the GPU loader
-@pytest.mark.parametrize("name", ["synth_cfg1_k31", "synth_cfg0_k53", "synth_cfg2_k95"])
-def test_reference_cli_with_gpu_loader(name, tmp_path):
+@pytest.mark.parametrize("name,devices", [("synth_cfg1_k31", None), ("synth_cfg0_k53", None), ("synth_cfg2_k95", None),
+                                          ("synth_cfg0_k53", "0,0,0,0"), ("synth_cfg1_k31", "all")])
+def test_reference_cli_with_gpu_loader(name, devices, tmp_path, monkeypatch):
     """integration/_build/dB_graph_gpu_*: reference main(), cmd-line parsing, cleaning,
     supernode walk and .ctx dump compiled from the reference sources, with ONLY the
-    two loader symbols coming from liblasv_b200.so (INTEGRATION.md level A)."""
+    two loader symbols coming from liblasv_b200.so (INTEGRATION.md level A).  With LASV_B200_DEVICES the same
+    main() builds on a hash-sharded multi-GPU graph (four shards on device 0 / every GPU of the box)."""
     from pathlib import Path
+    if devices:
+        monkeypatch.setenv("LASV_B200_DEVICES", devices)
     meta = util.case_meta(name)
     k, L, W = meta["k"], meta["L"], meta["W"]
     exe = Path(__file__).resolve().parents[1] / "integration" / "_build" / f"dB_graph_gpu_{O.MAXK_OF_N[O.words_per_kmer(k)]}"
