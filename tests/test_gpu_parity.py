@@ -1002,6 +1002,31 @@ def test_reference_cli_with_gpu_loader(name, devices, tmp_path, monkeypatch):
     assert tries == meta["inserts"]
 
 
+@pytest.mark.parametrize("devices", [None, "0,0"])
+def test_reference_assembly_mode_runs_unchanged_on_the_gpu_built_table(devices, tmp_path, monkeypatch):
+    """SURVEY 8f rank 3, second half: the read-span linkage table and the linkage-guided BFS contig assembly
+    (`--mode assembly --read_span_file`: build_linkage_from_files.c:411-499, linkage_operations.c:167-541,
+    little_hash_for_linkage.c:227) are consumers of the graph -- sequential, order-dependent host code that runs
+    UNCHANGED (the reference's own main() and functions) on the HashTable the GPU loader fills.  A diploid genome
+    with SNPs and a duplicated segment keeps branching nodes after the cleaning, so the BFS consults the linkage
+    table: contigs.fa must hold the same contigs as the all-CPU reference binary's."""
+    import importlib.util
+    from pathlib import Path
+    root = Path(__file__).resolve().parents[1]
+    spec = importlib.util.spec_from_file_location("assembly_mode_check", root / "tests" / "perf" / "assembly_mode_check.py")
+    A = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(A)
+    exe = root / "integration" / "_build" / "dB_graph_gpu_63"
+    if not exe.exists() or not O.ref_available(53):
+        pytest.skip("integration/_build or oracle/_ref not built (both need /root/reference at build time)")
+    w = A.make_branching_inputs(tmp_path, 8000, 2000, 7)
+    ref = A.run(O.REF_DIR / "dB_graph_63", tmp_path, w, "ref")
+    env = dict(os.environ, LASV_B200_DEVICES=devices) if devices else None
+    got = A.run(exe, tmp_path, w, "gpu", env)
+    assert ref.count(b">") > 100                      # the BFS branched
+    assert A.contig_set(got) == A.contig_set(ref)
+
+
 @pytest.mark.parametrize("name", ["synth_cfg1_k31", "synth_cfg0_k53", "synth_cfg2_k95"])
 @pytest.mark.parametrize("clean", [False, True])
 def test_reference_cli_prints_supernodes_through_the_gpu(name, clean, tmp_path):
