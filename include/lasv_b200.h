@@ -43,6 +43,7 @@ extern "C" {
 #define LASV_ERR_IO (-4)         /* file could not be opened / parsed */
 #define LASV_ERR_STATE (-5)      /* e.g. inserting into a finalised table */
 #define LASV_ERR_CAPACITY (-6)   /* caller-provided output buffer too small */
+#define LASV_ERR_LIMIT (-7)      /* *_strict / *_limited calls: a walk exceeds the reference's --max_var_len; nothing was done */
 
 typedef struct lasv_graph lasv_graph;
 
@@ -315,6 +316,13 @@ typedef struct {
 } lasv_supernode_stats;
 int lasv_graph_write_supernodes(lasv_graph *g, const char *fasta_path, int max_length,
                                 lasv_supernode_stats *stats /* may be NULL */);
+/* The same, but if any supernode has more than max_length edges nothing is written and LASV_ERR_LIMIT is
+ * returned (stats->over_max_length is set): that is where the reference's output turns into overlapping pieces
+ * of max_length edges (dB_graph_population.c:2739-2767, "contig length equals max length").  The reference-side
+ * binding (integration/supernode_shim.c) then runs the reference's own CPU printer, so the file is the
+ * reference's in every case. */
+int lasv_graph_write_supernodes_strict(lasv_graph *g, const char *fasta_path, int max_length,
+                                       lasv_supernode_stats *stats /* may be NULL */);
 
 /* `--health_check` (db_graph_health_check, dB_graph_population.c:6274-6350) on the device graph, in
  * either arrangement: every edge of every node (pruned ones have none) must lead to a node that is in
@@ -405,6 +413,10 @@ long long lasv_ref_hash_table_load_ctx_records(lasv_ref_hash_table *t, const cha
  * modified.  integration/supernode_shim.c is the reference-side binding. */
 int lasv_ref_hash_table_write_supernodes(lasv_ref_hash_table *t, const char *fasta_path, int max_length,
                                          lasv_supernode_stats *stats /* may be NULL */);
+/* ... failing with LASV_ERR_LIMIT instead of printing a supernode of more than max_length edges whole
+ * (lasv_graph_write_supernodes_strict). */
+int lasv_ref_hash_table_write_supernodes_strict(lasv_ref_hash_table *t, const char *fasta_path, int max_length,
+                                                lasv_supernode_stats *stats /* may be NULL */);
 
 /* The cleaning laSV always runs, `--remove_low_coverage_supernodes T` (graph_operations.c:
  * 1069-1090), on the caller's reference-layout table:
@@ -428,6 +440,13 @@ typedef struct {
   uint64_t nodes_pruned;     /* all nodes that went from none to pruned */
 } lasv_clean_stats;
 int lasv_ref_hash_table_clean(lasv_ref_hash_table *t, int what, int threshold, lasv_clean_stats *stats /* may be NULL */);
+/* The same with the reference's walk limit (`max_expected_sup` = --max_var_len, dB_graph_population.c:3595-3649):
+ * the reference judges a supernode from a walk of at most max_length edges each way, starting at a node with
+ * 0 < coverage <= threshold.  If such a walk would be cut short -- a path of more than max_length edges with a
+ * low-coverage node inside or at an end -- LASV_ERR_LIMIT is returned and the table is left as it was
+ * (integration/clean_shim.c then runs the reference's own CPU function).  max_length <= 0: no limit. */
+int lasv_ref_hash_table_clean_limited(lasv_ref_hash_table *t, int what, int threshold, int max_length,
+                                      lasv_clean_stats *stats /* may be NULL */);
 /* The same on a graph handle, in either arrangement of the device table -- no host copy of the table.
  * Pruned nodes stay in the table with status `pruned` and no edges, as in the reference: they are
  * skipped by lasv_graph_dump_ctx_records / lasv_graph_write_ctx (db_node_check_status_not_pruned,
@@ -438,6 +457,7 @@ int lasv_ref_hash_table_clean(lasv_ref_hash_table *t, int what, int threshold, l
  * (file_reader.c:2930-2994, graph_operations.c:1084-1088).  With lasv_graph_write_branches this is the
  * whole of `--mode build` after the load (run_laSV.sh:178) on the device. */
 int lasv_graph_clean(lasv_graph *g, int what, int threshold, lasv_clean_stats *stats /* may be NULL */);
+int lasv_graph_clean_limited(lasv_graph *g, int what, int threshold, int max_length, lasv_clean_stats *stats /* may be NULL */);
 
 /* db_graph_print_all_branches_for_specific_person_or_pop (print_branches.c:131-199) on the
  * caller's reference-layout table (lasv_graph_write_branches above, in the caller's slot

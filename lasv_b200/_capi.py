@@ -21,6 +21,7 @@ LASV_ERR_CUDA = -2
 LASV_ERR_TABLE_FULL = -3
 LASV_ERR_IO = -4
 LASV_ERR_STATE = -5
+LASV_ERR_LIMIT = -7
 LASV_ERR_CAPACITY = -6
 
 
@@ -117,6 +118,8 @@ EXPORTS = [
     "lasv_multi_graph_load_se_filelist", "lasv_multi_graph_load_pe_filelists", "lasv_multi_graph_flush",
     "lasv_multi_graph_stats", "lasv_multi_graph_rehash_histogram", "lasv_multi_graph_summary",
     "lasv_multi_graph_export_table",
+    "lasv_graph_write_supernodes_strict", "lasv_ref_hash_table_write_supernodes_strict", "lasv_graph_clean_limited",
+    "lasv_ref_hash_table_clean_limited",
 ]
 
 INSERT_AUTO, INSERT_RANDOM, INSERT_STREAMED = 0, 1, 2
@@ -203,6 +206,7 @@ def lib() -> C.CDLL:
     L.lasv_graph_write_ctx.argtypes = [vp, C.c_char_p, C.c_uint32, u64]
     L.lasv_ctx_header.argtypes = [i32, C.c_uint32, u64, vp]
     L.lasv_graph_write_supernodes.argtypes = [vp, C.c_char_p, i32, C.POINTER(SupernodeStats)]
+    L.lasv_graph_write_supernodes_strict.argtypes = [vp, C.c_char_p, i32, C.POINTER(SupernodeStats)]
     L.lasv_graph_load_ctx_records.argtypes = [vp, vp, u64]
     L.lasv_graph_load_ctx_file.argtypes = [vp, C.c_char_p, C.POINTER(C.c_uint32), C.POINTER(u64)]
     L.lasv_graph_load_se_file.argtypes = [vp, C.c_char_p, i32, C.POINTER(LoadStats)]
@@ -234,6 +238,7 @@ def lib() -> C.CDLL:
     L.lasv_graph_group_records_device.argtypes = [vp, vp, u64, C.c_uint32, vp, vp, vp]
     L.lasv_graph_insert_grouped_records_device.argtypes = [vp, vp, u64, vp, C.c_uint32, C.POINTER(C.c_uint64), vp]
     L.lasv_graph_clean.argtypes = [vp, i32, i32, C.POINTER(CleanStats)]
+    L.lasv_graph_clean_limited.argtypes = [vp, i32, i32, i32, C.POINTER(CleanStats)]
     L.lasv_graph_write_branches.argtypes = [vp, C.c_char_p, i32, C.POINTER(BranchStats)]
     L.lasv_ref_hash_table_write_branches.argtypes = [C.POINTER(RefHashTable), C.c_char_p, C.POINTER(BranchStats)]
     L.lasv_ref_hash_table_load_ctx_records.restype = C.c_longlong

@@ -176,6 +176,11 @@ struct lasv_graph {
     uint64_t bound = 0;         // k-mer bounds of the batches binned since the last exchange
   } *sink = nullptr;
   struct lasv_multi_graph *multi = nullptr;  // set on shard 0 while a file loader drives the multi graph through it
+  // the *_strict / *_limited entry points: the reference's walk limit (--max_var_len).  Where a walk of the reference
+  // would be cut short by it (and the output would become the reference's overlapping pieces), they return
+  // LASV_ERR_LIMIT and change / write nothing -- the reference-side shims then run the reference's own CPU function
+  bool sn_strict = false;
+  int walk_limit = 0;
   Knobs knobs;
   // optional per-launch timing of the two kernels of the partitioned path (bench: roofline of the
   // dominant kernel from CUDA events on the stream the kernel is launched on)
@@ -1654,6 +1659,11 @@ int lasv_graph_write_supernodes(lasv_graph *g, const char *fasta_path, int max_l
     prints.swap(replayer.prints);
     end_keys.swap(replayer.end_keys);
     for (const SnPrint &p : prints) over += max_length > 0 && p.len > (uint32_t)max_length;
+    if (over && g->sn_strict) {
+      if (stats) stats->over_max_length = over;
+      return fail(LASV_ERR_LIMIT, "%llu supernodes have more than %d edges: the reference cuts its walks there (--max_var_len)",
+                  (unsigned long long)over, max_length);
+    }
     const uint64_t image_bytes = sn_layout_fasta(prints, g->k);
     stage("replay the traversal (host)");
 
@@ -3027,6 +3037,19 @@ static int clean_pass(lasv_graph *g, int what, uint32_t threshold, lasv_clean_st
       c.both_ways = (recs[i].bits & SNB_BOTH_WAYS) ? 1u : 0u;
       cg.cycles.push_back(c);
     }
+    if (what == LASV_CLEAN_SUPERNODES && g->walk_limit > 0) {
+      // the reference walks a supernode only from a node with 0 < coverage <= T, for at most walk_limit edges each way
+      // (dB_graph_population.c:3371-3462): a longer path with such a node inside, or at one of its ends, is where it
+      // would judge a PIECE of the supernode
+      uint64_t cut = 0;
+      auto low_node = [&](int32_t i) { return i >= 0 && cg.nodes[(size_t)i].covg > 0 && cg.nodes[(size_t)i].covg <= threshold; };
+      for (const ClPath &pth : cg.paths)
+        cut += pth.len > (uint32_t)g->walk_limit && (pth.min_low_q != SN_NONE || low_node(pth.a) || low_node(pth.b));
+      for (const ClCycle &c : cg.cycles) cut += c.len > (uint32_t)g->walk_limit && c.min_low_q != SN_NONE;
+      if (cut)
+        return fail(LASV_ERR_LIMIT, "%llu supernodes with a low-coverage node have more than %d edges: the reference cuts "
+                    "its walks there (--max_var_len)", (unsigned long long)cut, g->walk_limit);
+    }
     ClActions act;
     if (what == LASV_CLEAN_TIPS) cg.clip_tips(g->k, act);
     else cg.remove_low_coverage_supernodes(g->k, threshold, act);
@@ -3148,11 +3171,24 @@ static int download_reference_table(lasv_graph *g, lasv_ref_hash_table *t) {
 }
 
 int lasv_ref_hash_table_clean(lasv_ref_hash_table *t, int what, int threshold, lasv_clean_stats *stats) {
+  return lasv_ref_hash_table_clean_limited(t, what, threshold, 0, stats);
+}
+
+int lasv_graph_clean_limited(lasv_graph *g, int what, int threshold, int max_length, lasv_clean_stats *stats) {
+  if (!g) return fail(LASV_ERR_ARG, "NULL graph");
+  g->walk_limit = max_length;
+  const int rc = lasv_graph_clean(g, what, threshold, stats);
+  g->walk_limit = 0;
+  return rc;
+}
+
+int lasv_ref_hash_table_clean_limited(lasv_ref_hash_table *t, int what, int threshold, int max_length, lasv_clean_stats *stats) {
   if (!(what & (LASV_CLEAN_TIPS | LASV_CLEAN_SUPERNODES)) || (what & ~(LASV_CLEAN_TIPS | LASV_CLEAN_SUPERNODES)))
     return fail(LASV_ERR_ARG, "what must be LASV_CLEAN_TIPS, LASV_CLEAN_SUPERNODES or both");
   if ((what & LASV_CLEAN_SUPERNODES) && threshold < 0) return fail(LASV_ERR_ARG, "negative coverage threshold");
   lasv_graph *g = graph_for_reference_table(t);
   if (!g) return last_error_code();
+  g->walk_limit = max_length;
   if (stats) memset(stats, 0, sizeof *stats);
   int rc = [&]() -> int {
     if (int e = upload_reference_table(g, t)) return e;
@@ -3313,13 +3349,32 @@ int lasv_ref_hash_table_write_branches(lasv_ref_hash_table *t, const char *fasta
   return rc;
 }
 
-int lasv_ref_hash_table_write_supernodes(lasv_ref_hash_table *t, const char *fasta_path, int max_length,
-                                         lasv_supernode_stats *stats) {
+static int ref_write_supernodes(lasv_ref_hash_table *t, const char *fasta_path, int max_length,
+                                lasv_supernode_stats *stats, bool strict) {
   lasv_graph *g = graph_for_reference_table(t);
   if (!g) return last_error_code();
+  g->sn_strict = strict;
   int rc = upload_reference_table(g, t);
   if (rc == LASV_OK) rc = lasv_graph_write_supernodes(g, fasta_path, max_length, stats);
   lasv_graph_free(&g);
+  return rc;
+}
+
+int lasv_ref_hash_table_write_supernodes(lasv_ref_hash_table *t, const char *fasta_path, int max_length,
+                                         lasv_supernode_stats *stats) {
+  return ref_write_supernodes(t, fasta_path, max_length, stats, false);
+}
+
+int lasv_ref_hash_table_write_supernodes_strict(lasv_ref_hash_table *t, const char *fasta_path, int max_length,
+                                                lasv_supernode_stats *stats) {
+  return ref_write_supernodes(t, fasta_path, max_length, stats, true);
+}
+
+int lasv_graph_write_supernodes_strict(lasv_graph *g, const char *fasta_path, int max_length, lasv_supernode_stats *stats) {
+  if (!g) return fail(LASV_ERR_ARG, "NULL graph");
+  g->sn_strict = true;
+  const int rc = lasv_graph_write_supernodes(g, fasta_path, max_length, stats);
+  g->sn_strict = false;
   return rc;
 }
 

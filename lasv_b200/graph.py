@@ -289,11 +289,12 @@ class DBGraph:
         """The `.ctx` records of this table, appended to `path` (one shard of a sharded dump)."""
         return check(self._lib.lasv_graph_append_ctx_records(self._h, str(path).encode()))
 
-    def output_supernodes(self, path, max_length: int = 10000) -> dict:
+    def output_supernodes(self, path, max_length: int = 10000, strict: bool = False) -> dict:
         """`--output_supernodes path` (graph_operations.c:1276-1293): the reference's FASTA of
         maximal unambiguous contigs for a traversal in table (= dumped .ctx) order."""
         st = _capi.SupernodeStats()
-        check(self._lib.lasv_graph_write_supernodes(self._h, str(path).encode(), max_length, C.byref(st)))
+        fn = self._lib.lasv_graph_write_supernodes_strict if strict else self._lib.lasv_graph_write_supernodes
+        check(fn(self._h, str(path).encode(), max_length, C.byref(st)))
         return st.as_dict()
 
     def health_check(self) -> dict:
@@ -303,11 +304,13 @@ class DBGraph:
         check(self._lib.lasv_graph_health_check(self._h, C.byref(st)))
         return st.as_dict()
 
-    def clean(self, threshold: int, what: int = _capi.CLEAN_TIPS | _capi.CLEAN_SUPERNODES) -> dict:
+    def clean(self, threshold: int, what: int = _capi.CLEAN_TIPS | _capi.CLEAN_SUPERNODES, max_length: int = 0) -> dict:
         """`--remove_low_coverage_supernodes threshold` (graph_operations.c:1069-1090) on the device table: tip
-        clipping, then low-coverage supernode removal, exact for the table's slot order."""
+        clipping, then low-coverage supernode removal, exact for the table's slot order.  max_length > 0: the
+        reference's walk limit (--max_var_len); LasvError(LASV_ERR_LIMIT), graph unchanged by that pass, where the
+        reference would judge a piece of a longer supernode."""
         st = _capi.CleanStats()
-        check(self._lib.lasv_graph_clean(self._h, what, threshold, C.byref(st)))
+        check(self._lib.lasv_graph_clean_limited(self._h, what, threshold, max_length, C.byref(st)))
         return st.as_dict()
 
     def output_branches(self, path, mark_visited: bool = False) -> dict:

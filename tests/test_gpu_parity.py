@@ -1068,6 +1068,88 @@ def test_reference_cli_prints_supernodes_through_the_gpu(name, clean, tmp_path):
     assert (tmp_path / "sup.fa").read_bytes() == (tmp_path / "oracle.fa").read_bytes()
 
 
+def test_walk_limit_is_reported_not_ignored(tmp_path):
+    """--max_var_len (default 10 000 edges): the reference cuts its supernode walks there and prints / judges
+    overlapping pieces (dB_graph_population.c:2739-2767, 3371-3462).  The *_strict / *_limited calls refuse such
+    a graph (LASV_ERR_LIMIT, nothing written or changed) instead of silently printing the supernode whole; with
+    a limit nothing exceeds they are the plain calls."""
+    name = "synth_cfg0_k53"
+    meta = util.case_meta(name)
+    seq, qual, offs = util.case_streams(name)
+    with DBGraph(meta["k"], meta["L"], meta["W"]) as g:
+        g.load_reads_host(seq, qual, offs, util.cutoff_of(meta))
+        whole = g.output_supernodes(tmp_path / "whole.fa", max_length=50)
+        assert whole["over_max_length"] > 0 and whole["longest_edges"] > 50
+        with pytest.raises(_capi.LasvError) as e:
+            g.output_supernodes(tmp_path / "strict.fa", max_length=50, strict=True)
+        assert e.value.code == _capi.LASV_ERR_LIMIT and not (tmp_path / "strict.fa").exists()
+        ok = g.output_supernodes(tmp_path / "ok.fa", max_length=int(whole["longest_edges"]), strict=True)
+        assert ok["over_max_length"] == 0
+        assert (tmp_path / "ok.fa").read_bytes() == (tmp_path / "whole.fa").read_bytes()
+        before = O.sort_records(g.records())
+        g.clean(2, what=_capi.CLEAN_TIPS)
+        tipped = O.sort_records(g.records())
+        with pytest.raises(_capi.LasvError) as e:
+            g.clean(2, what=_capi.CLEAN_SUPERNODES, max_length=5)     # error paths are ~k edges long
+        assert e.value.code == _capi.LASV_ERR_LIMIT
+        assert np.array_equal(O.sort_records(g.records()), tipped) and len(tipped) <= len(before)
+        st = g.clean(2, what=_capi.CLEAN_SUPERNODES, max_length=10000)
+        assert st["supernodes_pruned"] > 0 and len(g.records()) < len(tipped)
+
+
+def test_reference_cli_supernodes_beyond_the_walk_limit(tmp_path):
+    """The reference's main() with the GPU supernode printer and --max_var_len 50: supernodes of this graph have
+    up to ~440 edges, so the GPU call refuses (LASV_ERR_LIMIT) and integration/supernode_shim.c lets the reference's
+    own printer take over, so whatever is printed beyond the limit is the reference's doing.  With the default
+    limit the GPU prints, byte for byte what the all-CPU reference prints for the same table (it reloads the .ctx
+    the same run dumped: same slot order)."""
+    from pathlib import Path
+    name = "synth_cfg0_k53"
+    meta = util.case_meta(name)
+    k, L, W = meta["k"], meta["L"], meta["W"]
+    exe = Path(__file__).resolve().parents[1] / "integration" / "_build" / "dB_graph_gpusn_63"
+    if not exe.exists() or not O.ref_available(k):
+        pytest.skip("integration/_build or oracle/_ref not built (both need /root/reference at build time)")
+    seq, qual, _ = util.case_streams(name)
+    rl = meta["workload"]["read_len"]
+    s2, q2 = seq.reshape(-1, rl + 1), qual.reshape(-1, rl + 1)
+    O.write_fastq_fixed(tmp_path / "a.fq", s2[0::2].reshape(-1), q2[0::2].reshape(-1), rl)
+    O.write_fastq_fixed(tmp_path / "b.fq", s2[1::2].reshape(-1), q2[1::2].reshape(-1), rl)
+    (tmp_path / "l").write_text(f"{tmp_path / 'a.fq'}\n")
+    (tmp_path / "r").write_text(f"{tmp_path / 'b.fq'}\n")
+    geo = ["--kmer_size", str(k), "--mem_height", str(L), "--mem_width", str(W)]
+    p = subprocess.run([str(exe)] + geo + ["--pe_list", f"{tmp_path / 'l'},{tmp_path / 'r'}", "--quality_score_threshold",
+                                           str(meta["q_thresh"]), "--dump_binary", str(tmp_path / "out.ctx"),
+                                           "--output_supernodes", str(tmp_path / "gpu.fa"), "--max_var_len", "50"],
+                       cwd=tmp_path, capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stderr[-2000:] + p.stdout[-2000:]
+    assert "the reference's own printer takes over" in p.stdout and "contig length equals max length" in p.stdout
+    q = subprocess.run([str(O.ref_binary(k))] + geo + ["--multicolour_bin", str(tmp_path / "out.ctx"), "--output_supernodes",
+                                                       str(tmp_path / "ref.fa"), "--max_var_len", "50"],
+                       cwd=tmp_path, capture_output=True, text=True, timeout=600)
+    # Beyond the limit the reference itself is on thin ice: its path arrays hold max_length entries and the walk
+    # writes entry [max_length] (dB_graph_population.c:2739-2742 vs :864) -- with glibc the all-CPU binary prints
+    # its pieces and then dies in free().  If it survives, the bytes must agree; either way it was the reference's
+    # own code that produced them, not a silent GPU approximation.
+    if q.returncode == 0:
+        assert (tmp_path / "gpu.fa").read_bytes() == (tmp_path / "ref.fa").read_bytes()
+    else:
+        assert q.returncode < 0 and "contig length equals max length" in q.stdout
+    # and with the default limit the GPU prints: same bytes as the reference
+    for f in ("out.ctx",):
+        (tmp_path / f).unlink()
+    p = subprocess.run([str(exe)] + geo + ["--pe_list", f"{tmp_path / 'l'},{tmp_path / 'r'}", "--quality_score_threshold",
+                                           str(meta["q_thresh"]), "--dump_binary", str(tmp_path / "out.ctx"),
+                                           "--output_supernodes", str(tmp_path / "gpu2.fa")],
+                       cwd=tmp_path, capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0 and "takes over" not in p.stdout
+    q = subprocess.run([str(O.ref_binary(k))] + geo + ["--multicolour_bin", str(tmp_path / "out.ctx"), "--output_supernodes",
+                                                       str(tmp_path / "ref2.fa")],
+                       cwd=tmp_path, capture_output=True, text=True, timeout=600)
+    assert q.returncode == 0
+    assert (tmp_path / "gpu2.fa").read_bytes() == (tmp_path / "ref2.fa").read_bytes()
+
+
 def _table_records(table):
     occ = table[table["status"] == 1]
     out = np.zeros(len(occ), dtype=lasv_b200.record_dtype(table["kmer"].shape[1]))
