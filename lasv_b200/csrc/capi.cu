@@ -88,6 +88,7 @@ struct Knobs {
   int passes = 0;
   long chunk_mb = 0;
   long chunk_kb = 0;  // tests: chunks of a few KB make a small input wrap the staging ring many times
+  int pipe_ctas = 2;  // LASV_B200_PIPE_CTAS: CTAs per SM of the partition kernel when an insert may run beside it
 };
 struct Staging {  // one leg of the double-buffered host->device pipeline
   uint8_t *d_seq = nullptr, *d_qual = nullptr;
@@ -361,6 +362,7 @@ Knobs read_knobs(int *insert_mode) {
   if (const char *e = getenv("LASV_B200_PASSES")) k.passes = atoi(e);
   if (const char *e = getenv("LASV_B200_CHUNK_MB")) k.chunk_mb = atol(e);
   if (const char *e = getenv("LASV_B200_CHUNK_KB")) k.chunk_kb = atol(e);
+  if (const char *e = getenv("LASV_B200_PIPE_CTAS")) k.pipe_ctas = std::max(0, std::min(8, atoi(e)));
   return k;
 }
 
@@ -1272,7 +1274,7 @@ int bin_reads_impl(lasv_graph *g, const uint8_t *d_seq, const uint8_t *d_qual,
   p.bins.bins_per_src = n_bins;
   p.bins.block_shift = (uint32_t)log2_u32(bins_per_owner);
   p.bins.rec_words = bin_record_words(g->N, g->k);
-  p.ctas_per_sm = g->pipeline ? 2 : 0;
+  p.ctas_per_sm = g->pipeline ? g->knobs.pipe_ctas : 0;
   Span sp(g, LASV_T_PARTITION, st);
   launch_build(g->N, MODE_BIN, p, st);
   if (int e = check_launch()) return e;
