@@ -75,6 +75,7 @@ def parse_args():
     ap.add_argument("--no-pipeline", action="store_true",
                     help="insert each batch before the next one is partitioned (one stream)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--trace", action="store_true", help="cfg4, N>1: CUDA-event timeline of rank 0's rounds (bin / exchange / insert)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-pairs", type=int, default=100_000)
     return ap.parse_args()
@@ -651,7 +652,7 @@ def main_job(args, w):
     # window's timed region starts.  N = 1: R = 1 -- everything runs on one stream, so the generator of the next
     # step simply queues behind this step's kernels and no flush is needed between steps.  N > 1: the exchange and
     # the inserts run on side streams, so a timed region must end with everything joined; R is as many steps as
-    # fit in an eighth of the memory next to the shard (N >= 4: the whole job), and the steps inside a window follow
+    # fit in an eighth (N = 8: a sixth, the whole job) of the memory next to the shard, and the steps inside a window follow
     # each other without a flush.
     free0, _ = torch.cuda.mem_get_info()
     shard_bytes = (1 << w.number_bits) // world * ((w.bucket_size + 4) // 5) * 128
@@ -659,7 +660,7 @@ def main_job(args, w):
         R = 1
         resident = local_per_step * batch_dev_bytes <= max(0, free0 - shard_bytes - (36 << 30))
     else:
-        budget = min(48 << 30, (free0 - shard_bytes) // 8)
+        budget = min(48 << 30, (free0 - shard_bytes) // (8 if world <= 4 else 6))
         R = int(max(1, min(K, budget // max(1, local_per_step * batch_dev_bytes))))
         resident = True
     windows = [(s0, min(K, s0 + R)) for s0 in range(0, K, R)]
@@ -743,6 +744,8 @@ def main_job(args, w):
         g.enable_kernel_timing(True)
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in windows]
     launches = 0
+    if args.trace and world > 1:
+        graph.trace = []
     barrier()
     wall0 = time.monotonic()
     torch.cuda.profiler.start()        # `ncu --profile-from-start off` sees the timed steps only
@@ -754,6 +757,10 @@ def main_job(args, w):
     wall1 = time.monotonic()
     step_ms = max_over_ranks(e0.elapsed_time(e1) for e0, e1 in ev)
     dt = sum(step_ms) * 1e-3
+    timeline = None
+    if args.trace and world > 1:
+        timeline = [[round(x, 2) for x in row] for row in graph.timeline()]
+        graph.trace = None
     kinds = g.kernel_times_by_kind() if world == 1 else None
     if world == 1:
         g.enable_kernel_timing(False)
@@ -964,7 +971,8 @@ def main_job(args, w):
                     "fingerprint": f"{summary['fingerprint']:016x}", "inputs_resident_before_each_step": bool(resident),
                     "accumulate_stream_bytes_granted": granted, "inserts_by_kind": inserts_by_kind,
                     "wall_seconds_incl_read_generation": wall1 - wall0, "window_ms": step_ms, "steps_per_window": R,
-                    "batches_accumulated_per_exchange": acc_batches if world > 1 else None},
+                    "batches_accumulated_per_exchange": acc_batches if world > 1 else None,
+                    "round_timeline_ms_rank0": timeline},
             "fingerprint": f"{summary['fingerprint']:016x}",
             "parity": (("ok" if all(x["status"] == "ok" for x in (parity, parity_full) if x) else "FAILED")
                        if (parity or parity_full) else None),
