@@ -2877,7 +2877,9 @@ void dropin_load(lasv_ref_hash_table *t, const char *list1, const char *list2, i
   } else {
     lasv_graph *g = lasv_graph_new(t->kmer_size, L, t->bucket_size, t->max_rehash_tries, devs.size() == 1 ? devs[0] : dev);
     if (!g) die_like_reference(lasv_last_error());
-    if (t->unique_kmers > 0 && lasv_graph_import_table(g, t->table) != LASV_OK)
+    long long coll0[16] = {0};  // rehashes of the import itself: the caller's collisions[] holds those already
+    if (t->unique_kmers > 0 &&
+        (lasv_graph_import_table(g, t->table) != LASV_OK || lasv_graph_rehash_histogram(g, coll0) != LASV_OK))
       die_like_reference(lasv_last_error());
     const int rc = list2 ? lasv_graph_load_pe_filelists(g, list1, list2, qual_thresh, ascii_fq_offset, &n, &s)
                          : lasv_graph_load_se_filelist(g, list1, qual_thresh, ascii_fq_offset, &n, &s);
@@ -2889,6 +2891,10 @@ void dropin_load(lasv_ref_hash_table *t, const char *list1, const char *list2, i
       for (unsigned long i = 0; i < hist_size; i++) hist[i] += (unsigned long)h[i];
     }
     if (lasv_graph_rehash_histogram(g, coll) != LASV_OK) die_like_reference(lasv_last_error());
+    for (int r = 1; r < 16; r++) {  // (entry 0 is derived from the k-mers the loaders counted, which the import does not touch)
+      coll[r] -= coll0[r];
+      coll[0] += coll0[r];
+    }
     uniq = lasv_graph_unique_kmers(g);
     if (lasv_graph_export_table(g, t->table, t->next_element) != LASV_OK)
       die_like_reference(lasv_last_error());
@@ -3399,11 +3405,17 @@ long long lasv_ref_hash_table_load_ctx_records(lasv_ref_hash_table *t, const cha
   }
   unsigned long long n = 0;
   int rc = LASV_OK;
-  if (t->unique_kmers > 0) rc = lasv_graph_import_table(g, t->table);
+  long long coll0[16] = {0};  // rehashes of the import itself: the caller's collisions[] counted those when they happened
+  if (t->unique_kmers > 0) {
+    rc = lasv_graph_import_table(g, t->table);
+    if (rc == LASV_OK) rc = lasv_graph_rehash_histogram(g, coll0);
+  }
   if (rc == LASV_OK) rc = stream_ctx_records(g, fp, &n);
   fclose(fp);
   long long coll[16];
   if (rc == LASV_OK) rc = lasv_graph_rehash_histogram(g, coll);
+  if (rc == LASV_OK)
+    for (int r = 1; r < 16; r++) coll[r] -= coll0[r];
   const long long uniq = rc == LASV_OK ? lasv_graph_unique_kmers(g) : -1;
   if (rc == LASV_OK) rc = lasv_graph_export_table(g, t->table, t->next_element);
   if (rc == LASV_OK) {

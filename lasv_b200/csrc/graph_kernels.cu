@@ -948,6 +948,25 @@ __global__ void __launch_bounds__(THREADS, 5) ingest_elements_kernel(const uint8
   if (lane_id() == 0 && my_new) atomicAdd(&ctr->unique_kmers, my_new);
 }
 
+// Second pass of the import: an Element the caller's cleaning left `pruned` (element.h:57-75; edges reset, not part
+// of the graph any more) stays pruned -- the reference keeps such nodes pruned when more reads are loaded onto a
+// cleaned graph and leaves them out of dumps and supernodes.  Runs after ingest_elements_kernel (no insert in flight).
+template <int N>
+__global__ void __launch_bounds__(THREADS) mark_pruned_elements_kernel(const uint8_t *__restrict__ elems, const uint64_t n_slots,
+                                                                      const TableView t) {
+  constexpr uint32_t STRIDE = 8 * N + 8;
+  for (uint64_t i = (uint64_t)blockIdx.x * THREADS + threadIdx.x; i < n_slots; i += (uint64_t)gridDim.x * THREADS) {
+    const uint64_t *src = reinterpret_cast<const uint64_t *>(elems + i * STRIDE);
+    if (meta_status(src[N]) != ST_PRUNED) continue;
+    uint64_t key[N];
+#pragma unroll
+    for (int w = 0; w < N; w++) key[w] = src[w];
+    uint64_t m = 0, *slot = nullptr;
+    if (table_find<N, DeviceOps>(t, key, m, &slot) && meta_status(m) == ST_NONE)
+      DeviceOps::xor32(reinterpret_cast<uint32_t *>(slot + N) + 1, (ST_NONE ^ ST_PRUNED) << 8);
+  }
+}
+
 // hash_table_find for a batch of canonical keys (keys: n x N words).
 // finalized != 0: reference layout (scan each bucket from slot 0 to the first
 // empty slot, hash_table.c:84-111); else the hashed-start device layout.
@@ -1186,6 +1205,7 @@ void launch_ingest_elements(int N, const uint8_t *elements, uint64_t n_slots, co
     constexpr int NN = decltype(n)::value;
     ingest_elements_kernel<NN><<<resident_grid(ingest_elements_kernel<NN>), THREADS, 0, st>>>(
         elements, n_slots, t, ctr);
+    mark_pruned_elements_kernel<NN><<<resident_grid(mark_pruned_elements_kernel<NN>), THREADS, 0, st>>>(elements, n_slots, t);
   });
 }
 

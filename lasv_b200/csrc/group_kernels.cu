@@ -6,6 +6,7 @@
 //   insert_groups_bulk_kernel  the same with cp.async.bulk staging, double buffered (LASV_B200_GROUPS_BULK=1)
 //   insert_spilled_kernel  the records whose bucket was full, through the ordinary table_upsert
 #include <stdint.h>
+#include <stdio.h>
 #include <stdlib.h>
 
 #include <type_traits>
@@ -218,10 +219,13 @@ void launch_insert_groups(int N, const uint32_t *recs, const uint64_t *group_off
   gr_dispatch(N, [&](auto nn) {
     constexpr int NN = decltype(nn)::value;
     auto kernel = bulk ? insert_groups_bulk_kernel<NN> : insert_groups_kernel<NN>;
-    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     int per_sm = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, GR_THREADS, smem);
-    if (per_sm < 1) per_sm = 1;
+    if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, GR_THREADS, smem) != cudaSuccess || per_sm < 1) {
+      fprintf(stderr, "lasv_b200: grouped-insert prototype: %zu bytes of shared memory per CTA cannot be set up: %s\n", smem,
+              cudaGetErrorString(cudaPeekAtLastError()));
+      return;  // nothing is launched; the caller's check of the launch reports the error left in the runtime
+    }
     uint64_t grid = (uint64_t)per_sm * (uint64_t)sm_count();  // persistent: resident CTAs x SMs
     if (grid > n_groups) grid = n_groups;
     kernel<<<(unsigned)grid, GR_THREADS, smem, st>>>(recs, group_offsets, n_groups, buckets_per_group, t, ctr, spill, n_spill,

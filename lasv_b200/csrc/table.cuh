@@ -313,7 +313,7 @@ LASV_HD int table_upsert(const TableView &t, GraphCounters *ctr, const uint64_t 
 // no insert in flight.  Returns true and the meta word if present.
 #pragma nv_exec_check_disable
 template <int N, class Ops>
-LASV_HD bool table_find(const TableView &t, const uint64_t (&key)[N], uint64_t &meta_out) {
+LASV_HD bool table_find(const TableView &t, const uint64_t (&key)[N], uint64_t &meta_out, uint64_t **slot_out = nullptr) {
   constexpr uint32_t SLOT = LineLayout<N>::SLOT, G = LineLayout<N>::G;
   const Probe pr = probe_of_key<N>(key);
   const uint64_t rep = (uint64_t)pr.tag8 * 0x0101010101010101ull;
@@ -332,7 +332,11 @@ LASV_HD bool table_find(const TableView &t, const uint64_t (&key)[N], uint64_t &
         bool same = true;
 #pragma unroll
         for (int w = 0; w < N; w++) same &= (Ops::load(slot + w) == key[w]);
-        if (same) { meta_out = Ops::load(slot + N); return true; }
+        if (same) {
+          meta_out = Ops::load(slot + N);
+          if (slot_out) *slot_out = slot;
+          return true;
+        }
       }
       if (zero_bytes64(hdr) & valid) return false;  // a claimable slot ends the probe
       line = (line + 1 == t.NL) ? 0u : line + 1;

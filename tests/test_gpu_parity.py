@@ -785,6 +785,27 @@ def test_multi_gpu_graph_in_one_process(name, shards, monkeypatch):
     _reference_finds_every_key(table, nxt, gold, k, L, W)
 
 
+def test_import_keeps_pruned_nodes_pruned():
+    """A reference-layout table that went through the cleaning holds `pruned` Elements (edges reset, not part of the
+    graph: element.h:57-75).  Importing it -- what the drop-ins do when more reads or a .ctx are loaded onto a graph
+    that is not empty -- must keep them pruned: out of the dumps, and not counted as rehashes a second time."""
+    name = "synth_cfg0_k53"
+    meta = util.case_meta(name)
+    seq, qual, offs = util.case_streams(name)
+    with DBGraph(meta["k"], meta["L"], meta["W"]) as g:
+        g.load_reads_host(seq, qual, offs, util.cutoff_of(meta))
+        raw = len(g.records())
+        g.clean(2)
+        cleaned = O.sort_records(g.records())
+        table, nxt = g.export_table()
+    assert (table["status"] == 3).sum() == raw - len(cleaned) > 0
+    with DBGraph(meta["k"], meta["L"], meta["W"]) as g2:
+        g2.import_table(table)
+        assert np.array_equal(O.sort_records(g2.records()), cleaned)
+        t2, _ = g2.export_table()
+        assert (t2["status"] == 3).sum() == (table["status"] == 3).sum()
+
+
 @pytest.mark.parametrize("devices", [None, "0,0", "all"])
 def test_dropin_loader_fills_a_reference_hash_table(devices, tmp_path, monkeypatch):
     """(A) of include/lasv_b200.h: the reference-named loader on a calloc'ed
