@@ -376,8 +376,8 @@ def run_reference_arm(args, w):
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
-        "data": "synthetic",
+        "higher_is_better": True, "scaling": "strong" if args.workload in ("cfg4", "cfg0") else "weak",
+        "vs_baseline": None, "dtype": "u64", "data": "synthetic",
         "config": workload_config(args, w, args.gpus),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": ref.kind,
                          "sample": f"{sample_pairs} read pairs ({2 * sample_pairs * w.read_len} bases) per step of the "
