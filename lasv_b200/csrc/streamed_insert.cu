@@ -37,7 +37,10 @@ constexpr int SG_THREADS = 256;        // direct sorting kernels, drain kernel
 constexpr int SO_THREADS = 512;        // fused sorting kernel
 constexpr uint32_t SO_MAXB = 4096;     // buckets per region the fused sorting kernel handles
 constexpr uint32_t SO_SMEM = 100u << 10;  // its shared memory (two CTAs per SM)
-constexpr int SO_U = 4;                // record loads in flight per thread
+#ifndef LASV_SO_U
+#define LASV_SO_U 4
+#endif
+constexpr int SO_U = LASV_SO_U;        // record loads in flight per thread
 constexpr int SI_UNITS = 4;            // units a CTA of the insert kernel works on at a time
 constexpr int SI_TEAM = 2;             // warps that share one unit (occupancy: the staging buffers bound the units per
                                        // SM at 16, and 16 warps leave every scheduler with 4 -- too few to cover the
