@@ -648,23 +648,27 @@ def main_job(args, w):
     p = w.params()
     batch_dev_bytes = 2 * (n_bytes + 16)
 
-    # The reads of R consecutive steps (a "window") are generated on the device and are resident in HBM before the
-    # window's timed region starts.  N = 1: R = 1 -- everything runs on one stream, so the generator of the next
-    # step simply queues behind this step's kernels and no flush is needed between steps.  N > 1: the exchange and
-    # the inserts run on side streams, so a timed region must end with everything joined; R is as many steps as
-    # fit in an eighth (N = 8: a sixth, the whole job) of the memory next to the shard, and the steps inside a window follow
-    # each other without a flush.
+    # The reads of a WINDOW of consecutive batches are generated on the device and are resident in HBM before the
+    # window's timed region starts; a window is as many batches as the pool holds, whatever K is (the K steps are
+    # the job cut into equal parts, the windows are what is timed, back to back).  N = 1: 16 batches (10 GB) --
+    # everything runs on one stream, so the generator of the next window simply queues behind this window's kernels
+    # and no flush is needed in between.  N > 1: the exchange and the inserts run on side streams, so a timed
+    # region must end with everything joined; the pool is an eighth (N = 8: a sixth, the whole job) of the memory
+    # next to the shard, and the batches inside a window follow each other without a flush.
     free0, _ = torch.cuda.mem_get_info()
     shard_bytes = (1 << w.number_bits) // world * ((w.bucket_size + 4) // 5) * 128
     if world == 1:
-        R = 1
-        resident = local_per_step * batch_dev_bytes <= max(0, free0 - shard_bytes - (36 << 30))
+        pool_cap = 16
+        resident = pool_cap * batch_dev_bytes <= max(0, free0 - shard_bytes - (36 << 30))
     else:
         budget = min(48 << 30, (free0 - shard_bytes) // (8 if world <= 4 else 6))
-        R = int(max(1, min(K, budget // max(1, local_per_step * batch_dev_bytes))))
+        pool_cap = int(max(1, budget // batch_dev_bytes))
         resident = True
-    windows = [(s0, min(K, s0 + R)) for s0 in range(0, K, R)]
-    n_pool = R * local_per_step if resident else 2
+    pool_cap = max(1, min(pool_cap, geo["per_rank"]))
+    job_items = [(s_, i) for s_ in range(K) for i in range(geo["step_counts"][s_])]
+    windows = [job_items[x: x + pool_cap] for x in range(0, len(job_items), pool_cap)]
+    n_pool = max(2, pool_cap) if resident else 2
+    R = pool_cap / max(1, local_per_step)          # steps per window (reported)
 
     # N > 1: a rank bins A batches into the same stripes before ONE exchange and ONE insert on the owners (two buffer
     # sets: the next A batches are binned while the previous ones travel and are inserted).  A from the memory next
@@ -702,12 +706,11 @@ def main_job(args, w):
             mine = geo["per_rank"] + (step - K) * local_per_step + i
         return (mine * world + rank) * reads_per_batch
 
-    def run_window(s0, s1, e0=None, e1=None, flush=True):
-        """Steps s0 .. s1-1: their batches through the hot path.  The stripes are inserted whenever they are full
+    def run_window(todo, e0=None, e1=None, flush=True):
+        """The batches `todo` = [(step, i)] through the hot path.  The stripes are inserted whenever they are full
         (N=1: lasv_graph_set_accumulation; N>1: every `acc_batches` batches); at the end of the window everything
         queued on side streams is joined (N>1: what the stripes still hold is exchanged and inserted first), and
         with `flush` (the end of the job) the same happens at N=1."""
-        todo = [(s_, i) for s_ in range(s0, s1) for i in range(step_count(s_))]
         if resident:
             for slot_, (s_, i) in enumerate(todo):
                 synth.reads_device(p, first_read(s_, i), reads_per_batch, pool[slot_][0], pool[slot_][1], stream)
@@ -733,7 +736,7 @@ def main_job(args, w):
 
     # ---------------------------------------------------------------- warm-up, then an empty table again
     for _ in range(Wm):
-        run_window(0, 1)
+        run_window(windows[0])
     barrier()
     graph.stats()                      # (raises if anything overflowed)
     g.clear(stream)
@@ -749,9 +752,9 @@ def main_job(args, w):
     barrier()
     wall0 = time.monotonic()
     torch.cuda.profiler.start()        # `ncu --profile-from-start off` sees the timed steps only
-    # K steps in windows of R; the job ends with the insert of what the stripes still hold
-    for wi, (s0, s1) in enumerate(windows):
-        launches += run_window(s0, s1, *ev[wi], flush=(s1 == K))
+    # the K steps, window by window; the job ends with the insert of what the stripes still hold
+    for wi, items in enumerate(windows):
+        launches += run_window(items, *ev[wi], flush=(wi == len(windows) - 1))
     barrier()
     torch.cuda.profiler.stop()
     wall1 = time.monotonic()
@@ -774,10 +777,11 @@ def main_job(args, w):
     # ---------------------------------------------------------------- steady state on the finished table
     steady = None
     if args.steady_steps > 0:
-        sw = [(s0, min(args.steady_steps, s0 + R)) for s0 in range(0, args.steady_steps, R)]
+        st_items = [(K + s_, i) for s_ in range(args.steady_steps) for i in range(local_per_step)]
+        sw = [st_items[x: x + pool_cap] for x in range(0, len(st_items), pool_cap)]
         evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in sw]
-        for wi, (s0, s1) in enumerate(sw):
-            run_window(K + s0, K + s1, *evs[wi], flush=(s1 == args.steady_steps))
+        for wi, items in enumerate(sw):
+            run_window(items, *evs[wi], flush=(wi == len(sw) - 1))
         barrier()
         sms = max_over_ranks(e0.elapsed_time(e1) for e0, e1 in evs)
         st2 = graph.stats()
@@ -970,7 +974,7 @@ def main_job(args, w):
                     "covg_equals_inserts": summary["sum_covg"] == kmers, "bad_reads": st_job["bad_reads"],
                     "fingerprint": f"{summary['fingerprint']:016x}", "inputs_resident_before_each_step": bool(resident),
                     "accumulate_stream_bytes_granted": granted, "inserts_by_kind": inserts_by_kind,
-                    "wall_seconds_incl_read_generation": wall1 - wall0, "window_ms": step_ms, "steps_per_window": R,
+                    "wall_seconds_incl_read_generation": wall1 - wall0, "window_ms": step_ms, "steps_per_window": R, "batches_per_window": pool_cap,
                     "batches_accumulated_per_exchange": acc_batches if world > 1 else None,
                     "round_timeline_ms_rank0": timeline},
             "fingerprint": f"{summary['fingerprint']:016x}",
