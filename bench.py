@@ -709,8 +709,8 @@ def main_job(args, w):
     def run_window(todo, e0=None, e1=None, flush=True):
         """The batches `todo` = [(step, i)] through the hot path.  The stripes are inserted whenever they are full
         (N=1: lasv_graph_set_accumulation; N>1: every `acc_batches` batches); at the end of the window everything
-        queued on side streams is joined (N>1: what the stripes still hold is exchanged and inserted first), and
-        with `flush` (the end of the job) the same happens at N=1."""
+        queued on side streams is joined (batches binned but not yet exchanged stay in the stripes), and with `flush`
+        (the end of the job) what the stripes still hold is inserted too."""
         if resident:
             for slot_, (s_, i) in enumerate(todo):
                 synth.reads_device(p, first_read(s_, i), reads_per_batch, pool[slot_][0], pool[slot_][1], stream)
@@ -724,8 +724,10 @@ def main_job(args, w):
             if not resident:
                 synth.reads_device(p, first_read(s_, i), reads_per_batch, sq[0], sq[1], stream)
             graph.load_reads_device(sq[0], sq[1], n_bytes, w.cutoff, offs_dev, reads_per_batch)
-        if flush or world > 1:
+        if flush:
             graph.flush()
+        elif world > 1:
+            graph.join()               # rounds already shipped complete inside this window; pending batches stay binned
         if e1 is not None:
             e1.record()
         return lib.lasv_kernel_launches() - l0

@@ -344,6 +344,15 @@ class ShardedDBGraph:
         t0 = self.trace[0][0]
         return [[t0.elapsed_time(e) for e in ev] for ev in self.trace]
 
+    def join(self):
+        """The caller's current stream waits for the exchanges and inserts queued so far; batches that were binned
+        but not yet exchanged stay in the stripes (flush() ships them too)."""
+        if self.world > 1 and self.pipeline:
+            cur = torch.cuda.current_stream()
+            for buf in self.buffers:
+                if buf.inserted is not None:
+                    cur.wait_event(buf.inserted)
+
     def flush(self):
         """Make the caller's current stream wait for everything queued on the side streams."""
         cur = torch.cuda.current_stream()
