@@ -676,7 +676,9 @@ def main_job(args, w):
     # scratch), at least ~6 rounds per job.
     acc_batches = 1
     if world > 1 and args.accumulate_gb:
-        per_batch = 4 * 1.04 * 16 * reads_per_batch * (w.read_len - w.kmer_size + 1) * 1.13
+        # (LASV_B200_EXCHANGE=stores: no send stripes, half the memory per batch)
+        n_sets = 2 if os.environ.get("LASV_B200_EXCHANGE") == "stores" else 4
+        per_batch = n_sets * 1.04 * 16 * reads_per_batch * (w.read_len - w.kmer_size + 1) * 1.13
         room = free0 - shard_bytes - n_pool * batch_dev_bytes - (16 << 30)
         acc_batches = int(max(1, min(room / per_batch, (geo["per_rank"] + 5) // 6, 16)))
         if args.accumulate_batches > 0:
@@ -978,6 +980,7 @@ def main_job(args, w):
                     "accumulate_stream_bytes_granted": granted, "inserts_by_kind": inserts_by_kind,
                     "wall_seconds_incl_read_generation": wall1 - wall0, "window_ms": step_ms, "steps_per_window": R, "batches_per_window": pool_cap,
                     "batches_accumulated_per_exchange": acc_batches if world > 1 else None,
+                    "exchange": getattr(graph, "exchange", None) if world > 1 else None,
                     "round_timeline_ms_rank0": timeline},
             "fingerprint": f"{summary['fingerprint']:016x}",
             "parity": (("ok" if all(x["status"] == "ok" for x in (parity, parity_full) if x) else "FAILED")

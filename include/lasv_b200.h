@@ -269,6 +269,18 @@ int lasv_graph_bin_reads_append_device(lasv_graph *g, const uint8_t *d_seq, cons
                                        uint32_t bins_per_owner, uint32_t stripe_capacity_records,
                                        uint32_t spill_capacity_records, void *d_records, void *d_counts,
                                        void *cuda_stream);
+/* FUSED producer -> exchange: the partition kernel stores every record straight into its OWNER's
+ * receive stripes -- owner_records[o] (host array of n_owners device pointers) is the block that sender `this rank`
+ * has in owner o's receive buffer, mapped into this process (CUDA peer access / symmetric memory), so the stores to
+ * remote owners travel over NVLink while the kernel runs and no send buffer or block copy exists.  The slot
+ * reservations stay local (the counters are this sender's; they are copied to the owners afterwards, a few KB).
+ * The owners must not read the blocks before every sender's kernel has completed (a barrier between the ranks),
+ * and no sender may start before the owner has finished inserting the previous contents.  append as above. */
+int lasv_graph_bin_reads_peers_device(lasv_graph *g, const uint8_t *d_seq, const uint8_t *d_qual,
+                                      uint64_t n_bytes, int quality_cutoff, int n_owners,
+                                      uint32_t bins_per_owner, uint32_t stripe_capacity_records,
+                                      uint32_t spill_capacity_records, void *const *owner_records, void *d_counts,
+                                      void *cuda_stream, int append);
 int lasv_graph_insert_bins_device(lasv_graph *g, const void *d_records, const void *d_counts, int n_src,
                                   uint32_t bins_per_src, uint32_t stripe_capacity_records,
                                   uint32_t spill_capacity_records, void *cuda_stream);

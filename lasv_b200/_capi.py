@@ -119,7 +119,7 @@ EXPORTS = [
     "lasv_multi_graph_stats", "lasv_multi_graph_rehash_histogram", "lasv_multi_graph_summary",
     "lasv_multi_graph_export_table",
     "lasv_graph_write_supernodes_strict", "lasv_ref_hash_table_write_supernodes_strict", "lasv_graph_clean_limited",
-    "lasv_ref_hash_table_clean_limited",
+    "lasv_ref_hash_table_clean_limited", "lasv_graph_bin_reads_peers_device",
 ]
 
 INSERT_AUTO, INSERT_RANDOM, INSERT_STREAMED = 0, 1, 2
@@ -180,6 +180,8 @@ def lib() -> C.CDLL:
     L.lasv_graph_bin_geometry.argtypes = [vp, i32, u64, u64, u32p, u32p, u32p, u32p, u32p]
     L.lasv_graph_bin_reads_device.argtypes = [vp, vp, vp, u64, i32, i32, C.c_uint32, C.c_uint32, C.c_uint32, vp, vp, vp]
     L.lasv_graph_bin_reads_append_device.argtypes = L.lasv_graph_bin_reads_device.argtypes
+    L.lasv_graph_bin_reads_peers_device.argtypes = [vp, vp, vp, u64, i32, i32, C.c_uint32, C.c_uint32, C.c_uint32,
+                                                    C.POINTER(vp), vp, vp, i32]
     L.lasv_multi_graph_new.restype = vp
     L.lasv_multi_graph_new.argtypes = [i32, i32, i32, i32, C.POINTER(i32), i32, u64]
     L.lasv_multi_graph_free.argtypes = [C.POINTER(vp)]

@@ -206,7 +206,8 @@ int use_hot(lasv_graph *g) {
 int flush_accumulated(lasv_graph *g, cudaStream_t st);
 int bin_reads_impl(lasv_graph *g, const uint8_t *d_seq, const uint8_t *d_qual, uint64_t n_bytes, int quality_cutoff,
                    int n_owners, uint32_t bins_per_owner, uint32_t stripe_capacity_records,
-                   uint32_t spill_capacity_records, void *d_records, void *d_counts, void *cuda_stream, bool append);
+                   uint32_t spill_capacity_records, void *d_records, void *d_counts, void *cuda_stream, bool append,
+                   void *const *owner_records = nullptr);
 // Every other entry point: records that were partitioned but not inserted yet (lasv_graph_set_accumulation) go into
 // the table first, so that whatever reads the table or its counters sees every read loaded so far.
 int use(lasv_graph *g) {
@@ -1244,13 +1245,16 @@ int bin_reads_impl(lasv_graph *g, const uint8_t *d_seq, const uint8_t *d_qual,
                    uint64_t n_bytes, int quality_cutoff, int n_owners,
                    uint32_t bins_per_owner, uint32_t stripe_capacity_records,
                    uint32_t spill_capacity_records, void *d_records, void *d_counts,
-                   void *cuda_stream, bool append) {
+                   void *cuda_stream, bool append, void *const *owner_records) {
   if (int e = use(g)) return e;
   if (n_owners < 1 || n_owners > 16 || (n_owners & (n_owners - 1)) || !bins_per_owner ||
       (bins_per_owner & (bins_per_owner - 1)) || bins_per_owner > g->n_buckets || !stripe_capacity_records)
     return fail(LASV_ERR_ARG, "bad bin geometry: %d owners x %u bins x %u records", n_owners, bins_per_owner,
                 stripe_capacity_records);
-  if (!d_records || !d_counts) return fail(LASV_ERR_ARG, "NULL bin buffers");
+  if ((!d_records && !owner_records) || !d_counts) return fail(LASV_ERR_ARG, "NULL bin buffers");
+  if (owner_records)
+    for (int o = 0; o < n_owners; o++)
+      if (!owner_records[o]) return fail(LASV_ERR_ARG, "NULL receive block of owner %d", o);
   if (stripe_capacity_records % STRIPE_RUN || spill_capacity_records % STRIPE_RUN)
     return fail(LASV_ERR_ARG, "stripe and spill capacities must be multiples of %u records", STRIPE_RUN);
   if (int e = check_streams(d_seq, d_qual)) return e;
@@ -1261,6 +1265,10 @@ int bin_reads_impl(lasv_graph *g, const uint8_t *d_seq, const uint8_t *d_qual,
   if (!n_bytes) return LASV_OK;
   BuildParams p = build_params(g, d_seq, d_qual, n_bytes, quality_cutoff);
   p.bins.recs = (uint64_t *)d_records;
+  if (owner_records) {  // fused producer -> exchange: every owner's block at its own (peer) address
+    p.bins.direct = 1;
+    for (int o = 0; o < n_owners; o++) p.bins.owner_recs[o] = (uint64_t *)owner_records[o];
+  }
   p.bins.count = (unsigned int *)d_counts;
   p.bins.cap = stripe_capacity_records;
   p.bins.n_bins = n_bins;
@@ -1300,6 +1308,16 @@ int lasv_graph_bin_reads_append_device(lasv_graph *g, const uint8_t *d_seq, cons
                                        void *cuda_stream) {
   return bin_reads_impl(g, d_seq, d_qual, n_bytes, quality_cutoff, n_owners, bins_per_owner, stripe_capacity_records,
                         spill_capacity_records, d_records, d_counts, cuda_stream, true);
+}
+
+int lasv_graph_bin_reads_peers_device(lasv_graph *g, const uint8_t *d_seq, const uint8_t *d_qual,
+                                      uint64_t n_bytes, int quality_cutoff, int n_owners,
+                                      uint32_t bins_per_owner, uint32_t stripe_capacity_records,
+                                      uint32_t spill_capacity_records, void *const *owner_records, void *d_counts,
+                                      void *cuda_stream, int append) {
+  if (!owner_records) return fail(LASV_ERR_ARG, "NULL owner_records");
+  return bin_reads_impl(g, d_seq, d_qual, n_bytes, quality_cutoff, n_owners, bins_per_owner, stripe_capacity_records,
+                        spill_capacity_records, nullptr, d_counts, cuda_stream, append != 0, owner_records);
 }
 
 int lasv_graph_insert_bins_device(lasv_graph *g, const void *d_records, const void *d_counts, int n_src,

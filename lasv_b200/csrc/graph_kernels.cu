@@ -387,8 +387,7 @@ build_kernel(const BuildParams p, const uint64_t n_tiles) {
           if (!lead[u]) continue;
           const uint32_t bin = (hc[u] & p.bins.bin_mask) >> p.bins.bin_shift;
           if (idx[u] < p.bins.cap) {
-            store_bin_record<N>(p.bins.recs + stripe_record_at(p.bins, bin, idx[u]) * p.bins.rec_words,
-                                p.bins.rec_words, key[u], hc[u], edge[u], count[u]);
+            store_bin_record<N>(stripe_record_ptr(p.bins, bin, idx[u]), p.bins.rec_words, key[u], hc[u], edge[u], count[u]);
           } else if (p.bins.spill_ok) {  // stripe full (skewed batch): straight into the table
             const int r = table_upsert_hashed<N, DeviceOps>(p.table, p.ctr, key[u], hc[u], edge[u], count[u]);
             my_new += (r == 1);
@@ -396,8 +395,7 @@ build_kernel(const BuildParams p, const uint64_t n_tiles) {
             const uint32_t owner = bin >> p.bins.block_shift;
             const uint32_t si = atomicAdd(&p.bins.count[stripe_counter_at(p.bins, owner, 1u << p.bins.block_shift)], 1u);
             if (si < p.bins.spill_cap)
-              store_bin_record<N>(p.bins.recs + spill_record_at(p.bins, owner, si) * p.bins.rec_words,
-                                  p.bins.rec_words, key[u], hc[u], edge[u], count[u]);
+              store_bin_record<N>(spill_record_ptr(p.bins, owner, si), p.bins.rec_words, key[u], hc[u], edge[u], count[u]);
             else
               atomicExch(p.rec_overflow, 1ull);
           }

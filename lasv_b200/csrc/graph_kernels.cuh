@@ -60,6 +60,12 @@ struct BinView {
   // regions.  owner_stride = (cap << block_shift) + spill_cap records; every owner has block+1 counters.
   uint32_t block_shift;
   uint32_t spill_cap;
+  // Fused producer -> exchange (hash-sharded build over peer memory): owner_recs[o] != nullptr for all owners means
+  // that owner o's block (its stripes + spill area) does not live at recs + o * owner_stride but at owner_recs[o] --
+  // the slot of THIS sender in owner o's receive stripes, mapped into this process (symmetric memory / peer access),
+  // so that the partition kernel's stores ARE the exchange (NVLink stores for the remote owners).
+  uint64_t *owner_recs[16];
+  uint32_t direct;      // 1: use owner_recs
 };
 constexpr uint32_t STRIPE_RUN = 128;  // records; cap and spill_cap are multiples of it
 __host__ __device__ inline uint64_t owner_stride_records(const BinView &b) {
@@ -69,6 +75,18 @@ __host__ __device__ inline uint64_t stripe_record_at(const BinView &b, uint32_t 
   const uint32_t o = stripe >> b.block_shift, r = stripe & ((1u << b.block_shift) - 1u);
   return (uint64_t)o * owner_stride_records(b) + (((uint64_t)(idx / STRIPE_RUN) * STRIPE_RUN) << b.block_shift) +
          (uint64_t)r * STRIPE_RUN + (idx % STRIPE_RUN);
+}
+// address of record idx of stripe `stripe` (producer side): through the owner's own base pointer in the fused mode
+__device__ __forceinline__ uint64_t *stripe_record_ptr(const BinView &b, uint32_t stripe, uint32_t idx) {
+  if (!b.direct) return b.recs + stripe_record_at(b, stripe, idx) * b.rec_words;
+  const uint32_t o = stripe >> b.block_shift, r = stripe & ((1u << b.block_shift) - 1u);
+  const uint64_t in_block = (((uint64_t)(idx / STRIPE_RUN) * STRIPE_RUN) << b.block_shift) + (uint64_t)r * STRIPE_RUN + (idx % STRIPE_RUN);
+  return b.owner_recs[o] + in_block * b.rec_words;
+}
+__device__ __forceinline__ uint64_t *spill_record_ptr(const BinView &b, uint32_t owner, uint32_t idx) {
+  const uint64_t in_block = ((uint64_t)b.cap << b.block_shift) + idx;
+  if (!b.direct) return b.recs + ((uint64_t)owner * owner_stride_records(b) + in_block) * b.rec_words;
+  return b.owner_recs[owner] + in_block * b.rec_words;
 }
 __host__ __device__ inline uint64_t spill_record_at(const BinView &b, uint32_t owner, uint32_t idx) {
   return (uint64_t)owner * owner_stride_records(b) + ((uint64_t)b.cap << b.block_shift) + idx;

@@ -234,6 +234,15 @@ class DBGraph:
         check(fn(self._h, _ptr(d_seq), _ptr(d_qual), n_bytes, quality_cutoff,
                  n_owners, bins_per_owner, stripe_capacity, spill_capacity, _ptr(d_records), _ptr(d_counts), stream))
 
+    def bin_reads_peers_device(self, d_seq, d_qual, n_bytes, quality_cutoff, n_owners, bins_per_owner,
+                               stripe_capacity, spill_capacity, owner_blocks, d_counts, stream=None, append=False):
+        """Fused producer -> exchange: records go straight into owner_blocks[o] (this sender's block in owner o's
+        receive stripes, peer memory mapped into this process)."""
+        ptrs = (C.c_void_p * n_owners)(*[_ptr(b) for b in owner_blocks])
+        check(self._lib.lasv_graph_bin_reads_peers_device(self._h, _ptr(d_seq), _ptr(d_qual), n_bytes, quality_cutoff,
+                                                          n_owners, bins_per_owner, stripe_capacity, spill_capacity, ptrs,
+                                                          _ptr(d_counts), stream, 1 if append else 0))
+
     def insert_bins_device(self, d_records, d_counts, n_src, bins_per_src, stripe_capacity, spill_capacity,
                            stream=None):
         check(self._lib.lasv_graph_insert_bins_device(self._h, _ptr(d_records), _ptr(d_counts), n_src,

@@ -132,9 +132,10 @@ def write_sharded_ctx(path, header: bytes, append_records, group=None) -> int:
 
 
 class _StripeBuffers:
-    def __init__(self, world, geo, device):
+    def __init__(self, world, geo, device, with_send=True):
+        # (no send stripes in the fused mode: the partition kernel stores into the owners' receive stripes)
         self.send = torch.empty((world, geo["records_per_owner"], geo["record_bytes"] // 8), dtype=torch.int64,
-                                device=device)
+                                device=device) if with_send else None
         self.recv = None                     # allocated by the exchange set-up: symmetric memory or plain
         self.send_counts = torch.zeros((world, geo["counters_per_owner"], geo["count_stride_bytes"] // 4),
                                        dtype=torch.int32, device=device)
@@ -182,21 +183,27 @@ class ShardedDBGraph:
                                           self.accumulate * max_reads_per_batch)
             self.bins_per_owner, self.cap, self.spill = geo["bins_per_owner"], geo["stripe_capacity"], geo["spill_capacity"]
             self.rec_bytes = geo["record_bytes"]
+            # LASV_B200_EXCHANGE = p2p (default): blocks pushed by peer-to-peer DMA copies; stores: FUSED producer ->
+            # exchange, the partition kernel stores every record straight into its owner's receive stripes over
+            # peer memory (no send stripes, no block copies; lasv_graph_bin_reads_peers_device); nccl: all_to_all_single
+            want = os.environ.get("LASV_B200_EXCHANGE", "p2p")
             for _ in range(2 if self.pipeline else 1):
-                self.buffers.append(_StripeBuffers(world, geo, self.device))
+                self.buffers.append(_StripeBuffers(world, geo, self.device, with_send=(want != "stores")))
             self.comm_stream = torch.cuda.Stream(device=self.device)
             self.insert_stream = torch.cuda.Stream(device=self.device)
             self.exchange = "nccl"
-            want = os.environ.get("LASV_B200_EXCHANGE", "p2p")
-            if want == "p2p":
+            if want in ("p2p", "stores"):
                 try:
                     self._setup_p2p(geo)
-                    self.exchange = "p2p"
+                    self.exchange = want
                 except Exception as ex:           # no peer access / no symmetric memory: NCCL does the job
                     print(f"[lasv_b200] peer-memory exchange unavailable ({type(ex).__name__}: {ex}); using NCCL",
                           file=sys.stderr)
             if self.exchange == "nccl":
                 for buf in self.buffers:
+                    if buf.send is None:
+                        buf.send = torch.empty((world, geo["records_per_owner"], geo["record_bytes"] // 8),
+                                               dtype=torch.int64, device=self.device)
                     buf.recv = torch.empty_like(buf.send)
                     buf.recv_counts = torch.zeros_like(buf.send_counts)
 
@@ -229,7 +236,13 @@ class ShardedDBGraph:
 
     def _exchange(self, buf, k):
         """On the current (communication) stream: blocks and counters of `buf.send*` to their owners."""
-        if self.exchange == "p2p":
+        if self.exchange == "stores":
+            self.symm_hdl.barrier(k)                 # every rank's partition kernels of this round are complete:
+            for i in range(self.world):              # all records sit in their owners' receive stripes already
+                d = (self.rank + i) % self.world
+                buf.peer_counts[d].copy_(buf.send_counts64[d], non_blocking=True)
+            self.symm_hdl.barrier(k)                 # every sender's counters have landed here
+        elif self.exchange == "p2p":
             self.symm_hdl.barrier(k)                 # every rank's receive buffer of this set is free
             for i in range(self.world):
                 d = (self.rank + i) % self.world     # start with the local block, spread the peers
@@ -275,8 +288,17 @@ class ShardedDBGraph:
             ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
             self.trace.append(ev)
             ev[0].record(cur)
-        g.bin_reads_device(d_seq, d_qual, n_bytes, quality_cutoff, self.world, self.bins_per_owner, self.cap,
-                           self.spill, buf.send, buf.send_counts, stream, append=not first)
+        if self.exchange == "stores":
+            if first:
+                # the owners must have inserted what this buffer set held before anybody stores into it again
+                if buf.inserted is not None:
+                    cur.wait_event(buf.inserted)
+                self.symm_hdl.barrier(2 + self.turn % len(self.buffers))
+            g.bin_reads_peers_device(d_seq, d_qual, n_bytes, quality_cutoff, self.world, self.bins_per_owner, self.cap,
+                                     self.spill, buf.peer_recv, buf.send_counts, stream, append=not first)
+        else:
+            g.bin_reads_device(d_seq, d_qual, n_bytes, quality_cutoff, self.world, self.bins_per_owner, self.cap,
+                               self.spill, buf.send, buf.send_counts, stream, append=not first)
         if d_offsets is not None and n_reads:
             g.read_stats_device(d_seq, d_qual, d_offsets, n_reads, quality_cutoff, stream)
         self.pending += 1

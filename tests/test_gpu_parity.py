@@ -319,6 +319,15 @@ def test_binned_exchange_matches_oracle(base, world, bins, tiny_stripes, insert,
             lo, hi = r * per, ((r + 1) * per if r < world - 1 else len(seq))
             # in two batches: the second one is APPENDED to the stripes of the first (accumulation before the exchange)
             mid = lo + (per_reads // 2) * (w.read_len + 1)
+            if insert == "streamed" and world > 1:
+                # fused producer -> exchange: the records go straight to per-owner blocks (on a multi-GPU box: the
+                # owners' receive stripes over peer memory); here the blocks are this sender's rows of `send`
+                blocks = [send[r, o] for o in range(world)]
+                graphs[r].bin_reads_peers_device(d_seq[lo:], d_qual[lo:], mid - lo, w.cutoff, world, B, cap, spill, blocks,
+                                                 send_counts[r], st_)
+                graphs[r].bin_reads_peers_device(d_seq[mid:], d_qual[mid:], hi - mid, w.cutoff, world, B, cap, spill, blocks,
+                                                 send_counts[r], st_, append=True)
+                continue
             graphs[r].bin_reads_device(d_seq[lo:], d_qual[lo:], mid - lo, w.cutoff, world, B, cap, spill, send[r],
                                        send_counts[r], st_)
             graphs[r].bin_reads_device(d_seq[mid:], d_qual[mid:], hi - mid, w.cutoff, world, B, cap, spill, send[r],
