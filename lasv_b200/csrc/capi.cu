@@ -34,6 +34,7 @@
 #include "branches_host.h"
 #include "groups.cuh"
 #include "streamed_insert.cuh"
+#include "fastq_parse.cuh"
 #include "ranking.cuh"
 #include "seq_reader.h"
 
@@ -95,6 +96,10 @@ struct Staging {  // one leg of the double-buffered host->device pipeline
   uint64_t *d_offsets = nullptr;
   cudaEvent_t copied = nullptr, consumed = nullptr;
   uint64_t *h_offsets = nullptr;  // pinned: a pageable source would make the "async" copy block the host
+  // device-side FASTQ parse (fastq_parse.cuh), allocated on the first raw chunk: the chunk's text and the parse scratch
+  uint8_t *d_raw = nullptr;
+  FqScratch fq;
+  FqResult *h_fq = nullptr;  // pinned
 };
 
 }  // namespace
@@ -204,6 +209,7 @@ int use_hot(lasv_graph *g) {
   return LASV_OK;
 }
 int flush_accumulated(lasv_graph *g, cudaStream_t st);
+int load_raw_fastq_host(lasv_graph *g, const uint8_t *text, uint64_t n_bytes, int quality_cutoff, uint64_t *n_reads_out);
 int bin_reads_impl(lasv_graph *g, const uint8_t *d_seq, const uint8_t *d_qual, uint64_t n_bytes, int quality_cutoff,
                    int n_owners, uint32_t bins_per_owner, uint32_t stripe_capacity_records,
                    uint32_t spill_capacity_records, void *d_records, void *d_counts, void *cuda_stream, bool append,
@@ -230,6 +236,8 @@ void free_staging(lasv_graph *g) {
     cudaFree(s.d_qual);
     cudaFree(s.d_offsets);
     if (s.h_offsets) cudaFreeHost(s.h_offsets);
+    cudaFree(s.d_raw); cudaFree(s.fq.nl); cudaFree(s.fq.n_nl); cudaFree(s.fq.lens); cudaFree(s.fq.result); cudaFree(s.fq.temp);
+    if (s.h_fq) cudaFreeHost(s.h_fq);
     if (s.copied) cudaEventDestroy(s.copied);
     if (s.consumed) cudaEventDestroy(s.consumed);
     s = Staging{};
@@ -908,6 +916,29 @@ int lasv_graph_set_staging(lasv_graph *g, uint64_t bytes, uint64_t *granted) {
 
 extern "C++" {
 namespace {
+// The chunk that sits in staging leg `s` (streams + offsets, its copy or device parse ordered before s.copied) goes
+// through the hot path on the compute stream: into this graph, or -- a shard of a multi-GPU graph -- into the send
+// stripes of its device.
+int consume_staged(lasv_graph *g, Staging &s, bool has_qual, uint64_t bytes, uint64_t nr, int quality_cutoff) {
+  CUDA_TRY(cudaStreamWaitEvent(g->compute, s.copied, 0));
+  if (g->sink) {
+    lasv_graph::ShardSink &k = *g->sink;
+    if (int e = bin_reads_impl(g, s.d_seq, has_qual ? s.d_qual : nullptr, bytes, quality_cutoff, k.n_owners, k.bins_per_owner,
+                               k.cap, k.spill, k.records, k.counts, g->compute, !k.fresh))
+      return e;
+    k.fresh = false;
+    k.bound += kmer_bound(g, bytes, nr);
+    launch_read_stats(s.d_seq, has_qual ? s.d_qual : nullptr, s.d_offsets, nr, 1, g->k, quality_cutoff, g->d_stats, g->d_hist,
+                      HIST_BINS, g->compute);
+    if (int e = check_launch()) return e;
+  } else if (int e = lasv_graph_load_reads_device(g, s.d_seq, has_qual ? s.d_qual : nullptr, bytes, s.d_offsets, nr,
+                                                  quality_cutoff, g->compute)) {
+    return e;
+  }
+  CUDA_TRY(cudaEventRecord(s.consumed, g->compute));
+  return LASV_OK;
+}
+
 // Both host-buffer calls.  async: nothing here waits for a kernel -- the call returns once its last copy has left
 // the host buffers (copy stream drained); statistics, if wanted, are copied to pinned memory behind the kernels.
 int load_reads_host_impl(lasv_graph *g, const uint8_t *seq, const uint8_t *qual,
@@ -991,22 +1022,7 @@ int load_reads_host_impl(lasv_graph *g, const uint8_t *seq, const uint8_t *qual,
     CUDA_TRY(cudaMemcpyAsync(s.d_offsets, s.h_offsets, (nr + 1) * sizeof(uint64_t),
                              cudaMemcpyHostToDevice, g->copy));
     CUDA_TRY(cudaEventRecord(s.copied, g->copy));
-    CUDA_TRY(cudaStreamWaitEvent(g->compute, s.copied, 0));
-    if (g->sink) {
-      lasv_graph::ShardSink &k = *g->sink;
-      if (int e = bin_reads_impl(g, s.d_seq, qual ? s.d_qual : nullptr, bytes, quality_cutoff, k.n_owners, k.bins_per_owner,
-                                 k.cap, k.spill, k.records, k.counts, g->compute, !k.fresh))
-        return e;
-      k.fresh = false;
-      k.bound += kmer_bound(g, bytes, nr);
-      launch_read_stats(s.d_seq, qual ? s.d_qual : nullptr, s.d_offsets, nr, 1, g->k, quality_cutoff, g->d_stats, g->d_hist,
-                        HIST_BINS, g->compute);
-      if (int e = check_launch()) return e;
-    } else if (int e = lasv_graph_load_reads_device(g, s.d_seq, qual ? s.d_qual : nullptr, bytes,
-                                                    s.d_offsets, nr, quality_cutoff, g->compute)) {
-      return e;
-    }
-    CUDA_TRY(cudaEventRecord(s.consumed, g->compute));
+    if (int e = consume_staged(g, s, qual != nullptr, bytes, nr, quality_cutoff)) return e;
     // h_offsets of this leg must stay alive until its copy completed: the next
     // use of the leg waits on `consumed`, which is ordered after `copied`.
     g->stage_turn = (leg + 1) % (int)g->stage.size();
@@ -1050,6 +1066,58 @@ int lasv_graph_load_reads_host_async(lasv_graph *g, const uint8_t *seq, const ui
                                      uint64_t n_bytes, const uint64_t *offsets, uint64_t n_reads,
                                      int quality_cutoff, uint64_t *pinned_stats9) {
   return load_reads_host_impl(g, seq, qual, n_bytes, offsets, n_reads, quality_cutoff, nullptr, true, pinned_stats9);
+}
+
+extern "C++" {
+namespace {
+constexpr uint64_t RAW_CHUNK_BYTES = 32ull << 20;  // largest chunk of FASTQ text the device parse takes (= a loader batch)
+
+int ensure_raw(lasv_graph *g, Staging &s) {
+  if (s.d_raw) return LASV_OK;
+  const uint32_t rec_cap = (uint32_t)g->stage_reads;
+  CUDA_TRY(cudaMalloc(&s.d_raw, RAW_CHUNK_BYTES + 256));
+  CUDA_TRY(cudaMalloc(&s.fq.nl, RAW_CHUNK_BYTES * sizeof(uint32_t)));
+  CUDA_TRY(cudaMalloc(&s.fq.n_nl, sizeof(uint32_t)));
+  CUDA_TRY(cudaMalloc(&s.fq.lens, ((size_t)rec_cap + 1) * sizeof(uint64_t)));
+  CUDA_TRY(cudaMalloc(&s.fq.result, sizeof(FqResult)));
+  s.fq.temp_bytes = fq_temp_bytes((uint32_t)RAW_CHUNK_BYTES, rec_cap);
+  CUDA_TRY(cudaMalloc(&s.fq.temp, s.fq.temp_bytes));
+  CUDA_TRY(cudaMallocHost(&s.h_fq, sizeof(FqResult)));
+  s.fq.nl_cap = (uint32_t)RAW_CHUNK_BYTES;
+  s.fq.rec_cap = rec_cap;
+  return LASV_OK;
+}
+
+// One chunk of plain four-line FASTQ text (whole records, ending with '\n', pinned for full speed): copied to the
+// device as it is, taken apart there (fastq_parse.cu) and sent through the hot path.  Returns LASV_OK and the number
+// of reads, or 1 if the text is not plain four-line FASTQ throughout -- nothing was loaded then and the caller's
+// host parser (the reference's full grammar) takes the chunk.  The buffer may be reused when the call returns.
+int load_raw_fastq_host(lasv_graph *g, const uint8_t *text, uint64_t n_bytes, int quality_cutoff, uint64_t *n_reads_out) {
+  if (int e = use_hot(g)) return e;
+  if (g->finalized) return fail(LASV_ERR_STATE, "graph is finalised; no further inserts");
+  if (!n_bytes) { *n_reads_out = 0; return LASV_OK; }
+  if (n_bytes > RAW_CHUNK_BYTES || text[n_bytes - 1] != '\n') return 1;
+  if (int e = ensure_staging(g)) return e;
+  Staging &s = g->stage[(size_t)g->stage_turn % g->stage.size()];
+  if (int e = ensure_raw(g, s)) return e;
+  CUDA_TRY(cudaEventSynchronize(s.consumed));  // the kernels that read this leg's streams are done
+  CUDA_TRY(cudaMemcpyAsync(s.d_raw, text, n_bytes, cudaMemcpyHostToDevice, g->copy));
+  const cudaError_t pe = fq_parse_chunk(s.d_raw, (uint32_t)n_bytes, s.fq, s.d_seq, s.d_qual, s.d_offsets, CHUNK_BYTES, g->copy);
+  if (pe != cudaSuccess) return fail(LASV_ERR_CUDA, "device FASTQ parse: %s", cudaGetErrorString(pe));
+  g_launches.fetch_add(2, std::memory_order_relaxed);
+  CUDA_TRY(cudaMemcpyAsync(s.h_fq, s.fq.result, sizeof(FqResult), cudaMemcpyDeviceToHost, g->copy));
+  CUDA_TRY(cudaEventRecord(s.copied, g->copy));
+  CUDA_TRY(cudaStreamSynchronize(g->copy));  // (a copy and four small kernels: the streams are still to be consumed)
+  const FqResult r = *s.h_fq;
+  if (r.bad) return 1;
+  *n_reads_out = r.n_records;
+  if (!r.n_records) return LASV_OK;
+  // the chunks of a file accumulate like the chunks of a host-buffer call (the loaders set the accumulation up)
+  if (int e = consume_staged(g, s, true, r.n_bytes, r.n_records, quality_cutoff)) return e;
+  g->stage_turn = (g->stage_turn + 1) % (int)g->stage.size();
+  return LASV_OK;
+}
+}  // namespace
 }
 
 int lasv_graph_stats(lasv_graph *g, lasv_load_stats *out, uint64_t *contig_hist, uint64_t hist_size,
@@ -2097,6 +2165,24 @@ int multi_load_host(lasv_multi_graph *m, const uint8_t *seq, const uint8_t *qual
   return load_reads_host_impl(g, seq, qual, n_bytes, offsets, n_reads, cutoff, nullptr, true, nullptr);
 }
 
+// A chunk of FASTQ text to the next device in turn (device parse there); 1 = not plain four-line FASTQ, nothing loaded.
+int multi_load_raw(lasv_multi_graph *m, const uint8_t *text, uint64_t n_bytes, int cutoff, uint64_t *n_reads) {
+  if (!n_bytes) return LASV_OK;
+  const int d = m->turn;
+  lasv_graph *g = m->shard[d];
+  const uint64_t bound = n_bytes / 2;  // the sequence lines are less than half of the text
+  if (bound > m->round_bound) return fail(LASV_ERR_ARG, "a FASTQ chunk of %llu bytes exceeds the exchange stripes of the multi-GPU graph",
+                                          (unsigned long long)n_bytes);
+  if (m->dev[d].sink.bound + bound > m->round_bound)
+    if (int e = multi_ship(m)) return e;
+  const int rc = load_raw_fastq_host(g, text, n_bytes, cutoff, n_reads);
+  if (rc == LASV_OK && *n_reads) {
+    m->turn = (d + 1) % m->n;
+    m->any_binned = true;
+  }
+  return rc;
+}
+
 int multi_sync(lasv_multi_graph *m) {
   if (int e = multi_ship(m)) return e;
   for (int d = 0; d < m->n; d++) {
@@ -2343,7 +2429,44 @@ namespace {
 constexpr uint64_t LOADER_BATCH_BYTES = 32ull << 20;  // x 2 slots x parser threads, pinned, kept by the graph
 constexpr uint64_t LOADER_BATCH_READS = 4ull << 20;
 
-int flush_batch(lasv_graph *g, HostBatch &b, bool with_qual, int cutoff) {
+// A raw chunk (FASTQ text) through the device parse; *n_reads receives its read count.  Falls back to the host
+// parser (the reference's full grammar, pageable buffers: rare) if the chunk is not plain four-line FASTQ.
+int flush_raw_batch(lasv_graph *g, HostBatch &b, int cutoff, uint64_t *n_reads) {
+  int rc = g->multi ? multi_load_raw(g->multi, b.seq, b.n_bytes, cutoff, n_reads) : load_raw_fastq_host(g, b.seq, b.n_bytes, cutoff, n_reads);
+  if (rc != 1) return rc;
+  std::vector<uint8_t> sq(b.n_bytes + 16), ql(b.n_bytes + 16);
+  std::vector<uint64_t> off(b.n_bytes / 4 + 2);
+  HostBatch t;
+  t.seq = sq.data();
+  t.qual = ql.data();
+  t.offsets = off.data();
+  t.cap_bytes = b.n_bytes + 8;
+  t.cap_reads = off.size() - 1;
+  t.reset();
+  SeqReader rd;
+  rd.open_memory(b.seq, b.n_bytes, "FASTQ chunk");
+  std::string err;
+  uint64_t n = rd.fill_batch_fast(t, true);
+  while (rd.next(err)) {
+    if (!rd.append_to(t, true)) return fail(LASV_ERR_IO, "a FASTQ chunk does not fit its own size when parsed");
+    n++;
+    n += rd.fill_batch_fast(t, true);
+  }
+  if (!err.empty()) return fail(LASV_ERR_IO, "%s", err.c_str());
+  *n_reads = n;
+  if (!t.n_reads) return LASV_OK;
+  if (g->multi) return multi_load_host(g->multi, t.seq, t.qual, t.n_bytes, t.offsets, t.n_reads, cutoff);
+  return lasv_graph_load_reads_host(g, t.seq, t.qual, t.n_bytes, t.offsets, t.n_reads, cutoff, nullptr);
+}
+
+int flush_batch(lasv_graph *g, HostBatch &b, bool with_qual, int cutoff, uint64_t *raw_reads) {
+  if (b.raw) {
+    uint64_t n = 0;
+    const int rc = b.n_bytes ? flush_raw_batch(g, b, cutoff, &n) : LASV_OK;
+    if (raw_reads) *raw_reads += n;
+    b.reset();
+    return rc;
+  }
   if (!b.n_reads) return LASV_OK;
   int rc;
   if (g->multi)  // shard 0 of a multi-GPU graph stands in for the whole graph: the batch goes to the next device in turn
@@ -2359,6 +2482,8 @@ int loader_stats(lasv_graph *g, lasv_load_stats *s) {
   return lasv_graph_stats(g, s, nullptr, 0, nullptr);
 }
 
+size_t find_fastq_record(const unsigned char *d, size_t n, size_t from);
+
 // One parser thread per file: it fills two pinned batches in turn while the caller's thread hands the
 // full ones to the GPU.  (The text parse is the slow end of the file loaders by two orders of magnitude;
 // the two mates of a pair need not be interleaved -- the order of reads is irrelevant to the graph,
@@ -2371,14 +2496,27 @@ struct FileProducer {
   int full[2] = {0, 0};  // guarded by m
   bool done = false;     // guarded by m: no further batches will be produced
   bool too_long = false;
-  uint64_t reads = 0;
+  std::atomic<uint64_t> reads{0};  // (raw mode: counted by the consumer, else by the parser thread)
   std::mutex m;
   std::condition_variable cv;
   std::thread th;
+  // raw mode (a slice of a mapped plain four-line FASTQ file): the thread only copies whole records of text into the
+  // pinned batches, the device takes them apart (fastq_parse.cu); `reads` is then counted by the consumer
+  const unsigned char *raw_data = nullptr;
+  size_t raw_size = 0;
+
+  // end of the longest run of whole records in raw_data[pos, ...) that fits `cap` bytes; 0 if none is found
+  size_t raw_cut(size_t pos, size_t cap) const {
+    if (raw_size - pos <= cap) return raw_size;
+    const size_t back = std::min<size_t>(cap / 2, 1u << 16);  // a record boundary within the last 64 KB of the window
+    const size_t c = find_fastq_record(raw_data, raw_size, pos + cap - back);
+    return (c == SIZE_MAX || c <= pos || c - pos > cap) ? 0 : c;
+  }
 
   void run() {
     int k = 0;
     bool have = false;  // a parsed read waits for room
+    size_t raw_pos = 0;
     for (;;) {
       {
         std::unique_lock<std::mutex> lk(m);
@@ -2387,6 +2525,31 @@ struct FileProducer {
       HostBatch &b = *slot[k];
       b.reset();
       bool eof = false;
+      if (raw_data) {
+        const size_t cap = (size_t)std::min<uint64_t>(b.cap_bytes - 1, (32ull << 20) - 1);
+        const size_t end = raw_cut(raw_pos, cap);
+        if (end) {
+          const size_t n = end - raw_pos;
+          memcpy(b.seq, raw_data + raw_pos, n);
+          b.n_bytes = n;
+          if (b.seq[n - 1] != '\n') b.seq[b.n_bytes++] = '\n';  // the file's last line
+          b.raw = true;
+          raw_pos = end;
+          eof = raw_pos >= raw_size;
+          {
+            std::lock_guard<std::mutex> lk(m);
+            full[k] = 1;
+            if (eof) done = true;
+          }
+          cv.notify_all();
+          if (eof) return;
+          k ^= 1;
+          continue;
+        }
+        // no record boundary where one should be: the rest of the slice goes through the host parser
+        reader.open_memory(raw_data + raw_pos, raw_size - raw_pos, reader.path());
+        raw_data = nullptr;
+      }
       for (;;) {
         if (!have) {
           reads += reader.fill_batch_fast(b, with_qual);  // plain four-line records of a mapped slice
@@ -2484,8 +2647,9 @@ struct ParseJob {
 
   // entries: (file 1, file 2 or "") -- every file of every entry is parsed concurrently; `threads` parser
   // threads per large uncompressed FASTQ file (>= 1); `alloc` hands out the two batches of every producer
+  // raw_slices: the slices of a mapped plain FASTQ file are handed over as TEXT (HostBatch::raw) for the device parse
   bool open(const std::vector<std::pair<std::string, std::string>> &entries, int threads, size_t min_slice_bytes,
-            const std::function<HostBatch *()> &alloc) {
+            const std::function<HostBatch *()> &alloc, bool raw_slices = false) {
     for (size_t e = 0; e < entries.size(); e++) {
       const std::string paths[2] = {entries[e].first, entries[e].second};
       const int n_files = paths[1].empty() ? 1 : 2;
@@ -2514,9 +2678,15 @@ struct ParseJob {
         const size_t first = prod.size();
         if (cuts.size() > 1) {
           cuts.push_back(m.size);
+          const char *dp = getenv("LASV_B200_DEVICE_PARSE");  // 0: the parser threads take the slices apart on the host
+          const bool device_parse = raw_slices && (!dp || atoi(dp) != 0);
           for (size_t w = 0; w + 1 < cuts.size(); w++) {
             prod.emplace_back(new FileProducer());
             prod.back()->reader.open_memory(m.data + cuts[w], cuts[w + 1] - cuts[w], paths[f]);
+            if (device_parse && with_qual) {  // the text goes to the device as it is (fastq_parse.cu)
+              prod.back()->raw_data = m.data + cuts[w];
+              prod.back()->raw_size = cuts[w + 1] - cuts[w];
+            }
           }
         } else {
           prod.emplace_back(std::move(heads[f]));
@@ -2537,7 +2707,7 @@ struct ParseJob {
   }
 
   // runs the producers; `consume(batch)` is called from this thread for every full batch
-  void run(const std::function<void(HostBatch &, const FileProducer &)> &consume) {
+  void run(const std::function<void(HostBatch &, FileProducer &)> &consume) {
     for (auto &p : prod) {
       FileProducer *fp = p.get();
       fp->th = std::thread([fp] { fp->run(); });
@@ -2639,15 +2809,39 @@ int load_file_group(lasv_graph *g, const std::vector<std::pair<std::string, std:
           }
         }
         return g->host_pool[pool_next++].get();
-      }))
+      }, true))
     return fail(job.err.find("batch buffers") != std::string::npos ? LASV_ERR_CUDA : LASV_ERR_IO, "%s",
                 job.err.c_str());
   lasv_load_stats before;
   if (int e = loader_stats(g, &before)) return e;
+  // Large tables: the batches of the whole group accumulate in the graph's stripes and are inserted when those are
+  // full and at the end of the group (the streamed insert pays from about a record per table line on); sized from
+  // the files' bytes, which bound the stream bytes.
+  bool group_accumulates = false;
+  if (!g->multi && !g->pipeline && g->acc_limit == 0) {
+    uint64_t file_bytes = 0;
+    for (auto &e : entries)
+      for (const std::string *pth : {&e.first, &e.second}) {
+        struct stat sb;
+        if (!pth->empty() && stat(pth->c_str(), &sb) == 0) file_bytes += (uint64_t)sb.st_size;
+      }
+    uint32_t nb = 0;
+    if (file_bytes && want_binned(g, file_bytes, &nb) && g->table_bytes >= (256ull << 20)) {
+      if (int e = lasv_graph_set_accumulation(g, file_bytes, nullptr)) return e;
+      group_accumulates = true;
+    }
+  }
   int rc = LASV_OK;
-  job.run([&](HostBatch &b, const FileProducer &p) {
-    if (rc == LASV_OK) rc = flush_batch(g, b, p.with_qual, cutoff);  // after an error: just drain
+  job.run([&](HostBatch &b, FileProducer &p) {
+    uint64_t raw_reads = 0;
+    if (rc == LASV_OK) rc = flush_batch(g, b, p.with_qual, cutoff, &raw_reads);  // after an error: just drain
+    else b.reset();
+    p.reads += raw_reads;
   });
+  if (group_accumulates) {
+    const int e2 = lasv_graph_set_accumulation(g, 0, nullptr);  // inserts what the stripes hold, accumulation off again
+    if (rc == LASV_OK) rc = e2;
+  }
   if (rc != LASV_OK) return rc;
   for (size_t i = 0; i < job.prod.size(); i++) {
     const auto &e = entries[(size_t)job.file_of[i] / 2];

@@ -21,7 +21,10 @@ struct HostBatch {
   uint64_t *offsets = nullptr;  // cap_reads + 1 entries
   uint64_t cap_bytes = 0, cap_reads = 0;
   uint64_t n_bytes = 0, n_reads = 0;
-  void reset() { n_bytes = 0; n_reads = 0; if (offsets) offsets[0] = 0; }
+  // raw: `seq` holds n_bytes of plain four-line FASTQ TEXT (whole records, ending with '\n') instead of parsed
+  // streams; it is taken apart on the device (fastq_parse.cu)
+  bool raw = false;
+  void reset() { n_bytes = 0; n_reads = 0; raw = false; if (offsets) offsets[0] = 0; }
 };
 
 class SeqReader {

@@ -106,6 +106,49 @@ def test_file_loaders_with_many_small_batches(name, batch_bytes, tmp_path, monke
         assert st["n_reads"] == len(s2) // 2
 
 
+@pytest.mark.parametrize("batch_bytes,spoil", [(0, False), (150_000, False), (150_000, True)])
+def test_file_loaders_parse_fastq_text_on_the_device(batch_bytes, spoil, tmp_path, monkeypatch):
+    """Large uncompressed FASTQ files are mapped, cut into slices at record boundaries, and the slices go to the
+    device as TEXT (HostBatch::raw): newline index, record shape check, offsets, stream copy (fastq_parse.cu).
+    Same graph and statistics as the host parse of the same files; a chunk that is not plain four-line FASTQ
+    (one multi-line record in the middle of a file) falls back to the host parser for that chunk only."""
+    monkeypatch.setenv("LASV_B200_PARSE_THREADS", "2")           # slices from 1 MB on
+    if batch_bytes:
+        monkeypatch.setenv("LASV_B200_LOADER_BATCH_BYTES", str(batch_bytes))
+    name = "synth_cfg0_k53"
+    meta = util.case_meta(name)
+    seq, qual, _ = util.case_streams(name)
+    rl = meta["workload"]["read_len"]
+    s2, q2 = seq.reshape(-1, rl + 1), qual.reshape(-1, rl + 1)
+    reps = 32                                                    # 32 x 84 KB per file: two slices each
+    for f, sel in (("a.fq", slice(0, None, 2)), ("b.fq", slice(1, None, 2))):
+        O.write_fastq_fixed(tmp_path / "one.fq", s2[sel].reshape(-1), q2[sel].reshape(-1), rl)
+        text = (tmp_path / "one.fq").read_bytes()
+        if spoil and f == "a.fq":
+            # the 200th record with its sequence and quality wrapped over two lines: legal FASTQ, not four-line
+            lines = text.split(b"\n")
+            i = 4 * 200
+            lines[i + 1: i + 2] = [lines[i + 1][:40], lines[i + 1][40:]]
+            lines[i + 4: i + 5] = [lines[i + 4][:55], lines[i + 4][55:]]
+            text = b"\n".join(lines)
+        one = (tmp_path / "one.fq").read_bytes()
+        (tmp_path / f).write_bytes(one * 9 + text + one * (reps - 10))      # (the wrapped record sits in the first slice)
+    gold = util.case_records(name).copy()
+    gold["covg"] *= reps
+    results = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("LASV_B200_DEVICE_PARSE", mode)
+        with DBGraph(meta["k"], meta["L"], meta["W"]) as g:
+            l0 = _capi.lib().lasv_kernel_launches()
+            st = g.load_pe_seq_data(tmp_path / "a.fq", tmp_path / "b.fq", util.cutoff_of(meta))
+            results[mode] = (st, _capi.lib().lasv_kernel_launches() - l0)
+            assert st["n_reads"] == reps * len(s2) and st["kmers_inserted"] == reps * meta["inserts"]
+            assert st["bad_reads"] == reps * meta["bad_reads"] and st["bases_loaded"] == reps * meta["bases_loaded"]
+            util.assert_same_records(g.records(), gold, name)
+    assert results["1"][0] == results["0"][0]
+    assert results["1"][1] > results["0"][1]                     # the parse kernels ran
+
+
 def _merge_records(*arrays):
     acc = {}
     for a in arrays:

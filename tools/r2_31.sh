@@ -1,0 +1,3 @@
+out=gpurun_out/$1; mkdir -p $out
+timeout 1200 python -m pytest tests -m gpu -x -q -k "parse_fastq_text" > $out/pytest.log 2>&1; echo "rc=$?" >> $out/pytest.log
+tail -25 $out/pytest.log
