@@ -67,6 +67,7 @@ def parse_args():
     ap.add_argument("--insert", choices=["auto", "random", "streamed"], default="auto")
     ap.add_argument("--steady-steps", type=int, default=3)
     ap.add_argument("--e2e-pairs", type=int, default=4 << 20, help="cfg4: read pairs per host-buffer call of the e2e leg")
+    ap.add_argument("--pool-batches", type=int, default=8, help="cfg4, N=1: batches of reads resident per timed window")
     ap.add_argument("--e2e-steps", type=int, default=0, help="cfg4, N=1: host-buffer calls of the e2e leg (0: --steps)")
     ap.add_argument("--e2e-staging-gb", type=float, default=6.0, help="cfg4, N=1: device staging ring of the host-buffer calls")
     ap.add_argument("--parity-pairs", type=int, default=20_000)
@@ -650,7 +651,7 @@ def main_job(args, w):
 
     # The reads of a WINDOW of consecutive batches are generated on the device and are resident in HBM before the
     # window's timed region starts; a window is as many batches as the pool holds, whatever K is (the K steps are
-    # the job cut into equal parts, the windows are what is timed, back to back).  N = 1: 16 batches (10 GB) --
+    # the job cut into equal parts, the windows are what is timed, back to back).  N = 1: 8 batches (5 GB) --
     # everything runs on one stream, so the generator of the next window simply queues behind this window's kernels
     # and no flush is needed in between.  N > 1: the exchange and the inserts run on side streams, so a timed
     # region must end with everything joined; the pool is an eighth (N = 8: a sixth, the whole job) of the memory
@@ -658,7 +659,7 @@ def main_job(args, w):
     free0, _ = torch.cuda.mem_get_info()
     shard_bytes = (1 << w.number_bits) // world * ((w.bucket_size + 4) // 5) * 128
     if world == 1:
-        pool_cap = 16
+        pool_cap = max(1, args.pool_batches)
         resident = pool_cap * batch_dev_bytes <= max(0, free0 - shard_bytes - (36 << 30))
     else:
         budget = min(48 << 30, (free0 - shard_bytes) // (8 if world <= 4 else 6))
