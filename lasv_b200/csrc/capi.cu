@@ -174,6 +174,15 @@ struct lasv_graph {
   // probe of the k-mer counter queued in front of every insert).  Quality filtering, Ns and errors keep real reads
   // ~12 % under the bound, which is 12 % more batches per pass over the table.  An underestimate is harmless: a
   // record that finds its stripe full goes straight into the table (spill_ok).
+  // The accumulating stripes are divided into up to 32 SLOTS, each a complete set of stripes of its own (the consumer
+  // sees them as 32 "senders" of one region each, the layout of the multi-GPU receive side): a batch goes into the
+  // current slot, the next slot is taken when that one is booked out.  The write frontiers of a slot's stripes start
+  // together and drift apart only as far as one slot's worth of records lets them, so the partition kernel's scattered
+  // stores stay inside a few hundred 2 MB pages however much the accumulation holds (with ONE set of stripes the
+  // kernel went from 3.2 ms for the first batch of an accumulation to 4.65 ms for the 17th).
+  uint32_t acc_slots = 0, acc_slot = 0;
+  uint64_t acc_slot_records = 0, acc_slot_booked = 0;
+  double acc_fill_sized = 0.0;  // acc_fill the slots were sized with
   double acc_fill = 1.0;
   uint64_t acc_bound_sum = 0, probe_bound = 0, probe_prev_kmers = 0;
   unsigned long long *h_probe = nullptr;  // pinned
@@ -466,6 +475,70 @@ int ensure_bins(lasv_graph *g, lasv_graph::BinLeg &l, uint64_t bound, uint32_t n
   return LASV_OK;
 }
 
+// bytes of the counters a view's consumer reads: (stripes + spill counter) per sender
+size_t view_counter_bytes(const BinView &v) {
+  const uint32_t per = 1u << v.block_shift;
+  return (size_t)(v.n_bins / per) * (per + 1u) * COUNT_STRIDE * sizeof(unsigned int);
+}
+
+// Records per stripe of one SLOT of the accumulation (see lasv_graph::acc_slots): mean + 4 sigma -- a few dozen of the
+// 65 536 x slots stripes overflow by a few records per accumulation, and a record that finds its stripe full goes
+// straight into the table (spill_ok), so this is a sizing choice, not a limit; every per cent of slack here is a per
+// cent fewer batches per pass over the table.
+uint64_t slot_stripe_capacity(uint64_t slot_records, uint32_t n_bins) {
+  const double mean = (double)slot_records / n_bins;
+  const uint64_t cap = (uint64_t)(mean * 1.005 + 4.0 * sqrt(mean) + 8.0);
+  return (cap + STRIPE_RUN - 1) / STRIPE_RUN * STRIPE_RUN;
+}
+
+// The accumulating stripes of leg 0: n_slots complete sets of n_bins stripes for slot_records records each.  l.v is
+// the CONSUMER's view (n_slots rounded up to a power of two "senders"; the extra ones never receive anything).
+int ensure_acc_bins(lasv_graph *g, lasv_graph::BinLeg &l, uint64_t slot_records, uint32_t n_bins, uint32_t n_slots) {
+  const uint64_t cap = slot_stripe_capacity(slot_records, n_bins);
+  if (cap > 0xFFFFFFF0ull) return fail(LASV_ERR_ARG, "batch too large for the bin stripes");
+  uint32_t s2 = 1;
+  while (s2 < n_slots) s2 <<= 1;
+  const uint64_t want = cap * n_bins * n_slots;
+  const uint32_t want_n = n_bins * s2;
+  if (l.alloc_records < want || l.alloc_n != want_n) {
+    CUDA_TRY(cudaDeviceSynchronize());
+    cudaFree(l.v.recs);
+    cudaFree(l.v.count);
+    l.v = BinView{};
+    l.alloc_records = 0;
+    CUDA_TRY(cudaMalloc(&l.v.recs, want * (size_t)bin_record_words(g->N, g->k) * sizeof(uint64_t)));
+    const size_t cbytes = (size_t)(n_bins + 1) * s2 * COUNT_STRIDE * sizeof(unsigned int);
+    CUDA_TRY(cudaMalloc(&l.v.count, cbytes));
+    CUDA_TRY(cudaMemset(l.v.count, 0, cbytes));
+    l.alloc_records = want;
+    l.alloc_n = want_n;
+  }
+  l.v.cap = (uint32_t)cap;
+  l.v.block_shift = (uint32_t)log2_u32(n_bins);
+  l.v.rec_words = bin_record_words(g->N, g->k);
+  l.v.spill_cap = 0;  // one owner: an overfull stripe spills straight into the table
+  l.v.n_bins = want_n;
+  l.v.bin_mask = (uint32_t)(g->n_buckets - 1);
+  l.v.bin_shift = (uint32_t)(g->L - log2_u32(n_bins));
+  l.v.spill_ok = 1;
+  l.v.src_shift = (uint32_t)log2_u32(s2);
+  l.v.src_used = n_slots;
+  l.v.bins_per_src = n_bins;
+  return LASV_OK;
+}
+
+// the PRODUCER's view of slot `slot` of those stripes: one set of n_bins stripes, its own counters
+BinView acc_slot_view(const BinView &c, uint32_t slot) {
+  BinView p = c;
+  const uint32_t n_bins = c.bins_per_src;
+  p.recs = c.recs + (uint64_t)slot * ((uint64_t)c.cap << c.block_shift) * c.rec_words;
+  p.count = c.count + (size_t)slot * (n_bins + 1u) * COUNT_STRIDE;
+  p.n_bins = n_bins;
+  p.src_shift = 0;
+  p.src_used = 0;
+  return p;
+}
+
 // Streamed or random-access insert for these stripes?  Streaming costs two passes over the table's lines
 // whatever the batch; it pays from about 0.75 records per line on.
 bool want_streamed(const lasv_graph *g, const BinView &v, uint64_t n_records, StreamedGeom *geom) {
@@ -622,9 +695,11 @@ int lasv_graph_clear(lasv_graph *g, void *cuda_stream) {
   CUDA_TRY(cudaMemsetAsync(g->d_overflow, 0, sizeof(unsigned long long), st));
   if (g->acc_records) {  // records binned but not yet inserted belong to the graph that is being cleared
     CUDA_TRY(cudaStreamSynchronize(g->acc_stream));
-    CUDA_TRY(cudaMemsetAsync(g->leg[0].v.count, 0, (size_t)(g->leg[0].v.n_bins + 1) * COUNT_STRIDE * sizeof(unsigned int), st));
+    CUDA_TRY(cudaMemsetAsync(g->leg[0].v.count, 0, view_counter_bytes(g->leg[0].v), st));
     g->acc_records = 0;
     g->acc_bytes = 0;
+    g->acc_slot = 0;
+    g->acc_slot_booked = 0;
   }
   if (g->probe_pending) {  // a probe of the counters that were just reset: let it land, then forget it
     CUDA_TRY(cudaEventSynchronize(g->probe_ev));
@@ -760,7 +835,7 @@ int insert_stripes(lasv_graph *g, const BinView &v, uint64_t n_records, int ctas
   }
   total.end();
   if (own_counters)
-    CUDA_TRY(cudaMemsetAsync(v.count, 0, (size_t)(v.n_bins + 1) * COUNT_STRIDE * sizeof(unsigned int), st));
+    CUDA_TRY(cudaMemsetAsync(v.count, 0, view_counter_bytes(v), st));
   return LASV_OK;
 }
 
@@ -774,8 +849,9 @@ uint64_t accumulation_records(lasv_graph *g, uint64_t want) {
   const uint64_t reserve = 3ull << 30;  // staging legs, statistics, the caller's next buffers
   if (free_b + have <= reserve) return 0;
   const double budget = (double)(free_b + have - reserve);
-  // stripes (1.03: mean + 8 sigma + whole runs) and one slab (<= 1/8 of them) of sorted records + spill indices
-  const double per_record = 1.03 * ((double)rec_bytes + ((double)rec_bytes + 4.0) / 8.0);
+  // stripes (1.09: the slots' stripes hold mean + 4 sigma in whole runs of 128 records) and one slab (<= 1/8 of them)
+  // of sorted records + spill indices
+  const double per_record = 1.09 * ((double)rec_bytes + ((double)rec_bytes + 4.0) / 8.0);
   const uint64_t fit = (uint64_t)(budget / per_record);
   return std::min(want, fit);
 }
@@ -790,6 +866,8 @@ int flush_accumulated(lasv_graph *g, cudaStream_t st) {
   const uint64_t n = g->acc_records;
   g->acc_records = 0;
   g->acc_bytes = 0;
+  g->acc_slot = 0;
+  g->acc_slot_booked = 0;
   if (g->h_probe && g->probe_ev && !g->probe_pending && g->acc_bound_sum) {
     // the k-mer counter as it stands behind this accumulation's partition launches (counted there, not at the insert)
     CUDA_TRY(cudaMemcpyAsync(g->h_probe, &g->d_ctr->kmers_inserted, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
@@ -813,7 +891,7 @@ void poll_fill_probe(lasv_graph *g) {
   const uint64_t now = *g->h_probe;
   if (now >= g->probe_prev_kmers && g->probe_bound) {
     const double ratio = (double)(now - g->probe_prev_kmers) / (double)g->probe_bound;
-    g->acc_fill = std::min(1.0, std::max(0.05, ratio * 1.03));
+    g->acc_fill = std::min(1.0, std::max(0.05, ratio * 1.02));
   }
   g->probe_prev_kmers = now;
 }
@@ -855,29 +933,57 @@ int lasv_graph_load_reads_device(lasv_graph *g, const uint8_t *d_seq, const uint
       if (accumulate) {
         poll_fill_probe(g);
         booked = std::min<uint64_t>(bound, (uint64_t)((double)bound * g->acc_fill) + 1);
-        // several partition launches fill the same stripes; ONE insert when the next batch might not fit
-        if (g->acc_records && (g->acc_stream != st || g->acc_records + booked > g->acc_cap_records))
+        // several partition launches fill the stripes, slot by slot; ONE insert when the next batch does not fit
+        // (the slots are re-cut, while they are empty, when the fill estimate has moved since they were sized)
+        const bool stale = g->acc_slots && fabs(g->acc_fill - g->acc_fill_sized) > 0.03 * g->acc_fill_sized;
+        bool fits = g->acc_slots && booked <= g->acc_slot_records &&
+                    g->acc_bytes + n_bytes <= std::max(g->acc_limit, n_bytes) &&  // the caller's limit, in stream bytes
+                    (g->acc_slot_booked + booked <= g->acc_slot_records || g->acc_slot + 1 < g->acc_slots);
+        if (g->acc_records && (g->acc_stream != st || !fits)) {
+          static const bool trace = getenv("LASV_B200_ACC_TRACE") != nullptr;
+          if (trace)
+            fprintf(stderr, "[acc] flush: booked %llu slot %u/%u booked-in-slot %llu slot-records %llu bytes %llu+%llu limit %llu fill %.3f\n",
+                    (unsigned long long)booked, g->acc_slot, g->acc_slots, (unsigned long long)g->acc_slot_booked,
+                    (unsigned long long)g->acc_slot_records, (unsigned long long)g->acc_bytes, (unsigned long long)n_bytes,
+                    (unsigned long long)g->acc_limit, g->acc_fill);
           if (int e = flush_accumulated(g, g->acc_stream)) return e;
+        }
+        const bool resize = !g->acc_records && stale;
         if (!g->acc_records) {
           if (g->acc_stream != st && g->acc_stream_used) {  // the insert just queued there reads the stripes
             CUDA_TRY(cudaEventRecord(l.inserted, g->acc_stream));
             CUDA_TRY(cudaStreamWaitEvent(st, l.inserted, 0));
           }
-          if (!g->acc_cap_records || bound > g->acc_cap_records) {
+          if (!g->acc_cap_records || !g->acc_slots || resize || booked > g->acc_slot_records) {
             // as many records as `acc_limit` stream bytes of batches like this one hold, if they fit in memory
-            const double ratio = (double)bound / (double)n_bytes;
+            const double ratio = (double)booked / (double)n_bytes;
             const double want_d = (double)std::max(g->acc_limit, n_bytes) * ratio;
             const uint64_t want = want_d >= 1.8e19 ? ~0ull : (uint64_t)want_d + 1;
-            g->acc_cap_records = std::max(bound, accumulation_records(g, want));
+            const uint64_t fit = accumulation_records(g, ~0ull);  // what the memory holds
+            g->acc_cap_records = std::max(booked, std::min(want, fit));
+            // slots: one per batch like this one (a little more: batches cut at read boundaries differ by a read or
+            // two), at most 32 (smaller batches then share a slot); when memory is not the limit, the last slot may
+            // reach beyond what was asked for
+            g->acc_slot_records = std::max<uint64_t>(booked + booked / 100 + 1024, (g->acc_cap_records + 31) / 32);
+            // (a slot holds whole batches: count batches, not records, when memory is not the limit)
+            const uint64_t per_slot = std::max<uint64_t>(1, g->acc_slot_records / std::max<uint64_t>(booked, 1));
+            const uint64_t n_batches = (g->acc_cap_records + booked - 1) / std::max<uint64_t>(booked, 1);
+            const uint64_t n_sl = want <= fit ? (n_batches + per_slot - 1) / per_slot : g->acc_cap_records / g->acc_slot_records;
+            g->acc_slots = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(32, n_sl));
+            g->acc_fill_sized = g->acc_fill;
           }
-          if (int e = ensure_bins(g, l, g->acc_cap_records, n_bins)) return e;
+          if (int e = ensure_acc_bins(g, l, g->acc_slot_records, n_bins, g->acc_slots)) return e;
+        }
+        if (g->acc_slot_booked + booked > g->acc_slot_records) {  // (there is a next slot: `fits`)
+          g->acc_slot++;
+          g->acc_slot_booked = 0;
         }
         g->acc_stream = st;
         g->acc_stream_used = true;
       } else {
         if (int e = ensure_bins(g, l, bound, n_bins)) return e;
       }
-      p.bins = l.v;
+      p.bins = accumulate ? acc_slot_view(l.v, g->acc_slot) : l.v;
       p.ctas_per_sm = g->pipeline ? 2 : 0;  // pipelined: this kernel shares the SMs with the previous batch's insert
       {
         Span sp(g, LASV_T_PARTITION, st);
@@ -888,6 +994,7 @@ int lasv_graph_load_reads_device(lasv_graph *g, const uint8_t *d_seq, const uint
       if (accumulate) {
         g->acc_bytes += n_bytes;
         g->acc_records += booked;
+        g->acc_slot_booked += booked;
         g->acc_bound_sum += bound;
       } else if (!g->pipeline) {
         if (int e = insert_stripes(g, l.v, bound, 0, true, true, st)) return e;
@@ -1024,9 +1131,11 @@ int load_reads_host_impl(lasv_graph *g, const uint8_t *seq, const uint8_t *qual,
       if (!mine) return;
       if (g->acc_records) {  // error exit: drop what was binned but not inserted
         cudaStreamSynchronize(g->compute);
-        cudaMemset(g->leg[0].v.count, 0, (size_t)(g->leg[0].v.n_bins + 1) * COUNT_STRIDE * sizeof(unsigned int));
+        cudaMemset(g->leg[0].v.count, 0, view_counter_bytes(g->leg[0].v));
         g->acc_records = 0;
         g->acc_bytes = 0;
+        g->acc_slot = 0;
+        g->acc_slot_booked = 0;
       }
       g->acc_limit = 0;
       g->acc_cap_records = 0;

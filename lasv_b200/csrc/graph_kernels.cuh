@@ -66,6 +66,7 @@ struct BinView {
   // so that the partition kernel's stores ARE the exchange (NVLink stores for the remote owners).
   uint64_t *owner_recs[16];
   uint32_t direct;      // 1: use owner_recs
+  uint32_t src_used;    // consumer side: senders that can hold records (0: all 1 << src_shift of them) -- sizes the scratch
 };
 constexpr uint32_t STRIPE_RUN = 128;  // records; cap and spill_cap are multiples of it
 __host__ __device__ inline uint64_t owner_stride_records(const BinView &b) {

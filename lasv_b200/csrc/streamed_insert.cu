@@ -609,13 +609,14 @@ bool streamed_geometry(const TableView &t, const BinView &b, StreamedGeom *out) 
     const long v = e ? atol(e) : 0;
     return v > 0 ? (uint64_t)v : (uint64_t)(1u << 20);
   }();
+  const uint64_t n_src = b.src_used ? b.src_used : (1ull << b.src_shift);  // senders that can hold records
   while (rps < b.bins_per_src && (uint64_t)(2 * rps) * buckets_per_region <= slab_buckets &&
-         (((uint64_t)(2 * rps) << b.src_shift) * b.cap) < 0x7FFFFF00ull)
+         ((uint64_t)(2 * rps) * n_src * b.cap) < 0x7FFFFF00ull)
     rps <<= 1;
   g.regions_per_slab = rps;
   g.buckets_per_slab = (uint32_t)(rps * buckets_per_region);
   g.n_slabs = b.bins_per_src / rps;
-  g.slab_cap = ((uint64_t)rps << b.src_shift) * b.cap;
+  g.slab_cap = (uint64_t)rps * n_src * b.cap;
   g.fused = buckets_per_region <= SO_MAXB ? 1u : 0u;
   *out = g;
   return g.slab_cap < 0xFFFFFF00ull && (uint64_t)rps * buckets_per_region < 0xFFFFFF00ull;  // 32-bit offsets inside a slab
