@@ -1195,7 +1195,9 @@ def test_reference_cli_supernodes_beyond_the_walk_limit(tmp_path):
                                            str(meta["q_thresh"]), "--dump_binary", str(tmp_path / "out.ctx"),
                                            "--output_supernodes", str(tmp_path / "gpu.fa"), "--max_var_len", "50"],
                        cwd=tmp_path, capture_output=True, text=True, timeout=600)
-    assert p.returncode == 0, p.stderr[-2000:] + p.stdout[-2000:]
+    # (the reference's printer overruns its own arrays beyond the limit, see below: our binary, which runs that very
+    # code after the hand-over, may die in free() just like the all-CPU binary)
+    assert p.returncode <= 0, p.stderr[-2000:] + p.stdout[-2000:]
     assert "the reference's own printer takes over" in p.stdout and "contig length equals max length" in p.stdout
     q = subprocess.run([str(O.ref_binary(k))] + geo + ["--multicolour_bin", str(tmp_path / "out.ctx"), "--output_supernodes",
                                                        str(tmp_path / "ref.fa"), "--max_var_len", "50"],
@@ -1204,7 +1206,7 @@ def test_reference_cli_supernodes_beyond_the_walk_limit(tmp_path):
     # writes entry [max_length] (dB_graph_population.c:2739-2742 vs :864) -- with glibc the all-CPU binary prints
     # its pieces and then dies in free().  If it survives, the bytes must agree; either way it was the reference's
     # own code that produced them, not a silent GPU approximation.
-    if q.returncode == 0:
+    if q.returncode == 0 and p.returncode == 0:
         assert (tmp_path / "gpu.fa").read_bytes() == (tmp_path / "ref.fa").read_bytes()
     else:
         assert q.returncode < 0 and "contig length equals max length" in q.stdout
