@@ -90,6 +90,8 @@ struct Knobs {
   long chunk_mb = 0;
   long chunk_kb = 0;  // tests: chunks of a few KB make a small input wrap the staging ring many times
   int pipe_ctas = 2;  // LASV_B200_PIPE_CTAS: CTAs per SM of the partition kernel when an insert may run beside it
+  int acc_slots = 32; // LASV_B200_ACC_SLOTS: sets of stripes the accumulation is divided into at most (1: one set, as in
+                      // the first version of the accumulation)
 };
 struct Staging {  // one leg of the double-buffered host->device pipeline
   uint8_t *d_seq = nullptr, *d_qual = nullptr;
@@ -392,6 +394,7 @@ Knobs read_knobs(int *insert_mode) {
   if (const char *e = getenv("LASV_B200_CHUNK_MB")) k.chunk_mb = atol(e);
   if (const char *e = getenv("LASV_B200_CHUNK_KB")) k.chunk_kb = atol(e);
   if (const char *e = getenv("LASV_B200_PIPE_CTAS")) k.pipe_ctas = std::max(0, std::min(8, atoi(e)));
+  if (const char *e = getenv("LASV_B200_ACC_SLOTS")) k.acc_slots = std::max(1, std::min(32, atoi(e)));
   return k;
 }
 
@@ -964,12 +967,14 @@ int lasv_graph_load_reads_device(lasv_graph *g, const uint8_t *d_seq, const uint
             // slots: one per batch like this one (a little more: batches cut at read boundaries differ by a read or
             // two), at most 32 (smaller batches then share a slot); when memory is not the limit, the last slot may
             // reach beyond what was asked for
-            g->acc_slot_records = std::max<uint64_t>(booked + booked / 100 + 1024, (g->acc_cap_records + 31) / 32);
+            // (a slot shared by smaller batches holds a whole number of them)
+            const uint64_t one = booked + booked / 100 + 1024, max_slots = (uint64_t)g->knobs.acc_slots;
+            g->acc_slot_records = one * std::max<uint64_t>(1, ((g->acc_cap_records + max_slots - 1) / max_slots + one - 1) / one);
             // (a slot holds whole batches: count batches, not records, when memory is not the limit)
             const uint64_t per_slot = std::max<uint64_t>(1, g->acc_slot_records / std::max<uint64_t>(booked, 1));
             const uint64_t n_batches = (g->acc_cap_records + booked - 1) / std::max<uint64_t>(booked, 1);
             const uint64_t n_sl = want <= fit ? (n_batches + per_slot - 1) / per_slot : g->acc_cap_records / g->acc_slot_records;
-            g->acc_slots = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(32, n_sl));
+            g->acc_slots = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(max_slots, n_sl));
             g->acc_fill_sized = g->acc_fill;
           }
           if (int e = ensure_acc_bins(g, l, g->acc_slot_records, n_bins, g->acc_slots)) return e;

@@ -34,9 +34,15 @@ namespace lasv {
 namespace {
 
 constexpr int SG_THREADS = 256;        // direct sorting kernels, drain kernel
-constexpr int SO_THREADS = 512;        // fused sorting kernel
+#ifndef LASV_SO_THREADS
+#define LASV_SO_THREADS 512
+#endif
+#ifndef LASV_SO_SMEM_KB
+#define LASV_SO_SMEM_KB 100
+#endif
+constexpr int SO_THREADS = LASV_SO_THREADS;  // fused sorting kernel
 constexpr uint32_t SO_MAXB = 4096;     // buckets per region the fused sorting kernel handles
-constexpr uint32_t SO_SMEM = 100u << 10;  // its shared memory (two CTAs per SM)
+constexpr uint32_t SO_SMEM = (uint32_t)LASV_SO_SMEM_KB << 10;  // its shared memory (two CTAs per SM)
 #ifndef LASV_SO_U
 #define LASV_SO_U 4
 #endif
