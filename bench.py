@@ -46,6 +46,9 @@ ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
 METRIC = "kmers_inserted_per_s_k53"
+# order-independent fingerprint of the complete default cfg-4 graph (296 batches of 2^20 pairs): the same at N = 1, 2, 4, 8,
+# with the random-access insert of round 1 and with the streamed insert -- any run of the default job must reproduce it
+CFG4_FINGERPRINT = "b6385601b9dfaa1e"
 UNIT = "k-mers/s"
 
 
@@ -984,6 +987,9 @@ def main_job(args, w):
                     "exchange": getattr(graph, "exchange", None) if world > 1 else None,
                     "round_timeline_ms_rank0": timeline},
             "fingerprint": f"{summary['fingerprint']:016x}",
+            "fingerprint_expected": (CFG4_FINGERPRINT if args.fraction == 1.0 and args.pairs_per_batch == 1 << 20 else None),
+            "fingerprint_ok": ((f"{summary['fingerprint']:016x}" == CFG4_FINGERPRINT)
+                               if args.fraction == 1.0 and args.pairs_per_batch == 1 << 20 else None),
             "parity": (("ok" if all(x["status"] == "ok" for x in (parity, parity_full) if x) else "FAILED")
                        if (parity or parity_full) else None),
             "parity_detail": parity, "parity_full_geometry": parity_full,
