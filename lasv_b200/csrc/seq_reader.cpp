@@ -1,9 +1,133 @@
 // seq_reader.cpp -- see seq_reader.h
 #include "seq_reader.h"
+#include <fcntl.h>
+#include <stdlib.h>
 #include <string.h>
 #include <strings.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <atomic>
+#include <thread>
 
 namespace lasv {
+
+// ------------------------------------------------------------------ BGZF
+namespace {
+struct BgzfBlock {
+  size_t cdata;      // offset of the deflate stream in the file
+  uint32_t clen;     // its length
+  uint32_t isize;    // bytes it inflates to
+  uint32_t crc;
+  size_t out;        // offset in the window
+};
+
+// Header of the BGZF block at d[0..n): its total size, or 0 if this is not a BGZF block (SAM spec 4.1: gzip member
+// with FLG.FEXTRA and a 'B','C' subfield of 2 bytes holding the block size minus one).
+size_t bgzf_block_size(const unsigned char *d, size_t n, size_t *cdata_off) {
+  if (n < 18 || d[0] != 0x1f || d[1] != 0x8b || d[2] != 8 || !(d[3] & 4)) return 0;
+  const size_t xlen = (size_t)d[10] | ((size_t)d[11] << 8);
+  if (12 + xlen > n) return 0;
+  size_t bsize = 0;
+  for (size_t p = 12; p + 4 <= 12 + xlen;) {
+    const size_t slen = (size_t)d[p + 2] | ((size_t)d[p + 3] << 8);
+    if (d[p] == 'B' && d[p + 1] == 'C' && slen == 2 && p + 6 <= 12 + xlen) bsize = ((size_t)d[p + 4] | ((size_t)d[p + 5] << 8)) + 1;
+    p += 4 + slen;
+  }
+  if (!bsize || bsize > n || bsize < 12 + xlen + 8) return 0;
+  // FNAME / FCOMMENT / FHCRC are not used by BGZF writers; a member that has them is left to zlib
+  if (d[3] & ~4) return 0;
+  *cdata_off = 12 + xlen;
+  return bsize;
+}
+}  // namespace
+
+BgzfStream::~BgzfStream() {
+  if (data_) munmap((void *)data_, size_);
+  if (fd_ >= 0) ::close(fd_);
+}
+
+bool BgzfStream::open(const char *path, int threads) {
+  fd_ = ::open(path, O_RDONLY);
+  if (fd_ < 0) return false;
+  struct stat st;
+  if (fstat(fd_, &st) != 0 || st.st_size < 28) { ::close(fd_); fd_ = -1; return false; }
+  void *p = mmap(nullptr, (size_t)st.st_size, PROT_READ, MAP_PRIVATE, fd_, 0);
+  if (p == MAP_FAILED) { ::close(fd_); fd_ = -1; return false; }
+  data_ = (const unsigned char *)p;
+  size_ = (size_t)st.st_size;
+  size_t off = 0;
+  if (!bgzf_block_size(data_, size_, &off)) {
+    munmap(p, size_);
+    data_ = nullptr;
+    ::close(fd_);
+    fd_ = -1;
+    return false;
+  }
+  madvise(p, size_, MADV_SEQUENTIAL);
+  threads_ = threads < 1 ? 1 : threads;
+  pos_ = 0;
+  return true;
+}
+
+bool BgzfStream::next(std::vector<unsigned char> &out, std::string &err) {
+  constexpr size_t WINDOW = 8u << 20;
+  std::vector<BgzfBlock> blocks;
+  size_t total = 0;
+  while (pos_ < size_ && total < WINDOW) {
+    size_t off = 0;
+    const size_t bs = bgzf_block_size(data_ + pos_, size_ - pos_, &off);
+    if (!bs) {
+      err = "not a BGZF block where one should start (truncated or mixed gzip file)";
+      return false;
+    }
+    const unsigned char *t = data_ + pos_ + bs - 8;
+    BgzfBlock b;
+    b.cdata = pos_ + off;
+    b.clen = (uint32_t)(bs - off - 8);
+    b.crc = (uint32_t)t[0] | ((uint32_t)t[1] << 8) | ((uint32_t)t[2] << 16) | ((uint32_t)t[3] << 24);
+    b.isize = (uint32_t)t[4] | ((uint32_t)t[5] << 8) | ((uint32_t)t[6] << 16) | ((uint32_t)t[7] << 24);
+    b.out = total;
+    total += b.isize;
+    pos_ += bs;
+    if (b.isize) blocks.push_back(b);  // (the empty block that ends a BGZF file)
+  }
+  if (blocks.empty()) return false;
+  out.resize(total);
+  std::atomic<size_t> next_block{0};
+  std::atomic<int> failed{0};
+  auto work = [&]() {
+    z_stream z;
+    memset(&z, 0, sizeof z);
+    if (inflateInit2(&z, -15) != Z_OK) { failed = 1; return; }
+    for (;;) {
+      const size_t i = next_block.fetch_add(1);
+      if (i >= blocks.size() || failed) break;
+      const BgzfBlock &b = blocks[i];
+      inflateReset(&z);
+      z.next_in = const_cast<unsigned char *>(data_ + b.cdata);
+      z.avail_in = b.clen;
+      z.next_out = out.data() + b.out;
+      z.avail_out = b.isize;
+      const int rc = inflate(&z, Z_FINISH);
+      if (rc != Z_STREAM_END || z.avail_out != 0 ||
+          (uint32_t)crc32(crc32(0L, Z_NULL, 0), out.data() + b.out, b.isize) != b.crc)
+        failed = 1;
+    }
+    inflateEnd(&z);
+  };
+  const int n_thr = (int)std::min<size_t>((size_t)threads_, blocks.size());
+  std::vector<std::thread> pool;
+  for (int t = 1; t < n_thr; t++) pool.emplace_back(work);
+  work();
+  for (auto &t : pool) t.join();
+  if (failed) {
+    err = "corrupt BGZF block (inflate or CRC error)";
+    return false;
+  }
+  return true;
+}
 
 static bool path_has_ext(const std::string &p, const char *ext) {
   const size_t n = strlen(ext);
@@ -22,7 +146,13 @@ bool SeqReader::open(const std::string &path, std::string &err) {
     err = "SAM/BAM input is not supported by the GPU loader: " + path;
     return false;
   }
-  gz_ = gzopen(path.c_str(), "r");
+  {
+    int thr = 4;
+    if (const char *e = getenv("LASV_B200_GZ_THREADS")) thr = atoi(e);
+    std::unique_ptr<BgzfStream> b(new BgzfStream());
+    if (thr > 0 && b->open(path.c_str(), thr)) bgzf_ = std::move(b);
+  }
+  gz_ = gzopen(path.c_str(), "r");  // (kept open in BGZF mode too: the reader's "is open" handle)
   if (!gz_) {
     err = "Couldn't open sequence file '" + path + "'";
     return false;
@@ -67,6 +197,7 @@ void SeqReader::open_memory(const unsigned char *data, size_t n, const std::stri
 void SeqReader::close() {
   if (gz_) gzclose(gz_);
   gz_ = nullptr;
+  bgzf_.reset();
   type_ = UNKNOWN;
   memory_ = false;
 }
@@ -77,6 +208,19 @@ bool SeqReader::fill_() {
     eof_ = true;
     pos_ = end_ = 0;
     return false;
+  }
+  if (bgzf_) {  // the next window of blocks, inflated by several threads
+    std::string err;
+    if (!bgzf_->next(own_, err)) {
+      if (!err.empty()) io_error_ = err + " [file: " + path_ + "]";
+      eof_ = true;
+      pos_ = end_ = 0;
+      return false;
+    }
+    buf_ = own_.data();
+    pos_ = 0;
+    end_ = own_.size();
+    return true;
   }
   const int n = gzread(gz_, own_.data(), (unsigned)own_.size());
   if (n <= 0) {
@@ -121,6 +265,12 @@ void SeqReader::read_line_(std::string *dst) {
 }
 
 bool SeqReader::next(std::string &err) {
+  const bool ok = next_record_(err);
+  if (!ok && err.empty() && !io_error_.empty()) err = io_error_;  // the compressed stream broke off: not a clean end of file
+  return ok;
+}
+
+bool SeqReader::next_record_(std::string &err) {
   seq_.clear();
   qual_.clear();
   if (!gz_ && !memory_) return false;

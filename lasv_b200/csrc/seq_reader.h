@@ -8,11 +8,33 @@
 // kernel consumes -- instead of being handed out base by base.
 #pragma once
 #include <stdint.h>
+#include <memory>
 #include <string>
 #include <vector>
 #include <zlib.h>
 
 namespace lasv {
+
+// Block-parallel inflate of BGZF files (the blocked gzip of bgzip / htslib that sequencing pipelines write:
+// a series of gzip members of <= 64 KB, each carrying its own compressed size in a 'BC' extra field, so the members
+// can be found without inflating anything).  The reference reads compressed input one byte at a time through
+// gzgetc (libs/seq_file/seq_common.h:102-103, seq_file.c:170); ordinary single-stream gzip cannot be split and
+// stays with zlib's gzread, one stream per file and thread.
+class BgzfStream {
+ public:
+  ~BgzfStream();
+  // maps the file; false (and nothing kept open) unless it starts with a BGZF block
+  bool open(const char *path, int threads);
+  // inflates the next window of blocks (about 8 MB of text) into `out`; false at the end of the file or on error
+  // (then err is set)
+  bool next(std::vector<unsigned char> &out, std::string &err);
+
+ private:
+  int fd_ = -1;
+  const unsigned char *data_ = nullptr;
+  size_t size_ = 0, pos_ = 0;
+  int threads_ = 1;
+};
 
 // Pinned (or plain) host buffers for one batch of reads.
 struct HostBatch {
@@ -38,7 +60,7 @@ class SeqReader {
   // starts at a record header): the parallel loader gives every parser thread its own slice.
   void open_memory(const unsigned char *data, size_t n, const std::string &path);
   // True if the file is stored uncompressed (gzopen reads it transparently either way).
-  bool is_plain_file() const { return gz_ && gzdirect(gz_) == 1; }
+  bool is_plain_file() const { return !bgzf_ && gz_ && gzdirect(gz_) == 1; }
   void close();
   bool has_quality() const { return type_ == FASTQ; }
   Type type() const { return type_; }
@@ -61,12 +83,14 @@ class SeqReader {
   bool append_to(HostBatch &b, bool with_qual) const;
 
  private:
+  bool next_record_(std::string &err);
   int getc_();
   int peekc_();
   bool fill_();
   void read_line_(std::string *dst);  // rest of the current line, chomped; dst may be null
 
   gzFile gz_ = nullptr;
+  std::unique_ptr<BgzfStream> bgzf_;    // BGZF input: windows of blocks inflated by several threads
   std::string path_;
   Type type_ = UNKNOWN;
   std::vector<unsigned char> own_;      // gz mode: the refill buffer
@@ -74,6 +98,7 @@ class SeqReader {
   bool memory_ = false;
   size_t pos_ = 0, end_ = 0;
   bool eof_ = false;
+  std::string io_error_;                // a read error of the compressed stream (reported by next())
   bool at_record_start_ = false;  // header marker already consumed (seq_file.c: read_line_start)
   std::string seq_, qual_;
   uint64_t n_reads_ = 0;

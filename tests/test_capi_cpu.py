@@ -261,3 +261,54 @@ def test_parallel_fastq_parse_equals_sequential(tmp_path):
         one, u1 = _parse_check(util.GOLDEN / f, None, 1)
         four, u4 = _parse_check(util.GOLDEN / f, None, 4)
         assert one == four and u1 == u4 == 1
+
+
+def _bgzf(data: bytes, block: int = 65280, eof_marker: bool = True) -> bytes:
+    """BGZF (SAM spec 4.1): gzip members of <= 64 KB with a 'BC' extra field holding the member's size - 1."""
+    import struct
+    import zlib
+    out = bytearray()
+    for i in list(range(0, len(data), block)) + ([None] if eof_marker else []):
+        chunk = b"" if i is None else data[i: i + block]
+        co = zlib.compressobj(6, zlib.DEFLATED, -15)
+        c = co.compress(chunk) + co.flush()
+        out += (b"\x1f\x8b\x08\x04\x00\x00\x00\x00\x00\xff\x06\x00BC\x02\x00" + struct.pack("<H", len(c) + 25) + c +
+                struct.pack("<II", zlib.crc32(chunk) & 0xFFFFFFFF, len(chunk)))
+    return bytes(out)
+
+
+def test_bgzf_input_is_inflated_block_parallel(tmp_path, monkeypatch):
+    """Blocked gzip (bgzip / htslib) is inflated a window of blocks at a time by several threads (seq_reader.cpp:
+    BgzfStream); ordinary gzip keeps zlib's single stream.  Same reads, bases and checksum as the plain file for any
+    number of threads, for odd block sizes, and through zlib (LASV_B200_GZ_THREADS=0); a corrupt or truncated block is
+    an error, never a short file."""
+    rng = np.random.default_rng(5)
+    n = 40_000
+    lens = rng.integers(1, 200, n)
+    with open(tmp_path / "a.fq", "w") as fa:
+        for i, ln in enumerate(lens):
+            s = "".join(rng.choice(list("ACGTN"), ln))
+            q = "".join(rng.choice(list("@+IIIIIIFF#5&'"), ln))
+            fa.write(f"@r{i}\n{s}\n+\n{q}\n")
+    text = (tmp_path / "a.fq").read_bytes()
+    ref, _ = _parse_check(tmp_path / "a.fq", None, 1)
+    assert ref[0] == n
+    (tmp_path / "a.fq.gz").write_bytes(_bgzf(text))
+    (tmp_path / "odd.fq.gz").write_bytes(_bgzf(text, block=7919, eof_marker=False))
+    for thr in ("8", "3", "1", "0"):
+        monkeypatch.setenv("LASV_B200_GZ_THREADS", thr)
+        for f in ("a.fq.gz", "odd.fq.gz"):
+            got, used = _parse_check(tmp_path / f, None, 4)
+            assert used == 1 and got == ref, (thr, f, got, ref)
+    monkeypatch.setenv("LASV_B200_GZ_THREADS", "4")
+    import ctypes as C
+    lib = _capi.lib()
+    blob = bytearray(_bgzf(text))
+    blob[len(blob) // 2] ^= 0x55                                  # a flipped byte in the middle of a block
+    (tmp_path / "bad.fq.gz").write_bytes(bytes(blob))
+    out = (C.c_uint64 * 4)()
+    used = C.c_int(0)
+    assert lib.lasv_seqfile_parse_check(str(tmp_path / "bad.fq.gz").encode(), None, 1, 1 << 20, out, C.byref(used)) < 0
+    assert b"BGZF" in lib.lasv_last_error()
+    (tmp_path / "cut.fq.gz").write_bytes(_bgzf(text)[: len(blob) // 2])   # the file ends inside a block
+    assert lib.lasv_seqfile_parse_check(str(tmp_path / "cut.fq.gz").encode(), None, 1, 1 << 20, out, C.byref(used)) < 0
