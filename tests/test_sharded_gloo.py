@@ -177,21 +177,30 @@ def _stripe_worker(rank, world, port, name, outdir):
     send = torch.zeros((world, per_owner, rw), dtype=torch.int32)
     send_counts = torch.zeros((world, B + 1, cstride), dtype=torch.int32)
     region_shift = L - bits - 2                        # B = 4 regions per owner
-    for i in range(n):
-        key = np.zeros(N, dtype=np.uint64)
-        for w in range(N):
-            key[w] = np.uint64(recs[i, 2 * w]) | (np.uint64(recs[i, 2 * w + 1]) << np.uint64(32))
-        c = emul.emul_hash_c(key.ctypes.data, N, 0) & ((1 << L) - 1)
-        owner, region = c >> (L - bits), (c >> region_shift) & (B - 1)
-        idx = int(send_counts[owner, region, 0])
-        send_counts[owner, region, 0] += 1
-        if idx < cap:
-            send[owner, region * cap + idx] = torch.from_numpy(recs[i].view(np.int32).copy())
-        else:
-            si = int(send_counts[owner, B, 0])
-            send_counts[owner, B, 0] += 1
-            assert si < spill
-            send[owner, B * cap + si] = torch.from_numpy(recs[i].view(np.int32).copy())
+    # two batches, the second APPENDED to the stripes of the first (ShardedDBGraph(accumulate_batches=2):
+    # lasv_graph_bin_reads_append_device keeps the counters), then ONE exchange and one insert per owner
+    batches = [range(0, n // 2), range(n // 2, n)]
+    counts_after_first = None
+    for bi, batch in enumerate(batches):
+      if bi == 1:
+        counts_after_first = send_counts.clone()
+      for i in batch:
+          key = np.zeros(N, dtype=np.uint64)
+          for w in range(N):
+              key[w] = np.uint64(recs[i, 2 * w]) | (np.uint64(recs[i, 2 * w + 1]) << np.uint64(32))
+          c = emul.emul_hash_c(key.ctypes.data, N, 0) & ((1 << L) - 1)
+          owner, region = c >> (L - bits), (c >> region_shift) & (B - 1)
+          idx = int(send_counts[owner, region, 0])
+          send_counts[owner, region, 0] += 1
+          if idx < cap:
+              send[owner, region * cap + idx] = torch.from_numpy(recs[i].view(np.int32).copy())
+          else:
+              si = int(send_counts[owner, B, 0])
+              send_counts[owner, B, 0] += 1
+              assert si < spill
+              send[owner, B * cap + si] = torch.from_numpy(recs[i].view(np.int32).copy())
+    # (every record asks its stripe's counter for a place; the ones that found it full also ask the spill counter)
+    assert counts_after_first is not None and int((send_counts - counts_after_first)[:, :B, 0].sum()) == n - n // 2
     recv, recv_counts = torch.zeros_like(send), torch.zeros_like(send_counts)
     exchange_stripes(send, recv, None)
     exchange_stripes(send_counts, recv_counts, None)
