@@ -2668,6 +2668,10 @@ struct FileProducer {
   // pinned batches, the device takes them apart (fastq_parse.cu); `reads` is then counted by the consumer
   const unsigned char *raw_data = nullptr;
   size_t raw_size = 0;
+  // raw mode on a BGZF file: windows of inflated text (seq_reader.cpp: BgzfStream, several inflate threads), cut at
+  // the last record boundary; the tail is carried into the next batch
+  bool raw_bgzf = false;
+  std::vector<unsigned char> raw_carry;
 
   // end of the longest run of whole records in raw_data[pos, ...) that fits `cap` bytes; 0 if none is found
   size_t raw_cut(size_t pos, size_t cap) const {
@@ -2681,6 +2685,10 @@ struct FileProducer {
     int k = 0;
     bool have = false;  // a parsed read waits for room
     size_t raw_pos = 0;
+    if (raw_bgzf) {
+      if (slot[0]->cap_bytes < (20u << 20)) raw_bgzf = false;  // small batches (tests): the reader parses on the host
+      else reader.bgzf()->rewind();                            // (open() had a look at the first window)
+    }
     for (;;) {
       {
         std::unique_lock<std::mutex> lk(m);
@@ -2689,6 +2697,53 @@ struct FileProducer {
       HostBatch &b = *slot[k];
       b.reset();
       bool eof = false;
+      if (raw_bgzf) {
+        const size_t cap = (size_t)std::min<uint64_t>(b.cap_bytes - 1, (32ull << 20) - 1);
+        // text = carry + windows, up to the batch's capacity (a window is ~8 MB)
+        size_t n = raw_carry.size();
+        bool more = true;
+        if (n) memcpy(b.seq, raw_carry.data(), n);
+        raw_carry.clear();
+        std::string berr;
+        while (more && n + (9u << 20) <= cap) {  // (inflated straight into the pinned batch)
+          size_t got = 0;
+          more = reader.bgzf()->next_into(b.seq + n, cap - n, &got, berr);
+          if (!more) break;
+          n += got;
+        }
+        if (!berr.empty()) {
+          err = berr + " [file: " + reader.path() + "]";
+          eof = true;
+          more = false;
+          n = 0;
+        }
+        size_t end = n;
+        if (more && n) {  // not the end of the file: cut at a record boundary within the last 64 KB
+          const size_t back = std::min<size_t>(n / 2, 1u << 16);
+          const size_t c = find_fastq_record(b.seq, n, n - back);
+          end = (c == SIZE_MAX || c == 0 || c > n) ? 0 : c;
+        }
+        if (n && !end) {
+          // no record boundary where one should be (multi-line records ...): the host parser takes over from here
+          raw_bgzf = false;
+          reader.seed(std::vector<unsigned char>(b.seq, b.seq + n));
+        } else {
+          if (end < n) raw_carry.assign(b.seq + end, b.seq + n);
+          b.n_bytes = end;
+          if (end && b.seq[end - 1] != '\n') b.seq[b.n_bytes++] = '\n';  // the file's last line
+          b.raw = true;
+          if (!more) eof = true;
+          {
+            std::lock_guard<std::mutex> lk(m);
+            if (b.n_bytes) full[k] = 1;
+            if (eof) done = true;
+          }
+          cv.notify_all();
+          if (eof) return;
+          if (b.n_bytes) k ^= 1;
+          continue;
+        }
+      }
       if (raw_data) {
         const size_t cap = (size_t)std::min<uint64_t>(b.cap_bytes - 1, (32ull << 20) - 1);
         const size_t end = raw_cut(raw_pos, cap);
@@ -2854,6 +2909,11 @@ struct ParseJob {
           }
         } else {
           prod.emplace_back(std::move(heads[f]));
+          const char *dp = getenv("LASV_B200_DEVICE_PARSE");
+          FileProducer &hp = *prod.back();
+          if (raw_slices && (!dp || atoi(dp) != 0) && with_qual && hp.reader.type() == SeqReader::FASTQ && hp.reader.bgzf()) {
+            hp.raw_bgzf = true;  // (decided for good when the thread starts: the batches must hold a window)
+          }
         }
         for (size_t i = first; i < prod.size(); i++) {
           file_of.push_back((int)(2 * e) + f);

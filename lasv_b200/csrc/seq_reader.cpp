@@ -8,6 +8,7 @@
 #include <sys/stat.h>
 #include <unistd.h>
 
+#include <algorithm>
 #include <atomic>
 #include <thread>
 
@@ -71,7 +72,7 @@ bool BgzfStream::open(const char *path, int threads) {
   return true;
 }
 
-bool BgzfStream::next(std::vector<unsigned char> &out, std::string &err) {
+bool BgzfStream::next_impl(std::vector<unsigned char> *outv, unsigned char *dst, size_t dst_cap, size_t *n_out, std::string &err) {
   constexpr size_t WINDOW = 8u << 20;
   std::vector<BgzfBlock> blocks;
   size_t total = 0;
@@ -94,7 +95,14 @@ bool BgzfStream::next(std::vector<unsigned char> &out, std::string &err) {
     if (b.isize) blocks.push_back(b);  // (the empty block that ends a BGZF file)
   }
   if (blocks.empty()) return false;
-  out.resize(total);
+  if (outv) {
+    outv->resize(total);
+    dst = outv->data();
+  } else if (total > dst_cap) {
+    err = "a window of BGZF blocks does not fit the caller's buffer";
+    return false;
+  }
+  if (n_out) *n_out = total;
   std::atomic<size_t> next_block{0};
   std::atomic<int> failed{0};
   auto work = [&]() {
@@ -108,11 +116,11 @@ bool BgzfStream::next(std::vector<unsigned char> &out, std::string &err) {
       inflateReset(&z);
       z.next_in = const_cast<unsigned char *>(data_ + b.cdata);
       z.avail_in = b.clen;
-      z.next_out = out.data() + b.out;
+      z.next_out = dst + b.out;
       z.avail_out = b.isize;
       const int rc = inflate(&z, Z_FINISH);
       if (rc != Z_STREAM_END || z.avail_out != 0 ||
-          (uint32_t)crc32(crc32(0L, Z_NULL, 0), out.data() + b.out, b.isize) != b.crc)
+          (uint32_t)crc32(crc32(0L, Z_NULL, 0), dst + b.out, b.isize) != b.crc)
         failed = 1;
     }
     inflateEnd(&z);
@@ -147,7 +155,8 @@ bool SeqReader::open(const std::string &path, std::string &err) {
     return false;
   }
   {
-    int thr = 4;
+    const unsigned hw = std::thread::hardware_concurrency();
+    int thr = (int)std::min(8u, std::max(2u, hw / 2));  // inflate threads of a BGZF file
     if (const char *e = getenv("LASV_B200_GZ_THREADS")) thr = atoi(e);
     std::unique_ptr<BgzfStream> b(new BgzfStream());
     if (thr > 0 && b->open(path.c_str(), thr)) bgzf_ = std::move(b);
@@ -192,6 +201,16 @@ void SeqReader::open_memory(const unsigned char *data, size_t n, const std::stri
   n_reads_ = 0;
   type_ = FASTQ;
   at_record_start_ = false;  // the slice begins AT the '@' of a record header
+}
+
+void SeqReader::seed(std::vector<unsigned char> &&text) {
+  own_ = std::move(text);
+  buf_ = own_.data();
+  memory_ = false;
+  pos_ = 0;
+  end_ = own_.size();
+  eof_ = false;
+  at_record_start_ = false;  // the text begins AT the '@' of a record header
 }
 
 void SeqReader::close() {

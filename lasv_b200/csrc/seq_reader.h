@@ -27,9 +27,13 @@ class BgzfStream {
   bool open(const char *path, int threads);
   // inflates the next window of blocks (about 8 MB of text) into `out`; false at the end of the file or on error
   // (then err is set)
-  bool next(std::vector<unsigned char> &out, std::string &err);
+  bool next(std::vector<unsigned char> &out, std::string &err) { return next_impl(&out, nullptr, 0, nullptr, err); }
+  // the same straight into the caller's buffer (dst_cap >= 8 MB + 64 KB): *n receives the bytes written
+  bool next_into(unsigned char *dst, size_t dst_cap, size_t *n, std::string &err) { return next_impl(nullptr, dst, dst_cap, n, err); }
+  void rewind() { pos_ = 0; }
 
  private:
+  bool next_impl(std::vector<unsigned char> *out, unsigned char *dst, size_t dst_cap, size_t *n, std::string &err);
   int fd_ = -1;
   const unsigned char *data_ = nullptr;
   size_t size_ = 0, pos_ = 0;
@@ -61,6 +65,10 @@ class SeqReader {
   void open_memory(const unsigned char *data, size_t n, const std::string &path);
   // True if the file is stored uncompressed (gzopen reads it transparently either way).
   bool is_plain_file() const { return !bgzf_ && gz_ && gzdirect(gz_) == 1; }
+  // BGZF input: the block stream (the loader pulls whole windows of text from it for the device parse), and the way
+  // back: continue parsing on the host from `text` (starts at a record header) followed by the stream's next windows
+  BgzfStream *bgzf() { return bgzf_.get(); }
+  void seed(std::vector<unsigned char> &&text);
   void close();
   bool has_quality() const { return type_ == FASTQ; }
   Type type() const { return type_; }

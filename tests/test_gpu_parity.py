@@ -149,6 +149,37 @@ def test_file_loaders_parse_fastq_text_on_the_device(batch_bytes, spoil, tmp_pat
     assert results["1"][1] > results["0"][1]                     # the parse kernels ran
 
 
+def test_bgzf_fastq_goes_to_the_device_parse(tmp_path, monkeypatch):
+    """BGZF-compressed FASTQ: several threads inflate windows of blocks (BgzfStream), the text goes to the device parse
+    like the slices of plain files (cut at the last record boundary of a window, the tail carried over).  Same graph and
+    statistics as the uncompressed files; a multi-line record hands the rest of that file to the host parser."""
+    from tests.test_capi_cpu import _bgzf
+    name = "synth_cfg0_k53"
+    meta = util.case_meta(name)
+    seq, qual, _ = util.case_streams(name)
+    rl = meta["workload"]["read_len"]
+    s2, q2 = seq.reshape(-1, rl + 1), qual.reshape(-1, rl + 1)
+    reps = 260                                                   # 22 MB of text per file: three windows
+    gold = util.case_records(name).copy()
+    gold["covg"] *= reps
+    for f, sel in (("a", slice(0, None, 2)), ("b", slice(1, None, 2))):
+        O.write_fastq_fixed(tmp_path / "one.fq", s2[sel].reshape(-1), q2[sel].reshape(-1), rl)
+        one = (tmp_path / "one.fq").read_bytes()
+        (tmp_path / f"{f}.fq.gz").write_bytes(_bgzf(one * reps))
+        if f == "a":                                             # the same reads with one record wrapped, late in the file
+            lines = one.split(b"\n")
+            i = 4 * 100
+            lines[i + 1: i + 2] = [lines[i + 1][:30], lines[i + 1][30:]]
+            lines[i + 3: i + 4] = [lines[i + 3][:70], lines[i + 3][70:]]
+            (tmp_path / "w.fq.gz").write_bytes(_bgzf(one * 200 + b"\n".join(lines) + one * (reps - 201)))
+    for first in ("a.fq.gz", "w.fq.gz"):
+        with DBGraph(meta["k"], meta["L"], meta["W"]) as g:
+            st = g.load_pe_seq_data(tmp_path / first, tmp_path / "b.fq.gz", util.cutoff_of(meta))
+            assert st["n_reads"] == reps * len(s2) and st["kmers_inserted"] == reps * meta["inserts"]
+            assert st["bad_reads"] == reps * meta["bad_reads"] and st["bases_loaded"] == reps * meta["bases_loaded"]
+            util.assert_same_records(g.records(), gold, first)
+
+
 def _merge_records(*arrays):
     acc = {}
     for a in arrays:
