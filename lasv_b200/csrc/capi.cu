@@ -230,6 +230,7 @@ int use_hot(lasv_graph *g) {
   return LASV_OK;
 }
 int flush_accumulated(lasv_graph *g, cudaStream_t st);
+int queue_fill_probe(lasv_graph *g, cudaStream_t st);
 void poll_fill_probe(lasv_graph *g);
 int load_raw_fastq_host(lasv_graph *g, const uint8_t *text, uint64_t n_bytes, int quality_cutoff, uint64_t *n_reads_out);
 int bin_reads_impl(lasv_graph *g, const uint8_t *d_seq, const uint8_t *d_qual, uint64_t n_bytes, int quality_cutoff,
@@ -398,7 +399,9 @@ Knobs read_knobs(int *insert_mode) {
   return k;
 }
 
-uint32_t region_count(const lasv_graph *g) {
+// dense: the stripes are meant for the streamed insert (about a record or more per table line); a sparse batch goes
+// through the random-access insert, which sweeps the stripes one by one and pays for every stripe it looks at.
+uint32_t region_count(const lasv_graph *g, bool dense = true) {
   uint32_t n_bins = 1;
   // regions of <= 64 MB: the random-access insert doubles its rate once the region all SMs work on at a time is
   // ~100 MB or less and is flat below that (profiles/: bins sweep), while fewer bins keep the scatter's open
@@ -407,7 +410,7 @@ uint32_t region_count(const lasv_graph *g) {
   // ... and of <= 256 buckets on large tables: the sorting passes of the streamed insert rank a chunk of one
   // region's records by bucket in shared memory, and their output runs are chunk / buckets-per-region records long
   // (the partition kernel costs the same from 2 K to 16 K stripes, +11 % at 64 K: profiles/r2)
-  if (g->table_bytes >= (256ull << 20))
+  if (dense && g->table_bytes >= (256ull << 20))
     while ((uint64_t)n_bins * 256u < g->n_buckets && n_bins < 65536u) n_bins <<= 1;
   const long v = g->knobs.bins;  // tests: force a bin count on small tables
   if (v >= 1 && v <= 65536 && (v & (v - 1)) == 0 && (uint64_t)v <= g->n_buckets) n_bins = (uint32_t)v;
@@ -416,8 +419,8 @@ uint32_t region_count(const lasv_graph *g) {
 
 // Partitioned insert applies when the table is much larger than L2 and the batch
 // puts a useful number of records into every region.
-bool want_binned(const lasv_graph *g, uint64_t n_bytes, uint32_t *n_bins_out) {
-  const uint32_t n_bins = region_count(g);
+bool want_binned(const lasv_graph *g, uint64_t n_bytes, uint32_t *n_bins_out, bool dense = true) {
+  const uint32_t n_bins = region_count(g, dense);
   *n_bins_out = n_bins;
   bool binned = g->table_bytes >= (256ull << 20) && n_bytes >= (uint64_t)n_bins * 256u;
   if (g->knobs.insert == 1) binned = false;
@@ -704,9 +707,9 @@ int lasv_graph_clear(lasv_graph *g, void *cuda_stream) {
     g->acc_slot = 0;
     g->acc_slot_booked = 0;
   }
-  if (g->probe_pending) {  // a probe of the counters that were just reset: let it land, then forget it
+  if (g->probe_pending) {  // a probe of the counters that are being reset: let it land and use it (the read set may go on)
     CUDA_TRY(cudaEventSynchronize(g->probe_ev));
-    g->probe_pending = false;
+    poll_fill_probe(g);
   }
   g->probe_prev_kmers = 0;
   g->acc_bound_sum = 0;
@@ -871,15 +874,21 @@ int flush_accumulated(lasv_graph *g, cudaStream_t st) {
   g->acc_bytes = 0;
   g->acc_slot = 0;
   g->acc_slot_booked = 0;
+  if (int e = queue_fill_probe(g, st)) return e;
+  return insert_stripes(g, g->leg[0].v, n, 0, true, true, st);
+}
+
+// Queue a read-back of the k-mer counter as it stands behind the partition launches since the last probe (the
+// counter is kept by the partition kernel, not by the insert): k-mers / bound of those launches is the fill estimate.
+int queue_fill_probe(lasv_graph *g, cudaStream_t st) {
   if (g->h_probe && g->probe_ev && !g->probe_pending && g->acc_bound_sum) {
-    // the k-mer counter as it stands behind this accumulation's partition launches (counted there, not at the insert)
     CUDA_TRY(cudaMemcpyAsync(g->h_probe, &g->d_ctr->kmers_inserted, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaEventRecord(g->probe_ev, st));
     g->probe_bound = g->acc_bound_sum;
     g->probe_pending = true;
+    g->acc_bound_sum = 0;
   }
-  g->acc_bound_sum = 0;
-  return insert_stripes(g, g->leg[0].v, n, 0, true, true, st);
+  return LASV_OK;
 }
 
 // a finished probe updates the fill estimate (never waits)
@@ -925,17 +934,22 @@ int lasv_graph_load_reads_device(lasv_graph *g, const uint8_t *d_seq, const uint
     BuildParams p = build_params(g, d_seq, d_qual, n_bytes, quality_cutoff);
     uint32_t n_bins = 1;
     const bool accumulate = g->acc_limit != 0 && !g->pipeline;
-    if (want_binned(g, accumulate ? std::max(g->acc_limit, n_bytes) : n_bytes, &n_bins)) {
+    // what the batch is expected to put into the stripes: its bound times the fill earlier batches showed (a
+    // filter-heavy read set stays far below bytes - reads * k); a batch that will be inserted by random access (too
+    // few records per table line for the streamed insert) is partitioned into the few 64 MB regions of round 1
+    poll_fill_probe(g);
+    const uint64_t bound = kmer_bound(g, n_bytes, d_offsets ? n_reads : 0);
+    const uint64_t booked = std::min<uint64_t>(bound, (uint64_t)((double)bound * g->acc_fill) + 1);
+    const bool dense = accumulate || g->pipeline || g->insert_mode == LASV_INSERT_STREAMED ||
+                       (g->insert_mode == LASV_INSERT_AUTO &&
+                        (double)booked >= g->streamed_min_per_line * ((double)g->table_bytes / LINE_BYTES));
+    if (want_binned(g, accumulate ? std::max(g->acc_limit, n_bytes) : n_bytes, &n_bins, dense)) {
       // Partitioned insert: group the batch's k-mers by 64 MB table region, then insert region by
       // region: streamed through shared memory when the batch is dense on the table's lines
       // (streamed_insert.cuh), at random inside one region at a time otherwise.
       lasv_graph::BinLeg &l = g->leg[(g->pipeline && !accumulate) ? (g->turn++ & 1) : 0];
       if (l.in_flight) CUDA_TRY(cudaStreamWaitEvent(st, l.inserted, 0));  // the insert that read this leg
-      const uint64_t bound = kmer_bound(g, n_bytes, d_offsets ? n_reads : 0);
-      uint64_t booked = bound;  // what the batch is expected to put into the stripes
       if (accumulate) {
-        poll_fill_probe(g);
-        booked = std::min<uint64_t>(bound, (uint64_t)((double)bound * g->acc_fill) + 1);
         // several partition launches fill the stripes, slot by slot; ONE insert when the next batch does not fit
         // (the slots are re-cut, while they are empty, when the fill estimate has moved since they were sized)
         const bool stale = g->acc_slots && fabs(g->acc_fill - g->acc_fill_sized) > 0.03 * g->acc_fill_sized;
@@ -1002,7 +1016,10 @@ int lasv_graph_load_reads_device(lasv_graph *g, const uint8_t *d_seq, const uint
         g->acc_slot_booked += booked;
         g->acc_bound_sum += bound;
       } else if (!g->pipeline) {
-        if (int e = insert_stripes(g, l.v, bound, 0, true, true, st)) return e;
+        // (the stripes are sized for the bound; the CHOICE of the insert goes by what they are expected to hold)
+        g->acc_bound_sum += bound;
+        if (int e = queue_fill_probe(g, st)) return e;
+        if (int e = insert_stripes(g, l.v, booked, 0, true, true, st)) return e;
       } else {
         // (random access only: the next batch's partition kernel may spill straight into the table while
         // this insert runs, which the streamed insert's staged copies would overwrite)
