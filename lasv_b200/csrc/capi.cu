@@ -477,6 +477,8 @@ int ensure_bins(lasv_graph *g, lasv_graph::BinLeg &l, uint64_t bound, uint32_t n
   l.v.bin_shift = (uint32_t)(g->L - log2_u32(n_bins));
   l.v.spill_ok = 1;
   l.v.src_shift = 0;
+  l.v.src_used = 0;
+  l.v.direct = 0;
   l.v.bins_per_src = n_bins;
   return LASV_OK;
 }
