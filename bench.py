@@ -4,21 +4,25 @@
 Workload (default `cfg4`, BASELINE.json configs[4]): THE WHOLE JOB -- the complete 30x build of the human-scale
 graph from an EMPTY table (k=53, L=24, W=250 -> 4.19 G slots x 24 B = 100.7 GB, hash-sharded over the N GPUs;
 310 M pairs of 2x150 bp reads drawn by a counter-based generator from a synthetic 3.1 Gbp genome; 53 G k-mer
-insertions).  The job is cut into K equal steps (`--steps`); the reads of a step are generated on the device and
-are resident in HBM before the step's timed region starts; a step partitions its batches (2^20 read pairs each)
-into the graph's region stripes and ends with the insert of what the stripes hold (N=1: streamed insert over
-the accumulated stripes, lasv_graph_set_accumulation; N>1: bin / exchange / insert per batch).  The W warm-up
-steps run the first step's reads into the table, which is then cleared (untimed).  The same read set is used for
-every N (strong scaling), so the graph's order-independent fingerprint must be equal at N = 1, 2, 4, 8.
+insertions; 296 batches of 2^20 pairs).  The job is cut into K equal steps (`--steps`); what is timed, back to back,
+are WINDOWS of consecutive batches whose reads were generated on the device and are resident in HBM before the
+window's timed region starts (as many batches as the pool holds, whatever K is).  A batch is partitioned into the
+graph's region stripes; the stripes accumulate batches and are inserted whenever they are full and at the end of
+the job (N=1: lasv_graph_set_accumulation, streamed insert; N>1: every rank bins A batches, ONE exchange and ONE
+insert on the owners per A batches, two buffer sets).  The W warm-up steps run the first window's reads into the
+table, which is then cleared (untimed).  The same read set is used for every N (strong scaling), so the graph's
+order-independent fingerprint must be equal at N = 1, 2, 4, 8 -- and equal to CFG4_FINGERPRINT.
 
-  value : k-mers/s of the whole job, reads already resident in HBM (CUDA events around every step, max over ranks)
+  value : k-mers/s of the whole job, reads already resident in HBM (CUDA events around every window, max over ranks)
   steady_state : the same after the job, on the finished table (99 % of the operations update an existing node)
-  e2e   : k-mers/s through the C-ABI host-buffer call (pinned host memory -> device copies and the statistics
-          read-back inside the timed region), on the finished table
+  e2e   : k-mers/s through the C-ABI host-buffer call (N=1: lasv_graph_load_reads_host_async through a staging ring;
+          pinned host memory -> device copies and the statistics read-back inside the timed region, which ends with
+          a flush and a device synchronisation), on the finished table
   roofline    : dominant kernel of the job, algorithmic bytes / CUDA-event kernel time over the measured HBM
                 copy bandwidth (MEASURED_PEAKS.json); the other kernels' shares next to it
-  parity      : a fixed small read set through the same (sharded) path into a second small graph, its sorted
-                records compared on rank 0 with the compiled reference's own table (oracle/_ref)
+  parity      : every 64th pair of the job's reads through the same (sharded, accumulating) path into a second small
+                graph, and at N=1 also into the job's own 2^24 x 250 table: every node compared on rank 0 with the
+                compiled reference's own table (oracle/_ref)
   cpu_baseline: the compiled reference (oracle/_ref/libref_63.so) timed on one host core on a bounded sample
                 of the same reads (N=1 only)
 
