@@ -312,3 +312,30 @@ def test_bgzf_input_is_inflated_block_parallel(tmp_path, monkeypatch):
     assert b"BGZF" in lib.lasv_last_error()
     (tmp_path / "cut.fq.gz").write_bytes(_bgzf(text)[: len(blob) // 2])   # the file ends inside a block
     assert lib.lasv_seqfile_parse_check(str(tmp_path / "cut.fq.gz").encode(), None, 1, 1 << 20, out, C.byref(used)) < 0
+
+
+def test_bench_job_geometry_is_the_same_read_set_at_every_n():
+    """bench.py: the cfg-4 job is the same set of batches at N = 1, 2, 4, 8 (a multiple of 8 batches), whatever K is;
+    a rank's batches of step s are consecutive, and all ranks together cover every batch exactly once."""
+    import argparse
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", Path(__file__).resolve().parents[1] / "bench.py")
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    w = synth.WORKLOADS["cfg4"]
+    totals = set()
+    for steps in (3, 7, 20):
+        for world in (1, 2, 4, 8):
+            args = argparse.Namespace(steps=steps, fraction=1.0, pairs_per_batch=1 << 20)
+            geo = bench.job_geometry(args, w, world)
+            totals.add(geo["batches"])
+            assert geo["batches"] % 8 == 0 and geo["per_rank"] * world == geo["batches"]
+            assert sum(geo["step_counts"]) == geo["per_rank"] and len(geo["step_counts"]) == steps
+            assert max(geo["step_counts"]) - min(geo["step_counts"]) <= 1
+            seen = set()
+            for rank in range(world):
+                for s_ in range(steps):
+                    for i in range(geo["step_counts"][s_]):
+                        seen.add((geo["step_prefix"][s_] + i) * world + rank)
+            assert seen == set(range(geo["batches"]))
+    assert totals == {296}
