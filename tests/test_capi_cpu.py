@@ -312,6 +312,26 @@ def test_bgzf_input_is_inflated_block_parallel(tmp_path, monkeypatch):
     assert b"BGZF" in lib.lasv_last_error()
     (tmp_path / "cut.fq.gz").write_bytes(_bgzf(text)[: len(blob) // 2])   # the file ends inside a block
     assert lib.lasv_seqfile_parse_check(str(tmp_path / "cut.fq.gz").encode(), None, 1, 1 << 20, out, C.byref(used)) < 0
+    # nothing but the end-of-file block: an empty file, not an error
+    (tmp_path / "empty.fq.gz").write_bytes(_bgzf(b""))
+    got, _ = _parse_check(tmp_path / "empty.fq.gz", None, 1)
+    assert got[0] == 0 and got[2] == 0
+    # another extra subfield in front of 'BC' (the gzip header allows any number of them)
+    import struct
+    import zlib
+
+    def member(chunk):
+        co = zlib.compressobj(6, zlib.DEFLATED, -15)
+        c = co.compress(chunk) + co.flush()
+        xtra = b"XY\x03\x00abc" + b"BC\x02\x00"
+        xlen = len(xtra) + 2
+        return (b"\x1f\x8b\x08\x04\x00\x00\x00\x00\x00\xff" + struct.pack("<H", xlen) + xtra +
+                struct.pack("<H", 12 + xlen + len(c) + 8 - 1) + c + struct.pack("<II", zlib.crc32(chunk) & 0xFFFFFFFF, len(chunk)))
+    small = text[:60000]
+    (tmp_path / "small.fq").write_bytes(small[: small.rfind(b"\n@") + 1])
+    body = (tmp_path / "small.fq").read_bytes()
+    (tmp_path / "xtra.fq.gz").write_bytes(member(body[:30000]) + member(body[30000:]) + member(b""))
+    assert _parse_check(tmp_path / "xtra.fq.gz", None, 1)[0] == _parse_check(tmp_path / "small.fq", None, 1)[0]
 
 
 def test_bench_job_geometry_is_the_same_read_set_at_every_n():
