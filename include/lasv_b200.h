@@ -588,6 +588,14 @@ int lasv_graph_insert_grouped_records_device(lasv_graph *g, const uint32_t *d_re
 int lasv_graph_group_records_device(lasv_graph *g, const uint32_t *d_records, uint64_t n_records,
                                     uint32_t buckets_per_group, uint32_t *d_sorted, uint64_t *d_group_offsets,
                                     void *cuda_stream);
+/* The parallel inflate of ordinary gzip files on its own (host only, no GPU): what the file loaders use for .gz
+ * input of 8 MB and more that is not BGZF (the reference: zlib's gzgetc, one byte at a time,
+ * libs/seq_file/seq_common.h:102-103).  The compressed stream is cut into chunks of chunk_kb KB; every thread but
+ * the first finds the start of a deflate block in its chunk and inflates from there without knowing the 32 KB of
+ * text before it (16-bit symbols; resolved when the chunk before it has met that start on the same bit, which also
+ * proves the start was one).  out4 = {bytes of text, CRC-32 of the text, chunks confirmed, chunks dropped}.
+ * LASV_ERR_IO: not a gzip file, or corrupt (a member's CRC-32 / length is checked like zlib does). */
+int lasv_seqfile_inflate_check(const char *path, int threads, uint64_t chunk_kb, uint64_t *out4);
 /* The file loaders' parser on its own (host only, no GPU): reads per file, bases and
  * an order-independent checksum of every (sequence, quality) pair, parsed with
  * `threads` parser threads per file exactly as the loaders do (large uncompressed
@@ -596,6 +604,12 @@ int lasv_graph_group_records_device(lasv_graph *g, const uint32_t *d_records, ui
  * checksum}.  Used by the tests to check the parallel parse against the sequential. */
 int lasv_seqfile_parse_check(const char *path1, const char *path2, int threads, uint64_t batch_bytes,
                              uint64_t *out4, int *producers_used);
+/* The same with the producers set up as the file loaders set them up for the device parse (fastq_parse.cu): batches
+ * of FASTQ TEXT -- slices of mapped plain files, windows of inflated BGZF / gzip text cut at record boundaries with
+ * the tail carried over.  The text batches are taken apart by the host parser here, so the producers' side of that
+ * path is checked without a GPU; *raw_batches (may be NULL) counts them. */
+int lasv_seqfile_parse_check_text(const char *path1, const char *path2, int threads, uint64_t batch_bytes,
+                                  uint64_t *out4, int *producers_used, uint64_t *raw_batches);
 
 /* Host-only: parse a whole sequence file with the loader's reader (FASTQ /
  * FASTA / plain, optionally gzipped; grammar of libs/seq_file) into the stream

@@ -110,7 +110,7 @@ EXPORTS = [
     "lasv_graph_record_buckets_device", "lasv_graph_bin_geometry", "lasv_graph_bin_reads_device",
     "lasv_graph_insert_bins_device", "lasv_graph_set_pipeline", "lasv_graph_flush",
     "lasv_graph_enable_kernel_timing", "lasv_graph_kernel_times", "lasv_graph_stats_async",
-    "lasv_ref_hash_table_load_ctx_records", "lasv_seqfile_parse_check",
+    "lasv_ref_hash_table_load_ctx_records", "lasv_seqfile_parse_check", "lasv_seqfile_inflate_check", "lasv_seqfile_parse_check_text",
     "lasv_graph_kernel_times_by_kind", "lasv_graph_set_insert_mode", "lasv_graph_insert_counts",
     "lasv_graph_set_accumulation", "lasv_graph_load_reads_host_async", "lasv_graph_set_staging",
     "lasv_graph_bin_reads_append_device",
@@ -234,6 +234,8 @@ def lib() -> C.CDLL:
     L.lasv_seqfile_to_streams.restype = C.c_longlong
     L.lasv_seqfile_to_streams.argtypes = [C.c_char_p, vp, vp, u64, vp, u64, C.POINTER(i32)]
     L.lasv_seqfile_parse_check.argtypes = [C.c_char_p, C.c_char_p, i32, u64, vp, C.POINTER(i32)]
+    L.lasv_seqfile_inflate_check.argtypes = [C.c_char_p, i32, u64, vp]
+    L.lasv_seqfile_parse_check_text.argtypes = [C.c_char_p, C.c_char_p, i32, u64, vp, C.POINTER(i32), vp]
     L.lasv_ref_hash_table_write_supernodes.argtypes = [C.POINTER(RefHashTable), C.c_char_p, i32, C.POINTER(SupernodeStats)]
     L.lasv_ref_hash_table_clean.argtypes = [C.POINTER(RefHashTable), i32, i32, C.POINTER(CleanStats)]
     L.lasv_graph_health_check.argtypes = [vp, C.POINTER(HealthStats)]

@@ -2706,7 +2706,7 @@ struct FileProducer {
     size_t raw_pos = 0;
     if (raw_bgzf) {
       if (slot[0]->cap_bytes < (20u << 20)) raw_bgzf = false;  // small batches (tests): the reader parses on the host
-      else reader.bgzf()->rewind();                            // (open() had a look at the first window)
+      else reader.windows()->rewind();                            // (open() had a look at the first window)
     }
     for (;;) {
       {
@@ -2726,7 +2726,7 @@ struct FileProducer {
         std::string berr;
         while (more && n + (9u << 20) <= cap) {  // (inflated straight into the pinned batch)
           size_t got = 0;
-          more = reader.bgzf()->next_into(b.seq + n, cap - n, &got, berr);
+          more = reader.windows()->next_into(b.seq + n, cap - n, &got, berr);
           if (!more) break;
           n += got;
         }
@@ -2930,7 +2930,7 @@ struct ParseJob {
           prod.emplace_back(std::move(heads[f]));
           const char *dp = getenv("LASV_B200_DEVICE_PARSE");
           FileProducer &hp = *prod.back();
-          if (raw_slices && (!dp || atoi(dp) != 0) && with_qual && hp.reader.type() == SeqReader::FASTQ && hp.reader.bgzf()) {
+          if (raw_slices && (!dp || atoi(dp) != 0) && with_qual && hp.reader.type() == SeqReader::FASTQ && hp.reader.windows()) {
             hp.raw_bgzf = true;  // (decided for good when the thread starts: the batches must hold a window)
           }
         }
@@ -3949,12 +3949,53 @@ int lasv_synth_reads_host(const lasv_synth_params *p, uint64_t first_read, uint6
   return LASV_OK;
 }
 
+/* The parallel gzip inflate on its own (no GPU; gz_parallel.h): the text of a gzip file inflated by `threads` threads
+ * in chunks of chunk_kb compressed KB.  out4 = {bytes of text, CRC-32 of the text, chunks whose guessed start was
+ * confirmed, chunks dropped}.  LASV_ERR_IO if the file is not gzip or is corrupt (lasv_last_error says which). */
+int lasv_seqfile_inflate_check(const char *path, int threads, uint64_t chunk_kb, uint64_t *out4) {
+  if (!path || !out4) return fail(LASV_ERR_ARG, "NULL argument");
+  PgzStream s;
+  if (!s.open(path, threads, 0, (size_t)chunk_kb << 10)) return fail(LASV_ERR_IO, "not a gzip file of at least 64 bytes: %s", path);
+  std::vector<unsigned char> w(9u << 20);
+  std::string err;
+  uint64_t total = 0;
+  uint32_t crc = (uint32_t)crc32(0L, Z_NULL, 0);
+  size_t got = 0;
+  while (s.next_into(w.data(), w.size(), &got, err)) {
+    crc = (uint32_t)crc32(crc, w.data(), (uInt)got);
+    total += got;
+  }
+  if (!err.empty()) return fail(LASV_ERR_IO, "%s [file: %s]", err.c_str(), path);
+  out4[0] = total;
+  out4[1] = crc;
+  out4[2] = s.chunks_confirmed();
+  out4[3] = s.chunks_dropped();
+  return LASV_OK;
+}
+
 /* The file loaders' parser on its own (no GPU): reads, bases and an order-independent checksum of all
  * (sequence, quality) pairs of one or two files, parsed with `threads` parser threads per file exactly as
  * the loaders do (threads <= 1: one sequential parser per file).  out4 = {reads of file 1, reads of file
  * 2, bases, checksum}; producers_used reports how many parser threads ran. */
+static int parse_check_impl(const char *path1, const char *path2, int threads, uint64_t batch_bytes, uint64_t *out4,
+                            int *producers_used, bool raw_slices, uint64_t *raw_batches);
+
 int lasv_seqfile_parse_check(const char *path1, const char *path2, int threads, uint64_t batch_bytes,
                              uint64_t *out4, int *producers_used) {
+  return parse_check_impl(path1, path2, threads, batch_bytes, out4, producers_used, false, nullptr);
+}
+
+/* The same with the producers set up as the file loaders set them up for the DEVICE parse: batches of FASTQ text
+ * (slices of mapped plain files, windows of inflated BGZF / gzip text cut at record boundaries, tails carried over).
+ * Here the text batches are taken apart by the host parser, so that the producers' side of that path can be checked
+ * without a GPU; *raw_batches counts them. */
+int lasv_seqfile_parse_check_text(const char *path1, const char *path2, int threads, uint64_t batch_bytes,
+                                  uint64_t *out4, int *producers_used, uint64_t *raw_batches) {
+  return parse_check_impl(path1, path2, threads, batch_bytes, out4, producers_used, true, raw_batches);
+}
+
+static int parse_check_impl(const char *path1, const char *path2, int threads, uint64_t batch_bytes, uint64_t *out4,
+                            int *producers_used, bool raw_slices, uint64_t *raw_batches) {
   if (!path1) return fail(LASV_ERR_ARG, "NULL argument");
   const bool checksum = out4 != nullptr;  // out4 == NULL: parse only (parser timing)
   if (batch_bytes < 1024) batch_bytes = 1024;
@@ -3973,11 +4014,30 @@ int lasv_seqfile_parse_check(const char *path1, const char *path2, int threads, 
                 [&]() -> HostBatch * {
                   batches.emplace_back(new PlainBatch(batch_bytes, batch_bytes / 16 + 16));
                   return batches.back().get();
-                }))
+                }, raw_slices))
     return fail(LASV_ERR_IO, "%s", job.err.c_str());
-  uint64_t bases = 0, sum = 0;
-  job.run([&](HostBatch &b, const FileProducer &fp) {
+  uint64_t bases = 0, sum = 0, n_raw = 0;
+  std::string raw_err;
+  job.run([&](HostBatch &b, FileProducer &fp) {
     const bool wq = fp.with_qual;
+    if (b.raw) {  // a batch of text: whole records (what fastq_parse.cu takes apart on the device)
+      n_raw++;
+      SeqReader mr;
+      mr.open_memory(b.seq, b.n_bytes, fp.reader.path());
+      std::string e2;
+      uint64_t n = 0;
+      while (mr.next(e2)) {
+        uint64_t h = 0xCBF29CE484222325ull;
+        for (unsigned char c : mr.seq()) h = (h ^ c) * 0x100000001B3ull;
+        if (wq) for (unsigned char c : mr.qual()) h = (h ^ c) * 0x100000001B3ull;
+        sum += mix64(h ^ (uint64_t)mr.seq().size());
+        bases += mr.seq().size();
+        n++;
+      }
+      if (!e2.empty() && raw_err.empty()) raw_err = e2;
+      fp.reads += n;
+      return;
+    }
     if (!checksum) { bases += b.n_bytes - b.n_reads; return; }
     for (uint64_t r = 0; r < b.n_reads; r++) {
       const uint64_t lo = b.offsets[r], hi = b.offsets[r + 1] - 1;  // without the separator
@@ -3990,6 +4050,8 @@ int lasv_seqfile_parse_check(const char *path1, const char *path2, int threads, 
   });
   for (auto &p : job.prod)
     if (!p->err.empty()) return fail(LASV_ERR_IO, "%s", p->err.c_str());
+  if (!raw_err.empty()) return fail(LASV_ERR_IO, "%s", raw_err.c_str());
+  if (raw_batches) *raw_batches = n_raw;
   if (out4) {
     out4[0] = job.reads_of_file(0);
     out4[1] = path2 ? job.reads_of_file(1) : 0;

@@ -159,7 +159,15 @@ bool SeqReader::open(const std::string &path, std::string &err) {
     int thr = (int)std::min(8u, std::max(2u, hw / 2));  // inflate threads of a BGZF file
     if (const char *e = getenv("LASV_B200_GZ_THREADS")) thr = atoi(e);
     std::unique_ptr<BgzfStream> b(new BgzfStream());
-    if (thr > 0 && b->open(path.c_str(), thr)) bgzf_ = std::move(b);
+    if (thr > 0 && b->open(path.c_str(), thr)) stream_ = std::move(b);
+    if (thr > 0 && !stream_) {
+      // ordinary gzip of some size: chunks of the compressed stream inflated by the same number of threads
+      size_t min_kb = 8192, chunk_kb = 1024;
+      if (const char *e = getenv("LASV_B200_PGZ_MIN_KB")) min_kb = (size_t)strtoull(e, nullptr, 10);
+      if (const char *e = getenv("LASV_B200_PGZ_CHUNK_KB")) chunk_kb = (size_t)strtoull(e, nullptr, 10);
+      std::unique_ptr<PgzStream> g(new PgzStream());
+      if (g->open(path.c_str(), thr, min_kb << 10, chunk_kb << 10)) stream_ = std::move(g);
+    }
   }
   gz_ = gzopen(path.c_str(), "r");  // (kept open in BGZF mode too: the reader's "is open" handle)
   if (!gz_) {
@@ -216,7 +224,7 @@ void SeqReader::seed(std::vector<unsigned char> &&text) {
 void SeqReader::close() {
   if (gz_) gzclose(gz_);
   gz_ = nullptr;
-  bgzf_.reset();
+  stream_.reset();
   type_ = UNKNOWN;
   memory_ = false;
 }
@@ -228,9 +236,9 @@ bool SeqReader::fill_() {
     pos_ = end_ = 0;
     return false;
   }
-  if (bgzf_) {  // the next window of blocks, inflated by several threads
+  if (stream_) {  // the next window of text, inflated by several threads
     std::string err;
-    if (!bgzf_->next(own_, err)) {
+    if (!stream_->next(own_, err)) {
       if (!err.empty()) io_error_ = err + " [file: " + path_ + "]";
       eof_ = true;
       pos_ = end_ = 0;
@@ -285,7 +293,8 @@ void SeqReader::read_line_(std::string *dst) {
 
 bool SeqReader::next(std::string &err) {
   const bool ok = next_record_(err);
-  if (!ok && err.empty() && !io_error_.empty()) err = io_error_;  // the compressed stream broke off: not a clean end of file
+  // the compressed stream broke off: not a clean end of file, and the cause of whatever the parser saw at the break
+  if (!ok && !io_error_.empty()) err = io_error_;
   return ok;
 }
 

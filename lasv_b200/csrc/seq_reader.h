@@ -13,27 +13,28 @@
 #include <vector>
 #include <zlib.h>
 
+#include "gz_parallel.h"
+
 namespace lasv {
 
 // Block-parallel inflate of BGZF files (the blocked gzip of bgzip / htslib that sequencing pipelines write:
 // a series of gzip members of <= 64 KB, each carrying its own compressed size in a 'BC' extra field, so the members
 // can be found without inflating anything).  The reference reads compressed input one byte at a time through
-// gzgetc (libs/seq_file/seq_common.h:102-103, seq_file.c:170); ordinary single-stream gzip cannot be split and
-// stays with zlib's gzread, one stream per file and thread.
-class BgzfStream {
+// gzgetc (libs/seq_file/seq_common.h:102-103, seq_file.c:170).  Ordinary single-stream gzip: PgzStream
+// (gz_parallel.h); small files and anything else zlib can read: zlib's gzread, one stream per file and thread.
+class BgzfStream : public TextStream {
  public:
-  ~BgzfStream();
+  ~BgzfStream() override;
   // maps the file; false (and nothing kept open) unless it starts with a BGZF block
   bool open(const char *path, int threads);
-  // inflates the next window of blocks (about 8 MB of text) into `out`; false at the end of the file or on error
-  // (then err is set)
-  bool next(std::vector<unsigned char> &out, std::string &err) { return next_impl(&out, nullptr, 0, nullptr, err); }
-  // the same straight into the caller's buffer (dst_cap >= 8 MB + 64 KB): *n receives the bytes written
-  bool next_into(unsigned char *dst, size_t dst_cap, size_t *n, std::string &err) { return next_impl(nullptr, dst, dst_cap, n, err); }
-  void rewind() { pos_ = 0; }
+  // (next / next_into: the next window of blocks, about 8 MB of text)
+  void rewind() override { pos_ = 0; }
+  const char *kind() const override { return "BGZF"; }
+
+ protected:
+  bool next_impl(std::vector<unsigned char> *out, unsigned char *dst, size_t dst_cap, size_t *n, std::string &err) override;
 
  private:
-  bool next_impl(std::vector<unsigned char> *out, unsigned char *dst, size_t dst_cap, size_t *n, std::string &err);
   int fd_ = -1;
   const unsigned char *data_ = nullptr;
   size_t size_ = 0, pos_ = 0;
@@ -64,10 +65,11 @@ class SeqReader {
   // starts at a record header): the parallel loader gives every parser thread its own slice.
   void open_memory(const unsigned char *data, size_t n, const std::string &path);
   // True if the file is stored uncompressed (gzopen reads it transparently either way).
-  bool is_plain_file() const { return !bgzf_ && gz_ && gzdirect(gz_) == 1; }
-  // BGZF input: the block stream (the loader pulls whole windows of text from it for the device parse), and the way
-  // back: continue parsing on the host from `text` (starts at a record header) followed by the stream's next windows
-  BgzfStream *bgzf() { return bgzf_.get(); }
+  bool is_plain_file() const { return !stream_ && gz_ && gzdirect(gz_) == 1; }
+  // BGZF or large gzip input: the stream of windows of text inflated by several threads (the loader pulls whole
+  // windows from it for the device parse), and the way back: continue parsing on the host from `text` (starts at a
+  // record header) followed by the stream's next windows
+  TextStream *windows() { return stream_.get(); }
   void seed(std::vector<unsigned char> &&text);
   void close();
   bool has_quality() const { return type_ == FASTQ; }
@@ -98,7 +100,7 @@ class SeqReader {
   void read_line_(std::string *dst);  // rest of the current line, chomped; dst may be null
 
   gzFile gz_ = nullptr;
-  std::unique_ptr<BgzfStream> bgzf_;    // BGZF input: windows of blocks inflated by several threads
+  std::unique_ptr<TextStream> stream_;  // BGZF / large gzip input: windows of text inflated by several threads
   std::string path_;
   Type type_ = UNKNOWN;
   std::vector<unsigned char> own_;      // gz mode: the refill buffer

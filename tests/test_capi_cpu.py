@@ -334,6 +334,165 @@ def test_bgzf_input_is_inflated_block_parallel(tmp_path, monkeypatch):
     assert _parse_check(tmp_path / "xtra.fq.gz", None, 1)[0] == _parse_check(tmp_path / "small.fq", None, 1)[0]
 
 
+def _fastq_text(n, seed, max_len=200):
+    rng = np.random.default_rng(seed)
+    lens = rng.integers(1, max_len, n)
+    out = []
+    for i, ln in enumerate(lens):
+        s = "".join(rng.choice(list("ACGTN"), ln))
+        q = "".join(rng.choice(list("@+IIIIIIFF#5&'"), ln))
+        out.append(f"@r{i} {i}/1\n{s}\n+\n{q}\n")
+    return "".join(out).encode()
+
+
+def _gz(data, level=6, flush_every=0, flush_mode=None, strategy=None):
+    import zlib
+    co = zlib.compressobj(level, zlib.DEFLATED, 31, 8, zlib.Z_DEFAULT_STRATEGY if strategy is None else strategy)
+    out = []
+    if flush_every:
+        for i in range(0, len(data), flush_every):
+            out.append(co.compress(data[i:i + flush_every]))
+            out.append(co.flush(flush_mode))
+    else:
+        out.append(co.compress(data))
+    out.append(co.flush())
+    return b"".join(out)
+
+
+def _inflate_check(path, threads, chunk_kb):
+    import ctypes as C
+    out = (C.c_uint64 * 4)()
+    rc = _capi.lib().lasv_seqfile_inflate_check(str(path).encode(), threads, chunk_kb, out)
+    return rc, tuple(int(x) for x in out)
+
+
+def test_ordinary_gzip_is_inflated_by_several_threads(tmp_path):
+    """Single-stream gzip (gz_parallel.cpp: PgzStream): threads that start in the middle of the deflate stream find
+    a block boundary, inflate into symbols without the 32 KB before them, and are resolved once the chunk in front
+    has met their start.  The text is byte for byte zlib's -- for any number of threads and any chunk size, across
+    compression levels and strategies, flush points (stored empty blocks), fixed-code and stored blocks, several
+    members, trailing garbage, and data that is not text (nothing is confirmed there: one thread carries on)."""
+    import os
+    import zlib
+    text = _fastq_text(60_000, 21)
+    cases = {
+        "l1": _gz(text, 1), "l6": _gz(text, 6), "l9": _gz(text, 9),
+        "sync": _gz(text, 6, 70_000, zlib.Z_SYNC_FLUSH), "full": _gz(text, 6, 50_001, zlib.Z_FULL_FLUSH),
+        "fixed": _gz(text[:2_000_000], 6, strategy=zlib.Z_FIXED), "huffman": _gz(text[:2_000_000], 6, strategy=zlib.Z_HUFFMAN_ONLY),
+        "stored": _gz(text[:1_000_000], 0),
+        "members": _gz(text[:3_000_001], 6) + _gz(text[3_000_001:5_000_000], 2) + _gz(b"") + _gz(text[5_000_000:], 9),
+        "tail": _gz(text, 6) + b"\0" * 777,
+        "binary": _gz(os.urandom(700_000) + text[:2_000_000] + os.urandom(300_000), 6),
+        "zeros": _gz(bytes(40_000_000), 6),
+    }
+    plain = {"fixed": text[:2_000_000], "huffman": text[:2_000_000], "stored": text[:1_000_000], "zeros": bytes(40_000_000)}
+    for name, blob in cases.items():
+        (tmp_path / f"{name}.gz").write_bytes(blob)
+        want = plain.get(name)
+        if want is None:
+            want = zlib.decompressobj(31)
+            # (all members, as gzread does; the trailing zeros are not one)
+            data, rest = b"", blob
+            while rest[:2] == b"\x1f\x8b":
+                d = zlib.decompressobj(31)
+                data += d.decompress(rest)
+                rest = d.unused_data
+            want = data
+        for threads, chunk_kb in ((4, 256), (8, 64), (3, 1024), (1, 512), (5, 4)):
+            rc, got = _inflate_check(tmp_path / f"{name}.gz", threads, chunk_kb)
+            assert rc == 0, (name, threads, chunk_kb, _capi.lib().lasv_last_error())
+            assert got[0] == len(want) and got[1] == zlib.crc32(want), (name, threads, chunk_kb, got)
+            if name in ("l1", "l6", "l9", "sync", "full", "members", "tail") and (threads, chunk_kb) in ((4, 256), (8, 64)):
+                assert got[2] >= 4, (name, threads, chunk_kb, got)      # the chunks really started in mid-stream
+    # a broken file is an error, never a short or a wrong text
+    good = cases["l6"]
+    bad = {}
+    b = bytearray(good); b[len(b) // 2] ^= 0x10; bad["flip"] = bytes(b)
+    b = bytearray(good); b[-6] ^= 1; bad["crc"] = bytes(b)
+    b = bytearray(good); b[-2] ^= 1; bad["isize"] = bytes(b)
+    bad["cut"] = good[: len(good) // 2]
+    bad["cut_trailer"] = good[:-3]
+    bad["second_header"] = good + b"\x1f\x8b\x07" + b"\0" * 20
+    for name, blob in bad.items():
+        (tmp_path / f"bad_{name}.gz").write_bytes(blob)
+        for threads, chunk_kb in ((4, 256), (1, 512), (8, 16)):
+            rc, _ = _inflate_check(tmp_path / f"bad_{name}.gz", threads, chunk_kb)
+            assert rc < 0 and b"gzip" in _capi.lib().lasv_last_error(), (name, threads, chunk_kb)
+
+
+def test_file_loaders_read_ordinary_gzip_through_the_parallel_inflate(tmp_path, monkeypatch):
+    """The reader behind the file loaders takes .gz input of some size through PgzStream (LASV_B200_PGZ_MIN_KB,
+    default 8 MB; LASV_B200_PGZ_CHUNK_KB) and smaller files, or everything with LASV_B200_GZ_THREADS=0, through
+    zlib: the same reads, bases and checksum as the plain file either way, and a truncated file is an error."""
+    text = _fastq_text(40_000, 22)
+    (tmp_path / "a.fq").write_bytes(text)
+    (tmp_path / "a.fq.gz").write_bytes(_gz(text, 6))
+    ref, _ = _parse_check(tmp_path / "a.fq", None, 1)
+    assert ref[0] == 40_000
+    for env in ({"LASV_B200_PGZ_MIN_KB": "0", "LASV_B200_PGZ_CHUNK_KB": "128", "LASV_B200_GZ_THREADS": "4"},
+                {"LASV_B200_PGZ_MIN_KB": "0", "LASV_B200_PGZ_CHUNK_KB": "16", "LASV_B200_GZ_THREADS": "7"},
+                {"LASV_B200_PGZ_MIN_KB": "0", "LASV_B200_GZ_THREADS": "1"},
+                {"LASV_B200_GZ_THREADS": "0"}, {}):
+        for k in ("LASV_B200_PGZ_MIN_KB", "LASV_B200_PGZ_CHUNK_KB", "LASV_B200_GZ_THREADS"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        got, used = _parse_check(tmp_path / "a.fq.gz", None, 4)
+        assert used == 1 and got == ref, (env, got, ref)
+    monkeypatch.setenv("LASV_B200_PGZ_MIN_KB", "0")
+    monkeypatch.setenv("LASV_B200_GZ_THREADS", "4")
+    blob = (tmp_path / "a.fq.gz").read_bytes()
+    (tmp_path / "cut.fq.gz").write_bytes(blob[: len(blob) // 2])
+    import ctypes as C
+    out = (C.c_uint64 * 4)()
+    used = C.c_int(0)
+    lib = _capi.lib()
+    assert lib.lasv_seqfile_parse_check(str(tmp_path / "cut.fq.gz").encode(), None, 1, 1 << 20, out, C.byref(used)) < 0
+    assert b"gzip" in lib.lasv_last_error()
+
+
+def test_text_batches_for_the_device_parse_hold_whole_records(tmp_path, monkeypatch):
+    """The producers of the device parse (capi.cu: FileProducer in raw mode) hand over batches of FASTQ text: slices of
+    a mapped plain file, windows of BGZF or gzip text cut at the last record boundary with the tail carried into the
+    next batch.  Parsed on the host here (lasv_seqfile_parse_check_text): the same reads, bases and checksum as the
+    sequential parse of the plain file, and a multi-line record late in a compressed file hands the rest of it to
+    the host parser without losing or repeating a read."""
+    import ctypes as C
+    text = _fastq_text(260_000, 23, max_len=160)                 # 44 MB of text: two batches of 24 MB
+    (tmp_path / "a.fq").write_bytes(text)
+    (tmp_path / "a.bgzf.fq.gz").write_bytes(_bgzf(text))
+    (tmp_path / "a.gzip.fq.gz").write_bytes(_gz(text, 1))
+    lines = text.split(b"\n")
+    i = 4 * 200_000
+    lines[i + 1: i + 2] = [lines[i + 1][:1], lines[i + 1][1:]] if len(lines[i + 1]) > 1 else [lines[i + 1], b""]
+    wrapped = b"\n".join(lines)
+    (tmp_path / "w.gzip.fq.gz").write_bytes(_gz(wrapped, 1))
+    ref, _ = _parse_check(tmp_path / "a.fq", None, 1)
+    assert ref[0] == 260_000
+    monkeypatch.setenv("LASV_B200_PGZ_MIN_KB", "0")
+    monkeypatch.setenv("LASV_B200_PGZ_CHUNK_KB", "512")
+    monkeypatch.setenv("LASV_B200_GZ_THREADS", "4")
+    lib = _capi.lib()
+
+    def text_check(path, threads):
+        out = (C.c_uint64 * 4)()
+        used = C.c_int(0)
+        raw = C.c_uint64(0)
+        rc = lib.lasv_seqfile_parse_check_text(str(path).encode(), None, threads, 24 << 20, out, C.byref(used), C.byref(raw))
+        assert rc == 0, lib.lasv_last_error()
+        return tuple(int(x) for x in out), raw.value
+    for f, min_raw in (("a.fq", 2), ("a.bgzf.fq.gz", 2), ("a.gzip.fq.gz", 2), ("w.gzip.fq.gz", 1)):
+        got, raw = text_check(tmp_path / f, 2)
+        assert got == ref and raw >= min_raw, (f, got, ref, raw)
+    # two mates through the same path
+    got, raw = text_check(tmp_path / "a.gzip.fq.gz", 2)
+    out = (C.c_uint64 * 4)()
+    used = C.c_int(0)
+    assert lib.lasv_seqfile_parse_check_text(str(tmp_path / "a.gzip.fq.gz").encode(), str(tmp_path / "a.bgzf.fq.gz").encode(),
+                                             2, 24 << 20, out, C.byref(used), None) == 0
+    assert out[0] == out[1] == ref[0] and out[2] == 2 * ref[2]
+
+
 def test_bench_job_geometry_is_the_same_read_set_at_every_n():
     """bench.py: the cfg-4 job is the same set of batches at N = 1, 2, 4, 8 (a multiple of 8 batches), whatever K is;
     a rank's batches of step s are consecutive, and all ranks together cover every batch exactly once."""

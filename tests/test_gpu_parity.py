@@ -149,11 +149,17 @@ def test_file_loaders_parse_fastq_text_on_the_device(batch_bytes, spoil, tmp_pat
     assert results["1"][1] > results["0"][1]                     # the parse kernels ran
 
 
-def test_bgzf_fastq_goes_to_the_device_parse(tmp_path, monkeypatch):
-    """BGZF-compressed FASTQ: several threads inflate windows of blocks (BgzfStream), the text goes to the device parse
-    like the slices of plain files (cut at the last record boundary of a window, the tail carried over).  Same graph and
-    statistics as the uncompressed files; a multi-line record hands the rest of that file to the host parser."""
-    from tests.test_capi_cpu import _bgzf
+@pytest.mark.parametrize("kind", ["bgzf", "gzip"])
+def test_bgzf_fastq_goes_to_the_device_parse(kind, tmp_path, monkeypatch):
+    """Compressed FASTQ: several threads inflate windows of text -- blocks of a BGZF file (BgzfStream), chunks of an
+    ordinary gzip stream (PgzStream, gz_parallel.cpp) -- and the text goes to the device parse like the slices of plain
+    files (cut at the last record boundary of a window, the tail carried over).  Same graph and statistics as the
+    uncompressed files; a multi-line record hands the rest of that file to the host parser."""
+    from tests.test_capi_cpu import _bgzf, _gz
+    if kind == "gzip":
+        monkeypatch.setenv("LASV_B200_PGZ_MIN_KB", "0")          # (the files are ~5 MB compressed)
+        monkeypatch.setenv("LASV_B200_PGZ_CHUNK_KB", "512")
+        _bgzf = lambda data: _gz(data, 1)                        # noqa: E731
     name = "synth_cfg0_k53"
     meta = util.case_meta(name)
     seq, qual, _ = util.case_streams(name)
