@@ -31,7 +31,14 @@ if "--bgzf" in sys.argv:   # blocked gzip (bgzip / htslib): inflated block-paral
         f.with_suffix(".fq.gz").write_bytes(bgzf(f.read_bytes()))
     text_size = os.path.getsize(f1) + os.path.getsize(f2)
     f1, f2 = f1.with_suffix(".fq.gz"), f2.with_suffix(".fq.gz")
+if "--gzip" in sys.argv:   # ordinary single-stream gzip (gzip -1): chunks of the stream inflated by several threads
+    import subprocess
+    procs = [subprocess.Popen(["gzip", "-1", "-k", "-f", str(f)]) for f in (f1, f2)]
+    assert all(p.wait() == 0 for p in procs)
+    text_size = os.path.getsize(f1) + os.path.getsize(f2)
+    f1, f2 = Path(str(f1) + ".gz"), Path(str(f2) + ".gz")
 size = os.path.getsize(f1) + os.path.getsize(f2)
+compressed = "--bgzf" in sys.argv or "--gzip" in sys.argv
 with DBGraph(w.kmer_size, L, 100) as g:
     for rep in range(2):
         g.clear()
@@ -40,4 +47,8 @@ with DBGraph(w.kmer_size, L, 100) as g:
         dt = time.perf_counter() - t
     print(json.dumps({"what": "lasv_graph_load_pe_files, uncompressed FASTQ pair", "pairs": n_pairs, "fastq_bytes": size,
                       "seconds": dt, "fastq_MBps": size / dt / 1e6, "kmers_per_s": st["kmers_inserted"] / dt,
-                      "bgzf": "--bgzf" in sys.argv, "text_MBps": (text_size if "--bgzf" in sys.argv else size) / dt / 1e6}))
+                      "bgzf": "--bgzf" in sys.argv, "gzip": "--gzip" in sys.argv,
+                      "text_MBps": (text_size if compressed else size) / dt / 1e6,
+                      "device_parse": int(os.environ.get("LASV_B200_DEVICE_PARSE", "1")),
+                      "gz_threads": os.environ.get("LASV_B200_GZ_THREADS", "default"),
+                      "pgz_chunk_kb": os.environ.get("LASV_B200_PGZ_CHUNK_KB", "default"), "host_cores": os.cpu_count()}))
