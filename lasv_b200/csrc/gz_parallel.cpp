@@ -119,10 +119,11 @@ int build_table(const uint8_t *lens, int n, int pb, uint32_t *table, bool is_dis
     if (!l) continue;
     const uint32_t nb = (uint32_t)(l > pb ? l - pb : l);
     uint32_t e;
-    if (is_dist) e = i < 30 ? entry(T_LIT, nb, DIST_EXTRA[i], DIST_BASE[i]) : entry(T_BAD, nb, 0, 0);
+    // (lengths and distances: bits = code + extra bits, consumed at once)
+    if (is_dist) e = i < 30 ? entry(T_LIT, nb + DIST_EXTRA[i], DIST_EXTRA[i], DIST_BASE[i]) : entry(T_BAD, nb, 0, 0);
     else if (i < 256) e = entry(T_LIT, nb, 0, (uint32_t)i);
     else if (i == 256) e = entry(T_EOB, nb, 0, 0);
-    else if (i < 286) e = entry(T_LEN, nb, LEN_EXTRA[i - 257], LEN_BASE[i - 257]);
+    else if (i < 286) e = entry(T_LEN, nb + LEN_EXTRA[i - 257], LEN_EXTRA[i - 257], LEN_BASE[i - 257]);
     else e = entry(T_BAD, nb, 0, 0);
     if (l <= pb) {
       for (int j = rev[i]; j < primary; j += 1 << l) table[j] = e;
@@ -249,44 +250,72 @@ struct Inflater {
     uint16_t *o = out;
     uint16_t *const lim = mem + cap - 300;
     const uint16_t *const omin = out_min;
+    constexpr uint32_t LM = (1u << LIT_PB) - 1, DM = (1u << DIST_PB) - 1;
     int rc;
+#define LASV_GZ_REFILL()                                  \
+  if (!CAREFUL) {                                         \
+    if ((size_t)(end - q) < 8) {                          \
+      rc = IR_CAREFUL;                                    \
+      break;                                              \
+    }                                                     \
+    b |= load64(q) << c;                                  \
+    q += (63 - c) >> 3;                                   \
+    c |= 56;                                              \
+  } else {                                                \
+    while (c <= 56) {                                     \
+      if (q < end) b |= (uint64_t)*q++ << c;              \
+      else over++;                                        \
+      c += 8;                                             \
+    }                                                     \
+    if (over > 8) {                                       \
+      rc = IR_TRUNC;                                      \
+      break;                                              \
+    }                                                     \
+  }
+    // e: the entry of the bits at the head of b, looked up ahead (a refill only adds bits above the ones it was
+    // looked up with, so it stays valid across one)
+    uint32_t e = lit[b & LM];
     for (;;) {
       if (o >= lim) {
         rc = IR_SPACE;
         break;
       }
       if (c < 48) {
-        if (!CAREFUL) {
-          if ((size_t)(end - q) < 8) {
-            rc = IR_CAREFUL;
-            break;
-          }
-          b |= load64(q) << c;
-          q += (63 - c) >> 3;
-          c |= 56;
-        } else {
-          while (c <= 56) {
-            if (q < end) b |= (uint64_t)*q++ << c;
-            else over++;
-            c += 8;
-          }
-          if (over > 8) {
-            rc = IR_TRUNC;
-            break;
+        LASV_GZ_REFILL();
+        e = lit[b & LM];  // (c may have been 0: nothing looked up yet)
+      }
+      // up to three literals of the first level on one refill (at most 11 bits each; a match needs 48)
+      if ((e & 0xf00u) == (T_LIT << 8)) {
+        b >>= e_bits(e);
+        c -= (int)e_bits(e);
+        *o++ = (uint16_t)e_value(e);
+        e = lit[b & LM];
+        if ((e & 0xf00u) == (T_LIT << 8)) {
+          b >>= e_bits(e);
+          c -= (int)e_bits(e);
+          *o++ = (uint16_t)e_value(e);
+          e = lit[b & LM];
+          if ((e & 0xf00u) == (T_LIT << 8)) {
+            b >>= e_bits(e);
+            c -= (int)e_bits(e);
+            *o++ = (uint16_t)e_value(e);
+            e = lit[b & LM];
           }
         }
+        continue;
       }
-      uint32_t e = lit[b & ((1u << LIT_PB) - 1)];
       if (e_type(e) == T_SUB) {
         b >>= LIT_PB;
         c -= LIT_PB;
         e = lit[e_value(e) + (uint32_t)(b & ((1u << e_extra(e)) - 1))];
       }
+      uint64_t sv = b;
       b >>= e_bits(e);
       c -= (int)e_bits(e);
       const uint32_t t = e_type(e);
-      if (t == T_LIT) {
+      if (t == T_LIT) {  // (a literal with a long code)
         *o++ = (uint16_t)e_value(e);
+        e = lit[b & LM];
         continue;
       }
       if (t == T_EOB) {
@@ -297,35 +326,49 @@ struct Inflater {
         rc = IR_ERR;
         break;
       }
-      uint32_t len = e_value(e) + (uint32_t)(b & ((1u << e_extra(e)) - 1));
-      b >>= e_extra(e);
-      c -= (int)e_extra(e);
-      uint32_t d = dist[b & ((1u << DIST_PB) - 1)];
+      // (entries of lengths and distances: bits = code + extra bits)
+      const uint32_t len = e_value(e) + (uint32_t)((sv >> (e_bits(e) - e_extra(e))) & ((1u << e_extra(e)) - 1));
+      uint32_t d = dist[b & DM];
       if (e_type(d) == T_SUB) {
         b >>= DIST_PB;
         c -= DIST_PB;
         d = dist[e_value(d) + (uint32_t)(b & ((1u << e_extra(d)) - 1))];
       }
+      sv = b;
       b >>= e_bits(d);
       c -= (int)e_bits(d);
       if (e_type(d) != T_LIT) {
         rc = IR_ERR;
         break;
       }
-      const uint32_t dd = e_value(d) + (uint32_t)(b & ((1u << e_extra(d)) - 1));
-      b >>= e_extra(d);
-      c -= (int)e_extra(d);
+      const uint32_t dd = e_value(d) + (uint32_t)((sv >> (e_bits(d) - e_extra(d))) & ((1u << e_extra(d)) - 1));
+      e = lit[b & LM];  // the next symbol's entry, on its way while the match is copied
       if ((size_t)(o - omin) < dd) {  // "invalid distance too far back"
         rc = IR_ERR;
         break;
       }
       const uint16_t *s = o - dd;
       uint16_t *const oe = o + len;
-      if (dd >= 4) {
-        do {  // four symbols at a time (the buffer has room behind the match)
+      if (dd >= 16) {  // sixteen symbols at once cover most matches (the buffer has room behind the match)
+        memcpy(o, s, 32);
+        if (len > 16) {
+          do {
+            o += 16;
+            s += 16;
+            memcpy(o, s, 32);
+          } while (o + 16 < oe);
+        }
+      } else if (dd >= 4) {
+        do {
           memcpy(o, s, 8);
           o += 4;
           s += 4;
+        } while (o < oe);
+      } else if (dd == 1) {  // a run of one symbol
+        const uint64_t v = (uint64_t)s[0] * 0x0001000100010001ull;
+        do {
+          memcpy(o, &v, 8);
+          o += 4;
         } while (o < oe);
       } else {
         do *o++ = *s++;
@@ -333,6 +376,7 @@ struct Inflater {
       }
       o = oe;
     }
+#undef LASV_GZ_REFILL
     buf = b;
     cnt = c;
     p = q;
