@@ -3962,7 +3962,7 @@ int lasv_seqfile_inflate_check(const char *path, int threads, uint64_t chunk_kb,
   uint32_t crc = (uint32_t)crc32(0L, Z_NULL, 0);
   size_t got = 0;
   while (s.next_into(w.data(), w.size(), &got, err)) {
-    crc = (uint32_t)crc32(crc, w.data(), (uInt)got);
+    crc = (uint32_t)crc32(crc, w.data(), (uInt)got);  // (zlib's own: the check does not lean on fast_crc32)
     total += got;
   }
   if (!err.empty()) return fail(LASV_ERR_IO, "%s [file: %s]", err.c_str(), path);

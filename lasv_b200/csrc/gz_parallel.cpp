@@ -11,7 +11,9 @@
 #include <unistd.h>
 #include <zlib.h>
 
-#if defined(__SSE2__)
+#if defined(__x86_64__)
+#include <immintrin.h>
+#elif defined(__SSE2__)
 #include <emmintrin.h>
 #endif
 
@@ -20,6 +22,92 @@
 #include <thread>
 
 namespace lasv {
+
+// ------------------------------------------------------------------ CRC-32 by carry-less multiplication
+// (gzip's CRC-32 folded 64 bytes at a time with PCLMULQDQ: Gopal et al., "Fast CRC computation for generic polynomials
+// using PCLMULQDQ instruction", Intel 2009; the constants are x^n mod P for the reflected polynomial 0x1DB710641.
+// Checked against zlib's crc32 when first used; zlib's is the fallback.)
+#if defined(__x86_64__)
+namespace {
+__attribute__((target("pclmul,sse4.1")))
+uint32_t crc32_clmul_core(uint32_t crc, const unsigned char *buf, size_t len) {  // len >= 64, multiple of 16; raw (not inverted) state
+  const __m128i k12 = _mm_set_epi64x(0x00000001c6e41596ll, 0x0000000154442bd4ll);
+  const __m128i k34 = _mm_set_epi64x(0x00000000ccaa009ell, 0x00000001751997d0ll);
+  const __m128i k5 = _mm_set_epi64x(0, 0x0000000163cd6124ll);
+  const __m128i poly = _mm_set_epi64x(0x00000001F7011641ll, 0x00000001DB710641ll);
+  const __m128i mask32 = _mm_set_epi32(0, 0, 0, -1);
+  __m128i x1 = _mm_loadu_si128((const __m128i *)buf), x2 = _mm_loadu_si128((const __m128i *)(buf + 16));
+  __m128i x3 = _mm_loadu_si128((const __m128i *)(buf + 32)), x4 = _mm_loadu_si128((const __m128i *)(buf + 48));
+  x1 = _mm_xor_si128(x1, _mm_cvtsi32_si128((int)crc));
+  buf += 64; len -= 64;
+  while (len >= 64) {
+    __m128i t1 = _mm_clmulepi64_si128(x1, k12, 0x00), t2 = _mm_clmulepi64_si128(x2, k12, 0x00);
+    __m128i t3 = _mm_clmulepi64_si128(x3, k12, 0x00), t4 = _mm_clmulepi64_si128(x4, k12, 0x00);
+    x1 = _mm_clmulepi64_si128(x1, k12, 0x11); x2 = _mm_clmulepi64_si128(x2, k12, 0x11);
+    x3 = _mm_clmulepi64_si128(x3, k12, 0x11); x4 = _mm_clmulepi64_si128(x4, k12, 0x11);
+    x1 = _mm_xor_si128(_mm_xor_si128(x1, t1), _mm_loadu_si128((const __m128i *)buf));
+    x2 = _mm_xor_si128(_mm_xor_si128(x2, t2), _mm_loadu_si128((const __m128i *)(buf + 16)));
+    x3 = _mm_xor_si128(_mm_xor_si128(x3, t3), _mm_loadu_si128((const __m128i *)(buf + 32)));
+    x4 = _mm_xor_si128(_mm_xor_si128(x4, t4), _mm_loadu_si128((const __m128i *)(buf + 48)));
+    buf += 64; len -= 64;
+  }
+  __m128i t = _mm_clmulepi64_si128(x1, k34, 0x00); x1 = _mm_clmulepi64_si128(x1, k34, 0x11); x1 = _mm_xor_si128(_mm_xor_si128(x1, t), x2);
+  t = _mm_clmulepi64_si128(x1, k34, 0x00); x1 = _mm_clmulepi64_si128(x1, k34, 0x11); x1 = _mm_xor_si128(_mm_xor_si128(x1, t), x3);
+  t = _mm_clmulepi64_si128(x1, k34, 0x00); x1 = _mm_clmulepi64_si128(x1, k34, 0x11); x1 = _mm_xor_si128(_mm_xor_si128(x1, t), x4);
+  while (len >= 16) {
+    t = _mm_clmulepi64_si128(x1, k34, 0x00); x1 = _mm_clmulepi64_si128(x1, k34, 0x11);
+    x1 = _mm_xor_si128(_mm_xor_si128(x1, t), _mm_loadu_si128((const __m128i *)buf));
+    buf += 16; len -= 16;
+  }
+  // 128 -> 64
+  x2 = _mm_clmulepi64_si128(x1, k34, 0x10);
+  x1 = _mm_xor_si128(_mm_srli_si128(x1, 8), x2);
+  // 64 -> 32
+  x2 = _mm_srli_si128(x1, 4);
+  x1 = _mm_and_si128(x1, mask32);
+  x1 = _mm_clmulepi64_si128(x1, k5, 0x00);
+  x1 = _mm_xor_si128(x1, x2);
+  // Barrett
+  x2 = x1;
+  x1 = _mm_and_si128(x1, mask32);
+  x1 = _mm_clmulepi64_si128(x1, poly, 0x10);
+  x1 = _mm_and_si128(x1, mask32);
+  x1 = _mm_clmulepi64_si128(x1, poly, 0x00);
+  x1 = _mm_xor_si128(x1, x2);
+  return (uint32_t)_mm_extract_epi32(x1, 1);
+}
+
+bool clmul_usable() {
+  if (!__builtin_cpu_supports("pclmul") || !__builtin_cpu_supports("sse4.1")) return false;
+  unsigned char t[211];
+  for (int i = 0; i < 211; i++) t[i] = (unsigned char)(i * 37 + 11);
+  for (size_t n : {64u, 80u, 208u}) {
+    const uint32_t want = (uint32_t)crc32(0x1234567u, t, (uInt)n);
+    if (~crc32_clmul_core(~0x1234567u, t, n) != want) return false;
+  }
+  return true;
+}
+}  // namespace
+#endif
+
+uint32_t fast_crc32(uint32_t crc, const unsigned char *buf, size_t len) {
+#if defined(__x86_64__)
+  static const bool usable = clmul_usable();
+  if (usable && len >= 64) {
+    const size_t n = len & ~(size_t)15;
+    crc = ~crc32_clmul_core(~crc, buf, n);
+    buf += n;
+    len -= n;
+  }
+#endif
+  while (len) {  // (zlib takes 32-bit lengths)
+    const size_t n = std::min<size_t>(len, 1u << 30);
+    crc = (uint32_t)crc32(crc, buf, (uInt)n);
+    buf += n;
+    len -= n;
+  }
+  return crc;
+}
 
 namespace {
 
@@ -156,37 +244,39 @@ long gzip_header_len(const uint8_t *d, size_t n) {
   return pos > n ? -1 : (long)pos;
 }
 
-// One deflate decoder: bits from a mapped file, 16-bit symbols out (see gz_parallel.h), block by block.
-struct Inflater {
+// One deflate decoder: bits from a mapped file, block by block; out come 16-bit symbols (see gz_parallel.h) where the
+// text in front is not known, plain bytes where it is (the members of a BGZF file).
+template <typename SYM>
+struct InflaterT {
   const uint8_t *base = nullptr, *end = nullptr, *p = nullptr;
   uint64_t buf = 0;
   int cnt = 0;        // valid bits in buf
   uint32_t over = 0;  // zero bytes fed behind the end of the file
-  uint16_t *mem = nullptr;  // [CTX symbols in front of the chunk][its output ...]
+  SYM *mem = nullptr;  // [CTX symbols in front of the chunk][its output ...]
   size_t cap = 0;
-  uint16_t *out = nullptr, *out_min = nullptr;  // next symbol; oldest symbol a distance may reach
+  SYM *out = nullptr, *out_min = nullptr;  // next symbol; oldest symbol a distance may reach
   size_t limit = 0;                             // symbols of output after which decoding fails (0: none)
   uint32_t lit[LIT_SIZE], dist[DIST_SIZE];
 
-  ~Inflater() { free(mem); }
-  Inflater() {}
-  Inflater(const Inflater &) = delete;
-  Inflater &operator=(const Inflater &) = delete;
+  ~InflaterT() { free(mem); }
+  InflaterT() {}
+  InflaterT(const InflaterT &) = delete;
+  InflaterT &operator=(const InflaterT &) = delete;
 
   bool alloc(size_t symbols) {
     cap = CTX + symbols + 1024;
-    mem = (uint16_t *)malloc(cap * sizeof(uint16_t));
+    mem = (SYM *)malloc(cap * sizeof(SYM));
     out = out_min = mem ? mem + CTX : nullptr;
     return mem != nullptr;
   }
   // a buffer used before (its pages are there already), and the way back
-  void adopt(uint16_t *m, size_t c) {
+  void adopt(SYM *m, size_t c) {
     mem = m;
     cap = c;
     out = out_min = mem + CTX;
   }
-  uint16_t *release(size_t *c) {
-    uint16_t *m = mem;
+  SYM *release(size_t *c) {
+    SYM *m = mem;
     *c = cap;
     mem = nullptr;
     cap = 0;
@@ -194,7 +284,7 @@ struct Inflater {
   }
   bool grow() {
     const size_t o = (size_t)(out - mem), m = (size_t)(out_min - mem);
-    uint16_t *n = (uint16_t *)realloc(mem, cap * 2 * sizeof(uint16_t));
+    SYM *n = (SYM *)realloc(mem, cap * 2 * sizeof(SYM));
     if (!n) return false;
     mem = n;
     cap *= 2;
@@ -247,9 +337,10 @@ struct Inflater {
     uint64_t b = buf;
     int c = cnt;
     const uint8_t *q = p;
-    uint16_t *o = out;
-    uint16_t *const lim = mem + cap - 300;
-    const uint16_t *const omin = out_min;
+    SYM *o = out;
+    SYM *const lim = mem + cap - 300;
+    const SYM *const omin = out_min;
+    constexpr uint32_t WIDE = 32 / sizeof(SYM), NARROW = 8 / sizeof(SYM);  // symbols per 32-byte / 8-byte copy
     constexpr uint32_t LM = (1u << LIT_PB) - 1, DM = (1u << DIST_PB) - 1;
     int rc;
 #define LASV_GZ_REFILL()                                  \
@@ -288,17 +379,17 @@ struct Inflater {
       if ((e & 0xf00u) == (T_LIT << 8)) {
         b >>= e_bits(e);
         c -= (int)e_bits(e);
-        *o++ = (uint16_t)e_value(e);
+        *o++ = (SYM)e_value(e);
         e = lit[b & LM];
         if ((e & 0xf00u) == (T_LIT << 8)) {
           b >>= e_bits(e);
           c -= (int)e_bits(e);
-          *o++ = (uint16_t)e_value(e);
+          *o++ = (SYM)e_value(e);
           e = lit[b & LM];
           if ((e & 0xf00u) == (T_LIT << 8)) {
             b >>= e_bits(e);
             c -= (int)e_bits(e);
-            *o++ = (uint16_t)e_value(e);
+            *o++ = (SYM)e_value(e);
             e = lit[b & LM];
           }
         }
@@ -314,7 +405,7 @@ struct Inflater {
       c -= (int)e_bits(e);
       const uint32_t t = e_type(e);
       if (t == T_LIT) {  // (a literal with a long code)
-        *o++ = (uint16_t)e_value(e);
+        *o++ = (SYM)e_value(e);
         e = lit[b & LM];
         continue;
       }
@@ -347,28 +438,28 @@ struct Inflater {
         rc = IR_ERR;
         break;
       }
-      const uint16_t *s = o - dd;
-      uint16_t *const oe = o + len;
-      if (dd >= 16) {  // sixteen symbols at once cover most matches (the buffer has room behind the match)
+      const SYM *s = o - dd;
+      SYM *const oe = o + len;
+      if (dd >= WIDE) {  // 32 bytes at once cover most matches (the buffer has room behind the match)
         memcpy(o, s, 32);
-        if (len > 16) {
+        if (len > WIDE) {
           do {
-            o += 16;
-            s += 16;
+            o += WIDE;
+            s += WIDE;
             memcpy(o, s, 32);
-          } while (o + 16 < oe);
+          } while (o + WIDE < oe);
         }
-      } else if (dd >= 4) {
+      } else if (dd >= NARROW) {
         do {
           memcpy(o, s, 8);
-          o += 4;
-          s += 4;
+          o += NARROW;
+          s += NARROW;
         } while (o < oe);
       } else if (dd == 1) {  // a run of one symbol
-        const uint64_t v = (uint64_t)s[0] * 0x0001000100010001ull;
+        const uint64_t v = (uint64_t)s[0] * (sizeof(SYM) == 2 ? 0x0001000100010001ull : 0x0101010101010101ull);
         do {
           memcpy(o, &v, 8);
-          o += 4;
+          o += NARROW;
         } while (o < oe);
       } else {
         do *o++ = *s++;
@@ -386,8 +477,8 @@ struct Inflater {
 
   int block_body() {
     for (;;) {
-      int rc = run<false>();
-      if (rc == IR_CAREFUL) rc = run<true>();
+      int rc = this->template run<false>();
+      if (rc == IR_CAREFUL) rc = this->template run<true>();
       if (rc != IR_SPACE) return rc;
       if (limit && produced() > limit) return IR_ERR;
       if (!grow()) return IR_ERR;
@@ -408,7 +499,7 @@ struct Inflater {
         if (!grow()) return IR_ERR;
       uint32_t left = len;
       while (left && cnt >= 8) {
-        *out++ = (uint16_t)(buf & 0xff);
+        *out++ = (SYM)(buf & 0xff);
         buf >>= 8;
         cnt -= 8;
         left--;
@@ -496,6 +587,8 @@ struct Inflater {
   }
 };
 
+typedef InflaterT<uint16_t> Inflater;
+
 struct TextTable {
   bool ok[256];
   TextTable() {
@@ -528,6 +621,30 @@ struct MemberEnd {
 };
 
 }  // namespace
+
+struct MemberInflater::Impl {
+  InflaterT<uint8_t> in;
+};
+
+MemberInflater::MemberInflater() : impl_(new Impl()) {}
+MemberInflater::~MemberInflater() {}
+
+bool MemberInflater::inflate(const unsigned char *src, size_t n, unsigned char *dst, size_t expect) {
+  InflaterT<uint8_t> &in = impl_->in;
+  // (inflated into a scratch buffer that stays in the cache and copied: the decoder writes up to 31 bytes behind a
+  // match, which must not touch the neighbouring block's text another thread is writing)
+  if (!in.mem && !in.alloc(std::max<size_t>(expect, 65536) + 4096)) return false;
+  in.start(src, src + n, 0);
+  in.out = in.out_min = in.mem + CTX;
+  in.limit = expect;
+  bool fin = false;
+  while (!fin) {
+    if (in.block(&fin) != IR_OK || in.produced() > expect) return false;
+  }
+  if (in.produced() != expect || in.past_end()) return false;
+  memcpy(dst, in.mem + CTX, expect);
+  return true;
+}
 
 struct PgzStream::Chunk {
   Inflater inf;
@@ -884,7 +1001,7 @@ bool PgzStream::next_impl(std::vector<unsigned char> *outv, unsigned char *dst, 
         const uint16_t *s = c.inf.mem + CTX + pc.off;
         unsigned char *d = dst + pc.at;
         translate(s, d, pc.n, c.lut);
-        pc.crc = (uint32_t)crc32(crc32(0L, Z_NULL, 0), d, (uInt)pc.n);
+        pc.crc = fast_crc32(0, d, pc.n);
       }
     };
     {

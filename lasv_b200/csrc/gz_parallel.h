@@ -28,6 +28,9 @@
 
 namespace lasv {
 
+// gzip's CRC-32, continued from `crc` like zlib's crc32() (carry-less multiplication where the CPU has it)
+uint32_t fast_crc32(uint32_t crc, const unsigned char *buf, size_t len);
+
 class TextStream {
  public:
   virtual ~TextStream() {}
@@ -42,6 +45,20 @@ class TextStream {
 
  protected:
   virtual bool next_impl(std::vector<unsigned char> *out, unsigned char *dst, size_t dst_cap, size_t *n, std::string &err) = 0;
+};
+
+// A raw deflate stream whose text depends on nothing in front of it (the body of a gzip member, e.g. a BGZF block),
+// inflated to bytes by this library's decoder.  One per thread.
+class MemberInflater {
+ public:
+  MemberInflater();
+  ~MemberInflater();
+  // src[0, n) must inflate to exactly `expect` bytes, which are written to dst; false if it does not (corrupt data)
+  bool inflate(const unsigned char *src, size_t n, unsigned char *dst, size_t expect);
+
+ private:
+  struct Impl;
+  std::unique_ptr<Impl> impl_;
 };
 
 class PgzStream : public TextStream {

@@ -441,6 +441,18 @@ def test_file_loaders_read_ordinary_gzip_through_the_parallel_inflate(tmp_path, 
         assert used == 1 and got == ref, (env, got, ref)
     monkeypatch.setenv("LASV_B200_PGZ_MIN_KB", "0")
     monkeypatch.setenv("LASV_B200_GZ_THREADS", "4")
+    # FASTA (multi-line records) and one-read-per-line text take the same way: the type is told from the first window
+    rng = np.random.default_rng(24)
+    fa = "".join(f">c{i} len\n" + "\n".join("".join(rng.choice(list("ACGTNacgt"), 60)) for _ in range(int(rng.integers(1, 40)))) + "\n"
+                 for i in range(600)).encode()
+    (tmp_path / "c.fa").write_bytes(fa)
+    (tmp_path / "c.fa.gz").write_bytes(_gz(fa, 6))
+    plain_reads = b"".join(bytes(rng.choice(list(b"ACGT"), int(rng.integers(0, 90))).astype(np.uint8)) + b"\n" for _ in range(20_000))
+    (tmp_path / "p.txt").write_bytes(plain_reads)
+    (tmp_path / "p.txt.gz").write_bytes(_gz(plain_reads, 6))
+    monkeypatch.setenv("LASV_B200_PGZ_CHUNK_KB", "64")
+    for a, b in (("c.fa", "c.fa.gz"), ("p.txt", "p.txt.gz")):
+        assert _parse_check(tmp_path / b, None, 1)[0] == _parse_check(tmp_path / a, None, 1)[0], a
     blob = (tmp_path / "a.fq.gz").read_bytes()
     (tmp_path / "cut.fq.gz").write_bytes(blob[: len(blob) // 2])
     import ctypes as C
