@@ -4009,6 +4009,7 @@ static int parse_check_impl(const char *path1, const char *path2, int threads, u
     }
   };
   std::vector<std::unique_ptr<PlainBatch>> batches;
+  const auto t_open0 = std::chrono::steady_clock::now();
   ParseJob job;
   if (!job.open({{std::string(path1), std::string(path2 ? path2 : "")}}, threads < 1 ? 1 : threads, 1u << 20,
                 [&]() -> HostBatch * {
@@ -4018,10 +4019,17 @@ static int parse_check_impl(const char *path1, const char *path2, int threads, u
     return fail(LASV_ERR_IO, "%s", job.err.c_str());
   uint64_t bases = 0, sum = 0, n_raw = 0;
   std::string raw_err;
+  const auto t_run0 = std::chrono::steady_clock::now();
+  if (getenv("LASV_B200_TRACE_PARSE"))
+    fprintf(stderr, "parse_check: open %.3f s\n", std::chrono::duration<double>(t_run0 - t_open0).count());
   job.run([&](HostBatch &b, FileProducer &fp) {
     const bool wq = fp.with_qual;
     if (b.raw) {  // a batch of text: whole records (what fastq_parse.cu takes apart on the device)
       n_raw++;
+      if (!checksum) {  // (producer timing)
+        bases += b.n_bytes;
+        return;
+      }
       SeqReader mr;
       mr.open_memory(b.seq, b.n_bytes, fp.reader.path());
       std::string e2;
@@ -4048,6 +4056,8 @@ static int parse_check_impl(const char *path1, const char *path2, int threads, u
       bases += hi - lo;
     }
   });
+  if (getenv("LASV_B200_TRACE_PARSE"))
+    fprintf(stderr, "parse_check: run %.3f s\n", std::chrono::duration<double>(std::chrono::steady_clock::now() - t_run0).count());
   for (auto &p : job.prod)
     if (!p->err.empty()) return fail(LASV_ERR_IO, "%s", p->err.c_str());
   if (!raw_err.empty()) return fail(LASV_ERR_IO, "%s", raw_err.c_str());

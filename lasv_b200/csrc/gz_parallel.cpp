@@ -709,6 +709,7 @@ bool PgzStream::open(const char *path, int threads, size_t min_bytes, size_t chu
 }
 
 void PgzStream::reset() {
+  for (auto &c : queue_) recycle(c);  // (the buffers stay for the next round)
   queue_.clear();
   q_chunk_ = q_off_ = q_end_ = 0;
   cur_bit_ = (uint64_t)gzip_header_len(data_, size_) * 8;

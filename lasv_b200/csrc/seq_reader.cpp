@@ -165,15 +165,25 @@ bool SeqReader::open(const std::string &path, std::string &err) {
     err = "Couldn't open sequence file '" + path + "'";
     return false;
   }
-  gzbuffer(gz_, 1u << 20);
-  own_.resize(4u << 20);
+  gzbuffer(gz_, stream_ ? 8192u : 1u << 20);
+  own_.resize(stream_ ? 0 : 4u << 20);
   buf_ = own_.data();
   memory_ = false;
   pos_ = end_ = 0;
   eof_ = false;
   n_reads_ = 0;
-  // type sniffing on the first byte (seq_file.c:215-259)
-  const int c = getc_();
+  skip_first_ = false;
+  // type sniffing on the first byte (seq_file.c:215-259).  With a stream of windows the byte comes from zlib (a few
+  // KB inflated) rather than from the stream, whose first window is a round of work of all its threads; the marker is
+  // then skipped when the first window arrives.
+  int c;
+  if (stream_) {
+    unsigned char first = 0;
+    c = gzread(gz_, &first, 1) == 1 ? (int)first : -1;
+    skip_first_ = (c == '>' || c == '@');
+  } else {
+    c = getc_();
+  }
   if (c == -1) {
     type_ = PLAIN;  // empty file: no reads
   } else if (c == '>') {
@@ -184,7 +194,7 @@ bool SeqReader::open(const std::string &path, std::string &err) {
     at_record_start_ = true;
   } else {
     type_ = PLAIN;
-    pos_--;  // unget
+    if (!stream_) pos_--;  // unget
   }
   return true;
 }
@@ -206,6 +216,7 @@ void SeqReader::seed(std::vector<unsigned char> &&text) {
   own_ = std::move(text);
   buf_ = own_.data();
   memory_ = false;
+  skip_first_ = false;
   pos_ = 0;
   end_ = own_.size();
   eof_ = false;
@@ -236,7 +247,8 @@ bool SeqReader::fill_() {
       return false;
     }
     buf_ = own_.data();
-    pos_ = 0;
+    pos_ = skip_first_ ? 1 : 0;  // (the record marker open() has seen)
+    skip_first_ = false;
     end_ = own_.size();
     return true;
   }

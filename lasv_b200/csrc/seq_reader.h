@@ -110,6 +110,7 @@ class SeqReader {
   bool eof_ = false;
   std::string io_error_;                // a read error of the compressed stream (reported by next())
   bool at_record_start_ = false;  // header marker already consumed (seq_file.c: read_line_start)
+  bool skip_first_ = false;       // stream mode: ... by open(), from zlib; the first window still holds it
   std::string seq_, qual_;
   uint64_t n_reads_ = 0;
 };
