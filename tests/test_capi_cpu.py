@@ -398,7 +398,7 @@ def test_ordinary_gzip_is_inflated_by_several_threads(tmp_path):
                 data += d.decompress(rest)
                 rest = d.unused_data
             want = data
-        for threads, chunk_kb in ((4, 256), (8, 64), (3, 1024), (1, 512), (5, 4)):
+        for threads, chunk_kb in ((4, 256), (8, 64), (3, 1024), (1, 512), (5, 4), (16, 32)):
             rc, got = _inflate_check(tmp_path / f"{name}.gz", threads, chunk_kb)
             assert rc == 0, (name, threads, chunk_kb, _capi.lib().lasv_last_error())
             assert got[0] == len(want) and got[1] == zlib.crc32(want), (name, threads, chunk_kb, got)
